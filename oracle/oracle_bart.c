@@ -1,0 +1,641 @@
+/*
+ * oracle/oracle_bart.c -- TEST INFRASTRUCTURE (CPU oracle), not product code.
+ *
+ * Single-threaded fp64 restatement of the dbarts sum-of-trees sampler as it is
+ * configured and called by stan4bart:
+ *   call sites   /root/reference/src/init.cpp:215-228 (init), :255-257 (setOffset,
+ *                setSigma), :261 (sampleTreesFromPrior), :273/:824
+ *                (runSamplerWithResults), :289/:845 (storeLatents), :398 (predict),
+ *                :577 (getTrees)
+ *   config       /root/reference/R/stan4bart_fit.R:437-479 (1 chain, 1 thread,
+ *                n.samples = 1, n.thin = skip.bart, cgm/normal/fixed(1) priors,
+ *                node.scale .5 | 3)
+ *   results      /root/reference/src/bart_util.hpp:14-64
+ * dbarts itself (>= 0.9-34) is an un-vendored dependency; the algorithm below
+ * follows SURVEY.md App. B / section 8 rows a3-a10 (upstream files named there:
+ * bartFit.cpp, tree.cpp, node.cpp, birthDeathRule.cpp, changeRule.cpp,
+ * swapRule.cpp, likelihood.cpp).  PARITY UNPINNED against real dbarts.
+ *
+ * Data model here is deliberately dbarts-like (per-node index partitions,
+ * per-tree fits, two-pass mean/variance) and therefore independent of the CUDA
+ * product's (full residual + on-the-fly tree traversal + one-pass sums).
+ */
+#include "s4b_oracle.h"
+#include "s4b_rng.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+typedef struct Node {
+  struct Node *parent, *left, *right;
+  int var, cut;
+  int* obs; int nobs;
+  double avg;
+  double mu;
+} Node;
+
+typedef struct Tree {
+  Node* top;
+  int* indices;
+} Tree;
+
+struct or_bart {
+  s4b_bart_config cfg;
+  int n, p, nt, T;
+  double *y, *x, *x_test, *offset;
+  int* ncuts; double** cuts;
+  uint8_t *xt, *xt_test;           /* [p][n], [p][nt] */
+  double *yresc, *treeY, *totalFits, *treeFits, *currFits, *totalTestFits, *currTestFits;
+  Tree* trees;
+  double sigma;                    /* scaled units */
+  double smin, smax, srange;
+  double leaf_prec;
+  s4b_rng rng;
+  uint32_t latent_epoch;
+  double* trace; size_t trace_cap, trace_len;
+};
+
+/* ---------- nodes ---------- */
+static Node* node_new(Node* parent, int* obs, int nobs) {
+  Node* nd = (Node*) calloc(1, sizeof(Node));
+  nd->parent = parent; nd->obs = obs; nd->nobs = nobs; nd->var = -1; nd->cut = -1;
+  return nd;
+}
+static void node_free(Node* nd) { if (!nd) return; node_free(nd->left); node_free(nd->right); free(nd); }
+static int is_bottom(const Node* nd) { return nd->left == NULL; }
+static int node_depth(const Node* nd) { int d = 0; while (nd->parent) { ++d; nd = nd->parent; } return d; }
+static int64_t node_heap(const Node* nd) {
+  if (!nd->parent) return 1;
+  int64_t ph = node_heap(nd->parent);
+  return nd == nd->parent->left ? 2 * ph : 2 * ph + 1;
+}
+static void orphan_children(Node* nd) { node_free(nd->left); node_free(nd->right); nd->left = nd->right = NULL; nd->var = nd->cut = -1; }
+
+static void partition_children(const or_bart* f, Node* nd) {
+  /* in-place partition of nd->obs: left iff xt[var][i] <= cut */
+  const uint8_t* col = f->xt + (size_t) nd->var * f->n;
+  int lo = 0, hi = nd->nobs - 1;
+  int* a = nd->obs;
+  while (lo <= hi) {
+    if (col[a[lo]] <= nd->cut) ++lo;
+    else { int tmp = a[lo]; a[lo] = a[hi]; a[hi] = tmp; --hi; }
+  }
+  nd->left->obs = a; nd->left->nobs = lo;
+  nd->right->obs = a + lo; nd->right->nobs = nd->nobs - lo;
+}
+static void repartition(const or_bart* f, Node* nd) {
+  if (is_bottom(nd)) return;
+  partition_children(f, nd);
+  repartition(f, nd->left); repartition(f, nd->right);
+}
+static void node_split(const or_bart* f, Node* nd, int var, int cut) {
+  nd->var = var; nd->cut = cut;
+  nd->left = node_new(nd, NULL, 0); nd->right = node_new(nd, NULL, 0);
+  partition_children(f, nd);
+}
+
+static void fill_bottom(Node* nd, Node** out, int* k) { if (is_bottom(nd)) out[(*k)++] = nd; else { fill_bottom(nd->left, out, k); fill_bottom(nd->right, out, k); } }
+static void fill_not_bottom(Node* nd, Node** out, int* k) { if (is_bottom(nd)) return; out[(*k)++] = nd; fill_not_bottom(nd->left, out, k); fill_not_bottom(nd->right, out, k); }
+static void fill_nog(Node* nd, Node** out, int* k) {
+  if (is_bottom(nd)) return;
+  if (is_bottom(nd->left) && is_bottom(nd->right)) { out[(*k)++] = nd; return; }
+  fill_nog(nd->left, out, k); fill_nog(nd->right, out, k);
+}
+static void fill_swappable(Node* nd, Node** out, int* k) {
+  if (is_bottom(nd)) return;
+  if (!is_bottom(nd->left) || !is_bottom(nd->right)) out[(*k)++] = nd;
+  fill_swappable(nd->left, out, k); fill_swappable(nd->right, out, k);
+}
+static int count_bottom(const Node* nd) { return is_bottom(nd) ? 1 : count_bottom(nd->left) + count_bottom(nd->right); }
+static int count_nodes(const Node* nd) { return is_bottom(nd) ? 1 : 1 + count_nodes(nd->left) + count_nodes(nd->right); }
+
+/* ---------- rule availability (data independent) ---------- */
+static void split_interval(const or_bart* f, const Node* nd, int var, int* lo, int* hi) {
+  *lo = 0; *hi = f->ncuts[var] - 1;
+  const Node* child = nd; const Node* par = nd->parent;
+  while (par) {
+    if (par->var == var) {
+      if (child == par->left) { if (par->cut - 1 < *hi) *hi = par->cut - 1; }
+      else                    { if (par->cut + 1 > *lo) *lo = par->cut + 1; }
+    }
+    child = par; par = par->parent;
+  }
+}
+static int num_vars_available(const or_bart* f, const Node* nd) {
+  int c = 0;
+  for (int j = 0; j < f->p; ++j) { int lo, hi; split_interval(f, nd, j, &lo, &hi); if (hi >= lo) ++c; }
+  return c;
+}
+static int ith_available_var(const or_bart* f, const Node* nd, int ith) {
+  for (int j = 0; j < f->p; ++j) { int lo, hi; split_interval(f, nd, j, &lo, &hi); if (hi >= lo) { if (ith == 0) return j; --ith; } }
+  return -1;
+}
+static double growth_prob(const or_bart* f, const Node* nd) {
+  if (num_vars_available(f, nd) == 0) return 0.0;
+  return f->cfg.base / pow(1.0 + (double) node_depth(nd), f->cfg.power);
+}
+static int is_birthable(const or_bart* f, const Node* nd, int num_leaves) {
+  return num_vars_available(f, nd) > 0 && node_depth(nd) < S4B_MAX_DEPTH && num_leaves < S4B_MAX_LEAVES;
+}
+
+/* ---------- likelihood ---------- */
+static void node_set_average(Node* nd, const double* ty) {
+  double s = 0.0;
+  for (int i = 0; i < nd->nobs; ++i) s += ty[nd->obs[i]];
+  nd->avg = nd->nobs > 0 ? s / (double) nd->nobs : 0.0;
+}
+static void set_averages(Node* nd, const double* ty) {
+  if (is_bottom(nd)) { node_set_average(nd, ty); return; }
+  set_averages(nd->left, ty); set_averages(nd->right, ty);
+}
+static double node_sumsq_dev(const Node* nd, const double* ty) {
+  double s = 0.0;
+  for (int i = 0; i < nd->nobs; ++i) { double d = ty[nd->obs[i]] - nd->avg; s += d * d; }
+  return s;
+}
+static double node_loglik(const or_bart* f, Node* nd, const double* ty) {
+  if (nd->nobs == 0) return 0.0;
+  node_set_average(nd, ty);
+  double sigsq = f->sigma * f->sigma;
+  double a = f->leaf_prec;
+  double dp = (double) nd->nobs / sigsq;
+  double r = 0.5 * log(a / (a + dp));
+  r -= 0.5 * node_sumsq_dev(nd, ty) / sigsq;
+  r -= 0.5 * ((a * nd->avg) * (dp * nd->avg)) / (a + dp);
+  return r;
+}
+static double branch_loglik(const or_bart* f, Node* nd, const double* ty) {
+  if (is_bottom(nd)) return node_loglik(f, nd, ty);
+  return branch_loglik(f, nd->left, ty) + branch_loglik(f, nd->right, ty);
+}
+static int branch_min_obs(const Node* nd) {
+  if (is_bottom(nd)) return nd->nobs;
+  int a = branch_min_obs(nd->left), b = branch_min_obs(nd->right);
+  return a < b ? a : b;
+}
+/* log prior of the branch below nd: growth / no-growth + rule probabilities */
+static double branch_log_prior(const or_bart* f, const Node* nd) {
+  double pg = growth_prob(f, nd);
+  if (is_bottom(nd)) return log(1.0 - pg);
+  int lo, hi; split_interval(f, nd, nd->var, &lo, &hi);
+  double r = log(pg) - log((double) num_vars_available(f, nd)) - log((double) (hi - lo + 1));
+  return r + branch_log_prior(f, nd->left) + branch_log_prior(f, nd->right);
+}
+
+/* ---------- tree cloning for change / swap ---------- */
+static Node* clone_rec(const Node* src, Node* parent, int* newbase, const int* oldbase) {
+  Node* nd = node_new(parent, newbase + (src->obs - oldbase), src->nobs);
+  nd->var = src->var; nd->cut = src->cut; nd->avg = src->avg; nd->mu = src->mu;
+  if (!is_bottom(src)) { nd->left = clone_rec(src->left, nd, newbase, oldbase); nd->right = clone_rec(src->right, nd, newbase, oldbase); }
+  return nd;
+}
+static void tree_clone(const or_bart* f, const Tree* src, Tree* dst) {
+  dst->indices = (int*) malloc(sizeof(int) * (size_t) (f->n > 0 ? f->n : 1));
+  memcpy(dst->indices, src->indices, sizeof(int) * (size_t) f->n);
+  dst->top = clone_rec(src->top, NULL, dst->indices, src->indices);
+}
+static void tree_release(Tree* t) { node_free(t->top); free(t->indices); t->top = NULL; t->indices = NULL; }
+static Node* find_by_heap(Node* top, int64_t heap) {
+  /* walk the bits of heap below the leading one */
+  int nb = 0; for (int64_t h = heap; h > 1; h >>= 1) ++nb;
+  Node* nd = top;
+  for (int b = nb - 1; b >= 0 && nd; --b) nd = ((heap >> b) & 1) ? nd->right : nd->left;
+  return nd;
+}
+
+/* ---------- trace ---------- */
+static double* trace_begin(or_bart* f) {
+  static double scratch[S4B_TRACE_LEN];
+  double* r = (f->trace && f->trace_len < f->trace_cap) ? f->trace + f->trace_len * S4B_TRACE_LEN : scratch;
+  for (int i = 0; i < S4B_TRACE_LEN; ++i) r[i] = 0.0;
+  r[0] = -1.0; r[5] = -1.0;
+  return r;
+}
+
+/* ---------- MH steps ---------- */
+static void draw_rule(or_bart* f, const Node* nd, int* var, int* cut) {
+  int navail = num_vars_available(f, nd);
+  int ith = (int) s4b_rng_index(&f->rng, (size_t) navail);
+  *var = ith_available_var(f, nd, ith);
+  int lo, hi; split_interval(f, nd, *var, &lo, &hi);
+  *cut = lo + (int) s4b_rng_index(&f->rng, (size_t) (hi - lo + 1));
+}
+
+static double prob_birth_step(const or_bart* f, const Tree* t) {
+  Node* bottoms[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(t->top, bottoms, &nb);
+  int any = 0; for (int i = 0; i < nb; ++i) if (is_birthable(f, bottoms[i], nb)) { any = 1; break; }
+  if (!any) return 0.0;
+  if (is_bottom(t->top)) return 1.0;
+  return f->cfg.birth_prob;
+}
+
+static void birth_or_death(or_bart* f, Tree* t, const double* ty, double* tr) {
+  double p_birth = prob_birth_step(f, t);
+  Node* bottoms[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(t->top, bottoms, &nb);
+  if (s4b_rng_uniform(&f->rng) < p_birth) {
+    /* birth */
+    Node* cand[S4B_MAX_LEAVES + 1]; int nc = 0;
+    for (int i = 0; i < nb; ++i) if (is_birthable(f, bottoms[i], nb)) cand[nc++] = bottoms[i];
+    Node* nd = cand[s4b_rng_index(&f->rng, (size_t) nc)];
+    double p_select = 1.0 / (double) nc;
+    double pg_parent = growth_prob(f, nd);
+    double old_ll = node_loglik(f, nd, ty);
+    int var, cut; draw_rule(f, nd, &var, &cut);
+    node_split(f, nd, var, cut);
+    double pg_l = growth_prob(f, nd->left), pg_r = growth_prob(f, nd->right);
+    double new_ll = node_loglik(f, nd->left, ty) + node_loglik(f, nd->right, ty);
+    double p_death_new = 1.0 - prob_birth_step(f, t);
+    Node* nogs[S4B_MAX_LEAVES + 1]; int nn = 0; fill_nog(t->top, nogs, &nn);
+    double p_select_death = 1.0 / (double) nn;
+    double prior_ratio = pg_parent * (1.0 - pg_l) * (1.0 - pg_r) / (1.0 - pg_parent);
+    double trans_ratio = (p_death_new * p_select_death) / (p_birth * p_select);
+    double ratio = prior_ratio * trans_ratio * exp(new_ll - old_ll);
+    if (nd->left->nobs < f->cfg.min_obs || nd->right->nobs < f->cfg.min_obs) ratio = 0.0;
+    double u = s4b_rng_uniform(&f->rng);
+    int accept = u < ratio;
+    tr[0] = 0; tr[1] = (double) node_heap(nd); tr[2] = var; tr[3] = cut; tr[4] = accept; tr[5] = ratio;
+    tr[6] = old_ll; tr[7] = new_ll; tr[9] = nd->left->nobs; tr[10] = nd->right->nobs;
+    if (!accept) orphan_children(nd);
+  } else {
+    /* death */
+    Node* nogs[S4B_MAX_LEAVES + 1]; int nn = 0; fill_nog(t->top, nogs, &nn);
+    Node* nd = nogs[s4b_rng_index(&f->rng, (size_t) nn)];
+    double p_select = 1.0 / (double) nn;
+    double pg_parent = growth_prob(f, nd);
+    double pg_l = growth_prob(f, nd->left), pg_r = growth_prob(f, nd->right);
+    double old_ll = node_loglik(f, nd->left, ty) + node_loglik(f, nd->right, ty);
+    double new_ll = node_loglik(f, nd, ty);
+    /* the tree as it would be after the death */
+    int nb_new = nb - 1;
+    int n_birthable_new = 0;
+    for (int i = 0; i < nb; ++i) if (bottoms[i] != nd->left && bottoms[i] != nd->right && is_birthable(f, bottoms[i], nb_new)) ++n_birthable_new;
+    /* the collapsed node has a valid rule, hence an available variable */
+    if (node_depth(nd) < S4B_MAX_DEPTH && nb_new < S4B_MAX_LEAVES) ++n_birthable_new;
+    double p_birth_new = (nd == t->top) ? 1.0 : f->cfg.birth_prob;
+    if (n_birthable_new == 0) p_birth_new = 0.0;
+    double p_select_birth = n_birthable_new > 0 ? 1.0 / (double) n_birthable_new : 0.0;
+    double p_death = 1.0 - p_birth;
+    double prior_ratio = (1.0 - pg_parent) / (pg_parent * (1.0 - pg_l) * (1.0 - pg_r));
+    double trans_ratio = (p_birth_new * p_select_birth) / (p_death * p_select);
+    double ratio = prior_ratio * trans_ratio * exp(new_ll - old_ll);
+    double u = s4b_rng_uniform(&f->rng);
+    int accept = u < ratio;
+    tr[0] = 1; tr[1] = (double) node_heap(nd); tr[2] = nd->var; tr[3] = nd->cut; tr[4] = accept; tr[5] = ratio;
+    tr[6] = old_ll; tr[7] = new_ll; tr[9] = nd->left->nobs; tr[10] = nd->right->nobs;
+    if (accept) orphan_children(nd);
+  }
+}
+
+static void desc_constraints(const Node* nd, int var, int* maxcut, int* mincut) {
+  /* max / min cut used on `var` among internal nodes of the branch */
+  if (is_bottom(nd)) return;
+  if (nd->var == var) { if (nd->cut > *maxcut) *maxcut = nd->cut; if (nd->cut < *mincut) *mincut = nd->cut; }
+  desc_constraints(nd->left, var, maxcut, mincut); desc_constraints(nd->right, var, maxcut, mincut);
+}
+
+static void finish_change_like(or_bart* f, Tree* t, Tree* saved, Node* nd, int64_t heap, const double* ty, double* tr) {
+  /* nd is in the modified tree t, saved holds the original */
+  Node* old_nd = find_by_heap(saved->top, heap);
+  double old_ll = branch_loglik(f, old_nd, ty);
+  double old_lp = branch_log_prior(f, old_nd);
+  repartition(f, nd);
+  double new_ll = branch_loglik(f, nd, ty);
+  double new_lp = branch_log_prior(f, nd);
+  double ratio = exp((new_lp - old_lp) + (new_ll - old_ll));
+  if (branch_min_obs(nd) < f->cfg.min_obs) ratio = 0.0;
+  double u = s4b_rng_uniform(&f->rng);
+  int accept = u < ratio;
+  tr[4] = accept; tr[5] = ratio; tr[6] = old_ll; tr[7] = new_ll;
+  Node* bl[S4B_MAX_LEAVES + 1]; int k = 0; fill_bottom(nd, bl, &k);
+  tr[9] = bl[0]->nobs; tr[10] = k > 1 ? bl[1]->nobs : 0;
+  if (accept) { tree_release(saved); }
+  else { tree_release(t); *t = *saved; saved->top = NULL; saved->indices = NULL; }
+}
+
+static void change_rule(or_bart* f, Tree* t, const double* ty, double* tr) {
+  Node* nbs[S4B_MAX_LEAVES + 1]; int nnb = 0; fill_not_bottom(t->top, nbs, &nnb);
+  tr[0] = 12;
+  if (nnb == 0) return;
+  Node* nd = nbs[s4b_rng_index(&f->rng, (size_t) nnb)];
+  int navail = num_vars_available(f, nd);
+  int new_var = ith_available_var(f, nd, (int) s4b_rng_index(&f->rng, (size_t) navail));
+  int lo, hi; split_interval(f, nd, new_var, &lo, &hi);
+  int maxl = -1, minl = 1 << 30, maxr = -1, minr = 1 << 30;
+  desc_constraints(nd->left, new_var, &maxl, &minl);
+  desc_constraints(nd->right, new_var, &maxr, &minr);
+  if (maxl + 1 > lo) lo = maxl + 1;
+  if (minr - 1 < hi) hi = minr - 1;
+  tr[1] = (double) node_heap(nd); tr[2] = new_var;
+  if (lo > hi) return;
+  int new_cut = lo + (int) s4b_rng_index(&f->rng, (size_t) (hi - lo + 1));
+  tr[0] = 2; tr[3] = new_cut;
+  Tree saved; tree_clone(f, t, &saved);
+  int64_t heap = node_heap(nd);
+  nd->var = new_var; nd->cut = new_cut;
+  finish_change_like(f, t, &saved, nd, heap, ty, tr);
+}
+
+static int rules_valid(const or_bart* f, const Node* nd) {
+  if (is_bottom(nd)) return 1;
+  int lo, hi; split_interval(f, nd, nd->var, &lo, &hi);
+  if (nd->cut < lo || nd->cut > hi) return 0;
+  return rules_valid(f, nd->left) && rules_valid(f, nd->right);
+}
+
+static void swap_rule(or_bart* f, Tree* t, const double* ty, double* tr) {
+  Node* sw[S4B_MAX_LEAVES + 1]; int ns = 0; fill_swappable(t->top, sw, &ns);
+  tr[0] = 13;
+  if (ns == 0) return;
+  Node* nd = sw[s4b_rng_index(&f->rng, (size_t) ns)];
+  tr[1] = (double) node_heap(nd);
+  int li = !is_bottom(nd->left), ri = !is_bottom(nd->right);
+  int both_same = li && ri && nd->left->var == nd->right->var && nd->left->cut == nd->right->cut;
+  Node* child = NULL;
+  if (!both_same) {
+    if (li && ri) child = s4b_rng_uniform(&f->rng) < 0.5 ? nd->left : nd->right;
+    else child = li ? nd->left : nd->right;
+  }
+  int pv = nd->var, pc = nd->cut;
+  int cv = both_same ? nd->left->var : child->var, cc = both_same ? nd->left->cut : child->cut;
+  tr[2] = both_same ? -1.0 : (double) node_heap(child);
+  /* apply, check logical validity, undo if invalid */
+  nd->var = cv; nd->cut = cc;
+  if (both_same) { nd->left->var = pv; nd->left->cut = pc; nd->right->var = pv; nd->right->cut = pc; }
+  else { child->var = pv; child->cut = pc; }
+  int ok = rules_valid(f, nd);
+  nd->var = pv; nd->cut = pc;
+  if (both_same) { nd->left->var = cv; nd->left->cut = cc; nd->right->var = cv; nd->right->cut = cc; }
+  else { child->var = cv; child->cut = cc; }
+  if (!ok) return;
+  tr[0] = 3;
+  Tree saved; tree_clone(f, t, &saved);
+  int64_t heap = node_heap(nd);
+  nd->var = cv; nd->cut = cc;
+  if (both_same) { nd->left->var = pv; nd->left->cut = pc; nd->right->var = pv; nd->right->cut = pc; }
+  else { child->var = pv; child->cut = pc; }
+  finish_change_like(f, t, &saved, nd, heap, ty, tr);
+}
+
+static void metropolis_jump(or_bart* f, Tree* t, const double* ty, double* tr) {
+  double u = s4b_rng_uniform(&f->rng);
+  if (u < f->cfg.birth_death_prob) birth_or_death(f, t, ty, tr);
+  else if (u < f->cfg.birth_death_prob + f->cfg.swap_prob) swap_rule(f, t, ty, tr);
+  else change_rule(f, t, ty, tr);
+}
+
+/* ---------- leaf draws and fits ---------- */
+static const Node* traverse_binned(const Node* nd, const uint8_t* xt, size_t stride, size_t i) {
+  while (!is_bottom(nd)) nd = xt[(size_t) nd->var * stride + i] <= nd->cut ? nd->left : nd->right;
+  return nd;
+}
+static void sample_parameters_and_set_fits(or_bart* f, Tree* t, const double* ty, double* fits, double* test_fits, double* tr) {
+  Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(t->top, bl, &nb);
+  double sigsq = f->sigma * f->sigma;
+  for (int k = 0; k < nb; ++k) {
+    Node* nd = bl[k];
+    node_set_average(nd, ty);
+    double dp = (double) nd->nobs / sigsq;
+    double post_mean = dp * nd->avg / (f->leaf_prec + dp);
+    double post_sd = 1.0 / sqrt(f->leaf_prec + dp);
+    nd->mu = post_mean + post_sd * s4b_rng_normal(&f->rng);
+    for (int i = 0; i < nd->nobs; ++i) fits[nd->obs[i]] = nd->mu;
+    if (tr && 11 + k < S4B_TRACE_LEN) tr[11 + k] = nd->mu;
+  }
+  if (tr) tr[8] = nb;
+  if (test_fits) for (int j = 0; j < f->nt; ++j) test_fits[j] = traverse_binned(t->top, f->xt_test, (size_t) f->nt, (size_t) j)->mu;
+}
+
+/* ---------- construction ---------- */
+static uint8_t bin_value(const double* cuts, int ncuts, double x) {
+  int k = 0; while (k < ncuts && x > cuts[k]) ++k; return (uint8_t) k;
+}
+
+or_bart* or_bart_create(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test)
+{
+  if (cfg->n_cuts < 1 || cfg->n_cuts > 255) return NULL;
+  or_bart* f = (or_bart*) calloc(1, sizeof(or_bart));
+  f->cfg = *cfg; f->n = (int) cfg->n; f->p = (int) cfg->p; f->nt = (int) cfg->n_test; f->T = cfg->num_trees;
+  size_t n = (size_t) f->n, p = (size_t) f->p, nt = (size_t) f->nt, T = (size_t) f->T;
+  f->y = (double*) malloc(sizeof(double) * (n ? n : 1)); memcpy(f->y, y, sizeof(double) * n);
+  f->x = (double*) malloc(sizeof(double) * (n * p + 1)); memcpy(f->x, x, sizeof(double) * n * p);
+  f->offset = (double*) calloc(n ? n : 1, sizeof(double));
+  f->ncuts = (int*) malloc(sizeof(int) * p); f->cuts = (double**) malloc(sizeof(double*) * p);
+  f->xt = (uint8_t*) malloc(n * p + 1);
+  for (size_t j = 0; j < p; ++j) {
+    const double* col = x + j * n;
+    double mn = col[0], mx = col[0];
+    for (size_t i = 1; i < n; ++i) { if (col[i] < mn) mn = col[i]; if (col[i] > mx) mx = col[i]; }
+    f->ncuts[j] = cfg->n_cuts;
+    f->cuts[j] = (double*) malloc(sizeof(double) * (size_t) cfg->n_cuts);
+    double inc = (mx - mn) / (double) (cfg->n_cuts + 1);
+    for (int k = 0; k < cfg->n_cuts; ++k) f->cuts[j][k] = mn + (double) (k + 1) * inc;
+    for (size_t i = 0; i < n; ++i) f->xt[j * n + i] = bin_value(f->cuts[j], cfg->n_cuts, col[i]);
+  }
+  if (nt > 0) {
+    f->x_test = (double*) malloc(sizeof(double) * nt * p); memcpy(f->x_test, x_test, sizeof(double) * nt * p);
+    f->xt_test = (uint8_t*) malloc(nt * p);
+    for (size_t j = 0; j < p; ++j) for (size_t i = 0; i < nt; ++i) f->xt_test[j * nt + i] = bin_value(f->cuts[j], cfg->n_cuts, x_test[j * nt + i]);
+    f->totalTestFits = (double*) calloc(nt, sizeof(double)); f->currTestFits = (double*) calloc(nt, sizeof(double));
+  }
+  f->yresc = (double*) calloc(n ? n : 1, sizeof(double)); f->treeY = (double*) calloc(n ? n : 1, sizeof(double));
+  f->totalFits = (double*) calloc(n ? n : 1, sizeof(double)); f->currFits = (double*) calloc(n ? n : 1, sizeof(double));
+  f->treeFits = (double*) calloc(n * T + 1, sizeof(double));
+  f->trees = (Tree*) calloc(T, sizeof(Tree));
+  for (size_t t = 0; t < T; ++t) {
+    f->trees[t].indices = (int*) malloc(sizeof(int) * (n ? n : 1));
+    for (size_t i = 0; i < n; ++i) f->trees[t].indices[i] = (int) i;
+    f->trees[t].top = node_new(NULL, f->trees[t].indices, f->n);
+  }
+  double sd_leaf = cfg->node_scale / (cfg->k * sqrt((double) cfg->num_trees));
+  f->leaf_prec = 1.0 / (sd_leaf * sd_leaf);
+  s4b_rng_init(&f->rng, cfg->seed, S4B_STREAM_BART);
+  f->sigma = 1.0;
+  if (cfg->is_binary) {
+    f->smin = -0.5; f->smax = 0.5; f->srange = 1.0;
+    for (size_t i = 0; i < n; ++i) f->yresc[i] = f->y[i] > 0.0 ? 1.0 : -1.0;
+  } else {
+    or_bart_set_offset(f, NULL, 1);
+  }
+  return f;
+}
+
+void or_bart_free(or_bart* f)
+{
+  if (!f) return;
+  for (int t = 0; t < f->T; ++t) tree_release(&f->trees[t]);
+  for (int j = 0; j < f->p; ++j) free(f->cuts[j]);
+  free(f->cuts); free(f->ncuts); free(f->trees);
+  free(f->y); free(f->x); free(f->x_test); free(f->offset); free(f->xt); free(f->xt_test);
+  free(f->yresc); free(f->treeY); free(f->totalFits); free(f->treeFits); free(f->currFits);
+  free(f->totalTestFits); free(f->currTestFits);
+  free(f);
+}
+
+void or_bart_set_tape(or_bart* f, const double* tape, size_t len) { f->rng.tape = tape; f->rng.tape_len = len; f->rng.tape_pos = 0; }
+void or_bart_set_record(or_bart* f, double* rec, size_t cap) { f->rng.rec = rec; f->rng.rec_cap = cap; f->rng.rec_len = 0; }
+size_t or_bart_record_len(const or_bart* f) { return f->rng.rec_len; }
+void or_bart_set_trace(or_bart* f, double* trace, size_t cap) { f->trace = trace; f->trace_cap = cap; f->trace_len = 0; }
+size_t or_bart_trace_len(const or_bart* f) { return f->trace_len; }
+uint64_t or_bart_rng_counter(const or_bart* f) { return f->rng.counter; }
+
+static void sample_latents(or_bart* f)
+{
+  /* z_i ~ TN(totalFits_i + offset_i, 1), sign by y_i; trees see z - offset */
+  uint32_t epoch = f->latent_epoch++;
+  for (int i = 0; i < f->n; ++i) {
+    double mean = f->totalFits[i] + f->offset[i];
+    double z = s4b_keyed_truncnorm(f->cfg.seed, (uint32_t) i, epoch, mean, f->y[i] > 0.0);
+    f->yresc[i] = z - f->offset[i];
+  }
+}
+
+void or_bart_set_offset(or_bart* f, const double* offset, int update_scale)
+{
+  int n = f->n;
+  if (f->cfg.is_binary) {
+    if (offset) memcpy(f->offset, offset, sizeof(double) * (size_t) n); else memset(f->offset, 0, sizeof(double) * (size_t) n);
+    sample_latents(f);
+    return;
+  }
+  double sigma_unscaled = f->srange > 0.0 ? f->sigma * f->srange : f->sigma;
+  double old_range = f->srange;
+  if (offset) memcpy(f->offset, offset, sizeof(double) * (size_t) n); else memset(f->offset, 0, sizeof(double) * (size_t) n);
+  if (update_scale || old_range == 0.0) {
+    double mn = f->y[0] - f->offset[0], mx = mn;
+    for (int i = 1; i < n; ++i) { double r = f->y[i] - f->offset[i]; if (r < mn) mn = r; if (r > mx) mx = r; }
+    f->smin = mn; f->smax = mx; f->srange = mx - mn;
+    if (f->srange <= 0.0) f->srange = 1.0;
+    if (old_range > 0.0) {
+      /* keep fits, leaf values and sigma fixed in original units */
+      double s = old_range / f->srange;
+      f->sigma = sigma_unscaled / f->srange;
+      for (int i = 0; i < n; ++i) f->totalFits[i] *= s;
+      for (size_t k = 0; k < (size_t) n * (size_t) f->T; ++k) f->treeFits[k] *= s;
+      for (int t = 0; t < f->T; ++t) { Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(f->trees[t].top, bl, &nb); for (int k = 0; k < nb; ++k) bl[k]->mu *= s; }
+    }
+  }
+  for (int i = 0; i < n; ++i) f->yresc[i] = (f->y[i] - f->offset[i] - f->smin) / f->srange - 0.5;
+}
+
+void or_bart_set_sigma(or_bart* f, double sigma) { f->sigma = f->cfg.is_binary ? 1.0 : sigma / f->srange; }
+
+static void grow_from_prior(or_bart* f, Tree* t, Node* nd)
+{
+  double pg = is_birthable(f, nd, count_bottom(t->top)) ? growth_prob(f, nd) : 0.0;
+  double u = s4b_rng_uniform(&f->rng);
+  if (!(u < pg)) return;
+  int var, cut; draw_rule(f, nd, &var, &cut);
+  node_split(f, nd, var, cut);
+  grow_from_prior(f, t, nd->left);
+  grow_from_prior(f, t, nd->right);
+}
+
+void or_bart_sample_trees_from_prior(or_bart* f)
+{
+  int n = f->n;
+  for (int t = 0; t < f->T; ++t) {
+    Tree* tr = &f->trees[t];
+    orphan_children(tr->top);
+    grow_from_prior(f, tr, tr->top);
+    Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(tr->top, bl, &nb);
+    double* tf = f->treeFits + (size_t) t * (size_t) n;
+    for (int k = 0; k < nb; ++k) {
+      bl[k]->mu = s4b_rng_normal(&f->rng) / sqrt(f->leaf_prec);
+      for (int i = 0; i < bl[k]->nobs; ++i) { int o = bl[k]->obs[i]; f->totalFits[o] += bl[k]->mu - tf[o]; tf[o] = bl[k]->mu; }
+    }
+  }
+}
+
+void or_bart_run(or_bart* f, double* train, double* test, uint32_t* varcount, double* sigma_out)
+{
+  int n = f->n, nt = f->nt;
+  for (int k = 0; k < f->cfg.thin; ++k) {
+    int is_thinning = ((k + 1) % f->cfg.thin) != 0;
+    if (!is_thinning && nt > 0) memset(f->totalTestFits, 0, sizeof(double) * (size_t) nt);
+    for (int t = 0; t < f->T; ++t) {
+      Tree* tree = &f->trees[t];
+      double* tf = f->treeFits + (size_t) t * (size_t) n;
+      for (int i = 0; i < n; ++i) f->treeY[i] = f->yresc[i] - (f->totalFits[i] - tf[i]);
+      set_averages(tree->top, f->treeY);
+      double* tr = trace_begin(f);
+      metropolis_jump(f, tree, f->treeY, tr);
+      sample_parameters_and_set_fits(f, tree, f->treeY, f->currFits, is_thinning ? NULL : f->currTestFits, tr);
+      if (f->trace && f->trace_len < f->trace_cap) f->trace_len++;
+      for (int i = 0; i < n; ++i) { f->totalFits[i] += f->currFits[i] - tf[i]; tf[i] = f->currFits[i]; }
+      if (!is_thinning) for (int j = 0; j < nt; ++j) f->totalTestFits[j] += f->currTestFits[j];
+    }
+    if (f->cfg.is_binary) sample_latents(f);
+    if (!is_thinning) {
+      if (train) for (int i = 0; i < n; ++i)
+        train[i] = (f->cfg.is_binary ? f->totalFits[i] : f->smin + (f->totalFits[i] + 0.5) * f->srange) + f->offset[i];
+      if (test) for (int j = 0; j < nt; ++j)
+        test[j] = f->cfg.is_binary ? f->totalTestFits[j] : f->smin + (f->totalTestFits[j] + 0.5) * f->srange;
+      if (sigma_out) *sigma_out = f->cfg.is_binary ? 1.0 : f->sigma * f->srange;
+      if (varcount) {
+        for (int j = 0; j < f->p; ++j) varcount[j] = 0;
+        for (int t = 0; t < f->T; ++t) { Node* nbs[S4B_MAX_LEAVES + 1]; int k2 = 0; fill_not_bottom(f->trees[t].top, nbs, &k2); for (int q = 0; q < k2; ++q) varcount[nbs[q]->var]++; }
+      }
+    }
+  }
+}
+
+void or_bart_store_latents(const or_bart* f, double* out) { for (int i = 0; i < f->n; ++i) out[i] = f->yresc[i] + f->offset[i]; }
+void or_bart_get_range(const or_bart* f, double* o) { o[0] = f->smin; o[1] = f->smax; o[2] = f->srange; }
+void or_bart_get_residual(const or_bart* f, double* out) { for (int i = 0; i < f->n; ++i) out[i] = f->yresc[i] - f->totalFits[i]; }
+
+void or_bart_node_assignment(const or_bart* f, int tree, int64_t* heap_index)
+{
+  Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(f->trees[tree].top, bl, &nb);
+  for (int k = 0; k < nb; ++k) { int64_t h = node_heap(bl[k]); for (int i = 0; i < bl[k]->nobs; ++i) heap_index[bl[k]->obs[i]] = h; }
+}
+
+void or_bart_leaf_stats(const or_bart* f, int tree, int max_leaves, int64_t* heap_index, int64_t* count, double* sum, double* sumsq, int* num_leaves)
+{
+  /* statistics of the partial residual treeY = yresc - (totalFits - treeFits[tree]) per leaf, two-pass */
+  Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(f->trees[tree].top, bl, &nb);
+  const double* tf = f->treeFits + (size_t) tree * (size_t) f->n;
+  *num_leaves = nb;
+  for (int k = 0; k < nb && k < max_leaves; ++k) {
+    double s = 0.0, ss = 0.0;
+    for (int i = 0; i < bl[k]->nobs; ++i) { int o = bl[k]->obs[i]; double v = f->yresc[o] - (f->totalFits[o] - tf[o]); s += v; ss += v * v; }
+    heap_index[k] = node_heap(bl[k]); count[k] = bl[k]->nobs; sum[k] = s; sumsq[k] = ss;
+  }
+}
+
+int64_t or_bart_num_nodes(const or_bart* f) { int64_t c = 0; for (int t = 0; t < f->T; ++t) c += count_nodes(f->trees[t].top); return c; }
+
+static void flatten(const or_bart* f, const Node* nd, int t, int64_t* pos, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value)
+{
+  int64_t k = (*pos)++;
+  tree_no[k] = t; n_obs[k] = nd->nobs;
+  if (is_bottom(nd)) { var[k] = -1; value[k] = nd->mu; return; }
+  var[k] = nd->var; value[k] = f->cuts[nd->var][nd->cut];
+  flatten(f, nd->left, t, pos, tree_no, n_obs, var, value); flatten(f, nd->right, t, pos, tree_no, n_obs, var, value);
+}
+void or_bart_get_trees(const or_bart* f, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value)
+{
+  int64_t pos = 0;
+  for (int t = 0; t < f->T; ++t) flatten(f, f->trees[t].top, t, &pos, tree_no, n_obs, var, value);
+}
+
+void or_bart_predict(const or_bart* f, const double* x_test, int64_t n, const double* test_offset, double* out)
+{
+  for (int64_t i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int t = 0; t < f->T; ++t) {
+      const Node* nd = f->trees[t].top;
+      while (!is_bottom(nd)) nd = x_test[(size_t) nd->var * (size_t) n + (size_t) i] <= f->cuts[nd->var][nd->cut] ? nd->left : nd->right;
+      s += nd->mu;
+    }
+    out[i] = (f->cfg.is_binary ? s : f->smin + (s + 0.5) * f->srange) + (test_offset ? test_offset[i] : 0.0);
+  }
+}
+
+double or_rng_qnorm(double p) { return s4b_qnorm(p); }
+void or_rng_uniforms(uint64_t seed, uint32_t stream, uint64_t start, int64_t n, double* out)
+{
+  s4b_rng g; s4b_rng_init(&g, seed, stream); g.counter = start;
+  for (int64_t i = 0; i < n; ++i) out[i] = s4b_rng_uniform(&g);
+}
+double or_rng_truncnorm(uint64_t seed, uint32_t obs, uint32_t epoch, double mean, int positive) { return s4b_keyed_truncnorm(seed, obs, epoch, mean, positive); }

@@ -1,0 +1,92 @@
+/*
+ * oracle/oracle_gibbs.c -- TEST INFRASTRUCTURE (CPU oracle), not product code.
+ *
+ * Restates the alternating BART <-> Stan loop of stan4bart's host sampler:
+ *   createSampler   /root/reference/src/init.cpp:190-310
+ *   run             /root/reference/src/init.cpp:678-965 (loop body :752-917)
+ *   disengage       /root/reference/src/init.cpp:995-1004
+ * with userOffset == NULL (offset_type variants are SURVEY 8f rank 4).
+ */
+#include "s4b_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+struct or_sampler {
+  s4b_common_control cc;
+  or_glmm* model; or_nuts* nuts; or_bart* bart;
+  int64_t n, n_test; int p;
+  double *bartOffset, *stanOffset, *bartLatents;
+  double* stan_curr;   /* last saved Stan draw */
+  int num_pars;
+};
+
+or_sampler* or_sampler_create(const s4b_bart_config* bcfg, const double* y_bart, const double* x_bart, const double* x_test,
+                              const s4b_glmm_data* gdata, const s4b_stan_control* sctl, const s4b_common_control* cctl,
+                              const double* bart_offset_init)
+{
+  or_sampler* s = (or_sampler*) calloc(1, sizeof(or_sampler));
+  s->cc = *cctl; s->n = bcfg->n; s->n_test = bcfg->n_test; s->p = (int) bcfg->p;
+  size_t n = (size_t) s->n;
+  s->model = or_glmm_create(gdata);
+  if (!s->model) { free(s); return NULL; }
+  s->nuts = or_nuts_create(s->model, sctl, 1, cctl->warmup);                        /* init.cpp:211-212 */
+  s->num_pars = or_nuts_num_pars(s->nuts);
+  s->stan_curr = (double*) calloc((size_t) s->num_pars, sizeof(double));
+  s->bart = or_bart_create(bcfg, y_bart, x_bart, x_test);                           /* :215-228 */
+  s->bartOffset = (double*) calloc(n ? n : 1, sizeof(double));
+  s->stanOffset = (double*) calloc(n ? n : 1, sizeof(double));
+  if (cctl->is_binary) s->bartLatents = (double*) calloc(n ? n : 1, sizeof(double));
+  if (bart_offset_init) memcpy(s->bartOffset, bart_offset_init, sizeof(double) * n);  /* :248-252 */
+  or_bart_set_offset(s->bart, s->bartOffset, 1);                                    /* :255 */
+  if (!cctl->is_binary) or_bart_set_sigma(s->bart, cctl->sigma_init);               /* :256-257 */
+  or_bart_sample_trees_from_prior(s->bart);                                         /* :261 */
+  double* first = (double*) calloc(n ? n : 1, sizeof(double));
+  or_bart_run(s->bart, first, NULL, NULL, NULL);                                    /* :273 */
+  for (size_t j = 0; j < n; ++j) s->stanOffset[j] = first[j] - s->bartOffset[j];    /* :275-281 */
+  free(first);
+  or_glmm_set_offset(s->model, s->stanOffset);                                      /* :287 */
+  if (cctl->is_binary) { or_bart_store_latents(s->bart, s->bartLatents); or_glmm_set_response(s->model, s->bartLatents); }  /* :288-291 */
+  return s;
+}
+
+void or_sampler_free(or_sampler* s)
+{
+  if (!s) return;
+  or_bart_free(s->bart); or_nuts_free(s->nuts); or_glmm_free(s->model);
+  free(s->bartOffset); free(s->stanOffset); free(s->bartLatents); free(s->stan_curr); free(s);
+}
+
+int or_sampler_num_stan_pars(const or_sampler* s) { return s->num_pars; }
+or_bart* or_sampler_bart(or_sampler* s) { return s->bart; }
+or_nuts* or_sampler_nuts(or_sampler* s) { return s->nuts; }
+void or_sampler_get_range(const or_sampler* s, double* out2) { double r[3]; or_bart_get_range(s->bart, r); out2[0] = r[0]; out2[1] = r[1]; }
+void or_sampler_disengage_adaptation(or_sampler* s) { or_nuts_disengage_adaptation(s->nuts); }
+
+void or_sampler_run(or_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma)
+{
+  size_t n = (size_t) s->n, nt = (size_t) s->n_test;
+  double* tmp_train = (double*) calloc(n ? n : 1, sizeof(double));
+  double* tmp_test = (double*) calloc(nt ? nt : 1, sizeof(double));
+  for (int iter = 0; iter < num_iter; ++iter) {
+    size_t slot = s->cc.keep_fits ? (size_t) iter : 0;
+    /* A. Stan block, init.cpp:758-819 */
+    or_nuts_run(s->nuts, is_warmup, s->stan_curr);
+    if (stan) memcpy(stan + slot * (size_t) s->num_pars, s->stan_curr, sizeof(double) * (size_t) s->num_pars);
+    or_glmm_parametric_mean(s->model, s->stan_curr + 7, s->bartOffset, 1, 1);       /* :764 */
+    if (!s->cc.is_binary) or_bart_set_sigma(s->bart, or_glmm_get_aux(s->model, s->stan_curr + 7));  /* :796-800 */
+    int update_scale_mod = 1 << (8 * iter / num_iter);                              /* :816 */
+    or_bart_set_offset(s->bart, s->bartOffset, is_warmup && iter % update_scale_mod == 0);
+    /* B. BART block, init.cpp:821-916 */
+    double sig;
+    or_bart_run(s->bart, tmp_train, nt ? tmp_test : NULL, varcount ? varcount + slot * (size_t) s->p : NULL, &sig);
+    for (size_t j = 0; j < n; ++j) tmp_train[j] -= s->bartOffset[j];                /* :828-829 */
+    memcpy(s->stanOffset, tmp_train, sizeof(double) * n);                           /* :835 */
+    or_glmm_set_offset(s->model, s->stanOffset);                                    /* :842 */
+    if (s->cc.is_binary) { or_bart_store_latents(s->bart, s->bartLatents); or_glmm_set_response(s->model, s->bartLatents); }
+    if (train) memcpy(train + slot * n, tmp_train, sizeof(double) * n);
+    if (test && nt) memcpy(test + slot * nt, tmp_test, sizeof(double) * nt);
+    if (sigma) sigma[slot] = sig;
+  }
+  free(tmp_train); free(tmp_test);
+}

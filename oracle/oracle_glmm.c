@@ -1,0 +1,326 @@
+/*
+ * oracle/oracle_glmm.c -- TEST INFRASTRUCTURE (CPU oracle), not product code.
+ *
+ * CPU restatement of the stan4bart GLMM density and its gradient on the default
+ * path (prior_dist in {0,1}, no intercept, no weights, ranef blocks with p <= 2):
+ *   maths          /root/reference/src/stan_files/continuous.stan:1-429
+ *   op order       /root/reference/src/stan_files/continuous.hpp:2168-2638 (log_prob_impl,
+ *                  lpdfs hard-coded <false> = all constants kept)
+ *   make_theta_L   continuous.stan:2-59      make_b  continuous.stan:61-94
+ *   decov_lp       continuous.stan:96-122 (continuous.hpp:823-916)
+ *   transforms     src/include/stan/math/prim/fun/lb_constrain.hpp:64 (exp, J = +x),
+ *                  lub_constrain.hpp:109-110 (inv_logit, J = -|x| - 2 log1p(exp(-|x|)))
+ *   write_array    continuous.hpp:2640-2938 (order: params, then aux, beta, b, theta_L)
+ *   set_offset / set_response / get_aux / get_parametric_mean  continuous.hpp:3626-3768
+ * The reference differentiates by reverse-mode AD (model/gradient.hpp:21-35); here the
+ * gradient is hand-derived.  Pinned by tests/golden/glmm_*.json (torch fp64 autograd).
+ */
+#include "s4b_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct or_glmm {
+  s4b_glmm_data d;
+  double *X, *y, *offset;
+  double *prior_scale, *prior_mean, *shape, *scale, *concentration, *regularization, *w, *delta;
+  int32_t *p, *l, *v, *u;
+  int len_rho, num_params, has_aux;
+};
+
+#define HALF_LOG_2PI 0.91893853320467274178
+
+static void* dup_mem(const void* src, size_t bytes) { void* r = malloc(bytes ? bytes : 1); if (bytes) memcpy(r, src, bytes); return r; }
+
+or_glmm* or_glmm_create(const s4b_glmm_data* d)
+{
+  for (int i = 0; i < d->t; ++i) if (d->p[i] > 2) return NULL;            /* z_T onion: SURVEY 8f rank 4 */
+  if (d->prior_dist < 0 || d->prior_dist > 1) return NULL;
+  or_glmm* m = (or_glmm*) calloc(1, sizeof(or_glmm));
+  m->d = *d;
+  size_t N = (size_t) d->N, K = (size_t) d->K, t = (size_t) d->t;
+  m->X = (double*) dup_mem(d->X, sizeof(double) * N * K);
+  m->y = (double*) dup_mem(d->y, sizeof(double) * N);
+  m->offset = (double*) calloc(N ? N : 1, sizeof(double));
+  m->prior_scale = (double*) dup_mem(d->prior_scale, sizeof(double) * K);
+  m->prior_mean = (double*) dup_mem(d->prior_mean, sizeof(double) * K);
+  m->p = (int32_t*) dup_mem(d->p, sizeof(int32_t) * t);
+  m->l = (int32_t*) dup_mem(d->l, sizeof(int32_t) * t);
+  m->shape = (double*) dup_mem(d->shape, sizeof(double) * t);
+  m->scale = (double*) dup_mem(d->scale, sizeof(double) * t);
+  m->concentration = (double*) dup_mem(d->concentration, sizeof(double) * (size_t) d->len_concentration);
+  m->regularization = (double*) dup_mem(d->regularization, sizeof(double) * (size_t) d->len_regularization);
+  m->w = (double*) dup_mem(d->w, sizeof(double) * (size_t) d->num_non_zero);
+  m->v = (int32_t*) dup_mem(d->v, sizeof(int32_t) * (size_t) d->num_non_zero);
+  m->u = (int32_t*) dup_mem(d->u, sizeof(int32_t) * (N + 1));
+  /* transformed data, src/stan_sampler.cpp:142-182: delta restarts at concentration[0] for every term */
+  m->delta = (double*) calloc((size_t) d->len_concentration + 1, sizeof(double));
+  int pos = 0, sum_p = 0;
+  for (int i = 0; i < d->t; ++i) {
+    if (d->p[i] > 1) for (int j = 0; j < d->p[i]; ++j) m->delta[pos++] = d->concentration[j];
+    sum_p += d->p[i];
+  }
+  m->len_rho = sum_p - d->t;
+  m->has_aux = d->is_binary ? 0 : 1;
+  m->num_params = d->K + d->q + m->len_rho + d->len_concentration + d->t + m->has_aux;
+  return m;
+}
+
+void or_glmm_free(or_glmm* m)
+{
+  if (!m) return;
+  free(m->X); free(m->y); free(m->offset); free(m->prior_scale); free(m->prior_mean); free(m->p); free(m->l);
+  free(m->shape); free(m->scale); free(m->concentration); free(m->regularization); free(m->w); free(m->v); free(m->u); free(m->delta);
+  free(m);
+}
+
+int or_glmm_num_params(const or_glmm* m) { return m->num_params; }
+int or_glmm_num_constrained(const or_glmm* m) { return m->num_params + m->has_aux + m->d.K + m->d.q + m->d.len_theta_L; }
+void or_glmm_set_offset(or_glmm* m, const double* offset) { memcpy(m->offset, offset, sizeof(double) * (size_t) m->d.N); }
+void or_glmm_set_response(or_glmm* m, const double* y) { memcpy(m->y, y, sizeof(double) * (size_t) m->d.N); }
+
+void or_glmm_data_terms(const or_glmm* m, const double* beta, const double* b, double* S, double* gbeta, double* gb)
+{
+  int64_t N = m->d.N; int K = m->d.K, q = m->d.q;
+  double s = 0.0;
+  for (int k = 0; k < K; ++k) gbeta[k] = 0.0;
+  for (int k = 0; k < q; ++k) gb[k] = 0.0;
+  for (int64_t i = 0; i < N; ++i) {
+    double eta = m->offset[i];
+    for (int k = 0; k < K; ++k) eta += m->X[(size_t) k * (size_t) N + (size_t) i] * beta[k];
+    for (int32_t z = m->u[i]; z < m->u[i + 1]; ++z) eta += m->w[z] * b[m->v[z]];
+    double e = m->y[i] - eta;
+    s += e * e;
+    for (int k = 0; k < K; ++k) gbeta[k] += m->X[(size_t) k * (size_t) N + (size_t) i] * e;
+    for (int32_t z = m->u[i]; z < m->u[i + 1]; ++z) gb[m->v[z]] += m->w[z] * e;
+  }
+  *S = s;
+}
+
+/* constrained and transformed quantities for a given unconstrained q */
+typedef struct {
+  const double *z_beta, *z_b, *rho_u, *zeta_u, *tau_u;
+  double aux_u;
+  double *rho, *zeta, *tau, *beta, *b, *theta_L;
+  double aux_unscaled, aux, disp;
+} Params;
+
+static void params_alloc(const or_glmm* m, Params* P)
+{
+  P->rho = (double*) calloc((size_t) m->len_rho + 1, sizeof(double));
+  P->zeta = (double*) calloc((size_t) m->d.len_concentration + 1, sizeof(double));
+  P->tau = (double*) calloc((size_t) m->d.t + 1, sizeof(double));
+  P->beta = (double*) calloc((size_t) m->d.K + 1, sizeof(double));
+  P->b = (double*) calloc((size_t) m->d.q + 1, sizeof(double));
+  P->theta_L = (double*) calloc((size_t) m->d.len_theta_L + 1, sizeof(double));
+}
+static void params_free(Params* P) { free(P->rho); free(P->zeta); free(P->tau); free(P->beta); free(P->b); free(P->theta_L); }
+
+static double inv_logit(double x) { return x >= 0.0 ? 1.0 / (1.0 + exp(-x)) : exp(x) / (1.0 + exp(x)); }
+
+static void transform(const or_glmm* m, const double* q, Params* P)
+{
+  const s4b_glmm_data* d = &m->d;
+  int pos = 0;
+  P->z_beta = q + pos; pos += d->K;
+  P->z_b = q + pos; pos += d->q;
+  P->rho_u = q + pos; pos += m->len_rho;
+  P->zeta_u = q + pos; pos += d->len_concentration;
+  P->tau_u = q + pos; pos += d->t;
+  P->aux_u = m->has_aux ? q[pos] : 0.0;
+  for (int i = 0; i < m->len_rho; ++i) P->rho[i] = inv_logit(P->rho_u[i]);
+  for (int i = 0; i < d->len_concentration; ++i) P->zeta[i] = exp(P->zeta_u[i]);
+  for (int i = 0; i < d->t; ++i) P->tau[i] = exp(P->tau_u[i]);
+  if (m->has_aux) {
+    P->aux_unscaled = exp(P->aux_u);
+    if (d->prior_dist_for_aux == 0) P->aux = P->aux_unscaled;
+    else {
+      P->aux = d->prior_scale_for_aux * P->aux_unscaled;
+      if (d->prior_dist_for_aux <= 2) P->aux += d->prior_mean_for_aux;
+    }
+    P->disp = P->aux;
+  } else { P->aux_unscaled = 0.0; P->aux = 1.0; P->disp = 1.0; }
+  for (int k = 0; k < d->K; ++k)
+    P->beta[k] = d->prior_dist == 0 ? P->z_beta[k] : P->z_beta[k] * m->prior_scale[k] + m->prior_mean[k];
+  /* make_theta_L (continuous.stan:2-59) and make_b (:61-94), p <= 2 */
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0;
+  for (int i = 0; i < d->t; ++i) {
+    if (m->p[i] == 1) {
+      double theta = P->tau[i] * m->scale[i] * P->disp;
+      P->theta_L[th++] = theta;
+      for (int s = 0; s < m->l[i]; ++s) P->b[b_mark + s] = theta * P->z_b[b_mark + s];
+      b_mark += m->l[i];
+    } else {
+      double c = P->tau[i] * m->scale[i] * P->disp;
+      double trace = c * c * 2.0;
+      double zs = P->zeta[zeta_mark] + P->zeta[zeta_mark + 1];
+      double pi1 = P->zeta[zeta_mark] / zs, pi2 = P->zeta[zeta_mark + 1] / zs;
+      zeta_mark += 2;
+      double sd1 = sqrt(pi1 * trace), sd2 = sqrt(pi2 * trace);
+      double T21c = 2.0 * P->rho[rho_mark++] - 1.0;
+      double T11 = sd1, T22 = sd2 * sqrt(1.0 - T21c * T21c), T21 = sd2 * T21c;
+      P->theta_L[th++] = T11; P->theta_L[th++] = T21; P->theta_L[th++] = T22;
+      for (int j = 0; j < m->l[i]; ++j) {
+        double z0 = P->z_b[b_mark], z1 = P->z_b[b_mark + 1];
+        P->b[b_mark] = T11 * z0; P->b[b_mark + 1] = T21 * z0 + T22 * z1;
+        b_mark += 2;
+      }
+    }
+  }
+}
+
+int or_glmm_log_prob_grad(const or_glmm* m, const double* q, double* lp_out, double* grad)
+{
+  const s4b_glmm_data* d = &m->d;
+  Params P; params_alloc(m, &P); transform(m, q, &P);
+  int K = d->K, nq = d->q, t = d->t;
+  double N = (double) d->N;
+  double lp = 0.0;
+  /* Jacobians */
+  for (int i = 0; i < m->len_rho; ++i) { double x = P.rho_u[i]; lp += -fabs(x) - 2.0 * log1p(exp(-fabs(x))); }
+  for (int i = 0; i < d->len_concentration; ++i) lp += P.zeta_u[i];
+  for (int i = 0; i < t; ++i) lp += P.tau_u[i];
+  if (m->has_aux) lp += P.aux_u;
+  /* likelihood */
+  double* gbeta = (double*) calloc((size_t) K + 1, sizeof(double));
+  double* gb = (double*) calloc((size_t) nq + 1, sizeof(double));
+  double S; or_glmm_data_terms(m, P.beta, P.b, &S, gbeta, gb);
+  double sigma = m->has_aux ? P.aux : 1.0;
+  lp += -0.5 * S / (sigma * sigma) - N * log(sigma) - N * HALF_LOG_2PI;
+  /* priors */
+  double d_au_prior = 0.0;
+  if (m->has_aux && d->prior_dist_for_aux > 0 && d->prior_scale_for_aux > 0.0) {
+    double au = P.aux_unscaled;
+    if (d->prior_dist_for_aux == 1) { lp += -0.5 * au * au - HALF_LOG_2PI + 0.693147180559945286; d_au_prior = -au; }
+    else if (d->prior_dist_for_aux == 2) {
+      double nu = d->prior_df_for_aux;
+      lp += lgamma(0.5 * (nu + 1.0)) - lgamma(0.5 * nu) - 0.5 * log(nu * 3.14159265358979323846) - 0.5 * (nu + 1.0) * log1p(au * au / nu) + 0.693147180559945286;
+      d_au_prior = -(nu + 1.0) * au / (nu + au * au);
+    } else { lp += -au; d_au_prior = -1.0; }
+  }
+  if (d->prior_dist == 1) { for (int k = 0; k < K; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= K * HALF_LOG_2PI; }
+  for (int k = 0; k < nq; ++k) lp += -0.5 * P.z_b[k] * P.z_b[k];
+  lp -= nq * HALF_LOG_2PI;
+  {
+    int pos_reg = 0, pos_rho = 0;
+    for (int i = 0; i < t; ++i) if (m->p[i] > 1) {
+      double nu = m->regularization[pos_reg++] + 0.5 * (m->p[i] - 2);
+      double r = P.rho[pos_rho++];
+      lp += (nu - 1.0) * log(r) + (nu - 1.0) * log1p(-r) + lgamma(2.0 * nu) - 2.0 * lgamma(nu);
+    }
+  }
+  for (int i = 0; i < d->len_concentration; ++i) lp += (m->delta[i] - 1.0) * log(P.zeta[i]) - P.zeta[i] - lgamma(m->delta[i]);
+  for (int i = 0; i < t; ++i) lp += (m->shape[i] - 1.0) * log(P.tau[i]) - P.tau[i] - lgamma(m->shape[i]);
+
+  /* ---- gradient ---- */
+  int pos = 0;
+  double* g_zbeta = grad + pos; pos += K;
+  double* g_zb = grad + pos; pos += nq;
+  double* g_rho = grad + pos; pos += m->len_rho;
+  double* g_zeta = grad + pos; pos += d->len_concentration;
+  double* g_tau = grad + pos; pos += t;
+  double inv_s2 = 1.0 / (sigma * sigma);
+  for (int k = 0; k < K; ++k) {
+    double dbeta = gbeta[k] * inv_s2;
+    g_zbeta[k] = d->prior_dist == 0 ? dbeta : dbeta * m->prior_scale[k] - P.z_beta[k];
+  }
+  double d_disp = 0.0;
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, pos_reg = 0;
+  for (int i = 0; i < t; ++i) {
+    if (m->p[i] == 1) {
+      double theta = P.theta_L[th++];
+      double d_theta = 0.0;
+      for (int s = 0; s < m->l[i]; ++s) {
+        double db = gb[b_mark + s] * inv_s2;
+        g_zb[b_mark + s] = theta * db - P.z_b[b_mark + s];
+        d_theta += db * P.z_b[b_mark + s];
+      }
+      b_mark += m->l[i];
+      double d_tau = d_theta * m->scale[i] * P.disp;
+      d_disp += d_theta * P.tau[i] * m->scale[i];
+      d_tau += (m->shape[i] - 1.0) / P.tau[i] - 1.0;
+      g_tau[i] = d_tau * P.tau[i] + 1.0;
+    } else {
+      double T11 = P.theta_L[th], T21 = P.theta_L[th + 1], T22 = P.theta_L[th + 2]; th += 3;
+      double dT11 = 0.0, dT21 = 0.0, dT22 = 0.0;
+      for (int j = 0; j < m->l[i]; ++j) {
+        double db0 = gb[b_mark] * inv_s2, db1 = gb[b_mark + 1] * inv_s2;
+        double z0 = P.z_b[b_mark], z1 = P.z_b[b_mark + 1];
+        g_zb[b_mark] = T11 * db0 + T21 * db1 - z0;
+        g_zb[b_mark + 1] = T22 * db1 - z1;
+        dT11 += db0 * z0; dT21 += db1 * z0; dT22 += db1 * z1;
+        b_mark += 2;
+      }
+      double c = P.tau[i] * m->scale[i] * P.disp;
+      double trace = 2.0 * c * c;
+      double z1v = P.zeta[zeta_mark], z2v = P.zeta[zeta_mark + 1], zs = z1v + z2v;
+      double pi1 = z1v / zs, pi2 = z2v / zs;
+      double sd1 = sqrt(pi1 * trace), sd2 = sqrt(pi2 * trace);
+      double rho = P.rho[rho_mark];
+      double r = 2.0 * rho - 1.0, sq = sqrt(1.0 - r * r);
+      double d_c = (dT11 * T11 + dT21 * T21 + dT22 * T22) / c;
+      double d_sd1 = dT11, d_sd2 = dT21 * r + dT22 * sq;
+      double d_pi1 = d_sd1 * sd1 / (2.0 * pi1), d_pi2 = d_sd2 * sd2 / (2.0 * pi2);
+      double dot = d_pi1 * pi1 + d_pi2 * pi2;
+      double d_z1 = (d_pi1 - dot) / zs, d_z2 = (d_pi2 - dot) / zs;
+      double d_r = dT21 * sd2 - dT22 * sd2 * r / sq;
+      double d_rho = 2.0 * d_r;
+      double nu = m->regularization[pos_reg++] + 0.5 * (m->p[i] - 2);
+      d_rho += (nu - 1.0) / rho - (nu - 1.0) / (1.0 - rho);
+      g_rho[rho_mark] = d_rho * rho * (1.0 - rho) + (1.0 - 2.0 * rho);
+      d_z1 += (m->delta[zeta_mark] - 1.0) / z1v - 1.0;
+      d_z2 += (m->delta[zeta_mark + 1] - 1.0) / z2v - 1.0;
+      g_zeta[zeta_mark] = d_z1 * z1v + 1.0;
+      g_zeta[zeta_mark + 1] = d_z2 * z2v + 1.0;
+      double d_tau = d_c * m->scale[i] * P.disp;
+      d_disp += d_c * P.tau[i] * m->scale[i];
+      d_tau += (m->shape[i] - 1.0) / P.tau[i] - 1.0;
+      g_tau[i] = d_tau * P.tau[i] + 1.0;
+      zeta_mark += 2; rho_mark += 1;
+    }
+  }
+  if (m->has_aux) {
+    double d_aux = d_disp + S / (sigma * sigma * sigma) - N / sigma;
+    double d_au = d_aux * (d->prior_dist_for_aux == 0 ? 1.0 : d->prior_scale_for_aux) + d_au_prior;
+    grad[pos] = d_au * P.aux_unscaled + 1.0;
+  }
+  *lp_out = lp;
+  int bad = !isfinite(lp);
+  for (int i = 0; i < m->num_params; ++i) if (!isfinite(grad[i])) bad = 1;
+  free(gbeta); free(gb); params_free(&P);
+  return bad;
+}
+
+void or_glmm_write_array(const or_glmm* m, const double* q, double* out)
+{
+  const s4b_glmm_data* d = &m->d;
+  Params P; params_alloc(m, &P); transform(m, q, &P);
+  int pos = 0;
+  for (int k = 0; k < d->K; ++k) out[pos++] = P.z_beta[k];
+  for (int k = 0; k < d->q; ++k) out[pos++] = P.z_b[k];
+  for (int k = 0; k < m->len_rho; ++k) out[pos++] = P.rho[k];
+  for (int k = 0; k < d->len_concentration; ++k) out[pos++] = P.zeta[k];
+  for (int k = 0; k < d->t; ++k) out[pos++] = P.tau[k];
+  if (m->has_aux) { out[pos++] = P.aux_unscaled; out[pos++] = P.aux; }
+  for (int k = 0; k < d->K; ++k) out[pos++] = P.beta[k];
+  for (int k = 0; k < d->q; ++k) out[pos++] = P.b[k];
+  for (int k = 0; k < d->len_theta_L; ++k) out[pos++] = P.theta_L[k];
+  params_free(&P);
+}
+
+double or_glmm_get_aux(const or_glmm* m, const double* constrained) { return constrained[m->num_params]; }
+
+void or_glmm_parametric_mean(const or_glmm* m, const double* constrained, double* out, int include_fixed, int include_random)
+{
+  const s4b_glmm_data* d = &m->d;
+  const double* beta = constrained + m->num_params + m->has_aux;
+  const double* b = beta + d->K;
+  int64_t N = d->N;
+  for (int64_t i = 0; i < N; ++i) {
+    double eta = 0.0;
+    if (include_fixed) for (int k = 0; k < d->K; ++k) eta += m->X[(size_t) k * (size_t) N + (size_t) i] * beta[k];
+    if (include_random && d->t > 0) for (int32_t z = m->u[i]; z < m->u[i + 1]; ++z) eta += m->w[z] * b[m->v[z]];
+    out[i] = eta;
+  }
+}
