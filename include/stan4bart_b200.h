@@ -1,0 +1,164 @@
+/*
+ * include/stan4bart_b200.h -- C ABI of the B200-native stan4bart Gibbs hot path.
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference interface it
+ * replaces (paths relative to /root/reference).  All functions return 0 on success and a
+ * non-zero code on failure; s4b_last_error() returns the message (thread local).  There is
+ * no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Three layers, mirroring the reference's own boundaries:
+ *   gpubart_*  : the dbarts C-callable table stan4bart binds at load time
+ *                (BARTFunctionTable, src/init.cpp:54-81, lookup :1113-1147)
+ *   glmm_*     : the Stan model / gradient hook (stan::model::gradient,
+ *                src/include/stan/model/gradient.hpp:21-35; continuous_model members
+ *                src/stan_files/continuous.hpp:3626-3768)
+ *   s4b_sampler_* : the .Call routines of the host sampler (src/init.cpp:1215-1229)
+ */
+#ifndef STAN4BART_B200_H
+#define STAN4BART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S4B_TRACE_RECORD_LEN 32
+
+/* dbarts Control + Model as configured by R/stan4bart_fit.R:437-479 */
+typedef struct s4b_bart_config {
+  int64_t n, p, n_test;
+  int32_t num_trees;       /* n.trees */
+  int32_t n_cuts;          /* n.cuts, uniform cut points, <= 255 */
+  int32_t thin;            /* n.thin = skip.bart */
+  int32_t min_obs;         /* minNumObservationsInNode (5) */
+  int32_t is_binary;
+  int32_t reserved;
+  double birth_death_prob, swap_prob, change_prob, birth_prob;   /* .5 .1 .4 .5 */
+  double base, power;      /* cgm tree prior */
+  double k;                /* normal(k) leaf prior */
+  double node_scale;       /* .5 continuous, 3 binary (R/stan4bart_fit.R:479) */
+  uint64_t seed;
+} s4b_bart_config;
+
+/* the `data.stan` list, R/stan4bart_fit.R:259-365 / src/stan_sampler.cpp:112-380 (default path) */
+typedef struct s4b_glmm_data {
+  int64_t N;
+  int32_t K, is_binary, prior_dist, prior_dist_for_aux, t, q, len_theta_L, len_concentration, len_regularization, reserved;
+  int64_t num_non_zero;
+  const double* X; const double* y; const double* prior_scale; const double* prior_mean;
+  double prior_scale_for_aux, prior_mean_for_aux, prior_df_for_aux;
+  const int32_t* p; const int32_t* l; const double* shape; const double* scale;
+  const double* concentration; const double* regularization;
+  const double* w; const int32_t* v; const int32_t* u;
+} s4b_glmm_data;
+
+/* StanControl, src/stan_sampler.hpp:28-42 */
+typedef struct s4b_stan_control {
+  uint32_t seed; int32_t skip;
+  double init_radius, adapt_gamma, adapt_delta, adapt_kappa, adapt_t0;
+  uint32_t adapt_init_buffer, adapt_term_buffer, adapt_window; int32_t max_treedepth;
+  double stepsize, stepsize_jitter;
+} s4b_stan_control;
+
+/* control.common, src/init.cpp:1015-1051 */
+typedef struct s4b_common_control {
+  int32_t warmup, iter, is_binary, keep_fits;
+  double sigma_init;
+} s4b_common_control;
+
+const char* s4b_last_error(void);
+int s4b_device_count(void);
+/* all later objects created on this thread use `cuda_stream` (a cudaStream_t; NULL = a private stream) */
+int s4b_set_stream(void* cuda_stream);
+
+/* ------------------------------------------------------------------ gpubart_* */
+typedef struct gpubart_fit gpubart_fit;
+/* initializeFit + initializeControl/Data/Model (init.cpp:215-228); x, x_test column major */
+int gpubart_create(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test, gpubart_fit** out);
+/* invalidateFit (init.cpp:161-164) */
+int gpubart_free(gpubart_fit* fit);
+/* setOffset(fit, offset, updateScale) (init.cpp:255, :817) */
+int gpubart_set_offset(gpubart_fit* fit, const double* offset, int update_scale);
+/* setSigma (init.cpp:257, :799) */
+int gpubart_set_sigma(gpubart_fit* fit, double sigma);
+/* sampleTreesFromPrior (init.cpp:261) */
+int gpubart_sample_trees_from_prior(gpubart_fit* fit);
+/* runSamplerWithResults(fit, 0, results[numSamples = 1]) (init.cpp:273, :824); layout src/bart_util.hpp:14-35 */
+int gpubart_run_sampler_with_results(gpubart_fit* fit, double* train, double* test, uint32_t* varcount, double* sigma);
+/* storeLatents / getLatentVariables (init.cpp:289, :845) */
+int gpubart_store_latents(gpubart_fit* fit, double* out);
+/* fit->sharedScratch.dataScale.{min,max,range} (init.cpp:324-325) */
+int gpubart_get_data_range(gpubart_fit* fit, double* min_max_range);
+/* predict(fit, x_test, n, testOffset, result) (init.cpp:398) */
+int gpubart_predict(gpubart_fit* fit, const double* x_test, int64_t n, const double* test_offset, double* out);
+/* getTrees -> FlattenedTrees (init.cpp:577-666): pre-order, var < 0 => leaf, value = cut point | leaf mu */
+int gpubart_num_nodes(gpubart_fit* fit, int64_t* out);
+int gpubart_get_trees(gpubart_fit* fit, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value);
+/* parity instrumentation (no reference counterpart) */
+int gpubart_node_assignment(gpubart_fit* fit, int tree, int64_t* heap_index);
+int gpubart_leaf_stats(gpubart_fit* fit, int tree, int max_leaves, int64_t* heap_index, int64_t* count, double* sum, double* sumsq, int* num_leaves);
+int gpubart_get_residual(gpubart_fit* fit, double* out);
+int gpubart_set_trace(gpubart_fit* fit, size_t cap_records);
+int gpubart_get_trace(gpubart_fit* fit, double* out, size_t cap_records, size_t* num_records);
+int gpubart_set_tape(gpubart_fit* fit, const double* tape, size_t len);
+int gpubart_set_record(gpubart_fit* fit, size_t cap);
+int gpubart_get_record(gpubart_fit* fit, double* out, size_t cap, size_t* len);
+int gpubart_rng_counter(gpubart_fit* fit, uint64_t* out);
+int gpubart_set_use_graph(gpubart_fit* fit, int use_graph);
+/* micro-benchmark hook: `reps` launches of the leaf-statistics pass for `tree`, returns mean ms per launch */
+int gpubart_time_leaf_stats(gpubart_fit* fit, int tree, int reps, double* ms_per_launch);
+int gpubart_num_tree_steps(gpubart_fit* fit, int64_t* out);
+
+/* ------------------------------------------------------------------ glmm_* */
+typedef struct glmm_model glmm_model;
+/* createStanModelFromExpression (src/stan_sampler.cpp:112-380) */
+int glmm_create(const s4b_glmm_data* data, glmm_model** out);
+int glmm_free(glmm_model* m);
+int glmm_num_params(glmm_model* m, int* d, int* num_constrained);
+/* set_offset / set_response (continuous.hpp:3626-3635), host pointers */
+int glmm_set_offset(glmm_model* m, const double* offset);
+int glmm_set_response(glmm_model* m, const double* y);
+/* stan::model::gradient (model/gradient.hpp:21-35): status != 0 <=> exception path (V = +inf) */
+int glmm_log_prob_grad(glmm_model* m, const double* q, double* lp, double* grad, int* status);
+/* write_array (continuous.hpp:2640-2938) */
+int glmm_write_array(glmm_model* m, const double* q, double* out);
+/* get_parametric_mean (continuous.hpp:3662-3768) */
+int glmm_parametric_mean(glmm_model* m, const double* constrained, double* out, int include_fixed, int include_random);
+/* device data terms only: S = sum e^2, X'e, Z'e */
+int glmm_data_terms(glmm_model* m, const double* beta, const double* b, double* S, double* gbeta, double* gb);
+int glmm_num_grad_evals(glmm_model* m, int64_t* out);
+
+/* ------------------------------------------------------------------ s4b_sampler_* */
+typedef struct s4b_sampler s4b_sampler;
+/* stan4bart_create (init.cpp:190-310) */
+int s4b_sampler_create(const s4b_bart_config* bcfg, const double* y_bart, const double* x_bart, const double* x_test,
+                       const s4b_glmm_data* gdata, const s4b_stan_control* sctl, const s4b_common_control* cctl,
+                       const double* bart_offset_init, s4b_sampler** out);
+/* stan4bart_finalize */
+int s4b_sampler_free(s4b_sampler* s);
+int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out);
+/* stan4bart_run(sampler, numIter, isWarmup, "both") (init.cpp:678-965).  Output buffers may be NULL.
+ * stan [num_pars x S], train [n x S], test [n_test x S], varcount [p x S], sigma [S]; S = keep_fits ? num_iter : 1 */
+int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma);
+/* stan4bart_disengageAdaptation (init.cpp:995-1004) */
+int s4b_sampler_disengage_adaptation(s4b_sampler* s);
+/* stan4bart_getBARTDataRange (init.cpp:316-330) */
+int s4b_sampler_get_bart_data_range(s4b_sampler* s, double* out2);
+/* stan4bart_getParametricMean (init.cpp:332-347) */
+int s4b_sampler_get_parametric_mean(s4b_sampler* s, double* out);
+/* stan4bart_predictBART (init.cpp:354-403), on the live sampler's current trees */
+int s4b_sampler_predict_bart(s4b_sampler* s, const double* x_test, int64_t n, const double* test_offset, double* out);
+gpubart_fit* s4b_sampler_bart(s4b_sampler* s);
+glmm_model* s4b_sampler_glmm(s4b_sampler* s);
+/* running posterior means kept on device (keep_fits = FALSE path): mean train / test BART fit
+ * and mean parametric part over the sampling-phase sweeps run so far */
+int s4b_sampler_get_means(s4b_sampler* s, double* mean_bart_train, double* mean_bart_test, double* mean_parametric, int64_t* num_draws);
+/* timing split of the last run: milliseconds in the Stan block and the BART block (CUDA events), leapfrog count */
+int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* n_grad_evals, int64_t* n_tree_steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,982 @@
+// stan4bart_b200/csrc/bart.cu
+// BART half of the Gibbs sweep on one B200: kernels + the host object that owns device state.
+// Mirrors the dbarts entry points stan4bart binds through BARTFunctionTable
+// (/root/reference/src/init.cpp:54-81): initializeFit, setOffset, setSigma, sampleTreesFromPrior,
+// runSamplerWithResults, storeLatents (getLatentVariables), predict, getTrees.
+#include "bart.hpp"
+#include "bart_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace s4b {
+
+constexpr int kBlock = 256;
+
+enum PassMode { kModeStep = 0, kModeStatsOnly = 1, kModeUpdateOnly = 2 };
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_words(void* dst, const void* src, int nbytes, int tid, int nthreads)
+{
+  uint32_t* d = (uint32_t*) dst; const uint32_t* s = (const uint32_t*) src;
+  for (int i = tid; i < nbytes / 4; i += nthreads) d[i] = s[i];
+}
+
+__device__ __forceinline__ void copy_trav(TravTree& dst, const TravTree& src, int tid, int nthreads, bool with_val, bool with_slot)
+{
+  int n = src.n;
+  if (tid == 0) dst.n = n;
+  for (int i = tid; i < n; i += nthreads) {
+    dst.trav[i] = src.trav[i];
+    if (with_val) dst.val[i] = src.val[i];
+    if (with_slot) dst.slot[i] = src.slot[i];
+  }
+}
+
+__device__ __forceinline__ int traverse(const uint32_t* __restrict__ trav, const uint8_t* __restrict__ xt, long long npad, long long i)
+{
+  int node = 0;
+  uint32_t tr = trav[0];
+  while ((tr >> 16) != 0xFFFFu) {
+    uint32_t x = __ldg(xt + (long long) (tr >> 16) * npad + i);
+    node = (x <= ((tr >> 8) & 0xFFu)) ? node + 1 : (int) (tr & 0xFFu);
+    tr = trav[node];
+  }
+  return node;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// the per-tree pass (see bart_kernels.cuh header comment)
+// algorithmic bytes per observation: R read 8 + R write 8 (when an update is pending) + one
+// u8 per tree level actually visited (typically 1-3)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, int propose_next)
+{
+  __shared__ StepDesc sd;
+  __shared__ StepDesc sd_out;
+  __shared__ DTree tree;
+  __shared__ LeafStat st[S4B_MAX_SLOTS];
+  __shared__ double red[kBlock / 32][3 * S4B_SLOT_CHUNK];
+  __shared__ BartParams prm;
+  __shared__ double pgrow[S4B_MAX_DEPTH + 2];
+  __shared__ unsigned int s_ticket;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- stage the step descriptor ----
+  if (tid == 0) {
+    const StepDesc& g = *dv.desc;
+    sd.a_valid = g.a_valid; sd.a_same = g.a_same;
+    sd.b_tree = g.b_tree; sd.b_kind = g.b_kind; sd.b_node = g.b_node; sd.b_var = g.b_var; sd.b_cut = g.b_cut;
+    sd.b_num_leaves = g.b_num_leaves; sd.b_nslots = g.b_nslots; sd.b_child = g.b_child;
+    sd.log_prior_trans = g.log_prior_trans; sd.new_var = g.new_var; sd.new_cut = g.new_cut;
+  }
+  __syncthreads();
+  const bool a_valid = sd.a_valid != 0 && mode != kModeStatsOnly;
+  const bool a_same = sd.a_same != 0;
+  const int kind = sd.b_kind;
+  if (a_valid) { copy_trav(sd.a_old, dv.desc->a_old, tid, kBlock, true, false); if (!a_same) copy_trav(sd.a_new, dv.desc->a_new, tid, kBlock, true, false); }
+  if (mode != kModeUpdateOnly) {
+    copy_trav(sd.b_cur, dv.desc->b_cur, tid, kBlock, true, true);
+    if (kind == 2 || kind == 3) copy_trav(sd.b_prop, dv.desc->b_prop, tid, kBlock, false, true);
+  }
+  __syncthreads();
+
+  const long long n = dv.n, npad = dv.npad;
+  const long long nquad = (n + 3) >> 2;
+  const uint8_t* __restrict__ xt = dv.xt;
+  double* __restrict__ R = dv.R;
+  const int L = sd.b_num_leaves;
+  const int nslots = mode == kModeUpdateOnly ? 0 : sd.b_nslots;
+  const int nchunks = mode == kModeUpdateOnly ? 1 : (nslots + S4B_SLOT_CHUNK - 1) / S4B_SLOT_CHUNK;
+  const bool two_trees = (kind == 2 || kind == 3);
+  const int birth_node = kind == 0 ? sd.b_node : -1;
+  const long long birth_col = (long long) (kind == 0 ? sd.b_var : 0) * npad;
+  const uint32_t birth_cut = (uint32_t) sd.b_cut;
+
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int base = chunk * S4B_SLOT_CHUNK;
+    int cnt[S4B_SLOT_CHUNK]; double s1[S4B_SLOT_CHUNK], s2[S4B_SLOT_CHUNK];
+#pragma unroll
+    for (int k = 0; k < S4B_SLOT_CHUNK; ++k) { cnt[k] = 0; s1[k] = 0.0; s2[k] = 0.0; }
+    const bool do_update = a_valid && chunk == 0;
+
+    for (long long qd = (long long) blockIdx.x * kBlock + tid; qd < nquad; qd += (long long) gridDim.x * kBlock) {
+      const long long i0 = qd << 2;
+      double2 ra = *reinterpret_cast<const double2*>(R + i0);
+      double2 rb = *reinterpret_cast<const double2*>(R + i0 + 2);
+      double r[4] = { ra.x, ra.y, rb.x, rb.y };
+      if (do_update) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int leaf = traverse(sd.a_old.trav, xt, npad, i0 + j);
+          r[j] += sd.a_old.val[leaf];
+          if (!a_same) { int l2 = traverse(sd.a_new.trav, xt, npad, i0 + j); r[j] -= sd.a_new.val[l2]; }
+        }
+        *reinterpret_cast<double2*>(R + i0) = make_double2(r[0], r[1]);
+        *reinterpret_cast<double2*>(R + i0 + 2) = make_double2(r[2], r[3]);
+      }
+      if (mode != kModeUpdateOnly) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long i = i0 + j;
+          int leaf = traverse(sd.b_cur.trav, xt, npad, i);
+          double pr = r[j] + sd.b_cur.val[leaf];
+          int sa = sd.b_cur.slot[leaf];
+          if (leaf == birth_node) sa = L + ((uint32_t) __ldg(xt + birth_col + i) > birth_cut ? 1 : 0);
+          int sb = 255;
+          if (two_trees) sb = sd.b_prop.slot[traverse(sd.b_prop.trav, xt, npad, i)];
+          if (i >= n) { sa = 255; sb = 255; }
+          sa -= base; sb -= base;
+          double pp = pr * pr;
+#pragma unroll
+          for (int k = 0; k < S4B_SLOT_CHUNK; ++k) {
+            bool m = (sa == k) | (sb == k);
+            cnt[k] += m ? 1 : 0;
+            s1[k] += m ? pr : 0.0;
+            s2[k] += m ? pp : 0.0;
+          }
+        }
+      }
+    }
+    if (mode == kModeUpdateOnly) return;
+
+    // ---- block reduction of this chunk, fixed order ----
+    const int kmax = min(S4B_SLOT_CHUNK, nslots - base);
+#pragma unroll
+    for (int k = 0; k < S4B_SLOT_CHUNK; ++k) {
+      if (k < kmax) {
+        int c = __reduce_add_sync(0xffffffffu, cnt[k]);
+        double a = warp_sum(s1[k]);
+        double b = warp_sum(s2[k]);
+        if (lane == 0) { red[warp][3 * k] = (double) c; red[warp][3 * k + 1] = a; red[warp][3 * k + 2] = b; }
+      }
+    }
+    __syncthreads();
+    if (tid < 3 * kmax) {
+      double acc = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) acc += red[w][tid];
+      dv.partials[(long long) (3 * base + tid) * gridDim.x + blockIdx.x] = acc;
+    }
+    __syncthreads();
+  }
+
+  // ---- last block to finish becomes the controller ----
+  __threadfence();
+  if (tid == 0) s_ticket = atomicAdd(dv.ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+
+  // phase 1: reduce per-block partials (value-major layout, lanes stride over blocks)
+  const int G = gridDim.x;
+  for (int v = warp; v < 3 * nslots; v += kBlock / 32) {
+    const double* src = dv.partials + (long long) v * G;
+    double acc = 0.0;
+    for (int b = lane; b < G; b += 32) acc += __ldcg(src + b);
+    acc = warp_sum(acc);
+    if (lane == 0) { double* dst = reinterpret_cast<double*>(&st[v / 3]); dst[v % 3] = acc; }
+  }
+  if (tid == 0) { prm = *dv.params; *dv.ticket = 0u; }
+  if (tid < S4B_MAX_DEPTH + 2) pgrow[tid] = dv.pgrow[tid];
+  __syncthreads();
+  if (mode == kModeStatsOnly) {
+    for (int v = tid; v < 3 * nslots; v += kBlock) dv.stats_out[v] = reinterpret_cast<double*>(st)[v];
+    return;
+  }
+  const int t_cur = sd.b_tree;
+  {
+    const DTree& g = dv.trees[t_cur];
+    int nn = g.num_nodes;
+    if (tid == 0) { tree.num_nodes = nn; tree.pad = 0; }
+    copy_words(tree.nodes, g.nodes, nn * (int) sizeof(DNode), tid, kBlock);
+  }
+  __syncthreads();
+
+  // phase 2: Metropolis decision + leaf draws (serial)
+  if (tid == 0) {
+    RngState rng = *dv.rng;
+    double* trec = nullptr;
+    if (dv.trace != nullptr) {
+      unsigned long long k = *dv.trace_len;
+      if (k < dv.trace_cap) { trec = dv.trace + k * S4B_TRACE_LEN; for (int i = 0; i < S4B_TRACE_LEN; ++i) trec[i] = 0.0; }
+      *dv.trace_len = k + 1;
+    }
+    decide_and_draw(tree, prm, rng, sd, st, sd_out, trec);
+    *dv.rng = rng;
+    if (rng.tape_underrun) dv.params->error_flag |= 2u;
+  }
+  __syncthreads();
+  // phase 3: write tree back, fetch the next one
+  {
+    DTree& g = dv.trees[t_cur];
+    int nn = tree.num_nodes;
+    if (tid == 0) g.num_nodes = nn;
+    copy_words(g.nodes, tree.nodes, nn * (int) sizeof(DNode), tid, kBlock);
+  }
+  __syncthreads();
+  if (propose_next) {
+    const int t_next = (t_cur + 1) % prm.num_trees;
+    const DTree& g = dv.trees[t_next];
+    int nn = g.num_nodes;
+    if (tid == 0) { tree.num_nodes = nn; }
+    copy_words(tree.nodes, g.nodes, nn * (int) sizeof(DNode), tid, kBlock);
+    __syncthreads();
+    if (tid == 0) {
+      RngState rng = *dv.rng;
+      propose_step(tree, prm, pgrow, rng, sd_out, t_next);
+      *dv.rng = rng;
+      if (rng.tape_underrun) dv.params->error_flag |= 2u;
+    }
+  } else if (tid == 0) {
+    sd_out.b_kind = -1; sd_out.b_tree = -1; sd_out.b_num_leaves = 0; sd_out.b_nslots = 0; sd_out.b_cur.n = 0; sd_out.b_prop.n = 0;
+  }
+  __syncthreads();
+  // phase 4: publish the descriptor for the next launch
+  {
+    StepDesc& g = *dv.desc;
+    if (tid == 0) {
+      g.a_valid = sd_out.a_valid; g.a_same = sd_out.a_same;
+      g.b_tree = sd_out.b_tree; g.b_kind = sd_out.b_kind; g.b_node = sd_out.b_node; g.b_var = sd_out.b_var; g.b_cut = sd_out.b_cut;
+      g.b_num_leaves = sd_out.b_num_leaves; g.b_nslots = sd_out.b_nslots; g.b_child = sd_out.b_child;
+      g.log_prior_trans = sd_out.log_prior_trans; g.new_var = sd_out.new_var; g.new_cut = sd_out.new_cut;
+    }
+    copy_trav(g.a_old, sd_out.a_old, tid, kBlock, true, false);
+    if (!sd_out.a_same) copy_trav(g.a_new, sd_out.a_new, tid, kBlock, true, false);
+    if (sd_out.b_kind != -1 || propose_next) {
+      copy_trav(g.b_cur, sd_out.b_cur, tid, kBlock, true, true);
+      if (sd_out.b_kind == 2 || sd_out.b_kind == 3) copy_trav(g.b_prop, sd_out.b_prop, tid, kBlock, false, true);
+    }
+  }
+}
+
+// first proposal of a sweep (tree 0); single block
+__global__ void __launch_bounds__(kBlock) k_propose_first(BartDev dv)
+{
+  __shared__ DTree tree;
+  __shared__ StepDesc sd_out;
+  __shared__ BartParams prm;
+  __shared__ double pgrow[S4B_MAX_DEPTH + 2];
+  const int tid = threadIdx.x;
+  if (tid == 0) prm = *dv.params;
+  if (tid < S4B_MAX_DEPTH + 2) pgrow[tid] = dv.pgrow[tid];
+  {
+    const DTree& g = dv.trees[0];
+    int nn = g.num_nodes;
+    if (tid == 0) tree.num_nodes = nn;
+    copy_words(tree.nodes, g.nodes, nn * (int) sizeof(DNode), tid, kBlock);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    RngState rng = *dv.rng;
+    sd_out.a_valid = 0; sd_out.a_same = 1; sd_out.a_old.n = 0; sd_out.a_new.n = 0;
+    propose_step(tree, prm, pgrow, rng, sd_out, 0);
+    *dv.rng = rng;
+    if (rng.tape_underrun) dv.params->error_flag |= 2u;
+  }
+  __syncthreads();
+  StepDesc& g = *dv.desc;
+  if (tid == 0) {
+    g.a_valid = 0; g.a_same = 1;
+    g.b_tree = sd_out.b_tree; g.b_kind = sd_out.b_kind; g.b_node = sd_out.b_node; g.b_var = sd_out.b_var; g.b_cut = sd_out.b_cut;
+    g.b_num_leaves = sd_out.b_num_leaves; g.b_nslots = sd_out.b_nslots; g.b_child = sd_out.b_child;
+    g.log_prior_trans = sd_out.log_prior_trans; g.new_var = sd_out.new_var; g.new_cut = sd_out.new_cut;
+  }
+  copy_trav(g.b_cur, sd_out.b_cur, tid, kBlock, true, true);
+  if (sd_out.b_kind == 2 || sd_out.b_kind == 3) copy_trav(g.b_prop, sd_out.b_prop, tid, kBlock, false, true);
+}
+
+// descriptor for a stand-alone statistics pass over the current leaves of one tree
+__global__ void k_build_stats_desc(BartDev dv, int tree_index)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  StepDesc& g = *dv.desc;
+  const DTree& t = dv.trees[tree_index];
+  g.a_valid = 0; g.a_same = 1; g.a_old.n = 0; g.a_new.n = 0;
+  g.b_tree = tree_index; g.b_kind = -1; g.b_node = -1; g.b_var = -1; g.b_cut = -1; g.b_child = -1;
+  g.log_prior_trans = 0.0; g.new_var = -1; g.new_cut = -1; g.b_prop.n = 0;
+  g.b_cur.n = t.num_nodes;
+  int leaf = 0;
+  for (int k = 0; k < t.num_nodes; ++k) {
+    const DNode& nd = t.nodes[k];
+    g.b_cur.trav[k] = pack_trav(nd.var, nd.cut, nd.right);
+    g.b_cur.val[k] = nd.mu;
+    g.b_cur.slot[k] = nd.var < 0 ? (uint8_t) leaf++ : (uint8_t) 255;
+  }
+  g.b_num_leaves = leaf; g.b_nslots = leaf;
+}
+
+// one tree drawn from the CGM prior + its leaf values; fills the (A) part for an update-only pass
+__global__ void k_prior_tree(BartDev dv, int tree_index)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  BartParams P = *dv.params;
+  RngState rng = *dv.rng;
+  DTree& t = dv.trees[tree_index];
+  StepDesc& g = *dv.desc;
+  // old tree -> a_old
+  g.a_valid = 1; g.a_same = 0; g.b_kind = -1; g.b_tree = tree_index;
+  g.a_old.n = t.num_nodes;
+  for (int k = 0; k < t.num_nodes; ++k) { g.a_old.trav[k] = pack_trav(t.nodes[k].var, t.nodes[k].cut, t.nodes[k].right); g.a_old.val[k] = t.nodes[k].mu; }
+  // collapse to the root, then grow in pre-order
+  t.num_nodes = 1;
+  DNode& root = t.nodes[0];
+  root.var = -1; root.cut = -1; root.right = -1; root.parent = -1; root.depth = 0; root.n = 0;
+  int leaves = 1;
+  for (int i = 0; i < t.num_nodes; ++i) {
+    int navail = t_num_vars_available(t, P, i);
+    bool birthable = navail > 0 && t.nodes[i].depth < S4B_MAX_DEPTH && leaves < S4B_MAX_LEAVES;
+    double pg = birthable ? t_growth_prob_depth(dv.pgrow, navail, t.nodes[i].depth) : 0.0;
+    double u = rng_uniform(rng);
+    if (!(u < pg)) continue;
+    int var = t_ith_available_var(t, P, i, rng_index(rng, navail));
+    int lo, hi; t_split_interval(t, P.n_cuts, i, var, lo, hi);
+    int cut = lo + rng_index(rng, hi - lo + 1);
+    t_insert_children(t, i, var, cut);
+    ++leaves;
+  }
+  for (int k = 0; k < t.num_nodes; ++k) if (t.nodes[k].var < 0) t.nodes[k].mu = rng_normal(rng) / sqrt(P.leaf_prec);
+  g.a_new.n = t.num_nodes;
+  for (int k = 0; k < t.num_nodes; ++k) { g.a_new.trav[k] = pack_trav(t.nodes[k].var, t.nodes[k].cut, t.nodes[k].right); g.a_new.val[k] = t.nodes[k].mu; }
+  *dv.rng = rng;
+  if (rng.tape_underrun) dv.params->error_flag |= 2u;
+}
+
+// ---------------------------------------------------------------------------------------
+// sweep epilogue: pending update of the last tree, probit latents, results
+//   train_out  = BART fit in original units (+ offset if add_offset)   [SURVEY a2]
+//   latent_out = full latent z (binary)                                [SURVEY a9]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_finish_sweep(BartDev dv, double* __restrict__ train_out, double* __restrict__ latent_out, int add_offset)
+{
+  __shared__ TravTree a_old, a_new;
+  __shared__ BartParams prm;
+  const int tid = threadIdx.x;
+  const StepDesc& g = *dv.desc;
+  const bool a_valid = g.a_valid != 0;
+  const bool a_same = g.a_same != 0;
+  if (tid == 0) prm = *dv.params;
+  if (a_valid) { copy_trav(a_old, g.a_old, tid, kBlock, true, false); if (!a_same) copy_trav(a_new, g.a_new, tid, kBlock, true, false); }
+  __syncthreads();
+  const long long n = dv.n, npad = dv.npad;
+  const bool binary = prm.is_binary != 0;
+  for (long long i = (long long) blockIdx.x * kBlock + tid; i < n; i += (long long) gridDim.x * kBlock) {
+    double r = dv.R[i];
+    if (a_valid) {
+      r += a_old.val[traverse(a_old.trav, dv.xt, npad, i)];
+      if (!a_same) r -= a_new.val[traverse(a_new.trav, dv.xt, npad, i)];
+    }
+    double yr = dv.yresc[i];
+    double tf = yr - r;                      // total fit, scaled units
+    double off = dv.offset[i];
+    if (binary) {
+      double z = keyed_truncnorm(prm.key0, prm.key1, (uint32_t) i, prm.latent_epoch, tf + off, dv.y[i] > 0.0);
+      yr = z - off;
+      dv.yresc[i] = yr;
+      r = yr - tf;
+      if (latent_out != nullptr) latent_out[i] = z;
+    }
+    dv.R[i] = r;
+    if (train_out != nullptr) {
+      double f = binary ? tf : prm.smin + (tf + 0.5) * prm.srange;
+      train_out[i] = add_offset ? f + off : f;
+    }
+  }
+}
+
+__global__ void k_bump_epoch_clear_update(BartDev dv, int bump)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) { if (bump) dv.params->latent_epoch += 1u; dv.desc->a_valid = 0; }
+}
+
+// test-sample fits: sum over all trees of the leaf value reached by each test row
+__global__ void __launch_bounds__(kBlock) k_test_fits(BartDev dv, const uint8_t* __restrict__ xt_test, long long n_test, long long npad_test,
+                                                      const double* __restrict__ test_offset, double* __restrict__ out, int unscale)
+{
+  extern __shared__ unsigned char smem_raw[];
+  // layout: uint32 trav[cap], double val[cap]
+  const int tid = threadIdx.x;
+  const int T = dv.params->num_trees;
+  const int cap_nodes = 2048;
+  uint32_t* trav = reinterpret_cast<uint32_t*>(smem_raw);
+  double* val = reinterpret_cast<double*>(smem_raw + sizeof(uint32_t) * cap_nodes);
+  __shared__ int tree_start[257];
+  const long long i = (long long) blockIdx.x * kBlock + tid;
+  double acc = 0.0;
+  int t0 = 0;
+  while (t0 < T) {
+    // pack as many trees as fit
+    __syncthreads();
+    if (tid == 0) {
+      int used = 0, t = t0, k = 0;
+      while (t < T && k < 256 && used + dv.trees[t].num_nodes <= cap_nodes) { tree_start[k++] = used; used += dv.trees[t].num_nodes; ++t; }
+      tree_start[k] = used;
+      tree_start[256] = k;
+    }
+    __syncthreads();
+    const int nt = tree_start[256];
+    for (int k = 0; k < nt; ++k) {
+      const DTree& g = dv.trees[t0 + k];
+      int base = tree_start[k];
+      for (int j = tid; j < g.num_nodes; j += kBlock) {
+        const DNode& nd = g.nodes[j];
+        trav[base + j] = pack_trav(nd.var, nd.cut, nd.right);
+        val[base + j] = nd.mu;
+      }
+    }
+    __syncthreads();
+    if (i < n_test) {
+      for (int k = 0; k < nt; ++k) {
+        const uint32_t* tv = trav + tree_start[k];
+        int leaf = traverse(tv, xt_test, npad_test, i);
+        acc += val[tree_start[k] + leaf];
+      }
+    }
+    t0 += nt;
+  }
+  if (i < n_test) {
+    const double smin = dv.params->smin, srange = dv.params->srange;
+    double f = unscale ? smin + (acc + 0.5) * srange : acc;
+    out[i] = f + (test_offset != nullptr ? test_offset[i] : 0.0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// setOffset / setSigma / rescale
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_minmax(BartDev dv, const double* __restrict__ new_offset, double* __restrict__ part /* [2][G] */)
+{
+  __shared__ double smin_s[kBlock / 32], smax_s[kBlock / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double mn = INFINITY, mx = -INFINITY;
+  for (long long i = (long long) blockIdx.x * kBlock + tid; i < dv.n; i += (long long) gridDim.x * kBlock) {
+    double v = dv.y[i] - (new_offset != nullptr ? new_offset[i] : 0.0);
+    mn = fmin(mn, v); mx = fmax(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if (lane == 0) { smin_s[warp] = mn; smax_s[warp] = mx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kBlock / 32; ++w) { mn = fmin(mn, smin_s[w]); mx = fmax(mx, smax_s[w]); }
+    part[blockIdx.x] = mn; part[gridDim.x + blockIdx.x] = mx;
+  }
+}
+
+// single thread: finish min/max, update the scale, sigma and (optionally) leaf values
+__global__ void k_update_scale(BartDev dv, const double* __restrict__ part, int G, double* __restrict__ scale_factor_out)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  BartParams& P = *dv.params;
+  double mn = INFINITY, mx = -INFINITY;
+  for (int b = 0; b < G; ++b) { mn = fmin(mn, part[b]); mx = fmax(mx, part[G + b]); }
+  double old_range = P.srange;
+  double sigma_unscaled = old_range > 0.0 ? P.sigma * old_range : P.sigma;
+  double range = mx - mn;
+  if (!(range > 0.0)) range = 1.0;
+  P.smin = mn; P.smax = mx; P.srange = range;
+  double s = 1.0;
+  if (old_range > 0.0) { s = old_range / range; P.sigma = sigma_unscaled / range; }
+  *scale_factor_out = s;
+}
+
+__global__ void k_scale_leaves(BartDev dv, const double* __restrict__ scale_factor)
+{
+  const double s = *scale_factor;
+  const int t = blockIdx.x;
+  DTree& tr = dv.trees[t];
+  for (int k = threadIdx.x; k < tr.num_nodes; k += blockDim.x) if (tr.nodes[k].var < 0) tr.nodes[k].mu *= s;
+}
+
+// yresc / R refresh for a new offset.  scale_factor == nullptr => scale unchanged.
+__global__ void __launch_bounds__(kBlock) k_apply_offset(BartDev dv, const double* __restrict__ new_offset, const double* __restrict__ scale_factor)
+{
+  const double s = scale_factor != nullptr ? *scale_factor : 1.0;
+  const double smin = dv.params->smin, srange = dv.params->srange;
+  for (long long i = (long long) blockIdx.x * kBlock + threadIdx.x; i < dv.n; i += (long long) gridDim.x * kBlock) {
+    double off = new_offset != nullptr ? new_offset[i] : 0.0;
+    double tf = (dv.yresc[i] - dv.R[i]) * s;
+    double yr = (dv.y[i] - off - smin) / srange - 0.5;
+    dv.yresc[i] = yr;
+    dv.R[i] = yr - tf;
+    dv.offset[i] = off;
+  }
+}
+
+// binary: new offset => redraw the latents around (fit + offset)  (oracle_bart.c sample_latents)
+__global__ void __launch_bounds__(kBlock) k_apply_offset_binary(BartDev dv, const double* __restrict__ new_offset, double* __restrict__ latent_out)
+{
+  const BartParams& P = *dv.params;
+  const uint32_t k0 = P.key0, k1 = P.key1, epoch = P.latent_epoch;
+  for (long long i = (long long) blockIdx.x * kBlock + threadIdx.x; i < dv.n; i += (long long) gridDim.x * kBlock) {
+    double off = new_offset != nullptr ? new_offset[i] : 0.0;
+    double tf = dv.yresc[i] - dv.R[i];
+    double z = keyed_truncnorm(k0, k1, (uint32_t) i, epoch, tf + off, dv.y[i] > 0.0);
+    double yr = z - off;
+    dv.yresc[i] = yr;
+    dv.R[i] = yr - tf;
+    dv.offset[i] = off;
+    if (latent_out != nullptr) latent_out[i] = z;
+  }
+}
+
+__global__ void k_set_sigma(BartDev dv, double sigma)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) dv.params->sigma = dv.params->is_binary ? 1.0 : sigma / dv.params->srange;
+}
+
+__global__ void k_store_latents(BartDev dv, double* __restrict__ out)
+{
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < dv.n; i += (long long) gridDim.x * blockDim.x) out[i] = dv.yresc[i] + dv.offset[i];
+}
+
+__global__ void k_varcount(BartDev dv, unsigned int* __restrict__ out)
+{
+  const int T = dv.params->num_trees;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const DTree& tr = dv.trees[t];
+    for (int k = 0; k < tr.num_nodes; ++k) if (tr.nodes[k].var >= 0) atomicAdd(out + tr.nodes[k].var, 1u);
+  }
+}
+
+// observation -> node partition of one tree as heap indices (integer, bit-exact contract)
+__global__ void __launch_bounds__(kBlock) k_node_assignment(BartDev dv, int tree_index, long long* __restrict__ out)
+{
+  __shared__ uint32_t trav[S4B_NODE_CAP];
+  const DTree& g = dv.trees[tree_index];
+  for (int k = threadIdx.x; k < g.num_nodes; k += kBlock) trav[k] = pack_trav(g.nodes[k].var, g.nodes[k].cut, g.nodes[k].right);
+  __syncthreads();
+  for (long long i = (long long) blockIdx.x * kBlock + threadIdx.x; i < dv.n; i += (long long) gridDim.x * kBlock) {
+    int node = 0; long long h = 1;
+    uint32_t tr = trav[0];
+    while ((tr >> 16) != 0xFFFFu) {
+      uint32_t x = __ldg(dv.xt + (long long) (tr >> 16) * dv.npad + i);
+      bool left = x <= ((tr >> 8) & 0xFFu);
+      node = left ? node + 1 : (int) (tr & 0xFFu);
+      h = 2 * h + (left ? 0 : 1);
+      tr = trav[node];
+    }
+    out[i] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host object
+// ---------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
+BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, const double* x_test, cudaStream_t stream)
+    : cfg_(cfg), stream_(stream)
+{
+  if (cfg.n_cuts < 1 || cfg.n_cuts > 255) throw std::invalid_argument("n_cuts must be in [1, 255] (u8 bins)");
+  if (cfg.p < 1 || cfg.p > 32767) throw std::invalid_argument("p out of range");
+  if (cfg.num_trees < 1) throw std::invalid_argument("num_trees < 1");
+  if (cfg.n < 1) throw std::invalid_argument("n < 1");
+  n_ = cfg.n; p_ = (int) cfg.p; nt_ = cfg.n_test; T_ = cfg.num_trees;
+  npad_ = (n_ + 15) / 16 * 16; npad_t_ = (nt_ + 15) / 16 * 16;
+  int dev = 0; S4B_CUDA(cudaGetDevice(&dev));
+  S4B_CUDA(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
+  blocks_per_sm_ = env_int("S4B_BLOCKS_PER_SM", 3);
+  long long want = ((n_ + 3) / 4 + kBlock - 1) / kBlock;
+  grid_ = (int) std::max<long long>(1, std::min<long long>(want, (long long) num_sms_ * blocks_per_sm_));
+  long long want1 = (n_ + kBlock - 1) / kBlock;
+  grid_ew_ = (int) std::max<long long>(1, std::min<long long>(want1, (long long) num_sms_ * 8));
+
+  // ---- cut points (uniform over the training range) and binning, host side (setup only) ----
+  cuts_.resize((size_t) p_ * cfg.n_cuts);
+  std::vector<uint8_t> xt((size_t) p_ * npad_, 0);
+  for (int j = 0; j < p_; ++j) {
+    const double* col = x + (size_t) j * n_;
+    double mn = col[0], mx = col[0];
+    for (long long i = 1; i < n_; ++i) { mn = std::min(mn, col[i]); mx = std::max(mx, col[i]); }
+    double inc = (mx - mn) / (double) (cfg.n_cuts + 1);
+    double* c = cuts_.data() + (size_t) j * cfg.n_cuts;
+    for (int k = 0; k < cfg.n_cuts; ++k) c[k] = mn + (double) (k + 1) * inc;
+    uint8_t* dst = xt.data() + (size_t) j * npad_;
+    for (long long i = 0; i < n_; ++i) dst[i] = (uint8_t) (std::lower_bound(c, c + cfg.n_cuts, col[i]) - c);
+  }
+  S4B_CUDA(cudaMalloc(&d_xt_, xt.size()));
+  S4B_CUDA(cudaMemcpy(d_xt_, xt.data(), xt.size(), cudaMemcpyHostToDevice));
+  if (nt_ > 0) {
+    std::vector<uint8_t> xtt; bin_matrix(x_test, nt_, npad_t_, xtt);
+    S4B_CUDA(cudaMalloc(&d_xt_test_, xtt.size()));
+    S4B_CUDA(cudaMemcpy(d_xt_test_, xtt.data(), xtt.size(), cudaMemcpyHostToDevice));
+    S4B_CUDA(cudaMalloc(&d_test_out_, sizeof(double) * (size_t) npad_t_));
+  }
+  auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * count)); S4B_CUDA(cudaMemset(*p, 0, sizeof(double) * count)); };
+  dalloc(&d_R_, (size_t) npad_); dalloc(&d_yresc_, (size_t) npad_); dalloc(&d_y_, (size_t) npad_); dalloc(&d_offset_, (size_t) npad_);
+  dalloc(&d_train_out_, (size_t) npad_); dalloc(&d_latent_out_, (size_t) npad_); dalloc(&d_offset_in_, (size_t) npad_);
+  S4B_CUDA(cudaMemcpy(d_y_, y, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice));
+  dalloc(&d_partials_, (size_t) 3 * S4B_MAX_SLOTS * grid_);
+  dalloc(&d_minmax_, (size_t) 2 * grid_ew_ + 8);
+  dalloc(&d_stats_out_, (size_t) 3 * S4B_MAX_SLOTS);
+  S4B_CUDA(cudaMalloc(&d_desc_, sizeof(StepDesc))); S4B_CUDA(cudaMemset(d_desc_, 0, sizeof(StepDesc)));
+  S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
+  S4B_CUDA(cudaMalloc(&d_trace_len_, sizeof(unsigned long long))); S4B_CUDA(cudaMemset(d_trace_len_, 0, sizeof(unsigned long long)));
+  S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
+  // trees: single root each
+  std::vector<DTree> trees((size_t) T_);
+  std::memset(trees.data(), 0, sizeof(DTree) * trees.size());
+  for (auto& t : trees) { t.num_nodes = 1; t.nodes[0].var = -1; t.nodes[0].cut = -1; t.nodes[0].right = -1; t.nodes[0].parent = -1; t.nodes[0].n = (int32_t) std::min<long long>(n_, 2147483647LL); }
+  S4B_CUDA(cudaMalloc(&d_trees_, sizeof(DTree) * trees.size()));
+  S4B_CUDA(cudaMemcpy(d_trees_, trees.data(), sizeof(DTree) * trees.size(), cudaMemcpyHostToDevice));
+  // params
+  BartParams P; std::memset(&P, 0, sizeof P);
+  P.n = n_; P.n_test = nt_; P.p = p_; P.num_trees = T_; P.n_cuts = cfg.n_cuts; P.min_obs = cfg.min_obs; P.is_binary = cfg.is_binary; P.thin = cfg.thin;
+  P.birth_death_prob = cfg.birth_death_prob; P.swap_prob = cfg.swap_prob; P.change_prob = cfg.change_prob; P.birth_prob = cfg.birth_prob;
+  P.base = cfg.base; P.power = cfg.power;
+  double sd_leaf = cfg.node_scale / (cfg.k * std::sqrt((double) cfg.num_trees));
+  P.leaf_prec = 1.0 / (sd_leaf * sd_leaf);
+  P.sigma = 1.0; P.smin = -0.5; P.smax = 0.5; P.srange = cfg.is_binary ? 1.0 : 0.0;
+  P.key0 = (uint32_t) cfg.seed; P.key1 = (uint32_t) (cfg.seed >> 32);
+  S4B_CUDA(cudaMalloc(&d_params_, sizeof(BartParams)));
+  S4B_CUDA(cudaMemcpy(d_params_, &P, sizeof P, cudaMemcpyHostToDevice));
+  std::vector<double> pg(S4B_MAX_DEPTH + 2);
+  for (int d = 0; d < S4B_MAX_DEPTH + 2; ++d) pg[d] = cfg.base / std::pow(1.0 + (double) d, cfg.power);
+  dalloc(&d_pgrow_, pg.size());
+  S4B_CUDA(cudaMemcpy(d_pgrow_, pg.data(), sizeof(double) * pg.size(), cudaMemcpyHostToDevice));
+  RngState rs; std::memset(&rs, 0, sizeof rs);
+  rs.key0 = P.key0; rs.key1 = P.key1; rs.stream = S4B_STREAM_BART;
+  S4B_CUDA(cudaMalloc(&d_rng_, sizeof(RngState)));
+  S4B_CUDA(cudaMemcpy(d_rng_, &rs, sizeof rs, cudaMemcpyHostToDevice));
+  S4B_CUDA(cudaMalloc(&d_scale_factor_, sizeof(double)));
+
+  if (cfg.is_binary) {
+    // latents start at +-1 with zero offset (oracle_bart.c or_bart_create)
+    std::vector<double> init((size_t) n_);
+    for (long long i = 0; i < n_; ++i) init[(size_t) i] = y[i] > 0.0 ? 1.0 : -1.0;
+    S4B_CUDA(cudaMemcpy(d_yresc_, init.data(), sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice));
+    S4B_CUDA(cudaMemcpy(d_R_, init.data(), sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice));
+  } else {
+    set_offset_device(nullptr, true);
+  }
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+}
+
+BartFit::~BartFit()
+{
+  if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+  if (graph_exec_thin_) cudaGraphExecDestroy(graph_exec_thin_);
+  cudaFree(d_xt_); cudaFree(d_xt_test_); cudaFree(d_R_); cudaFree(d_yresc_); cudaFree(d_y_); cudaFree(d_offset_);
+  cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
+  cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
+  cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
+  cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+}
+
+void BartFit::bin_matrix(const double* x, long long rows, long long rows_pad, std::vector<uint8_t>& out) const
+{
+  out.assign((size_t) p_ * rows_pad, 0);
+  for (int j = 0; j < p_; ++j) {
+    const double* c = cuts_.data() + (size_t) j * cfg_.n_cuts;
+    const double* col = x + (size_t) j * rows;
+    uint8_t* dst = out.data() + (size_t) j * rows_pad;
+    for (long long i = 0; i < rows; ++i) dst[i] = (uint8_t) (std::lower_bound(c, c + cfg_.n_cuts, col[i]) - c);
+  }
+}
+
+BartDev BartFit::dev() const
+{
+  BartDev d;
+  d.n = n_; d.npad = npad_; d.xt = d_xt_; d.R = d_R_; d.yresc = d_yresc_; d.y = d_y_; d.offset = d_offset_;
+  d.desc = d_desc_; d.trees = d_trees_; d.params = d_params_; d.pgrow = d_pgrow_; d.rng = d_rng_;
+  d.partials = d_partials_; d.ticket = d_ticket_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
+  d.stats_out = d_stats_out_;
+  return d;
+}
+
+void BartFit::invalidate_graph()
+{
+  if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+  if (graph_exec_thin_) { cudaGraphExecDestroy(graph_exec_thin_); graph_exec_thin_ = nullptr; }
+}
+
+void BartFit::set_trace(size_t cap_records)
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_trace_); d_trace_ = nullptr; trace_cap_ = cap_records;
+  if (cap_records) { S4B_CUDA(cudaMalloc(&d_trace_, sizeof(double) * S4B_TRACE_LEN * cap_records)); S4B_CUDA(cudaMemset(d_trace_, 0, sizeof(double) * S4B_TRACE_LEN * cap_records)); }
+  S4B_CUDA(cudaMemset(d_trace_len_, 0, sizeof(unsigned long long)));
+  invalidate_graph();
+}
+
+size_t BartFit::get_trace(double* out, size_t cap_records)
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  unsigned long long k = 0;
+  S4B_CUDA(cudaMemcpy(&k, d_trace_len_, sizeof k, cudaMemcpyDeviceToHost));
+  size_t m = std::min<size_t>({ (size_t) k, trace_cap_, cap_records });
+  if (m && out) S4B_CUDA(cudaMemcpy(out, d_trace_, sizeof(double) * S4B_TRACE_LEN * m, cudaMemcpyDeviceToHost));
+  return (size_t) k;
+}
+
+void BartFit::set_tape(const double* tape, size_t len)
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_tape_); d_tape_ = nullptr;
+  RngState rs; S4B_CUDA(cudaMemcpy(&rs, d_rng_, sizeof rs, cudaMemcpyDeviceToHost));
+  if (tape && len) {
+    S4B_CUDA(cudaMalloc(&d_tape_, sizeof(double) * len));
+    S4B_CUDA(cudaMemcpy(d_tape_, tape, sizeof(double) * len, cudaMemcpyHostToDevice));
+  }
+  rs.tape = d_tape_; rs.tape_len = d_tape_ ? len : 0; rs.tape_pos = 0; rs.tape_underrun = 0;
+  S4B_CUDA(cudaMemcpy(d_rng_, &rs, sizeof rs, cudaMemcpyHostToDevice));
+}
+
+void BartFit::set_record(size_t cap)
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_rec_); d_rec_ = nullptr;
+  RngState rs; S4B_CUDA(cudaMemcpy(&rs, d_rng_, sizeof rs, cudaMemcpyDeviceToHost));
+  if (cap) S4B_CUDA(cudaMalloc(&d_rec_, sizeof(double) * cap));
+  rs.rec = d_rec_; rs.rec_cap = cap; rs.rec_len = 0;
+  S4B_CUDA(cudaMemcpy(d_rng_, &rs, sizeof rs, cudaMemcpyHostToDevice));
+}
+
+size_t BartFit::get_record(double* out, size_t cap)
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  RngState rs; S4B_CUDA(cudaMemcpy(&rs, d_rng_, sizeof rs, cudaMemcpyDeviceToHost));
+  size_t m = std::min<size_t>({ (size_t) rs.rec_len, (size_t) rs.rec_cap, cap });
+  if (m && out) S4B_CUDA(cudaMemcpy(out, d_rec_, sizeof(double) * m, cudaMemcpyDeviceToHost));
+  return (size_t) rs.rec_len;
+}
+
+unsigned long long BartFit::rng_counter()
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  RngState rs; S4B_CUDA(cudaMemcpy(&rs, d_rng_, sizeof rs, cudaMemcpyDeviceToHost));
+  return rs.counter;
+}
+
+void BartFit::check_error_flag()
+{
+  BartParams P = params();
+  if (P.error_flag & 2u) throw std::runtime_error("s4b: RNG tape underrun in replay mode");
+  if (P.error_flag) throw std::runtime_error("s4b: device error flag set");
+}
+
+BartParams BartFit::params()
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  BartParams P; S4B_CUDA(cudaMemcpy(&P, d_params_, sizeof P, cudaMemcpyDeviceToHost));
+  return P;
+}
+
+void BartFit::set_offset_device(const double* d_offset, bool update_scale)
+{
+  BartDev dv = dev();
+  if (cfg_.is_binary) {
+    k_apply_offset_binary<<<grid_ew_, kBlock, 0, stream_>>>(dv, d_offset, d_latent_out_);
+    k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, 1);
+    S4B_CUDA(cudaGetLastError());
+    return;
+  }
+  bool first = !scale_initialised_;
+  if (update_scale || first) {
+    k_minmax<<<grid_ew_, kBlock, 0, stream_>>>(dv, d_offset, d_minmax_);
+    k_update_scale<<<1, 32, 0, stream_>>>(dv, d_minmax_, grid_ew_, d_scale_factor_);
+    if (!first) k_scale_leaves<<<T_, 128, 0, stream_>>>(dv, d_scale_factor_);
+    k_apply_offset<<<grid_ew_, kBlock, 0, stream_>>>(dv, d_offset, d_scale_factor_);
+    scale_initialised_ = true;
+  } else {
+    k_apply_offset<<<grid_ew_, kBlock, 0, stream_>>>(dv, d_offset, nullptr);
+  }
+  S4B_CUDA(cudaGetLastError());
+}
+
+void BartFit::set_offset_host(const double* offset, bool update_scale)
+{
+  if (offset) S4B_CUDA(cudaMemcpyAsync(d_offset_in_, offset, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice, stream_));
+  set_offset_device(offset ? d_offset_in_ : nullptr, update_scale);
+}
+
+void BartFit::set_sigma(double sigma)
+{
+  k_set_sigma<<<1, 32, 0, stream_>>>(dev(), sigma);
+  S4B_CUDA(cudaGetLastError());
+}
+
+void BartFit::sample_trees_from_prior()
+{
+  BartDev dv = dev();
+  for (int t = 0; t < T_; ++t) {
+    k_prior_tree<<<1, 32, 0, stream_>>>(dv, t);
+    k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeUpdateOnly, 0);
+  }
+  k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, 0);
+  S4B_CUDA(cudaGetLastError());
+}
+
+void BartFit::launch_sweep_kernels(bool last_thin)
+{
+  BartDev dv = dev();
+  k_propose_first<<<1, kBlock, 0, stream_>>>(dv);
+  for (int t = 0; t < T_; ++t) k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStep, t + 1 < T_ ? 1 : 0);
+  k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0);
+  k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
+}
+
+void BartFit::run_sweeps()
+{
+  // one runSamplerWithResults(fit, 0, results[numSamples = 1]): `thin` sweeps, the last one kept
+  const bool use_graph = use_graph_;
+  for (int k = 0; k < cfg_.thin; ++k) {
+    bool last = (k + 1) == cfg_.thin;
+    if (!use_graph) { launch_sweep_kernels(last); S4B_CUDA(cudaGetLastError()); continue; }
+    cudaGraphExec_t& ge = last ? graph_exec_ : graph_exec_thin_;
+    if (!ge) {
+      cudaGraph_t graph;
+      S4B_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      launch_sweep_kernels(last);
+      S4B_CUDA(cudaStreamEndCapture(stream_, &graph));
+      S4B_CUDA(cudaGraphInstantiate(&ge, graph, 0));
+      S4B_CUDA(cudaGraphDestroy(graph));
+    }
+    S4B_CUDA(cudaGraphLaunch(ge, stream_));
+  }
+  num_tree_steps_ += (long long) cfg_.thin * T_;
+  if (nt_ > 0) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
+}
+
+void BartFit::test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out)
+{
+  size_t smem = (sizeof(uint32_t) + sizeof(double)) * 2048;
+  int grid = (int) ((rows + kBlock - 1) / kBlock);
+  k_test_fits<<<grid, kBlock, smem, stream_>>>(dev(), d_xt, rows, rows_pad, d_off, d_out, cfg_.is_binary ? 0 : 1);
+  S4B_CUDA(cudaGetLastError());
+}
+
+void BartFit::run(double* train, double* test, uint32_t* varcount, double* sigma)
+{
+  run_sweeps();
+  if (train) S4B_CUDA(cudaMemcpyAsync(train, d_train_out_, sizeof(double) * (size_t) n_, cudaMemcpyDeviceToHost, stream_));
+  if (test && nt_ > 0) S4B_CUDA(cudaMemcpyAsync(test, d_test_out_, sizeof(double) * (size_t) nt_, cudaMemcpyDeviceToHost, stream_));
+  if (varcount) {
+    S4B_CUDA(cudaMemsetAsync(d_varcount_, 0, sizeof(unsigned int) * (size_t) p_, stream_));
+    k_varcount<<<1, 256, 0, stream_>>>(dev(), d_varcount_);
+    S4B_CUDA(cudaMemcpyAsync(varcount, d_varcount_, sizeof(unsigned int) * (size_t) p_, cudaMemcpyDeviceToHost, stream_));
+  }
+  BartParams P = params();   // synchronises
+  if (P.error_flag) check_error_flag();
+  if (sigma) *sigma = cfg_.is_binary ? 1.0 : P.sigma * P.srange;
+}
+
+void BartFit::varcount_device(unsigned int* d_out)
+{
+  S4B_CUDA(cudaMemsetAsync(d_out, 0, sizeof(unsigned int) * (size_t) p_, stream_));
+  k_varcount<<<1, 256, 0, stream_>>>(dev(), d_out);
+}
+
+void BartFit::store_latents(double* out)
+{
+  k_store_latents<<<grid_ew_, kBlock, 0, stream_>>>(dev(), d_latent_out_);
+  S4B_CUDA(cudaMemcpyAsync(out, d_latent_out_, sizeof(double) * (size_t) n_, cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void BartFit::get_residual(double* out)
+{
+  S4B_CUDA(cudaMemcpyAsync(out, d_R_, sizeof(double) * (size_t) n_, cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void BartFit::node_assignment(int tree, long long* out)
+{
+  if (tree < 0 || tree >= T_) throw std::invalid_argument("tree index out of range");
+  long long* d; S4B_CUDA(cudaMalloc(&d, sizeof(long long) * (size_t) n_));
+  k_node_assignment<<<grid_ew_, kBlock, 0, stream_>>>(dev(), tree, d);
+  S4B_CUDA(cudaMemcpyAsync(out, d, sizeof(long long) * (size_t) n_, cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d);
+}
+
+int BartFit::leaf_stats(int tree, int max_leaves, long long* heap, long long* count, double* sum, double* sumsq)
+{
+  if (tree < 0 || tree >= T_) throw std::invalid_argument("tree index out of range");
+  launch_leaf_stats(tree);
+  std::vector<double> st((size_t) 3 * S4B_MAX_SLOTS);
+  S4B_CUDA(cudaMemcpyAsync(st.data(), d_stats_out_, sizeof(double) * st.size(), cudaMemcpyDeviceToHost, stream_));
+  std::vector<DTree> trees = download_trees();
+  const DTree& t = trees[(size_t) tree];
+  int leaf = 0;
+  for (int k = 0; k < t.num_nodes; ++k) if (t.nodes[k].var < 0) {
+    if (leaf < max_leaves) {
+      // heap index by walking parents
+      long long path[64]; int len = 0; int child = k, par = t.nodes[k].parent;
+      while (par >= 0) { path[len++] = (child == par + 1) ? 0 : 1; child = par; par = t.nodes[par].parent; }
+      long long h = 1; for (int q = len - 1; q >= 0; --q) h = 2 * h + path[q];
+      heap[leaf] = h; count[leaf] = (long long) st[(size_t) 3 * leaf]; sum[leaf] = st[(size_t) 3 * leaf + 1]; sumsq[leaf] = st[(size_t) 3 * leaf + 2];
+    }
+    ++leaf;
+  }
+  return leaf;
+}
+
+void BartFit::launch_leaf_stats(int tree)
+{
+  BartDev dv = dev();
+  k_build_stats_desc<<<1, 32, 0, stream_>>>(dv, tree);
+  k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStatsOnly, 0);
+  k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, 0);
+  S4B_CUDA(cudaGetLastError());
+}
+
+std::vector<DTree> BartFit::download_trees()
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  std::vector<DTree> trees((size_t) T_);
+  S4B_CUDA(cudaMemcpy(trees.data(), d_trees_, sizeof(DTree) * trees.size(), cudaMemcpyDeviceToHost));
+  return trees;
+}
+
+long long BartFit::num_nodes()
+{
+  long long c = 0;
+  for (const auto& t : download_trees()) c += t.num_nodes;
+  return c;
+}
+
+void BartFit::get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double* value)
+{
+  long long pos = 0;
+  auto trees = download_trees();
+  for (int t = 0; t < T_; ++t) {
+    const DTree& tr = trees[(size_t) t];
+    for (int k = 0; k < tr.num_nodes; ++k, ++pos) {
+      const DNode& nd = tr.nodes[k];
+      tree_no[pos] = t; n_obs[pos] = nd.n;
+      if (nd.var < 0) { var[pos] = -1; value[pos] = nd.mu; }
+      else { var[pos] = nd.var; value[pos] = cuts_[(size_t) nd.var * cfg_.n_cuts + nd.cut]; }
+    }
+  }
+}
+
+void BartFit::predict(const double* x_test, long long rows, const double* test_offset, double* out)
+{
+  if (rows <= 0) return;
+  long long rows_pad = (rows + 15) / 16 * 16;
+  std::vector<uint8_t> xtt; bin_matrix(x_test, rows, rows_pad, xtt);
+  uint8_t* d_x; double* d_o; double* d_off = nullptr;
+  S4B_CUDA(cudaMalloc(&d_x, xtt.size())); S4B_CUDA(cudaMalloc(&d_o, sizeof(double) * (size_t) rows));
+  S4B_CUDA(cudaMemcpyAsync(d_x, xtt.data(), xtt.size(), cudaMemcpyHostToDevice, stream_));
+  if (test_offset) { S4B_CUDA(cudaMalloc(&d_off, sizeof(double) * (size_t) rows)); S4B_CUDA(cudaMemcpyAsync(d_off, test_offset, sizeof(double) * (size_t) rows, cudaMemcpyHostToDevice, stream_)); }
+  test_fits_device(d_x, rows, rows_pad, d_off, d_o);
+  S4B_CUDA(cudaMemcpyAsync(out, d_o, sizeof(double) * (size_t) rows, cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_x); cudaFree(d_o); cudaFree(d_off);
+}
+
+}  // namespace s4b

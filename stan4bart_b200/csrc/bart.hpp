@@ -1,0 +1,103 @@
+// stan4bart_b200/csrc/bart.hpp -- host object for the device-resident BART sampler.
+#pragma once
+
+#include "../../include/stan4bart_b200.h"
+#include "s4b_common.cuh"
+
+#include <vector>
+
+namespace s4b {
+
+// everything a kernel needs, passed by value
+struct BartDev {
+  long long n, npad;
+  const uint8_t* xt;
+  double* R; double* yresc; const double* y; double* offset;
+  StepDesc* desc; DTree* trees; BartParams* params; const double* pgrow; RngState* rng;
+  double* partials; unsigned int* ticket;
+  double* trace; unsigned long long trace_cap; unsigned long long* trace_len;
+  double* stats_out;
+};
+
+class BartFit {
+ public:
+  BartFit(const s4b_bart_config& cfg, const double* y, const double* x, const double* x_test, cudaStream_t stream);
+  ~BartFit();
+  BartFit(const BartFit&) = delete;
+  BartFit& operator=(const BartFit&) = delete;
+
+  void set_offset_host(const double* offset, bool update_scale);
+  void set_offset_device(const double* d_offset, bool update_scale);
+  void set_sigma(double sigma);
+  void sample_trees_from_prior();
+  // `thin` sweeps; results stay on device (train_out / test_out / latent_out)
+  void run_sweeps();
+  // runSamplerWithResults with host result buffers (any may be NULL)
+  void run(double* train, double* test, uint32_t* varcount, double* sigma);
+  void store_latents(double* out);
+  void predict(const double* x_test, long long rows, const double* test_offset, double* out);
+  void get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double* value);
+  long long num_nodes();
+  BartParams params();
+  void varcount_device(unsigned int* d_out);
+
+  // parity / measurement instrumentation
+  void node_assignment(int tree, long long* out);
+  int leaf_stats(int tree, int max_leaves, long long* heap, long long* count, double* sum, double* sumsq);
+  void launch_leaf_stats(int tree);
+  void get_residual(double* out);
+  void set_trace(size_t cap_records);
+  size_t get_trace(double* out, size_t cap_records);
+  void set_tape(const double* tape, size_t len);
+  void set_record(size_t cap);
+  size_t get_record(double* out, size_t cap);
+  unsigned long long rng_counter();
+  void set_use_graph(bool g) { use_graph_ = g; }
+  // dbarts returns training fits with the offset added (init.cpp:828-829 subtracts it again); the Gibbs
+  // loop asks for the tree-only fit directly
+  void set_add_offset(bool a) { if (a != add_offset_) { add_offset_ = a; invalidate_graph(); } }
+  void check_error_flag();
+
+  long long n() const { return n_; }
+  long long n_test() const { return nt_; }
+  int p() const { return p_; }
+  int num_trees() const { return T_; }
+  bool is_binary() const { return cfg_.is_binary != 0; }
+  cudaStream_t stream() const { return stream_; }
+  double* d_train_out() const { return d_train_out_; }     // BART fit + offset, original units
+  double* d_test_out() const { return d_test_out_; }
+  double* d_latent_out() const { return d_latent_out_; }   // full latents (binary)
+  double* d_offset() const { return d_offset_; }
+  int grid() const { return grid_; }
+  long long num_tree_steps() const { return num_tree_steps_; }
+
+ private:
+  BartDev dev() const;
+  void launch_sweep_kernels(bool last_thin);
+  void test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out);
+  void bin_matrix(const double* x, long long rows, long long rows_pad, std::vector<uint8_t>& out) const;
+  std::vector<DTree> download_trees();
+  void invalidate_graph();
+
+  s4b_bart_config cfg_;
+  cudaStream_t stream_;
+  long long n_ = 0, nt_ = 0, npad_ = 0, npad_t_ = 0;
+  int p_ = 0, T_ = 0, num_sms_ = 0, blocks_per_sm_ = 3, grid_ = 1, grid_ew_ = 1;
+  std::vector<double> cuts_;
+  bool scale_initialised_ = false;
+  bool use_graph_ = true;
+  bool add_offset_ = true;
+  long long num_tree_steps_ = 0;
+
+  uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;
+  double *d_R_ = nullptr, *d_yresc_ = nullptr, *d_y_ = nullptr, *d_offset_ = nullptr, *d_offset_in_ = nullptr;
+  double *d_train_out_ = nullptr, *d_test_out_ = nullptr, *d_latent_out_ = nullptr;
+  double *d_partials_ = nullptr, *d_minmax_ = nullptr, *d_stats_out_ = nullptr, *d_pgrow_ = nullptr, *d_scale_factor_ = nullptr;
+  StepDesc* d_desc_ = nullptr; DTree* d_trees_ = nullptr; BartParams* d_params_ = nullptr; RngState* d_rng_ = nullptr;
+  unsigned int* d_ticket_ = nullptr; unsigned long long* d_trace_len_ = nullptr; unsigned int* d_varcount_ = nullptr;
+  double* d_trace_ = nullptr; size_t trace_cap_ = 0;
+  double* d_tape_ = nullptr; double* d_rec_ = nullptr;
+  cudaGraphExec_t graph_exec_ = nullptr, graph_exec_thin_ = nullptr;
+};
+
+}  // namespace s4b

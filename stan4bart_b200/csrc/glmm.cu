@@ -1,0 +1,449 @@
+// stan4bart_b200/csrc/glmm.cu
+// Device evaluation of the GLMM log-density data terms for stan4bart's continuous.stan and
+// the O(d) host-side chain rule around them.
+//
+//   reference density   /root/reference/src/stan_files/continuous.stan:344-366 (eta, normal_lpdf),
+//                       continuous.hpp:2168-2638 (log_prob_impl), :528-806 (make_theta_L, make_b),
+//                       :823-916 (decov_lp), :2640-2938 (write_array), :3626-3768 (offset / response /
+//                       parametric mean)
+//   reference gradient  reverse-mode AD, src/include/stan/model/gradient.hpp:21-35
+//
+// Per evaluation one N-length pass produces S = sum e^2, X'e and Z'e (e = y - offset - X beta - Z b);
+// everything else is O(K + q) and stays on the host next to the NUTS control logic.
+// Z is stored as ELL (one int32 column index + one fp64 value per non-zero slot, slot-major so every
+// stream is coalesced); the per-column sums are segmented reductions into lane-private shared-memory
+// bins (no atomics, fixed order => deterministic).
+#include "glmm.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace s4b {
+
+constexpr int kGBlock = 256;
+
+__device__ __forceinline__ double g_warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// algorithmic bytes per observation: r 8 + X 8K + Z (4 + 8 [0 if the slot is an indicator]) per slot
+__global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
+{
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = g.K + g.q;
+  double* sth = smem;                                   // [nb] beta, b
+  double* wb = smem + nb + (size_t) warp * (nb + 1) * 32; // lane-private bins of this warp
+  for (int j = tid; j < nb; j += kGBlock) sth[j] = g.theta[j];
+  for (int j = lane; j < (nb + 1) * 32; j += 32) wb[j] = 0.0;
+  __syncthreads();
+
+  const long long N = g.N, npad = g.npad;
+  const int K = g.K, slots = g.slots;
+  double S = 0.0;
+  for (long long i = (long long) blockIdx.x * kGBlock + tid; i < N; i += (long long) gridDim.x * kGBlock) {
+    double eta = 0.0;
+    for (int k = 0; k < K; ++k) eta += __ldg(g.X + (long long) k * npad + i) * sth[k];
+    for (int s = 0; s < slots; ++s) {
+      int c = __ldg(g.zidx + (long long) s * npad + i);
+      double v = ((g.ones_mask >> s) & 1u) ? 1.0 : __ldg(g.zval + (long long) s * npad + i);
+      eta += v * sth[K + c];
+    }
+    double e = __ldg(g.r + i) - eta;
+    S += e * e;
+    for (int k = 0; k < K; ++k) wb[k * 32 + lane] += __ldg(g.X + (long long) k * npad + i) * e;
+    for (int s = 0; s < slots; ++s) {
+      int c = __ldg(g.zidx + (long long) s * npad + i);
+      double v = ((g.ones_mask >> s) & 1u) ? 1.0 : __ldg(g.zval + (long long) s * npad + i);
+      wb[(K + c) * 32 + lane] += v * e;
+    }
+  }
+  wb[nb * 32 + lane] = S;
+  __syncwarp();
+  for (int j = 0; j <= nb; ++j) {
+    double v = g_warp_sum(wb[j * 32 + lane]);
+    __syncwarp();
+    if (lane == 0) wb[j * 32] = v;
+  }
+  __syncthreads();
+  const int G = gridDim.x;
+  for (int j = tid; j <= nb; j += kGBlock) {
+    double acc = 0.0;
+    for (int w = 0; w < kGBlock / 32; ++w) acc += smem[nb + (size_t) w * (nb + 1) * 32 + j * 32];
+    // value order in partials / result: S, X'e, Z'e
+    int out_j = j == nb ? 0 : j + 1;
+    g.partials[(long long) out_j * G + blockIdx.x] = acc;
+  }
+  __shared__ unsigned int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(g.ticket, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned int) G - 1) return;
+  __threadfence();
+  for (int v = warp; v <= nb; v += kGBlock / 32) {
+    const double* src = g.partials + (long long) v * G;
+    double acc = 0.0;
+    for (int b = lane; b < G; b += 32) acc += __ldcg(src + b);
+    acc = g_warp_sum(acc);
+    if (lane == 0) g.result[v] = acc;
+  }
+  if (tid == 0) *g.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(kGBlock) k_glmm_linear_predictor(GlmmDev g, double* __restrict__ out, int include_fixed, int include_random)
+{
+  extern __shared__ double smem[];
+  const int nb = g.K + g.q;
+  for (int j = threadIdx.x; j < nb; j += kGBlock) smem[j] = g.theta[j];
+  __syncthreads();
+  for (long long i = (long long) blockIdx.x * kGBlock + threadIdx.x; i < g.N; i += (long long) gridDim.x * kGBlock) {
+    double eta = 0.0;
+    if (include_fixed) for (int k = 0; k < g.K; ++k) eta += __ldg(g.X + (long long) k * g.npad + i) * smem[k];
+    if (include_random) for (int s = 0; s < g.slots; ++s) {
+      int c = __ldg(g.zidx + (long long) s * g.npad + i);
+      double v = ((g.ones_mask >> s) & 1u) ? 1.0 : __ldg(g.zval + (long long) s * g.npad + i);
+      eta += v * smem[g.K + c];
+    }
+    out[i] = eta;
+  }
+}
+
+__global__ void k_glmm_residual(long long N, const double* __restrict__ y, const double* __restrict__ offset, double* __restrict__ r)
+{
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long) gridDim.x * blockDim.x) r[i] = y[i] - offset[i];
+}
+
+// ---------------------------------------------------------------------------------------
+struct GlmmModel::Params {
+  const double *z_beta, *z_b, *rho_u, *zeta_u, *tau_u;
+  double aux_u = 0, aux_unscaled = 0, aux = 1, disp = 1;
+  std::vector<double> rho, zeta, tau, beta, b, theta_L;
+};
+
+static const double kHalfLog2Pi = 0.91893853320467274178;
+static const double kLog2 = 0.693147180559945286;
+
+GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream) : stream_(stream)
+{
+  if (d.prior_dist < 0 || d.prior_dist > 1) throw std::invalid_argument("glmm: only prior_dist 0 (none) and 1 (normal) are implemented (SURVEY 8f rank 4)");
+  if (d.prior_dist_for_aux < 0 || d.prior_dist_for_aux > 3) throw std::invalid_argument("glmm: prior_dist_for_aux out of range");
+  for (int i = 0; i < d.t; ++i) {
+    if (d.p[i] < 1 || d.l[i] < 1) throw std::invalid_argument("glmm: p[i] / l[i] must be >= 1");
+    if (d.p[i] > 2) throw std::invalid_argument("glmm: ranef blocks with more than 2 coefficients (z_T onion) are not implemented (SURVEY 8f rank 4)");
+  }
+  N_ = d.N; K_ = d.K; q_ = d.q; t_ = d.t; len_theta_L_ = d.len_theta_L; len_conc_ = d.len_concentration;
+  is_binary_ = d.is_binary; prior_dist_ = d.prior_dist; prior_dist_for_aux_ = d.prior_dist_for_aux;
+  prior_scale_for_aux_ = d.prior_scale_for_aux; prior_mean_for_aux_ = d.prior_mean_for_aux; prior_df_for_aux_ = d.prior_df_for_aux;
+  prior_scale_.assign(d.prior_scale, d.prior_scale + K_); prior_mean_.assign(d.prior_mean, d.prior_mean + K_);
+  p_.assign(d.p, d.p + t_); l_.assign(d.l, d.l + t_);
+  shape_.assign(d.shape, d.shape + t_); scale_.assign(d.scale, d.scale + t_);
+  regularization_.assign(d.regularization, d.regularization + d.len_regularization);
+  // transformed data (src/stan_sampler.cpp:142-182): delta restarts at concentration[0] for every term
+  delta_.assign((size_t) len_conc_, 0.0);
+  int pos = 0, sum_p = 0, qq = 0;
+  for (int i = 0; i < t_; ++i) {
+    if (p_[i] > 1) for (int j = 0; j < p_[i]; ++j) delta_[(size_t) pos++] = d.concentration[j];
+    sum_p += p_[i]; qq += p_[i] * l_[i];
+  }
+  if (qq != q_) throw std::invalid_argument("glmm: q != sum(p * l)");
+  len_rho_ = sum_p - t_;
+  has_aux_ = is_binary_ ? 0 : 1;
+  num_params_ = K_ + q_ + len_rho_ + len_conc_ + t_ + has_aux_;
+
+  // ---- CSR (w, v, u) -> slot-major ELL ----
+  npad_ = (N_ + 15) / 16 * 16;
+  int max_nnz = 0;
+  for (long long i = 0; i < N_; ++i) max_nnz = std::max(max_nnz, d.u[i + 1] - d.u[i]);
+  slots_ = max_nnz;
+  if (slots_ > 32) throw std::invalid_argument("glmm: more than 32 non-zeros per row of Z");
+  std::vector<int> zidx((size_t) std::max(1, slots_) * npad_, 0);
+  std::vector<double> zval((size_t) std::max(1, slots_) * npad_, 0.0);
+  ones_mask_ = 0;
+  for (int s = 0; s < slots_; ++s) {
+    bool all_one = true;
+    for (long long i = 0; i < N_; ++i) {
+      int k = d.u[i] + s;
+      if (k < d.u[i + 1]) {
+        if (d.v[k] < 0 || d.v[k] >= q_) throw std::invalid_argument("glmm: column index out of range in v");
+        zidx[(size_t) s * npad_ + i] = d.v[k]; zval[(size_t) s * npad_ + i] = d.w[k];
+        if (d.w[k] != 1.0) all_one = false;
+      } else all_one = false;
+    }
+    if (all_one) ones_mask_ |= 1u << s;
+  }
+  auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); S4B_CUDA(cudaMemset(*p, 0, sizeof(double) * std::max<size_t>(count, 1))); };
+  dalloc(&d_X_, (size_t) std::max(1, K_) * npad_);
+  for (int k = 0; k < K_; ++k) S4B_CUDA(cudaMemcpy(d_X_ + (size_t) k * npad_, d.X + (size_t) k * N_, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice));
+  dalloc(&d_y_, (size_t) npad_); dalloc(&d_offset_, (size_t) npad_); dalloc(&d_r_, (size_t) npad_); dalloc(&d_tmp_, (size_t) npad_);
+  S4B_CUDA(cudaMemcpy(d_y_, d.y, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice));
+  dalloc(&d_zval_, zval.size());
+  S4B_CUDA(cudaMemcpy(d_zval_, zval.data(), sizeof(double) * zval.size(), cudaMemcpyHostToDevice));
+  S4B_CUDA(cudaMalloc(&d_zidx_, sizeof(int) * zidx.size()));
+  S4B_CUDA(cudaMemcpy(d_zidx_, zidx.data(), sizeof(int) * zidx.size(), cudaMemcpyHostToDevice));
+
+  int dev = 0, sms = 0; S4B_CUDA(cudaGetDevice(&dev));
+  S4B_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nb = K_ + q_;
+  smem_bytes_ = sizeof(double) * ((size_t) nb + (size_t) (kGBlock / 32) * (nb + 1) * 32);
+  int max_smem = 0; S4B_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem_bytes_ > (size_t) max_smem)
+    throw std::invalid_argument("glmm: K + q too large for the shared-memory binned reduction (sorted-segment path not implemented yet)");
+  S4B_CUDA(cudaFuncSetAttribute(k_glmm_data_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
+  int per_sm = (int) std::max<size_t>(1, std::min<size_t>(8, (size_t) (200 * 1024) / std::max<size_t>(smem_bytes_, 1)));
+  long long want = (N_ + kGBlock - 1) / kGBlock;
+  grid_ = (int) std::max<long long>(1, std::min<long long>(want, (long long) sms * per_sm));
+  dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) (nb + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
+  S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
+  S4B_CUDA(cudaMallocHost(&h_pinned_, sizeof(double) * 2 * ((size_t) nb + 1)));
+  refresh_r();
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+}
+
+GlmmModel::~GlmmModel()
+{
+  cudaFree(d_X_); cudaFree(d_y_); cudaFree(d_offset_); cudaFree(d_r_); cudaFree(d_tmp_); cudaFree(d_zval_); cudaFree(d_zidx_);
+  cudaFree(d_theta_); cudaFree(d_partials_); cudaFree(d_result_); cudaFree(d_ticket_); cudaFreeHost(h_pinned_);
+}
+
+void GlmmModel::refresh_r()
+{
+  int grid = (int) std::max<long long>(1, std::min<long long>((N_ + 255) / 256, 148 * 8));
+  k_glmm_residual<<<grid, 256, 0, stream_>>>(N_, d_y_, d_offset_, d_r_);
+  S4B_CUDA(cudaGetLastError());
+}
+
+void GlmmModel::set_offset_host(const double* offset) { S4B_CUDA(cudaMemcpyAsync(d_offset_, offset, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice, stream_)); refresh_r(); S4B_CUDA(cudaStreamSynchronize(stream_)); }
+void GlmmModel::set_response_host(const double* y) { S4B_CUDA(cudaMemcpyAsync(d_y_, y, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice, stream_)); refresh_r(); S4B_CUDA(cudaStreamSynchronize(stream_)); }
+void GlmmModel::set_offset_device(const double* d_offset) { S4B_CUDA(cudaMemcpyAsync(d_offset_, d_offset, sizeof(double) * (size_t) N_, cudaMemcpyDeviceToDevice, stream_)); refresh_r(); }
+void GlmmModel::set_response_device(const double* d_y) { S4B_CUDA(cudaMemcpyAsync(d_y_, d_y, sizeof(double) * (size_t) N_, cudaMemcpyDeviceToDevice, stream_)); refresh_r(); }
+
+void GlmmModel::data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb)
+{
+  const int nb = K_ + q_;
+  double* h_theta = h_pinned_;
+  double* h_res = h_pinned_ + nb + 1;
+  for (int k = 0; k < K_; ++k) h_theta[k] = beta[k];
+  for (int k = 0; k < q_; ++k) h_theta[K_ + k] = b[k];
+  if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
+  GlmmDev g;
+  g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.zidx = d_zidx_; g.zval = d_zval_;
+  g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
+  k_glmm_data_terms<<<grid_, kGBlock, smem_bytes_, stream_>>>(g);
+  S4B_CUDA(cudaGetLastError());
+  S4B_CUDA(cudaMemcpyAsync(h_res, d_result_, sizeof(double) * (size_t) (nb + 1), cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  *S = h_res[0];
+  for (int k = 0; k < K_; ++k) gbeta[k] = h_res[1 + k];
+  for (int k = 0; k < q_; ++k) gb[k] = h_res[1 + K_ + k];
+}
+
+void GlmmModel::parametric_mean_device(const double* beta, const double* b, double* d_out, bool include_fixed, bool include_random)
+{
+  const int nb = K_ + q_;
+  double* h_theta = h_pinned_;
+  for (int k = 0; k < K_; ++k) h_theta[k] = beta[k];
+  for (int k = 0; k < q_; ++k) h_theta[K_ + k] = b[k];
+  if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
+  GlmmDev g;
+  g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.zidx = d_zidx_; g.zval = d_zval_;
+  g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
+  int grid = (int) std::max<long long>(1, std::min<long long>((N_ + kGBlock - 1) / kGBlock, 148 * 8));
+  k_glmm_linear_predictor<<<grid, kGBlock, sizeof(double) * (size_t) std::max(1, nb), stream_>>>(g, d_out, include_fixed ? 1 : 0, include_random ? 1 : 0);
+  S4B_CUDA(cudaGetLastError());
+  // h_pinned_ is reused by the next call: make sure the H2D copy has been consumed
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void GlmmModel::parametric_mean_host(const double* constrained, double* out, bool include_fixed, bool include_random)
+{
+  const double* beta = constrained + num_params_ + has_aux_;
+  const double* b = beta + K_;
+  parametric_mean_device(beta, b, d_tmp_, include_fixed, include_random);
+  S4B_CUDA(cudaMemcpyAsync(out, d_tmp_, sizeof(double) * (size_t) N_, cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+}
+
+static inline double inv_logit(double x) { return x >= 0.0 ? 1.0 / (1.0 + std::exp(-x)) : std::exp(x) / (1.0 + std::exp(x)); }
+
+void GlmmModel::transform(const double* q, Params& P) const
+{
+  int pos = 0;
+  P.z_beta = q + pos; pos += K_;
+  P.z_b = q + pos; pos += q_;
+  P.rho_u = q + pos; pos += len_rho_;
+  P.zeta_u = q + pos; pos += len_conc_;
+  P.tau_u = q + pos; pos += t_;
+  P.aux_u = has_aux_ ? q[pos] : 0.0;
+  P.rho.resize((size_t) len_rho_); P.zeta.resize((size_t) len_conc_); P.tau.resize((size_t) t_);
+  P.beta.resize((size_t) K_); P.b.resize((size_t) q_); P.theta_L.resize((size_t) len_theta_L_);
+  for (int i = 0; i < len_rho_; ++i) P.rho[(size_t) i] = inv_logit(P.rho_u[i]);
+  for (int i = 0; i < len_conc_; ++i) P.zeta[(size_t) i] = std::exp(P.zeta_u[i]);
+  for (int i = 0; i < t_; ++i) P.tau[(size_t) i] = std::exp(P.tau_u[i]);
+  if (has_aux_) {
+    P.aux_unscaled = std::exp(P.aux_u);
+    if (prior_dist_for_aux_ == 0) P.aux = P.aux_unscaled;
+    else { P.aux = prior_scale_for_aux_ * P.aux_unscaled; if (prior_dist_for_aux_ <= 2) P.aux += prior_mean_for_aux_; }
+    P.disp = P.aux;
+  } else { P.aux_unscaled = 0.0; P.aux = 1.0; P.disp = 1.0; }
+  for (int k = 0; k < K_; ++k) P.beta[(size_t) k] = prior_dist_ == 0 ? P.z_beta[k] : P.z_beta[k] * prior_scale_[(size_t) k] + prior_mean_[(size_t) k];
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0;
+  for (int i = 0; i < t_; ++i) {
+    const double c = P.tau[(size_t) i] * scale_[(size_t) i] * P.disp;
+    if (p_[(size_t) i] == 1) {
+      P.theta_L[(size_t) th++] = c;
+      for (int s = 0; s < l_[(size_t) i]; ++s) P.b[(size_t) (b_mark + s)] = c * P.z_b[b_mark + s];
+      b_mark += l_[(size_t) i];
+    } else {
+      const double trace = c * c * 2.0;
+      const double zs = P.zeta[(size_t) zeta_mark] + P.zeta[(size_t) zeta_mark + 1];
+      const double pi1 = P.zeta[(size_t) zeta_mark] / zs, pi2 = P.zeta[(size_t) zeta_mark + 1] / zs;
+      zeta_mark += 2;
+      const double sd1 = std::sqrt(pi1 * trace), sd2 = std::sqrt(pi2 * trace);
+      const double r = 2.0 * P.rho[(size_t) rho_mark++] - 1.0;
+      const double T11 = sd1, T21 = sd2 * r, T22 = sd2 * std::sqrt(1.0 - r * r);
+      P.theta_L[(size_t) th++] = T11; P.theta_L[(size_t) th++] = T21; P.theta_L[(size_t) th++] = T22;
+      for (int j = 0; j < l_[(size_t) i]; ++j) {
+        const double z0 = P.z_b[b_mark], z1 = P.z_b[b_mark + 1];
+        P.b[(size_t) b_mark] = T11 * z0; P.b[(size_t) b_mark + 1] = T21 * z0 + T22 * z1;
+        b_mark += 2;
+      }
+    }
+  }
+}
+
+int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
+{
+  Params P; transform(q, P);
+  ++num_grad_;
+  const double N = (double) N_;
+  double lp = 0.0;
+  for (int i = 0; i < len_rho_; ++i) { double x = std::fabs(P.rho_u[i]); lp += -x - 2.0 * std::log1p(std::exp(-x)); }
+  for (int i = 0; i < len_conc_; ++i) lp += P.zeta_u[i];
+  for (int i = 0; i < t_; ++i) lp += P.tau_u[i];
+  if (has_aux_) lp += P.aux_u;
+
+  std::vector<double> gbeta((size_t) K_ + 1), gb((size_t) q_ + 1);
+  double S = 0.0;
+  data_terms(P.beta.data(), P.b.data(), &S, gbeta.data(), gb.data());
+  const double sigma = has_aux_ ? P.aux : 1.0;
+  lp += -0.5 * S / (sigma * sigma) - N * std::log(sigma) - N * kHalfLog2Pi;
+
+  double d_au_prior = 0.0;
+  if (has_aux_ && prior_dist_for_aux_ > 0 && prior_scale_for_aux_ > 0.0) {
+    const double au = P.aux_unscaled;
+    if (prior_dist_for_aux_ == 1) { lp += -0.5 * au * au - kHalfLog2Pi + kLog2; d_au_prior = -au; }
+    else if (prior_dist_for_aux_ == 2) {
+      const double nu = prior_df_for_aux_;
+      lp += std::lgamma(0.5 * (nu + 1.0)) - std::lgamma(0.5 * nu) - 0.5 * std::log(nu * 3.14159265358979323846) - 0.5 * (nu + 1.0) * std::log1p(au * au / nu) + kLog2;
+      d_au_prior = -(nu + 1.0) * au / (nu + au * au);
+    } else { lp += -au; d_au_prior = -1.0; }
+  }
+  if (prior_dist_ == 1) { for (int k = 0; k < K_; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= K_ * kHalfLog2Pi; }
+  for (int k = 0; k < q_; ++k) lp += -0.5 * P.z_b[k] * P.z_b[k];
+  lp -= q_ * kHalfLog2Pi;
+  {
+    int pos_reg = 0, pos_rho = 0;
+    for (int i = 0; i < t_; ++i) if (p_[(size_t) i] > 1) {
+      const double nu = regularization_[(size_t) pos_reg++] + 0.5 * (p_[(size_t) i] - 2);
+      const double r = P.rho[(size_t) pos_rho++];
+      lp += (nu - 1.0) * std::log(r) + (nu - 1.0) * std::log1p(-r) + std::lgamma(2.0 * nu) - 2.0 * std::lgamma(nu);
+    }
+  }
+  for (int i = 0; i < len_conc_; ++i) lp += (delta_[(size_t) i] - 1.0) * std::log(P.zeta[(size_t) i]) - P.zeta[(size_t) i] - std::lgamma(delta_[(size_t) i]);
+  for (int i = 0; i < t_; ++i) lp += (shape_[(size_t) i] - 1.0) * std::log(P.tau[(size_t) i]) - P.tau[(size_t) i] - std::lgamma(shape_[(size_t) i]);
+
+  // ---- adjoints ----
+  int pos = 0;
+  double* g_zbeta = grad + pos; pos += K_;
+  double* g_zb = grad + pos; pos += q_;
+  double* g_rho = grad + pos; pos += len_rho_;
+  double* g_zeta = grad + pos; pos += len_conc_;
+  double* g_tau = grad + pos; pos += t_;
+  const double inv_s2 = 1.0 / (sigma * sigma);
+  for (int k = 0; k < K_; ++k) {
+    const double dbeta = gbeta[(size_t) k] * inv_s2;
+    g_zbeta[k] = prior_dist_ == 0 ? dbeta : dbeta * prior_scale_[(size_t) k] - P.z_beta[k];
+  }
+  double adj_disp = 0.0;
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, pos_reg = 0;
+  for (int i = 0; i < t_; ++i) {
+    const double tau = P.tau[(size_t) i], sc = scale_[(size_t) i];
+    double adj_c = 0.0;     // adjoint of c = tau * scale * dispersion
+    if (p_[(size_t) i] == 1) {
+      const double theta = P.theta_L[(size_t) th++];
+      for (int s = 0; s < l_[(size_t) i]; ++s) {
+        const double db = gb[(size_t) (b_mark + s)] * inv_s2;
+        g_zb[b_mark + s] = theta * db - P.z_b[b_mark + s];
+        adj_c += db * P.z_b[b_mark + s];
+      }
+      b_mark += l_[(size_t) i];
+    } else {
+      const double T11 = P.theta_L[(size_t) th], T21 = P.theta_L[(size_t) th + 1], T22 = P.theta_L[(size_t) th + 2]; th += 3;
+      double a11 = 0.0, a21 = 0.0, a22 = 0.0;
+      for (int j = 0; j < l_[(size_t) i]; ++j) {
+        const double db0 = gb[(size_t) b_mark] * inv_s2, db1 = gb[(size_t) b_mark + 1] * inv_s2;
+        const double z0 = P.z_b[b_mark], z1 = P.z_b[b_mark + 1];
+        g_zb[b_mark] = T11 * db0 + T21 * db1 - z0;
+        g_zb[b_mark + 1] = T22 * db1 - z1;
+        a11 += db0 * z0; a21 += db1 * z0; a22 += db1 * z1;
+        b_mark += 2;
+      }
+      const double c = tau * sc * P.disp;
+      const double trace = 2.0 * c * c;
+      const double z1v = P.zeta[(size_t) zeta_mark], z2v = P.zeta[(size_t) zeta_mark + 1], zs = z1v + z2v;
+      const double pi1 = z1v / zs, pi2 = z2v / zs;
+      const double sd1 = std::sqrt(pi1 * trace), sd2 = std::sqrt(pi2 * trace);
+      const double rho = P.rho[(size_t) rho_mark];
+      const double r = 2.0 * rho - 1.0, sq = std::sqrt(1.0 - r * r);
+      adj_c = (a11 * T11 + a21 * T21 + a22 * T22) / c;        // every entry of T is linear in c
+      const double a_sd1 = a11, a_sd2 = a21 * r + a22 * sq;
+      const double a_pi1 = a_sd1 * sd1 / (2.0 * pi1), a_pi2 = a_sd2 * sd2 / (2.0 * pi2);
+      const double dot = a_pi1 * pi1 + a_pi2 * pi2;
+      double a_z1 = (a_pi1 - dot) / zs, a_z2 = (a_pi2 - dot) / zs;
+      double a_rho = 2.0 * (a21 * sd2 - a22 * sd2 * r / sq);
+      const double nu = regularization_[(size_t) pos_reg++] + 0.5 * (p_[(size_t) i] - 2);
+      a_rho += (nu - 1.0) / rho - (nu - 1.0) / (1.0 - rho);
+      g_rho[rho_mark] = a_rho * rho * (1.0 - rho) + (1.0 - 2.0 * rho);
+      a_z1 += (delta_[(size_t) zeta_mark] - 1.0) / z1v - 1.0;
+      a_z2 += (delta_[(size_t) zeta_mark + 1] - 1.0) / z2v - 1.0;
+      g_zeta[zeta_mark] = a_z1 * z1v + 1.0;
+      g_zeta[zeta_mark + 1] = a_z2 * z2v + 1.0;
+      zeta_mark += 2; rho_mark += 1;
+    }
+    double a_tau = adj_c * sc * P.disp + (shape_[(size_t) i] - 1.0) / tau - 1.0;
+    adj_disp += adj_c * tau * sc;
+    g_tau[i] = a_tau * tau + 1.0;
+  }
+  if (has_aux_) {
+    const double a_aux = adj_disp + S / (sigma * sigma * sigma) - N / sigma;
+    const double a_au = a_aux * (prior_dist_for_aux_ == 0 ? 1.0 : prior_scale_for_aux_) + d_au_prior;
+    grad[pos] = a_au * P.aux_unscaled + 1.0;
+  }
+  *lp_out = lp;
+  bool bad = !std::isfinite(lp);
+  for (int i = 0; i < num_params_; ++i) if (!std::isfinite(grad[i])) bad = true;
+  return bad ? 1 : 0;
+}
+
+void GlmmModel::write_array(const double* q, double* out) const
+{
+  Params P; transform(q, P);
+  int pos = 0;
+  for (int k = 0; k < K_; ++k) out[pos++] = P.z_beta[k];
+  for (int k = 0; k < q_; ++k) out[pos++] = P.z_b[k];
+  for (double v : P.rho) out[pos++] = v;
+  for (double v : P.zeta) out[pos++] = v;
+  for (double v : P.tau) out[pos++] = v;
+  if (has_aux_) { out[pos++] = P.aux_unscaled; out[pos++] = P.aux; }
+  for (double v : P.beta) out[pos++] = v;
+  for (double v : P.b) out[pos++] = v;
+  for (double v : P.theta_L) out[pos++] = v;
+}
+
+}  // namespace s4b

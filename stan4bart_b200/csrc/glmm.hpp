@@ -1,0 +1,77 @@
+// stan4bart_b200/csrc/glmm.hpp -- device-backed GLMM density (continuous.stan) for the host NUTS.
+#pragma once
+
+#include "../../include/stan4bart_b200.h"
+#include "s4b_common.cuh"
+
+#include <vector>
+
+namespace s4b {
+
+struct GlmmDev {
+  long long N, npad;
+  int K, q, slots, bins;
+  const double* X;        // [K][npad]
+  const double* r;        // y - offset, [npad]
+  const int* zidx;        // [slots][npad]   (ELL, padded rows point at column 0 with value 0)
+  const double* zval;     // [slots][npad]
+  unsigned int ones_mask; // bit s set => every stored value of slot s is exactly 1.0
+  const double* theta;    // [K + q] : beta then b
+  double* partials;       // [(1 + K + q)][G]
+  double* result;         // [1 + K + q]
+  unsigned int* ticket;
+};
+
+class GlmmModel {
+ public:
+  GlmmModel(const s4b_glmm_data& d, cudaStream_t stream);
+  ~GlmmModel();
+  GlmmModel(const GlmmModel&) = delete;
+  GlmmModel& operator=(const GlmmModel&) = delete;
+
+  int num_params() const { return num_params_; }
+  int num_constrained() const { return num_params_ + has_aux_ + K_ + q_ + len_theta_L_; }
+  long long N() const { return N_; }
+  int K() const { return K_; }
+  int q() const { return q_; }
+  bool has_aux() const { return has_aux_ != 0; }
+
+  void set_offset_host(const double* offset);
+  void set_response_host(const double* y);
+  void set_offset_device(const double* d_offset);     // copies
+  void set_response_device(const double* d_y);        // copies
+  // returns status: 0 ok, 1 non-finite lp / gradient (maps to V = +inf in the sampler)
+  int log_prob_grad(const double* q, double* lp, double* grad);
+  void write_array(const double* q, double* out) const;
+  // device result; beta / b are host pointers
+  void parametric_mean_device(const double* beta, const double* b, double* d_out, bool include_fixed, bool include_random);
+  void parametric_mean_host(const double* constrained, double* out, bool include_fixed, bool include_random);
+  void data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb);
+  long long num_grad_evals() const { return num_grad_; }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  struct Params;
+  void transform(const double* q, Params& P) const;
+  void refresh_r();
+
+  cudaStream_t stream_;
+  long long N_ = 0, npad_ = 0;
+  int K_ = 0, q_ = 0, t_ = 0, len_theta_L_ = 0, len_rho_ = 0, len_conc_ = 0, num_params_ = 0, has_aux_ = 0;
+  int is_binary_ = 0, prior_dist_ = 0, prior_dist_for_aux_ = 0;
+  double prior_scale_for_aux_ = 0, prior_mean_for_aux_ = 0, prior_df_for_aux_ = 0;
+  std::vector<double> prior_scale_, prior_mean_, shape_, scale_, delta_, regularization_;
+  std::vector<int> p_, l_;
+  int slots_ = 0, grid_ = 1, block_ = 256;
+  unsigned int ones_mask_ = 0;
+  size_t smem_bytes_ = 0;
+  long long num_grad_ = 0;
+
+  double *d_X_ = nullptr, *d_y_ = nullptr, *d_offset_ = nullptr, *d_r_ = nullptr, *d_zval_ = nullptr;
+  int* d_zidx_ = nullptr;
+  double *d_theta_ = nullptr, *d_partials_ = nullptr, *d_result_ = nullptr, *d_tmp_ = nullptr;
+  unsigned int* d_ticket_ = nullptr;
+  double* h_pinned_ = nullptr;   // [2 * (1 + K + q)] : theta out, result in
+};
+
+}  // namespace s4b

@@ -1,0 +1,301 @@
+// stan4bart_b200/csrc/sampler.cu
+// The alternating BART <-> Stan Gibbs loop and the extern "C" layer.
+//   createSampler  /root/reference/src/init.cpp:190-310
+//   run            /root/reference/src/init.cpp:678-965 (loop body :752-917)
+// All N-length vectors the reference keeps on the host (bartOffset, stanOffset, bartLatents,
+// init.cpp:143-145) live in HBM here; per iteration only the 58-odd Stan row and the tiny
+// gradient reductions cross PCIe unless the caller asked for the fits (keep_fits).
+#include "bart.hpp"
+#include "glmm.hpp"
+#include "nuts.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+
+namespace s4b {
+
+__global__ void k_accumulate(long long n, const double* __restrict__ src, double* __restrict__ acc)
+{
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) acc[i] += src[i];
+}
+
+class GibbsSampler {
+ public:
+  GibbsSampler(const s4b_bart_config& bcfg, const double* y_bart, const double* x_bart, const double* x_test, const s4b_glmm_data& gdata,
+               const s4b_stan_control& sctl, const s4b_common_control& cctl, const double* bart_offset_init, cudaStream_t stream)
+      : cc_(cctl), stream_(stream), glmm_(gdata, stream), nuts_(glmm_, sctl, 1, cctl.warmup), bart_(bcfg, y_bart, x_bart, x_test, stream)
+  {
+    n_ = bcfg.n; nt_ = bcfg.n_test; p_ = (int) bcfg.p;
+    if (gdata.N != n_) throw std::invalid_argument("sampler: BART and Stan data disagree on N");
+    num_pars_ = nuts_.num_pars();
+    stan_curr_.assign((size_t) num_pars_, 0.0);
+    auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); S4B_CUDA(cudaMemset(*p, 0, sizeof(double) * std::max<size_t>(count, 1))); };
+    dalloc(&d_bart_offset_, (size_t) n_); dalloc(&d_mean_train_, (size_t) n_); dalloc(&d_mean_param_, (size_t) n_); dalloc(&d_mean_test_, (size_t) std::max<long long>(nt_, 1));
+    S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
+    S4B_CUDA(cudaEventCreate(&ev_a_)); S4B_CUDA(cudaEventCreate(&ev_b_)); S4B_CUDA(cudaEventCreate(&ev_c_));
+    bart_.set_add_offset(false);
+    if (bart_offset_init) S4B_CUDA(cudaMemcpyAsync(d_bart_offset_, bart_offset_init, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice, stream_));
+    bart_.set_offset_device(d_bart_offset_, true);                         // init.cpp:255
+    if (!cc_.is_binary) bart_.set_sigma(cc_.sigma_init);                   // :256-257
+    bart_.sample_trees_from_prior();                                       // :261
+    bart_.run_sweeps();                                                    // :273  (first draw)
+    glmm_.set_offset_device(bart_.d_train_out());                          // :275-287 (fit without the offset)
+    if (cc_.is_binary) glmm_.set_response_device(bart_.d_latent_out());    // :288-291
+    S4B_CUDA(cudaStreamSynchronize(stream_));
+    bart_.check_error_flag();
+  }
+  ~GibbsSampler()
+  {
+    cudaFree(d_bart_offset_); cudaFree(d_mean_train_); cudaFree(d_mean_param_); cudaFree(d_mean_test_); cudaFree(d_varcount_);
+    cudaEventDestroy(ev_a_); cudaEventDestroy(ev_b_); cudaEventDestroy(ev_c_);
+  }
+
+  int num_pars() const { return num_pars_; }
+  BartFit& bart() { return bart_; }
+  GlmmModel& glmm() { return glmm_; }
+  NutsSampler& nuts() { return nuts_; }
+
+  void run(int num_iter, bool is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma)
+  {
+    if (num_iter < 1) throw std::invalid_argument("num_iter must be >= 1");
+    const size_t n = (size_t) n_, nt = (size_t) nt_;
+    ms_stan_ = ms_bart_ = 0.0;
+    const long long grad0 = glmm_.num_grad_evals(), steps0 = bart_.num_tree_steps();
+    const int acc_grid = (int) std::max<long long>(1, std::min<long long>((n_ + 255) / 256, 148 * 8));
+    for (int iter = 0; iter < num_iter; ++iter) {
+      const size_t slot = cc_.keep_fits ? (size_t) iter : 0;
+      auto t0 = std::chrono::steady_clock::now();
+      // ---- A. Stan block (init.cpp:758-819) ----
+      nuts_.run(is_warmup, stan_curr_.data());
+      if (stan) std::memcpy(stan + slot * (size_t) num_pars_, stan_curr_.data(), sizeof(double) * (size_t) num_pars_);
+      const double* constrained = stan_curr_.data() + 7;
+      const double* beta = constrained + glmm_.num_params() + (glmm_.has_aux() ? 1 : 0);
+      const double* b = beta + glmm_.K();
+      glmm_.parametric_mean_device(beta, b, d_bart_offset_, true, true);               // :764
+      double aux = 1.0;
+      if (!cc_.is_binary) { aux = constrained[glmm_.num_params()]; bart_.set_sigma(aux); }  // :796-800
+      const int update_scale_mod = 1 << (8 * iter / num_iter);                           // :816
+      bart_.set_offset_device(d_bart_offset_, is_warmup && (iter % update_scale_mod == 0));
+      auto t1 = std::chrono::steady_clock::now();
+      // ---- B. BART block (init.cpp:821-916) ----
+      bart_.run_sweeps();                                                                // :824
+      glmm_.set_offset_device(bart_.d_train_out());                                      // :828-842
+      if (cc_.is_binary) glmm_.set_response_device(bart_.d_latent_out());                // :843-847
+      if (!is_warmup) {
+        k_accumulate<<<acc_grid, 256, 0, stream_>>>(n_, bart_.d_train_out(), d_mean_train_);
+        k_accumulate<<<acc_grid, 256, 0, stream_>>>(n_, d_bart_offset_, d_mean_param_);
+        if (nt_ > 0) k_accumulate<<<acc_grid, 256, 0, stream_>>>(nt_, bart_.d_test_out(), d_mean_test_);
+        ++num_mean_draws_;
+      }
+      if (train) S4B_CUDA(cudaMemcpyAsync(train + slot * n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+      if (test && nt_ > 0) S4B_CUDA(cudaMemcpyAsync(test + slot * nt, bart_.d_test_out(), sizeof(double) * nt, cudaMemcpyDeviceToHost, stream_));
+      if (varcount) {
+        bart_.varcount_device(d_varcount_);
+        S4B_CUDA(cudaMemcpyAsync(varcount + slot * (size_t) p_, d_varcount_, sizeof(unsigned int) * (size_t) p_, cudaMemcpyDeviceToHost, stream_));
+      }
+      if (sigma) sigma[slot] = aux;
+      S4B_CUDA(cudaStreamSynchronize(stream_));
+      auto t2 = std::chrono::steady_clock::now();
+      ms_stan_ += std::chrono::duration<double, std::milli>(t1 - t0).count();
+      ms_bart_ += std::chrono::duration<double, std::milli>(t2 - t1).count();
+    }
+    bart_.check_error_flag();
+    last_grad_evals_ = glmm_.num_grad_evals() - grad0;
+    last_tree_steps_ = bart_.num_tree_steps() - steps0;
+  }
+
+  void disengage_adaptation() { nuts_.disengage_adaptation(); }
+  void parametric_mean(double* out) { glmm_.parametric_mean_host(stan_curr_.data() + 7, out, true, true); }
+  void means(double* mean_train, double* mean_test, double* mean_param, long long* num_draws)
+  {
+    S4B_CUDA(cudaStreamSynchronize(stream_));
+    const double inv = num_mean_draws_ > 0 ? 1.0 / (double) num_mean_draws_ : 0.0;
+    auto fetch = [&](double* dst, const double* src, size_t count) {
+      if (!dst || !count) return;
+      S4B_CUDA(cudaMemcpy(dst, src, sizeof(double) * count, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < count; ++i) dst[i] *= inv;
+    };
+    fetch(mean_train, d_mean_train_, (size_t) n_); fetch(mean_test, d_mean_test_, (size_t) nt_); fetch(mean_param, d_mean_param_, (size_t) n_);
+    if (num_draws) *num_draws = num_mean_draws_;
+  }
+  void last_run_stats(double* ms_stan, double* ms_bart, long long* n_grad, long long* n_steps) const
+  {
+    if (ms_stan) *ms_stan = ms_stan_; if (ms_bart) *ms_bart = ms_bart_;
+    if (n_grad) *n_grad = last_grad_evals_; if (n_steps) *n_steps = last_tree_steps_;
+  }
+
+ private:
+  s4b_common_control cc_;
+  cudaStream_t stream_;
+  GlmmModel glmm_;
+  NutsSampler nuts_;
+  BartFit bart_;
+  long long n_ = 0, nt_ = 0; int p_ = 0, num_pars_ = 0;
+  std::vector<double> stan_curr_;
+  double *d_bart_offset_ = nullptr, *d_mean_train_ = nullptr, *d_mean_param_ = nullptr, *d_mean_test_ = nullptr;
+  unsigned int* d_varcount_ = nullptr;
+  cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;
+  long long num_mean_draws_ = 0, last_grad_evals_ = 0, last_tree_steps_ = 0;
+  double ms_stan_ = 0.0, ms_bart_ = 0.0;
+};
+
+}  // namespace s4b
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace s4b;
+
+struct gpubart_fit { std::unique_ptr<BartFit> owned; BartFit* fit; };
+struct glmm_model { std::unique_ptr<GlmmModel> owned; GlmmModel* m; };
+struct s4b_sampler { std::unique_ptr<GibbsSampler> s; gpubart_fit bart_view; glmm_model glmm_view; };
+
+static thread_local std::string g_last_error;
+static thread_local cudaStream_t g_stream = nullptr;
+static thread_local bool g_stream_set = false;
+
+static cudaStream_t current_stream()
+{
+  if (!g_stream_set) { S4B_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking)); g_stream_set = true; }
+  return g_stream;
+}
+
+#define S4B_API_BEGIN try {
+#define S4B_API_END \
+  return 0; } catch (const std::exception& e) { g_last_error = e.what(); return 1; } catch (...) { g_last_error = "unknown error"; return 1; }
+#define S4B_REQUIRE(x) if (!(x)) throw std::invalid_argument("null or invalid argument: " #x)
+
+extern "C" {
+
+const char* s4b_last_error(void) { return g_last_error.c_str(); }
+
+int s4b_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int s4b_set_stream(void* cuda_stream)
+{
+  S4B_API_BEGIN
+  if (cuda_stream == nullptr) { g_stream_set = false; g_stream = nullptr; }
+  else { g_stream = (cudaStream_t) cuda_stream; g_stream_set = true; }
+  S4B_API_END
+}
+
+// ---- gpubart ----
+int gpubart_create(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test, gpubart_fit** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(cfg && y && x && out);
+  if (cfg->n_test > 0) S4B_REQUIRE(x_test);
+  if (s4b_device_count() < 1) throw std::runtime_error("no CUDA device: stan4bart_b200 has no CPU fallback");
+  auto* h = new gpubart_fit;
+  h->owned.reset(new BartFit(*cfg, y, x, x_test, current_stream()));
+  h->fit = h->owned.get();
+  *out = h;
+  S4B_API_END
+}
+int gpubart_free(gpubart_fit* f) { S4B_API_BEGIN if (f && f->owned) delete f; S4B_API_END }
+int gpubart_set_offset(gpubart_fit* f, const double* offset, int update_scale) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_offset_host(offset, update_scale != 0); S4B_API_END }
+int gpubart_set_sigma(gpubart_fit* f, double sigma) { S4B_API_BEGIN S4B_REQUIRE(f && sigma > 0); f->fit->set_sigma(sigma); S4B_API_END }
+int gpubart_sample_trees_from_prior(gpubart_fit* f) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->sample_trees_from_prior(); S4B_API_END }
+int gpubart_run_sampler_with_results(gpubart_fit* f, double* train, double* test, uint32_t* varcount, double* sigma)
+{ S4B_API_BEGIN S4B_REQUIRE(f); f->fit->run(train, test, varcount, sigma); S4B_API_END }
+int gpubart_store_latents(gpubart_fit* f, double* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); f->fit->store_latents(out); S4B_API_END }
+int gpubart_get_data_range(gpubart_fit* f, double* o) { S4B_API_BEGIN S4B_REQUIRE(f && o); BartParams P = f->fit->params(); o[0] = P.smin; o[1] = P.smax; o[2] = P.srange; S4B_API_END }
+int gpubart_predict(gpubart_fit* f, const double* x_test, int64_t n, const double* test_offset, double* out)
+{ S4B_API_BEGIN S4B_REQUIRE(f && x_test && out && n >= 0); f->fit->predict(x_test, n, test_offset, out); S4B_API_END }
+int gpubart_num_nodes(gpubart_fit* f, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); *out = f->fit->num_nodes(); S4B_API_END }
+int gpubart_get_trees(gpubart_fit* f, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value)
+{ S4B_API_BEGIN S4B_REQUIRE(f && tree_no && n_obs && var && value); f->fit->get_trees(tree_no, (long long*) n_obs, var, value); S4B_API_END }
+int gpubart_node_assignment(gpubart_fit* f, int tree, int64_t* heap) { S4B_API_BEGIN S4B_REQUIRE(f && heap); f->fit->node_assignment(tree, (long long*) heap); S4B_API_END }
+int gpubart_leaf_stats(gpubart_fit* f, int tree, int max_leaves, int64_t* heap, int64_t* count, double* sum, double* sumsq, int* num_leaves)
+{ S4B_API_BEGIN S4B_REQUIRE(f && heap && count && sum && sumsq && num_leaves); *num_leaves = f->fit->leaf_stats(tree, max_leaves, (long long*) heap, (long long*) count, sum, sumsq); S4B_API_END }
+int gpubart_get_residual(gpubart_fit* f, double* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); f->fit->get_residual(out); S4B_API_END }
+int gpubart_set_trace(gpubart_fit* f, size_t cap) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_trace(cap); S4B_API_END }
+int gpubart_get_trace(gpubart_fit* f, double* out, size_t cap, size_t* num) { S4B_API_BEGIN S4B_REQUIRE(f && num); *num = f->fit->get_trace(out, cap); S4B_API_END }
+int gpubart_set_tape(gpubart_fit* f, const double* tape, size_t len) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_tape(tape, len); S4B_API_END }
+int gpubart_set_record(gpubart_fit* f, size_t cap) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_record(cap); S4B_API_END }
+int gpubart_get_record(gpubart_fit* f, double* out, size_t cap, size_t* len) { S4B_API_BEGIN S4B_REQUIRE(f && len); *len = f->fit->get_record(out, cap); S4B_API_END }
+int gpubart_rng_counter(gpubart_fit* f, uint64_t* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); *out = f->fit->rng_counter(); S4B_API_END }
+int gpubart_set_use_graph(gpubart_fit* f, int g) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_use_graph(g != 0); S4B_API_END }
+int gpubart_num_tree_steps(gpubart_fit* f, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); *out = f->fit->num_tree_steps(); S4B_API_END }
+int gpubart_time_leaf_stats(gpubart_fit* f, int tree, int reps, double* ms)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(f && ms && reps > 0);
+  cudaStream_t st = f->fit->stream();
+  cudaEvent_t a, b; S4B_CUDA(cudaEventCreate(&a)); S4B_CUDA(cudaEventCreate(&b));
+  f->fit->launch_leaf_stats(tree);
+  S4B_CUDA(cudaStreamSynchronize(st));
+  S4B_CUDA(cudaEventRecord(a, st));
+  for (int r = 0; r < reps; ++r) f->fit->launch_leaf_stats(tree);
+  S4B_CUDA(cudaEventRecord(b, st));
+  S4B_CUDA(cudaEventSynchronize(b));
+  float t = 0.f; S4B_CUDA(cudaEventElapsedTime(&t, a, b));
+  *ms = (double) t / reps;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  S4B_API_END
+}
+
+// ---- glmm ----
+int glmm_create(const s4b_glmm_data* d, glmm_model** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(d && out);
+  if (s4b_device_count() < 1) throw std::runtime_error("no CUDA device: stan4bart_b200 has no CPU fallback");
+  auto* h = new glmm_model;
+  h->owned.reset(new GlmmModel(*d, current_stream()));
+  h->m = h->owned.get();
+  *out = h;
+  S4B_API_END
+}
+int glmm_free(glmm_model* m) { S4B_API_BEGIN if (m && m->owned) delete m; S4B_API_END }
+int glmm_num_params(glmm_model* m, int* d, int* nc) { S4B_API_BEGIN S4B_REQUIRE(m); if (d) *d = m->m->num_params(); if (nc) *nc = m->m->num_constrained(); S4B_API_END }
+int glmm_set_offset(glmm_model* m, const double* o) { S4B_API_BEGIN S4B_REQUIRE(m && o); m->m->set_offset_host(o); S4B_API_END }
+int glmm_set_response(glmm_model* m, const double* y) { S4B_API_BEGIN S4B_REQUIRE(m && y); m->m->set_response_host(y); S4B_API_END }
+int glmm_log_prob_grad(glmm_model* m, const double* q, double* lp, double* grad, int* status)
+{ S4B_API_BEGIN S4B_REQUIRE(m && q && lp && grad && status); *status = m->m->log_prob_grad(q, lp, grad); S4B_API_END }
+int glmm_write_array(glmm_model* m, const double* q, double* out) { S4B_API_BEGIN S4B_REQUIRE(m && q && out); m->m->write_array(q, out); S4B_API_END }
+int glmm_parametric_mean(glmm_model* m, const double* c, double* out, int f, int r) { S4B_API_BEGIN S4B_REQUIRE(m && c && out); m->m->parametric_mean_host(c, out, f != 0, r != 0); S4B_API_END }
+int glmm_data_terms(glmm_model* m, const double* beta, const double* b, double* S, double* gbeta, double* gb)
+{ S4B_API_BEGIN S4B_REQUIRE(m && S && gbeta && gb); m->m->data_terms(beta, b, S, gbeta, gb); S4B_API_END }
+int glmm_num_grad_evals(glmm_model* m, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(m && out); *out = m->m->num_grad_evals(); S4B_API_END }
+
+// ---- sampler ----
+int s4b_sampler_create(const s4b_bart_config* bcfg, const double* y_bart, const double* x_bart, const double* x_test,
+                       const s4b_glmm_data* gdata, const s4b_stan_control* sctl, const s4b_common_control* cctl,
+                       const double* bart_offset_init, s4b_sampler** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(bcfg && y_bart && x_bart && gdata && sctl && cctl && out);
+  if (bcfg->n_test > 0) S4B_REQUIRE(x_test);
+  if (s4b_device_count() < 1) throw std::runtime_error("no CUDA device: stan4bart_b200 has no CPU fallback");
+  auto* h = new s4b_sampler;
+  h->s.reset(new GibbsSampler(*bcfg, y_bart, x_bart, x_test, *gdata, *sctl, *cctl, bart_offset_init, current_stream()));
+  h->bart_view.fit = &h->s->bart();
+  h->glmm_view.m = &h->s->glmm();
+  *out = h;
+  S4B_API_END
+}
+int s4b_sampler_free(s4b_sampler* s) { S4B_API_BEGIN delete s; S4B_API_END }
+int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); *out = s->s->num_pars(); S4B_API_END }
+int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma)
+{ S4B_API_BEGIN S4B_REQUIRE(s); s->s->run(num_iter, is_warmup != 0, stan, train, test, varcount, sigma); S4B_API_END }
+int s4b_sampler_disengage_adaptation(s4b_sampler* s) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->disengage_adaptation(); S4B_API_END }
+int s4b_sampler_get_bart_data_range(s4b_sampler* s, double* o) { S4B_API_BEGIN S4B_REQUIRE(s && o); BartParams P = s->s->bart().params(); o[0] = P.smin; o[1] = P.smax; S4B_API_END }
+int s4b_sampler_get_parametric_mean(s4b_sampler* s, double* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); s->s->parametric_mean(out); S4B_API_END }
+int s4b_sampler_predict_bart(s4b_sampler* s, const double* x_test, int64_t n, const double* off, double* out)
+{ S4B_API_BEGIN S4B_REQUIRE(s && x_test && out); s->s->bart().predict(x_test, n, off, out); S4B_API_END }
+gpubart_fit* s4b_sampler_bart(s4b_sampler* s) { return s ? &s->bart_view : nullptr; }
+glmm_model* s4b_sampler_glmm(s4b_sampler* s) { return s ? &s->glmm_view : nullptr; }
+int s4b_sampler_get_means(s4b_sampler* s, double* mt, double* mte, double* mp, int64_t* nd)
+{ S4B_API_BEGIN S4B_REQUIRE(s); long long k = 0; s->s->means(mt, mte, mp, &k); if (nd) *nd = k; S4B_API_END }
+int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* ng, int64_t* ns)
+{ S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->last_run_stats(ms_stan, ms_bart, &a, &b); if (ng) *ng = a; if (ns) *ns = b; S4B_API_END }
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+"""Python mirror of the reference's host interface for the Gibbs hot path, over the C ABI.
+
+  GpuBart    the dbarts function table stan4bart binds (src/init.cpp:54-81)
+  GlmmModel  the Stan model / gradient hook (continuous.hpp; model/gradient.hpp:21-35)
+  Sampler    the `.Call` routines: stan4bart_create / _run / _disengageAdaptation /
+             _getParametricMean / _getBARTDataRange / _predictBART (src/init.cpp:1215-1229);
+             `run` returns the same named pieces as the reference's result list
+             (stan [pars x S]; bart: train [n x S], test [n_test x S], varcount [p x S], sigma [S])
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .structs import CommonControl, c_int32_p, c_int64_p, c_uint32_p, dptr, f64
+
+TRACE_LEN = 32
+
+
+class GpuBart:
+    def __init__(self, cfg, y, x, x_test=None, handle=None):
+        self.L = _lib.load()
+        self.cfg = cfg
+        self.n, self.p, self.nt = int(cfg.n), int(cfg.p), int(cfg.n_test)
+        self._owner = handle is None
+        if handle is not None:
+            self.h = handle
+            return
+        _lib.require_device()
+        y = f64(y)
+        x = np.asfortranarray(x, dtype=np.float64)
+        xt = np.asfortranarray(x_test, dtype=np.float64) if x_test is not None else None
+        if x.shape != (self.n, self.p):
+            raise ValueError("x must be n x p")
+        h = C.c_void_p()
+        _lib.check(self.L.gpubart_create(C.byref(cfg), dptr(y), dptr(x), dptr(xt), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None) and self._owner:
+            self.L.gpubart_free(self.h)
+            self.h = None
+
+    def set_offset(self, offset, update_scale):
+        o = f64(offset) if offset is not None else None
+        _lib.check(self.L.gpubart_set_offset(self.h, dptr(o), int(update_scale)))
+
+    def set_sigma(self, sigma):
+        _lib.check(self.L.gpubart_set_sigma(self.h, float(sigma)))
+
+    def sample_trees_from_prior(self):
+        _lib.check(self.L.gpubart_sample_trees_from_prior(self.h))
+
+    def run(self):
+        train = np.zeros(self.n)
+        test = np.zeros(self.nt) if self.nt else None
+        vc = np.zeros(self.p, dtype=np.uint32)
+        sig = C.c_double(0.0)
+        _lib.check(self.L.gpubart_run_sampler_with_results(self.h, dptr(train), dptr(test), vc.ctypes.data_as(c_uint32_p), C.byref(sig)))
+        return dict(train=train, test=test, varcount=vc, sigma=sig.value)
+
+    def latents(self):
+        out = np.zeros(self.n)
+        _lib.check(self.L.gpubart_store_latents(self.h, dptr(out)))
+        return out
+
+    def data_range(self):
+        out = np.zeros(3)
+        _lib.check(self.L.gpubart_get_data_range(self.h, dptr(out)))
+        return out
+
+    def predict(self, x_test, offset=None):
+        xt = np.asfortranarray(x_test, dtype=np.float64)
+        out = np.zeros(xt.shape[0])
+        o = f64(offset) if offset is not None else None
+        _lib.check(self.L.gpubart_predict(self.h, dptr(xt), xt.shape[0], dptr(o), dptr(out)))
+        return out
+
+    def trees(self):
+        k = C.c_int64(0)
+        _lib.check(self.L.gpubart_num_nodes(self.h, C.byref(k)))
+        k = k.value
+        tree_no = np.zeros(k, dtype=np.int32)
+        n_obs = np.zeros(k, dtype=np.int64)
+        var = np.zeros(k, dtype=np.int32)
+        value = np.zeros(k)
+        _lib.check(self.L.gpubart_get_trees(self.h, tree_no.ctypes.data_as(c_int32_p), n_obs.ctypes.data_as(c_int64_p),
+                                            var.ctypes.data_as(c_int32_p), dptr(value)))
+        return dict(tree=tree_no, n=n_obs, var=var, value=value)
+
+    # ---- parity instrumentation ----
+    def node_assignment(self, tree):
+        out = np.zeros(self.n, dtype=np.int64)
+        _lib.check(self.L.gpubart_node_assignment(self.h, tree, out.ctypes.data_as(c_int64_p)))
+        return out
+
+    def leaf_stats(self, tree, max_leaves=64):
+        heap = np.zeros(max_leaves, dtype=np.int64)
+        cnt = np.zeros(max_leaves, dtype=np.int64)
+        s = np.zeros(max_leaves)
+        ss = np.zeros(max_leaves)
+        nl = C.c_int(0)
+        _lib.check(self.L.gpubart_leaf_stats(self.h, tree, max_leaves, heap.ctypes.data_as(c_int64_p), cnt.ctypes.data_as(c_int64_p),
+                                             dptr(s), dptr(ss), C.byref(nl)))
+        k = nl.value
+        return heap[:k], cnt[:k], s[:k], ss[:k]
+
+    def residual(self):
+        out = np.zeros(self.n)
+        _lib.check(self.L.gpubart_get_residual(self.h, dptr(out)))
+        return out
+
+    def set_trace(self, cap):
+        self._trace_cap = cap
+        _lib.check(self.L.gpubart_set_trace(self.h, cap))
+
+    def trace(self):
+        out = np.zeros((self._trace_cap, TRACE_LEN))
+        k = C.c_size_t(0)
+        _lib.check(self.L.gpubart_get_trace(self.h, dptr(out), self._trace_cap, C.byref(k)))
+        return out[:min(k.value, self._trace_cap)]
+
+    def set_tape(self, tape):
+        t = f64(tape)
+        _lib.check(self.L.gpubart_set_tape(self.h, dptr(t), len(t)))
+
+    def set_record(self, cap):
+        self._rec_cap = cap
+        _lib.check(self.L.gpubart_set_record(self.h, cap))
+
+    def record(self):
+        out = np.zeros(self._rec_cap)
+        k = C.c_size_t(0)
+        _lib.check(self.L.gpubart_get_record(self.h, dptr(out), self._rec_cap, C.byref(k)))
+        if k.value > self._rec_cap:
+            raise _lib.S4BError("record buffer too small")
+        return out[:k.value]
+
+    def rng_counter(self):
+        k = C.c_uint64(0)
+        _lib.check(self.L.gpubart_rng_counter(self.h, C.byref(k)))
+        return int(k.value)
+
+    def set_use_graph(self, flag):
+        _lib.check(self.L.gpubart_set_use_graph(self.h, int(flag)))
+
+    def time_leaf_stats(self, tree=0, reps=20):
+        ms = C.c_double(0.0)
+        _lib.check(self.L.gpubart_time_leaf_stats(self.h, tree, reps, C.byref(ms)))
+        return ms.value
+
+    def num_tree_steps(self):
+        k = C.c_int64(0)
+        _lib.check(self.L.gpubart_num_tree_steps(self.h, C.byref(k)))
+        return int(k.value)
+
+
+class GlmmModel:
+    def __init__(self, stan_data, handle=None):
+        self.L = _lib.load()
+        self.sd = stan_data
+        self._owner = handle is None
+        if handle is None:
+            _lib.require_device()
+            self._struct = stan_data.struct()
+            h = C.c_void_p()
+            _lib.check(self.L.glmm_create(C.byref(self._struct), C.byref(h)))
+            self.h = h
+        else:
+            self.h = handle
+        d, nc = C.c_int(0), C.c_int(0)
+        _lib.check(self.L.glmm_num_params(self.h, C.byref(d), C.byref(nc)))
+        self.d, self.nc = d.value, nc.value
+
+    def __del__(self):
+        if getattr(self, "h", None) and self._owner:
+            self.L.glmm_free(self.h)
+            self.h = None
+
+    def set_offset(self, o):
+        _lib.check(self.L.glmm_set_offset(self.h, dptr(f64(o))))
+
+    def set_response(self, y):
+        _lib.check(self.L.glmm_set_response(self.h, dptr(f64(y))))
+
+    def log_prob_grad(self, q):
+        q = f64(q)
+        g = np.zeros(self.d)
+        lp = C.c_double(0.0)
+        st = C.c_int(0)
+        _lib.check(self.L.glmm_log_prob_grad(self.h, dptr(q), C.byref(lp), dptr(g), C.byref(st)))
+        return lp.value, g, st.value
+
+    def write_array(self, q):
+        out = np.zeros(self.nc)
+        _lib.check(self.L.glmm_write_array(self.h, dptr(f64(q)), dptr(out)))
+        return out
+
+    def parametric_mean(self, constrained, fixed=True, random=True):
+        out = np.zeros(self.sd.N)
+        _lib.check(self.L.glmm_parametric_mean(self.h, dptr(f64(constrained)), dptr(out), int(fixed), int(random)))
+        return out
+
+    def data_terms(self, beta, b):
+        S = C.c_double(0.0)
+        gbeta = np.zeros(max(1, self.sd.K))
+        gb = np.zeros(max(1, self.sd.q))
+        _lib.check(self.L.glmm_data_terms(self.h, dptr(f64(beta)), dptr(f64(b)), C.byref(S), dptr(gbeta), dptr(gb)))
+        return S.value, gbeta[:self.sd.K], gb[:self.sd.q]
+
+    def num_grad_evals(self):
+        k = C.c_int64(0)
+        _lib.check(self.L.glmm_num_grad_evals(self.h, C.byref(k)))
+        return int(k.value)
+
+
+class Sampler:
+    """stan4bart_create(...) -> sampler object with run / disengage_adaptation / ... methods."""
+
+    def __init__(self, bart_cfg, y, x_bart, x_test, stan_data, stan_ctl, warmup, iter_, keep_fits=True, sigma_init=1.0,
+                 bart_offset_init=None):
+        self.L = _lib.load()
+        _lib.require_device()
+        self.bcfg = bart_cfg
+        self.sd = stan_data
+        self._gs = stan_data.struct()
+        y = f64(y)
+        x = np.asfortranarray(x_bart, dtype=np.float64)
+        xt = np.asfortranarray(x_test, dtype=np.float64) if x_test is not None else None
+        off = f64(bart_offset_init) if bart_offset_init is not None else None
+        self.cc = CommonControl(warmup=warmup, iter=iter_, is_binary=int(stan_data.is_binary), keep_fits=int(keep_fits),
+                                sigma_init=float(sigma_init))
+        self.keep_fits = bool(keep_fits)
+        h = C.c_void_p()
+        _lib.check(self.L.s4b_sampler_create(C.byref(bart_cfg), dptr(y), dptr(x), dptr(xt), C.byref(self._gs), C.byref(stan_ctl),
+                                             C.byref(self.cc), dptr(off), C.byref(h)))
+        self.h = h
+        k = C.c_int(0)
+        _lib.check(self.L.s4b_sampler_num_stan_pars(self.h, C.byref(k)))
+        self.num_pars = k.value
+        self.n, self.nt, self.p = int(bart_cfg.n), int(bart_cfg.n_test), int(bart_cfg.p)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.s4b_sampler_free(self.h)
+            self.h = None
+
+    def bart(self):
+        return GpuBart(self.bcfg, None, None, handle=C.c_void_p(self.L.s4b_sampler_bart(self.h)))
+
+    def glmm(self):
+        return GlmmModel(self.sd, handle=C.c_void_p(self.L.s4b_sampler_glmm(self.h)))
+
+    def run(self, num_iter, is_warmup, results=True):
+        """results=False runs without copying any fits back (the keep_fits = FALSE path)."""
+        S = num_iter if self.keep_fits else 1
+        stan = np.zeros((S, self.num_pars))
+        if results:
+            train = np.zeros((S, self.n))
+            test = np.zeros((S, max(self.nt, 1)))
+            vc = np.zeros((S, self.p), dtype=np.uint32)
+        else:
+            train = test = vc = None
+        sigma = np.zeros(S)
+        _lib.check(self.L.s4b_sampler_run(self.h, num_iter, int(is_warmup), dptr(stan), dptr(train), dptr(test),
+                                          vc.ctypes.data_as(c_uint32_p) if vc is not None else c_uint32_p(), dptr(sigma)))
+        out = dict(stan=stan.T)
+        if results:
+            out["bart"] = dict(train=train.T, test=test.T[:self.nt], varcount=vc.T, sigma=sigma)
+        else:
+            out["bart"] = dict(sigma=sigma)
+        return out
+
+    def disengage_adaptation(self):
+        _lib.check(self.L.s4b_sampler_disengage_adaptation(self.h))
+
+    def data_range(self):
+        out = np.zeros(2)
+        _lib.check(self.L.s4b_sampler_get_bart_data_range(self.h, dptr(out)))
+        return out
+
+    def parametric_mean(self):
+        out = np.zeros(self.n)
+        _lib.check(self.L.s4b_sampler_get_parametric_mean(self.h, dptr(out)))
+        return out
+
+    def predict_bart(self, x_test, offset=None):
+        xt = np.asfortranarray(x_test, dtype=np.float64)
+        out = np.zeros(xt.shape[0])
+        o = f64(offset) if offset is not None else None
+        _lib.check(self.L.s4b_sampler_predict_bart(self.h, dptr(xt), xt.shape[0], dptr(o), dptr(out)))
+        return out
+
+    def means(self):
+        mt = np.zeros(self.n)
+        mte = np.zeros(max(self.nt, 1))
+        mp = np.zeros(self.n)
+        k = C.c_int64(0)
+        _lib.check(self.L.s4b_sampler_get_means(self.h, dptr(mt), dptr(mte) if self.nt else dptr(None), dptr(mp), C.byref(k)))
+        return dict(bart_train=mt, bart_test=mte[:self.nt], parametric=mp, num_draws=int(k.value))
+
+    def last_run_stats(self):
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        g, s = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.L.s4b_sampler_last_run_stats(self.h, C.byref(a), C.byref(b), C.byref(g), C.byref(s)))
+        return dict(ms_stan=a.value, ms_bart=b.value, grad_evals=int(g.value), tree_steps=int(s.value))

@@ -1,7 +1,7 @@
 """ctypes mirrors of the plain-C configuration structs in include/stan4bart_b200.h.
 
-The same layouts are used by the CPU oracle (oracle/s4b_oracle.h) so that tests can
-drive both sides with identical inputs.  Field meaning follows the reference:
+The test-side CPU checker declares identical layouts so that tests can drive both sides
+with the same inputs.  Field meaning follows the reference:
   BartConfig     dbarts Control/Model as set up by R/stan4bart_fit.R:437-479
   GlmmData       the 44-field `data.stan` list, R/stan4bart_fit.R:259-365,
                  parsed by src/stan_sampler.cpp:112-380

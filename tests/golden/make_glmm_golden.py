@@ -1,0 +1,224 @@
+"""Generates tests/golden/glmm_*.json: known-answer vectors for the GLMM log-density and its
+gradient, from an INDEPENDENT transcription of /root/reference/src/stan_files/continuous.stan
+into torch (float64) with autograd doing the differentiation -- the same division of labour
+as the reference (Stan program + reverse-mode AD, src/include/stan/model/gradient.hpp:21-35).
+
+The reference itself cannot be executed in this image (needs R, Eigen, Boost, TBB), so these
+vectors pin the oracle (oracle/oracle_glmm.c) and, through it, the CUDA path.  Every lpdf keeps
+its normalising constants because the generated C++ hard-codes `<false>` (continuous.hpp:2460,
+:853-909).  Run:  python tests/golden/make_glmm_golden.py
+"""
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from stan4bart_b200.frontend import build_stan_data  # noqa: E402
+
+torch.set_default_dtype(torch.float64)
+
+
+def normal_lpdf(y, mu, sigma):
+    # stan::math::normal_lpdf<false>: -0.5 z^2 - log(sigma) - 0.5 log(2 pi), summed
+    z = (y - mu) / sigma
+    n = y.numel()
+    return (-0.5 * z * z).sum() - n * torch.log(sigma) - n * 0.5 * math.log(2 * math.pi)
+
+
+def gamma_lpdf(y, alpha, beta=1.0):
+    alpha = torch.as_tensor(alpha)
+    return (alpha * math.log(beta) - torch.lgamma(alpha) + (alpha - 1) * torch.log(y) - beta * y).sum()
+
+
+def beta_lpdf(y, a, b):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    return (torch.lgamma(a + b) - torch.lgamma(a) - torch.lgamma(b) + (a - 1) * torch.log(y) + (b - 1) * torch.log1p(-y)).sum()
+
+
+def student_t_lpdf(y, nu, mu, sigma):
+    z = (y - mu) / sigma
+    return (math.lgamma((nu + 1) / 2) - math.lgamma(nu / 2) - 0.5 * math.log(nu * math.pi) - math.log(sigma)
+            - (nu + 1) / 2 * torch.log1p(z * z / nu)).sum()
+
+
+def make_theta_L(p, dispersion, tau, scale, zeta, rho):
+    out = []
+    zeta_mark = 0
+    rho_mark = 0
+    for i, nc in enumerate(p):
+        if nc == 1:
+            out.append(tau[i] * scale[i] * dispersion)
+        else:
+            trace = (tau[i] * scale[i] * dispersion) ** 2 * nc
+            pi = zeta[zeta_mark:zeta_mark + nc]
+            pi = pi / pi.sum()
+            zeta_mark += nc
+            std_dev = torch.sqrt(pi[0] * trace)
+            T11 = std_dev
+            std_dev = torch.sqrt(pi[1] * trace)
+            T21 = 2.0 * rho[rho_mark] - 1.0
+            rho_mark += 1
+            T22 = std_dev * torch.sqrt(1.0 - T21 ** 2)
+            T21 = std_dev * T21
+            assert nc == 2
+            out += [T11, T21, T22]     # vech, column major
+    return torch.stack(out) if out else torch.zeros(0)
+
+
+def make_b(z_b, theta_L, p, l):
+    b = []
+    b_mark = 0
+    th = 0
+    for i, nc in enumerate(p):
+        if nc == 1:
+            b.append(theta_L[th] * z_b[b_mark:b_mark + l[i]])
+            b_mark += l[i]
+            th += 1
+        else:
+            T = torch.zeros(nc, nc)
+            T = T.clone()
+            rows = []
+            T11, T21, T22 = theta_L[th], theta_L[th + 1], theta_L[th + 2]
+            th += 3
+            Tm = torch.stack([torch.stack([T11, torch.zeros(())]), torch.stack([T21, T22])])
+            for j in range(l[i]):
+                rows.append(Tm @ z_b[b_mark:b_mark + nc])
+                b_mark += nc
+            b.append(torch.cat(rows))
+    return torch.cat(b) if b else torch.zeros(0)
+
+
+def log_prob(sd, q, offset, y):
+    """continuous.stan, default path, jacobian = true."""
+    K, nq, t = sd.K, sd.q, sd.t
+    p, l = list(sd.p), list(sd.l)
+    len_rho = sum(p) - t
+    len_conc = len(sd.concentration)
+    pos = 0
+    z_beta = q[pos:pos + K]; pos += K
+    z_b = q[pos:pos + nq]; pos += nq
+    rho_u = q[pos:pos + len_rho]; pos += len_rho
+    zeta_u = q[pos:pos + len_conc]; pos += len_conc
+    tau_u = q[pos:pos + t]; pos += t
+    lp = torch.zeros(())
+    rho = torch.sigmoid(rho_u)
+    lp = lp + (torch.log(rho) + torch.log1p(-rho)).sum()          # lub_constrain(0, 1) Jacobian
+    zeta = torch.exp(zeta_u); lp = lp + zeta_u.sum()
+    tau = torch.exp(tau_u); lp = lp + tau_u.sum()
+    if not sd.is_binary:
+        aux_u = q[pos]
+        aux_unscaled = torch.exp(aux_u); lp = lp + aux_u
+        if sd.prior_dist_for_aux == 0:
+            aux = aux_unscaled
+        elif sd.prior_dist_for_aux <= 2:
+            aux = sd.prior_scale_for_aux * aux_unscaled + sd.prior_mean_for_aux
+        else:
+            aux = sd.prior_scale_for_aux * aux_unscaled
+        dispersion = aux
+    else:
+        aux = torch.ones(())
+        dispersion = torch.ones(())
+    if sd.prior_dist == 0:
+        beta = z_beta
+    else:
+        beta = z_beta * torch.as_tensor(sd.prior_scale) + torch.as_tensor(sd.prior_mean)
+    theta_L = make_theta_L(p, dispersion, tau, torch.as_tensor(sd.scale), zeta, rho)
+    b = make_b(z_b, theta_L, p, l)
+    # eta = offset + X beta + Z b   (CSR w, v, u)
+    eta = torch.as_tensor(offset).clone()
+    if K > 0:
+        eta = eta + torch.as_tensor(np.ascontiguousarray(sd.X)) @ beta
+    u = sd.u
+    rows = np.repeat(np.arange(sd.N), np.diff(u))
+    Zb = torch.zeros(sd.N).index_add(0, torch.as_tensor(rows), torch.as_tensor(sd.w) * b[torch.as_tensor(sd.v.astype(np.int64))])
+    eta = eta + Zb
+    lp = lp + normal_lpdf(torch.as_tensor(y), eta, aux if not sd.is_binary else torch.ones(()))
+    if (not sd.is_binary) and sd.prior_dist_for_aux > 0 and sd.prior_scale_for_aux > 0:
+        log_half = -0.693147180559945286
+        if sd.prior_dist_for_aux == 1:
+            lp = lp + normal_lpdf(aux_unscaled.reshape(1), torch.zeros(()), torch.ones(())) - log_half
+        elif sd.prior_dist_for_aux == 2:
+            lp = lp + student_t_lpdf(aux_unscaled.reshape(1), sd.prior_df_for_aux, 0.0, 1.0) - log_half
+        else:
+            lp = lp - aux_unscaled                                   # exponential_lpdf(. | 1)
+    if sd.prior_dist == 1:
+        lp = lp + normal_lpdf(z_beta, torch.zeros(()), torch.ones(()))
+    # decov_lp
+    lp = lp + normal_lpdf(z_b, torch.zeros(()), torch.ones(()))
+    pos_reg = 0
+    pos_rho = 0
+    for i in range(t):
+        if p[i] > 1:
+            nu = sd.regularization[pos_reg] + 0.5 * (p[i] - 2)
+            pos_reg += 1
+            lp = lp + beta_lpdf(rho[pos_rho:pos_rho + p[i] - 1], nu, nu)
+            pos_rho += p[i] - 1
+    delta = []
+    for i in range(t):
+        if p[i] > 1:
+            delta += [sd.concentration[j] for j in range(p[i])]
+    if len_conc:
+        lp = lp + gamma_lpdf(zeta, torch.as_tensor(np.array(delta)))
+    if t:
+        lp = lp + gamma_lpdf(tau, torch.as_tensor(sd.shape))
+    return lp, dict(beta=beta, b=b, theta_L=theta_L, aux=aux, rho=rho, zeta=zeta, tau=tau)
+
+
+def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1):
+    rng = np.random.default_rng(seed)
+    Xf = np.column_stack([rng.random(N), (rng.random(N) < 0.3).astype(float)])
+    terms = []
+    groups = []
+    for (nlev, pc) in terms_spec:
+        g = rng.integers(0, nlev, N)
+        g[:nlev] = np.arange(nlev)          # every level present
+        M = np.column_stack([np.ones(N)] + [rng.random(N) for _ in range(pc - 1)])
+        terms.append((g, M))
+        groups.append(dict(levels=int(nlev), g=g.tolist(), M=M.tolist()))
+    y = rng.standard_normal(N) * 2 + 3 * Xf[:, 0]
+    sd = build_stan_data(Xf, y, terms, is_binary=binary)
+    if not binary:
+        sd.prior_dist_for_aux = aux_prior
+        if aux_prior in (1, 2):
+            sd.prior_mean_for_aux = 0.4
+            sd.prior_df_for_aux = 4.0
+    sd.prior_dist = prior_dist
+    offset = rng.standard_normal(N) * 0.5
+    if binary:
+        y = rng.standard_normal(N) + 0.3      # latents
+        sd.y = y
+    qs, lps, grads, was = [], [], [], []
+    for k in range(3):
+        q = torch.tensor(rng.uniform(-1.5, 1.5, sd.num_params), requires_grad=True)
+        lp, tp = log_prob(sd, q, offset, y)
+        lp.backward()
+        qs.append(q.detach().numpy().tolist()); lps.append(float(lp)); grads.append(q.grad.numpy().tolist())
+        wa = q.detach().numpy().tolist()
+        # write_array order: params (constrained) then aux, beta, b, theta_L
+        K, nq = sd.K, sd.q
+        cons = list(q.detach().numpy()[:K + nq]) + tp["rho"].tolist() + tp["zeta"].tolist() + tp["tau"].tolist()
+        if not binary:
+            cons += [float(torch.exp(q[-1])), float(tp["aux"])]
+        cons += tp["beta"].tolist() + tp["b"].tolist() + tp["theta_L"].tolist()
+        was.append([float(v) for v in cons])
+    case = dict(name=name, N=N, binary=binary, X_fixed=Xf.tolist(), y=np.asarray(y).tolist(), y_for_scaling=None, offset=offset.tolist(),
+                groups=groups, aux_prior=aux_prior, prior_dist=prior_dist,
+                prior_scale=sd.prior_scale.tolist(), prior_scale_for_aux=sd.prior_scale_for_aux,
+                prior_mean_for_aux=sd.prior_mean_for_aux, prior_df_for_aux=sd.prior_df_for_aux,
+                q=qs, lp=lps, grad=grads, write_array=was)
+    with open(os.path.join(HERE, f"glmm_{name}.json"), "w") as f:
+        json.dump(case, f)
+    print(name, "d =", sd.num_params, "lp =", lps)
+
+
+if __name__ == "__main__":
+    make_case("friedman_like", 60, 1, False, [(5, 2), (8, 1)])
+    make_case("binary", 50, 2, True, [(4, 2), (6, 1)])
+    make_case("intercepts_only", 40, 3, False, [(3, 1), (7, 1)], aux_prior=1)
+    make_case("two_slopes_t_aux", 70, 4, False, [(4, 2), (5, 2), (3, 1)], aux_prior=2)
+    make_case("no_ranef_flat_prior", 30, 5, False, [], aux_prior=0, prior_dist=0)

@@ -1,0 +1,179 @@
+"""GPU parity tests for the BART half (CUDA path through the C ABI vs the CPU oracle)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from common import REL_TOL, bart_problem, compare_traces, rel_err
+from stan4bart_b200.sampler import GpuBart
+from stan4bart_b200.structs import bart_config
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(n=500, p=5, n_test=0, binary=False, num_trees=10, seed=11, thin=1, offset=True, **kw):
+    x, y, xt = bart_problem(n, p, n_test, binary)
+    cfg = bart_config(n, p, n_test=n_test, num_trees=num_trees, is_binary=binary, seed=seed, thin=thin, **kw)
+    o = O.OracleBart(cfg, y, x, xt)
+    g = GpuBart(cfg, y, x, xt)
+    if offset:
+        off = 0.3 * x[:, 3] - 0.1
+        o.set_offset(off, True); g.set_offset(off, True)
+    if not binary:
+        o.set_sigma(1.3); g.set_sigma(1.3)
+    return o, g, (x, y, xt)
+
+
+def assert_same_partition(o, g, num_trees):
+    for t in range(num_trees):
+        ao, ag = o.node_assignment(t), g.node_assignment(t)
+        assert np.array_equal(ao, ag), f"tree {t}: node assignment differs for {np.count_nonzero(ao != ag)} observations"
+
+
+def test_prior_trees_partition_and_residual():
+    o, g, _ = make_pair(n=777, num_trees=12)
+    o.sample_trees_from_prior(); g.sample_trees_from_prior()
+    assert o.rng_counter() == g.rng_counter()
+    assert_same_partition(o, g, 12)
+    to, tg = o.trees(), g.trees()
+    assert np.array_equal(to["var"], tg["var"]) and np.array_equal(to["tree"], tg["tree"])
+    assert rel_err(to["value"], tg["value"]) <= REL_TOL
+    assert rel_err(o.residual(), g.residual(), scale=1.0) <= 1e-12
+
+
+def test_leaf_stats_kernel():
+    o, g, _ = make_pair(n=2003, num_trees=8)
+    o.sample_trees_from_prior(); g.sample_trees_from_prior()
+    for t in range(8):
+        ho, co, so, sso = o.leaf_stats(t)
+        hg, cg, sg, ssg = g.leaf_stats(t)
+        assert np.array_equal(ho, hg) and np.array_equal(co, cg)           # counts bit exact
+        assert rel_err(sso, ssg) <= REL_TOL
+        # sums can cancel: measure against sum |x| <= sqrt(n * sumsq)
+        assert rel_err(so, sg, scale=np.sqrt(np.maximum(co, 1) * sso) + 1e-300) <= REL_TOL
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_stepwise_replay_native_rng(binary):
+    """Same counter-based RNG on both sides: every tree step of the first sweeps matches."""
+    T, sweeps = 10, 6
+    o, g, _ = make_pair(n=600, num_trees=T, binary=binary, n_test=50)
+    o.sample_trees_from_prior(); g.sample_trees_from_prior()
+    o.set_trace(T * sweeps); g.set_trace(T * sweeps)
+    for s in range(sweeps):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL, f"sweep {s}"
+        assert rel_err(ro["test"], rg["test"], scale=np.abs(ro["test"]) + 1.0) <= REL_TOL
+        assert np.array_equal(ro["varcount"], rg["varcount"])
+        assert ro["sigma"] == pytest.approx(rg["sigma"], rel=1e-14)
+    compare_traces(o.trace(), g.trace())
+    assert o.rng_counter() == g.rng_counter()
+    assert_same_partition(o, g, T)
+    if binary:
+        assert rel_err(o.latents(), g.latents(), scale=1.0) <= 1e-9
+
+
+def test_replay_from_tape():
+    """Replay mode: the GPU consumes the draws recorded by the oracle, not its own generator."""
+    T, sweeps = 7, 5
+    o, g, _ = make_pair(n=400, num_trees=T, seed=5)
+    o.set_record(200000)
+    o.sample_trees_from_prior()
+    o.set_trace(T * sweeps)
+    outs = [o.run() for _ in range(sweeps)]
+    tape = o.record()
+    g2 = g
+    g2.set_tape(tape)
+    g2.sample_trees_from_prior()
+    g2.set_trace(T * sweeps)
+    for s in range(sweeps):
+        rg = g2.run()
+        assert rel_err(outs[s]["train"], rg["train"], scale=np.abs(outs[s]["train"]) + 1.0) <= REL_TOL
+    compare_traces(o.trace(), g2.trace())
+
+
+def test_tape_underrun_is_an_error():
+    from stan4bart_b200._lib import S4BError
+    o, g, _ = make_pair(n=300, num_trees=4)
+    g.set_tape(np.full(3, 0.5))
+    with pytest.raises(S4BError):
+        g.sample_trees_from_prior()
+        g.run()
+
+
+def test_all_move_types_and_graph_vs_stream():
+    """Long enough that birth, death, change and swap are all proposed and accepted; the graph-captured
+    sweep and plain stream launches must agree bit for bit."""
+    T, sweeps = 20, 30
+    o, g, (x, y, xt) = make_pair(n=1500, p=6, num_trees=T, seed=21)
+    cfg = g.cfg
+    g_plain = GpuBart(cfg, y, x, xt)
+    off = 0.3 * x[:, 3] - 0.1
+    g_plain.set_offset(off, True); g_plain.set_sigma(1.3); g_plain.set_use_graph(False)
+    for b in (o, g, g_plain):
+        b.sample_trees_from_prior()
+    o.set_trace(T * sweeps); g.set_trace(T * sweeps)
+    for s in range(sweeps):
+        ro, rg, rp = o.run(), g.run(), g_plain.run()
+        assert np.array_equal(rg["train"], rp["train"])
+    tr = o.trace()
+    compare_traces(tr, g.trace())
+    kinds = tr[:, 0]
+    for k in (0, 1, 2, 3):
+        assert np.any((kinds == k) & (tr[:, 4] == 1)), f"move type {k} never accepted in this run"
+    assert_same_partition(o, g, T)
+
+
+def test_thinning_and_rescale_schedule():
+    T = 6
+    o, g, (x, y, _) = make_pair(n=500, num_trees=T, thin=3)
+    o.sample_trees_from_prior(); g.sample_trees_from_prior()
+    rng = np.random.default_rng(0)
+    for it in range(6):
+        off = 0.3 * x[:, 3] + 0.05 * rng.standard_normal(len(y))
+        upd = it % 2 == 0
+        o.set_offset(off, upd); g.set_offset(off, upd)
+        o.set_sigma(1.0 + 0.1 * it); g.set_sigma(1.0 + 0.1 * it)
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
+        assert rel_err(o.data_range(), g.data_range()) <= 1e-14
+    assert o.rng_counter() == g.rng_counter()
+
+
+def test_predict_matches_training_fits_and_oracle():
+    """test-01-continuous.R:212-254: predict(newdata = train) reproduces the stored training fits."""
+    o, g, (x, y, _) = make_pair(n=640, num_trees=15)
+    o.sample_trees_from_prior(); g.sample_trees_from_prior()
+    for _ in range(5):
+        ro, rg = o.run(), g.run()
+    off = 0.3 * x[:, 3] - 0.1
+    pg = g.predict(x, off)
+    assert rel_err(pg, rg["train"], scale=np.abs(pg) + 1.0) <= 1e-10
+    xnew = np.asfortranarray(np.random.default_rng(9).random((333, x.shape[1])))
+    assert rel_err(o.predict(xnew), g.predict(xnew), scale=1.0) <= 1e-10
+    to, tg = o.trees(), g.trees()
+    assert np.array_equal(to["var"], tg["var"]) and np.array_equal(to["n"], tg["n"])
+    assert rel_err(to["value"], tg["value"]) <= REL_TOL
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 17, 255, 256, 257, 1025])
+def test_ragged_sizes(n):
+    T = 3
+    x, y, xt = bart_problem(max(n, 1), 2, 0)
+    cfg = bart_config(n, 2, num_trees=T, seed=2, min_obs=1)
+    o, g = O.OracleBart(cfg, y, x), GpuBart(cfg, y, x)
+    o.set_sigma(0.7); g.set_sigma(0.7)
+    o.set_trace(T * 4); g.set_trace(T * 4)
+    for _ in range(4):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
+    compare_traces(o.trace(), g.trace())
+
+
+def test_bad_arguments_fail_loudly():
+    from stan4bart_b200._lib import S4BError
+    x, y, _ = bart_problem(50, 2)
+    with pytest.raises(S4BError):
+        GpuBart(bart_config(50, 2, n_cuts=300), y, x)
+    g = GpuBart(bart_config(50, 2, num_trees=2), y, x)
+    with pytest.raises(S4BError):
+        g.node_assignment(5)

@@ -1,0 +1,140 @@
+"""GPU parity of the whole Gibbs sweep (BART block + Stan block + plumbing) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from common import compare_traces, rel_err
+from stan4bart_b200.frontend import friedman_problem
+from stan4bart_b200.sampler import Sampler
+from stan4bart_b200.structs import bart_config, stan_control
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(n=100, binary=False, num_trees=11, warmup=7, iter_=13, keep_fits=True, seed=12345, thin=1):
+    pr = friedman_problem(n, binary=binary)
+    sd = pr["stan_data"]
+    cfg = bart_config(n, 9, n_test=n, num_trees=num_trees, is_binary=binary, seed=seed, thin=thin)
+    ctl = stan_control(seed=seed + 1)
+    kw = dict(warmup=warmup, iter_=iter_, keep_fits=keep_fits, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    g = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    return o, g, pr
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_first_sweeps_match_step_by_step(binary):
+    """README config A (n = 100), tests' tiny settings: first K Gibbs sweeps agree step by step."""
+    o, g, pr = make_pair(binary=binary)
+    K = 7
+    ob, gb = o.bart(), g.bart()
+    ob.set_trace(11 * K); gb.set_trace(11 * K)
+    ro, rg = o.run(K, True), g.run(K, True)
+    compare_traces(ob.trace(), gb.trace(), tol=1e-8)
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["test"], rg["bart"]["test"], scale=np.abs(ro["bart"]["test"]) + 1.0) <= 1e-8
+    assert np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"])
+    assert rel_err(ro["bart"]["sigma"], rg["bart"]["sigma"]) <= 1e-8
+    assert rel_err(o.data_range(), g.data_range()) <= 1e-10
+    # the saved 7 diagnostics are integers / booleans where they should be
+    names = pr["stan_data"].param_names()
+    for nm in ("treedepth__", "n_leapfrog__", "divergent__"):
+        assert np.array_equal(ro["stan"][names.index(nm)], rg["stan"][names.index(nm)])
+
+
+def test_result_layout_and_consistency():
+    """Shapes of the reference's result list and the invariants of test-01-continuous.R / test-11-callback.R."""
+    o, g, pr = make_pair(warmup=7, iter_=13)
+    sd = pr["stan_data"]
+    w = g.run(7, True)
+    g.disengage_adaptation()
+    r = g.run(6, False)
+    assert w["stan"].shape == (58, 7) and r["stan"].shape == (58, 6)           # 7 + 26 + 25 rows
+    assert r["bart"]["train"].shape == (100, 6) and r["bart"]["test"].shape == (100, 6)
+    assert r["bart"]["varcount"].shape == (9, 6) and r["bart"]["sigma"].shape == (6,)
+    names = sd.param_names()
+    assert len(names) == 58 and not any(nm.startswith("gamma") for nm in names)    # test-01:29-32: no intercept
+    # stored beta / b rows reproduce the parametric mean the BART block saw (test-11:57-66)
+    glmm = O.OracleGlmm(sd)
+    last = r["stan"][7:, -1]
+    assert rel_err(g.parametric_mean(), glmm.parametric_mean(last), scale=1.0) <= 1e-12
+    # sigma handed to BART is the stored aux row
+    assert np.allclose(r["bart"]["sigma"], r["stan"][names.index("aux.1")])
+    # predict on the training design reproduces the stored training fit of the last sweep (test-01:212-254)
+    rng_min, rng_max = g.data_range()
+    pred = g.predict_bart(pr["x_bart"])
+    assert rel_err(pred, r["bart"]["train"][:, -1], scale=np.abs(pred) + 1.0) <= 1e-10
+    # x_test == x_train for this design, so test fits equal training fits
+    assert rel_err(r["bart"]["test"][:, -1], r["bart"]["train"][:, -1], scale=1.0) <= 1e-10
+    # running means kept on device equal the mean of the stored draws (fitted == rowMeans(extract), test-01:34-57)
+    m = g.means()
+    assert m["num_draws"] == 6
+    assert rel_err(m["bart_train"], r["bart"]["train"].mean(axis=1), scale=1.0) <= 1e-12
+    assert rel_err(m["bart_test"], r["bart"]["test"].mean(axis=1), scale=1.0) <= 1e-12
+
+
+def test_keep_fits_false_and_seed_determinism():
+    _, g1, _ = make_pair(keep_fits=False)
+    _, g2, _ = make_pair(keep_fits=False)
+    _, g3, _ = make_pair(keep_fits=False, seed=777)
+    outs = []
+    for g in (g1, g2, g3):
+        g.run(5, True)
+        g.disengage_adaptation()
+        outs.append(g.run(5, False))
+    assert outs[0]["stan"].shape == (58, 1)
+    assert np.array_equal(outs[0]["stan"], outs[1]["stan"])                 # test-05-rng.R: same seed, same draws
+    assert np.array_equal(outs[0]["bart"]["train"], outs[1]["bart"]["train"])
+    assert not np.array_equal(outs[0]["bart"]["train"], outs[2]["bart"]["train"])
+
+
+def test_thin_and_larger_n():
+    o, g, _ = make_pair(n=3000, num_trees=20, thin=2)
+    ob, gb = o.bart(), g.bart()
+    ob.set_trace(20 * 2 * 3); gb.set_trace(20 * 2 * 3)
+    ro, rg = o.run(3, True), g.run(3, True)
+    compare_traces(ob.trace(), gb.trace(), tol=1e-7)
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
+
+
+def test_posterior_agreement_within_monte_carlo_error():
+    """north_star: posterior fitted means and CATE agree within 4 Monte-Carlo standard errors.
+    Independent seeds on the two sides, so this is a statistical, not a replay, check."""
+    n, warm, it = 200, 150, 300
+    pr = friedman_problem(n)
+    sd = pr["stan_data"]
+    kw = dict(warmup=warm, iter_=warm + it, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    d = pr["data"]
+
+    def cate_draws(run, glmm_mean):
+        # readme.md:57-64: icate = (mu.train - mu.test) * (2 z - 1); here the counterfactual differs only in z
+        names = sd.param_names()
+        beta_z = run["stan"][names.index("beta.2")]
+        return beta_z
+
+    draws = {}
+    for label, cls, seed in (("oracle", O.OracleSampler, 101), ("gpu", Sampler, 202)):
+        cfg = bart_config(n, 9, n_test=n, num_trees=30, seed=seed)
+        s = cls(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=seed), **kw)
+        s.run(warm, True)
+        s.disengage_adaptation()
+        r = s.run(it, False)
+        g = O.OracleGlmm(sd)
+        par = np.stack([g.parametric_mean(r["stan"][7:, k]) for k in range(it)], axis=1)
+        ev = r["bart"]["train"] + par
+        draws[label] = dict(ev=ev, cate=cate_draws(r, None))
+
+    def mcse(x):   # batch means
+        b = 10
+        m = x.reshape(*x.shape[:-1], b, -1).mean(axis=-1)
+        return m.std(axis=-1, ddof=1) / np.sqrt(b)
+
+    ev_o, ev_g = draws["oracle"]["ev"], draws["gpu"]["ev"]
+    diff = np.abs(ev_o.mean(axis=1) - ev_g.mean(axis=1))
+    se = np.sqrt(mcse(ev_o) ** 2 + mcse(ev_g) ** 2)
+    assert np.mean(diff <= 4 * se) >= 0.97        # fitted means, observation by observation
+    c_o, c_g = draws["oracle"]["cate"], draws["gpu"]["cate"]
+    assert abs(c_o.mean() - c_g.mean()) <= 4 * np.sqrt(mcse(c_o) ** 2 + mcse(c_g) ** 2)
+    mu_true = d["mu1"] * d["z"] + d["mu0"] * (1 - d["z"])
+    assert np.corrcoef(ev_g.mean(axis=1), mu_true)[0, 1] >= 0.95

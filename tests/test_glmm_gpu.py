@@ -1,0 +1,92 @@
+"""GPU parity: the device GLMM pass + host chain rule against the golden vectors and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from common import REL_TOL, golden_cases, load_glmm_case, rel_err
+from stan4bart_b200.frontend import friedman_problem
+from stan4bart_b200.sampler import GlmmModel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[5:-5])
+def test_gpu_matches_golden(path):
+    sd, c = load_glmm_case(path)
+    m = GlmmModel(sd)
+    m.set_offset(np.asarray(c["offset"]))
+    assert m.d == len(c["q"][0])
+    for q, lp, grad, wa in zip(c["q"], c["lp"], c["grad"], c["write_array"]):
+        lp_g, g_g, status = m.log_prob_grad(np.asarray(q))
+        assert status == 0
+        assert abs(lp_g - lp) <= REL_TOL * abs(lp)
+        assert rel_err(g_g, grad, scale=np.abs(grad) + 1e-8 * np.max(np.abs(grad))) <= REL_TOL
+        assert rel_err(m.write_array(np.asarray(q)), wa) <= 1e-12
+
+
+@pytest.mark.parametrize("n,binary", [(1, False), (31, False), (257, True), (20000, False), (100003, True)])
+def test_gpu_matches_oracle_on_friedman(n, binary):
+    pr = friedman_problem(max(n, 1), binary=binary, seed=5)
+    sd = pr["stan_data"]
+    rng = np.random.default_rng(n)
+    off = rng.standard_normal(sd.N)
+    mo, mg = O.OracleGlmm(sd), GlmmModel(sd)
+    mo.set_offset(off); mg.set_offset(off)
+    if binary:
+        z = rng.standard_normal(sd.N)
+        mo.set_response(z); mg.set_response(z)
+    for _ in range(3):
+        q = rng.uniform(-1, 1, mo.d)
+        lo, go, so = mo.log_prob_grad(q)
+        lg, gg, sg = mg.log_prob_grad(q)
+        assert so == sg == 0
+        assert abs(lo - lg) <= REL_TOL * abs(lo)
+        assert rel_err(go, gg, scale=np.abs(go) + 1e-8 * np.max(np.abs(go))) <= REL_TOL
+        wa = mo.write_array(q)
+        assert rel_err(mo.parametric_mean(wa), mg.parametric_mean(wa), scale=1.0) <= 1e-12
+        assert rel_err(mo.parametric_mean(wa, True, False), mg.parametric_mean(wa, True, False), scale=1.0) <= 1e-12
+        assert rel_err(mo.parametric_mean(wa, False, True), mg.parametric_mean(wa, False, True), scale=1.0) <= 1e-12
+
+
+def test_data_terms_linearity_at_scale():
+    """Size-independent property at a large N: S, X'e, Z'e are quadratic / linear in (beta, b)."""
+    pr = friedman_problem(300000, seed=8)
+    sd = pr["stan_data"]
+    m = GlmmModel(sd)
+    rng = np.random.default_rng(0)
+    m.set_offset(rng.standard_normal(sd.N))
+    z0, zb0 = np.zeros(sd.K), np.zeros(sd.q)
+    S0, gx0, gz0 = m.data_terms(z0, zb0)
+    beta, b = rng.standard_normal(sd.K), rng.standard_normal(sd.q)
+    S1, gx1, gz1 = m.data_terms(beta, b)
+    S2, gx2, gz2 = m.data_terms(2 * beta, 2 * b)
+    # e(theta) = e0 - A theta  =>  g(theta) affine, S quadratic
+    assert rel_err(gx2 - gx0, 2 * (gx1 - gx0), scale=np.abs(gx0) + np.abs(gx2)) <= 1e-11
+    assert rel_err(gz2 - gz0, 2 * (gz1 - gz0), scale=np.abs(gz0) + np.abs(gz2)) <= 1e-11
+    quad = S1 - S0 + 2 * (beta @ gx0 + b @ gz0)       # theta' A'A theta
+    quad2 = S2 - S0 + 4 * (beta @ gx0 + b @ gz0)
+    assert abs(quad2 - 4 * quad) <= 1e-10 * abs(quad2)
+    # deterministic: repeated evaluation is bit identical
+    assert m.data_terms(beta, b)[0] == S1
+
+
+def test_non_finite_maps_to_status():
+    sd, c = load_glmm_case(golden_cases()[1])
+    m = GlmmModel(sd)
+    q = np.asarray(c["q"][0]).copy()
+    q[-1] = 800.0
+    assert m.log_prob_grad(q)[2] != 0
+
+
+def test_unsupported_branches_fail_loudly():
+    from stan4bart_b200._lib import S4BError
+    from stan4bart_b200.frontend import build_stan_data
+    rng = np.random.default_rng(0)
+    N = 30
+    g = rng.integers(0, 3, N)
+    M = np.column_stack([np.ones(N), rng.random(N), rng.random(N)])
+    sd = build_stan_data(rng.random((N, 1)), rng.standard_normal(N), [(g, M)])
+    with pytest.raises(S4BError):
+        GlmmModel(sd)
