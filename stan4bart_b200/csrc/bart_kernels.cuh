@@ -426,6 +426,8 @@ __device__ inline void decide_and_draw(DTree& t, const BartParams& P, RngState& 
     if (trace_rec != nullptr && 11 + nleaf < S4B_TRACE_LEN) trace_rec[11 + nleaf] = mu;
     ++nleaf;
   }
+  // observation counts of internal nodes (FlattenedTrees numObservations, init.cpp:583-666)
+  for (int k = t.num_nodes - 1; k >= 0; --k) if (!t_is_leaf(t, k)) t.nodes[k].n = t.nodes[k + 1].n + t.nodes[t.nodes[k].right].n;
   if (structure_changed) {
     out.a_same = 0;
     t_fill_trav(t, out.a_new, true);

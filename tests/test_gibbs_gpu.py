@@ -100,41 +100,34 @@ def test_thin_and_larger_n():
 
 def test_posterior_agreement_within_monte_carlo_error():
     """north_star: posterior fitted means and CATE agree within 4 Monte-Carlo standard errors.
-    Independent seeds on the two sides, so this is a statistical, not a replay, check."""
-    n, warm, it = 200, 150, 300
+    Independent seeds on the two sides (a statistical, not a replay, check).  BART chains mix slowly, so
+    the Monte-Carlo error of a posterior mean is estimated from the spread of independent chains."""
+    n, warm, it, chains = 200, 150, 300, 4
     pr = friedman_problem(n)
     sd = pr["stan_data"]
     kw = dict(warmup=warm, iter_=warm + it, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
     d = pr["data"]
-
-    def cate_draws(run, glmm_mean):
-        # readme.md:57-64: icate = (mu.train - mu.test) * (2 z - 1); here the counterfactual differs only in z
-        names = sd.param_names()
-        beta_z = run["stan"][names.index("beta.2")]
-        return beta_z
-
-    draws = {}
-    for label, cls, seed in (("oracle", O.OracleSampler, 101), ("gpu", Sampler, 202)):
-        cfg = bart_config(n, 9, n_test=n, num_trees=30, seed=seed)
-        s = cls(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=seed), **kw)
-        s.run(warm, True)
-        s.disengage_adaptation()
-        r = s.run(it, False)
-        g = O.OracleGlmm(sd)
-        par = np.stack([g.parametric_mean(r["stan"][7:, k]) for k in range(it)], axis=1)
-        ev = r["bart"]["train"] + par
-        draws[label] = dict(ev=ev, cate=cate_draws(r, None))
-
-    def mcse(x):   # batch means
-        b = 10
-        m = x.reshape(*x.shape[:-1], b, -1).mean(axis=-1)
-        return m.std(axis=-1, ddof=1) / np.sqrt(b)
-
-    ev_o, ev_g = draws["oracle"]["ev"], draws["gpu"]["ev"]
-    diff = np.abs(ev_o.mean(axis=1) - ev_g.mean(axis=1))
-    se = np.sqrt(mcse(ev_o) ** 2 + mcse(ev_g) ** 2)
+    names = sd.param_names()
+    glmm = O.OracleGlmm(sd)
+    means = {"oracle": [], "gpu": []}
+    cates = {"oracle": [], "gpu": []}
+    for label, cls, seed0 in (("oracle", O.OracleSampler, 100), ("gpu", Sampler, 200)):
+        for c in range(chains):
+            seed = seed0 + c
+            cfg = bart_config(n, 9, n_test=n, num_trees=30, seed=seed)
+            s = cls(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=seed), **kw)
+            s.run(warm, True)
+            s.disengage_adaptation()
+            r = s.run(it, False)
+            par = np.stack([glmm.parametric_mean(r["stan"][7:, k]) for k in range(it)], axis=1)
+            means[label].append((r["bart"]["train"] + par).mean(axis=1))
+            # readme.md:57-64: icate = (mu.train - mu.test) * (2 z - 1); the counterfactual differs only in z => beta_z
+            cates[label].append(r["stan"][names.index("beta.2")].mean())
+    mo, mg = np.stack(means["oracle"]), np.stack(means["gpu"])
+    se = np.sqrt(mo.var(axis=0, ddof=1) / chains + mg.var(axis=0, ddof=1) / chains)
+    diff = np.abs(mo.mean(axis=0) - mg.mean(axis=0))
     assert np.mean(diff <= 4 * se) >= 0.97        # fitted means, observation by observation
-    c_o, c_g = draws["oracle"]["cate"], draws["gpu"]["cate"]
-    assert abs(c_o.mean() - c_g.mean()) <= 4 * np.sqrt(mcse(c_o) ** 2 + mcse(c_g) ** 2)
+    co, cg = np.array(cates["oracle"]), np.array(cates["gpu"])
+    assert abs(co.mean() - cg.mean()) <= 4 * np.sqrt(co.var(ddof=1) / chains + cg.var(ddof=1) / chains)
     mu_true = d["mu1"] * d["z"] + d["mu0"] * (1 - d["z"])
-    assert np.corrcoef(ev_g.mean(axis=1), mu_true)[0, 1] >= 0.95
+    assert np.corrcoef(mg.mean(axis=0), mu_true)[0, 1] >= 0.95

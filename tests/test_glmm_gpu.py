@@ -26,7 +26,7 @@ def test_gpu_matches_golden(path):
         assert rel_err(m.write_array(np.asarray(q)), wa) <= 1e-12
 
 
-@pytest.mark.parametrize("n,binary", [(1, False), (31, False), (257, True), (20000, False), (100003, True)])
+@pytest.mark.parametrize("n,binary", [(2, False), (31, False), (257, True), (20000, False), (100003, True)])
 def test_gpu_matches_oracle_on_friedman(n, binary):
     pr = friedman_problem(max(n, 1), binary=binary, seed=5)
     sd = pr["stan_data"]
