@@ -70,6 +70,8 @@ typedef struct s4b_common_control {
 
 const char* s4b_last_error(void);
 int s4b_device_count(void);
+/* cudaSetDevice for this library's runtime instance (one process per GPU: call once with LOCAL_RANK) */
+int s4b_set_device(int device);
 /* all later objects created on this thread use `cuda_stream` (a cudaStream_t; NULL = a private stream) */
 int s4b_set_stream(void* cuda_stream);
 
@@ -110,6 +112,8 @@ int gpubart_set_use_graph(gpubart_fit* fit, int use_graph);
 /* micro-benchmark hook: `reps` launches of the leaf-statistics pass for `tree`, returns mean ms per launch */
 int gpubart_time_leaf_stats(gpubart_fit* fit, int tree, int reps, double* ms_per_launch);
 int gpubart_num_tree_steps(gpubart_fit* fit, int64_t* out);
+/* device milliseconds (CUDA events on the launching stream) spent in the per-tree kernels since the last reset */
+int gpubart_tree_step_ms(gpubart_fit* fit, int reset, double* ms);
 
 /* ------------------------------------------------------------------ glmm_* */
 typedef struct glmm_model glmm_model;
@@ -155,6 +159,9 @@ glmm_model* s4b_sampler_glmm(s4b_sampler* s);
 /* running posterior means kept on device (keep_fits = FALSE path): mean train / test BART fit
  * and mean parametric part over the sampling-phase sweeps run so far */
 int s4b_sampler_get_means(s4b_sampler* s, double* mean_bart_train, double* mean_bart_test, double* mean_parametric, int64_t* num_draws);
+/* route every iteration's N-length vectors (parametric mean, BART fit, latents) through pinned host memory, as the
+ * reference's host-side vectors bartOffset / stanOffset / bartLatents do (init.cpp:143-145); reports bytes per iteration */
+int s4b_sampler_set_host_plumbing(s4b_sampler* s, int on, int64_t* h2d_bytes_per_iter, int64_t* d2h_bytes_per_iter);
 /* timing split of the last run: milliseconds in the Stan block and the BART block (CUDA events), leapfrog count */
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* n_grad_evals, int64_t* n_tree_steps);
 

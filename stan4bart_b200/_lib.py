@@ -21,6 +21,9 @@ SIGNATURES = {
     "s4b_last_error": (C.c_char_p, []),
     "s4b_device_count": (C.c_int, []),
     "s4b_set_stream": (C.c_int, [vp]),
+    "s4b_set_device": (C.c_int, [C.c_int]),
+    "gpubart_tree_step_ms": (C.c_int, [vp, C.c_int, c_double_p]),
+    "s4b_sampler_set_host_plumbing": (C.c_int, [vp, C.c_int, c_int64_p, c_int64_p]),
     "gpubart_create": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, vpp]),
     "gpubart_free": (C.c_int, [vp]),
     "gpubart_set_offset": (C.c_int, [vp, c_double_p, C.c_int]),

@@ -652,6 +652,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   S4B_CUDA(cudaMalloc(&d_rng_, sizeof(RngState)));
   S4B_CUDA(cudaMemcpy(d_rng_, &rs, sizeof rs, cudaMemcpyHostToDevice));
   S4B_CUDA(cudaMalloc(&d_scale_factor_, sizeof(double)));
+  S4B_CUDA(cudaEventCreate(&ev_start_)); S4B_CUDA(cudaEventCreate(&ev_end_));
 
   if (cfg.is_binary) {
     // latents start at +-1 with zero offset (oracle_bart.c or_bart_create)
@@ -669,6 +670,8 @@ BartFit::~BartFit()
 {
   if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
   if (graph_exec_thin_) cudaGraphExecDestroy(graph_exec_thin_);
+  if (ev_start_) cudaEventDestroy(ev_start_);
+  if (ev_end_) cudaEventDestroy(ev_end_);
   cudaFree(d_xt_); cudaFree(d_xt_test_); cudaFree(d_R_); cudaFree(d_yresc_); cudaFree(d_y_); cudaFree(d_offset_);
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
@@ -833,6 +836,8 @@ void BartFit::run_sweeps()
 {
   // one runSamplerWithResults(fit, 0, results[numSamples = 1]): `thin` sweeps, the last one kept
   const bool use_graph = use_graph_;
+  tree_step_ms(false);                       // fold in the previous sweep's event pair
+  S4B_CUDA(cudaEventRecord(ev_start_, stream_));
   for (int k = 0; k < cfg_.thin; ++k) {
     bool last = (k + 1) == cfg_.thin;
     if (!use_graph) { launch_sweep_kernels(last); S4B_CUDA(cudaGetLastError()); continue; }
@@ -847,8 +852,23 @@ void BartFit::run_sweeps()
     }
     S4B_CUDA(cudaGraphLaunch(ge, stream_));
   }
+  S4B_CUDA(cudaEventRecord(ev_end_, stream_));
+  ev_pending_ = true;
   num_tree_steps_ += (long long) cfg_.thin * T_;
   if (nt_ > 0) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
+}
+
+double BartFit::tree_step_ms(bool reset)
+{
+  if (ev_pending_) {
+    S4B_CUDA(cudaEventSynchronize(ev_end_));
+    float ms = 0.f; S4B_CUDA(cudaEventElapsedTime(&ms, ev_start_, ev_end_));
+    sweep_ms_ += (double) ms;
+    ev_pending_ = false;
+  }
+  double r = sweep_ms_;
+  if (reset) sweep_ms_ = 0.0;
+  return r;
 }
 
 void BartFit::test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out)

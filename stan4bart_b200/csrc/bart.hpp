@@ -70,6 +70,8 @@ class BartFit {
   double* d_offset() const { return d_offset_; }
   int grid() const { return grid_; }
   long long num_tree_steps() const { return num_tree_steps_; }
+  // device time (CUDA events on the launching stream) spent in the sweep graphs since the last reset
+  double tree_step_ms(bool reset);
 
  private:
   BartDev dev() const;
@@ -98,6 +100,9 @@ class BartFit {
   double* d_trace_ = nullptr; size_t trace_cap_ = 0;
   double* d_tape_ = nullptr; double* d_rec_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr, graph_exec_thin_ = nullptr;
+  cudaEvent_t ev_start_ = nullptr, ev_end_ = nullptr;
+  bool ev_pending_ = false;
+  double sweep_ms_ = 0.0;
 };
 
 }  // namespace s4b

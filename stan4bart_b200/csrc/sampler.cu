@@ -48,6 +48,7 @@ class GibbsSampler {
   }
   ~GibbsSampler()
   {
+    if (h_plumb_) cudaFreeHost(h_plumb_);
     cudaFree(d_bart_offset_); cudaFree(d_mean_train_); cudaFree(d_mean_param_); cudaFree(d_mean_test_); cudaFree(d_varcount_);
     cudaEventDestroy(ev_a_); cudaEventDestroy(ev_b_); cudaEventDestroy(ev_c_);
   }
@@ -74,6 +75,10 @@ class GibbsSampler {
       const double* beta = constrained + glmm_.num_params() + (glmm_.has_aux() ? 1 : 0);
       const double* b = beta + glmm_.K();
       glmm_.parametric_mean_device(beta, b, d_bart_offset_, true, true);               // :764
+      if (host_plumbing_) {   // the reference's host vector `bartOffset` (init.cpp:143): D2H, then H2D into BART
+        S4B_CUDA(cudaMemcpyAsync(h_plumb_, d_bart_offset_, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+        S4B_CUDA(cudaMemcpyAsync(d_bart_offset_, h_plumb_, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+      }
       double aux = 1.0;
       if (!cc_.is_binary) { aux = constrained[glmm_.num_params()]; bart_.set_sigma(aux); }  // :796-800
       const int update_scale_mod = 1 << (8 * iter / num_iter);                           // :816
@@ -81,6 +86,14 @@ class GibbsSampler {
       auto t1 = std::chrono::steady_clock::now();
       // ---- B. BART block (init.cpp:821-916) ----
       bart_.run_sweeps();                                                                // :824
+      if (host_plumbing_) {   // `stanOffset` and `bartLatents` as host vectors (init.cpp:144-145, :835, :845-846)
+        S4B_CUDA(cudaMemcpyAsync(h_plumb_ + n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+        S4B_CUDA(cudaMemcpyAsync(bart_.d_train_out(), h_plumb_ + n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+        if (cc_.is_binary) {
+          S4B_CUDA(cudaMemcpyAsync(h_plumb_ + 2 * n, bart_.d_latent_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+          S4B_CUDA(cudaMemcpyAsync(bart_.d_latent_out(), h_plumb_ + 2 * n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+        }
+      }
       glmm_.set_offset_device(bart_.d_train_out());                                      // :828-842
       if (cc_.is_binary) glmm_.set_response_device(bart_.d_latent_out());                // :843-847
       if (!is_warmup) {
@@ -107,6 +120,16 @@ class GibbsSampler {
   }
 
   void disengage_adaptation() { nuts_.disengage_adaptation(); }
+  // route the N-length vectors of every iteration through pinned host memory, as a drop-in at the reference's
+  // own host boundary would (bench.py's `e2e` leg); returns bytes moved per iteration in each direction
+  void set_host_plumbing(bool on, long long* h2d_bytes, long long* d2h_bytes)
+  {
+    host_plumbing_ = on;
+    if (on && !h_plumb_) S4B_CUDA(cudaMallocHost(&h_plumb_, sizeof(double) * 3 * (size_t) n_));
+    long long per = (long long) sizeof(double) * n_ * (cc_.is_binary ? 3 : 2);
+    if (h2d_bytes) *h2d_bytes = on ? per : 0;
+    if (d2h_bytes) *d2h_bytes = on ? per : 0;
+  }
   void parametric_mean(double* out) { glmm_.parametric_mean_host(stan_curr_.data() + 7, out, true, true); }
   void means(double* mean_train, double* mean_test, double* mean_param, long long* num_draws)
   {
@@ -139,6 +162,8 @@ class GibbsSampler {
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;
   long long num_mean_draws_ = 0, last_grad_evals_ = 0, last_tree_steps_ = 0;
   double ms_stan_ = 0.0, ms_bart_ = 0.0;
+  bool host_plumbing_ = false;
+  double* h_plumb_ = nullptr;
 };
 
 }  // namespace s4b
@@ -176,6 +201,13 @@ int s4b_device_count(void)
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
+}
+
+int s4b_set_device(int device)
+{
+  S4B_API_BEGIN
+  S4B_CUDA(cudaSetDevice(device));
+  S4B_API_END
 }
 
 int s4b_set_stream(void* cuda_stream)
@@ -295,6 +327,9 @@ gpubart_fit* s4b_sampler_bart(s4b_sampler* s) { return s ? &s->bart_view : nullp
 glmm_model* s4b_sampler_glmm(s4b_sampler* s) { return s ? &s->glmm_view : nullptr; }
 int s4b_sampler_get_means(s4b_sampler* s, double* mt, double* mte, double* mp, int64_t* nd)
 { S4B_API_BEGIN S4B_REQUIRE(s); long long k = 0; s->s->means(mt, mte, mp, &k); if (nd) *nd = k; S4B_API_END }
+int s4b_sampler_set_host_plumbing(s4b_sampler* s, int on, int64_t* h2d, int64_t* d2h)
+{ S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->set_host_plumbing(on != 0, &a, &b); if (h2d) *h2d = a; if (d2h) *d2h = b; S4B_API_END }
+int gpubart_tree_step_ms(gpubart_fit* f, int reset, double* ms) { S4B_API_BEGIN S4B_REQUIRE(f && ms); *ms = f->fit->tree_step_ms(reset != 0); S4B_API_END }
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* ng, int64_t* ns)
 { S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->last_run_stats(ms_stan, ms_bart, &a, &b); if (ng) *ng = a; if (ns) *ns = b; S4B_API_END }
 

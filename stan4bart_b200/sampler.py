@@ -149,6 +149,11 @@ class GpuBart:
         _lib.check(self.L.gpubart_time_leaf_stats(self.h, tree, reps, C.byref(ms)))
         return ms.value
 
+    def tree_step_ms(self, reset=True):
+        ms = C.c_double(0.0)
+        _lib.check(self.L.gpubart_tree_step_ms(self.h, int(reset), C.byref(ms)))
+        return ms.value
+
     def num_tree_steps(self):
         k = C.c_int64(0)
         _lib.check(self.L.gpubart_num_tree_steps(self.h, C.byref(k)))
@@ -298,6 +303,18 @@ class Sampler:
         k = C.c_int64(0)
         _lib.check(self.L.s4b_sampler_get_means(self.h, dptr(mt), dptr(mte) if self.nt else dptr(None), dptr(mp), C.byref(k)))
         return dict(bart_train=mt, bart_test=mte[:self.nt], parametric=mp, num_draws=int(k.value))
+
+    def set_host_plumbing(self, on):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.L.s4b_sampler_set_host_plumbing(self.h, int(on), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def run_into(self, num_iter, is_warmup, stan=None, train=None, test=None, varcount=None, sigma=None):
+        """stan4bart_run writing into caller-provided host buffers given as raw addresses (or None)."""
+        def p(addr, typ):
+            return C.cast(C.c_void_p(addr), typ) if addr else typ()
+        _lib.check(self.L.s4b_sampler_run(self.h, num_iter, int(is_warmup), p(stan, _lib.c_double_p), p(train, _lib.c_double_p),
+                                          p(test, _lib.c_double_p), p(varcount, c_uint32_p), p(sigma, _lib.c_double_p)))
 
     def last_run_stats(self):
         a, b = C.c_double(0.0), C.c_double(0.0)
