@@ -109,11 +109,18 @@ int gpubart_set_record(gpubart_fit* fit, size_t cap);
 int gpubart_get_record(gpubart_fit* fit, double* out, size_t cap, size_t* len);
 int gpubart_rng_counter(gpubart_fit* fit, uint64_t* out);
 int gpubart_set_use_graph(gpubart_fit* fit, int use_graph);
+/* 0: one kernel launch per tree step; 1: those launches captured in a CUDA graph; 2: persistent on-chip sweep kernel
+ * (default when the chain fits the register file + shared memory) */
+int gpubart_set_sweep_mode(gpubart_fit* fit, int mode);
+int gpubart_get_sweep_mode(gpubart_fit* fit, int* mode);
 /* micro-benchmark hook: `reps` launches of the leaf-statistics pass for `tree`, returns mean ms per launch */
 int gpubart_time_leaf_stats(gpubart_fit* fit, int tree, int reps, double* ms_per_launch);
 int gpubart_num_tree_steps(gpubart_fit* fit, int64_t* out);
 /* device milliseconds (CUDA events on the launching stream) spent in the per-tree kernels since the last reset */
 int gpubart_tree_step_ms(gpubart_fit* fit, int reset, double* ms);
+/* SM-cycle counters of the controller phases of k_tree_step: [0] pass of the last block, [1] partial reduction, [2] tree load,
+ * [3] MH decision + leaf draws, [4] write-back + next tree load, [5] next proposal, [6] descriptor publish, [7] steps counted */
+int gpubart_get_profile(gpubart_fit* fit, uint64_t* out8, int reset);
 
 /* ------------------------------------------------------------------ glmm_* */
 typedef struct glmm_model glmm_model;

@@ -53,6 +53,7 @@ struct or_bart {
   double leaf_prec;
   s4b_rng rng;
   uint32_t latent_epoch;
+  uint64_t step_id, prior_calls;
   double* trace; size_t trace_cap, trace_len;
 };
 
@@ -252,6 +253,7 @@ static void birth_or_death(or_bart* f, Tree* t, const double* ty, double* tr) {
     double trans_ratio = (p_death_new * p_select_death) / (p_birth * p_select);
     double ratio = prior_ratio * trans_ratio * exp(new_ll - old_ll);
     if (nd->left->nobs < f->cfg.min_obs || nd->right->nobs < f->cfg.min_obs) ratio = 0.0;
+    s4b_rng_enter(&f->rng, f->step_id, 1);
     double u = s4b_rng_uniform(&f->rng);
     int accept = u < ratio;
     tr[0] = 0; tr[1] = (double) node_heap(nd); tr[2] = var; tr[3] = cut; tr[4] = accept; tr[5] = ratio;
@@ -279,6 +281,7 @@ static void birth_or_death(or_bart* f, Tree* t, const double* ty, double* tr) {
     double prior_ratio = (1.0 - pg_parent) / (pg_parent * (1.0 - pg_l) * (1.0 - pg_r));
     double trans_ratio = (p_birth_new * p_select_birth) / (p_death * p_select);
     double ratio = prior_ratio * trans_ratio * exp(new_ll - old_ll);
+    s4b_rng_enter(&f->rng, f->step_id, 1);
     double u = s4b_rng_uniform(&f->rng);
     int accept = u < ratio;
     tr[0] = 1; tr[1] = (double) node_heap(nd); tr[2] = nd->var; tr[3] = nd->cut; tr[4] = accept; tr[5] = ratio;
@@ -304,6 +307,7 @@ static void finish_change_like(or_bart* f, Tree* t, Tree* saved, Node* nd, int64
   double new_lp = branch_log_prior(f, nd);
   double ratio = exp((new_lp - old_lp) + (new_ll - old_ll));
   if (branch_min_obs(nd) < f->cfg.min_obs) ratio = 0.0;
+  s4b_rng_enter(&f->rng, f->step_id, 1);
   double u = s4b_rng_uniform(&f->rng);
   int accept = u < ratio;
   tr[4] = accept; tr[5] = ratio; tr[6] = old_ll; tr[7] = new_ll;
@@ -378,6 +382,7 @@ static void swap_rule(or_bart* f, Tree* t, const double* ty, double* tr) {
 }
 
 static void metropolis_jump(or_bart* f, Tree* t, const double* ty, double* tr) {
+  s4b_rng_enter(&f->rng, f->step_id, 0);
   double u = s4b_rng_uniform(&f->rng);
   if (u < f->cfg.birth_death_prob) birth_or_death(f, t, ty, tr);
   else if (u < f->cfg.birth_death_prob + f->cfg.swap_prob) swap_rule(f, t, ty, tr);
@@ -392,6 +397,7 @@ static const Node* traverse_binned(const Node* nd, const uint8_t* xt, size_t str
 static void sample_parameters_and_set_fits(or_bart* f, Tree* t, const double* ty, double* fits, double* test_fits, double* tr) {
   Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(t->top, bl, &nb);
   double sigsq = f->sigma * f->sigma;
+  s4b_rng_enter(&f->rng, f->step_id, 1);
   for (int k = 0; k < nb; ++k) {
     Node* nd = bl[k];
     node_set_average(nd, ty);
@@ -536,6 +542,7 @@ void or_bart_sample_trees_from_prior(or_bart* f)
   int n = f->n;
   for (int t = 0; t < f->T; ++t) {
     Tree* tr = &f->trees[t];
+    s4b_rng_enter(&f->rng, f->prior_calls * (uint64_t) f->T + (uint64_t) t, 2);
     orphan_children(tr->top);
     grow_from_prior(f, tr, tr->top);
     Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(tr->top, bl, &nb);
@@ -545,6 +552,7 @@ void or_bart_sample_trees_from_prior(or_bart* f)
       for (int i = 0; i < bl[k]->nobs; ++i) { int o = bl[k]->obs[i]; f->totalFits[o] += bl[k]->mu - tf[o]; tf[o] = bl[k]->mu; }
     }
   }
+  f->prior_calls++;
 }
 
 void or_bart_run(or_bart* f, double* train, double* test, uint32_t* varcount, double* sigma_out)
@@ -562,6 +570,7 @@ void or_bart_run(or_bart* f, double* train, double* test, uint32_t* varcount, do
       metropolis_jump(f, tree, f->treeY, tr);
       sample_parameters_and_set_fits(f, tree, f->treeY, f->currFits, is_thinning ? NULL : f->currTestFits, tr);
       if (f->trace && f->trace_len < f->trace_cap) f->trace_len++;
+      f->step_id++;
       for (int i = 0; i < n; ++i) { f->totalFits[i] += f->currFits[i] - tf[i]; tf[i] = f->currFits[i]; }
       if (!is_thinning) for (int j = 0; j < nt; ++j) f->totalTestFits[j] += f->currTestFits[j];
     }
@@ -635,7 +644,7 @@ void or_bart_predict(const or_bart* f, const double* x_test, int64_t n, const do
 double or_rng_qnorm(double p) { return s4b_qnorm(p); }
 void or_rng_uniforms(uint64_t seed, uint32_t stream, uint64_t start, int64_t n, double* out)
 {
-  s4b_rng g; s4b_rng_init(&g, seed, stream); g.counter = start;
+  s4b_rng g; s4b_rng_init(&g, seed, stream); g.idx = (uint32_t) start; g.step = start >> 32;
   for (int64_t i = 0; i < n; ++i) out[i] = s4b_rng_uniform(&g);
 }
 double or_rng_truncnorm(uint64_t seed, uint32_t obs, uint32_t epoch, double mean, int positive) { return s4b_keyed_truncnorm(seed, obs, epoch, mean, positive); }

@@ -20,8 +20,15 @@
  *   exp(1)  : -log(u)
  *   index   : floor(u * n), clamped to n-1
  *
- * Sequential streams advance (c0,c1) by one per draw.  The probit-latent stream
- * is keyed per observation: counter = (sub-draw, epoch, obs index, stream 2).
+ * Counter layout of a stream: c0 = draw index inside a substream, c1 = low 32 bits of
+ * the substream's step number, c2 = (sub << 30) | high 30 bits of the step, c3 = stream.
+ * The BART stream is keyed by tree step so that independent pieces of work do not
+ * serialise on one counter: sub 0 = proposal draws of tree step `step`, sub 1 = its
+ * decision draws (accept uniform, then one normal per bottom node, left to right),
+ * sub 2 = sampleTreesFromPrior (step = call * numTrees + tree).  Inside a substream draws
+ * are consumed in order; the Stan stream uses (step 0, sub 0) and carries idx into step.
+ * The probit-latent stream is keyed per observation: counter = (sub-draw, epoch, obs
+ * index, stream 2).  A replay tape is consumed strictly in program order.
  */
 #ifndef S4B_ORACLE_RNG_H
 #define S4B_ORACLE_RNG_H
@@ -109,7 +116,9 @@ static inline double s4b_qnorm(double p)
 typedef struct s4b_rng {
   uint32_t key[2];
   uint32_t stream;
-  uint64_t counter;
+  uint32_t sub, idx;
+  uint64_t step;
+  uint64_t counter;      /* total number of draws consumed (for tests) */
   /* replay: if tape != NULL draws are read from it (uniforms and normals
      interleaved in consumption order); record: if rec != NULL every draw is
      appended (until rec_cap) */
@@ -121,22 +130,30 @@ typedef struct s4b_rng {
 static inline void s4b_rng_init(s4b_rng* g, uint64_t seed, uint32_t stream)
 {
   g->key[0] = (uint32_t) seed; g->key[1] = (uint32_t) (seed >> 32);
-  g->stream = stream; g->counter = 0;
+  g->stream = stream; g->counter = 0; g->step = 0; g->sub = 0; g->idx = 0;
   g->tape = NULL; g->tape_len = 0; g->tape_pos = 0;
   g->rec = NULL; g->rec_cap = 0; g->rec_len = 0; g->tape_underrun = 0;
 }
 
+/* switch to substream (step, sub); a no-op when already there */
+static inline void s4b_rng_enter(s4b_rng* g, uint64_t step, uint32_t sub)
+{
+  if (g->step != step || g->sub != sub) { g->step = step; g->sub = sub; g->idx = 0; }
+}
+
 static inline double s4b_rng_raw_uniform(s4b_rng* g)
 {
-  uint32_t ctr[4] = { (uint32_t) g->counter, (uint32_t) (g->counter >> 32), 0u, g->stream };
+  uint32_t ctr[4] = { g->idx, (uint32_t) g->step, (g->sub << 30) | (uint32_t) ((g->step >> 32) & 0x3FFFFFFFu), g->stream };
   uint32_t out[4];
   s4b_philox4x32_10(ctr, g->key, out);
-  g->counter++;
+  g->idx++;
+  if (g->idx == 0) g->step++;
   return s4b_bits_to_uniform(out[0], out[1]);
 }
 
 static inline double s4b_rng_record(s4b_rng* g, double v)
 {
+  g->counter++;
   if (g->rec != NULL && g->rec_len < g->rec_cap) g->rec[g->rec_len] = v;
   if (g->rec != NULL) g->rec_len++;
   return v;

@@ -23,6 +23,7 @@ SIGNATURES = {
     "s4b_set_stream": (C.c_int, [vp]),
     "s4b_set_device": (C.c_int, [C.c_int]),
     "gpubart_tree_step_ms": (C.c_int, [vp, C.c_int, c_double_p]),
+    "gpubart_get_profile": (C.c_int, [vp, c_uint64_p, C.c_int]),
     "s4b_sampler_set_host_plumbing": (C.c_int, [vp, C.c_int, c_int64_p, c_int64_p]),
     "gpubart_create": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, vpp]),
     "gpubart_free": (C.c_int, [vp]),
@@ -45,6 +46,8 @@ SIGNATURES = {
     "gpubart_get_record": (C.c_int, [vp, c_double_p, C.c_size_t, c_size_p]),
     "gpubart_rng_counter": (C.c_int, [vp, c_uint64_p]),
     "gpubart_set_use_graph": (C.c_int, [vp, C.c_int]),
+    "gpubart_set_sweep_mode": (C.c_int, [vp, C.c_int]),
+    "gpubart_get_sweep_mode": (C.c_int, [vp, c_int_p]),
     "gpubart_time_leaf_stats": (C.c_int, [vp, C.c_int, C.c_int, c_double_p]),
     "gpubart_num_tree_steps": (C.c_int, [vp, c_int64_p]),
     "glmm_create": (C.c_int, [C.POINTER(GlmmData), vpp]),

@@ -5,6 +5,7 @@
 // runSamplerWithResults, storeLatents (getLatentVariables), predict, getTrees.
 #include "bart.hpp"
 #include "bart_kernels.cuh"
+#include "sweep_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  const long long clk_start = clock64();
 
   // ---- stage the step descriptor ----
   if (tid == 0) {
@@ -180,6 +182,8 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
+  long long clk[8];
+  clk[0] = clock64();
 
   // phase 1: reduce per-block partials (value-major layout, lanes stride over blocks)
   const int G = gridDim.x;
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
   if (tid == 0) { prm = *dv.params; *dv.ticket = 0u; }
   if (tid < S4B_MAX_DEPTH + 2) pgrow[tid] = dv.pgrow[tid];
   __syncthreads();
+  clk[1] = clock64();
   if (mode == kModeStatsOnly) {
     for (int v = tid; v < 3 * nslots; v += kBlock) dv.stats_out[v] = reinterpret_cast<double*>(st)[v];
     return;
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
   }
   __syncthreads();
 
+  clk[2] = clock64();
   // phase 2: Metropolis decision + leaf draws (serial)
   if (tid == 0) {
     RngState rng = *dv.rng;
@@ -215,11 +221,13 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
       if (k < dv.trace_cap) { trec = dv.trace + k * S4B_TRACE_LEN; for (int i = 0; i < S4B_TRACE_LEN; ++i) trec[i] = 0.0; }
       *dv.trace_len = k + 1;
     }
-    decide_and_draw(tree, prm, rng, sd, st, sd_out, trec);
+    decide_and_draw(tree, prm, rng, sd, st, sd_out, trec, prm.step_id);
+    dv.params->step_id = prm.step_id + 1ull;
     *dv.rng = rng;
     if (rng.tape_underrun) dv.params->error_flag |= 2u;
   }
   __syncthreads();
+  clk[3] = clock64();
   // phase 3: write tree back, fetch the next one
   {
     DTree& g = dv.trees[t_cur];
@@ -235,16 +243,21 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
     if (tid == 0) { tree.num_nodes = nn; }
     copy_words(tree.nodes, g.nodes, nn * (int) sizeof(DNode), tid, kBlock);
     __syncthreads();
+    clk[4] = clock64();
     if (tid == 0) {
       RngState rng = *dv.rng;
-      propose_step(tree, prm, pgrow, rng, sd_out, t_next);
+      propose_step(tree, prm, pgrow, rng, sd_out, t_next, prm.step_id + 1ull);
       *dv.rng = rng;
       if (rng.tape_underrun) dv.params->error_flag |= 2u;
     }
-  } else if (tid == 0) {
+  } else {
+    clk[4] = clock64();
+  }
+  if (!propose_next && tid == 0) {
     sd_out.b_kind = -1; sd_out.b_tree = -1; sd_out.b_num_leaves = 0; sd_out.b_nslots = 0; sd_out.b_cur.n = 0; sd_out.b_prop.n = 0;
   }
   __syncthreads();
+  clk[5] = clock64();
   // phase 4: publish the descriptor for the next launch
   {
     StepDesc& g = *dv.desc;
@@ -260,6 +273,12 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
       copy_trav(g.b_cur, sd_out.b_cur, tid, kBlock, true, true);
       if (sd_out.b_kind == 2 || sd_out.b_kind == 3) copy_trav(g.b_prop, sd_out.b_prop, tid, kBlock, false, true);
     }
+  }
+  if (tid == 0 && dv.prof != nullptr) {
+    clk[6] = clock64();
+    dv.prof[0] += (unsigned long long) (clk[0] - clk_start);
+    for (int i = 1; i <= 6; ++i) dv.prof[i] += (unsigned long long) (clk[i] - clk[i - 1]);
+    dv.prof[7] += 1ull;
   }
 }
 
@@ -283,7 +302,7 @@ __global__ void __launch_bounds__(kBlock) k_propose_first(BartDev dv)
   if (tid == 0) {
     RngState rng = *dv.rng;
     sd_out.a_valid = 0; sd_out.a_same = 1; sd_out.a_old.n = 0; sd_out.a_new.n = 0;
-    propose_step(tree, prm, pgrow, rng, sd_out, 0);
+    propose_step(tree, prm, pgrow, rng, sd_out, 0, prm.step_id);
     *dv.rng = rng;
     if (rng.tape_underrun) dv.params->error_flag |= 2u;
   }
@@ -325,6 +344,8 @@ __global__ void k_prior_tree(BartDev dv, int tree_index)
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   BartParams P = *dv.params;
   RngState rng = *dv.rng;
+  rng_enter(rng, P.prior_calls * (unsigned long long) P.num_trees + (unsigned long long) tree_index, 2u);
+  if (tree_index == P.num_trees - 1) dv.params->prior_calls = P.prior_calls + 1ull;
   DTree& t = dv.trees[tree_index];
   StepDesc& g = *dv.desc;
   // old tree -> a_old
@@ -624,6 +645,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   dalloc(&d_stats_out_, (size_t) 3 * S4B_MAX_SLOTS);
   S4B_CUDA(cudaMalloc(&d_desc_, sizeof(StepDesc))); S4B_CUDA(cudaMemset(d_desc_, 0, sizeof(StepDesc)));
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
+  S4B_CUDA(cudaMalloc(&d_prof_, sizeof(unsigned long long) * 8)); S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 8));
   S4B_CUDA(cudaMalloc(&d_trace_len_, sizeof(unsigned long long))); S4B_CUDA(cudaMemset(d_trace_len_, 0, sizeof(unsigned long long)));
   S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
   // trees: single root each
@@ -654,6 +676,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   S4B_CUDA(cudaMalloc(&d_scale_factor_, sizeof(double)));
   S4B_CUDA(cudaEventCreate(&ev_start_)); S4B_CUDA(cudaEventCreate(&ev_end_));
 
+  setup_persistent();
   if (cfg.is_binary) {
     // latents start at +-1 with zero offset (oracle_bart.c or_bart_create)
     std::vector<double> init((size_t) n_);
@@ -676,7 +699,85 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+}
+
+template <int NQ>
+static size_t sweep_smem_bytes(int p)
+{
+  size_t base = ((sizeof(SweepSmem) + 15) / 16) * 16;
+  size_t bins = (size_t) kBinSlots * kWorkers * (sizeof(double2) + sizeof(int));
+  size_t tile = (size_t) p * NQ * kWorkers * sizeof(uint32_t);
+  return base + bins + tile;
+}
+
+void BartFit::setup_persistent()
+{
+  // the persistent sweep needs every CTA co-resident and the chain's residuals / predictors on chip
+  persistent_nq_ = 0;
+  const char* env = getenv("S4B_SWEEP_MODE");
+  int dev = 0; S4B_CUDA(cudaGetDevice(&dev));
+  int coop = 0; S4B_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  int max_smem = 0; S4B_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (coop) {
+    const long long nquad = (n_ + 3) / 4;
+    auto try_nq = [&](int nq, size_t smem, const void* fn) -> bool {
+      if (smem > (size_t) max_smem) return false;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); return false; }
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (per_sm < 1) return false;
+      long long grid = num_sms_;                       // one CTA per SM
+      long long need = (nquad + (long long) nq * kWorkers - 1) / ((long long) nq * kWorkers);
+      if (need > grid) return false;
+      persistent_nq_ = nq; persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(grid, (nquad + kWorkers - 1) / kWorkers)); persistent_smem_ = smem;
+      return true;
+    };
+    if (!try_nq(1, sweep_smem_bytes<1>(p_), (const void*) k_sweep<1>))
+      if (!try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2>))
+        try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4>);
+  }
+  if (persistent_nq_ > 0) {
+    partial_stride_ = 3 * S4B_MAX_SLOTS * persistent_grid_;
+    S4B_CUDA(cudaMalloc(&d_partials2_, sizeof(double) * 2 * (size_t) partial_stride_));
+    S4B_CUDA(cudaMemset(d_partials2_, 0, sizeof(double) * 2 * (size_t) partial_stride_));
+    S4B_CUDA(cudaMalloc(&d_barrier_, sizeof(unsigned int)));
+    S4B_CUDA(cudaMemset(d_barrier_, 0, sizeof(unsigned int)));
+    // host-side tables (glibc): growth probabilities by depth, their logs, log of small integers
+    std::vector<double> tab((size_t) kTabSize, 0.0);
+    for (int d = 0; d < 32; ++d) {
+      double pg = cfg_.base / std::pow(1.0 + (double) d, cfg_.power);
+      tab[(size_t) kTabPg + d] = pg; tab[(size_t) kTabLogPg + d] = std::log(pg); tab[(size_t) kTabLog1mPg + d] = std::log(1.0 - pg);
+    }
+    for (int i = 1; i < kLogTab; ++i) tab[(size_t) kTabLogInt + i] = std::log((double) i);
+    S4B_CUDA(cudaMalloc(&d_tables_, sizeof(double) * tab.size()));
+    S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    sweep_mode_ = 2;
+  }
+  if (env) set_sweep_mode(atoi(env));
+}
+
+void BartFit::set_sweep_mode(int m)
+{
+  if (m == 2 && persistent_nq_ == 0) throw std::invalid_argument("persistent sweep kernel does not fit this problem (n, p) on this GPU");
+  if (m < 0 || m > 2) throw std::invalid_argument("sweep mode must be 0, 1 or 2");
+  sweep_mode_ = m; use_graph_ = m != 0;
+}
+
+void BartFit::launch_persistent_sweep(bool last_thin)
+{
+  BartDev dv = dev();
+  dv.partials = d_partials2_;
+  S4B_CUDA(cudaMemsetAsync(d_barrier_, 0, sizeof(unsigned int), stream_));
+  unsigned int* bar = d_barrier_;
+  int stride = partial_stride_;
+  const double* tabs = d_tables_;
+  void* args[] = { &dv, &bar, &stride, &tabs };
+  const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep<1> : (persistent_nq_ == 2 ? (const void*) k_sweep<2> : (const void*) k_sweep<4>);
+  S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
+  k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0);
+  k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
+  S4B_CUDA(cudaGetLastError());
 }
 
 void BartFit::bin_matrix(const double* x, long long rows, long long rows_pad, std::vector<uint8_t>& out) const
@@ -696,7 +797,7 @@ BartDev BartFit::dev() const
   d.n = n_; d.npad = npad_; d.xt = d_xt_; d.R = d_R_; d.yresc = d_yresc_; d.y = d_y_; d.offset = d_offset_;
   d.desc = d_desc_; d.trees = d_trees_; d.params = d_params_; d.pgrow = d_pgrow_; d.rng = d_rng_;
   d.partials = d_partials_; d.ticket = d_ticket_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
-  d.stats_out = d_stats_out_;
+  d.stats_out = d_stats_out_; d.prof = d_prof_;
   return d;
 }
 
@@ -840,6 +941,7 @@ void BartFit::run_sweeps()
   S4B_CUDA(cudaEventRecord(ev_start_, stream_));
   for (int k = 0; k < cfg_.thin; ++k) {
     bool last = (k + 1) == cfg_.thin;
+    if (sweep_mode_ == 2) { launch_persistent_sweep(last); continue; }
     if (!use_graph) { launch_sweep_kernels(last); S4B_CUDA(cudaGetLastError()); continue; }
     cudaGraphExec_t& ge = last ? graph_exec_ : graph_exec_thin_;
     if (!ge) {
@@ -856,6 +958,13 @@ void BartFit::run_sweeps()
   ev_pending_ = true;
   num_tree_steps_ += (long long) cfg_.thin * T_;
   if (nt_ > 0) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
+}
+
+void BartFit::get_profile(unsigned long long* out8, bool reset)
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  S4B_CUDA(cudaMemcpy(out8, d_prof_, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
+  if (reset) S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 8));
 }
 
 double BartFit::tree_step_ms(bool reset)
@@ -974,7 +1083,9 @@ void BartFit::get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double
   long long pos = 0;
   auto trees = download_trees();
   for (int t = 0; t < T_; ++t) {
-    const DTree& tr = trees[(size_t) t];
+    DTree& tr = trees[(size_t) t];
+    // the device keeps observation counts for bottom nodes only; internal nodes are the sum of their children
+    for (int k = tr.num_nodes - 1; k >= 0; --k) if (tr.nodes[k].var >= 0) tr.nodes[k].n = tr.nodes[k + 1].n + tr.nodes[tr.nodes[k].right].n;
     for (int k = 0; k < tr.num_nodes; ++k, ++pos) {
       const DNode& nd = tr.nodes[k];
       tree_no[pos] = t; n_obs[pos] = nd.n;

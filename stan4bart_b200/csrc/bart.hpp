@@ -17,6 +17,7 @@ struct BartDev {
   double* partials; unsigned int* ticket;
   double* trace; unsigned long long trace_cap; unsigned long long* trace_len;
   double* stats_out;
+  unsigned long long* prof;   // cycle counters of the controller phases (last block, thread 0)
 };
 
 class BartFit {
@@ -52,7 +53,12 @@ class BartFit {
   void set_record(size_t cap);
   size_t get_record(double* out, size_t cap);
   unsigned long long rng_counter();
-  void set_use_graph(bool g) { use_graph_ = g; }
+  void set_use_graph(bool g) { use_graph_ = g; if (!g) sweep_mode_ = 0; else if (sweep_mode_ == 0) sweep_mode_ = 1; }
+  // 0: one launch per tree step; 1: the same kernels captured in a CUDA graph; 2: persistent on-chip sweep kernel
+  // (sweep_kernel.cuh), the default whenever the chain fits
+  void set_sweep_mode(int m);
+  int sweep_mode() const { return sweep_mode_; }
+  bool persistent_fits() const { return persistent_nq_ > 0; }
   // dbarts returns training fits with the offset added (init.cpp:828-829 subtracts it again); the Gibbs
   // loop asks for the tree-only fit directly
   void set_add_offset(bool a) { if (a != add_offset_) { add_offset_ = a; invalidate_graph(); } }
@@ -72,10 +78,15 @@ class BartFit {
   long long num_tree_steps() const { return num_tree_steps_; }
   // device time (CUDA events on the launching stream) spent in the sweep graphs since the last reset
   double tree_step_ms(bool reset);
+  // cycles spent by the last block in: [0] its own pass, [1] partial reduction, [2] tree load, [3] decision + leaf draws,
+  // [4] write-back + next tree load, [5] proposal, [6] descriptor publish, [7] number of steps
+  void get_profile(unsigned long long* out8, bool reset);
 
  private:
   BartDev dev() const;
   void launch_sweep_kernels(bool last_thin);
+  void launch_persistent_sweep(bool last_thin);
+  void setup_persistent();
   void test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out);
   void bin_matrix(const double* x, long long rows, long long rows_pad, std::vector<uint8_t>& out) const;
   std::vector<DTree> download_trees();
@@ -89,6 +100,13 @@ class BartFit {
   bool scale_initialised_ = false;
   bool use_graph_ = true;
   bool add_offset_ = true;
+  int sweep_mode_ = 1;
+  int persistent_nq_ = 0, persistent_grid_ = 0;
+  size_t persistent_smem_ = 0;
+  unsigned int* d_barrier_ = nullptr;
+  double* d_partials2_ = nullptr;
+  double* d_tables_ = nullptr;
+  int partial_stride_ = 0;
   long long num_tree_steps_ = 0;
 
   uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;
@@ -96,6 +114,7 @@ class BartFit {
   double *d_train_out_ = nullptr, *d_test_out_ = nullptr, *d_latent_out_ = nullptr;
   double *d_partials_ = nullptr, *d_minmax_ = nullptr, *d_stats_out_ = nullptr, *d_pgrow_ = nullptr, *d_scale_factor_ = nullptr;
   StepDesc* d_desc_ = nullptr; DTree* d_trees_ = nullptr; BartParams* d_params_ = nullptr; RngState* d_rng_ = nullptr;
+  unsigned long long* d_prof_ = nullptr;
   unsigned int* d_ticket_ = nullptr; unsigned long long* d_trace_len_ = nullptr; unsigned int* d_varcount_ = nullptr;
   double* d_trace_ = nullptr; size_t trace_cap_ = 0;
   double* d_tape_ = nullptr; double* d_rec_ = nullptr;

@@ -185,8 +185,9 @@ __device__ inline double leaf_loglik(const LeafStat& s, double sigma, double lea
 // proposal for the tree held in `t` (thread 0 of the controller block)
 // RNG consumption order mirrors the CPU oracle / dbarts step functions exactly.
 // --------------------------------------------------------------------------------------
-__device__ inline void propose_step(DTree& t, const BartParams& P, const double* pgrow, RngState& rng, StepDesc& d, int tree_index)
+__device__ inline void propose_step(DTree& t, const BartParams& P, const double* pgrow, RngState& rng, StepDesc& d, int tree_index, unsigned long long step_id)
 {
+  rng_enter(rng, step_id, 0u);
   d.b_tree = tree_index;
   d.b_kind = -1; d.b_node = -1; d.b_var = -1; d.b_cut = -1; d.b_child = -1; d.new_var = -1; d.new_cut = -1;
   d.log_prior_trans = 0.0;
@@ -334,8 +335,9 @@ __device__ inline void propose_step(DTree& t, const BartParams& P, const double*
 // `stats[slot]` are the reduced sufficient statistics.  Fills the (A) part of `out`.
 // --------------------------------------------------------------------------------------
 __device__ inline void decide_and_draw(DTree& t, const BartParams& P, RngState& rng, const StepDesc& in, const LeafStat* stats,
-                                       StepDesc& out, double* trace_rec)
+                                       StepDesc& out, double* trace_rec, unsigned long long step_id)
 {
+  rng_enter(rng, step_id, 1u);
   const int L = in.b_num_leaves;
   const int kind = in.b_kind;
   const int node = in.b_node;

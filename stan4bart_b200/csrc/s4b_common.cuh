@@ -98,26 +98,42 @@ __host__ __device__ inline double qnorm_as241(double p)
 }
 
 // sequential stream state (lives in device memory for the BART stream, host memory for NUTS)
+// Counter layout (spec "s4b-rng v1"): c0 = draw index inside the substream, c1 = low 32 bits of the step,
+// c2 = (sub << 30) | high 30 bits of the step, c3 = stream.  BART stream: sub 0 = proposal draws of a tree
+// step, sub 1 = its decision draws (accept uniform, leaf normals), sub 2 = sampleTreesFromPrior.
 struct RngState {
   uint32_t key0, key1;
   uint32_t stream;
   uint32_t tape_underrun;
-  unsigned long long counter;
+  uint32_t sub, idx;
+  unsigned long long step;
+  unsigned long long counter;   // total draws consumed
   const double* tape;           // replay: interleaved uniforms / normals in consumption order
   unsigned long long tape_len, tape_pos;
   double* rec;                  // optional recording of every draw
   unsigned long long rec_cap, rec_len;
 };
 
-__host__ __device__ inline double rng_raw_uniform(RngState& g)
+__host__ __device__ inline void rng_enter(RngState& g, unsigned long long step, uint32_t sub)
+{
+  if (g.step != step || g.sub != sub) { g.step = step; g.sub = sub; g.idx = 0; }
+}
+__host__ __device__ inline double keyed_stream_uniform(uint32_t k0, uint32_t k1, uint32_t stream, unsigned long long step, uint32_t sub, uint32_t idx)
 {
   uint32_t o0, o1;
-  philox4x32_10((uint32_t) g.counter, (uint32_t) (g.counter >> 32), 0u, g.stream, g.key0, g.key1, o0, o1);
-  g.counter++;
+  philox4x32_10(idx, (uint32_t) step, (sub << 30) | (uint32_t) ((step >> 32) & 0x3FFFFFFFu), stream, k0, k1, o0, o1);
   return bits_to_uniform(o0, o1);
+}
+__host__ __device__ inline double rng_raw_uniform(RngState& g)
+{
+  double u = keyed_stream_uniform(g.key0, g.key1, g.stream, g.step, g.sub, g.idx);
+  g.idx++;
+  if (g.idx == 0) g.step++;
+  return u;
 }
 __host__ __device__ inline double rng_note(RngState& g, double v)
 {
+  g.counter++;
   if (g.rec != nullptr) { if (g.rec_len < g.rec_cap) g.rec[g.rec_len] = v; g.rec_len++; }
   return v;
 }
@@ -236,6 +252,8 @@ struct BartParams {
   uint32_t key0, key1;
   uint32_t latent_epoch;
   uint32_t error_flag;      // set by kernels on capacity / tape problems
+  unsigned long long step_id;     // tree steps taken so far (keys the BART RNG substreams)
+  unsigned long long prior_calls; // sampleTreesFromPrior calls so far
 };
 
 }  // namespace s4b

@@ -1,0 +1,885 @@
+// stan4bart_b200/csrc/sweep_kernel.cuh
+// Persistent, on-chip BART sweep for sm_100a: the primary path whenever one chain's working set fits the
+// register file + shared memory of the GPU (n <= 148 x 480 x 16 ~ 1.1 M observations per GPU).
+//
+//   * ONE cooperative launch per sweep, one CTA per SM: 15 worker warps + 1 helper warp;
+//   * every worker thread owns NQ x 4 observations for the whole sweep: their residuals R live in REGISTERS,
+//     their binned predictors in a shared-memory tile (filled once per sweep with coalesced 32-bit loads);
+//     inside the 200-tree loop nothing is read from global memory except the tiny per-CTA partials;
+//   * per tree step
+//       workers : walk the tree for 4 observations at a time (shared memory only, 4-way ILP), accumulate
+//                 (n, sum, sum^2) per leaf slot in registers, warp-shuffle + fixed-order CTA reduction, write
+//                 one row of partials, grid barrier;
+//       helper  : meanwhile fetches the next tree, pre-computes the decision draws of this step and draws
+//                 the PROPOSAL OF THE NEXT TREE (keyed RNG substreams make it independent of this step);
+//       all CTAs: reduce all partial rows in the same fixed order and run the same warp-parallel Metropolis
+//                 decision + leaf draws: bitwise identical everywhere, so no broadcast / second barrier;
+//       workers : R += mu_old[leaf] - mu_new[leaf'] from the leaf indices cached during the walk.
+//
+// Arithmetic follows the reference path restated in oracle/oracle_bart.c (dbarts).
+#pragma once
+
+#include "bart_kernels.cuh"
+
+namespace s4b {
+
+constexpr int kWorkers = 480;               // 15 worker warps + 1 helper warp = 512 threads => 128 registers per thread
+constexpr int kWorkerWarps = kWorkers / 32;
+constexpr int kSweepBlock = kWorkers + 32;     // + helper warp
+constexpr int kSweepWarps = kSweepBlock / 32;
+constexpr int kBinSlots = 8;                   // lane-private shared-memory bins per thread and pass
+constexpr int kLogTab = 1024;
+
+// host-computed tables (glibc log, so they are bit-identical to the CPU oracle's calls):
+// [0,32) growth probability by depth, [32,64) its log, [64,96) log(1 - p), [96, 96 + kLogTab) log(i)
+constexpr int kTabPg = 0, kTabLogPg = 32, kTabLog1mPg = 64, kTabLogInt = 96, kTabSize = 96 + kLogTab;
+
+struct UpdateDesc {                 // how to apply the accepted / rejected step to the residuals
+  int32_t mode;                     // 0: structure unchanged; 1: birth accepted; 2: death accepted; 3: change / swap accepted
+  int32_t node;
+  double val_old[S4B_NODE_CAP];     // mu before the step, by old node index
+  double val_new[S4B_NODE_CAP];     // mu after the step, by new node index
+  uint8_t remap[S4B_NODE_CAP];      // old leaf index -> new leaf index (modes 0-2)
+};
+
+struct CtlScratch {
+  int16_t navail[S4B_NODE_CAP];
+  uint8_t flag[S4B_NODE_CAP];
+  double ubuf[32], zbuf[32];        // pre-generated draws of the current substream
+  double ll[S4B_MAX_SLOTS];
+  DNode tmp[S4B_NODE_CAP];
+  int32_t draw_pos;                 // consumed from ubuf / zbuf
+  int32_t draws_total;              // draws consumed through this scratch since kernel start
+};
+
+// ---------------------------------------------------------------------------------------
+// warp-cooperative RNG over one substream: 32 draws are generated at once (lane i -> draw base + i)
+// and consumed in order.  Replay (tape) and recording force strictly sequential program order.
+// ---------------------------------------------------------------------------------------
+struct WarpRng {
+  RngState* g;        // shared-memory copy (tape / record bookkeeping), identical in every CTA
+  CtlScratch* cs;
+  unsigned long long step;
+  uint32_t sub, base; // buffer holds draws [base, base + 32) of (step, sub)
+  int lane;
+  bool writer;        // CTA 0 appends to the record buffer
+
+  __device__ void fill()
+  {
+    const RngState& r = *g;
+    double u, z;
+    if (r.tape != nullptr) {
+      unsigned long long idx = r.tape_pos + (unsigned long long) lane;
+      u = idx < r.tape_len ? r.tape[idx] : 0.5;
+      z = idx < r.tape_len ? u : 0.0;
+    } else {
+      u = keyed_stream_uniform(r.key0, r.key1, r.stream, step, sub, base + (uint32_t) lane);
+      z = qnorm_as241(u);
+    }
+    cs->ubuf[lane] = u; cs->zbuf[lane] = z;
+    if (lane == 0) cs->draw_pos = 0;
+    __syncwarp();
+  }
+  __device__ void enter(unsigned long long s, uint32_t sb) { step = s; sub = sb; base = 0; }
+  // account for the consumed prefix (all lanes call)
+  __device__ void commit()
+  {
+    __syncwarp();
+    const int k = cs->draw_pos;
+    base += (uint32_t) k;
+    __syncwarp();
+    if (lane == 0) {
+      RngState& r = *g;
+      if (r.tape != nullptr) { if (r.tape_pos + (unsigned long long) k > r.tape_len) r.tape_underrun = 1; r.tape_pos += (unsigned long long) k; }
+      cs->draws_total += k;
+      cs->draw_pos = 0;
+    }
+    __syncwarp();
+  }
+  __device__ void note(double v)
+  {
+    RngState& r = *g;
+    if (r.rec != nullptr && lane == 0) { if (writer && r.rec_len < r.rec_cap) r.rec[r.rec_len] = v; r.rec_len++; }
+  }
+  __device__ double uniform()
+  {
+    __syncwarp();
+    if (cs->draw_pos >= 32) { commit(); fill(); }
+    const int p = cs->draw_pos;
+    const double v = cs->ubuf[p];
+    __syncwarp();
+    if (lane == 0) { cs->draw_pos = p + 1; note(v); }
+    __syncwarp();
+    return v;
+  }
+  __device__ int index(int n) { int k = (int) (uniform() * (double) n); return k >= n ? n - 1 : k; }
+  // reserve `count` (<= 32) consecutive normal draws; returns the buffer position of the first one
+  __device__ int reserve_normals(int count)
+  {
+    __syncwarp();
+    if (cs->draw_pos + count > 32) { commit(); fill(); }
+    const int p = cs->draw_pos;
+    __syncwarp();
+    if (lane == 0) { cs->draw_pos = p + count; for (int i = 0; i < count; ++i) note(cs->zbuf[p + i]); }
+    __syncwarp();
+    return p;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int w_count_flag(const CtlScratch& cs, int nn, uint8_t bit, int lane)
+{
+  int c = 0;
+  for (int base = 0; base < nn; base += 32) {
+    int k = base + lane;
+    c += __popc(__ballot_sync(0xffffffffu, k < nn && (cs.flag[k] & bit)));
+  }
+  return c;
+}
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n)
+{
+  for (int i = 0; i < n; ++i) m &= m - 1;
+  return __ffs(m) - 1;
+}
+// index of the pick-th node (in index order) whose flag has `bit`
+__device__ __forceinline__ int w_select_flag(const CtlScratch& cs, int nn, uint8_t bit, int pick, int lane)
+{
+  int found = -1;
+  for (int base = 0; base < nn; base += 32) {
+    int k = base + lane;
+    unsigned m = __ballot_sync(0xffffffffu, k < nn && (cs.flag[k] & bit));
+    int c = __popc(m);
+    if (found < 0) { if (pick < c) found = base + nth_set_bit(m, pick); else pick -= c; }
+  }
+  return found;
+}
+__device__ __forceinline__ double w_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double w_min(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int w_maxi(int v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int w_mini(int v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+enum : uint8_t { kFLeaf = 1, kFBirthable = 2, kFNog = 4, kFSwappable = 8, kFInternal = 16 };
+
+// per-node attributes, one lane per node
+__device__ inline void w_node_attrs(const DTree& t, const BartParams& P, CtlScratch& cs, int num_leaves_for_cap, int lane)
+{
+  const int nn = t.num_nodes;
+  for (int k = lane; k < nn; k += 32) {
+    int na = t_num_vars_available(t, P, k);
+    cs.navail[k] = (int16_t) na;
+    uint8_t f = 0;
+    if (t.nodes[k].var < 0) {
+      f |= kFLeaf;
+      if (na > 0 && t.nodes[k].depth < S4B_MAX_DEPTH && num_leaves_for_cap < S4B_MAX_LEAVES) f |= kFBirthable;
+    } else {
+      f |= kFInternal;
+      bool ll = t.nodes[k + 1].var < 0, rl = t.nodes[t.nodes[k].right].var < 0;
+      if (ll && rl) f |= kFNog;
+      if (!ll || !rl) f |= kFSwappable;
+    }
+    cs.flag[k] = f;
+  }
+  __syncwarp();
+}
+
+// fills trav / val / slot of a TravTree (one lane per node); tv.pad receives the depth of the deepest leaf;
+// returns the number of leaves
+__device__ inline int w_fill_trav(const DTree& t, TravTree& tv, bool with_mu, int lane)
+{
+  const int nn = t.num_nodes;
+  int leaves = 0, maxd = 0;
+  for (int base = 0; base < nn; base += 32) {
+    int k = base + lane;
+    bool leaf = k < nn && t.nodes[k].var < 0;
+    unsigned m = __ballot_sync(0xffffffffu, leaf);
+    if (k < nn) {
+      const DNode& nd = t.nodes[k];
+      tv.trav[k] = pack_trav(nd.var, nd.cut, nd.right);
+      if (leaf) { tv.slot[k] = (uint8_t) (leaves + __popc(m & ((1u << lane) - 1u))); if (with_mu) tv.val[k] = nd.mu; maxd = max(maxd, nd.depth); }
+      else tv.slot[k] = 255;
+    }
+    leaves += __popc(m);
+  }
+  maxd = w_maxi(maxd);
+  if (lane == 0) { tv.n = nn; tv.pad = maxd; }
+  __syncwarp();
+  return leaves;
+}
+
+// i-th available variable at node `node` (lanes scan variables)
+__device__ inline int w_ith_available_var(const DTree& t, const BartParams& P, int node, int ith, int lane)
+{
+  int found = -1;
+  for (int base = 0; base < P.p; base += 32) {
+    int j = base + lane;
+    bool avail = false;
+    if (j < P.p) {
+      bool used = false;
+      for (int a = t.nodes[node].parent; a >= 0; a = t.nodes[a].parent) if (t.nodes[a].var == j) { used = true; break; }
+      avail = true;
+      if (used) { int lo, hi; t_split_interval(t, P.n_cuts, node, j, lo, hi); avail = hi >= lo; }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, avail);
+    int c = __popc(m);
+    if (found < 0) { if (ith < c) found = base + nth_set_bit(m, ith); else ith -= c; }
+  }
+  return found;
+}
+
+__device__ __forceinline__ double tab_log_int(const double* tab, int i) { return i < kLogTab ? tab[kTabLogInt + i] : log((double) i); }
+
+// log prior of the branch [node, end): lanes over nodes, table look-ups, fixed-order warp sum
+__device__ inline double w_branch_log_prior(const DTree& t, const BartParams& P, const double* tab, int node, int end, int lane)
+{
+  double acc = 0.0;
+  for (int base = node; base < end; base += 32) {
+    int k = base + lane;
+    double term = 0.0;
+    if (k < end) {
+      int navail = t_num_vars_available(t, P, k);
+      int d = t.nodes[k].depth;
+      if (t.nodes[k].var < 0) term = navail > 0 ? tab[kTabLog1mPg + d] : 0.0;
+      else { int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi); term = tab[kTabLogPg + d] - tab_log_int(tab, navail) - tab_log_int(tab, hi - lo + 1); }
+    }
+    acc += w_sum(term);
+  }
+  return acc;
+}
+
+// slots of the proposed tree: L + rank for leaves below `node`, 255 elsewhere; returns the slot count
+__device__ inline int w_assign_prop_slots(const DTree& t, TravTree& prop, int node, int end, int L, int lane)
+{
+  const int nn = t.num_nodes;
+  int s = L;
+  for (int base = 0; base < nn; base += 32) {
+    int k = base + lane;
+    bool in = k < nn && k >= node && k < end && t.nodes[k].var < 0;
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    if (k < nn) prop.slot[k] = in ? (uint8_t) (s + __popc(m & ((1u << lane) - 1u))) : (uint8_t) 255;
+    s += __popc(m);
+  }
+  __syncwarp();
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// proposal (warp-cooperative; same draw order as oracle_bart.c metropolis_jump)
+// ---------------------------------------------------------------------------------------
+__device__ inline void w_propose(DTree& t, const BartParams& P, const double* tab, WarpRng& rng, StepDesc& d, CtlScratch& cs, int tree_index, int lane)
+{
+  const int nn = t.num_nodes;
+  const int L = w_fill_trav(t, d.b_cur, true, lane);
+  w_node_attrs(t, P, cs, L, lane);
+  int kind = -1, node = -1, b_var = -1, b_cut = -1, child = -1, new_var = -1, new_cut = -1, nslots = L;
+  double lpt = 0.0;
+
+  const double u = rng.uniform();
+  if (u < P.birth_death_prob) {
+    const int n_birthable = w_count_flag(cs, nn, kFBirthable, lane);
+    const double p_birth = n_birthable == 0 ? 0.0 : (nn == 1 ? 1.0 : P.birth_prob);
+    const int n_nog = w_count_flag(cs, nn, kFNog, lane);
+    if (rng.uniform() < p_birth) {
+      node = w_select_flag(cs, nn, kFBirthable, rng.index(n_birthable), lane);
+      const int navail = cs.navail[node];
+      const int depth = t.nodes[node].depth;
+      const double pg_parent = t_growth_prob_depth(tab + kTabPg, navail, depth);
+      b_var = w_ith_available_var(t, P, node, rng.index(navail), lane);
+      int lo, hi; t_split_interval(t, P.n_cuts, node, b_var, lo, hi);
+      b_cut = lo + rng.index(hi - lo + 1);
+      const int navail_l = navail - ((b_cut - 1 < lo) ? 1 : 0);
+      const int navail_r = navail - ((b_cut + 1 > hi) ? 1 : 0);
+      const double pg_l = t_growth_prob_depth(tab + kTabPg, navail_l, depth + 1), pg_r = t_growth_prob_depth(tab + kTabPg, navail_r, depth + 1);
+      const int Lnew = L + 1;
+      bool any_new = false;
+      for (int base = 0; base < nn; base += 32) {
+        int k = base + lane;
+        bool b = k < nn && k != node && (cs.flag[k] & kFLeaf) && cs.navail[k] > 0 && t.nodes[k].depth < S4B_MAX_DEPTH && Lnew < S4B_MAX_LEAVES;
+        if (__ballot_sync(0xffffffffu, b)) any_new = true;
+      }
+      if (!any_new && depth + 1 < S4B_MAX_DEPTH && Lnew < S4B_MAX_LEAVES && (navail_l > 0 || navail_r > 0)) any_new = true;
+      const double p_death_new = 1.0 - (any_new ? P.birth_prob : 0.0);
+      const int par = t.nodes[node].parent;
+      const bool parent_was_nog = par >= 0 && (cs.flag[par] & kFNog);
+      const int n_nog_new = n_nog + 1 - (parent_was_nog ? 1 : 0);
+      const double prior_ratio = pg_parent * (1.0 - pg_l) * (1.0 - pg_r) / (1.0 - pg_parent);
+      const double trans_ratio = (p_death_new * (1.0 / (double) n_nog_new)) / (p_birth * (1.0 / (double) n_birthable));
+      kind = 0; nslots = L + 2; lpt = prior_ratio * trans_ratio;
+    } else {
+      node = w_select_flag(cs, nn, kFNog, rng.index(n_nog), lane);
+      const int left = node + 1, right = t.nodes[node].right;
+      const double pg_parent = t_growth_prob_depth(tab + kTabPg, cs.navail[node], t.nodes[node].depth);
+      const double pg_l = t_growth_prob_depth(tab + kTabPg, cs.navail[left], t.nodes[left].depth);
+      const double pg_r = t_growth_prob_depth(tab + kTabPg, cs.navail[right], t.nodes[right].depth);
+      const int Lnew = L - 1;
+      int n_birthable_new = 0;
+      for (int base = 0; base < nn; base += 32) {
+        int k = base + lane;
+        bool b = k < nn && k != left && k != right && (cs.flag[k] & kFLeaf) && cs.navail[k] > 0 && t.nodes[k].depth < S4B_MAX_DEPTH && Lnew < S4B_MAX_LEAVES;
+        n_birthable_new += __popc(__ballot_sync(0xffffffffu, b));
+      }
+      if (t.nodes[node].depth < S4B_MAX_DEPTH && Lnew < S4B_MAX_LEAVES) ++n_birthable_new;
+      double p_birth_new = node == 0 ? 1.0 : P.birth_prob;
+      if (n_birthable_new == 0) p_birth_new = 0.0;
+      const double p_select_birth = n_birthable_new > 0 ? 1.0 / (double) n_birthable_new : 0.0;
+      const double p_death = 1.0 - p_birth;
+      const double prior_ratio = (1.0 - pg_parent) / (pg_parent * (1.0 - pg_l) * (1.0 - pg_r));
+      const double trans_ratio = (p_birth_new * p_select_birth) / (p_death * (1.0 / (double) n_nog));
+      kind = 1; b_var = t.nodes[node].var; b_cut = t.nodes[node].cut; lpt = prior_ratio * trans_ratio;
+    }
+  } else if (u < P.birth_death_prob + P.swap_prob) {
+    // ---- swap ----
+    kind = 13;
+    const int n_sw = w_count_flag(cs, nn, kFSwappable, lane);
+    if (n_sw > 0) {
+      node = w_select_flag(cs, nn, kFSwappable, rng.index(n_sw), lane);
+      const int left = node + 1, right = t.nodes[node].right;
+      const bool li = t.nodes[left].var >= 0, ri = t.nodes[right].var >= 0;
+      const bool both_same = li && ri && t.nodes[left].var == t.nodes[right].var && t.nodes[left].cut == t.nodes[right].cut;
+      if (!both_same) {
+        if (li && ri) child = rng.uniform() < 0.5 ? left : right;
+        else child = li ? left : right;
+      }
+      const int end = t_subtree_end(t, node);
+      const int pv = t.nodes[node].var, pc = t.nodes[node].cut;
+      const int cv = both_same ? t.nodes[left].var : t.nodes[child].var, cc = both_same ? t.nodes[left].cut : t.nodes[child].cut;
+      const double old_lp = w_branch_log_prior(t, P, tab, node, end, lane);
+      __syncwarp();
+      if (lane == 0) {
+        t.nodes[node].var = (int16_t) cv; t.nodes[node].cut = (int16_t) cc;
+        if (both_same) { t.nodes[left].var = (int16_t) pv; t.nodes[left].cut = (int16_t) pc; t.nodes[right].var = (int16_t) pv; t.nodes[right].cut = (int16_t) pc; }
+        else { t.nodes[child].var = (int16_t) pv; t.nodes[child].cut = (int16_t) pc; }
+      }
+      __syncwarp();
+      bool bad = false;
+      for (int base = node; base < end; base += 32) {
+        int k = base + lane;
+        bool b = false;
+        if (k < end && t.nodes[k].var >= 0) { int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi); b = t.nodes[k].cut < lo || t.nodes[k].cut > hi; }
+        if (__ballot_sync(0xffffffffu, b)) bad = true;
+      }
+      double new_lp = 0.0;
+      if (!bad) {
+        new_lp = w_branch_log_prior(t, P, tab, node, end, lane);
+        w_fill_trav(t, d.b_prop, false, lane);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        t.nodes[node].var = (int16_t) pv; t.nodes[node].cut = (int16_t) pc;
+        if (both_same) { t.nodes[left].var = (int16_t) cv; t.nodes[left].cut = (int16_t) cc; t.nodes[right].var = (int16_t) cv; t.nodes[right].cut = (int16_t) cc; }
+        else { t.nodes[child].var = (int16_t) cv; t.nodes[child].cut = (int16_t) cc; }
+      }
+      __syncwarp();
+      if (!bad) { nslots = w_assign_prop_slots(t, d.b_prop, node, end, L, lane); kind = 3; lpt = new_lp - old_lp; }
+    }
+  } else {
+    // ---- change ----
+    kind = 12;
+    const int n_nb = w_count_flag(cs, nn, kFInternal, lane);
+    if (n_nb > 0) {
+      node = w_select_flag(cs, nn, kFInternal, rng.index(n_nb), lane);
+      new_var = w_ith_available_var(t, P, node, rng.index(cs.navail[node]), lane);
+      int lo, hi; t_split_interval(t, P.n_cuts, node, new_var, lo, hi);
+      const int end = t_subtree_end(t, node), rstart = t.nodes[node].right;
+      int lo_c = lo, hi_c = hi;
+      for (int base = node + 1; base < end; base += 32) {
+        int k = base + lane;
+        if (k < end && t.nodes[k].var == new_var) {
+          int c = t.nodes[k].cut;
+          if (k < rstart) lo_c = max(lo_c, c + 1); else hi_c = min(hi_c, c - 1);
+        }
+      }
+      lo = w_maxi(lo_c); hi = w_mini(hi_c);
+      if (lo <= hi) {
+        new_cut = lo + rng.index(hi - lo + 1);
+        const double old_lp = w_branch_log_prior(t, P, tab, node, end, lane);
+        const int ov = t.nodes[node].var, oc = t.nodes[node].cut;
+        __syncwarp();
+        if (lane == 0) { t.nodes[node].var = (int16_t) new_var; t.nodes[node].cut = (int16_t) new_cut; }
+        __syncwarp();
+        const double new_lp = w_branch_log_prior(t, P, tab, node, end, lane);
+        w_fill_trav(t, d.b_prop, false, lane);
+        if (lane == 0) { t.nodes[node].var = (int16_t) ov; t.nodes[node].cut = (int16_t) oc; }
+        __syncwarp();
+        nslots = w_assign_prop_slots(t, d.b_prop, node, end, L, lane);
+        kind = 2; lpt = new_lp - old_lp;
+      }
+    }
+  }
+  if (lane == 0) {
+    d.a_valid = 0; d.a_same = 1;
+    d.b_tree = tree_index; d.b_kind = kind; d.b_node = node; d.b_var = b_var; d.b_cut = b_cut; d.b_child = child;
+    d.b_num_leaves = L; d.b_nslots = nslots; d.log_prior_trans = lpt; d.new_var = new_var; d.new_cut = new_cut;
+    if (kind != 2 && kind != 3) d.b_prop.n = 0;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------
+// decision + leaf draws (warp-cooperative)
+// ---------------------------------------------------------------------------------------
+__device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, const StepDesc& in, const LeafStat* stats, UpdateDesc& upd,
+                                CtlScratch& cs, double* trace_rec, int lane)
+{
+  const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
+  const int nn_old = t.num_nodes;
+  for (int s = lane; s < nslots; s += 32) cs.ll[s] = leaf_loglik(stats[s], P.sigma, P.leaf_prec);
+  for (int k = lane; k < nn_old; k += 32) upd.val_old[k] = in.b_cur.val[k];
+  __syncwarp();
+  bool accept = false;
+  double ratio = -1.0, old_ll = 0.0, new_ll = 0.0, n_first = 0.0, n_second = 0.0;
+  if (kind == 0 || kind == 1) {
+    const int sl = kind == 0 ? L : in.b_cur.slot[node + 1];
+    const int sr = kind == 0 ? L + 1 : in.b_cur.slot[t.nodes[node].right];
+    const LeafStat l = stats[sl], r = stats[sr];
+    const LeafStat par = { l.n + r.n, l.sum + r.sum, l.sumsq + r.sumsq };
+    const double ll_par = leaf_loglik(par, P.sigma, P.leaf_prec);
+    const double ll_ch = cs.ll[sl] + cs.ll[sr];
+    if (kind == 0) { old_ll = ll_par; new_ll = ll_ch; } else { old_ll = ll_ch; new_ll = ll_par; }
+    ratio = in.log_prior_trans * exp(new_ll - old_ll);
+    if (kind == 0 && (l.n < (double) P.min_obs || r.n < (double) P.min_obs)) ratio = 0.0;
+    accept = rng.uniform() < ratio;
+    n_first = l.n; n_second = r.n;
+  } else if (kind == 2 || kind == 3) {
+    const int end = t_subtree_end(t, node);
+    double a_old = 0.0, a_new = 0.0, mn = 1e300;
+    int first_leaf = -1, second_leaf = -1, seen = 0;
+    for (int base = node; base < end; base += 32) {
+      int k = base + lane;
+      bool leaf = k < end && t.nodes[k].var < 0;
+      double to = 0.0, tn = 0.0, nk = 1e300;
+      if (leaf) { to = cs.ll[in.b_cur.slot[k]]; tn = cs.ll[in.b_prop.slot[k]]; nk = stats[in.b_prop.slot[k]].n; }
+      a_old += w_sum(to); a_new += w_sum(tn); mn = fmin(mn, w_min(nk));
+      unsigned m = __ballot_sync(0xffffffffu, leaf);
+      while (m && seen < 2) { int b = __ffs(m) - 1; if (seen == 0) first_leaf = base + b; else second_leaf = base + b; ++seen; m &= m - 1; }
+    }
+    old_ll = a_old; new_ll = a_new;
+    ratio = exp(in.log_prior_trans + (new_ll - old_ll));
+    if (mn < (double) P.min_obs) ratio = 0.0;
+    accept = rng.uniform() < ratio;
+    if (first_leaf >= 0) n_first = stats[in.b_prop.slot[first_leaf]].n;
+    if (second_leaf >= 0) n_second = stats[in.b_prop.slot[second_leaf]].n;
+  }
+
+  // ---- structural change, all lanes ----
+  const int amode = !accept ? 0 : (kind == 0 ? 1 : (kind == 1 ? 2 : 3));
+  if (amode == 1 || amode == 2) {
+    for (int k = lane; k < nn_old; k += 32) cs.tmp[k] = t.nodes[k];
+    __syncwarp();
+    const int shift = amode == 1 ? 2 : -2;
+    const int pivot = amode == 1 ? node : node + 2;     // indices > pivot move
+    for (int k = lane; k < nn_old; k += 32) {
+      if (amode == 2 && (k == node + 1 || k == node + 2)) continue;
+      DNode nd = cs.tmp[k];
+      if (nd.var >= 0 && nd.right > pivot) nd.right = (int16_t) (nd.right + shift);
+      if (nd.parent > pivot) nd.parent = (int16_t) (nd.parent + shift);
+      t.nodes[k > pivot ? k + shift : k] = nd;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      DNode& nd = t.nodes[node];
+      if (amode == 1) {
+        nd.var = (int16_t) in.b_var; nd.cut = (int16_t) in.b_cut; nd.right = (int16_t) (node + 2);
+        for (int c = 1; c <= 2; ++c) { DNode& ch = t.nodes[node + c]; ch.var = -1; ch.cut = -1; ch.right = -1; ch.parent = (int16_t) node; ch.n = 0; ch.depth = nd.depth + 1; ch.mu = 0.0; }
+      } else { nd.var = -1; nd.cut = -1; nd.right = -1; }
+      t.num_nodes = nn_old + shift;
+    }
+    __syncwarp();
+  } else if (amode == 3) {
+    const int end = t_subtree_end(t, node);
+    for (int k = node + lane; k < end; k += 32) if (t.nodes[k].var >= 0) { uint32_t tv = in.b_prop.trav[k]; t.nodes[k].var = (int16_t) (tv >> 16); t.nodes[k].cut = (int16_t) ((tv >> 8) & 0xFF); }
+    __syncwarp();
+  }
+
+  // ---- leaf draws: one lane per node of the final tree ----
+  const int nn = t.num_nodes;
+  const double sigsq = P.sigma * P.sigma;
+  int leaves_before = 0;
+  for (int base = 0; base < nn; base += 32) {
+    const int k = base + lane;
+    const bool leaf = k < nn && t.nodes[k].var < 0;
+    const unsigned m = __ballot_sync(0xffffffffu, leaf);
+    const int cnt = __popc(m);
+    const int p0 = cnt > 0 ? rng.reserve_normals(cnt) : 0;
+    if (leaf) {
+      const int j = __popc(m & ((1u << lane) - 1u));
+      int old_k = k;
+      if (amode == 1) old_k = (k <= node) ? k : (k <= node + 2 ? node : k - 2);
+      else if (amode == 2) old_k = (k <= node) ? k : k + 2;
+      LeafStat s;
+      if (kind == 0) {
+        if (accept && k == node + 1) s = stats[L];
+        else if (accept && k == node + 2) s = stats[L + 1];
+        else if (!accept && k == node) { s.n = stats[L].n + stats[L + 1].n; s.sum = stats[L].sum + stats[L + 1].sum; s.sumsq = stats[L].sumsq + stats[L + 1].sumsq; }
+        else s = stats[in.b_cur.slot[old_k]];
+      } else if (kind == 1 && accept && k == node) {
+        const LeafStat& a = stats[in.b_cur.slot[node + 1]];
+        const LeafStat& b = stats[in.b_cur.slot[node + 2]];
+        s.n = a.n + b.n; s.sum = a.sum + b.sum; s.sumsq = a.sumsq + b.sumsq;
+      } else if ((kind == 2 || kind == 3) && accept && in.b_prop.slot[k] != 255) s = stats[in.b_prop.slot[k]];
+      else s = stats[in.b_cur.slot[old_k]];
+      const double avg = s.n > 0.0 ? s.sum / s.n : 0.0;
+      const double dp = s.n / sigsq;
+      const double mu = dp * avg / (P.leaf_prec + dp) + (1.0 / sqrt(P.leaf_prec + dp)) * cs.zbuf[p0 + j];
+      t.nodes[k].mu = mu;
+      t.nodes[k].n = (int32_t) s.n;
+      upd.val_new[k] = mu;
+      if (trace_rec != nullptr && 11 + leaves_before + j < S4B_TRACE_LEN) trace_rec[11 + leaves_before + j] = mu;
+    }
+    leaves_before += cnt;
+  }
+  // ---- residual update descriptor ----
+  for (int k = lane; k < nn_old; k += 32) {
+    int nk = k;
+    if (amode == 1) nk = k > node ? k + 2 : k;                                   // the split leaf itself is resolved by the caller
+    else if (amode == 2) nk = (k == node + 1 || k == node + 2) ? node : (k > node + 2 ? k - 2 : k);
+    upd.remap[k] = (uint8_t) nk;
+  }
+  if (lane == 0) { upd.mode = amode; upd.node = node; }
+  if (trace_rec != nullptr && lane == 0) {
+    trace_rec[0] = (double) kind;
+    trace_rec[1] = (kind >= 0 && node >= 0) ? (double) t_heap_index(t, node) : 0.0;
+    if (kind == 0 || kind == 1) { trace_rec[2] = in.b_var; trace_rec[3] = in.b_cut; }
+    else if (kind == 2 || kind == 12) { trace_rec[2] = node >= 0 ? in.new_var : 0; trace_rec[3] = kind == 2 ? in.new_cut : 0; }
+    else if ((kind == 3 || kind == 13) && node >= 0) { trace_rec[2] = in.b_child >= 0 ? (double) t_heap_index(t, in.b_child) : -1.0; }
+    trace_rec[4] = accept ? 1.0 : 0.0; trace_rec[5] = ratio; trace_rec[6] = old_ll; trace_rec[7] = new_ll;
+    trace_rec[8] = (double) leaves_before; trace_rec[9] = n_first; trace_rec[10] = n_second;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+struct SweepSmem {
+  StepDesc sd[2];
+  DTree tree[2];
+  UpdateDesc upd;
+  CtlScratch csd;      // decision (warp 0)
+  CtlScratch csp;      // proposal (helper warp)
+  LeafStat st[S4B_MAX_SLOTS];
+  RngState rng;
+  BartParams prm;
+  double tab[kTabSize];
+  double red[kWorkerWarps][3 * kBinSlots];
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
+  // lane-private statistic bins: [slot][thread] -> (sum, sum^2) and count; no atomics, no bank conflicts
+  double2* bin_s = reinterpret_cast<double2*>(smem_raw + ((sizeof(SweepSmem) + 15) / 16) * 16);
+  int* bin_n = reinterpret_cast<int*>(bin_s + kBinSlots * kWorkers);
+  uint32_t* tile = reinterpret_cast<uint32_t*>(bin_n + kBinSlots * kWorkers);                          // [p][NQ * kWorkers]
+  constexpr int tile_stride = NQ * kWorkers;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_worker = tid < kWorkers;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const long long n = dv.n, npad = dv.npad;
+  const long long nquad = (n + 3) >> 2;
+
+  // ---- one-time loads: residuals -> registers, binned predictors -> shared tile, controller state ----
+  double R[NQ][4];
+  long long qidx[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
+    qidx[j] = (is_worker && q < nquad) ? q : -1;
+    if (qidx[j] >= 0) {
+      double2 a = *reinterpret_cast<const double2*>(dv.R + 4 * q), b = *reinterpret_cast<const double2*>(dv.R + 4 * q + 2);
+      R[j][0] = a.x; R[j][1] = a.y; R[j][2] = b.x; R[j][3] = b.y;
+    } else { R[j][0] = R[j][1] = R[j][2] = R[j][3] = 0.0; }
+  }
+  if (tid == 0) { S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; }
+  for (int i = tid; i < kTabSize; i += kSweepBlock) S.tab[i] = tables[i];
+  __syncthreads();
+  const int p = S.prm.p, T = S.prm.num_trees;
+  const unsigned long long step0 = S.prm.step_id;
+  const bool sequential_rng = S.rng.tape != nullptr || S.rng.rec != nullptr;   // replay / record: strict program order
+  if (is_worker) {
+    const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(dv.xt);
+    const long long col_words = npad >> 2;
+    for (int v = 0; v < p; ++v)
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) tile[v * tile_stride + j * kWorkers + tid] = qidx[j] >= 0 ? __ldg(xt32 + (long long) v * col_words + qidx[j]) : 0u;
+  }
+  {
+    const DTree& g = dv.trees[0];
+    int nn = g.num_nodes;
+    if (tid == 0) { S.tree[0].num_nodes = nn; S.tree[0].pad = 0; }
+    for (int i = tid; i < nn * (int) (sizeof(DNode) / 4); i += kSweepBlock) reinterpret_cast<uint32_t*>(S.tree[0].nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+  }
+  __syncthreads();
+  WarpRng rngp; rngp.g = &S.rng; rngp.cs = &S.csp; rngp.lane = lane; rngp.writer = cta == 0;     // proposals (helper, or warp 0 when sequential)
+  WarpRng rngd; rngd.g = &S.rng; rngd.cs = &S.csd; rngd.lane = lane; rngd.writer = cta == 0;     // decisions (warp 0)
+  if (warp == kWorkerWarps) {
+    rngp.enter(step0, 0u); rngp.fill();
+    w_propose(S.tree[0], S.prm, S.tab, rngp, S.sd[0], S.csp, 0, lane);
+    rngp.commit();
+  }
+  __syncthreads();
+
+  unsigned int bar_k = 0;
+  long long pc[6] = { 0, 0, 0, 0, 0, 0 };
+  for (int t = 0; t < T; ++t) {
+    const long long c0 = clock64();
+    StepDesc& sd = S.sd[t & 1];
+    StepDesc& sd_next = S.sd[(t + 1) & 1];
+    DTree& tree = S.tree[t & 1];
+    DTree& tree_next = S.tree[(t + 1) & 1];
+    const int kind = sd.b_kind;
+    const int L = sd.b_num_leaves;
+    const int nslots = sd.b_nslots;
+    const bool two_trees = (kind == 2 || kind == 3);
+    const int birth_node = kind == 0 ? sd.b_node : -1;
+    const int birth_var = kind == 0 ? sd.b_var : 0;
+    const uint32_t birth_cut = (uint32_t) sd.b_cut;
+    const int depth_cur = sd.b_cur.pad;
+    double* partials = dv.partials + (size_t) (t & 1) * partial_stride;
+    uint32_t leaf_pack[NQ], aux_pack[NQ];
+
+    if (is_worker) {
+      // ---- statistics walk (4 observations interleaved); leaf indices are cached for later passes and the update ----
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        uint32_t lp = 0, ap = 0;
+        if (qidx[j] >= 0) {
+          const int qslot = j * kWorkers + tid;
+          int node[4] = { 0, 0, 0, 0 };
+          for (int lvl = 0; lvl < depth_cur; ++lvl) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const uint32_t tr = sd.b_cur.trav[node[o]];
+              if ((tr >> 16) != 0xFFFFu) {
+                const uint32_t x = (tile[(tr >> 16) * tile_stride + qslot] >> (8 * o)) & 0xFFu;
+                node[o] = (x <= ((tr >> 8) & 0xFFu)) ? node[o] + 1 : (int) (tr & 0xFFu);
+              }
+            }
+          }
+          int aux[4] = { 0, 0, 0, 0 };
+          if (two_trees) {
+            for (int lvl = 0; lvl < depth_cur; ++lvl) {
+#pragma unroll
+              for (int o = 0; o < 4; ++o) {
+                const uint32_t tr = sd.b_prop.trav[aux[o]];
+                if ((tr >> 16) != 0xFFFFu) {
+                  const uint32_t x = (tile[(tr >> 16) * tile_stride + qslot] >> (8 * o)) & 0xFFu;
+                  aux[o] = (x <= ((tr >> 8) & 0xFFu)) ? aux[o] + 1 : (int) (tr & 0xFFu);
+                }
+              }
+            }
+          } else if (birth_node >= 0) {
+            const uint32_t w = tile[birth_var * tile_stride + qslot];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) aux[o] = (((w >> (8 * o)) & 0xFFu) > birth_cut) ? 1 : 0;
+          }
+#pragma unroll
+          for (int o = 0; o < 4; ++o) { lp |= (uint32_t) node[o] << (8 * o); ap |= (uint32_t) aux[o] << (8 * o); }
+        }
+        leaf_pack[j] = lp; aux_pack[j] = ap;
+      }
+      const int nchunks = (nslots + kBinSlots - 1) / kBinSlots;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int base = chunk * kBinSlots;
+        const int kmax = min(kBinSlots, nslots - base);
+        for (int k = 0; k < kmax; ++k) { bin_s[k * kWorkers + tid] = make_double2(0.0, 0.0); bin_n[k * kWorkers + tid] = 0; }
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          if (qidx[j] >= 0) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
+              const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
+              const double pr = R[j][o] + sd.b_cur.val[leaf];
+              int sa = sd.b_cur.slot[leaf];
+              if (leaf == birth_node) sa = L + aux;
+              int sb = two_trees ? (int) sd.b_prop.slot[aux] : 255;
+              if (4 * qidx[j] + o >= n) { sa = 255; sb = 255; }
+              sa -= base; sb -= base;
+              if (sa >= 0 && sa < kmax) {
+                double2 v = bin_s[sa * kWorkers + tid]; v.x += pr; v.y += pr * pr; bin_s[sa * kWorkers + tid] = v;
+                bin_n[sa * kWorkers + tid] += 1;
+              }
+              if (sb >= 0 && sb < kmax) {
+                double2 v = bin_s[sb * kWorkers + tid]; v.x += pr; v.y += pr * pr; bin_s[sb * kWorkers + tid] = v;
+                bin_n[sb * kWorkers + tid] += 1;
+              }
+            }
+          }
+        }
+        // warp reduction of the lane-private bins (fixed order)
+        for (int k0 = 0; k0 < kmax; k0 += 4) {
+          int cnt[4]; double s1[4], s2[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool ok = k0 + k < kmax;
+            double2 v = ok ? bin_s[(k0 + k) * kWorkers + tid] : make_double2(0.0, 0.0);
+            cnt[k] = ok ? bin_n[(k0 + k) * kWorkers + tid] : 0; s1[k] = v.x; s2[k] = v.y;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+            }
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k0 + k < kmax) { S.red[warp][3 * (k0 + k)] = (double) cnt[k]; S.red[warp][3 * (k0 + k) + 1] = s1[k]; S.red[warp][3 * (k0 + k) + 2] = s2[k]; }
+          }
+        }
+        named_bar_sync(1, kWorkers);
+        if (tid < 3 * kmax) {
+          double acc = 0.0;
+#pragma unroll
+          for (int w = 0; w < kWorkerWarps; ++w) acc += S.red[w][tid];
+          partials[(size_t) (3 * base + tid) * G + cta] = acc;
+        }
+        named_bar_sync(1, kWorkers);
+      }
+      // ---- arrive at the grid barrier and wait for every CTA's partial row ----
+      if (tid == 0) {
+        pc[0] += clock64() - c0;
+        __threadfence();
+        atomicAdd(barrier_counter, 1u);
+        const unsigned int target = (unsigned int) (t + 1) * (unsigned int) G;
+        unsigned int v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(barrier_counter) : "memory"); } while (v < target);
+        __threadfence();
+      }
+    } else {
+      // ---- helper warp: persist tree t-1, fetch tree t+1, pre-compute this step's decision draws, propose for t+1 ----
+      if (t + 1 < T) {
+        const DTree& g = dv.trees[t + 1];
+        int nn = g.num_nodes;
+        if (lane == 0) { tree_next.num_nodes = nn; tree_next.pad = 0; }
+        for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(tree_next.nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+        __syncwarp();
+      }
+      if (!sequential_rng) {
+        rngd.enter(step0 + (unsigned long long) t, 1u); rngd.fill();
+        if (t + 1 < T) {
+          rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
+          w_propose(tree_next, S.prm, S.tab, rngp, sd_next, S.csp, t + 1, lane);
+          rngp.commit();
+        }
+      }
+    }
+    (void) bar_k;
+    __syncthreads();                                                        // [A] partials complete, next proposal ready
+    const long long c2 = clock64();
+
+    // ---- every CTA: reduce all partial rows in the same fixed order ----
+    for (int v = warp; v < 3 * nslots; v += kSweepWarps) {
+      const double* src = partials + (size_t) v * G;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+      // G <= 160: five predicated loads per lane, issued together
+      { int b = lane;       if (b < G) a0 = __ldcg(src + b); }
+      { int b = lane + 32;  if (b < G) a1 = __ldcg(src + b); }
+      { int b = lane + 64;  if (b < G) a2 = __ldcg(src + b); }
+      { int b = lane + 96;  if (b < G) a3 = __ldcg(src + b); }
+      { int b = lane + 128; if (b < G) a4 = __ldcg(src + b); }
+      double acc = (((a0 + a1) + a2) + a3) + a4;
+      for (int b = lane + 160; b < G; b += 32) acc += __ldcg(src + b);
+      acc = w_sum(acc);
+      if (lane == 0) reinterpret_cast<double*>(&S.st[v / 3])[v % 3] = acc;
+    }
+    __syncthreads();                                                        // [B]
+    const long long c3 = clock64();
+    long long c4 = c3;
+    if (warp == 0) {
+      double* trec = nullptr;
+      if (dv.trace != nullptr && cta == 0) {
+        unsigned long long k = *dv.trace_len;
+        if (k < dv.trace_cap) { trec = dv.trace + k * S4B_TRACE_LEN; for (int i = lane; i < S4B_TRACE_LEN; i += 32) trec[i] = 0.0; }
+        __syncwarp();
+        if (lane == 0) *dv.trace_len = k + 1;
+      }
+      rngd.enter(step0 + (unsigned long long) t, 1u);
+      if (sequential_rng) rngd.fill();
+      w_decide(tree, S.prm, rngd, sd, S.st, S.upd, S.csd, trec, lane);
+      rngd.commit();
+      c4 = clock64();
+      if (sequential_rng && t + 1 < T) {
+        rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
+        w_propose(tree_next, S.prm, S.tab, rngp, sd_next, S.csp, t + 1, lane);
+        rngp.commit();
+      }
+    }
+    __syncthreads();                                                        // [C]
+    const long long c5 = clock64();
+    if (is_worker) {
+      // ---- fit / residual update from the cached leaf indices ----
+      const int amode = S.upd.mode, unode = S.upd.node;
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
+          const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
+          int nl;
+          if (amode == 3) nl = aux;
+          else if (amode == 1 && leaf == unode) nl = unode + 1 + aux;
+          else nl = S.upd.remap[leaf];
+          R[j][o] += S.upd.val_old[leaf] - S.upd.val_new[nl];
+        }
+      }
+    } else if (cta == 0) {
+      // helper of CTA 0 persists the tree that was just decided
+      DTree& g = dv.trees[t];
+      int nn = tree.num_nodes;
+      if (lane == 0) g.num_nodes = nn;
+      for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(g.nodes)[i] = reinterpret_cast<const uint32_t*>(tree.nodes)[i];
+    }
+    __syncthreads();                                                        // [D] upd / tree buffers free again
+    if (cta == 0 && tid == 0) { pc[1] += c2 - c0 - 0; pc[2] += c3 - c2; pc[3] += c4 - c3; pc[4] += c5 - c4; pc[5] += clock64() - c5; }
+  }
+
+  // ---- write back ----
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) if (qidx[j] >= 0) {
+    *reinterpret_cast<double2*>(dv.R + 4 * qidx[j]) = make_double2(R[j][0], R[j][1]);
+    *reinterpret_cast<double2*>(dv.R + 4 * qidx[j] + 2) = make_double2(R[j][2], R[j][3]);
+  }
+  if (cta == 0 && tid == 0) {
+    RngState out = S.rng;
+    out.counter += (unsigned long long) (S.csd.draws_total + S.csp.draws_total);
+    *dv.rng = out;
+    if (out.tape_underrun) dv.params->error_flag |= 2u;
+    dv.params->step_id = step0 + (unsigned long long) T;
+    dv.desc->a_valid = 0;
+    if (dv.prof != nullptr) {
+      // [0] pass (CTA 0), [1] pass + barrier wait, [2] reduce, [3] decide, [4] sequential-mode proposal, [5] update, [7] steps
+      for (int i = 0; i < 6; ++i) dv.prof[i] += (unsigned long long) pc[i];
+      dv.prof[7] += (unsigned long long) T;
+    }
+  }
+}
+
+}  // namespace s4b

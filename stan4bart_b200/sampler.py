@@ -144,6 +144,14 @@ class GpuBart:
     def set_use_graph(self, flag):
         _lib.check(self.L.gpubart_set_use_graph(self.h, int(flag)))
 
+    def set_sweep_mode(self, mode):
+        _lib.check(self.L.gpubart_set_sweep_mode(self.h, int(mode)))
+
+    def sweep_mode(self):
+        m = C.c_int(0)
+        _lib.check(self.L.gpubart_get_sweep_mode(self.h, C.byref(m)))
+        return m.value
+
     def time_leaf_stats(self, tree=0, reps=20):
         ms = C.c_double(0.0)
         _lib.check(self.L.gpubart_time_leaf_stats(self.h, tree, reps, C.byref(ms)))
@@ -153,6 +161,14 @@ class GpuBart:
         ms = C.c_double(0.0)
         _lib.check(self.L.gpubart_tree_step_ms(self.h, int(reset), C.byref(ms)))
         return ms.value
+
+    def profile(self, reset=True):
+        out = (C.c_uint64 * 8)()
+        _lib.check(self.L.gpubart_get_profile(self.h, out, int(reset)))
+        v = [int(x) for x in out]
+        steps = max(1, v[7])
+        names = ["pass", "reduce", "tree_load_or_barrier", "decide", "writeback_or_update", "propose", "publish"]
+        return {"steps": v[7], "cycles_per_step": {k: v[i] / steps for i, k in enumerate(names)}}
 
     def num_tree_steps(self):
         k = C.c_int64(0)

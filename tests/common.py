@@ -36,10 +36,17 @@ def compare_traces(tr_o, tr_g, tol=REL_TOL):
     for c in int_cols:
         bad = np.nonzero(tr_o[:, c] != tr_g[:, c])[0]
         assert bad.size == 0, f"trace column {c} differs first at step {bad[0]}: oracle {tr_o[bad[0]]} gpu {tr_g[bad[0]]}"
-    for c in [5, 6, 7] + list(range(11, tr_o.shape[1])):
+    # the MH ratio is exp(delta log-lik): compare it on the log scale, relative to the size of the log-likelihoods
+    ra, rb = tr_o[:, 5], tr_g[:, 5]
+    pos = (ra > 0) & (rb > 0) & np.isfinite(ra) & np.isfinite(rb)
+    assert np.array_equal(ra[~pos], rb[~pos]), "zero / infinite / absent ratios differ"
+    ll_scale = np.maximum(1.0, np.maximum(np.abs(tr_o[:, 6]), np.abs(tr_o[:, 7])))
+    lerr = np.abs(np.log(ra[pos]) - np.log(rb[pos])) / ll_scale[pos]
+    assert lerr.size == 0 or lerr.max() <= tol, f"log ratio differs by {lerr.max():.3e} (relative to |log-lik|)"
+    for c in [6, 7] + list(range(11, tr_o.shape[1])):
         a, b = tr_o[:, c], tr_g[:, c]
         # floors: log-likelihood sums and leaf draws are differences that can cancel to ~0
-        floor = 1.0 if c in (6, 7) else (1e-3 if c >= 11 else 1e-300)
+        floor = 1.0 if c in (6, 7) else 1e-3
         scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
         with np.errstate(invalid="ignore"):
             err = np.where(a == b, 0.0, np.abs(a - b) / scale)      # equal infinities (overflowing ratios) are equal

@@ -100,26 +100,55 @@ def test_tape_underrun_is_an_error():
         g.run()
 
 
-def test_all_move_types_and_graph_vs_stream():
-    """Long enough that birth, death, change and swap are all proposed and accepted; the graph-captured
-    sweep and plain stream launches must agree bit for bit."""
+def test_all_move_types_and_all_sweep_modes():
+    """Long enough that birth, death, change and swap are all proposed and accepted.  The three execution
+    modes (persistent on-chip sweep, per-tree kernels in a CUDA graph, per-tree kernels on the stream) all
+    match the oracle; graph and stream launches of the same kernels agree bit for bit."""
     T, sweeps = 20, 30
     o, g, (x, y, xt) = make_pair(n=1500, p=6, num_trees=T, seed=21)
+    assert g.sweep_mode() == 2
     cfg = g.cfg
-    g_plain = GpuBart(cfg, y, x, xt)
     off = 0.3 * x[:, 3] - 0.1
-    g_plain.set_offset(off, True); g_plain.set_sigma(1.3); g_plain.set_use_graph(False)
-    for b in (o, g, g_plain):
+    others = []
+    for mode in (1, 0):
+        h = GpuBart(cfg, y, x, xt)
+        h.set_offset(off, True); h.set_sigma(1.3); h.set_sweep_mode(mode)
+        others.append(h)
+    for b in [o, g] + others:
         b.sample_trees_from_prior()
-    o.set_trace(T * sweeps); g.set_trace(T * sweeps)
+        b.set_trace(T * sweeps)
     for s in range(sweeps):
-        ro, rg, rp = o.run(), g.run(), g_plain.run()
-        assert np.array_equal(rg["train"], rp["train"])
+        ro, rg = o.run(), g.run()
+        r1, r0 = others[0].run(), others[1].run()
+        assert np.array_equal(r1["train"], r0["train"])
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
+        assert rel_err(ro["train"], r1["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
     tr = o.trace()
     compare_traces(tr, g.trace())
+    compare_traces(tr, others[0].trace())
     kinds = tr[:, 0]
     for k in (0, 1, 2, 3):
         assert np.any((kinds == k) & (tr[:, 4] == 1)), f"move type {k} never accepted in this run"
+    assert_same_partition(o, g, T)
+    assert_same_partition(o, others[0], T)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_deep_trees_many_slots(mode):
+    """Weak leaf prior + tiny min_obs grows trees past 8 statistic slots (several bin passes)."""
+    T, sweeps = 4, 60
+    x, y, _ = bart_problem(3000, 4, 0)
+    cfg = bart_config(3000, 4, num_trees=T, seed=8, min_obs=1, base=0.99, power=0.5, k=0.5)
+    o, g = O.OracleBart(cfg, y, x), GpuBart(cfg, y, x)
+    g.set_sweep_mode(mode)
+    o.set_sigma(0.3); g.set_sigma(0.3)
+    o.set_trace(T * sweeps); g.set_trace(T * sweeps)
+    for _ in range(sweeps):
+        ro, rg = o.run(), g.run()
+    tr = o.trace()
+    assert tr[:, 8].max() > 9, "trees did not grow deep enough for this test to bite"
+    compare_traces(tr, g.trace())
+    assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
     assert_same_partition(o, g, T)
 
 
