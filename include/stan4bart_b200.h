@@ -119,8 +119,9 @@ int gpubart_num_tree_steps(gpubart_fit* fit, int64_t* out);
 /* device milliseconds (CUDA events on the launching stream) spent in the per-tree kernels since the last reset */
 int gpubart_tree_step_ms(gpubart_fit* fit, int reset, double* ms);
 /* SM-cycle counters of the controller phases of k_tree_step: [0] pass of the last block, [1] partial reduction, [2] tree load,
- * [3] MH decision + leaf draws, [4] write-back + next tree load, [5] next proposal, [6] descriptor publish, [7] steps counted */
-int gpubart_get_profile(gpubart_fit* fit, uint64_t* out8, int reset);
+ * [3] MH decision + leaf draws, [4] write-back + next tree load, [5] next proposal / update, [6] descriptor publish, [7] steps counted,
+ * [8..15] finer controller counters of the persistent kernel (see sweep_kernel.cuh); out16 has 16 entries */
+int gpubart_get_profile(gpubart_fit* fit, uint64_t* out16, int reset);
 
 /* ------------------------------------------------------------------ glmm_* */
 typedef struct glmm_model glmm_model;

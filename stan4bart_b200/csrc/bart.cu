@@ -381,7 +381,8 @@ __global__ void k_prior_tree(BartDev dv, int tree_index)
 //   train_out  = BART fit in original units (+ offset if add_offset)   [SURVEY a2]
 //   latent_out = full latent z (binary)                                [SURVEY a9]
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_finish_sweep(BartDev dv, double* __restrict__ train_out, double* __restrict__ latent_out, int add_offset)
+__global__ void __launch_bounds__(kBlock) k_finish_sweep(BartDev dv, double* __restrict__ train_out, double* __restrict__ latent_out, int add_offset,
+                                                         double* __restrict__ test_alias_out)
 {
   __shared__ TravTree a_old, a_new;
   __shared__ BartParams prm;
@@ -414,6 +415,8 @@ __global__ void __launch_bounds__(kBlock) k_finish_sweep(BartDev dv, double* __r
     if (train_out != nullptr) {
       double f = binary ? tf : prm.smin + (tf + 0.5) * prm.srange;
       train_out[i] = add_offset ? f + off : f;
+      // test design identical to the training design (same binned rows): the test fit is the training fit
+      if (test_alias_out != nullptr) test_alias_out[i] = f;
     }
   }
 }
@@ -423,23 +426,24 @@ __global__ void k_bump_epoch_clear_update(BartDev dv, int bump)
   if (threadIdx.x == 0 && blockIdx.x == 0) { if (bump) dv.params->latent_epoch += 1u; dv.desc->a_valid = 0; }
 }
 
-// test-sample fits: sum over all trees of the leaf value reached by each test row
+// test-sample fits: sum over all trees of the leaf value reached by each test row.  The block's rows are staged in
+// shared memory (p bytes per row), the trees are streamed through shared memory in batches; all walks are on chip.
 __global__ void __launch_bounds__(kBlock) k_test_fits(BartDev dv, const uint8_t* __restrict__ xt_test, long long n_test, long long npad_test,
-                                                      const double* __restrict__ test_offset, double* __restrict__ out, int unscale)
+                                                      const double* __restrict__ test_offset, double* __restrict__ out, int unscale, int p)
 {
   extern __shared__ unsigned char smem_raw[];
-  // layout: uint32 trav[cap], double val[cap]
   const int tid = threadIdx.x;
   const int T = dv.params->num_trees;
   const int cap_nodes = 2048;
   uint32_t* trav = reinterpret_cast<uint32_t*>(smem_raw);
   double* val = reinterpret_cast<double*>(smem_raw + sizeof(uint32_t) * cap_nodes);
+  uint8_t* rows = smem_raw + (sizeof(uint32_t) + sizeof(double)) * cap_nodes;      // [p][kBlock]
   __shared__ int tree_start[257];
   const long long i = (long long) blockIdx.x * kBlock + tid;
+  for (int v = 0; v < p; ++v) rows[v * kBlock + tid] = i < n_test ? xt_test[(long long) v * npad_test + i] : (uint8_t) 0;
   double acc = 0.0;
   int t0 = 0;
   while (t0 < T) {
-    // pack as many trees as fit
     __syncthreads();
     if (tid == 0) {
       int used = 0, t = t0, k = 0;
@@ -449,21 +453,25 @@ __global__ void __launch_bounds__(kBlock) k_test_fits(BartDev dv, const uint8_t*
     }
     __syncthreads();
     const int nt = tree_start[256];
-    for (int k = 0; k < nt; ++k) {
-      const DTree& g = dv.trees[t0 + k];
-      int base = tree_start[k];
-      for (int j = tid; j < g.num_nodes; j += kBlock) {
-        const DNode& nd = g.nodes[j];
-        trav[base + j] = pack_trav(nd.var, nd.cut, nd.right);
-        val[base + j] = nd.mu;
-      }
+    for (int k = tid; k < nt * 8; k += kBlock) {
+      // 8 threads per tree copy its nodes
+      const int tr = k >> 3, sub = k & 7;
+      const DTree& g = dv.trees[t0 + tr];
+      const int base = tree_start[tr];
+      for (int j = sub; j < g.num_nodes; j += 8) { const DNode& nd = g.nodes[j]; trav[base + j] = pack_trav(nd.var, nd.cut, nd.right); val[base + j] = nd.mu; }
     }
     __syncthreads();
     if (i < n_test) {
       for (int k = 0; k < nt; ++k) {
         const uint32_t* tv = trav + tree_start[k];
-        int leaf = traverse(tv, xt_test, npad_test, i);
-        acc += val[tree_start[k] + leaf];
+        int node = 0;
+        uint32_t tr = tv[0];
+        while ((tr >> 16) != 0xFFFFu) {
+          const uint32_t x = rows[(tr >> 16) * kBlock + tid];
+          node = (x <= ((tr >> 8) & 0xFFu)) ? node + 1 : (int) (tr & 0xFFu);
+          tr = tv[node];
+        }
+        acc += val[tree_start[k] + node];
       }
     }
     t0 += nt;
@@ -632,6 +640,9 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   S4B_CUDA(cudaMemcpy(d_xt_, xt.data(), xt.size(), cudaMemcpyHostToDevice));
   if (nt_ > 0) {
     std::vector<uint8_t> xtt; bin_matrix(x_test, nt_, npad_t_, xtt);
+    // counterfactual designs that differ from the training design only outside the BART covariates (README example,
+    // treatment = z) bin to identical rows: their test fits equal the training fits and need no second traversal
+    test_aliases_train_ = nt_ == n_ && xtt.size() == xt.size() && std::memcmp(xtt.data(), xt.data(), xt.size()) == 0 && getenv("S4B_NO_TEST_ALIAS") == nullptr;
     S4B_CUDA(cudaMalloc(&d_xt_test_, xtt.size()));
     S4B_CUDA(cudaMemcpy(d_xt_test_, xtt.data(), xtt.size(), cudaMemcpyHostToDevice));
     S4B_CUDA(cudaMalloc(&d_test_out_, sizeof(double) * (size_t) npad_t_));
@@ -645,7 +656,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   dalloc(&d_stats_out_, (size_t) 3 * S4B_MAX_SLOTS);
   S4B_CUDA(cudaMalloc(&d_desc_, sizeof(StepDesc))); S4B_CUDA(cudaMemset(d_desc_, 0, sizeof(StepDesc)));
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
-  S4B_CUDA(cudaMalloc(&d_prof_, sizeof(unsigned long long) * 8)); S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 8));
+  S4B_CUDA(cudaMalloc(&d_prof_, sizeof(unsigned long long) * 16)); S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 16));
   S4B_CUDA(cudaMalloc(&d_trace_len_, sizeof(unsigned long long))); S4B_CUDA(cudaMemset(d_trace_len_, 0, sizeof(unsigned long long)));
   S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
   // trees: single root each
@@ -699,7 +710,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -722,7 +733,7 @@ void BartFit::setup_persistent()
   if (coop) {
     const long long nquad = (n_ + 3) / 4;
     auto try_nq = [&](int nq, size_t smem, const void* fn) -> bool {
-      if (smem > (size_t) max_smem) return false;
+      if (smem > (size_t) max_smem || p_ > 511) return false;      // traversal records carry 9 bits of variable index
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); return false; }
       int per_sm = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -750,6 +761,13 @@ void BartFit::setup_persistent()
       tab[(size_t) kTabPg + d] = pg; tab[(size_t) kTabLogPg + d] = std::log(pg); tab[(size_t) kTabLog1mPg + d] = std::log(1.0 - pg);
     }
     for (int i = 1; i < kLogTab; ++i) tab[(size_t) kTabLogInt + i] = std::log((double) i);
+    S4B_CUDA(cudaMalloc(&d_descs_, sizeof(StepDesc) * (size_t) T_));
+    S4B_CUDA(cudaMemset(d_descs_, 0, sizeof(StepDesc) * (size_t) T_));
+    S4B_CUDA(cudaMalloc(&d_draws_, sizeof(double2) * 32 * (size_t) T_));
+    {
+      size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
+      S4B_CUDA(cudaFuncSetAttribute(k_prepare_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) psmem));
+    }
     S4B_CUDA(cudaMalloc(&d_tables_, sizeof(double) * tab.size()));
     S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     sweep_mode_ = 2;
@@ -772,10 +790,18 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   unsigned int* bar = d_barrier_;
   int stride = partial_stride_;
   const double* tabs = d_tables_;
-  void* args[] = { &dv, &bar, &stride, &tabs };
+  // replay / record keep strict program order inside the kernel; otherwise proposals and decision draws are produced up front
+  const StepDesc* descs = sequential_rng_ ? nullptr : d_descs_;
+  const double2* draws = sequential_rng_ ? nullptr : d_draws_;
+  if (!sequential_rng_) {
+    size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
+    k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_);
+  }
+  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws };
   const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep<1> : (persistent_nq_ == 2 ? (const void*) k_sweep<2> : (const void*) k_sweep<4>);
   S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
-  k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0);
+  k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
+                                                   (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
   S4B_CUDA(cudaGetLastError());
 }
@@ -836,6 +862,7 @@ void BartFit::set_tape(const double* tape, size_t len)
     S4B_CUDA(cudaMemcpy(d_tape_, tape, sizeof(double) * len, cudaMemcpyHostToDevice));
   }
   rs.tape = d_tape_; rs.tape_len = d_tape_ ? len : 0; rs.tape_pos = 0; rs.tape_underrun = 0;
+  tape_set_ = d_tape_ != nullptr; sequential_rng_ = tape_set_ || rec_set_;
   S4B_CUDA(cudaMemcpy(d_rng_, &rs, sizeof rs, cudaMemcpyHostToDevice));
 }
 
@@ -846,6 +873,7 @@ void BartFit::set_record(size_t cap)
   RngState rs; S4B_CUDA(cudaMemcpy(&rs, d_rng_, sizeof rs, cudaMemcpyDeviceToHost));
   if (cap) S4B_CUDA(cudaMalloc(&d_rec_, sizeof(double) * cap));
   rs.rec = d_rec_; rs.rec_cap = cap; rs.rec_len = 0;
+  rec_set_ = d_rec_ != nullptr; sequential_rng_ = tape_set_ || rec_set_;
   S4B_CUDA(cudaMemcpy(d_rng_, &rs, sizeof rs, cudaMemcpyHostToDevice));
 }
 
@@ -929,7 +957,8 @@ void BartFit::launch_sweep_kernels(bool last_thin)
   BartDev dv = dev();
   k_propose_first<<<1, kBlock, 0, stream_>>>(dv);
   for (int t = 0; t < T_; ++t) k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStep, t + 1 < T_ ? 1 : 0);
-  k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0);
+  k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
+                                                   (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
 }
 
@@ -957,14 +986,14 @@ void BartFit::run_sweeps()
   S4B_CUDA(cudaEventRecord(ev_end_, stream_));
   ev_pending_ = true;
   num_tree_steps_ += (long long) cfg_.thin * T_;
-  if (nt_ > 0) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
+  if (nt_ > 0 && !test_aliases_train_) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
 }
 
 void BartFit::get_profile(unsigned long long* out8, bool reset)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));
-  S4B_CUDA(cudaMemcpy(out8, d_prof_, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
-  if (reset) S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 8));
+  S4B_CUDA(cudaMemcpy(out8, d_prof_, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
+  if (reset) S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 16));
 }
 
 double BartFit::tree_step_ms(bool reset)
@@ -982,9 +1011,10 @@ double BartFit::tree_step_ms(bool reset)
 
 void BartFit::test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out)
 {
-  size_t smem = (sizeof(uint32_t) + sizeof(double)) * 2048;
+  size_t smem = (sizeof(uint32_t) + sizeof(double)) * 2048 + (size_t) p_ * kBlock;
+  if (smem > 48 * 1024) S4B_CUDA(cudaFuncSetAttribute(k_test_fits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int grid = (int) ((rows + kBlock - 1) / kBlock);
-  k_test_fits<<<grid, kBlock, smem, stream_>>>(dev(), d_xt, rows, rows_pad, d_off, d_out, cfg_.is_binary ? 0 : 1);
+  k_test_fits<<<grid, kBlock, smem, stream_>>>(dev(), d_xt, rows, rows_pad, d_off, d_out, cfg_.is_binary ? 0 : 1, p_);
   S4B_CUDA(cudaGetLastError());
 }
 

@@ -80,7 +80,7 @@ class BartFit {
   double tree_step_ms(bool reset);
   // cycles spent by the last block in: [0] its own pass, [1] partial reduction, [2] tree load, [3] decision + leaf draws,
   // [4] write-back + next tree load, [5] proposal, [6] descriptor publish, [7] number of steps
-  void get_profile(unsigned long long* out8, bool reset);
+  void get_profile(unsigned long long* out16, bool reset);
 
  private:
   BartDev dev() const;
@@ -100,12 +100,16 @@ class BartFit {
   bool scale_initialised_ = false;
   bool use_graph_ = true;
   bool add_offset_ = true;
+  bool test_aliases_train_ = false;
   int sweep_mode_ = 1;
   int persistent_nq_ = 0, persistent_grid_ = 0;
   size_t persistent_smem_ = 0;
   unsigned int* d_barrier_ = nullptr;
   double* d_partials2_ = nullptr;
   double* d_tables_ = nullptr;
+  StepDesc* d_descs_ = nullptr;
+  double2* d_draws_ = nullptr;
+  bool tape_set_ = false, rec_set_ = false, sequential_rng_ = false;
   int partial_stride_ = 0;
   long long num_tree_steps_ = 0;
 

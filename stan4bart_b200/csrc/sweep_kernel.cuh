@@ -37,6 +37,7 @@ constexpr int kTabPg = 0, kTabLogPg = 32, kTabLog1mPg = 64, kTabLogInt = 96, kTa
 struct UpdateDesc {                 // how to apply the accepted / rejected step to the residuals
   int32_t mode;                     // 0: structure unchanged; 1: birth accepted; 2: death accepted; 3: change / swap accepted
   int32_t node;
+  double delta[S4B_NODE_CAP];       // mode 0: mu_old - mu_new by node index
   double val_old[S4B_NODE_CAP];     // mu before the step, by old node index
   double val_new[S4B_NODE_CAP];     // mu after the step, by new node index
   uint8_t remap[S4B_NODE_CAP];      // old leaf index -> new leaf index (modes 0-2)
@@ -46,10 +47,13 @@ struct CtlScratch {
   int16_t navail[S4B_NODE_CAP];
   uint8_t flag[S4B_NODE_CAP];
   double ubuf[32], zbuf[32];        // pre-generated draws of the current substream
-  double ll[S4B_MAX_SLOTS];
+  double ll[S4B_MAX_SLOTS];         // per statistic slot: integrated log-likelihood,
+  double pmean[S4B_MAX_SLOTS + 1];  //   posterior mean of the leaf value,
+  double psd[S4B_MAX_SLOTS + 1];    //   posterior sd (entry [nslots] describes the merged parent of a birth / death)
   DNode tmp[S4B_NODE_CAP];
   int32_t draw_pos;                 // consumed from ubuf / zbuf
   int32_t draws_total;              // draws consumed through this scratch since kernel start
+  long long dbg[8];                 // cycle counters (diagnostics)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -120,7 +124,7 @@ struct WarpRng {
     if (cs->draw_pos + count > 32) { commit(); fill(); }
     const int p = cs->draw_pos;
     __syncwarp();
-    if (lane == 0) { cs->draw_pos = p + count; for (int i = 0; i < count; ++i) note(cs->zbuf[p + i]); }
+    if (lane == 0) { cs->draw_pos = p + count; if (g->rec != nullptr) for (int i = 0; i < count; ++i) note(cs->zbuf[p + i]); }
     __syncwarp();
     return p;
   }
@@ -180,6 +184,14 @@ __device__ __forceinline__ int w_mini(int v)
   return v;
 }
 
+// branch-free traversal record: var (9 bits) | cut (8) | left (7) | pad (1) | right (7); a leaf points at itself with cut 255
+__host__ __device__ inline uint32_t pack_trav2(int var, int cut, int left, int right)
+{
+  return ((uint32_t) (var & 0x1FF) << 23) | ((uint32_t) (cut & 0xFF) << 15) | ((uint32_t) (left & 0x7F) << 8) | (uint32_t) (right & 0x7F);
+}
+__device__ __forceinline__ int trav2_var(uint32_t tr) { return (int) (tr >> 23); }
+__device__ __forceinline__ int trav2_cut(uint32_t tr) { return (int) ((tr >> 15) & 0xFFu); }
+
 enum : uint8_t { kFLeaf = 1, kFBirthable = 2, kFNog = 4, kFSwappable = 8, kFInternal = 16 };
 
 // per-node attributes, one lane per node
@@ -216,7 +228,7 @@ __device__ inline int w_fill_trav(const DTree& t, TravTree& tv, bool with_mu, in
     unsigned m = __ballot_sync(0xffffffffu, leaf);
     if (k < nn) {
       const DNode& nd = t.nodes[k];
-      tv.trav[k] = pack_trav(nd.var, nd.cut, nd.right);
+      tv.trav[k] = leaf ? pack_trav2(0, 255, k, k) : pack_trav2(nd.var, nd.cut, k + 1, nd.right);
       if (leaf) { tv.slot[k] = (uint8_t) (leaves + __popc(m & ((1u << lane) - 1u))); if (with_mu) tv.val[k] = nd.mu; maxd = max(maxd, nd.depth); }
       else tv.slot[k] = 255;
     }
@@ -436,6 +448,20 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
   __syncwarp();
 }
 
+// posterior mean / sd of the leaf value and integrated log-likelihood of one leaf (two divisions, one log, one sqrt)
+__device__ __forceinline__ void slot_summary(const LeafStat& s, double inv_sigsq, double leaf_prec, double& pmean, double& psd, double& ll)
+{
+  const double dp = s.n * inv_sigsq;
+  const double rinv = 1.0 / (leaf_prec + dp);
+  psd = sqrt(rinv);
+  if (s.n <= 0.0) { pmean = 0.0; ll = 0.0; return; }
+  const double avg = s.sum / s.n;
+  double ss = s.sumsq - s.n * avg * avg;
+  if (ss < 0.0) ss = 0.0;
+  pmean = dp * avg * rinv;
+  ll = 0.5 * log(leaf_prec * rinv) - 0.5 * ss * inv_sigsq - 0.5 * ((leaf_prec * avg) * (dp * avg)) * rinv;
+}
+
 // ---------------------------------------------------------------------------------------
 // decision + leaf draws (warp-cooperative)
 // ---------------------------------------------------------------------------------------
@@ -444,17 +470,24 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
 {
   const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
   const int nn_old = t.num_nodes;
-  for (int s = lane; s < nslots; s += 32) cs.ll[s] = leaf_loglik(stats[s], P.sigma, P.leaf_prec);
+  const long long d0 = clock64();
+  const double inv_sigsq = 1.0 / (P.sigma * P.sigma);
+  // slot nslots = the merged parent of a birth / death step, summarised in the same parallel pass
+  int sl_bd = 0, sr_bd = 0;
+  if (kind == 0 || kind == 1) { sl_bd = kind == 0 ? L : in.b_cur.slot[node + 1]; sr_bd = kind == 0 ? L + 1 : in.b_cur.slot[t.nodes[node].right]; }
+  const int nsum = nslots + ((kind == 0 || kind == 1) ? 1 : 0);
+  for (int s = lane; s < nsum; s += 32) {
+    LeafStat st = s < nslots ? stats[s] : LeafStat{ stats[sl_bd].n + stats[sr_bd].n, stats[sl_bd].sum + stats[sr_bd].sum, stats[sl_bd].sumsq + stats[sr_bd].sumsq };
+    slot_summary(st, inv_sigsq, P.leaf_prec, cs.pmean[s], cs.psd[s], cs.ll[s]);
+  }
   for (int k = lane; k < nn_old; k += 32) upd.val_old[k] = in.b_cur.val[k];
   __syncwarp();
   bool accept = false;
   double ratio = -1.0, old_ll = 0.0, new_ll = 0.0, n_first = 0.0, n_second = 0.0;
   if (kind == 0 || kind == 1) {
-    const int sl = kind == 0 ? L : in.b_cur.slot[node + 1];
-    const int sr = kind == 0 ? L + 1 : in.b_cur.slot[t.nodes[node].right];
+    const int sl = sl_bd, sr = sr_bd;
     const LeafStat l = stats[sl], r = stats[sr];
-    const LeafStat par = { l.n + r.n, l.sum + r.sum, l.sumsq + r.sumsq };
-    const double ll_par = leaf_loglik(par, P.sigma, P.leaf_prec);
+    const double ll_par = cs.ll[nslots];
     const double ll_ch = cs.ll[sl] + cs.ll[sr];
     if (kind == 0) { old_ll = ll_par; new_ll = ll_ch; } else { old_ll = ll_ch; new_ll = ll_par; }
     ratio = in.log_prior_trans * exp(new_ll - old_ll);
@@ -483,6 +516,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
   }
 
   // ---- structural change, all lanes ----
+  const long long d1 = clock64();
   const int amode = !accept ? 0 : (kind == 0 ? 1 : (kind == 1 ? 2 : 3));
   if (amode == 1 || amode == 2) {
     for (int k = lane; k < nn_old; k += 32) cs.tmp[k] = t.nodes[k];
@@ -508,11 +542,12 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     __syncwarp();
   } else if (amode == 3) {
     const int end = t_subtree_end(t, node);
-    for (int k = node + lane; k < end; k += 32) if (t.nodes[k].var >= 0) { uint32_t tv = in.b_prop.trav[k]; t.nodes[k].var = (int16_t) (tv >> 16); t.nodes[k].cut = (int16_t) ((tv >> 8) & 0xFF); }
+    for (int k = node + lane; k < end; k += 32) if (t.nodes[k].var >= 0) { uint32_t tv = in.b_prop.trav[k]; t.nodes[k].var = (int16_t) trav2_var(tv); t.nodes[k].cut = (int16_t) trav2_cut(tv); }
     __syncwarp();
   }
 
   // ---- leaf draws: one lane per node of the final tree ----
+  const long long d2 = clock64();
   const int nn = t.num_nodes;
   const double sigsq = P.sigma * P.sigma;
   int leaves_before = 0;
@@ -527,34 +562,34 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
       int old_k = k;
       if (amode == 1) old_k = (k <= node) ? k : (k <= node + 2 ? node : k - 2);
       else if (amode == 2) old_k = (k <= node) ? k : k + 2;
-      LeafStat s;
+      // which statistic slot describes this leaf (-1: the merged parent of a rejected birth / accepted death)
+      int sl;
       if (kind == 0) {
-        if (accept && k == node + 1) s = stats[L];
-        else if (accept && k == node + 2) s = stats[L + 1];
-        else if (!accept && k == node) { s.n = stats[L].n + stats[L + 1].n; s.sum = stats[L].sum + stats[L + 1].sum; s.sumsq = stats[L].sumsq + stats[L + 1].sumsq; }
-        else s = stats[in.b_cur.slot[old_k]];
-      } else if (kind == 1 && accept && k == node) {
-        const LeafStat& a = stats[in.b_cur.slot[node + 1]];
-        const LeafStat& b = stats[in.b_cur.slot[node + 2]];
-        s.n = a.n + b.n; s.sum = a.sum + b.sum; s.sumsq = a.sumsq + b.sumsq;
-      } else if ((kind == 2 || kind == 3) && accept && in.b_prop.slot[k] != 255) s = stats[in.b_prop.slot[k]];
-      else s = stats[in.b_cur.slot[old_k]];
-      const double avg = s.n > 0.0 ? s.sum / s.n : 0.0;
-      const double dp = s.n / sigsq;
-      const double mu = dp * avg / (P.leaf_prec + dp) + (1.0 / sqrt(P.leaf_prec + dp)) * cs.zbuf[p0 + j];
+        if (accept && k == node + 1) sl = L;
+        else if (accept && k == node + 2) sl = L + 1;
+        else if (!accept && k == node) sl = -1;
+        else sl = in.b_cur.slot[old_k];
+      } else if (kind == 1 && accept && k == node) sl = -1;
+      else if ((kind == 2 || kind == 3) && accept && in.b_prop.slot[k] != 255) sl = in.b_prop.slot[k];
+      else sl = in.b_cur.slot[old_k];
+      const int ss = sl >= 0 ? sl : nslots;
+      const double nobs = sl >= 0 ? stats[sl].n : stats[sl_bd].n + stats[sr_bd].n;
+      const double mu = cs.pmean[ss] + cs.psd[ss] * cs.zbuf[p0 + j];
       t.nodes[k].mu = mu;
-      t.nodes[k].n = (int32_t) s.n;
+      t.nodes[k].n = (int32_t) nobs;
       upd.val_new[k] = mu;
       if (trace_rec != nullptr && 11 + leaves_before + j < S4B_TRACE_LEN) trace_rec[11 + leaves_before + j] = mu;
     }
     leaves_before += cnt;
   }
   // ---- residual update descriptor ----
+  const long long d3 = clock64();
   for (int k = lane; k < nn_old; k += 32) {
     int nk = k;
     if (amode == 1) nk = k > node ? k + 2 : k;                                   // the split leaf itself is resolved by the caller
     else if (amode == 2) nk = (k == node + 1 || k == node + 2) ? node : (k > node + 2 ? k - 2 : k);
     upd.remap[k] = (uint8_t) nk;
+    if (amode == 0) upd.delta[k] = t.nodes[k].var < 0 ? in.b_cur.val[k] - t.nodes[k].mu : 0.0;
   }
   if (lane == 0) { upd.mode = amode; upd.node = node; }
   if (trace_rec != nullptr && lane == 0) {
@@ -567,6 +602,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     trace_rec[8] = (double) leaves_before; trace_rec[9] = n_first; trace_rec[10] = n_second;
   }
   __syncwarp();
+  if (lane == 0) { const long long d4 = clock64(); cs.dbg[0] += d1 - d0; cs.dbg[1] += d2 - d1; cs.dbg[2] += d3 - d2; cs.dbg[3] += d4 - d3; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -576,17 +612,119 @@ struct SweepSmem {
   StepDesc sd[2];
   DTree tree[2];
   UpdateDesc upd;
-  CtlScratch csd;      // decision (warp 0)
-  CtlScratch csp;      // proposal (helper warp)
+  CtlScratch csd;      // decision scratch
+  CtlScratch csp;      // proposal scratch
   LeafStat st[S4B_MAX_SLOTS];
   RngState rng;
   BartParams prm;
   double tab[kTabSize];
-  double red[kWorkerWarps][3 * kBinSlots];
 };
 
+// walk one tree for the four observations of a quad (branch-free records, 4-way ILP); returns packed node indices
+__device__ __forceinline__ uint32_t walk_quad(const uint32_t* __restrict__ trav, const uint32_t* __restrict__ tile, int tile_stride, int qslot, int depth)
+{
+  int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+  for (int lvl = 0; lvl < depth; ++lvl) {
+    const uint32_t t0 = trav[n0], t1 = trav[n1], t2 = trav[n2], t3 = trav[n3];
+    const uint32_t w0 = tile[(t0 >> 23) * tile_stride + qslot], w1 = tile[(t1 >> 23) * tile_stride + qslot];
+    const uint32_t w2 = tile[(t2 >> 23) * tile_stride + qslot], w3 = tile[(t3 >> 23) * tile_stride + qslot];
+    n0 = ((w0 & 0xFFu) <= ((t0 >> 15) & 0xFFu)) ? (int) ((t0 >> 8) & 0x7Fu) : (int) (t0 & 0x7Fu);
+    n1 = (((w1 >> 8) & 0xFFu) <= ((t1 >> 15) & 0xFFu)) ? (int) ((t1 >> 8) & 0x7Fu) : (int) (t1 & 0x7Fu);
+    n2 = (((w2 >> 16) & 0xFFu) <= ((t2 >> 15) & 0xFFu)) ? (int) ((t2 >> 8) & 0x7Fu) : (int) (t2 & 0x7Fu);
+    n3 = ((w3 >> 24) <= ((t3 >> 15) & 0xFFu)) ? (int) ((t3 >> 8) & 0x7Fu) : (int) (t3 & 0x7Fu);
+  }
+  return (uint32_t) n0 | ((uint32_t) n1 << 8) | ((uint32_t) n2 << 16) | ((uint32_t) n3 << 24);
+}
+
+// leaf indices (and the auxiliary byte: proposed-tree leaf for change / swap, split side for a birth) of every owned quad
 template <int NQ>
-__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables)
+__device__ __forceinline__ void walk_step(const StepDesc& sd, const uint32_t* __restrict__ tile, int tile_stride, int tid, unsigned valid_mask,
+                                          uint32_t (&leaf_pack)[NQ], uint32_t (&aux_pack)[NQ])
+{
+  const int kind = sd.b_kind;
+  const int depth = sd.b_cur.pad;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    uint32_t lp = 0, ap = 0;
+    if ((valid_mask >> j) & 1u) {
+      const int qslot = j * kWorkers + tid;
+      lp = walk_quad(sd.b_cur.trav, tile, tile_stride, qslot, depth);
+      if (kind == 2 || kind == 3) ap = walk_quad(sd.b_prop.trav, tile, tile_stride, qslot, depth);
+      else if (kind == 0) {
+        const uint32_t w = tile[sd.b_var * tile_stride + qslot];
+        const uint32_t c = (uint32_t) sd.b_cut;
+        ap = ((w & 0xFFu) > c ? 1u : 0u) | (((w >> 8) & 0xFFu) > c ? 0x100u : 0u) | (((w >> 16) & 0xFFu) > c ? 0x10000u : 0u) | ((w >> 24) > c ? 0x1000000u : 0u);
+      }
+    }
+    leaf_pack[j] = lp; aux_pack[j] = ap;
+  }
+}
+
+// warp-cooperative copy of the used part of a step descriptor
+__device__ inline void w_copy_desc(StepDesc& dst, const StepDesc& src, int lane)
+{
+  const int kind = src.b_kind;
+  const int n = src.b_cur.n;
+  if (lane == 0) {
+    dst.a_valid = 0; dst.a_same = 1;
+    dst.b_tree = src.b_tree; dst.b_kind = kind; dst.b_node = src.b_node; dst.b_var = src.b_var; dst.b_cut = src.b_cut;
+    dst.b_num_leaves = src.b_num_leaves; dst.b_nslots = src.b_nslots; dst.b_child = src.b_child;
+    dst.log_prior_trans = src.log_prior_trans; dst.new_var = src.new_var; dst.new_cut = src.new_cut;
+    dst.b_cur.n = n; dst.b_cur.pad = src.b_cur.pad;
+    dst.b_prop.n = (kind == 2 || kind == 3) ? n : 0; dst.b_prop.pad = src.b_cur.pad;
+  }
+  for (int k = lane; k < n; k += 32) {
+    dst.b_cur.trav[k] = src.b_cur.trav[k]; dst.b_cur.val[k] = src.b_cur.val[k]; dst.b_cur.slot[k] = src.b_cur.slot[k];
+    if (kind == 2 || kind == 3) { dst.b_prop.trav[k] = src.b_prop.trav[k]; dst.b_prop.slot[k] = src.b_prop.slot[k]; }
+  }
+  __syncwarp();
+}
+
+// Everything of a sweep that does not depend on the data: with keyed RNG substreams the proposal of every tree (it needs
+// only that tree's structure) and the decision draws of every step can be produced before the sweep, one warp per tree.
+constexpr int kPrepWarps = 4;
+struct PrepSmemWarp { DTree tree; CtlScratch cs; StepDesc sd; };
+
+__global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, StepDesc* __restrict__ descs, double2* __restrict__ draws,
+                                                                   const double* __restrict__ tables)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tab = reinterpret_cast<double*>(smem_raw);
+  BartParams* prm = reinterpret_cast<BartParams*>(tab + kTabSize);
+  RngState* rng = reinterpret_cast<RngState*>(prm + 1);
+  PrepSmemWarp* pw = reinterpret_cast<PrepSmemWarp*>(smem_raw + ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kTabSize; i += kPrepWarps * 32) tab[i] = tables[i];
+  if (tid == 0) { *prm = *dv.params; *rng = *dv.rng; }
+  __syncthreads();
+  const int T = prm->num_trees;
+  const int t = blockIdx.x * kPrepWarps + warp;
+  if (t >= T) return;
+  PrepSmemWarp& W = pw[warp];
+  {
+    const DTree& g = dv.trees[t];
+    int nn = g.num_nodes;
+    if (lane == 0) { W.tree.num_nodes = nn; W.tree.pad = 0; W.cs.draws_total = 0; }
+    for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(W.tree.nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+    __syncwarp();
+  }
+  const unsigned long long step = prm->step_id + (unsigned long long) t;
+  WarpRng rngp; rngp.g = rng; rngp.cs = &W.cs; rngp.lane = lane; rngp.writer = false;
+  rngp.enter(step, 0u); rngp.fill();
+  w_propose(W.tree, *prm, tab, rngp, W.sd, W.cs, t, lane);
+  rngp.commit();
+  w_copy_desc(descs[t], W.sd, lane);
+  // decision draws of this step: (uniform, normal) pairs for draw indices 0..31
+  {
+    const double u = keyed_stream_uniform(rng->key0, rng->key1, rng->stream, step, 1u, (uint32_t) lane);
+    draws[t * 32 + lane] = make_double2(u, qnorm_as241(u));
+  }
+  if (lane == 0) atomicAdd(&dv.rng->counter, (unsigned long long) W.cs.draws_total);
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
+                                                               const StepDesc* __restrict__ descs, const double2* __restrict__ draws)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
@@ -597,35 +735,41 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   constexpr int tile_stride = NQ * kWorkers;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool is_worker = tid < kWorkers;
+  const bool is_worker = tid < kWorkers;            // warps 0..14: observations; warp 15: controller (proposals + decisions)
   const int G = gridDim.x, cta = blockIdx.x;
   const long long n = dv.n, npad = dv.npad;
   const long long nquad = (n + 3) >> 2;
 
   // ---- one-time loads: residuals -> registers, binned predictors -> shared tile, controller state ----
   double R[NQ][4];
-  long long qidx[NQ];
+  unsigned valid_mask = 0;       // bit j: quad j exists
+  unsigned obs_mask = 0;         // bit 4j + o: observation is a real one (not padding)
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
-    qidx[j] = (is_worker && q < nquad) ? q : -1;
-    if (qidx[j] >= 0) {
+    const long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
+    if (is_worker && q < nquad) {
+      valid_mask |= 1u << j;
+      for (int o = 0; o < 4; ++o) if (4 * q + o < n) obs_mask |= 1u << (4 * j + o);
       double2 a = *reinterpret_cast<const double2*>(dv.R + 4 * q), b = *reinterpret_cast<const double2*>(dv.R + 4 * q + 2);
       R[j][0] = a.x; R[j][1] = a.y; R[j][2] = b.x; R[j][3] = b.y;
     } else { R[j][0] = R[j][1] = R[j][2] = R[j][3] = 0.0; }
   }
-  if (tid == 0) { S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; }
+  if (tid == 0) { S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; }
   for (int i = tid; i < kTabSize; i += kSweepBlock) S.tab[i] = tables[i];
   __syncthreads();
   const int p = S.prm.p, T = S.prm.num_trees;
   const unsigned long long step0 = S.prm.step_id;
-  const bool sequential_rng = S.rng.tape != nullptr || S.rng.rec != nullptr;   // replay / record: strict program order
+  // replay / record need strict program order: proposals and draws are then produced inside the loop
+  const bool sequential_rng = descs == nullptr;
   if (is_worker) {
     const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(dv.xt);
     const long long col_words = npad >> 2;
     for (int v = 0; v < p; ++v)
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) tile[v * tile_stride + j * kWorkers + tid] = qidx[j] >= 0 ? __ldg(xt32 + (long long) v * col_words + qidx[j]) : 0u;
+      for (int j = 0; j < NQ; ++j) {
+        const long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
+        tile[v * tile_stride + j * kWorkers + tid] = ((valid_mask >> j) & 1u) ? __ldg(xt32 + (long long) v * col_words + q) : 0u;
+      }
   }
   {
     const DTree& g = dv.trees[0];
@@ -634,16 +778,19 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     for (int i = tid; i < nn * (int) (sizeof(DNode) / 4); i += kSweepBlock) reinterpret_cast<uint32_t*>(S.tree[0].nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
   }
   __syncthreads();
-  WarpRng rngp; rngp.g = &S.rng; rngp.cs = &S.csp; rngp.lane = lane; rngp.writer = cta == 0;     // proposals (helper, or warp 0 when sequential)
-  WarpRng rngd; rngd.g = &S.rng; rngd.cs = &S.csd; rngd.lane = lane; rngd.writer = cta == 0;     // decisions (warp 0)
-  if (warp == kWorkerWarps) {
-    rngp.enter(step0, 0u); rngp.fill();
-    w_propose(S.tree[0], S.prm, S.tab, rngp, S.sd[0], S.csp, 0, lane);
-    rngp.commit();
+  WarpRng rngp; rngp.g = &S.rng; rngp.cs = &S.csp; rngp.lane = lane; rngp.writer = cta == 0;     // proposal draws
+  WarpRng rngd; rngd.g = &S.rng; rngd.cs = &S.csd; rngd.lane = lane; rngd.writer = cta == 0;     // decision draws
+  if (!is_worker) {
+    if (sequential_rng) {
+      rngp.enter(step0, 0u); rngp.fill();
+      w_propose(S.tree[0], S.prm, S.tab, rngp, S.sd[0], S.csp, 0, lane);
+      rngp.commit();
+    } else w_copy_desc(S.sd[0], descs[0], lane);
   }
   __syncthreads();
+  uint32_t leaf_pack[NQ], aux_pack[NQ];
+  if (is_worker) walk_step<NQ>(S.sd[0], tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
 
-  unsigned int bar_k = 0;
   long long pc[6] = { 0, 0, 0, 0, 0, 0 };
   for (int t = 0; t < T; ++t) {
     const long long c0 = clock64();
@@ -656,52 +803,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     const int nslots = sd.b_nslots;
     const bool two_trees = (kind == 2 || kind == 3);
     const int birth_node = kind == 0 ? sd.b_node : -1;
-    const int birth_var = kind == 0 ? sd.b_var : 0;
-    const uint32_t birth_cut = (uint32_t) sd.b_cut;
-    const int depth_cur = sd.b_cur.pad;
     double* partials = dv.partials + (size_t) (t & 1) * partial_stride;
-    uint32_t leaf_pack[NQ], aux_pack[NQ];
 
     if (is_worker) {
-      // ---- statistics walk (4 observations interleaved); leaf indices are cached for later passes and the update ----
-#pragma unroll
-      for (int j = 0; j < NQ; ++j) {
-        uint32_t lp = 0, ap = 0;
-        if (qidx[j] >= 0) {
-          const int qslot = j * kWorkers + tid;
-          int node[4] = { 0, 0, 0, 0 };
-          for (int lvl = 0; lvl < depth_cur; ++lvl) {
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              const uint32_t tr = sd.b_cur.trav[node[o]];
-              if ((tr >> 16) != 0xFFFFu) {
-                const uint32_t x = (tile[(tr >> 16) * tile_stride + qslot] >> (8 * o)) & 0xFFu;
-                node[o] = (x <= ((tr >> 8) & 0xFFu)) ? node[o] + 1 : (int) (tr & 0xFFu);
-              }
-            }
-          }
-          int aux[4] = { 0, 0, 0, 0 };
-          if (two_trees) {
-            for (int lvl = 0; lvl < depth_cur; ++lvl) {
-#pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                const uint32_t tr = sd.b_prop.trav[aux[o]];
-                if ((tr >> 16) != 0xFFFFu) {
-                  const uint32_t x = (tile[(tr >> 16) * tile_stride + qslot] >> (8 * o)) & 0xFFu;
-                  aux[o] = (x <= ((tr >> 8) & 0xFFu)) ? aux[o] + 1 : (int) (tr & 0xFFu);
-                }
-              }
-            }
-          } else if (birth_node >= 0) {
-            const uint32_t w = tile[birth_var * tile_stride + qslot];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) aux[o] = (((w >> (8 * o)) & 0xFFu) > birth_cut) ? 1 : 0;
-          }
-#pragma unroll
-          for (int o = 0; o < 4; ++o) { lp |= (uint32_t) node[o] << (8 * o); ap |= (uint32_t) aux[o] << (8 * o); }
-        }
-        leaf_pack[j] = lp; aux_pack[j] = ap;
-      }
+      // ---- accumulate (n, sum, sum^2) per statistic slot from the cached leaf indices ----
       const int nchunks = (nslots + kBinSlots - 1) / kBinSlots;
       for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int base = chunk * kBinSlots;
@@ -709,57 +814,44 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         for (int k = 0; k < kmax; ++k) { bin_s[k * kWorkers + tid] = make_double2(0.0, 0.0); bin_n[k * kWorkers + tid] = 0; }
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
-          if (qidx[j] >= 0) {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
+          for (int o = 0; o < 4; ++o) {
+            if ((obs_mask >> (4 * j + o)) & 1u) {
               const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
               const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
               const double pr = R[j][o] + sd.b_cur.val[leaf];
-              int sa = sd.b_cur.slot[leaf];
-              if (leaf == birth_node) sa = L + aux;
-              int sb = two_trees ? (int) sd.b_prop.slot[aux] : 255;
-              if (4 * qidx[j] + o >= n) { sa = 255; sb = 255; }
-              sa -= base; sb -= base;
-              if (sa >= 0 && sa < kmax) {
+              int sa = (leaf == birth_node ? L + aux : (int) sd.b_cur.slot[leaf]) - base;
+              if ((unsigned) sa < (unsigned) kmax) {
                 double2 v = bin_s[sa * kWorkers + tid]; v.x += pr; v.y += pr * pr; bin_s[sa * kWorkers + tid] = v;
                 bin_n[sa * kWorkers + tid] += 1;
               }
-              if (sb >= 0 && sb < kmax) {
-                double2 v = bin_s[sb * kWorkers + tid]; v.x += pr; v.y += pr * pr; bin_s[sb * kWorkers + tid] = v;
-                bin_n[sb * kWorkers + tid] += 1;
+              if (two_trees) {
+                const int sb = (int) sd.b_prop.slot[aux] - base;
+                if ((unsigned) sb < (unsigned) kmax) {
+                  double2 v = bin_s[sb * kWorkers + tid]; v.x += pr; v.y += pr * pr; bin_s[sb * kWorkers + tid] = v;
+                  bin_n[sb * kWorkers + tid] += 1;
+                }
               }
             }
           }
         }
-        // warp reduction of the lane-private bins (fixed order)
-        for (int k0 = 0; k0 < kmax; k0 += 4) {
-          int cnt[4]; double s1[4], s2[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool ok = k0 + k < kmax;
-            double2 v = ok ? bin_s[(k0 + k) * kWorkers + tid] : make_double2(0.0, 0.0);
-            cnt[k] = ok ? bin_n[(k0 + k) * kWorkers + tid] : 0; s1[k] = v.x; s2[k] = v.y;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
-              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
-              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
-            }
-          }
-          if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (k0 + k < kmax) { S.red[warp][3 * (k0 + k)] = (double) cnt[k]; S.red[warp][3 * (k0 + k) + 1] = s1[k]; S.red[warp][3 * (k0 + k) + 2] = s2[k]; }
-          }
-        }
         named_bar_sync(1, kWorkers);
-        if (tid < 3 * kmax) {
-          double acc = 0.0;
+        // row-wise reduction: task r < kmax sums (sum, sum^2) of slot r over the CTA's threads, task kmax + r its counts
+        for (int task = warp; task < 2 * kmax; task += kWorkerWarps) {
+          if (task < kmax) {
+            double a = 0.0, b = 0.0;
 #pragma unroll
-          for (int w = 0; w < kWorkerWarps; ++w) acc += S.red[w][tid];
-          partials[(size_t) (3 * base + tid) * G + cta] = acc;
+            for (int i = 0; i < kWorkerWarps; ++i) { const double2 v = bin_s[task * kWorkers + i * 32 + lane]; a += v.x; b += v.y; }
+            a = w_sum(a); b = w_sum(b);
+            if (lane == 0) { partials[(size_t) (3 * (base + task) + 1) * G + cta] = a; partials[(size_t) (3 * (base + task) + 2) * G + cta] = b; }
+          } else {
+            const int r = task - kmax;
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < kWorkerWarps; ++i) c += bin_n[r * kWorkers + i * 32 + lane];
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) partials[(size_t) (3 * (base + r)) * G + cta] = (double) c;
+          }
         }
         named_bar_sync(1, kWorkers);
       }
@@ -774,7 +866,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         __threadfence();
       }
     } else {
-      // ---- helper warp: persist tree t-1, fetch tree t+1, pre-compute this step's decision draws, propose for t+1 ----
+      // ---- controller warp: fetch tree t+1, pre-compute this step's decision draws, propose for t+1 ----
+      const long long h0 = clock64();
       if (t + 1 < T) {
         const DTree& g = dv.trees[t + 1];
         int nn = g.num_nodes;
@@ -782,24 +875,26 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(tree_next.nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
         __syncwarp();
       }
+      const long long h1 = clock64();
+      rngd.enter(step0 + (unsigned long long) t, 1u);
       if (!sequential_rng) {
-        rngd.enter(step0 + (unsigned long long) t, 1u); rngd.fill();
-        if (t + 1 < T) {
-          rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
-          w_propose(tree_next, S.prm, S.tab, rngp, sd_next, S.csp, t + 1, lane);
-          rngp.commit();
-        }
+        // pre-computed by k_prepare_sweep: this step's decision draws and the next tree's proposal
+        const double2 dz = __ldcg(draws + t * 32 + lane);
+        S.csd.ubuf[lane] = dz.x; S.csd.zbuf[lane] = dz.y;
+        if (lane == 0) S.csd.draw_pos = 0;
+        __syncwarp();
+        const long long h2 = clock64();
+        if (t + 1 < T) w_copy_desc(sd_next, descs[t + 1], lane);
+        if (lane == 0) { S.csd.dbg[4] += h1 - h0; S.csd.dbg[5] += h2 - h1; S.csd.dbg[7] += clock64() - h2; }
       }
     }
-    (void) bar_k;
-    __syncthreads();                                                        // [A] partials complete, next proposal ready
+    __syncthreads();                                                        // [A] partials complete everywhere, next proposal ready
     const long long c2 = clock64();
 
     // ---- every CTA: reduce all partial rows in the same fixed order ----
     for (int v = warp; v < 3 * nslots; v += kSweepWarps) {
       const double* src = partials + (size_t) v * G;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
-      // G <= 160: five predicated loads per lane, issued together
       { int b = lane;       if (b < G) a0 = __ldcg(src + b); }
       { int b = lane + 32;  if (b < G) a1 = __ldcg(src + b); }
       { int b = lane + 64;  if (b < G) a2 = __ldcg(src + b); }
@@ -810,10 +905,11 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       acc = w_sum(acc);
       if (lane == 0) reinterpret_cast<double*>(&S.st[v / 3])[v % 3] = acc;
     }
-    __syncthreads();                                                        // [B]
+    __syncthreads();                                                        // [B] statistics in shared memory
     const long long c3 = clock64();
-    long long c4 = c3;
-    if (warp == 0) {
+    uint32_t leaf_next[NQ], aux_next[NQ];
+    if (!is_worker) {
+      // ---- controller: Metropolis decision + leaf draws for tree t ----
       double* trec = nullptr;
       if (dv.trace != nullptr && cta == 0) {
         unsigned long long k = *dv.trace_len;
@@ -821,51 +917,67 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         __syncwarp();
         if (lane == 0) *dv.trace_len = k + 1;
       }
-      rngd.enter(step0 + (unsigned long long) t, 1u);
       if (sequential_rng) rngd.fill();
       w_decide(tree, S.prm, rngd, sd, S.st, S.upd, S.csd, trec, lane);
       rngd.commit();
-      c4 = clock64();
       if (sequential_rng && t + 1 < T) {
         rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
         w_propose(tree_next, S.prm, S.tab, rngp, sd_next, S.csp, t + 1, lane);
         rngp.commit();
       }
+    } else if (!sequential_rng && t + 1 < T) {
+      // ---- workers, concurrently: walk tree t+1 (independent of this step's decision) ----
+      walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_next, aux_next);
     }
-    __syncthreads();                                                        // [C]
+    __syncthreads();                                                        // [C] decision known
     const long long c5 = clock64();
     if (is_worker) {
       // ---- fit / residual update from the cached leaf indices ----
       const int amode = S.upd.mode, unode = S.upd.node;
+      if (amode == 0) {
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) {
+        for (int j = 0; j < NQ; ++j)
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
-          const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
-          int nl;
-          if (amode == 3) nl = aux;
-          else if (amode == 1 && leaf == unode) nl = unode + 1 + aux;
-          else nl = S.upd.remap[leaf];
-          R[j][o] += S.upd.val_old[leaf] - S.upd.val_new[nl];
+          for (int o = 0; o < 4; ++o) R[j][o] += S.upd.delta[(leaf_pack[j] >> (8 * o)) & 0xFF];
+      } else {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
+            const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
+            int nl;
+            if (amode == 3) nl = aux;
+            else if (amode == 1 && leaf == unode) nl = unode + 1 + aux;
+            else nl = S.upd.remap[leaf];
+            R[j][o] += S.upd.val_old[leaf] - S.upd.val_new[nl];
+          }
+        }
+      }
+      if (t + 1 < T) {
+        if (sequential_rng) walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
+        else {
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) { leaf_pack[j] = leaf_next[j]; aux_pack[j] = aux_next[j]; }
         }
       }
     } else if (cta == 0) {
-      // helper of CTA 0 persists the tree that was just decided
+      // controller of CTA 0 persists the tree that was just decided
       DTree& g = dv.trees[t];
       int nn = tree.num_nodes;
       if (lane == 0) g.num_nodes = nn;
       for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(g.nodes)[i] = reinterpret_cast<const uint32_t*>(tree.nodes)[i];
     }
-    __syncthreads();                                                        // [D] upd / tree buffers free again
-    if (cta == 0 && tid == 0) { pc[1] += c2 - c0 - 0; pc[2] += c3 - c2; pc[3] += c4 - c3; pc[4] += c5 - c4; pc[5] += clock64() - c5; }
+    __syncthreads();                                                        // [D] upd / tree / descriptor buffers free again
+    if (cta == 0 && tid == 0) { pc[1] += c2 - c0; pc[2] += c3 - c2; pc[3] += c5 - c3; pc[5] += clock64() - c5; }
   }
 
   // ---- write back ----
 #pragma unroll
-  for (int j = 0; j < NQ; ++j) if (qidx[j] >= 0) {
-    *reinterpret_cast<double2*>(dv.R + 4 * qidx[j]) = make_double2(R[j][0], R[j][1]);
-    *reinterpret_cast<double2*>(dv.R + 4 * qidx[j] + 2) = make_double2(R[j][2], R[j][3]);
+  for (int j = 0; j < NQ; ++j) if ((valid_mask >> j) & 1u) {
+    const long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
+    *reinterpret_cast<double2*>(dv.R + 4 * q) = make_double2(R[j][0], R[j][1]);
+    *reinterpret_cast<double2*>(dv.R + 4 * q + 2) = make_double2(R[j][2], R[j][3]);
   }
   if (cta == 0 && tid == 0) {
     RngState out = S.rng;
@@ -875,9 +987,13 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     dv.params->step_id = step0 + (unsigned long long) T;
     dv.desc->a_valid = 0;
     if (dv.prof != nullptr) {
-      // [0] pass (CTA 0), [1] pass + barrier wait, [2] reduce, [3] decide, [4] sequential-mode proposal, [5] update, [7] steps
+      // [0] accumulate + CTA reduction (CTA 0), [1] ... + grid barrier + controller wait, [2] statistics reduce,
+      // [3] decision (overlapped with the next walk), [5] update, [7] steps
       for (int i = 0; i < 6; ++i) dv.prof[i] += (unsigned long long) pc[i];
       dv.prof[7] += (unsigned long long) T;
+      // [8..11] decision: slot summaries + accept, structure, leaf draws, update descriptor; [12..15] controller before the
+      // barrier: tree fetch, decision-draw prefill, proposal-draw prefill, proposal
+      for (int i = 0; i < 8; ++i) dv.prof[8 + i] += (unsigned long long) S.csd.dbg[i];
     }
   }
 }

@@ -163,12 +163,15 @@ class GpuBart:
         return ms.value
 
     def profile(self, reset=True):
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 16)()
         _lib.check(self.L.gpubart_get_profile(self.h, out, int(reset)))
         v = [int(x) for x in out]
         steps = max(1, v[7])
-        names = ["pass", "reduce", "tree_load_or_barrier", "decide", "writeback_or_update", "propose", "publish"]
-        return {"steps": v[7], "cycles_per_step": {k: v[i] / steps for i, k in enumerate(names)}}
+        names = ["p0", "p1", "p2", "p3", "p4", "p5", "p6"]
+        fine = ["dec_summaries_accept", "dec_structure", "dec_leaf_draws", "dec_update_desc", "ctl_tree_fetch", "ctl_fill_decision_draws",
+                "ctl_fill_proposal_draws", "ctl_propose"]
+        return {"steps": v[7], "cycles_per_step": {k: v[i] / steps for i, k in enumerate(names)},
+                "controller_cycles_per_step": {k: v[8 + i] / steps for i, k in enumerate(fine)}}
 
     def num_tree_steps(self):
         k = C.c_int64(0)
