@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--trees", type=int, default=200)
-    ap.add_argument("--adapt", type=int, default=40, help="adaptation sweeps before adaptation is disengaged (untimed)")
+    ap.add_argument("--adapt", type=int, default=200, help="adaptation sweeps before adaptation is disengaged (untimed; >= 150 so that the metric windows of Stan run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
@@ -143,7 +143,8 @@ def cpu_baseline(args, pr, budget_s):
     dt = time.time() - t0
     return {"value": k / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "CPU restatement of the reference algorithm (oracle/, not the reference binary): same n=%d, %d trees, "
-                      "1 chain on 1 thread, %d full sweeps after 1 warm-up sweep (setup %.1f s excluded)" % (args.n, args.trees, k, t_create)}
+                      "1 chain on 1 thread, %d full sweeps after 1 warm-up sweep (setup %.1f s excluded); these are early, "
+                      "un-adapted sweeps with few leapfrogs each, i.e. the CPU's best case" % (args.n, args.trees, k, t_create)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -244,26 +245,16 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     _lib.check(L.s4b_set_stream(stream.cuda_stream))
 
-    def barrier():
-        if world > 1:
-            t = torch.zeros(1, device="cuda")
-            dist.all_reduce(t)
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world > 1:
-            t = torch.tensor([x], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return x
+    from stan4bart_b200.dist import barrier, chain_seed, max_over_ranks
 
     pr = make_problem(args)
     sd = pr["stan_data"]
     n, T = args.n, args.trees
-    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=True, seed=12345 + rank)
-    s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=1000 + rank), warmup=args.adapt, iter_=args.adapt + args.steps,
+    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=True, seed=chain_seed(12345, rank))
+    s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=chain_seed(1000, rank)), warmup=args.adapt, iter_=args.adapt + args.steps,
                 keep_fits=False)
     bart = s.bart()
+    glmm = s.glmm()
     s.run(args.adapt, True, results=False)
     s.disengage_adaptation()
     W, K = max(3, args.warmup), args.steps
@@ -272,6 +263,7 @@ def run_ours(args):
     s.run(W, False, results=False)
     bart.tree_step_ms(reset=True)
     clocks = ClockSampler(local_rank)
+    passes0 = glmm.num_device_passes()
     barrier()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,30 +277,35 @@ def run_ours(args):
     clocks.stop_flag.set()
     ms = max_over_ranks(float(ev0.elapsed_time(ev1)))
     stats = s.last_run_stats()
+    glmm_passes = glmm.num_device_passes() - passes0
     sweep_ms = bart.tree_step_ms(reset=True)
     names = sd.param_names()
     n_leapfrog = float(out["stan"][names.index("n_leapfrog__")][-1])
     value = world * K / (ms / 1000.0)
 
-    # ---- roofline of the dominant kernel (k_tree_step) ----
+    # ---- roofline of the dominant kernel ----
     trees = bart.trees()
     lv = avg_levels(trees, n)
-    bytes_per_obs = 16.0 + 2.0 * lv           # R read + write, one u8 per level for the update walk and the statistics walk
-    launch_ms = sweep_ms / (K * T)             # CUDA-event time of the sweep graphs / tree steps (includes propose + epilogue)
+    bytes_per_obs = 16.0 + 2.0 * lv           # per tree x observation: R read + write, one u8 per level for each of the two walks
     peak, peak_src = measured_peak()
-    achieved = bytes_per_obs * n / (launch_ms * 1e-3) / 1e9
+    persistent = bart.sweep_mode() == 2
+    launch_ms = sweep_ms / K if persistent else sweep_ms / (K * T)    # CUDA events around the sweep launches on the launching stream
+    units_per_launch = (T if persistent else 1) * n
+    achieved = bytes_per_obs * units_per_launch / (launch_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_tree_step_dram_bytes_per_launch")
+            traffic = json.load(f).get("k_sweep_dram_bytes_per_launch" if persistent else "k_tree_step_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_tree_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_obs": bytes_per_obs, "avg_tree_levels": lv,
-                "launch_us": launch_ms * 1e3,
-                "achieved_survey_model_gbs": 29.0 * n / (launch_ms * 1e-3) / 1e9,
-                "note": "bytes are served largely from L2 at this n (R + binned X = 17 MB); sequential tree steps make the "
-                        "kernel latency-bound, see DESIGN.md"}
+    roofline = {"bound": "hbm", "kernel": "k_sweep<4> (one launch = one 200-tree sweep)" if persistent else "k_tree_step (one launch = one tree)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_tree_obs": bytes_per_obs, "avg_tree_levels": lv,
+                "launch_us": launch_ms * 1e3, "tree_step_us": sweep_ms / (K * T) * 1e3,
+                "achieved_survey_model_gbs": 29.0 * units_per_launch / (launch_ms * 1e-3) / 1e9,
+                "note": "algorithmic bytes are what a per-tree streaming pass must move; the persistent kernel keeps residuals in registers "
+                        "and predictors in shared memory, so DRAM traffic per launch is ~17 MB and the binding limit is the latency of "
+                        "200 sequential reduce + Metropolis decisions, not HBM (DESIGN.md section 4)"}
 
     # ---- end-to-end leg through the C ABI with host buffers ----
     h2d, d2h = s.set_host_plumbing(True)
@@ -326,16 +323,18 @@ def run_ours(args):
            "note": "s4b_sampler_run with host result buffers (train + test fits, Stan row) and every N-vector of the sweep "
                    "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors"}
 
-    # kernels launched inside the timed region (per sweep: propose + T tree steps + epilogue + epoch bump + test fits,
-    # 2 offset kernels, parametric mean, 2 residual refreshes, 3 running-mean accumulations, one pass per gradient)
-    launches = K * (T + 3 + 1 + 2 + 1 + 2 + 3) + stats["grad_evals"]
+    # kernels launched inside the timed region, per sweep: k_prepare_sweep + k_sweep + epilogue + epoch bump (BART),
+    # 2 offset kernels, parametric mean, 2 residual refreshes, 3 running-mean accumulations, plus the GLMM data passes
+    per_sweep_bart = 4 if bart.sweep_mode() == 2 else T + 3
+    launches = K * (per_sweep_bart + 2 + 1 + 2 + 3) + glmm_passes
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
             "breakdown": {"ms_stan_block": stats["ms_stan"] / K, "ms_bart_block": stats["ms_bart"] / K, "grad_evals_per_sweep": stats["grad_evals"] / K,
-                          "n_leapfrog_last": n_leapfrog, "wall_s": t_wall, "tree_step_us": launch_ms * 1e3}}
+                          "glmm_device_passes_per_sweep": glmm_passes / K, "glmm_mode": glmm.mode(), "bart_sweep_mode": bart.sweep_mode(),
+                          "n_leapfrog_last": n_leapfrog, "wall_s": t_wall, "tree_step_us": sweep_ms / (K * T) * 1e3}}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, pr, args.cpu_budget_s)

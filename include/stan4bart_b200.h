@@ -120,8 +120,8 @@ int gpubart_num_tree_steps(gpubart_fit* fit, int64_t* out);
 int gpubart_tree_step_ms(gpubart_fit* fit, int reset, double* ms);
 /* SM-cycle counters of the controller phases of k_tree_step: [0] pass of the last block, [1] partial reduction, [2] tree load,
  * [3] MH decision + leaf draws, [4] write-back + next tree load, [5] next proposal / update, [6] descriptor publish, [7] steps counted,
- * [8..15] finer controller counters of the persistent kernel (see sweep_kernel.cuh); out16 has 16 entries */
-int gpubart_get_profile(gpubart_fit* fit, uint64_t* out16, int reset);
+ * [8..15] finer controller counters of the persistent kernel (see sweep_kernel.cuh); [16..19] worker sub-phases; out24 has 24 entries */
+int gpubart_get_profile(gpubart_fit* fit, uint64_t* out24, int reset);
 
 /* ------------------------------------------------------------------ glmm_* */
 typedef struct glmm_model glmm_model;
@@ -141,6 +141,12 @@ int glmm_parametric_mean(glmm_model* m, const double* constrained, double* out, 
 /* device data terms only: S = sum e^2, X'e, Z'e */
 int glmm_data_terms(glmm_model* m, const double* beta, const double* b, double* S, double* gbeta, double* gb);
 int glmm_num_grad_evals(glmm_model* m, int64_t* out);
+/* 0: one device pass per evaluation (the literal north-star path); 1 (default when K + q <= 512): one device pass per Gibbs
+ * sweep anchors an exact quadratic expansion of the data terms in (beta, b), every further evaluation of the sweep is O((K+q)^2)
+ * on the host */
+int glmm_set_mode(glmm_model* m, int mode);
+int glmm_get_mode(glmm_model* m, int* mode);
+int glmm_num_device_passes(glmm_model* m, int64_t* out);
 
 /* ------------------------------------------------------------------ s4b_sampler_* */
 typedef struct s4b_sampler s4b_sampler;

@@ -656,7 +656,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   dalloc(&d_stats_out_, (size_t) 3 * S4B_MAX_SLOTS);
   S4B_CUDA(cudaMalloc(&d_desc_, sizeof(StepDesc))); S4B_CUDA(cudaMemset(d_desc_, 0, sizeof(StepDesc)));
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
-  S4B_CUDA(cudaMalloc(&d_prof_, sizeof(unsigned long long) * 16)); S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 16));
+  S4B_CUDA(cudaMalloc(&d_prof_, sizeof(unsigned long long) * 24)); S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 24));
   S4B_CUDA(cudaMalloc(&d_trace_len_, sizeof(unsigned long long))); S4B_CUDA(cudaMemset(d_trace_len_, 0, sizeof(unsigned long long)));
   S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
   // trees: single root each
@@ -717,7 +717,7 @@ template <int NQ>
 static size_t sweep_smem_bytes(int p)
 {
   size_t base = ((sizeof(SweepSmem) + 15) / 16) * 16;
-  size_t bins = (size_t) kBinSlots * kWorkers * (sizeof(double2) + sizeof(int));
+  size_t bins = (size_t) (kBinSlots + 1) * kWorkers * (sizeof(double2) + sizeof(int));
   size_t tile = (size_t) p * NQ * kWorkers * sizeof(uint32_t);
   return base + bins + tile;
 }
@@ -992,8 +992,8 @@ void BartFit::run_sweeps()
 void BartFit::get_profile(unsigned long long* out8, bool reset)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));
-  S4B_CUDA(cudaMemcpy(out8, d_prof_, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
-  if (reset) S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 16));
+  S4B_CUDA(cudaMemcpy(out8, d_prof_, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost));
+  if (reset) S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 24));
 }
 
 double BartFit::tree_step_ms(bool reset)

@@ -80,7 +80,7 @@ class BartFit {
   double tree_step_ms(bool reset);
   // cycles spent by the last block in: [0] its own pass, [1] partial reduction, [2] tree load, [3] decision + leaf draws,
   // [4] write-back + next tree load, [5] proposal, [6] descriptor publish, [7] number of steps
-  void get_profile(unsigned long long* out16, bool reset);
+  void get_profile(unsigned long long* out24, bool reset);
 
  private:
   BartDev dev() const;

@@ -201,6 +201,20 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream) : stream_(stre
   dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) (nb + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
   S4B_CUDA(cudaMallocHost(&h_pinned_, sizeof(double) * 2 * ((size_t) nb + 1)));
+  // Gram matrix G = [X Z]'[X Z] (host, once): the model matrices never change during sampling
+  if (nb > 0 && nb <= 512) {
+    gram_.assign((size_t) nb * nb, 0.0);
+    std::vector<int> cols((size_t) K_ + slots_);
+    std::vector<double> vals((size_t) K_ + slots_);
+    for (long long i = 0; i < N_; ++i) {
+      int m = 0;
+      for (int k = 0; k < K_; ++k) { cols[(size_t) m] = k; vals[(size_t) m] = d.X[(size_t) k * N_ + i]; ++m; }
+      for (int z = d.u[i]; z < d.u[i + 1]; ++z) { cols[(size_t) m] = K_ + d.v[z]; vals[(size_t) m] = d.w[z]; ++m; }
+      for (int a = 0; a < m; ++a) for (int bb = 0; bb < m; ++bb) gram_[(size_t) cols[(size_t) a] * nb + cols[(size_t) bb]] += vals[(size_t) a] * vals[(size_t) bb];
+    }
+    theta0_.assign((size_t) nb, 0.0); g0_.assign((size_t) nb, 0.0);
+    mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : 1;
+  }
   refresh_r();
   S4B_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -211,8 +225,46 @@ GlmmModel::~GlmmModel()
   cudaFree(d_theta_); cudaFree(d_partials_); cudaFree(d_result_); cudaFree(d_ticket_); cudaFreeHost(h_pinned_);
 }
 
+void GlmmModel::set_mode(int mode)
+{
+  if (mode != 0 && mode != 1) throw std::invalid_argument("glmm mode must be 0 (pass per evaluation) or 1 (pass per sweep)");
+  if (mode == 1 && gram_.empty()) throw std::invalid_argument("glmm: sweep-level expansion unavailable (K + q > 512)");
+  mode_ = mode; expansion_valid_ = false;
+}
+
+void GlmmModel::data_terms_auto(const double* beta, const double* b, double* S, double* gbeta, double* gb)
+{
+  if (mode_ == 0) { data_terms(beta, b, S, gbeta, gb); return; }
+  const int nb = K_ + q_;
+  if (!expansion_valid_) {
+    // first evaluation after the residual changed: one device pass anchors the expansion at this point
+    data_terms(beta, b, &S0_, g0_.data(), g0_.data() + K_);
+    for (int k = 0; k < K_; ++k) theta0_[(size_t) k] = beta[k];
+    for (int k = 0; k < q_; ++k) theta0_[(size_t) (K_ + k)] = b[k];
+    expansion_valid_ = true;
+    *S = S0_;
+    for (int k = 0; k < K_; ++k) gbeta[k] = g0_[(size_t) k];
+    for (int k = 0; k < q_; ++k) gb[k] = g0_[(size_t) (K_ + k)];
+    return;
+  }
+  double dl[512], Gd[512];
+  for (int k = 0; k < K_; ++k) dl[k] = beta[k] - theta0_[(size_t) k];
+  for (int k = 0; k < q_; ++k) dl[K_ + k] = b[k] - theta0_[(size_t) (K_ + k)];
+  double quad = 0.0, lin = 0.0;
+  for (int a = 0; a < nb; ++a) {
+    const double* row = gram_.data() + (size_t) a * nb;
+    double acc = 0.0;
+    for (int c = 0; c < nb; ++c) acc += row[c] * dl[c];
+    Gd[a] = acc; quad += dl[a] * acc; lin += g0_[(size_t) a] * dl[a];
+  }
+  *S = S0_ - 2.0 * lin + quad;
+  for (int k = 0; k < K_; ++k) gbeta[k] = g0_[(size_t) k] - Gd[k];
+  for (int k = 0; k < q_; ++k) gb[k] = g0_[(size_t) (K_ + k)] - Gd[K_ + k];
+}
+
 void GlmmModel::refresh_r()
 {
+  expansion_valid_ = false;
   int grid = (int) std::max<long long>(1, std::min<long long>((N_ + 255) / 256, 148 * 8));
   k_glmm_residual<<<grid, 256, 0, stream_>>>(N_, d_y_, d_offset_, d_r_);
   S4B_CUDA(cudaGetLastError());
@@ -225,6 +277,7 @@ void GlmmModel::set_response_device(const double* d_y) { S4B_CUDA(cudaMemcpyAsyn
 
 void GlmmModel::data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb)
 {
+  ++num_passes_;
   const int nb = K_ + q_;
   double* h_theta = h_pinned_;
   double* h_res = h_pinned_ + nb + 1;
@@ -330,7 +383,7 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
 
   std::vector<double> gbeta((size_t) K_ + 1), gb((size_t) q_ + 1);
   double S = 0.0;
-  data_terms(P.beta.data(), P.b.data(), &S, gbeta.data(), gb.data());
+  data_terms_auto(P.beta.data(), P.b.data(), &S, gbeta.data(), gb.data());
   const double sigma = has_aux_ ? P.aux : 1.0;
   lp += -0.5 * S / (sigma * sigma) - N * std::log(sigma) - N * kHalfLog2Pi;
 

@@ -46,7 +46,14 @@ class GlmmModel {
   // device result; beta / b are host pointers
   void parametric_mean_device(const double* beta, const double* b, double* d_out, bool include_fixed, bool include_random);
   void parametric_mean_host(const double* constrained, double* out, bool include_fixed, bool include_random);
+  // device pass: S = sum e^2, X'e, Z'e at (beta, b)
   void data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb);
+  // the same three quantities through the sweep-level expansion (mode 1) or the device pass (mode 0)
+  void data_terms_auto(const double* beta, const double* b, double* S, double* gbeta, double* gb);
+  // 0: one device pass per evaluation; 1: one device pass per Gibbs sweep + exact quadratic expansion (default when K + q is small)
+  void set_mode(int mode);
+  int mode() const { return mode_; }
+  long long num_device_passes() const { return num_passes_; }
   long long num_grad_evals() const { return num_grad_; }
   cudaStream_t stream() const { return stream_; }
 
@@ -65,7 +72,13 @@ class GlmmModel {
   int slots_ = 0, grid_ = 1, block_ = 256;
   unsigned int ones_mask_ = 0;
   size_t smem_bytes_ = 0;
-  long long num_grad_ = 0;
+  long long num_grad_ = 0, num_passes_ = 0;
+  // sweep-level sufficient statistics: with e = r - A theta (A = [X Z]) the data terms are an exact quadratic in theta,
+  //   S(theta0 + d) = S0 - 2 g0'd + d'G d,   A'e(theta0 + d) = g0 - G d,   G = A'A (fixed), (S0, g0) from one pass at theta0
+  int mode_ = 0;
+  bool expansion_valid_ = false;
+  std::vector<double> gram_, theta0_, g0_;
+  double S0_ = 0.0;
 
   double *d_X_ = nullptr, *d_y_ = nullptr, *d_offset_ = nullptr, *d_r_ = nullptr, *d_zval_ = nullptr;
   int* d_zidx_ = nullptr;

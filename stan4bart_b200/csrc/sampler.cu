@@ -298,6 +298,9 @@ int glmm_write_array(glmm_model* m, const double* q, double* out) { S4B_API_BEGI
 int glmm_parametric_mean(glmm_model* m, const double* c, double* out, int f, int r) { S4B_API_BEGIN S4B_REQUIRE(m && c && out); m->m->parametric_mean_host(c, out, f != 0, r != 0); S4B_API_END }
 int glmm_data_terms(glmm_model* m, const double* beta, const double* b, double* S, double* gbeta, double* gb)
 { S4B_API_BEGIN S4B_REQUIRE(m && S && gbeta && gb); m->m->data_terms(beta, b, S, gbeta, gb); S4B_API_END }
+int glmm_set_mode(glmm_model* m, int mode) { S4B_API_BEGIN S4B_REQUIRE(m); m->m->set_mode(mode); S4B_API_END }
+int glmm_get_mode(glmm_model* m, int* mode) { S4B_API_BEGIN S4B_REQUIRE(m && mode); *mode = m->m->mode(); S4B_API_END }
+int glmm_num_device_passes(glmm_model* m, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(m && out); *out = m->m->num_device_passes(); S4B_API_END }
 int glmm_num_grad_evals(glmm_model* m, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(m && out); *out = m->m->num_grad_evals(); S4B_API_END }
 
 // ---- sampler ----
@@ -331,7 +334,7 @@ int s4b_sampler_get_means(s4b_sampler* s, double* mt, double* mte, double* mp, i
 { S4B_API_BEGIN S4B_REQUIRE(s); long long k = 0; s->s->means(mt, mte, mp, &k); if (nd) *nd = k; S4B_API_END }
 int s4b_sampler_set_host_plumbing(s4b_sampler* s, int on, int64_t* h2d, int64_t* d2h)
 { S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->set_host_plumbing(on != 0, &a, &b); if (h2d) *h2d = a; if (d2h) *d2h = b; S4B_API_END }
-int gpubart_get_profile(gpubart_fit* f, uint64_t* out16, int reset) { S4B_API_BEGIN S4B_REQUIRE(f && out16); f->fit->get_profile((unsigned long long*) out16, reset != 0); S4B_API_END }
+int gpubart_get_profile(gpubart_fit* f, uint64_t* out24, int reset) { S4B_API_BEGIN S4B_REQUIRE(f && out24); f->fit->get_profile((unsigned long long*) out24, reset != 0); S4B_API_END }
 int gpubart_tree_step_ms(gpubart_fit* f, int reset, double* ms) { S4B_API_BEGIN S4B_REQUIRE(f && ms); *ms = f->fit->tree_step_ms(reset != 0); S4B_API_END }
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* ng, int64_t* ns)
 { S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->last_run_stats(ms_stan, ms_bart, &a, &b); if (ng) *ng = a; if (ns) *ns = b; S4B_API_END }

@@ -7,9 +7,9 @@
 //     their binned predictors in a shared-memory tile (filled once per sweep with coalesced 32-bit loads);
 //     inside the 200-tree loop nothing is read from global memory except the tiny per-CTA partials;
 //   * per tree step
-//       workers : walk the tree for 4 observations at a time (shared memory only, 4-way ILP), accumulate
-//                 (n, sum, sum^2) per leaf slot in registers, warp-shuffle + fixed-order CTA reduction, write
-//                 one row of partials, grid barrier;
+//       workers : accumulate (n, sum, sum^2) per leaf slot in lane-private shared-memory bins keyed by the cached leaf
+//                 index (no atomics, branch-free), fixed-order row reduction, one row of partials, grid barrier; the
+//                 walk of the NEXT tree (shared memory only, 4-way ILP) overlaps the controller's decision;
 //       helper  : meanwhile fetches the next tree, pre-computes the decision draws of this step and draws
 //                 the PROPOSAL OF THE NEXT TREE (keyed RNG substreams make it independent of this step);
 //       all CTAs: reduce all partial rows in the same fixed order and run the same warp-parallel Metropolis
@@ -27,7 +27,7 @@ constexpr int kWorkers = 480;               // 15 worker warps + 1 helper warp =
 constexpr int kWorkerWarps = kWorkers / 32;
 constexpr int kSweepBlock = kWorkers + 32;     // + helper warp
 constexpr int kSweepWarps = kSweepBlock / 32;
-constexpr int kBinSlots = 8;                   // lane-private shared-memory bins per thread and pass
+constexpr int kBinSlots = 8;                   // lane-private shared-memory bin rows per pass (+ 1 trash row)
 constexpr int kLogTab = 1024;
 
 // host-computed tables (glibc log, so they are bit-identical to the CPU oracle's calls):
@@ -730,8 +730,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
   // lane-private statistic bins: [slot][thread] -> (sum, sum^2) and count; no atomics, no bank conflicts
   double2* bin_s = reinterpret_cast<double2*>(smem_raw + ((sizeof(SweepSmem) + 15) / 16) * 16);
-  int* bin_n = reinterpret_cast<int*>(bin_s + kBinSlots * kWorkers);
-  uint32_t* tile = reinterpret_cast<uint32_t*>(bin_n + kBinSlots * kWorkers);                          // [p][NQ * kWorkers]
+  int* bin_n = reinterpret_cast<int*>(bin_s + (kBinSlots + 1) * kWorkers);
+  uint32_t* tile = reinterpret_cast<uint32_t*>(bin_n + (kBinSlots + 1) * kWorkers);                    // [p][NQ * kWorkers]
   constexpr int tile_stride = NQ * kWorkers;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -792,6 +792,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   if (is_worker) walk_step<NQ>(S.sd[0], tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
 
   long long pc[6] = { 0, 0, 0, 0, 0, 0 };
+  long long pw[4] = { 0, 0, 0, 0 };     // worker sub-phases (CTA 0, thread 0): zero bins, accumulate, wait + row reduce, second barrier
   for (int t = 0; t < T; ++t) {
     const long long c0 = clock64();
     StepDesc& sd = S.sd[t & 1];
@@ -811,30 +812,57 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int base = chunk * kBinSlots;
         const int kmax = min(kBinSlots, nslots - base);
+        const long long w0 = clock64();
         for (int k = 0; k < kmax; ++k) { bin_s[k * kWorkers + tid] = make_double2(0.0, 0.0); bin_n[k * kWorkers + tid] = 0; }
+        const long long w1 = clock64();
+        // branch-free: every observation adds into exactly one bin row (row kBinSlots is a trash row for padding and for
+        // slots outside this pass); loads first (independent), then the read-modify-write chain
+        if (!two_trees) {
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
+          for (int j = 0; j < NQ; ++j) {
+            double pr[4]; int row[4];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            if ((obs_mask >> (4 * j + o)) & 1u) {
+            for (int o = 0; o < 4; ++o) {
               const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
               const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
-              const double pr = R[j][o] + sd.b_cur.val[leaf];
-              int sa = (leaf == birth_node ? L + aux : (int) sd.b_cur.slot[leaf]) - base;
-              if ((unsigned) sa < (unsigned) kmax) {
-                double2 v = bin_s[sa * kWorkers + tid]; v.x += pr; v.y += pr * pr; bin_s[sa * kWorkers + tid] = v;
-                bin_n[sa * kWorkers + tid] += 1;
-              }
-              if (two_trees) {
-                const int sb = (int) sd.b_prop.slot[aux] - base;
-                if ((unsigned) sb < (unsigned) kmax) {
-                  double2 v = bin_s[sb * kWorkers + tid]; v.x += pr; v.y += pr * pr; bin_s[sb * kWorkers + tid] = v;
-                  bin_n[sb * kWorkers + tid] += 1;
-                }
-              }
+              pr[o] = R[j][o] + sd.b_cur.val[leaf];
+              const int sa = (leaf == birth_node ? L + aux : (int) sd.b_cur.slot[leaf]) - base;
+              row[o] = ((unsigned) sa < (unsigned) kmax && ((obs_mask >> (4 * j + o)) & 1u)) ? sa : kBinSlots;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int idx = row[o] * kWorkers + tid;
+              double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+              bin_n[idx] += 1;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) {
+            double pr[4]; int row[4], row2[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
+              const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
+              pr[o] = R[j][o] + sd.b_cur.val[leaf];
+              const bool ok = (obs_mask >> (4 * j + o)) & 1u;
+              const int sa = (int) sd.b_cur.slot[leaf] - base;
+              const int sb = (int) sd.b_prop.slot[aux] - base;
+              row[o] = ((unsigned) sa < (unsigned) kmax && ok) ? sa : kBinSlots;
+              row2[o] = ((unsigned) sb < (unsigned) kmax && ok) ? sb : kBinSlots;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              int idx = row[o] * kWorkers + tid;
+              double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+              bin_n[idx] += 1;
+              idx = row2[o] * kWorkers + tid;
+              v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+              bin_n[idx] += 1;
             }
           }
         }
+        const long long w2 = clock64();
         named_bar_sync(1, kWorkers);
         // row-wise reduction: task r < kmax sums (sum, sum^2) of slot r over the CTA's threads, task kmax + r its counts
         for (int task = warp; task < 2 * kmax; task += kWorkerWarps) {
@@ -853,7 +881,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             if (lane == 0) partials[(size_t) (3 * (base + r)) * G + cta] = (double) c;
           }
         }
-        named_bar_sync(1, kWorkers);
+        const long long w3 = clock64();
+        if (chunk + 1 < nchunks) named_bar_sync(1, kWorkers);        // the bins are reused by the next pass
+        if (tid == 0) { pw[0] += w1 - w0; pw[1] += w2 - w1; pw[2] += w3 - w2; pw[3] += clock64() - w3; }
       }
       // ---- arrive at the grid barrier and wait for every CTA's partial row ----
       if (tid == 0) {
@@ -994,6 +1024,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       // [8..11] decision: slot summaries + accept, structure, leaf draws, update descriptor; [12..15] controller before the
       // barrier: tree fetch, decision-draw prefill, proposal-draw prefill, proposal
       for (int i = 0; i < 8; ++i) dv.prof[8 + i] += (unsigned long long) S.csd.dbg[i];
+      for (int i = 0; i < 4; ++i) dv.prof[16 + i] += (unsigned long long) pw[i];
     }
   }
 }

@@ -163,7 +163,7 @@ class GpuBart:
         return ms.value
 
     def profile(self, reset=True):
-        out = (C.c_uint64 * 16)()
+        out = (C.c_uint64 * 24)()
         _lib.check(self.L.gpubart_get_profile(self.h, out, int(reset)))
         v = [int(x) for x in out]
         steps = max(1, v[7])
@@ -171,7 +171,8 @@ class GpuBart:
         fine = ["dec_summaries_accept", "dec_structure", "dec_leaf_draws", "dec_update_desc", "ctl_tree_fetch", "ctl_fill_decision_draws",
                 "ctl_fill_proposal_draws", "ctl_propose"]
         return {"steps": v[7], "cycles_per_step": {k: v[i] / steps for i, k in enumerate(names)},
-                "controller_cycles_per_step": {k: v[8 + i] / steps for i, k in enumerate(fine)}}
+                "controller_cycles_per_step": {k: v[8 + i] / steps for i, k in enumerate(fine)},
+                "worker_cycles_per_step": {k: v[16 + i] / steps for i, k in enumerate(["zero_bins", "accumulate", "barrier_and_row_reduce", "second_barrier"])}}
 
     def num_tree_steps(self):
         k = C.c_int64(0)
@@ -236,6 +237,19 @@ class GlmmModel:
         k = C.c_int64(0)
         _lib.check(self.L.glmm_num_grad_evals(self.h, C.byref(k)))
         return int(k.value)
+
+    def num_device_passes(self):
+        k = C.c_int64(0)
+        _lib.check(self.L.glmm_num_device_passes(self.h, C.byref(k)))
+        return int(k.value)
+
+    def set_mode(self, mode):
+        _lib.check(self.L.glmm_set_mode(self.h, int(mode)))
+
+    def mode(self):
+        m = C.c_int(0)
+        _lib.check(self.L.glmm_get_mode(self.h, C.byref(m)))
+        return m.value
 
 
 class Sampler:

@@ -12,10 +12,13 @@ from stan4bart_b200.sampler import GlmmModel
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[5:-5])
-def test_gpu_matches_golden(path):
+def test_gpu_matches_golden(path, mode):
     sd, c = load_glmm_case(path)
     m = GlmmModel(sd)
+    if sd.K + sd.q > 0:
+        m.set_mode(mode)
     m.set_offset(np.asarray(c["offset"]))
     assert m.d == len(c["q"][0])
     for q, lp, grad, wa in zip(c["q"], c["lp"], c["grad"], c["write_array"]):
@@ -48,6 +51,32 @@ def test_gpu_matches_oracle_on_friedman(n, binary):
         assert rel_err(mo.parametric_mean(wa), mg.parametric_mean(wa), scale=1.0) <= 1e-12
         assert rel_err(mo.parametric_mean(wa, True, False), mg.parametric_mean(wa, True, False), scale=1.0) <= 1e-12
         assert rel_err(mo.parametric_mean(wa, False, True), mg.parametric_mean(wa, False, True), scale=1.0) <= 1e-12
+
+
+def test_sweep_level_expansion_equals_per_evaluation_pass():
+    """Mode 1 (one device pass per sweep + exact quadratic expansion) against mode 0 (a pass per evaluation),
+    near the anchor point (NUTS-sized moves) and far from it."""
+    pr = friedman_problem(50000, seed=11)
+    sd = pr["stan_data"]
+    rng = np.random.default_rng(1)
+    m0, m1 = GlmmModel(sd), GlmmModel(sd)
+    m0.set_mode(0); m1.set_mode(1)
+    off = rng.standard_normal(sd.N)
+    m0.set_offset(off); m1.set_offset(off)
+    q0 = rng.uniform(-0.5, 0.5, m0.d)
+    passes0 = m1.num_device_passes()
+    for scale in (0.0, 1e-4, 1e-2, 1.0):
+        for _ in range(3):
+            q = q0 + scale * rng.standard_normal(m0.d)
+            la, ga, sa = m0.log_prob_grad(q)
+            lb, gb, sb = m1.log_prob_grad(q)
+            assert sa == sb == 0
+            assert abs(la - lb) <= 1e-12 * abs(la)
+            assert rel_err(ga, gb, scale=np.abs(ga) + 1e-9 * np.max(np.abs(ga))) <= REL_TOL
+    assert m1.num_device_passes() == passes0 + 1          # one pass for the whole "sweep"
+    m1.set_offset(off + 0.1)                              # new residual => new anchor
+    m1.log_prob_grad(q0); m1.log_prob_grad(q0 + 0.01)
+    assert m1.num_device_passes() == passes0 + 2
 
 
 def test_data_terms_linearity_at_scale():
