@@ -58,36 +58,56 @@ def make_problem(args):
 
 
 # ------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.stop_flag = threading.Event()
+class ClockSampler:
+    """`nvidia-smi -lms 100` running from before the warm-up steps until after the timed region (the timed region itself
+    is only tens of milliseconds, shorter than one nvidia-smi start-up)."""
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag.is_set():
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.25)            # let at least one more sample land
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                self.proc.kill()
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+        samples = [[x.strip() for x in ln.split(",")] for ln in self.lines if ln]
+        sm, mx, reasons = [], [], set()
+        for smp in samples:
+            try:
+                sm.append(float(smp[0])); mx.append(float(smp[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), smp[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "sampled every 100 ms from the warm-up steps through the timed and e2e regions"}
 
 
 def measured_peak():
@@ -260,12 +280,12 @@ def run_ours(args):
     W, K = max(3, args.warmup), args.steps
 
     # ---- device-resident leg: `value` ----
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     s.run(W, False, results=False)
     bart.tree_step_ms(reset=True)
-    clocks = ClockSampler(local_rank)
     passes0 = glmm.num_device_passes()
     barrier()
-    clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
@@ -274,7 +294,6 @@ def run_ours(args):
         ev1.record(stream)
     barrier()
     t_wall = time.time() - t_wall0
-    clocks.stop_flag.set()
     ms = max_over_ranks(float(ev0.elapsed_time(ev1)))
     stats = s.last_run_stats()
     glmm_passes = glmm.num_device_passes() - passes0
@@ -319,6 +338,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.time() - t0)
     s.set_host_plumbing(False)
+    clocks.stop()
     e2e = {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + 2 * 8 * n + 8 * s.num_pars),
            "note": "s4b_sampler_run with host result buffers (train + test fits, Stan row) and every N-vector of the sweep "
                    "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors"}

@@ -773,6 +773,7 @@ void BartFit::setup_persistent()
     sweep_mode_ = 2;
   }
   if (env) set_sweep_mode(atoi(env));
+  if (getenv("S4B_OVERLAP_WALK")) overlap_walk_ = atoi(getenv("S4B_OVERLAP_WALK"));
 }
 
 void BartFit::set_sweep_mode(int m)
@@ -797,7 +798,8 @@ void BartFit::launch_persistent_sweep(bool last_thin)
     size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
     k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_);
   }
-  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws };
+  int overlap = overlap_walk_;
+  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap };
   const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep<1> : (persistent_nq_ == 2 ? (const void*) k_sweep<2> : (const void*) k_sweep<4>);
   S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,

@@ -111,6 +111,7 @@ class BartFit {
   double2* d_draws_ = nullptr;
   bool tape_set_ = false, rec_set_ = false, sequential_rng_ = false;
   int partial_stride_ = 0;
+  int overlap_walk_ = 1;
   long long num_tree_steps_ = 0;
 
   uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;

@@ -240,7 +240,8 @@ struct StepDesc {
   TravTree b_prop;         // proposed tree (change / swap): slot = L + rank for leaves below b_node, 255 elsewhere
   double log_prior_trans;  // data-independent part of the log MH ratio
   int32_t new_var, new_cut;// change: proposed rule
-  int32_t pad0, pad1;
+  int32_t b_end;           // change / swap: one past the last pre-order index of the branch below b_node
+  int32_t pad1;
 };
 
 struct BartParams {

@@ -51,7 +51,7 @@ struct CtlScratch {
   double pmean[S4B_MAX_SLOTS + 1];  //   posterior mean of the leaf value,
   double psd[S4B_MAX_SLOTS + 1];    //   posterior sd (entry [nslots] describes the merged parent of a birth / death)
   DNode tmp[S4B_NODE_CAP];
-  int32_t draw_pos;                 // consumed from ubuf / zbuf
+  int32_t pad0;
   int32_t draws_total;              // draws consumed through this scratch since kernel start
   long long dbg[8];                 // cycle counters (diagnostics)
 };
@@ -65,8 +65,10 @@ struct WarpRng {
   CtlScratch* cs;
   unsigned long long step;
   uint32_t sub, base; // buffer holds draws [base, base + 32) of (step, sub)
+  int pos;            // consumed from the buffer (warp-uniform register)
   int lane;
   bool writer;        // CTA 0 appends to the record buffer
+  bool recording;
 
   __device__ void fill()
   {
@@ -80,52 +82,47 @@ struct WarpRng {
       u = keyed_stream_uniform(r.key0, r.key1, r.stream, step, sub, base + (uint32_t) lane);
       z = qnorm_as241(u);
     }
+    __syncwarp();
     cs->ubuf[lane] = u; cs->zbuf[lane] = z;
-    if (lane == 0) cs->draw_pos = 0;
+    pos = 0;
     __syncwarp();
   }
-  __device__ void enter(unsigned long long s, uint32_t sb) { step = s; sub = sb; base = 0; }
+  // the buffer was filled by someone else (pre-computed draws): start consuming at its beginning
+  __device__ void adopt() { pos = 0; __syncwarp(); }
+  __device__ void enter(unsigned long long s, uint32_t sb) { step = s; sub = sb; base = 0; pos = 0; recording = g->rec != nullptr; }
   // account for the consumed prefix (all lanes call)
   __device__ void commit()
   {
-    __syncwarp();
-    const int k = cs->draw_pos;
+    const int k = pos;
     base += (uint32_t) k;
-    __syncwarp();
     if (lane == 0) {
       RngState& r = *g;
       if (r.tape != nullptr) { if (r.tape_pos + (unsigned long long) k > r.tape_len) r.tape_underrun = 1; r.tape_pos += (unsigned long long) k; }
       cs->draws_total += k;
-      cs->draw_pos = 0;
     }
+    pos = 0;
     __syncwarp();
   }
   __device__ void note(double v)
   {
     RngState& r = *g;
-    if (r.rec != nullptr && lane == 0) { if (writer && r.rec_len < r.rec_cap) r.rec[r.rec_len] = v; r.rec_len++; }
+    if (lane == 0) { if (writer && r.rec_len < r.rec_cap) r.rec[r.rec_len] = v; r.rec_len++; }
   }
   __device__ double uniform()
   {
-    __syncwarp();
-    if (cs->draw_pos >= 32) { commit(); fill(); }
-    const int p = cs->draw_pos;
-    const double v = cs->ubuf[p];
-    __syncwarp();
-    if (lane == 0) { cs->draw_pos = p + 1; note(v); }
-    __syncwarp();
+    if (pos >= 32) { commit(); fill(); }
+    const double v = cs->ubuf[pos++];
+    if (recording) note(v);
     return v;
   }
   __device__ int index(int n) { int k = (int) (uniform() * (double) n); return k >= n ? n - 1 : k; }
   // reserve `count` (<= 32) consecutive normal draws; returns the buffer position of the first one
   __device__ int reserve_normals(int count)
   {
-    __syncwarp();
-    if (cs->draw_pos + count > 32) { commit(); fill(); }
-    const int p = cs->draw_pos;
-    __syncwarp();
-    if (lane == 0) { cs->draw_pos = p + count; if (g->rec != nullptr) for (int i = 0; i < count; ++i) note(cs->zbuf[p + i]); }
-    __syncwarp();
+    if (pos + count > 32) { commit(); fill(); }
+    const int p = pos;
+    pos += count;
+    if (recording) for (int i = 0; i < count; ++i) note(cs->zbuf[p + i]);
     return p;
   }
 };
@@ -304,7 +301,7 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
   const int nn = t.num_nodes;
   const int L = w_fill_trav(t, d.b_cur, true, lane);
   w_node_attrs(t, P, cs, L, lane);
-  int kind = -1, node = -1, b_var = -1, b_cut = -1, child = -1, new_var = -1, new_cut = -1, nslots = L;
+  int kind = -1, node = -1, b_var = -1, b_cut = -1, child = -1, new_var = -1, new_cut = -1, nslots = L, b_end = -1;
   double lpt = 0.0;
 
   const double u = rng.uniform();
@@ -403,7 +400,7 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
         else { t.nodes[child].var = (int16_t) cv; t.nodes[child].cut = (int16_t) cc; }
       }
       __syncwarp();
-      if (!bad) { nslots = w_assign_prop_slots(t, d.b_prop, node, end, L, lane); kind = 3; lpt = new_lp - old_lp; }
+      if (!bad) { nslots = w_assign_prop_slots(t, d.b_prop, node, end, L, lane); kind = 3; lpt = new_lp - old_lp; b_end = end; }
     }
   } else {
     // ---- change ----
@@ -435,14 +432,14 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
         if (lane == 0) { t.nodes[node].var = (int16_t) ov; t.nodes[node].cut = (int16_t) oc; }
         __syncwarp();
         nslots = w_assign_prop_slots(t, d.b_prop, node, end, L, lane);
-        kind = 2; lpt = new_lp - old_lp;
+        kind = 2; lpt = new_lp - old_lp; b_end = end;
       }
     }
   }
   if (lane == 0) {
     d.a_valid = 0; d.a_same = 1;
     d.b_tree = tree_index; d.b_kind = kind; d.b_node = node; d.b_var = b_var; d.b_cut = b_cut; d.b_child = child;
-    d.b_num_leaves = L; d.b_nslots = nslots; d.log_prior_trans = lpt; d.new_var = new_var; d.new_cut = new_cut;
+    d.b_num_leaves = L; d.b_nslots = nslots; d.log_prior_trans = lpt; d.new_var = new_var; d.new_cut = new_cut; d.b_end = b_end;
     if (kind != 2 && kind != 3) d.b_prop.n = 0;
   }
   __syncwarp();
@@ -495,7 +492,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     accept = rng.uniform() < ratio;
     n_first = l.n; n_second = r.n;
   } else if (kind == 2 || kind == 3) {
-    const int end = t_subtree_end(t, node);
+    const int end = in.b_end;
     double a_old = 0.0, a_new = 0.0, mn = 1e300;
     int first_leaf = -1, second_leaf = -1, seen = 0;
     for (int base = node; base < end; base += 32) {
@@ -541,7 +538,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     }
     __syncwarp();
   } else if (amode == 3) {
-    const int end = t_subtree_end(t, node);
+    const int end = in.b_end;
     for (int k = node + lane; k < end; k += 32) if (t.nodes[k].var >= 0) { uint32_t tv = in.b_prop.trav[k]; t.nodes[k].var = (int16_t) trav2_var(tv); t.nodes[k].cut = (int16_t) trav2_cut(tv); }
     __syncwarp();
   }
@@ -669,7 +666,7 @@ __device__ inline void w_copy_desc(StepDesc& dst, const StepDesc& src, int lane)
     dst.a_valid = 0; dst.a_same = 1;
     dst.b_tree = src.b_tree; dst.b_kind = kind; dst.b_node = src.b_node; dst.b_var = src.b_var; dst.b_cut = src.b_cut;
     dst.b_num_leaves = src.b_num_leaves; dst.b_nslots = src.b_nslots; dst.b_child = src.b_child;
-    dst.log_prior_trans = src.log_prior_trans; dst.new_var = src.new_var; dst.new_cut = src.new_cut;
+    dst.log_prior_trans = src.log_prior_trans; dst.new_var = src.new_var; dst.new_cut = src.new_cut; dst.b_end = src.b_end;
     dst.b_cur.n = n; dst.b_cur.pad = src.b_cur.pad;
     dst.b_prop.n = (kind == 2 || kind == 3) ? n : 0; dst.b_prop.pad = src.b_cur.pad;
   }
@@ -724,7 +721,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
 
 template <int NQ>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
-                                                               const StepDesc* __restrict__ descs, const double2* __restrict__ draws)
+                                                               const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
@@ -911,8 +908,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         // pre-computed by k_prepare_sweep: this step's decision draws and the next tree's proposal
         const double2 dz = __ldcg(draws + t * 32 + lane);
         S.csd.ubuf[lane] = dz.x; S.csd.zbuf[lane] = dz.y;
-        if (lane == 0) S.csd.draw_pos = 0;
-        __syncwarp();
+        rngd.adopt();
         const long long h2 = clock64();
         if (t + 1 < T) w_copy_desc(sd_next, descs[t + 1], lane);
         if (lane == 0) { S.csd.dbg[4] += h1 - h0; S.csd.dbg[5] += h2 - h1; S.csd.dbg[7] += clock64() - h2; }
@@ -955,7 +951,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         w_propose(tree_next, S.prm, S.tab, rngp, sd_next, S.csp, t + 1, lane);
         rngp.commit();
       }
-    } else if (!sequential_rng && t + 1 < T) {
+    } else if (!sequential_rng && overlap_walk && t + 1 < T) {
       // ---- workers, concurrently: walk tree t+1 (independent of this step's decision) ----
       walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_next, aux_next);
     }
@@ -985,7 +981,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         }
       }
       if (t + 1 < T) {
-        if (sequential_rng) walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
+        if (sequential_rng || !overlap_walk) walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
         else {
 #pragma unroll
           for (int j = 0; j < NQ; ++j) { leaf_pack[j] = leaf_next[j]; aux_pack[j] = aux_next[j]; }
