@@ -179,6 +179,31 @@ int s4b_sampler_set_host_plumbing(s4b_sampler* s, int on, int64_t* h2d_bytes_per
 /* timing split of the last run: milliseconds in the Stan block and the BART block (CUDA events), leapfrog count */
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* n_grad_evals, int64_t* n_tree_steps);
 
+/* ------------------------------------------------------------------ s4b_shard_*  (observation-sharded chains)
+ * No counterpart in the reference: stan4bart runs one chain on one host thread (R/stan4bart.R:288-300 fans whole chains
+ * out with parallel::clusterMap).  BASELINE config E / SURVEY.md 8(e) shard the ROWS of one chain over the GPUs of an
+ * NVSwitch box: one process per GPU, trees / RNG / NUTS state replicated, per-node statistics and GLMM reductions
+ * exchanged through peer-mapped mailboxes inside the kernels (csrc/shard.hpp).  Set-up: every rank creates a context,
+ * publishes its 64-byte IPC handle (any transport: torch.distributed all_gather, MPI, a file), attaches the world's
+ * handles, states its row range, then creates the sampler with the *_sharded constructors.  All ranks must make the
+ * same sequence of calls with the same seeds. */
+typedef struct s4b_shard s4b_shard;
+int s4b_shard_create(int rank, int world, s4b_shard** out);
+int s4b_shard_free(s4b_shard* sh);
+int s4b_shard_ipc_handle(s4b_shard* sh, unsigned char* out64);
+/* handles: world x 64 bytes, ordered by rank (the own entry is ignored) */
+int s4b_shard_attach(s4b_shard* sh, const unsigned char* handles);
+/* this rank holds rows [first_obs, first_obs + n_local) of total_obs */
+int s4b_shard_set_obs_range(s4b_shard* sh, int64_t first_obs, int64_t total_obs);
+/* in-place all-reduce of a host vector over the ranks (op 0 = sum in rank order, 1 = max); collective */
+int s4b_shard_allreduce(s4b_shard* sh, double* vec, int64_t n, int op);
+/* initializeFit / glmm / stan4bart_create on this rank's rows; n, N are the local row counts */
+int gpubart_create_sharded(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test, s4b_shard* sh, gpubart_fit** out);
+int glmm_create_sharded(const s4b_glmm_data* d, s4b_shard* sh, glmm_model** out);
+int s4b_sampler_create_sharded(const s4b_bart_config* bcfg, const double* y_bart, const double* x_bart, const double* x_test,
+                               const s4b_glmm_data* gdata, const s4b_stan_control* sctl, const s4b_common_control* cctl,
+                               const double* bart_offset_init, s4b_shard* sh, s4b_sampler** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ vpp = C.POINTER(C.c_void_p)
 c_size_p = C.POINTER(C.c_size_t)
 c_int_p = C.POINTER(C.c_int)
 c_uint64_p = C.POINTER(C.c_uint64)
+c_ubyte_p = C.POINTER(C.c_ubyte)
 
 # name -> (restype, argtypes); every symbol declared in include/stan4bart_b200.h
 SIGNATURES = {
@@ -76,6 +77,16 @@ SIGNATURES = {
     "s4b_sampler_glmm": (vp, [vp]),
     "s4b_sampler_get_means": (C.c_int, [vp, c_double_p, c_double_p, c_double_p, c_int64_p]),
     "s4b_sampler_last_run_stats": (C.c_int, [vp, c_double_p, c_double_p, c_int64_p, c_int64_p]),
+    "s4b_shard_create": (C.c_int, [C.c_int, C.c_int, vpp]),
+    "s4b_shard_free": (C.c_int, [vp]),
+    "s4b_shard_ipc_handle": (C.c_int, [vp, c_ubyte_p]),
+    "s4b_shard_attach": (C.c_int, [vp, c_ubyte_p]),
+    "s4b_shard_set_obs_range": (C.c_int, [vp, C.c_int64, C.c_int64]),
+    "s4b_shard_allreduce": (C.c_int, [vp, c_double_p, C.c_int64, C.c_int]),
+    "gpubart_create_sharded": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, vp, vpp]),
+    "glmm_create_sharded": (C.c_int, [C.POINTER(GlmmData), vp, vpp]),
+    "s4b_sampler_create_sharded": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, C.POINTER(GlmmData),
+                                             C.POINTER(StanControl), C.POINTER(CommonControl), c_double_p, vp, vpp]),
 }
 
 _lib = None

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libstan4bart_b200.so")
-SOURCES = ["bart.cu", "glmm.cu", "nuts.cu", "sampler.cu"]
+SOURCES = ["bart.cu", "glmm.cu", "nuts.cu", "sampler.cu", "shard.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kBlock) k_finish_sweep(BartDev dv, double* __r
     double tf = yr - r;                      // total fit, scaled units
     double off = dv.offset[i];
     if (binary) {
-      double z = keyed_truncnorm(prm.key0, prm.key1, (uint32_t) i, prm.latent_epoch, tf + off, dv.y[i] > 0.0);
+      double z = keyed_truncnorm(prm.key0, prm.key1, (uint32_t) (i + dv.obs_offset), prm.latent_epoch, tf + off, dv.y[i] > 0.0);
       yr = z - off;
       dv.yresc[i] = yr;
       r = yr - tf;
@@ -504,6 +504,20 @@ __global__ void __launch_bounds__(kBlock) k_minmax(BartDev dv, const double* __r
   }
 }
 
+// sharded chains: fold the block partials into (-min, max) so that one max-reduction over the ranks finishes both, then
+// unpack into the [2][1] layout k_update_scale reads
+__global__ void k_minmax_pack(const double* __restrict__ part, int G, double* __restrict__ packed)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mn = INFINITY, mx = -INFINITY;
+  for (int b = 0; b < G; ++b) { mn = fmin(mn, part[b]); mx = fmax(mx, part[G + b]); }
+  packed[0] = -mn; packed[1] = mx;
+}
+__global__ void k_minmax_unpack(const double* __restrict__ packed, double* __restrict__ part1)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) { part1[0] = -packed[0]; part1[1] = packed[1]; }
+}
+
 // single thread: finish min/max, update the scale, sigma and (optionally) leaf values
 __global__ void k_update_scale(BartDev dv, const double* __restrict__ part, int G, double* __restrict__ scale_factor_out)
 {
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(kBlock) k_apply_offset_binary(BartDev dv, cons
   for (long long i = (long long) blockIdx.x * kBlock + threadIdx.x; i < dv.n; i += (long long) gridDim.x * kBlock) {
     double off = new_offset != nullptr ? new_offset[i] : 0.0;
     double tf = dv.yresc[i] - dv.R[i];
-    double z = keyed_truncnorm(k0, k1, (uint32_t) i, epoch, tf + off, dv.y[i] > 0.0);
+    double z = keyed_truncnorm(k0, k1, (uint32_t) (i + dv.obs_offset), epoch, tf + off, dv.y[i] > 0.0);
     double yr = z - off;
     dv.yresc[i] = yr;
     dv.R[i] = yr - tf;
@@ -606,9 +620,10 @@ __global__ void __launch_bounds__(kBlock) k_node_assignment(BartDev dv, int tree
 // ---------------------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
-BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, const double* x_test, cudaStream_t stream)
-    : cfg_(cfg), stream_(stream)
+BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, const double* x_test, cudaStream_t stream, ShardContext* shard)
+    : cfg_(cfg), stream_(stream), shard_(shard)
 {
+  if (shard_ != nullptr && !shard_->attached()) throw std::invalid_argument("sharded fit: attach the peer mailboxes first");
   if (cfg.n_cuts < 1 || cfg.n_cuts > 255) throw std::invalid_argument("n_cuts must be in [1, 255] (u8 bins)");
   if (cfg.p < 1 || cfg.p > 32767) throw std::invalid_argument("p out of range");
   if (cfg.num_trees < 1) throw std::invalid_argument("num_trees < 1");
@@ -626,10 +641,17 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   // ---- cut points (uniform over the training range) and binning, host side (setup only) ----
   cuts_.resize((size_t) p_ * cfg.n_cuts);
   std::vector<uint8_t> xt((size_t) p_ * npad_, 0);
+  std::vector<double> range((size_t) 2 * p_);          // (-min, max) per predictor: one max-reduction over the shards
   for (int j = 0; j < p_; ++j) {
     const double* col = x + (size_t) j * n_;
     double mn = col[0], mx = col[0];
     for (long long i = 1; i < n_; ++i) { mn = std::min(mn, col[i]); mx = std::max(mx, col[i]); }
+    range[(size_t) 2 * j] = -mn; range[(size_t) 2 * j + 1] = mx;
+  }
+  if (sharded()) shard_->allreduce_host(range.data(), (long long) range.size(), kOpMax, stream_);
+  for (int j = 0; j < p_; ++j) {
+    const double* col = x + (size_t) j * n_;
+    const double mn = -range[(size_t) 2 * j], mx = range[(size_t) 2 * j + 1];
     double inc = (mx - mn) / (double) (cfg.n_cuts + 1);
     double* c = cuts_.data() + (size_t) j * cfg.n_cuts;
     for (int k = 0; k < cfg.n_cuts; ++k) c[k] = mn + (double) (k + 1) * inc;
@@ -662,7 +684,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   // trees: single root each
   std::vector<DTree> trees((size_t) T_);
   std::memset(trees.data(), 0, sizeof(DTree) * trees.size());
-  for (auto& t : trees) { t.num_nodes = 1; t.nodes[0].var = -1; t.nodes[0].cut = -1; t.nodes[0].right = -1; t.nodes[0].parent = -1; t.nodes[0].n = (int32_t) std::min<long long>(n_, 2147483647LL); }
+  for (auto& t : trees) { t.num_nodes = 1; t.nodes[0].var = -1; t.nodes[0].cut = -1; t.nodes[0].right = -1; t.nodes[0].parent = -1; t.nodes[0].n = (int32_t) std::min<long long>(sharded() ? shard_->total_obs() : n_, 2147483647LL); }
   S4B_CUDA(cudaMalloc(&d_trees_, sizeof(DTree) * trees.size()));
   S4B_CUDA(cudaMemcpy(d_trees_, trees.data(), sizeof(DTree) * trees.size(), cudaMemcpyHostToDevice));
   // params
@@ -772,7 +794,8 @@ void BartFit::setup_persistent()
     S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     sweep_mode_ = 2;
   }
-  if (env) set_sweep_mode(atoi(env));
+  if (sharded() && persistent_nq_ == 0) throw std::invalid_argument("sharded fit: the local shard does not fit the persistent sweep kernel (rows per GPU or p too large)");
+  if (env && !sharded()) set_sweep_mode(atoi(env));
   if (getenv("S4B_OVERLAP_WALK")) overlap_walk_ = atoi(getenv("S4B_OVERLAP_WALK"));
 }
 
@@ -780,6 +803,7 @@ void BartFit::set_sweep_mode(int m)
 {
   if (m == 2 && persistent_nq_ == 0) throw std::invalid_argument("persistent sweep kernel does not fit this problem (n, p) on this GPU");
   if (m < 0 || m > 2) throw std::invalid_argument("sweep mode must be 0, 1 or 2");
+  if (m != 2 && sharded()) throw std::invalid_argument("observation-sharded chains run the persistent sweep kernel only (mode 2)");
   sweep_mode_ = m; use_graph_ = m != 0;
 }
 
@@ -799,7 +823,10 @@ void BartFit::launch_persistent_sweep(bool last_thin)
     k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_);
   }
   int overlap = overlap_walk_;
-  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap };
+  ShardDev sh; std::memset(&sh, 0, sizeof sh); sh.world = 1;
+  unsigned long long seq_base = 0;
+  if (sharded()) { sh = shard_->dev(); seq_base = shard_->reserve_step_seq(T_); }
+  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &seq_base };
   const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep<1> : (persistent_nq_ == 2 ? (const void*) k_sweep<2> : (const void*) k_sweep<4>);
   S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
@@ -822,7 +849,7 @@ void BartFit::bin_matrix(const double* x, long long rows, long long rows_pad, st
 BartDev BartFit::dev() const
 {
   BartDev d;
-  d.n = n_; d.npad = npad_; d.xt = d_xt_; d.R = d_R_; d.yresc = d_yresc_; d.y = d_y_; d.offset = d_offset_;
+  d.n = n_; d.npad = npad_; d.obs_offset = shard_ != nullptr ? shard_->obs_offset() : 0; d.xt = d_xt_; d.R = d_R_; d.yresc = d_yresc_; d.y = d_y_; d.offset = d_offset_;
   d.desc = d_desc_; d.trees = d_trees_; d.params = d_params_; d.pgrow = d_pgrow_; d.rng = d_rng_;
   d.partials = d_partials_; d.ticket = d_ticket_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
   d.stats_out = d_stats_out_; d.prof = d_prof_;
@@ -899,6 +926,7 @@ void BartFit::check_error_flag()
 {
   BartParams P = params();
   if (P.error_flag & 2u) throw std::runtime_error("s4b: RNG tape underrun in replay mode");
+  if (P.error_flag & 4u) throw std::runtime_error("s4b: a peer rank stopped answering during a sharded sweep");
   if (P.error_flag) throw std::runtime_error("s4b: device error flag set");
 }
 
@@ -921,7 +949,15 @@ void BartFit::set_offset_device(const double* d_offset, bool update_scale)
   bool first = !scale_initialised_;
   if (update_scale || first) {
     k_minmax<<<grid_ew_, kBlock, 0, stream_>>>(dv, d_offset, d_minmax_);
-    k_update_scale<<<1, 32, 0, stream_>>>(dv, d_minmax_, grid_ew_, d_scale_factor_);
+    if (sharded()) {
+      // the response range is a property of the whole data set: max-reduce (-min, max) over the ranks
+      double* packed = d_minmax_ + 2 * (size_t) grid_ew_;
+      k_minmax_pack<<<1, 32, 0, stream_>>>(d_minmax_, grid_ew_, packed);
+      shard_->allreduce(packed, 2, kOpMax, stream_);
+      k_minmax_unpack<<<1, 32, 0, stream_>>>(packed, packed + 2);
+      k_update_scale<<<1, 32, 0, stream_>>>(dv, packed + 2, 1, d_scale_factor_);
+    } else
+      k_update_scale<<<1, 32, 0, stream_>>>(dv, d_minmax_, grid_ew_, d_scale_factor_);
     if (!first) k_scale_leaves<<<T_, 128, 0, stream_>>>(dv, d_scale_factor_);
     k_apply_offset<<<grid_ew_, kBlock, 0, stream_>>>(dv, d_offset, d_scale_factor_);
     scale_initialised_ = true;
@@ -1071,6 +1107,7 @@ int BartFit::leaf_stats(int tree, int max_leaves, long long* heap, long long* co
   std::vector<double> st((size_t) 3 * S4B_MAX_SLOTS);
   S4B_CUDA(cudaMemcpyAsync(st.data(), d_stats_out_, sizeof(double) * st.size(), cudaMemcpyDeviceToHost, stream_));
   std::vector<DTree> trees = download_trees();
+  if (sharded()) shard_->allreduce_host(st.data(), (long long) st.size(), kOpSum, stream_);     // statistics of the whole data set
   const DTree& t = trees[(size_t) tree];
   int leaf = 0;
   for (int k = 0; k < t.num_nodes; ++k) if (t.nodes[k].var < 0) {

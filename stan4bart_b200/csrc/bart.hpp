@@ -3,6 +3,7 @@
 
 #include "../../include/stan4bart_b200.h"
 #include "s4b_common.cuh"
+#include "shard.hpp"
 
 #include <vector>
 
@@ -11,6 +12,7 @@ namespace s4b {
 // everything a kernel needs, passed by value
 struct BartDev {
   long long n, npad;
+  long long obs_offset;       // global index of local row 0 (sharded chains; keys the latent draws)
   const uint8_t* xt;
   double* R; double* yresc; const double* y; double* offset;
   StepDesc* desc; DTree* trees; BartParams* params; const double* pgrow; RngState* rng;
@@ -22,7 +24,9 @@ struct BartDev {
 
 class BartFit {
  public:
-  BartFit(const s4b_bart_config& cfg, const double* y, const double* x, const double* x_test, cudaStream_t stream);
+  // `shard` != nullptr: this fit holds rows [obs_offset, obs_offset + n) of an observation-sharded chain (shard.hpp);
+  // every rank must then make the same sequence of calls
+  BartFit(const s4b_bart_config& cfg, const double* y, const double* x, const double* x_test, cudaStream_t stream, ShardContext* shard = nullptr);
   ~BartFit();
   BartFit(const BartFit&) = delete;
   BartFit& operator=(const BartFit&) = delete;
@@ -53,7 +57,7 @@ class BartFit {
   void set_record(size_t cap);
   size_t get_record(double* out, size_t cap);
   unsigned long long rng_counter();
-  void set_use_graph(bool g) { use_graph_ = g; if (!g) sweep_mode_ = 0; else if (sweep_mode_ == 0) sweep_mode_ = 1; }
+  void set_use_graph(bool g) { if (sharded()) throw std::invalid_argument("observation-sharded chains run the persistent sweep kernel only"); use_graph_ = g; if (!g) sweep_mode_ = 0; else if (sweep_mode_ == 0) sweep_mode_ = 1; }
   // 0: one launch per tree step; 1: the same kernels captured in a CUDA graph; 2: persistent on-chip sweep kernel
   // (sweep_kernel.cuh), the default whenever the chain fits
   void set_sweep_mode(int m);
@@ -75,6 +79,7 @@ class BartFit {
   double* d_latent_out() const { return d_latent_out_; }   // full latents (binary)
   double* d_offset() const { return d_offset_; }
   int grid() const { return grid_; }
+  bool sharded() const { return shard_ != nullptr && shard_->world() > 1; }
   long long num_tree_steps() const { return num_tree_steps_; }
   // device time (CUDA events on the launching stream) spent in the sweep graphs since the last reset
   double tree_step_ms(bool reset);
@@ -94,6 +99,7 @@ class BartFit {
 
   s4b_bart_config cfg_;
   cudaStream_t stream_;
+  ShardContext* shard_ = nullptr;
   long long n_ = 0, nt_ = 0, npad_ = 0, npad_t_ = 0;
   int p_ = 0, T_ = 0, num_sms_ = 0, blocks_per_sm_ = 3, grid_ = 1, grid_ew_ = 1;
   std::vector<double> cuts_;

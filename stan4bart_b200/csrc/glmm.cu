@@ -129,15 +129,16 @@ struct GlmmModel::Params {
 static const double kHalfLog2Pi = 0.91893853320467274178;
 static const double kLog2 = 0.693147180559945286;
 
-GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream) : stream_(stream)
+GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* shard) : stream_(stream), shard_(shard)
 {
+  if (shard_ != nullptr && !shard_->attached()) throw std::invalid_argument("sharded glmm: attach the peer mailboxes first");
   if (d.prior_dist < 0 || d.prior_dist > 1) throw std::invalid_argument("glmm: only prior_dist 0 (none) and 1 (normal) are implemented (SURVEY 8f rank 4)");
   if (d.prior_dist_for_aux < 0 || d.prior_dist_for_aux > 3) throw std::invalid_argument("glmm: prior_dist_for_aux out of range");
   for (int i = 0; i < d.t; ++i) {
     if (d.p[i] < 1 || d.l[i] < 1) throw std::invalid_argument("glmm: p[i] / l[i] must be >= 1");
     if (d.p[i] > 2) throw std::invalid_argument("glmm: ranef blocks with more than 2 coefficients (z_T onion) are not implemented (SURVEY 8f rank 4)");
   }
-  N_ = d.N; K_ = d.K; q_ = d.q; t_ = d.t; len_theta_L_ = d.len_theta_L; len_conc_ = d.len_concentration;
+  N_ = d.N; N_total_ = sharded() ? shard_->total_obs() : d.N; K_ = d.K; q_ = d.q; t_ = d.t; len_theta_L_ = d.len_theta_L; len_conc_ = d.len_concentration;
   is_binary_ = d.is_binary; prior_dist_ = d.prior_dist; prior_dist_for_aux_ = d.prior_dist_for_aux;
   prior_scale_for_aux_ = d.prior_scale_for_aux; prior_mean_for_aux_ = d.prior_mean_for_aux; prior_df_for_aux_ = d.prior_df_for_aux;
   prior_scale_.assign(d.prior_scale, d.prior_scale + K_); prior_mean_.assign(d.prior_mean, d.prior_mean + K_);
@@ -212,6 +213,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream) : stream_(stre
       for (int z = d.u[i]; z < d.u[i + 1]; ++z) { cols[(size_t) m] = K_ + d.v[z]; vals[(size_t) m] = d.w[z]; ++m; }
       for (int a = 0; a < m; ++a) for (int bb = 0; bb < m; ++bb) gram_[(size_t) cols[(size_t) a] * nb + cols[(size_t) bb]] += vals[(size_t) a] * vals[(size_t) bb];
     }
+    if (sharded()) shard_->allreduce_host(gram_.data(), (long long) gram_.size(), kOpSum, stream_);
     theta0_.assign((size_t) nb, 0.0); g0_.assign((size_t) nb, 0.0);
     mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : 1;
   }
@@ -289,6 +291,7 @@ void GlmmModel::data_terms(const double* beta, const double* b, double* S, doubl
   g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
   k_glmm_data_terms<<<grid_, kGBlock, smem_bytes_, stream_>>>(g);
   S4B_CUDA(cudaGetLastError());
+  if (sharded()) for (int off = 0; off < nb + 1; off += kMailVec) shard_->allreduce(d_result_ + off, std::min(kMailVec, nb + 1 - off), kOpSum, stream_);
   S4B_CUDA(cudaMemcpyAsync(h_res, d_result_, sizeof(double) * (size_t) (nb + 1), cudaMemcpyDeviceToHost, stream_));
   S4B_CUDA(cudaStreamSynchronize(stream_));
   *S = h_res[0];
@@ -374,7 +377,7 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
 {
   Params P; transform(q, P);
   ++num_grad_;
-  const double N = (double) N_;
+  const double N = (double) N_total_;
   double lp = 0.0;
   for (int i = 0; i < len_rho_; ++i) { double x = std::fabs(P.rho_u[i]); lp += -x - 2.0 * std::log1p(std::exp(-x)); }
   for (int i = 0; i < len_conc_; ++i) lp += P.zeta_u[i];

@@ -3,6 +3,7 @@
 
 #include "../../include/stan4bart_b200.h"
 #include "s4b_common.cuh"
+#include "shard.hpp"
 
 #include <vector>
 
@@ -24,7 +25,9 @@ struct GlmmDev {
 
 class GlmmModel {
  public:
-  GlmmModel(const s4b_glmm_data& d, cudaStream_t stream);
+  // `shard` != nullptr: d holds this rank's rows of an observation-sharded model; the (1 + K + q) data-term reductions and
+  // the Gram matrix are summed over the ranks in rank order (shard.hpp), so every rank evaluates the same density
+  GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* shard = nullptr);
   ~GlmmModel();
   GlmmModel(const GlmmModel&) = delete;
   GlmmModel& operator=(const GlmmModel&) = delete;
@@ -62,8 +65,11 @@ class GlmmModel {
   void transform(const double* q, Params& P) const;
   void refresh_r();
 
+  bool sharded() const { return shard_ != nullptr && shard_->world() > 1; }
+
   cudaStream_t stream_;
-  long long N_ = 0, npad_ = 0;
+  ShardContext* shard_ = nullptr;
+  long long N_ = 0, npad_ = 0, N_total_ = 0;
   int K_ = 0, q_ = 0, t_ = 0, len_theta_L_ = 0, len_rho_ = 0, len_conc_ = 0, num_params_ = 0, has_aux_ = 0;
   int is_binary_ = 0, prior_dist_ = 0, prior_dist_for_aux_ = 0;
   double prior_scale_for_aux_ = 0, prior_mean_for_aux_ = 0, prior_df_for_aux_ = 0;

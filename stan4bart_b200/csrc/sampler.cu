@@ -24,8 +24,9 @@ __global__ void k_accumulate(long long n, const double* __restrict__ src, double
 class GibbsSampler {
  public:
   GibbsSampler(const s4b_bart_config& bcfg, const double* y_bart, const double* x_bart, const double* x_test, const s4b_glmm_data& gdata,
-               const s4b_stan_control& sctl, const s4b_common_control& cctl, const double* bart_offset_init, cudaStream_t stream)
-      : cc_(cctl), stream_(stream), glmm_(gdata, stream), nuts_(glmm_, sctl, 1, cctl.warmup), bart_(bcfg, y_bart, x_bart, x_test, stream)
+               const s4b_stan_control& sctl, const s4b_common_control& cctl, const double* bart_offset_init, cudaStream_t stream,
+               ShardContext* shard = nullptr)
+      : cc_(cctl), stream_(stream), glmm_(gdata, stream, shard), nuts_(glmm_, sctl, 1, cctl.warmup), bart_(bcfg, y_bart, x_bart, x_test, stream, shard)
   {
     n_ = bcfg.n; nt_ = bcfg.n_test; p_ = (int) bcfg.p;
     if (gdata.N != n_) throw std::invalid_argument("sampler: BART and Stan data disagree on N");
@@ -175,6 +176,7 @@ using namespace s4b;
 
 struct gpubart_fit { std::unique_ptr<BartFit> owned; BartFit* fit; };
 struct glmm_model { std::unique_ptr<GlmmModel> owned; GlmmModel* m; };
+struct s4b_shard { std::unique_ptr<ShardContext> ctx; };
 struct s4b_sampler { std::unique_ptr<GibbsSampler> s; gpubart_fit bart_view; glmm_model glmm_view; };
 
 static thread_local std::string g_last_error;
@@ -338,5 +340,59 @@ int gpubart_get_profile(gpubart_fit* f, uint64_t* out24, int reset) { S4B_API_BE
 int gpubart_tree_step_ms(gpubart_fit* f, int reset, double* ms) { S4B_API_BEGIN S4B_REQUIRE(f && ms); *ms = f->fit->tree_step_ms(reset != 0); S4B_API_END }
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* ng, int64_t* ns)
 { S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->last_run_stats(ms_stan, ms_bart, &a, &b); if (ng) *ng = a; if (ns) *ns = b; S4B_API_END }
+
+// ---- observation-sharded chains ----
+int s4b_shard_create(int rank, int world, s4b_shard** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(out);
+  if (s4b_device_count() < 1) throw std::runtime_error("no CUDA device: stan4bart_b200 has no CPU fallback");
+  auto* h = new s4b_shard;
+  h->ctx.reset(new ShardContext(rank, world));
+  *out = h;
+  S4B_API_END
+}
+int s4b_shard_free(s4b_shard* sh) { S4B_API_BEGIN delete sh; S4B_API_END }
+int s4b_shard_ipc_handle(s4b_shard* sh, unsigned char* out64) { S4B_API_BEGIN S4B_REQUIRE(sh && out64); sh->ctx->ipc_handle(out64); S4B_API_END }
+int s4b_shard_attach(s4b_shard* sh, const unsigned char* handles) { S4B_API_BEGIN S4B_REQUIRE(sh && handles); sh->ctx->attach(handles); S4B_API_END }
+int s4b_shard_set_obs_range(s4b_shard* sh, int64_t first_obs, int64_t total_obs)
+{ S4B_API_BEGIN S4B_REQUIRE(sh && first_obs >= 0 && total_obs >= first_obs); sh->ctx->set_obs_range(first_obs, total_obs); S4B_API_END }
+int s4b_shard_allreduce(s4b_shard* sh, double* vec, int64_t n, int op)
+{ S4B_API_BEGIN S4B_REQUIRE(sh && vec && n >= 0 && (op == 0 || op == 1)); sh->ctx->allreduce_host(vec, n, op == 0 ? kOpSum : kOpMax, current_stream()); S4B_API_END }
+int gpubart_create_sharded(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test, s4b_shard* sh, gpubart_fit** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(cfg && y && x && sh && out);
+  if (cfg->n_test > 0) S4B_REQUIRE(x_test);
+  auto* h = new gpubart_fit;
+  h->owned.reset(new BartFit(*cfg, y, x, x_test, current_stream(), sh->ctx.get()));
+  h->fit = h->owned.get();
+  *out = h;
+  S4B_API_END
+}
+int glmm_create_sharded(const s4b_glmm_data* d, s4b_shard* sh, glmm_model** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(d && sh && out);
+  auto* h = new glmm_model;
+  h->owned.reset(new GlmmModel(*d, current_stream(), sh->ctx.get()));
+  h->m = h->owned.get();
+  *out = h;
+  S4B_API_END
+}
+int s4b_sampler_create_sharded(const s4b_bart_config* bcfg, const double* y_bart, const double* x_bart, const double* x_test,
+                               const s4b_glmm_data* gdata, const s4b_stan_control* sctl, const s4b_common_control* cctl,
+                               const double* bart_offset_init, s4b_shard* sh, s4b_sampler** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(bcfg && y_bart && x_bart && gdata && sctl && cctl && sh && out);
+  if (bcfg->n_test > 0) S4B_REQUIRE(x_test);
+  auto* h = new s4b_sampler;
+  h->s.reset(new GibbsSampler(*bcfg, y_bart, x_bart, x_test, *gdata, *sctl, *cctl, bart_offset_init, current_stream(), sh->ctx.get()));
+  h->bart_view.fit = &h->s->bart();
+  h->glmm_view.m = &h->s->glmm();
+  *out = h;
+  S4B_API_END
+}
 
 }  // extern "C"

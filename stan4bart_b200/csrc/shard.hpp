@@ -1,0 +1,106 @@
+// stan4bart_b200/csrc/shard.hpp
+// Observation-sharded mode (BASELINE config E): rows are split over the GPUs of one NVSwitch box, trees /
+// RNG / NUTS state are replicated, and the only data exchanged are the tiny per-node sufficient statistics of every tree
+// step and the (1 + K + q) GLMM reductions.  The exchange does not go through NCCL: every rank owns a "mailbox" in its
+// HBM that all peers map through CUDA IPC; a rank stores its contribution directly into every peer's mailbox over NVLink
+// (one-shot all-gather), then each rank sums the contributions in rank order, so all ranks obtain bitwise identical
+// results and take identical Metropolis decisions.  The per-tree exchange happens INSIDE the persistent sweep kernel.
+#pragma once
+
+#include "s4b_common.cuh"
+
+#include <stdexcept>
+
+namespace s4b {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMailVec = 1024;     // capacity of the generic small all-reduce
+
+struct Mailbox {
+  // per-tree-step statistics, double buffered by step parity; flag = sequence number of the step
+  unsigned long long step_flag[2][kMaxRanks];
+  double step_data[2][kMaxRanks][3 * S4B_MAX_SLOTS];
+  // generic small vectors (GLMM reductions, min / max for the rescale, cut-point ranges)
+  unsigned long long vec_flag[2][kMaxRanks];
+  double vec_data[2][kMaxRanks][kMailVec];
+};
+
+struct ShardDev {
+  int rank, world;
+  long long obs_offset;            // global index of this rank's first observation (keys the latent draws)
+  Mailbox* mail[kMaxRanks];        // mail[r] = rank r's mailbox as mapped into this process (mail[rank] is local)
+};
+
+enum ReduceOp { kOpSum = 0, kOpMax = 1 };
+
+class ShardContext {
+ public:
+  ShardContext(int rank, int world);
+  ~ShardContext();
+  ShardContext(const ShardContext&) = delete;
+  ShardContext& operator=(const ShardContext&) = delete;
+  void ipc_handle(void* out64) const;                       // cudaIpcMemHandle_t of the local mailbox
+  void attach(const void* handles64_by_rank);               // world handles, 64 bytes each
+  bool attached() const { return attached_; }
+  int rank() const { return dev_.rank; }
+  int world() const { return dev_.world; }
+  // this rank's rows are [first_obs, first_obs + n_local) of total_obs
+  void set_obs_range(long long first_obs, long long total_obs) { dev_.obs_offset = first_obs; total_obs_ = total_obs; }
+  long long obs_offset() const { return dev_.obs_offset; }
+  long long total_obs() const { return total_obs_; }
+  // sequence numbers for the per-tree-step exchange of one sweep (monotone over the context's lifetime)
+  unsigned long long reserve_step_seq(int steps) { unsigned long long b = step_seq_; step_seq_ += (unsigned long long) steps; return b; }
+  void check_error();
+  const ShardDev& dev() const { return dev_; }
+  // in-place all-reduce of a small device vector (n <= kMailVec), identical result on every rank
+  void allreduce(double* d_vec, int n, ReduceOp op, cudaStream_t stream);
+  // host convenience (any length; chunks of kMailVec)
+  void allreduce_host(double* h_vec, long long n, ReduceOp op, cudaStream_t stream);
+
+ private:
+  ShardDev dev_;
+  Mailbox* local_ = nullptr;
+  bool attached_ = false;
+  unsigned long long vec_seq_ = 0, step_seq_ = 0;
+  long long total_obs_ = 0;
+  double* d_tmp_ = nullptr;
+  unsigned int* d_err_ = nullptr;
+};
+
+// device side of the generic all-reduce, callable from any single CTA
+__device__ inline unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until the flag reaches `seq`; gives up after kPeerTimeoutNs (a peer died or never launched) so that a broken
+// job fails with an error instead of hanging the GPU
+constexpr unsigned long long kPeerTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ inline bool mailbox_wait(const unsigned long long* flag, unsigned long long seq)
+{
+  unsigned long long v;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= seq) return true;
+    if ((++spins & 1023u) == 0u) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kPeerTimeoutNs) return false;
+    }
+  }
+}
+__device__ inline void mailbox_post(unsigned long long* flag, unsigned long long seq)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+}
+__device__ inline double mailbox_load(const double* p)
+{
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+}  // namespace s4b

@@ -20,6 +20,7 @@
 #pragma once
 
 #include "bart_kernels.cuh"
+#include "shard.hpp"
 
 namespace s4b {
 
@@ -612,6 +613,8 @@ struct SweepSmem {
   CtlScratch csd;      // decision scratch
   CtlScratch csp;      // proposal scratch
   LeafStat st[S4B_MAX_SLOTS];
+  int peer_dead;       // a peer rank stopped answering (sharded mode): stop waiting, flag the error
+  ShardDev sh;         // copy of the kernel parameter (indexed dynamically; keeps it out of local memory)
   RngState rng;
   BartParams prm;
   double tab[kTabSize];
@@ -721,7 +724,8 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
 
 template <int NQ>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
-                                                               const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk)
+                                                               const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
+                                                               const __grid_constant__ ShardDev sh_param, unsigned long long seq_base)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
@@ -751,7 +755,13 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       R[j][0] = a.x; R[j][1] = a.y; R[j][2] = b.x; R[j][3] = b.y;
     } else { R[j][0] = R[j][1] = R[j][2] = R[j][3] = 0.0; }
   }
-  if (tid == 0) { S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; }
+  if (tid == 0) {
+    S.sh.rank = sh_param.rank; S.sh.world = sh_param.world; S.sh.obs_offset = sh_param.obs_offset;
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r) S.sh.mail[r] = sh_param.mail[r];
+  }
+  const int world = sh_param.world;
+  if (tid == 0) { S.peer_dead = 0; S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; }
   for (int i = tid; i < kTabSize; i += kSweepBlock) S.tab[i] = tables[i];
   __syncthreads();
   const int p = S.prm.p, T = S.prm.num_trees;
@@ -932,6 +942,37 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       if (lane == 0) reinterpret_cast<double*>(&S.st[v / 3])[v % 3] = acc;
     }
     __syncthreads();                                                        // [B] statistics in shared memory
+    if (world > 1) {
+      const ShardDev& sh = S.sh;
+      // ---- observation-sharded chain: exchange the per-slot statistics with the peer GPUs (shard.hpp).  CTA 0 stores
+      // this rank's sums straight into every rank's mailbox over NVLink and posts the step's sequence number; every CTA
+      // waits for all ranks' flags in the local mailbox and adds the contributions in rank order, so all CTAs of all
+      // ranks hold bitwise identical statistics and take the same decision ----
+      const unsigned long long seq = seq_base + (unsigned long long) t + 1ull;
+      const int par = (int) (seq & 1ull);
+      const int cnt = 3 * nslots;
+      double* stv = reinterpret_cast<double*>(S.st);
+      if (cta == 0) {
+        for (int i = tid; i < world * cnt; i += kSweepBlock) {
+          const int dst = i / cnt, k = i - dst * cnt;
+          sh.mail[dst]->step_data[par][sh.rank][k] = stv[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence_system();
+          for (int dst = 0; dst < world; ++dst) mailbox_post(&sh.mail[dst]->step_flag[par][sh.rank], seq);
+        }
+      }
+      if (tid < world && !S.peer_dead) { if (!mailbox_wait(&sh.mail[sh.rank]->step_flag[par][tid], seq)) S.peer_dead = 1; }
+      __syncthreads();
+      const Mailbox* mine = sh.mail[sh.rank];
+      for (int i = tid; i < cnt; i += kSweepBlock) {
+        double acc = mailbox_load(&mine->step_data[par][0][i]);
+        for (int src = 1; src < world; ++src) acc += mailbox_load(&mine->step_data[par][src][i]);
+        stv[i] = acc;
+      }
+      __syncthreads();
+    }
     const long long c3 = clock64();
     uint32_t leaf_next[NQ], aux_next[NQ];
     if (!is_worker) {
@@ -1010,6 +1051,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     out.counter += (unsigned long long) (S.csd.draws_total + S.csp.draws_total);
     *dv.rng = out;
     if (out.tape_underrun) dv.params->error_flag |= 2u;
+    if (S.peer_dead) dv.params->error_flag |= 4u;
     dv.params->step_id = step0 + (unsigned long long) T;
     dv.desc->a_valid = 0;
     if (dv.prof != nullptr) {

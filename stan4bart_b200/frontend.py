@@ -163,3 +163,15 @@ def friedman_problem(n, binary=False, seed=99, n_g1=5, n_g2=8, with_test=True):
     offset_init, sigma_init = init_fit(sd, binary)
     return dict(data=d, x_bart=x_bart, x_test=x_test, stan_data=sd, y=np.ascontiguousarray(d["y"]),
                 bart_offset_init=offset_init, sigma_init=sigma_init)
+
+
+def shard_problem(prob, lo, hi):
+    """Rows [lo, hi) of a problem built by `friedman_problem` (or laid out like it): what one rank of an
+    observation-sharded chain holds.  The initial offset / sigma come from the whole-data fit."""
+    out = dict(prob)
+    out["x_bart"] = np.asfortranarray(prob["x_bart"][lo:hi])
+    out["x_test"] = np.asfortranarray(prob["x_test"][lo:hi]) if prob.get("x_test") is not None else None
+    out["stan_data"] = prob["stan_data"].rows(lo, hi)
+    out["y"] = np.ascontiguousarray(prob["y"][lo:hi])
+    out["bart_offset_init"] = np.ascontiguousarray(prob["bart_offset_init"][lo:hi])
+    return out

@@ -18,7 +18,7 @@ TRACE_LEN = 32
 
 
 class GpuBart:
-    def __init__(self, cfg, y, x, x_test=None, handle=None):
+    def __init__(self, cfg, y, x, x_test=None, handle=None, shard=None):
         self.L = _lib.load()
         self.cfg = cfg
         self.n, self.p, self.nt = int(cfg.n), int(cfg.p), int(cfg.n_test)
@@ -33,7 +33,11 @@ class GpuBart:
         if x.shape != (self.n, self.p):
             raise ValueError("x must be n x p")
         h = C.c_void_p()
-        _lib.check(self.L.gpubart_create(C.byref(cfg), dptr(y), dptr(x), dptr(xt), C.byref(h)))
+        if shard is None:
+            _lib.check(self.L.gpubart_create(C.byref(cfg), dptr(y), dptr(x), dptr(xt), C.byref(h)))
+        else:       # this rank's rows of an observation-sharded chain (shard.py)
+            _lib.check(self.L.gpubart_create_sharded(C.byref(cfg), dptr(y), dptr(x), dptr(xt), shard.h, C.byref(h)))
+        self._shard = shard
         self.h = h
 
     def __del__(self):
@@ -181,7 +185,7 @@ class GpuBart:
 
 
 class GlmmModel:
-    def __init__(self, stan_data, handle=None):
+    def __init__(self, stan_data, handle=None, shard=None):
         self.L = _lib.load()
         self.sd = stan_data
         self._owner = handle is None
@@ -189,7 +193,11 @@ class GlmmModel:
             _lib.require_device()
             self._struct = stan_data.struct()
             h = C.c_void_p()
-            _lib.check(self.L.glmm_create(C.byref(self._struct), C.byref(h)))
+            if shard is None:
+                _lib.check(self.L.glmm_create(C.byref(self._struct), C.byref(h)))
+            else:
+                _lib.check(self.L.glmm_create_sharded(C.byref(self._struct), shard.h, C.byref(h)))
+            self._shard = shard
             self.h = h
         else:
             self.h = handle
@@ -256,8 +264,9 @@ class Sampler:
     """stan4bart_create(...) -> sampler object with run / disengage_adaptation / ... methods."""
 
     def __init__(self, bart_cfg, y, x_bart, x_test, stan_data, stan_ctl, warmup, iter_, keep_fits=True, sigma_init=1.0,
-                 bart_offset_init=None):
+                 bart_offset_init=None, shard=None):
         self.L = _lib.load()
+        self._shard = shard
         _lib.require_device()
         self.bcfg = bart_cfg
         self.sd = stan_data
@@ -270,8 +279,12 @@ class Sampler:
                                 sigma_init=float(sigma_init))
         self.keep_fits = bool(keep_fits)
         h = C.c_void_p()
-        _lib.check(self.L.s4b_sampler_create(C.byref(bart_cfg), dptr(y), dptr(x), dptr(xt), C.byref(self._gs), C.byref(stan_ctl),
-                                             C.byref(self.cc), dptr(off), C.byref(h)))
+        if shard is None:
+            _lib.check(self.L.s4b_sampler_create(C.byref(bart_cfg), dptr(y), dptr(x), dptr(xt), C.byref(self._gs), C.byref(stan_ctl),
+                                                 C.byref(self.cc), dptr(off), C.byref(h)))
+        else:
+            _lib.check(self.L.s4b_sampler_create_sharded(C.byref(bart_cfg), dptr(y), dptr(x), dptr(xt), C.byref(self._gs),
+                                                         C.byref(stan_ctl), C.byref(self.cc), dptr(off), shard.h, C.byref(h)))
         self.h = h
         k = C.c_int(0)
         _lib.check(self.L.s4b_sampler_num_stan_pars(self.h, C.byref(k)))

@@ -129,6 +129,20 @@ class StanData:
         self.num_params = self.K + self.q + self.len_rho + len(self.concentration) + self.t + (0 if self.is_binary else 1)
         self.num_constrained = self.num_params + (0 if self.is_binary else 1) + self.K + self.q + self.len_theta_L
 
+    def rows(self, lo, hi):
+        """The same model restricted to observations [lo, hi): the shard of one rank of an observation-sharded chain.
+        Priors, the ranef layout and the column space of Z (q) are those of the whole data set."""
+        lo, hi = int(lo), int(hi)
+        k0, k1 = int(self.u[lo]), int(self.u[hi])
+        out = StanData(self.X[lo:hi], self.y[lo:hi], self.is_binary, self.prior_dist, self.prior_scale, self.prior_mean,
+                       self.prior_dist_for_aux, self.prior_scale_for_aux, self.prior_mean_for_aux, self.prior_df_for_aux,
+                       self.p, self.l, self.shape, self.scale, self.concentration, self.regularization,
+                       self.w[k0:k1], self.v[k0:k1], self.u[lo:hi + 1] - k0, self.q)
+        for name in ("xbar", "term_order"):
+            if hasattr(self, name):
+                setattr(out, name, getattr(self, name))
+        return out
+
     def struct(self):
         return GlmmData(
             N=self.N, K=self.K, is_binary=int(self.is_binary), prior_dist=self.prior_dist,

@@ -2,6 +2,7 @@
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -61,3 +62,48 @@ def test_single_process_fallbacks():
     assert max_over_ranks(3.5) == 3.5
     v, ms = aggregate_throughput(40, 20.0)
     assert v == 2000.0 and ms == 20.0
+
+
+# ---- observation-sharded chains: host-side row partition (stan4bart_b200/shard.py, frontend.shard_problem) ----
+def test_row_range_covers_everything_once():
+    from stan4bart_b200.shard import row_range
+    for n in (1, 2, 7, 100, 1501, 1000000):
+        for world in (1, 2, 3, 8):
+            edges = [row_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for a, b in zip(edges[:-1], edges[1:]):
+                assert a[1] == b[0]
+            assert all(lo % 4 == 0 for lo, _ in edges if lo < n)
+    with pytest.raises(ValueError):
+        row_range(10, 2, 2)
+
+
+def test_sharded_stan_data_terms_add_up_to_the_whole():
+    """The GLMM reductions a sharded chain all-reduces (S, X'e, Z'e) are sums over rows: the row shards produced by
+    StanData.rows() must add up to the whole-data terms on the CPU oracle."""
+    import oracle_lib as O
+    from stan4bart_b200.frontend import friedman_problem, shard_problem
+    from stan4bart_b200.shard import row_range
+    n, world = 403, 3
+    pr = friedman_problem(n)
+    sd = pr["stan_data"]
+    rng = np.random.default_rng(1)
+    beta, b = rng.standard_normal(sd.K), rng.standard_normal(sd.q)
+    off = rng.standard_normal(n)
+    whole = O.OracleGlmm(sd)
+    whole.set_offset(off)
+    S, gbeta, gb = whole.data_terms(beta, b)
+    S2, gbeta2, gb2 = 0.0, np.zeros(sd.K), np.zeros(sd.q)
+    rows = 0
+    for r in range(world):
+        lo, hi = row_range(n, r, world)
+        sp = shard_problem(pr, lo, hi)
+        assert sp["stan_data"].q == sd.q and sp["stan_data"].N == hi - lo and len(sp["y"]) == hi - lo
+        part = O.OracleGlmm(sp["stan_data"])
+        part.set_offset(off[lo:hi])
+        s_, a_, b_ = part.data_terms(beta, b)
+        S2 += s_; gbeta2 += a_; gb2 += b_
+        rows += hi - lo
+    assert rows == n
+    assert abs(S - S2) <= 1e-10 * abs(S)
+    assert np.allclose(gbeta, gbeta2, rtol=1e-10, atol=1e-10) and np.allclose(gb, gb2, rtol=1e-10, atol=1e-10)

@@ -1,0 +1,148 @@
+"""Observation-sharded chains on 2 GPUs: one process per GPU, rows split in contiguous blocks,
+per-tree statistics and GLMM reductions exchanged through peer-mapped mailboxes inside the kernels.  Every rank must
+reproduce the CPU oracle run on the WHOLE data set (integer fields exact, floating fields to the usual tolerance;
+the only difference to the single-GPU path is the order of the final sums).  Skipped on boxes with fewer than 2 GPUs:
+run with `gpurun --gpus 2 -- python -m pytest tests/test_shard_gpu.py -m gpu`."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import shard_cases as SC
+from common import compare_traces, rel_err
+from stan4bart_b200.frontend import friedman_problem
+from stan4bart_b200.shard import row_range
+from stan4bart_b200.structs import bart_config, stan_control
+
+pytestmark = pytest.mark.gpu
+WORLD = 2
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _device_count():
+    from stan4bart_b200 import _lib
+    return _lib.load().s4b_device_count()
+
+
+@pytest.fixture(scope="module")
+def ranks():
+    if _device_count() < WORLD:
+        pytest.skip("needs 2 GPUs on one box")
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "shard")
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={WORLD}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.join(HERE, "shard_worker.py"), "--out", out]
+        # the kernels give up on a silent peer after 30 s; the outer limit only guards the launch itself
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-4000:] + "\n" + p.stderr[-4000:]
+        yield [dict(np.load(f"{out}.rank{r}.npz")) for r in range(WORLD)]
+
+
+def _cat(ranks, key, axis=0):
+    return np.concatenate([r[key] for r in ranks], axis=axis)
+
+
+def test_small_allreduce_is_rank_ordered_and_identical(ranks):
+    v = [SC.allreduce_input(r) for r in range(WORLD)]
+    want = v[0].copy()
+    for r in range(1, WORLD):
+        want = want + v[r]
+    for r in ranks:
+        assert np.array_equal(r["allreduce_sum"], want)                    # same order of additions: bit-exact
+        assert np.array_equal(r["allreduce_max"], np.maximum.reduce(v))
+    long_want = SC.allreduce_long_input(0)
+    for r in range(1, WORLD):
+        long_want = long_want + SC.allreduce_long_input(r)
+    for r in ranks:
+        assert np.array_equal(r["allreduce_long"], long_want)              # chunked path (> 1024 entries)
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_sharded_bart_matches_whole_data_oracle(ranks, binary):
+    tag = "bin" if binary else "cont"
+    x, y, off = SC.bart_data(binary)
+    cfg = bart_config(len(y), x.shape[1], n_test=0, num_trees=SC.BART_TREES, is_binary=binary, seed=SC.BART_SEED)
+    o = O.OracleBart(cfg, y, x)
+    o.set_offset(off, True)
+    if not binary:
+        o.set_sigma(1.3)
+    o.sample_trees_from_prior()
+    o.set_trace(SC.BART_TREES * SC.BART_SWEEPS)
+    for _ in range(SC.BART_SWEEPS):
+        ro = o.run()
+    tr_o = o.trace()
+    for r in ranks:
+        compare_traces(tr_o, r[f"bart_{tag}_trace"], tol=1e-8)
+        assert rel_err(o.data_range(), r[f"bart_{tag}_range"]) <= 1e-12
+    assert np.array_equal(ranks[0][f"bart_{tag}_trace"], ranks[1][f"bart_{tag}_trace"])     # ranks agree bit for bit
+    train = _cat(ranks, f"bart_{tag}_train")
+    assert rel_err(ro["train"], train, scale=np.abs(ro["train"]) + 1.0) <= 1e-8
+    res = _cat(ranks, f"bart_{tag}_residual")
+    assert rel_err(o.residual(), res, scale=np.abs(o.residual()) + 1.0) <= 1e-8
+    # leaf statistics of tree 0 are those of the whole data set, on every rank
+    heap, cnt, s, ss = o.leaf_stats(0)
+    for r in ranks:
+        ls = r[f"bart_{tag}_leafstats"]
+        assert np.array_equal(ls[:, 0].astype(np.int64), heap) and np.array_equal(ls[:, 1].astype(np.int64), cnt)
+        assert rel_err(s, ls[:, 2], scale=np.abs(s) + 1e-3 * cnt) <= 1e-10 and rel_err(ss, ls[:, 3]) <= 1e-10
+    to = o.trees()
+    for r in ranks:
+        assert np.array_equal(to["var"], r[f"bart_{tag}_trees_var"])
+        assert np.array_equal(to["n"], r[f"bart_{tag}_trees_n"])            # counts of the whole data set
+        assert rel_err(to["value"], r[f"bart_{tag}_trees_value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-8
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sharded_glmm_density_matches_whole_data_oracle(ranks, mode):
+    pr = friedman_problem(SC.GLMM_N)
+    g = O.OracleGlmm(pr["stan_data"])
+    g.set_offset(SC.glmm_offset())
+    for k, q in enumerate(SC.glmm_points(g.d)):
+        lp, grad, st = g.log_prob_grad(q)
+        for r in ranks:
+            row = r[f"glmm_mode{mode}"][k]
+            assert int(row[1]) == st
+            assert abs(row[0] - lp) <= 1e-10 * max(1.0, abs(lp))
+            assert rel_err(grad, row[2:], scale=np.abs(grad) + 1.0) <= 1e-10
+    assert np.array_equal(ranks[0][f"glmm_mode{mode}"], ranks[1][f"glmm_mode{mode}"])
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_sharded_gibbs_matches_whole_data_oracle(ranks, binary):
+    tag = "bin" if binary else "cont"
+    n = SC.GIBBS_N
+    pr = friedman_problem(n, binary=binary)
+    cfg = bart_config(n, 9, n_test=n, num_trees=SC.GIBBS_TREES, is_binary=binary, seed=SC.GIBBS_SEED)
+    ctl = stan_control(seed=SC.GIBBS_SEED + 1)
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, warmup=SC.GIBBS_WARMUP, iter_=SC.GIBBS_ITER,
+                        keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    ob = o.bart()
+    ob.set_trace(SC.GIBBS_TREES * (SC.GIBBS_WARMUP + SC.GIBBS_SAMPLES))
+    w = o.run(SC.GIBBS_WARMUP, True)
+    o.disengage_adaptation()
+    s = o.run(SC.GIBBS_SAMPLES, False)
+    tr_o = ob.trace()
+    for r in ranks:
+        compare_traces(tr_o, r[f"gibbs_{tag}_trace"], tol=1e-7)
+        for nm, part in (("w", w), ("r", s)):
+            assert rel_err(part["stan"], r[f"gibbs_{tag}_{nm}_stan"], scale=np.abs(part["stan"]) + 1.0) <= 1e-7
+            assert np.array_equal(part["bart"]["varcount"], r[f"gibbs_{tag}_{nm}_varcount"])
+            assert rel_err(part["bart"]["sigma"], r[f"gibbs_{tag}_{nm}_sigma"]) <= 1e-7
+        assert rel_err(o.data_range(), r[f"gibbs_{tag}_range"]) <= 1e-10
+    # replicated state is bitwise identical on the two ranks
+    for key in (f"gibbs_{tag}_trace", f"gibbs_{tag}_w_stan", f"gibbs_{tag}_r_stan"):
+        assert np.array_equal(ranks[0][key], ranks[1][key]), key
+    for nm, part in (("w", w), ("r", s)):
+        for which in ("train", "test"):
+            got = _cat(ranks, f"gibbs_{tag}_{nm}_{which}", axis=0)
+            want = part["bart"][which]
+            assert rel_err(want, got, scale=np.abs(want) + 1.0) <= 1e-7
+    lo, hi = row_range(n, 1, WORLD)
+    assert ranks[1][f"gibbs_{tag}_parmean"].shape == (hi - lo,)
+    got = _cat(ranks, f"gibbs_{tag}_mean_train")
+    assert rel_err(s["bart"]["train"].mean(axis=1), got, scale=1.0) <= 1e-7
