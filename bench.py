@@ -35,10 +35,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=1_000_000, help="observations (use --rows under torchrun: its parser trips over --n)")
     ap.add_argument("--trees", type=int, default=200)
     ap.add_argument("--adapt", type=int, default=200, help="adaptation sweeps before adaptation is disengaged (untimed; >= 150 so that the metric windows of Stan run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-rows", action="store_true",
+                    help="N > 1 only: ONE chain whose --n rows are sharded over the N GPUs (BASELINE config E; strong scaling) instead of "
+                         "one independent chain per GPU")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -268,11 +271,24 @@ def run_ours(args):
     from stan4bart_b200.dist import barrier, chain_seed, max_over_ranks
 
     pr = make_problem(args)
-    sd = pr["stan_data"]
     n, T = args.n, args.trees
-    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=True, seed=chain_seed(12345, rank))
-    s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=chain_seed(1000, rank)), warmup=args.adapt, iter_=args.adapt + args.steps,
-                keep_fits=False)
+    sharded = bool(args.shard_rows) and world > 1
+    shard_ctx = None
+    chains = world
+    if sharded:
+        # one chain, rows dealt out in contiguous blocks; every rank runs the replicated controller with the same seeds
+        from stan4bart_b200.frontend import shard_problem
+        from stan4bart_b200.shard import ShardContext, row_range
+        shard_ctx = ShardContext.from_torch_distributed(total_obs=n)
+        lo, hi = row_range(n, rank, world)
+        pr = shard_problem(pr, lo, hi)
+        n = hi - lo
+        chains = 1
+    seed_rank = 0 if sharded else rank
+    sd = pr["stan_data"]
+    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=True, seed=chain_seed(12345, seed_rank))
+    s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=chain_seed(1000, seed_rank)), warmup=args.adapt,
+                iter_=args.adapt + args.steps, keep_fits=False, shard=shard_ctx)
     bart = s.bart()
     glmm = s.glmm()
     s.run(args.adapt, True, results=False)
@@ -300,7 +316,7 @@ def run_ours(args):
     sweep_ms = bart.tree_step_ms(reset=True)
     names = sd.param_names()
     n_leapfrog = float(out["stan"][names.index("n_leapfrog__")][-1])
-    value = world * K / (ms / 1000.0)
+    value = chains * K / (ms / 1000.0)
 
     # ---- roofline of the dominant kernel ----
     trees = bart.trees()
@@ -339,7 +355,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.time() - t0)
     s.set_host_plumbing(False)
     clocks.stop()
-    e2e = {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + 2 * 8 * n + 8 * s.num_pars),
+    e2e = {"value": chains * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + 2 * 8 * n + 8 * s.num_pars),
            "note": "s4b_sampler_run with host result buffers (train + test fits, Stan row) and every N-vector of the sweep "
                    "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors"}
 
@@ -349,8 +365,9 @@ def run_ours(args):
     launches = K * (per_sweep_bart + 2 + 1 + 2 + 3) + glmm_passes
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args), **({"sharding": f"one chain, rows sharded over {world} GPUs ({n} rows on rank 0)"} if sharded else {})),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
             "breakdown": {"ms_stan_block": stats["ms_stan"] / K, "ms_bart_block": stats["ms_bart"] / K, "grad_evals_per_sweep": stats["grad_evals"] / K,
                           "glmm_device_passes_per_sweep": glmm_passes / K, "glmm_mode": glmm.mode(), "bart_sweep_mode": bart.sweep_mode(),

@@ -17,9 +17,10 @@ constexpr int kMaxRanks = 8;
 constexpr int kMailVec = 1024;     // capacity of the generic small all-reduce
 
 struct Mailbox {
-  // per-tree-step statistics, double buffered by step parity; flag = sequence number of the step
-  unsigned long long step_flag[2][kMaxRanks];
-  double step_data[2][kMaxRanks][3 * S4B_MAX_SLOTS];
+  // per-tree-step statistics, double buffered by step parity.  Low-latency layout: every double travels as two 8-byte
+  // words (flag32 << 32 | half32) so that data and flag arrive in the same store -- no fence and no second hop between
+  // "data written" and "flag visible"; the flag is the low 32 bits of the step's sequence number
+  ulonglong2 step_ll[2][kMaxRanks][3 * S4B_MAX_SLOTS];
   // generic small vectors (GLMM reductions, min / max for the rescale, cut-point ranges)
   unsigned long long vec_flag[2][kMaxRanks];
   double vec_data[2][kMaxRanks][kMailVec];
@@ -91,6 +92,31 @@ __device__ inline bool mailbox_wait(const unsigned long long* flag, unsigned lon
       else if (now - t0 > kPeerTimeoutNs) return false;
     }
   }
+}
+// flag-in-word transport of one double (see Mailbox::step_ll)
+__device__ inline void mailbox_send_ll(ulonglong2* slot, double v, unsigned int seq32)
+{
+  const unsigned long long bits = (unsigned long long) __double_as_longlong(v);
+  const unsigned long long f = (unsigned long long) seq32 << 32;
+  const unsigned long long lo = f | (bits & 0xFFFFFFFFull), hi = f | (bits >> 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(lo), "l"(hi) : "memory");
+}
+__device__ inline bool mailbox_recv_ll(const ulonglong2* slot, unsigned int seq32, double* out)
+{
+  unsigned long long lo, hi;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(slot) : "memory");
+    if ((unsigned int) (lo >> 32) == seq32 && (unsigned int) (hi >> 32) == seq32) break;
+    if ((++spins & 1023u) == 0u) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kPeerTimeoutNs) return false;
+    }
+  }
+  *out = __longlong_as_double((long long) ((hi << 32) | (lo & 0xFFFFFFFFull)));
+  return true;
 }
 __device__ inline void mailbox_post(unsigned long long* flag, unsigned long long seq)
 {

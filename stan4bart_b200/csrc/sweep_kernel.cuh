@@ -942,33 +942,36 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       if (lane == 0) reinterpret_cast<double*>(&S.st[v / 3])[v % 3] = acc;
     }
     __syncthreads();                                                        // [B] statistics in shared memory
+    const long long cx = clock64();
     if (world > 1) {
       const ShardDev& sh = S.sh;
       // ---- observation-sharded chain: exchange the per-slot statistics with the peer GPUs (shard.hpp).  CTA 0 stores
-      // this rank's sums straight into every rank's mailbox over NVLink and posts the step's sequence number; every CTA
-      // waits for all ranks' flags in the local mailbox and adds the contributions in rank order, so all CTAs of all
-      // ranks hold bitwise identical statistics and take the same decision ----
+      // this rank's sums straight into every peer's mailbox over NVLink, each double as two flag-carrying 8-byte words
+      // (no fence, one hop); every CTA polls the local mailbox and adds the contributions in rank order, so all CTAs
+      // of all ranks hold bitwise identical statistics and take the same decision ----
       const unsigned long long seq = seq_base + (unsigned long long) t + 1ull;
+      const unsigned int seq32 = (unsigned int) seq;
       const int par = (int) (seq & 1ull);
       const int cnt = 3 * nslots;
       double* stv = reinterpret_cast<double*>(S.st);
+      double mine_k = 0.0;
+      if (tid < cnt) mine_k = stv[tid];
       if (cta == 0) {
         for (int i = tid; i < world * cnt; i += kSweepBlock) {
           const int dst = i / cnt, k = i - dst * cnt;
-          sh.mail[dst]->step_data[par][sh.rank][k] = stv[k];
-        }
-        __syncthreads();
-        if (tid == 0) {
-          __threadfence_system();
-          for (int dst = 0; dst < world; ++dst) mailbox_post(&sh.mail[dst]->step_flag[par][sh.rank], seq);
+          mailbox_send_ll(&sh.mail[dst]->step_ll[par][sh.rank][k], stv[k], seq32);
         }
       }
-      if (tid < world && !S.peer_dead) { if (!mailbox_wait(&sh.mail[sh.rank]->step_flag[par][tid], seq)) S.peer_dead = 1; }
-      __syncthreads();
+      __syncthreads();                                   // everyone has read the local sums before they are overwritten
       const Mailbox* mine = sh.mail[sh.rank];
       for (int i = tid; i < cnt; i += kSweepBlock) {
-        double acc = mailbox_load(&mine->step_data[par][0][i]);
-        for (int src = 1; src < world; ++src) acc += mailbox_load(&mine->step_data[par][src][i]);
+        double acc = 0.0;
+        for (int src = 0; src < world; ++src) {
+          double v = 0.0;
+          if (src == sh.rank && i == tid) v = mine_k;    // own contribution needs no round trip
+          else if (!S.peer_dead && !mailbox_recv_ll(&mine->step_ll[par][src][i], seq32, &v)) S.peer_dead = 1;
+          acc = src == 0 ? v : acc + v;
+        }
         stv[i] = acc;
       }
       __syncthreads();
@@ -1036,7 +1039,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(g.nodes)[i] = reinterpret_cast<const uint32_t*>(tree.nodes)[i];
     }
     __syncthreads();                                                        // [D] upd / tree / descriptor buffers free again
-    if (cta == 0 && tid == 0) { pc[1] += c2 - c0; pc[2] += c3 - c2; pc[3] += c5 - c3; pc[5] += clock64() - c5; }
+    if (cta == 0 && tid == 0) { pc[1] += c2 - c0; pc[2] += cx - c2; pc[4] += c3 - cx; pc[3] += c5 - c3; pc[5] += clock64() - c5; }
   }
 
   // ---- write back ----
@@ -1056,7 +1059,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     dv.desc->a_valid = 0;
     if (dv.prof != nullptr) {
       // [0] accumulate + CTA reduction (CTA 0), [1] ... + grid barrier + controller wait, [2] statistics reduce,
-      // [3] decision (overlapped with the next walk), [5] update, [7] steps
+      // [3] decision (overlapped with the next walk), [4] cross-rank exchange (sharded chains), [5] update, [7] steps
       for (int i = 0; i < 6; ++i) dv.prof[i] += (unsigned long long) pc[i];
       dv.prof[7] += (unsigned long long) T;
       // [8..11] decision: slot summaries + accept, structure, leaf draws, update descriptor; [12..15] controller before the
