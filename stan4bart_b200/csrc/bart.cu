@@ -739,7 +739,7 @@ template <int NQ>
 static size_t sweep_smem_bytes(int p)
 {
   size_t base = ((sizeof(SweepSmem) + 15) / 16) * 16;
-  size_t bins = (size_t) (kBinSlots + 1) * kWorkers * (sizeof(double2) + sizeof(int));
+  size_t bins = (size_t) (kBinSlots + 1) * kWorkers * sizeof(double2) + (size_t) kWorkers * sizeof(unsigned long long);
   size_t tile = (size_t) p * NQ * kWorkers * sizeof(uint32_t);
   return base + bins + tile;
 }
@@ -754,21 +754,23 @@ void BartFit::setup_persistent()
   int max_smem = 0; S4B_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if (coop) {
     const long long nquad = (n_ + 3) / 4;
-    auto try_nq = [&](int nq, size_t smem, const void* fn) -> bool {
+    auto try_nq = [&](int nq, size_t smem, const void* fn, const void* fn_seq) -> bool {
       if (smem > (size_t) max_smem || p_ > 511) return false;      // traversal records carry 9 bits of variable index
-      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); return false; }
-      int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) != cudaSuccess) { cudaGetLastError(); return false; }
-      if (per_sm < 1) return false;
+      for (const void* f : { fn, fn_seq }) {
+        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); return false; }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, kSweepBlock, smem) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (per_sm < 1) return false;
+      }
       long long grid = num_sms_;                       // one CTA per SM
       long long need = (nquad + (long long) nq * kWorkers - 1) / ((long long) nq * kWorkers);
       if (need > grid) return false;
       persistent_nq_ = nq; persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(grid, (nquad + kWorkers - 1) / kWorkers)); persistent_smem_ = smem;
       return true;
     };
-    if (!try_nq(1, sweep_smem_bytes<1>(p_), (const void*) k_sweep<1>))
-      if (!try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2>))
-        try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4>);
+    if (!try_nq(1, sweep_smem_bytes<1>(p_), (const void*) k_sweep<1, false>, (const void*) k_sweep<1, true>))
+      if (!try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2, false>, (const void*) k_sweep<2, true>))
+        try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4, false>, (const void*) k_sweep<4, true>);
   }
   if (persistent_nq_ > 0) {
     partial_stride_ = 3 * S4B_MAX_SLOTS * persistent_grid_;
@@ -827,7 +829,9 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   unsigned long long seq_base = 0;
   if (sharded()) { sh = shard_->dev(); seq_base = shard_->reserve_step_seq(T_); }
   void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &seq_base };
-  const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep<1> : (persistent_nq_ == 2 ? (const void*) k_sweep<2> : (const void*) k_sweep<4>);
+  const void* fn;
+  if (sequential_rng_) fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, true> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, true> : (const void*) k_sweep<4, true>);
+  else fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, false> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, false> : (const void*) k_sweep<4, false>);
   S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
                                                    (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);

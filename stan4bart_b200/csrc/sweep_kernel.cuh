@@ -55,12 +55,32 @@ struct CtlScratch {
   int32_t pad0;
   int32_t draws_total;              // draws consumed through this scratch since kernel start
   long long dbg[8];                 // cycle counters (diagnostics)
+  long long fine[4];                // decision, first part: slot summaries, staging, ratio, accept
 };
 
 // ---------------------------------------------------------------------------------------
 // warp-cooperative RNG over one substream: 32 draws are generated at once (lane i -> draw base + i)
 // and consumed in order.  Replay (tape) and recording force strictly sequential program order.
 // ---------------------------------------------------------------------------------------
+// one out-of-line copy: Philox + AS241 are ~500 instructions and the refill sits on many rarely taken paths of the
+// controller, whose instruction footprint is what its latency is made of
+__device__ __noinline__ void warp_rng_fill(const RngState* g, CtlScratch* cs, unsigned long long step, uint32_t sub, uint32_t base, int lane)
+{
+  const RngState& r = *g;
+  double u, z;
+  if (r.tape != nullptr) {
+    unsigned long long idx = r.tape_pos + (unsigned long long) lane;
+    u = idx < r.tape_len ? r.tape[idx] : 0.5;
+    z = idx < r.tape_len ? u : 0.0;
+  } else {
+    u = keyed_stream_uniform(r.key0, r.key1, r.stream, step, sub, base + (uint32_t) lane);
+    z = qnorm_as241(u);
+  }
+  __syncwarp();
+  cs->ubuf[lane] = u; cs->zbuf[lane] = z;
+  __syncwarp();
+}
+
 struct WarpRng {
   RngState* g;        // shared-memory copy (tape / record bookkeeping), identical in every CTA
   CtlScratch* cs;
@@ -73,20 +93,8 @@ struct WarpRng {
 
   __device__ void fill()
   {
-    const RngState& r = *g;
-    double u, z;
-    if (r.tape != nullptr) {
-      unsigned long long idx = r.tape_pos + (unsigned long long) lane;
-      u = idx < r.tape_len ? r.tape[idx] : 0.5;
-      z = idx < r.tape_len ? u : 0.0;
-    } else {
-      u = keyed_stream_uniform(r.key0, r.key1, r.stream, step, sub, base + (uint32_t) lane);
-      z = qnorm_as241(u);
-    }
-    __syncwarp();
-    cs->ubuf[lane] = u; cs->zbuf[lane] = z;
+    warp_rng_fill(g, cs, step, sub, base, lane);
     pos = 0;
-    __syncwarp();
   }
   // the buffer was filled by someone else (pre-computed draws): start consuming at its beginning
   __device__ void adopt() { pos = 0; __syncwarp(); }
@@ -478,8 +486,10 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     LeafStat st = s < nslots ? stats[s] : LeafStat{ stats[sl_bd].n + stats[sr_bd].n, stats[sl_bd].sum + stats[sr_bd].sum, stats[sl_bd].sumsq + stats[sr_bd].sumsq };
     slot_summary(st, inv_sigsq, P.leaf_prec, cs.pmean[s], cs.psd[s], cs.ll[s]);
   }
+  const long long f1 = clock64();
   for (int k = lane; k < nn_old; k += 32) upd.val_old[k] = in.b_cur.val[k];
   __syncwarp();
+  const long long f2 = clock64();
   bool accept = false;
   double ratio = -1.0, old_ll = 0.0, new_ll = 0.0, n_first = 0.0, n_second = 0.0;
   if (kind == 0 || kind == 1) {
@@ -515,6 +525,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
 
   // ---- structural change, all lanes ----
   const long long d1 = clock64();
+  if (lane == 0) { cs.fine[0] += f1 - d0; cs.fine[1] += f2 - f1; cs.fine[2] += d1 - f2; }
   const int amode = !accept ? 0 : (kind == 0 ? 1 : (kind == 1 ? 2 : 3));
   if (amode == 1 || amode == 2) {
     for (int k = lane; k < nn_old; k += 32) cs.tmp[k] = t.nodes[k];
@@ -624,6 +635,7 @@ struct SweepSmem {
 __device__ __forceinline__ uint32_t walk_quad(const uint32_t* __restrict__ trav, const uint32_t* __restrict__ tile, int tile_stride, int qslot, int depth)
 {
   int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll 1
   for (int lvl = 0; lvl < depth; ++lvl) {
     const uint32_t t0 = trav[n0], t1 = trav[n1], t2 = trav[n2], t3 = trav[n3];
     const uint32_t w0 = tile[(t0 >> 23) * tile_stride + qslot], w1 = tile[(t1 >> 23) * tile_stride + qslot];
@@ -722,7 +734,9 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
   if (lane == 0) atomicAdd(&dv.rng->counter, (unsigned long long) W.cs.draws_total);
 }
 
-template <int NQ>
+// SEQ: replay / record keep the strict program order of the draws (proposals and draws produced inside the loop);
+// the production instantiation (SEQ = false) carries none of that code
+template <int NQ, bool SEQ>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
                                                                const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
                                                                const __grid_constant__ ShardDev sh_param, unsigned long long seq_base)
@@ -731,8 +745,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
   // lane-private statistic bins: [slot][thread] -> (sum, sum^2) and count; no atomics, no bank conflicts
   double2* bin_s = reinterpret_cast<double2*>(smem_raw + ((sizeof(SweepSmem) + 15) / 16) * 16);
-  int* bin_n = reinterpret_cast<int*>(bin_s + (kBinSlots + 1) * kWorkers);
-  uint32_t* tile = reinterpret_cast<uint32_t*>(bin_n + (kBinSlots + 1) * kWorkers);                    // [p][NQ * kWorkers]
+  unsigned long long* bin_c = reinterpret_cast<unsigned long long*>(bin_s + (kBinSlots + 1) * kWorkers);   // packed per-thread counts
+  uint32_t* tile = reinterpret_cast<uint32_t*>(bin_c + kWorkers);                                      // [p][NQ * kWorkers]
   constexpr int tile_stride = NQ * kWorkers;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -761,13 +775,13 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     for (int r = 0; r < kMaxRanks; ++r) S.sh.mail[r] = sh_param.mail[r];
   }
   const int world = sh_param.world;
-  if (tid == 0) { S.peer_dead = 0; S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; }
+  if (tid == 0) { S.peer_dead = 0; S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; for (int i = 0; i < 4; ++i) S.csd.fine[i] = 0; }
   for (int i = tid; i < kTabSize; i += kSweepBlock) S.tab[i] = tables[i];
   __syncthreads();
   const int p = S.prm.p, T = S.prm.num_trees;
   const unsigned long long step0 = S.prm.step_id;
   // replay / record need strict program order: proposals and draws are then produced inside the loop
-  const bool sequential_rng = descs == nullptr;
+  constexpr bool sequential_rng = SEQ;
   if (is_worker) {
     const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(dv.xt);
     const long long col_words = npad >> 2;
@@ -820,7 +834,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         const int base = chunk * kBinSlots;
         const int kmax = min(kBinSlots, nslots - base);
         const long long w0 = clock64();
-        for (int k = 0; k < kmax; ++k) { bin_s[k * kWorkers + tid] = make_double2(0.0, 0.0); bin_n[k * kWorkers + tid] = 0; }
+        for (int k = 0; k < kmax; ++k) bin_s[k * kWorkers + tid] = make_double2(0.0, 0.0);
+        // observation counts stay in a register: one 6-bit field per bin row (a thread adds at most 32 to a row)
+        unsigned long long cpk = 0ull;
         const long long w1 = clock64();
         // branch-free: every observation adds into exactly one bin row (row kBinSlots is a trash row for padding and for
         // slots outside this pass); loads first (independent), then the read-modify-write chain
@@ -840,7 +856,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             for (int o = 0; o < 4; ++o) {
               const int idx = row[o] * kWorkers + tid;
               double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
-              bin_n[idx] += 1;
+              cpk += 1ull << (6 * row[o]);
             }
           }
         } else {
@@ -862,13 +878,13 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             for (int o = 0; o < 4; ++o) {
               int idx = row[o] * kWorkers + tid;
               double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
-              bin_n[idx] += 1;
               idx = row2[o] * kWorkers + tid;
               v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
-              bin_n[idx] += 1;
+              cpk += (1ull << (6 * row[o])) + (1ull << (6 * row2[o]));
             }
           }
         }
+        bin_c[tid] = cpk;
         const long long w2 = clock64();
         named_bar_sync(1, kWorkers);
         // row-wise reduction: task r < kmax sums (sum, sum^2) of slot r over the CTA's threads, task kmax + r its counts
@@ -883,7 +899,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             const int r = task - kmax;
             int c = 0;
 #pragma unroll
-            for (int i = 0; i < kWorkerWarps; ++i) c += bin_n[r * kWorkers + i * 32 + lane];
+            for (int i = 0; i < kWorkerWarps; ++i) c += (int) ((bin_c[i * 32 + lane] >> (6 * r)) & 63ull);
             c = __reduce_add_sync(0xffffffffu, c);
             if (lane == 0) partials[(size_t) (3 * (base + r)) * G + cta] = (double) c;
           }
@@ -892,14 +908,20 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         if (chunk + 1 < nchunks) named_bar_sync(1, kWorkers);        // the bins are reused by the next pass
         if (tid == 0) { pw[0] += w1 - w0; pw[1] += w2 - w1; pw[2] += w3 - w2; pw[3] += clock64() - w3; }
       }
-      // ---- arrive at the grid barrier and wait for every CTA's partial row ----
+      // ---- arrive at the grid barrier and wait for every CTA's partial rows.  The rows are stored by lane 0 of
+      // several warps: all of them must have issued their stores before thread 0 publishes them (fence + arrive) ----
+      named_bar_sync(1, kWorkers);
       if (tid == 0) {
         pc[0] += clock64() - c0;
         __threadfence();
         atomicAdd(barrier_counter, 1u);
         const unsigned int target = (unsigned int) (t + 1) * (unsigned int) G;
         unsigned int v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(barrier_counter) : "memory"); } while (v < target);
+        const long long w0 = clock64();
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(barrier_counter) : "memory");
+          if (v < target && (S.peer_dead || clock64() - w0 > 4000000000LL)) { S.peer_dead = 2; break; }     // a CTA never arrived: fail, do not hang
+        } while (v < target);
         __threadfence();
       }
     } else {
@@ -1054,7 +1076,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     out.counter += (unsigned long long) (S.csd.draws_total + S.csp.draws_total);
     *dv.rng = out;
     if (out.tape_underrun) dv.params->error_flag |= 2u;
-    if (S.peer_dead) dv.params->error_flag |= 4u;
+    if (S.peer_dead) dv.params->error_flag |= (S.peer_dead == 2 ? 8u : 4u);
     dv.params->step_id = step0 + (unsigned long long) T;
     dv.desc->a_valid = 0;
     if (dv.prof != nullptr) {
@@ -1066,6 +1088,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       // barrier: tree fetch, decision-draw prefill, proposal-draw prefill, proposal
       for (int i = 0; i < 8; ++i) dv.prof[8 + i] += (unsigned long long) S.csd.dbg[i];
       for (int i = 0; i < 4; ++i) dv.prof[16 + i] += (unsigned long long) pw[i];
+      for (int i = 0; i < 4; ++i) dv.prof[20 + i] += (unsigned long long) S.csd.fine[i];
     }
   }
 }

@@ -176,7 +176,8 @@ class GpuBart:
                 "ctl_fill_proposal_draws", "ctl_propose"]
         return {"steps": v[7], "cycles_per_step": {k: v[i] / steps for i, k in enumerate(names)},
                 "controller_cycles_per_step": {k: v[8 + i] / steps for i, k in enumerate(fine)},
-                "worker_cycles_per_step": {k: v[16 + i] / steps for i, k in enumerate(["zero_bins", "accumulate", "barrier_and_row_reduce", "second_barrier"])}}
+                "worker_cycles_per_step": {k: v[16 + i] / steps for i, k in enumerate(["zero_bins", "accumulate", "barrier_and_row_reduce", "second_barrier"])},
+                "decision_fine_cycles_per_step": {k: v[20 + i] / steps for i, k in enumerate(["slot_summaries", "stage_old_values", "ratio_accept", "-"])}}
 
     def num_tree_steps(self):
         k = C.c_int64(0)

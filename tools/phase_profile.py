@@ -41,6 +41,6 @@ else:
 prof = g.profile()
 names = ["pass(cta0)", "pass+barrier+helper", "reduce", "decide", "seq_propose", "update", "-"]
 print(json.dumps({"steps": prof["steps"], "cycles_per_step": dict(zip(names, prof["cycles_per_step"].values())),
-                  "controller": prof["controller_cycles_per_step"], "worker": prof["worker_cycles_per_step"]}, indent=1))
+                  "controller": prof["controller_cycles_per_step"], "worker": prof["worker_cycles_per_step"], "decision_fine": prof["decision_fine_cycles_per_step"]}, indent=1))
 tr = g.trees()
 print("nodes per tree", len(tr["var"]) / 200, "sweep mode", g.sweep_mode())
