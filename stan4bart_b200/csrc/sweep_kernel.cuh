@@ -472,37 +472,47 @@ __device__ __forceinline__ void slot_summary(const LeafStat& s, double inv_sigsq
 // decision + leaf draws (warp-cooperative)
 // ---------------------------------------------------------------------------------------
 __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, const StepDesc& in, const LeafStat* stats, UpdateDesc& upd,
-                                CtlScratch& cs, double* trace_rec, int lane)
+                                CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq)
 {
   const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
   const int nn_old = t.num_nodes;
   const long long d0 = clock64();
-  const double inv_sigsq = 1.0 / (P.sigma * P.sigma);
   // slot nslots = the merged parent of a birth / death step, summarised in the same parallel pass
   int sl_bd = 0, sr_bd = 0;
   if (kind == 0 || kind == 1) { sl_bd = kind == 0 ? L : in.b_cur.slot[node + 1]; sr_bd = kind == 0 ? L + 1 : in.b_cur.slot[t.nodes[node].right]; }
   const int nsum = nslots + ((kind == 0 || kind == 1) ? 1 : 0);
+  // lane s summarises slot s; with at most 32 slots (nearly always) the summaries also stay in registers and the
+  // decision below reads them with shuffles instead of a shared-memory round trip
+  const bool small = nsum <= 32;
+  double my_ll = 0.0, my_n = 0.0;
   for (int s = lane; s < nsum; s += 32) {
     LeafStat st = s < nslots ? stats[s] : LeafStat{ stats[sl_bd].n + stats[sr_bd].n, stats[sl_bd].sum + stats[sr_bd].sum, stats[sl_bd].sumsq + stats[sr_bd].sumsq };
-    slot_summary(st, inv_sigsq, P.leaf_prec, cs.pmean[s], cs.psd[s], cs.ll[s]);
+    double pm, ps, ll;
+    slot_summary(st, inv_sigsq, P.leaf_prec, pm, ps, ll);
+    cs.pmean[s] = pm; cs.psd[s] = ps; cs.ll[s] = ll;
+    my_ll = ll; my_n = st.n;
   }
   const long long f1 = clock64();
   for (int k = lane; k < nn_old; k += 32) upd.val_old[k] = in.b_cur.val[k];
-  __syncwarp();
+  if (!small) __syncwarp();
   const long long f2 = clock64();
   bool accept = false;
   double ratio = -1.0, old_ll = 0.0, new_ll = 0.0, n_first = 0.0, n_second = 0.0;
   if (kind == 0 || kind == 1) {
     const int sl = sl_bd, sr = sr_bd;
-    const LeafStat l = stats[sl], r = stats[sr];
-    const double ll_par = cs.ll[nslots];
-    const double ll_ch = cs.ll[sl] + cs.ll[sr];
+    double ll_par, ll_l, ll_r, n_l, n_r;
+    if (small) {
+      ll_par = __shfl_sync(0xffffffffu, my_ll, nslots); ll_l = __shfl_sync(0xffffffffu, my_ll, sl); ll_r = __shfl_sync(0xffffffffu, my_ll, sr);
+      n_l = __shfl_sync(0xffffffffu, my_n, sl); n_r = __shfl_sync(0xffffffffu, my_n, sr);
+    } else { ll_par = cs.ll[nslots]; ll_l = cs.ll[sl]; ll_r = cs.ll[sr]; n_l = stats[sl].n; n_r = stats[sr].n; }
+    const double ll_ch = ll_l + ll_r;
     if (kind == 0) { old_ll = ll_par; new_ll = ll_ch; } else { old_ll = ll_ch; new_ll = ll_par; }
     ratio = in.log_prior_trans * exp(new_ll - old_ll);
-    if (kind == 0 && (l.n < (double) P.min_obs || r.n < (double) P.min_obs)) ratio = 0.0;
+    if (kind == 0 && (n_l < (double) P.min_obs || n_r < (double) P.min_obs)) ratio = 0.0;
     accept = rng.uniform() < ratio;
-    n_first = l.n; n_second = r.n;
+    n_first = n_l; n_second = n_r;
   } else if (kind == 2 || kind == 3) {
+    if (small) __syncwarp();
     const int end = in.b_end;
     double a_old = 0.0, a_new = 0.0, mn = 1e300;
     int first_leaf = -1, second_leaf = -1, seen = 0;
@@ -522,6 +532,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     if (first_leaf >= 0) n_first = stats[in.b_prop.slot[first_leaf]].n;
     if (second_leaf >= 0) n_second = stats[in.b_prop.slot[second_leaf]].n;
   }
+  __syncwarp();        // summaries and staged leaf values visible to all lanes
 
   // ---- structural change, all lanes ----
   const long long d1 = clock64();
@@ -558,7 +569,6 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
   // ---- leaf draws: one lane per node of the final tree ----
   const long long d2 = clock64();
   const int nn = t.num_nodes;
-  const double sigsq = P.sigma * P.sigma;
   int leaves_before = 0;
   for (int base = 0; base < nn; base += 32) {
     const int k = base + lane;
@@ -615,6 +625,214 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
 }
 
 // ---------------------------------------------------------------------------------------
+// Fast path of the decision for trees of at most 30 nodes (practically all of them): everything that depends only on
+// the tree and its proposal -- the node array of the accepted outcome, which statistic slot and which normal draw
+// belong to every bottom node under either outcome, the index remap of the residual update -- is prepared by the
+// controller BEFORE the grid barrier, while it would otherwise idle.  After the barrier what is left is the arithmetic
+// on the statistics: lane s summarises slot s in registers, the ratio is assembled with shuffles, and lane k finishes
+// node k of the final tree.  Results are identical to w_decide (same formulas, same draw positions).
+// ---------------------------------------------------------------------------------------
+struct FastPlan {
+  bool valid;               // warp-uniform
+  int nn_acc;               // nodes of the tree if the proposal is accepted
+  int sl_bd, sr_bd;         // birth / death: slots of the two children
+  unsigned mask_rej, mask_acc;   // bottom nodes of the final tree under either outcome (bit k = node k)
+  unsigned mask_under;      // change / swap: bottom nodes below the proposal node
+  int slot_rej, slot_acc;   // lane k: statistic slot of node k as a bottom node of the final tree (nslots = merged parent)
+  int slot_cur, slot_prop;  // lane k: slots under the current / proposed rule (change / swap ratio)
+};
+
+// the plan crosses the grid barrier in shared memory: held in registers it would be live across the workers' code and
+// cost every thread of the block a dozen registers
+struct FastPlanSmem {
+  int valid, nn_acc, sl_bd, sr_bd;
+  unsigned mask_rej, mask_acc, mask_under;
+  int pad;
+  uint8_t slot_rej[32], slot_acc[32], slot_cur[32], slot_prop[32];
+};
+__device__ inline void plan_store(FastPlanSmem& d, const FastPlan& pl, int lane)
+{
+  if (lane == 0) { d.valid = pl.valid ? 1 : 0; d.nn_acc = pl.nn_acc; d.sl_bd = pl.sl_bd; d.sr_bd = pl.sr_bd; d.mask_rej = pl.mask_rej; d.mask_acc = pl.mask_acc; d.mask_under = pl.mask_under; }
+  d.slot_rej[lane] = (uint8_t) pl.slot_rej; d.slot_acc[lane] = (uint8_t) pl.slot_acc; d.slot_cur[lane] = (uint8_t) pl.slot_cur; d.slot_prop[lane] = (uint8_t) pl.slot_prop;
+  __syncwarp();
+}
+__device__ inline FastPlan plan_load(const FastPlanSmem& d, int lane)
+{
+  FastPlan pl;
+  pl.valid = d.valid != 0; pl.nn_acc = d.nn_acc; pl.sl_bd = d.sl_bd; pl.sr_bd = d.sr_bd; pl.mask_rej = d.mask_rej; pl.mask_acc = d.mask_acc; pl.mask_under = d.mask_under;
+  pl.slot_rej = d.slot_rej[lane]; pl.slot_acc = d.slot_acc[lane]; pl.slot_cur = d.slot_cur[lane]; pl.slot_prop = d.slot_prop[lane];
+  return pl;
+}
+
+__device__ inline FastPlan w_plan(const DTree& t, const StepDesc& in, UpdateDesc& upd, CtlScratch& cs, int lane)
+{
+  FastPlan pl;
+  const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
+  const int nn_old = t.num_nodes;
+  const bool bd = kind == 0 || kind == 1;
+  const int nsum = nslots + (bd ? 1 : 0);
+  pl.valid = nn_old + 2 <= 32 && nsum <= 32;
+  pl.nn_acc = nn_old; pl.sl_bd = 0; pl.sr_bd = 0; pl.mask_rej = 0; pl.mask_acc = 0; pl.mask_under = 0;
+  pl.slot_rej = 0; pl.slot_acc = 0; pl.slot_cur = 0; pl.slot_prop = 0;
+  if (!pl.valid) return pl;
+  const int k = lane;
+  DNode me; me.var = -1; me.cut = -1; me.right = -1; me.parent = -1; me.n = 0; me.depth = 0; me.mu = 0.0;
+  if (k < nn_old) me = t.nodes[k];
+  const bool leaf_old = k < nn_old && me.var < 0;
+  const int my_slot = k < nn_old ? (int) in.b_cur.slot[k] : 0;
+  pl.mask_rej = __ballot_sync(0xffffffffu, leaf_old);
+  pl.slot_cur = my_slot;
+  // staged values the residual update reads whatever the outcome
+  if (k < nn_old) upd.val_old[k] = in.b_cur.val[k];
+  if (kind == 0) {
+    pl.sl_bd = L; pl.sr_bd = L + 1;
+    pl.nn_acc = nn_old + 2;
+    // accepted tree: nodes after `node` move up by two, `node` becomes internal with two fresh bottom children
+    const int depth_node = __shfl_sync(0xffffffffu, me.depth, node);
+    if (k < nn_old) {
+      DNode nd = me;
+      if (nd.var >= 0 && nd.right > node) nd.right = (int16_t) (nd.right + 2);
+      if (nd.parent > node) nd.parent = (int16_t) (nd.parent + 2);
+      if (k == node) { nd.var = (int16_t) in.b_var; nd.cut = (int16_t) in.b_cut; nd.right = (int16_t) (node + 2); }
+      cs.tmp[k > node ? k + 2 : k] = nd;
+      upd.remap[k] = (uint8_t) (k > node ? k + 2 : k);
+    }
+    if (k == 0) {
+      for (int c = 1; c <= 2; ++c) { DNode& ch = cs.tmp[node + c]; ch.var = -1; ch.cut = -1; ch.right = -1; ch.parent = (int16_t) node; ch.n = 0; ch.depth = depth_node + 1; ch.mu = 0.0; }
+    }
+    pl.slot_rej = k == node ? nslots : my_slot;
+    const int old_k = (k <= node) ? k : (k <= node + 2 ? node : k - 2);
+    const int old_slot = __shfl_sync(0xffffffffu, my_slot, old_k & 31);
+    const bool old_leaf = (pl.mask_rej >> (old_k & 31)) & 1u;
+    const bool leaf_acc = k < pl.nn_acc && (k == node + 1 || k == node + 2 || (k != node && old_leaf));
+    pl.slot_acc = k == node + 1 ? L : (k == node + 2 ? L + 1 : old_slot);
+    pl.mask_acc = __ballot_sync(0xffffffffu, leaf_acc);
+  } else if (kind == 1) {
+    const int right = __shfl_sync(0xffffffffu, (int) me.right, node);
+    pl.sl_bd = __shfl_sync(0xffffffffu, my_slot, node + 1); pl.sr_bd = __shfl_sync(0xffffffffu, my_slot, right & 31);
+    pl.nn_acc = nn_old - 2;
+    if (k < nn_old && k != node + 1 && k != node + 2) {
+      DNode nd = me;
+      if (nd.var >= 0 && nd.right > node + 2) nd.right = (int16_t) (nd.right - 2);
+      if (nd.parent > node + 2) nd.parent = (int16_t) (nd.parent - 2);
+      if (k == node) { nd.var = -1; nd.cut = -1; nd.right = -1; }
+      cs.tmp[k > node + 2 ? k - 2 : k] = nd;
+    }
+    if (k < nn_old) upd.remap[k] = (uint8_t) ((k == node + 1 || k == node + 2) ? node : (k > node + 2 ? k - 2 : k));
+    pl.slot_rej = my_slot;
+    const int old_k = (k <= node) ? k : k + 2;
+    const int old_slot = __shfl_sync(0xffffffffu, my_slot, old_k & 31);
+    const bool old_leaf = old_k < 32 && ((pl.mask_rej >> (old_k & 31)) & 1u);
+    const bool leaf_acc = k < pl.nn_acc && (k == node || old_leaf);
+    pl.slot_acc = k == node ? nslots : old_slot;
+    pl.mask_acc = __ballot_sync(0xffffffffu, leaf_acc);
+  } else if (kind == 2 || kind == 3) {
+    const int end = in.b_end;
+    if (k < nn_old) {
+      DNode nd = me;
+      if (k >= node && k < end && nd.var >= 0) { const uint32_t tv = in.b_prop.trav[k]; nd.var = (int16_t) trav2_var(tv); nd.cut = (int16_t) trav2_cut(tv); }
+      cs.tmp[k] = nd;
+      upd.remap[k] = (uint8_t) k;
+    }
+    const int ps = k < nn_old ? (int) in.b_prop.slot[k] : 255;
+    pl.slot_prop = ps == 255 ? 0 : ps;
+    pl.slot_rej = my_slot;
+    pl.slot_acc = ps != 255 ? ps : my_slot;
+    pl.mask_acc = pl.mask_rej;
+    pl.mask_under = __ballot_sync(0xffffffffu, leaf_old && k >= node && k < end);
+  } else {
+    if (k < nn_old) upd.remap[k] = (uint8_t) k;
+    pl.slot_rej = my_slot; pl.slot_acc = my_slot; pl.mask_acc = pl.mask_rej;
+  }
+  __syncwarp();
+  return pl;
+}
+
+__device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartParams& P, WarpRng& rng, const StepDesc& in, const LeafStat* stats,
+                                     UpdateDesc& upd, CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq)
+{
+  const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
+  const bool bd = kind == 0 || kind == 1;
+  const int nsum = nslots + (bd ? 1 : 0);
+  const long long d0 = clock64();
+  // ---- lane s: summary of slot s (slot nslots = the merged parent of a birth / death step) ----
+  double my_ll = 0.0, my_n = 0.0, my_pm = 0.0, my_ps = 0.0;
+  if (lane < nsum) {
+    LeafStat st;
+    if (lane < nslots) st = stats[lane];
+    else { const LeafStat a = stats[pl.sl_bd], b = stats[pl.sr_bd]; st.n = a.n + b.n; st.sum = a.sum + b.sum; st.sumsq = a.sumsq + b.sumsq; }
+    slot_summary(st, inv_sigsq, P.leaf_prec, my_pm, my_ps, my_ll);
+    my_n = st.n;
+  }
+  const long long f1 = clock64();
+  // ---- Metropolis ratio ----
+  bool accept = false;
+  double ratio = -1.0, old_ll = 0.0, new_ll = 0.0, n_first = 0.0, n_second = 0.0;
+  if (bd) {
+    const double ll_par = __shfl_sync(0xffffffffu, my_ll, nslots), ll_l = __shfl_sync(0xffffffffu, my_ll, pl.sl_bd), ll_r = __shfl_sync(0xffffffffu, my_ll, pl.sr_bd);
+    const double n_l = __shfl_sync(0xffffffffu, my_n, pl.sl_bd), n_r = __shfl_sync(0xffffffffu, my_n, pl.sr_bd);
+    const double ll_ch = ll_l + ll_r;
+    if (kind == 0) { old_ll = ll_par; new_ll = ll_ch; } else { old_ll = ll_ch; new_ll = ll_par; }
+    ratio = in.log_prior_trans * exp(new_ll - old_ll);
+    if (kind == 0 && (n_l < (double) P.min_obs || n_r < (double) P.min_obs)) ratio = 0.0;
+    accept = rng.uniform() < ratio;
+    n_first = n_l; n_second = n_r;
+  } else if (kind == 2 || kind == 3) {
+    const bool under = (pl.mask_under >> lane) & 1u;
+    const double to_ = __shfl_sync(0xffffffffu, my_ll, pl.slot_cur & 31), tn_ = __shfl_sync(0xffffffffu, my_ll, pl.slot_prop & 31);
+    const double nk_ = __shfl_sync(0xffffffffu, my_n, pl.slot_prop & 31);
+    old_ll = w_sum(under ? to_ : 0.0); new_ll = w_sum(under ? tn_ : 0.0);
+    const double mn = w_min(under ? nk_ : 1e300);
+    ratio = exp(in.log_prior_trans + (new_ll - old_ll));
+    if (mn < (double) P.min_obs) ratio = 0.0;
+    accept = rng.uniform() < ratio;
+    if (trace_rec != nullptr) {
+      unsigned m = pl.mask_under;
+      if (m) { const int b = __ffs(m) - 1; n_first = __shfl_sync(0xffffffffu, nk_, b); m &= m - 1; }
+      if (m) { const int b = __ffs(m) - 1; n_second = __shfl_sync(0xffffffffu, nk_, b); }
+    }
+  }
+  const long long d1 = clock64();
+  // ---- final tree: lane k finishes node k ----
+  const int amode = !accept ? 0 : (kind == 0 ? 1 : (kind == 1 ? 2 : 3));
+  const unsigned mask = accept ? pl.mask_acc : pl.mask_rej;
+  const int ss = accept ? pl.slot_acc : pl.slot_rej;
+  const int cnt = __popc(mask);
+  const int p0 = cnt > 0 ? rng.reserve_normals(cnt) : 0;
+  const bool leaf = (mask >> lane) & 1u;
+  const int j = __popc(mask & ((1u << lane) - 1u));
+  const double pm = __shfl_sync(0xffffffffu, my_pm, ss & 31), ps = __shfl_sync(0xffffffffu, my_ps, ss & 31), nobs = __shfl_sync(0xffffffffu, my_n, ss & 31);
+  const double mu = leaf ? pm + ps * cs.zbuf[p0 + j] : 0.0;
+  const int nn_old = t.num_nodes;
+  if (amode != 0) {
+    const int nn = pl.nn_acc;
+    if (lane < nn) { DNode nd = cs.tmp[lane]; if (leaf) { nd.mu = mu; nd.n = (int32_t) nobs; } t.nodes[lane] = nd; }
+    if (lane == 0) t.num_nodes = nn;
+    if (leaf) upd.val_new[lane] = mu;
+  } else if (leaf) {
+    t.nodes[lane].mu = mu; t.nodes[lane].n = (int32_t) nobs;
+    upd.val_new[lane] = mu;
+  }
+  if (amode == 0 && lane < nn_old) upd.delta[lane] = leaf ? in.b_cur.val[lane] - mu : 0.0;
+  if (lane == 0) { upd.mode = amode; upd.node = node; }
+  if (trace_rec != nullptr) {
+    if (leaf && 11 + j < S4B_TRACE_LEN) trace_rec[11 + j] = mu;
+    __syncwarp();
+    if (lane == 0) {
+      trace_rec[0] = (double) kind;
+      trace_rec[1] = (kind >= 0 && node >= 0) ? (double) t_heap_index(t, node) : 0.0;
+      if (kind == 0 || kind == 1) { trace_rec[2] = in.b_var; trace_rec[3] = in.b_cut; }
+      else if (kind == 2 || kind == 12) { trace_rec[2] = node >= 0 ? in.new_var : 0; trace_rec[3] = kind == 2 ? in.new_cut : 0; }
+      else if ((kind == 3 || kind == 13) && node >= 0) { trace_rec[2] = in.b_child >= 0 ? (double) t_heap_index(t, in.b_child) : -1.0; }
+      trace_rec[4] = accept ? 1.0 : 0.0; trace_rec[5] = ratio; trace_rec[6] = old_ll; trace_rec[7] = new_ll;
+      trace_rec[8] = (double) cnt; trace_rec[9] = n_first; trace_rec[10] = n_second;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) { const long long d4 = clock64(); cs.dbg[0] += d1 - d0; cs.dbg[2] += d4 - d1; cs.fine[0] += f1 - d0; cs.fine[2] += d1 - f1; }
+}
+
+// ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 struct SweepSmem {
@@ -624,6 +842,8 @@ struct SweepSmem {
   CtlScratch csd;      // decision scratch
   CtlScratch csp;      // proposal scratch
   LeafStat st[S4B_MAX_SLOTS];
+  double inv_sigsq;    // 1 / sigma^2, fixed for the whole sweep
+  FastPlanSmem plan;   // this step's decision plan (controller, written before the grid barrier)
   int peer_dead;       // a peer rank stopped answering (sharded mode): stop waiting, flag the error
   ShardDev sh;         // copy of the kernel parameter (indexed dynamically; keeps it out of local memory)
   RngState rng;
@@ -754,6 +974,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   const int G = gridDim.x, cta = blockIdx.x;
   const long long n = dv.n, npad = dv.npad;
   const long long nquad = (n + 3) >> 2;
+  // balanced partition: CTA c owns the contiguous quads [c nquad / G, (c + 1) nquad / G), dealt to its threads in rounds of
+  // kWorkers (coalesced); every SM then moves the same number of observations through its shared-memory bins
+  const long long q_lo = nquad * cta / G, q_hi = nquad * (cta + 1) / G;
 
   // ---- one-time loads: residuals -> registers, binned predictors -> shared tile, controller state ----
   double R[NQ][4];
@@ -761,8 +984,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   unsigned obs_mask = 0;         // bit 4j + o: observation is a real one (not padding)
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    const long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
-    if (is_worker && q < nquad) {
+    const long long q = q_lo + (long long) j * kWorkers + tid;
+    if (is_worker && q < q_hi) {
       valid_mask |= 1u << j;
       for (int o = 0; o < 4; ++o) if (4 * q + o < n) obs_mask |= 1u << (4 * j + o);
       double2 a = *reinterpret_cast<const double2*>(dv.R + 4 * q), b = *reinterpret_cast<const double2*>(dv.R + 4 * q + 2);
@@ -775,6 +998,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     for (int r = 0; r < kMaxRanks; ++r) S.sh.mail[r] = sh_param.mail[r];
   }
   const int world = sh_param.world;
+  if (tid == 0) { const double sg = dv.params->sigma; S.inv_sigsq = 1.0 / (sg * sg); }
   if (tid == 0) { S.peer_dead = 0; S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; for (int i = 0; i < 4; ++i) S.csd.fine[i] = 0; }
   for (int i = tid; i < kTabSize; i += kSweepBlock) S.tab[i] = tables[i];
   __syncthreads();
@@ -788,7 +1012,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     for (int v = 0; v < p; ++v)
 #pragma unroll
       for (int j = 0; j < NQ; ++j) {
-        const long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
+        const long long q = q_lo + (long long) j * kWorkers + tid;
         tile[v * tile_stride + j * kWorkers + tid] = ((valid_mask >> j) & 1u) ? __ldg(xt32 + (long long) v * col_words + q) : 0u;
       }
   }
@@ -913,8 +1137,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       named_bar_sync(1, kWorkers);
       if (tid == 0) {
         pc[0] += clock64() - c0;
-        __threadfence();
-        atomicAdd(barrier_counter, 1u);
+        // release-arrive: orders this CTA's partial rows (made visible to thread 0 by the named barrier) before the count
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(barrier_counter) : "memory");
         const unsigned int target = (unsigned int) (t + 1) * (unsigned int) G;
         unsigned int v;
         const long long w0 = clock64();
@@ -922,10 +1146,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(barrier_counter) : "memory");
           if (v < target && (S.peer_dead || clock64() - w0 > 4000000000LL)) { S.peer_dead = 2; break; }     // a CTA never arrived: fail, do not hang
         } while (v < target);
-        __threadfence();
       }
     } else {
-      // ---- controller warp: fetch tree t+1, pre-compute this step's decision draws, propose for t+1 ----
+      // ---- controller warp: plan this step's decision, fetch tree t+1, pre-compute this step's decision draws, propose for t+1 ----
+      { const FastPlan pl = w_plan(tree, sd, S.upd, S.csd, lane); plan_store(S.plan, pl, lane); }
       const long long h0 = clock64();
       if (t + 1 < T) {
         const DTree& g = dv.trees[t + 1];
@@ -1010,7 +1234,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         if (lane == 0) *dv.trace_len = k + 1;
       }
       if (sequential_rng) rngd.fill();
-      w_decide(tree, S.prm, rngd, sd, S.st, S.upd, S.csd, trec, lane);
+      if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast(plan, tree, S.prm, rngd, sd, S.st, S.upd, S.csd, trec, lane, S.inv_sigsq); }
+      else w_decide(tree, S.prm, rngd, sd, S.st, S.upd, S.csd, trec, lane, S.inv_sigsq);
       rngd.commit();
       if (sequential_rng && t + 1 < T) {
         rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
@@ -1067,7 +1292,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   // ---- write back ----
 #pragma unroll
   for (int j = 0; j < NQ; ++j) if ((valid_mask >> j) & 1u) {
-    const long long q = (long long) j * G * kWorkers + (long long) cta * kWorkers + tid;
+    const long long q = q_lo + (long long) j * kWorkers + tid;
     *reinterpret_cast<double2*>(dv.R + 4 * q) = make_double2(R[j][0], R[j][1]);
     *reinterpret_cast<double2*>(dv.R + 4 * q + 2) = make_double2(R[j][2], R[j][3]);
   }
