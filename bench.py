@@ -321,7 +321,11 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ----
     trees = bart.trees()
     lv = avg_levels(trees, n)
-    bytes_per_obs = 16.0 + 2.0 * lv           # per tree x observation: R read + write, one u8 per level for each of the two walks
+    # 29 algorithmic bytes per (tree x observation) -- statistics pass 11 B (residual 8 + node id 2 + split column 1)
+    # + update pass 18 B (residual read 8 + write 8 + node id 2).  The leaner count for THIS design (residual read + write and
+    # one u8 per tree level of the two walks) is reported beside it.
+    bytes_per_obs = 29.0
+    bytes_per_obs_lean = 16.0 + 2.0 * lv
     peak, peak_src = measured_peak()
     persistent = bart.sweep_mode() == 2
     launch_ms = sweep_ms / K if persistent else sweep_ms / (K * T)    # CUDA events around the sweep launches on the launching stream
@@ -335,12 +339,14 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "kernel": "k_sweep<4> (one launch = one 200-tree sweep)" if persistent else "k_tree_step (one launch = one tree)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_tree_obs": bytes_per_obs, "avg_tree_levels": lv,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_tree_obs": bytes_per_obs,
+                "units_per_launch": units_per_launch, "avg_tree_levels": lv,
                 "launch_us": launch_ms * 1e3, "tree_step_us": sweep_ms / (K * T) * 1e3,
-                "achieved_survey_model_gbs": 29.0 * units_per_launch / (launch_ms * 1e-3) / 1e9,
-                "note": "algorithmic bytes are what a per-tree streaming pass must move; the persistent kernel keeps residuals in registers "
-                        "and predictors in shared memory, so DRAM traffic per launch is ~17 MB and the binding limit is the latency of "
-                        "200 sequential reduce + Metropolis decisions, not HBM (DESIGN.md section 4)"}
+                "achieved_lean_model_gbs": bytes_per_obs_lean * units_per_launch / (launch_ms * 1e-3) / 1e9,
+                "lean_bytes_per_tree_obs": bytes_per_obs_lean,
+                "note": "algorithmic bytes are what per-tree streaming passes must move (SURVEY.md 8d); the persistent kernel keeps residuals "
+                        "in registers and predictors in shared memory, so DRAM traffic per launch is ~17 MB and the binding limit is the "
+                        "latency of 200 sequential reduce + Metropolis decisions, not HBM (DESIGN.md section 4)"}
 
     # ---- end-to-end leg through the C ABI with host buffers ----
     h2d, d2h = s.set_host_plumbing(True)

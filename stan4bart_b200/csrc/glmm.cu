@@ -225,6 +225,7 @@ GlmmModel::~GlmmModel()
 {
   cudaFree(d_X_); cudaFree(d_y_); cudaFree(d_offset_); cudaFree(d_r_); cudaFree(d_tmp_); cudaFree(d_zval_); cudaFree(d_zidx_);
   cudaFree(d_theta_); cudaFree(d_partials_); cudaFree(d_result_); cudaFree(d_ticket_); cudaFreeHost(h_pinned_);
+  delete scratch_;
 }
 
 void GlmmModel::set_mode(int mode)
@@ -375,7 +376,8 @@ void GlmmModel::transform(const double* q, Params& P) const
 
 int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
 {
-  Params P; transform(q, P);
+  if (scratch_ == nullptr) { scratch_ = new Params; gbeta_.assign((size_t) K_ + 1, 0.0); gb_.assign((size_t) q_ + 1, 0.0); }
+  Params& P = *scratch_; transform(q, P);
   ++num_grad_;
   const double N = (double) N_total_;
   double lp = 0.0;
@@ -384,7 +386,7 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
   for (int i = 0; i < t_; ++i) lp += P.tau_u[i];
   if (has_aux_) lp += P.aux_u;
 
-  std::vector<double> gbeta((size_t) K_ + 1), gb((size_t) q_ + 1);
+  std::vector<double>& gbeta = gbeta_; std::vector<double>& gb = gb_;
   double S = 0.0;
   data_terms_auto(P.beta.data(), P.b.data(), &S, gbeta.data(), gb.data());
   const double sigma = has_aux_ ? P.aux : 1.0;

@@ -63,6 +63,8 @@ class GlmmModel {
  private:
   struct Params;
   void transform(const double* q, Params& P) const;
+  Params* scratch_ = nullptr;                 // reused by log_prob_grad: no heap traffic per evaluation
+  std::vector<double> gbeta_, gb_;
   void refresh_r();
 
   bool sharded() const { return shard_ != nullptr && shard_->world() > 1; }

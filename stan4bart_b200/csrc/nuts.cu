@@ -40,6 +40,7 @@ NutsSampler::NutsSampler(GlmmModel& model, const s4b_stan_control& ctl, int chai
   if (ctl.stepsize > 0) nom_epsilon_ = ctl.stepsize;
   if (ctl.stepsize_jitter > 0 && ctl.stepsize_jitter < 1) epsilon_jitter_ = ctl.stepsize_jitter;
   if (ctl.max_treedepth > 0) max_depth_ = ctl.max_treedepth;
+  levels_.resize((size_t) max_depth_ + 2);       // never resized while build_tree holds references into it
   sa_mu_ = std::log(10 * ctl.stepsize);
   if (ctl.adapt_delta > 0 && ctl.adapt_delta < 1) sa_delta_ = ctl.adapt_delta;
   if (ctl.adapt_gamma > 0) sa_gamma_ = ctl.adapt_gamma;
@@ -111,17 +112,24 @@ bool NutsSampler::build_tree(int depth, Point& z_propose, Vec& p_sharp_beg, Vec&
     return !divergent_;
   }
   double lsw_init = -kInf;
-  Vec p_init_end((size_t) d_), p_sharp_init_end((size_t) d_), rho_init((size_t) d_, 0.0);
+  if ((int) levels_.size() <= depth) levels_.resize((size_t) depth + 1);
+  Level& W = levels_[(size_t) depth];
+  const size_t d = (size_t) d_;
+  Vec& p_init_end = W.p_init_end; Vec& p_sharp_init_end = W.p_sharp_init_end; Vec& rho_init = W.rho_init;
+  p_init_end.resize(d); p_sharp_init_end.resize(d); rho_init.assign(d, 0.0);
   if (!build_tree(depth - 1, z_propose, p_sharp_beg, p_sharp_init_end, rho_init, p_beg, p_init_end, H0, sign, n_leapfrog, lsw_init, sum_metro_prob)) return false;
-  Point z_propose_final = z_;
+  Point& z_propose_final = W.z_propose_final;
+  z_propose_final = z_;
   double lsw_final = -kInf;
-  Vec p_final_beg((size_t) d_), p_sharp_final_beg((size_t) d_), rho_final((size_t) d_, 0.0);
+  Vec& p_final_beg = W.p_final_beg; Vec& p_sharp_final_beg = W.p_sharp_final_beg; Vec& rho_final = W.rho_final;
+  p_final_beg.resize(d); p_sharp_final_beg.resize(d); rho_final.assign(d, 0.0);
   if (!build_tree(depth - 1, z_propose_final, p_sharp_final_beg, p_sharp_end, rho_final, p_final_beg, p_end, H0, sign, n_leapfrog, lsw_final, sum_metro_prob)) return false;
   double lsw_subtree = log_sum_exp(lsw_init, lsw_final);
   log_sum_weight = log_sum_exp(log_sum_weight, lsw_subtree);
   if (lsw_final > lsw_subtree) z_propose = z_propose_final;
   else if (rng_uniform(rng_) < std::exp(lsw_final - lsw_subtree)) z_propose = z_propose_final;
-  Vec rho_subtree((size_t) d_);
+  Vec& rho_subtree = W.rho_subtree;
+  rho_subtree.resize(d);
   for (int i = 0; i < d_; ++i) { rho_subtree[(size_t) i] = rho_init[(size_t) i] + rho_final[(size_t) i]; rho[(size_t) i] += rho_subtree[(size_t) i]; }
   bool persist = no_u_turn(p_sharp_beg, p_sharp_end, rho_subtree);
   for (int i = 0; i < d_; ++i) rho_subtree[(size_t) i] = rho_init[(size_t) i] + p_final_beg[(size_t) i];

@@ -46,6 +46,11 @@ class NutsSampler {
   void set_window_params(uint32_t num_warmup, uint32_t init_buffer, uint32_t term_buffer, uint32_t base_window);
   void compute_next_window();
 
+  // scratch of one recursion level of build_tree (depth is unique along the call stack): allocated once, so that the
+  // ~1000 leapfrogs of a deep transition do not touch the heap
+  struct Level { Vec p_init_end, p_sharp_init_end, rho_init, p_final_beg, p_sharp_final_beg, rho_final, rho_subtree; Point z_propose_final; };
+  std::vector<Level> levels_;
+
   GlmmModel& model_;
   s4b_stan_control ctl_;
   int d_;
