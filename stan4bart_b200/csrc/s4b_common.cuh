@@ -214,12 +214,19 @@ __host__ __device__ inline uint32_t pack_trav(int var, int cut, int right)
   return ((uint32_t) (var < 0 ? 0xFFFF : var) << 16) | ((uint32_t) (cut & 0xFF) << 8) | (uint32_t) (right & 0xFF);
 }
 
+// Trees with at most S4B_BITMAP_INT internal nodes (nearly all of them) are also described for the "bitmap walk" of the
+// persistent sweep kernel: every internal node's rule is evaluated for an observation (bit i = 1 iff x[var_i] <= cut_i,
+// i = rank of the node among the internal nodes in index order) and the bit pattern indexes a table of bottom nodes.
+#define S4B_BITMAP_INT 8
 struct TravTree {
   int32_t n;
   int32_t pad;
   uint32_t trav[S4B_NODE_CAP];
   double val[S4B_NODE_CAP];
   uint8_t slot[S4B_NODE_CAP];
+  int32_t n_int;                               // internal nodes, or 255 when the tree is too large for the bitmap walk
+  uint32_t irec[S4B_BITMAP_INT];               // var << 8 | cut of internal node i
+  uint8_t table[1 << S4B_BITMAP_INT];          // rule pattern -> index of the bottom node reached
 };
 
 // what the N-length pass of tree step t needs; written by the controller of step t - 1

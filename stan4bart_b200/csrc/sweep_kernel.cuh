@@ -241,7 +241,22 @@ __device__ inline int w_fill_trav(const DTree& t, TravTree& tv, bool with_mu, in
     leaves += __popc(m);
   }
   maxd = w_maxi(maxd);
-  if (lane == 0) { tv.n = nn; tv.pad = maxd; }
+  const int n_int = nn - leaves;
+  const bool bitmap = nn <= 32 && n_int <= S4B_BITMAP_INT;
+  if (lane == 0) { tv.n = nn; tv.pad = maxd; tv.n_int = bitmap ? n_int : 255; }
+  if (bitmap) {
+    // rule records in internal-node order and the pattern -> bottom-node table of the bitmap walk
+    const unsigned imask = __ballot_sync(0xffffffffu, lane < nn && t.nodes[lane].var >= 0);
+    if ((imask >> lane) & 1u) tv.irec[__popc(imask & ((1u << lane) - 1u))] = ((uint32_t) t.nodes[lane].var << 8) | (uint32_t) (t.nodes[lane].cut & 0xFF);
+    for (int e = lane; e < (1 << n_int); e += 32) {
+      int node = 0;
+      while ((imask >> node) & 1u) {
+        const int id = __popc(imask & ((1u << node) - 1u));
+        node = ((e >> id) & 1) ? node + 1 : (int) t.nodes[node].right;
+      }
+      tv.table[e] = (uint8_t) node;
+    }
+  }
   __syncwarp();
   return leaves;
 }
@@ -869,12 +884,51 @@ __device__ __forceinline__ uint32_t walk_quad(const uint32_t* __restrict__ trav,
 }
 
 // leaf indices (and the auxiliary byte: proposed-tree leaf for change / swap, split side for a birth) of every owned quad
+// bitmap walk: evaluate every internal node's rule for the 4 observations of each quad (one shared-memory word per rule
+// and quad), collect the outcomes as one bit pattern per observation, look the bottom node up
+template <int NQ>
+__device__ __forceinline__ void bitmap_walk(const TravTree& tv, const uint8_t* __restrict__ table, const uint32_t* __restrict__ tile, int tile_stride, int tid,
+                                            uint32_t (&pack)[NQ])
+{
+  uint32_t pat[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) pat[j] = 0u;
+  const int n_int = tv.n_int;
+#pragma unroll 1
+  for (int i = 0; i < n_int; ++i) {
+    const uint32_t rec = tv.irec[i];
+    const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
+    const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+  }
+#pragma unroll
+  for (int j = 0; j < NQ; ++j)
+    pack[j] = (uint32_t) table[pat[j] & 0xFFu] | ((uint32_t) table[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) table[(pat[j] >> 16) & 0xFFu] << 16) |
+              ((uint32_t) table[pat[j] >> 24] << 24);
+}
+
 template <int NQ>
 __device__ __forceinline__ void walk_step(const StepDesc& sd, const uint32_t* __restrict__ tile, int tile_stride, int tid, unsigned valid_mask,
                                           uint32_t (&leaf_pack)[NQ], uint32_t (&aux_pack)[NQ])
 {
   const int kind = sd.b_kind;
   const int depth = sd.b_cur.pad;
+  if (sd.b_cur.n_int <= S4B_BITMAP_INT) {
+    // (quads beyond the data hold zeros in the tile: walking them is harmless, nothing of theirs is ever used)
+    bitmap_walk<NQ>(sd.b_cur, sd.b_cur.table, tile, tile_stride, tid, leaf_pack);
+    if (kind == 2 || kind == 3) bitmap_walk<NQ>(sd.b_prop, sd.b_cur.table, tile, tile_stride, tid, aux_pack);
+    else if (kind == 0) {
+      const uint32_t* col = tile + sd.b_var * tile_stride + tid;
+      const uint32_t cut4 = (uint32_t) sd.b_cut * 0x01010101u;
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) aux_pack[j] = __vcmpgtu4(col[j * kWorkers], cut4) & 0x01010101u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) aux_pack[j] = 0u;
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     uint32_t lp = 0, ap = 0;
@@ -904,6 +958,15 @@ __device__ inline void w_copy_desc(StepDesc& dst, const StepDesc& src, int lane)
     dst.log_prior_trans = src.log_prior_trans; dst.new_var = src.new_var; dst.new_cut = src.new_cut; dst.b_end = src.b_end;
     dst.b_cur.n = n; dst.b_cur.pad = src.b_cur.pad;
     dst.b_prop.n = (kind == 2 || kind == 3) ? n : 0; dst.b_prop.pad = src.b_cur.pad;
+    dst.b_cur.n_int = src.b_cur.n_int; dst.b_prop.n_int = src.b_cur.n_int;
+  }
+  {
+    const int n_int = src.b_cur.n_int;
+    if (n_int <= S4B_BITMAP_INT) {
+      if (lane < n_int) { dst.b_cur.irec[lane] = src.b_cur.irec[lane]; if (kind == 2 || kind == 3) dst.b_prop.irec[lane] = src.b_prop.irec[lane]; }
+      // the structure of the proposed tree of a change / swap step is that of the current one: one table serves both
+      for (int e = lane * 4; e < (1 << n_int); e += 128) *reinterpret_cast<uint32_t*>(&dst.b_cur.table[e]) = *reinterpret_cast<const uint32_t*>(&src.b_cur.table[e]);
+    }
   }
   for (int k = lane; k < n; k += 32) {
     dst.b_cur.trav[k] = src.b_cur.trav[k]; dst.b_cur.val[k] = src.b_cur.val[k]; dst.b_cur.slot[k] = src.b_cur.slot[k];
