@@ -122,6 +122,8 @@ int gpubart_tree_step_ms(gpubart_fit* fit, int reset, double* ms);
  * [3] MH decision + leaf draws, [4] write-back + next tree load, [5] next proposal / update, [6] descriptor publish, [7] steps counted,
  * [8..15] finer controller counters of the persistent kernel (see sweep_kernel.cuh); [16..19] worker sub-phases; out24 has 24 entries */
 int gpubart_get_profile(gpubart_fit* fit, uint64_t* out24, int reset);
+/* the cycle counters cost a few percent of the controller's time: off by default, switch on before the sweeps to profile */
+int gpubart_set_profile(gpubart_fit* fit, int on);
 
 /* ------------------------------------------------------------------ glmm_* */
 typedef struct glmm_model glmm_model;

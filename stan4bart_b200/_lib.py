@@ -25,6 +25,7 @@ SIGNATURES = {
     "s4b_set_device": (C.c_int, [C.c_int]),
     "gpubart_tree_step_ms": (C.c_int, [vp, C.c_int, c_double_p]),
     "gpubart_get_profile": (C.c_int, [vp, c_uint64_p, C.c_int]),
+    "gpubart_set_profile": (C.c_int, [vp, C.c_int]),
     "s4b_sampler_set_host_plumbing": (C.c_int, [vp, C.c_int, c_int64_p, c_int64_p]),
     "gpubart_create": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, vpp]),
     "gpubart_free": (C.c_int, [vp]),

@@ -856,7 +856,7 @@ BartDev BartFit::dev() const
   d.n = n_; d.npad = npad_; d.obs_offset = shard_ != nullptr ? shard_->obs_offset() : 0; d.xt = d_xt_; d.R = d_R_; d.yresc = d_yresc_; d.y = d_y_; d.offset = d_offset_;
   d.desc = d_desc_; d.trees = d_trees_; d.params = d_params_; d.pgrow = d_pgrow_; d.rng = d_rng_;
   d.partials = d_partials_; d.ticket = d_ticket_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
-  d.stats_out = d_stats_out_; d.prof = d_prof_;
+  d.stats_out = d_stats_out_; d.prof = profile_on_ ? d_prof_ : nullptr;
   return d;
 }
 

@@ -86,6 +86,7 @@ class BartFit {
   // cycles spent by the last block in: [0] its own pass, [1] partial reduction, [2] tree load, [3] decision + leaf draws,
   // [4] write-back + next tree load, [5] proposal, [6] descriptor publish, [7] number of steps
   void get_profile(unsigned long long* out24, bool reset);
+  void set_profile(bool on) { if (on != profile_on_) { profile_on_ = on; invalidate_graph(); } }
 
  private:
   BartDev dev() const;
@@ -118,6 +119,7 @@ class BartFit {
   bool tape_set_ = false, rec_set_ = false, sequential_rng_ = false;
   int partial_stride_ = 0;
   int overlap_walk_ = 1;
+  bool profile_on_ = false;
   long long num_tree_steps_ = 0;
 
   uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;

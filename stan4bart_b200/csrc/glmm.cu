@@ -376,6 +376,13 @@ void GlmmModel::transform(const double* q, Params& P) const
 
 int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
 {
+  if (scratch_ == nullptr) {
+    // log-gamma values of the hyper-parameters never change: look them up instead of ~6 lgamma calls per evaluation
+    lg_delta_.resize(delta_.size()); for (size_t i = 0; i < delta_.size(); ++i) lg_delta_[i] = std::lgamma(delta_[i]);
+    lg_shape_.resize(shape_.size()); for (size_t i = 0; i < shape_.size(); ++i) lg_shape_[i] = std::lgamma(shape_[i]);
+    lg_reg_.clear(); lg_reg2_.clear();
+    { int pr = 0; for (int i = 0; i < t_; ++i) if (p_[(size_t) i] > 1) { const double nu = regularization_[(size_t) pr++] + 0.5 * (p_[(size_t) i] - 2); lg_reg_.push_back(std::lgamma(nu)); lg_reg2_.push_back(std::lgamma(2.0 * nu)); } }
+  }
   if (scratch_ == nullptr) { scratch_ = new Params; gbeta_.assign((size_t) K_ + 1, 0.0); gb_.assign((size_t) q_ + 1, 0.0); }
   Params& P = *scratch_; transform(q, P);
   ++num_grad_;
@@ -410,11 +417,11 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
     for (int i = 0; i < t_; ++i) if (p_[(size_t) i] > 1) {
       const double nu = regularization_[(size_t) pos_reg++] + 0.5 * (p_[(size_t) i] - 2);
       const double r = P.rho[(size_t) pos_rho++];
-      lp += (nu - 1.0) * std::log(r) + (nu - 1.0) * std::log1p(-r) + std::lgamma(2.0 * nu) - 2.0 * std::lgamma(nu);
+      lp += (nu - 1.0) * std::log(r) + (nu - 1.0) * std::log1p(-r) + lg_reg2_[(size_t) (pos_reg - 1)] - 2.0 * lg_reg_[(size_t) (pos_reg - 1)];
     }
   }
-  for (int i = 0; i < len_conc_; ++i) lp += (delta_[(size_t) i] - 1.0) * std::log(P.zeta[(size_t) i]) - P.zeta[(size_t) i] - std::lgamma(delta_[(size_t) i]);
-  for (int i = 0; i < t_; ++i) lp += (shape_[(size_t) i] - 1.0) * std::log(P.tau[(size_t) i]) - P.tau[(size_t) i] - std::lgamma(shape_[(size_t) i]);
+  for (int i = 0; i < len_conc_; ++i) lp += (delta_[(size_t) i] - 1.0) * std::log(P.zeta[(size_t) i]) - P.zeta[(size_t) i] - lg_delta_[(size_t) i];
+  for (int i = 0; i < t_; ++i) lp += (shape_[(size_t) i] - 1.0) * std::log(P.tau[(size_t) i]) - P.tau[(size_t) i] - lg_shape_[(size_t) i];
 
   // ---- adjoints ----
   int pos = 0;

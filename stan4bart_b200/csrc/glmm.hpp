@@ -64,7 +64,7 @@ class GlmmModel {
   struct Params;
   void transform(const double* q, Params& P) const;
   Params* scratch_ = nullptr;                 // reused by log_prob_grad: no heap traffic per evaluation
-  std::vector<double> gbeta_, gb_;
+  std::vector<double> gbeta_, gb_, lg_delta_, lg_shape_, lg_reg_, lg_reg2_;
   void refresh_r();
 
   bool sharded() const { return shard_ != nullptr && shard_->world() > 1; }

@@ -54,6 +54,7 @@ struct CtlScratch {
   DNode tmp[S4B_NODE_CAP];
   int32_t pad0;
   int32_t draws_total;              // draws consumed through this scratch since kernel start
+  int32_t prof_on, pad1;            // cycle counters below are kept only when profiling is enabled (gpubart_set_profile)
   long long dbg[8];                 // cycle counters (diagnostics)
   long long fine[4];                // decision, first part: slot summaries, staging, ratio, accept
 };
@@ -551,7 +552,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
 
   // ---- structural change, all lanes ----
   const long long d1 = clock64();
-  if (lane == 0) { cs.fine[0] += f1 - d0; cs.fine[1] += f2 - f1; cs.fine[2] += d1 - f2; }
+  if (lane == 0 && cs.prof_on) { cs.fine[0] += f1 - d0; cs.fine[1] += f2 - f1; cs.fine[2] += d1 - f2; }
   const int amode = !accept ? 0 : (kind == 0 ? 1 : (kind == 1 ? 2 : 3));
   if (amode == 1 || amode == 2) {
     for (int k = lane; k < nn_old; k += 32) cs.tmp[k] = t.nodes[k];
@@ -636,7 +637,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     trace_rec[8] = (double) leaves_before; trace_rec[9] = n_first; trace_rec[10] = n_second;
   }
   __syncwarp();
-  if (lane == 0) { const long long d4 = clock64(); cs.dbg[0] += d1 - d0; cs.dbg[1] += d2 - d1; cs.dbg[2] += d3 - d2; cs.dbg[3] += d4 - d3; }
+  if (lane == 0 && cs.prof_on) { const long long d4 = clock64(); cs.dbg[0] += d1 - d0; cs.dbg[1] += d2 - d1; cs.dbg[2] += d3 - d2; cs.dbg[3] += d4 - d3; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -844,7 +845,7 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
     }
   }
   __syncwarp();
-  if (lane == 0) { const long long d4 = clock64(); cs.dbg[0] += d1 - d0; cs.dbg[2] += d4 - d1; cs.fine[0] += f1 - d0; cs.fine[2] += d1 - f1; }
+  if (lane == 0 && cs.prof_on) { const long long d4 = clock64(); cs.dbg[0] += d1 - d0; cs.dbg[2] += d4 - d1; cs.fine[0] += f1 - d0; cs.fine[2] += d1 - f1; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -858,6 +859,7 @@ struct SweepSmem {
   CtlScratch csp;      // proposal scratch
   LeafStat st[S4B_MAX_SLOTS];
   double inv_sigsq;    // 1 / sigma^2, fixed for the whole sweep
+  long long pc[6], wk[4];   // phase cycle counters (profiling runs)
   FastPlanSmem plan;   // this step's decision plan (controller, written before the grid barrier)
   int peer_dead;       // a peer rank stopped answering (sharded mode): stop waiting, flag the error
   ShardDev sh;         // copy of the kernel parameter (indexed dynamically; keeps it out of local memory)
@@ -1061,8 +1063,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     for (int r = 0; r < kMaxRanks; ++r) S.sh.mail[r] = sh_param.mail[r];
   }
   const int world = sh_param.world;
-  if (tid == 0) { const double sg = dv.params->sigma; S.inv_sigsq = 1.0 / (sg * sg); }
-  if (tid == 0) { S.peer_dead = 0; S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; for (int i = 0; i < 4; ++i) S.csd.fine[i] = 0; }
+  if (tid == 0) { const double sg = dv.params->sigma; S.inv_sigsq = 1.0 / (sg * sg); for (int i = 0; i < 6; ++i) S.pc[i] = 0; for (int i = 0; i < 4; ++i) S.wk[i] = 0; }
+  if (tid == 0) { S.peer_dead = 0; S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; S.csd.prof_on = dv.prof != nullptr ? 1 : 0; S.csp.prof_on = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; for (int i = 0; i < 4; ++i) S.csd.fine[i] = 0; }
   for (int i = tid; i < kTabSize; i += kSweepBlock) S.tab[i] = tables[i];
   __syncthreads();
   const int p = S.prm.p, T = S.prm.num_trees;
@@ -1099,8 +1101,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   uint32_t leaf_pack[NQ], aux_pack[NQ];
   if (is_worker) walk_step<NQ>(S.sd[0], tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
 
-  long long pc[6] = { 0, 0, 0, 0, 0, 0 };
-  long long pw[4] = { 0, 0, 0, 0 };     // worker sub-phases (CTA 0, thread 0): zero bins, accumulate, wait + row reduce, second barrier
+  // phase counters live in shared memory (thread 0, profiling runs only): as registers they would be carried through the
+  // whole loop by every thread.  S.wk[0..3]: worker sub-phases (zero bins, accumulate, wait + row reduce, second barrier)
+  const bool prof_on = dv.prof != nullptr;
   for (int t = 0; t < T; ++t) {
     const long long c0 = clock64();
     StepDesc& sd = S.sd[t & 1];
@@ -1193,13 +1196,13 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         }
         const long long w3 = clock64();
         if (chunk + 1 < nchunks) named_bar_sync(1, kWorkers);        // the bins are reused by the next pass
-        if (tid == 0) { pw[0] += w1 - w0; pw[1] += w2 - w1; pw[2] += w3 - w2; pw[3] += clock64() - w3; }
+        if (tid == 0 && prof_on) { S.wk[0] += w1 - w0; S.wk[1] += w2 - w1; S.wk[2] += w3 - w2; S.wk[3] += clock64() - w3; }
       }
       // ---- arrive at the grid barrier and wait for every CTA's partial rows.  The rows are stored by lane 0 of
       // several warps: all of them must have issued their stores before thread 0 publishes them (fence + arrive) ----
       named_bar_sync(1, kWorkers);
       if (tid == 0) {
-        pc[0] += clock64() - c0;
+        if (prof_on) S.pc[0] += clock64() - c0;
         // release-arrive: orders this CTA's partial rows (made visible to thread 0 by the named barrier) before the count
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(barrier_counter) : "memory");
         const unsigned int target = (unsigned int) (t + 1) * (unsigned int) G;
@@ -1230,7 +1233,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         rngd.adopt();
         const long long h2 = clock64();
         if (t + 1 < T) w_copy_desc(sd_next, descs[t + 1], lane);
-        if (lane == 0) { S.csd.dbg[4] += h1 - h0; S.csd.dbg[5] += h2 - h1; S.csd.dbg[7] += clock64() - h2; }
+        if (lane == 0 && S.csd.prof_on) { S.csd.dbg[4] += h1 - h0; S.csd.dbg[5] += h2 - h1; S.csd.dbg[7] += clock64() - h2; }
       }
     }
     __syncthreads();                                                        // [A] partials complete everywhere, next proposal ready
@@ -1349,7 +1352,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(g.nodes)[i] = reinterpret_cast<const uint32_t*>(tree.nodes)[i];
     }
     __syncthreads();                                                        // [D] upd / tree / descriptor buffers free again
-    if (cta == 0 && tid == 0) { pc[1] += c2 - c0; pc[2] += cx - c2; pc[4] += c3 - cx; pc[3] += c5 - c3; pc[5] += clock64() - c5; }
+    if (tid == 0 && prof_on) { S.pc[1] += c2 - c0; S.pc[2] += cx - c2; S.pc[4] += c3 - cx; S.pc[3] += c5 - c3; S.pc[5] += clock64() - c5; }
   }
 
   // ---- write back ----
@@ -1370,12 +1373,12 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     if (dv.prof != nullptr) {
       // [0] accumulate + CTA reduction (CTA 0), [1] ... + grid barrier + controller wait, [2] statistics reduce,
       // [3] decision (overlapped with the next walk), [4] cross-rank exchange (sharded chains), [5] update, [7] steps
-      for (int i = 0; i < 6; ++i) dv.prof[i] += (unsigned long long) pc[i];
+      for (int i = 0; i < 6; ++i) dv.prof[i] += (unsigned long long) S.pc[i];
       dv.prof[7] += (unsigned long long) T;
       // [8..11] decision: slot summaries + accept, structure, leaf draws, update descriptor; [12..15] controller before the
       // barrier: tree fetch, decision-draw prefill, proposal-draw prefill, proposal
       for (int i = 0; i < 8; ++i) dv.prof[8 + i] += (unsigned long long) S.csd.dbg[i];
-      for (int i = 0; i < 4; ++i) dv.prof[16 + i] += (unsigned long long) pw[i];
+      for (int i = 0; i < 4; ++i) dv.prof[16 + i] += (unsigned long long) S.wk[i];
       for (int i = 0; i < 4; ++i) dv.prof[20 + i] += (unsigned long long) S.csd.fine[i];
     }
   }

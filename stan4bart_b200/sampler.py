@@ -166,6 +166,9 @@ class GpuBart:
         _lib.check(self.L.gpubart_tree_step_ms(self.h, int(reset), C.byref(ms)))
         return ms.value
 
+    def set_profile(self, on=True):
+        _lib.check(self.L.gpubart_set_profile(self.h, int(on)))
+
     def profile(self, reset=True):
         out = (C.c_uint64 * 24)()
         _lib.check(self.L.gpubart_get_profile(self.h, out, int(reset)))

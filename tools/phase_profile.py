@@ -21,7 +21,7 @@ if what == "gibbs":
     s.run(40, True, results=False)
     s.disengage_adaptation()
     g = s.bart()
-    g.profile(); g.tree_step_ms()
+    g.set_profile(True); g.profile(); g.tree_step_ms()
     t0 = time.time()
     s.run(20, False, results=False)
     dt = time.time() - t0
@@ -32,7 +32,7 @@ else:
         g.set_sigma(1.0)
     for _ in range(30):
         g.run()
-    g.profile(); g.tree_step_ms()
+    g.set_profile(True); g.profile(); g.tree_step_ms()
     t0 = time.time()
     for _ in range(20):
         g.run()

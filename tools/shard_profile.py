@@ -26,7 +26,7 @@ g = GpuBart(cfg, pr["y"][lo:hi], pr["x_bart"][lo:hi], shard=ctx if world > 1 els
 g.set_sigma(1.0)
 for _ in range(30):
     g.run()
-g.profile(); g.tree_step_ms()
+g.set_profile(True); g.profile(); g.tree_step_ms()
 dist.barrier()
 for _ in range(20):
     g.run()
