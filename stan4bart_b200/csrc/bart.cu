@@ -62,8 +62,11 @@ __device__ __forceinline__ double warp_sum(double v)
 // algorithmic bytes per observation: R read 8 + R write 8 (when an update is pending) + one
 // u8 per tree level actually visited (typically 1-3)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, int propose_next)
+__global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, int propose_next, const __grid_constant__ ShardDev sh_param)
 {
+  __shared__ ShardDev sh;
+  __shared__ unsigned long long s_seq;
+  __shared__ int s_dead;
   __shared__ StepDesc sd;
   __shared__ StepDesc sd_out;
   __shared__ DTree tree;
@@ -197,6 +200,34 @@ __global__ void __launch_bounds__(kBlock, 3) k_tree_step(BartDev dv, int mode, i
   if (tid == 0) { prm = *dv.params; *dv.ticket = 0u; }
   if (tid < S4B_MAX_DEPTH + 2) pgrow[tid] = dv.pgrow[tid];
   __syncthreads();
+  if (sh_param.world > 1) {
+    // observation-sharded chain: the controller blocks of all ranks exchange their statistics through the peer-mapped
+    // mailboxes (flag-carrying words, see shard.hpp) and add them in rank order -> identical decisions everywhere
+    if (tid == 0) {
+      sh.rank = sh_param.rank; sh.world = sh_param.world;
+      for (int r = 0; r < kMaxRanks; ++r) sh.mail[r] = sh_param.mail[r];
+      s_seq = sh_param.mail[sh_param.rank]->kseq + 1ull; s_dead = 0;
+    }
+    __syncthreads();
+    const unsigned int seq32 = (unsigned int) s_seq;
+    const int par = (int) (s_seq & 1ull);
+    const int cnt = 3 * nslots, world = sh.world;
+    double* stv = reinterpret_cast<double*>(st);
+    for (int i = tid; i < world * cnt; i += kBlock) { const int dst = i / cnt, k = i - dst * cnt; mailbox_send_ll(&sh.mail[dst]->step_ll[par][sh.rank][k], stv[k], seq32); }
+    __syncthreads();
+    const Mailbox* mine = sh.mail[sh.rank];
+    for (int i = tid; i < cnt; i += kBlock) {
+      double acc = 0.0;
+      for (int src = 0; src < world; ++src) {
+        double v = 0.0;
+        if (!s_dead && !mailbox_recv_ll(&mine->step_ll[par][src][i], seq32, &v)) s_dead = 1;
+        acc = src == 0 ? v : acc + v;
+      }
+      stv[i] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) { sh.mail[sh.rank]->kseq = s_seq; if (s_dead) dv.params->error_flag |= 4u; }
+  }
   clk[1] = clock64();
   if (mode == kModeStatsOnly) {
     for (int v = tid; v < 3 * nslots; v += kBlock) dv.stats_out[v] = reinterpret_cast<double*>(st)[v];
@@ -770,7 +801,8 @@ void BartFit::setup_persistent()
     };
     if (!try_nq(1, sweep_smem_bytes<1>(p_), (const void*) k_sweep<1, false>, (const void*) k_sweep<1, true>))
       if (!try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2, false>, (const void*) k_sweep<2, true>))
-        try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4, false>, (const void*) k_sweep<4, true>);
+        if (!try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4, false>, (const void*) k_sweep<4, true>))
+          try_nq(6, sweep_smem_bytes<6>(p_), (const void*) k_sweep<6, false>, (const void*) k_sweep<6, true>);
   }
   if (persistent_nq_ > 0) {
     partial_stride_ = 3 * S4B_MAX_SLOTS * persistent_grid_;
@@ -796,8 +828,7 @@ void BartFit::setup_persistent()
     S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     sweep_mode_ = 2;
   }
-  if (sharded() && persistent_nq_ == 0) throw std::invalid_argument("sharded fit: the local shard does not fit the persistent sweep kernel (rows per GPU or p too large)");
-  if (env && !sharded()) set_sweep_mode(atoi(env));
+  if (env) set_sweep_mode(atoi(env));
   if (getenv("S4B_OVERLAP_WALK")) overlap_walk_ = atoi(getenv("S4B_OVERLAP_WALK"));
 }
 
@@ -805,7 +836,6 @@ void BartFit::set_sweep_mode(int m)
 {
   if (m == 2 && persistent_nq_ == 0) throw std::invalid_argument("persistent sweep kernel does not fit this problem (n, p) on this GPU");
   if (m < 0 || m > 2) throw std::invalid_argument("sweep mode must be 0, 1 or 2");
-  if (m != 2 && sharded()) throw std::invalid_argument("observation-sharded chains run the persistent sweep kernel only (mode 2)");
   sweep_mode_ = m; use_graph_ = m != 0;
 }
 
@@ -825,13 +855,11 @@ void BartFit::launch_persistent_sweep(bool last_thin)
     k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_);
   }
   int overlap = overlap_walk_;
-  ShardDev sh; std::memset(&sh, 0, sizeof sh); sh.world = 1;
-  unsigned long long seq_base = 0;
-  if (sharded()) { sh = shard_->dev(); seq_base = shard_->reserve_step_seq(T_); }
-  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &seq_base };
+  ShardDev sh = shard_dev();
+  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh };
   const void* fn;
-  if (sequential_rng_) fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, true> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, true> : (const void*) k_sweep<4, true>);
-  else fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, false> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, false> : (const void*) k_sweep<4, false>);
+  if (sequential_rng_) fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, true> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, true> : (persistent_nq_ == 4 ? (const void*) k_sweep<4, true> : (const void*) k_sweep<6, true>));
+  else fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, false> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, false> : (persistent_nq_ == 4 ? (const void*) k_sweep<4, false> : (const void*) k_sweep<6, false>));
   S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
                                                    (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);
@@ -848,6 +876,13 @@ void BartFit::bin_matrix(const double* x, long long rows, long long rows_pad, st
     uint8_t* dst = out.data() + (size_t) j * rows_pad;
     for (long long i = 0; i < rows; ++i) dst[i] = (uint8_t) (std::lower_bound(c, c + cfg_.n_cuts, col[i]) - c);
   }
+}
+
+ShardDev BartFit::shard_dev() const
+{
+  ShardDev sh; std::memset(&sh, 0, sizeof sh); sh.world = 1;
+  if (sharded()) sh = shard_->dev();
+  return sh;
 }
 
 BartDev BartFit::dev() const
@@ -931,6 +966,7 @@ void BartFit::check_error_flag()
   BartParams P = params();
   if (P.error_flag & 2u) throw std::runtime_error("s4b: RNG tape underrun in replay mode");
   if (P.error_flag & 4u) throw std::runtime_error("s4b: a peer rank stopped answering during a sharded sweep");
+  if (P.error_flag & 8u) throw std::runtime_error("s4b: a CTA never reached the grid barrier of the sweep kernel");
   if (P.error_flag) throw std::runtime_error("s4b: device error flag set");
 }
 
@@ -988,7 +1024,7 @@ void BartFit::sample_trees_from_prior()
   BartDev dv = dev();
   for (int t = 0; t < T_; ++t) {
     k_prior_tree<<<1, 32, 0, stream_>>>(dv, t);
-    k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeUpdateOnly, 0);
+    k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeUpdateOnly, 0, shard_dev());
   }
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, 0);
   S4B_CUDA(cudaGetLastError());
@@ -998,7 +1034,7 @@ void BartFit::launch_sweep_kernels(bool last_thin)
 {
   BartDev dv = dev();
   k_propose_first<<<1, kBlock, 0, stream_>>>(dv);
-  for (int t = 0; t < T_; ++t) k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStep, t + 1 < T_ ? 1 : 0);
+  for (int t = 0; t < T_; ++t) k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStep, t + 1 < T_ ? 1 : 0, shard_dev());
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
                                                    (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
@@ -1110,8 +1146,7 @@ int BartFit::leaf_stats(int tree, int max_leaves, long long* heap, long long* co
   launch_leaf_stats(tree);
   std::vector<double> st((size_t) 3 * S4B_MAX_SLOTS);
   S4B_CUDA(cudaMemcpyAsync(st.data(), d_stats_out_, sizeof(double) * st.size(), cudaMemcpyDeviceToHost, stream_));
-  std::vector<DTree> trees = download_trees();
-  if (sharded()) shard_->allreduce_host(st.data(), (long long) st.size(), kOpSum, stream_);     // statistics of the whole data set
+  std::vector<DTree> trees = download_trees();       // (sharded chains: the kernel already exchanged the statistics)
   const DTree& t = trees[(size_t) tree];
   int leaf = 0;
   for (int k = 0; k < t.num_nodes; ++k) if (t.nodes[k].var < 0) {
@@ -1131,7 +1166,7 @@ void BartFit::launch_leaf_stats(int tree)
 {
   BartDev dv = dev();
   k_build_stats_desc<<<1, 32, 0, stream_>>>(dv, tree);
-  k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStatsOnly, 0);
+  k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStatsOnly, 0, shard_dev());
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, 0);
   S4B_CUDA(cudaGetLastError());
 }

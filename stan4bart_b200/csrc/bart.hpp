@@ -57,7 +57,7 @@ class BartFit {
   void set_record(size_t cap);
   size_t get_record(double* out, size_t cap);
   unsigned long long rng_counter();
-  void set_use_graph(bool g) { if (sharded()) throw std::invalid_argument("observation-sharded chains run the persistent sweep kernel only"); use_graph_ = g; if (!g) sweep_mode_ = 0; else if (sweep_mode_ == 0) sweep_mode_ = 1; }
+  void set_use_graph(bool g) { use_graph_ = g; if (!g) sweep_mode_ = 0; else if (sweep_mode_ == 0) sweep_mode_ = 1; }
   // 0: one launch per tree step; 1: the same kernels captured in a CUDA graph; 2: persistent on-chip sweep kernel
   // (sweep_kernel.cuh), the default whenever the chain fits
   void set_sweep_mode(int m);
@@ -90,6 +90,7 @@ class BartFit {
 
  private:
   BartDev dev() const;
+  ShardDev shard_dev() const;
   void launch_sweep_kernels(bool last_thin);
   void launch_persistent_sweep(bool last_thin);
   void setup_persistent();

@@ -21,6 +21,9 @@ struct Mailbox {
   // words (flag32 << 32 | half32) so that data and flag arrive in the same store -- no fence and no second hop between
   // "data written" and "flag visible"; the flag is the low 32 bits of the step's sequence number
   ulonglong2 step_ll[2][kMaxRanks][3 * S4B_MAX_SLOTS];
+  // number of per-tree-step exchanges this rank has completed: the next exchange uses kseq + 1.  Kept on the device so that
+  // graph-captured launches need no per-launch argument; identical on all ranks because they make identical call sequences
+  unsigned long long kseq;
   // generic small vectors (GLMM reductions, min / max for the rescale, cut-point ranges)
   unsigned long long vec_flag[2][kMaxRanks];
   double vec_data[2][kMaxRanks][kMailVec];
@@ -49,8 +52,6 @@ class ShardContext {
   void set_obs_range(long long first_obs, long long total_obs) { dev_.obs_offset = first_obs; total_obs_ = total_obs; }
   long long obs_offset() const { return dev_.obs_offset; }
   long long total_obs() const { return total_obs_; }
-  // sequence numbers for the per-tree-step exchange of one sweep (monotone over the context's lifetime)
-  unsigned long long reserve_step_seq(int steps) { unsigned long long b = step_seq_; step_seq_ += (unsigned long long) steps; return b; }
   void check_error();
   const ShardDev& dev() const { return dev_; }
   // in-place all-reduce of a small device vector (n <= kMailVec), identical result on every rank
@@ -62,7 +63,7 @@ class ShardContext {
   ShardDev dev_;
   Mailbox* local_ = nullptr;
   bool attached_ = false;
-  unsigned long long vec_seq_ = 0, step_seq_ = 0;
+  unsigned long long vec_seq_ = 0;
   long long total_obs_ = 0;
   double* d_tmp_ = nullptr;
   unsigned int* d_err_ = nullptr;

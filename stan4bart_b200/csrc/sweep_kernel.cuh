@@ -862,6 +862,7 @@ struct SweepSmem {
   long long pc[6], wk[4];   // phase cycle counters (profiling runs)
   FastPlanSmem plan;   // this step's decision plan (controller, written before the grid barrier)
   int peer_dead;       // a peer rank stopped answering (sharded mode): stop waiting, flag the error
+  unsigned long long seq_base;   // sharded chains: exchanges completed before this launch (Mailbox::kseq)
   ShardDev sh;         // copy of the kernel parameter (indexed dynamically; keeps it out of local memory)
   RngState rng;
   BartParams prm;
@@ -1024,7 +1025,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
 template <int NQ, bool SEQ>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
                                                                const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
-                                                               const __grid_constant__ ShardDev sh_param, unsigned long long seq_base)
+                                                               const __grid_constant__ ShardDev sh_param)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
@@ -1061,6 +1062,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     S.sh.rank = sh_param.rank; S.sh.world = sh_param.world; S.sh.obs_offset = sh_param.obs_offset;
 #pragma unroll
     for (int r = 0; r < kMaxRanks; ++r) S.sh.mail[r] = sh_param.mail[r];
+    S.seq_base = sh_param.world > 1 ? sh_param.mail[sh_param.rank]->kseq : 0ull;
   }
   const int world = sh_param.world;
   if (tid == 0) { const double sg = dv.params->sigma; S.inv_sigsq = 1.0 / (sg * sg); for (int i = 0; i < 6; ++i) S.pc[i] = 0; for (int i = 0; i < 4; ++i) S.wk[i] = 0; }
@@ -1261,7 +1263,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       // this rank's sums straight into every peer's mailbox over NVLink, each double as two flag-carrying 8-byte words
       // (no fence, one hop); every CTA polls the local mailbox and adds the contributions in rank order, so all CTAs
       // of all ranks hold bitwise identical statistics and take the same decision ----
-      const unsigned long long seq = seq_base + (unsigned long long) t + 1ull;
+      const unsigned long long seq = S.seq_base + (unsigned long long) t + 1ull;
       const unsigned int seq32 = (unsigned int) seq;
       const int par = (int) (seq & 1ull);
       const int cnt = 3 * nslots;
@@ -1369,6 +1371,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     if (out.tape_underrun) dv.params->error_flag |= 2u;
     if (S.peer_dead) dv.params->error_flag |= (S.peer_dead == 2 ? 8u : 4u);
     dv.params->step_id = step0 + (unsigned long long) T;
+    if (world > 1) S.sh.mail[S.sh.rank]->kseq = S.seq_base + (unsigned long long) T;
     dv.desc->a_valid = 0;
     if (dv.prof != nullptr) {
       // [0] accumulate + CTA reduction (CTA 0), [1] ... + grid barrier + controller wait, [2] statistics reduce,

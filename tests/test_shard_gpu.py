@@ -80,6 +80,11 @@ def test_sharded_bart_matches_whole_data_oracle(ranks, binary):
         compare_traces(tr_o, r[f"bart_{tag}_trace"], tol=1e-8)
         assert rel_err(o.data_range(), r[f"bart_{tag}_range"]) <= 1e-12
     assert np.array_equal(ranks[0][f"bart_{tag}_trace"], ranks[1][f"bart_{tag}_trace"])     # ranks agree bit for bit
+    for mode in (0, 1):      # streaming per-tree kernels, sharded
+        for r in ranks:
+            compare_traces(tr_o, r[f"bart_{tag}_trace_mode{mode}"], tol=1e-8)
+        got = _cat(ranks, f"bart_{tag}_train_mode{mode}")
+        assert rel_err(ro["train"], got, scale=np.abs(ro["train"]) + 1.0) <= 1e-8
     train = _cat(ranks, f"bart_{tag}_train")
     assert rel_err(ro["train"], train, scale=np.abs(ro["train"]) + 1.0) <= 1e-8
     res = _cat(ranks, f"bart_{tag}_residual")
