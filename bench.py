@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--n", "--rows", dest="n", type=int, default=1_000_000, help="observations (use --rows under torchrun: its parser trips over --n)")
     ap.add_argument("--trees", type=int, default=200)
     ap.add_argument("--adapt", type=int, default=200, help="adaptation sweeps before adaptation is disengaged (untimed; >= 150 so that the metric windows of Stan run)")
+    ap.add_argument("--continuous", action="store_true", help="continuous response (configs B / E) instead of the probit model of config C")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-rows", action="store_true",
                     help="N > 1 only: ONE chain whose --n rows are sharded over the N GPUs (BASELINE config E; strong scaling) instead of "
@@ -48,8 +49,9 @@ def parse_args():
 
 
 def workload_config(args):
-    return {"workload": "config C: binary probit Friedman causal, n=%d, %d trees, p_bart=9, K=2, q=18, n_test=%d, "
-                        "1 chain per GPU" % (args.n, args.trees, args.n),
+    what = "continuous Friedman causal" if args.continuous else "config C: binary probit Friedman causal"
+    return {"workload": "%s, n=%d, %d trees, p_bart=9, K=2, q=18, n_test=%d, "
+                        "1 chain per GPU" % (what, args.n, args.trees, args.n),
             "n": args.n, "trees": args.trees, "chains_per_gpu": 1, "parallelism": "chain-per-GPU, no data-path collective",
             "l2": "working set of a sweep is re-read 200x by design (R 8 MB + binned X 9 MB resident in L2); "
                   "no flush between steps because that is the workload", "adapt_sweeps": args.adapt}
@@ -57,7 +59,7 @@ def workload_config(args):
 
 def make_problem(args):
     from stan4bart_b200.frontend import friedman_problem
-    return friedman_problem(args.n, binary=True, seed=99)
+    return friedman_problem(args.n, binary=not args.continuous, seed=99)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -153,9 +155,10 @@ def cpu_baseline(args, pr, budget_s):
     import oracle_lib as O
     from stan4bart_b200.structs import bart_config, stan_control
     sd = pr["stan_data"]
-    cfg = bart_config(args.n, 9, n_test=args.n, num_trees=args.trees, is_binary=True, seed=12345)
+    cfg = bart_config(args.n, 9, n_test=args.n, num_trees=args.trees, is_binary=not args.continuous, seed=12345)
+    extra = {"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}
     t0 = time.time()
-    s = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=1), warmup=10, iter_=20, keep_fits=False)
+    s = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=1), warmup=10, iter_=20, keep_fits=False, **extra)
     t_create = time.time() - t0
     t0 = time.time()
     s.run(1, True)
@@ -177,10 +180,12 @@ def _ref_worker(args_dict, seed, conn):
         from stan4bart_b200.frontend import friedman_problem
         from stan4bart_b200.structs import bart_config, stan_control
         n, trees = args_dict["n"], args_dict["trees"]
-        pr = friedman_problem(n, binary=True, seed=99)
-        cfg = bart_config(n, 9, n_test=n, num_trees=trees, is_binary=True, seed=seed)
+        binary = not args_dict.get("continuous", False)
+        pr = friedman_problem(n, binary=binary, seed=99)
+        cfg = bart_config(n, 9, n_test=n, num_trees=trees, is_binary=binary, seed=seed)
+        extra = {} if binary else {"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]}
         s = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=seed), warmup=10, iter_=20,
-                            keep_fits=False)
+                            keep_fits=False, **extra)
         conn.send(("ready", 0.0))
         while True:
             cmd = conn.recv()
@@ -209,7 +214,7 @@ def run_reference(args):
     workers = []
     for c in range(procs):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(dict(n=args.n, trees=args.trees), 12345 + c, b), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(dict(n=args.n, trees=args.trees, continuous=args.continuous), 12345 + c, b), daemon=True)
         p.start()
         workers.append((p, a))
     for _, a in workers:
@@ -286,9 +291,10 @@ def run_ours(args):
         chains = 1
     seed_rank = 0 if sharded else rank
     sd = pr["stan_data"]
-    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=True, seed=chain_seed(12345, seed_rank))
+    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=not args.continuous, seed=chain_seed(12345, seed_rank))
     s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=chain_seed(1000, seed_rank)), warmup=args.adapt,
-                iter_=args.adapt + args.steps, keep_fits=False, shard=shard_ctx)
+                iter_=args.adapt + args.steps, keep_fits=False, shard=shard_ctx,
+                **({"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}))
     bart = s.bart()
     glmm = s.glmm()
     s.run(args.adapt, True, results=False)
@@ -337,7 +343,7 @@ def run_ours(args):
             traffic = json.load(f).get("k_sweep_dram_bytes_per_launch" if persistent else "k_tree_step_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_sweep<4> (one launch = one 200-tree sweep)" if persistent else "k_tree_step (one launch = one tree)",
+    roofline = {"bound": "hbm", "kernel": "k_sweep (one launch = one %d-tree sweep)" % T if persistent else "k_tree_step (one launch = one tree)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_tree_obs": bytes_per_obs,
                 "units_per_launch": units_per_launch, "avg_tree_levels": lv,
