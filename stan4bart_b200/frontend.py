@@ -175,3 +175,26 @@ def shard_problem(prob, lo, hi):
     out["y"] = np.ascontiguousarray(prob["y"][lo:hi])
     out["bart_offset_init"] = np.ascontiguousarray(prob["bart_offset_init"][lo:hi])
     return out
+
+
+def ihdp_problem(n, seed=7, n_sites=8, with_test=True):
+    """BASELINE config D: an IHDP-shaped causal problem (/root/reference/ihdp/data.R:7-10: 6 continuous + 19 binary
+    covariates; treatment z; site-level random intercept), scaled to n rows with synthetic covariates.  Model:
+    `y ~ bart(. - site - z) + z + (1 | site)`; the counterfactual test design flips nothing BART sees, so it aliases
+    the training design exactly as in the Friedman causal example."""
+    rng = np.random.default_rng(seed)
+    xc = rng.standard_normal((n, 6))
+    xb = (rng.random((n, 19)) < rng.uniform(0.1, 0.9, 19)).astype(np.float64)
+    x = np.column_stack([xc, xb])
+    site = rng.integers(0, n_sites, n)
+    b_site = rng.standard_normal(n_sites) * 0.8
+    z = (rng.random(n) < ndtr(0.4 * xc[:, 0] - 0.3 * xb[:, 0] - 0.6)).astype(np.float64)
+    mu0 = np.exp((xc[:, :3] + 0.5) @ np.array([0.3, 0.2, 0.1])) + xb[:, :5] @ np.array([0.5, -0.4, 0.3, 0.2, -0.1]) + b_site[site]
+    y = mu0 + 4.0 * z + rng.standard_normal(n)
+    x_bart = np.asfortranarray(x)
+    x_test = np.asfortranarray(x_bart.copy()) if with_test else None
+    terms = [(site, np.ones((n, 1)))]
+    sd = build_stan_data(z.reshape(n, 1), y, terms, is_binary=False)
+    offset_init, sigma_init = init_fit(sd, False)
+    return dict(data=dict(x=x, z=z, site=site, y=y), x_bart=x_bart, x_test=x_test, stan_data=sd, y=np.ascontiguousarray(y),
+                bart_offset_init=offset_init, sigma_init=sigma_init)

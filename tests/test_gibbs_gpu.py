@@ -131,3 +131,61 @@ def test_posterior_agreement_within_monte_carlo_error():
     assert abs(co.mean() - cg.mean()) <= 4 * np.sqrt(co.var(ddof=1) / chains + cg.var(ddof=1) / chains)
     mu_true = d["mu1"] * d["z"] + d["mu0"] * (1 - d["z"])
     assert np.corrcoef(mg.mean(axis=0), mu_true)[0, 1] >= 0.95
+
+
+def _ihdp_pair(n=400, num_trees=9, seed=4321, warmup=6, iter_=11):
+    from stan4bart_b200.frontend import ihdp_problem
+    pr = ihdp_problem(n)
+    cfg = bart_config(n, 25, n_test=n, num_trees=num_trees, is_binary=False, seed=seed)
+    ctl = stan_control(seed=seed + 1)
+    kw = dict(warmup=warmup, iter_=iter_, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    return pr, cfg, ctl, kw
+
+
+def test_config_d_ihdp_shaped_first_sweeps():
+    """BASELINE config D shape (25 covariates: 6 continuous + 19 binary, site-level random intercept, treatment as the
+    only fixed effect): first sweeps agree with the oracle step by step; binary covariates bin to two levels."""
+    pr, cfg, ctl, kw = _ihdp_pair()
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, **kw)
+    g = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, **kw)
+    K = 6
+    ob, gb = o.bart(), g.bart()
+    ob.set_trace(9 * K); gb.set_trace(9 * K)
+    ro, rg = o.run(K, True), g.run(K, True)
+    compare_traces(ob.trace(), gb.trace(), tol=1e-8)
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-8
+    assert np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"])
+
+
+def test_chains_on_concurrent_host_threads_match_sequential_runs():
+    """Config D runs several chains per GPU: every chain is driven by its own host thread on its own stream (the C ABI
+    keeps stream and error state per thread), so one chain's host NUTS overlaps another chain's sweep kernel.  The draws
+    must not depend on the interleaving."""
+    import threading
+    pr, cfg0, ctl0, kw = _ihdp_pair(n=600)
+
+    def make(c):
+        cfg = bart_config(600, 25, n_test=600, num_trees=9, is_binary=False, seed=100 + c)
+        return Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=200 + c), **kw)
+
+    seq = []
+    for c in range(3):
+        s = make(c)
+        seq.append(s.run(6, True))
+        del s
+    out = [None] * 3
+
+    def work(c):
+        s = make(c)
+        out[c] = s.run(6, True)
+
+    th = [threading.Thread(target=work, args=(c,)) for c in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for c in range(3):
+        assert out[c] is not None
+        assert np.array_equal(seq[c]["stan"], out[c]["stan"])
+        assert np.array_equal(seq[c]["bart"]["train"], out[c]["bart"]["train"])

@@ -1,0 +1,58 @@
+"""Several chains per GPU (BASELINE config D: IHDP-shaped, n = 500 000, 25 covariates, 8 chains per GPU): every chain has its
+own host thread and stream, so one chain's host-side NUTS overlaps another chain's sweep kernel on the device.
+usage: python tools/multi_chain_bench.py [n] [chains] [sweeps] [trees]"""
+import json
+import os
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stan4bart_b200.frontend import ihdp_problem
+from stan4bart_b200.sampler import Sampler
+from stan4bart_b200.structs import bart_config, stan_control
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 500000
+chains = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+trees = int(sys.argv[4]) if len(sys.argv) > 4 else 200
+adapt = 160
+pr = ihdp_problem(n)
+kw = dict(warmup=adapt, iter_=adapt + 3 * sweeps, keep_fits=False, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+samplers = [None] * chains
+barrier = threading.Barrier(chains + 1)
+times = {}
+
+
+def work(c):
+    cfg = bart_config(n, 25, n_test=n, num_trees=trees, is_binary=False, seed=100 + c)
+    s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=200 + c), **kw)
+    s.run(adapt, True, results=False)
+    s.disengage_adaptation()
+    s.run(5, False, results=False)
+    samplers[c] = s
+    barrier.wait()          # everybody adapted
+    barrier.wait()          # sequential leg done by the main thread
+    s.run(sweeps, False, results=False)
+    barrier.wait()
+
+
+th = [threading.Thread(target=work, args=(c,)) for c in range(chains)]
+for t in th:
+    t.start()
+barrier.wait()
+t0 = time.time()
+for s in samplers:          # one chain after the other on the main thread
+    s.run(sweeps, False, results=False)
+t_seq = time.time() - t0
+stats = samplers[0].last_run_stats()
+barrier.wait()
+t0 = time.time()
+barrier.wait()
+t_par = time.time() - t0
+for t in th:
+    t.join()
+print(json.dumps({"workload": "config D shape: IHDP-like continuous, n=%d, p=25, %d trees, %d chains on one GPU" % (n, trees, chains),
+                  "sweeps_per_s_sequential": chains * sweeps / t_seq, "sweeps_per_s_threaded": chains * sweeps / t_par,
+                  "ms_stan_block": stats["ms_stan"] / sweeps, "ms_bart_block": stats["ms_bart"] / sweeps,
+                  "bart_sweep_mode": samplers[0].bart().sweep_mode()}))
