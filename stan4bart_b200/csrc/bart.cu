@@ -15,6 +15,7 @@
 namespace s4b {
 
 constexpr int kBlock = 256;
+constexpr int kStreamNq = 99;      // persistent_nq_ value of the streamed sweep variant
 
 enum PassMode { kModeStep = 0, kModeStatsOnly = 1, kModeUpdateOnly = 2 };
 
@@ -763,7 +764,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -803,6 +804,25 @@ void BartFit::setup_persistent()
       if (!try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2, false>, (const void*) k_sweep<2, true>))
         if (!try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4, false>, (const void*) k_sweep<4, true>))
           try_nq(6, sweep_smem_bytes<6>(p_), (const void*) k_sweep<6, false>, (const void*) k_sweep<6, true>);
+    // shards beyond the register file (or when forced, for the tests): residuals and node indices streamed from global memory
+    const bool force_stream = getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0;
+    if (persistent_nq_ == 0 || force_stream) {
+      const size_t smem = sweep_smem_bytes<1>(0);
+      const long long rounds = (nquad / num_sms_ + 1 + kWorkers - 1) / kWorkers;
+      bool ok = smem <= (size_t) max_smem && p_ <= 511 && rounds <= 63;      // 8-bit count fields: at most 63 rounds of 4 observations
+      for (const void* f : { (const void*) k_sweep<1, false, true>, (const void*) k_sweep<1, true, true> }) {
+        if (!ok) break;
+        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, kSweepBlock, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); ok = false; }
+      }
+      if (ok) {
+        persistent_nq_ = kStreamNq; persistent_smem_ = smem;
+        persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(num_sms_, (nquad + kWorkers - 1) / kWorkers));
+        S4B_CUDA(cudaMalloc(&d_packs_, sizeof(uint2) * 2 * (size_t) nquad));
+        S4B_CUDA(cudaMemset(d_packs_, 0, sizeof(uint2) * 2 * (size_t) nquad));
+      }
+    }
   }
   if (persistent_nq_ > 0) {
     partial_stride_ = 3 * S4B_MAX_SLOTS * persistent_grid_;
@@ -858,7 +878,8 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   ShardDev sh = shard_dev();
   void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh };
   const void* fn;
-  if (sequential_rng_) fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, true> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, true> : (persistent_nq_ == 4 ? (const void*) k_sweep<4, true> : (const void*) k_sweep<6, true>));
+  if (persistent_nq_ == kStreamNq) fn = sequential_rng_ ? (const void*) k_sweep<1, true, true> : (const void*) k_sweep<1, false, true>;
+  else if (sequential_rng_) fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, true> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, true> : (persistent_nq_ == 4 ? (const void*) k_sweep<4, true> : (const void*) k_sweep<6, true>));
   else fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, false> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, false> : (persistent_nq_ == 4 ? (const void*) k_sweep<4, false> : (const void*) k_sweep<6, false>));
   S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
@@ -890,7 +911,7 @@ BartDev BartFit::dev() const
   BartDev d;
   d.n = n_; d.npad = npad_; d.obs_offset = shard_ != nullptr ? shard_->obs_offset() : 0; d.xt = d_xt_; d.R = d_R_; d.yresc = d_yresc_; d.y = d_y_; d.offset = d_offset_;
   d.desc = d_desc_; d.trees = d_trees_; d.params = d_params_; d.pgrow = d_pgrow_; d.rng = d_rng_;
-  d.partials = d_partials_; d.ticket = d_ticket_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
+  d.partials = d_partials_; d.ticket = d_ticket_; d.packs = d_packs_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
   d.stats_out = d_stats_out_; d.prof = profile_on_ ? d_prof_ : nullptr;
   return d;
 }

@@ -17,6 +17,7 @@ struct BartDev {
   double* R; double* yresc; const double* y; double* offset;
   StepDesc* desc; DTree* trees; BartParams* params; const double* pgrow; RngState* rng;
   double* partials; unsigned int* ticket;
+  uint2* packs;               // streamed sweep: cached node indices of every quad, two buffers of nquad entries
   double* trace; unsigned long long trace_cap; unsigned long long* trace_len;
   double* stats_out;
   unsigned long long* prof;   // cycle counters of the controller phases (last block, thread 0)
@@ -110,7 +111,8 @@ class BartFit {
   bool add_offset_ = true;
   bool test_aliases_train_ = false;
   int sweep_mode_ = 1;
-  int persistent_nq_ = 0, persistent_grid_ = 0;
+  int persistent_nq_ = 0, persistent_grid_ = 0;       // nq = kStreamNq: residuals streamed from global memory (L2)
+  uint2* d_packs_ = nullptr;
   size_t persistent_smem_ = 0;
   unsigned int* d_barrier_ = nullptr;
   double* d_partials2_ = nullptr;

@@ -119,6 +119,18 @@ __global__ void k_glmm_residual(long long N, const double* __restrict__ y, const
   for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long) gridDim.x * blockDim.x) r[i] = y[i] - offset[i];
 }
 
+// new offset and / or response in one pass: copies what changed into the model's own buffers and refreshes r = y - offset
+__global__ void k_glmm_set_inputs(long long N, const double* __restrict__ new_offset, const double* __restrict__ new_y, double* __restrict__ offset,
+                                  double* __restrict__ y, double* __restrict__ r)
+{
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long) gridDim.x * blockDim.x) {
+    double o, v;
+    if (new_offset != nullptr) { o = new_offset[i]; offset[i] = o; } else o = offset[i];
+    if (new_y != nullptr) { v = new_y[i]; y[i] = v; } else v = y[i];
+    r[i] = v - o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 struct GlmmModel::Params {
   const double *z_beta, *z_b, *rho_u, *zeta_u, *tau_u;
@@ -275,8 +287,15 @@ void GlmmModel::refresh_r()
 
 void GlmmModel::set_offset_host(const double* offset) { S4B_CUDA(cudaMemcpyAsync(d_offset_, offset, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice, stream_)); refresh_r(); S4B_CUDA(cudaStreamSynchronize(stream_)); }
 void GlmmModel::set_response_host(const double* y) { S4B_CUDA(cudaMemcpyAsync(d_y_, y, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice, stream_)); refresh_r(); S4B_CUDA(cudaStreamSynchronize(stream_)); }
-void GlmmModel::set_offset_device(const double* d_offset) { S4B_CUDA(cudaMemcpyAsync(d_offset_, d_offset, sizeof(double) * (size_t) N_, cudaMemcpyDeviceToDevice, stream_)); refresh_r(); }
-void GlmmModel::set_response_device(const double* d_y) { S4B_CUDA(cudaMemcpyAsync(d_y_, d_y, sizeof(double) * (size_t) N_, cudaMemcpyDeviceToDevice, stream_)); refresh_r(); }
+void GlmmModel::set_inputs_device(const double* d_offset, const double* d_y)
+{
+  expansion_valid_ = false;
+  int grid = (int) std::max<long long>(1, std::min<long long>((N_ + 255) / 256, 148 * 8));
+  k_glmm_set_inputs<<<grid, 256, 0, stream_>>>(N_, d_offset, d_y, d_offset_, d_y_, d_r_);
+  S4B_CUDA(cudaGetLastError());
+}
+void GlmmModel::set_offset_device(const double* d_offset) { set_inputs_device(d_offset, nullptr); }
+void GlmmModel::set_response_device(const double* d_y) { set_inputs_device(nullptr, d_y); }
 
 void GlmmModel::data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb)
 {

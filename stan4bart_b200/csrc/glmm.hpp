@@ -43,6 +43,7 @@ class GlmmModel {
   void set_response_host(const double* y);
   void set_offset_device(const double* d_offset);     // copies
   void set_response_device(const double* d_y);        // copies
+  void set_inputs_device(const double* d_offset, const double* d_y);   // either may be NULL (unchanged); one fused pass
   // returns status: 0 ok, 1 non-finite lp / gradient (maps to V = +inf in the sampler)
   int log_prob_grad(const double* q, double* lp, double* grad);
   void write_array(const double* q, double* out) const;

@@ -16,9 +16,15 @@
 
 namespace s4b {
 
-__global__ void k_accumulate(long long n, const double* __restrict__ src, double* __restrict__ acc)
+// running sums of the kept draws (training fit, parametric mean, test fit) in one launch
+__global__ void k_accumulate3(long long n, const double* __restrict__ s0, double* __restrict__ a0, const double* __restrict__ s1, double* __restrict__ a1,
+                              long long n2, const double* __restrict__ s2, double* __restrict__ a2)
 {
-  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) acc[i] += src[i];
+  const long long m = n > n2 ? n : n2;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long) gridDim.x * blockDim.x) {
+    if (i < n) { a0[i] += s0[i]; a1[i] += s1[i]; }
+    if (i < n2) a2[i] += s2[i];
+  }
 }
 
 class GibbsSampler {
@@ -42,8 +48,7 @@ class GibbsSampler {
     if (!cc_.is_binary) bart_.set_sigma(cc_.sigma_init);                   // :256-257
     bart_.sample_trees_from_prior();                                       // :261
     bart_.run_sweeps();                                                    // :273  (first draw)
-    glmm_.set_offset_device(bart_.d_train_out());                          // :275-287 (fit without the offset)
-    if (cc_.is_binary) glmm_.set_response_device(bart_.d_latent_out());    // :288-291
+    glmm_.set_inputs_device(bart_.d_train_out(), cc_.is_binary ? bart_.d_latent_out() : nullptr);    // :275-291 (fit without the offset)
     S4B_CUDA(cudaStreamSynchronize(stream_));
     bart_.check_error_flag();
   }
@@ -95,12 +100,10 @@ class GibbsSampler {
           S4B_CUDA(cudaMemcpyAsync(bart_.d_latent_out(), h_plumb_ + 2 * n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
         }
       }
-      glmm_.set_offset_device(bart_.d_train_out());                                      // :828-842
-      if (cc_.is_binary) glmm_.set_response_device(bart_.d_latent_out());                // :843-847
+      glmm_.set_inputs_device(bart_.d_train_out(), cc_.is_binary ? bart_.d_latent_out() : nullptr);   // :828-847
       if (!is_warmup) {
-        k_accumulate<<<acc_grid, 256, 0, stream_>>>(n_, bart_.d_train_out(), d_mean_train_);
-        k_accumulate<<<acc_grid, 256, 0, stream_>>>(n_, d_bart_offset_, d_mean_param_);
-        if (nt_ > 0) k_accumulate<<<acc_grid, 256, 0, stream_>>>(nt_, bart_.d_test_out(), d_mean_test_);
+        k_accumulate3<<<acc_grid, 256, 0, stream_>>>(n_, bart_.d_train_out(), d_mean_train_, d_bart_offset_, d_mean_param_,
+                                                     nt_, nt_ > 0 ? bart_.d_test_out() : nullptr, d_mean_test_);
         ++num_mean_draws_;
       }
       if (train) S4B_CUDA(cudaMemcpyAsync(train + slot * n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));

@@ -1020,9 +1020,95 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
   if (lane == 0) atomicAdd(&dv.rng->counter, (unsigned long long) W.cs.draws_total);
 }
 
+// ---------------------------------------------------------------------------------------
+// Streamed variant (STREAM = true): shards that do not fit the register file keep the residuals and the cached node
+// indices in global memory (L2 resident up to a few million rows) and stream them through the same per-step phases in
+// rounds of kWorkers quads; the binned predictors are read from global memory by the walks.  Every quad is owned by one
+// thread for the whole sweep, so no synchronisation is needed for R or the node-index buffers.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void stream_walk(const StepDesc& sd, const uint32_t* __restrict__ xt32, int col_words, long long q_lo, long long q_hi, int tid,
+                                            uint2* packs_out)
+{
+  for (long long q0 = q_lo; q0 < q_hi; q0 += kWorkers) {
+    const long long q = q0 + tid;
+    if (q < q_hi) {
+      uint32_t lp[1], ap[1];
+      walk_step<1>(sd, xt32 + q0, col_words, tid, 1u, lp, ap);
+      packs_out[q] = make_uint2(lp[0], ap[0]);
+    }
+  }
+}
+
+// (no __restrict__ / read-only qualifiers on R and the node-index buffers: they are rewritten inside the same kernel, and a
+// non-coherent load would return stale values)
+__device__ __forceinline__ void stream_accumulate(const StepDesc& sd, const double* Rg, const uint2* packs, long long q_lo, long long q_hi,
+                                                  long long n, int tid, int base, int kmax, double2* __restrict__ bin_s, unsigned long long& cpk)
+{
+  const int kind = sd.b_kind, L = sd.b_num_leaves;
+  const bool two_trees = (kind == 2 || kind == 3);
+  const int birth_node = kind == 0 ? sd.b_node : -1;
+  for (long long q0 = q_lo; q0 < q_hi; q0 += kWorkers) {
+    const long long q = q0 + tid;
+    if (q >= q_hi) continue;
+    const double2 ra = *reinterpret_cast<const double2*>(Rg + 4 * q), rb = *reinterpret_cast<const double2*>(Rg + 4 * q + 2);
+    const double r[4] = { ra.x, ra.y, rb.x, rb.y };
+    const uint2 pk = packs[q];
+    double pr[4]; int row[4], row2[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int leaf = (pk.x >> (8 * o)) & 0xFF;
+      const int aux = (pk.y >> (8 * o)) & 0xFF;
+      pr[o] = r[o] + sd.b_cur.val[leaf];
+      const bool ok = 4 * q + o < n;
+      const int sa = (two_trees ? (int) sd.b_cur.slot[leaf] : (leaf == birth_node ? L + aux : (int) sd.b_cur.slot[leaf])) - base;
+      row[o] = ((unsigned) sa < (unsigned) kmax && ok) ? sa : kBinSlots;
+      row2[o] = kBinSlots;
+      if (two_trees) { const int sb = (int) sd.b_prop.slot[aux] - base; row2[o] = ((unsigned) sb < (unsigned) kmax && ok) ? sb : kBinSlots; }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      int idx = row[o] * kWorkers + tid;
+      double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+      if (row[o] < kBinSlots) cpk += 1ull << (8 * row[o]);
+      if (two_trees) {
+        idx = row2[o] * kWorkers + tid;
+        v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+        if (row2[o] < kBinSlots) cpk += 1ull << (8 * row2[o]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void stream_update(const UpdateDesc& upd, double* Rg, const uint2* packs, long long q_lo, long long q_hi, int tid)
+{
+  const int amode = upd.mode, unode = upd.node;
+  for (long long q0 = q_lo; q0 < q_hi; q0 += kWorkers) {
+    const long long q = q0 + tid;
+    if (q >= q_hi) continue;
+    double2 ra = *reinterpret_cast<const double2*>(Rg + 4 * q), rb = *reinterpret_cast<const double2*>(Rg + 4 * q + 2);
+    double r[4] = { ra.x, ra.y, rb.x, rb.y };
+    const uint2 pk = packs[q];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int leaf = (pk.x >> (8 * o)) & 0xFF;
+      const int aux = (pk.y >> (8 * o)) & 0xFF;
+      if (amode == 0) r[o] += upd.delta[leaf];
+      else {
+        int nl;
+        if (amode == 3) nl = aux;
+        else if (amode == 1 && leaf == unode) nl = unode + 1 + aux;
+        else nl = upd.remap[leaf];
+        r[o] += upd.val_old[leaf] - upd.val_new[nl];
+      }
+    }
+    *reinterpret_cast<double2*>(Rg + 4 * q) = make_double2(r[0], r[1]);
+    *reinterpret_cast<double2*>(Rg + 4 * q + 2) = make_double2(r[2], r[3]);
+  }
+}
+
 // SEQ: replay / record keep the strict program order of the draws (proposals and draws produced inside the loop);
 // the production instantiation (SEQ = false) carries none of that code
-template <int NQ, bool SEQ>
+template <int NQ, bool SEQ, bool STREAM = false>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
                                                                const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
                                                                const __grid_constant__ ShardDev sh_param)
@@ -1051,7 +1137,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     const long long q = q_lo + (long long) j * kWorkers + tid;
-    if (is_worker && q < q_hi) {
+    if (!STREAM && is_worker && q < q_hi) {
       valid_mask |= 1u << j;
       for (int o = 0; o < 4; ++o) if (4 * q + o < n) obs_mask |= 1u << (4 * j + o);
       double2 a = *reinterpret_cast<const double2*>(dv.R + 4 * q), b = *reinterpret_cast<const double2*>(dv.R + 4 * q + 2);
@@ -1073,9 +1159,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   const unsigned long long step0 = S.prm.step_id;
   // replay / record need strict program order: proposals and draws are then produced inside the loop
   constexpr bool sequential_rng = SEQ;
-  if (is_worker) {
-    const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(dv.xt);
-    const long long col_words = npad >> 2;
+  const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(dv.xt);
+  const int col_words = (int) (npad >> 2);
+  if (!STREAM && is_worker) {
     for (int v = 0; v < p; ++v)
 #pragma unroll
       for (int j = 0; j < NQ; ++j) {
@@ -1101,7 +1187,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   }
   __syncthreads();
   uint32_t leaf_pack[NQ], aux_pack[NQ];
-  if (is_worker) walk_step<NQ>(S.sd[0], tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
+  if (is_worker) {
+    if (STREAM) stream_walk(S.sd[0], xt32, col_words, q_lo, q_hi, tid, dv.packs);
+    else walk_step<NQ>(S.sd[0], tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
+  }
 
   // phase counters live in shared memory (thread 0, profiling runs only): as registers they would be carried through the
   // whole loop by every thread.  S.wk[0..3]: worker sub-phases (zero bins, accumulate, wait + row reduce, second barrier)
@@ -1132,7 +1221,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         const long long w1 = clock64();
         // branch-free: every observation adds into exactly one bin row (row kBinSlots is a trash row for padding and for
         // slots outside this pass); loads first (independent), then the read-modify-write chain
-        if (!two_trees) {
+        if (STREAM) {
+          stream_accumulate(sd, dv.R, dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, n, tid, base, kmax, bin_s, cpk);
+        } else if (!two_trees) {
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {
             double pr[4]; int row[4];
@@ -1191,7 +1282,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             const int r = task - kmax;
             int c = 0;
 #pragma unroll
-            for (int i = 0; i < kWorkerWarps; ++i) c += (int) ((bin_c[i * 32 + lane] >> (6 * r)) & 63ull);
+            for (int i = 0; i < kWorkerWarps; ++i) c += STREAM ? (int) ((bin_c[i * 32 + lane] >> (8 * r)) & 255ull) : (int) ((bin_c[i * 32 + lane] >> (6 * r)) & 63ull);
             c = __reduce_add_sync(0xffffffffu, c);
             if (lane == 0) partials[(size_t) (3 * (base + r)) * G + cta] = (double) c;
           }
@@ -1312,14 +1403,17 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       }
     } else if (!sequential_rng && overlap_walk && t + 1 < T) {
       // ---- workers, concurrently: walk tree t+1 (independent of this step's decision) ----
-      walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_next, aux_next);
+      if (STREAM) stream_walk(sd_next, xt32, col_words, q_lo, q_hi, tid, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad);
+      else walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_next, aux_next);
     }
     __syncthreads();                                                        // [C] decision known
     const long long c5 = clock64();
     if (is_worker) {
       // ---- fit / residual update from the cached leaf indices ----
       const int amode = S.upd.mode, unode = S.upd.node;
-      if (amode == 0) {
+      if (STREAM) {
+        stream_update(S.upd, dv.R, dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, tid);
+      } else if (amode == 0) {
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
 #pragma unroll
@@ -1339,7 +1433,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
           }
         }
       }
-      if (t + 1 < T) {
+      if (STREAM) {
+        if (t + 1 < T && (sequential_rng || !overlap_walk)) stream_walk(sd_next, xt32, col_words, q_lo, q_hi, tid, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad);
+      } else if (t + 1 < T) {
         if (sequential_rng || !overlap_walk) walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
         else {
 #pragma unroll

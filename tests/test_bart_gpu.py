@@ -206,3 +206,54 @@ def test_bad_arguments_fail_loudly():
     g = GpuBart(bart_config(50, 2, num_trees=2), y, x)
     with pytest.raises(S4BError):
         g.node_assignment(5)
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_streamed_sweep_variant(monkeypatch, binary):
+    """Shards beyond the register file run the same persistent sweep with residuals and cached node indices streamed
+    from global memory (S4B_FORCE_STREAM selects it at any size): all move types, n not a multiple of anything, and
+    bit-for-bit agreement with the register-resident variant (same arithmetic in the same order)."""
+    T, sweeps = 12, 25
+    x, y, xt = bart_problem(2777, 6, 0, binary, seed=21)
+    cfg = bart_config(2777, 6, num_trees=T, is_binary=binary, seed=33)
+    off = 0.3 * x[:, 3] - 0.1
+    o = O.OracleBart(cfg, y, x, xt)
+    g_reg = GpuBart(cfg, y, x, xt)
+    monkeypatch.setenv("S4B_FORCE_STREAM", "1")
+    g_str = GpuBart(cfg, y, x, xt)
+    monkeypatch.delenv("S4B_FORCE_STREAM")
+    assert g_str.sweep_mode() == 2
+    for b in (o, g_reg, g_str):
+        b.set_offset(off, True)
+        if not binary:
+            b.set_sigma(1.3)
+        b.sample_trees_from_prior()
+        b.set_trace(T * sweeps)
+    for s in range(sweeps):
+        ro, r1, r2 = o.run(), g_reg.run(), g_str.run()
+        assert np.array_equal(r1["train"], r2["train"]), f"sweep {s}"
+        assert rel_err(ro["train"], r2["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
+    compare_traces(o.trace(), g_str.trace())
+    assert np.array_equal(g_reg.trace(), g_str.trace())
+    assert_same_partition(o, g_str, T)
+
+
+def test_streamed_sweep_variant_replays_a_tape(monkeypatch):
+    T, sweeps = 7, 5
+    o, _, (x, y, xt) = make_pair(n=900, num_trees=T, seed=5)
+    monkeypatch.setenv("S4B_FORCE_STREAM", "1")
+    g = GpuBart(o.cfg, y, x, xt)
+    monkeypatch.delenv("S4B_FORCE_STREAM")
+    off = 0.3 * x[:, 3] - 0.1
+    g.set_offset(off, True); g.set_sigma(1.3)
+    o.set_record(200000)
+    o.sample_trees_from_prior()
+    o.set_trace(T * sweeps)
+    outs = [o.run() for _ in range(sweeps)]
+    g.set_tape(o.record())
+    g.sample_trees_from_prior()
+    g.set_trace(T * sweeps)
+    for s in range(sweeps):
+        rg = g.run()
+        assert rel_err(outs[s]["train"], rg["train"], scale=np.abs(outs[s]["train"]) + 1.0) <= REL_TOL
+    compare_traces(o.trace(), g.trace())
