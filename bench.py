@@ -371,10 +371,11 @@ def run_ours(args):
            "note": "s4b_sampler_run with host result buffers (train + test fits, Stan row) and every N-vector of the sweep "
                    "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors"}
 
-    # kernels launched inside the timed region, per sweep: k_prepare_sweep + k_sweep + epilogue + epoch bump (BART),
-    # 2 offset kernels, parametric mean, 2 residual refreshes, 3 running-mean accumulations, plus the GLMM data passes
+    # kernels launched inside the timed region, per sweep: k_prepare_sweep + k_sweep + epilogue + epoch bump (BART block),
+    # the offset kernel + its epoch bump (1 kernel for a continuous response), parametric mean, the fused GLMM input refresh,
+    # the fused running-mean accumulation, plus the GLMM data passes
     per_sweep_bart = 4 if bart.sweep_mode() == 2 else T + 3
-    launches = K * (per_sweep_bart + 2 + 1 + 2 + 3) + glmm_passes
+    launches = K * (per_sweep_bart + (1 if args.continuous else 2) + 1 + 1 + 1) + glmm_passes
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -41,7 +41,9 @@ class GibbsSampler {
     auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); S4B_CUDA(cudaMemset(*p, 0, sizeof(double) * std::max<size_t>(count, 1))); };
     dalloc(&d_bart_offset_, (size_t) n_); dalloc(&d_mean_train_, (size_t) n_); dalloc(&d_mean_param_, (size_t) n_); dalloc(&d_mean_test_, (size_t) std::max<long long>(nt_, 1));
     S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
-    S4B_CUDA(cudaEventCreate(&ev_a_)); S4B_CUDA(cudaEventCreate(&ev_b_)); S4B_CUDA(cudaEventCreate(&ev_c_));
+    S4B_CUDA(cudaEventCreateWithFlags(&ev_a_, cudaEventDisableTiming)); S4B_CUDA(cudaEventCreateWithFlags(&ev_b_, cudaEventDisableTiming));
+    S4B_CUDA(cudaEventCreateWithFlags(&ev_c_, cudaEventDisableTiming));
+    S4B_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     bart_.set_add_offset(false);
     if (bart_offset_init) S4B_CUDA(cudaMemcpyAsync(d_bart_offset_, bart_offset_init, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice, stream_));
     bart_.set_offset_device(d_bart_offset_, true);                         // init.cpp:255
@@ -57,6 +59,7 @@ class GibbsSampler {
     if (h_plumb_) cudaFreeHost(h_plumb_);
     cudaFree(d_bart_offset_); cudaFree(d_mean_train_); cudaFree(d_mean_param_); cudaFree(d_mean_test_); cudaFree(d_varcount_);
     cudaEventDestroy(ev_a_); cudaEventDestroy(ev_b_); cudaEventDestroy(ev_c_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
   }
 
   int num_pars() const { return num_pars_; }
@@ -91,12 +94,21 @@ class GibbsSampler {
       bart_.set_offset_device(d_bart_offset_, is_warmup && (iter % update_scale_mod == 0));
       auto t1 = std::chrono::steady_clock::now();
       // ---- B. BART block (init.cpp:821-916) ----
+      // the previous iteration's result copies (second stream) must be out of the fit buffers before they are rewritten
+      if (copy_pending_) { S4B_CUDA(cudaStreamWaitEvent(stream_, ev_c_, 0)); copy_pending_ = false; }
       bart_.run_sweeps();                                                                // :824
       if (host_plumbing_) {   // `stanOffset` and `bartLatents` as host vectors (init.cpp:144-145, :835, :845-846)
+        // the latents leave on the copy stream while the fit makes its round trip on the main stream: PCIe is full duplex
+        if (cc_.is_binary) {
+          S4B_CUDA(cudaEventRecord(ev_a_, stream_));
+          S4B_CUDA(cudaStreamWaitEvent(copy_stream_, ev_a_, 0));
+          S4B_CUDA(cudaMemcpyAsync(h_plumb_ + 2 * n, bart_.d_latent_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, copy_stream_));
+          S4B_CUDA(cudaEventRecord(ev_b_, copy_stream_));
+        }
         S4B_CUDA(cudaMemcpyAsync(h_plumb_ + n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
         S4B_CUDA(cudaMemcpyAsync(bart_.d_train_out(), h_plumb_ + n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
         if (cc_.is_binary) {
-          S4B_CUDA(cudaMemcpyAsync(h_plumb_ + 2 * n, bart_.d_latent_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+          S4B_CUDA(cudaStreamWaitEvent(stream_, ev_b_, 0));
           S4B_CUDA(cudaMemcpyAsync(bart_.d_latent_out(), h_plumb_ + 2 * n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
         }
       }
@@ -106,8 +118,15 @@ class GibbsSampler {
                                                      nt_, nt_ > 0 ? bart_.d_test_out() : nullptr, d_mean_test_);
         ++num_mean_draws_;
       }
-      if (train) S4B_CUDA(cudaMemcpyAsync(train + slot * n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
-      if (test && nt_ > 0) S4B_CUDA(cudaMemcpyAsync(test + slot * nt, bart_.d_test_out(), sizeof(double) * nt, cudaMemcpyDeviceToHost, stream_));
+      if (train || (test && nt_ > 0)) {
+        // the N-length results leave on the copy stream and overlap the next iteration's Stan block
+        S4B_CUDA(cudaEventRecord(ev_a_, stream_));
+        S4B_CUDA(cudaStreamWaitEvent(copy_stream_, ev_a_, 0));
+        if (train) S4B_CUDA(cudaMemcpyAsync(train + slot * n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, copy_stream_));
+        if (test && nt_ > 0) S4B_CUDA(cudaMemcpyAsync(test + slot * nt, bart_.d_test_out(), sizeof(double) * nt, cudaMemcpyDeviceToHost, copy_stream_));
+        S4B_CUDA(cudaEventRecord(ev_c_, copy_stream_));
+        copy_pending_ = true;
+      }
       if (varcount) {
         bart_.varcount_device(d_varcount_);
         S4B_CUDA(cudaMemcpyAsync(varcount + slot * (size_t) p_, d_varcount_, sizeof(unsigned int) * (size_t) p_, cudaMemcpyDeviceToHost, stream_));
@@ -118,6 +137,8 @@ class GibbsSampler {
       ms_stan_ += std::chrono::duration<double, std::milli>(t1 - t0).count();
       ms_bart_ += std::chrono::duration<double, std::milli>(t2 - t1).count();
     }
+    S4B_CUDA(cudaStreamSynchronize(copy_stream_));        // results are in the caller's buffers when run() returns
+    copy_pending_ = false;
     bart_.check_error_flag();
     last_grad_evals_ = glmm_.num_grad_evals() - grad0;
     last_tree_steps_ = bart_.num_tree_steps() - steps0;
@@ -166,7 +187,8 @@ class GibbsSampler {
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;
   long long num_mean_draws_ = 0, last_grad_evals_ = 0, last_tree_steps_ = 0;
   double ms_stan_ = 0.0, ms_bart_ = 0.0;
-  bool host_plumbing_ = false;
+  bool host_plumbing_ = false, copy_pending_ = false;
+  cudaStream_t copy_stream_ = nullptr;
   double* h_plumb_ = nullptr;
 };
 

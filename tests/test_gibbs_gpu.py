@@ -189,3 +189,26 @@ def test_chains_on_concurrent_host_threads_match_sequential_runs():
         assert out[c] is not None
         assert np.array_equal(seq[c]["stan"], out[c]["stan"])
         assert np.array_equal(seq[c]["bart"]["train"], out[c]["bart"]["train"])
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_host_boundary_path_gives_the_same_draws(binary):
+    """bench.py's `e2e` leg: results written into caller-provided host buffers (on a second stream, overlapping the next
+    Stan block) and every N-vector of the sweep round-tripped through pinned host memory like the reference's host
+    vectors.  The draws must be exactly those of the device-resident path."""
+    _, g1, pr = make_pair(n=1201, binary=binary, num_trees=9, keep_fits=False)
+    _, g2, _ = make_pair(n=1201, binary=binary, num_trees=9, keep_fits=False)
+    h2d, d2h = g2.set_host_plumbing(True)
+    assert h2d == d2h == 8 * 1201 * (3 if binary else 2)
+    stan = np.zeros(g2.num_pars)
+    train = np.zeros(1201)
+    test = np.zeros(1201)
+    for k in range(4):
+        r1 = g1.run(3, k < 2)
+        g2.run_into(3, k < 2, stan=stan.ctypes.data, train=train.ctypes.data, test=test.ctypes.data)
+        assert np.array_equal(r1["stan"][:, -1], stan)
+        assert np.array_equal(r1["bart"]["train"][:, -1], train)
+        assert np.array_equal(r1["bart"]["test"][:, -1], test)
+    g2.set_host_plumbing(False)
+    r1, r2 = g1.run(2, False), g2.run(2, False)
+    assert np.array_equal(r1["stan"], r2["stan"]) and np.array_equal(r1["bart"]["train"], r2["bart"]["train"])
