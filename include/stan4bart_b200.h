@@ -96,6 +96,15 @@ int gpubart_get_data_range(gpubart_fit* fit, double* min_max_range);
 /* predict(fit, x_test, n, testOffset, result) (init.cpp:398) */
 int gpubart_predict(gpubart_fit* fit, const double* x_test, int64_t n, const double* test_offset, double* out);
 /* getTrees -> FlattenedTrees (init.cpp:577-666): pre-order, var < 0 => leaf, value = cut point | leaf mu */
+/* keepTrees (dbarts control$keepTrees; stan4bart_exportBARTState / stan4bart_createStoredBARTSampler / stan4bart_predictBART on a
+ * stored sampler, init.cpp:354-446; stan4bart_getTrees on stored samples, :514-671).  With a store of `capacity` draws every
+ * runSamplerWithResults call (and every s4b_sampler_run iteration) appends the trees of its kept draw; capacity 0 frees it.
+ * predict_stored: out [n x count], draws first .. first + count - 1; get_stored_trees: the flattened table of one draw. */
+int gpubart_set_keep_trees(gpubart_fit* fit, int64_t capacity);
+int gpubart_num_stored(gpubart_fit* fit, int64_t* out);
+int gpubart_predict_stored(gpubart_fit* fit, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out);
+int gpubart_num_stored_nodes(gpubart_fit* fit, int64_t sample, int64_t* out);
+int gpubart_get_stored_trees(gpubart_fit* fit, int64_t sample, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value);
 int gpubart_num_nodes(gpubart_fit* fit, int64_t* out);
 int gpubart_get_trees(gpubart_fit* fit, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value);
 /* parity instrumentation (no reference counterpart) */

@@ -26,6 +26,11 @@ SIGNATURES = {
     "gpubart_tree_step_ms": (C.c_int, [vp, C.c_int, c_double_p]),
     "gpubart_get_profile": (C.c_int, [vp, c_uint64_p, C.c_int]),
     "gpubart_set_profile": (C.c_int, [vp, C.c_int]),
+    "gpubart_set_keep_trees": (C.c_int, [vp, C.c_int64]),
+    "gpubart_num_stored": (C.c_int, [vp, c_int64_p]),
+    "gpubart_predict_stored": (C.c_int, [vp, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int64, c_double_p]),
+    "gpubart_num_stored_nodes": (C.c_int, [vp, C.c_int64, c_int64_p]),
+    "gpubart_get_stored_trees": (C.c_int, [vp, C.c_int64, c_int32_p, c_int64_p, c_int32_p, c_double_p]),
     "s4b_sampler_set_host_plumbing": (C.c_int, [vp, C.c_int, c_int64_p, c_int64_p]),
     "gpubart_create": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, vpp]),
     "gpubart_free": (C.c_int, [vp]),

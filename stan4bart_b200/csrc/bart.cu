@@ -460,9 +460,12 @@ __global__ void k_bump_epoch_clear_update(BartDev dv, int bump)
 
 // test-sample fits: sum over all trees of the leaf value reached by each test row.  The block's rows are staged in
 // shared memory (p bytes per row), the trees are streamed through shared memory in batches; all walks are on chip.
+// `trees` / `scale` (smin, srange) default to the live sampler state; stored samples (keepTrees) pass their own
 __global__ void __launch_bounds__(kBlock) k_test_fits(BartDev dv, const uint8_t* __restrict__ xt_test, long long n_test, long long npad_test,
-                                                      const double* __restrict__ test_offset, double* __restrict__ out, int unscale, int p)
+                                                      const double* __restrict__ test_offset, double* __restrict__ out, int unscale, int p,
+                                                      const DTree* __restrict__ trees_in, const double* __restrict__ scale_in)
 {
+  const DTree* __restrict__ trees = trees_in != nullptr ? trees_in : dv.trees;
   extern __shared__ unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int T = dv.params->num_trees;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(kBlock) k_test_fits(BartDev dv, const uint8_t*
     __syncthreads();
     if (tid == 0) {
       int used = 0, t = t0, k = 0;
-      while (t < T && k < 256 && used + dv.trees[t].num_nodes <= cap_nodes) { tree_start[k++] = used; used += dv.trees[t].num_nodes; ++t; }
+      while (t < T && k < 256 && used + trees[t].num_nodes <= cap_nodes) { tree_start[k++] = used; used += trees[t].num_nodes; ++t; }
       tree_start[k] = used;
       tree_start[256] = k;
     }
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(kBlock) k_test_fits(BartDev dv, const uint8_t*
     for (int k = tid; k < nt * 8; k += kBlock) {
       // 8 threads per tree copy its nodes
       const int tr = k >> 3, sub = k & 7;
-      const DTree& g = dv.trees[t0 + tr];
+      const DTree& g = trees[t0 + tr];
       const int base = tree_start[tr];
       for (int j = sub; j < g.num_nodes; j += 8) { const DNode& nd = g.nodes[j]; trav[base + j] = pack_trav(nd.var, nd.cut, nd.right); val[base + j] = nd.mu; }
     }
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(kBlock) k_test_fits(BartDev dv, const uint8_t*
     t0 += nt;
   }
   if (i < n_test) {
-    const double smin = dv.params->smin, srange = dv.params->srange;
+    const double smin = scale_in != nullptr ? scale_in[0] : dv.params->smin, srange = scale_in != nullptr ? scale_in[1] : dv.params->srange;
     double f = unscale ? smin + (acc + 0.5) * srange : acc;
     out[i] = f + (test_offset != nullptr ? test_offset[i] : 0.0);
   }
@@ -615,6 +618,18 @@ __global__ void k_set_sigma(BartDev dv, double sigma)
 __global__ void k_store_latents(BartDev dv, double* __restrict__ out)
 {
   for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < dv.n; i += (long long) gridDim.x * blockDim.x) out[i] = dv.yresc[i] + dv.offset[i];
+}
+
+// keepTrees: copy the current trees and the current response scale into slot `slot` of the store
+__global__ void k_snapshot_trees(BartDev dv, DTree* __restrict__ store, double* __restrict__ scales)
+{
+  const int t = blockIdx.x;
+  const DTree& g = dv.trees[t];
+  DTree& d = store[t];
+  const int nn = g.num_nodes;
+  if (threadIdx.x == 0) { d.num_nodes = nn; d.pad = 0; }
+  for (int i = threadIdx.x; i < nn * (int) (sizeof(DNode) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(d.nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+  if (t == 0 && threadIdx.x == 0) { scales[0] = dv.params->smin; scales[1] = dv.params->srange; }
 }
 
 __global__ void k_varcount(BartDev dv, unsigned int* __restrict__ out)
@@ -764,7 +779,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -1086,6 +1101,67 @@ void BartFit::run_sweeps()
   ev_pending_ = true;
   num_tree_steps_ += (long long) cfg_.thin * T_;
   if (nt_ > 0 && !test_aliases_train_) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
+  snapshot_trees();                      // keepTrees (no-op unless a store was requested)
+}
+
+void BartFit::set_keep_trees(long long capacity)
+{
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_store_); cudaFree(d_store_scale_); d_store_ = nullptr; d_store_scale_ = nullptr;
+  store_cap_ = capacity > 0 ? capacity : 0; store_len_ = 0;
+  if (store_cap_ > 0) {
+    S4B_CUDA(cudaMalloc(&d_store_, sizeof(DTree) * (size_t) T_ * (size_t) store_cap_));
+    S4B_CUDA(cudaMalloc(&d_store_scale_, sizeof(double) * 2 * (size_t) store_cap_));
+  }
+}
+
+void BartFit::snapshot_trees()
+{
+  if (store_cap_ == 0) return;
+  if (store_len_ >= store_cap_) throw std::runtime_error("keepTrees: the tree store is full (gpubart_set_keep_trees capacity)");
+  k_snapshot_trees<<<T_, 128, 0, stream_>>>(dev(), d_store_ + (size_t) store_len_ * (size_t) T_, d_store_scale_ + 2 * (size_t) store_len_);
+  S4B_CUDA(cudaGetLastError());
+  ++store_len_;
+}
+
+void BartFit::predict_stored(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out)
+{
+  if (first < 0 || count < 0 || first + count > store_len_) throw std::invalid_argument("stored sample range out of bounds");
+  if (rows <= 0 || count == 0) return;
+  long long rows_pad = (rows + 15) / 16 * 16;
+  std::vector<uint8_t> xtt; bin_matrix(x_test, rows, rows_pad, xtt);
+  uint8_t* d_x; double* d_o; double* d_off = nullptr;
+  S4B_CUDA(cudaMalloc(&d_x, xtt.size())); S4B_CUDA(cudaMalloc(&d_o, sizeof(double) * (size_t) rows));
+  S4B_CUDA(cudaMemcpyAsync(d_x, xtt.data(), xtt.size(), cudaMemcpyHostToDevice, stream_));
+  if (test_offset) { S4B_CUDA(cudaMalloc(&d_off, sizeof(double) * (size_t) rows)); S4B_CUDA(cudaMemcpyAsync(d_off, test_offset, sizeof(double) * (size_t) rows, cudaMemcpyHostToDevice, stream_)); }
+  for (long long s = 0; s < count; ++s) {
+    test_fits_device(d_x, rows, rows_pad, d_off, d_o, d_store_ + (size_t) (first + s) * (size_t) T_, d_store_scale_ + 2 * (size_t) (first + s));
+    S4B_CUDA(cudaMemcpyAsync(out + (size_t) s * (size_t) rows, d_o, sizeof(double) * (size_t) rows, cudaMemcpyDeviceToHost, stream_));
+  }
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_x); cudaFree(d_o); cudaFree(d_off);
+}
+
+std::vector<DTree> BartFit::download_stored(long long sample)
+{
+  if (sample < 0 || sample >= store_len_) throw std::invalid_argument("stored sample index out of bounds");
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  std::vector<DTree> trees((size_t) T_);
+  S4B_CUDA(cudaMemcpy(trees.data(), d_store_ + (size_t) sample * (size_t) T_, sizeof(DTree) * trees.size(), cudaMemcpyDeviceToHost));
+  return trees;
+}
+
+long long BartFit::num_stored_nodes(long long sample)
+{
+  long long c = 0;
+  for (const auto& t : download_stored(sample)) c += t.num_nodes;
+  return c;
+}
+
+void BartFit::get_stored_trees(long long sample, int32_t* tree_no, long long* n_obs, int32_t* var, double* value)
+{
+  auto trees = download_stored(sample);
+  flatten_trees(trees, tree_no, n_obs, var, value);
 }
 
 void BartFit::get_profile(unsigned long long* out8, bool reset)
@@ -1108,12 +1184,13 @@ double BartFit::tree_step_ms(bool reset)
   return r;
 }
 
-void BartFit::test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out)
+void BartFit::test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out, const DTree* trees,
+                               const double* scale)
 {
   size_t smem = (sizeof(uint32_t) + sizeof(double)) * 2048 + (size_t) p_ * kBlock;
   if (smem > 48 * 1024) S4B_CUDA(cudaFuncSetAttribute(k_test_fits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int grid = (int) ((rows + kBlock - 1) / kBlock);
-  k_test_fits<<<grid, kBlock, smem, stream_>>>(dev(), d_xt, rows, rows_pad, d_off, d_out, cfg_.is_binary ? 0 : 1, p_);
+  k_test_fits<<<grid, kBlock, smem, stream_>>>(dev(), d_xt, rows, rows_pad, d_off, d_out, cfg_.is_binary ? 0 : 1, p_, trees, scale);
   S4B_CUDA(cudaGetLastError());
 }
 
@@ -1207,10 +1284,9 @@ long long BartFit::num_nodes()
   return c;
 }
 
-void BartFit::get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double* value)
+void BartFit::flatten_trees(std::vector<DTree>& trees, int32_t* tree_no, long long* n_obs, int32_t* var, double* value) const
 {
   long long pos = 0;
-  auto trees = download_trees();
   for (int t = 0; t < T_; ++t) {
     DTree& tr = trees[(size_t) t];
     // the device keeps observation counts for bottom nodes only; internal nodes are the sum of their children
@@ -1222,6 +1298,12 @@ void BartFit::get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double
       else { var[pos] = nd.var; value[pos] = cuts_[(size_t) nd.var * cfg_.n_cuts + nd.cut]; }
     }
   }
+}
+
+void BartFit::get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double* value)
+{
+  auto trees = download_trees();
+  flatten_trees(trees, tree_no, n_obs, var, value);
 }
 
 void BartFit::predict(const double* x_test, long long rows, const double* test_offset, double* out)

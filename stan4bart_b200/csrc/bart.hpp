@@ -44,6 +44,14 @@ class BartFit {
   void predict(const double* x_test, long long rows, const double* test_offset, double* out);
   void get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double* value);
   long long num_nodes();
+  // keepTrees (dbarts control$keepTrees; stan4bart_exportBARTState / createStoredBARTSampler / predictBART, init.cpp:354-446):
+  // with a store of `capacity` samples every runSamplerWithResults call appends the trees and the response scale of its
+  // kept draw; stored draws can be predicted from and flattened like the live sampler
+  void set_keep_trees(long long capacity);
+  long long num_stored() const { return store_len_; }
+  void predict_stored(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out);
+  long long num_stored_nodes(long long sample);
+  void get_stored_trees(long long sample, int32_t* tree_no, long long* n_obs, int32_t* var, double* value);
   BartParams params();
   void varcount_device(unsigned int* d_out);
 
@@ -95,7 +103,11 @@ class BartFit {
   void launch_sweep_kernels(bool last_thin);
   void launch_persistent_sweep(bool last_thin);
   void setup_persistent();
-  void test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out);
+  void test_fits_device(const uint8_t* d_xt, long long rows, long long rows_pad, const double* d_off, double* d_out, const DTree* trees = nullptr,
+                        const double* scale = nullptr);
+  void snapshot_trees();
+  std::vector<DTree> download_stored(long long sample);
+  void flatten_trees(std::vector<DTree>& trees, int32_t* tree_no, long long* n_obs, int32_t* var, double* value) const;
   void bin_matrix(const double* x, long long rows, long long rows_pad, std::vector<uint8_t>& out) const;
   std::vector<DTree> download_trees();
   void invalidate_graph();
@@ -113,6 +125,7 @@ class BartFit {
   int sweep_mode_ = 1;
   int persistent_nq_ = 0, persistent_grid_ = 0;       // nq = kStreamNq: residuals streamed from global memory (L2)
   uint2* d_packs_ = nullptr;
+  DTree* d_store_ = nullptr; double* d_store_scale_ = nullptr; long long store_cap_ = 0, store_len_ = 0;
   size_t persistent_smem_ = 0;
   unsigned int* d_barrier_ = nullptr;
   double* d_partials2_ = nullptr;

@@ -362,6 +362,13 @@ int s4b_sampler_get_means(s4b_sampler* s, double* mt, double* mte, double* mp, i
 int s4b_sampler_set_host_plumbing(s4b_sampler* s, int on, int64_t* h2d, int64_t* d2h)
 { S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->set_host_plumbing(on != 0, &a, &b); if (h2d) *h2d = a; if (d2h) *d2h = b; S4B_API_END }
 int gpubart_get_profile(gpubart_fit* f, uint64_t* out24, int reset) { S4B_API_BEGIN S4B_REQUIRE(f && out24); f->fit->get_profile((unsigned long long*) out24, reset != 0); S4B_API_END }
+int gpubart_set_keep_trees(gpubart_fit* f, int64_t capacity) { S4B_API_BEGIN S4B_REQUIRE(f && capacity >= 0); f->fit->set_keep_trees(capacity); S4B_API_END }
+int gpubart_num_stored(gpubart_fit* f, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); *out = f->fit->num_stored(); S4B_API_END }
+int gpubart_predict_stored(gpubart_fit* f, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out)
+{ S4B_API_BEGIN S4B_REQUIRE(f && x_test && out && n >= 0); f->fit->predict_stored(x_test, n, test_offset, first, count, out); S4B_API_END }
+int gpubart_num_stored_nodes(gpubart_fit* f, int64_t sample, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); *out = f->fit->num_stored_nodes(sample); S4B_API_END }
+int gpubart_get_stored_trees(gpubart_fit* f, int64_t sample, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value)
+{ S4B_API_BEGIN S4B_REQUIRE(f && tree_no && n_obs && var && value); f->fit->get_stored_trees(sample, tree_no, (long long*) n_obs, var, value); S4B_API_END }
 int gpubart_set_profile(gpubart_fit* f, int on) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_profile(on != 0); S4B_API_END }
 int gpubart_tree_step_ms(gpubart_fit* f, int reset, double* ms) { S4B_API_BEGIN S4B_REQUIRE(f && ms); *ms = f->fit->tree_step_ms(reset != 0); S4B_API_END }
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* ng, int64_t* ns)

@@ -92,6 +92,36 @@ class GpuBart:
                                             var.ctypes.data_as(c_int32_p), dptr(value)))
         return dict(tree=tree_no, n=n_obs, var=var, value=value)
 
+    # ---- keepTrees: stored draws ----
+    def set_keep_trees(self, capacity):
+        _lib.check(self.L.gpubart_set_keep_trees(self.h, int(capacity)))
+
+    def num_stored(self):
+        k = C.c_int64(0)
+        _lib.check(self.L.gpubart_num_stored(self.h, C.byref(k)))
+        return int(k.value)
+
+    def predict_stored(self, x_test, first=0, count=None, offset=None):
+        """Predictions of stored draws first .. first + count - 1 on new rows: array [rows x count]."""
+        xt = np.asfortranarray(x_test, dtype=np.float64)
+        count = self.num_stored() - first if count is None else count
+        out = np.zeros((count, xt.shape[0]))
+        o = f64(offset) if offset is not None else None
+        _lib.check(self.L.gpubart_predict_stored(self.h, dptr(xt), xt.shape[0], dptr(o), int(first), int(count), dptr(out)))
+        return out.T
+
+    def stored_trees(self, sample):
+        k = C.c_int64(0)
+        _lib.check(self.L.gpubart_num_stored_nodes(self.h, int(sample), C.byref(k)))
+        k = k.value
+        tree_no = np.zeros(k, dtype=np.int32)
+        n_obs = np.zeros(k, dtype=np.int64)
+        var = np.zeros(k, dtype=np.int32)
+        value = np.zeros(k)
+        _lib.check(self.L.gpubart_get_stored_trees(self.h, int(sample), tree_no.ctypes.data_as(c_int32_p), n_obs.ctypes.data_as(c_int64_p),
+                                                   var.ctypes.data_as(c_int32_p), dptr(value)))
+        return dict(tree=tree_no, n=n_obs, var=var, value=value)
+
     # ---- parity instrumentation ----
     def node_assignment(self, tree):
         out = np.zeros(self.n, dtype=np.int64)

@@ -212,3 +212,33 @@ def test_host_boundary_path_gives_the_same_draws(binary):
     g2.set_host_plumbing(False)
     r1, r2 = g1.run(2, False), g2.run(2, False)
     assert np.array_equal(r1["stan"], r2["stan"]) and np.array_equal(r1["bart"]["train"], r2["bart"]["train"])
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_keep_trees_stored_draws_predict_their_own_training_fits(binary):
+    """keepTrees (the reference's strongest self-consistency check, tests/testthat/test-01-continuous.R:212-254):
+    predicting from the stored trees of draw s on the training design reproduces the stored training fit of draw s, the
+    flattened tree table of the last stored draw is the live sampler's, and the store refuses to overflow."""
+    from stan4bart_b200._lib import S4BError
+    _, g, pr = make_pair(n=700, binary=binary, num_trees=9, warmup=8, iter_=14)
+    g.run(8, True)                                  # warm-up draws are not stored
+    g.disengage_adaptation()
+    b = g.bart()
+    b.set_keep_trees(6)
+    r = g.run(6, False)
+    assert b.num_stored() == 6
+    pred = b.predict_stored(pr["x_bart"])
+    assert pred.shape == (700, 6)
+    assert rel_err(pred, r["bart"]["train"], scale=np.abs(r["bart"]["train"]) + 1.0) <= 1e-10
+    # a different design goes through the same trees: stored draw 5 == the live sampler's current state
+    xnew = np.asfortranarray(np.random.default_rng(0).random((50, 9)))
+    assert rel_err(b.predict_stored(xnew, first=5, count=1)[:, 0], g.predict_bart(xnew), scale=1.0) <= 1e-12
+    live, last = b.trees(), b.stored_trees(5)
+    for key in ("tree", "n", "var", "value"):
+        assert np.array_equal(live[key], last[key]), key
+    assert not np.array_equal(b.stored_trees(0)["value"], last["value"])
+    with pytest.raises(S4BError):
+        g.run(1, False)                             # a seventh draw does not fit the store
+    b.set_keep_trees(0)
+    g.run(1, False)
+    assert b.num_stored() == 0
