@@ -23,6 +23,7 @@
 namespace s4b {
 
 constexpr int kGBlock = 256;
+constexpr int kGFast = 4;          // fast path of the data pass: K and non-zeros per row of Z up to this
 
 __device__ __forceinline__ double g_warp_sum(double v)
 {
@@ -46,6 +47,51 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
   const long long N = g.N, npad = g.npad;
   const int K = g.K, slots = g.slots;
   double S = 0.0;
+  if (K <= kGFast && slots <= kGFast) {
+    // fast path (K, non-zeros per row <= 4: every BASELINE config): two observations per thread and load, two such pairs
+    // in flight per iteration, every global load of the iteration issued before the first use -- the pass is bound by
+    // memory latency otherwise (ncu: long-scoreboard stalls, 1.1 TB/s)
+    const long long stride = (long long) gridDim.x * kGBlock * 2;
+    for (long long i0 = ((long long) blockIdx.x * kGBlock + tid) * 2; i0 < N; i0 += 2 * stride) {
+      double2 r2[2], x2[2][kGFast], v2[2][kGFast]; int2 c2[2][kGFast];
+      bool live[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const long long i = i0 + u * stride;
+        live[u] = i < N;
+        if (live[u]) {
+          r2[u] = __ldg(reinterpret_cast<const double2*>(g.r + i));
+#pragma unroll
+          for (int k = 0; k < kGFast; ++k) if (k < K) x2[u][k] = __ldg(reinterpret_cast<const double2*>(g.X + (long long) k * npad + i));
+#pragma unroll
+          for (int s_ = 0; s_ < kGFast; ++s_) if (s_ < slots) {
+            c2[u][s_] = __ldg(reinterpret_cast<const int2*>(g.zidx + (long long) s_ * npad + i));
+            v2[u][s_] = ((g.ones_mask >> s_) & 1u) ? make_double2(1.0, 1.0) : __ldg(reinterpret_cast<const double2*>(g.zval + (long long) s_ * npad + i));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!live[u]) continue;
+        const long long i = i0 + u * stride;
+        const bool second = i + 1 < N;            // the padded tail holds zeros, but indicator slots are forced to 1
+        double eta0 = 0.0, eta1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < kGFast; ++k) if (k < K) { eta0 += x2[u][k].x * sth[k]; eta1 += x2[u][k].y * sth[k]; }
+#pragma unroll
+        for (int s_ = 0; s_ < kGFast; ++s_) if (s_ < slots) { eta0 += v2[u][s_].x * sth[K + c2[u][s_].x]; eta1 += v2[u][s_].y * sth[K + c2[u][s_].y]; }
+        const double e0 = r2[u].x - eta0, e1 = second ? r2[u].y - eta1 : 0.0;
+        S += e0 * e0; S += e1 * e1;
+#pragma unroll
+        for (int k = 0; k < kGFast; ++k) if (k < K) { double a = wb[k * 32 + lane]; a += x2[u][k].x * e0; a += x2[u][k].y * e1; wb[k * 32 + lane] = a; }
+#pragma unroll
+        for (int s_ = 0; s_ < kGFast; ++s_) if (s_ < slots) {
+          wb[(K + c2[u][s_].x) * 32 + lane] += v2[u][s_].x * e0;
+          wb[(K + c2[u][s_].y) * 32 + lane] += v2[u][s_].y * e1;
+        }
+      }
+    }
+  } else
   for (long long i = (long long) blockIdx.x * kGBlock + tid; i < N; i += (long long) gridDim.x * kGBlock) {
     double eta = 0.0;
     for (int k = 0; k < K; ++k) eta += __ldg(g.X + (long long) k * npad + i) * sth[k];
@@ -208,8 +254,9 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   if (smem_bytes_ > (size_t) max_smem)
     throw std::invalid_argument("glmm: K + q too large for the shared-memory binned reduction (sorted-segment path not implemented yet)");
   S4B_CUDA(cudaFuncSetAttribute(k_glmm_data_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
-  int per_sm = (int) std::max<size_t>(1, std::min<size_t>(8, (size_t) (200 * 1024) / std::max<size_t>(smem_bytes_, 1)));
-  long long want = (N_ + kGBlock - 1) / kGBlock;
+  int per_sm = 1;      // resident blocks per SM (registers and shared memory): the grid is one full wave
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_glmm_data_terms, kGBlock, smem_bytes_) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+  long long want = (N_ + 2 * kGBlock - 1) / (2 * kGBlock);
   grid_ = (int) std::max<long long>(1, std::min<long long>(want, (long long) sms * per_sm));
   dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) (nb + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
