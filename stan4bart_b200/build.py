@@ -15,8 +15,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libstan4bart_b200.so")
 SOURCES = ["bart.cu", "glmm.cu", "nuts.cu", "sampler.cu", "shard.cu"]
+# host side: the NUTS control and the GLMM's O((K+q)^2) expansion run on the CPU ~1000 times per sweep; AVX2 + FMA is safe on
+# every host a B200 sits in
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-mavx2", "-Xcompiler", "-mfma", "--expt-relaxed-constexpr"]
 
 
 def _nvcc():

@@ -1,7 +1,10 @@
 // stan4bart_b200/csrc/nuts.cu -- see nuts.hpp.  Host code only (compiled by nvcc for the shared headers).
 #include "nuts.hpp"
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -55,7 +58,11 @@ NutsSampler::NutsSampler(GlmmModel& model, const s4b_stan_control& ctl, int chai
 void NutsSampler::update_potential_gradient(Point& z)
 {
   double lp = 0.0;
+  static const bool host_prof = getenv("S4B_HOST_PROF") != nullptr;
+  std::chrono::steady_clock::time_point t0;
+  if (host_prof) t0 = std::chrono::steady_clock::now();
   int status = model_.log_prob_grad(z.q.data(), &lp, grad_tmp_.data());
+  if (host_prof) { prof_lp_ns_ += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count(); ++prof_lp_calls_; }
   if (status == 0) { z.V = -lp; for (int i = 0; i < d_; ++i) z.g[(size_t) i] = -grad_tmp_[(size_t) i]; }
   else { z.V = kInf; for (int i = 0; i < d_; ++i) z.g[(size_t) i] = -z.g[(size_t) i]; }   // base_hamiltonian.hpp:61-70
 }
@@ -255,8 +262,18 @@ void NutsSampler::learn_stepsize(double adapt_stat)
 void NutsSampler::run(bool warmup, double* out)
 {
   (void) warmup;
+  static const bool host_prof = getenv("S4B_HOST_PROF") != nullptr;
   for (int m = 0; m < ctl_.skip; ++m) {
+    std::chrono::steady_clock::time_point t0;
+    if (host_prof) t0 = std::chrono::steady_clock::now();
     transition();
+    if (host_prof) {
+      prof_tr_ns_ += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+      if (++prof_tr_calls_ % 50 == 0)
+        fprintf(stderr, "[s4b host prof] transitions %lld: %.1f us each, %.1f evaluations each, %.0f ns per evaluation inside log_prob_grad, %.0f ns per evaluation around it\n",
+                prof_tr_calls_, prof_tr_ns_ / prof_tr_calls_ / 1e3, (double) prof_lp_calls_ / prof_tr_calls_, prof_lp_ns_ / prof_lp_calls_,
+                (prof_tr_ns_ - prof_lp_ns_) / prof_lp_calls_);
+    }
     if (adapt_flag_) {
       learn_stepsize(accept_stat_);
       if (learn_variance()) {

@@ -67,6 +67,7 @@ class NutsSampler {
   uint32_t num_warmup_ = 0, init_buffer_ = 0, term_buffer_ = 0, base_window_ = 0, window_counter_ = 0, next_window_ = 0, window_size_ = 0;
   double wf_n_ = 0; Vec wf_m_, wf_m2_;
   bool adapt_flag_ = true;
+  double prof_lp_ns_ = 0, prof_tr_ns_ = 0; long long prof_lp_calls_ = 0, prof_tr_calls_ = 0;   // S4B_HOST_PROF=1 diagnostics
 };
 
 }  // namespace s4b
