@@ -1041,68 +1041,83 @@ __device__ __forceinline__ void stream_walk(const StepDesc& sd, const uint32_t* 
 
 // (no __restrict__ / read-only qualifiers on R and the node-index buffers: they are rewritten inside the same kernel, and a
 // non-coherent load would return stale values)
+__device__ __forceinline__ void stream_acc_quad(const StepDesc& sd, const double2 ra, const double2 rb, const uint2 pk, long long q, long long n, int tid, int base,
+                                                int kmax, bool two_trees, int birth_node, int L, double2* __restrict__ bin_s, unsigned long long& cpk)
+{
+  const double r[4] = { ra.x, ra.y, rb.x, rb.y };
+  double pr[4]; int row[4], row2[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int leaf = (pk.x >> (8 * o)) & 0xFF;
+    const int aux = (pk.y >> (8 * o)) & 0xFF;
+    pr[o] = r[o] + sd.b_cur.val[leaf];
+    const bool ok = 4 * q + o < n;
+    const int sa = (two_trees ? (int) sd.b_cur.slot[leaf] : (leaf == birth_node ? L + aux : (int) sd.b_cur.slot[leaf])) - base;
+    row[o] = ((unsigned) sa < (unsigned) kmax && ok) ? sa : kBinSlots;
+    row2[o] = kBinSlots;
+    if (two_trees) { const int sb = (int) sd.b_prop.slot[aux] - base; row2[o] = ((unsigned) sb < (unsigned) kmax && ok) ? sb : kBinSlots; }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    int idx = row[o] * kWorkers + tid;
+    double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+    if (row[o] < kBinSlots) cpk += 1ull << (8 * row[o]);
+    if (two_trees) {
+      idx = row2[o] * kWorkers + tid;
+      v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+      if (row2[o] < kBinSlots) cpk += 1ull << (8 * row2[o]);
+    }
+  }
+}
+
+// two rounds per iteration: all global loads of both rounds are in flight before the first is used
 __device__ __forceinline__ void stream_accumulate(const StepDesc& sd, const double* Rg, const uint2* packs, long long q_lo, long long q_hi,
                                                   long long n, int tid, int base, int kmax, double2* __restrict__ bin_s, unsigned long long& cpk)
 {
   const int kind = sd.b_kind, L = sd.b_num_leaves;
   const bool two_trees = (kind == 2 || kind == 3);
   const int birth_node = kind == 0 ? sd.b_node : -1;
-  for (long long q0 = q_lo; q0 < q_hi; q0 += kWorkers) {
-    const long long q = q0 + tid;
-    if (q >= q_hi) continue;
-    const double2 ra = *reinterpret_cast<const double2*>(Rg + 4 * q), rb = *reinterpret_cast<const double2*>(Rg + 4 * q + 2);
-    const double r[4] = { ra.x, ra.y, rb.x, rb.y };
-    const uint2 pk = packs[q];
-    double pr[4]; int row[4], row2[4];
+  for (long long q0 = q_lo; q0 < q_hi; q0 += 2 * kWorkers) {
+    const long long qa = q0 + tid, qb = qa + kWorkers;
+    const bool la = qa < q_hi, lb = qb < q_hi;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0; uint2 pa = make_uint2(0u, 0u), pb = pa;
+    if (la) { a0 = *reinterpret_cast<const double2*>(Rg + 4 * qa); a1 = *reinterpret_cast<const double2*>(Rg + 4 * qa + 2); pa = packs[qa]; }
+    if (lb) { b0 = *reinterpret_cast<const double2*>(Rg + 4 * qb); b1 = *reinterpret_cast<const double2*>(Rg + 4 * qb + 2); pb = packs[qb]; }
+    if (la) stream_acc_quad(sd, a0, a1, pa, qa, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+    if (lb) stream_acc_quad(sd, b0, b1, pb, qb, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+  }
+}
+
+__device__ __forceinline__ void stream_upd_quad(const UpdateDesc& upd, double2& ra, double2& rb, const uint2 pk, int amode, int unode)
+{
+  double r[4] = { ra.x, ra.y, rb.x, rb.y };
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const int leaf = (pk.x >> (8 * o)) & 0xFF;
-      const int aux = (pk.y >> (8 * o)) & 0xFF;
-      pr[o] = r[o] + sd.b_cur.val[leaf];
-      const bool ok = 4 * q + o < n;
-      const int sa = (two_trees ? (int) sd.b_cur.slot[leaf] : (leaf == birth_node ? L + aux : (int) sd.b_cur.slot[leaf])) - base;
-      row[o] = ((unsigned) sa < (unsigned) kmax && ok) ? sa : kBinSlots;
-      row2[o] = kBinSlots;
-      if (two_trees) { const int sb = (int) sd.b_prop.slot[aux] - base; row2[o] = ((unsigned) sb < (unsigned) kmax && ok) ? sb : kBinSlots; }
-    }
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      int idx = row[o] * kWorkers + tid;
-      double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
-      if (row[o] < kBinSlots) cpk += 1ull << (8 * row[o]);
-      if (two_trees) {
-        idx = row2[o] * kWorkers + tid;
-        v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
-        if (row2[o] < kBinSlots) cpk += 1ull << (8 * row2[o]);
-      }
+  for (int o = 0; o < 4; ++o) {
+    const int leaf = (pk.x >> (8 * o)) & 0xFF;
+    const int aux = (pk.y >> (8 * o)) & 0xFF;
+    if (amode == 0) r[o] += upd.delta[leaf];
+    else {
+      int nl;
+      if (amode == 3) nl = aux;
+      else if (amode == 1 && leaf == unode) nl = unode + 1 + aux;
+      else nl = upd.remap[leaf];
+      r[o] += upd.val_old[leaf] - upd.val_new[nl];
     }
   }
+  ra = make_double2(r[0], r[1]); rb = make_double2(r[2], r[3]);
 }
 
 __device__ __forceinline__ void stream_update(const UpdateDesc& upd, double* Rg, const uint2* packs, long long q_lo, long long q_hi, int tid)
 {
   const int amode = upd.mode, unode = upd.node;
-  for (long long q0 = q_lo; q0 < q_hi; q0 += kWorkers) {
-    const long long q = q0 + tid;
-    if (q >= q_hi) continue;
-    double2 ra = *reinterpret_cast<const double2*>(Rg + 4 * q), rb = *reinterpret_cast<const double2*>(Rg + 4 * q + 2);
-    double r[4] = { ra.x, ra.y, rb.x, rb.y };
-    const uint2 pk = packs[q];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const int leaf = (pk.x >> (8 * o)) & 0xFF;
-      const int aux = (pk.y >> (8 * o)) & 0xFF;
-      if (amode == 0) r[o] += upd.delta[leaf];
-      else {
-        int nl;
-        if (amode == 3) nl = aux;
-        else if (amode == 1 && leaf == unode) nl = unode + 1 + aux;
-        else nl = upd.remap[leaf];
-        r[o] += upd.val_old[leaf] - upd.val_new[nl];
-      }
-    }
-    *reinterpret_cast<double2*>(Rg + 4 * q) = make_double2(r[0], r[1]);
-    *reinterpret_cast<double2*>(Rg + 4 * q + 2) = make_double2(r[2], r[3]);
+  for (long long q0 = q_lo; q0 < q_hi; q0 += 2 * kWorkers) {
+    const long long qa = q0 + tid, qb = qa + kWorkers;
+    const bool la = qa < q_hi, lb = qb < q_hi;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0; uint2 pa = make_uint2(0u, 0u), pb = pa;
+    if (la) { a0 = *reinterpret_cast<const double2*>(Rg + 4 * qa); a1 = *reinterpret_cast<const double2*>(Rg + 4 * qa + 2); pa = packs[qa]; }
+    if (lb) { b0 = *reinterpret_cast<const double2*>(Rg + 4 * qb); b1 = *reinterpret_cast<const double2*>(Rg + 4 * qb + 2); pb = packs[qb]; }
+    if (la) { stream_upd_quad(upd, a0, a1, pa, amode, unode); *reinterpret_cast<double2*>(Rg + 4 * qa) = a0; *reinterpret_cast<double2*>(Rg + 4 * qa + 2) = a1; }
+    if (lb) { stream_upd_quad(upd, b0, b1, pb, amode, unode); *reinterpret_cast<double2*>(Rg + 4 * qb) = b0; *reinterpret_cast<double2*>(Rg + 4 * qb + 2) = b1; }
   }
 }
 
