@@ -53,8 +53,11 @@ def workload_config(args):
     return {"workload": "%s, n=%d, %d trees, p_bart=9, K=2, q=18, n_test=%d, "
                         "1 chain per GPU" % (what, args.n, args.trees, args.n),
             "n": args.n, "trees": args.trees, "chains_per_gpu": 1, "parallelism": "chain-per-GPU, no data-path collective",
-            "l2": "working set of a sweep is re-read 200x by design (R 8 MB + binned X 9 MB resident in L2); "
-                  "no flush between steps because that is the workload", "adapt_sweeps": args.adapt}
+            "l2": "inputs larger than L2, no explicit flush: one sweep streams ~%d MB of distinct N-length arrays (BART: binned X, "
+                  "residual, response, offset, fits, latents; GLMM: X, Z index / value streams, response, offset, residual; running "
+                  "means) against 126 MB of L2, so every step's kernels start from HBM; inside k_sweep the chain's residuals and "
+                  "predictors are then held on chip for the 200 tree steps by design" % int(round((9 + 8 * 19 + 12 + 8) * args.n / 1e6)),
+            "adapt_sweeps": args.adapt}
 
 
 def make_problem(args):
