@@ -854,7 +854,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 struct SweepSmem {
   StepDesc sd[2];
   DTree tree[2];
-  UpdateDesc upd;
+  UpdateDesc upd[2];   // by step parity: the streamed variant applies step t's update while it accumulates step t + 1
   CtlScratch csd;      // decision scratch
   CtlScratch csp;      // proposal scratch
   LeafStat st[S4B_MAX_SLOTS];
@@ -1070,21 +1070,33 @@ __device__ __forceinline__ void stream_acc_quad(const StepDesc& sd, const double
   }
 }
 
-// two rounds per iteration: all global loads of both rounds are in flight before the first is used
-__device__ __forceinline__ void stream_accumulate(const StepDesc& sd, const double* Rg, const uint2* packs, long long q_lo, long long q_hi,
-                                                  long long n, int tid, int base, int kmax, double2* __restrict__ bin_s, unsigned long long& cpk)
+__device__ __forceinline__ void stream_upd_quad(const UpdateDesc& upd, double2& ra, double2& rb, const uint2 pk, int amode, int unode);
+
+// two rounds per iteration: all global loads of both rounds are in flight before the first is used.  `upd_prev` != nullptr:
+// the previous step's residual update (node indices in packs_prev) is applied on the way, R is read and written once
+__device__ __forceinline__ void stream_accumulate(const StepDesc& sd, const UpdateDesc* upd_prev, double* Rg, const uint2* packs_prev, const uint2* packs,
+                                                  long long q_lo, long long q_hi, long long n, int tid, int base, int kmax, double2* __restrict__ bin_s,
+                                                  unsigned long long& cpk)
 {
   const int kind = sd.b_kind, L = sd.b_num_leaves;
   const bool two_trees = (kind == 2 || kind == 3);
   const int birth_node = kind == 0 ? sd.b_node : -1;
+  const bool fused = upd_prev != nullptr;
+  const int pmode = fused ? upd_prev->mode : 0, pnode = fused ? upd_prev->node : 0;
   for (long long q0 = q_lo; q0 < q_hi; q0 += 2 * kWorkers) {
     const long long qa = q0 + tid, qb = qa + kWorkers;
     const bool la = qa < q_hi, lb = qb < q_hi;
-    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0; uint2 pa = make_uint2(0u, 0u), pb = pa;
-    if (la) { a0 = *reinterpret_cast<const double2*>(Rg + 4 * qa); a1 = *reinterpret_cast<const double2*>(Rg + 4 * qa + 2); pa = packs[qa]; }
-    if (lb) { b0 = *reinterpret_cast<const double2*>(Rg + 4 * qb); b1 = *reinterpret_cast<const double2*>(Rg + 4 * qb + 2); pb = packs[qb]; }
-    if (la) stream_acc_quad(sd, a0, a1, pa, qa, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
-    if (lb) stream_acc_quad(sd, b0, b1, pb, qb, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0; uint2 pa = make_uint2(0u, 0u), pb = pa, ua = pa, ub = pa;
+    if (la) { a0 = *reinterpret_cast<const double2*>(Rg + 4 * qa); a1 = *reinterpret_cast<const double2*>(Rg + 4 * qa + 2); pa = packs[qa]; if (fused) ua = packs_prev[qa]; }
+    if (lb) { b0 = *reinterpret_cast<const double2*>(Rg + 4 * qb); b1 = *reinterpret_cast<const double2*>(Rg + 4 * qb + 2); pb = packs[qb]; if (fused) ub = packs_prev[qb]; }
+    if (la) {
+      if (fused) { stream_upd_quad(*upd_prev, a0, a1, ua, pmode, pnode); *reinterpret_cast<double2*>(Rg + 4 * qa) = a0; *reinterpret_cast<double2*>(Rg + 4 * qa + 2) = a1; }
+      stream_acc_quad(sd, a0, a1, pa, qa, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+    }
+    if (lb) {
+      if (fused) { stream_upd_quad(*upd_prev, b0, b1, ub, pmode, pnode); *reinterpret_cast<double2*>(Rg + 4 * qb) = b0; *reinterpret_cast<double2*>(Rg + 4 * qb + 2) = b1; }
+      stream_acc_quad(sd, b0, b1, pb, qb, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+    }
   }
 }
 
@@ -1237,7 +1249,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         // branch-free: every observation adds into exactly one bin row (row kBinSlots is a trash row for padding and for
         // slots outside this pass); loads first (independent), then the read-modify-write chain
         if (STREAM) {
-          stream_accumulate(sd, dv.R, dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, n, tid, base, kmax, bin_s, cpk);
+          stream_accumulate(sd, (t > 0 && chunk == 0) ? &S.upd[(t - 1) & 1] : nullptr, dv.R, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad,
+                            dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, n, tid, base, kmax, bin_s, cpk);
         } else if (!two_trees) {
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {
@@ -1323,7 +1336,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       }
     } else {
       // ---- controller warp: plan this step's decision, fetch tree t+1, pre-compute this step's decision draws, propose for t+1 ----
-      { const FastPlan pl = w_plan(tree, sd, S.upd, S.csd, lane); plan_store(S.plan, pl, lane); }
+      { const FastPlan pl = w_plan(tree, sd, S.upd[t & 1], S.csd, lane); plan_store(S.plan, pl, lane); }
       const long long h0 = clock64();
       if (t + 1 < T) {
         const DTree& g = dv.trees[t + 1];
@@ -1408,8 +1421,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         if (lane == 0) *dv.trace_len = k + 1;
       }
       if (sequential_rng) rngd.fill();
-      if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast(plan, tree, S.prm, rngd, sd, S.st, S.upd, S.csd, trec, lane, S.inv_sigsq); }
-      else w_decide(tree, S.prm, rngd, sd, S.st, S.upd, S.csd, trec, lane, S.inv_sigsq);
+      if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast(plan, tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq); }
+      else w_decide(tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq);
       rngd.commit();
       if (sequential_rng && t + 1 < T) {
         rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
@@ -1425,14 +1438,16 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     const long long c5 = clock64();
     if (is_worker) {
       // ---- fit / residual update from the cached leaf indices ----
-      const int amode = S.upd.mode, unode = S.upd.node;
+      const UpdateDesc& upd = S.upd[t & 1];
+      const int amode = upd.mode, unode = upd.node;
       if (STREAM) {
-        stream_update(S.upd, dv.R, dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, tid);
+        // applied together with the next step's accumulation (one read and one write of R per step); the last step has no successor
+        if (t + 1 == T) stream_update(upd, dv.R, dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, tid);
       } else if (amode == 0) {
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
 #pragma unroll
-          for (int o = 0; o < 4; ++o) R[j][o] += S.upd.delta[(leaf_pack[j] >> (8 * o)) & 0xFF];
+          for (int o = 0; o < 4; ++o) R[j][o] += upd.delta[(leaf_pack[j] >> (8 * o)) & 0xFF];
       } else {
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
@@ -1443,8 +1458,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             int nl;
             if (amode == 3) nl = aux;
             else if (amode == 1 && leaf == unode) nl = unode + 1 + aux;
-            else nl = S.upd.remap[leaf];
-            R[j][o] += S.upd.val_old[leaf] - S.upd.val_new[nl];
+            else nl = upd.remap[leaf];
+            R[j][o] += upd.val_old[leaf] - upd.val_new[nl];
           }
         }
       }
