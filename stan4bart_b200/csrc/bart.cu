@@ -815,10 +815,11 @@ void BartFit::setup_persistent()
       persistent_nq_ = nq; persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(grid, (nquad + kWorkers - 1) / kWorkers)); persistent_smem_ = smem;
       return true;
     };
-    if (!try_nq(1, sweep_smem_bytes<1>(p_), (const void*) k_sweep<1, false>, (const void*) k_sweep<1, true>))
-      if (!try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2, false>, (const void*) k_sweep<2, true>))
-        if (!try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4, false>, (const void*) k_sweep<4, true>))
-          try_nq(6, sweep_smem_bytes<6>(p_), (const void*) k_sweep<6, false>, (const void*) k_sweep<6, true>);
+    const int force_nq = getenv("S4B_FORCE_NQ") ? atoi(getenv("S4B_FORCE_NQ")) : 0;      // tests: a given register variant at any size
+    if ((force_nq != 0 && force_nq != 1) || !try_nq(1, sweep_smem_bytes<1>(p_), (const void*) k_sweep<1, false>, (const void*) k_sweep<1, true>))
+      if ((force_nq != 0 && force_nq != 2) || !try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2, false>, (const void*) k_sweep<2, true>))
+        if ((force_nq != 0 && force_nq != 4) || !try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4, false>, (const void*) k_sweep<4, true>))
+          if (force_nq == 0 || force_nq == 6) try_nq(6, sweep_smem_bytes<6>(p_), (const void*) k_sweep<6, false>, (const void*) k_sweep<6, true>);
     // shards beyond the register file (or when forced, for the tests): residuals and node indices streamed from global memory
     const bool force_stream = getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0;
     if (persistent_nq_ == 0 || force_stream) {

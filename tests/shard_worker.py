@@ -68,6 +68,20 @@ def main():
         res[f"bart_{tag}_trees_n"] = tr["n"]
         res[f"bart_{tag}_trees_value"] = tr["value"]
         del g
+        # the streamed sweep variant (shards beyond the register file), sharded
+        os.environ["S4B_FORCE_STREAM"] = "1"
+        g = GpuBart(cfg, y[lo:hi], x[lo:hi], shard=ctx)
+        del os.environ["S4B_FORCE_STREAM"]
+        g.set_offset(off[lo:hi], True)
+        if not binary:
+            g.set_sigma(1.3)
+        g.sample_trees_from_prior()
+        g.set_trace(SC.BART_TREES * SC.BART_SWEEPS)
+        for _ in range(SC.BART_SWEEPS):
+            r = g.run()
+        res[f"bart_{tag}_trace_streamed"] = g.trace()
+        res[f"bart_{tag}_train_streamed"] = r["train"]
+        del g
         # the streaming per-tree kernels (shards too large for the on-chip sweep) exchange through the same mailboxes
         for mode in (0, 1):
             g = GpuBart(cfg, y[lo:hi], x[lo:hi], shard=ctx)

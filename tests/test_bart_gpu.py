@@ -257,3 +257,50 @@ def test_streamed_sweep_variant_replays_a_tape(monkeypatch):
         rg = g.run()
         assert rel_err(outs[s]["train"], rg["train"], scale=np.abs(outs[s]["train"]) + 1.0) <= REL_TOL
     compare_traces(o.trace(), g.trace())
+
+
+@pytest.mark.parametrize("nq", [2, 4, 6])
+def test_register_variants_of_the_sweep_kernel(monkeypatch, nq):
+    """The sweep kernel keeps 4 * NQ observations per thread in registers (NQ grows with the shard); S4B_FORCE_NQ selects an
+    instantiation at any size.  Every instantiation reproduces the oracle and the NQ = 1 run bit for bit."""
+    T, sweeps = 10, 12
+    x, y, xt = bart_problem(5003, 6, 0, False, seed=9)
+    cfg = bart_config(5003, 6, num_trees=T, seed=77)
+    off = 0.3 * x[:, 3] - 0.1
+    o = O.OracleBart(cfg, y, x, xt)
+    g1 = GpuBart(cfg, y, x, xt)
+    monkeypatch.setenv("S4B_FORCE_NQ", str(nq))
+    g2 = GpuBart(cfg, y, x, xt)
+    monkeypatch.delenv("S4B_FORCE_NQ")
+    for b in (o, g1, g2):
+        b.set_offset(off, True); b.set_sigma(1.3)
+        b.sample_trees_from_prior()
+        b.set_trace(T * sweeps)
+    for s in range(sweeps):
+        ro, r1, r2 = o.run(), g1.run(), g2.run()
+        assert np.array_equal(r1["train"], r2["train"]), f"sweep {s}"
+        assert rel_err(ro["train"], r2["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
+    compare_traces(o.trace(), g2.trace())
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_full_grid_at_scale(binary):
+    """n = 600 000 rows: all 148 CTAs, 16 observations per thread (the instantiation of the n = 1 M benchmark), the
+    grid-wide barrier and reduction at full width.  First sweeps against the oracle; partitions bit-exact."""
+    T, sweeps = 8, 3
+    n = 600000
+    x, y, xt = bart_problem(n, 5, 0, binary, seed=4)
+    cfg = bart_config(n, 5, num_trees=T, is_binary=binary, seed=5)
+    o = O.OracleBart(cfg, y, x, xt)
+    g = GpuBart(cfg, y, x, xt)
+    assert g.sweep_mode() == 2
+    for b in (o, g):
+        if not binary:
+            b.set_sigma(1.1)
+        b.sample_trees_from_prior()
+        b.set_trace(T * sweeps)
+    for s in range(sweeps):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9, f"sweep {s}"
+    compare_traces(o.trace(), g.trace(), tol=1e-9)
+    assert_same_partition(o, g, T)

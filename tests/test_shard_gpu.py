@@ -80,6 +80,9 @@ def test_sharded_bart_matches_whole_data_oracle(ranks, binary):
         compare_traces(tr_o, r[f"bart_{tag}_trace"], tol=1e-8)
         assert rel_err(o.data_range(), r[f"bart_{tag}_range"]) <= 1e-12
     assert np.array_equal(ranks[0][f"bart_{tag}_trace"], ranks[1][f"bart_{tag}_trace"])     # ranks agree bit for bit
+    for r in ranks:          # streamed sweep variant, sharded: same arithmetic as the register variant
+        assert np.array_equal(r[f"bart_{tag}_trace"], r[f"bart_{tag}_trace_streamed"])
+    assert np.array_equal(_cat(ranks, f"bart_{tag}_train"), _cat(ranks, f"bart_{tag}_train_streamed"))
     for mode in (0, 1):      # streaming per-tree kernels, sharded
         for r in ranks:
             compare_traces(tr_o, r[f"bart_{tag}_trace_mode{mode}"], tol=1e-8)
