@@ -193,31 +193,20 @@ static inline double s4b_keyed_uniform(uint64_t seed, uint32_t obs, uint32_t epo
   return s4b_bits_to_uniform(out[0], out[1]);
 }
 
-/* z ~ N(mean, 1) truncated to z > 0 (positive != 0) or z < 0 (positive == 0).
- * Robert (1995) rejection sampler as used by dbarts'
- * ext_rng_simulate{Lower,Upper}TruncatedNormalScale1 (un-vendored; restated
- * from upstream).  Sub-draw counter advances per uniform. */
+/* z ~ N(mean, 1) truncated to z > 0 (positive != 0) or z < 0 (positive == 0), by inversion from ONE keyed uniform
+ * (sub-draw 0): with m = +-mean, x = m - Phi^-1(u Phi(m)) is N(m, 1) conditioned on x > 0 for every m (Phi(m) from erfc, so
+ * the far tail m << 0 keeps full relative accuracy).  dbarts draws the same distribution with Robert's (1995) rejection
+ * sampler (ext_rng_simulate{Lower,Upper}TruncatedNormalScale1, un-vendored); its stream cannot be reproduced anyway, and
+ * a fixed one-draw recipe has no data-dependent loop on the GPU. */
 static inline double s4b_keyed_truncnorm(uint64_t seed, uint32_t obs, uint32_t epoch, double mean, int positive)
 {
   double m = positive ? mean : -mean;   /* reduce to lower truncation at 0 of N(m,1) */
-  double lb = -m;                        /* standardised lower bound */
-  uint32_t sub = 0;
-  double x;
-  if (lb < 0.0) {
-    do {
-      x = s4b_qnorm(s4b_keyed_uniform(seed, obs, epoch, sub++));
-    } while (x < lb && sub < 4096u);
-  } else {
-    double alpha = 0.5 * (lb + sqrt(lb * lb + 4.0));
-    double u, rho;
-    do {
-      double e = -log(s4b_keyed_uniform(seed, obs, epoch, sub++));
-      x = lb + e / alpha;
-      u = s4b_keyed_uniform(seed, obs, epoch, sub++);
-      rho = exp(-0.5 * (x - alpha) * (x - alpha));
-    } while (u > rho && sub < 4096u);
-  }
-  x += m;
+  double u = s4b_keyed_uniform(seed, obs, epoch, 0u);
+  double pm = 0.5 * erfc(-m * 0.70710678118654752440);
+  double arg = u * pm;
+  if (arg < 1e-300) arg = 1e-300;
+  double x = m - s4b_qnorm(arg);
+  if (!(x > 0.0)) x = 0.0;               /* rounding at the boundary */
   return positive ? x : -x;
 }
 

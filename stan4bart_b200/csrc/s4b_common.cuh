@@ -166,26 +166,17 @@ __host__ __device__ inline double keyed_uniform(uint32_t k0, uint32_t k1, uint32
   return bits_to_uniform(o0, o1);
 }
 
-// z ~ N(mean, 1) truncated to (0, inf) if positive else (-inf, 0); Robert (1995) rejection
+// z ~ N(mean, 1) truncated to (0, inf) if positive else (-inf, 0), by inversion from one keyed uniform:
+// x = m - Phi^-1(u Phi(m)) with m = +-mean (oracle/s4b_rng.h s4b_keyed_truncnorm); no data-dependent loop
 __host__ __device__ inline double keyed_truncnorm(uint32_t k0, uint32_t k1, uint32_t obs, uint32_t epoch, double mean, bool positive)
 {
-  double m = positive ? mean : -mean;
-  double lb = -m;
-  uint32_t sub = 0;
-  double x;
-  if (lb < 0.0) {
-    do { x = qnorm_as241(keyed_uniform(k0, k1, obs, epoch, sub++)); } while (x < lb && sub < 4096u);
-  } else {
-    double alpha = 0.5 * (lb + sqrt(lb * lb + 4.0));
-    double u, rho;
-    do {
-      double e = -log(keyed_uniform(k0, k1, obs, epoch, sub++));
-      x = lb + e / alpha;
-      u = keyed_uniform(k0, k1, obs, epoch, sub++);
-      rho = exp(-0.5 * (x - alpha) * (x - alpha));
-    } while (u > rho && sub < 4096u);
-  }
-  x += m;
+  const double m = positive ? mean : -mean;
+  const double u = keyed_uniform(k0, k1, obs, epoch, 0u);
+  const double pm = 0.5 * erfc(-m * 0.70710678118654752440);
+  double arg = u * pm;
+  if (arg < 1e-300) arg = 1e-300;
+  double x = m - qnorm_as241(arg);
+  if (!(x > 0.0)) x = 0.0;
   return positive ? x : -x;
 }
 

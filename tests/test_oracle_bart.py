@@ -39,6 +39,18 @@ def test_truncated_normal_moments():
         assert abs(z.mean() - want_m) < 5 * want_s / np.sqrt(len(z))
 
 
+def test_truncated_normal_law_including_far_tails():
+    """The one-draw inversion x = m - qnorm(u Phi(m)) has exactly the law of N(m, 1) | x > 0: Kolmogorov-Smirnov against
+    scipy for means from deep inside the truncated region to far outside it."""
+    from scipy.stats import kstest, truncnorm
+    for mean, positive in [(0.0, 1), (2.0, 1), (-3.0, 1), (-8.0, 1), (8.0, 1), (6.0, 0), (-6.0, 0)]:
+        z = np.array([O.lib().or_rng_truncnorm(123, i, 1, mean, positive) for i in range(20000)])
+        assert np.all(np.isfinite(z))
+        a, b = (-mean, np.inf) if positive else (-np.inf, -mean)
+        stat, pval = kstest(z, truncnorm(a, b, loc=mean).cdf)
+        assert pval > 1e-3, (mean, positive, stat, pval)
+
+
 def make(n=300, p=4, n_test=40, num_trees=15, seed=4, binary=False, **kw):
     x, y, xt = bart_problem(n, p, n_test, binary)
     cfg = bart_config(n, p, n_test=n_test, num_trees=num_trees, seed=seed, is_binary=binary, **kw)
