@@ -1479,7 +1479,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       if (lane == 0) g.num_nodes = nn;
       for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(g.nodes)[i] = reinterpret_cast<const uint32_t*>(tree.nodes)[i];
     }
-    __syncthreads();                                                        // [D] upd / tree / descriptor buffers free again
+    // (no barrier here: the update tables are double buffered, and the tree / descriptor buffers of step t are touched by
+    // the controller alone from now on, so workers run straight into the next accumulation)
     if (tid == 0 && prof_on) { S.pc[1] += c2 - c0; S.pc[2] += cx - c2; S.pc[4] += c3 - cx; S.pc[3] += c5 - c3; S.pc[5] += clock64() - c5; }
   }
 
