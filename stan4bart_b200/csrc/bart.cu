@@ -801,9 +801,9 @@ void BartFit::setup_persistent()
   int max_smem = 0; S4B_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if (coop) {
     const long long nquad = (n_ + 3) / 4;
-    auto try_nq = [&](int nq, size_t smem, const void* fn, const void* fn_seq) -> bool {
+    auto try_nq = [&](int nq, size_t smem, const void* fn, const void* fn_seq, const void* fn_nosq) -> bool {
       if (smem > (size_t) max_smem || p_ > 511) return false;      // traversal records carry 9 bits of variable index
-      for (const void* f : { fn, fn_seq }) {
+      for (const void* f : { fn, fn_seq, fn_nosq }) {
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); return false; }
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, kSweepBlock, smem) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -816,17 +816,19 @@ void BartFit::setup_persistent()
       return true;
     };
     const int force_nq = getenv("S4B_FORCE_NQ") ? atoi(getenv("S4B_FORCE_NQ")) : 0;      // tests: a given register variant at any size
-    if ((force_nq != 0 && force_nq != 1) || !try_nq(1, sweep_smem_bytes<1>(p_), (const void*) k_sweep<1, false>, (const void*) k_sweep<1, true>))
-      if ((force_nq != 0 && force_nq != 2) || !try_nq(2, sweep_smem_bytes<2>(p_), (const void*) k_sweep<2, false>, (const void*) k_sweep<2, true>))
-        if ((force_nq != 0 && force_nq != 4) || !try_nq(4, sweep_smem_bytes<4>(p_), (const void*) k_sweep<4, false>, (const void*) k_sweep<4, true>))
-          if (force_nq == 0 || force_nq == 6) try_nq(6, sweep_smem_bytes<6>(p_), (const void*) k_sweep<6, false>, (const void*) k_sweep<6, true>);
+#define S4B_SWEEP_FNS(NQ) (const void*) k_sweep<NQ, false>, (const void*) k_sweep<NQ, true>, (const void*) k_sweep<NQ, false, false, false>
+    if ((force_nq != 0 && force_nq != 1) || !try_nq(1, sweep_smem_bytes<1>(p_), S4B_SWEEP_FNS(1)))
+      if ((force_nq != 0 && force_nq != 2) || !try_nq(2, sweep_smem_bytes<2>(p_), S4B_SWEEP_FNS(2)))
+        if ((force_nq != 0 && force_nq != 4) || !try_nq(4, sweep_smem_bytes<4>(p_), S4B_SWEEP_FNS(4)))
+          if (force_nq == 0 || force_nq == 6) try_nq(6, sweep_smem_bytes<6>(p_), S4B_SWEEP_FNS(6));
+#undef S4B_SWEEP_FNS
     // shards beyond the register file (or when forced, for the tests): residuals and node indices streamed from global memory
     const bool force_stream = getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0;
     if (persistent_nq_ == 0 || force_stream) {
       const size_t smem = sweep_smem_bytes<1>(0);
       const long long rounds = (nquad / num_sms_ + 1 + kWorkers - 1) / kWorkers;
       bool ok = smem <= (size_t) max_smem && p_ <= 511 && rounds <= 63;      // 8-bit count fields: at most 63 rounds of 4 observations
-      for (const void* f : { (const void*) k_sweep<1, false, true>, (const void*) k_sweep<1, true, true> }) {
+      for (const void* f : { (const void*) k_sweep<1, false, true>, (const void*) k_sweep<1, true, true>, (const void*) k_sweep<1, false, true, false> }) {
         if (!ok) break;
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         int per_sm = 0;
@@ -893,10 +895,16 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   int overlap = overlap_walk_;
   ShardDev sh = shard_dev();
   void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh };
+  // the sums of squares are accumulated only when the parity trace (which reports the individual log-likelihoods) is on
+  const bool sq = trace_cap_ > 0 || sequential_rng_;
   const void* fn;
-  if (persistent_nq_ == kStreamNq) fn = sequential_rng_ ? (const void*) k_sweep<1, true, true> : (const void*) k_sweep<1, false, true>;
-  else if (sequential_rng_) fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, true> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, true> : (persistent_nq_ == 4 ? (const void*) k_sweep<4, true> : (const void*) k_sweep<6, true>));
-  else fn = persistent_nq_ == 1 ? (const void*) k_sweep<1, false> : (persistent_nq_ == 2 ? (const void*) k_sweep<2, false> : (persistent_nq_ == 4 ? (const void*) k_sweep<4, false> : (const void*) k_sweep<6, false>));
+#define S4B_PICK(NQ) (sequential_rng_ ? (const void*) k_sweep<NQ, true> : (sq ? (const void*) k_sweep<NQ, false> : (const void*) k_sweep<NQ, false, false, false>))
+  if (persistent_nq_ == kStreamNq) fn = sequential_rng_ ? (const void*) k_sweep<1, true, true> : (sq ? (const void*) k_sweep<1, false, true> : (const void*) k_sweep<1, false, true, false>);
+  else if (persistent_nq_ == 1) fn = S4B_PICK(1);
+  else if (persistent_nq_ == 2) fn = S4B_PICK(2);
+  else if (persistent_nq_ == 4) fn = S4B_PICK(4);
+  else fn = S4B_PICK(6);
+#undef S4B_PICK
   S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
                                                    (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);

@@ -470,7 +470,11 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
   __syncwarp();
 }
 
-// posterior mean / sd of the leaf value and integrated log-likelihood of one leaf (two divisions, one log, one sqrt)
+// posterior mean / sd of the leaf value and integrated log-likelihood of one leaf (two divisions, one log, one sqrt).
+// SQ = false: the sum of squares is not available and not needed -- every Metropolis ratio compares two partitions of the
+// SAME observations, so the -sum(r^2) / (2 sigma^2) terms of the two sides cancel exactly; `ll` is then the integrated
+// log-likelihood without that common term: 1/2 log(a / (a + n/s2)) + 1/2 (n/s2)^2 avg^2 / (a + n/s2)
+template <bool SQ>
 __device__ __forceinline__ void slot_summary(const LeafStat& s, double inv_sigsq, double leaf_prec, double& pmean, double& psd, double& ll)
 {
   const double dp = s.n * inv_sigsq;
@@ -478,15 +482,20 @@ __device__ __forceinline__ void slot_summary(const LeafStat& s, double inv_sigsq
   psd = sqrt(rinv);
   if (s.n <= 0.0) { pmean = 0.0; ll = 0.0; return; }
   const double avg = s.sum / s.n;
-  double ss = s.sumsq - s.n * avg * avg;
-  if (ss < 0.0) ss = 0.0;
   pmean = dp * avg * rinv;
-  ll = 0.5 * log(leaf_prec * rinv) - 0.5 * ss * inv_sigsq - 0.5 * ((leaf_prec * avg) * (dp * avg)) * rinv;
+  if (SQ) {
+    double ss = s.sumsq - s.n * avg * avg;
+    if (ss < 0.0) ss = 0.0;
+    ll = 0.5 * log(leaf_prec * rinv) - 0.5 * ss * inv_sigsq - 0.5 * ((leaf_prec * avg) * (dp * avg)) * rinv;
+  } else {
+    ll = 0.5 * log(leaf_prec * rinv) + 0.5 * ((dp * avg) * (dp * avg)) * rinv;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
 // decision + leaf draws (warp-cooperative)
 // ---------------------------------------------------------------------------------------
+template <bool SQ>
 __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, const StepDesc& in, const LeafStat* stats, UpdateDesc& upd,
                                 CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq)
 {
@@ -504,7 +513,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
   for (int s = lane; s < nsum; s += 32) {
     LeafStat st = s < nslots ? stats[s] : LeafStat{ stats[sl_bd].n + stats[sr_bd].n, stats[sl_bd].sum + stats[sr_bd].sum, stats[sl_bd].sumsq + stats[sr_bd].sumsq };
     double pm, ps, ll;
-    slot_summary(st, inv_sigsq, P.leaf_prec, pm, ps, ll);
+    slot_summary<SQ>(st, inv_sigsq, P.leaf_prec, pm, ps, ll);
     cs.pmean[s] = pm; cs.psd[s] = ps; cs.ll[s] = ll;
     my_ll = ll; my_n = st.n;
   }
@@ -764,6 +773,7 @@ __device__ inline FastPlan w_plan(const DTree& t, const StepDesc& in, UpdateDesc
   return pl;
 }
 
+template <bool SQ>
 __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartParams& P, WarpRng& rng, const StepDesc& in, const LeafStat* stats,
                                      UpdateDesc& upd, CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq)
 {
@@ -777,7 +787,7 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
     LeafStat st;
     if (lane < nslots) st = stats[lane];
     else { const LeafStat a = stats[pl.sl_bd], b = stats[pl.sr_bd]; st.n = a.n + b.n; st.sum = a.sum + b.sum; st.sumsq = a.sumsq + b.sumsq; }
-    slot_summary(st, inv_sigsq, P.leaf_prec, my_pm, my_ps, my_ll);
+    slot_summary<SQ>(st, inv_sigsq, P.leaf_prec, my_pm, my_ps, my_ll);
     my_n = st.n;
   }
   const long long f1 = clock64();
@@ -1039,8 +1049,18 @@ __device__ __forceinline__ void stream_walk(const StepDesc& sd, const uint32_t* 
   }
 }
 
+// one observation into its lane-private bin: (sum, sum^2) as one 16-byte read-modify-write, or the sum alone (SQ = false:
+// half the shared-memory traffic of the accumulation)
+template <bool SQ>
+__device__ __forceinline__ void bin_add(double2* __restrict__ bin_s, int idx, double pr)
+{
+  if (SQ) { double2 v = bin_s[idx]; v.x += pr; v.y = fma(pr, pr, v.y); bin_s[idx] = v; }
+  else { double* b1 = reinterpret_cast<double*>(bin_s); b1[idx] += pr; }
+}
+
 // (no __restrict__ / read-only qualifiers on R and the node-index buffers: they are rewritten inside the same kernel, and a
 // non-coherent load would return stale values)
+template <bool SQ>
 __device__ __forceinline__ void stream_acc_quad(const StepDesc& sd, const double2 ra, const double2 rb, const uint2 pk, long long q, long long n, int tid, int base,
                                                 int kmax, bool two_trees, int birth_node, int L, double2* __restrict__ bin_s, unsigned long long& cpk)
 {
@@ -1059,12 +1079,10 @@ __device__ __forceinline__ void stream_acc_quad(const StepDesc& sd, const double
   }
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
-    int idx = row[o] * kWorkers + tid;
-    double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+    bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
     if (row[o] < kBinSlots) cpk += 1ull << (8 * row[o]);
     if (two_trees) {
-      idx = row2[o] * kWorkers + tid;
-      v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+      bin_add<SQ>(bin_s, row2[o] * kWorkers + tid, pr[o]);
       if (row2[o] < kBinSlots) cpk += 1ull << (8 * row2[o]);
     }
   }
@@ -1074,6 +1092,7 @@ __device__ __forceinline__ void stream_upd_quad(const UpdateDesc& upd, double2& 
 
 // two rounds per iteration: all global loads of both rounds are in flight before the first is used.  `upd_prev` != nullptr:
 // the previous step's residual update (node indices in packs_prev) is applied on the way, R is read and written once
+template <bool SQ>
 __device__ __forceinline__ void stream_accumulate(const StepDesc& sd, const UpdateDesc* upd_prev, double* Rg, const uint2* packs_prev, const uint2* packs,
                                                   long long q_lo, long long q_hi, long long n, int tid, int base, int kmax, double2* __restrict__ bin_s,
                                                   unsigned long long& cpk)
@@ -1091,11 +1110,11 @@ __device__ __forceinline__ void stream_accumulate(const StepDesc& sd, const Upda
     if (lb) { b0 = *reinterpret_cast<const double2*>(Rg + 4 * qb); b1 = *reinterpret_cast<const double2*>(Rg + 4 * qb + 2); pb = packs[qb]; if (fused) ub = packs_prev[qb]; }
     if (la) {
       if (fused) { stream_upd_quad(*upd_prev, a0, a1, ua, pmode, pnode); *reinterpret_cast<double2*>(Rg + 4 * qa) = a0; *reinterpret_cast<double2*>(Rg + 4 * qa + 2) = a1; }
-      stream_acc_quad(sd, a0, a1, pa, qa, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+      stream_acc_quad<SQ>(sd, a0, a1, pa, qa, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
     }
     if (lb) {
       if (fused) { stream_upd_quad(*upd_prev, b0, b1, ub, pmode, pnode); *reinterpret_cast<double2*>(Rg + 4 * qb) = b0; *reinterpret_cast<double2*>(Rg + 4 * qb + 2) = b1; }
-      stream_acc_quad(sd, b0, b1, pb, qb, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+      stream_acc_quad<SQ>(sd, b0, b1, pb, qb, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
     }
   }
 }
@@ -1135,7 +1154,9 @@ __device__ __forceinline__ void stream_update(const UpdateDesc& upd, double* Rg,
 
 // SEQ: replay / record keep the strict program order of the draws (proposals and draws produced inside the loop);
 // the production instantiation (SEQ = false) carries none of that code
-template <int NQ, bool SEQ, bool STREAM = false>
+// SQ: also accumulate the per-slot sums of squares (needed only to report the individual log-likelihoods in the parity
+// trace; the Metropolis ratios do not depend on them, see slot_summary)
+template <int NQ, bool SEQ, bool STREAM = false, bool SQ = true>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
                                                                const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
                                                                const __grid_constant__ ShardDev sh_param)
@@ -1181,6 +1202,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   if (tid == 0) { const double sg = dv.params->sigma; S.inv_sigsq = 1.0 / (sg * sg); for (int i = 0; i < 6; ++i) S.pc[i] = 0; for (int i = 0; i < 4; ++i) S.wk[i] = 0; }
   if (tid == 0) { S.peer_dead = 0; S.prm = *dv.params; S.rng = *dv.rng; S.csd.draws_total = 0; S.csp.draws_total = 0; S.csd.prof_on = dv.prof != nullptr ? 1 : 0; S.csp.prof_on = 0; for (int i = 0; i < 8; ++i) S.csd.dbg[i] = 0; for (int i = 0; i < 4; ++i) S.csd.fine[i] = 0; }
   for (int i = tid; i < kTabSize; i += kSweepBlock) S.tab[i] = tables[i];
+  for (int i = tid; i < 3 * S4B_MAX_SLOTS; i += kSweepBlock) reinterpret_cast<double*>(S.st)[i] = 0.0;
   __syncthreads();
   const int p = S.prm.p, T = S.prm.num_trees;
   const unsigned long long step0 = S.prm.step_id;
@@ -1242,14 +1264,15 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         const int base = chunk * kBinSlots;
         const int kmax = min(kBinSlots, nslots - base);
         const long long w0 = clock64();
-        for (int k = 0; k < kmax; ++k) bin_s[k * kWorkers + tid] = make_double2(0.0, 0.0);
+        if (SQ) { for (int k = 0; k < kmax; ++k) bin_s[k * kWorkers + tid] = make_double2(0.0, 0.0); }
+        else { for (int k = 0; k < kmax; ++k) reinterpret_cast<double*>(bin_s)[k * kWorkers + tid] = 0.0; }
         // observation counts stay in a register: one 6-bit field per bin row (a thread adds at most 32 to a row)
         unsigned long long cpk = 0ull;
         const long long w1 = clock64();
         // branch-free: every observation adds into exactly one bin row (row kBinSlots is a trash row for padding and for
         // slots outside this pass); loads first (independent), then the read-modify-write chain
         if (STREAM) {
-          stream_accumulate(sd, (t > 0 && chunk == 0) ? &S.upd[(t - 1) & 1] : nullptr, dv.R, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad,
+          stream_accumulate<SQ>(sd, (t > 0 && chunk == 0) ? &S.upd[(t - 1) & 1] : nullptr, dv.R, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad,
                             dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, n, tid, base, kmax, bin_s, cpk);
         } else if (!two_trees) {
 #pragma unroll
@@ -1265,8 +1288,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             }
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              const int idx = row[o] * kWorkers + tid;
-              double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+              bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
               cpk += 1ull << (6 * row[o]);
             }
           }
@@ -1287,10 +1309,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             }
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              int idx = row[o] * kWorkers + tid;
-              double2 v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
-              idx = row2[o] * kWorkers + tid;
-              v = bin_s[idx]; v.x += pr[o]; v.y = fma(pr[o], pr[o], v.y); bin_s[idx] = v;
+              bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
+              bin_add<SQ>(bin_s, row2[o] * kWorkers + tid, pr[o]);
               cpk += (1ull << (6 * row[o])) + (1ull << (6 * row2[o]));
             }
           }
@@ -1301,11 +1321,19 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         // row-wise reduction: task r < kmax sums (sum, sum^2) of slot r over the CTA's threads, task kmax + r its counts
         for (int task = warp; task < 2 * kmax; task += kWorkerWarps) {
           if (task < kmax) {
-            double a = 0.0, b = 0.0;
+            if (SQ) {
+              double a = 0.0, b = 0.0;
 #pragma unroll
-            for (int i = 0; i < kWorkerWarps; ++i) { const double2 v = bin_s[task * kWorkers + i * 32 + lane]; a += v.x; b += v.y; }
-            a = w_sum(a); b = w_sum(b);
-            if (lane == 0) { partials[(size_t) (3 * (base + task) + 1) * G + cta] = a; partials[(size_t) (3 * (base + task) + 2) * G + cta] = b; }
+              for (int i = 0; i < kWorkerWarps; ++i) { const double2 v = bin_s[task * kWorkers + i * 32 + lane]; a += v.x; b += v.y; }
+              a = w_sum(a); b = w_sum(b);
+              if (lane == 0) { partials[(size_t) (3 * (base + task) + 1) * G + cta] = a; partials[(size_t) (3 * (base + task) + 2) * G + cta] = b; }
+            } else {
+              double a = 0.0;
+#pragma unroll
+              for (int i = 0; i < kWorkerWarps; ++i) a += reinterpret_cast<const double*>(bin_s)[task * kWorkers + i * 32 + lane];
+              a = w_sum(a);
+              if (lane == 0) partials[(size_t) (3 * (base + task) + 1) * G + cta] = a;
+            }
           } else {
             const int r = task - kmax;
             int c = 0;
@@ -1361,7 +1389,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     const long long c2 = clock64();
 
     // ---- every CTA: reduce all partial rows in the same fixed order ----
-    for (int v = warp; v < 3 * nslots; v += kSweepWarps) {
+    for (int w = warp; w < (SQ ? 3 : 2) * nslots; w += kSweepWarps) {
+      const int v = SQ ? w : (w >> 1) * 3 + (w & 1);          // without sums of squares only the (n, sum) rows exist
       const double* src = partials + (size_t) v * G;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
       { int b = lane;       if (b < G) a0 = __ldcg(src + b); }
@@ -1414,15 +1443,15 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     if (!is_worker) {
       // ---- controller: Metropolis decision + leaf draws for tree t ----
       double* trec = nullptr;
-      if (dv.trace != nullptr && cta == 0) {
+      if (SQ && dv.trace != nullptr && cta == 0) {
         unsigned long long k = *dv.trace_len;
         if (k < dv.trace_cap) { trec = dv.trace + k * S4B_TRACE_LEN; for (int i = lane; i < S4B_TRACE_LEN; i += 32) trec[i] = 0.0; }
         __syncwarp();
         if (lane == 0) *dv.trace_len = k + 1;
       }
       if (sequential_rng) rngd.fill();
-      if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast(plan, tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq); }
-      else w_decide(tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq);
+      if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast<SQ>(plan, tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq); }
+      else w_decide<SQ>(tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq);
       rngd.commit();
       if (sequential_rng && t + 1 < T) {
         rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();

@@ -304,3 +304,31 @@ def test_full_grid_at_scale(binary):
         assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9, f"sweep {s}"
     compare_traces(o.trace(), g.trace(), tol=1e-9)
     assert_same_partition(o, g, T)
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_production_path_without_sums_of_squares(binary):
+    """Without the parity trace the sweep kernel does not accumulate sum(r^2): every Metropolis ratio compares two partitions
+    of the same observations, so those terms cancel.  The untraced (production) run must take the same decisions as the
+    traced run and as the oracle: same trees, fits equal to rounding."""
+    T, sweeps = 15, 30
+    x, y, xt = bart_problem(3001, 6, 0, binary, seed=13)
+    cfg = bart_config(3001, 6, num_trees=T, is_binary=binary, seed=99)
+    off = 0.3 * x[:, 3] - 0.1
+    o = O.OracleBart(cfg, y, x, xt)
+    g_tr, g_pl = GpuBart(cfg, y, x, xt), GpuBart(cfg, y, x, xt)
+    for b in (o, g_tr, g_pl):
+        b.set_offset(off, True)
+        if not binary:
+            b.set_sigma(1.3)
+        b.sample_trees_from_prior()
+    g_tr.set_trace(T * sweeps)
+    for s in range(sweeps):
+        ro, r1, r2 = o.run(), g_tr.run(), g_pl.run()
+        assert rel_err(r1["train"], r2["train"], scale=np.abs(r1["train"]) + 1.0) <= 1e-10, f"sweep {s}"
+        assert rel_err(ro["train"], r2["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9, f"sweep {s}"
+        assert np.array_equal(ro["varcount"], r2["varcount"])
+    to, t2 = o.trees(), g_pl.trees()
+    assert np.array_equal(to["var"], t2["var"]) and np.array_equal(to["n"], t2["n"])
+    assert_same_partition(o, g_pl, T)
+    assert g_tr.rng_counter() == g_pl.rng_counter() == o.rng_counter()
