@@ -780,6 +780,7 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
   const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
   const bool bd = kind == 0 || kind == 1;
   const int nsum = nslots + (bd ? 1 : 0);
+  const int nn_old = t.num_nodes;          // read by every lane before lane 0 rewrites it below
   const long long d0 = clock64();
   // ---- lane s: summary of slot s (slot nslots = the merged parent of a birth / death step) ----
   double my_ll = 0.0, my_n = 0.0, my_pm = 0.0, my_ps = 0.0;
@@ -829,7 +830,6 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
   const int j = __popc(mask & ((1u << lane) - 1u));
   const double pm = __shfl_sync(0xffffffffu, my_pm, ss & 31), ps = __shfl_sync(0xffffffffu, my_ps, ss & 31), nobs = __shfl_sync(0xffffffffu, my_n, ss & 31);
   const double mu = leaf ? pm + ps * cs.zbuf[p0 + j] : 0.0;
-  const int nn_old = t.num_nodes;
   if (amode != 0) {
     const int nn = pl.nn_acc;
     if (lane < nn) { DNode nd = cs.tmp[lane]; if (leaf) { nd.mu = mu; nd.n = (int32_t) nobs; } t.nodes[lane] = nd; }
