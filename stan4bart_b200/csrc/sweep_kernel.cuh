@@ -781,6 +781,7 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
   const bool bd = kind == 0 || kind == 1;
   const int nsum = nslots + (bd ? 1 : 0);
   const int nn_old = t.num_nodes;          // read by every lane before lane 0 rewrites it below
+  __syncwarp();
   const long long d0 = clock64();
   // ---- lane s: summary of slot s (slot nslots = the merged parent of a birth / death step) ----
   double my_ll = 0.0, my_n = 0.0, my_pm = 0.0, my_ps = 0.0;
