@@ -98,12 +98,14 @@ def test_thin_and_larger_n():
     assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
 
 
-def test_posterior_agreement_within_monte_carlo_error():
+@pytest.mark.parametrize("binary", [False, True])
+def test_posterior_agreement_within_monte_carlo_error(binary):
     """north_star: posterior fitted means and CATE agree within 4 Monte-Carlo standard errors.
     Independent seeds on the two sides (a statistical, not a replay, check).  BART chains mix slowly, so
-    the Monte-Carlo error of a posterior mean is estimated from the spread of independent chains."""
+    the Monte-Carlo error of a posterior mean is estimated from the spread of independent chains.
+    (Probit: fitted means and the treatment coefficient on the latent scale.)"""
     n, warm, it, chains = 200, 150, 300, 4
-    pr = friedman_problem(n)
+    pr = friedman_problem(n, binary=binary)
     sd = pr["stan_data"]
     kw = dict(warmup=warm, iter_=warm + it, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
     d = pr["data"]
@@ -114,7 +116,7 @@ def test_posterior_agreement_within_monte_carlo_error():
     for label, cls, seed0 in (("oracle", O.OracleSampler, 100), ("gpu", Sampler, 200)):
         for c in range(chains):
             seed = seed0 + c
-            cfg = bart_config(n, 9, n_test=n, num_trees=30, seed=seed)
+            cfg = bart_config(n, 9, n_test=n, num_trees=30, seed=seed, is_binary=binary)
             s = cls(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=seed), **kw)
             s.run(warm, True)
             s.disengage_adaptation()
@@ -130,7 +132,7 @@ def test_posterior_agreement_within_monte_carlo_error():
     co, cg = np.array(cates["oracle"]), np.array(cates["gpu"])
     assert abs(co.mean() - cg.mean()) <= 4 * np.sqrt(co.var(ddof=1) / chains + cg.var(ddof=1) / chains)
     mu_true = d["mu1"] * d["z"] + d["mu0"] * (1 - d["z"])
-    assert np.corrcoef(mg.mean(axis=0), mu_true)[0, 1] >= 0.95
+    assert np.corrcoef(mg.mean(axis=0), mu_true)[0, 1] >= (0.6 if binary else 0.95)
 
 
 def _ihdp_pair(n=400, num_trees=9, seed=4321, warmup=6, iter_=11):
