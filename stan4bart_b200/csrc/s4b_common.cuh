@@ -236,7 +236,8 @@ struct StepDesc {
   int32_t b_child;         // swap: child index or -1 (both)
   TravTree b_cur;          // current tree, val = mu, slot = leaf slot
   TravTree b_prop;         // proposed tree (change / swap): slot = L + rank for leaves below b_node, 255 elsewhere
-  double log_prior_trans;  // data-independent part of the log MH ratio
+  double log_prior_trans;  // data-independent part of the MH ratio (plain ratio for birth / death, log for change / swap)
+  double accept_thr;       // persistent sweep: log(u) - log(data-independent part): the step is accepted iff this is < delta log-lik
   int32_t new_var, new_cut;// change: proposed rule
   int32_t b_end;           // change / swap: one past the last pre-order index of the branch below b_node
   int32_t pad1;

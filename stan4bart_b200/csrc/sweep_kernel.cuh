@@ -470,6 +470,13 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
   __syncwarp();
 }
 
+// the data-independent side of the Metropolis test, on the log scale (no exp on the decision's critical path)
+__device__ __forceinline__ double accept_threshold(double u, int kind, double prior_trans)
+{
+  if (kind == 0 || kind == 1) return prior_trans > 0.0 ? log(u) - log(prior_trans) : INFINITY;
+  return log(u) - prior_trans;
+}
+
 // posterior mean / sd of the leaf value and integrated log-likelihood of one leaf (two divisions, one log, one sqrt).
 // SQ = false: the sum of squares is not available and not needed -- every Metropolis ratio compares two partitions of the
 // SAME observations, so the -sum(r^2) / (2 sigma^2) terms of the two sides cancel exactly; `ll` is then the integrated
@@ -497,7 +504,7 @@ __device__ __forceinline__ void slot_summary(const LeafStat& s, double inv_sigsq
 // ---------------------------------------------------------------------------------------
 template <bool SQ>
 __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, const StepDesc& in, const LeafStat* stats, UpdateDesc& upd,
-                                CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq)
+                                CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq, double accept_thr)
 {
   const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
   const int nn_old = t.num_nodes;
@@ -533,8 +540,10 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     const double ll_ch = ll_l + ll_r;
     if (kind == 0) { old_ll = ll_par; new_ll = ll_ch; } else { old_ll = ll_ch; new_ll = ll_par; }
     ratio = in.log_prior_trans * exp(new_ll - old_ll);
-    if (kind == 0 && (n_l < (double) P.min_obs || n_r < (double) P.min_obs)) ratio = 0.0;
-    accept = rng.uniform() < ratio;
+    const bool too_small = kind == 0 && (n_l < (double) P.min_obs || n_r < (double) P.min_obs);
+    if (too_small) ratio = 0.0;
+    (void) rng.uniform();
+    accept = !too_small && accept_thr < new_ll - old_ll;
     n_first = n_l; n_second = n_r;
   } else if (kind == 2 || kind == 3) {
     if (small) __syncwarp();
@@ -552,8 +561,10 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
     }
     old_ll = a_old; new_ll = a_new;
     ratio = exp(in.log_prior_trans + (new_ll - old_ll));
-    if (mn < (double) P.min_obs) ratio = 0.0;
-    accept = rng.uniform() < ratio;
+    const bool too_small = mn < (double) P.min_obs;
+    if (too_small) ratio = 0.0;
+    (void) rng.uniform();
+    accept = !too_small && accept_thr < new_ll - old_ll;
     if (first_leaf >= 0) n_first = stats[in.b_prop.slot[first_leaf]].n;
     if (second_leaf >= 0) n_second = stats[in.b_prop.slot[second_leaf]].n;
   }
@@ -775,7 +786,7 @@ __device__ inline FastPlan w_plan(const DTree& t, const StepDesc& in, UpdateDesc
 
 template <bool SQ>
 __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartParams& P, WarpRng& rng, const StepDesc& in, const LeafStat* stats,
-                                     UpdateDesc& upd, CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq)
+                                     UpdateDesc& upd, CtlScratch& cs, double* trace_rec, int lane, double inv_sigsq, double accept_thr)
 {
   const int L = in.b_num_leaves, kind = in.b_kind, node = in.b_node, nslots = in.b_nslots;
   const bool bd = kind == 0 || kind == 1;
@@ -793,7 +804,17 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
     my_n = st.n;
   }
   const long long f1 = clock64();
-  // ---- Metropolis ratio ----
+  // ---- leaf values of node `lane` under BOTH outcomes, issued before the ratio chain so that their shuffles and loads
+  // complete in its shadow.  The accept uniform (if any) is draw 0, the normals follow at the same positions either way ----
+  const bool has_u = kind >= 0 && kind <= 3;
+  const int z0 = has_u ? 1 : 0;
+  const int j_rej = __popc(pl.mask_rej & ((1u << lane) - 1u)), j_acc = __popc(pl.mask_acc & ((1u << lane) - 1u));
+  const double pm_r = __shfl_sync(0xffffffffu, my_pm, pl.slot_rej & 31), ps_r = __shfl_sync(0xffffffffu, my_ps, pl.slot_rej & 31);
+  const double n_r_ = __shfl_sync(0xffffffffu, my_n, pl.slot_rej & 31);
+  const double pm_a = __shfl_sync(0xffffffffu, my_pm, pl.slot_acc & 31), ps_a = __shfl_sync(0xffffffffu, my_ps, pl.slot_acc & 31);
+  const double n_a_ = __shfl_sync(0xffffffffu, my_n, pl.slot_acc & 31);
+  const double mu_rej = pm_r + ps_r * cs.zbuf[(z0 + j_rej) & 31], mu_acc = pm_a + ps_a * cs.zbuf[(z0 + j_acc) & 31];
+  // ---- Metropolis test on the log scale: accept iff log u - log(prior x transition) < delta log-likelihood ----
   bool accept = false;
   double ratio = -1.0, old_ll = 0.0, new_ll = 0.0, n_first = 0.0, n_second = 0.0;
   if (bd) {
@@ -801,9 +822,10 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
     const double n_l = __shfl_sync(0xffffffffu, my_n, pl.sl_bd), n_r = __shfl_sync(0xffffffffu, my_n, pl.sr_bd);
     const double ll_ch = ll_l + ll_r;
     if (kind == 0) { old_ll = ll_par; new_ll = ll_ch; } else { old_ll = ll_ch; new_ll = ll_par; }
-    ratio = in.log_prior_trans * exp(new_ll - old_ll);
-    if (kind == 0 && (n_l < (double) P.min_obs || n_r < (double) P.min_obs)) ratio = 0.0;
-    accept = rng.uniform() < ratio;
+    const bool too_small = kind == 0 && (n_l < (double) P.min_obs || n_r < (double) P.min_obs);
+    (void) rng.uniform();
+    accept = !too_small && accept_thr < new_ll - old_ll;
+    if (trace_rec != nullptr) ratio = too_small ? 0.0 : in.log_prior_trans * exp(new_ll - old_ll);
     n_first = n_l; n_second = n_r;
   } else if (kind == 2 || kind == 3) {
     const bool under = (pl.mask_under >> lane) & 1u;
@@ -811,10 +833,11 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
     const double nk_ = __shfl_sync(0xffffffffu, my_n, pl.slot_prop & 31);
     old_ll = w_sum(under ? to_ : 0.0); new_ll = w_sum(under ? tn_ : 0.0);
     const double mn = w_min(under ? nk_ : 1e300);
-    ratio = exp(in.log_prior_trans + (new_ll - old_ll));
-    if (mn < (double) P.min_obs) ratio = 0.0;
-    accept = rng.uniform() < ratio;
+    const bool too_small = mn < (double) P.min_obs;
+    (void) rng.uniform();
+    accept = !too_small && accept_thr < new_ll - old_ll;
     if (trace_rec != nullptr) {
+      ratio = too_small ? 0.0 : exp(in.log_prior_trans + (new_ll - old_ll));
       unsigned m = pl.mask_under;
       if (m) { const int b = __ffs(m) - 1; n_first = __shfl_sync(0xffffffffu, nk_, b); m &= m - 1; }
       if (m) { const int b = __ffs(m) - 1; n_second = __shfl_sync(0xffffffffu, nk_, b); }
@@ -824,13 +847,12 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
   // ---- final tree: lane k finishes node k ----
   const int amode = !accept ? 0 : (kind == 0 ? 1 : (kind == 1 ? 2 : 3));
   const unsigned mask = accept ? pl.mask_acc : pl.mask_rej;
-  const int ss = accept ? pl.slot_acc : pl.slot_rej;
   const int cnt = __popc(mask);
-  const int p0 = cnt > 0 ? rng.reserve_normals(cnt) : 0;
+  if (cnt > 0) (void) rng.reserve_normals(cnt);          // bookkeeping: the positions were fixed above
   const bool leaf = (mask >> lane) & 1u;
-  const int j = __popc(mask & ((1u << lane) - 1u));
-  const double pm = __shfl_sync(0xffffffffu, my_pm, ss & 31), ps = __shfl_sync(0xffffffffu, my_ps, ss & 31), nobs = __shfl_sync(0xffffffffu, my_n, ss & 31);
-  const double mu = leaf ? pm + ps * cs.zbuf[p0 + j] : 0.0;
+  const int j = accept ? j_acc : j_rej;
+  const double nobs = accept ? n_a_ : n_r_;
+  const double mu = leaf ? (accept ? mu_acc : mu_rej) : 0.0;
   if (amode != 0) {
     const int nn = pl.nn_acc;
     if (lane < nn) { DNode nd = cs.tmp[lane]; if (leaf) { nd.mu = mu; nd.n = (int32_t) nobs; } t.nodes[lane] = nd; }
@@ -969,7 +991,7 @@ __device__ inline void w_copy_desc(StepDesc& dst, const StepDesc& src, int lane)
     dst.a_valid = 0; dst.a_same = 1;
     dst.b_tree = src.b_tree; dst.b_kind = kind; dst.b_node = src.b_node; dst.b_var = src.b_var; dst.b_cut = src.b_cut;
     dst.b_num_leaves = src.b_num_leaves; dst.b_nslots = src.b_nslots; dst.b_child = src.b_child;
-    dst.log_prior_trans = src.log_prior_trans; dst.new_var = src.new_var; dst.new_cut = src.new_cut; dst.b_end = src.b_end;
+    dst.log_prior_trans = src.log_prior_trans; dst.accept_thr = src.accept_thr; dst.new_var = src.new_var; dst.new_cut = src.new_cut; dst.b_end = src.b_end;
     dst.b_cur.n = n; dst.b_cur.pad = src.b_cur.pad;
     dst.b_prop.n = (kind == 2 || kind == 3) ? n : 0; dst.b_prop.pad = src.b_cur.pad;
     dst.b_cur.n_int = src.b_cur.n_int; dst.b_prop.n_int = src.b_cur.n_int;
@@ -1027,6 +1049,8 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
   {
     const double u = keyed_stream_uniform(rng->key0, rng->key1, rng->stream, step, 1u, (uint32_t) lane);
     draws[t * 32 + lane] = make_double2(u, qnorm_as241(u));
+    // draw 0 is the accept uniform of a birth / death / change / swap step: u < prior x exp(delta) <=> log u - log prior < delta
+    if (lane == 0) descs[t].accept_thr = accept_threshold(u, W.sd.b_kind, W.sd.log_prior_trans);
   }
   if (lane == 0) atomicAdd(&dv.rng->counter, (unsigned long long) W.cs.draws_total);
 }
@@ -1451,8 +1475,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         if (lane == 0) *dv.trace_len = k + 1;
       }
       if (sequential_rng) rngd.fill();
-      if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast<SQ>(plan, tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq); }
-      else w_decide<SQ>(tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq);
+      // replay / record draw in program order: the threshold is formed here; otherwise k_prepare_sweep stored it with the proposal
+      const double thr = sequential_rng ? accept_threshold(S.csd.ubuf[0], sd.b_kind, sd.log_prior_trans) : sd.accept_thr;
+      if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast<SQ>(plan, tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq, thr); }
+      else w_decide<SQ>(tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq, thr);
       rngd.commit();
       if (sequential_rng && t + 1 < T) {
         rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
