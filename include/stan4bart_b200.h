@@ -40,6 +40,10 @@ typedef struct s4b_bart_config {
   double k;                /* normal(k) leaf prior */
   double node_scale;       /* .5 continuous, 3 binary (R/stan4bart_fit.R:479) */
   uint64_t seed;
+  /* bart_args split.probs (R/stan4bart_fit.R:466, tests/testthat/test-09-bartArgs.R:20-39): relative probability of every
+   * predictor when a splitting variable is drawn and in the rule prior; NULL = uniform.  Normalised internally to integer
+   * weights summing to ~2^30, so that the CPU oracle and the device select and weigh variables identically. */
+  const double* split_probs;
 } s4b_bart_config;
 
 /* the `data.stan` list, R/stan4bart_fit.R:259-365 / src/stan_sampler.cpp:112-380 (default path) */

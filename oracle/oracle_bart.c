@@ -45,6 +45,7 @@ struct or_bart {
   int n, p, nt, T;
   double *y, *x, *x_test, *offset;
   int* ncuts; double** cuts;
+  uint32_t* split_w;               /* integer split weights (bart_args split.probs), NULL = uniform */
   uint8_t *xt, *xt_test;           /* [p][n], [p][nt] */
   double *yresc, *treeY, *totalFits, *treeFits, *currFits, *totalTestFits, *currTestFits;
   Tree* trees;
@@ -123,14 +124,41 @@ static void split_interval(const or_bart* f, const Node* nd, int var, int* lo, i
     child = par; par = par->parent;
   }
 }
+/* a predictor is available below nd when a cut point is left for it (and, with split.probs, its weight is positive) */
+static int var_available(const or_bart* f, const Node* nd, int j) {
+  if (f->split_w && f->split_w[j] == 0u) return 0;
+  int lo, hi; split_interval(f, nd, j, &lo, &hi);
+  return hi >= lo;
+}
 static int num_vars_available(const or_bart* f, const Node* nd) {
   int c = 0;
-  for (int j = 0; j < f->p; ++j) { int lo, hi; split_interval(f, nd, j, &lo, &hi); if (hi >= lo) ++c; }
+  for (int j = 0; j < f->p; ++j) if (var_available(f, nd, j)) ++c;
   return c;
 }
 static int ith_available_var(const or_bart* f, const Node* nd, int ith) {
-  for (int j = 0; j < f->p; ++j) { int lo, hi; split_interval(f, nd, j, &lo, &hi); if (hi >= lo) { if (ith == 0) return j; --ith; } }
+  for (int j = 0; j < f->p; ++j) if (var_available(f, nd, j)) { if (ith == 0) return j; --ith; }
   return -1;
+}
+/* split.probs: total integer weight of the available predictors, and the weighted draw (one uniform, like the unweighted one) */
+static uint64_t avail_weight(const or_bart* f, const Node* nd) {
+  uint64_t w = 0;
+  for (int j = 0; j < f->p; ++j) if (var_available(f, nd, j)) w += f->split_w[j];
+  return w;
+}
+static int draw_available_var(or_bart* f, const Node* nd) {
+  if (!f->split_w) return ith_available_var(f, nd, (int) s4b_rng_index(&f->rng, (size_t) num_vars_available(f, nd)));
+  uint64_t W = avail_weight(f, nd);
+  uint64_t r = (uint64_t) (s4b_rng_uniform(&f->rng) * (double) W);
+  if (r >= W) r = W - 1;
+  uint64_t cum = 0;
+  int last = -1;
+  for (int j = 0; j < f->p; ++j) if (var_available(f, nd, j)) { last = j; cum += f->split_w[j]; if (cum > r) return j; }
+  return last;
+}
+/* log prior probability of the splitting variable of an internal node */
+static double log_var_prior(const or_bart* f, const Node* nd) {
+  if (!f->split_w) return -log((double) num_vars_available(f, nd));
+  return log((double) f->split_w[nd->var] / (double) avail_weight(f, nd));
 }
 static double growth_prob(const or_bart* f, const Node* nd) {
   if (num_vars_available(f, nd) == 0) return 0.0;
@@ -180,7 +208,7 @@ static double branch_log_prior(const or_bart* f, const Node* nd) {
   double pg = growth_prob(f, nd);
   if (is_bottom(nd)) return log(1.0 - pg);
   int lo, hi; split_interval(f, nd, nd->var, &lo, &hi);
-  double r = log(pg) - log((double) num_vars_available(f, nd)) - log((double) (hi - lo + 1));
+  double r = log(pg) + log_var_prior(f, nd) - log((double) (hi - lo + 1));
   return r + branch_log_prior(f, nd->left) + branch_log_prior(f, nd->right);
 }
 
@@ -216,9 +244,7 @@ static double* trace_begin(or_bart* f) {
 
 /* ---------- MH steps ---------- */
 static void draw_rule(or_bart* f, const Node* nd, int* var, int* cut) {
-  int navail = num_vars_available(f, nd);
-  int ith = (int) s4b_rng_index(&f->rng, (size_t) navail);
-  *var = ith_available_var(f, nd, ith);
+  *var = draw_available_var(f, nd);
   int lo, hi; split_interval(f, nd, *var, &lo, &hi);
   *cut = lo + (int) s4b_rng_index(&f->rng, (size_t) (hi - lo + 1));
 }
@@ -322,8 +348,7 @@ static void change_rule(or_bart* f, Tree* t, const double* ty, double* tr) {
   tr[0] = 12;
   if (nnb == 0) return;
   Node* nd = nbs[s4b_rng_index(&f->rng, (size_t) nnb)];
-  int navail = num_vars_available(f, nd);
-  int new_var = ith_available_var(f, nd, (int) s4b_rng_index(&f->rng, (size_t) navail));
+  int new_var = draw_available_var(f, nd);
   int lo, hi; split_interval(f, nd, new_var, &lo, &hi);
   int maxl = -1, minl = 1 << 30, maxr = -1, minr = 1 << 30;
   desc_constraints(nd->left, new_var, &maxl, &minl);
@@ -427,6 +452,19 @@ or_bart* or_bart_create(const s4b_bart_config* cfg, const double* y, const doubl
   f->x = (double*) malloc(sizeof(double) * (n * p + 1)); memcpy(f->x, x, sizeof(double) * n * p);
   f->offset = (double*) calloc(n ? n : 1, sizeof(double));
   f->ncuts = (int*) malloc(sizeof(int) * p); f->cuts = (double**) malloc(sizeof(double*) * p);
+  f->split_w = NULL;
+  if (cfg->split_probs) {
+    /* integer weights: round(2^30 sp_j / sum sp), at least 1 for a positive probability */
+    double sum = 0.0;
+    for (size_t j = 0; j < p; ++j) sum += cfg->split_probs[j];
+    f->split_w = (uint32_t*) malloc(sizeof(uint32_t) * p);
+    for (size_t j = 0; j < p; ++j) {
+      double t = cfg->split_probs[j] / sum;
+      double w = floor(ldexp(t, 30) + 0.5);
+      f->split_w[j] = cfg->split_probs[j] > 0.0 ? (w < 1.0 ? 1u : (uint32_t) w) : 0u;
+    }
+  }
+  f->cfg.split_probs = NULL;       /* the caller's array is not kept */
   f->xt = (uint8_t*) malloc(n * p + 1);
   for (size_t j = 0; j < p; ++j) {
     const double* col = x + j * n;
@@ -471,7 +509,7 @@ void or_bart_free(or_bart* f)
   if (!f) return;
   for (int t = 0; t < f->T; ++t) tree_release(&f->trees[t]);
   for (int j = 0; j < f->p; ++j) free(f->cuts[j]);
-  free(f->cuts); free(f->ncuts); free(f->trees);
+  free(f->cuts); free(f->ncuts); free(f->trees); free(f->split_w);
   free(f->y); free(f->x); free(f->x_test); free(f->offset); free(f->xt); free(f->xt_test);
   free(f->yresc); free(f->treeY); free(f->totalFits); free(f->treeFits); free(f->currFits);
   free(f->totalTestFits); free(f->currTestFits);

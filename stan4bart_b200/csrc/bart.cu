@@ -395,7 +395,7 @@ __global__ void k_prior_tree(BartDev dv, int tree_index)
     double pg = birthable ? t_growth_prob_depth(dv.pgrow, navail, t.nodes[i].depth) : 0.0;
     double u = rng_uniform(rng);
     if (!(u < pg)) continue;
-    int var = t_ith_available_var(t, P, i, rng_index(rng, navail));
+    int var = t_draw_var(t, P, i, navail, rng);
     int lo, hi; t_split_interval(t, P.n_cuts, i, var, lo, hi);
     int cut = lo + rng_index(rng, hi - lo + 1);
     t_insert_children(t, i, var, cut);
@@ -743,6 +743,25 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   P.leaf_prec = 1.0 / (sd_leaf * sd_leaf);
   P.sigma = 1.0; P.smin = -0.5; P.smax = 0.5; P.srange = cfg.is_binary ? 1.0 : 0.0;
   P.key0 = (uint32_t) cfg.seed; P.key1 = (uint32_t) (cfg.seed >> 32);
+  if (cfg.split_probs != nullptr) {
+    // bart_args split.probs -> integer weights round(2^30 p_j / sum p), at least 1 for a positive probability (same recipe
+    // as the oracle: selection and rule priors are then exact integer arithmetic on both sides)
+    double sum = 0.0;
+    for (int j = 0; j < p_; ++j) { if (!(cfg.split_probs[j] >= 0.0)) throw std::invalid_argument("split_probs must be non-negative"); sum += cfg.split_probs[j]; }
+    if (!(sum > 0.0)) throw std::invalid_argument("split_probs must not all be zero");
+    std::vector<uint32_t> w((size_t) p_);
+    unsigned long long total = 0; int pos = 0;
+    for (int j = 0; j < p_; ++j) {
+      const double tj = cfg.split_probs[j] / sum;
+      const double wj = std::floor(std::ldexp(tj, 30) + 0.5);
+      w[(size_t) j] = cfg.split_probs[j] > 0.0 ? (wj < 1.0 ? 1u : (uint32_t) wj) : 0u;
+      total += w[(size_t) j]; pos += w[(size_t) j] != 0u;
+    }
+    S4B_CUDA(cudaMalloc(&d_split_w_, sizeof(uint32_t) * (size_t) p_));
+    S4B_CUDA(cudaMemcpy(d_split_w_, w.data(), sizeof(uint32_t) * (size_t) p_, cudaMemcpyHostToDevice));
+    P.split_w = d_split_w_; P.split_total = total; P.p_pos = pos;
+  }
+  cfg_.split_probs = nullptr;        // the caller's array is not kept
   S4B_CUDA(cudaMalloc(&d_params_, sizeof(BartParams)));
   S4B_CUDA(cudaMemcpy(d_params_, &P, sizeof P, cudaMemcpyHostToDevice));
   std::vector<double> pg(S4B_MAX_DEPTH + 2);
@@ -779,7 +798,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -1116,7 +1135,7 @@ void BartFit::run_sweeps()
 void BartFit::set_keep_trees(long long capacity)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));
-  cudaFree(d_store_); cudaFree(d_store_scale_); d_store_ = nullptr; d_store_scale_ = nullptr;
+  cudaFree(d_split_w_); cudaFree(d_store_); cudaFree(d_store_scale_); d_store_ = nullptr; d_store_scale_ = nullptr;
   store_cap_ = capacity > 0 ? capacity : 0; store_len_ = 0;
   if (store_cap_ > 0) {
     S4B_CUDA(cudaMalloc(&d_store_, sizeof(DTree) * (size_t) T_ * (size_t) store_cap_));

@@ -125,6 +125,7 @@ class BartFit {
   int sweep_mode_ = 1;
   int persistent_nq_ = 0, persistent_grid_ = 0;       // nq = kStreamNq: residuals streamed from global memory (L2)
   uint2* d_packs_ = nullptr;
+  uint32_t* d_split_w_ = nullptr;
   DTree* d_store_ = nullptr; double* d_store_scale_ = nullptr; long long store_cap_ = 0, store_len_ = 0;
   size_t persistent_smem_ = 0;
   unsigned int* d_barrier_ = nullptr;

@@ -42,7 +42,8 @@ __device__ inline void t_split_interval(const DTree& t, int n_cuts, int i, int v
   }
 }
 
-// number of predictors that still have a cut available below node i (data independent)
+// number of predictors that still have a cut available below node i (data independent); with split weights only
+// predictors of positive weight count
 __device__ inline int t_num_vars_available(const DTree& t, const BartParams& P, int i)
 {
   int blocked = 0;
@@ -52,22 +53,67 @@ __device__ inline int t_num_vars_available(const DTree& t, const BartParams& P, 
     int v = t.nodes[par].var;
     bool seen = false;
     for (int a = t.nodes[i].parent; a != par; a = t.nodes[a].parent) if (t.nodes[a].var == v) { seen = true; break; }
-    if (!seen) { int lo, hi; t_split_interval(t, P.n_cuts, i, v, lo, hi); if (hi < lo) ++blocked; }
+    if (!seen && (P.split_w == nullptr || P.split_w[v] != 0u)) { int lo, hi; t_split_interval(t, P.n_cuts, i, v, lo, hi); if (hi < lo) ++blocked; }
     par = t.nodes[par].parent;
   }
-  return P.p - blocked;
+  return (P.split_w != nullptr ? P.p_pos : P.p) - blocked;
+}
+
+__device__ inline bool t_var_available(const DTree& t, const BartParams& P, int i, int j)
+{
+  if (P.split_w != nullptr && P.split_w[j] == 0u) return false;
+  bool used = false;
+  for (int a = t.nodes[i].parent; a >= 0; a = t.nodes[a].parent) if (t.nodes[a].var == j) { used = true; break; }
+  if (!used) return true;
+  int lo, hi; t_split_interval(t, P.n_cuts, i, j, lo, hi);
+  return hi >= lo;
 }
 
 __device__ inline int t_ith_available_var(const DTree& t, const BartParams& P, int i, int ith)
 {
-  for (int j = 0; j < P.p; ++j) {
-    bool used = false;
-    for (int a = t.nodes[i].parent; a >= 0; a = t.nodes[a].parent) if (t.nodes[a].var == j) { used = true; break; }
-    bool avail = true;
-    if (used) { int lo, hi; t_split_interval(t, P.n_cuts, i, j, lo, hi); avail = hi >= lo; }
-    if (avail) { if (ith == 0) return j; --ith; }
-  }
+  for (int j = 0; j < P.p; ++j) if (t_var_available(t, P, i, j)) { if (ith == 0) return j; --ith; }
   return -1;
+}
+
+// split weights: total weight of the predictors available below node i
+__device__ inline unsigned long long t_avail_weight(const DTree& t, const BartParams& P, int i)
+{
+  unsigned long long w = P.split_total;
+  int par = t.nodes[i].parent;
+  while (par >= 0) {
+    int v = t.nodes[par].var;
+    bool seen = false;
+    for (int a = t.nodes[i].parent; a != par; a = t.nodes[a].parent) if (t.nodes[a].var == v) { seen = true; break; }
+    if (!seen && P.split_w[v] != 0u) { int lo, hi; t_split_interval(t, P.n_cuts, i, v, lo, hi); if (hi < lo) w -= P.split_w[v]; }
+    par = t.nodes[par].parent;
+  }
+  return w;
+}
+// position r in [0, W) of the cumulative weights of the available predictors (index order)
+__device__ inline unsigned long long weighted_position(double u, unsigned long long W)
+{
+  unsigned long long r = (unsigned long long) (u * (double) W);
+  return r >= W ? W - 1ull : r;
+}
+__device__ inline int t_weighted_var(const DTree& t, const BartParams& P, int i, unsigned long long r)
+{
+  unsigned long long cum = 0ull;
+  int last = -1;
+  for (int j = 0; j < P.p; ++j) if (t_var_available(t, P, i, j)) { last = j; cum += P.split_w[j]; if (cum > r) return j; }
+  return last;
+}
+// one draw from the rule prior's variable distribution at node i (one uniform either way)
+__device__ inline int t_draw_var(const DTree& t, const BartParams& P, int i, int navail, RngState& rng)
+{
+  if (P.split_w == nullptr) return t_ith_available_var(t, P, i, rng_index(rng, navail));
+  const unsigned long long W = t_avail_weight(t, P, i);
+  return t_weighted_var(t, P, i, weighted_position(rng_uniform(rng), W));
+}
+// log prior probability of the splitting variable of internal node i
+__device__ inline double t_log_var_prior(const DTree& t, const BartParams& P, int i, int navail)
+{
+  if (P.split_w == nullptr) return -log((double) navail);
+  return log((double) P.split_w[t.nodes[i].var] / (double) t_avail_weight(t, P, i));
 }
 
 __device__ inline double t_growth_prob_depth(const double* pgrow, int navail, int depth) { return navail > 0 ? pgrow[depth] : 0.0; }
@@ -138,7 +184,7 @@ __device__ inline double t_branch_log_prior(const DTree& t, const BartParams& P,
     if (t_is_leaf(t, k)) r += log(1.0 - pg);
     else {
       int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi);
-      r += log(pg) - log((double) navail) - log((double) (hi - lo + 1));
+      r += log(pg) + t_log_var_prior(t, P, k, navail) - log((double) (hi - lo + 1));
     }
   }
   return r;
@@ -210,7 +256,7 @@ __device__ inline void propose_step(DTree& t, const BartParams& P, const double*
       int navail = t_num_vars_available(t, P, node);
       int depth = t.nodes[node].depth;
       double pg_parent = t_growth_prob_depth(pgrow, navail, depth);
-      int var = t_ith_available_var(t, P, node, rng_index(rng, navail));
+      int var = t_draw_var(t, P, node, navail, rng);
       int lo, hi; t_split_interval(t, P.n_cuts, node, var, lo, hi);
       int cut = lo + rng_index(rng, hi - lo + 1);
       // children: same availability except possibly `var`
@@ -269,7 +315,7 @@ __device__ inline void propose_step(DTree& t, const BartParams& P, const double*
     int node = -1;
     for (int k = 0; k < t.num_nodes; ++k) if (!t_is_leaf(t, k)) { if (pick == 0) { node = k; break; } --pick; }
     int navail = t_num_vars_available(t, P, node);
-    int new_var = t_ith_available_var(t, P, node, rng_index(rng, navail));
+    int new_var = t_draw_var(t, P, node, navail, rng);
     int lo, hi; t_split_interval(t, P.n_cuts, node, new_var, lo, hi);
     int end = t_subtree_end(t, node), rstart = t.nodes[node].right;
     for (int k = node + 1; k < end; ++k) if (!t_is_leaf(t, k) && t.nodes[k].var == new_var) {

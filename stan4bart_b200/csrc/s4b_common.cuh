@@ -254,6 +254,10 @@ struct BartParams {
   uint32_t error_flag;      // set by kernels on capacity / tape problems
   unsigned long long step_id;     // tree steps taken so far (keys the BART RNG substreams)
   unsigned long long prior_calls; // sampleTreesFromPrior calls so far
+  // bart_args split.probs as integer weights (round(2^30 p_j / sum p), >= 1 when p_j > 0), nullptr = uniform
+  const uint32_t* split_w;
+  unsigned long long split_total; // sum of the weights
+  int p_pos, pad_sw;              // predictors with a positive weight
 };
 
 }  // namespace s4b

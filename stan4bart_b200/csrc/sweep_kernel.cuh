@@ -268,18 +268,41 @@ __device__ inline int w_ith_available_var(const DTree& t, const BartParams& P, i
   int found = -1;
   for (int base = 0; base < P.p; base += 32) {
     int j = base + lane;
-    bool avail = false;
-    if (j < P.p) {
-      bool used = false;
-      for (int a = t.nodes[node].parent; a >= 0; a = t.nodes[a].parent) if (t.nodes[a].var == j) { used = true; break; }
-      avail = true;
-      if (used) { int lo, hi; t_split_interval(t, P.n_cuts, node, j, lo, hi); avail = hi >= lo; }
-    }
+    const bool avail = j < P.p && t_var_available(t, P, node, j);
     unsigned m = __ballot_sync(0xffffffffu, avail);
     int c = __popc(m);
     if (found < 0) { if (ith < c) found = base + nth_set_bit(m, ith); else ith -= c; }
   }
   return found;
+}
+
+// split weights: the available variable whose cumulative weight (index order) first exceeds r; integer arithmetic, so the
+// warp scan gives exactly the oracle's sequential result
+__device__ inline int w_weighted_var(const DTree& t, const BartParams& P, int node, unsigned long long r, int lane)
+{
+  int found = -1, last = -1;
+  unsigned long long carried = 0ull;
+  for (int base = 0; base < P.p; base += 32) {
+    int j = base + lane;
+    const bool avail = j < P.p && t_var_available(t, P, node, j);
+    unsigned long long cum = avail ? (unsigned long long) P.split_w[j] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long up = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += up; }
+    const unsigned hit = __ballot_sync(0xffffffffu, avail && carried + cum > r);
+    const unsigned am = __ballot_sync(0xffffffffu, avail);
+    if (found < 0 && hit) found = base + __ffs(hit) - 1;
+    if (am) last = base + 31 - __clz(am);
+    carried += __shfl_sync(0xffffffffu, cum, 31);
+  }
+  return found >= 0 ? found : last;
+}
+
+// one draw of a splitting variable at `node` (one uniform either way)
+__device__ inline int w_draw_var(const DTree& t, const BartParams& P, int node, int navail, WarpRng& rng, int lane)
+{
+  if (P.split_w == nullptr) return w_ith_available_var(t, P, node, rng.index(navail), lane);
+  const unsigned long long W = t_avail_weight(t, P, node);
+  return w_weighted_var(t, P, node, weighted_position(rng.uniform(), W), lane);
 }
 
 __device__ __forceinline__ double tab_log_int(const double* tab, int i) { return i < kLogTab ? tab[kTabLogInt + i] : log((double) i); }
@@ -295,7 +318,11 @@ __device__ inline double w_branch_log_prior(const DTree& t, const BartParams& P,
       int navail = t_num_vars_available(t, P, k);
       int d = t.nodes[k].depth;
       if (t.nodes[k].var < 0) term = navail > 0 ? tab[kTabLog1mPg + d] : 0.0;
-      else { int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi); term = tab[kTabLogPg + d] - tab_log_int(tab, navail) - tab_log_int(tab, hi - lo + 1); }
+      else {
+        int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi);
+        const double lvar = P.split_w == nullptr ? -tab_log_int(tab, navail) : log((double) P.split_w[t.nodes[k].var] / (double) t_avail_weight(t, P, k));
+        term = tab[kTabLogPg + d] + lvar - tab_log_int(tab, hi - lo + 1);
+      }
     }
     acc += w_sum(term);
   }
@@ -339,7 +366,7 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
       const int navail = cs.navail[node];
       const int depth = t.nodes[node].depth;
       const double pg_parent = t_growth_prob_depth(tab + kTabPg, navail, depth);
-      b_var = w_ith_available_var(t, P, node, rng.index(navail), lane);
+      b_var = w_draw_var(t, P, node, navail, rng, lane);
       int lo, hi; t_split_interval(t, P.n_cuts, node, b_var, lo, hi);
       b_cut = lo + rng.index(hi - lo + 1);
       const int navail_l = navail - ((b_cut - 1 < lo) ? 1 : 0);
@@ -433,7 +460,7 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
     const int n_nb = w_count_flag(cs, nn, kFInternal, lane);
     if (n_nb > 0) {
       node = w_select_flag(cs, nn, kFInternal, rng.index(n_nb), lane);
-      new_var = w_ith_available_var(t, P, node, rng.index(cs.navail[node]), lane);
+      new_var = w_draw_var(t, P, node, cs.navail[node], rng, lane);
       int lo, hi; t_split_interval(t, P.n_cuts, node, new_var, lo, hi);
       const int end = t_subtree_end(t, node), rstart = t.nodes[node].right;
       int lo_c = lo, hi_c = hi;

@@ -25,7 +25,7 @@ class BartConfig(C.Structure):
         ("is_binary", C.c_int32), ("reserved", C.c_int32),
         ("birth_death_prob", C.c_double), ("swap_prob", C.c_double), ("change_prob", C.c_double),
         ("birth_prob", C.c_double), ("base", C.c_double), ("power", C.c_double), ("k", C.c_double),
-        ("node_scale", C.c_double), ("seed", C.c_uint64),
+        ("node_scale", C.c_double), ("seed", C.c_uint64), ("split_probs", C.POINTER(C.c_double)),
     ]
 
 
@@ -77,14 +77,22 @@ def i32(a):
 
 def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_binary=False,
                 base=0.95, power=2.0, k=2.0, node_scale=None, seed=0,
-                birth_death_prob=0.5, swap_prob=0.1, change_prob=0.4, birth_prob=0.5):
-    """dbarts defaults as used by stan4bart (R/stan4bart_fit.R:437-479)."""
+                birth_death_prob=0.5, swap_prob=0.1, change_prob=0.4, birth_prob=0.5, split_probs=None):
+    """dbarts defaults as used by stan4bart (R/stan4bart_fit.R:437-479).  split_probs: relative probabilities of the p
+    predictors (bart_args split.probs), None = uniform."""
     if node_scale is None:
         node_scale = 3.0 if is_binary else 0.5
-    return BartConfig(n=n, p=p, n_test=n_test, num_trees=num_trees, n_cuts=n_cuts, thin=thin, min_obs=min_obs,
-                      is_binary=int(is_binary), reserved=0, birth_death_prob=birth_death_prob, swap_prob=swap_prob,
-                      change_prob=change_prob, birth_prob=birth_prob, base=base, power=power, k=k,
-                      node_scale=node_scale, seed=seed)
+    cfg = BartConfig(n=n, p=p, n_test=n_test, num_trees=num_trees, n_cuts=n_cuts, thin=thin, min_obs=min_obs,
+                     is_binary=int(is_binary), reserved=0, birth_death_prob=birth_death_prob, swap_prob=swap_prob,
+                     change_prob=change_prob, birth_prob=birth_prob, base=base, power=power, k=k,
+                     node_scale=node_scale, seed=seed)
+    if split_probs is not None:
+        sp = np.ascontiguousarray(split_probs, dtype=np.float64)
+        if sp.shape != (p,) or np.any(sp < 0) or not np.any(sp > 0):
+            raise ValueError("split_probs must be p non-negative numbers, not all zero")
+        cfg._split_probs = sp                       # keeps the array alive with the struct
+        cfg.split_probs = sp.ctypes.data_as(C.POINTER(C.c_double))
+    return cfg
 
 
 def stan_control(seed=0, skip=1, init_radius=2.0, adapt_gamma=0.05, adapt_delta=0.8, adapt_kappa=0.75, adapt_t0=10.0,

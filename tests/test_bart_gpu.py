@@ -332,3 +332,31 @@ def test_production_path_without_sums_of_squares(binary):
     assert np.array_equal(to["var"], t2["var"]) and np.array_equal(to["n"], t2["n"])
     assert_same_partition(o, g_pl, T)
     assert g_tr.rng_counter() == g_pl.rng_counter() == o.rng_counter()
+
+
+def test_split_probs_weighted_variable_selection():
+    """bart_args split.probs (tests/testthat/test-09-bartArgs.R:20-39): predictors are drawn, and enter the rule prior, with the
+    given relative probabilities.  Integer weights make the choice exact on both sides: every step matches the oracle in the
+    persistent kernel and in the per-tree kernels; a predictor of probability zero is never split on."""
+    T, sweeps = 12, 25
+    x, y, xt = bart_problem(1500, 6, 0, False, seed=31)
+    sp = [1.0, 1.0, 2.0, 0.0, 1.0, 3.0]
+    cfg = bart_config(1500, 6, num_trees=T, seed=8, split_probs=sp)
+    o = O.OracleBart(cfg, y, x, xt)
+    g2, g1 = GpuBart(cfg, y, x, xt), GpuBart(cfg, y, x, xt)
+    g1.set_sweep_mode(1)
+    for b in (o, g2, g1):
+        b.set_sigma(1.2)
+        b.sample_trees_from_prior()
+        b.set_trace(T * sweeps)
+    used = np.zeros(6)
+    for s in range(sweeps):
+        ro, r2, r1 = o.run(), g2.run(), g1.run()
+        assert np.array_equal(ro["varcount"], r2["varcount"]) and np.array_equal(ro["varcount"], r1["varcount"])
+        assert rel_err(ro["train"], r2["train"], scale=np.abs(ro["train"]) + 1.0) <= REL_TOL
+        used += ro["varcount"]
+    compare_traces(o.trace(), g2.trace())
+    compare_traces(o.trace(), g1.trace())
+    assert used[3] == 0 and used.sum() > 0
+    kinds = o.trace()[:, 0]
+    assert np.any(kinds == 2) and np.any(kinds == 0)          # change and birth steps drew weighted variables

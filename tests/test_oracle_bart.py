@@ -156,3 +156,23 @@ def test_trace_covers_all_move_types():
     # min_obs is respected by every accepted birth
     births = tr[(tr[:, 0] == 0) & (tr[:, 4] == 1)]
     assert np.all(births[:, 9] >= 5) and np.all(births[:, 10] >= 5)
+
+
+def test_split_probs_prior_frequencies():
+    """Trees drawn from the prior split on predictor j with probability proportional to split.probs (root rules: no
+    predictor is exhausted there), and never on a predictor of probability zero."""
+    x, y, _ = bart_problem(300, 5, 0, False)
+    sp = np.array([1.0, 1.0, 2.0, 0.0, 4.0])
+    cfg = bart_config(300, 5, num_trees=200, seed=17, split_probs=sp)
+    o = O.OracleBart(cfg, y, x, None)
+    counts = np.zeros(5)
+    for _ in range(30):
+        o.sample_trees_from_prior()
+        tr = o.trees()
+        roots = np.concatenate([[0], np.nonzero(np.diff(tr["tree"]))[0] + 1])
+        rv = tr["var"][roots]
+        counts += np.bincount(rv[rv >= 0], minlength=5)
+    assert counts[3] == 0
+    freq = counts / counts.sum()
+    want = sp / sp.sum()
+    assert np.all(np.abs(freq - want) < 4 * np.sqrt(want * (1 - want) / counts.sum()) + 1e-9)
