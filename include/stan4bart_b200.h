@@ -67,9 +67,15 @@ typedef struct s4b_stan_control {
 } s4b_stan_control;
 
 /* control.common, src/init.cpp:1015-1051 */
+/* commonControl (init.cpp:1010-1040).  user_offset / offset_type: the `offset` argument of stan4bart() and its debugging
+ * variants (init.cpp:84-88, :236-252, :762-795, :831-839): 0 default (added to both halves' offsets), 1 fixef / 2 ranef (the
+ * user vector stands in for that part of the parametric mean), 3 bart (it replaces the BART fit seen by Stan), 4 parametric
+ * (it replaces the whole Stan part seen by BART).  user_offset NULL = none. */
 typedef struct s4b_common_control {
   int32_t warmup, iter, is_binary, keep_fits;
   double sigma_init;
+  int32_t offset_type, reserved;
+  const double* user_offset;
 } s4b_common_control;
 
 const char* s4b_last_error(void);

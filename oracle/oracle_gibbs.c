@@ -5,7 +5,7 @@
  *   createSampler   /root/reference/src/init.cpp:190-310
  *   run             /root/reference/src/init.cpp:678-965 (loop body :752-917)
  *   disengage       /root/reference/src/init.cpp:995-1004
- * with userOffset == NULL (offset_type variants are SURVEY 8f rank 4).
+ * including the user offset and its offset_type variants (init.cpp:84-88, :236-252, :762-795, :831-839).
  */
 #include "s4b_oracle.h"
 
@@ -19,7 +19,21 @@ struct or_sampler {
   double *bartOffset, *stanOffset, *bartLatents;
   double* stan_curr;   /* last saved Stan draw */
   int num_pars;
+  double* userOffset;  /* copy of cc.user_offset or NULL */
 };
+enum { OFFSET_DEFAULT = 0, OFFSET_FIXEF, OFFSET_RANEF, OFFSET_BART, OFFSET_PARAMETRIC };
+
+/* stanOffset from the tree-only training fit (init.cpp:277-285, :831-839) */
+static void set_stan_offset(or_sampler* s, const double* tree_fit)
+{
+  size_t n = (size_t) s->n;
+  if (s->userOffset && s->cc.offset_type == OFFSET_BART) memcpy(s->stanOffset, s->userOffset, sizeof(double) * n);
+  else {
+    memcpy(s->stanOffset, tree_fit, sizeof(double) * n);
+    if (s->userOffset && s->cc.offset_type == OFFSET_DEFAULT) for (size_t j = 0; j < n; ++j) s->stanOffset[j] += s->userOffset[j];
+  }
+  or_glmm_set_offset(s->model, s->stanOffset);
+}
 
 or_sampler* or_sampler_create(const s4b_bart_config* bcfg, const double* y_bart, const double* x_bart, const double* x_test,
                               const s4b_glmm_data* gdata, const s4b_stan_control* sctl, const s4b_common_control* cctl,
@@ -37,15 +51,20 @@ or_sampler* or_sampler_create(const s4b_bart_config* bcfg, const double* y_bart,
   s->bartOffset = (double*) calloc(n ? n : 1, sizeof(double));
   s->stanOffset = (double*) calloc(n ? n : 1, sizeof(double));
   if (cctl->is_binary) s->bartLatents = (double*) calloc(n ? n : 1, sizeof(double));
-  if (bart_offset_init) memcpy(s->bartOffset, bart_offset_init, sizeof(double) * n);  /* :248-252 */
+  if (cctl->user_offset) { s->userOffset = (double*) malloc(sizeof(double) * (n ? n : 1)); memcpy(s->userOffset, cctl->user_offset, sizeof(double) * n); }
+  s->cc.user_offset = NULL;
+  if (s->userOffset && s->cc.offset_type != OFFSET_BART) {                          /* :236-247 */
+    memcpy(s->bartOffset, s->userOffset, sizeof(double) * n);
+    if (bart_offset_init && s->cc.offset_type == OFFSET_DEFAULT) for (size_t j = 0; j < n; ++j) s->bartOffset[j] += bart_offset_init[j];
+  } else if (bart_offset_init) memcpy(s->bartOffset, bart_offset_init, sizeof(double) * n);  /* :248-252 */
   or_bart_set_offset(s->bart, s->bartOffset, 1);                                    /* :255 */
   if (!cctl->is_binary) or_bart_set_sigma(s->bart, cctl->sigma_init);               /* :256-257 */
   or_bart_sample_trees_from_prior(s->bart);                                         /* :261 */
   double* first = (double*) calloc(n ? n : 1, sizeof(double));
   or_bart_run(s->bart, first, NULL, NULL, NULL);                                    /* :273 */
-  for (size_t j = 0; j < n; ++j) s->stanOffset[j] = first[j] - s->bartOffset[j];    /* :275-281 */
+  for (size_t j = 0; j < n; ++j) first[j] -= s->bartOffset[j];                      /* :275 */
+  set_stan_offset(s, first);                                                        /* :277-287 */
   free(first);
-  or_glmm_set_offset(s->model, s->stanOffset);                                      /* :287 */
   if (cctl->is_binary) { or_bart_store_latents(s->bart, s->bartLatents); or_glmm_set_response(s->model, s->bartLatents); }  /* :288-291 */
   return s;
 }
@@ -54,7 +73,7 @@ void or_sampler_free(or_sampler* s)
 {
   if (!s) return;
   or_bart_free(s->bart); or_nuts_free(s->nuts); or_glmm_free(s->model);
-  free(s->bartOffset); free(s->stanOffset); free(s->bartLatents); free(s->stan_curr); free(s);
+  free(s->bartOffset); free(s->stanOffset); free(s->bartLatents); free(s->stan_curr); free(s->userOffset); free(s);
 }
 
 int or_sampler_num_stan_pars(const or_sampler* s) { return s->num_pars; }
@@ -73,7 +92,14 @@ void or_sampler_run(or_sampler* s, int num_iter, int is_warmup, double* stan, do
     /* A. Stan block, init.cpp:758-819 */
     or_nuts_run(s->nuts, is_warmup, s->stan_curr);
     if (stan) memcpy(stan + slot * (size_t) s->num_pars, s->stan_curr, sizeof(double) * (size_t) s->num_pars);
-    or_glmm_parametric_mean(s->model, s->stan_curr + 7, s->bartOffset, 1, 1);       /* :764 */
+    if (!s->userOffset || s->cc.offset_type == OFFSET_DEFAULT || s->cc.offset_type == OFFSET_BART)   /* :762-776 */
+      or_glmm_parametric_mean(s->model, s->stan_curr + 7, s->bartOffset, 1, 1);
+    else if (s->cc.offset_type == OFFSET_RANEF) or_glmm_parametric_mean(s->model, s->stan_curr + 7, s->bartOffset, 1, 0);   /* :778-782 */
+    else if (s->cc.offset_type == OFFSET_FIXEF) or_glmm_parametric_mean(s->model, s->stan_curr + 7, s->bartOffset, 0, 1);   /* :784-788 */
+    if (s->userOffset) {
+      if (s->cc.offset_type == OFFSET_PARAMETRIC) memcpy(s->bartOffset, s->userOffset, sizeof(double) * n);               /* :790-793 */
+      else if (s->cc.offset_type != OFFSET_BART) for (size_t j = 0; j < n; ++j) s->bartOffset[j] += s->userOffset[j];
+    }
     if (!s->cc.is_binary) or_bart_set_sigma(s->bart, or_glmm_get_aux(s->model, s->stan_curr + 7));  /* :796-800 */
     int update_scale_mod = 1 << (8 * iter / num_iter);                              /* :816 */
     or_bart_set_offset(s->bart, s->bartOffset, is_warmup && iter % update_scale_mod == 0);
@@ -81,8 +107,7 @@ void or_sampler_run(or_sampler* s, int num_iter, int is_warmup, double* stan, do
     double sig;
     or_bart_run(s->bart, tmp_train, nt ? tmp_test : NULL, varcount ? varcount + slot * (size_t) s->p : NULL, &sig);
     for (size_t j = 0; j < n; ++j) tmp_train[j] -= s->bartOffset[j];                /* :828-829 */
-    memcpy(s->stanOffset, tmp_train, sizeof(double) * n);                           /* :835 */
-    or_glmm_set_offset(s->model, s->stanOffset);                                    /* :842 */
+    set_stan_offset(s, tmp_train);                                                  /* :831-842 */
     if (s->cc.is_binary) { or_bart_store_latents(s->bart, s->bartLatents); or_glmm_set_response(s->model, s->bartLatents); }
     if (train) memcpy(train + slot * n, tmp_train, sizeof(double) * n);
     if (test && nt) memcpy(test + slot * nt, tmp_test, sizeof(double) * nt);

@@ -16,6 +16,14 @@
 
 namespace s4b {
 
+// dst = a + b (b may be NULL: plain copy)
+__global__ void k_sum2(long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ dst)
+{
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) dst[i] = b != nullptr ? a[i] + b[i] : a[i];
+}
+
+enum { kOffsetDefault = 0, kOffsetFixef = 1, kOffsetRanef = 2, kOffsetBart = 3, kOffsetParametric = 4 };   // init.cpp:84-88
+
 // running sums of the kept draws (training fit, parametric mean, test fit) in one launch
 __global__ void k_accumulate3(long long n, const double* __restrict__ s0, double* __restrict__ a0, const double* __restrict__ s1, double* __restrict__ a1,
                               long long n2, const double* __restrict__ s2, double* __restrict__ a2)
@@ -45,18 +53,28 @@ class GibbsSampler {
     S4B_CUDA(cudaEventCreateWithFlags(&ev_c_, cudaEventDisableTiming));
     S4B_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     bart_.set_add_offset(false);
+    if (cc_.offset_type < kOffsetDefault || cc_.offset_type > kOffsetParametric) throw std::invalid_argument("sampler: offset_type out of range");
+    const int ew_grid = (int) std::max<long long>(1, std::min<long long>((n_ + 255) / 256, 148 * 8));
+    if (cc_.user_offset != nullptr) {
+      dalloc(&d_user_offset_, (size_t) n_); dalloc(&d_stan_offset_, (size_t) n_);
+      S4B_CUDA(cudaMemcpyAsync(d_user_offset_, cc_.user_offset, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice, stream_));
+    }
+    cc_.user_offset = nullptr;                                             // the caller's array is not kept
     if (bart_offset_init) S4B_CUDA(cudaMemcpyAsync(d_bart_offset_, bart_offset_init, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice, stream_));
+    if (d_user_offset_ != nullptr && cc_.offset_type != kOffsetBart)       // init.cpp:236-247
+      k_sum2<<<ew_grid, 256, 0, stream_>>>(n_, d_user_offset_, (bart_offset_init && cc_.offset_type == kOffsetDefault) ? d_bart_offset_ : nullptr, d_bart_offset_);
     bart_.set_offset_device(d_bart_offset_, true);                         // init.cpp:255
     if (!cc_.is_binary) bart_.set_sigma(cc_.sigma_init);                   // :256-257
     bart_.sample_trees_from_prior();                                       // :261
     bart_.run_sweeps();                                                    // :273  (first draw)
-    glmm_.set_inputs_device(bart_.d_train_out(), cc_.is_binary ? bart_.d_latent_out() : nullptr);    // :275-291 (fit without the offset)
+    glmm_.set_inputs_device(stan_offset_source(), cc_.is_binary ? bart_.d_latent_out() : nullptr);    // :275-291 (fit without the offset)
     S4B_CUDA(cudaStreamSynchronize(stream_));
     bart_.check_error_flag();
   }
   ~GibbsSampler()
   {
     if (h_plumb_) cudaFreeHost(h_plumb_);
+    cudaFree(d_user_offset_); cudaFree(d_stan_offset_);
     cudaFree(d_bart_offset_); cudaFree(d_mean_train_); cudaFree(d_mean_param_); cudaFree(d_mean_test_); cudaFree(d_varcount_);
     cudaEventDestroy(ev_a_); cudaEventDestroy(ev_b_); cudaEventDestroy(ev_c_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -83,7 +101,15 @@ class GibbsSampler {
       const double* constrained = stan_curr_.data() + 7;
       const double* beta = constrained + glmm_.num_params() + (glmm_.has_aux() ? 1 : 0);
       const double* b = beta + glmm_.K();
-      glmm_.parametric_mean_device(beta, b, d_bart_offset_, true, true);               // :764
+      if (d_user_offset_ == nullptr) glmm_.parametric_mean_device(beta, b, d_bart_offset_, true, true);               // :764
+      else {                                                                             // :766-794
+        const int ot = cc_.offset_type;
+        if (ot == kOffsetParametric) S4B_CUDA(cudaMemcpyAsync(d_bart_offset_, d_user_offset_, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream_));
+        else {
+          glmm_.parametric_mean_device(beta, b, d_bart_offset_, ot != kOffsetFixef, ot != kOffsetRanef);
+          if (ot != kOffsetBart) k_sum2<<<acc_grid, 256, 0, stream_>>>(n_, d_bart_offset_, d_user_offset_, d_bart_offset_);
+        }
+      }
       if (host_plumbing_) {   // the reference's host vector `bartOffset` (init.cpp:143): D2H, then H2D into BART
         S4B_CUDA(cudaMemcpyAsync(h_plumb_, d_bart_offset_, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
         S4B_CUDA(cudaMemcpyAsync(d_bart_offset_, h_plumb_, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
@@ -112,7 +138,7 @@ class GibbsSampler {
           S4B_CUDA(cudaMemcpyAsync(bart_.d_latent_out(), h_plumb_ + 2 * n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
         }
       }
-      glmm_.set_inputs_device(bart_.d_train_out(), cc_.is_binary ? bart_.d_latent_out() : nullptr);   // :828-847
+      glmm_.set_inputs_device(stan_offset_source(), cc_.is_binary ? bart_.d_latent_out() : nullptr);   // :828-847
       if (!is_warmup) {
         k_accumulate3<<<acc_grid, 256, 0, stream_>>>(n_, bart_.d_train_out(), d_mean_train_, d_bart_offset_, d_mean_param_,
                                                      nt_, nt_ > 0 ? bart_.d_test_out() : nullptr, d_mean_test_);
@@ -144,6 +170,16 @@ class GibbsSampler {
     last_tree_steps_ = bart_.num_tree_steps() - steps0;
   }
 
+  // what Stan sees as its offset (init.cpp:277-285, :831-839): the tree-only fit, plus / replaced by the user offset
+  const double* stan_offset_source()
+  {
+    if (d_user_offset_ == nullptr) return bart_.d_train_out();
+    if (cc_.offset_type == kOffsetBart) return d_user_offset_;
+    if (cc_.offset_type != kOffsetDefault) return bart_.d_train_out();
+    const int grid = (int) std::max<long long>(1, std::min<long long>((n_ + 255) / 256, 148 * 8));
+    k_sum2<<<grid, 256, 0, stream_>>>(n_, bart_.d_train_out(), d_user_offset_, d_stan_offset_);
+    return d_stan_offset_;
+  }
   void disengage_adaptation() { nuts_.disengage_adaptation(); }
   // route the N-length vectors of every iteration through pinned host memory, as a drop-in at the reference's
   // own host boundary would (bench.py's `e2e` leg); returns bytes moved per iteration in each direction
@@ -182,6 +218,7 @@ class GibbsSampler {
   BartFit bart_;
   long long n_ = 0, nt_ = 0; int p_ = 0, num_pars_ = 0;
   std::vector<double> stan_curr_;
+  double *d_user_offset_ = nullptr, *d_stan_offset_ = nullptr;
   double *d_bart_offset_ = nullptr, *d_mean_train_ = nullptr, *d_mean_param_ = nullptr, *d_mean_test_ = nullptr;
   unsigned int* d_varcount_ = nullptr;
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;

@@ -298,7 +298,7 @@ class Sampler:
     """stan4bart_create(...) -> sampler object with run / disengage_adaptation / ... methods."""
 
     def __init__(self, bart_cfg, y, x_bart, x_test, stan_data, stan_ctl, warmup, iter_, keep_fits=True, sigma_init=1.0,
-                 bart_offset_init=None, shard=None):
+                 bart_offset_init=None, shard=None, offset=None, offset_type=0):
         self.L = _lib.load()
         self._shard = shard
         _lib.require_device()
@@ -309,8 +309,9 @@ class Sampler:
         x = np.asfortranarray(x_bart, dtype=np.float64)
         xt = np.asfortranarray(x_test, dtype=np.float64) if x_test is not None else None
         off = f64(bart_offset_init) if bart_offset_init is not None else None
+        self._user_offset = f64(offset) if offset is not None else None
         self.cc = CommonControl(warmup=warmup, iter=iter_, is_binary=int(stan_data.is_binary), keep_fits=int(keep_fits),
-                                sigma_init=float(sigma_init))
+                                sigma_init=float(sigma_init), offset_type=int(offset_type), reserved=0, user_offset=dptr(self._user_offset))
         self.keep_fits = bool(keep_fits)
         h = C.c_void_p()
         if shard is None:

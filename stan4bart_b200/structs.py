@@ -55,7 +55,7 @@ class StanControl(C.Structure):
 class CommonControl(C.Structure):
     _fields_ = [
         ("warmup", C.c_int32), ("iter", C.c_int32), ("is_binary", C.c_int32), ("keep_fits", C.c_int32),
-        ("sigma_init", C.c_double),
+        ("sigma_init", C.c_double), ("offset_type", C.c_int32), ("reserved", C.c_int32), ("user_offset", C.POINTER(C.c_double)),
     ]
 
 

@@ -289,7 +289,7 @@ class OracleSampler:
     """Mirror of the reference's `.Call` surface (src/init.cpp:1215-1229) on the CPU oracle."""
 
     def __init__(self, bart_cfg, y, x_bart, x_test, stan_data, stan_ctl, warmup, iter_, keep_fits=True, sigma_init=1.0,
-                 bart_offset_init=None):
+                 bart_offset_init=None, offset=None, offset_type=0):
         self.bcfg = bart_cfg
         self.sd = stan_data
         self._gs = stan_data.struct()
@@ -297,8 +297,9 @@ class OracleSampler:
         self._x = np.asfortranarray(x_bart, dtype=np.float64)
         self._xt = np.asfortranarray(x_test, dtype=np.float64) if x_test is not None else None
         self._off = f64(bart_offset_init) if bart_offset_init is not None else None
+        self._user_offset = f64(offset) if offset is not None else None
         self.cc = CommonControl(warmup=warmup, iter=iter_, is_binary=int(stan_data.is_binary), keep_fits=int(keep_fits),
-                                sigma_init=float(sigma_init))
+                                sigma_init=float(sigma_init), offset_type=int(offset_type), reserved=0, user_offset=dptr(self._user_offset))
         self.keep_fits = keep_fits
         self.h = lib().or_sampler_create(C.byref(bart_cfg), dptr(self._y), dptr(self._x), dptr(self._xt), C.byref(self._gs),
                                          C.byref(stan_ctl), C.byref(self.cc), dptr(self._off))

@@ -244,3 +244,31 @@ def test_keep_trees_stored_draws_predict_their_own_training_fits(binary):
     b.set_keep_trees(0)
     g.run(1, False)
     assert b.num_stored() == 0
+
+
+@pytest.mark.parametrize("offset_type", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("binary", [False, True])
+def test_user_offset_and_offset_types(offset_type, binary):
+    """stan4bart(offset = ...) and its offset_type variants (init.cpp:84-88, :236-252, :762-795, :831-839): default (added to
+    both halves), fixef / ranef (stands in for that part of the parametric mean), bart (replaces the BART fit Stan sees),
+    parametric (replaces the Stan part BART sees).  First sweeps against the oracle, step by step."""
+    n, T, K = 400, 9, 6
+    pr = friedman_problem(n, binary=binary)
+    sd = pr["stan_data"]
+    user = 0.4 * np.sin(np.arange(n) * 0.05) + 0.1
+    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=binary, seed=321)
+    ctl = stan_control(seed=654)
+    kw = dict(warmup=K, iter_=2 * K, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"],
+              offset=user, offset_type=offset_type)
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    g = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    ob, gb = o.bart(), g.bart()
+    ob.set_trace(T * K); gb.set_trace(T * K)
+    ro, rg = o.run(K, True), g.run(K, True)
+    compare_traces(ob.trace(), gb.trace(), tol=1e-8)
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-8
+    # the offset changes the chain (it is not silently ignored)
+    base = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, warmup=K, iter_=2 * K, keep_fits=True, sigma_init=pr["sigma_init"],
+                   bart_offset_init=pr["bart_offset_init"]).run(K, True)
+    assert not np.allclose(base["bart"]["train"], rg["bart"]["train"])
