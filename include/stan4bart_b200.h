@@ -181,6 +181,12 @@ int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out);
 /* stan4bart_run(sampler, numIter, isWarmup, "both") (init.cpp:678-965).  Output buffers may be NULL.
  * stan [num_pars x S], train [n x S], test [n_test x S], varcount [p x S], sigma [S]; S = keep_fits ? num_iter : 1 */
 int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma);
+/* the per-iteration callback of stan4bart_run (init.cpp:849-911: an R closure evaluated with yhat.train, yhat.test and the Stan
+ * draw of the iteration in scope).  `fn` is called on the host after every iteration with host copies of the iteration's
+ * training fit [n], test fit [n_test] (NULL when there is no test sample) and Stan row [num_pars]; a non-zero return value
+ * stops the run with an error.  fn == NULL removes the callback. */
+typedef int (*s4b_iteration_callback)(void* user, int iteration, const double* stan_row, const double* yhat_train, const double* yhat_test);
+int s4b_sampler_set_callback(s4b_sampler* s, s4b_iteration_callback fn, void* user);
 /* stan4bart_disengageAdaptation (init.cpp:995-1004) */
 int s4b_sampler_disengage_adaptation(s4b_sampler* s);
 /* stan4bart_getBARTDataRange (init.cpp:316-330) */

@@ -16,6 +16,7 @@ c_size_p = C.POINTER(C.c_size_t)
 c_int_p = C.POINTER(C.c_int)
 c_uint64_p = C.POINTER(C.c_uint64)
 c_ubyte_p = C.POINTER(C.c_ubyte)
+ITERATION_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p)
 
 # name -> (restype, argtypes); every symbol declared in include/stan4bart_b200.h
 SIGNATURES = {
@@ -83,6 +84,7 @@ SIGNATURES = {
     "s4b_sampler_glmm": (vp, [vp]),
     "s4b_sampler_get_means": (C.c_int, [vp, c_double_p, c_double_p, c_double_p, c_int64_p]),
     "s4b_sampler_last_run_stats": (C.c_int, [vp, c_double_p, c_double_p, c_int64_p, c_int64_p]),
+    "s4b_sampler_set_callback": (C.c_int, [vp, ITERATION_CALLBACK, vp]),
     "s4b_shard_create": (C.c_int, [C.c_int, C.c_int, vpp]),
     "s4b_shard_free": (C.c_int, [vp]),
     "s4b_shard_ipc_handle": (C.c_int, [vp, c_ubyte_p]),

@@ -74,6 +74,7 @@ class GibbsSampler {
   ~GibbsSampler()
   {
     if (h_plumb_) cudaFreeHost(h_plumb_);
+    if (h_cb_) cudaFreeHost(h_cb_);
     cudaFree(d_user_offset_); cudaFree(d_stan_offset_);
     cudaFree(d_bart_offset_); cudaFree(d_mean_train_); cudaFree(d_mean_param_); cudaFree(d_mean_test_); cudaFree(d_varcount_);
     cudaEventDestroy(ev_a_); cudaEventDestroy(ev_b_); cudaEventDestroy(ev_c_);
@@ -159,6 +160,14 @@ class GibbsSampler {
       }
       if (sigma) sigma[slot] = aux;
       S4B_CUDA(cudaStreamSynchronize(stream_));
+      if (callback_ != nullptr) {                                                        // init.cpp:849-911
+        if (!h_cb_) S4B_CUDA(cudaMallocHost(&h_cb_, sizeof(double) * (n + std::max<size_t>(nt, 1))));
+        S4B_CUDA(cudaMemcpyAsync(h_cb_, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+        if (nt_ > 0) S4B_CUDA(cudaMemcpyAsync(h_cb_ + n, bart_.d_test_out(), sizeof(double) * nt, cudaMemcpyDeviceToHost, stream_));
+        S4B_CUDA(cudaStreamSynchronize(stream_));
+        if (callback_(callback_user_, iter, stan_curr_.data(), h_cb_, nt_ > 0 ? h_cb_ + n : nullptr) != 0)
+          throw std::runtime_error("the iteration callback asked to stop");
+      }
       auto t2 = std::chrono::steady_clock::now();
       ms_stan_ += std::chrono::duration<double, std::milli>(t1 - t0).count();
       ms_bart_ += std::chrono::duration<double, std::milli>(t2 - t1).count();
@@ -180,6 +189,7 @@ class GibbsSampler {
     k_sum2<<<grid, 256, 0, stream_>>>(n_, bart_.d_train_out(), d_user_offset_, d_stan_offset_);
     return d_stan_offset_;
   }
+  void set_callback(s4b_iteration_callback fn, void* user) { callback_ = fn; callback_user_ = user; }
   void disengage_adaptation() { nuts_.disengage_adaptation(); }
   // route the N-length vectors of every iteration through pinned host memory, as a drop-in at the reference's
   // own host boundary would (bench.py's `e2e` leg); returns bytes moved per iteration in each direction
@@ -219,6 +229,7 @@ class GibbsSampler {
   long long n_ = 0, nt_ = 0; int p_ = 0, num_pars_ = 0;
   std::vector<double> stan_curr_;
   double *d_user_offset_ = nullptr, *d_stan_offset_ = nullptr;
+  s4b_iteration_callback callback_ = nullptr; void* callback_user_ = nullptr; double* h_cb_ = nullptr;
   double *d_bart_offset_ = nullptr, *d_mean_train_ = nullptr, *d_mean_param_ = nullptr, *d_mean_test_ = nullptr;
   unsigned int* d_varcount_ = nullptr;
   cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr, ev_c_ = nullptr;
@@ -387,6 +398,7 @@ int s4b_sampler_free(s4b_sampler* s) { S4B_API_BEGIN delete s; S4B_API_END }
 int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); *out = s->s->num_pars(); S4B_API_END }
 int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma)
 { S4B_API_BEGIN S4B_REQUIRE(s); s->s->run(num_iter, is_warmup != 0, stan, train, test, varcount, sigma); S4B_API_END }
+int s4b_sampler_set_callback(s4b_sampler* s, s4b_iteration_callback fn, void* user) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->set_callback(fn, user); S4B_API_END }
 int s4b_sampler_disengage_adaptation(s4b_sampler* s) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->disengage_adaptation(); S4B_API_END }
 int s4b_sampler_get_bart_data_range(s4b_sampler* s, double* o) { S4B_API_BEGIN S4B_REQUIRE(s && o); BartParams P = s->s->bart().params(); o[0] = P.smin; o[1] = P.smax; S4B_API_END }
 int s4b_sampler_get_parametric_mean(s4b_sampler* s, double* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); s->s->parametric_mean(out); S4B_API_END }

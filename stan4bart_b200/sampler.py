@@ -357,6 +357,24 @@ class Sampler:
             out["bart"] = dict(sigma=sigma)
         return out
 
+    def set_callback(self, fn):
+        """fn(iteration, stan_row, yhat_train, yhat_test) is called on the host after every iteration (numpy views valid
+        during the call only; yhat_test is None without a test sample); a truthy return value stops the run.  None removes it."""
+        if fn is None:
+            self._cb = None
+            _lib.check(self.L.s4b_sampler_set_callback(self.h, _lib.ITERATION_CALLBACK(), None))
+            return
+        n, nt, npar = self.n, self.nt, self.num_pars
+
+        def tramp(_user, it, stan_p, train_p, test_p):
+            stan = np.ctypeslib.as_array(stan_p, shape=(npar,))
+            train = np.ctypeslib.as_array(train_p, shape=(n,))
+            test = np.ctypeslib.as_array(test_p, shape=(nt,)) if nt and test_p else None
+            return 1 if fn(it, stan, train, test) else 0
+
+        self._cb = _lib.ITERATION_CALLBACK(tramp)          # keep the trampoline alive
+        _lib.check(self.L.s4b_sampler_set_callback(self.h, self._cb, None))
+
     def disengage_adaptation(self):
         _lib.check(self.L.s4b_sampler_disengage_adaptation(self.h))
 

@@ -272,3 +272,22 @@ def test_user_offset_and_offset_types(offset_type, binary):
     base = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, warmup=K, iter_=2 * K, keep_fits=True, sigma_init=pr["sigma_init"],
                    bart_offset_init=pr["bart_offset_init"]).run(K, True)
     assert not np.allclose(base["bart"]["train"], rg["bart"]["train"])
+
+
+def test_iteration_callback_sees_each_draw():
+    """The per-iteration callback of stan4bart_run (init.cpp:849-911, tests/testthat/test-11-callback.R): called after every
+    iteration with that iteration's Stan row and fits; a truthy return stops the run."""
+    from stan4bart_b200._lib import S4BError
+    _, g, pr = make_pair(n=300, num_trees=7, warmup=4, iter_=9)
+    seen = []
+    g.set_callback(lambda it, stan, train, test: seen.append((it, stan.copy(), train.copy(), test.copy())) and False)
+    r = g.run(4, True)
+    assert [s[0] for s in seen] == [0, 1, 2, 3]
+    for k, (_, stan, train, test) in enumerate(seen):
+        assert np.array_equal(stan, r["stan"][:, k]) and np.array_equal(train, r["bart"]["train"][:, k])
+        assert np.array_equal(test, r["bart"]["test"][:, k])
+    g.set_callback(lambda it, stan, train, test: it == 1)
+    with pytest.raises(S4BError):
+        g.run(4, True)
+    g.set_callback(None)
+    g.run(2, True)
