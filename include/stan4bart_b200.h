@@ -115,6 +115,15 @@ int gpubart_num_stored(gpubart_fit* fit, int64_t* out);
 int gpubart_predict_stored(gpubart_fit* fit, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out);
 int gpubart_num_stored_nodes(gpubart_fit* fit, int64_t sample, int64_t* out);
 int gpubart_get_stored_trees(gpubart_fit* fit, int64_t sample, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value);
+/* stan4bart_exportBARTState -> a host blob (cut points + stored draws); stan4bart_createStoredBARTSampler -> a prediction-only
+ * object rebuilt from such a blob in any later process (R: the state saved inside the fitted object, R/generics.R:183-190) */
+typedef struct gpubart_stored gpubart_stored;
+int gpubart_stored_export_size(gpubart_fit* fit, int64_t* bytes);
+int gpubart_stored_export(gpubart_fit* fit, void* out, int64_t bytes);
+int gpubart_stored_import(const void* blob, int64_t bytes, gpubart_stored** out);
+int gpubart_stored_free(gpubart_stored* st);
+int gpubart_stored_count(gpubart_stored* st, int64_t* out);
+int gpubart_stored_predict(gpubart_stored* st, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out);
 int gpubart_num_nodes(gpubart_fit* fit, int64_t* out);
 int gpubart_get_trees(gpubart_fit* fit, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value);
 /* parity instrumentation (no reference counterpart) */

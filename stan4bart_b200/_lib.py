@@ -27,6 +27,12 @@ SIGNATURES = {
     "gpubart_tree_step_ms": (C.c_int, [vp, C.c_int, c_double_p]),
     "gpubart_get_profile": (C.c_int, [vp, c_uint64_p, C.c_int]),
     "gpubart_set_profile": (C.c_int, [vp, C.c_int]),
+    "gpubart_stored_export_size": (C.c_int, [vp, c_int64_p]),
+    "gpubart_stored_export": (C.c_int, [vp, vp, C.c_int64]),
+    "gpubart_stored_import": (C.c_int, [vp, C.c_int64, vpp]),
+    "gpubart_stored_free": (C.c_int, [vp]),
+    "gpubart_stored_count": (C.c_int, [vp, c_int64_p]),
+    "gpubart_stored_predict": (C.c_int, [vp, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int64, c_double_p]),
     "gpubart_set_keep_trees": (C.c_int, [vp, C.c_int64]),
     "gpubart_num_stored": (C.c_int, [vp, c_int64_p]),
     "gpubart_predict_stored": (C.c_int, [vp, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int64, c_double_p]),

@@ -1192,6 +1192,111 @@ void BartFit::get_stored_trees(long long sample, int32_t* tree_no, long long* n_
   flatten_trees(trees, tree_no, n_obs, var, value);
 }
 
+// ---- exported draws: header, cut points, then per draw the response scale and the trees (used nodes only) ----
+struct StoredHeader { unsigned long long magic; int p, T, n_cuts, is_binary; long long count; };
+static const unsigned long long kStoredMagic = 0x5334425354524545ull;      // "S4BSTREE"
+
+long long BartFit::stored_export_size()
+{
+  long long bytes = (long long) sizeof(StoredHeader) + (long long) sizeof(double) * (long long) cuts_.size();
+  for (long long s = 0; s < store_len_; ++s) {
+    bytes += 2 * (long long) sizeof(double);
+    for (const auto& t : download_stored(s)) bytes += (long long) sizeof(int32_t) * 2 + (long long) sizeof(DNode) * t.num_nodes;
+  }
+  return bytes;
+}
+
+void BartFit::stored_export(void* out, long long bytes)
+{
+  if (bytes < stored_export_size()) throw std::invalid_argument("stored_export: buffer too small");
+  unsigned char* w = static_cast<unsigned char*>(out);
+  StoredHeader h; std::memset(&h, 0, sizeof h);
+  h.magic = kStoredMagic; h.p = p_; h.T = T_; h.n_cuts = cfg_.n_cuts; h.is_binary = cfg_.is_binary; h.count = store_len_;
+  std::memcpy(w, &h, sizeof h); w += sizeof h;
+  std::memcpy(w, cuts_.data(), sizeof(double) * cuts_.size()); w += sizeof(double) * cuts_.size();
+  std::vector<double> scales((size_t) 2 * (size_t) std::max<long long>(store_len_, 1));
+  if (store_len_ > 0) S4B_CUDA(cudaMemcpy(scales.data(), d_store_scale_, sizeof(double) * 2 * (size_t) store_len_, cudaMemcpyDeviceToHost));
+  for (long long s = 0; s < store_len_; ++s) {
+    std::memcpy(w, scales.data() + 2 * s, 2 * sizeof(double)); w += 2 * sizeof(double);
+    for (const auto& t : download_stored(s)) {
+      int32_t hdr[2] = { t.num_nodes, 0 };
+      std::memcpy(w, hdr, sizeof hdr); w += sizeof hdr;
+      std::memcpy(w, t.nodes, sizeof(DNode) * (size_t) t.num_nodes); w += sizeof(DNode) * (size_t) t.num_nodes;
+    }
+  }
+}
+
+StoredBart::StoredBart(const void* blob, long long bytes, cudaStream_t stream) : stream_(stream)
+{
+  const unsigned char* r = static_cast<const unsigned char*>(blob);
+  const unsigned char* end = r + bytes;
+  StoredHeader h;
+  if (bytes < (long long) sizeof h) throw std::invalid_argument("stored sampler: blob too short");
+  std::memcpy(&h, r, sizeof h); r += sizeof h;
+  if (h.magic != kStoredMagic || h.p < 1 || h.T < 1 || h.n_cuts < 1 || h.n_cuts > 255 || h.count < 0) throw std::invalid_argument("stored sampler: not an exported BART state");
+  p_ = h.p; T_ = h.T; n_cuts_ = h.n_cuts; is_binary_ = h.is_binary; count_ = h.count;
+  const size_t ncut = (size_t) p_ * (size_t) n_cuts_;
+  if (r + sizeof(double) * ncut > end) throw std::invalid_argument("stored sampler: truncated blob");
+  cuts_.resize(ncut); std::memcpy(cuts_.data(), r, sizeof(double) * ncut); r += sizeof(double) * ncut;
+  std::vector<DTree> trees((size_t) T_ * (size_t) std::max<long long>(count_, 1));
+  std::memset(trees.data(), 0, sizeof(DTree) * trees.size());
+  std::vector<double> scales((size_t) 2 * (size_t) std::max<long long>(count_, 1), 0.0);
+  for (long long s = 0; s < count_; ++s) {
+    if (r + 2 * sizeof(double) > end) throw std::invalid_argument("stored sampler: truncated blob");
+    std::memcpy(scales.data() + 2 * s, r, 2 * sizeof(double)); r += 2 * sizeof(double);
+    for (int t = 0; t < T_; ++t) {
+      int32_t hdr[2];
+      if (r + sizeof hdr > end) throw std::invalid_argument("stored sampler: truncated blob");
+      std::memcpy(hdr, r, sizeof hdr); r += sizeof hdr;
+      if (hdr[0] < 1 || hdr[0] > S4B_NODE_CAP || r + sizeof(DNode) * (size_t) hdr[0] > end) throw std::invalid_argument("stored sampler: corrupt tree record");
+      DTree& d = trees[(size_t) s * (size_t) T_ + (size_t) t];
+      d.num_nodes = hdr[0];
+      std::memcpy(d.nodes, r, sizeof(DNode) * (size_t) hdr[0]); r += sizeof(DNode) * (size_t) hdr[0];
+    }
+  }
+  S4B_CUDA(cudaMalloc(&d_store_, sizeof(DTree) * trees.size()));
+  S4B_CUDA(cudaMemcpy(d_store_, trees.data(), sizeof(DTree) * trees.size(), cudaMemcpyHostToDevice));
+  S4B_CUDA(cudaMalloc(&d_scale_, sizeof(double) * scales.size()));
+  S4B_CUDA(cudaMemcpy(d_scale_, scales.data(), sizeof(double) * scales.size(), cudaMemcpyHostToDevice));
+  BartParams P; std::memset(&P, 0, sizeof P);
+  P.p = p_; P.num_trees = T_; P.n_cuts = n_cuts_; P.is_binary = is_binary_; P.smin = -0.5; P.smax = 0.5; P.srange = 1.0;
+  S4B_CUDA(cudaMalloc(&d_params_, sizeof(BartParams)));
+  S4B_CUDA(cudaMemcpy(d_params_, &P, sizeof P, cudaMemcpyHostToDevice));
+}
+
+StoredBart::~StoredBart() { cudaFree(d_store_); cudaFree(d_scale_); cudaFree(d_params_); }
+
+void StoredBart::predict(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out)
+{
+  if (first < 0 || count < 0 || first + count > count_) throw std::invalid_argument("stored sample range out of bounds");
+  if (rows <= 0 || count == 0) return;
+  const long long rows_pad = (rows + 15) / 16 * 16;
+  std::vector<uint8_t> xtt((size_t) p_ * (size_t) rows_pad, 0);
+  for (int j = 0; j < p_; ++j) {
+    const double* c = cuts_.data() + (size_t) j * n_cuts_;
+    const double* col = x_test + (size_t) j * rows;
+    uint8_t* dst = xtt.data() + (size_t) j * rows_pad;
+    for (long long i = 0; i < rows; ++i) dst[i] = (uint8_t) (std::lower_bound(c, c + n_cuts_, col[i]) - c);
+  }
+  uint8_t* d_x; double* d_o; double* d_off = nullptr;
+  S4B_CUDA(cudaMalloc(&d_x, xtt.size())); S4B_CUDA(cudaMalloc(&d_o, sizeof(double) * (size_t) rows));
+  S4B_CUDA(cudaMemcpyAsync(d_x, xtt.data(), xtt.size(), cudaMemcpyHostToDevice, stream_));
+  if (test_offset) { S4B_CUDA(cudaMalloc(&d_off, sizeof(double) * (size_t) rows)); S4B_CUDA(cudaMemcpyAsync(d_off, test_offset, sizeof(double) * (size_t) rows, cudaMemcpyHostToDevice, stream_)); }
+  BartDev dv; std::memset(&dv, 0, sizeof dv);
+  dv.params = d_params_;
+  const size_t smem = (sizeof(uint32_t) + sizeof(double)) * 2048 + (size_t) p_ * kBlock;
+  if (smem > 48 * 1024) S4B_CUDA(cudaFuncSetAttribute(k_test_fits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const int grid = (int) ((rows + kBlock - 1) / kBlock);
+  for (long long s = 0; s < count; ++s) {
+    k_test_fits<<<grid, kBlock, smem, stream_>>>(dv, d_x, rows, rows_pad, d_off, d_o, is_binary_ ? 0 : 1, p_, d_store_ + (size_t) (first + s) * (size_t) T_,
+                                                 d_scale_ + 2 * (size_t) (first + s));
+    S4B_CUDA(cudaGetLastError());
+    S4B_CUDA(cudaMemcpyAsync(out + (size_t) s * (size_t) rows, d_o, sizeof(double) * (size_t) rows, cudaMemcpyDeviceToHost, stream_));
+  }
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  cudaFree(d_x); cudaFree(d_o); cudaFree(d_off);
+}
+
 void BartFit::get_profile(unsigned long long* out8, bool reset)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));

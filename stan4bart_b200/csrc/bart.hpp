@@ -52,6 +52,9 @@ class BartFit {
   void predict_stored(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out);
   long long num_stored_nodes(long long sample);
   void get_stored_trees(long long sample, int32_t* tree_no, long long* n_obs, int32_t* var, double* value);
+  // exportBARTState (init.cpp:409-446): the stored draws, the cut points and what prediction needs, as one host blob
+  long long stored_export_size();
+  void stored_export(void* out, long long bytes);
   BartParams params();
   void varcount_device(unsigned int* d_out);
 
@@ -152,6 +155,25 @@ class BartFit {
   cudaEvent_t ev_start_ = nullptr, ev_end_ = nullptr;
   bool ev_pending_ = false;
   double sweep_ms_ = 0.0;
+};
+
+// createStoredBARTSampler (init.cpp:409-446): prediction from exported draws without the training data or a live sampler
+class StoredBart {
+ public:
+  StoredBart(const void* blob, long long bytes, cudaStream_t stream);
+  ~StoredBart();
+  StoredBart(const StoredBart&) = delete;
+  StoredBart& operator=(const StoredBart&) = delete;
+  long long count() const { return count_; }
+  int p() const { return p_; }
+  void predict(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out);
+
+ private:
+  cudaStream_t stream_;
+  int p_ = 0, T_ = 0, n_cuts_ = 0, is_binary_ = 0;
+  long long count_ = 0;
+  std::vector<double> cuts_;
+  DTree* d_store_ = nullptr; double* d_scale_ = nullptr; BartParams* d_params_ = nullptr;
 };
 
 }  // namespace s4b

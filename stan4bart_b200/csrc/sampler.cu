@@ -250,6 +250,7 @@ using namespace s4b;
 struct gpubart_fit { std::unique_ptr<BartFit> owned; BartFit* fit; };
 struct glmm_model { std::unique_ptr<GlmmModel> owned; GlmmModel* m; };
 struct s4b_shard { std::unique_ptr<ShardContext> ctx; };
+struct gpubart_stored { std::unique_ptr<StoredBart> st; };
 struct s4b_sampler { std::unique_ptr<GibbsSampler> s; gpubart_fit bart_view; glmm_model glmm_view; };
 
 static thread_local std::string g_last_error;
@@ -418,6 +419,22 @@ int gpubart_predict_stored(gpubart_fit* f, const double* x_test, int64_t n, cons
 int gpubart_num_stored_nodes(gpubart_fit* f, int64_t sample, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); *out = f->fit->num_stored_nodes(sample); S4B_API_END }
 int gpubart_get_stored_trees(gpubart_fit* f, int64_t sample, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value)
 { S4B_API_BEGIN S4B_REQUIRE(f && tree_no && n_obs && var && value); f->fit->get_stored_trees(sample, tree_no, (long long*) n_obs, var, value); S4B_API_END }
+int gpubart_stored_export_size(gpubart_fit* f, int64_t* bytes) { S4B_API_BEGIN S4B_REQUIRE(f && bytes); *bytes = f->fit->stored_export_size(); S4B_API_END }
+int gpubart_stored_export(gpubart_fit* f, void* out, int64_t bytes) { S4B_API_BEGIN S4B_REQUIRE(f && out); f->fit->stored_export(out, bytes); S4B_API_END }
+int gpubart_stored_import(const void* blob, int64_t bytes, gpubart_stored** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(blob && out);
+  if (s4b_device_count() < 1) throw std::runtime_error("no CUDA device: stan4bart_b200 has no CPU fallback");
+  auto* h = new gpubart_stored;
+  h->st.reset(new StoredBart(blob, bytes, current_stream()));
+  *out = h;
+  S4B_API_END
+}
+int gpubart_stored_free(gpubart_stored* st) { S4B_API_BEGIN delete st; S4B_API_END }
+int gpubart_stored_count(gpubart_stored* st, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(st && out); *out = st->st->count(); S4B_API_END }
+int gpubart_stored_predict(gpubart_stored* st, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out)
+{ S4B_API_BEGIN S4B_REQUIRE(st && x_test && out && n >= 0); st->st->predict(x_test, n, test_offset, first, count, out); S4B_API_END }
 int gpubart_set_profile(gpubart_fit* f, int on) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_profile(on != 0); S4B_API_END }
 int gpubart_tree_step_ms(gpubart_fit* f, int reset, double* ms) { S4B_API_BEGIN S4B_REQUIRE(f && ms); *ms = f->fit->tree_step_ms(reset != 0); S4B_API_END }
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* ng, int64_t* ns)

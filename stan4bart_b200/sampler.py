@@ -122,6 +122,14 @@ class GpuBart:
                                                    var.ctypes.data_as(c_int32_p), dptr(value)))
         return dict(tree=tree_no, n=n_obs, var=var, value=value)
 
+    def export_stored(self):
+        """stan4bart_exportBARTState: the stored draws (and the cut points) as bytes."""
+        k = C.c_int64(0)
+        _lib.check(self.L.gpubart_stored_export_size(self.h, C.byref(k)))
+        buf = (C.c_ubyte * k.value)()
+        _lib.check(self.L.gpubart_stored_export(self.h, buf, k.value))
+        return bytes(buf)
+
     # ---- parity instrumentation ----
     def node_assignment(self, tree):
         out = np.zeros(self.n, dtype=np.int64)
@@ -216,6 +224,36 @@ class GpuBart:
         k = C.c_int64(0)
         _lib.check(self.L.gpubart_num_tree_steps(self.h, C.byref(k)))
         return int(k.value)
+
+
+class StoredBart:
+    """stan4bart_createStoredBARTSampler: prediction from exported draws, no training data or live sampler needed."""
+
+    def __init__(self, blob):
+        self.L = _lib.load()
+        _lib.require_device()
+        self._blob = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        h = C.c_void_p()
+        _lib.check(self.L.gpubart_stored_import(self._blob, len(blob), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.gpubart_stored_free(self.h)
+            self.h = None
+
+    def count(self):
+        k = C.c_int64(0)
+        _lib.check(self.L.gpubart_stored_count(self.h, C.byref(k)))
+        return int(k.value)
+
+    def predict(self, x_test, first=0, count=None, offset=None):
+        xt = np.asfortranarray(x_test, dtype=np.float64)
+        count = self.count() - first if count is None else count
+        out = np.zeros((count, xt.shape[0]))
+        o = f64(offset) if offset is not None else None
+        _lib.check(self.L.gpubart_stored_predict(self.h, dptr(xt), xt.shape[0], dptr(o), int(first), int(count), dptr(out)))
+        return out.T
 
 
 class GlmmModel:

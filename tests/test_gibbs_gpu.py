@@ -241,6 +241,15 @@ def test_keep_trees_stored_draws_predict_their_own_training_fits(binary):
     assert not np.array_equal(b.stored_trees(0)["value"], last["value"])
     with pytest.raises(S4BError):
         g.run(1, False)                             # a seventh draw does not fit the store
+    # exportBARTState / createStoredBARTSampler: the blob predicts on its own, also after the live sampler is gone
+    from stan4bart_b200.sampler import StoredBart
+    blob = b.export_stored()
+    st = StoredBart(blob)
+    assert st.count() == 6
+    assert np.array_equal(st.predict(xnew), b.predict_stored(xnew))
+    assert np.array_equal(st.predict(pr["x_bart"], first=2, count=3), pred[:, 2:5])
+    with pytest.raises(S4BError):
+        StoredBart(blob[:100])
     b.set_keep_trees(0)
     g.run(1, False)
     assert b.num_stored() == 0
