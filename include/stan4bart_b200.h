@@ -124,6 +124,10 @@ int gpubart_stored_import(const void* blob, int64_t bytes, gpubart_stored** out)
 int gpubart_stored_free(gpubart_stored* st);
 int gpubart_stored_count(gpubart_stored* st, int64_t* out);
 int gpubart_stored_predict(gpubart_stored* st, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out);
+/* printInitialSummary (dbarts table entry called by stan4bart_printInitialSummary, init.cpp:981): the text of the summary,
+ * including the "power and base for tree prior:" and "tree split probabilities:" lines that tests/testthat/test-09-bartArgs.R
+ * parses.  *needed = bytes including the terminator; out may be NULL to query. */
+int gpubart_summary(gpubart_fit* fit, char* out, size_t cap, size_t* needed);
 int gpubart_num_nodes(gpubart_fit* fit, int64_t* out);
 int gpubart_get_trees(gpubart_fit* fit, int32_t* tree_no, int64_t* n_obs, int32_t* var, double* value);
 /* parity instrumentation (no reference counterpart) */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "gpubart_stored_free": (C.c_int, [vp]),
     "gpubart_stored_count": (C.c_int, [vp, c_int64_p]),
     "gpubart_stored_predict": (C.c_int, [vp, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int64, c_double_p]),
+    "gpubart_summary": (C.c_int, [vp, C.c_char_p, C.c_size_t, c_size_p]),
     "gpubart_set_keep_trees": (C.c_int, [vp, C.c_int64]),
     "gpubart_num_stored": (C.c_int, [vp, c_int64_p]),
     "gpubart_predict_stored": (C.c_int, [vp, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int64, c_double_p]),

@@ -760,6 +760,8 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
     S4B_CUDA(cudaMalloc(&d_split_w_, sizeof(uint32_t) * (size_t) p_));
     S4B_CUDA(cudaMemcpy(d_split_w_, w.data(), sizeof(uint32_t) * (size_t) p_, cudaMemcpyHostToDevice));
     P.split_w = d_split_w_; P.split_total = total; P.p_pos = pos;
+    split_probs_.resize((size_t) p_);
+    for (int j = 0; j < p_; ++j) split_probs_[(size_t) j] = cfg.split_probs[j] / sum;
   }
   cfg_.split_probs = nullptr;        // the caller's array is not kept
   S4B_CUDA(cudaMalloc(&d_params_, sizeof(BartParams)));
@@ -1408,6 +1410,29 @@ std::vector<DTree> BartFit::download_trees()
   std::vector<DTree> trees((size_t) T_);
   S4B_CUDA(cudaMemcpy(trees.data(), d_trees_, sizeof(DTree) * trees.size(), cudaMemcpyDeviceToHost));
   return trees;
+}
+
+std::string BartFit::summary() const
+{
+  char line[256];
+  std::string out = "Running BART with ";
+  out += cfg_.is_binary ? "binary" : "numeric"; out += " y\n\n";
+  snprintf(line, sizeof line, "number of trees: %d\nnumber of training observations: %lld\nnumber of test observations: %lld\nnumber of explanatory variables: %d\n",
+           T_, n_, nt_, p_);
+  out += line;
+  snprintf(line, sizeof line, "Prior:\n\tk prior fixed to %g\n\tpower and base for tree prior: %g %g\n", cfg_.k, cfg_.power, cfg_.base);
+  out += line;
+  out += "\ttree split probabilities: ";
+  for (int j = 0; j < p_; ++j) {
+    snprintf(line, sizeof line, "%g%s", split_probs_.empty() ? 1.0 / (double) p_ : split_probs_[(size_t) j], j + 1 < p_ ? ", " : "\n");
+    out += line;
+  }
+  snprintf(line, sizeof line, "\tuse quantiles for rule cut points: false\n\tproposal probabilities: birth/death %.2f, swap %.2f, change %.2f; birth %.2f\n",
+           cfg_.birth_death_prob, cfg_.swap_prob, cfg_.change_prob, cfg_.birth_prob);
+  out += line;
+  snprintf(line, sizeof line, "Cutoff rules c in x<=c vs x>c\nnumber of cuts: %d per predictor (uniform over the training range)\n", cfg_.n_cuts);
+  out += line;
+  return out;
 }
 
 long long BartFit::num_nodes()

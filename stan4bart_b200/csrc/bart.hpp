@@ -5,6 +5,7 @@
 #include "s4b_common.cuh"
 #include "shard.hpp"
 
+#include <string>
 #include <vector>
 
 namespace s4b {
@@ -44,6 +45,8 @@ class BartFit {
   void predict(const double* x_test, long long rows, const double* test_offset, double* out);
   void get_trees(int32_t* tree_no, long long* n_obs, int32_t* var, double* value);
   long long num_nodes();
+  // printInitialSummary (the dbarts table entry stan4bart calls at init.cpp:981): the lines the reference's tests parse
+  std::string summary() const;
   // keepTrees (dbarts control$keepTrees; stan4bart_exportBARTState / createStoredBARTSampler / predictBART, init.cpp:354-446):
   // with a store of `capacity` samples every runSamplerWithResults call appends the trees and the response scale of its
   // kept draw; stored draws can be predicted from and flattened like the live sampler
@@ -129,6 +132,7 @@ class BartFit {
   int persistent_nq_ = 0, persistent_grid_ = 0;       // nq = kStreamNq: residuals streamed from global memory (L2)
   uint2* d_packs_ = nullptr;
   uint32_t* d_split_w_ = nullptr;
+  std::vector<double> split_probs_;       // normalised bart_args split.probs (empty = uniform)
   DTree* d_store_ = nullptr; double* d_store_scale_ = nullptr; long long store_cap_ = 0, store_len_ = 0;
   size_t persistent_smem_ = 0;
   unsigned int* d_barrier_ = nullptr;

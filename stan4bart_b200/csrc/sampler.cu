@@ -435,6 +435,15 @@ int gpubart_stored_free(gpubart_stored* st) { S4B_API_BEGIN delete st; S4B_API_E
 int gpubart_stored_count(gpubart_stored* st, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(st && out); *out = st->st->count(); S4B_API_END }
 int gpubart_stored_predict(gpubart_stored* st, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out)
 { S4B_API_BEGIN S4B_REQUIRE(st && x_test && out && n >= 0); st->st->predict(x_test, n, test_offset, first, count, out); S4B_API_END }
+int gpubart_summary(gpubart_fit* f, char* out, size_t cap, size_t* needed)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(f && needed);
+  const std::string sm = f->fit->summary();
+  *needed = sm.size() + 1;
+  if (out != nullptr && cap > 0) { const size_t k = std::min(cap - 1, sm.size()); std::memcpy(out, sm.data(), k); out[k] = 0; }
+  S4B_API_END
+}
 int gpubart_set_profile(gpubart_fit* f, int on) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_profile(on != 0); S4B_API_END }
 int gpubart_tree_step_ms(gpubart_fit* f, int reset, double* ms) { S4B_API_BEGIN S4B_REQUIRE(f && ms); *ms = f->fit->tree_step_ms(reset != 0); S4B_API_END }
 int s4b_sampler_last_run_stats(s4b_sampler* s, double* ms_stan, double* ms_bart, int64_t* ng, int64_t* ns)

@@ -122,6 +122,14 @@ class GpuBart:
                                                    var.ctypes.data_as(c_int32_p), dptr(value)))
         return dict(tree=tree_no, n=n_obs, var=var, value=value)
 
+    def summary(self):
+        """printInitialSummary: the text dbarts prints for a fit (prior, tree prior parameters, split probabilities)."""
+        need = C.c_size_t(0)
+        _lib.check(self.L.gpubart_summary(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _lib.check(self.L.gpubart_summary(self.h, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
     def export_stored(self):
         """stan4bart_exportBARTState: the stored draws (and the cut points) as bytes."""
         k = C.c_int64(0)

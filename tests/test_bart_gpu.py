@@ -360,3 +360,22 @@ def test_split_probs_weighted_variable_selection():
     assert used[3] == 0 and used.sum() > 0
     kinds = o.trace()[:, 0]
     assert np.any(kinds == 2) and np.any(kinds == 0)          # change and birth steps drew weighted variables
+
+
+def test_bart_args_plumb_through_like_test_09():
+    """tests/testthat/test-09-bartArgs.R:20-39: bart_args n.trees = 2, power = 2.5, base = 0.9, split.probs = c(X3 = 2, .default = 1)
+    must reach the tree sampler; the reference checks it by parsing the initial summary."""
+    import re
+    x, y, xt = bart_problem(200, 5, 0, False)
+    cfg = bart_config(200, 5, num_trees=2, power=2.5, base=0.9, split_probs=[1, 1, 2, 1, 1], seed=1)
+    g = GpuBart(cfg, y, x, xt)
+    out = g.summary().splitlines()
+    pb = [ln for ln in out if "\tpower and base for tree prior:" in ln]
+    assert len(pb) == 1
+    power, base = (float(v) for v in re.sub(r"^[^0-9]+([0-9.]+ [0-9.]+)$", r"\1", pb[0]).split(" "))
+    assert (power, base) == (2.5, 0.9)
+    sp = [ln for ln in out if "\ttree split probabilities:" in ln]
+    assert len(sp) == 1
+    probs = [float(v) for v in re.sub(r"^[^0-9]+((?:[0-9.]+, )*[0-9.]+)$", r"\1", sp[0]).split(", ")]
+    assert np.allclose(probs, [1 / 6, 1 / 6, 2 / 6, 1 / 6, 1 / 6], atol=1e-5)
+    assert "number of trees: 2" in "\n".join(out)
