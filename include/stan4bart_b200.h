@@ -34,7 +34,7 @@ typedef struct s4b_bart_config {
   int32_t thin;            /* n.thin = skip.bart */
   int32_t min_obs;         /* minNumObservationsInNode (5) */
   int32_t is_binary;
-  int32_t reserved;
+  int32_t max_ctas;        /* 0 = the whole GPU; > 0 confines this chain's sweep kernel to that many SMs (several chains per GPU) */
   double birth_death_prob, swap_prob, change_prob, birth_prob;   /* .5 .1 .4 .5 */
   double base, power;      /* cgm tree prior */
   double k;                /* normal(k) leaf prior */

@@ -822,6 +822,12 @@ void BartFit::setup_persistent()
   int max_smem = 0; S4B_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if (coop) {
     const long long nquad = (n_ + 3) / 4;
+    // several chains per GPU (config D): every chain can be confined to a share of the SMs (s4b_bart_config::max_ctas, or
+    // S4B_MAX_CTAS), so that the sweep kernels of different chains, launched from their own host threads and streams, are
+    // resident side by side and hide each other's barrier / decision latency
+    long long cta_cap = num_sms_;
+    if (cfg_.max_ctas > 0) cta_cap = std::min<long long>(cta_cap, cfg_.max_ctas);
+    if (getenv("S4B_MAX_CTAS") && atoi(getenv("S4B_MAX_CTAS")) > 0) cta_cap = std::min<long long>(cta_cap, atoi(getenv("S4B_MAX_CTAS")));
     auto try_nq = [&](int nq, size_t smem, const void* fn, const void* fn_seq, const void* fn_nosq) -> bool {
       if (smem > (size_t) max_smem || p_ > 511) return false;      // traversal records carry 9 bits of variable index
       for (const void* f : { fn, fn_seq, fn_nosq }) {
@@ -830,7 +836,7 @@ void BartFit::setup_persistent()
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, kSweepBlock, smem) != cudaSuccess) { cudaGetLastError(); return false; }
         if (per_sm < 1) return false;
       }
-      long long grid = num_sms_;                       // one CTA per SM
+      long long grid = cta_cap;                        // one CTA per SM (or the share of the SMs this chain was given)
       long long need = (nquad + (long long) nq * kWorkers - 1) / ((long long) nq * kWorkers);
       if (need > grid) return false;
       persistent_nq_ = nq; persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(grid, (nquad + kWorkers - 1) / kWorkers)); persistent_smem_ = smem;
@@ -847,7 +853,7 @@ void BartFit::setup_persistent()
     const bool force_stream = getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0;
     if (persistent_nq_ == 0 || force_stream) {
       const size_t smem = sweep_smem_bytes<1>(0);
-      const long long rounds = (nquad / num_sms_ + 1 + kWorkers - 1) / kWorkers;
+      const long long rounds = (nquad / cta_cap + 1 + kWorkers - 1) / kWorkers;
       bool ok = smem <= (size_t) max_smem && p_ <= 511 && rounds <= 63;      // 8-bit count fields: at most 63 rounds of 4 observations
       for (const void* f : { (const void*) k_sweep<1, false, true>, (const void*) k_sweep<1, true, true>, (const void*) k_sweep<1, false, true, false> }) {
         if (!ok) break;
@@ -857,7 +863,7 @@ void BartFit::setup_persistent()
       }
       if (ok) {
         persistent_nq_ = kStreamNq; persistent_smem_ = smem;
-        persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(num_sms_, (nquad + kWorkers - 1) / kWorkers));
+        persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(cta_cap, (nquad + kWorkers - 1) / kWorkers));
         S4B_CUDA(cudaMalloc(&d_packs_, sizeof(uint2) * 2 * (size_t) nquad));
         S4B_CUDA(cudaMemset(d_packs_, 0, sizeof(uint2) * 2 * (size_t) nquad));
       }

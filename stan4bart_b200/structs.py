@@ -22,7 +22,7 @@ class BartConfig(C.Structure):
     _fields_ = [
         ("n", C.c_int64), ("p", C.c_int64), ("n_test", C.c_int64),
         ("num_trees", C.c_int32), ("n_cuts", C.c_int32), ("thin", C.c_int32), ("min_obs", C.c_int32),
-        ("is_binary", C.c_int32), ("reserved", C.c_int32),
+        ("is_binary", C.c_int32), ("max_ctas", C.c_int32),
         ("birth_death_prob", C.c_double), ("swap_prob", C.c_double), ("change_prob", C.c_double),
         ("birth_prob", C.c_double), ("base", C.c_double), ("power", C.c_double), ("k", C.c_double),
         ("node_scale", C.c_double), ("seed", C.c_uint64), ("split_probs", C.POINTER(C.c_double)),
@@ -77,13 +77,13 @@ def i32(a):
 
 def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_binary=False,
                 base=0.95, power=2.0, k=2.0, node_scale=None, seed=0,
-                birth_death_prob=0.5, swap_prob=0.1, change_prob=0.4, birth_prob=0.5, split_probs=None):
+                birth_death_prob=0.5, swap_prob=0.1, change_prob=0.4, birth_prob=0.5, split_probs=None, max_ctas=0):
     """dbarts defaults as used by stan4bart (R/stan4bart_fit.R:437-479).  split_probs: relative probabilities of the p
     predictors (bart_args split.probs), None = uniform."""
     if node_scale is None:
         node_scale = 3.0 if is_binary else 0.5
     cfg = BartConfig(n=n, p=p, n_test=n_test, num_trees=num_trees, n_cuts=n_cuts, thin=thin, min_obs=min_obs,
-                     is_binary=int(is_binary), reserved=0, birth_death_prob=birth_death_prob, swap_prob=swap_prob,
+                     is_binary=int(is_binary), max_ctas=int(max_ctas), birth_death_prob=birth_death_prob, swap_prob=swap_prob,
                      change_prob=change_prob, birth_prob=birth_prob, base=base, power=power, k=k,
                      node_scale=node_scale, seed=seed)
     if split_probs is not None:

@@ -379,3 +379,26 @@ def test_bart_args_plumb_through_like_test_09():
     probs = [float(v) for v in re.sub(r"^[^0-9]+((?:[0-9.]+, )*[0-9.]+)$", r"\1", sp[0]).split(", ")]
     assert np.allclose(probs, [1 / 6, 1 / 6, 2 / 6, 1 / 6, 1 / 6], atol=1e-5)
     assert "number of trees: 2" in "\n".join(out)
+
+
+def test_chain_confined_to_a_share_of_the_sms(monkeypatch):
+    """Several chains per GPU (config D): max_ctas confines a chain's sweep kernel to a few SMs (register or streamed variant,
+    whichever holds the rows); the draws do not depend on the grid size beyond the order of the final sums."""
+    T, sweeps = 10, 8
+    n = 60000
+    x, y, xt = bart_problem(n, 5, 0, False, seed=2)
+    o = O.OracleBart(bart_config(n, 5, num_trees=T, seed=6), y, x, xt)
+    fits = [o]
+    for cap in (0, 7, 2):
+        fits.append(GpuBart(bart_config(n, 5, num_trees=T, seed=6, max_ctas=cap), y, x, xt))
+    for b in fits:
+        b.set_sigma(1.1)
+        b.sample_trees_from_prior()
+        b.set_trace(T * sweeps)
+    for s in range(sweeps):
+        rs = [b.run() for b in fits]
+        for r in rs[1:]:
+            assert rel_err(rs[0]["train"], r["train"], scale=np.abs(rs[0]["train"]) + 1.0) <= 1e-9, f"sweep {s}"
+    for b in fits[1:]:
+        compare_traces(o.trace(), b.trace(), tol=1e-9)
+        assert b.sweep_mode() == 2

@@ -1,6 +1,8 @@
 """Several chains per GPU (BASELINE config D: IHDP-shaped, n = 500 000, 25 covariates, 8 chains per GPU): every chain has its
 own host thread and stream, so one chain's host-side NUTS overlaps another chain's sweep kernel on the device.
-usage: python tools/multi_chain_bench.py [n] [chains] [sweeps] [trees]"""
+With max_ctas > 0 every chain's sweep kernel is confined to that many SMs, so that the kernels of different chains are
+resident side by side (8 chains x 18 SMs on a 148-SM B200) and hide each other's barrier and decision latency.
+usage: python tools/multi_chain_bench.py [n] [chains] [sweeps] [trees] [max_ctas]"""
 import json
 import os
 import sys
@@ -16,6 +18,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 500000
 chains = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 trees = int(sys.argv[4]) if len(sys.argv) > 4 else 200
+max_ctas = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 adapt = 160
 pr = ihdp_problem(n)
 kw = dict(warmup=adapt, iter_=adapt + 3 * sweeps, keep_fits=False, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
@@ -25,7 +28,7 @@ times = {}
 
 
 def work(c):
-    cfg = bart_config(n, 25, n_test=n, num_trees=trees, is_binary=False, seed=100 + c)
+    cfg = bart_config(n, 25, n_test=n, num_trees=trees, is_binary=False, seed=100 + c, max_ctas=max_ctas)
     s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=200 + c), **kw)
     s.run(adapt, True, results=False)
     s.disengage_adaptation()
@@ -52,7 +55,7 @@ barrier.wait()
 t_par = time.time() - t0
 for t in th:
     t.join()
-print(json.dumps({"workload": "config D shape: IHDP-like continuous, n=%d, p=25, %d trees, %d chains on one GPU" % (n, trees, chains),
+print(json.dumps({"workload": "config D shape: IHDP-like continuous, n=%d, p=25, %d trees, %d chains on one GPU, %s SMs per chain" % (n, trees, chains, max_ctas or "all"),
                   "sweeps_per_s_sequential": chains * sweeps / t_seq, "sweeps_per_s_threaded": chains * sweeps / t_par,
                   "ms_stan_block": stats["ms_stan"] / sweeps, "ms_bart_block": stats["ms_bart"] / sweeps,
                   "bart_sweep_mode": samplers[0].bart().sweep_mode()}))
