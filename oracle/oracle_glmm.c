@@ -2,7 +2,8 @@
  * oracle/oracle_glmm.c -- TEST INFRASTRUCTURE (CPU oracle), not product code.
  *
  * CPU restatement of the stan4bart GLMM density and its gradient on the default
- * path (prior_dist in {0,1}, no intercept, no weights, ranef blocks with p <= 2):
+ * path (prior_dist in {0,1}, no intercept, no weights; ranef blocks of any size, the ones with more than two
+ * coefficients through the scaled onion rows of make_theta_L):
  *   maths          /root/reference/src/stan_files/continuous.stan:1-429
  *   op order       /root/reference/src/stan_files/continuous.hpp:2168-2638 (log_prob_impl,
  *                  lpdfs hard-coded <false> = all constants kept)
@@ -13,10 +14,13 @@
  *   write_array    continuous.hpp:2640-2938 (order: params, then aux, beta, b, theta_L)
  *   set_offset / set_response / get_aux / get_parametric_mean  continuous.hpp:3626-3768
  * The reference differentiates by reverse-mode AD (model/gradient.hpp:21-35); here the
- * gradient is hand-derived.  Pinned by tests/golden/glmm_*.json (torch fp64 autograd).
+ * gradient is hand-derived; for blocks with more than two coefficients the Jacobian of the block factor T with
+ * respect to its parameters is taken by the complex-step method (exact to rounding: no subtraction), everything
+ * around it stays analytic.  Pinned by tests/golden/glmm_*.json (torch fp64 autograd).
  */
 #include "s4b_oracle.h"
 
+#include <complex.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,8 +30,9 @@ struct or_glmm {
   double *X, *y, *offset;
   double *prior_scale, *prior_mean, *shape, *scale, *concentration, *regularization, *w, *delta;
   int32_t *p, *l, *v, *u;
-  int len_rho, num_params, has_aux;
+  int len_rho, len_z_T, num_params, has_aux;
 };
+#define OR_MAX_NC 16
 
 #define HALF_LOG_2PI 0.91893853320467274178
 
@@ -35,7 +40,7 @@ static void* dup_mem(const void* src, size_t bytes) { void* r = malloc(bytes ? b
 
 or_glmm* or_glmm_create(const s4b_glmm_data* d)
 {
-  for (int i = 0; i < d->t; ++i) if (d->p[i] > 2) return NULL;            /* z_T onion: SURVEY 8f rank 4 */
+  for (int i = 0; i < d->t; ++i) if (d->p[i] < 1 || d->p[i] > OR_MAX_NC) return NULL;
   if (d->prior_dist < 0 || d->prior_dist > 1) return NULL;
   or_glmm* m = (or_glmm*) calloc(1, sizeof(or_glmm));
   m->d = *d;
@@ -62,8 +67,10 @@ or_glmm* or_glmm_create(const s4b_glmm_data* d)
     sum_p += d->p[i];
   }
   m->len_rho = sum_p - d->t;
+  m->len_z_T = 0;
+  for (int i = 0; i < d->t; ++i) if (d->p[i] > 2) m->len_z_T += (d->p[i] - 2) * (d->p[i] - 1);      /* continuous.stan:258 */
   m->has_aux = d->is_binary ? 0 : 1;
-  m->num_params = d->K + d->q + m->len_rho + d->len_concentration + d->t + m->has_aux;
+  m->num_params = d->K + d->q + m->len_z_T + m->len_rho + d->len_concentration + d->t + m->has_aux;
   return m;
 }
 
@@ -100,7 +107,7 @@ void or_glmm_data_terms(const or_glmm* m, const double* beta, const double* b, d
 
 /* constrained and transformed quantities for a given unconstrained q */
 typedef struct {
-  const double *z_beta, *z_b, *rho_u, *zeta_u, *tau_u;
+  const double *z_beta, *z_b, *z_T, *rho_u, *zeta_u, *tau_u;
   double aux_u;
   double *rho, *zeta, *tau, *beta, *b, *theta_L;
   double aux_unscaled, aux, disp;
@@ -117,6 +124,32 @@ static void params_alloc(const or_glmm* m, Params* P)
 }
 static void params_free(Params* P) { free(P->rho); free(P->zeta); free(P->tau); free(P->beta); free(P->b); free(P->theta_L); }
 
+/* lower-triangular factor T (row major, nc x nc) of one ranef block with nc >= 2 coefficients: continuous.stan:20-50.
+ * The off-diagonal entries of row r + 1 are scaled with the standard deviation of row r, exactly as the Stan program
+ * does.  Complex arguments: the imaginary part carries the complex-step derivative. */
+static void block_T(int nc, double complex c, const double complex* zeta, const double complex* rho, const double complex* zT, double complex* T)
+{
+  double complex trace = c * c * (double) nc, zs = 0.0;
+  for (int k = 0; k < nc; ++k) zs += zeta[k];
+  for (int k = 0; k < nc * nc; ++k) T[k] = 0.0;
+  double complex sd = csqrt(zeta[0] / zs * trace);
+  T[0] = sd;
+  sd = csqrt(zeta[1] / zs * trace);
+  double complex r21 = 2.0 * rho[0] - 1.0;
+  T[nc + 1] = sd * csqrt(1.0 - r21 * r21);
+  T[nc] = sd * r21;
+  int zmark = 0;
+  for (int r = 2; r < nc; ++r) {
+    double complex dot = 0.0;
+    for (int k = 0; k < r; ++k) dot += zT[zmark + k] * zT[zmark + k];
+    double complex sf = csqrt(rho[r - 1] / dot) * sd;
+    sd = csqrt(zeta[r] / zs * trace);
+    for (int k = 0; k < r; ++k) T[r * nc + k] = zT[zmark + k] * sf;
+    T[r * nc + r] = csqrt(1.0 - rho[r - 1]) * sd;
+    zmark += r;
+  }
+}
+
 static double inv_logit(double x) { return x >= 0.0 ? 1.0 / (1.0 + exp(-x)) : exp(x) / (1.0 + exp(x)); }
 
 static void transform(const or_glmm* m, const double* q, Params* P)
@@ -125,6 +158,7 @@ static void transform(const or_glmm* m, const double* q, Params* P)
   int pos = 0;
   P->z_beta = q + pos; pos += d->K;
   P->z_b = q + pos; pos += d->q;
+  P->z_T = q + pos; pos += m->len_z_T;
   P->rho_u = q + pos; pos += m->len_rho;
   P->zeta_u = q + pos; pos += d->len_concentration;
   P->tau_u = q + pos; pos += d->t;
@@ -143,14 +177,28 @@ static void transform(const or_glmm* m, const double* q, Params* P)
   } else { P->aux_unscaled = 0.0; P->aux = 1.0; P->disp = 1.0; }
   for (int k = 0; k < d->K; ++k)
     P->beta[k] = d->prior_dist == 0 ? P->z_beta[k] : P->z_beta[k] * m->prior_scale[k] + m->prior_mean[k];
-  /* make_theta_L (continuous.stan:2-59) and make_b (:61-94), p <= 2 */
-  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0;
+  /* make_theta_L (continuous.stan:2-59) and make_b (:61-94) */
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, zT_mark = 0;
   for (int i = 0; i < d->t; ++i) {
     if (m->p[i] == 1) {
       double theta = P->tau[i] * m->scale[i] * P->disp;
       P->theta_L[th++] = theta;
       for (int s = 0; s < m->l[i]; ++s) P->b[b_mark + s] = theta * P->z_b[b_mark + s];
       b_mark += m->l[i];
+    } else if (m->p[i] > 2) {
+      const int nc = m->p[i];
+      double complex T[OR_MAX_NC * OR_MAX_NC], zc[OR_MAX_NC], rc[OR_MAX_NC], tc[OR_MAX_NC * OR_MAX_NC];
+      const int nzT = (nc - 2) * (nc + 1) / 2;          /* 2 + 3 + ... + (nc - 1) */
+      for (int k = 0; k < nc; ++k) zc[k] = P->zeta[zeta_mark + k];
+      for (int k = 0; k < nc - 1; ++k) rc[k] = P->rho[rho_mark + k];
+      for (int k = 0; k < nzT; ++k) tc[k] = P->z_T[zT_mark + k];
+      block_T(nc, P->tau[i] * m->scale[i] * P->disp, zc, rc, tc, T);
+      for (int c2 = 0; c2 < nc; ++c2) for (int r = c2; r < nc; ++r) P->theta_L[th++] = creal(T[r * nc + c2]);     /* vech */
+      for (int j = 0; j < m->l[i]; ++j) {
+        for (int r = 0; r < nc; ++r) { double acc = 0.0; for (int k = 0; k <= r; ++k) acc += creal(T[r * nc + k]) * P->z_b[b_mark + k]; P->b[b_mark + r] = acc; }
+        b_mark += nc;
+      }
+      zeta_mark += nc; rho_mark += nc - 1; zT_mark += nzT;
     } else {
       double c = P->tau[i] * m->scale[i] * P->disp;
       double trace = c * c * 2.0;
@@ -202,12 +250,20 @@ int or_glmm_log_prob_grad(const or_glmm* m, const double* q, double* lp_out, dou
   if (d->prior_dist == 1) { for (int k = 0; k < K; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= K * HALF_LOG_2PI; }
   for (int k = 0; k < nq; ++k) lp += -0.5 * P.z_b[k] * P.z_b[k];
   lp -= nq * HALF_LOG_2PI;
+  for (int k = 0; k < m->len_z_T; ++k) lp += -0.5 * P.z_T[k] * P.z_T[k];
+  lp -= m->len_z_T * HALF_LOG_2PI;
   {
     int pos_reg = 0, pos_rho = 0;
     for (int i = 0; i < t; ++i) if (m->p[i] > 1) {
       double nu = m->regularization[pos_reg++] + 0.5 * (m->p[i] - 2);
       double r = P.rho[pos_rho++];
       lp += (nu - 1.0) * log(r) + (nu - 1.0) * log1p(-r) + lgamma(2.0 * nu) - 2.0 * lgamma(nu);
+      for (int j = 2; j < m->p[i]; ++j) {            /* continuous.stan:111-115: shape1 = j / 2, shape2 = nu - (j - 1) / 2 */
+        nu -= 0.5;
+        double s1 = 0.5 * j, s2 = nu;
+        r = P.rho[pos_rho++];
+        lp += (s1 - 1.0) * log(r) + (s2 - 1.0) * log1p(-r) + lgamma(s1 + s2) - lgamma(s1) - lgamma(s2);
+      }
     }
   }
   for (int i = 0; i < d->len_concentration; ++i) lp += (m->delta[i] - 1.0) * log(P.zeta[i]) - P.zeta[i] - lgamma(m->delta[i]);
@@ -217,6 +273,7 @@ int or_glmm_log_prob_grad(const or_glmm* m, const double* q, double* lp_out, dou
   int pos = 0;
   double* g_zbeta = grad + pos; pos += K;
   double* g_zb = grad + pos; pos += nq;
+  double* g_zT = grad + pos; pos += m->len_z_T;
   double* g_rho = grad + pos; pos += m->len_rho;
   double* g_zeta = grad + pos; pos += d->len_concentration;
   double* g_tau = grad + pos; pos += t;
@@ -226,9 +283,69 @@ int or_glmm_log_prob_grad(const or_glmm* m, const double* q, double* lp_out, dou
     g_zbeta[k] = d->prior_dist == 0 ? dbeta : dbeta * m->prior_scale[k] - P.z_beta[k];
   }
   double d_disp = 0.0;
-  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, pos_reg = 0;
+  /* the Stan program declares (p - 2)(p - 1) elements of z_T per block but its onion rows consume 2 + ... + (p - 1) of them
+   * through one running mark (continuous.stan:9, :41-44, :258): the surplus elements only see their normal prior */
+  for (int k = 0; k < m->len_z_T; ++k) g_zT[k] = -P.z_T[k];
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, pos_reg = 0, zT_mark = 0;
   for (int i = 0; i < t; ++i) {
-    if (m->p[i] == 1) {
+    if (m->p[i] > 2) {
+      const int nc = m->p[i];
+      const int nzT = (nc - 2) * (nc + 1) / 2;
+      double Tr[OR_MAX_NC * OR_MAX_NC], A[OR_MAX_NC * OR_MAX_NC];
+      for (int k = 0; k < nc * nc; ++k) { Tr[k] = 0.0; A[k] = 0.0; }
+      { int thk = th; for (int c2 = 0; c2 < nc; ++c2) for (int r = c2; r < nc; ++r) Tr[r * nc + c2] = P.theta_L[thk++]; th = thk; }
+      for (int j = 0; j < m->l[i]; ++j) {
+        for (int k = 0; k < nc; ++k) {              /* g_zb = T' db - z ; A[r][k] += db[r] z[k] */
+          double acc = 0.0;
+          for (int r = k; r < nc; ++r) acc += Tr[r * nc + k] * (gb[b_mark + r] * inv_s2);
+          g_zb[b_mark + k] = acc - P.z_b[b_mark + k];
+        }
+        for (int r = 0; r < nc; ++r) for (int k = 0; k <= r; ++k) A[r * nc + k] += (gb[b_mark + r] * inv_s2) * P.z_b[b_mark + k];
+        b_mark += nc;
+      }
+      /* d L / d (c, zeta, rho, z_T) = sum A .* dT/dparam, dT/dparam by complex step */
+      const double h = 1e-20;
+      double complex Tc[OR_MAX_NC * OR_MAX_NC], zc[OR_MAX_NC], rc[OR_MAX_NC], tc[OR_MAX_NC * OR_MAX_NC];
+      const double cval = P.tau[i] * m->scale[i] * P.disp;
+      const int npar = 1 + nc + (nc - 1) + nzT;
+      double dpar[1 + OR_MAX_NC + OR_MAX_NC + OR_MAX_NC * OR_MAX_NC];
+      for (int ip = 0; ip < npar; ++ip) {
+        double complex cc = cval;
+        for (int k = 0; k < nc; ++k) zc[k] = P.zeta[zeta_mark + k];
+        for (int k = 0; k < nc - 1; ++k) rc[k] = P.rho[rho_mark + k];
+        for (int k = 0; k < nzT; ++k) tc[k] = P.z_T[zT_mark + k];
+        if (ip == 0) cc += I * h;
+        else if (ip < 1 + nc) zc[ip - 1] += I * h;
+        else if (ip < 1 + nc + nc - 1) rc[ip - 1 - nc] += I * h;
+        else tc[ip - 1 - nc - (nc - 1)] += I * h;
+        block_T(nc, cc, zc, rc, tc, Tc);
+        double acc = 0.0;
+        for (int r = 0; r < nc; ++r) for (int k = 0; k <= r; ++k) acc += A[r * nc + k] * (cimag(Tc[r * nc + k]) / h);
+        dpar[ip] = acc;
+      }
+      const double d_c = dpar[0];
+      for (int k = 0; k < nc; ++k) {
+        const double zv = P.zeta[zeta_mark + k];
+        const double d_z = dpar[1 + k] + (m->delta[zeta_mark + k] - 1.0) / zv - 1.0;
+        g_zeta[zeta_mark + k] = d_z * zv + 1.0;
+      }
+      {
+        double nu = m->regularization[pos_reg++] + 0.5 * (nc - 2);
+        for (int k = 0; k < nc - 1; ++k) {
+          double s1, s2;
+          if (k == 0) { s1 = nu; s2 = nu; } else { nu -= 0.5; s1 = 0.5 * (k + 1); s2 = nu; }
+          const double rho = P.rho[rho_mark + k];
+          const double d_rho = dpar[1 + nc + k] + (s1 - 1.0) / rho - (s2 - 1.0) / (1.0 - rho);
+          g_rho[rho_mark + k] = d_rho * rho * (1.0 - rho) + (1.0 - 2.0 * rho);
+        }
+      }
+      for (int k = 0; k < nzT; ++k) g_zT[zT_mark + k] += dpar[1 + nc + (nc - 1) + k];
+      double d_tau = d_c * m->scale[i] * P.disp;
+      d_disp += d_c * P.tau[i] * m->scale[i];
+      d_tau += (m->shape[i] - 1.0) / P.tau[i] - 1.0;
+      g_tau[i] = d_tau * P.tau[i] + 1.0;
+      zeta_mark += nc; rho_mark += nc - 1; zT_mark += nzT;
+    } else if (m->p[i] == 1) {
       double theta = P.theta_L[th++];
       double d_theta = 0.0;
       for (int s = 0; s < m->l[i]; ++s) {
@@ -299,6 +416,7 @@ void or_glmm_write_array(const or_glmm* m, const double* q, double* out)
   int pos = 0;
   for (int k = 0; k < d->K; ++k) out[pos++] = P.z_beta[k];
   for (int k = 0; k < d->q; ++k) out[pos++] = P.z_b[k];
+  for (int k = 0; k < m->len_z_T; ++k) out[pos++] = P.z_T[k];
   for (int k = 0; k < m->len_rho; ++k) out[pos++] = P.rho[k];
   for (int k = 0; k < d->len_concentration; ++k) out[pos++] = P.zeta[k];
   for (int k = 0; k < d->t; ++k) out[pos++] = P.tau[k];

@@ -17,12 +17,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <stdexcept>
 
 namespace s4b {
 
 constexpr int kGBlock = 256;
+constexpr int kMaxNc = 16;         // coefficients per ranef block
 constexpr int kGFast = 4;          // fast path of the data pass: K and non-zeros per row of Z up to this
 
 __device__ __forceinline__ double g_warp_sum(double v)
@@ -179,7 +181,7 @@ __global__ void k_glmm_set_inputs(long long N, const double* __restrict__ new_of
 
 // ---------------------------------------------------------------------------------------
 struct GlmmModel::Params {
-  const double *z_beta, *z_b, *rho_u, *zeta_u, *tau_u;
+  const double *z_beta, *z_b, *z_T, *rho_u, *zeta_u, *tau_u;
   double aux_u = 0, aux_unscaled = 0, aux = 1, disp = 1;
   std::vector<double> rho, zeta, tau, beta, b, theta_L;
 };
@@ -194,7 +196,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   if (d.prior_dist_for_aux < 0 || d.prior_dist_for_aux > 3) throw std::invalid_argument("glmm: prior_dist_for_aux out of range");
   for (int i = 0; i < d.t; ++i) {
     if (d.p[i] < 1 || d.l[i] < 1) throw std::invalid_argument("glmm: p[i] / l[i] must be >= 1");
-    if (d.p[i] > 2) throw std::invalid_argument("glmm: ranef blocks with more than 2 coefficients (z_T onion) are not implemented (SURVEY 8f rank 4)");
+    if (d.p[i] > kMaxNc) throw std::invalid_argument("glmm: ranef blocks with more than 16 coefficients are not supported");
   }
   N_ = d.N; N_total_ = sharded() ? shard_->total_obs() : d.N; K_ = d.K; q_ = d.q; t_ = d.t; len_theta_L_ = d.len_theta_L; len_conc_ = d.len_concentration;
   is_binary_ = d.is_binary; prior_dist_ = d.prior_dist; prior_dist_for_aux_ = d.prior_dist_for_aux;
@@ -212,8 +214,10 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   }
   if (qq != q_) throw std::invalid_argument("glmm: q != sum(p * l)");
   len_rho_ = sum_p - t_;
+  len_z_T_ = 0;
+  for (int i = 0; i < t_; ++i) if (p_[i] > 2) len_z_T_ += (p_[i] - 2) * (p_[i] - 1);      // continuous.stan:258
   has_aux_ = is_binary_ ? 0 : 1;
-  num_params_ = K_ + q_ + len_rho_ + len_conc_ + t_ + has_aux_;
+  num_params_ = K_ + q_ + len_z_T_ + len_rho_ + len_conc_ + t_ + has_aux_;
 
   // ---- CSR (w, v, u) -> slot-major ELL ----
   npad_ = (N_ + 15) / 16 * 16;
@@ -399,6 +403,34 @@ void GlmmModel::parametric_mean_host(const double* constrained, double* out, boo
   S4B_CUDA(cudaStreamSynchronize(stream_));
 }
 
+// Lower-triangular factor T (row major, nc x nc) of one ranef block with nc >= 2 coefficients (continuous.stan:20-50, the
+// scaled onion rows for nc > 2; the off-diagonal entries of row r + 1 are scaled with the standard deviation of row r, as
+// the Stan program does).  Complex arguments: the imaginary part carries the complex-step derivative used for the adjoint.
+using cplx = std::complex<double>;
+static void block_T(int nc, cplx c, const cplx* zeta, const cplx* rho, const cplx* zT, cplx* T)
+{
+  const cplx trace = c * c * (double) nc;
+  cplx zs = 0.0;
+  for (int k = 0; k < nc; ++k) zs += zeta[k];
+  for (int k = 0; k < nc * nc; ++k) T[k] = 0.0;
+  cplx sd = std::sqrt(zeta[0] / zs * trace);
+  T[0] = sd;
+  sd = std::sqrt(zeta[1] / zs * trace);
+  const cplx r21 = 2.0 * rho[0] - 1.0;
+  T[nc + 1] = sd * std::sqrt(1.0 - r21 * r21);
+  T[nc] = sd * r21;
+  int zmark = 0;
+  for (int r = 2; r < nc; ++r) {
+    cplx dot = 0.0;
+    for (int k = 0; k < r; ++k) dot += zT[zmark + k] * zT[zmark + k];
+    const cplx sf = std::sqrt(rho[r - 1] / dot) * sd;
+    sd = std::sqrt(zeta[r] / zs * trace);
+    for (int k = 0; k < r; ++k) T[r * nc + k] = zT[zmark + k] * sf;
+    T[r * nc + r] = std::sqrt(1.0 - rho[r - 1]) * sd;
+    zmark += r;
+  }
+}
+
 static inline double inv_logit(double x) { return x >= 0.0 ? 1.0 / (1.0 + std::exp(-x)) : std::exp(x) / (1.0 + std::exp(x)); }
 
 void GlmmModel::transform(const double* q, Params& P) const
@@ -406,6 +438,7 @@ void GlmmModel::transform(const double* q, Params& P) const
   int pos = 0;
   P.z_beta = q + pos; pos += K_;
   P.z_b = q + pos; pos += q_;
+  P.z_T = q + pos; pos += len_z_T_;
   P.rho_u = q + pos; pos += len_rho_;
   P.zeta_u = q + pos; pos += len_conc_;
   P.tau_u = q + pos; pos += t_;
@@ -422,13 +455,27 @@ void GlmmModel::transform(const double* q, Params& P) const
     P.disp = P.aux;
   } else { P.aux_unscaled = 0.0; P.aux = 1.0; P.disp = 1.0; }
   for (int k = 0; k < K_; ++k) P.beta[(size_t) k] = prior_dist_ == 0 ? P.z_beta[k] : P.z_beta[k] * prior_scale_[(size_t) k] + prior_mean_[(size_t) k];
-  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0;
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, zT_mark = 0;
   for (int i = 0; i < t_; ++i) {
     const double c = P.tau[(size_t) i] * scale_[(size_t) i] * P.disp;
     if (p_[(size_t) i] == 1) {
       P.theta_L[(size_t) th++] = c;
       for (int s = 0; s < l_[(size_t) i]; ++s) P.b[(size_t) (b_mark + s)] = c * P.z_b[b_mark + s];
       b_mark += l_[(size_t) i];
+    } else if (p_[(size_t) i] > 2) {
+      const int nc = p_[(size_t) i];
+      const int nzT = (nc - 2) * (nc + 1) / 2;          // 2 + 3 + ... + (nc - 1) elements of z_T, one running mark
+      cplx T[kMaxNc * kMaxNc], zc[kMaxNc], rc[kMaxNc], tc[kMaxNc * kMaxNc];
+      for (int k = 0; k < nc; ++k) zc[k] = P.zeta[(size_t) (zeta_mark + k)];
+      for (int k = 0; k < nc - 1; ++k) rc[k] = P.rho[(size_t) (rho_mark + k)];
+      for (int k = 0; k < nzT; ++k) tc[k] = P.z_T[zT_mark + k];
+      block_T(nc, c, zc, rc, tc, T);
+      for (int c2 = 0; c2 < nc; ++c2) for (int r = c2; r < nc; ++r) P.theta_L[(size_t) th++] = T[r * nc + c2].real();     // vech
+      for (int j = 0; j < l_[(size_t) i]; ++j) {
+        for (int r = 0; r < nc; ++r) { double acc = 0.0; for (int k = 0; k <= r; ++k) acc += T[r * nc + k].real() * P.z_b[b_mark + k]; P.b[(size_t) (b_mark + r)] = acc; }
+        b_mark += nc;
+      }
+      zeta_mark += nc; rho_mark += nc - 1; zT_mark += nzT;
     } else {
       const double trace = c * c * 2.0;
       const double zs = P.zeta[(size_t) zeta_mark] + P.zeta[(size_t) zeta_mark + 1];
@@ -485,11 +532,21 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
   if (prior_dist_ == 1) { for (int k = 0; k < K_; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= K_ * kHalfLog2Pi; }
   for (int k = 0; k < q_; ++k) lp += -0.5 * P.z_b[k] * P.z_b[k];
   lp -= q_ * kHalfLog2Pi;
+  for (int k = 0; k < len_z_T_; ++k) lp += -0.5 * P.z_T[k] * P.z_T[k];
+  lp -= len_z_T_ * kHalfLog2Pi;
   {
     int pos_reg = 0, pos_rho = 0;
     for (int i = 0; i < t_; ++i) if (p_[(size_t) i] > 1) {
       const double nu = regularization_[(size_t) pos_reg++] + 0.5 * (p_[(size_t) i] - 2);
       const double r = P.rho[(size_t) pos_rho++];
+      {   // continuous.stan:111-115: the further correlations of a block with more than two coefficients
+        double nuj = nu;
+        for (int j = 2; j < p_[(size_t) i]; ++j) {
+          nuj -= 0.5;
+          const double s1 = 0.5 * j, s2 = nuj, rj = P.rho[(size_t) pos_rho++];
+          lp += (s1 - 1.0) * std::log(rj) + (s2 - 1.0) * std::log1p(-rj) + std::lgamma(s1 + s2) - std::lgamma(s1) - std::lgamma(s2);
+        }
+      }
       // a zero coefficient contributes exactly 0 (Stan's multiply_log(0, .) convention): the default decov(1, 1, 1, 1) then
       // needs none of these logarithms
       const double kl = nu - 1.0;
@@ -503,6 +560,7 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
   int pos = 0;
   double* g_zbeta = grad + pos; pos += K_;
   double* g_zb = grad + pos; pos += q_;
+  double* g_zT = grad + pos; pos += len_z_T_;
   double* g_rho = grad + pos; pos += len_rho_;
   double* g_zeta = grad + pos; pos += len_conc_;
   double* g_tau = grad + pos; pos += t_;
@@ -512,11 +570,67 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
     g_zbeta[k] = prior_dist_ == 0 ? dbeta : dbeta * prior_scale_[(size_t) k] - P.z_beta[k];
   }
   double adj_disp = 0.0;
-  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, pos_reg = 0;
+  // the Stan program declares (p - 2)(p - 1) elements of z_T per block but its onion rows consume 2 + ... + (p - 1) of them
+  // through one running mark: the surplus elements only see their normal prior
+  for (int k = 0; k < len_z_T_; ++k) g_zT[k] = -P.z_T[k];
+  int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, pos_reg = 0, zT_mark = 0;
   for (int i = 0; i < t_; ++i) {
     const double tau = P.tau[(size_t) i], sc = scale_[(size_t) i];
     double adj_c = 0.0;     // adjoint of c = tau * scale * dispersion
-    if (p_[(size_t) i] == 1) {
+    if (p_[(size_t) i] > 2) {
+      const int nc = p_[(size_t) i];
+      const int nzT = (nc - 2) * (nc + 1) / 2;
+      double Tr[kMaxNc * kMaxNc], A[kMaxNc * kMaxNc];
+      for (int k = 0; k < nc * nc; ++k) { Tr[k] = 0.0; A[k] = 0.0; }
+      for (int c2 = 0; c2 < nc; ++c2) for (int r = c2; r < nc; ++r) Tr[r * nc + c2] = P.theta_L[(size_t) th++];
+      for (int j = 0; j < l_[(size_t) i]; ++j) {
+        for (int k = 0; k < nc; ++k) {              // g_zb = T' db - z ;  A[r][k] += db[r] z[k]
+          double acc = 0.0;
+          for (int r = k; r < nc; ++r) acc += Tr[r * nc + k] * (gb[(size_t) (b_mark + r)] * inv_s2);
+          g_zb[b_mark + k] = acc - P.z_b[b_mark + k];
+        }
+        for (int r = 0; r < nc; ++r) for (int k = 0; k <= r; ++k) A[r * nc + k] += (gb[(size_t) (b_mark + r)] * inv_s2) * P.z_b[b_mark + k];
+        b_mark += nc;
+      }
+      // dL / d(c, zeta, rho, z_T) = sum A .* dT/dparam, with dT/dparam by the complex-step method (exact to rounding)
+      const double h = 1e-20;
+      cplx Tc[kMaxNc * kMaxNc], zc[kMaxNc], rc[kMaxNc], tc[kMaxNc * kMaxNc];
+      const double cval = tau * sc * P.disp;
+      const int npar = 1 + nc + (nc - 1) + nzT;
+      double dpar[1 + kMaxNc + kMaxNc + kMaxNc * kMaxNc];
+      for (int ip = 0; ip < npar; ++ip) {
+        cplx cc = cval;
+        for (int k = 0; k < nc; ++k) zc[k] = P.zeta[(size_t) (zeta_mark + k)];
+        for (int k = 0; k < nc - 1; ++k) rc[k] = P.rho[(size_t) (rho_mark + k)];
+        for (int k = 0; k < nzT; ++k) tc[k] = P.z_T[zT_mark + k];
+        if (ip == 0) cc += cplx(0.0, h);
+        else if (ip < 1 + nc) zc[ip - 1] += cplx(0.0, h);
+        else if (ip < 1 + nc + nc - 1) rc[ip - 1 - nc] += cplx(0.0, h);
+        else tc[ip - 1 - nc - (nc - 1)] += cplx(0.0, h);
+        block_T(nc, cc, zc, rc, tc, Tc);
+        double acc = 0.0;
+        for (int r = 0; r < nc; ++r) for (int k = 0; k <= r; ++k) acc += A[r * nc + k] * (Tc[r * nc + k].imag() / h);
+        dpar[ip] = acc;
+      }
+      adj_c = dpar[0];
+      for (int k = 0; k < nc; ++k) {
+        const double zv = P.zeta[(size_t) (zeta_mark + k)];
+        const double d_z = dpar[1 + k] + (delta_[(size_t) (zeta_mark + k)] - 1.0) / zv - 1.0;
+        g_zeta[zeta_mark + k] = d_z * zv + 1.0;
+      }
+      {
+        double nu = regularization_[(size_t) pos_reg++] + 0.5 * (nc - 2);
+        for (int k = 0; k < nc - 1; ++k) {
+          double s1, s2;
+          if (k == 0) { s1 = nu; s2 = nu; } else { nu -= 0.5; s1 = 0.5 * (k + 1); s2 = nu; }
+          const double rho = P.rho[(size_t) (rho_mark + k)];
+          const double d_rho = dpar[1 + nc + k] + (s1 - 1.0) / rho - (s2 - 1.0) / (1.0 - rho);
+          g_rho[rho_mark + k] = d_rho * rho * (1.0 - rho) + (1.0 - 2.0 * rho);
+        }
+      }
+      for (int k = 0; k < nzT; ++k) g_zT[zT_mark + k] += dpar[1 + nc + (nc - 1) + k];
+      zeta_mark += nc; rho_mark += nc - 1; zT_mark += nzT;
+    } else if (p_[(size_t) i] == 1) {
       const double theta = P.theta_L[(size_t) th++];
       for (int s = 0; s < l_[(size_t) i]; ++s) {
         const double db = gb[(size_t) (b_mark + s)] * inv_s2;
@@ -578,6 +692,7 @@ void GlmmModel::write_array(const double* q, double* out) const
   int pos = 0;
   for (int k = 0; k < K_; ++k) out[pos++] = P.z_beta[k];
   for (int k = 0; k < q_; ++k) out[pos++] = P.z_b[k];
+  for (int k = 0; k < len_z_T_; ++k) out[pos++] = P.z_T[k];
   for (double v : P.rho) out[pos++] = v;
   for (double v : P.zeta) out[pos++] = v;
   for (double v : P.tau) out[pos++] = v;

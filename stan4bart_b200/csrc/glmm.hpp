@@ -73,7 +73,7 @@ class GlmmModel {
   cudaStream_t stream_;
   ShardContext* shard_ = nullptr;
   long long N_ = 0, npad_ = 0, N_total_ = 0;
-  int K_ = 0, q_ = 0, t_ = 0, len_theta_L_ = 0, len_rho_ = 0, len_conc_ = 0, num_params_ = 0, has_aux_ = 0;
+  int K_ = 0, q_ = 0, t_ = 0, len_theta_L_ = 0, len_rho_ = 0, len_z_T_ = 0, len_conc_ = 0, num_params_ = 0, has_aux_ = 0;
   int is_binary_ = 0, prior_dist_ = 0, prior_dist_for_aux_ = 0;
   double prior_scale_for_aux_ = 0, prior_mean_for_aux_ = 0, prior_df_for_aux_ = 0;
   std::vector<double> prior_scale_, prior_mean_, shape_, scale_, delta_, regularization_;

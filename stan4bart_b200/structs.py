@@ -134,7 +134,8 @@ class StanData:
         self.v = i32(v)
         self.u = i32(u)
         self.len_rho = int(sum(self.p) - self.t)
-        self.num_params = self.K + self.q + self.len_rho + len(self.concentration) + self.t + (0 if self.is_binary else 1)
+        self.len_z_T = int(sum((pi - 2) * (pi - 1) for pi in self.p if pi > 2))        # continuous.stan:258
+        self.num_params = self.K + self.q + self.len_z_T + self.len_rho + len(self.concentration) + self.t + (0 if self.is_binary else 1)
         self.num_constrained = self.num_params + (0 if self.is_binary else 1) + self.K + self.q + self.len_theta_L
 
     def rows(self, lo, hi):
@@ -169,6 +170,7 @@ class StanData:
         names = ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"]
         names += [f"z_beta.{i + 1}" for i in range(self.K)]
         names += [f"z_b.{i + 1}" for i in range(self.q)]
+        names += [f"z_T.{i + 1}" for i in range(self.len_z_T)]
         names += [f"rho.{i + 1}" for i in range(self.len_rho)]
         names += [f"zeta.{i + 1}" for i in range(len(self.concentration))]
         names += [f"tau.{i + 1}" for i in range(self.t)]

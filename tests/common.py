@@ -79,3 +79,9 @@ def golden_cases():
     import os
     here = os.path.dirname(os.path.abspath(__file__))
     return sorted(glob.glob(os.path.join(here, "golden", "glmm_*.json")))
+
+
+def golden_case(name):
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    return os.path.join(here, "golden", f"glmm_{name}.json")

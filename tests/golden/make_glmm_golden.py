@@ -46,10 +46,13 @@ def student_t_lpdf(y, nu, mu, sigma):
             - (nu + 1) / 2 * torch.log1p(z * z / nu)).sum()
 
 
-def make_theta_L(p, dispersion, tau, scale, zeta, rho):
+def make_theta_L(p, dispersion, tau, scale, zeta, rho, z_T):
+    """continuous.stan:2-59, including the scaled onion rows of blocks with more than two coefficients (note that the
+    off-diagonal entries of row r + 1 are scaled with the standard deviation of row r, as the Stan program does)."""
     out = []
     zeta_mark = 0
     rho_mark = 0
+    z_T_mark = 0
     for i, nc in enumerate(p):
         if nc == 1:
             out.append(tau[i] * scale[i] * dispersion)
@@ -58,15 +61,26 @@ def make_theta_L(p, dispersion, tau, scale, zeta, rho):
             pi = zeta[zeta_mark:zeta_mark + nc]
             pi = pi / pi.sum()
             zeta_mark += nc
+            T = [[None] * nc for _ in range(nc)]
             std_dev = torch.sqrt(pi[0] * trace)
-            T11 = std_dev
+            T[0][0] = std_dev
             std_dev = torch.sqrt(pi[1] * trace)
             T21 = 2.0 * rho[rho_mark] - 1.0
             rho_mark += 1
-            T22 = std_dev * torch.sqrt(1.0 - T21 ** 2)
-            T21 = std_dev * T21
-            assert nc == 2
-            out += [T11, T21, T22]     # vech, column major
+            T[1][1] = std_dev * torch.sqrt(1.0 - T21 ** 2)
+            T[1][0] = std_dev * T21
+            for r in range(2, nc):          # stan r = 2 .. nc - 1, rp1 = r + 1 (1-based) -> row index r (0-based)
+                T_row = z_T[z_T_mark:z_T_mark + r]
+                scale_factor = torch.sqrt(rho[rho_mark] / (T_row * T_row).sum()) * std_dev
+                z_T_mark += r
+                std_dev = torch.sqrt(pi[r] * trace)
+                for c in range(r):
+                    T[r][c] = T_row[c] * scale_factor
+                T[r][r] = torch.sqrt(1.0 - rho[rho_mark]) * std_dev
+                rho_mark += 1
+            for c in range(nc):             # vech, column major
+                for r in range(c, nc):
+                    out.append(T[r][c])
     return torch.stack(out) if out else torch.zeros(0)
 
 
@@ -80,12 +94,13 @@ def make_b(z_b, theta_L, p, l):
             b_mark += l[i]
             th += 1
         else:
-            T = torch.zeros(nc, nc)
-            T = T.clone()
+            rows_T = [[torch.zeros(()) for _ in range(nc)] for _ in range(nc)]
+            for c in range(nc):
+                for r in range(c, nc):
+                    rows_T[r][c] = theta_L[th]
+                    th += 1
+            Tm = torch.stack([torch.stack(row) for row in rows_T])
             rows = []
-            T11, T21, T22 = theta_L[th], theta_L[th + 1], theta_L[th + 2]
-            th += 3
-            Tm = torch.stack([torch.stack([T11, torch.zeros(())]), torch.stack([T21, T22])])
             for j in range(l[i]):
                 rows.append(Tm @ z_b[b_mark:b_mark + nc])
                 b_mark += nc
@@ -102,6 +117,8 @@ def log_prob(sd, q, offset, y):
     pos = 0
     z_beta = q[pos:pos + K]; pos += K
     z_b = q[pos:pos + nq]; pos += nq
+    len_z_T = sum((pi - 2) * (pi - 1) for pi in p if pi > 2)        # continuous.stan:258
+    z_T = q[pos:pos + len_z_T]; pos += len_z_T
     rho_u = q[pos:pos + len_rho]; pos += len_rho
     zeta_u = q[pos:pos + len_conc]; pos += len_conc
     tau_u = q[pos:pos + t]; pos += t
@@ -127,7 +144,7 @@ def log_prob(sd, q, offset, y):
         beta = z_beta
     else:
         beta = z_beta * torch.as_tensor(sd.prior_scale) + torch.as_tensor(sd.prior_mean)
-    theta_L = make_theta_L(p, dispersion, tau, torch.as_tensor(sd.scale), zeta, rho)
+    theta_L = make_theta_L(p, dispersion, tau, torch.as_tensor(sd.scale), zeta, rho, z_T)
     b = make_b(z_b, theta_L, p, l)
     # eta = offset + X beta + Z b   (CSR w, v, u)
     eta = torch.as_tensor(offset).clone()
@@ -150,13 +167,20 @@ def log_prob(sd, q, offset, y):
         lp = lp + normal_lpdf(z_beta, torch.zeros(()), torch.ones(()))
     # decov_lp
     lp = lp + normal_lpdf(z_b, torch.zeros(()), torch.ones(()))
+    if len_z_T:
+        lp = lp + normal_lpdf(z_T, torch.zeros(()), torch.ones(()))
     pos_reg = 0
     pos_rho = 0
     for i in range(t):
         if p[i] > 1:
             nu = sd.regularization[pos_reg] + 0.5 * (p[i] - 2)
             pos_reg += 1
-            lp = lp + beta_lpdf(rho[pos_rho:pos_rho + p[i] - 1], nu, nu)
+            shape1, shape2 = [nu], [nu]
+            for j in range(2, p[i]):          # stan j = 2 .. p - 1
+                nu -= 0.5
+                shape1.append(0.5 * j)
+                shape2.append(nu)
+            lp = lp + beta_lpdf(rho[pos_rho:pos_rho + p[i] - 1], np.array(shape1), np.array(shape2))
             pos_rho += p[i] - 1
     delta = []
     for i in range(t):
@@ -166,7 +190,7 @@ def log_prob(sd, q, offset, y):
         lp = lp + gamma_lpdf(zeta, torch.as_tensor(np.array(delta)))
     if t:
         lp = lp + gamma_lpdf(tau, torch.as_tensor(sd.shape))
-    return lp, dict(beta=beta, b=b, theta_L=theta_L, aux=aux, rho=rho, zeta=zeta, tau=tau)
+    return lp, dict(beta=beta, b=b, theta_L=theta_L, aux=aux, rho=rho, zeta=zeta, tau=tau, z_T=z_T)
 
 
 def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1):
@@ -201,7 +225,7 @@ def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1):
         wa = q.detach().numpy().tolist()
         # write_array order: params (constrained) then aux, beta, b, theta_L
         K, nq = sd.K, sd.q
-        cons = list(q.detach().numpy()[:K + nq]) + tp["rho"].tolist() + tp["zeta"].tolist() + tp["tau"].tolist()
+        cons = list(q.detach().numpy()[:K + nq]) + tp["z_T"].tolist() + tp["rho"].tolist() + tp["zeta"].tolist() + tp["tau"].tolist()
         if not binary:
             cons += [float(torch.exp(q[-1])), float(tp["aux"])]
         cons += tp["beta"].tolist() + tp["b"].tolist() + tp["theta_L"].tolist()
@@ -222,3 +246,5 @@ if __name__ == "__main__":
     make_case("intercepts_only", 40, 3, False, [(3, 1), (7, 1)], aux_prior=1)
     make_case("two_slopes_t_aux", 70, 4, False, [(4, 2), (5, 2), (3, 1)], aux_prior=2)
     make_case("no_ranef_flat_prior", 30, 5, False, [], aux_prior=0, prior_dist=0)
+    make_case("three_coefficients", 80, 6, False, [(4, 3), (6, 1)])
+    make_case("four_and_three_binary", 90, 7, True, [(3, 4), (5, 3), (4, 2)])

@@ -300,3 +300,33 @@ def test_iteration_callback_sees_each_draw():
         g.run(4, True)
     g.set_callback(None)
     g.run(2, True)
+
+
+def test_three_coefficient_block_first_sweeps():
+    """`(1 + X4 + X5 | g.1)`: a grouping term with three coefficients (onion rows through z_T) through the whole Gibbs
+    sweep, step by step against the oracle."""
+    from stan4bart_b200.frontend import build_stan_data, friedman_data, init_fit
+    n, nt, seed = 300, 9, 777
+    d = friedman_data(n, ranef=True, causal=True, binary=False, seed=3)
+    x = d["x"]
+    x_bart = np.asfortranarray(x[:, [0, 1, 2, 5, 6, 7, 8, 9]])
+    ones = np.ones(n)
+    terms = [(d["g1"], np.column_stack([ones, x[:, 3], x[:, 4]])), (d["g2"], ones.reshape(n, 1))]
+    sd = build_stan_data(np.column_stack([x[:, 3], d["z"]]), d["y"], terms, is_binary=False)
+    offset_init, sigma_init = init_fit(sd, False)
+    cfg = bart_config(n, 8, n_test=n, num_trees=nt, is_binary=False, seed=seed)
+    ctl = stan_control(seed=seed + 1)
+    kw = dict(warmup=6, iter_=8, keep_fits=True, sigma_init=sigma_init, bart_offset_init=offset_init)
+    y = np.ascontiguousarray(d["y"])
+    o = O.OracleSampler(cfg, y, x_bart, x_bart.copy(order="F"), sd, ctl, **kw)
+    g = Sampler(cfg, y, x_bart, x_bart.copy(order="F"), sd, ctl, **kw)
+    K = 6
+    ob, gb = o.bart(), g.bart()
+    ob.set_trace(nt * K); gb.set_trace(nt * K)
+    ro, rg = o.run(K, True), g.run(K, True)
+    compare_traces(ob.trace(), gb.trace(), tol=1e-8)
+    assert ro["stan"].shape == rg["stan"].shape
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-8
+    names = sd.param_names()
+    assert sum(nm.startswith("z_T") for nm in names) == 2

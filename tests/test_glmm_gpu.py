@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from common import REL_TOL, golden_cases, load_glmm_case, rel_err
+from common import REL_TOL, golden_case, golden_cases, load_glmm_case, rel_err
 from stan4bart_b200.frontend import friedman_problem
 from stan4bart_b200.sampler import GlmmModel
 
@@ -102,7 +102,7 @@ def test_data_terms_linearity_at_scale():
 
 
 def test_non_finite_maps_to_status():
-    sd, c = load_glmm_case(golden_cases()[1])
+    sd, c = load_glmm_case(golden_case("friedman_like"))
     m = GlmmModel(sd)
     q = np.asarray(c["q"][0]).copy()
     q[-1] = 800.0
@@ -110,12 +110,39 @@ def test_non_finite_maps_to_status():
 
 
 def test_unsupported_branches_fail_loudly():
+    """A grouping term with more coefficients than the host's fixed-size onion scratch (16) is refused, not truncated."""
     from stan4bart_b200._lib import S4BError
     from stan4bart_b200.frontend import build_stan_data
     rng = np.random.default_rng(0)
-    N = 30
+    N = 60
     g = rng.integers(0, 3, N)
-    M = np.column_stack([np.ones(N), rng.random(N), rng.random(N)])
+    M = np.column_stack([np.ones(N)] + [rng.random(N) for _ in range(16)])
     sd = build_stan_data(rng.random((N, 1)), rng.standard_normal(N), [(g, M)])
     with pytest.raises(S4BError):
         GlmmModel(sd)
+
+
+@pytest.mark.parametrize("ncoef", [3, 5])
+def test_blocks_with_more_than_two_coefficients_match_oracle(ncoef):
+    """continuous.stan:44-70 (scaled onion rows through z_T) at sizes beyond the golden vectors."""
+    from stan4bart_b200.frontend import build_stan_data
+    rng = np.random.default_rng(ncoef)
+    N = 4000
+    g1, g2 = rng.integers(0, 7, N), rng.integers(0, 4, N)
+    M1 = np.column_stack([np.ones(N)] + [rng.standard_normal(N) for _ in range(ncoef - 1)])
+    M2 = np.column_stack([np.ones(N), rng.standard_normal(N)])
+    sd = build_stan_data(rng.standard_normal((N, 2)), rng.standard_normal(N), [(g1, M1), (g2, M2)])
+    off = rng.standard_normal(N)
+    mo, mg = O.OracleGlmm(sd), GlmmModel(sd)
+    mo.set_offset(off); mg.set_offset(off)
+    assert mo.d == mg.d
+    for mode in (0, 1):
+        mg.set_mode(mode)
+        for _ in range(3):
+            q = rng.uniform(-1, 1, mo.d)
+            lo, go, so = mo.log_prob_grad(q)
+            lg, gg, sg = mg.log_prob_grad(q)
+            assert so == sg == 0
+            assert abs(lo - lg) <= REL_TOL * abs(lo)
+            assert rel_err(go, gg, scale=np.abs(go) + 1e-8 * np.max(np.abs(go))) <= REL_TOL
+            assert rel_err(mo.write_array(q), mg.write_array(q)) <= 1e-12

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from common import golden_cases, load_glmm_case, rel_err
+from common import golden_case, golden_cases, load_glmm_case, rel_err
 
 
 @pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[5:-5])
@@ -24,7 +24,7 @@ def test_oracle_matches_golden(path):
 
 
 def test_gradient_matches_finite_differences():
-    sd, c = load_glmm_case(golden_cases()[1])
+    sd, c = load_glmm_case(golden_case("friedman_like"))
     m = O.OracleGlmm(sd)
     m.set_offset(np.asarray(c["offset"]))
     q = np.asarray(c["q"][0])
@@ -38,7 +38,7 @@ def test_gradient_matches_finite_differences():
 
 
 def test_parametric_mean_and_aux():
-    sd, c = load_glmm_case(golden_cases()[1])
+    sd, c = load_glmm_case(golden_case("friedman_like"))
     m = O.OracleGlmm(sd)
     q = np.asarray(c["q"][0])
     wa = m.write_array(q)
@@ -58,7 +58,7 @@ def test_parametric_mean_and_aux():
 
 
 def test_non_finite_maps_to_error_status():
-    sd, c = load_glmm_case(golden_cases()[1])
+    sd, c = load_glmm_case(golden_case("friedman_like"))
     m = O.OracleGlmm(sd)
     q = np.asarray(c["q"][0]).copy()
     q[-1] = 800.0          # aux overflows
@@ -70,8 +70,27 @@ def test_unsupported_branches_are_rejected():
     rng = np.random.default_rng(0)
     N = 30
     g = rng.integers(0, 3, N)
-    M = np.column_stack([np.ones(N), rng.random(N), rng.random(N)])      # p = 3 needs the z_T onion
+    M = np.column_stack([np.ones(N), rng.random(N)])
     sd = build_stan_data(rng.random((N, 1)), rng.standard_normal(N), [(g, M)])
+    sd.prior_dist = 3                                   # hs prior: not implemented
     s = sd.struct()
     import ctypes as C
     assert not O.lib().or_glmm_create(C.byref(s))
+
+
+def test_onion_blocks_gradient_by_finite_differences():
+    """Ranef blocks with more than two coefficients (scaled onion rows, z_T): the hand-derived / complex-step gradient against
+    central differences of the log density, including the surplus z_T element that the Stan program declares but never uses."""
+    sd, c = load_glmm_case(golden_case("four_and_three_binary"))
+    assert sd.len_z_T == 8 and list(sd.p) == [4, 3, 2] or sd.len_z_T == 8
+    m = O.OracleGlmm(sd)
+    m.set_offset(np.asarray(c["offset"]))
+    q = np.asarray(c["q"][1])
+    lp, g, st = m.log_prob_grad(q)
+    assert st == 0
+    for k in range(len(q)):
+        h = 1e-6
+        qp, qm = q.copy(), q.copy()
+        qp[k] += h; qm[k] -= h
+        fd = (m.log_prob_grad(qp)[0] - m.log_prob_grad(qm)[0]) / (2 * h)
+        assert abs(fd - g[k]) <= 1e-5 * max(1.0, abs(g[k])), (k, fd, g[k])
