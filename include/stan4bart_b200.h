@@ -44,6 +44,10 @@ typedef struct s4b_bart_config {
    * predictor when a splitting variable is drawn and in the rule prior; NULL = uniform.  Normalised internally to integer
    * weights summing to ~2^30, so that the CPU oracle and the device select and weigh variables identically. */
   const double* split_probs;
+  /* observation weights (`weights` of stan4bart(), handed to dbarts as data weights: R/stan4bart_fit.R:449): y_i ~ N(f(x_i),
+   * sigma^2 / w_i), leaf statistics become sum w, sum w r; n rows, finite and >= 0; NULL = unweighted.  Weighted fits run the
+   * streamed variant of the sweep kernel. */
+  const double* weights;
 } s4b_bart_config;
 
 /* the `data.stan` list, R/stan4bart_fit.R:259-365 / src/stan_sampler.cpp:112-380 (default path) */
@@ -56,6 +60,8 @@ typedef struct s4b_glmm_data {
   const int32_t* p; const int32_t* l; const double* shape; const double* scale;
   const double* concentration; const double* regularization;
   const double* w; const int32_t* v; const int32_t* u;
+  /* data.stan `has_weights` / `weights` (R/stan4bart_fit.R:255-262, continuous.stan:358-366): NULL = unweighted */
+  const double* weights;
 } s4b_glmm_data;
 
 /* StanControl, src/stan_sampler.hpp:28-42 */

@@ -31,7 +31,7 @@ typedef struct Node {
   struct Node *parent, *left, *right;
   int var, cut;
   int* obs; int nobs;
-  double avg;
+  double avg, neff;
   double mu;
 } Node;
 
@@ -46,6 +46,7 @@ struct or_bart {
   double *y, *x, *x_test, *offset;
   int* ncuts; double** cuts;
   uint32_t* split_w;               /* integer split weights (bart_args split.probs), NULL = uniform */
+  double* weights;                 /* observation weights, NULL = unweighted */
   uint8_t *xt, *xt_test;           /* [p][n], [p][nt] */
   double *yresc, *treeY, *totalFits, *treeFits, *currFits, *totalTestFits, *currTestFits;
   Tree* trees;
@@ -169,28 +170,39 @@ static int is_birthable(const or_bart* f, const Node* nd, int num_leaves) {
 }
 
 /* ---------- likelihood ---------- */
-static void node_set_average(Node* nd, const double* ty) {
+/* observation weights (dbarts data weights, R/stan4bart_fit.R:449): y_i ~ N(mu, sigma^2 / w_i), so a leaf's sufficient
+ * statistics are n_eff = sum w, the weighted mean, and sum w (y - mean)^2; without weights n_eff is the count */
+static void node_set_average(const or_bart* f, Node* nd, const double* ty) {
   double s = 0.0;
+  if (f->weights) {
+    double sw = 0.0;
+    for (int i = 0; i < nd->nobs; ++i) { double w = f->weights[nd->obs[i]]; s += w * ty[nd->obs[i]]; sw += w; }
+    nd->neff = sw;
+    nd->avg = sw > 0.0 ? s / sw : 0.0;
+    return;
+  }
   for (int i = 0; i < nd->nobs; ++i) s += ty[nd->obs[i]];
+  nd->neff = (double) nd->nobs;
   nd->avg = nd->nobs > 0 ? s / (double) nd->nobs : 0.0;
 }
-static void set_averages(Node* nd, const double* ty) {
-  if (is_bottom(nd)) { node_set_average(nd, ty); return; }
-  set_averages(nd->left, ty); set_averages(nd->right, ty);
+static void set_averages(const or_bart* f, Node* nd, const double* ty) {
+  if (is_bottom(nd)) { node_set_average(f, nd, ty); return; }
+  set_averages(f, nd->left, ty); set_averages(f, nd->right, ty);
 }
-static double node_sumsq_dev(const Node* nd, const double* ty) {
+static double node_sumsq_dev(const or_bart* f, const Node* nd, const double* ty) {
   double s = 0.0;
+  if (f->weights) { for (int i = 0; i < nd->nobs; ++i) { double d = ty[nd->obs[i]] - nd->avg; s += f->weights[nd->obs[i]] * d * d; } return s; }
   for (int i = 0; i < nd->nobs; ++i) { double d = ty[nd->obs[i]] - nd->avg; s += d * d; }
   return s;
 }
 static double node_loglik(const or_bart* f, Node* nd, const double* ty) {
   if (nd->nobs == 0) return 0.0;
-  node_set_average(nd, ty);
+  node_set_average(f, nd, ty);
   double sigsq = f->sigma * f->sigma;
   double a = f->leaf_prec;
-  double dp = (double) nd->nobs / sigsq;
+  double dp = nd->neff / sigsq;
   double r = 0.5 * log(a / (a + dp));
-  r -= 0.5 * node_sumsq_dev(nd, ty) / sigsq;
+  r -= 0.5 * node_sumsq_dev(f, nd, ty) / sigsq;
   r -= 0.5 * ((a * nd->avg) * (dp * nd->avg)) / (a + dp);
   return r;
 }
@@ -215,7 +227,7 @@ static double branch_log_prior(const or_bart* f, const Node* nd) {
 /* ---------- tree cloning for change / swap ---------- */
 static Node* clone_rec(const Node* src, Node* parent, int* newbase, const int* oldbase) {
   Node* nd = node_new(parent, newbase + (src->obs - oldbase), src->nobs);
-  nd->var = src->var; nd->cut = src->cut; nd->avg = src->avg; nd->mu = src->mu;
+  nd->var = src->var; nd->cut = src->cut; nd->avg = src->avg; nd->neff = src->neff; nd->mu = src->mu;
   if (!is_bottom(src)) { nd->left = clone_rec(src->left, nd, newbase, oldbase); nd->right = clone_rec(src->right, nd, newbase, oldbase); }
   return nd;
 }
@@ -425,8 +437,8 @@ static void sample_parameters_and_set_fits(or_bart* f, Tree* t, const double* ty
   s4b_rng_enter(&f->rng, f->step_id, 1);
   for (int k = 0; k < nb; ++k) {
     Node* nd = bl[k];
-    node_set_average(nd, ty);
-    double dp = (double) nd->nobs / sigsq;
+    node_set_average(f, nd, ty);
+    double dp = nd->neff / sigsq;
     double post_mean = dp * nd->avg / (f->leaf_prec + dp);
     double post_sd = 1.0 / sqrt(f->leaf_prec + dp);
     nd->mu = post_mean + post_sd * s4b_rng_normal(&f->rng);
@@ -465,6 +477,9 @@ or_bart* or_bart_create(const s4b_bart_config* cfg, const double* y, const doubl
     }
   }
   f->cfg.split_probs = NULL;       /* the caller's array is not kept */
+  f->weights = NULL;
+  if (cfg->weights) { f->weights = (double*) malloc(sizeof(double) * (n ? n : 1)); memcpy(f->weights, cfg->weights, sizeof(double) * n); }
+  f->cfg.weights = NULL;
   f->xt = (uint8_t*) malloc(n * p + 1);
   for (size_t j = 0; j < p; ++j) {
     const double* col = x + j * n;
@@ -509,7 +524,7 @@ void or_bart_free(or_bart* f)
   if (!f) return;
   for (int t = 0; t < f->T; ++t) tree_release(&f->trees[t]);
   for (int j = 0; j < f->p; ++j) free(f->cuts[j]);
-  free(f->cuts); free(f->ncuts); free(f->trees); free(f->split_w);
+  free(f->cuts); free(f->ncuts); free(f->trees); free(f->split_w); free(f->weights);
   free(f->y); free(f->x); free(f->x_test); free(f->offset); free(f->xt); free(f->xt_test);
   free(f->yresc); free(f->treeY); free(f->totalFits); free(f->treeFits); free(f->currFits);
   free(f->totalTestFits); free(f->currTestFits);
@@ -603,7 +618,7 @@ void or_bart_run(or_bart* f, double* train, double* test, uint32_t* varcount, do
       Tree* tree = &f->trees[t];
       double* tf = f->treeFits + (size_t) t * (size_t) n;
       for (int i = 0; i < n; ++i) f->treeY[i] = f->yresc[i] - (f->totalFits[i] - tf[i]);
-      set_averages(tree->top, f->treeY);
+      set_averages(f, tree->top, f->treeY);
       double* tr = trace_begin(f);
       metropolis_jump(f, tree, f->treeY, tr);
       sample_parameters_and_set_fits(f, tree, f->treeY, f->currFits, is_thinning ? NULL : f->currTestFits, tr);

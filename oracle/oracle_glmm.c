@@ -2,7 +2,7 @@
  * oracle/oracle_glmm.c -- TEST INFRASTRUCTURE (CPU oracle), not product code.
  *
  * CPU restatement of the stan4bart GLMM density and its gradient on the default
- * path (prior_dist in {0,1}, no intercept, no weights; ranef blocks of any size, the ones with more than two
+ * path (prior_dist in {0,1}, no intercept, optional observation weights; ranef blocks of any size, the ones with more than two
  * coefficients through the scaled onion rows of make_theta_L):
  *   maths          /root/reference/src/stan_files/continuous.stan:1-429
  *   op order       /root/reference/src/stan_files/continuous.hpp:2168-2638 (log_prob_impl,
@@ -27,7 +27,7 @@
 
 struct or_glmm {
   s4b_glmm_data d;
-  double *X, *y, *offset;
+  double *X, *y, *offset, *weights;
   double *prior_scale, *prior_mean, *shape, *scale, *concentration, *regularization, *w, *delta;
   int32_t *p, *l, *v, *u;
   int len_rho, len_z_T, num_params, has_aux;
@@ -48,6 +48,7 @@ or_glmm* or_glmm_create(const s4b_glmm_data* d)
   m->X = (double*) dup_mem(d->X, sizeof(double) * N * K);
   m->y = (double*) dup_mem(d->y, sizeof(double) * N);
   m->offset = (double*) calloc(N ? N : 1, sizeof(double));
+  m->weights = d->weights ? (double*) dup_mem(d->weights, sizeof(double) * N) : NULL;
   m->prior_scale = (double*) dup_mem(d->prior_scale, sizeof(double) * K);
   m->prior_mean = (double*) dup_mem(d->prior_mean, sizeof(double) * K);
   m->p = (int32_t*) dup_mem(d->p, sizeof(int32_t) * t);
@@ -77,7 +78,7 @@ or_glmm* or_glmm_create(const s4b_glmm_data* d)
 void or_glmm_free(or_glmm* m)
 {
   if (!m) return;
-  free(m->X); free(m->y); free(m->offset); free(m->prior_scale); free(m->prior_mean); free(m->p); free(m->l);
+  free(m->X); free(m->y); free(m->offset); free(m->weights); free(m->prior_scale); free(m->prior_mean); free(m->p); free(m->l);
   free(m->shape); free(m->scale); free(m->concentration); free(m->regularization); free(m->w); free(m->v); free(m->u); free(m->delta);
   free(m);
 }
@@ -98,7 +99,11 @@ void or_glmm_data_terms(const or_glmm* m, const double* beta, const double* b, d
     for (int k = 0; k < K; ++k) eta += m->X[(size_t) k * (size_t) N + (size_t) i] * beta[k];
     for (int32_t z = m->u[i]; z < m->u[i + 1]; ++z) eta += m->w[z] * b[m->v[z]];
     double e = m->y[i] - eta;
-    s += e * e;
+    if (m->weights) {            /* continuous.stan:358-366: -0.5 sum w (y - eta)^2 / sigma^2 */
+      double we = m->weights[i] * e;
+      s += we * e;
+      e = we;
+    } else s += e * e;
     for (int k = 0; k < K; ++k) gbeta[k] += m->X[(size_t) k * (size_t) N + (size_t) i] * e;
     for (int32_t z = m->u[i]; z < m->u[i + 1]; ++z) gb[m->v[z]] += m->w[z] * e;
   }

@@ -764,6 +764,14 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
     for (int j = 0; j < p_; ++j) split_probs_[(size_t) j] = cfg.split_probs[j] / sum;
   }
   cfg_.split_probs = nullptr;        // the caller's array is not kept
+  if (cfg.weights != nullptr) {
+    // dbarts data weights (R/stan4bart_fit.R:449): y_i ~ N(f(x_i), sigma^2 / w_i)
+    for (long long i = 0; i < n_; ++i) if (!(cfg.weights[i] >= 0.0) || !std::isfinite(cfg.weights[i])) throw std::invalid_argument("weights must be finite and non-negative");
+    dalloc(&d_wt_, (size_t) npad_);
+    S4B_CUDA(cudaMemcpy(d_wt_, cfg.weights, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice));
+    P.weighted = 1;
+  }
+  cfg_.weights = nullptr;
   S4B_CUDA(cudaMalloc(&d_params_, sizeof(BartParams)));
   S4B_CUDA(cudaMemcpy(d_params_, &P, sizeof P, cudaMemcpyHostToDevice));
   std::vector<double> pg(S4B_MAX_DEPTH + 2);
@@ -800,7 +808,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_split_w_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -850,7 +858,8 @@ void BartFit::setup_persistent()
           if (force_nq == 0 || force_nq == 6) try_nq(6, sweep_smem_bytes<6>(p_), S4B_SWEEP_FNS(6));
 #undef S4B_SWEEP_FNS
     // shards beyond the register file (or when forced, for the tests): residuals and node indices streamed from global memory
-    const bool force_stream = getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0;
+    // weighted fits: only the streamed variant reads the observation weights
+    const bool force_stream = (getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0) || d_wt_ != nullptr;
     if (persistent_nq_ == 0 || force_stream) {
       const size_t smem = sweep_smem_bytes<1>(0);
       const long long rounds = (nquad / cta_cap + 1 + kWorkers - 1) / kWorkers;
@@ -893,6 +902,8 @@ void BartFit::setup_persistent()
     S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     sweep_mode_ = 2;
   }
+  if (d_wt_ != nullptr && persistent_nq_ != kStreamNq)
+    throw std::invalid_argument("weighted fit: the streamed sweep kernel does not fit this many rows on one GPU (shard the chain by rows)");
   if (env) set_sweep_mode(atoi(env));
   if (getenv("S4B_OVERLAP_WALK")) overlap_walk_ = atoi(getenv("S4B_OVERLAP_WALK"));
 }
@@ -901,6 +912,7 @@ void BartFit::set_sweep_mode(int m)
 {
   if (m == 2 && persistent_nq_ == 0) throw std::invalid_argument("persistent sweep kernel does not fit this problem (n, p) on this GPU");
   if (m < 0 || m > 2) throw std::invalid_argument("sweep mode must be 0, 1 or 2");
+  if (m != 2 && d_wt_ != nullptr) throw std::invalid_argument("weighted fits run the persistent sweep kernel only (sweep mode 2)");
   sweep_mode_ = m; use_graph_ = m != 0;
 }
 
@@ -923,7 +935,8 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   ShardDev sh = shard_dev();
   void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh };
   // the sums of squares are accumulated only when the parity trace (which reports the individual log-likelihoods) is on
-  const bool sq = trace_cap_ > 0 || sequential_rng_;
+  // (weighted fits use the two-value bins for sum w r and sum w)
+  const bool sq = trace_cap_ > 0 || sequential_rng_ || d_wt_ != nullptr;
   const void* fn;
 #define S4B_PICK(NQ) (sequential_rng_ ? (const void*) k_sweep<NQ, true> : (sq ? (const void*) k_sweep<NQ, false> : (const void*) k_sweep<NQ, false, false, false>))
   if (persistent_nq_ == kStreamNq) fn = sequential_rng_ ? (const void*) k_sweep<1, true, true> : (sq ? (const void*) k_sweep<1, false, true> : (const void*) k_sweep<1, false, true, false>);
@@ -962,7 +975,7 @@ BartDev BartFit::dev() const
   BartDev d;
   d.n = n_; d.npad = npad_; d.obs_offset = shard_ != nullptr ? shard_->obs_offset() : 0; d.xt = d_xt_; d.R = d_R_; d.yresc = d_yresc_; d.y = d_y_; d.offset = d_offset_;
   d.desc = d_desc_; d.trees = d_trees_; d.params = d_params_; d.pgrow = d_pgrow_; d.rng = d_rng_;
-  d.partials = d_partials_; d.ticket = d_ticket_; d.packs = d_packs_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
+  d.partials = d_partials_; d.ticket = d_ticket_; d.packs = d_packs_; d.wt = d_wt_; d.trace = d_trace_; d.trace_cap = trace_cap_; d.trace_len = d_trace_len_;
   d.stats_out = d_stats_out_; d.prof = profile_on_ ? d_prof_ : nullptr;
   return d;
 }
@@ -1143,7 +1156,7 @@ void BartFit::run_sweeps()
 void BartFit::set_keep_trees(long long capacity)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));
-  cudaFree(d_split_w_); cudaFree(d_store_); cudaFree(d_store_scale_); d_store_ = nullptr; d_store_scale_ = nullptr;
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_store_); cudaFree(d_store_scale_); d_store_ = nullptr; d_store_scale_ = nullptr;
   store_cap_ = capacity > 0 ? capacity : 0; store_len_ = 0;
   if (store_cap_ > 0) {
     S4B_CUDA(cudaMalloc(&d_store_, sizeof(DTree) * (size_t) T_ * (size_t) store_cap_));

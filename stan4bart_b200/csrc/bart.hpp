@@ -19,6 +19,7 @@ struct BartDev {
   StepDesc* desc; DTree* trees; BartParams* params; const double* pgrow; RngState* rng;
   double* partials; unsigned int* ticket;
   uint2* packs;               // streamed sweep: cached node indices of every quad, two buffers of nquad entries
+  const double* wt;           // observation weights [npad] (zero padded), nullptr = unweighted
   double* trace; unsigned long long trace_cap; unsigned long long* trace_len;
   double* stats_out;
   unsigned long long* prof;   // cycle counters of the controller phases (last block, thread 0)
@@ -131,6 +132,7 @@ class BartFit {
   int sweep_mode_ = 1;
   int persistent_nq_ = 0, persistent_grid_ = 0;       // nq = kStreamNq: residuals streamed from global memory (L2)
   uint2* d_packs_ = nullptr;
+  double* d_wt_ = nullptr;       // observation weights (zero padded), nullptr = unweighted
   uint32_t* d_split_w_ = nullptr;
   std::vector<double> split_probs_;       // normalised bart_args split.probs (empty = uniform)
   DTree* d_store_ = nullptr; double* d_store_scale_ = nullptr; long long store_cap_ = 0, store_len_ = 0;

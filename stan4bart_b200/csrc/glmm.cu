@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
     // memory latency otherwise (ncu: long-scoreboard stalls, 1.1 TB/s)
     const long long stride = (long long) gridDim.x * kGBlock * 2;
     for (long long i0 = ((long long) blockIdx.x * kGBlock + tid) * 2; i0 < N; i0 += 2 * stride) {
-      double2 r2[2], x2[2][kGFast], v2[2][kGFast]; int2 c2[2][kGFast];
+      double2 r2[2], w2[2], x2[2][kGFast], v2[2][kGFast]; int2 c2[2][kGFast];
       bool live[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
         live[u] = i < N;
         if (live[u]) {
           r2[u] = __ldg(reinterpret_cast<const double2*>(g.r + i));
+          w2[u] = g.wt != nullptr ? __ldg(reinterpret_cast<const double2*>(g.wt + i)) : make_double2(1.0, 1.0);
 #pragma unroll
           for (int k = 0; k < kGFast; ++k) if (k < K) x2[u][k] = __ldg(reinterpret_cast<const double2*>(g.X + (long long) k * npad + i));
 #pragma unroll
@@ -82,8 +83,12 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
         for (int k = 0; k < kGFast; ++k) if (k < K) { eta0 += x2[u][k].x * sth[k]; eta1 += x2[u][k].y * sth[k]; }
 #pragma unroll
         for (int s_ = 0; s_ < kGFast; ++s_) if (s_ < slots) { eta0 += v2[u][s_].x * sth[K + c2[u][s_].x]; eta1 += v2[u][s_].y * sth[K + c2[u][s_].y]; }
-        const double e0 = r2[u].x - eta0, e1 = second ? r2[u].y - eta1 : 0.0;
-        S += e0 * e0; S += e1 * e1;
+        double e0 = r2[u].x - eta0, e1 = second ? r2[u].y - eta1 : 0.0;
+        if (g.wt != nullptr) {       // continuous.stan:365: sum w e^2; its gradient carries w e
+          const double we0 = w2[u].x * e0, we1 = w2[u].y * e1;
+          S += we0 * e0; S += we1 * e1;
+          e0 = we0; e1 = we1;
+        } else { S += e0 * e0; S += e1 * e1; }
 #pragma unroll
         for (int k = 0; k < kGFast; ++k) if (k < K) { double a = wb[k * 32 + lane]; a += x2[u][k].x * e0; a += x2[u][k].y * e1; wb[k * 32 + lane] = a; }
 #pragma unroll
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
       eta += v * sth[K + c];
     }
     double e = __ldg(g.r + i) - eta;
-    S += e * e;
+    if (g.wt != nullptr) { const double we = __ldg(g.wt + i) * e; S += we * e; e = we; } else S += e * e;
     for (int k = 0; k < K; ++k) wb[k * 32 + lane] += __ldg(g.X + (long long) k * npad + i) * e;
     for (int s = 0; s < slots; ++s) {
       int c = __ldg(g.zidx + (long long) s * npad + i);
@@ -245,6 +250,11 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   for (int k = 0; k < K_; ++k) S4B_CUDA(cudaMemcpy(d_X_ + (size_t) k * npad_, d.X + (size_t) k * N_, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice));
   dalloc(&d_y_, (size_t) npad_); dalloc(&d_offset_, (size_t) npad_); dalloc(&d_r_, (size_t) npad_); dalloc(&d_tmp_, (size_t) npad_);
   S4B_CUDA(cudaMemcpy(d_y_, d.y, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice));
+  if (d.weights != nullptr) {
+    for (long long i = 0; i < N_; ++i) if (!(d.weights[i] >= 0.0) || !std::isfinite(d.weights[i])) throw std::invalid_argument("glmm: weights must be finite and non-negative");
+    dalloc(&d_wt_, (size_t) npad_);
+    S4B_CUDA(cudaMemcpy(d_wt_, d.weights, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice));
+  }
   dalloc(&d_zval_, zval.size());
   S4B_CUDA(cudaMemcpy(d_zval_, zval.data(), sizeof(double) * zval.size(), cudaMemcpyHostToDevice));
   S4B_CUDA(cudaMalloc(&d_zidx_, sizeof(int) * zidx.size()));
@@ -265,7 +275,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) (nb + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
   S4B_CUDA(cudaMallocHost(&h_pinned_, sizeof(double) * 2 * ((size_t) nb + 1)));
-  // Gram matrix G = [X Z]'[X Z] (host, once): the model matrices never change during sampling
+  // Gram matrix G = [X Z]' W [X Z] (host, once): the model matrices never change during sampling
   if (nb > 0 && nb <= 512) {
     gram_.assign((size_t) nb * nb, 0.0);
     std::vector<int> cols((size_t) K_ + slots_);
@@ -274,7 +284,8 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
       int m = 0;
       for (int k = 0; k < K_; ++k) { cols[(size_t) m] = k; vals[(size_t) m] = d.X[(size_t) k * N_ + i]; ++m; }
       for (int z = d.u[i]; z < d.u[i + 1]; ++z) { cols[(size_t) m] = K_ + d.v[z]; vals[(size_t) m] = d.w[z]; ++m; }
-      for (int a = 0; a < m; ++a) for (int bb = 0; bb < m; ++bb) gram_[(size_t) cols[(size_t) a] * nb + cols[(size_t) bb]] += vals[(size_t) a] * vals[(size_t) bb];
+      const double wi = d.weights != nullptr ? d.weights[i] : 1.0;
+      for (int a = 0; a < m; ++a) for (int bb = 0; bb < m; ++bb) gram_[(size_t) cols[(size_t) a] * nb + cols[(size_t) bb]] += wi * vals[(size_t) a] * vals[(size_t) bb];
     }
     if (sharded()) shard_->allreduce_host(gram_.data(), (long long) gram_.size(), kOpSum, stream_);
     theta0_.assign((size_t) nb, 0.0); g0_.assign((size_t) nb, 0.0);
@@ -286,7 +297,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
 
 GlmmModel::~GlmmModel()
 {
-  cudaFree(d_X_); cudaFree(d_y_); cudaFree(d_offset_); cudaFree(d_r_); cudaFree(d_tmp_); cudaFree(d_zval_); cudaFree(d_zidx_);
+  cudaFree(d_X_); cudaFree(d_y_); cudaFree(d_offset_); cudaFree(d_r_); cudaFree(d_wt_); cudaFree(d_tmp_); cudaFree(d_zval_); cudaFree(d_zidx_);
   cudaFree(d_theta_); cudaFree(d_partials_); cudaFree(d_result_); cudaFree(d_ticket_); cudaFreeHost(h_pinned_);
   delete scratch_;
 }
@@ -365,7 +376,7 @@ void GlmmModel::data_terms(const double* beta, const double* b, double* S, doubl
   for (int k = 0; k < q_; ++k) h_theta[K_ + k] = b[k];
   if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
   GlmmDev g;
-  g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.zidx = d_zidx_; g.zval = d_zval_;
+  g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
   g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
   k_glmm_data_terms<<<grid_, kGBlock, smem_bytes_, stream_>>>(g);
   S4B_CUDA(cudaGetLastError());
@@ -385,7 +396,7 @@ void GlmmModel::parametric_mean_device(const double* beta, const double* b, doub
   for (int k = 0; k < q_; ++k) h_theta[K_ + k] = b[k];
   if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
   GlmmDev g;
-  g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.zidx = d_zidx_; g.zval = d_zval_;
+  g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
   g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
   int grid = (int) std::max<long long>(1, std::min<long long>((N_ + kGBlock - 1) / kGBlock, 148 * 8));
   k_glmm_linear_predictor<<<grid, kGBlock, sizeof(double) * (size_t) std::max(1, nb), stream_>>>(g, d_out, include_fixed ? 1 : 0, include_random ? 1 : 0);

@@ -14,6 +14,7 @@ struct GlmmDev {
   int K, q, slots, bins;
   const double* X;        // [K][npad]
   const double* r;        // y - offset, [npad]
+  const double* wt;       // observation weights [npad], nullptr = unweighted
   const int* zidx;        // [slots][npad]   (ELL, padded rows point at column 0 with value 0)
   const double* zval;     // [slots][npad]
   unsigned int ones_mask; // bit s set => every stored value of slot s is exactly 1.0
@@ -89,7 +90,7 @@ class GlmmModel {
   std::vector<double> gram_, theta0_, g0_;
   double S0_ = 0.0;
 
-  double *d_X_ = nullptr, *d_y_ = nullptr, *d_offset_ = nullptr, *d_r_ = nullptr, *d_zval_ = nullptr;
+  double *d_X_ = nullptr, *d_y_ = nullptr, *d_offset_ = nullptr, *d_r_ = nullptr, *d_wt_ = nullptr, *d_zval_ = nullptr;
   int* d_zidx_ = nullptr;
   double *d_theta_ = nullptr, *d_partials_ = nullptr, *d_result_ = nullptr, *d_tmp_ = nullptr;
   unsigned int* d_ticket_ = nullptr;

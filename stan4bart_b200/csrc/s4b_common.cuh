@@ -257,7 +257,8 @@ struct BartParams {
   // bart_args split.probs as integer weights (round(2^30 p_j / sum p), >= 1 when p_j > 0), nullptr = uniform
   const uint32_t* split_w;
   unsigned long long split_total; // sum of the weights
-  int p_pos, pad_sw;              // predictors with a positive weight
+  int p_pos;                      // predictors with a positive weight
+  int weighted;                   // observation weights present: leaf statistics are (count, sum w r, sum w)
 };
 
 }  // namespace s4b

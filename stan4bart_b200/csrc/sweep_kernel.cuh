@@ -508,16 +508,19 @@ __device__ __forceinline__ double accept_threshold(double u, int kind, double pr
 // SQ = false: the sum of squares is not available and not needed -- every Metropolis ratio compares two partitions of the
 // SAME observations, so the -sum(r^2) / (2 sigma^2) terms of the two sides cancel exactly; `ll` is then the integrated
 // log-likelihood without that common term: 1/2 log(a / (a + n/s2)) + 1/2 (n/s2)^2 avg^2 / (a + n/s2)
+// weighted: the slot holds (count, sum w r, sum w) -- y_i ~ N(mu, sigma^2 / w_i), so sum w takes the place of the count in the
+// data precision and the mean is the weighted one; the (cancelling) sum w r^2 is never formed
 template <bool SQ>
-__device__ __forceinline__ void slot_summary(const LeafStat& s, double inv_sigsq, double leaf_prec, double& pmean, double& psd, double& ll)
+__device__ __forceinline__ void slot_summary(const LeafStat& s, double inv_sigsq, double leaf_prec, bool weighted, double& pmean, double& psd, double& ll)
 {
-  const double dp = s.n * inv_sigsq;
+  const double neff = (SQ && weighted) ? s.sumsq : s.n;
+  const double dp = neff * inv_sigsq;
   const double rinv = 1.0 / (leaf_prec + dp);
   psd = sqrt(rinv);
-  if (s.n <= 0.0) { pmean = 0.0; ll = 0.0; return; }
-  const double avg = s.sum / s.n;
+  if (neff <= 0.0) { pmean = 0.0; ll = 0.0; return; }
+  const double avg = s.sum / neff;
   pmean = dp * avg * rinv;
-  if (SQ) {
+  if (SQ && !weighted) {
     double ss = s.sumsq - s.n * avg * avg;
     if (ss < 0.0) ss = 0.0;
     ll = 0.5 * log(leaf_prec * rinv) - 0.5 * ss * inv_sigsq - 0.5 * ((leaf_prec * avg) * (dp * avg)) * rinv;
@@ -547,7 +550,7 @@ __device__ inline void w_decide(DTree& t, const BartParams& P, WarpRng& rng, con
   for (int s = lane; s < nsum; s += 32) {
     LeafStat st = s < nslots ? stats[s] : LeafStat{ stats[sl_bd].n + stats[sr_bd].n, stats[sl_bd].sum + stats[sr_bd].sum, stats[sl_bd].sumsq + stats[sr_bd].sumsq };
     double pm, ps, ll;
-    slot_summary<SQ>(st, inv_sigsq, P.leaf_prec, pm, ps, ll);
+    slot_summary<SQ>(st, inv_sigsq, P.leaf_prec, P.weighted != 0, pm, ps, ll);
     cs.pmean[s] = pm; cs.psd[s] = ps; cs.ll[s] = ll;
     my_ll = ll; my_n = st.n;
   }
@@ -827,7 +830,7 @@ __device__ inline void w_decide_fast(const FastPlan& pl, DTree& t, const BartPar
     LeafStat st;
     if (lane < nslots) st = stats[lane];
     else { const LeafStat a = stats[pl.sl_bd], b = stats[pl.sr_bd]; st.n = a.n + b.n; st.sum = a.sum + b.sum; st.sumsq = a.sumsq + b.sumsq; }
-    slot_summary<SQ>(st, inv_sigsq, P.leaf_prec, my_pm, my_ps, my_ll);
+    slot_summary<SQ>(st, inv_sigsq, P.leaf_prec, P.weighted != 0, my_pm, my_ps, my_ll);
     my_n = st.n;
   }
   const long long f1 = clock64();
@@ -1110,13 +1113,21 @@ __device__ __forceinline__ void bin_add(double2* __restrict__ bin_s, int idx, do
   else { double* b1 = reinterpret_cast<double*>(bin_s); b1[idx] += pr; }
 }
 
+// weighted observation (SQ layout only): (sum w r, sum w)
+__device__ __forceinline__ void bin_add_w(double2* __restrict__ bin_s, int idx, double pr, double w)
+{
+  double2 v = bin_s[idx]; v.x = fma(w, pr, v.x); v.y += w; bin_s[idx] = v;
+}
+
 // (no __restrict__ / read-only qualifiers on R and the node-index buffers: they are rewritten inside the same kernel, and a
 // non-coherent load would return stale values)
 template <bool SQ>
 __device__ __forceinline__ void stream_acc_quad(const StepDesc& sd, const double2 ra, const double2 rb, const uint2 pk, long long q, long long n, int tid, int base,
-                                                int kmax, bool two_trees, int birth_node, int L, double2* __restrict__ bin_s, unsigned long long& cpk)
+                                                int kmax, bool two_trees, int birth_node, int L, double2* __restrict__ bin_s, unsigned long long& cpk,
+                                                const bool weighted, const double2 wa, const double2 wb)
 {
   const double r[4] = { ra.x, ra.y, rb.x, rb.y };
+  const double w[4] = { wa.x, wa.y, wb.x, wb.y };
   double pr[4]; int row[4], row2[4];
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
@@ -1131,10 +1142,10 @@ __device__ __forceinline__ void stream_acc_quad(const StepDesc& sd, const double
   }
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
-    bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
+    if (SQ && weighted) bin_add_w(bin_s, row[o] * kWorkers + tid, pr[o], w[o]); else bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
     if (row[o] < kBinSlots) cpk += 1ull << (8 * row[o]);
     if (two_trees) {
-      bin_add<SQ>(bin_s, row2[o] * kWorkers + tid, pr[o]);
+      if (SQ && weighted) bin_add_w(bin_s, row2[o] * kWorkers + tid, pr[o], w[o]); else bin_add<SQ>(bin_s, row2[o] * kWorkers + tid, pr[o]);
       if (row2[o] < kBinSlots) cpk += 1ull << (8 * row2[o]);
     }
   }
@@ -1147,26 +1158,32 @@ __device__ __forceinline__ void stream_upd_quad(const UpdateDesc& upd, double2& 
 template <bool SQ>
 __device__ __forceinline__ void stream_accumulate(const StepDesc& sd, const UpdateDesc* upd_prev, double* Rg, const uint2* packs_prev, const uint2* packs,
                                                   long long q_lo, long long q_hi, long long n, int tid, int base, int kmax, double2* __restrict__ bin_s,
-                                                  unsigned long long& cpk)
+                                                  unsigned long long& cpk, const double* __restrict__ wt)
 {
   const int kind = sd.b_kind, L = sd.b_num_leaves;
   const bool two_trees = (kind == 2 || kind == 3);
   const int birth_node = kind == 0 ? sd.b_node : -1;
   const bool fused = upd_prev != nullptr;
+  const bool weighted = wt != nullptr;
   const int pmode = fused ? upd_prev->mode : 0, pnode = fused ? upd_prev->node : 0;
   for (long long q0 = q_lo; q0 < q_hi; q0 += 2 * kWorkers) {
     const long long qa = q0 + tid, qb = qa + kWorkers;
     const bool la = qa < q_hi, lb = qb < q_hi;
     double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0; uint2 pa = make_uint2(0u, 0u), pb = pa, ua = pa, ub = pa;
+    double2 wa0 = make_double2(1.0, 1.0), wa1 = wa0, wb0 = wa0, wb1 = wa0;
     if (la) { a0 = *reinterpret_cast<const double2*>(Rg + 4 * qa); a1 = *reinterpret_cast<const double2*>(Rg + 4 * qa + 2); pa = packs[qa]; if (fused) ua = packs_prev[qa]; }
     if (lb) { b0 = *reinterpret_cast<const double2*>(Rg + 4 * qb); b1 = *reinterpret_cast<const double2*>(Rg + 4 * qb + 2); pb = packs[qb]; if (fused) ub = packs_prev[qb]; }
+    if (SQ && weighted) {
+      if (la) { wa0 = __ldg(reinterpret_cast<const double2*>(wt + 4 * qa)); wa1 = __ldg(reinterpret_cast<const double2*>(wt + 4 * qa + 2)); }
+      if (lb) { wb0 = __ldg(reinterpret_cast<const double2*>(wt + 4 * qb)); wb1 = __ldg(reinterpret_cast<const double2*>(wt + 4 * qb + 2)); }
+    }
     if (la) {
       if (fused) { stream_upd_quad(*upd_prev, a0, a1, ua, pmode, pnode); *reinterpret_cast<double2*>(Rg + 4 * qa) = a0; *reinterpret_cast<double2*>(Rg + 4 * qa + 2) = a1; }
-      stream_acc_quad<SQ>(sd, a0, a1, pa, qa, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+      stream_acc_quad<SQ>(sd, a0, a1, pa, qa, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk, weighted, wa0, wa1);
     }
     if (lb) {
       if (fused) { stream_upd_quad(*upd_prev, b0, b1, ub, pmode, pnode); *reinterpret_cast<double2*>(Rg + 4 * qb) = b0; *reinterpret_cast<double2*>(Rg + 4 * qb + 2) = b1; }
-      stream_acc_quad<SQ>(sd, b0, b1, pb, qb, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk);
+      stream_acc_quad<SQ>(sd, b0, b1, pb, qb, n, tid, base, kmax, two_trees, birth_node, L, bin_s, cpk, weighted, wb0, wb1);
     }
   }
 }
@@ -1325,7 +1342,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         // slots outside this pass); loads first (independent), then the read-modify-write chain
         if (STREAM) {
           stream_accumulate<SQ>(sd, (t > 0 && chunk == 0) ? &S.upd[(t - 1) & 1] : nullptr, dv.R, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad,
-                            dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, n, tid, base, kmax, bin_s, cpk);
+                            dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, n, tid, base, kmax, bin_s, cpk, dv.wt);
         } else if (!two_trees) {
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {

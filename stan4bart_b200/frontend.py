@@ -98,8 +98,9 @@ def _ranef_terms_to_csr(n, terms):
 
 
 def build_stan_data(X_fixed, y, ranef_terms, is_binary=False, prior_scale=2.5, autoscale=True,
-                    decov=(1.0, 1.0, 1.0, 1.0)):
-    """Mirror of the data.stan list built at R/stan4bart_fit.R:259-365 on the default path."""
+                    decov=(1.0, 1.0, 1.0, 1.0), weights=None):
+    """Mirror of the data.stan list built at R/stan4bart_fit.R:259-365 on the default path.  weights: observation weights
+    (`has_weights` / `weights`); all-one weights are dropped as at R/stan4bart_fit.R:255."""
     X_fixed = np.asarray(X_fixed, dtype=np.float64)
     n = len(y)
     if X_fixed.ndim == 1:
@@ -130,6 +131,8 @@ def build_stan_data(X_fixed, y, ranef_terms, is_binary=False, prior_scale=2.5, a
         p=p, l=l, shape=np.full(t, shape), scale=np.full(t, scale), concentration=np.full(len_conc, conc),
         regularization=np.full(len_reg, reg), w=w, v=v, u=u, q=q)
     sd.xbar = xbar
+    if weights is not None and len(weights) > 0 and not np.all(np.asarray(weights) == 1):
+        sd.weights = np.ascontiguousarray(weights, dtype=np.float64)
     sd.term_order = order
     return sd
 

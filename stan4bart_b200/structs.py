@@ -26,6 +26,7 @@ class BartConfig(C.Structure):
         ("birth_death_prob", C.c_double), ("swap_prob", C.c_double), ("change_prob", C.c_double),
         ("birth_prob", C.c_double), ("base", C.c_double), ("power", C.c_double), ("k", C.c_double),
         ("node_scale", C.c_double), ("seed", C.c_uint64), ("split_probs", C.POINTER(C.c_double)),
+        ("weights", C.POINTER(C.c_double)),
     ]
 
 
@@ -39,7 +40,7 @@ class GlmmData(C.Structure):
         ("prior_scale_for_aux", C.c_double), ("prior_mean_for_aux", C.c_double), ("prior_df_for_aux", C.c_double),
         ("p", c_int32_p), ("l", c_int32_p), ("shape", c_double_p), ("scale", c_double_p),
         ("concentration", c_double_p), ("regularization", c_double_p),
-        ("w", c_double_p), ("v", c_int32_p), ("u", c_int32_p),
+        ("w", c_double_p), ("v", c_int32_p), ("u", c_int32_p), ("weights", c_double_p),
     ]
 
 
@@ -77,7 +78,7 @@ def i32(a):
 
 def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_binary=False,
                 base=0.95, power=2.0, k=2.0, node_scale=None, seed=0,
-                birth_death_prob=0.5, swap_prob=0.1, change_prob=0.4, birth_prob=0.5, split_probs=None, max_ctas=0):
+                birth_death_prob=0.5, swap_prob=0.1, change_prob=0.4, birth_prob=0.5, split_probs=None, max_ctas=0, weights=None):
     """dbarts defaults as used by stan4bart (R/stan4bart_fit.R:437-479).  split_probs: relative probabilities of the p
     predictors (bart_args split.probs), None = uniform."""
     if node_scale is None:
@@ -92,6 +93,12 @@ def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_
             raise ValueError("split_probs must be p non-negative numbers, not all zero")
         cfg._split_probs = sp                       # keeps the array alive with the struct
         cfg.split_probs = sp.ctypes.data_as(C.POINTER(C.c_double))
+    if weights is not None:
+        wt = np.ascontiguousarray(weights, dtype=np.float64)
+        if wt.shape != (n,) or not np.all(np.isfinite(wt)) or np.any(wt < 0):
+            raise ValueError("weights must be n finite non-negative numbers")
+        cfg._weights = wt
+        cfg.weights = wt.ctypes.data_as(C.POINTER(C.c_double))
     return cfg
 
 
@@ -150,6 +157,8 @@ class StanData:
         for name in ("xbar", "term_order"):
             if hasattr(self, name):
                 setattr(out, name, getattr(self, name))
+        if getattr(self, "weights", None) is not None:
+            out.weights = np.ascontiguousarray(self.weights[lo:hi])
         return out
 
     def struct(self):
@@ -163,7 +172,17 @@ class StanData:
             prior_df_for_aux=self.prior_df_for_aux,
             p=i32ptr(self.p), l=i32ptr(self.l), shape=dptr(self.shape), scale=dptr(self.scale),
             concentration=dptr(self.concentration), regularization=dptr(self.regularization),
-            w=dptr(self.w), v=i32ptr(self.v), u=i32ptr(self.u))
+            w=dptr(self.w), v=i32ptr(self.v), u=i32ptr(self.u), weights=self._weights_ptr())
+
+    def _weights_ptr(self):
+        """data.stan `weights` (R/stan4bart_fit.R:255-262): None = unweighted (a NULL pointer)."""
+        wt = getattr(self, "weights", None)
+        if wt is None:
+            return None
+        self.weights = np.ascontiguousarray(wt, dtype=np.float64)
+        if self.weights.shape != (self.N,):
+            raise ValueError("weights must have one entry per observation")
+        return dptr(self.weights)
 
     def param_names(self):
         """Names of the stored Stan rows, continuous.hpp:3115-3204 (constrained_param_names)."""

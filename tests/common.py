@@ -28,9 +28,10 @@ def bart_problem(n=500, p=5, n_test=0, binary=False, seed=3):
     return x, y, xt
 
 
-def compare_traces(tr_o, tr_g, tol=REL_TOL):
+def compare_traces(tr_o, tr_g, tol=REL_TOL, ll_difference_only=False):
     """Integer fields exact, floating fields to `tol` (relative, with a small absolute floor for
-    log-likelihood sums that can be near zero)."""
+    log-likelihood sums that can be near zero).  ll_difference_only (weighted fits): the device never forms the
+    sum w r^2 term that is common to both sides of a Metropolis ratio, so only new - old log-likelihood is comparable."""
     assert tr_o.shape == tr_g.shape, (tr_o.shape, tr_g.shape)
     int_cols = [0, 1, 2, 3, 4, 8, 9, 10]
     for c in int_cols:
@@ -43,7 +44,13 @@ def compare_traces(tr_o, tr_g, tol=REL_TOL):
     ll_scale = np.maximum(1.0, np.maximum(np.abs(tr_o[:, 6]), np.abs(tr_o[:, 7])))
     lerr = np.abs(np.log(ra[pos]) - np.log(rb[pos])) / ll_scale[pos]
     assert lerr.size == 0 or lerr.max() <= tol, f"log ratio differs by {lerr.max():.3e} (relative to |log-lik|)"
-    for c in [6, 7] + list(range(11, tr_o.shape[1])):
+    if ll_difference_only:
+        do, dg = tr_o[:, 7] - tr_o[:, 6], tr_g[:, 7] - tr_g[:, 6]
+        fin = np.isfinite(do) & np.isfinite(dg)
+        assert np.array_equal(fin, np.isfinite(do) | np.isfinite(dg))
+        derr = np.abs(do[fin] - dg[fin]) / ll_scale[fin]
+        assert derr.size == 0 or derr.max() <= tol, f"log-likelihood difference differs by {derr.max():.3e}"
+    for c in ([] if ll_difference_only else [6, 7]) + list(range(11, tr_o.shape[1])):
         a, b = tr_o[:, c], tr_g[:, c]
         # floors: log-likelihood sums and leaf draws are differences that can cancel to ~0
         floor = 1.0 if c in (6, 7) else 1e-3
@@ -71,6 +78,8 @@ def load_glmm_case(path):
         sd.prior_scale_for_aux = c["prior_scale_for_aux"]
     sd.prior_dist = c["prior_dist"]
     sd.prior_scale = np.asarray(c["prior_scale"], dtype=np.float64)
+    if "weights" in c:
+        sd.weights = np.asarray(c["weights"], dtype=np.float64)
     return sd, c
 
 

@@ -154,7 +154,14 @@ def log_prob(sd, q, offset, y):
     rows = np.repeat(np.arange(sd.N), np.diff(u))
     Zb = torch.zeros(sd.N).index_add(0, torch.as_tensor(rows), torch.as_tensor(sd.w) * b[torch.as_tensor(sd.v.astype(np.int64))])
     eta = eta + Zb
-    lp = lp + normal_lpdf(torch.as_tensor(y), eta, aux if not sd.is_binary else torch.ones(()))
+    actual_aux = aux if not sd.is_binary else torch.ones(())
+    if getattr(sd, "weights", None) is None:
+        lp = lp + normal_lpdf(torch.as_tensor(y), eta, actual_aux)
+    else:
+        # continuous.stan:358-366 (the sum of the log weights is dropped there)
+        wt = torch.as_tensor(sd.weights)
+        lp = lp + (-0.5 * sd.N * torch.log(6.283185307179586232 * actual_aux * actual_aux)
+                   - 0.5 * (wt * (torch.as_tensor(y) - eta) ** 2).sum() / (actual_aux * actual_aux))
     if (not sd.is_binary) and sd.prior_dist_for_aux > 0 and sd.prior_scale_for_aux > 0:
         log_half = -0.693147180559945286
         if sd.prior_dist_for_aux == 1:
@@ -193,7 +200,7 @@ def log_prob(sd, q, offset, y):
     return lp, dict(beta=beta, b=b, theta_L=theta_L, aux=aux, rho=rho, zeta=zeta, tau=tau, z_T=z_T)
 
 
-def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1):
+def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1, weighted=False):
     rng = np.random.default_rng(seed)
     Xf = np.column_stack([rng.random(N), (rng.random(N) < 0.3).astype(float)])
     terms = []
@@ -216,6 +223,9 @@ def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1):
     if binary:
         y = rng.standard_normal(N) + 0.3      # latents
         sd.y = y
+    if weighted:
+        sd.weights = rng.gamma(2.0, 0.5, N)
+        sd.weights[:3] = [0.0, 1.0, 2.5]
     qs, lps, grads, was = [], [], [], []
     for k in range(3):
         q = torch.tensor(rng.uniform(-1.5, 1.5, sd.num_params), requires_grad=True)
@@ -232,6 +242,7 @@ def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1):
         was.append([float(v) for v in cons])
     case = dict(name=name, N=N, binary=binary, X_fixed=Xf.tolist(), y=np.asarray(y).tolist(), y_for_scaling=None, offset=offset.tolist(),
                 groups=groups, aux_prior=aux_prior, prior_dist=prior_dist,
+                **(dict(weights=sd.weights.tolist()) if weighted else {}),
                 prior_scale=sd.prior_scale.tolist(), prior_scale_for_aux=sd.prior_scale_for_aux,
                 prior_mean_for_aux=sd.prior_mean_for_aux, prior_df_for_aux=sd.prior_df_for_aux,
                 q=qs, lp=lps, grad=grads, write_array=was)
@@ -248,3 +259,5 @@ if __name__ == "__main__":
     make_case("no_ranef_flat_prior", 30, 5, False, [], aux_prior=0, prior_dist=0)
     make_case("three_coefficients", 80, 6, False, [(4, 3), (6, 1)])
     make_case("four_and_three_binary", 90, 7, True, [(3, 4), (5, 3), (4, 2)])
+    make_case("weighted", 64, 8, False, [(5, 2), (6, 1)], weighted=True)
+    make_case("weighted_binary", 55, 9, True, [(4, 3), (3, 1)], weighted=True)

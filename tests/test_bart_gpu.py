@@ -402,3 +402,67 @@ def test_chain_confined_to_a_share_of_the_sms(monkeypatch):
     for b in fits[1:]:
         compare_traces(o.trace(), b.trace(), tol=1e-9)
         assert b.sweep_mode() == 2
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_observation_weights(binary):
+    """`weights` of stan4bart() as dbarts data weights: leaf statistics sum w / sum w r; same decisions, partitions and
+    leaf draws as the oracle, traced and untraced.  Some zero weights: such rows follow the trees but carry no information."""
+    T, sweeps, n = 12, 8, 2500
+    x, y, xt = bart_problem(n, 6, 40, binary, seed=21)
+    rng = np.random.default_rng(5)
+    wt = rng.gamma(2.0, 0.5, n)
+    wt[rng.random(n) < 0.05] = 0.0
+    cfg = bart_config(n, 6, n_test=40, num_trees=T, is_binary=binary, seed=77, weights=wt)
+    off = 0.3 * x[:, 3] - 0.1
+    o = O.OracleBart(cfg, y, x, xt)
+    g_tr, g_pl = GpuBart(cfg, y, x, xt), GpuBart(cfg, y, x, xt)
+    for b in (o, g_tr, g_pl):
+        b.set_offset(off, True)
+        if not binary:
+            b.set_sigma(1.3)
+        b.sample_trees_from_prior()
+    o.set_trace(T * sweeps); g_tr.set_trace(T * sweeps)
+    for s in range(sweeps):
+        ro, r1, r2 = o.run(), g_tr.run(), g_pl.run()
+        assert rel_err(ro["train"], r1["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9, f"sweep {s}"
+        assert rel_err(r1["train"], r2["train"], scale=np.abs(r1["train"]) + 1.0) <= 1e-10, f"sweep {s}"
+        assert rel_err(ro["test"], r2["test"], scale=np.abs(ro["test"]) + 1.0) <= 1e-9
+        assert np.array_equal(ro["varcount"], r2["varcount"])
+    compare_traces(o.trace(), g_tr.trace(), ll_difference_only=True)
+    assert_same_partition(o, g_pl, T)
+    assert g_tr.rng_counter() == g_pl.rng_counter() == o.rng_counter()
+    # the weights matter: an unweighted chain from the same seed takes other decisions
+    cfg_u = bart_config(n, 6, n_test=40, num_trees=T, is_binary=binary, seed=77)
+    u = GpuBart(cfg_u, y, x, xt)
+    u.set_offset(off, True)
+    if not binary:
+        u.set_sigma(1.3)
+    u.sample_trees_from_prior()
+    for s in range(sweeps):
+        ru = u.run()
+    assert not np.array_equal(ru["train"], r2["train"])
+
+
+def test_constant_weights_rescale_sigma():
+    """y_i ~ N(mu, sigma^2 / c) for every i is the unweighted model with sigma / sqrt(c)."""
+    T, n, c = 10, 1500, 4.0
+    x, y, xt = bart_problem(n, 5, 0, False, seed=8)
+    gw = GpuBart(bart_config(n, 5, num_trees=T, seed=5, weights=np.full(n, c)), y, x, xt)
+    gu = GpuBart(bart_config(n, 5, num_trees=T, seed=5), y, x, xt)
+    gw.set_sigma(1.3); gu.set_sigma(1.3 / np.sqrt(c))
+    gw.sample_trees_from_prior(); gu.sample_trees_from_prior()
+    for s in range(6):
+        rw, ru = gw.run(), gu.run()
+        assert rel_err(rw["train"], ru["train"], scale=np.abs(ru["train"]) + 1.0) <= 1e-9
+    assert np.array_equal(gw.trees()["var"], gu.trees()["var"])
+
+
+def test_weighted_fit_refuses_the_per_tree_modes():
+    from stan4bart_b200._lib import S4BError
+    x, y, xt = bart_problem(300, 5, 0, False)
+    g = GpuBart(bart_config(300, 5, num_trees=5, weights=np.ones(300)), y, x, xt)
+    with pytest.raises(S4BError):
+        g.set_sweep_mode(0)
+    with pytest.raises(ValueError):
+        bart_config(300, 5, weights=-np.ones(300))

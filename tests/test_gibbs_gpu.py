@@ -330,3 +330,34 @@ def test_three_coefficient_block_first_sweeps():
     assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-8
     names = sd.param_names()
     assert sum(nm.startswith("z_T") for nm in names) == 2
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_observation_weights_first_sweeps(binary):
+    """`stan4bart(weights = ...)` (R/stan4bart_fit.R:255-262, :449): the weights reach both halves -- dbarts data weights in
+    the tree statistics and `weights` of continuous.stan:358-366 -- and the sweeps agree with the oracle step by step."""
+    n, nt, seed, K = 500, 9, 31, 6
+    pr = friedman_problem(n, binary=binary)
+    rng = np.random.default_rng(17)
+    wt = rng.gamma(3.0, 1.0 / 3.0, n)
+    sd = pr["stan_data"]
+    sd.weights = wt
+    cfg = bart_config(n, 9, n_test=n, num_trees=nt, is_binary=binary, seed=seed, weights=wt)
+    ctl = stan_control(seed=seed + 1)
+    kw = dict(warmup=K, iter_=8, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    g = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    ob, gb = o.bart(), g.bart()
+    ob.set_trace(nt * K); gb.set_trace(nt * K)
+    ro, rg = o.run(K, True), g.run(K, True)
+    compare_traces(ob.trace(), gb.trace(), tol=1e-8, ll_difference_only=True)
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["test"], rg["bart"]["test"], scale=np.abs(ro["bart"]["test"]) + 1.0) <= 1e-8
+    assert np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"])
+    # and they matter: the unweighted chain from the same seeds differs
+    sd.weights = None
+    cfg_u = bart_config(n, 9, n_test=n, num_trees=nt, is_binary=binary, seed=seed)
+    u = Sampler(cfg_u, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    ru = u.run(K, True)
+    assert not np.allclose(ru["stan"], rg["stan"])

@@ -146,3 +146,27 @@ def test_blocks_with_more_than_two_coefficients_match_oracle(ncoef):
             assert abs(lo - lg) <= REL_TOL * abs(lo)
             assert rel_err(go, gg, scale=np.abs(go) + 1e-8 * np.max(np.abs(go))) <= REL_TOL
             assert rel_err(mo.write_array(q), mg.write_array(q)) <= 1e-12
+
+
+def test_weighted_data_pass_general_path_and_scale():
+    """Observation weights outside the fast path (K > 4) and at a size with many blocks, both evaluation modes."""
+    from stan4bart_b200.frontend import build_stan_data
+    rng = np.random.default_rng(3)
+    N = 50001
+    g1 = rng.integers(0, 9, N)
+    M1 = np.column_stack([np.ones(N), rng.standard_normal(N)])
+    wt = rng.gamma(2.0, 0.5, N)
+    wt[::97] = 0.0
+    sd = build_stan_data(rng.standard_normal((N, 6)), rng.standard_normal(N), [(g1, M1)], weights=wt)
+    off = rng.standard_normal(N)
+    mo, mg = O.OracleGlmm(sd), GlmmModel(sd)
+    mo.set_offset(off); mg.set_offset(off)
+    for mode in (0, 1):
+        mg.set_mode(mode)
+        for _ in range(3):
+            q = rng.uniform(-1, 1, mo.d)
+            lo, go, so = mo.log_prob_grad(q)
+            lg, gg, sg = mg.log_prob_grad(q)
+            assert so == sg == 0
+            assert abs(lo - lg) <= REL_TOL * abs(lo)
+            assert rel_err(go, gg, scale=np.abs(go) + 1e-8 * np.max(np.abs(go))) <= REL_TOL

@@ -176,3 +176,28 @@ def test_split_probs_prior_frequencies():
     freq = counts / counts.sum()
     want = sp / sp.sum()
     assert np.all(np.abs(freq - want) < 4 * np.sqrt(want * (1 - want) / counts.sum()) + 1e-9)
+
+
+def test_observation_weights_semantics():
+    """Unit weights are the unweighted model (bit for bit); a constant weight c is sigma / sqrt(c); the leaf statistics of a
+    weighted fit are the weighted mean with effective count sum w."""
+    n, T = 400, 8
+    x, y, xt = bart_problem(n, 4, 0, False, seed=2)
+
+    def run(weights, sigma, sweeps=5):
+        o = O.OracleBart(bart_config(n, 4, num_trees=T, seed=9, weights=weights), y, x, xt)
+        o.set_sigma(sigma)
+        o.sample_trees_from_prior()
+        o.set_trace(T * sweeps)
+        out = [o.run()["train"].copy() for _ in range(sweeps)]
+        return out, o.trace()
+
+    base, tr0 = run(None, 1.1)
+    ones, tr1 = run(np.ones(n), 1.1)
+    assert all(np.array_equal(a, b) for a, b in zip(base, ones)) and np.array_equal(tr0, tr1)
+    c = 2.5
+    scaled, _ = run(np.full(n, c), 1.1 * np.sqrt(c))
+    assert max(rel_err(a, b, scale=np.abs(a) + 1.0) for a, b in zip(base, scaled)) <= 1e-9
+    rng = np.random.default_rng(0)
+    other, _ = run(rng.gamma(2.0, 0.5, n), 1.1)
+    assert not np.array_equal(other[-1], base[-1])
