@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--trees", type=int, default=200)
     ap.add_argument("--adapt", type=int, default=200, help="adaptation sweeps before adaptation is disengaged (untimed; >= 150 so that the metric windows of Stan run)")
     ap.add_argument("--continuous", action="store_true", help="continuous response (configs B / E) instead of the probit model of config C")
+    ap.add_argument("--weighted", action="store_true", help="observation weights (`weights` of stan4bart()): a non-default branch, not the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-rows", action="store_true",
                     help="N > 1 only: ONE chain whose --n rows are sharded over the N GPUs (BASELINE config E; strong scaling) instead of "
@@ -50,6 +51,8 @@ def parse_args():
 
 def workload_config(args):
     what = "continuous Friedman causal" if args.continuous else "config C: binary probit Friedman causal"
+    if args.weighted:
+        what += " with observation weights"
     return {"workload": "%s, n=%d, %d trees, p_bart=9, K=2, q=18, n_test=%d, "
                         "1 chain per GPU" % (what, args.n, args.trees, args.n),
             "n": args.n, "trees": args.trees, "chains_per_gpu": 1, "parallelism": "chain-per-GPU, no data-path collective",
@@ -62,7 +65,14 @@ def workload_config(args):
 
 def make_problem(args):
     from stan4bart_b200.frontend import friedman_problem
-    return friedman_problem(args.n, binary=not args.continuous, seed=99)
+    pr = friedman_problem(args.n, binary=not args.continuous, seed=99)
+    return add_weights(pr, args.n) if args.weighted else pr
+
+
+def add_weights(pr, n):
+    pr["weights"] = np.random.default_rng(4).gamma(3.0, 1.0 / 3.0, n)
+    pr["stan_data"].weights = pr["weights"]
+    return pr
 
 
 # ------------------------------------------------------------------------------------------------
@@ -158,7 +168,7 @@ def cpu_baseline(args, pr, budget_s):
     import oracle_lib as O
     from stan4bart_b200.structs import bart_config, stan_control
     sd = pr["stan_data"]
-    cfg = bart_config(args.n, 9, n_test=args.n, num_trees=args.trees, is_binary=not args.continuous, seed=12345)
+    cfg = bart_config(args.n, 9, n_test=args.n, num_trees=args.trees, is_binary=not args.continuous, seed=12345, weights=pr.get("weights"))
     extra = {"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}
     t0 = time.time()
     s = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=1), warmup=10, iter_=20, keep_fits=False, **extra)
@@ -185,7 +195,9 @@ def _ref_worker(args_dict, seed, conn):
         n, trees = args_dict["n"], args_dict["trees"]
         binary = not args_dict.get("continuous", False)
         pr = friedman_problem(n, binary=binary, seed=99)
-        cfg = bart_config(n, 9, n_test=n, num_trees=trees, is_binary=binary, seed=seed)
+        if args_dict.get("weighted"):
+            pr = add_weights(pr, n)
+        cfg = bart_config(n, 9, n_test=n, num_trees=trees, is_binary=binary, seed=seed, weights=pr.get("weights"))
         extra = {} if binary else {"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]}
         s = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=seed), warmup=10, iter_=20,
                             keep_fits=False, **extra)
@@ -217,7 +229,7 @@ def run_reference(args):
     workers = []
     for c in range(procs):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(dict(n=args.n, trees=args.trees, continuous=args.continuous), 12345 + c, b), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(dict(n=args.n, trees=args.trees, continuous=args.continuous, weighted=args.weighted), 12345 + c, b), daemon=True)
         p.start()
         workers.append((p, a))
     for _, a in workers:
@@ -298,7 +310,7 @@ def run_ours(args):
         chains = 1
     seed_rank = 0 if sharded else rank
     sd = pr["stan_data"]
-    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=not args.continuous, seed=chain_seed(12345, seed_rank))
+    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=not args.continuous, seed=chain_seed(12345, seed_rank), weights=pr.get("weights"))
     s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=chain_seed(1000, seed_rank)), warmup=args.adapt,
                 iter_=args.adapt + args.steps, keep_fits=False, shard=shard_ctx,
                 **({"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}))

@@ -177,6 +177,8 @@ def shard_problem(prob, lo, hi):
     out["stan_data"] = prob["stan_data"].rows(lo, hi)
     out["y"] = np.ascontiguousarray(prob["y"][lo:hi])
     out["bart_offset_init"] = np.ascontiguousarray(prob["bart_offset_init"][lo:hi])
+    if prob.get("weights") is not None:
+        out["weights"] = np.ascontiguousarray(prob["weights"][lo:hi])
     return out
 
 

@@ -31,3 +31,8 @@ def glmm_offset():
 def glmm_points(d):
     rng = np.random.default_rng(5)
     return [rng.uniform(-1.0, 1.0, d) for _ in range(3)]
+
+
+def gibbs_weights():
+    rng = np.random.default_rng(77)
+    return rng.gamma(3.0, 1.0 / 3.0, GIBBS_N)

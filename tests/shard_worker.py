@@ -142,6 +142,24 @@ def main():
         res[f"gibbs_{tag}_mean_train"] = m["bart_train"]
         del b, s
 
+    # ---- the same with observation weights (weighted leaf statistics cross the ranks as sum w r / sum w) ----
+    pr = friedman_problem(SC.GIBBS_N)
+    pr["stan_data"].weights = SC.gibbs_weights()
+    lo, hi = row_range(SC.GIBBS_N, rank, world)
+    ctx.set_obs_range(lo, SC.GIBBS_N)
+    sp = shard_problem(pr, lo, hi)
+    cfg = bart_config(hi - lo, 9, n_test=hi - lo, num_trees=SC.GIBBS_TREES, seed=SC.GIBBS_SEED, weights=SC.gibbs_weights()[lo:hi])
+    ctl = stan_control(seed=SC.GIBBS_SEED + 1)
+    s = Sampler(cfg, sp["y"], sp["x_bart"], sp["x_test"], sp["stan_data"], ctl, warmup=SC.GIBBS_WARMUP, iter_=SC.GIBBS_ITER,
+                keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=sp["bart_offset_init"], shard=ctx)
+    b = s.bart()
+    b.set_trace(SC.GIBBS_TREES * SC.GIBBS_WARMUP)
+    w = s.run(SC.GIBBS_WARMUP, True)
+    res["gibbs_wt_trace"] = b.trace()
+    res["gibbs_wt_stan"] = w["stan"]
+    res["gibbs_wt_train"] = w["bart"]["train"]
+    del b, s
+
     np.savez(f"{args.out}.rank{rank}.npz", **res)
     dist.barrier()
     dist.destroy_process_group()

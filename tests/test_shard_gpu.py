@@ -154,3 +154,23 @@ def test_sharded_gibbs_matches_whole_data_oracle(ranks, binary):
     assert ranks[1][f"gibbs_{tag}_parmean"].shape == (hi - lo,)
     got = _cat(ranks, f"gibbs_{tag}_mean_train")
     assert rel_err(s["bart"]["train"].mean(axis=1), got, scale=1.0) <= 1e-7
+
+
+def test_sharded_weighted_gibbs_matches_whole_data_oracle(ranks):
+    n = SC.GIBBS_N
+    pr = friedman_problem(n)
+    wt = SC.gibbs_weights()
+    pr["stan_data"].weights = wt
+    cfg = bart_config(n, 9, n_test=n, num_trees=SC.GIBBS_TREES, seed=SC.GIBBS_SEED, weights=wt)
+    ctl = stan_control(seed=SC.GIBBS_SEED + 1)
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, warmup=SC.GIBBS_WARMUP, iter_=SC.GIBBS_ITER,
+                        keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    ob = o.bart()
+    ob.set_trace(SC.GIBBS_TREES * SC.GIBBS_WARMUP)
+    w = o.run(SC.GIBBS_WARMUP, True)
+    for r in ranks:
+        compare_traces(ob.trace(), r["gibbs_wt_trace"], tol=1e-7, ll_difference_only=True)
+        assert rel_err(w["stan"], r["gibbs_wt_stan"], scale=np.abs(w["stan"]) + 1.0) <= 1e-7
+    assert np.array_equal(ranks[0]["gibbs_wt_trace"], ranks[1]["gibbs_wt_trace"])
+    got = _cat(ranks, "gibbs_wt_train", axis=0)
+    assert rel_err(w["bart"]["train"], got, scale=np.abs(w["bart"]["train"]) + 1.0) <= 1e-7
