@@ -62,6 +62,11 @@ typedef struct s4b_glmm_data {
   const double* w; const int32_t* v; const int32_t* u;
   /* data.stan `has_weights` / `weights` (R/stan4bart_fit.R:255-262, continuous.stan:358-366): NULL = unweighted */
   const double* weights;
+  /* non-default coefficient priors (continuous.stan:184-186, :207-215): prior_dist 2 student_t (prior_df), 3 hs / 4 hs_plus
+   * (prior_df, global_prior_df, global_prior_scale, slab_df, slab_scale; hs_plus reads prior_scale as a second df), 5 laplace,
+   * 6 lasso (prior_df[0]), 7 product_normal (num_normals, K entries >= 2).  prior_df / num_normals may be NULL when unused. */
+  const double* prior_df; const int32_t* num_normals;
+  double global_prior_df, global_prior_scale, slab_df, slab_scale;
 } s4b_glmm_data;
 
 /* StanControl, src/stan_sampler.hpp:28-42 */

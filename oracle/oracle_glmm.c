@@ -31,6 +31,10 @@ struct or_glmm {
   double *prior_scale, *prior_mean, *shape, *scale, *concentration, *regularization, *w, *delta;
   int32_t *p, *l, *v, *u;
   int len_rho, len_z_T, num_params, has_aux;
+  /* coefficient priors beyond normal (continuous.stan:262-270): z_beta may be longer than K (product_normal) and the
+   * shrinkage priors add positive parameters global[hs], local[hs][K], caux[hs > 0], mix[K], one_over_lambda */
+  double* prior_df; int32_t* num_normals;
+  int hs, len_zbeta, len_extra;
 };
 #define OR_MAX_NC 16
 
@@ -41,7 +45,10 @@ static void* dup_mem(const void* src, size_t bytes) { void* r = malloc(bytes ? b
 or_glmm* or_glmm_create(const s4b_glmm_data* d)
 {
   for (int i = 0; i < d->t; ++i) if (d->p[i] < 1 || d->p[i] > OR_MAX_NC) return NULL;
-  if (d->prior_dist < 0 || d->prior_dist > 1) return NULL;
+  if (d->prior_dist < 0 || d->prior_dist > 7) return NULL;
+  if ((d->prior_dist == 3 || d->prior_dist == 4) && d->is_binary) return NULL;      /* hs_prior reads aux[1] */
+  if ((d->prior_dist == 2 || d->prior_dist == 3 || d->prior_dist == 4 || d->prior_dist == 6) && d->K > 0 && !d->prior_df) return NULL;
+  if (d->prior_dist == 7 && d->K > 0 && !d->num_normals) return NULL;
   or_glmm* m = (or_glmm*) calloc(1, sizeof(or_glmm));
   m->d = *d;
   size_t N = (size_t) d->N, K = (size_t) d->K, t = (size_t) d->t;
@@ -71,14 +78,20 @@ or_glmm* or_glmm_create(const s4b_glmm_data* d)
   m->len_z_T = 0;
   for (int i = 0; i < d->t; ++i) if (d->p[i] > 2) m->len_z_T += (d->p[i] - 2) * (d->p[i] - 1);      /* continuous.stan:258 */
   m->has_aux = d->is_binary ? 0 : 1;
-  m->num_params = d->K + d->q + m->len_z_T + m->len_rho + d->len_concentration + d->t + m->has_aux;
+  m->prior_df = d->prior_df ? (double*) dup_mem(d->prior_df, sizeof(double) * K) : NULL;
+  m->num_normals = d->num_normals ? (int32_t*) dup_mem(d->num_normals, sizeof(int32_t) * K) : NULL;
+  m->hs = d->prior_dist == 3 ? 2 : (d->prior_dist == 4 ? 4 : 0);
+  m->len_zbeta = d->K;
+  if (d->prior_dist == 7) { m->len_zbeta = 0; for (int k = 0; k < d->K; ++k) { if (d->num_normals[k] < 2) { or_glmm_free(m); return NULL; } m->len_zbeta += d->num_normals[k]; } }
+  m->len_extra = m->hs + m->hs * d->K + (m->hs > 0) + ((d->prior_dist == 5 || d->prior_dist == 6) ? d->K : 0) + (d->prior_dist == 6);
+  m->num_params = m->len_zbeta + m->len_extra + d->q + m->len_z_T + m->len_rho + d->len_concentration + d->t + m->has_aux;
   return m;
 }
 
 void or_glmm_free(or_glmm* m)
 {
   if (!m) return;
-  free(m->X); free(m->y); free(m->offset); free(m->weights); free(m->prior_scale); free(m->prior_mean); free(m->p); free(m->l);
+  free(m->X); free(m->y); free(m->offset); free(m->weights); free(m->prior_df); free(m->num_normals); free(m->prior_scale); free(m->prior_mean); free(m->p); free(m->l);
   free(m->shape); free(m->scale); free(m->concentration); free(m->regularization); free(m->w); free(m->v); free(m->u); free(m->delta);
   free(m);
 }
@@ -112,9 +125,9 @@ void or_glmm_data_terms(const or_glmm* m, const double* beta, const double* b, d
 
 /* constrained and transformed quantities for a given unconstrained q */
 typedef struct {
-  const double *z_beta, *z_b, *z_T, *rho_u, *zeta_u, *tau_u;
+  const double *z_beta, *extra_u, *z_b, *z_T, *rho_u, *zeta_u, *tau_u;
   double aux_u;
-  double *rho, *zeta, *tau, *beta, *b, *theta_L;
+  double *rho, *zeta, *tau, *beta, *b, *theta_L, *extra;
   double aux_unscaled, aux, disp;
 } Params;
 
@@ -126,8 +139,9 @@ static void params_alloc(const or_glmm* m, Params* P)
   P->beta = (double*) calloc((size_t) m->d.K + 1, sizeof(double));
   P->b = (double*) calloc((size_t) m->d.q + 1, sizeof(double));
   P->theta_L = (double*) calloc((size_t) m->d.len_theta_L + 1, sizeof(double));
+  P->extra = (double*) calloc((size_t) m->len_extra + 1, sizeof(double));
 }
-static void params_free(Params* P) { free(P->rho); free(P->zeta); free(P->tau); free(P->beta); free(P->b); free(P->theta_L); }
+static void params_free(Params* P) { free(P->rho); free(P->zeta); free(P->tau); free(P->beta); free(P->b); free(P->theta_L); free(P->extra); }
 
 /* lower-triangular factor T (row major, nc x nc) of one ranef block with nc >= 2 coefficients: continuous.stan:20-50.
  * The off-diagonal entries of row r + 1 are scaled with the standard deviation of row r, exactly as the Stan program
@@ -155,13 +169,62 @@ static void block_T(int nc, double complex c, const double complex* zeta, const 
   }
 }
 
+/* beta as a function of z_beta, the constrained extra parameters and aux: continuous.stan:293-322 with hs_prior /
+ * hsplus_prior (:123-143) and CFt (:146-158).  Complex arguments carry the complex-step derivative. */
+static void coef_beta(const or_glmm* m, const double complex* z, const double complex* ex, double complex aux, double complex* beta)
+{
+  const s4b_glmm_data* d = &m->d;
+  const int K = d->K, hs = m->hs;
+  switch (d->prior_dist) {
+  case 0: for (int k = 0; k < K; ++k) beta[k] = z[k]; break;
+  case 1: for (int k = 0; k < K; ++k) beta[k] = z[k] * m->prior_scale[k] + m->prior_mean[k]; break;
+  case 2:
+    for (int k = 0; k < K; ++k) {
+      double complex z1 = z[k], z2 = z1 * z1, z3 = z2 * z1, z5 = z2 * z3, z7 = z2 * z5, z9 = z2 * z7;
+      double df = m->prior_df[k], df2 = df * df, df3 = df2 * df, df4 = df2 * df2;
+      double complex cft = z1 + (z3 + z1) / (4 * df) + (5 * z5 + 16 * z3 + 3 * z1) / (96 * df2)
+                           + (3 * z7 + 19 * z5 + 17 * z3 - 15 * z1) / (384 * df3)
+                           + (79 * z9 + 776 * z7 + 1482 * z5 - 1920 * z3 - 945 * z1) / (92160 * df4);
+      beta[k] = cft * m->prior_scale[k] + m->prior_mean[k];
+    }
+    break;
+  case 3: case 4: {
+    const double complex* global = ex;
+    const double complex* local = ex + hs;              /* local[j][k] = local[j * K + k] */
+    double complex caux = ex[hs + hs * K];
+    double complex c2 = d->slab_scale * d->slab_scale * caux;
+    double complex tau = global[0] * csqrt(global[1]) * d->global_prior_scale * aux;
+    for (int k = 0; k < K; ++k) {
+      double complex lambda = local[k] * csqrt(local[K + k]);
+      if (hs == 4) lambda = lambda * (local[2 * K + k] * csqrt(local[3 * K + k]));
+      double complex l2 = lambda * lambda;
+      double complex lt = csqrt(c2 * l2 / (c2 + tau * tau * l2));
+      beta[k] = z[k] * lt * tau;
+    }
+    break;
+  }
+  case 5: for (int k = 0; k < K; ++k) beta[k] = m->prior_mean[k] + m->prior_scale[k] * csqrt(2.0 * ex[k]) * z[k]; break;
+  case 6: for (int k = 0; k < K; ++k) beta[k] = m->prior_mean[k] + ex[K] * m->prior_scale[k] * csqrt(2.0 * ex[k]) * z[k]; break;
+  default: {
+    int zp = 0;
+    for (int k = 0; k < K; ++k) {
+      double complex v = z[zp++];
+      for (int n = 2; n <= m->num_normals[k]; ++n) v = v * z[zp++];
+      beta[k] = v * pow(m->prior_scale[k], (double) m->num_normals[k]) + m->prior_mean[k];
+    }
+  }
+  }
+}
+
 static double inv_logit(double x) { return x >= 0.0 ? 1.0 / (1.0 + exp(-x)) : exp(x) / (1.0 + exp(x)); }
 
 static void transform(const or_glmm* m, const double* q, Params* P)
 {
   const s4b_glmm_data* d = &m->d;
   int pos = 0;
-  P->z_beta = q + pos; pos += d->K;
+  P->z_beta = q + pos; pos += m->len_zbeta;
+  P->extra_u = q + pos; pos += m->len_extra;
+  for (int i = 0; i < m->len_extra; ++i) P->extra[i] = exp(P->extra_u[i]);
   P->z_b = q + pos; pos += d->q;
   P->z_T = q + pos; pos += m->len_z_T;
   P->rho_u = q + pos; pos += m->len_rho;
@@ -180,8 +243,15 @@ static void transform(const or_glmm* m, const double* q, Params* P)
     }
     P->disp = P->aux;
   } else { P->aux_unscaled = 0.0; P->aux = 1.0; P->disp = 1.0; }
-  for (int k = 0; k < d->K; ++k)
-    P->beta[k] = d->prior_dist == 0 ? P->z_beta[k] : P->z_beta[k] * m->prior_scale[k] + m->prior_mean[k];
+  {
+    int nin = m->len_zbeta + m->len_extra;
+    double complex* in = (double complex*) malloc(sizeof(double complex) * (size_t) (nin + d->K + 1));
+    for (int i = 0; i < m->len_zbeta; ++i) in[i] = P->z_beta[i];
+    for (int i = 0; i < m->len_extra; ++i) in[m->len_zbeta + i] = P->extra[i];
+    coef_beta(m, in, in + m->len_zbeta, P->aux, in + nin);
+    for (int k = 0; k < d->K; ++k) P->beta[k] = creal(in[nin + k]);
+    free(in);
+  }
   /* make_theta_L (continuous.stan:2-59) and make_b (:61-94) */
   int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, zT_mark = 0;
   for (int i = 0; i < d->t; ++i) {
@@ -252,7 +322,36 @@ int or_glmm_log_prob_grad(const or_glmm* m, const double* q, double* lp_out, dou
       d_au_prior = -(nu + 1.0) * au / (nu + au * au);
     } else { lp += -au; d_au_prior = -1.0; }
   }
-  if (d->prior_dist == 1) { for (int k = 0; k < K; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= K * HALF_LOG_2PI; }
+  if (d->prior_dist >= 1) { for (int k = 0; k < m->len_zbeta; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= m->len_zbeta * HALF_LOG_2PI; }
+  /* the extra parameters of the shrinkage priors: lb_constrain Jacobian + their priors (continuous.stan:381-408);
+   * d_extra[i] = d prior / d (constrained value) */
+  double* d_extra = (double*) calloc((size_t) m->len_extra + 1, sizeof(double));
+  for (int i = 0; i < m->len_extra; ++i) lp += P.extra_u[i];
+  if (m->hs > 0) {
+    const int hs = m->hs;
+    const double* local = P.extra + hs;
+    double* d_local = d_extra + hs;
+    for (int j = 0; j < hs; ++j) for (int k = 0; k < K; ++k) {
+      double x = local[j * K + k];
+      if ((j & 1) == 0) { lp += -0.5 * x * x - HALF_LOG_2PI; d_local[j * K + k] = -x; }   /* normal_lpdf(local[j] | 0, 1), - log_half once below */
+      else {
+        double a = 0.5 * (j == 1 ? m->prior_df[k] : m->prior_scale[k]);        /* hs_plus: prior_scale as a second df */
+        lp += a * log(a) - lgamma(a) - (a + 1.0) * log(x) - a / x;
+        d_local[j * K + k] = -(a + 1.0) / x + a / (x * x);
+      }
+    }
+    lp += 0.693147180559945286 * (hs / 2);       /* "- log_half" is subtracted once per vector statement (continuous.stan:384, :393, :395) */
+    { double x = P.extra[0]; lp += -0.5 * x * x - HALF_LOG_2PI + 0.693147180559945286; d_extra[0] = -x; }
+    { double x = P.extra[1], a = 0.5 * d->global_prior_df; lp += a * log(a) - lgamma(a) - (a + 1.0) * log(x) - a / x; d_extra[1] = -(a + 1.0) / x + a / (x * x); }
+    { double x = P.extra[hs + hs * K], a = 0.5 * d->slab_df; lp += a * log(a) - lgamma(a) - (a + 1.0) * log(x) - a / x; d_extra[hs + hs * K] = -(a + 1.0) / x + a / (x * x); }
+  } else if (d->prior_dist == 5 || d->prior_dist == 6) {
+    for (int k = 0; k < K; ++k) { lp += -P.extra[k]; d_extra[k] = -1.0; }
+    if (d->prior_dist == 6) {
+      double nu = m->prior_df[0], x = P.extra[K];
+      lp += -(0.5 * nu) * 0.693147180559945286 - lgamma(0.5 * nu) + (0.5 * nu - 1.0) * log(x) - 0.5 * x;
+      d_extra[K] = (0.5 * nu - 1.0) / x - 0.5;
+    }
+  }
   for (int k = 0; k < nq; ++k) lp += -0.5 * P.z_b[k] * P.z_b[k];
   lp -= nq * HALF_LOG_2PI;
   for (int k = 0; k < m->len_z_T; ++k) lp += -0.5 * P.z_T[k] * P.z_T[k];
@@ -276,18 +375,39 @@ int or_glmm_log_prob_grad(const or_glmm* m, const double* q, double* lp_out, dou
 
   /* ---- gradient ---- */
   int pos = 0;
-  double* g_zbeta = grad + pos; pos += K;
+  double* g_zbeta = grad + pos; pos += m->len_zbeta;
+  double* g_extra = grad + pos; pos += m->len_extra;
   double* g_zb = grad + pos; pos += nq;
   double* g_zT = grad + pos; pos += m->len_z_T;
   double* g_rho = grad + pos; pos += m->len_rho;
   double* g_zeta = grad + pos; pos += d->len_concentration;
   double* g_tau = grad + pos; pos += t;
   double inv_s2 = 1.0 / (sigma * sigma);
-  for (int k = 0; k < K; ++k) {
-    double dbeta = gbeta[k] * inv_s2;
-    g_zbeta[k] = d->prior_dist == 0 ? dbeta : dbeta * m->prior_scale[k] - P.z_beta[k];
-  }
   double d_disp = 0.0;
+  if (d->prior_dist <= 1) {
+    for (int k = 0; k < K; ++k) {
+      double dbeta = gbeta[k] * inv_s2;
+      g_zbeta[k] = d->prior_dist == 0 ? dbeta : dbeta * m->prior_scale[k] - P.z_beta[k];
+    }
+  } else {
+    /* d beta / d (z_beta, extras, aux) by the complex-step method: the map is a handful of elementary functions of K numbers */
+    const double h = 1e-20;
+    int nin = m->len_zbeta + m->len_extra;
+    double complex* in = (double complex*) malloc(sizeof(double complex) * (size_t) (nin + K + 1));
+    for (int ip = 0; ip < nin + (m->hs > 0 ? 1 : 0); ++ip) {
+      for (int i = 0; i < m->len_zbeta; ++i) in[i] = P.z_beta[i];
+      for (int i = 0; i < m->len_extra; ++i) in[m->len_zbeta + i] = P.extra[i];
+      double complex aux = P.aux;
+      if (ip < nin) in[ip] += h * I; else aux += h * I;
+      coef_beta(m, in, in + m->len_zbeta, aux, in + nin);
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) acc += gbeta[k] * inv_s2 * (cimag(in[nin + k]) / h);
+      if (ip < m->len_zbeta) g_zbeta[ip] = acc - P.z_beta[ip];
+      else if (ip < nin) { int e = ip - m->len_zbeta; g_extra[e] = (acc + d_extra[e]) * P.extra[e] + 1.0; }
+      else d_disp += acc;                               /* hs_prior's error_scale is aux */
+    }
+    free(in);
+  }
   /* the Stan program declares (p - 2)(p - 1) elements of z_T per block but its onion rows consume 2 + ... + (p - 1) of them
    * through one running mark (continuous.stan:9, :41-44, :258): the surplus elements only see their normal prior */
   for (int k = 0; k < m->len_z_T; ++k) g_zT[k] = -P.z_T[k];
@@ -410,7 +530,7 @@ int or_glmm_log_prob_grad(const or_glmm* m, const double* q, double* lp_out, dou
   *lp_out = lp;
   int bad = !isfinite(lp);
   for (int i = 0; i < m->num_params; ++i) if (!isfinite(grad[i])) bad = 1;
-  free(gbeta); free(gb); params_free(&P);
+  free(gbeta); free(gb); free(d_extra); params_free(&P);
   return bad;
 }
 
@@ -419,7 +539,8 @@ void or_glmm_write_array(const or_glmm* m, const double* q, double* out)
   const s4b_glmm_data* d = &m->d;
   Params P; params_alloc(m, &P); transform(m, q, &P);
   int pos = 0;
-  for (int k = 0; k < d->K; ++k) out[pos++] = P.z_beta[k];
+  for (int k = 0; k < m->len_zbeta; ++k) out[pos++] = P.z_beta[k];
+  for (int k = 0; k < m->len_extra; ++k) out[pos++] = P.extra[k];
   for (int k = 0; k < d->q; ++k) out[pos++] = P.z_b[k];
   for (int k = 0; k < m->len_z_T; ++k) out[pos++] = P.z_T[k];
   for (int k = 0; k < m->len_rho; ++k) out[pos++] = P.rho[k];

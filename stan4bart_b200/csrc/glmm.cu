@@ -186,9 +186,10 @@ __global__ void k_glmm_set_inputs(long long N, const double* __restrict__ new_of
 
 // ---------------------------------------------------------------------------------------
 struct GlmmModel::Params {
-  const double *z_beta, *z_b, *z_T, *rho_u, *zeta_u, *tau_u;
+  const double *z_beta, *extra_u, *z_b, *z_T, *rho_u, *zeta_u, *tau_u;
   double aux_u = 0, aux_unscaled = 0, aux = 1, disp = 1;
-  std::vector<double> rho, zeta, tau, beta, b, theta_L;
+  std::vector<double> rho, zeta, tau, beta, b, theta_L, extra;
+  std::vector<std::complex<double>> cin;        // complex-step scratch of the coefficient-prior map
 };
 
 static const double kHalfLog2Pi = 0.91893853320467274178;
@@ -197,7 +198,11 @@ static const double kLog2 = 0.693147180559945286;
 GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* shard) : stream_(stream), shard_(shard)
 {
   if (shard_ != nullptr && !shard_->attached()) throw std::invalid_argument("sharded glmm: attach the peer mailboxes first");
-  if (d.prior_dist < 0 || d.prior_dist > 1) throw std::invalid_argument("glmm: only prior_dist 0 (none) and 1 (normal) are implemented (SURVEY 8f rank 4)");
+  if (d.prior_dist < 0 || d.prior_dist > 7) throw std::invalid_argument("glmm: prior_dist out of range (0 none, 1 normal, 2 student_t, 3 hs, 4 hs_plus, 5 laplace, 6 lasso, 7 product_normal)");
+  if ((d.prior_dist == 3 || d.prior_dist == 4) && d.is_binary)
+    throw std::invalid_argument("glmm: the horseshoe priors scale with the error sd aux[1] (continuous.stan:300), which a binary response does not have");
+  if ((d.prior_dist == 2 || d.prior_dist == 3 || d.prior_dist == 4 || d.prior_dist == 6) && d.K > 0 && d.prior_df == nullptr) throw std::invalid_argument("glmm: this prior_dist needs prior_df");
+  if (d.prior_dist == 7 && d.K > 0 && d.num_normals == nullptr) throw std::invalid_argument("glmm: product_normal needs num_normals");
   if (d.prior_dist_for_aux < 0 || d.prior_dist_for_aux > 3) throw std::invalid_argument("glmm: prior_dist_for_aux out of range");
   for (int i = 0; i < d.t; ++i) {
     if (d.p[i] < 1 || d.l[i] < 1) throw std::invalid_argument("glmm: p[i] / l[i] must be >= 1");
@@ -222,7 +227,16 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   len_z_T_ = 0;
   for (int i = 0; i < t_; ++i) if (p_[i] > 2) len_z_T_ += (p_[i] - 2) * (p_[i] - 1);      // continuous.stan:258
   has_aux_ = is_binary_ ? 0 : 1;
-  num_params_ = K_ + q_ + len_z_T_ + len_rho_ + len_conc_ + t_ + has_aux_;
+  // coefficient priors beyond normal (continuous.stan:262-270): z_beta may be longer than K (product_normal) and the
+  // shrinkage priors add positive parameters global[hs], local[hs][K], caux[hs > 0], mix[K], one_over_lambda
+  if (d.prior_df != nullptr) prior_df_.assign(d.prior_df, d.prior_df + K_);
+  if (d.num_normals != nullptr) num_normals_.assign(d.num_normals, d.num_normals + K_);
+  global_prior_df_ = d.global_prior_df; global_prior_scale_ = d.global_prior_scale; slab_df_ = d.slab_df; slab_scale_ = d.slab_scale;
+  hs_ = prior_dist_ == 3 ? 2 : (prior_dist_ == 4 ? 4 : 0);
+  len_zbeta_ = K_;
+  if (prior_dist_ == 7) { len_zbeta_ = 0; for (int k = 0; k < K_; ++k) { if (num_normals_[(size_t) k] < 2) throw std::invalid_argument("glmm: num_normals must be >= 2"); len_zbeta_ += num_normals_[(size_t) k]; } }
+  len_extra_ = hs_ + hs_ * K_ + (hs_ > 0 ? 1 : 0) + ((prior_dist_ == 5 || prior_dist_ == 6) ? K_ : 0) + (prior_dist_ == 6 ? 1 : 0);
+  num_params_ = len_zbeta_ + len_extra_ + q_ + len_z_T_ + len_rho_ + len_conc_ + t_ + has_aux_;
 
   // ---- CSR (w, v, u) -> slot-major ELL ----
   npad_ = (N_ + 15) / 16 * 16;
@@ -442,12 +456,59 @@ static void block_T(int nc, cplx c, const cplx* zeta, const cplx* rho, const cpl
   }
 }
 
+// beta as a function of z_beta, the constrained extra parameters and aux: continuous.stan:293-322 with hs_prior / hsplus_prior
+// (:123-143) and CFt (:146-158).  Complex arguments carry the complex-step derivative of the host chain rule.
+void GlmmModel::coef_beta(const cplx* z, const cplx* ex, cplx aux, cplx* beta) const
+{
+  const int K = K_, hs = hs_;
+  switch (prior_dist_) {
+    case 0: for (int k = 0; k < K; ++k) beta[k] = z[k]; break;
+    case 1: for (int k = 0; k < K; ++k) beta[k] = z[k] * prior_scale_[(size_t) k] + prior_mean_[(size_t) k]; break;
+    case 2:
+      for (int k = 0; k < K; ++k) {
+        const cplx z1 = z[k], z2 = z1 * z1, z3 = z2 * z1, z5 = z2 * z3, z7 = z2 * z5, z9 = z2 * z7;
+        const double df = prior_df_[(size_t) k], df2 = df * df, df3 = df2 * df, df4 = df2 * df2;
+        const cplx cft = z1 + (z3 + z1) / (4.0 * df) + (5.0 * z5 + 16.0 * z3 + 3.0 * z1) / (96.0 * df2)
+                         + (3.0 * z7 + 19.0 * z5 + 17.0 * z3 - 15.0 * z1) / (384.0 * df3)
+                         + (79.0 * z9 + 776.0 * z7 + 1482.0 * z5 - 1920.0 * z3 - 945.0 * z1) / (92160.0 * df4);
+        beta[k] = cft * prior_scale_[(size_t) k] + prior_mean_[(size_t) k];
+      }
+      break;
+    case 3: case 4: {
+      const cplx* global = ex;
+      const cplx* local = ex + hs;                 // local[j][k] = local[j * K + k]
+      const cplx c2 = slab_scale_ * slab_scale_ * ex[hs + hs * K];
+      const cplx tau = global[0] * std::sqrt(global[1]) * global_prior_scale_ * aux;
+      for (int k = 0; k < K; ++k) {
+        cplx lambda = local[k] * std::sqrt(local[K + k]);
+        if (hs == 4) lambda = lambda * (local[2 * K + k] * std::sqrt(local[3 * K + k]));
+        const cplx l2 = lambda * lambda;
+        beta[k] = z[k] * std::sqrt(c2 * l2 / (c2 + tau * tau * l2)) * tau;
+      }
+      break;
+    }
+    case 5: for (int k = 0; k < K; ++k) beta[k] = prior_mean_[(size_t) k] + prior_scale_[(size_t) k] * std::sqrt(2.0 * ex[k]) * z[k]; break;
+    case 6: for (int k = 0; k < K; ++k) beta[k] = prior_mean_[(size_t) k] + ex[K] * prior_scale_[(size_t) k] * std::sqrt(2.0 * ex[k]) * z[k]; break;
+    default: {
+      int zp = 0;
+      for (int k = 0; k < K; ++k) {
+        cplx v = z[zp++];
+        for (int n = 2; n <= num_normals_[(size_t) k]; ++n) v = v * z[zp++];
+        beta[k] = v * std::pow(prior_scale_[(size_t) k], (double) num_normals_[(size_t) k]) + prior_mean_[(size_t) k];
+      }
+    }
+  }
+}
+
 static inline double inv_logit(double x) { return x >= 0.0 ? 1.0 / (1.0 + std::exp(-x)) : std::exp(x) / (1.0 + std::exp(x)); }
 
 void GlmmModel::transform(const double* q, Params& P) const
 {
   int pos = 0;
-  P.z_beta = q + pos; pos += K_;
+  P.z_beta = q + pos; pos += len_zbeta_;
+  P.extra_u = q + pos; pos += len_extra_;
+  P.extra.resize((size_t) len_extra_);
+  for (int i = 0; i < len_extra_; ++i) P.extra[(size_t) i] = std::exp(P.extra_u[i]);
   P.z_b = q + pos; pos += q_;
   P.z_T = q + pos; pos += len_z_T_;
   P.rho_u = q + pos; pos += len_rho_;
@@ -465,7 +526,16 @@ void GlmmModel::transform(const double* q, Params& P) const
     else { P.aux = prior_scale_for_aux_ * P.aux_unscaled; if (prior_dist_for_aux_ <= 2) P.aux += prior_mean_for_aux_; }
     P.disp = P.aux;
   } else { P.aux_unscaled = 0.0; P.aux = 1.0; P.disp = 1.0; }
-  for (int k = 0; k < K_; ++k) P.beta[(size_t) k] = prior_dist_ == 0 ? P.z_beta[k] : P.z_beta[k] * prior_scale_[(size_t) k] + prior_mean_[(size_t) k];
+  if (prior_dist_ <= 1) {
+    for (int k = 0; k < K_; ++k) P.beta[(size_t) k] = prior_dist_ == 0 ? P.z_beta[k] : P.z_beta[k] * prior_scale_[(size_t) k] + prior_mean_[(size_t) k];
+  } else {
+    const int nin = len_zbeta_ + len_extra_;
+    P.cin.resize((size_t) (nin + K_ + 1));
+    for (int i = 0; i < len_zbeta_; ++i) P.cin[(size_t) i] = P.z_beta[i];
+    for (int i = 0; i < len_extra_; ++i) P.cin[(size_t) (len_zbeta_ + i)] = P.extra[(size_t) i];
+    coef_beta(P.cin.data(), P.cin.data() + len_zbeta_, P.aux, P.cin.data() + nin);
+    for (int k = 0; k < K_; ++k) P.beta[(size_t) k] = P.cin[(size_t) (nin + k)].real();
+  }
   int zeta_mark = 0, rho_mark = 0, th = 0, b_mark = 0, zT_mark = 0;
   for (int i = 0; i < t_; ++i) {
     const double c = P.tau[(size_t) i] * scale_[(size_t) i] * P.disp;
@@ -540,7 +610,32 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
       d_au_prior = -(nu + 1.0) * au / (nu + au * au);
     } else { lp += -au; d_au_prior = -1.0; }
   }
-  if (prior_dist_ == 1) { for (int k = 0; k < K_; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= K_ * kHalfLog2Pi; }
+  if (prior_dist_ >= 1) { for (int k = 0; k < len_zbeta_; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= len_zbeta_ * kHalfLog2Pi; }
+  // the extra parameters of the shrinkage priors: lb_constrain Jacobian + their priors (continuous.stan:381-408);
+  // d_extra[i] = d prior / d (constrained value)
+  d_extra_.assign((size_t) len_extra_ + 1, 0.0);
+  for (int i = 0; i < len_extra_; ++i) lp += P.extra_u[i];
+  if (hs_ > 0) {
+    auto inv_gamma = [&](double x, double a, double& dx) { dx = -(a + 1.0) / x + a / (x * x); return a * std::log(a) - std::lgamma(a) - (a + 1.0) * std::log(x) - a / x; };
+    const double* local = P.extra.data() + hs_;
+    double* d_local = d_extra_.data() + hs_;
+    for (int j = 0; j < hs_; ++j) for (int k = 0; k < K_; ++k) {
+      const double x = local[j * K_ + k];
+      if ((j & 1) == 0) { lp += -0.5 * x * x - kHalfLog2Pi; d_local[j * K_ + k] = -x; }      // normal_lpdf(local[j] | 0, 1); - log_half once per statement
+      else lp += inv_gamma(x, 0.5 * (j == 1 ? prior_df_[(size_t) k] : prior_scale_[(size_t) k]), d_local[j * K_ + k]);   // hs_plus: prior_scale as a second df
+    }
+    lp += kLog2 * (hs_ / 2);
+    { const double x = P.extra[0]; lp += -0.5 * x * x - kHalfLog2Pi + kLog2; d_extra_[0] = -x; }
+    lp += inv_gamma(P.extra[1], 0.5 * global_prior_df_, d_extra_[1]);
+    lp += inv_gamma(P.extra[(size_t) (hs_ + hs_ * K_)], 0.5 * slab_df_, d_extra_[(size_t) (hs_ + hs_ * K_)]);
+  } else if (prior_dist_ == 5 || prior_dist_ == 6) {
+    for (int k = 0; k < K_; ++k) { lp += -P.extra[(size_t) k]; d_extra_[(size_t) k] = -1.0; }      // exponential_lpdf(mix | 1)
+    if (prior_dist_ == 6) {                                                                        // chi_square_lpdf(one_over_lambda | prior_df[1])
+      const double nu = prior_df_[0], x = P.extra[(size_t) K_];
+      lp += -(0.5 * nu) * kLog2 - std::lgamma(0.5 * nu) + (0.5 * nu - 1.0) * std::log(x) - 0.5 * x;
+      d_extra_[(size_t) K_] = (0.5 * nu - 1.0) / x - 0.5;
+    }
+  }
   for (int k = 0; k < q_; ++k) lp += -0.5 * P.z_b[k] * P.z_b[k];
   lp -= q_ * kHalfLog2Pi;
   for (int k = 0; k < len_z_T_; ++k) lp += -0.5 * P.z_T[k] * P.z_T[k];
@@ -569,18 +664,38 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
 
   // ---- adjoints ----
   int pos = 0;
-  double* g_zbeta = grad + pos; pos += K_;
+  double* g_zbeta = grad + pos; pos += len_zbeta_;
+  double* g_extra = grad + pos; pos += len_extra_;
   double* g_zb = grad + pos; pos += q_;
   double* g_zT = grad + pos; pos += len_z_T_;
   double* g_rho = grad + pos; pos += len_rho_;
   double* g_zeta = grad + pos; pos += len_conc_;
   double* g_tau = grad + pos; pos += t_;
   const double inv_s2 = 1.0 / (sigma * sigma);
-  for (int k = 0; k < K_; ++k) {
-    const double dbeta = gbeta[(size_t) k] * inv_s2;
-    g_zbeta[k] = prior_dist_ == 0 ? dbeta : dbeta * prior_scale_[(size_t) k] - P.z_beta[k];
-  }
   double adj_disp = 0.0;
+  if (prior_dist_ <= 1) {
+    for (int k = 0; k < K_; ++k) {
+      const double dbeta = gbeta[(size_t) k] * inv_s2;
+      g_zbeta[k] = prior_dist_ == 0 ? dbeta : dbeta * prior_scale_[(size_t) k] - P.z_beta[k];
+    }
+  } else {
+    // d beta / d (z_beta, extras, aux) by the complex-step method: the map is a handful of elementary functions of K numbers
+    const double h = 1e-20;
+    const int nin = len_zbeta_ + len_extra_;
+    cplx* in = P.cin.data();
+    for (int ip = 0; ip < nin + (hs_ > 0 ? 1 : 0); ++ip) {
+      for (int i = 0; i < len_zbeta_; ++i) in[i] = P.z_beta[i];
+      for (int i = 0; i < len_extra_; ++i) in[len_zbeta_ + i] = P.extra[(size_t) i];
+      cplx aux = P.aux;
+      if (ip < nin) in[ip] += cplx(0.0, h); else aux += cplx(0.0, h);
+      coef_beta(in, in + len_zbeta_, aux, in + nin);
+      double acc = 0.0;
+      for (int k = 0; k < K_; ++k) acc += gbeta[(size_t) k] * inv_s2 * (in[nin + k].imag() / h);
+      if (ip < len_zbeta_) g_zbeta[ip] = acc - P.z_beta[ip];
+      else if (ip < nin) { const int e = ip - len_zbeta_; g_extra[e] = (acc + d_extra_[(size_t) e]) * P.extra[(size_t) e] + 1.0; }
+      else adj_disp += acc;                           // hs_prior's error_scale is aux
+    }
+  }
   // the Stan program declares (p - 2)(p - 1) elements of z_T per block but its onion rows consume 2 + ... + (p - 1) of them
   // through one running mark: the surplus elements only see their normal prior
   for (int k = 0; k < len_z_T_; ++k) g_zT[k] = -P.z_T[k];
@@ -701,7 +816,8 @@ void GlmmModel::write_array(const double* q, double* out) const
 {
   Params P; transform(q, P);
   int pos = 0;
-  for (int k = 0; k < K_; ++k) out[pos++] = P.z_beta[k];
+  for (int k = 0; k < len_zbeta_; ++k) out[pos++] = P.z_beta[k];
+  for (int k = 0; k < len_extra_; ++k) out[pos++] = P.extra[(size_t) k];
   for (int k = 0; k < q_; ++k) out[pos++] = P.z_b[k];
   for (int k = 0; k < len_z_T_; ++k) out[pos++] = P.z_T[k];
   for (double v : P.rho) out[pos++] = v;

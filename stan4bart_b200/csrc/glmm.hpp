@@ -5,6 +5,7 @@
 #include "s4b_common.cuh"
 #include "shard.hpp"
 
+#include <complex>
 #include <vector>
 
 namespace s4b {
@@ -74,6 +75,10 @@ class GlmmModel {
   cudaStream_t stream_;
   ShardContext* shard_ = nullptr;
   long long N_ = 0, npad_ = 0, N_total_ = 0;
+  std::vector<double> prior_df_, d_extra_; std::vector<int> num_normals_;
+  double global_prior_df_ = 0, global_prior_scale_ = 0, slab_df_ = 0, slab_scale_ = 0;
+  int hs_ = 0, len_zbeta_ = 0, len_extra_ = 0;
+  void coef_beta(const std::complex<double>* z, const std::complex<double>* ex, std::complex<double> aux, std::complex<double>* beta) const;
   int K_ = 0, q_ = 0, t_ = 0, len_theta_L_ = 0, len_rho_ = 0, len_z_T_ = 0, len_conc_ = 0, num_params_ = 0, has_aux_ = 0;
   int is_binary_ = 0, prior_dist_ = 0, prior_dist_for_aux_ = 0;
   double prior_scale_for_aux_ = 0, prior_mean_for_aux_ = 0, prior_df_for_aux_ = 0;

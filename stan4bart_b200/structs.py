@@ -41,6 +41,8 @@ class GlmmData(C.Structure):
         ("p", c_int32_p), ("l", c_int32_p), ("shape", c_double_p), ("scale", c_double_p),
         ("concentration", c_double_p), ("regularization", c_double_p),
         ("w", c_double_p), ("v", c_int32_p), ("u", c_int32_p), ("weights", c_double_p),
+        ("prior_df", c_double_p), ("num_normals", c_int32_p),
+        ("global_prior_df", C.c_double), ("global_prior_scale", C.c_double), ("slab_df", C.c_double), ("slab_scale", C.c_double),
     ]
 
 
@@ -142,8 +144,42 @@ class StanData:
         self.u = i32(u)
         self.len_rho = int(sum(self.p) - self.t)
         self.len_z_T = int(sum((pi - 2) * (pi - 1) for pi in self.p if pi > 2))        # continuous.stan:258
-        self.num_params = self.K + self.q + self.len_z_T + self.len_rho + len(self.concentration) + self.t + (0 if self.is_binary else 1)
-        self.num_constrained = self.num_params + (0 if self.is_binary else 1) + self.K + self.q + self.len_theta_L
+        # hyper-parameters of the non-default coefficient priors (continuous.stan:207-215; prior_dist 2 .. 7)
+        self.prior_df = np.ones(self.K)
+        self.global_prior_df = 1.0
+        self.global_prior_scale = 0.01
+        self.slab_df = 4.0
+        self.slab_scale = 2.5
+        self.num_normals = np.full(self.K, 2, dtype=np.int32)
+
+    # parameter block of continuous.stan:262-279 ------------------------------------------------------------
+    @property
+    def hs(self):
+        return {3: 2, 4: 4}.get(self.prior_dist, 0)
+
+    @property
+    def len_z_beta(self):
+        return int(np.sum(self.num_normals)) if self.prior_dist == 7 else self.K
+
+    @property
+    def coef_extra_names(self):
+        """global, local, caux, mix, one_over_lambda: the extra parameters of the shrinkage priors, in declaration order."""
+        hs, K = self.hs, self.K
+        names = [f"global.{i + 1}" for i in range(hs)]
+        names += [f"local.{j + 1}.{k + 1}" for j in range(hs) for k in range(K)]
+        names += ["caux.1"] if hs > 0 else []
+        names += [f"mix.1.{k + 1}" for k in range(K)] if self.prior_dist in (5, 6) else []
+        names += ["one_over_lambda.1"] if self.prior_dist == 6 else []
+        return names
+
+    @property
+    def num_params(self):
+        return (self.len_z_beta + len(self.coef_extra_names) + self.q + self.len_z_T + self.len_rho + len(self.concentration)
+                + self.t + (0 if self.is_binary else 1))
+
+    @property
+    def num_constrained(self):
+        return self.num_params + (0 if self.is_binary else 1) + self.K + self.q + self.len_theta_L
 
     def rows(self, lo, hi):
         """The same model restricted to observations [lo, hi): the shard of one rank of an observation-sharded chain.
@@ -154,7 +190,7 @@ class StanData:
                        self.prior_dist_for_aux, self.prior_scale_for_aux, self.prior_mean_for_aux, self.prior_df_for_aux,
                        self.p, self.l, self.shape, self.scale, self.concentration, self.regularization,
                        self.w[k0:k1], self.v[k0:k1], self.u[lo:hi + 1] - k0, self.q)
-        for name in ("xbar", "term_order"):
+        for name in ("xbar", "term_order", "prior_df", "global_prior_df", "global_prior_scale", "slab_df", "slab_scale", "num_normals"):
             if hasattr(self, name):
                 setattr(out, name, getattr(self, name))
         if getattr(self, "weights", None) is not None:
@@ -172,7 +208,17 @@ class StanData:
             prior_df_for_aux=self.prior_df_for_aux,
             p=i32ptr(self.p), l=i32ptr(self.l), shape=dptr(self.shape), scale=dptr(self.scale),
             concentration=dptr(self.concentration), regularization=dptr(self.regularization),
-            w=dptr(self.w), v=i32ptr(self.v), u=i32ptr(self.u), weights=self._weights_ptr())
+            w=dptr(self.w), v=i32ptr(self.v), u=i32ptr(self.u), weights=self._weights_ptr(),
+            prior_df=self._keep("prior_df", np.float64, dptr), num_normals=self._keep("num_normals", np.int32, i32ptr),
+            global_prior_df=self.global_prior_df, global_prior_scale=self.global_prior_scale, slab_df=self.slab_df,
+            slab_scale=self.slab_scale)
+
+    def _keep(self, name, dtype, to_ptr):
+        arr = np.ascontiguousarray(getattr(self, name), dtype=dtype)
+        if arr.shape != (self.K,):
+            raise ValueError(f"{name} must have one entry per fixed-effect coefficient")
+        setattr(self, name, arr)
+        return to_ptr(arr)
 
     def _weights_ptr(self):
         """data.stan `weights` (R/stan4bart_fit.R:255-262): None = unweighted (a NULL pointer)."""
@@ -187,7 +233,8 @@ class StanData:
     def param_names(self):
         """Names of the stored Stan rows, continuous.hpp:3115-3204 (constrained_param_names)."""
         names = ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"]
-        names += [f"z_beta.{i + 1}" for i in range(self.K)]
+        names += [f"z_beta.{i + 1}" for i in range(self.len_z_beta)]
+        names += self.coef_extra_names
         names += [f"z_b.{i + 1}" for i in range(self.q)]
         names += [f"z_T.{i + 1}" for i in range(self.len_z_T)]
         names += [f"rho.{i + 1}" for i in range(self.len_rho)]

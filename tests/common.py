@@ -78,6 +78,8 @@ def load_glmm_case(path):
         sd.prior_scale_for_aux = c["prior_scale_for_aux"]
     sd.prior_dist = c["prior_dist"]
     sd.prior_scale = np.asarray(c["prior_scale"], dtype=np.float64)
+    for key, val in c.get("coef", {}).items():
+        setattr(sd, key, np.asarray(val) if isinstance(val, list) else val)
     if "weights" in c:
         sd.weights = np.asarray(c["weights"], dtype=np.float64)
     return sd, c

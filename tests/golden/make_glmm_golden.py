@@ -40,6 +40,11 @@ def beta_lpdf(y, a, b):
     return (torch.lgamma(a + b) - torch.lgamma(a) - torch.lgamma(b) + (a - 1) * torch.log(y) + (b - 1) * torch.log1p(-y)).sum()
 
 
+def inv_gamma_lpdf(y, a, b):
+    # stan::math::inv_gamma_lpdf<false>
+    return (a * torch.log(b) - torch.lgamma(a) - (a + 1) * torch.log(y) - b / y).sum()
+
+
 def student_t_lpdf(y, nu, mu, sigma):
     z = (y - mu) / sigma
     return (math.lgamma((nu + 1) / 2) - math.lgamma(nu / 2) - 0.5 * math.log(nu * math.pi) - math.log(sigma)
@@ -115,14 +120,27 @@ def log_prob(sd, q, offset, y):
     len_rho = sum(p) - t
     len_conc = len(sd.concentration)
     pos = 0
-    z_beta = q[pos:pos + K]; pos += K
+    lp = torch.zeros(())
+    nzb = sd.len_z_beta
+    z_beta = q[pos:pos + nzb]; pos += nzb
+    # parameters of the shrinkage priors, all <lower=0>: exp transform, Jacobian + u   (continuous.stan:265-270)
+    hs = sd.hs
+    def lower0(count):
+        nonlocal pos, lp
+        u = q[pos:pos + count]; pos += count
+        lp = lp + u.sum()
+        return torch.exp(u)
+    glob = lower0(hs)
+    local = [lower0(K) for _ in range(hs)]
+    caux = lower0(1 if hs > 0 else 0)
+    mix = lower0(K) if sd.prior_dist in (5, 6) else None
+    ool = lower0(1) if sd.prior_dist == 6 else None
     z_b = q[pos:pos + nq]; pos += nq
     len_z_T = sum((pi - 2) * (pi - 1) for pi in p if pi > 2)        # continuous.stan:258
     z_T = q[pos:pos + len_z_T]; pos += len_z_T
     rho_u = q[pos:pos + len_rho]; pos += len_rho
     zeta_u = q[pos:pos + len_conc]; pos += len_conc
     tau_u = q[pos:pos + t]; pos += t
-    lp = torch.zeros(())
     rho = torch.sigmoid(rho_u)
     lp = lp + (torch.log(rho) + torch.log1p(-rho)).sum()          # lub_constrain(0, 1) Jacobian
     zeta = torch.exp(zeta_u); lp = lp + zeta_u.sum()
@@ -140,10 +158,39 @@ def log_prob(sd, q, offset, y):
     else:
         aux = torch.ones(())
         dispersion = torch.ones(())
+    pscale, pmean, pdf = torch.as_tensor(sd.prior_scale), torch.as_tensor(sd.prior_mean), torch.as_tensor(np.asarray(sd.prior_df, dtype=np.float64))
     if sd.prior_dist == 0:
         beta = z_beta
-    else:
-        beta = z_beta * torch.as_tensor(sd.prior_scale) + torch.as_tensor(sd.prior_mean)
+    elif sd.prior_dist == 1:
+        beta = z_beta * pscale + pmean
+    elif sd.prior_dist == 2:                                   # continuous.stan:146-158, :295-297
+        z = z_beta; df = pdf
+        z2 = z * z; z3 = z2 * z; z5 = z2 * z3; z7 = z2 * z5; z9 = z2 * z7
+        df2 = df * df; df3 = df2 * df; df4 = df2 * df2
+        cft = (z + (z3 + z) / (4 * df) + (5 * z5 + 16 * z3 + 3 * z) / (96 * df2)
+               + (3 * z7 + 19 * z5 + 17 * z3 - 15 * z) / (384 * df3)
+               + (79 * z9 + 776 * z7 + 1482 * z5 - 1920 * z3 - 945 * z) / (92160 * df4))
+        beta = cft * pscale + pmean
+    elif sd.prior_dist in (3, 4):                              # continuous.stan:123-143, :298-305
+        c2 = sd.slab_scale ** 2 * caux[0]
+        lam = local[0] * torch.sqrt(local[1])
+        if sd.prior_dist == 4:
+            lam = lam * (local[2] * torch.sqrt(local[3]))
+        tau_g = glob[0] * torch.sqrt(glob[1]) * sd.global_prior_scale * aux
+        lam2 = lam * lam
+        lam_tilde = torch.sqrt(c2 * lam2 / (c2 + tau_g * tau_g * lam2))
+        beta = z_beta * lam_tilde * tau_g
+    elif sd.prior_dist == 5:
+        beta = pmean + pscale * torch.sqrt(2 * mix) * z_beta
+    elif sd.prior_dist == 6:
+        beta = pmean + ool[0] * pscale * torch.sqrt(2 * mix) * z_beta
+    else:                                                      # product_normal, continuous.stan:310-322
+        parts, zp = [], 0
+        for k in range(K):
+            nn = int(sd.num_normals[k])
+            parts.append(torch.prod(z_beta[zp:zp + nn]) * float(sd.prior_scale[k]) ** nn + float(sd.prior_mean[k]))
+            zp += nn
+        beta = torch.stack(parts) if parts else z_beta[:0]
     theta_L = make_theta_L(p, dispersion, tau, torch.as_tensor(sd.scale), zeta, rho, z_T)
     b = make_b(z_b, theta_L, p, l)
     # eta = offset + X beta + Z b   (CSR w, v, u)
@@ -170,8 +217,22 @@ def log_prob(sd, q, offset, y):
             lp = lp + student_t_lpdf(aux_unscaled.reshape(1), sd.prior_df_for_aux, 0.0, 1.0) - log_half
         else:
             lp = lp - aux_unscaled                                   # exponential_lpdf(. | 1)
-    if sd.prior_dist == 1:
+    if sd.prior_dist >= 1:
         lp = lp + normal_lpdf(z_beta, torch.zeros(()), torch.ones(()))
+    log_half = -0.693147180559945286
+    def half_normal(x):
+        return normal_lpdf(x, torch.zeros(()), torch.ones(())) - log_half
+    if sd.prior_dist in (3, 4):                                # continuous.stan:381-401
+        lp = lp + half_normal(local[0]) + inv_gamma_lpdf(local[1], 0.5 * pdf, 0.5 * pdf)
+        if sd.prior_dist == 4:
+            lp = lp + half_normal(local[2]) + inv_gamma_lpdf(local[3], 0.5 * pscale, 0.5 * pscale)
+        lp = lp + half_normal(glob[0:1]) + inv_gamma_lpdf(glob[1:2], torch.tensor([0.5 * sd.global_prior_df]), torch.tensor([0.5 * sd.global_prior_df]))
+        lp = lp + inv_gamma_lpdf(caux, torch.tensor([0.5 * sd.slab_df]), torch.tensor([0.5 * sd.slab_df]))
+    elif sd.prior_dist in (5, 6):
+        lp = lp - mix.sum()                                    # exponential_lpdf(. | 1)
+        if sd.prior_dist == 6:
+            nu = float(sd.prior_df[0])                         # chi_square_lpdf
+            lp = lp + (-(nu / 2) * math.log(2.0) - math.lgamma(nu / 2) + (nu / 2 - 1) * torch.log(ool[0]) - ool[0] / 2)
     # decov_lp
     lp = lp + normal_lpdf(z_b, torch.zeros(()), torch.ones(()))
     if len_z_T:
@@ -197,10 +258,11 @@ def log_prob(sd, q, offset, y):
         lp = lp + gamma_lpdf(zeta, torch.as_tensor(np.array(delta)))
     if t:
         lp = lp + gamma_lpdf(tau, torch.as_tensor(sd.shape))
-    return lp, dict(beta=beta, b=b, theta_L=theta_L, aux=aux, rho=rho, zeta=zeta, tau=tau, z_T=z_T)
+    extras = torch.cat([glob] + local + [caux] + ([mix] if mix is not None else []) + ([ool] if ool is not None else []))
+    return lp, dict(beta=beta, b=b, theta_L=theta_L, aux=aux, rho=rho, zeta=zeta, tau=tau, z_T=z_T, extras=extras)
 
 
-def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1, weighted=False):
+def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1, weighted=False, coef=None):
     rng = np.random.default_rng(seed)
     Xf = np.column_stack([rng.random(N), (rng.random(N) < 0.3).astype(float)])
     terms = []
@@ -219,6 +281,9 @@ def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1, weig
             sd.prior_mean_for_aux = 0.4
             sd.prior_df_for_aux = 4.0
     sd.prior_dist = prior_dist
+    if coef:
+        for key, val in coef.items():
+            setattr(sd, key, np.asarray(val) if isinstance(val, list) else val)
     offset = rng.standard_normal(N) * 0.5
     if binary:
         y = rng.standard_normal(N) + 0.3      # latents
@@ -235,14 +300,17 @@ def make_case(name, N, seed, binary, terms_spec, aux_prior=3, prior_dist=1, weig
         wa = q.detach().numpy().tolist()
         # write_array order: params (constrained) then aux, beta, b, theta_L
         K, nq = sd.K, sd.q
-        cons = list(q.detach().numpy()[:K + nq]) + tp["z_T"].tolist() + tp["rho"].tolist() + tp["zeta"].tolist() + tp["tau"].tolist()
+        nzb = sd.len_z_beta
+        qn = q.detach().numpy()
+        ne = len(tp["extras"])
+        cons = list(qn[:nzb]) + tp["extras"].tolist() + list(qn[nzb + ne:nzb + ne + nq]) + tp["z_T"].tolist() + tp["rho"].tolist() + tp["zeta"].tolist() + tp["tau"].tolist()
         if not binary:
             cons += [float(torch.exp(q[-1])), float(tp["aux"])]
         cons += tp["beta"].tolist() + tp["b"].tolist() + tp["theta_L"].tolist()
         was.append([float(v) for v in cons])
     case = dict(name=name, N=N, binary=binary, X_fixed=Xf.tolist(), y=np.asarray(y).tolist(), y_for_scaling=None, offset=offset.tolist(),
                 groups=groups, aux_prior=aux_prior, prior_dist=prior_dist,
-                **(dict(weights=sd.weights.tolist()) if weighted else {}),
+                **(dict(weights=sd.weights.tolist()) if weighted else {}), **(dict(coef=coef) if coef else {}),
                 prior_scale=sd.prior_scale.tolist(), prior_scale_for_aux=sd.prior_scale_for_aux,
                 prior_mean_for_aux=sd.prior_mean_for_aux, prior_df_for_aux=sd.prior_df_for_aux,
                 q=qs, lp=lps, grad=grads, write_array=was)
@@ -261,3 +329,11 @@ if __name__ == "__main__":
     make_case("four_and_three_binary", 90, 7, True, [(3, 4), (5, 3), (4, 2)])
     make_case("weighted", 64, 8, False, [(5, 2), (6, 1)], weighted=True)
     make_case("weighted_binary", 55, 9, True, [(4, 3), (3, 1)], weighted=True)
+    make_case("coef_student_t", 45, 10, False, [(4, 1)], prior_dist=2, coef=dict(prior_df=[3.0, 7.0]))
+    make_case("coef_hs", 50, 11, False, [(4, 2)], prior_dist=3,
+              coef=dict(prior_df=[1.0, 3.0], global_prior_df=1.0, global_prior_scale=0.05, slab_df=4.0, slab_scale=2.5))
+    make_case("coef_hs_plus", 50, 12, False, [(5, 1)], prior_dist=4,
+              coef=dict(prior_df=[1.0, 2.0], global_prior_df=2.0, global_prior_scale=0.1, slab_df=3.0, slab_scale=2.0))
+    make_case("coef_laplace_binary", 48, 13, True, [(4, 1)], prior_dist=5)
+    make_case("coef_lasso", 52, 14, False, [(3, 2)], prior_dist=6, coef=dict(prior_df=[2.0, 2.0]))
+    make_case("coef_product_normal", 44, 15, False, [(4, 1)], prior_dist=7, coef=dict(num_normals=[2, 3]))

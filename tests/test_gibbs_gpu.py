@@ -361,3 +361,25 @@ def test_observation_weights_first_sweeps(binary):
     u = Sampler(cfg_u, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
     ru = u.run(K, True)
     assert not np.allclose(ru["stan"], rg["stan"])
+
+
+@pytest.mark.parametrize("prior_dist", [3, 6, 7])
+def test_shrinkage_coefficient_priors_first_sweeps(prior_dist):
+    """`stan_args = list(prior = hs() / lasso() / product_normal())` (R/stan4bart_fit.R:129-142): the extra parameters of the
+    prior travel through NUTS and the stored Stan rows; sweeps agree with the oracle step by step."""
+    n, nt, seed, K = 300, 7, 55, 5
+    pr = friedman_problem(n, binary=False)
+    sd = pr["stan_data"]
+    sd.prior_dist = prior_dist
+    sd.prior_df = np.array([1.0, 3.0])
+    sd.num_normals = np.array([2, 3], dtype=np.int32)
+    cfg = bart_config(n, 9, n_test=n, num_trees=nt, seed=seed)
+    ctl = stan_control(seed=seed + 1)
+    kw = dict(warmup=K, iter_=8, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    g = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, ctl, **kw)
+    ro, rg = o.run(K, True), g.run(K, True)
+    assert ro["stan"].shape == rg["stan"].shape == (len(sd.param_names()), K)
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-7
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
+    assert np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"])

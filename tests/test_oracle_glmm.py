@@ -72,10 +72,42 @@ def test_unsupported_branches_are_rejected():
     g = rng.integers(0, 3, N)
     M = np.column_stack([np.ones(N), rng.random(N)])
     sd = build_stan_data(rng.random((N, 1)), rng.standard_normal(N), [(g, M)])
-    sd.prior_dist = 3                                   # hs prior: not implemented
-    s = sd.struct()
     import ctypes as C
+    sd.prior_dist = 8                                   # no such prior family
+    s = sd.struct()
     assert not O.lib().or_glmm_create(C.byref(s))
+    # the horseshoe priors read the error scale aux[1] (continuous.stan:300, :304): undefined for a binary response
+    sb = build_stan_data(rng.random((N, 1)), (rng.random(N) < 0.5).astype(float), [(g, M)], is_binary=True)
+    sb.prior_dist = 3
+    s = sb.struct()
+    assert not O.lib().or_glmm_create(C.byref(s))
+
+
+@pytest.mark.parametrize("prior_dist", [2, 3, 4, 5, 6, 7])
+def test_coefficient_priors_gradient_by_finite_differences(prior_dist):
+    """student_t / hs / hs_plus / laplace / lasso / product_normal coefficient priors: gradient against central differences
+    of the log density (the goldens pin the values; this covers other sizes, K = 3)."""
+    from stan4bart_b200.frontend import build_stan_data
+    rng = np.random.default_rng(prior_dist)
+    N = 80
+    g = rng.integers(0, 4, N)
+    sd = build_stan_data(rng.standard_normal((N, 3)), rng.standard_normal(N), [(g, np.ones((N, 1)))])
+    sd.prior_dist = prior_dist
+    sd.prior_df = np.array([3.0, 1.0, 5.0])
+    sd.num_normals = np.array([2, 3, 2], dtype=np.int32)
+    m = O.OracleGlmm(sd)
+    assert m.d == sd.num_params
+    m.set_offset(rng.standard_normal(N) * 0.3)
+    q = rng.uniform(-0.7, 0.7, m.d)
+    lp, grad, st = m.log_prob_grad(q)
+    assert st == 0
+    h = 1e-6
+    for i in range(m.d):
+        qp, qm = q.copy(), q.copy()
+        qp[i] += h; qm[i] -= h
+        fd = (m.log_prob_grad(qp)[0] - m.log_prob_grad(qm)[0]) / (2 * h)
+        assert abs(fd - grad[i]) <= 2e-5 * max(1.0, abs(grad[i])), (i, fd, grad[i])
+    assert len(sd.param_names()) == 7 + m.nc == 7 + sd.num_constrained
 
 
 def test_onion_blocks_gradient_by_finite_differences():
