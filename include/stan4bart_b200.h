@@ -48,6 +48,9 @@ typedef struct s4b_bart_config {
    * sigma^2 / w_i), leaf statistics become sum w, sum w r; n rows, finite and >= 0; NULL = unweighted.  Weighted fits run the
    * streamed variant of the sweep kernel. */
   const double* weights;
+  /* bart_args k = chi(degreesOfFreedom, scale) (the `!kPrior->isFixed` of src/init.cpp:731): k_df > 0 => k is sampled after every
+   * sweep, starting from `k`; k_scale <= 0 or infinite => the improper chi(df, Inf).  k_df = 0 => fixed k. */
+  double k_df, k_scale;
 } s4b_bart_config;
 
 /* the `data.stan` list, R/stan4bart_fit.R:259-365 / src/stan_sampler.cpp:112-380 (default path) */
@@ -106,6 +109,8 @@ int gpubart_free(gpubart_fit* fit);
 int gpubart_set_offset(gpubart_fit* fit, const double* offset, int update_scale);
 /* setSigma (init.cpp:257, :799) */
 int gpubart_set_sigma(gpubart_fit* fit, double sigma);
+/* current k of the leaf prior (a draw when k is modelled) */
+int gpubart_get_k(gpubart_fit* fit, double* k);
 /* sampleTreesFromPrior (init.cpp:261) */
 int gpubart_sample_trees_from_prior(gpubart_fit* fit);
 /* runSamplerWithResults(fit, 0, results[numSamples = 1]) (init.cpp:273, :824); layout src/bart_util.hpp:14-35 */
@@ -205,6 +210,9 @@ int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out);
 /* stan4bart_run(sampler, numIter, isWarmup, "both") (init.cpp:678-965).  Output buffers may be NULL.
  * stan [num_pars x S], train [n x S], test [n_test x S], varcount [p x S], sigma [S]; S = keep_fits ? num_iter : 1 */
 int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma);
+/* k of every iteration of the last s4b_sampler_run (the `k` row of the reference's BART results when k is modelled,
+ * src/bart_util.hpp:25); *count = how many were written (<= capacity) */
+int s4b_sampler_last_k(s4b_sampler* s, double* out, int capacity, int* count);
 /* the per-iteration callback of stan4bart_run (init.cpp:849-911: an R closure evaluated with yhat.train, yhat.test and the Stan
  * draw of the iteration in scope).  `fn` is called on the host after every iteration with host copies of the iteration's
  * training fit [n], test fit [n_test] (NULL when there is no test sample) and Stan row [num_pars]; a non-zero return value

@@ -47,6 +47,7 @@ struct or_bart {
   int* ncuts; double** cuts;
   uint32_t* split_w;               /* integer split weights (bart_args split.probs), NULL = uniform */
   double* weights;                 /* observation weights, NULL = unweighted */
+  double k;                        /* current k of the leaf prior normal(k): fixed, or sampled under the chi hyperprior */
   uint8_t *xt, *xt_test;           /* [p][n], [p][nt] */
   double *yresc, *treeY, *totalFits, *treeFits, *currFits, *totalTestFits, *currTestFits;
   Tree* trees;
@@ -508,6 +509,7 @@ or_bart* or_bart_create(const s4b_bart_config* cfg, const double* y, const doubl
   }
   double sd_leaf = cfg->node_scale / (cfg->k * sqrt((double) cfg->num_trees));
   f->leaf_prec = 1.0 / (sd_leaf * sd_leaf);
+  f->k = cfg->k;
   s4b_rng_init(&f->rng, cfg->seed, S4B_STREAM_BART);
   f->sigma = 1.0;
   if (cfg->is_binary) {
@@ -608,6 +610,27 @@ void or_bart_sample_trees_from_prior(or_bart* f)
   f->prior_calls++;
 }
 
+/* k ~ chi(df, scale) hyperprior of the leaf prior mu ~ N(0, (node_scale / (k sqrt(T)))^2) (bart_args k = chi(1.25, Inf),
+ * the reference's `!kPrior->isFixed` at src/init.cpp:731).  dbarts is not vendored; this is the conjugate update the model
+ * implies: given the L leaf values of all trees, k^2 ~ Gamma((L + df) / 2, rate = T sum mu^2 / (2 node_scale^2) + 1 / (2 scale^2)). */
+static void sample_k(or_bart* f)
+{
+  double sumsq = 0.0; int L = 0;
+  for (int t = 0; t < f->T; ++t) {
+    Node* bl[S4B_MAX_LEAVES + 1]; int nb = 0; fill_bottom(f->trees[t].top, bl, &nb);
+    for (int k = 0; k < nb; ++k) { sumsq += bl[k]->mu * bl[k]->mu; ++L; }
+  }
+  double ns = f->cfg.node_scale;
+  double inv_scale2 = (f->cfg.k_scale > 0.0 && isfinite(f->cfg.k_scale)) ? 1.0 / (f->cfg.k_scale * f->cfg.k_scale) : 0.0;
+  double shape = 0.5 * ((double) L + f->cfg.k_df);
+  double rate = 0.5 * (sumsq * (double) f->T / (ns * ns) + inv_scale2);
+  s4b_rng_enter(&f->rng, f->step_id, 3);
+  f->k = sqrt(s4b_rng_gamma(&f->rng, shape) / rate);
+  double sd_leaf = ns / (f->k * sqrt((double) f->T));
+  f->leaf_prec = 1.0 / (sd_leaf * sd_leaf);
+}
+double or_bart_get_k(const or_bart* f) { return f->k; }
+
 void or_bart_run(or_bart* f, double* train, double* test, uint32_t* varcount, double* sigma_out)
 {
   int n = f->n, nt = f->nt;
@@ -628,6 +651,7 @@ void or_bart_run(or_bart* f, double* train, double* test, uint32_t* varcount, do
       if (!is_thinning) for (int j = 0; j < nt; ++j) f->totalTestFits[j] += f->currTestFits[j];
     }
     if (f->cfg.is_binary) sample_latents(f);
+    if (f->cfg.k_df > 0.0) sample_k(f);
     if (!is_thinning) {
       if (train) for (int i = 0; i < n; ++i)
         train[i] = (f->cfg.is_binary ? f->totalFits[i] : f->smin + (f->totalFits[i] + 0.5) * f->srange) + f->offset[i];

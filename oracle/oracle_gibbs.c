@@ -20,6 +20,7 @@ struct or_sampler {
   double* stan_curr;   /* last saved Stan draw */
   int num_pars;
   double* userOffset;  /* copy of cc.user_offset or NULL */
+  double* k_samples; int num_k;   /* k of every iteration of the last run */
 };
 enum { OFFSET_DEFAULT = 0, OFFSET_FIXEF, OFFSET_RANEF, OFFSET_BART, OFFSET_PARAMETRIC };
 
@@ -73,7 +74,7 @@ void or_sampler_free(or_sampler* s)
 {
   if (!s) return;
   or_bart_free(s->bart); or_nuts_free(s->nuts); or_glmm_free(s->model);
-  free(s->bartOffset); free(s->stanOffset); free(s->bartLatents); free(s->stan_curr); free(s->userOffset); free(s);
+  free(s->bartOffset); free(s->stanOffset); free(s->bartLatents); free(s->stan_curr); free(s->userOffset); free(s->k_samples); free(s);
 }
 
 int or_sampler_num_stan_pars(const or_sampler* s) { return s->num_pars; }
@@ -87,6 +88,8 @@ void or_sampler_run(or_sampler* s, int num_iter, int is_warmup, double* stan, do
   size_t n = (size_t) s->n, nt = (size_t) s->n_test;
   double* tmp_train = (double*) calloc(n ? n : 1, sizeof(double));
   double* tmp_test = (double*) calloc(nt ? nt : 1, sizeof(double));
+  free(s->k_samples);
+  s->k_samples = (double*) calloc((size_t) (num_iter > 0 ? num_iter : 1), sizeof(double)); s->num_k = num_iter;
   for (int iter = 0; iter < num_iter; ++iter) {
     size_t slot = s->cc.keep_fits ? (size_t) iter : 0;
     /* A. Stan block, init.cpp:758-819 */
@@ -112,6 +115,14 @@ void or_sampler_run(or_sampler* s, int num_iter, int is_warmup, double* stan, do
     if (train) memcpy(train + slot * n, tmp_train, sizeof(double) * n);
     if (test && nt) memcpy(test + slot * nt, tmp_test, sizeof(double) * nt);
     if (sigma) sigma[slot] = sig;
+    s->k_samples[iter] = or_bart_get_k(s->bart);
   }
   free(tmp_train); free(tmp_test);
+}
+
+int or_sampler_last_k(const or_sampler* s, double* out, int capacity)
+{
+  int m = s->num_k < capacity ? s->num_k : capacity;
+  for (int i = 0; i < m; ++i) out[i] = s->k_samples[i];
+  return m;
 }

@@ -177,6 +177,24 @@ static inline double s4b_rng_normal(s4b_rng* g)
   return s4b_rng_record(g, s4b_qnorm(s4b_rng_raw_uniform(g)));
 }
 
+/* Gamma(shape, 1) by Marsaglia & Tsang (2000) on the stream's normal and uniform draws (shape < 1 through the usual
+ * U^(1/shape) boost); used for the k hyperprior of the leaf prior */
+static inline double s4b_rng_gamma(s4b_rng* g, double shape)
+{
+  double boost = 1.0;
+  if (shape < 1.0) { boost = pow(s4b_rng_uniform(g), 1.0 / shape); shape += 1.0; }
+  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (;;) {
+    double x = s4b_rng_normal(g);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = s4b_rng_uniform(g);
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+    if (g->tape != NULL && g->tape_underrun) return boost * d;
+  }
+}
+
 static inline size_t s4b_rng_index(s4b_rng* g, size_t n)
 {
   size_t k = (size_t) (s4b_rng_uniform(g) * (double) n);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "gpubart_free": (C.c_int, [vp]),
     "gpubart_set_offset": (C.c_int, [vp, c_double_p, C.c_int]),
     "gpubart_set_sigma": (C.c_int, [vp, C.c_double]),
+    "gpubart_get_k": (C.c_int, [vp, c_double_p]),
     "gpubart_sample_trees_from_prior": (C.c_int, [vp]),
     "gpubart_run_sampler_with_results": (C.c_int, [vp, c_double_p, c_double_p, c_uint32_p, c_double_p]),
     "gpubart_store_latents": (C.c_int, [vp, c_double_p]),
@@ -92,6 +93,7 @@ SIGNATURES = {
     "s4b_sampler_get_means": (C.c_int, [vp, c_double_p, c_double_p, c_double_p, c_int64_p]),
     "s4b_sampler_last_run_stats": (C.c_int, [vp, c_double_p, c_double_p, c_int64_p, c_int64_p]),
     "s4b_sampler_set_callback": (C.c_int, [vp, ITERATION_CALLBACK, vp]),
+    "s4b_sampler_last_k": (C.c_int, [vp, c_double_p, C.c_int, C.POINTER(C.c_int)]),
     "s4b_shard_create": (C.c_int, [C.c_int, C.c_int, vpp]),
     "s4b_shard_free": (C.c_int, [vp]),
     "s4b_shard_ipc_handle": (C.c_int, [vp, c_ubyte_p]),

@@ -453,6 +453,37 @@ __global__ void __launch_bounds__(kBlock) k_finish_sweep(BartDev dv, double* __r
   }
 }
 
+// k ~ chi(df, scale) hyperprior of the leaf prior (bart_args k = chi(1.25, Inf); the reference's `!kPrior->isFixed`,
+// src/init.cpp:731): given the L leaf values of all trees, k^2 ~ Gamma((L + df) / 2, rate = T sum mu^2 / (2 node_scale^2)
+// + 1 / (2 scale^2)).  One block; the per-thread partial sums are added in thread order (deterministic).
+__global__ void __launch_bounds__(256) k_draw_k(BartDev dv)
+{
+  __shared__ double s_sum[256];
+  __shared__ int s_cnt[256];
+  const int tid = threadIdx.x;
+  BartParams& P = *dv.params;
+  double sum = 0.0; int cnt = 0;
+  for (int t = tid; t < P.num_trees; t += 256) {
+    const DTree& tr = dv.trees[t];
+    for (int k = 0; k < tr.num_nodes; ++k) if (tr.nodes[k].var < 0) { const double mu = tr.nodes[k].mu; sum += mu * mu; ++cnt; }
+  }
+  s_sum[tid] = sum; s_cnt[tid] = cnt;
+  __syncthreads();
+  if (tid != 0) return;
+  double S = 0.0; int L = 0;
+  for (int i = 0; i < 256; ++i) { S += s_sum[i]; L += s_cnt[i]; }
+  RngState rng = *dv.rng;
+  rng_enter(rng, P.step_id, 3);
+  const double shape = 0.5 * ((double) L + P.k_df);
+  const double rate = 0.5 * (S * (double) P.num_trees / (P.node_scale * P.node_scale) + P.k_inv_scale2);
+  const double k = sqrt(rng_gamma(rng, shape) / rate);
+  const double sd_leaf = P.node_scale / (k * sqrt((double) P.num_trees));
+  P.k = k;
+  P.leaf_prec = 1.0 / (sd_leaf * sd_leaf);
+  if (rng.tape_underrun) P.error_flag |= 2u;
+  *dv.rng = rng;
+}
+
 __global__ void k_bump_epoch_clear_update(BartDev dv, int bump)
 {
   if (threadIdx.x == 0 && blockIdx.x == 0) { if (bump) dv.params->latent_epoch += 1u; dv.desc->a_valid = 0; }
@@ -741,6 +772,10 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   P.base = cfg.base; P.power = cfg.power;
   double sd_leaf = cfg.node_scale / (cfg.k * std::sqrt((double) cfg.num_trees));
   P.leaf_prec = 1.0 / (sd_leaf * sd_leaf);
+  P.k = cfg.k; P.node_scale = cfg.node_scale;
+  if (cfg.k_df < 0.0 || !std::isfinite(cfg.k_df)) throw std::invalid_argument("k_df must be >= 0");
+  P.k_df = cfg.k_df;
+  P.k_inv_scale2 = (cfg.k_scale > 0.0 && std::isfinite(cfg.k_scale)) ? 1.0 / (cfg.k_scale * cfg.k_scale) : 0.0;
   P.sigma = 1.0; P.smin = -0.5; P.smax = 0.5; P.srange = cfg.is_binary ? 1.0 : 0.0;
   P.key0 = (uint32_t) cfg.seed; P.key1 = (uint32_t) (cfg.seed >> 32);
   if (cfg.split_probs != nullptr) {
@@ -1133,6 +1168,7 @@ void BartFit::run_sweeps()
   S4B_CUDA(cudaEventRecord(ev_start_, stream_));
   for (int k = 0; k < cfg_.thin; ++k) {
     bool last = (k + 1) == cfg_.thin;
+    if (k > 0) draw_k();                   // k of the previous (thinned) sweep; the last one is drawn after the loop
     if (sweep_mode_ == 2) { launch_persistent_sweep(last); continue; }
     if (!use_graph) { launch_sweep_kernels(last); S4B_CUDA(cudaGetLastError()); continue; }
     cudaGraphExec_t& ge = last ? graph_exec_ : graph_exec_thin_;
@@ -1146,6 +1182,7 @@ void BartFit::run_sweeps()
     }
     S4B_CUDA(cudaGraphLaunch(ge, stream_));
   }
+  draw_k();
   S4B_CUDA(cudaEventRecord(ev_end_, stream_));
   ev_pending_ = true;
   num_tree_steps_ += (long long) cfg_.thin * T_;
@@ -1153,10 +1190,25 @@ void BartFit::run_sweeps()
   snapshot_trees();                      // keepTrees (no-op unless a store was requested)
 }
 
+void BartFit::draw_k()
+{
+  if (!(cfg_.k_df > 0.0)) return;
+  k_draw_k<<<1, 256, 0, stream_>>>(dev());
+  S4B_CUDA(cudaGetLastError());
+}
+
+double BartFit::current_k()
+{
+  double k = 0.0;
+  S4B_CUDA(cudaMemcpyAsync(&k, d_k_ptr(), sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  return k;
+}
+
 void BartFit::set_keep_trees(long long capacity)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));
-  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_store_); cudaFree(d_store_scale_); d_store_ = nullptr; d_store_scale_ = nullptr;
+  cudaFree(d_store_); cudaFree(d_store_scale_); d_store_ = nullptr; d_store_scale_ = nullptr;
   store_cap_ = capacity > 0 ? capacity : 0; store_len_ = 0;
   if (store_cap_ > 0) {
     S4B_CUDA(cudaMalloc(&d_store_, sizeof(DTree) * (size_t) T_ * (size_t) store_cap_));

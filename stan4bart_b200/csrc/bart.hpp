@@ -38,6 +38,12 @@ class BartFit {
   void set_offset_device(const double* d_offset, bool update_scale);
   void set_sigma(double sigma);
   void sample_trees_from_prior();
+  // k of the leaf prior (a draw per sweep when cfg.k_df > 0)
+  double current_k();
+  const double* d_k_ptr() const { return &d_params_->k; }
+  void draw_k();
+  bool k_modeled() const { return cfg_.k_df > 0.0; }
+  double config_k() const { return cfg_.k; }
   // `thin` sweeps; results stay on device (train_out / test_out / latent_out)
   void run_sweeps();
   // runSamplerWithResults with host result buffers (any may be NULL)

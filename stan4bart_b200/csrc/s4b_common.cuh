@@ -153,6 +153,22 @@ __host__ __device__ inline double rng_normal(RngState& g)
   }
   return rng_note(g, qnorm_as241(rng_raw_uniform(g)));
 }
+// Gamma(shape, 1) by Marsaglia & Tsang (2000) on the stream's normal and uniform draws (same recipe as oracle/s4b_rng.h)
+__host__ __device__ inline double rng_gamma(RngState& g, double shape)
+{
+  double boost = 1.0;
+  if (shape < 1.0) { boost = pow(rng_uniform(g), 1.0 / shape); shape += 1.0; }
+  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (;;) {
+    const double x = rng_normal(g);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const double u = rng_uniform(g);
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+    if (g.tape != nullptr && g.tape_underrun) return boost * d;
+  }
+}
 __host__ __device__ inline int rng_index(RngState& g, int n)
 {
   int k = (int) (rng_uniform(g) * (double) n);
@@ -259,6 +275,8 @@ struct BartParams {
   unsigned long long split_total; // sum of the weights
   int p_pos;                      // predictors with a positive weight
   int weighted;                   // observation weights present: leaf statistics are (count, sum w r, sum w)
+  // leaf prior mu ~ N(0, (node_scale / (k sqrt(T)))^2); k_df > 0: k is sampled after every sweep under k ~ chi(k_df, scale)
+  double k, k_df, k_inv_scale2, node_scale;
 };
 
 }  // namespace s4b

@@ -75,6 +75,7 @@ class GibbsSampler {
   {
     if (h_plumb_) cudaFreeHost(h_plumb_);
     if (h_cb_) cudaFreeHost(h_cb_);
+    if (h_k_) cudaFreeHost(h_k_);
     cudaFree(d_user_offset_); cudaFree(d_stan_offset_);
     cudaFree(d_bart_offset_); cudaFree(d_mean_train_); cudaFree(d_mean_param_); cudaFree(d_mean_test_); cudaFree(d_varcount_);
     cudaEventDestroy(ev_a_); cudaEventDestroy(ev_b_); cudaEventDestroy(ev_c_);
@@ -93,6 +94,12 @@ class GibbsSampler {
     ms_stan_ = ms_bart_ = 0.0;
     const long long grad0 = glmm_.num_grad_evals(), steps0 = bart_.num_tree_steps();
     const int acc_grid = (int) std::max<long long>(1, std::min<long long>((n_ + 255) / 256, 148 * 8));
+    const bool k_modeled = bart_.k_modeled();
+    if (k_modeled && (size_t) num_iter > h_k_cap_) {
+      if (h_k_) cudaFreeHost(h_k_);
+      S4B_CUDA(cudaMallocHost(&h_k_, sizeof(double) * (size_t) num_iter)); h_k_cap_ = (size_t) num_iter;
+    }
+    last_k_.clear();
     for (int iter = 0; iter < num_iter; ++iter) {
       const size_t slot = cc_.keep_fits ? (size_t) iter : 0;
       auto t0 = std::chrono::steady_clock::now();
@@ -159,6 +166,7 @@ class GibbsSampler {
         S4B_CUDA(cudaMemcpyAsync(varcount + slot * (size_t) p_, d_varcount_, sizeof(unsigned int) * (size_t) p_, cudaMemcpyDeviceToHost, stream_));
       }
       if (sigma) sigma[slot] = aux;
+      if (k_modeled) S4B_CUDA(cudaMemcpyAsync(h_k_ + iter, bart_.d_k_ptr(), sizeof(double), cudaMemcpyDeviceToHost, stream_));
       S4B_CUDA(cudaStreamSynchronize(stream_));
       if (callback_ != nullptr) {                                                        // init.cpp:849-911
         if (!h_cb_) S4B_CUDA(cudaMallocHost(&h_cb_, sizeof(double) * (n + std::max<size_t>(nt, 1))));
@@ -174,6 +182,7 @@ class GibbsSampler {
     }
     S4B_CUDA(cudaStreamSynchronize(copy_stream_));        // results are in the caller's buffers when run() returns
     copy_pending_ = false;
+    if (k_modeled) last_k_.assign(h_k_, h_k_ + num_iter); else last_k_.assign((size_t) num_iter, bart_.config_k());
     bart_.check_error_flag();
     last_grad_evals_ = glmm_.num_grad_evals() - grad0;
     last_tree_steps_ = bart_.num_tree_steps() - steps0;
@@ -190,6 +199,7 @@ class GibbsSampler {
     return d_stan_offset_;
   }
   void set_callback(s4b_iteration_callback fn, void* user) { callback_ = fn; callback_user_ = user; }
+  const std::vector<double>& last_k() const { return last_k_; }
   void disengage_adaptation() { nuts_.disengage_adaptation(); }
   // route the N-length vectors of every iteration through pinned host memory, as a drop-in at the reference's
   // own host boundary would (bench.py's `e2e` leg); returns bytes moved per iteration in each direction
@@ -227,7 +237,8 @@ class GibbsSampler {
   NutsSampler nuts_;
   BartFit bart_;
   long long n_ = 0, nt_ = 0; int p_ = 0, num_pars_ = 0;
-  std::vector<double> stan_curr_;
+  std::vector<double> stan_curr_, last_k_;
+  double* h_k_ = nullptr; size_t h_k_cap_ = 0;
   double *d_user_offset_ = nullptr, *d_stan_offset_ = nullptr;
   s4b_iteration_callback callback_ = nullptr; void* callback_user_ = nullptr; double* h_cb_ = nullptr;
   double *d_bart_offset_ = nullptr, *d_mean_train_ = nullptr, *d_mean_param_ = nullptr, *d_mean_test_ = nullptr;
@@ -309,6 +320,7 @@ int gpubart_create(const s4b_bart_config* cfg, const double* y, const double* x,
 }
 int gpubart_free(gpubart_fit* f) { S4B_API_BEGIN if (f && f->owned) delete f; S4B_API_END }
 int gpubart_set_offset(gpubart_fit* f, const double* offset, int update_scale) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_offset_host(offset, update_scale != 0); S4B_API_END }
+int gpubart_get_k(gpubart_fit* f, double* k) { S4B_API_BEGIN S4B_REQUIRE(f && k); *k = f->fit->current_k(); S4B_API_END }
 int gpubart_set_sigma(gpubart_fit* f, double sigma) { S4B_API_BEGIN S4B_REQUIRE(f && sigma > 0); f->fit->set_sigma(sigma); S4B_API_END }
 int gpubart_sample_trees_from_prior(gpubart_fit* f) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->sample_trees_from_prior(); S4B_API_END }
 int gpubart_run_sampler_with_results(gpubart_fit* f, double* train, double* test, uint32_t* varcount, double* sigma)
@@ -399,6 +411,16 @@ int s4b_sampler_free(s4b_sampler* s) { S4B_API_BEGIN delete s; S4B_API_END }
 int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); *out = s->s->num_pars(); S4B_API_END }
 int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma)
 { S4B_API_BEGIN S4B_REQUIRE(s); s->s->run(num_iter, is_warmup != 0, stan, train, test, varcount, sigma); S4B_API_END }
+int s4b_sampler_last_k(s4b_sampler* s, double* out, int capacity, int* count)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(s && out && capacity >= 0);
+  const std::vector<double>& k = s->s->last_k();
+  const int m = std::min<int>(capacity, (int) k.size());
+  for (int i = 0; i < m; ++i) out[i] = k[(size_t) i];
+  if (count) *count = m;
+  S4B_API_END
+}
 int s4b_sampler_set_callback(s4b_sampler* s, s4b_iteration_callback fn, void* user) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->set_callback(fn, user); S4B_API_END }
 int s4b_sampler_disengage_adaptation(s4b_sampler* s) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->disengage_adaptation(); S4B_API_END }
 int s4b_sampler_get_bart_data_range(s4b_sampler* s, double* o) { S4B_API_BEGIN S4B_REQUIRE(s && o); BartParams P = s->s->bart().params(); o[0] = P.smin; o[1] = P.smax; S4B_API_END }

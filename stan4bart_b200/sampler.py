@@ -52,6 +52,12 @@ class GpuBart:
     def set_sigma(self, sigma):
         _lib.check(self.L.gpubart_set_sigma(self.h, float(sigma)))
 
+    def k(self):
+        """Current k of the leaf prior normal(k): the configured value, or the latest draw under the chi hyperprior."""
+        v = C.c_double(0.0)
+        _lib.check(self.L.gpubart_get_k(self.h, C.byref(v)))
+        return v.value
+
     def sample_trees_from_prior(self):
         _lib.check(self.L.gpubart_sample_trees_from_prior(self.h))
 
@@ -401,6 +407,11 @@ class Sampler:
             out["bart"] = dict(train=train.T, test=test.T[:self.nt], varcount=vc.T, sigma=sigma)
         else:
             out["bart"] = dict(sigma=sigma)
+        # the `k` row of the BART results (src/bart_util.hpp:25: present when k is modelled; here always, constant otherwise)
+        k = np.zeros(num_iter)
+        cnt = C.c_int(0)
+        _lib.check(self.L.s4b_sampler_last_k(self.h, dptr(k), num_iter, C.byref(cnt)))
+        out["bart"]["k"] = k[:cnt.value]
         return out
 
     def set_callback(self, fn):

@@ -53,6 +53,8 @@ def lib():
             "or_bart_predict": (None, [vp, c_double_p, C.c_int64, c_double_p, c_double_p]),
             "or_bart_get_residual": (None, [vp, c_double_p]),
             "or_bart_rng_counter": (C.c_uint64, [vp]),
+            "or_bart_get_k": (C.c_double, [vp]),
+            "or_sampler_last_k": (C.c_int, [vp, c_double_p, C.c_int]),
             "or_glmm_create": (vp, [C.POINTER(GlmmData)]),
             "or_glmm_free": (None, [vp]),
             "or_glmm_num_params": (C.c_int, [vp]),
@@ -202,6 +204,9 @@ class OracleBart:
     def rng_counter(self):
         return int(lib().or_bart_rng_counter(self.h))
 
+    def k(self):
+        return float(lib().or_bart_get_k(self.h))
+
 
 class OracleGlmm:
     def __init__(self, stan_data):
@@ -324,7 +329,9 @@ class OracleSampler:
         sigma = np.zeros(S)
         lib().or_sampler_run(self.h, num_iter, int(is_warmup), dptr(stan), dptr(train), dptr(test),
                              vc.ctypes.data_as(c_uint32_p), dptr(sigma))
-        return dict(stan=stan.T, bart=dict(train=train.T, test=test.T[:self.nt], varcount=vc.T, sigma=sigma))
+        k = np.zeros(num_iter)
+        m = lib().or_sampler_last_k(self.h, dptr(k), num_iter)
+        return dict(stan=stan.T, bart=dict(train=train.T, test=test.T[:self.nt], varcount=vc.T, sigma=sigma, k=k[:m]))
 
     def disengage_adaptation(self):
         lib().or_sampler_disengage_adaptation(self.h)

@@ -466,3 +466,39 @@ def test_weighted_fit_refuses_the_per_tree_modes():
         g.set_sweep_mode(0)
     with pytest.raises(ValueError):
         bart_config(300, 5, weights=-np.ones(300))
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_modelled_k_matches_oracle(binary):
+    """bart_args k = chi(1.25, Inf): the k draw after every sweep (its own RNG substream) and the leaf prior it feeds."""
+    T, sweeps = 12, 10
+    o, g, _ = make_pair(n=900, num_trees=T, binary=binary, k_df=1.25)
+    o.sample_trees_from_prior(); g.sample_trees_from_prior()
+    o.set_trace(T * sweeps); g.set_trace(T * sweeps)
+    assert o.k() == g.k() == 2.0
+    ks = []
+    for s in range(sweeps):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9, f"sweep {s}"
+        assert abs(o.k() - g.k()) <= 1e-10 * o.k(), f"sweep {s}"
+        ks.append(g.k())
+    compare_traces(o.trace(), g.trace())
+    assert o.rng_counter() == g.rng_counter()
+    assert len(set(ks)) == sweeps
+
+
+def test_keep_trees_leaves_the_split_and_observation_weights_alone():
+    """Regression: asking for a tree store must not release the split weights / observation weights of the fit."""
+    n, T = 800, 8
+    x, y, xt = bart_problem(n, 5, 0, False, seed=4)
+    wt = np.random.default_rng(1).gamma(2.0, 0.5, n)
+    cfg = bart_config(n, 5, num_trees=T, seed=21, weights=wt, split_probs=[0.4, 0.1, 0.2, 0.2, 0.1])
+    o, g = O.OracleBart(cfg, y, x, xt), GpuBart(cfg, y, x, xt)
+    for b in (o, g):
+        b.set_sigma(1.2); b.sample_trees_from_prior()
+    g.set_keep_trees(4)
+    for s in range(4):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9
+        assert np.array_equal(ro["varcount"], rg["varcount"])
+    assert_same_partition(o, g, T)

@@ -383,3 +383,24 @@ def test_shrinkage_coefficient_priors_first_sweeps(prior_dist):
     assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-7
     assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
     assert np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"])
+
+
+def test_modelled_k_through_the_gibbs_loop():
+    """`bart_args = list(k = chi(1.25, Inf))`: the per-iteration k row of the BART results (src/bart_util.hpp:25)."""
+    n, nt, seed, K = 300, 8, 91, 6
+    pr = friedman_problem(n, binary=False)
+    cfg = bart_config(n, 9, n_test=n, num_trees=nt, seed=seed, k_df=1.25)
+    ctl = stan_control(seed=seed + 1)
+    kw = dict(warmup=K, iter_=8, keep_fits=True, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+    o = O.OracleSampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, **kw)
+    g = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, **kw)
+    ro, rg = o.run(K, True), g.run(K, True)
+    assert ro["bart"]["k"].shape == rg["bart"]["k"].shape == (K,)
+    assert rel_err(ro["bart"]["k"], rg["bart"]["k"]) <= 1e-8
+    assert len(set(rg["bart"]["k"])) == K
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-8
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-8
+    # fixed k: the row is the configured constant
+    cfg_f = bart_config(n, 9, n_test=n, num_trees=nt, seed=seed, k=3.0)
+    f = Sampler(cfg_f, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, **kw)
+    assert np.array_equal(f.run(2, True)["bart"]["k"], [3.0, 3.0])

@@ -201,3 +201,23 @@ def test_observation_weights_semantics():
     rng = np.random.default_rng(0)
     other, _ = run(rng.gamma(2.0, 0.5, n), 1.1)
     assert not np.array_equal(other[-1], base[-1])
+
+
+def test_modelled_k_hyperprior():
+    """bart_args k = chi(df, scale): k is redrawn after every sweep from its conjugate conditional; a prior that dominates
+    pins it at sqrt(df) * scale, the improper chi(1.25, Inf) lets the leaf values speak."""
+    n, T = 300, 10
+    x, y, xt = bart_problem(n, 4, 0, False, seed=6)
+    fixed = O.OracleBart(bart_config(n, 4, num_trees=T, seed=3), y, x, xt)
+    assert fixed.k() == 2.0
+    tight = O.OracleBart(bart_config(n, 4, num_trees=T, seed=3, k_df=1e6, k_scale=0.003), y, x, xt)
+    free = O.OracleBart(bart_config(n, 4, num_trees=T, seed=3, k_df=1.25), y, x, xt)
+    for o in (fixed, tight, free):
+        o.set_sigma(1.0); o.sample_trees_from_prior()
+    ks = []
+    for s in range(12):
+        fixed.run(); tight.run(); free.run()
+        assert fixed.k() == 2.0
+        assert abs(tight.k() - 3.0) < 0.02
+        ks.append(free.k())
+    assert all(np.isfinite(k) and k > 0 for k in ks) and len(set(ks)) == len(ks)

@@ -2,7 +2,8 @@
 own host thread and stream, so one chain's host-side NUTS overlaps another chain's sweep kernel on the device.
 With max_ctas > 0 every chain's sweep kernel is confined to that many SMs, so that the kernels of different chains are
 resident side by side (8 chains x 18 SMs on a 148-SM B200) and hide each other's barrier and decision latency.
-usage: python tools/multi_chain_bench.py [n] [chains] [sweeps] [trees] [max_ctas]"""
+usage: python tools/multi_chain_bench.py [n] [chains] [sweeps] [trees] [max_ctas] [ihdp|configC]
+(configC: the binary probit Friedman problem of the headline bench, to see what a second chain on the same GPU adds)"""
 import json
 import os
 import sys
@@ -10,7 +11,7 @@ import threading
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from stan4bart_b200.frontend import ihdp_problem
+from stan4bart_b200.frontend import friedman_problem, ihdp_problem
 from stan4bart_b200.sampler import Sampler
 from stan4bart_b200.structs import bart_config, stan_control
 
@@ -19,16 +20,21 @@ chains = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 trees = int(sys.argv[4]) if len(sys.argv) > 4 else 200
 max_ctas = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+problem = sys.argv[6] if len(sys.argv) > 6 else "ihdp"
 adapt = 160
-pr = ihdp_problem(n)
-kw = dict(warmup=adapt, iter_=adapt + 3 * sweeps, keep_fits=False, sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
+binary = problem == "configC"
+pr = friedman_problem(n, binary=True, seed=99) if binary else ihdp_problem(n)
+p_bart = pr["x_bart"].shape[1]
+kw = dict(warmup=adapt, iter_=adapt + 3 * sweeps, keep_fits=False)
+if not binary:
+    kw.update(sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
 samplers = [None] * chains
 barrier = threading.Barrier(chains + 1)
 times = {}
 
 
 def work(c):
-    cfg = bart_config(n, 25, n_test=n, num_trees=trees, is_binary=False, seed=100 + c, max_ctas=max_ctas)
+    cfg = bart_config(n, p_bart, n_test=n, num_trees=trees, is_binary=binary, seed=100 + c, max_ctas=max_ctas)
     s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=200 + c), **kw)
     s.run(adapt, True, results=False)
     s.disengage_adaptation()
@@ -55,7 +61,8 @@ barrier.wait()
 t_par = time.time() - t0
 for t in th:
     t.join()
-print(json.dumps({"workload": "config D shape: IHDP-like continuous, n=%d, p=25, %d trees, %d chains on one GPU, %s SMs per chain" % (n, trees, chains, max_ctas or "all"),
+what = "config C: binary probit Friedman" if binary else "config D shape: IHDP-like continuous"
+print(json.dumps({"workload": "%s, n=%d, p=%d, %d trees, %d chains on one GPU, %s SMs per chain" % (what, n, p_bart, trees, chains, max_ctas or "all"),
                   "sweeps_per_s_sequential": chains * sweeps / t_seq, "sweeps_per_s_threaded": chains * sweeps / t_par,
                   "ms_stan_block": stats["ms_stan"] / sweeps, "ms_bart_block": stats["ms_bart"] / sweeps,
                   "bart_sweep_mode": samplers[0].bart().sweep_mode()}))
