@@ -502,3 +502,56 @@ def test_keep_trees_leaves_the_split_and_observation_weights_alone():
         assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9
         assert np.array_equal(ro["varcount"], rg["varcount"])
     assert_same_partition(o, g, T)
+
+
+@pytest.mark.parametrize("case", range(14))
+def test_randomised_configurations_against_the_oracle(case, monkeypatch):
+    """Random draws over the configuration space (size, predictors, trees, response type, thinning, n.cuts, min leaf size,
+    tree prior, move probabilities, split.probs, weights, modelled k, sweep kernel variant): decisions, partitions and fits."""
+    rng = np.random.default_rng(1000 + case)
+    n = int(rng.choice([37, 150, 600, 2100, 5003]))
+    p = int(rng.integers(1, 12))
+    T = int(rng.integers(1, 14))
+    binary = bool(rng.integers(0, 2))
+    n_test = int(rng.choice([0, 1, 33]))
+    kw = dict(thin=int(rng.choice([1, 1, 2, 3])), n_cuts=int(rng.choice([1, 3, 20, 100, 255])), min_obs=int(rng.choice([1, 5, 20])),
+              base=float(rng.uniform(0.5, 0.99)), power=float(rng.uniform(0.5, 3.0)), k=float(rng.uniform(1.0, 4.0)))
+    if rng.random() < 0.4:
+        sp = rng.random(p) + 0.05
+        sp[rng.random(p) < 0.2] = 0.0
+        if not np.any(sp > 0):
+            sp[0] = 1.0
+        kw["split_probs"] = sp
+    if rng.random() < 0.4:
+        kw["weights"] = rng.gamma(2.0, 0.5, n)
+    if rng.random() < 0.3:
+        kw["k_df"] = float(rng.uniform(0.5, 3.0))
+    variant = rng.choice(["auto", "stream", "nq2", "nq6"])
+    if variant == "stream":
+        monkeypatch.setenv("S4B_FORCE_STREAM", "1")
+    elif variant.startswith("nq") and "weights" not in kw:
+        monkeypatch.setenv("S4B_FORCE_NQ", variant[2:])
+    x, y, xt = bart_problem(n, p, n_test, binary, seed=case)
+    cfg = bart_config(n, p, n_test=n_test, num_trees=T, is_binary=binary, seed=500 + case, **kw)
+    o, g = O.OracleBart(cfg, y, x, xt), GpuBart(cfg, y, x, xt)
+    off = 0.2 * np.sin(np.arange(n))
+    sweeps = 5
+    for b in (o, g):
+        b.set_offset(off, True)
+        if not binary:
+            b.set_sigma(float(0.5 + case % 3))
+        b.sample_trees_from_prior()
+    traced = case % 2 == 0
+    if traced:
+        o.set_trace(T * sweeps * kw["thin"]); g.set_trace(T * sweeps * kw["thin"])
+    for s in range(sweeps):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-8, f"sweep {s}"
+        if n_test:
+            assert rel_err(ro["test"], rg["test"], scale=np.abs(ro["test"]) + 1.0) <= 1e-8
+        assert np.array_equal(ro["varcount"], rg["varcount"])
+        assert abs(o.k() - g.k()) <= 1e-9 * o.k()
+    if traced:
+        compare_traces(o.trace(), g.trace(), tol=1e-8, ll_difference_only="weights" in kw)
+    assert_same_partition(o, g, T)
+    assert o.rng_counter() == g.rng_counter()

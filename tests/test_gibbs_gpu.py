@@ -404,3 +404,46 @@ def test_modelled_k_through_the_gibbs_loop():
     cfg_f = bart_config(n, 9, n_test=n, num_trees=nt, seed=seed, k=3.0)
     f = Sampler(cfg_f, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], ctl, **kw)
     assert np.array_equal(f.run(2, True)["bart"]["k"], [3.0, 3.0])
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_randomised_models_against_the_oracle(case):
+    """Random model structures through the whole sweep: grouping terms with 1-4 coefficients, coefficient prior family,
+    aux prior, response type, weights, user offset, thinning of both halves; a few sweeps step by step."""
+    from stan4bart_b200.frontend import build_stan_data, init_fit
+    rng = np.random.default_rng(7000 + case)
+    n = int(rng.choice([120, 400, 1500]))
+    binary = bool(rng.integers(0, 2))
+    p_bart, Kf = int(rng.integers(2, 8)), int(rng.integers(0, 4))
+    xb = np.asfortranarray(rng.random((n, p_bart)))
+    Xf = rng.standard_normal((n, Kf))
+    terms = []
+    for _ in range(int(rng.integers(0, 3))):
+        nc, nlev = int(rng.integers(1, 5)), int(rng.integers(2, 7))
+        g = rng.integers(0, nlev, n); g[:nlev] = np.arange(nlev)
+        terms.append((g, np.column_stack([np.ones(n)] + [rng.standard_normal(n) for _ in range(nc - 1)])))
+    f = 3 * np.sin(3 * xb[:, 0]) + xb[:, 1] + (Xf @ rng.standard_normal(Kf) if Kf else 0.0)
+    y = (rng.random(n) < 1 / (1 + np.exp(-f))).astype(float) if binary else f + rng.standard_normal(n)
+    wt = rng.gamma(3.0, 1.0 / 3.0, n) if rng.random() < 0.4 else None
+    sd = build_stan_data(Xf, y, terms, is_binary=binary, weights=wt)
+    sd.prior_dist = int(rng.choice([0, 1, 1, 2, 5, 6, 7] + ([] if binary else [3, 4]))) if Kf else 1
+    sd.prior_df = rng.uniform(1.0, 6.0, Kf)
+    sd.num_normals = rng.integers(2, 4, Kf).astype(np.int32)
+    if not binary:
+        sd.prior_dist_for_aux = int(rng.integers(0, 4))
+        sd.prior_mean_for_aux, sd.prior_df_for_aux = 0.3, 4.0
+    offset_init, sigma_init = init_fit(sd, binary)
+    nt = int(rng.integers(2, 9))
+    cfg = bart_config(n, p_bart, n_test=n, num_trees=nt, is_binary=binary, seed=case, thin=int(rng.choice([1, 2])), weights=wt)
+    ctl = stan_control(seed=case + 50, skip=int(rng.choice([1, 2])))
+    kw = dict(warmup=5, iter_=7, keep_fits=True, sigma_init=sigma_init, bart_offset_init=offset_init)
+    if rng.random() < 0.3:
+        kw.update(offset=rng.standard_normal(n) * 0.2, offset_type=int(rng.integers(0, 5)))
+    o = O.OracleSampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
+    g = Sampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
+    ro, rg = o.run(5, True), g.run(5, True)
+    assert ro["stan"].shape == rg["stan"].shape == (len(sd.param_names()), 5)
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-7
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
+    assert rel_err(ro["bart"]["test"], rg["bart"]["test"], scale=np.abs(ro["bart"]["test"]) + 1.0) <= 1e-7
+    assert np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"])
