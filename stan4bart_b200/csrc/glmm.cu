@@ -25,6 +25,7 @@ namespace s4b {
 
 constexpr int kGBlock = 256;
 constexpr int kMaxNc = 16;         // coefficients per ranef block
+constexpr size_t kThetaSmemMax = 40 * 1024;   // coefficient vector staged in (default-limit) shared memory up to this size
 constexpr int kGFast = 4;          // fast path of the data pass: K and non-zeros per row of Z up to this
 
 __device__ __forceinline__ double g_warp_sum(double v)
@@ -149,19 +150,103 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
   if (tid == 0) *g.ticket = 0u;
 }
 
+// ---------------------------------------------------------------------------------------
+// Column path of the data pass: models whose K + q exceeds what the lane-private shared-memory bins hold (~110 columns)
+// -- many grouping levels.  Pass 1 writes the weighted residual w e and block partials of S = sum w e^2; the dense columns
+// X'(w e) are chunked dot products; every column of Z (compressed sparse columns, entries in observation order, built once)
+// is summed by one warp in a fixed order.  No atomics: results are deterministic.
+// algorithmic bytes per observation: pass 1 as the binned pass + 8 (w e written), pass 2: 16 K + (4 + 8 + 8) per non-zero of Z
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double g_block_sum(double v, double* red /* [kGBlock / 32] */)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = g_warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double acc = 0.0;
+  for (int w = 0; w < kGBlock / 32; ++w) acc += red[w];
+  return acc;
+}
+
+__global__ void __launch_bounds__(kGBlock) k_glmm_resid_we(GlmmDev g, double* __restrict__ we_out, double* __restrict__ partials)
+{
+  __shared__ double red[kGBlock / 32];
+  const long long N = g.N, npad = g.npad;
+  const int K = g.K, slots = g.slots;
+  double S = 0.0;
+  for (long long i = (long long) blockIdx.x * kGBlock + threadIdx.x; i < N; i += (long long) gridDim.x * kGBlock) {
+    double eta = 0.0;
+    for (int k = 0; k < K; ++k) eta += __ldg(g.X + (long long) k * npad + i) * __ldg(g.theta + k);
+    for (int s = 0; s < slots; ++s) {
+      const int c = __ldg(g.zidx + (long long) s * npad + i);
+      const double v = ((g.ones_mask >> s) & 1u) ? 1.0 : __ldg(g.zval + (long long) s * npad + i);
+      eta += v * __ldg(g.theta + K + c);
+    }
+    const double e = __ldg(g.r + i) - eta;
+    const double we = g.wt != nullptr ? __ldg(g.wt + i) * e : e;
+    we_out[i] = we;
+    S += we * e;
+  }
+  S = g_block_sum(S, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = S;
+}
+
+// block (c, j): partial dot product of dense column j with w e over chunk c
+__global__ void __launch_bounds__(kGBlock) k_glmm_dense_cols(GlmmDev g, const double* __restrict__ we, double* __restrict__ partials /* [(1 + K)][G] */)
+{
+  __shared__ double red[kGBlock / 32];
+  const int j = blockIdx.y, G = gridDim.x;
+  const double* __restrict__ col = g.X + (long long) j * g.npad;
+  double acc = 0.0;
+  for (long long i = (long long) blockIdx.x * kGBlock + threadIdx.x; i < g.N; i += (long long) G * kGBlock) acc += __ldg(col + i) * __ldg(we + i);
+  acc = g_block_sum(acc, red);
+  if (threadIdx.x == 0) partials[(long long) (1 + j) * G + blockIdx.x] = acc;
+}
+
+// rows 0 .. K of the partials (S and the dense columns): one warp per row, lanes stride over the blocks
+__global__ void __launch_bounds__(kGBlock) k_glmm_finish_dense(int rows, int G, const double* __restrict__ partials, double* __restrict__ result)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v = warp; v < rows; v += kGBlock / 32) {
+    double acc = 0.0;
+    for (int b = lane; b < G; b += 32) acc += partials[(long long) v * G + b];
+    acc = g_warp_sum(acc);
+    if (lane == 0) result[v] = acc;
+  }
+}
+
+// one warp per column of Z: sum of value * (w e)[observation] over the column's entries
+__global__ void __launch_bounds__(kGBlock) k_glmm_z_cols(int q, const long long* __restrict__ col_ptr, const int* __restrict__ obs, const double* __restrict__ val,
+                                                        const double* __restrict__ we, double* __restrict__ result_z)
+{
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long) blockIdx.x * kGBlock + threadIdx.x) >> 5, nwarps = ((long long) gridDim.x * kGBlock) >> 5;
+  for (long long c = warp0; c < q; c += nwarps) {
+    const long long lo = col_ptr[c], hi = col_ptr[c + 1];
+    double a0 = 0.0, a1 = 0.0;
+    long long k = lo + lane;
+    for (; k + 32 < hi; k += 64) { a0 += __ldg(val + k) * __ldg(we + __ldg(obs + k)); a1 += __ldg(val + k + 32) * __ldg(we + __ldg(obs + k + 32)); }
+    if (k < hi) a0 += __ldg(val + k) * __ldg(we + __ldg(obs + k));
+    const double acc = g_warp_sum(a0 + a1);
+    if (lane == 0) result_z[c] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(kGBlock) k_glmm_linear_predictor(GlmmDev g, double* __restrict__ out, int include_fixed, int include_random)
 {
   extern __shared__ double smem[];
   const int nb = g.K + g.q;
-  for (int j = threadIdx.x; j < nb; j += kGBlock) smem[j] = g.theta[j];
-  __syncthreads();
+  const bool staged = (size_t) nb * sizeof(double) <= kThetaSmemMax;      // otherwise the coefficients are read through L1 / L2
+  if (staged) { for (int j = threadIdx.x; j < nb; j += kGBlock) smem[j] = g.theta[j]; __syncthreads(); }
+  const double* th = staged ? smem : g.theta;
   for (long long i = (long long) blockIdx.x * kGBlock + threadIdx.x; i < g.N; i += (long long) gridDim.x * kGBlock) {
     double eta = 0.0;
-    if (include_fixed) for (int k = 0; k < g.K; ++k) eta += __ldg(g.X + (long long) k * g.npad + i) * smem[k];
+    if (include_fixed) for (int k = 0; k < g.K; ++k) eta += __ldg(g.X + (long long) k * g.npad + i) * th[k];
     if (include_random) for (int s = 0; s < g.slots; ++s) {
       int c = __ldg(g.zidx + (long long) s * g.npad + i);
       double v = ((g.ones_mask >> s) & 1u) ? 1.0 : __ldg(g.zval + (long long) s * g.npad + i);
-      eta += v * smem[g.K + c];
+      eta += v * th[g.K + c];
     }
     out[i] = eta;
   }
@@ -279,14 +364,32 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   const int nb = K_ + q_;
   smem_bytes_ = sizeof(double) * ((size_t) nb + (size_t) (kGBlock / 32) * (nb + 1) * 32);
   int max_smem = 0; S4B_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (smem_bytes_ > (size_t) max_smem)
-    throw std::invalid_argument("glmm: K + q too large for the shared-memory binned reduction (sorted-segment path not implemented yet)");
-  S4B_CUDA(cudaFuncSetAttribute(k_glmm_data_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
+  // more columns than the lane-private shared-memory bins hold (or forced, for the tests): the column path
+  columns_ = smem_bytes_ > (size_t) max_smem || (getenv("S4B_GLMM_COLUMNS") != nullptr && atoi(getenv("S4B_GLMM_COLUMNS")) != 0);
   int per_sm = 1;      // resident blocks per SM (registers and shared memory): the grid is one full wave
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_glmm_data_terms, kGBlock, smem_bytes_) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+  if (columns_) {
+    // compressed sparse columns of Z, entries of a column in observation order
+    std::vector<long long> col_ptr((size_t) q_ + 1, 0);
+    for (long long k = 0; k < d.num_non_zero; ++k) ++col_ptr[(size_t) d.v[k] + 1];
+    for (int c = 0; c < q_; ++c) col_ptr[(size_t) c + 1] += col_ptr[(size_t) c];
+    std::vector<long long> fill(col_ptr.begin(), col_ptr.end() - 1);
+    std::vector<int> obs((size_t) std::max<long long>(1, d.num_non_zero)); std::vector<double> val(obs.size(), 0.0);
+    for (long long i = 0; i < N_; ++i) for (int k = d.u[i]; k < d.u[i + 1]; ++k) { const long long at = fill[(size_t) d.v[k]]++; obs[(size_t) at] = (int) i; val[(size_t) at] = d.w[k]; }
+    S4B_CUDA(cudaMalloc(&d_col_ptr_, sizeof(long long) * col_ptr.size()));
+    S4B_CUDA(cudaMemcpy(d_col_ptr_, col_ptr.data(), sizeof(long long) * col_ptr.size(), cudaMemcpyHostToDevice));
+    S4B_CUDA(cudaMalloc(&d_col_obs_, sizeof(int) * obs.size()));
+    S4B_CUDA(cudaMemcpy(d_col_obs_, obs.data(), sizeof(int) * obs.size(), cudaMemcpyHostToDevice));
+    dalloc(&d_col_val_, val.size());
+    S4B_CUDA(cudaMemcpy(d_col_val_, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice));
+    dalloc(&d_we_, (size_t) npad_);
+    per_sm = 4;
+  } else {
+    S4B_CUDA(cudaFuncSetAttribute(k_glmm_data_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_glmm_data_terms, kGBlock, smem_bytes_) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+  }
   long long want = (N_ + 2 * kGBlock - 1) / (2 * kGBlock);
   grid_ = (int) std::max<long long>(1, std::min<long long>(want, (long long) sms * per_sm));
-  dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) (nb + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
+  dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) ((columns_ ? K_ : nb) + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
   S4B_CUDA(cudaMallocHost(&h_pinned_, sizeof(double) * 2 * ((size_t) nb + 1)));
   // Gram matrix G = [X Z]' W [X Z] (host, once): the model matrices never change during sampling
@@ -311,7 +414,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
 
 GlmmModel::~GlmmModel()
 {
-  cudaFree(d_X_); cudaFree(d_y_); cudaFree(d_offset_); cudaFree(d_r_); cudaFree(d_wt_); cudaFree(d_tmp_); cudaFree(d_zval_); cudaFree(d_zidx_);
+  cudaFree(d_X_); cudaFree(d_y_); cudaFree(d_offset_); cudaFree(d_r_); cudaFree(d_wt_); cudaFree(d_we_); cudaFree(d_col_ptr_); cudaFree(d_col_obs_); cudaFree(d_col_val_); cudaFree(d_tmp_); cudaFree(d_zval_); cudaFree(d_zidx_);
   cudaFree(d_theta_); cudaFree(d_partials_); cudaFree(d_result_); cudaFree(d_ticket_); cudaFreeHost(h_pinned_);
   delete scratch_;
 }
@@ -392,7 +495,16 @@ void GlmmModel::data_terms(const double* beta, const double* b, double* S, doubl
   GlmmDev g;
   g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
   g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
-  k_glmm_data_terms<<<grid_, kGBlock, smem_bytes_, stream_>>>(g);
+  if (!columns_) k_glmm_data_terms<<<grid_, kGBlock, smem_bytes_, stream_>>>(g);
+  else {
+    k_glmm_resid_we<<<grid_, kGBlock, 0, stream_>>>(g, d_we_, d_partials_);
+    if (K_ > 0) k_glmm_dense_cols<<<dim3((unsigned) grid_, (unsigned) K_), kGBlock, 0, stream_>>>(g, d_we_, d_partials_);
+    k_glmm_finish_dense<<<1, kGBlock, 0, stream_>>>(K_ + 1, grid_, d_partials_, d_result_);
+    if (q_ > 0) {
+      const int zgrid = (int) std::max<long long>(1, std::min<long long>(((long long) q_ * 32 + kGBlock - 1) / kGBlock, 148 * 8));
+      k_glmm_z_cols<<<zgrid, kGBlock, 0, stream_>>>(q_, d_col_ptr_, d_col_obs_, d_col_val_, d_we_, d_result_ + 1 + K_);
+    }
+  }
   S4B_CUDA(cudaGetLastError());
   if (sharded()) for (int off = 0; off < nb + 1; off += kMailVec) shard_->allreduce(d_result_ + off, std::min(kMailVec, nb + 1 - off), kOpSum, stream_);
   S4B_CUDA(cudaMemcpyAsync(h_res, d_result_, sizeof(double) * (size_t) (nb + 1), cudaMemcpyDeviceToHost, stream_));
@@ -413,7 +525,7 @@ void GlmmModel::parametric_mean_device(const double* beta, const double* b, doub
   g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
   g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
   int grid = (int) std::max<long long>(1, std::min<long long>((N_ + kGBlock - 1) / kGBlock, 148 * 8));
-  k_glmm_linear_predictor<<<grid, kGBlock, sizeof(double) * (size_t) std::max(1, nb), stream_>>>(g, d_out, include_fixed ? 1 : 0, include_random ? 1 : 0);
+  k_glmm_linear_predictor<<<grid, kGBlock, (size_t) nb * sizeof(double) <= kThetaSmemMax ? sizeof(double) * (size_t) std::max(1, nb) : 8, stream_>>>(g, d_out, include_fixed ? 1 : 0, include_random ? 1 : 0);
   S4B_CUDA(cudaGetLastError());
   // h_pinned_ is reused by the next call: make sure the H2D copy has been consumed
   S4B_CUDA(cudaStreamSynchronize(stream_));

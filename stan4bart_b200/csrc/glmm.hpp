@@ -97,6 +97,9 @@ class GlmmModel {
 
   double *d_X_ = nullptr, *d_y_ = nullptr, *d_offset_ = nullptr, *d_r_ = nullptr, *d_wt_ = nullptr, *d_zval_ = nullptr;
   int* d_zidx_ = nullptr;
+  // column path of the data pass (K + q beyond the shared-memory bins): w e, and Z as compressed sparse columns
+  bool columns_ = false;
+  double *d_we_ = nullptr, *d_col_val_ = nullptr; long long* d_col_ptr_ = nullptr; int* d_col_obs_ = nullptr;
   double *d_theta_ = nullptr, *d_partials_ = nullptr, *d_result_ = nullptr, *d_tmp_ = nullptr;
   unsigned int* d_ticket_ = nullptr;
   double* h_pinned_ = nullptr;   // [2 * (1 + K + q)] : theta out, result in

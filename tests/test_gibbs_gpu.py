@@ -447,3 +447,26 @@ def test_randomised_models_against_the_oracle(case):
     assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
     assert rel_err(ro["bart"]["test"], rg["bart"]["test"], scale=np.abs(ro["bart"]["test"]) + 1.0) <= 1e-7
     assert np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"])
+
+
+def test_many_grouping_levels_through_the_gibbs_loop():
+    """A grouping factor with 400 levels and a random slope (q = 800): the column path of the GLMM data pass, one device pass
+    per gradient evaluation (the sweep-level expansion stops at K + q = 512)."""
+    from stan4bart_b200.frontend import build_stan_data, init_fit
+    rng = np.random.default_rng(3)
+    n, levels, nt = 6000, 400, 6
+    xb = np.asfortranarray(rng.random((n, 4)))
+    g = rng.integers(0, levels, n); g[:levels] = np.arange(levels)
+    Xf = rng.standard_normal((n, 1))
+    b = rng.standard_normal(levels) * 0.5
+    y = 3 * np.sin(3 * xb[:, 0]) + Xf[:, 0] + b[g] + rng.standard_normal(n)
+    sd = build_stan_data(Xf, y, [(g, np.column_stack([np.ones(n), xb[:, 1]]))])
+    offset_init, sigma_init = init_fit(sd, False)
+    cfg = bart_config(n, 4, n_test=n, num_trees=nt, seed=8)
+    ctl = stan_control(seed=9, max_treedepth=5)
+    kw = dict(warmup=4, iter_=6, keep_fits=True, sigma_init=sigma_init, bart_offset_init=offset_init)
+    o = O.OracleSampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
+    s = Sampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
+    ro, rg = o.run(4, True), s.run(4, True)
+    assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-7
+    assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
