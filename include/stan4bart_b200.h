@@ -46,7 +46,7 @@ typedef struct s4b_bart_config {
   const double* split_probs;
   /* observation weights (`weights` of stan4bart(), handed to dbarts as data weights: R/stan4bart_fit.R:449): y_i ~ N(f(x_i),
    * sigma^2 / w_i), leaf statistics become sum w, sum w r; n rows, finite and >= 0; NULL = unweighted.  Weighted fits run the
-   * streamed variant of the sweep kernel. */
+   * persistent sweep kernel with two-value bins (sum w r, sum w). */
   const double* weights;
   /* bart_args k = chi(degreesOfFreedom, scale) (the `!kPrior->isFixed` of src/init.cpp:731): k_df > 0 => k is sampled after every
    * sweep, starting from `k`; k_scale <= 0 or infinite => the improper chi(df, Inf).  k_df = 0 => fixed k. */

@@ -893,8 +893,7 @@ void BartFit::setup_persistent()
           if (force_nq == 0 || force_nq == 6) try_nq(6, sweep_smem_bytes<6>(p_), S4B_SWEEP_FNS(6));
 #undef S4B_SWEEP_FNS
     // shards beyond the register file (or when forced, for the tests): residuals and node indices streamed from global memory
-    // weighted fits: only the streamed variant reads the observation weights
-    const bool force_stream = (getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0) || d_wt_ != nullptr;
+    const bool force_stream = getenv("S4B_FORCE_STREAM") != nullptr && atoi(getenv("S4B_FORCE_STREAM")) != 0;
     if (persistent_nq_ == 0 || force_stream) {
       const size_t smem = sweep_smem_bytes<1>(0);
       const long long rounds = (nquad / cta_cap + 1 + kWorkers - 1) / kWorkers;
@@ -937,8 +936,8 @@ void BartFit::setup_persistent()
     S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     sweep_mode_ = 2;
   }
-  if (d_wt_ != nullptr && persistent_nq_ != kStreamNq)
-    throw std::invalid_argument("weighted fit: the streamed sweep kernel does not fit this many rows on one GPU (shard the chain by rows)");
+  if (d_wt_ != nullptr && persistent_nq_ == 0)
+    throw std::invalid_argument("weighted fit: the sweep kernel does not fit this many rows on one GPU (shard the chain by rows)");
   if (env) set_sweep_mode(atoi(env));
   if (getenv("S4B_OVERLAP_WALK")) overlap_walk_ = atoi(getenv("S4B_OVERLAP_WALK"));
 }

@@ -1119,6 +1119,14 @@ __device__ __forceinline__ void bin_add_w(double2* __restrict__ bin_s, int idx, 
   double2 v = bin_s[idx]; v.x = fma(w, pr, v.x); v.y += w; bin_s[idx] = v;
 }
 
+// register-resident variants: the residuals live in registers, the weights of a quad are re-read (L2) at every tree step
+__device__ __forceinline__ void reg_quad_weights(const double* __restrict__ wt, long long q, unsigned int live, double (&w)[4])
+{
+  if (live == 0u) return;
+  const double2 a = __ldg(reinterpret_cast<const double2*>(wt + 4 * q)), b = __ldg(reinterpret_cast<const double2*>(wt + 4 * q + 2));
+  w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+}
+
 // (no __restrict__ / read-only qualifiers on R and the node-index buffers: they are rewritten inside the same kernel, and a
 // non-coherent load would return stale values)
 template <bool SQ>
@@ -1337,6 +1345,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         else { for (int k = 0; k < kmax; ++k) reinterpret_cast<double*>(bin_s)[k * kWorkers + tid] = 0.0; }
         // observation counts stay in a register: one 6-bit field per bin row (a thread adds at most 32 to a row)
         unsigned long long cpk = 0ull;
+        const bool weighted = dv.wt != nullptr;
         const long long w1 = clock64();
         // branch-free: every observation adds into exactly one bin row (row kBinSlots is a trash row for padding and for
         // slots outside this pass); loads first (independent), then the read-modify-write chain
@@ -1347,6 +1356,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {
             double pr[4]; int row[4];
+            double wq[4] = { 1.0, 1.0, 1.0, 1.0 };
+            if (SQ && weighted) reg_quad_weights(dv.wt, q_lo + (long long) j * kWorkers + tid, (obs_mask >> (4 * j)) & 0xFu, wq);
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
@@ -1357,7 +1368,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             }
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
+              if (SQ && weighted) bin_add_w(bin_s, row[o] * kWorkers + tid, pr[o], wq[o]); else bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
               cpk += 1ull << (6 * row[o]);
             }
           }
@@ -1365,6 +1376,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {
             double pr[4]; int row[4], row2[4];
+            double wq[4] = { 1.0, 1.0, 1.0, 1.0 };
+            if (SQ && weighted) reg_quad_weights(dv.wt, q_lo + (long long) j * kWorkers + tid, (obs_mask >> (4 * j)) & 0xFu, wq);
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
@@ -1378,8 +1391,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
             }
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]);
-              bin_add<SQ>(bin_s, row2[o] * kWorkers + tid, pr[o]);
+              if (SQ && weighted) { bin_add_w(bin_s, row[o] * kWorkers + tid, pr[o], wq[o]); bin_add_w(bin_s, row2[o] * kWorkers + tid, pr[o], wq[o]); }
+              else { bin_add<SQ>(bin_s, row[o] * kWorkers + tid, pr[o]); bin_add<SQ>(bin_s, row2[o] * kWorkers + tid, pr[o]); }
               cpk += (1ull << (6 * row[o])) + (1ull << (6 * row2[o]));
             }
           }
