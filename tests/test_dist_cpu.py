@@ -78,9 +78,11 @@ def test_row_range_covers_everything_once():
         row_range(10, 2, 2)
 
 
-def test_sharded_stan_data_terms_add_up_to_the_whole():
+@pytest.mark.parametrize("weighted", [False, True])
+def test_sharded_stan_data_terms_add_up_to_the_whole(weighted):
     """The GLMM reductions a sharded chain all-reduces (S, X'e, Z'e) are sums over rows: the row shards produced by
-    StanData.rows() must add up to the whole-data terms on the CPU oracle."""
+    StanData.rows() must add up to the whole-data terms on the CPU oracle (with observation weights: each shard carries
+    its own rows' weights)."""
     import oracle_lib as O
     from stan4bart_b200.frontend import friedman_problem, shard_problem
     from stan4bart_b200.shard import row_range
@@ -88,6 +90,9 @@ def test_sharded_stan_data_terms_add_up_to_the_whole():
     pr = friedman_problem(n)
     sd = pr["stan_data"]
     rng = np.random.default_rng(1)
+    if weighted:
+        pr["weights"] = rng.gamma(2.0, 0.5, n)
+        sd.weights = pr["weights"]
     beta, b = rng.standard_normal(sd.K), rng.standard_normal(sd.q)
     off = rng.standard_normal(n)
     whole = O.OracleGlmm(sd)
@@ -99,6 +104,8 @@ def test_sharded_stan_data_terms_add_up_to_the_whole():
         lo, hi = row_range(n, r, world)
         sp = shard_problem(pr, lo, hi)
         assert sp["stan_data"].q == sd.q and sp["stan_data"].N == hi - lo and len(sp["y"]) == hi - lo
+        if weighted:
+            assert np.array_equal(sp["stan_data"].weights, pr["weights"][lo:hi]) and np.array_equal(sp["weights"], pr["weights"][lo:hi])
         part = O.OracleGlmm(sp["stan_data"])
         part.set_offset(off[lo:hi])
         s_, a_, b_ = part.data_terms(beta, b)
