@@ -407,7 +407,39 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     if (sharded()) shard_->allreduce_host(gram_.data(), (long long) gram_.size(), kOpSum, stream_);
     theta0_.assign((size_t) nb, 0.0); g0_.assign((size_t) nb, 0.0);
     mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : 1;
+  } else if (nb > 512 && !sharded()) {
+    // many grouping levels: the Gram matrix is kept in pieces -- X'WX and X'WZ dense (K is small), Z'WZ sparse (an
+    // observation touches one level per grouping term, so a row of Z'WZ has a handful of entries per term it shares rows
+    // with).  Triples (row, column, w z_a z_b) in observation order, sorted by position and merged: a fixed summation order.
+    const size_t K = (size_t) K_, q = (size_t) q_;
+    gxx_.assign(K * K, 0.0); gxz_.assign(K * q, 0.0);
+    struct Trip { unsigned long long key; double val; };
+    std::vector<Trip> trips;
+    trips.reserve((size_t) d.num_non_zero * (size_t) std::max(1, slots_));
+    for (long long i = 0; i < N_; ++i) {
+      const double wi = d.weights != nullptr ? d.weights[i] : 1.0;
+      for (size_t a = 0; a < K; ++a) {
+        const double xa = wi * d.X[a * (size_t) N_ + (size_t) i];
+        for (size_t bb = 0; bb < K; ++bb) gxx_[a * K + bb] += xa * d.X[bb * (size_t) N_ + (size_t) i];
+        for (int z = d.u[i]; z < d.u[i + 1]; ++z) gxz_[a * q + (size_t) d.v[z]] += xa * d.w[z];
+      }
+      for (int za = d.u[i]; za < d.u[i + 1]; ++za) for (int zb = d.u[i]; zb < d.u[i + 1]; ++zb)
+        trips.push_back({ (unsigned long long) d.v[za] * q + (unsigned long long) d.v[zb], wi * d.w[za] * d.w[zb] });
+    }
+    std::stable_sort(trips.begin(), trips.end(), [](const Trip& a, const Trip& b) { return a.key < b.key; });
+    gz_ptr_.assign(q + 1, 0);
+    for (size_t k = 0; k < trips.size();) {
+      size_t e = k; double acc = 0.0;
+      while (e < trips.size() && trips[e].key == trips[k].key) acc += trips[e++].val;
+      gz_col_.push_back((int) (trips[k].key % q)); gz_val_.push_back(acc); ++gz_ptr_[(size_t) (trips[k].key / q) + 1];
+      k = e;
+    }
+    for (size_t c = 0; c < q; ++c) gz_ptr_[c + 1] += gz_ptr_[c];
+    sparse_gram_ = true;
+    theta0_.assign((size_t) nb, 0.0); g0_.assign((size_t) nb, 0.0);
+    mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : 1;
   }
+  dl_.assign((size_t) nb + 1, 0.0); Gd_.assign((size_t) nb + 1, 0.0);
   refresh_r();
   S4B_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -422,7 +454,7 @@ GlmmModel::~GlmmModel()
 void GlmmModel::set_mode(int mode)
 {
   if (mode != 0 && mode != 1) throw std::invalid_argument("glmm mode must be 0 (pass per evaluation) or 1 (pass per sweep)");
-  if (mode == 1 && gram_.empty()) throw std::invalid_argument("glmm: sweep-level expansion unavailable (K + q > 512)");
+  if (mode == 1 && gram_.empty() && !sparse_gram_) throw std::invalid_argument("glmm: sweep-level expansion unavailable (K + q > 512 on a sharded chain)");
   mode_ = mode; expansion_valid_ = false;
 }
 
@@ -441,13 +473,32 @@ void GlmmModel::data_terms_auto(const double* beta, const double* b, double* S, 
     for (int k = 0; k < q_; ++k) gb[k] = g0_[(size_t) (K_ + k)];
     return;
   }
-  double dl[512], Gd[512];
+  double* dl = dl_.data(); double* Gd = Gd_.data();
   for (int k = 0; k < K_; ++k) dl[k] = beta[k] - theta0_[(size_t) k];
   for (int k = 0; k < q_; ++k) dl[K_ + k] = b[k] - theta0_[(size_t) (K_ + k)];
   // G d accumulated column by column (G is symmetric: column c is row c): the inner loop has no loop-carried dependency
   // and vectorises, unlike a row-wise dot product whose additions form one latency-bound chain per row
   for (int a = 0; a < nb; ++a) Gd[a] = 0.0;
-  {
+  if (sparse_gram_) {
+    const size_t K = (size_t) K_, q = (size_t) q_;
+    const double* db = dl + K;
+    for (size_t a = 0; a < K; ++a) {
+      double acc = 0.0;
+      for (size_t bb = 0; bb < K; ++bb) acc += gxx_[a * K + bb] * dl[bb];
+      const double* __restrict__ row = gxz_.data() + a * q;
+      double acc2 = 0.0;
+      for (size_t c = 0; c < q; ++c) acc2 += row[c] * db[c];
+      Gd[a] = acc + acc2;
+      const double da = dl[a];
+      double* __restrict__ out = Gd + K;
+      for (size_t c = 0; c < q; ++c) out[c] += row[c] * da;           // (X'WZ)' d_beta
+    }
+    for (size_t r = 0; r < q; ++r) {
+      double acc = 0.0;
+      for (long long k = gz_ptr_[r]; k < gz_ptr_[r + 1]; ++k) acc += gz_val_[(size_t) k] * db[gz_col_[(size_t) k]];
+      Gd[K + r] += acc;
+    }
+  } else {
     const double* __restrict__ G = gram_.data();
     double* __restrict__ out = Gd;
     for (int c = 0; c < nb; ++c) {

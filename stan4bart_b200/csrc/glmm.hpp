@@ -92,7 +92,10 @@ class GlmmModel {
   //   S(theta0 + d) = S0 - 2 g0'd + d'G d,   A'e(theta0 + d) = g0 - G d,   G = A'A (fixed), (S0, g0) from one pass at theta0
   int mode_ = 0;
   bool expansion_valid_ = false;
-  std::vector<double> gram_, theta0_, g0_;
+  std::vector<double> gram_, theta0_, g0_, dl_, Gd_;
+  // K + q > 512: the Gram matrix in pieces -- X'WX, X'WZ dense, Z'WZ as compressed sparse rows
+  bool sparse_gram_ = false;
+  std::vector<double> gxx_, gxz_, gz_val_; std::vector<long long> gz_ptr_; std::vector<int> gz_col_;
   double S0_ = 0.0;
 
   double *d_X_ = nullptr, *d_y_ = nullptr, *d_offset_ = nullptr, *d_r_ = nullptr, *d_wt_ = nullptr, *d_zval_ = nullptr;

@@ -450,8 +450,8 @@ def test_randomised_models_against_the_oracle(case):
 
 
 def test_many_grouping_levels_through_the_gibbs_loop():
-    """A grouping factor with 400 levels and a random slope (q = 800): the column path of the GLMM data pass, one device pass
-    per gradient evaluation (the sweep-level expansion stops at K + q = 512)."""
+    """A grouping factor with 400 levels and a random slope (q = 800): the column path of the GLMM data pass and the
+    sweep-level expansion with the Gram matrix in pieces (X'WX, X'WZ dense, Z'WZ sparse)."""
     from stan4bart_b200.frontend import build_stan_data, init_fit
     rng = np.random.default_rng(3)
     n, levels, nt = 6000, 400, 6
@@ -467,6 +467,7 @@ def test_many_grouping_levels_through_the_gibbs_loop():
     kw = dict(warmup=4, iter_=6, keep_fits=True, sigma_init=sigma_init, bart_offset_init=offset_init)
     o = O.OracleSampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
     s = Sampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
+    assert s.glmm().mode() == 1
     ro, rg = o.run(4, True), s.run(4, True)
     assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-7
     assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
