@@ -473,32 +473,14 @@ void GlmmModel::data_terms_auto(const double* beta, const double* b, double* S, 
     for (int k = 0; k < q_; ++k) gb[k] = g0_[(size_t) (K_ + k)];
     return;
   }
-  double* dl = dl_.data(); double* Gd = Gd_.data();
+  if (sparse_gram_) { expand_sparse(beta, b, S, gbeta, gb); return; }
+  double dl[512], Gd[512];
   for (int k = 0; k < K_; ++k) dl[k] = beta[k] - theta0_[(size_t) k];
   for (int k = 0; k < q_; ++k) dl[K_ + k] = b[k] - theta0_[(size_t) (K_ + k)];
   // G d accumulated column by column (G is symmetric: column c is row c): the inner loop has no loop-carried dependency
   // and vectorises, unlike a row-wise dot product whose additions form one latency-bound chain per row
   for (int a = 0; a < nb; ++a) Gd[a] = 0.0;
-  if (sparse_gram_) {
-    const size_t K = (size_t) K_, q = (size_t) q_;
-    const double* db = dl + K;
-    for (size_t a = 0; a < K; ++a) {
-      double acc = 0.0;
-      for (size_t bb = 0; bb < K; ++bb) acc += gxx_[a * K + bb] * dl[bb];
-      const double* __restrict__ row = gxz_.data() + a * q;
-      double acc2 = 0.0;
-      for (size_t c = 0; c < q; ++c) acc2 += row[c] * db[c];
-      Gd[a] = acc + acc2;
-      const double da = dl[a];
-      double* __restrict__ out = Gd + K;
-      for (size_t c = 0; c < q; ++c) out[c] += row[c] * da;           // (X'WZ)' d_beta
-    }
-    for (size_t r = 0; r < q; ++r) {
-      double acc = 0.0;
-      for (long long k = gz_ptr_[r]; k < gz_ptr_[r + 1]; ++k) acc += gz_val_[(size_t) k] * db[gz_col_[(size_t) k]];
-      Gd[K + r] += acc;
-    }
-  } else {
+  {
     const double* __restrict__ G = gram_.data();
     double* __restrict__ out = Gd;
     for (int c = 0; c < nb; ++c) {
@@ -506,6 +488,39 @@ void GlmmModel::data_terms_auto(const double* beta, const double* b, double* S, 
       const double* __restrict__ col = G + (size_t) c * nb;
       for (int a = 0; a < nb; ++a) out[a] += col[a] * dc;
     }
+  }
+  double quad = 0.0, lin = 0.0;
+  for (int a = 0; a < nb; ++a) { quad += dl[a] * Gd[a]; lin += g0_[(size_t) a] * dl[a]; }
+  *S = S0_ - 2.0 * lin + quad;
+  for (int k = 0; k < K_; ++k) gbeta[k] = g0_[(size_t) k] - Gd[k];
+  for (int k = 0; k < q_; ++k) gb[k] = g0_[(size_t) (K_ + k)] - Gd[K_ + k];
+}
+
+// the same expansion with the Gram matrix in pieces (K + q > 512): X'WX and X'WZ dense, Z'WZ compressed sparse rows
+void GlmmModel::expand_sparse(const double* beta, const double* b, double* S, double* gbeta, double* gb)
+{
+  const int nb = K_ + q_;
+  const size_t K = (size_t) K_, q = (size_t) q_;
+  double* dl = dl_.data(); double* Gd = Gd_.data();
+  for (int k = 0; k < K_; ++k) dl[k] = beta[k] - theta0_[(size_t) k];
+  for (int k = 0; k < q_; ++k) dl[K_ + k] = b[k] - theta0_[(size_t) (K_ + k)];
+  for (int a = 0; a < nb; ++a) Gd[a] = 0.0;
+  const double* db = dl + K;
+  for (size_t a = 0; a < K; ++a) {
+    double acc = 0.0;
+    for (size_t bb = 0; bb < K; ++bb) acc += gxx_[a * K + bb] * dl[bb];
+    const double* __restrict__ row = gxz_.data() + a * q;
+    double acc2 = 0.0;
+    for (size_t c = 0; c < q; ++c) acc2 += row[c] * db[c];
+    Gd[a] = acc + acc2;
+    const double da = dl[a];
+    double* __restrict__ out = Gd + K;
+    for (size_t c = 0; c < q; ++c) out[c] += row[c] * da;           // (X'WZ)' d_beta
+  }
+  for (size_t r = 0; r < q; ++r) {
+    double acc = 0.0;
+    for (long long k = gz_ptr_[r]; k < gz_ptr_[r + 1]; ++k) acc += gz_val_[(size_t) k] * db[gz_col_[(size_t) k]];
+    Gd[K + r] += acc;
   }
   double quad = 0.0, lin = 0.0;
   for (int a = 0; a < nb; ++a) { quad += dl[a] * Gd[a]; lin += g0_[(size_t) a] * dl[a]; }
@@ -776,7 +791,7 @@ int GlmmModel::log_prob_grad(const double* q, double* lp_out, double* grad)
   if (prior_dist_ >= 1) { for (int k = 0; k < len_zbeta_; ++k) lp += -0.5 * P.z_beta[k] * P.z_beta[k]; lp -= len_zbeta_ * kHalfLog2Pi; }
   // the extra parameters of the shrinkage priors: lb_constrain Jacobian + their priors (continuous.stan:381-408);
   // d_extra[i] = d prior / d (constrained value)
-  d_extra_.assign((size_t) len_extra_ + 1, 0.0);
+  if (len_extra_ > 0) d_extra_.assign((size_t) len_extra_ + 1, 0.0);
   for (int i = 0; i < len_extra_; ++i) lp += P.extra_u[i];
   if (hs_ > 0) {
     auto inv_gamma = [&](double x, double a, double& dx) { dx = -(a + 1.0) / x + a / (x * x); return a * std::log(a) - std::lgamma(a) - (a + 1.0) * std::log(x) - a / x; };
