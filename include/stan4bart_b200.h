@@ -51,6 +51,9 @@ typedef struct s4b_bart_config {
   /* bart_args k = chi(degreesOfFreedom, scale) (the `!kPrior->isFixed` of src/init.cpp:731): k_df > 0 => k is sampled after every
    * sweep, starting from `k`; k_scale <= 0 or infinite => the improper chi(df, Inf).  k_df = 0 => fixed k. */
   double k_df, k_scale;
+  /* bart_args n.cuts given per predictor (R/stan4bart_fit.R:446-451 recycles it over the columns): p entries in [1, n_cuts],
+   * n_cuts being the largest; NULL = n_cuts for every predictor */
+  const int32_t* n_cuts_var;
 } s4b_bart_config;
 
 /* the `data.stan` list, R/stan4bart_fit.R:259-365 / src/stan_sampler.cpp:112-380 (default path) */

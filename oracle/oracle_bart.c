@@ -458,6 +458,7 @@ static uint8_t bin_value(const double* cuts, int ncuts, double x) {
 or_bart* or_bart_create(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test)
 {
   if (cfg->n_cuts < 1 || cfg->n_cuts > 255) return NULL;
+  if (cfg->n_cuts_var) for (int64_t j = 0; j < cfg->p; ++j) if (cfg->n_cuts_var[j] < 1 || cfg->n_cuts_var[j] > cfg->n_cuts) return NULL;
   or_bart* f = (or_bart*) calloc(1, sizeof(or_bart));
   f->cfg = *cfg; f->n = (int) cfg->n; f->p = (int) cfg->p; f->nt = (int) cfg->n_test; f->T = cfg->num_trees;
   size_t n = (size_t) f->n, p = (size_t) f->p, nt = (size_t) f->nt, T = (size_t) f->T;
@@ -481,21 +482,22 @@ or_bart* or_bart_create(const s4b_bart_config* cfg, const double* y, const doubl
   f->weights = NULL;
   if (cfg->weights) { f->weights = (double*) malloc(sizeof(double) * (n ? n : 1)); memcpy(f->weights, cfg->weights, sizeof(double) * n); }
   f->cfg.weights = NULL;
+  f->cfg.n_cuts_var = NULL;
   f->xt = (uint8_t*) malloc(n * p + 1);
   for (size_t j = 0; j < p; ++j) {
     const double* col = x + j * n;
     double mn = col[0], mx = col[0];
     for (size_t i = 1; i < n; ++i) { if (col[i] < mn) mn = col[i]; if (col[i] > mx) mx = col[i]; }
-    f->ncuts[j] = cfg->n_cuts;
+    f->ncuts[j] = cfg->n_cuts_var ? cfg->n_cuts_var[j] : cfg->n_cuts;      /* bart_args n.cuts, possibly one count per predictor */
     f->cuts[j] = (double*) malloc(sizeof(double) * (size_t) cfg->n_cuts);
-    double inc = (mx - mn) / (double) (cfg->n_cuts + 1);
-    for (int k = 0; k < cfg->n_cuts; ++k) f->cuts[j][k] = mn + (double) (k + 1) * inc;
-    for (size_t i = 0; i < n; ++i) f->xt[j * n + i] = bin_value(f->cuts[j], cfg->n_cuts, col[i]);
+    double inc = (mx - mn) / (double) (f->ncuts[j] + 1);
+    for (int k = 0; k < f->ncuts[j]; ++k) f->cuts[j][k] = mn + (double) (k + 1) * inc;
+    for (size_t i = 0; i < n; ++i) f->xt[j * n + i] = bin_value(f->cuts[j], f->ncuts[j], col[i]);
   }
   if (nt > 0) {
     f->x_test = (double*) malloc(sizeof(double) * nt * p); memcpy(f->x_test, x_test, sizeof(double) * nt * p);
     f->xt_test = (uint8_t*) malloc(nt * p);
-    for (size_t j = 0; j < p; ++j) for (size_t i = 0; i < nt; ++i) f->xt_test[j * nt + i] = bin_value(f->cuts[j], cfg->n_cuts, x_test[j * nt + i]);
+    for (size_t j = 0; j < p; ++j) for (size_t i = 0; i < nt; ++i) f->xt_test[j * nt + i] = bin_value(f->cuts[j], f->ncuts[j], x_test[j * nt + i]);
     f->totalTestFits = (double*) calloc(nt, sizeof(double)); f->currTestFits = (double*) calloc(nt, sizeof(double));
   }
   f->yresc = (double*) calloc(n ? n : 1, sizeof(double)); f->treeY = (double*) calloc(n ? n : 1, sizeof(double));

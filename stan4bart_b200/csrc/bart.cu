@@ -396,7 +396,7 @@ __global__ void k_prior_tree(BartDev dv, int tree_index)
     double u = rng_uniform(rng);
     if (!(u < pg)) continue;
     int var = t_draw_var(t, P, i, navail, rng);
-    int lo, hi; t_split_interval(t, P.n_cuts, i, var, lo, hi);
+    int lo, hi; t_split_interval(t, s4b_ncuts(P, var), i, var, lo, hi);
     int cut = lo + rng_index(rng, hi - lo + 1);
     t_insert_children(t, i, var, cut);
     ++leaves;
@@ -716,6 +716,13 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   long long want1 = (n_ + kBlock - 1) / kBlock;
   grid_ew_ = (int) std::max<long long>(1, std::min<long long>(want1, (long long) num_sms_ * 8));
 
+  if (cfg.n_cuts_var != nullptr) {
+    ncuts_var_.assign(cfg.n_cuts_var, cfg.n_cuts_var + p_);
+    for (int j = 0; j < p_; ++j) if (ncuts_var_[(size_t) j] < 1 || ncuts_var_[(size_t) j] > cfg.n_cuts) throw std::invalid_argument("n_cuts_var entries must be in [1, n_cuts]");
+    S4B_CUDA(cudaMalloc(&d_ncuts_var_, sizeof(int) * (size_t) p_));
+    S4B_CUDA(cudaMemcpy(d_ncuts_var_, ncuts_var_.data(), sizeof(int) * (size_t) p_, cudaMemcpyHostToDevice));
+  }
+  cfg_.n_cuts_var = nullptr;
   // ---- cut points (uniform over the training range) and binning, host side (setup only) ----
   cuts_.resize((size_t) p_ * cfg.n_cuts);
   std::vector<uint8_t> xt((size_t) p_ * npad_, 0);
@@ -730,9 +737,11 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   for (int j = 0; j < p_; ++j) {
     const double* col = x + (size_t) j * n_;
     const double mn = -range[(size_t) 2 * j], mx = range[(size_t) 2 * j + 1];
-    double inc = (mx - mn) / (double) (cfg.n_cuts + 1);
+    // a predictor with fewer cuts than n_cuts (bart_args n.cuts as a vector) pads its row with +inf: binning never goes past its last cut
+    const int mj = ncuts_var_.empty() ? cfg.n_cuts : ncuts_var_[(size_t) j];
+    double inc = (mx - mn) / (double) (mj + 1);
     double* c = cuts_.data() + (size_t) j * cfg.n_cuts;
-    for (int k = 0; k < cfg.n_cuts; ++k) c[k] = mn + (double) (k + 1) * inc;
+    for (int k = 0; k < cfg.n_cuts; ++k) c[k] = k < mj ? mn + (double) (k + 1) * inc : std::numeric_limits<double>::infinity();
     uint8_t* dst = xt.data() + (size_t) j * npad_;
     for (long long i = 0; i < n_; ++i) dst[i] = (uint8_t) (std::lower_bound(c, c + cfg.n_cuts, col[i]) - c);
   }
@@ -772,7 +781,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   P.base = cfg.base; P.power = cfg.power;
   double sd_leaf = cfg.node_scale / (cfg.k * std::sqrt((double) cfg.num_trees));
   P.leaf_prec = 1.0 / (sd_leaf * sd_leaf);
-  P.k = cfg.k; P.node_scale = cfg.node_scale;
+  P.k = cfg.k; P.node_scale = cfg.node_scale; P.ncuts_var = d_ncuts_var_;
   if (cfg.k_df < 0.0 || !std::isfinite(cfg.k_df)) throw std::invalid_argument("k_df must be >= 0");
   P.k_df = cfg.k_df;
   P.k_inv_scale2 = (cfg.k_scale > 0.0 && std::isfinite(cfg.k_scale)) ? 1.0 / (cfg.k_scale * cfg.k_scale) : 0.0;
@@ -843,7 +852,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>

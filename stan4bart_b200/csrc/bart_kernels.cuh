@@ -28,6 +28,9 @@ namespace s4b {
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ bool t_is_leaf(const DTree& t, int i) { return t.nodes[i].var < 0; }
 
+// cut points of predictor `var` (bart_args n.cuts may name one count per predictor)
+__device__ __forceinline__ int s4b_ncuts(const BartParams& P, int var) { return P.ncuts_var != nullptr ? P.ncuts_var[var] : P.n_cuts; }
+
 __device__ inline void t_split_interval(const DTree& t, int n_cuts, int i, int var, int& lo, int& hi)
 {
   lo = 0; hi = n_cuts - 1;
@@ -53,7 +56,7 @@ __device__ inline int t_num_vars_available(const DTree& t, const BartParams& P, 
     int v = t.nodes[par].var;
     bool seen = false;
     for (int a = t.nodes[i].parent; a != par; a = t.nodes[a].parent) if (t.nodes[a].var == v) { seen = true; break; }
-    if (!seen && (P.split_w == nullptr || P.split_w[v] != 0u)) { int lo, hi; t_split_interval(t, P.n_cuts, i, v, lo, hi); if (hi < lo) ++blocked; }
+    if (!seen && (P.split_w == nullptr || P.split_w[v] != 0u)) { int lo, hi; t_split_interval(t, s4b_ncuts(P, v), i, v, lo, hi); if (hi < lo) ++blocked; }
     par = t.nodes[par].parent;
   }
   return (P.split_w != nullptr ? P.p_pos : P.p) - blocked;
@@ -65,7 +68,7 @@ __device__ inline bool t_var_available(const DTree& t, const BartParams& P, int 
   bool used = false;
   for (int a = t.nodes[i].parent; a >= 0; a = t.nodes[a].parent) if (t.nodes[a].var == j) { used = true; break; }
   if (!used) return true;
-  int lo, hi; t_split_interval(t, P.n_cuts, i, j, lo, hi);
+  int lo, hi; t_split_interval(t, s4b_ncuts(P, j), i, j, lo, hi);
   return hi >= lo;
 }
 
@@ -84,7 +87,7 @@ __device__ inline unsigned long long t_avail_weight(const DTree& t, const BartPa
     int v = t.nodes[par].var;
     bool seen = false;
     for (int a = t.nodes[i].parent; a != par; a = t.nodes[a].parent) if (t.nodes[a].var == v) { seen = true; break; }
-    if (!seen && P.split_w[v] != 0u) { int lo, hi; t_split_interval(t, P.n_cuts, i, v, lo, hi); if (hi < lo) w -= P.split_w[v]; }
+    if (!seen && P.split_w[v] != 0u) { int lo, hi; t_split_interval(t, s4b_ncuts(P, v), i, v, lo, hi); if (hi < lo) w -= P.split_w[v]; }
     par = t.nodes[par].parent;
   }
   return w;
@@ -183,7 +186,7 @@ __device__ inline double t_branch_log_prior(const DTree& t, const BartParams& P,
     double pg = t_growth_prob_depth(pgrow, navail, t.nodes[k].depth);
     if (t_is_leaf(t, k)) r += log(1.0 - pg);
     else {
-      int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi);
+      int lo, hi; t_split_interval(t, s4b_ncuts(P, t.nodes[k].var), k, t.nodes[k].var, lo, hi);
       r += log(pg) + t_log_var_prior(t, P, k, navail) - log((double) (hi - lo + 1));
     }
   }
@@ -193,7 +196,7 @@ __device__ inline bool t_rules_valid(const DTree& t, const BartParams& P, int i)
 {
   int end = t_subtree_end(t, i);
   for (int k = i; k < end; ++k) if (!t_is_leaf(t, k)) {
-    int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi);
+    int lo, hi; t_split_interval(t, s4b_ncuts(P, t.nodes[k].var), k, t.nodes[k].var, lo, hi);
     if (t.nodes[k].cut < lo || t.nodes[k].cut > hi) return false;
   }
   return true;
@@ -257,7 +260,7 @@ __device__ inline void propose_step(DTree& t, const BartParams& P, const double*
       int depth = t.nodes[node].depth;
       double pg_parent = t_growth_prob_depth(pgrow, navail, depth);
       int var = t_draw_var(t, P, node, navail, rng);
-      int lo, hi; t_split_interval(t, P.n_cuts, node, var, lo, hi);
+      int lo, hi; t_split_interval(t, s4b_ncuts(P, var), node, var, lo, hi);
       int cut = lo + rng_index(rng, hi - lo + 1);
       // children: same availability except possibly `var`
       int navail_l = navail - ((cut - 1 < lo) ? 1 : 0);
@@ -316,7 +319,7 @@ __device__ inline void propose_step(DTree& t, const BartParams& P, const double*
     for (int k = 0; k < t.num_nodes; ++k) if (!t_is_leaf(t, k)) { if (pick == 0) { node = k; break; } --pick; }
     int navail = t_num_vars_available(t, P, node);
     int new_var = t_draw_var(t, P, node, navail, rng);
-    int lo, hi; t_split_interval(t, P.n_cuts, node, new_var, lo, hi);
+    int lo, hi; t_split_interval(t, s4b_ncuts(P, new_var), node, new_var, lo, hi);
     int end = t_subtree_end(t, node), rstart = t.nodes[node].right;
     for (int k = node + 1; k < end; ++k) if (!t_is_leaf(t, k) && t.nodes[k].var == new_var) {
       int c = t.nodes[k].cut;

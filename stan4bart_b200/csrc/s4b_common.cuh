@@ -275,6 +275,7 @@ struct BartParams {
   unsigned long long split_total; // sum of the weights
   int p_pos;                      // predictors with a positive weight
   int weighted;                   // observation weights present: leaf statistics are (count, sum w r, sum w)
+  const int* ncuts_var;           // bart_args n.cuts given per predictor (each <= n_cuts), nullptr = n_cuts everywhere
   // leaf prior mu ~ N(0, (node_scale / (k sqrt(T)))^2); k_df > 0: k is sampled after every sweep under k ~ chi(k_df, scale)
   double k, k_df, k_inv_scale2, node_scale;
 };

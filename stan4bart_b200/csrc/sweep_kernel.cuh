@@ -319,7 +319,7 @@ __device__ inline double w_branch_log_prior(const DTree& t, const BartParams& P,
       int d = t.nodes[k].depth;
       if (t.nodes[k].var < 0) term = navail > 0 ? tab[kTabLog1mPg + d] : 0.0;
       else {
-        int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi);
+        int lo, hi; t_split_interval(t, s4b_ncuts(P, t.nodes[k].var), k, t.nodes[k].var, lo, hi);
         const double lvar = P.split_w == nullptr ? -tab_log_int(tab, navail) : log((double) P.split_w[t.nodes[k].var] / (double) t_avail_weight(t, P, k));
         term = tab[kTabLogPg + d] + lvar - tab_log_int(tab, hi - lo + 1);
       }
@@ -367,7 +367,7 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
       const int depth = t.nodes[node].depth;
       const double pg_parent = t_growth_prob_depth(tab + kTabPg, navail, depth);
       b_var = w_draw_var(t, P, node, navail, rng, lane);
-      int lo, hi; t_split_interval(t, P.n_cuts, node, b_var, lo, hi);
+      int lo, hi; t_split_interval(t, s4b_ncuts(P, b_var), node, b_var, lo, hi);
       b_cut = lo + rng.index(hi - lo + 1);
       const int navail_l = navail - ((b_cut - 1 < lo) ? 1 : 0);
       const int navail_r = navail - ((b_cut + 1 > hi) ? 1 : 0);
@@ -437,7 +437,7 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
       for (int base = node; base < end; base += 32) {
         int k = base + lane;
         bool b = false;
-        if (k < end && t.nodes[k].var >= 0) { int lo, hi; t_split_interval(t, P.n_cuts, k, t.nodes[k].var, lo, hi); b = t.nodes[k].cut < lo || t.nodes[k].cut > hi; }
+        if (k < end && t.nodes[k].var >= 0) { int lo, hi; t_split_interval(t, s4b_ncuts(P, t.nodes[k].var), k, t.nodes[k].var, lo, hi); b = t.nodes[k].cut < lo || t.nodes[k].cut > hi; }
         if (__ballot_sync(0xffffffffu, b)) bad = true;
       }
       double new_lp = 0.0;
@@ -461,7 +461,7 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
     if (n_nb > 0) {
       node = w_select_flag(cs, nn, kFInternal, rng.index(n_nb), lane);
       new_var = w_draw_var(t, P, node, cs.navail[node], rng, lane);
-      int lo, hi; t_split_interval(t, P.n_cuts, node, new_var, lo, hi);
+      int lo, hi; t_split_interval(t, s4b_ncuts(P, new_var), node, new_var, lo, hi);
       const int end = t_subtree_end(t, node), rstart = t.nodes[node].right;
       int lo_c = lo, hi_c = hi;
       for (int base = node + 1; base < end; base += 32) {

@@ -27,6 +27,7 @@ class BartConfig(C.Structure):
         ("birth_prob", C.c_double), ("base", C.c_double), ("power", C.c_double), ("k", C.c_double),
         ("node_scale", C.c_double), ("seed", C.c_uint64), ("split_probs", C.POINTER(C.c_double)),
         ("weights", C.POINTER(C.c_double)), ("k_df", C.c_double), ("k_scale", C.c_double),
+        ("n_cuts_var", C.POINTER(C.c_int32)),
     ]
 
 
@@ -86,6 +87,10 @@ def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_
     predictors (bart_args split.probs), None = uniform."""
     if node_scale is None:
         node_scale = 3.0 if is_binary else 0.5
+    n_cuts_var = None
+    if np.ndim(n_cuts) > 0:          # bart_args n.cuts as a vector: recycled over the predictors (R/stan4bart_fit.R:451)
+        n_cuts_var = np.ascontiguousarray(np.resize(np.asarray(n_cuts, dtype=np.int32), p))
+        n_cuts = int(n_cuts_var.max())
     cfg = BartConfig(n=n, p=p, n_test=n_test, num_trees=num_trees, n_cuts=n_cuts, thin=thin, min_obs=min_obs,
                      is_binary=int(is_binary), max_ctas=int(max_ctas), birth_death_prob=birth_death_prob, swap_prob=swap_prob,
                      change_prob=change_prob, birth_prob=birth_prob, base=base, power=power, k=k,
@@ -96,6 +101,9 @@ def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_
             raise ValueError("split_probs must be p non-negative numbers, not all zero")
         cfg._split_probs = sp                       # keeps the array alive with the struct
         cfg.split_probs = sp.ctypes.data_as(C.POINTER(C.c_double))
+    if n_cuts_var is not None:
+        cfg._n_cuts_var = n_cuts_var
+        cfg.n_cuts_var = n_cuts_var.ctypes.data_as(C.POINTER(C.c_int32))
     if weights is not None:
         wt = np.ascontiguousarray(weights, dtype=np.float64)
         if wt.shape != (n,) or not np.all(np.isfinite(wt)) or np.any(wt < 0):

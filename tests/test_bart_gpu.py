@@ -504,7 +504,7 @@ def test_keep_trees_leaves_the_split_and_observation_weights_alone():
     assert_same_partition(o, g, T)
 
 
-@pytest.mark.parametrize("case", range(14))
+@pytest.mark.parametrize("case", range(16))
 def test_randomised_configurations_against_the_oracle(case, monkeypatch):
     """Random draws over the configuration space (size, predictors, trees, response type, thinning, n.cuts, min leaf size,
     tree prior, move probabilities, split.probs, weights, modelled k, sweep kernel variant): decisions, partitions and fits."""
@@ -526,6 +526,8 @@ def test_randomised_configurations_against_the_oracle(case, monkeypatch):
         kw["weights"] = rng.gamma(2.0, 0.5, n)
     if rng.random() < 0.3:
         kw["k_df"] = float(rng.uniform(0.5, 3.0))
+    if case >= 10:               # bart_args n.cuts as a vector: one count per predictor
+        kw["n_cuts"] = rng.integers(1, 60, p)
     variant = rng.choice(["auto", "stream", "nq2", "nq6"])
     if variant == "stream":
         monkeypatch.setenv("S4B_FORCE_STREAM", "1")
@@ -555,3 +557,27 @@ def test_randomised_configurations_against_the_oracle(case, monkeypatch):
         compare_traces(o.trace(), g.trace(), tol=1e-8, ll_difference_only="weights" in kw)
     assert_same_partition(o, g, T)
     assert o.rng_counter() == g.rng_counter()
+
+
+def test_cut_counts_per_predictor():
+    """bart_args n.cuts as a vector (R/stan4bart_fit.R:446-451): every predictor has its own number of uniform cut points;
+    splits on a predictor never use a cut index beyond its own count."""
+    n, T = 1200, 12
+    x, y, xt = bart_problem(n, 4, 25, False, seed=5)
+    counts = np.array([1, 2, 100, 7])
+    cfg = bart_config(n, 4, n_test=25, num_trees=T, seed=3, n_cuts=counts)
+    o, g = O.OracleBart(cfg, y, x, xt), GpuBart(cfg, y, x, xt)
+    for b in (o, g):
+        b.set_sigma(1.0); b.sample_trees_from_prior()
+    o.set_trace(T * 8); g.set_trace(T * 8)
+    for s in range(8):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9
+        assert rel_err(ro["test"], rg["test"], scale=np.abs(ro["test"]) + 1.0) <= 1e-9
+    compare_traces(o.trace(), g.trace())
+    assert_same_partition(o, g, T)
+    tr = g.trace()
+    births = tr[(tr[:, 0] == 0) & (tr[:, 2] >= 0)]
+    assert births.shape[0] > 0 and np.all(births[:, 3] < counts[births[:, 2].astype(int)])
+    tg, to = g.trees(), o.trees()
+    assert np.array_equal(tg["var"], to["var"]) and rel_err(tg["value"], to["value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-9

@@ -221,3 +221,19 @@ def test_modelled_k_hyperprior():
         assert abs(tight.k() - 3.0) < 0.02
         ks.append(free.k())
     assert all(np.isfinite(k) and k > 0 for k in ks) and len(set(ks)) == len(ks)
+
+
+def test_cut_counts_per_predictor_in_the_oracle():
+    n, T = 500, 10
+    x, y, xt = bart_problem(n, 3, 0, False, seed=5)
+    counts = np.array([1, 3, 50])
+    o = O.OracleBart(bart_config(n, 3, num_trees=T, seed=3, n_cuts=counts), y, x, xt)
+    o.set_sigma(1.0); o.sample_trees_from_prior()
+    o.set_trace(T * 10)
+    for s in range(10):
+        o.run()
+    tr = o.trace()
+    rules = tr[(tr[:, 0] == 0) & (tr[:, 2] >= 0)]
+    assert rules.shape[0] > 0 and np.all(rules[:, 3] < counts[rules[:, 2].astype(int)])
+    with pytest.raises(Exception):
+        O.OracleBart(bart_config(n, 3, num_trees=T, n_cuts=np.array([0, 3, 50])), y, x, xt)
