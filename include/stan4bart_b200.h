@@ -54,6 +54,13 @@ typedef struct s4b_bart_config {
   /* bart_args n.cuts given per predictor (R/stan4bart_fit.R:446-451 recycles it over the columns): p entries in [1, n_cuts],
    * n_cuts being the largest; NULL = n_cuts for every predictor */
   const int32_t* n_cuts_var;
+  /* change rule: 0 (default) = Metropolis-Hastings ratio including the proposal term |I_new| P(old var) / (|I_old| P(new var))
+   * (the cut of the new rule is drawn from the interval that ancestors and descendants leave for the NEW variable, the reverse
+   * move draws from the interval of the OLD one): the chain then has the model's exact posterior as its stationary law, which
+   * tests/test_exact_posterior.py checks by brute-force enumeration.  1 = prior x likelihood ratio only, the form the change
+   * step is remembered to have in dbarts / BayesTree (not verifiable here: dbarts is not vendored); exact only for p = 1. */
+  int32_t change_symmetric;
+  int32_t reserved;
 } s4b_bart_config;
 
 /* the `data.stan` list, R/stan4bart_fit.R:259-365 / src/stan_sampler.cpp:112-380 (default path) */

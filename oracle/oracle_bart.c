@@ -336,15 +336,15 @@ static void desc_constraints(const Node* nd, int var, int* maxcut, int* mincut) 
   desc_constraints(nd->left, var, maxcut, mincut); desc_constraints(nd->right, var, maxcut, mincut);
 }
 
-static void finish_change_like(or_bart* f, Tree* t, Tree* saved, Node* nd, int64_t heap, const double* ty, double* tr) {
-  /* nd is in the modified tree t, saved holds the original */
+static void finish_change_like(or_bart* f, Tree* t, Tree* saved, Node* nd, int64_t heap, const double* ty, double* tr, double log_hastings) {
+  /* nd is in the modified tree t, saved holds the original; log_hastings = log q(new -> old) - log q(old -> new) */
   Node* old_nd = find_by_heap(saved->top, heap);
   double old_ll = branch_loglik(f, old_nd, ty);
   double old_lp = branch_log_prior(f, old_nd);
   repartition(f, nd);
   double new_ll = branch_loglik(f, nd, ty);
   double new_lp = branch_log_prior(f, nd);
-  double ratio = exp((new_lp - old_lp) + (new_ll - old_ll));
+  double ratio = exp(((new_lp - old_lp) + log_hastings) + (new_ll - old_ll));
   if (branch_min_obs(nd) < f->cfg.min_obs) ratio = 0.0;
   s4b_rng_enter(&f->rng, f->step_id, 1);
   double u = s4b_rng_uniform(&f->rng);
@@ -372,10 +372,27 @@ static void change_rule(or_bart* f, Tree* t, const double* ty, double* tr) {
   if (lo > hi) return;
   int new_cut = lo + (int) s4b_rng_index(&f->rng, (size_t) (hi - lo + 1));
   tr[0] = 2; tr[3] = new_cut;
+  /* Proposal ratio.  The new rule is drawn as (variable | node) x (cut uniform on the interval that ancestors AND
+   * descendants leave for that variable); the reverse move has to draw the old variable and the old cut from ITS
+   * interval, and the two intervals differ when the variable changes:
+   *   q(new -> old) / q(old -> new) = [P(old var) / |I_old|] / [P(new var) / |I_new|].
+   * Without this term the chain does not have the model's posterior as its stationary law once p >= 2
+   * (tests/test_exact_posterior.py); change_symmetric = 1 keeps the uncorrected ratio (prior x likelihood only). */
+  double log_hastings = 0.0;
+  if (!f->cfg.change_symmetric && new_var != nd->var) {
+    int olo, ohi; split_interval(f, nd, nd->var, &olo, &ohi);
+    int omaxl = -1, ominl = 1 << 30, omaxr = -1, ominr = 1 << 30;
+    desc_constraints(nd->left, nd->var, &omaxl, &ominl);
+    desc_constraints(nd->right, nd->var, &omaxr, &ominr);
+    if (omaxl + 1 > olo) olo = omaxl + 1;
+    if (ominr - 1 < ohi) ohi = ominr - 1;
+    log_hastings = log((double) (hi - lo + 1)) - log((double) (ohi - olo + 1));
+    if (f->split_w) log_hastings += log((double) f->split_w[nd->var] / (double) f->split_w[new_var]);
+  }
   Tree saved; tree_clone(f, t, &saved);
   int64_t heap = node_heap(nd);
   nd->var = new_var; nd->cut = new_cut;
-  finish_change_like(f, t, &saved, nd, heap, ty, tr);
+  finish_change_like(f, t, &saved, nd, heap, ty, tr, log_hastings);
 }
 
 static int rules_valid(const or_bart* f, const Node* nd) {
@@ -416,7 +433,7 @@ static void swap_rule(or_bart* f, Tree* t, const double* ty, double* tr) {
   nd->var = cv; nd->cut = cc;
   if (both_same) { nd->left->var = pv; nd->left->cut = pc; nd->right->var = pv; nd->right->cut = pc; }
   else { child->var = pv; child->cut = pc; }
-  finish_change_like(f, t, &saved, nd, heap, ty, tr);
+  finish_change_like(f, t, &saved, nd, heap, ty, tr, 0.0);
 }
 
 static void metropolis_jump(or_bart* f, Tree* t, const double* ty, double* tr) {

@@ -756,17 +756,17 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
     S4B_CUDA(cudaMemcpy(d_xt_test_, xtt.data(), xtt.size(), cudaMemcpyHostToDevice));
     S4B_CUDA(cudaMalloc(&d_test_out_, sizeof(double) * (size_t) npad_t_));
   }
-  auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * count)); S4B_CUDA(cudaMemset(*p, 0, sizeof(double) * count)); };
+  auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * count)); zero_device_sync(*p, sizeof(double) * count, stream_); };
   dalloc(&d_R_, (size_t) npad_); dalloc(&d_yresc_, (size_t) npad_); dalloc(&d_y_, (size_t) npad_); dalloc(&d_offset_, (size_t) npad_);
   dalloc(&d_train_out_, (size_t) npad_); dalloc(&d_latent_out_, (size_t) npad_); dalloc(&d_offset_in_, (size_t) npad_);
   S4B_CUDA(cudaMemcpy(d_y_, y, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice));
   dalloc(&d_partials_, (size_t) 3 * S4B_MAX_SLOTS * grid_);
   dalloc(&d_minmax_, (size_t) 2 * grid_ew_ + 8);
   dalloc(&d_stats_out_, (size_t) 3 * S4B_MAX_SLOTS);
-  S4B_CUDA(cudaMalloc(&d_desc_, sizeof(StepDesc))); S4B_CUDA(cudaMemset(d_desc_, 0, sizeof(StepDesc)));
-  S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
-  S4B_CUDA(cudaMalloc(&d_prof_, sizeof(unsigned long long) * 24)); S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 24));
-  S4B_CUDA(cudaMalloc(&d_trace_len_, sizeof(unsigned long long))); S4B_CUDA(cudaMemset(d_trace_len_, 0, sizeof(unsigned long long)));
+  S4B_CUDA(cudaMalloc(&d_desc_, sizeof(StepDesc))); zero_device_sync(d_desc_, sizeof(StepDesc), stream_);
+  S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); zero_device_sync(d_ticket_, sizeof(unsigned int), stream_);
+  S4B_CUDA(cudaMalloc(&d_prof_, sizeof(unsigned long long) * 24)); zero_device_sync(d_prof_, sizeof(unsigned long long) * 24, stream_);
+  S4B_CUDA(cudaMalloc(&d_trace_len_, sizeof(unsigned long long))); zero_device_sync(d_trace_len_, sizeof(unsigned long long), stream_);
   S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
   // trees: single root each
   std::vector<DTree> trees((size_t) T_);
@@ -784,6 +784,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   P.k = cfg.k; P.node_scale = cfg.node_scale; P.ncuts_var = d_ncuts_var_;
   if (cfg.k_df < 0.0 || !std::isfinite(cfg.k_df)) throw std::invalid_argument("k_df must be >= 0");
   P.k_df = cfg.k_df;
+  P.change_symmetric = cfg.change_symmetric != 0 ? 1 : 0; P.pad_cs = 0;
   P.k_inv_scale2 = (cfg.k_scale > 0.0 && std::isfinite(cfg.k_scale)) ? 1.0 / (cfg.k_scale * cfg.k_scale) : 0.0;
   P.sigma = 1.0; P.smin = -0.5; P.smax = 0.5; P.srange = cfg.is_binary ? 1.0 : 0.0;
   P.key0 = (uint32_t) cfg.seed; P.key1 = (uint32_t) (cfg.seed >> 32);
@@ -917,16 +918,16 @@ void BartFit::setup_persistent()
         persistent_nq_ = kStreamNq; persistent_smem_ = smem;
         persistent_grid_ = (int) std::max<long long>(1, std::min<long long>(cta_cap, (nquad + kWorkers - 1) / kWorkers));
         S4B_CUDA(cudaMalloc(&d_packs_, sizeof(uint2) * 2 * (size_t) nquad));
-        S4B_CUDA(cudaMemset(d_packs_, 0, sizeof(uint2) * 2 * (size_t) nquad));
+        zero_device_sync(d_packs_, sizeof(uint2) * 2 * (size_t) nquad, stream_);
       }
     }
   }
   if (persistent_nq_ > 0) {
     partial_stride_ = 3 * S4B_MAX_SLOTS * persistent_grid_;
     S4B_CUDA(cudaMalloc(&d_partials2_, sizeof(double) * 2 * (size_t) partial_stride_));
-    S4B_CUDA(cudaMemset(d_partials2_, 0, sizeof(double) * 2 * (size_t) partial_stride_));
+    zero_device_sync(d_partials2_, sizeof(double) * 2 * (size_t) partial_stride_, stream_);
     S4B_CUDA(cudaMalloc(&d_barrier_, sizeof(unsigned int)));
-    S4B_CUDA(cudaMemset(d_barrier_, 0, sizeof(unsigned int)));
+    zero_device_sync(d_barrier_, sizeof(unsigned int), stream_);
     // host-side tables (glibc): growth probabilities by depth, their logs, log of small integers
     std::vector<double> tab((size_t) kTabSize, 0.0);
     for (int d = 0; d < 32; ++d) {
@@ -935,7 +936,7 @@ void BartFit::setup_persistent()
     }
     for (int i = 1; i < kLogTab; ++i) tab[(size_t) kTabLogInt + i] = std::log((double) i);
     S4B_CUDA(cudaMalloc(&d_descs_, sizeof(StepDesc) * (size_t) T_));
-    S4B_CUDA(cudaMemset(d_descs_, 0, sizeof(StepDesc) * (size_t) T_));
+    zero_device_sync(d_descs_, sizeof(StepDesc) * (size_t) T_, stream_);
     S4B_CUDA(cudaMalloc(&d_draws_, sizeof(double2) * 32 * (size_t) T_));
     {
       size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
@@ -1033,8 +1034,8 @@ void BartFit::set_trace(size_t cap_records)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));
   cudaFree(d_trace_); d_trace_ = nullptr; trace_cap_ = cap_records;
-  if (cap_records) { S4B_CUDA(cudaMalloc(&d_trace_, sizeof(double) * S4B_TRACE_LEN * cap_records)); S4B_CUDA(cudaMemset(d_trace_, 0, sizeof(double) * S4B_TRACE_LEN * cap_records)); }
-  S4B_CUDA(cudaMemset(d_trace_len_, 0, sizeof(unsigned long long)));
+  if (cap_records) { S4B_CUDA(cudaMalloc(&d_trace_, sizeof(double) * S4B_TRACE_LEN * cap_records)); zero_device_sync(d_trace_, sizeof(double) * S4B_TRACE_LEN * cap_records, stream_); }
+  zero_device_sync(d_trace_len_, sizeof(unsigned long long), stream_);
   invalidate_graph();
 }
 
@@ -1195,7 +1196,9 @@ void BartFit::run_sweeps()
   ev_pending_ = true;
   num_tree_steps_ += (long long) cfg_.thin * T_;
   if (nt_ > 0 && !test_aliases_train_) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
-  snapshot_trees();                      // keepTrees (no-op unless a store was requested)
+  // keepTrees (no-op unless a store was requested); the reference switches dbarts' keepTrees off for warm-up runs
+  // (init.cpp:737-744), so warm-up sweeps never take slots of the store
+  if (keep_trees_active_) snapshot_trees();
 }
 
 void BartFit::draw_k()
@@ -1382,7 +1385,7 @@ void BartFit::get_profile(unsigned long long* out8, bool reset)
 {
   S4B_CUDA(cudaStreamSynchronize(stream_));
   S4B_CUDA(cudaMemcpy(out8, d_prof_, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost));
-  if (reset) S4B_CUDA(cudaMemset(d_prof_, 0, sizeof(unsigned long long) * 24));
+  if (reset) zero_device_sync(d_prof_, sizeof(unsigned long long) * 24, stream_);
 }
 
 double BartFit::tree_step_ms(bool reset)

@@ -59,6 +59,8 @@ class BartFit {
   // kept draw; stored draws can be predicted from and flattened like the live sampler
   void set_keep_trees(long long capacity);
   long long num_stored() const { return store_len_; }
+  // setControl(keepTrees = ...) as the Gibbs loop uses it (init.cpp:737-744): warm-up runs do not append to the store
+  void set_keep_trees_active(bool on) { keep_trees_active_ = on; }
   void predict_stored(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out);
   long long num_stored_nodes(long long sample);
   void get_stored_trees(long long sample, int32_t* tree_no, long long* n_obs, int32_t* var, double* value);
@@ -153,6 +155,7 @@ class BartFit {
   int partial_stride_ = 0;
   int overlap_walk_ = 1;
   bool profile_on_ = false;
+  bool keep_trees_active_ = true;
   long long num_tree_steps_ = 0;
 
   uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;

@@ -338,7 +338,21 @@ __device__ inline void propose_step(DTree& t, const BartParams& P, const double*
     t.nodes[node].var = (int16_t) ov; t.nodes[node].cut = (int16_t) oc;
     int s = L;
     for (int k = 0; k < t.num_nodes; ++k) d.b_prop.slot[k] = (k >= node && k < end && t_is_leaf(t, k)) ? (uint8_t) s++ : (uint8_t) 255;
-    d.b_kind = 2; d.b_nslots = s; d.log_prior_trans = new_lp - old_lp;
+    // proposal (Hastings) term of the change step: the cut of the new rule was drawn from the interval that ancestors and
+    // descendants leave for new_var, the reverse move draws the old cut from the interval of the old variable
+    // (oracle_bart.c change_rule; exactness: tests/test_exact_posterior.py)
+    double log_hastings = 0.0;
+    if (!P.change_symmetric && new_var != ov) {
+      int olo, ohi; t_split_interval(t, s4b_ncuts(P, ov), node, ov, olo, ohi);
+      for (int k = node + 1; k < end; ++k) if (!t_is_leaf(t, k) && t.nodes[k].var == ov) {
+        int c = t.nodes[k].cut;
+        if (k < rstart) { if (c + 1 > olo) olo = c + 1; }
+        else            { if (c - 1 < ohi) ohi = c - 1; }
+      }
+      log_hastings = log((double) (hi - lo + 1)) - log((double) (ohi - olo + 1));
+      if (P.split_w != nullptr) log_hastings += log((double) P.split_w[ov] / (double) P.split_w[new_var]);
+    }
+    d.b_kind = 2; d.b_nslots = s; d.log_prior_trans = (new_lp - old_lp) + log_hastings;
     return;
   }
 

@@ -344,7 +344,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     }
     if (all_one) ones_mask_ |= 1u << s;
   }
-  auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); S4B_CUDA(cudaMemset(*p, 0, sizeof(double) * std::max<size_t>(count, 1))); };
+  auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); zero_device_sync(*p, sizeof(double) * std::max<size_t>(count, 1), stream_); };
   dalloc(&d_X_, (size_t) std::max(1, K_) * npad_);
   for (int k = 0; k < K_; ++k) S4B_CUDA(cudaMemcpy(d_X_ + (size_t) k * npad_, d.X + (size_t) k * N_, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice));
   dalloc(&d_y_, (size_t) npad_); dalloc(&d_offset_, (size_t) npad_); dalloc(&d_r_, (size_t) npad_); dalloc(&d_tmp_, (size_t) npad_);
@@ -387,10 +387,11 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     S4B_CUDA(cudaFuncSetAttribute(k_glmm_data_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_glmm_data_terms, kGBlock, smem_bytes_) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
   }
+  num_sms_ = sms;
   long long want = (N_ + 2 * kGBlock - 1) / (2 * kGBlock);
   grid_ = (int) std::max<long long>(1, std::min<long long>(want, (long long) sms * per_sm));
   dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) ((columns_ ? K_ : nb) + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
-  S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); S4B_CUDA(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
+  S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); zero_device_sync(d_ticket_, sizeof(unsigned int), stream_);
   S4B_CUDA(cudaMallocHost(&h_pinned_, sizeof(double) * 2 * ((size_t) nb + 1)));
   // Gram matrix G = [X Z]' W [X Z] (host, once): the model matrices never change during sampling
   if (nb > 0 && nb <= 512) {
@@ -532,7 +533,7 @@ void GlmmModel::expand_sparse(const double* beta, const double* b, double* S, do
 void GlmmModel::refresh_r()
 {
   expansion_valid_ = false;
-  int grid = (int) std::max<long long>(1, std::min<long long>((N_ + 255) / 256, 148 * 8));
+  int grid = elementwise_grid(N_, 256, num_sms_);
   k_glmm_residual<<<grid, 256, 0, stream_>>>(N_, d_y_, d_offset_, d_r_);
   S4B_CUDA(cudaGetLastError());
 }
@@ -542,7 +543,7 @@ void GlmmModel::set_response_host(const double* y) { S4B_CUDA(cudaMemcpyAsync(d_
 void GlmmModel::set_inputs_device(const double* d_offset, const double* d_y)
 {
   expansion_valid_ = false;
-  int grid = (int) std::max<long long>(1, std::min<long long>((N_ + 255) / 256, 148 * 8));
+  int grid = elementwise_grid(N_, 256, num_sms_);
   k_glmm_set_inputs<<<grid, 256, 0, stream_>>>(N_, d_offset, d_y, d_offset_, d_y_, d_r_);
   S4B_CUDA(cudaGetLastError());
 }
@@ -567,7 +568,7 @@ void GlmmModel::data_terms(const double* beta, const double* b, double* S, doubl
     if (K_ > 0) k_glmm_dense_cols<<<dim3((unsigned) grid_, (unsigned) K_), kGBlock, 0, stream_>>>(g, d_we_, d_partials_);
     k_glmm_finish_dense<<<1, kGBlock, 0, stream_>>>(K_ + 1, grid_, d_partials_, d_result_);
     if (q_ > 0) {
-      const int zgrid = (int) std::max<long long>(1, std::min<long long>(((long long) q_ * 32 + kGBlock - 1) / kGBlock, 148 * 8));
+      const int zgrid = elementwise_grid((long long) q_ * 32, kGBlock, num_sms_);
       k_glmm_z_cols<<<zgrid, kGBlock, 0, stream_>>>(q_, d_col_ptr_, d_col_obs_, d_col_val_, d_we_, d_result_ + 1 + K_);
     }
   }
@@ -590,7 +591,7 @@ void GlmmModel::parametric_mean_device(const double* beta, const double* b, doub
   GlmmDev g;
   g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
   g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
-  int grid = (int) std::max<long long>(1, std::min<long long>((N_ + kGBlock - 1) / kGBlock, 148 * 8));
+  int grid = elementwise_grid(N_, kGBlock, num_sms_);
   k_glmm_linear_predictor<<<grid, kGBlock, (size_t) nb * sizeof(double) <= kThetaSmemMax ? sizeof(double) * (size_t) std::max(1, nb) : 8, stream_>>>(g, d_out, include_fixed ? 1 : 0, include_random ? 1 : 0);
   S4B_CUDA(cudaGetLastError());
   // h_pinned_ is reused by the next call: make sure the H2D copy has been consumed

@@ -84,7 +84,7 @@ class GlmmModel {
   double prior_scale_for_aux_ = 0, prior_mean_for_aux_ = 0, prior_df_for_aux_ = 0;
   std::vector<double> prior_scale_, prior_mean_, shape_, scale_, delta_, regularization_;
   std::vector<int> p_, l_;
-  int slots_ = 0, grid_ = 1, block_ = 256;
+  int slots_ = 0, grid_ = 1, block_ = 256, num_sms_ = 1;
   unsigned int ones_mask_ = 0;
   size_t smem_bytes_ = 0;
   long long num_grad_ = 0, num_passes_ = 0;

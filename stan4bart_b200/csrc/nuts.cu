@@ -35,11 +35,14 @@ NutsSampler::NutsSampler(GlmmModel& model, const s4b_stan_control& ctl, int chai
   inv_metric_.assign(d, 1.0); cont_params_.assign(d, 0.0); grad_tmp_.assign(d + 1, 0.0);
   wf_m_.assign(d, 0.0); wf_m2_.assign(d, 0.0);
   // services/util/initialize.hpp:86-216: uniform(-R, R) inits, at most 100 attempts
-  for (int attempt = 0; attempt < 100; ++attempt) {
+  bool initialised = false;
+  for (int attempt = 0; attempt < 100 && !initialised; ++attempt) {
     for (size_t i = 0; i < d; ++i) cont_params_[i] = ctl.init_radius == 0.0 ? 0.0 : -ctl.init_radius + 2.0 * ctl.init_radius * rng_uniform(rng_);
     double lp;
-    if (model_.log_prob_grad(cont_params_.data(), &lp, grad_tmp_.data()) == 0) break;
+    initialised = model_.log_prob_grad(cont_params_.data(), &lp, grad_tmp_.data()) == 0;
   }
+  // initialize.hpp:186-195: after 100 rejected points Stan gives up with "Initialization failed."
+  if (!initialised) throw std::domain_error("Initialization failed. (100 attempts: no point with a finite log density and gradient)");
   if (ctl.stepsize > 0) nom_epsilon_ = ctl.stepsize;
   if (ctl.stepsize_jitter > 0 && ctl.stepsize_jitter < 1) epsilon_jitter_ = ctl.stepsize_jitter;
   if (ctl.max_treedepth > 0) max_depth_ = ctl.max_treedepth;
@@ -97,7 +100,9 @@ void NutsSampler::init_stepsize()
     if (direction == 1 && !(delta_H > log08)) break;
     else if (direction == -1 && !(delta_H < log08)) break;
     else nom_epsilon_ = direction == 1 ? 2.0 * nom_epsilon_ : 0.5 * nom_epsilon_;
-    if (nom_epsilon_ > 1e7 || nom_epsilon_ == 0) break;
+    // base_hmc.hpp:131-139
+    if (nom_epsilon_ > 1e7) throw std::runtime_error("Posterior is improper. Please check your model.");
+    if (nom_epsilon_ == 0) throw std::runtime_error("No acceptably small step size could be found. Perhaps the posterior is not continuous?");
   }
   z_ = z_init;
 }

@@ -39,6 +39,31 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 }
 #define S4B_CUDA(x) ::s4b::cuda_check((x), #x, __FILE__, __LINE__)
 
+// Zero a fresh allocation ON THE OBJECT'S STREAM and wait for it.  A plain cudaMemset runs asynchronously on the legacy
+// default stream, which the library's non-blocking streams do not synchronise with: the memset could land after a
+// stream-ordered copy into the same buffer (seen as a lost offset vector when two ranks time-share one GPU).
+inline void zero_device_sync(void* p, size_t bytes, cudaStream_t stream)
+{
+  S4B_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+  S4B_CUDA(cudaStreamSynchronize(stream));
+}
+
+// SM count of the current device (grids of the element-wise kernels are sized in multiples of it)
+inline int device_sm_count()
+{
+  int dev = 0, sms = 0;
+  S4B_CUDA(cudaGetDevice(&dev));
+  S4B_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return sms > 0 ? sms : 1;
+}
+// grid of an element-wise kernel over `items` with `block` threads: at most 8 resident blocks per SM
+inline int elementwise_grid(long long items, int block, int num_sms)
+{
+  const long long want = (items + block - 1) / block;
+  const long long cap = (long long) num_sms * 8;
+  return (int) (want < 1 ? 1 : (want > cap ? cap : want));
+}
+
 // ---------------------------------------------------------------------------------------
 // RNG (spec "s4b-rng v1")
 // ---------------------------------------------------------------------------------------
@@ -278,6 +303,8 @@ struct BartParams {
   const int* ncuts_var;           // bart_args n.cuts given per predictor (each <= n_cuts), nullptr = n_cuts everywhere
   // leaf prior mu ~ N(0, (node_scale / (k sqrt(T)))^2); k_df > 0: k is sampled after every sweep under k ~ chi(k_df, scale)
   double k, k_df, k_inv_scale2, node_scale;
+  // change rule without its proposal (Hastings) term: see s4b_bart_config::change_symmetric
+  int change_symmetric, pad_cs;
 };
 
 }  // namespace s4b

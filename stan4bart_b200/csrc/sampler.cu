@@ -16,8 +16,8 @@
 
 namespace s4b {
 
-// dst = a + b (b may be NULL: plain copy)
-__global__ void k_sum2(long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ dst)
+// dst = a + b (b may be NULL: plain copy).  dst may alias a or b (in-place sums of the offset vectors): no __restrict__
+__global__ void k_sum2(long long n, const double* a, const double* b, double* dst)
 {
   for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) dst[i] = b != nullptr ? a[i] + b[i] : a[i];
 }
@@ -46,7 +46,7 @@ class GibbsSampler {
     if (gdata.N != n_) throw std::invalid_argument("sampler: BART and Stan data disagree on N");
     num_pars_ = nuts_.num_pars();
     stan_curr_.assign((size_t) num_pars_, 0.0);
-    auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); S4B_CUDA(cudaMemset(*p, 0, sizeof(double) * std::max<size_t>(count, 1))); };
+    auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); zero_device_sync(*p, sizeof(double) * std::max<size_t>(count, 1), stream_); };
     dalloc(&d_bart_offset_, (size_t) n_); dalloc(&d_mean_train_, (size_t) n_); dalloc(&d_mean_param_, (size_t) n_); dalloc(&d_mean_test_, (size_t) std::max<long long>(nt_, 1));
     S4B_CUDA(cudaMalloc(&d_varcount_, sizeof(unsigned int) * (size_t) p_));
     S4B_CUDA(cudaEventCreateWithFlags(&ev_a_, cudaEventDisableTiming)); S4B_CUDA(cudaEventCreateWithFlags(&ev_b_, cudaEventDisableTiming));
@@ -54,7 +54,8 @@ class GibbsSampler {
     S4B_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     bart_.set_add_offset(false);
     if (cc_.offset_type < kOffsetDefault || cc_.offset_type > kOffsetParametric) throw std::invalid_argument("sampler: offset_type out of range");
-    const int ew_grid = (int) std::max<long long>(1, std::min<long long>((n_ + 255) / 256, 148 * 8));
+    num_sms_ = device_sm_count();
+    const int ew_grid = elementwise_grid(n_, 256, num_sms_);
     if (cc_.user_offset != nullptr) {
       dalloc(&d_user_offset_, (size_t) n_); dalloc(&d_stan_offset_, (size_t) n_);
       S4B_CUDA(cudaMemcpyAsync(d_user_offset_, cc_.user_offset, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice, stream_));
@@ -93,13 +94,20 @@ class GibbsSampler {
     const size_t n = (size_t) n_, nt = (size_t) nt_;
     ms_stan_ = ms_bart_ = 0.0;
     const long long grad0 = glmm_.num_grad_evals(), steps0 = bart_.num_tree_steps();
-    const int acc_grid = (int) std::max<long long>(1, std::min<long long>((n_ + 255) / 256, 148 * 8));
+    const int acc_grid = elementwise_grid(n_, 256, num_sms_);
     const bool k_modeled = bart_.k_modeled();
     if (k_modeled && (size_t) num_iter > h_k_cap_) {
       if (h_k_) cudaFreeHost(h_k_);
       S4B_CUDA(cudaMallocHost(&h_k_, sizeof(double) * (size_t) num_iter)); h_k_cap_ = (size_t) num_iter;
     }
     last_k_.clear();
+    bart_.set_keep_trees_active(!is_warmup);                                             // init.cpp:737-744
+    // whatever ends the loop (an exception from a kernel, the callback asking to stop), no copy into the caller's buffers may
+    // still be in flight when run() returns
+    struct DrainCopies {
+      GibbsSampler* s;
+      ~DrainCopies() { cudaStreamSynchronize(s->copy_stream_); cudaStreamSynchronize(s->stream_); s->copy_pending_ = false; s->bart_.set_keep_trees_active(true); }
+    } drain{this};
     for (int iter = 0; iter < num_iter; ++iter) {
       const size_t slot = cc_.keep_fits ? (size_t) iter : 0;
       auto t0 = std::chrono::steady_clock::now();
@@ -194,7 +202,7 @@ class GibbsSampler {
     if (d_user_offset_ == nullptr) return bart_.d_train_out();
     if (cc_.offset_type == kOffsetBart) return d_user_offset_;
     if (cc_.offset_type != kOffsetDefault) return bart_.d_train_out();
-    const int grid = (int) std::max<long long>(1, std::min<long long>((n_ + 255) / 256, 148 * 8));
+    const int grid = elementwise_grid(n_, 256, num_sms_);
     k_sum2<<<grid, 256, 0, stream_>>>(n_, bart_.d_train_out(), d_user_offset_, d_stan_offset_);
     return d_stan_offset_;
   }
@@ -236,7 +244,7 @@ class GibbsSampler {
   GlmmModel glmm_;
   NutsSampler nuts_;
   BartFit bart_;
-  long long n_ = 0, nt_ = 0; int p_ = 0, num_pars_ = 0;
+  long long n_ = 0, nt_ = 0; int p_ = 0, num_pars_ = 0, num_sms_ = 1;
   std::vector<double> stan_curr_, last_k_;
   double* h_k_ = nullptr; size_t h_k_cap_ = 0;
   double *d_user_offset_ = nullptr, *d_stan_offset_ = nullptr;

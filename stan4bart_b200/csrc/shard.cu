@@ -2,6 +2,8 @@
 #include "shard.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -85,6 +87,8 @@ void ShardContext::allreduce(double* d_vec, int n, ReduceOp op, cudaStream_t str
   if (!attached_) throw std::runtime_error("shard context: peers not attached");
   if (n < 0 || n > kMailVec) throw std::invalid_argument("shard all-reduce: vector too long");
   ++vec_seq_;
+  static const bool debug = getenv("S4B_SHARD_DEBUG") != nullptr;
+  if (debug) fprintf(stderr, "[s4b shard] rank %d allreduce seq %llu n %d op %d\n", dev_.rank, vec_seq_, n, (int) op);
   k_allreduce_small<<<1, 256, 0, stream>>>(dev_, d_vec, n, (int) op, vec_seq_, d_err_);
   S4B_CUDA(cudaGetLastError());
 }

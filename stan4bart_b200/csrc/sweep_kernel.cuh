@@ -484,7 +484,23 @@ __device__ inline void w_propose(DTree& t, const BartParams& P, const double* ta
         if (lane == 0) { t.nodes[node].var = (int16_t) ov; t.nodes[node].cut = (int16_t) oc; }
         __syncwarp();
         nslots = w_assign_prop_slots(t, d.b_prop, node, end, L, lane);
-        kind = 2; lpt = new_lp - old_lp; b_end = end;
+        // proposal (Hastings) term: |I_new| P(old var) / (|I_old| P(new var)), I = interval left by ancestors and descendants
+        double log_hastings = 0.0;
+        if (!P.change_symmetric && new_var != ov) {
+          int olo, ohi; t_split_interval(t, s4b_ncuts(P, ov), node, ov, olo, ohi);
+          int olo_c = olo, ohi_c = ohi;
+          for (int base = node + 1; base < end; base += 32) {
+            int k = base + lane;
+            if (k < end && t.nodes[k].var == ov) {
+              int c = t.nodes[k].cut;
+              if (k < rstart) olo_c = max(olo_c, c + 1); else ohi_c = min(ohi_c, c - 1);
+            }
+          }
+          olo = w_maxi(olo_c); ohi = w_mini(ohi_c);
+          log_hastings = tab_log_int(tab, hi - lo + 1) - tab_log_int(tab, ohi - olo + 1);
+          if (P.split_w != nullptr) log_hastings += log((double) P.split_w[ov] / (double) P.split_w[new_var]);
+        }
+        kind = 2; lpt = (new_lp - old_lp) + log_hastings; b_end = end;
       }
     }
   }

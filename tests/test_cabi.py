@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     import ctypes as C
     from stan4bart_b200.structs import BartConfig, CommonControl, GlmmData, StanControl
-    assert C.sizeof(BartConfig) == 3 * 8 + 6 * 4 + 8 * 8 + 8 + 8 + 8 + 2 * 8 + 8    # + the split_probs and weights pointers, k_df, k_scale, n_cuts_var
+    assert C.sizeof(BartConfig) == 3 * 8 + 6 * 4 + 8 * 8 + 8 + 8 + 8 + 2 * 8 + 8 + 2 * 4    # + the split_probs and weights pointers, k_df, k_scale, n_cuts_var, change_symmetric + pad
     assert C.sizeof(StanControl) == 2 * 4 + 5 * 8 + 4 * 4 + 2 * 8
     assert C.sizeof(CommonControl) == 4 * 4 + 8 + 2 * 4 + 8            # + offset_type, reserved, user_offset
     assert C.sizeof(GlmmData) == 8 + 10 * 4 + 8 + 4 * 8 + 3 * 8 + 9 * 8 + 8 + 2 * 8 + 4 * 8   # + weights, prior_df, num_normals, hs hyper-parameters

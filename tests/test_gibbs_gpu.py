@@ -439,6 +439,13 @@ def test_randomised_models_against_the_oracle(case):
     kw = dict(warmup=5, iter_=7, keep_fits=True, sigma_init=sigma_init, bart_offset_init=offset_init)
     if rng.random() < 0.3:
         kw.update(offset=rng.standard_normal(n) * 0.2, offset_type=int(rng.integers(0, 5)))
+    if Kf == 0 and not terms:
+        # no parametric component at all: the reference's front end refuses such a formula (R/lme4_functions.R:205) and Stan's
+        # step-size search throws on the parameter-free density (base_hmc.hpp:131-134); the sampler must fail the same way
+        from stan4bart_b200._lib import S4BError
+        with pytest.raises(S4BError, match="Posterior is improper"):
+            Sampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
+        return
     o = O.OracleSampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
     g = Sampler(cfg, y, xb, xb.copy(order="F"), sd, ctl, **kw)
     ro, rg = o.run(5, True), g.run(5, True)

@@ -1,8 +1,10 @@
 """Observation-sharded chains on 2 GPUs: one process per GPU, rows split in contiguous blocks,
 per-tree statistics and GLMM reductions exchanged through peer-mapped mailboxes inside the kernels.  Every rank must
 reproduce the CPU oracle run on the WHOLE data set (integer fields exact, floating fields to the usual tolerance;
-the only difference to the single-GPU path is the order of the final sums).  Skipped on boxes with fewer than 2 GPUs:
-run with `gpurun --gpus 2 -- python -m pytest tests/test_shard_gpu.py -m gpu`."""
+the only difference to the single-GPU path is the order of the final sums).  On a box with one GPU both ranks run on that
+device as two time-sliced processes (the peer mailboxes are still mapped through CUDA IPC and every exchange still crosses
+the process boundary), so the suite never skips; `gpurun --gpus 2 -- python -m pytest tests/test_shard_gpu.py -m gpu` runs it
+over NVLink."""
 import os
 import subprocess
 import sys
@@ -30,15 +32,15 @@ def _device_count():
 
 @pytest.fixture(scope="module")
 def ranks():
-    if _device_count() < WORLD:
-        pytest.skip("needs 2 GPUs on one box")
+    if _device_count() < 1:
+        pytest.skip("needs a CUDA device")
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, "shard")
         port = 29500 + os.getpid() % 2000
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={WORLD}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.join(HERE, "shard_worker.py"), "--out", out]
         # the kernels give up on a silent peer after 30 s; the outer limit only guards the launch itself
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
         assert p.returncode == 0, p.stdout[-4000:] + "\n" + p.stderr[-4000:]
         yield [dict(np.load(f"{out}.rank{r}.npz")) for r in range(WORLD)]
 
