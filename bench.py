@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--continuous", action="store_true", help="continuous response (configs B / E) instead of the probit model of config C")
     ap.add_argument("--weighted", action="store_true", help="observation weights (`weights` of stan4bart()): a non-default branch, not the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chains-per-gpu", type=int, default=2,
+                    help="chains resident on every GPU, each on its own host thread and stream (value = aggregate over all chains; the "
+                         "one-chain-per-GPU figure is reported beside it)")
+    ap.add_argument("--no-mode0", action="store_true", help="skip the glmm mode 0 leg (one device pass per gradient evaluation)")
     ap.add_argument("--shard-rows", action="store_true",
                     help="N > 1 only: ONE chain whose --n rows are sharded over the N GPUs (BASELINE config E; strong scaling) instead of "
                          "one independent chain per GPU")
@@ -55,7 +59,7 @@ def workload_config(args):
         what += " with observation weights"
     return {"workload": "%s, n=%d, %d trees, p_bart=9, K=2, q=18, n_test=%d, "
                         "1 chain per GPU" % (what, args.n, args.trees, args.n),
-            "n": args.n, "trees": args.trees, "chains_per_gpu": 1, "parallelism": "chain-per-GPU, no data-path collective",
+            "n": args.n, "trees": args.trees, "chains_per_gpu": 1, "parallelism": "chains over GPUs, no data-path collective",
             "l2": "inputs larger than L2, no explicit flush: one sweep streams ~%d MB of distinct N-length arrays (BART: binned X, "
                   "residual, response, offset, fits, latents; GLMM: X, Z index / value streams, response, offset, residual; running "
                   "means) against 126 MB of L2, so every step's kernels start from HBM; inside k_sweep the chain's residuals and "
@@ -167,6 +171,9 @@ def cpu_baseline(args, pr, budget_s):
     R/stan4bart_fit.R:437-439) timed on a bounded sample of the same workload."""
     import oracle_lib as O
     from stan4bart_b200.structs import bart_config, stan_control
+    O.use_fast(True)                # the -O3 -march=native build of the same sources (oracle/Makefile); parity checks use the strict one
+    O.lib()
+    build = "-O3 -march=native" if O.fast_build_is_native() else "-O2 (strict build: the native one was compiled for another CPU)"
     sd = pr["stan_data"]
     cfg = bart_config(args.n, 9, n_test=args.n, num_trees=args.trees, is_binary=not args.continuous, seed=12345, weights=pr.get("weights"))
     extra = {"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}
@@ -181,15 +188,16 @@ def cpu_baseline(args, pr, budget_s):
     s.run(k, True)
     dt = time.time() - t0
     return {"value": k / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "CPU restatement of the reference algorithm (oracle/, not the reference binary): same n=%d, %d trees, "
+            "sample": "CPU restatement of the reference algorithm (oracle/, gcc %s, not the reference binary): same n=%d, %d trees, "
                       "1 chain on 1 thread, %d full sweeps after 1 warm-up sweep (setup %.1f s excluded); these are early, "
-                      "un-adapted sweeps with few leapfrogs each, i.e. the CPU's best case" % (args.n, args.trees, k, t_create)}
+                      "un-adapted sweeps with few leapfrogs each, i.e. the CPU's best case" % (build, args.n, args.trees, k, t_create)}
 
 
 # ------------------------------------------------------------------------------------------------
 def _ref_worker(args_dict, seed, conn):
     try:
         import oracle_lib as O
+        O.use_fast(True)
         from stan4bart_b200.frontend import friedman_problem
         from stan4bart_b200.structs import bart_config, stan_control
         n, trees = args_dict["n"], args_dict["trees"]
@@ -222,6 +230,11 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
+
+    import oracle_lib as O
+    O.use_fast(True)
+    O.lib()                 # loaded in this process too (the workers are forked from it): the CPU arm's native code is visible here
+    build = "-O3 -march=native" if O.fast_build_is_native() else "-O2 (strict build)"
     chains = max(1, args.gpus)
     cores = os.cpu_count() or 1
     procs = min(chains, cores)
@@ -254,9 +267,9 @@ def run_reference(args):
     for _, a in workers:
         a.send(("stop",))
     value = procs * k / dt
-    sample = ("oracle port (CPU restatement of the reference algorithm, not the reference binary), %d chain(s) in %d "
+    sample = ("oracle port (CPU restatement of the reference algorithm, gcc %s, not the reference binary), %d chain(s) in %d "
               "single-threaded process(es), n=%d, %d trees, %d full sweeps timed after %d warm-up sweep "
-              "(requested steps=%d warmup=%d bounded by --ref-budget-s)" % (procs, procs, args.n, args.trees, k, warm_done, args.steps, args.warmup))
+              "(requested steps=%d warmup=%d bounded by --ref-budget-s)" % (build, procs, procs, args.n, args.trees, k, warm_done, args.steps, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": warm_done,
             "ms_per_step": 1000.0 * dt / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args),
@@ -267,6 +280,135 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def pin_rank_to_cores(local_rank, local_world):
+    """Every rank gets its own slice of the host's cores (its chain threads and their NUTS run there): eight ranks sharing one
+    NUMA node's scheduler was what bent the 8-GPU curve."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, local_world))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except (AttributeError, OSError):
+        return None
+
+
+class ChainThread(threading.Thread):
+    """One chain = one host thread + one CUDA stream (the reference runs one worker process per chain, R/stan4bart_fit.R:495-542).
+    Chains of one GPU overlap: while one chain's NUTS runs on the host, the other chain's sweep kernel has the device."""
+
+    def __init__(self, index, device, make_sampler):
+        super().__init__(daemon=True)
+        self.index, self.device, self.make_sampler = index, device, make_sampler
+        self.cmd, self.done = None, threading.Event()
+        self.go = threading.Event()
+        self.sampler = None
+        self.stream = None
+        self.error = None
+        self.result = None
+
+    def run(self):
+        import torch
+
+        from stan4bart_b200 import _lib
+        try:
+            torch.cuda.set_device(self.device)
+            L = _lib.load()
+            _lib.check(L.s4b_set_device(self.device))
+            self.stream = torch.cuda.Stream()
+            _lib.check(L.s4b_set_stream(self.stream.cuda_stream))
+            self.sampler = self.make_sampler(self.index)
+        except Exception as e:      # pragma: no cover
+            self.error = e
+        self.done.set()
+        while True:
+            self.go.wait()
+            self.go.clear()
+            if self.cmd is None:
+                return
+            try:
+                self.result = self.cmd(self)
+            except Exception as e:  # pragma: no cover
+                self.error = e
+            self.done.set()
+
+    def submit(self, fn):
+        self.done.clear()
+        self.cmd = fn
+        self.go.set()
+
+    def wait(self):
+        self.done.wait()
+        if self.error is not None:
+            raise self.error
+        return self.result
+
+
+def run_all(chains, fn):
+    for c in chains:
+        c.submit(fn)
+    return [c.wait() for c in chains]
+
+
+def timed_concurrent(torch, chains, fn):
+    """Device time (CUDA events) from a common start to the completion of the last chain's work on its stream."""
+    tstream = torch.cuda.Stream()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(tstream)
+    for c in chains:
+        c.stream.wait_event(ev0)
+
+    def work(c):
+        out = fn(c)
+        e = torch.cuda.Event()
+        e.record(c.stream)
+        return out, e
+    res = run_all(chains, work)
+    for _, e in res:
+        tstream.wait_event(e)
+    ev1.record(tstream)
+    ev1.synchronize()
+    return float(ev0.elapsed_time(ev1)), [r for r, _ in res]
+
+
+def parity_at_config(args, pr, sweeps=2):
+    """The first Gibbs sweeps AT THE BENCHMARKED CONFIGURATION (same n, trees, kernel instantiation, GLMM mode), CUDA path against
+    the strict build of the CPU oracle with the same seeds: Stan rows, fits, variable counts and trees after every sweep."""
+    import oracle_lib as O
+    from stan4bart_b200.sampler import Sampler
+    from stan4bart_b200.structs import bart_config, stan_control
+    O.use_fast(False)
+    t0 = time.time()
+    mk = lambda: bart_config(args.n, 9, n_test=args.n, num_trees=args.trees, is_binary=not args.continuous, seed=4711, weights=pr.get("weights"))
+    extra = {"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}
+    kw = dict(warmup=10, iter_=20, keep_fits=False, **extra)
+    o = O.OracleSampler(mk(), pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=4712), **kw)
+    g = Sampler(mk(), pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=4712), **kw)
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / (np.abs(np.asarray(a)) + 1.0))) if np.size(a) else 0.0
+    worst = {"stan": 0.0, "train": 0.0, "test": 0.0, "tree_values": 0.0}
+    status = "ok"
+    for k in range(sweeps):
+        ro, rg = o.run(1, True), g.run(1, True)
+        worst["stan"] = max(worst["stan"], rel(ro["stan"], rg["stan"]))
+        worst["train"] = max(worst["train"], rel(ro["bart"]["train"], rg["bart"]["train"]))
+        worst["test"] = max(worst["test"], rel(ro["bart"]["test"], rg["bart"]["test"]))
+        to, tg = o.bart().trees(), g.bart().trees()
+        same_structure = np.array_equal(to["var"], tg["var"]) and np.array_equal(to["n"], tg["n"]) and np.array_equal(to["tree"], tg["tree"])
+        if same_structure:
+            worst["tree_values"] = max(worst["tree_values"], rel(to["value"], tg["value"]))
+        if not same_structure or not np.array_equal(ro["bart"]["varcount"], rg["bart"]["varcount"]):
+            status = "FAILED: tree structures / node counts / variable counts differ after sweep %d" % (k + 1)
+            break
+    tol = 1e-8
+    if status == "ok" and max(worst.values()) > tol:
+        status = "FAILED: %s differs by %.3e (tolerance %.0e)" % (max(worst, key=worst.get), max(worst.values()), tol)
+    glmm_mode, sweep_mode = g.glmm().mode(), g.bart().sweep_mode()
+    del o, g
+    return {"status": status, "sweeps": sweeps, "tolerance": tol, "max_rel_err": worst, "bit_exact": "tree structures, per-node row counts, variable counts",
+            "glmm_mode": glmm_mode, "bart_sweep_mode": sweep_mode, "seconds": time.time() - t0,
+            "what": "CUDA path vs CPU oracle (strict build), same seeds, n=%d, %d trees: every sweep's Stan row, train / test fits, trees" % (args.n, args.trees)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -278,6 +420,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    cores_per_rank = pin_rank_to_cores(local_rank, local_world)
     # stdout carries exactly one line, the JSON: anything libraries print on fd 1 meanwhile (NCCL's version banner) goes to stderr
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -292,13 +436,14 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     _lib.check(L.s4b_set_stream(stream.cuda_stream))
 
-    from stan4bart_b200.dist import barrier, chain_seed, max_over_ranks
+    from stan4bart_b200.dist import barrier, chain_seed, max_over_ranks, min_over_ranks
 
     pr = make_problem(args)
     n, T = args.n, args.trees
     sharded = bool(args.shard_rows) and world > 1
     shard_ctx = None
-    chains = world
+    cpg = 1 if sharded else max(1, args.chains_per_gpu)
+    chains_total = 1 if sharded else world * cpg
     if sharded:
         # one chain, rows dealt out in contiguous blocks; every rank runs the replicated controller with the same seeds
         from stan4bart_b200.frontend import shard_problem
@@ -307,41 +452,86 @@ def run_ours(args):
         lo, hi = row_range(n, rank, world)
         pr = shard_problem(pr, lo, hi)
         n = hi - lo
-        chains = 1
-    seed_rank = 0 if sharded else rank
     sd = pr["stan_data"]
-    cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=not args.continuous, seed=chain_seed(12345, seed_rank), weights=pr.get("weights"))
-    s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=chain_seed(1000, seed_rank)), warmup=args.adapt,
-                iter_=args.adapt + args.steps, keep_fits=False, shard=shard_ctx,
-                **({"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}))
-    bart = s.bart()
-    glmm = s.glmm()
-    s.run(args.adapt, True, results=False)
-    s.disengage_adaptation()
-    W, K = max(3, args.warmup), args.steps
+    extra = {"sigma_init": pr["sigma_init"], "bart_offset_init": pr["bart_offset_init"]} if args.continuous else {}
 
-    # ---- device-resident leg: `value` ----
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    s.run(W, False, results=False)
-    bart.tree_step_ms(reset=True)
-    passes0 = glmm.num_device_passes()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        t_wall0 = time.time()
-        out = s.run(K, False, results=False)
-        ev1.record(stream)
-    barrier()
-    t_wall = time.time() - t_wall0
-    ms = max_over_ranks(float(ev0.elapsed_time(ev1)))
-    stats = s.last_run_stats()
-    glmm_passes = glmm.num_device_passes() - passes0
-    sweep_ms = bart.tree_step_ms(reset=True)
+    def make_sampler(c):
+        chain = 0 if sharded else rank * cpg + c
+        cfg = bart_config(n, 9, n_test=n, num_trees=T, is_binary=not args.continuous, seed=chain_seed(12345, chain), weights=pr.get("weights"))
+        s = Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], sd, stan_control(seed=chain_seed(1000, chain)), warmup=args.adapt,
+                    iter_=args.adapt + args.steps, keep_fits=False, shard=shard_ctx, **extra)
+        s.run(args.adapt, True, results=False)
+        s.disengage_adaptation()
+        return s
+
+    W, K = max(3, args.warmup), args.steps
+    if sharded:
+        # the sharded constructors are collective over the ranks: keep them on this thread and stream
+        class Inline:
+            pass
+        ch = Inline()
+        ch.sampler, ch.stream = make_sampler(0), stream
+        chains = [ch]
+
+        def run_all_local(fn):
+            return [fn(ch)]
+    else:
+        chains = [ChainThread(c, local_rank, make_sampler) for c in range(cpg)]
+        for c in chains:
+            c.start()
+        for c in chains:
+            c.wait()
+        run_all_local = lambda fn: run_all(chains, fn)
+    s0 = chains[0].sampler
+    bart, glmm = s0.bart(), s0.glmm()
     names = sd.param_names()
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None          # one nvidia-smi poller per job, not one per rank
+    if clocks:
+        clocks.start()
+
+    # ---- leg A: ONE chain alone on the GPU.  The sweep kernel's launch time (roofline) is measured here, where no other
+    # chain's kernel can sit between its events ----
+    s0.run(W, False, results=False)
+    bart.tree_step_ms(reset=True)
+    passes_before_a = glmm.num_device_passes()
+    barrier()
+    evA0, evA1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evA0.record(chains[0].stream)
+    if sharded:
+        outA = s0.run(K, False, results=False)
+    else:
+        chains[0].submit(lambda c: c.sampler.run(K, False, results=False))
+        outA = chains[0].wait()
+    evA1.record(chains[0].stream)
+    evA1.synchronize()
+    barrier()
+    ms_one = max_over_ranks(float(evA0.elapsed_time(evA1)))
+    sweep_ms = bart.tree_step_ms(reset=True)
+    statsA = s0.last_run_stats()
+    value_one = (1 if sharded else world) * K / (ms_one / 1000.0)
+
+    # ---- leg B (the headline when chains_per_gpu > 1): every chain of this GPU at once ----
+    passes0 = sum(c.sampler.glmm().num_device_passes() for c in chains)
+    if cpg > 1:
+        run_all_local(lambda c: c.sampler.run(W, False, results=False))
+        barrier()
+        t_wall0 = time.time()
+        ms_loc, outs = timed_concurrent(torch, chains, lambda c: c.sampler.run(K, False, results=False))
+        barrier()
+        t_wall = time.time() - t_wall0
+        ms = max_over_ranks(ms_loc)
+        stats = [c.sampler.last_run_stats() for c in chains]
+        out = outs[0]
+    else:
+        ms, out, stats, t_wall = ms_one, outA, [statsA], ms_one / 1000.0
+        passes0 = passes_before_a       # leg A is the timed region
+    glmm_passes = sum(c.sampler.glmm().num_device_passes() for c in chains) - passes0
     n_leapfrog = float(out["stan"][names.index("n_leapfrog__")][-1])
-    value = chains * K / (ms / 1000.0)
+    value = chains_total * K / (ms / 1000.0)
+    ms_stan = float(np.mean([st["ms_stan"] for st in stats])) / K
+    ms_bart = float(np.mean([st["ms_bart"] for st in stats])) / K
+    grad_evals = float(np.mean([st["grad_evals"] for st in stats])) / K
 
     # ---- roofline of the dominant kernel ----
     trees = bart.trees()
@@ -356,62 +546,122 @@ def run_ours(args):
     launch_ms = sweep_ms / K if persistent else sweep_ms / (K * T)    # CUDA events around the sweep launches on the launching stream
     units_per_launch = (T if persistent else 1) * n
     achieved = bytes_per_obs * units_per_launch / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_file = None, {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_sweep_dram_bytes_per_launch" if persistent else "k_tree_step_dram_bytes_per_launch")
+            traffic_file = json.load(f)
+            traffic = traffic_file.get("k_sweep_dram_bytes_per_launch" if persistent else "k_tree_step_dram_bytes_per_launch")
     except Exception:
         pass
+    # the metric's second half: "leaf-stat HBM GB/s vs peak" -- the stand-alone leaf-statistics pass (one launch streams the
+    # residuals and the binned predictor columns of the tree's rules: 11 B per observation in the SURVEY model)
+    leaf_stat = None
+    if not sharded:
+        try:
+            reps = 50
+            leaf_ms = float(np.median([bart.time_leaf_stats(t, reps) for t in (0, T // 2, T - 1)]))
+            leaf_gbs = 11.0 * n / (leaf_ms * 1e-3) / 1e9
+            leaf_stat = {"kernel": "k_tree_step (statistics only): one launch = one tree's per-leaf (n, sum r, sum r^2) over all rows",
+                         "algorithmic_bytes_per_obs": 11.0, "launch_us": leaf_ms * 1e3, "achieved": leaf_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": leaf_gbs / peak, "traffic": traffic_file.get("k_tree_step_dram_bytes_per_launch"),
+                         "timing": "CUDA events around %d back-to-back launches on the launching stream, median over 3 trees; the 9 MB + 8 MB "
+                                   "working set stays in the 126 MB L2 between launches, so this is an L2-resident rate unless flushed" % reps}
+        except Exception as e:      # pragma: no cover
+            leaf_stat = {"error": repr(e)}
     roofline = {"bound": "hbm", "kernel": "k_sweep (one launch = one %d-tree sweep)" % T if persistent else "k_tree_step (one launch = one tree)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_tree_obs": bytes_per_obs,
                 "units_per_launch": units_per_launch, "avg_tree_levels": lv,
                 "launch_us": launch_ms * 1e3, "tree_step_us": sweep_ms / (K * T) * 1e3,
+                "launch_timing": "CUDA events on the launching stream around every sweep launch of the one-chain leg (%d sweeps)" % K,
                 "achieved_lean_model_gbs": bytes_per_obs_lean * units_per_launch / (launch_ms * 1e-3) / 1e9,
                 "lean_bytes_per_tree_obs": bytes_per_obs_lean,
+                "whole_sweep_frac": bytes_per_obs * T * n * (value / max(1, world)) / 1e9 / peak,
+                "leaf_stat": leaf_stat,
+                # where a sweep's time goes, per rank (max / min over ranks): kept here so that the scaling record can attribute a loss
+                "step_breakdown": {"ms_stan_block_max": max_over_ranks(ms_stan), "ms_stan_block_min": min_over_ranks(ms_stan),
+                                   "ms_bart_block_max": max_over_ranks(ms_bart), "ms_bart_block_min": min_over_ranks(ms_bart),
+                                   "ms_per_step_max": max_over_ranks(ms / K), "ms_per_step_min": min_over_ranks(ms / K),
+                                   "grad_evals_per_sweep": grad_evals, "host_cores_per_rank": cores_per_rank},
                 "note": "algorithmic bytes are what per-tree streaming passes must move (SURVEY.md 8d); the persistent kernel keeps residuals "
                         "in registers and predictors in shared memory, so DRAM traffic per launch is ~17 MB and the binding limit is the "
                         "latency of 200 sequential reduce + Metropolis decisions, not HBM (DESIGN.md section 4)"}
 
+    # ---- the literal north-star Stan path beside it: one device pass per gradient evaluation (glmm mode 0) ----
+    value_mode0 = None
+    if not sharded and not args.no_mode0:
+        k0 = max(2, min(4, K))
+        for c in chains:
+            c.sampler.glmm().set_mode(0)
+        run_all_local(lambda c: c.sampler.run(1, False, results=False))
+        ms0, _ = timed_concurrent(torch, chains, lambda c: c.sampler.run(k0, False, results=False))
+        for c in chains:
+            c.sampler.glmm().set_mode(1)
+        value_mode0 = {"value": chains_total * k0 / (max_over_ranks(ms0) / 1000.0), "unit": UNIT, "steps": k0,
+                       "note": "glmm_mode 0: k_glmm_data_terms launched for EVERY gradient evaluation (~%d per sweep) instead of once per "
+                               "sweep; same chain, same draws to rounding" % int(round(grad_evals))}
+
     # ---- end-to-end leg through the C ABI with host buffers ----
-    h2d, d2h = s.set_host_plumbing(True)
-    pin_train = torch.empty(n, dtype=torch.float64).pin_memory()
-    pin_test = torch.empty(n, dtype=torch.float64).pin_memory()
-    pin_stan = torch.empty(s.num_pars, dtype=torch.float64).pin_memory()
-    s.run_into(W, False, stan=pin_stan.data_ptr(), train=pin_train.data_ptr(), test=pin_test.data_ptr())
+    pins = []
+    for c in chains:
+        h2d, d2h = c.sampler.set_host_plumbing(True)
+        pins.append((torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory(),
+                     torch.empty(c.sampler.num_pars, dtype=torch.float64).pin_memory()))
+    for c, pin in zip(chains, pins):
+        c.pin = pin
+    e2e_run = lambda k: (lambda c: c.sampler.run_into(k, False, stan=c.pin[2].data_ptr(), train=c.pin[0].data_ptr(), test=c.pin[1].data_ptr()))
+    run_all_local(e2e_run(W))
     barrier()
     t0 = time.time()
-    s.run_into(K, False, stan=pin_stan.data_ptr(), train=pin_train.data_ptr(), test=pin_test.data_ptr())
+    run_all_local(e2e_run(K))
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.time() - t0)
-    s.set_host_plumbing(False)
-    clocks.stop()
-    e2e = {"value": chains * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + 2 * 8 * n + 8 * s.num_pars),
+    for c in chains:
+        c.sampler.set_host_plumbing(False)
+    if clocks:
+        clocks.stop()
+    e2e = {"value": chains_total * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * cpg, "d2h_bytes_per_step": int(d2h + 2 * 8 * n + 8 * s0.num_pars) * cpg,
            "note": "s4b_sampler_run with host result buffers (train + test fits, Stan row) and every N-vector of the sweep "
-                   "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors"}
+                   "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors; "
+                   "bytes are per step of the GPU (all %d chain(s) on it advance one sweep)" % cpg}
 
-    # kernels launched inside the timed region, per sweep: k_prepare_sweep + k_sweep + epilogue + epoch bump (BART block),
+    # kernels launched inside the timed region, per sweep and chain: k_prepare_sweep + k_sweep + epilogue + epoch bump (BART block),
     # the offset kernel + its epoch bump (1 kernel for a continuous response), parametric mean, the fused GLMM input refresh,
     # the fused running-mean accumulation, plus the GLMM data passes
     per_sweep_bart = 4 if bart.sweep_mode() == 2 else T + 3
-    launches = K * (per_sweep_bart + (1 if args.continuous else 2) + 1 + 1 + 1) + glmm_passes
+    launches = cpg * K * (per_sweep_bart + (1 if args.continuous else 2) + 1 + 1 + 1) + glmm_passes
 
+    cfg_out = workload_config(args)
+    cfg_out["chains_per_gpu"] = cpg
+    cfg_out["workload"] = cfg_out["workload"].replace("1 chain per GPU", "%d chain(s) per GPU" % cpg)
+    if sharded:
+        cfg_out["sharding"] = f"one chain, rows sharded over {world} GPUs ({n} rows on rank 0)"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args), **({"sharding": f"one chain, rows sharded over {world} GPUs ({n} rows on rank 0)"} if sharded else {})),
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "config": cfg_out,
+            "clocks": clocks.summary() if clocks else None, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
-            "breakdown": {"ms_stan_block": stats["ms_stan"] / K, "ms_bart_block": stats["ms_bart"] / K, "grad_evals_per_sweep": stats["grad_evals"] / K,
-                          "glmm_device_passes_per_sweep": glmm_passes / K, "glmm_mode": glmm.mode(), "bart_sweep_mode": bart.sweep_mode(),
+            "per_chain": {"chains_total": chains_total, "sweeps_per_s_per_chain": value / chains_total,
+                          "value_one_chain_per_gpu": value_one, "ms_per_sweep_one_chain_per_gpu": ms_one / K,
+                          "note": "a step of the job = every chain advances one Gibbs sweep; with %d chains per GPU one chain's host-side NUTS "
+                                  "overlaps the other chain's sweep kernel (the reference also runs its chains side by side, one process each)" % cpg},
+            "value_mode0": value_mode0,
+            "breakdown": {"ms_stan_block": ms_stan, "ms_bart_block": ms_bart, "grad_evals_per_sweep": grad_evals,
+                          "glmm_device_passes_per_sweep": glmm_passes / (K * cpg), "glmm_mode": glmm.mode(), "bart_sweep_mode": bart.sweep_mode(),
                           "n_leapfrog_last": n_leapfrog, "wall_s": t_wall, "tree_step_us": sweep_ms / (K * T) * 1e3}}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            line["parity_at_config"] = parity_at_config(args, pr)
             line["cpu_baseline"] = cpu_baseline(args, pr, args.cpu_budget_s)
         else:
             line["cpu_baseline"] = None
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+    if not sharded:
+        for c in chains:
+            c.cmd = None
+            c.go.set()
     if world > 1:
         dist.destroy_process_group()
 

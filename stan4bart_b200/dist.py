@@ -38,6 +38,14 @@ def max_over_ranks(x):
     return float(x)
 
 
+def min_over_ranks(x):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([float(x)], dtype=torch.float64, device=_device_for_backend())
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+    return float(x)
+
+
 def sum_over_ranks(x):
     if dist.is_initialized() and dist.get_world_size() > 1:
         t = torch.tensor([float(x)], dtype=torch.float64, device=_device_for_backend())

@@ -13,24 +13,69 @@ from stan4bart_b200.structs import (BartConfig, CommonControl, GlmmData, StanCon
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "_build", "libs4b_oracle.so")
+FAST_LIB_PATH = os.path.join(ORACLE_DIR, "_build", "libs4b_oracle_fast.so")     # -O3 -march=native: the build bench.py TIMES
 TRACE_LEN = 32
+
+
+def _cpu_signature():
+    """The fast build uses -march=native, so it is only valid on the CPU model it was compiled on (the in-tree .so travels
+    from the build container to the GPU box): remember which CPU that was."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.md5(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def build_oracle(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
-    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+    if force or any(not os.path.exists(q) or any(os.path.getmtime(s) > os.path.getmtime(q) for s in srcs) for q in (LIB_PATH, FAST_LIB_PATH)):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    stamp = os.path.join(ORACLE_DIR, "_build", "fast.cpu")
+    sig = _cpu_signature()
+    try:
+        have = open(stamp).read().strip() if os.path.exists(stamp) else ""
+        if have != sig:
+            if have:        # built on another CPU model: rebuild for this one
+                subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "_build/libs4b_oracle_fast.so"])
+            with open(stamp, "w") as f:
+                f.write(sig)
+    except (OSError, subprocess.CalledProcessError):
+        pass
     return LIB_PATH
 
 
+def fast_build_is_native():
+    """True when the -O3 -march=native build was compiled for the CPU this process runs on."""
+    stamp = os.path.join(ORACLE_DIR, "_build", "fast.cpu")
+    try:
+        return open(stamp).read().strip() == _cpu_signature()
+    except OSError:
+        return False
+
+
 _lib = None
+_libs = {}
+_fast = False
+
+
+def use_fast(on):
+    """Switch between the strict build (parity checks: the default) and the -O3 -march=native build (timing).  Objects
+    must be used with the build that created them: switch only when none are alive."""
+    global _fast, _lib
+    _fast = bool(on)
+    _lib = _libs.get(_fast)
 
 
 def lib():
     global _lib
     if _lib is None:
         build_oracle()
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(FAST_LIB_PATH if (_fast and fast_build_is_native()) else LIB_PATH)
         vp = C.c_void_p
         sigs = {
             "or_bart_create": (vp, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p]),
@@ -93,6 +138,7 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        _libs[_fast] = L
     return _lib
 
 

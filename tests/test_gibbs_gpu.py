@@ -478,3 +478,18 @@ def test_many_grouping_levels_through_the_gibbs_loop():
     ro, rg = o.run(4, True), s.run(4, True)
     assert rel_err(ro["stan"], rg["stan"], scale=np.abs(ro["stan"]) + 1.0) <= 1e-7
     assert rel_err(ro["bart"]["train"], rg["bart"]["train"], scale=np.abs(ro["bart"]["train"]) + 1.0) <= 1e-7
+
+
+def test_headline_configuration_first_sweeps_match_the_oracle():
+    """The configuration BASELINE.json's metric is quoted on and bench.py times -- binary probit Friedman, n = 1 000 000, 200 trees,
+    n_test = n, the NQ = 4 register-resident sweep kernel without the parity trace, GLMM sweep-level expansion (mode 1) -- against the
+    CPU oracle with the same seeds: every sweep's Stan row, train / test fits, trees (structures and node counts bit-exact).
+    bench.py runs the same check before it times the CPU arm and reports it as `parity_at_config`."""
+    import argparse
+
+    import bench
+    args = argparse.Namespace(n=1_000_000, trees=200, continuous=False, weighted=False)
+    res = bench.parity_at_config(args, bench.make_problem(args), sweeps=2)
+    assert res["status"] == "ok", res
+    assert res["bart_sweep_mode"] == 2 and res["glmm_mode"] == 1
+    assert max(res["max_rel_err"].values()) <= 1e-8
