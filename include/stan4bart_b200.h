@@ -117,6 +117,8 @@ int gpubart_create(const s4b_bart_config* cfg, const double* y, const double* x,
 int gpubart_free(gpubart_fit* fit);
 /* setOffset(fit, offset, updateScale) (init.cpp:255, :817) */
 int gpubart_set_offset(gpubart_fit* fit, const double* offset, int update_scale);
+/* setResponse(fit, response) (BARTFunctionTable, init.cpp:68): a new response vector, n entries */
+int gpubart_set_response(gpubart_fit* fit, const double* y);
 /* setSigma (init.cpp:257, :799) */
 int gpubart_set_sigma(gpubart_fit* fit, double sigma);
 /* current k of the leaf prior (a draw when k is modelled) */
@@ -137,6 +139,11 @@ int gpubart_predict(gpubart_fit* fit, const double* x_test, int64_t n, const dou
  * runSamplerWithResults call (and every s4b_sampler_run iteration) appends the trees of its kept draw; capacity 0 frees it.
  * predict_stored: out [n x count], draws first .. first + count - 1; get_stored_trees: the flattened table of one draw. */
 int gpubart_set_keep_trees(gpubart_fit* fit, int64_t capacity);
+/* setControl(fit, control) with control->keepTrees toggled (init.cpp:737-744: off for warm-up runs, on for sampling): whether
+ * runSamplerWithResults appends to the store */
+int gpubart_set_keep_trees_active(gpubart_fit* fit, int on);
+/* (min, range) of the response scale each stored draw's leaf values are expressed in; out2 has 2 * count entries */
+int gpubart_get_stored_scales(gpubart_fit* fit, int64_t first, int64_t count, double* out2);
 int gpubart_num_stored(gpubart_fit* fit, int64_t* out);
 int gpubart_predict_stored(gpubart_fit* fit, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out);
 int gpubart_num_stored_nodes(gpubart_fit* fit, int64_t sample, int64_t* out);
@@ -149,6 +156,7 @@ int gpubart_stored_export(gpubart_fit* fit, void* out, int64_t bytes);
 int gpubart_stored_import(const void* blob, int64_t bytes, gpubart_stored** out);
 int gpubart_stored_free(gpubart_stored* st);
 int gpubart_stored_count(gpubart_stored* st, int64_t* out);
+int gpubart_stored_get_scales(gpubart_stored* st, int64_t first, int64_t count, double* out2);
 int gpubart_stored_predict(gpubart_stored* st, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out);
 /* printInitialSummary (dbarts table entry called by stan4bart_printInitialSummary, init.cpp:981): the text of the summary,
  * including the "power and base for tree prior:" and "tree split probabilities:" lines that tests/testthat/test-09-bartArgs.R
@@ -196,6 +204,9 @@ int glmm_set_response(glmm_model* m, const double* y);
 int glmm_log_prob_grad(glmm_model* m, const double* q, double* lp, double* grad, int* status);
 /* write_array (continuous.hpp:2640-2938) */
 int glmm_write_array(glmm_model* m, const double* q, double* out);
+/* names of the stored Stan rows ('\n' separated; lp__ ... energy__, then constrained_param_names, continuous.hpp:3115-3204):
+ * the dimnames of the reference's `stan` result (src/stan_sampler.cpp:478-489, :577-596).  *needed = bytes incl. terminator */
+int glmm_stan_row_names(glmm_model* m, char* out, size_t cap, size_t* needed);
 /* get_parametric_mean (continuous.hpp:3662-3768) */
 int glmm_parametric_mean(glmm_model* m, const double* constrained, double* out, int include_fixed, int include_random);
 /* device data terms only: S = sum e^2, X'e, Z'e */

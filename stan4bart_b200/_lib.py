@@ -100,6 +100,11 @@ SIGNATURES = {
     "s4b_shard_attach": (C.c_int, [vp, c_ubyte_p]),
     "s4b_shard_set_obs_range": (C.c_int, [vp, C.c_int64, C.c_int64]),
     "s4b_shard_allreduce": (C.c_int, [vp, c_double_p, C.c_int64, C.c_int]),
+    "glmm_stan_row_names": (C.c_int, [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gpubart_set_keep_trees_active": (C.c_int, [vp, C.c_int]),
+    "gpubart_set_response": (C.c_int, [vp, c_double_p]),
+    "gpubart_get_stored_scales": (C.c_int, [vp, C.c_int64, C.c_int64, c_double_p]),
+    "gpubart_stored_get_scales": (C.c_int, [vp, C.c_int64, C.c_int64, c_double_p]),
     "gpubart_create_sharded": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, vp, vpp]),
     "glmm_create_sharded": (C.c_int, [C.POINTER(GlmmData), vp, vpp]),
     "s4b_sampler_create_sharded": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, C.POINTER(GlmmData),

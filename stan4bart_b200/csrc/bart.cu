@@ -1142,6 +1142,16 @@ void BartFit::set_offset_host(const double* offset, bool update_scale)
   set_offset_device(offset ? d_offset_in_ : nullptr, update_scale);
 }
 
+void BartFit::set_response_host(const double* y)
+{
+  // the new response replaces y; re-applying the current offset refreshes the rescaled response and the residuals
+  // (binary: the latents are redrawn for the new signs), exactly what a setOffset with unchanged values does
+  S4B_CUDA(cudaMemcpyAsync(d_y_, y, sizeof(double) * (size_t) n_, cudaMemcpyHostToDevice, stream_));
+  S4B_CUDA(cudaMemcpyAsync(d_offset_in_, d_offset_, sizeof(double) * (size_t) n_, cudaMemcpyDeviceToDevice, stream_));
+  set_offset_device(d_offset_in_, false);
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+}
+
 void BartFit::set_sigma(double sigma)
 {
   k_set_sigma<<<1, 32, 0, stream_>>>(dev(), sigma);
@@ -1254,6 +1264,14 @@ void BartFit::predict_stored(const double* x_test, long long rows, const double*
   cudaFree(d_x); cudaFree(d_o); cudaFree(d_off);
 }
 
+void BartFit::get_stored_scales(long long first, long long count, double* out2)
+{
+  if (first < 0 || count < 0 || first + count > store_len_) throw std::invalid_argument("stored sample range out of bounds");
+  if (count == 0) return;
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  S4B_CUDA(cudaMemcpy(out2, d_store_scale_ + 2 * (size_t) first, sizeof(double) * 2 * (size_t) count, cudaMemcpyDeviceToHost));
+}
+
 std::vector<DTree> BartFit::download_stored(long long sample)
 {
   if (sample < 0 || sample >= store_len_) throw std::invalid_argument("stored sample index out of bounds");
@@ -1342,6 +1360,7 @@ StoredBart::StoredBart(const void* blob, long long bytes, cudaStream_t stream) :
   S4B_CUDA(cudaMemcpy(d_store_, trees.data(), sizeof(DTree) * trees.size(), cudaMemcpyHostToDevice));
   S4B_CUDA(cudaMalloc(&d_scale_, sizeof(double) * scales.size()));
   S4B_CUDA(cudaMemcpy(d_scale_, scales.data(), sizeof(double) * scales.size(), cudaMemcpyHostToDevice));
+  scales_ = scales;
   BartParams P; std::memset(&P, 0, sizeof P);
   P.p = p_; P.num_trees = T_; P.n_cuts = n_cuts_; P.is_binary = is_binary_; P.smin = -0.5; P.smax = 0.5; P.srange = 1.0;
   S4B_CUDA(cudaMalloc(&d_params_, sizeof(BartParams)));
@@ -1349,6 +1368,12 @@ StoredBart::StoredBart(const void* blob, long long bytes, cudaStream_t stream) :
 }
 
 StoredBart::~StoredBart() { cudaFree(d_store_); cudaFree(d_scale_); cudaFree(d_params_); }
+
+void StoredBart::get_scales(long long first, long long count, double* out2) const
+{
+  if (first < 0 || count < 0 || first + count > count_) throw std::invalid_argument("stored sample range out of bounds");
+  for (long long i = 0; i < 2 * count; ++i) out2[i] = scales_[(size_t) (2 * first + i)];
+}
 
 void StoredBart::predict(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out)
 {

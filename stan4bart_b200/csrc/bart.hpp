@@ -37,6 +37,8 @@ class BartFit {
   void set_offset_host(const double* offset, bool update_scale);
   void set_offset_device(const double* d_offset, bool update_scale);
   void set_sigma(double sigma);
+  // setResponse (dbarts table entry, init.cpp:68): a new response vector, fits and offset unchanged
+  void set_response_host(const double* y);
   void sample_trees_from_prior();
   // k of the leaf prior (a draw per sweep when cfg.k_df > 0)
   double current_k();
@@ -63,6 +65,8 @@ class BartFit {
   void set_keep_trees_active(bool on) { keep_trees_active_ = on; }
   void predict_stored(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out);
   long long num_stored_nodes(long long sample);
+  // (min, range) of the response scale of stored draws first .. first + count - 1 (what their leaf values are expressed in)
+  void get_stored_scales(long long first, long long count, double* out2);
   void get_stored_trees(long long sample, int32_t* tree_no, long long* n_obs, int32_t* var, double* value);
   // exportBARTState (init.cpp:409-446): the stored draws, the cut points and what prediction needs, as one host blob
   long long stored_export_size();
@@ -182,13 +186,14 @@ class StoredBart {
   StoredBart& operator=(const StoredBart&) = delete;
   long long count() const { return count_; }
   int p() const { return p_; }
+  void get_scales(long long first, long long count, double* out2) const;
   void predict(const double* x_test, long long rows, const double* test_offset, long long first, long long count, double* out);
 
  private:
   cudaStream_t stream_;
   int p_ = 0, T_ = 0, n_cuts_ = 0, is_binary_ = 0;
   long long count_ = 0;
-  std::vector<double> cuts_;
+  std::vector<double> cuts_, scales_;
   DTree* d_store_ = nullptr; double* d_scale_ = nullptr; BartParams* d_params_ = nullptr;
 };
 

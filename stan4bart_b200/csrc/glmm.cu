@@ -530,6 +530,22 @@ void GlmmModel::expand_sparse(const double* beta, const double* b, double* S, do
   for (int k = 0; k < q_; ++k) gb[k] = g0_[(size_t) (K_ + k)] - Gd[K_ + k];
 }
 
+std::vector<std::string> GlmmModel::param_names() const
+{
+  std::vector<std::string> out;
+  auto add = [&](const char* base, int count) { for (int i = 0; i < count; ++i) out.push_back(std::string(base) + "." + std::to_string(i + 1)); };
+  add("z_beta", len_zbeta_);
+  add("global", hs_);
+  for (int j = 0; j < hs_; ++j) for (int k = 0; k < K_; ++k) out.push_back("local." + std::to_string(j + 1) + "." + std::to_string(k + 1));
+  if (hs_ > 0) out.push_back("caux.1");
+  if (prior_dist_ == 5 || prior_dist_ == 6) for (int k = 0; k < K_; ++k) out.push_back("mix.1." + std::to_string(k + 1));
+  if (prior_dist_ == 6) out.push_back("one_over_lambda.1");
+  add("z_b", q_); add("z_T", len_z_T_); add("rho", len_rho_); add("zeta", len_conc_); add("tau", t_);
+  if (has_aux_) { out.push_back("aux_unscaled.1"); out.push_back("aux.1"); }
+  add("beta", K_); add("b", q_); add("theta_L", len_theta_L_);
+  return out;
+}
+
 void GlmmModel::refresh_r()
 {
   expansion_valid_ = false;

@@ -6,6 +6,7 @@
 #include "shard.hpp"
 
 #include <complex>
+#include <string>
 #include <vector>
 
 namespace s4b {
@@ -49,6 +50,8 @@ class GlmmModel {
   // returns status: 0 ok, 1 non-finite lp / gradient (maps to V = +inf in the sampler)
   int log_prob_grad(const double* q, double* lp, double* grad);
   void write_array(const double* q, double* out) const;
+  // names of the rows of write_array (constrained_param_names, continuous.hpp:3115-3204), in order
+  std::vector<std::string> param_names() const;
   // device result; beta / b are host pointers
   void parametric_mean_device(const double* beta, const double* b, double* d_out, bool include_fixed, bool include_random);
   void parametric_mean_host(const double* constrained, double* out, bool include_fixed, bool include_random);

@@ -394,6 +394,19 @@ int glmm_write_array(glmm_model* m, const double* q, double* out) { S4B_API_BEGI
 int glmm_parametric_mean(glmm_model* m, const double* c, double* out, int f, int r) { S4B_API_BEGIN S4B_REQUIRE(m && c && out); m->m->parametric_mean_host(c, out, f != 0, r != 0); S4B_API_END }
 int glmm_data_terms(glmm_model* m, const double* beta, const double* b, double* S, double* gbeta, double* gb)
 { S4B_API_BEGIN S4B_REQUIRE(m && S && gbeta && gb); m->m->data_terms(beta, b, S, gbeta, gb); S4B_API_END }
+// names of the stored Stan rows, '\n' separated: the 7 sampler diagnostics (mcmc/sample.hpp:43-44, base_nuts get_sampler_param_names)
+// followed by the constrained parameter names -- what the reference puts into the dimnames of its `stan` result
+// (src/stan_sampler.cpp:478-489, :577-596) and R splits with the regexes of R/stan4bart.R:241-246
+int glmm_stan_row_names(glmm_model* m, char* out, size_t cap, size_t* needed)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(m && needed);
+  std::string all = "lp__\naccept_stat__\nstepsize__\ntreedepth__\nn_leapfrog__\ndivergent__\nenergy__";
+  for (const std::string& nm : m->m->param_names()) { all += "\n"; all += nm; }
+  *needed = all.size() + 1;
+  if (out != nullptr && cap > 0) { const size_t k = std::min(cap - 1, all.size()); std::memcpy(out, all.data(), k); out[k] = 0; }
+  S4B_API_END
+}
 int glmm_set_mode(glmm_model* m, int mode) { S4B_API_BEGIN S4B_REQUIRE(m); m->m->set_mode(mode); S4B_API_END }
 int glmm_get_mode(glmm_model* m, int* mode) { S4B_API_BEGIN S4B_REQUIRE(m && mode); *mode = m->m->mode(); S4B_API_END }
 int glmm_num_device_passes(glmm_model* m, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(m && out); *out = m->m->num_device_passes(); S4B_API_END }
@@ -443,6 +456,12 @@ int s4b_sampler_set_host_plumbing(s4b_sampler* s, int on, int64_t* h2d, int64_t*
 { S4B_API_BEGIN S4B_REQUIRE(s); long long a = 0, b = 0; s->s->set_host_plumbing(on != 0, &a, &b); if (h2d) *h2d = a; if (d2h) *d2h = b; S4B_API_END }
 int gpubart_get_profile(gpubart_fit* f, uint64_t* out24, int reset) { S4B_API_BEGIN S4B_REQUIRE(f && out24); f->fit->get_profile((unsigned long long*) out24, reset != 0); S4B_API_END }
 int gpubart_set_keep_trees(gpubart_fit* f, int64_t capacity) { S4B_API_BEGIN S4B_REQUIRE(f && capacity >= 0); f->fit->set_keep_trees(capacity); S4B_API_END }
+int gpubart_set_keep_trees_active(gpubart_fit* f, int on) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_keep_trees_active(on != 0); S4B_API_END }
+int gpubart_set_response(gpubart_fit* f, const double* y) { S4B_API_BEGIN S4B_REQUIRE(f && y); f->fit->set_response_host(y); S4B_API_END }
+int gpubart_get_stored_scales(gpubart_fit* f, int64_t first, int64_t count, double* out2)
+{ S4B_API_BEGIN S4B_REQUIRE(f && out2); f->fit->get_stored_scales(first, count, out2); S4B_API_END }
+int gpubart_stored_get_scales(gpubart_stored* st, int64_t first, int64_t count, double* out2)
+{ S4B_API_BEGIN S4B_REQUIRE(st && out2); st->st->get_scales(first, count, out2); S4B_API_END }
 int gpubart_num_stored(gpubart_fit* f, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); *out = f->fit->num_stored(); S4B_API_END }
 int gpubart_predict_stored(gpubart_fit* f, const double* x_test, int64_t n, const double* test_offset, int64_t first, int64_t count, double* out)
 { S4B_API_BEGIN S4B_REQUIRE(f && x_test && out && n >= 0); f->fit->predict_stored(x_test, n, test_offset, first, count, out); S4B_API_END }

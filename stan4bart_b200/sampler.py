@@ -52,6 +52,20 @@ class GpuBart:
     def set_sigma(self, sigma):
         _lib.check(self.L.gpubart_set_sigma(self.h, float(sigma)))
 
+    def set_response(self, y):
+        """setResponse of the dbarts table (init.cpp:68): a new response vector, fits and offset unchanged."""
+        _lib.check(self.L.gpubart_set_response(self.h, dptr(f64(y))))
+
+    def set_keep_trees_active(self, on):
+        """setControl(keepTrees = on): whether the following runs append their draw to the tree store (init.cpp:737-744)."""
+        _lib.check(self.L.gpubart_set_keep_trees_active(self.h, int(bool(on))))
+
+    def stored_scales(self, first=0, count=None):
+        count = self.num_stored() - first if count is None else count
+        out = np.zeros((count, 2))
+        _lib.check(self.L.gpubart_get_stored_scales(self.h, int(first), int(count), dptr(out)))
+        return out
+
     def k(self):
         """Current k of the leaf prior normal(k): the configured value, or the latest draw under the chi hyperprior."""
         v = C.c_double(0.0)
@@ -326,6 +340,14 @@ class GlmmModel:
         gb = np.zeros(max(1, self.sd.q))
         _lib.check(self.L.glmm_data_terms(self.h, dptr(f64(beta)), dptr(f64(b)), C.byref(S), dptr(gbeta), dptr(gb)))
         return S.value, gbeta[:self.sd.K], gb[:self.sd.q]
+
+    def stan_row_names(self):
+        """Names of the stored Stan rows as the library reports them (the dimnames of the reference's `stan` result)."""
+        need = C.c_size_t(0)
+        _lib.check(self.L.glmm_stan_row_names(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _lib.check(self.L.glmm_stan_row_names(self.h, buf, need.value, C.byref(need)))
+        return buf.value.decode().split("\n")
 
     def num_grad_evals(self):
         k = C.c_int64(0)

@@ -220,3 +220,18 @@ def test_many_grouping_levels(levels, weighted):
     # deterministic: repeated evaluation is bit identical
     a, b = mg.log_prob_grad(q), mg.log_prob_grad(q)
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("prior_dist", [1, 3, 4, 5, 6, 7])
+def test_stan_row_names_match_the_reference_naming(prior_dist):
+    """The names the library reports for the stored Stan rows (dimnames of the reference's `stan` result, src/stan_sampler.cpp:478-489,
+    continuous.hpp:3115-3204) equal the front end's list for every coefficient prior family."""
+    from stan4bart_b200.sampler import GlmmModel
+    pr = friedman_problem(300)
+    sd = pr["stan_data"]
+    sd.prior_dist = prior_dist
+    sd.prior_df = np.full(sd.K, 3.0)
+    sd.num_normals = np.full(sd.K, 2, dtype=np.int32)
+    sd.global_prior_df, sd.global_prior_scale, sd.slab_df, sd.slab_scale = 1.0, 0.1, 4.0, 2.5
+    m = GlmmModel(sd)
+    assert m.stan_row_names() == sd.param_names()
