@@ -101,6 +101,8 @@ SIGNATURES = {
     "s4b_shard_set_obs_range": (C.c_int, [vp, C.c_int64, C.c_int64]),
     "s4b_shard_allreduce": (C.c_int, [vp, c_double_p, C.c_int64, C.c_int]),
     "glmm_stan_row_names": (C.c_int, [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gpubart_set_pipeline": (C.c_int, [vp, C.c_int]),
+    "gpubart_get_pipeline": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gpubart_set_keep_trees_active": (C.c_int, [vp, C.c_int]),
     "gpubart_set_response": (C.c_int, [vp, c_double_p]),
     "gpubart_get_stored_scales": (C.c_int, [vp, C.c_int64, C.c_int64, c_double_p]),

@@ -6,6 +6,7 @@
 #include "bart.hpp"
 #include "bart_kernels.cuh"
 #include "sweep_kernel.cuh"
+#include "sweep_pipe.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -853,7 +854,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_counters_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -945,6 +946,32 @@ void BartFit::setup_persistent()
     S4B_CUDA(cudaMalloc(&d_tables_, sizeof(double) * tab.size()));
     S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     sweep_mode_ = 2;
+    // ---- pipelined kernel: register-resident, unweighted, unsharded chains; the cross table gets what shared memory is left ----
+    if (persistent_nq_ != kStreamNq && d_wt_ == nullptr && !sharded() && !(getenv("S4B_PIPE") && atoi(getenv("S4B_PIPE")) == 0)) {
+      const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
+                     : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
+      const size_t fixed = ((sizeof(PipeSmem) + 15) / 16) * 16 + (size_t) (kBinSlots + 1) * kWorkers * sizeof(double)
+                         + (size_t) p_ * persistent_nq_ * kWorkers * sizeof(uint32_t);
+      int words = 0;
+      if (fixed < (size_t) max_smem) words = (int) std::min<size_t>(32, ((size_t) max_smem - fixed) / (kWorkers * sizeof(uint32_t))) - 1;
+      if (words >= 8) {
+        const size_t smem = fixed + (size_t) (words + 1) * kWorkers * sizeof(uint32_t);
+        int per_sm = 0;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) == cudaSuccess && per_sm >= 1) {
+          pipe_count_words_ = words; pipe_smem_ = smem; pipe_ring_stride_ = (kBinSlots + words) * persistent_grid_;
+          S4B_CUDA(cudaMalloc(&d_pipe_ring_, sizeof(double) * kPipeRing * (size_t) pipe_ring_stride_));
+          zero_device_sync(d_pipe_ring_, sizeof(double) * kPipeRing * (size_t) pipe_ring_stride_, stream_);
+          S4B_CUDA(cudaMalloc(&d_pipe_counters_, sizeof(unsigned int) * kPipeRing));
+          S4B_CUDA(cudaMalloc(&d_pipe_flag_, sizeof(unsigned int)));
+          S4B_CUDA(cudaMalloc(&d_pipe_infos_, sizeof(PipeInfo) * (size_t) T_));
+          zero_device_sync(d_pipe_infos_, sizeof(PipeInfo) * (size_t) T_, stream_);
+          S4B_CUDA(cudaMalloc(&d_pipe_ran_, sizeof(unsigned long long)));
+          zero_device_sync(d_pipe_ran_, sizeof(unsigned long long), stream_);
+          pipe_enabled_ = true;
+        } else cudaGetLastError();
+      }
+    }
   }
   if (d_wt_ != nullptr && persistent_nq_ == 0)
     throw std::invalid_argument("weighted fit: the sweep kernel does not fit this many rows on one GPU (shard the chain by rows)");
@@ -971,13 +998,35 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   // replay / record keep strict program order inside the kernel; otherwise proposals and decision draws are produced up front
   const StepDesc* descs = sequential_rng_ ? nullptr : d_descs_;
   const double2* draws = sequential_rng_ ? nullptr : d_draws_;
+  // the pipelined kernel takes the sweep when this is a production run (no parity trace, no replay, no cycle counters) and,
+  // decided on the device by k_prepare_sweep, every tree of the sweep is small enough for it; otherwise it returns at once
+  // and the synchronous kernel below does the sweep (it returns at once in the other case)
+  const bool pipe = pipe_enabled_ && !sequential_rng_ && trace_cap_ == 0 && !profile_on_;
+  PipeInfo* infos = pipe ? static_cast<PipeInfo*>(d_pipe_infos_) : nullptr;
+  unsigned int* flag = pipe ? d_pipe_flag_ : nullptr;
   if (!sequential_rng_) {
     size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
-    k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_);
+    if (pipe) {
+      S4B_CUDA(cudaMemsetAsync(d_pipe_flag_, 0, sizeof(unsigned int), stream_));
+      S4B_CUDA(cudaMemsetAsync(d_pipe_counters_, 0, sizeof(unsigned int) * kPipeRing, stream_));
+    }
+    k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_, infos, flag,
+                                                                                         std::min(kPipeCells, 4 * pipe_count_words_ / kBinSlots));
+  }
+  if (pipe) {
+    const void* pfn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
+                    : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
+    unsigned int* ctrs = d_pipe_counters_; double* ring = d_pipe_ring_; int rstride = pipe_ring_stride_; int words = pipe_count_words_;
+    const StepDesc* pdescs = d_descs_; const PipeInfo* pinfos = infos; const double2* pdraws = d_draws_; const unsigned int* pflag = flag;
+    unsigned long long* ran = d_pipe_ran_;
+    void* pargs[] = { &dv, &ctrs, &ring, &rstride, &pdescs, &pinfos, &pdraws, &pflag, &words, &ran };
+    S4B_CUDA(cudaLaunchCooperativeKernel(pfn, dim3(persistent_grid_), dim3(kSweepBlock), pargs, pipe_smem_, stream_));
+    ++pipe_sweeps_;
   }
   int overlap = overlap_walk_;
   ShardDev sh = shard_dev();
-  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh };
+  const unsigned int* run_flag = flag;
+  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &run_flag };
   // the sums of squares are accumulated only when the parity trace (which reports the individual log-likelihoods) is on
   // (weighted fits use the two-value bins for sum w r and sum w)
   const bool sq = trace_cap_ > 0 || sequential_rng_ || d_wt_ != nullptr;
@@ -994,6 +1043,15 @@ void BartFit::launch_persistent_sweep(bool last_thin)
                                                    (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
   S4B_CUDA(cudaGetLastError());
+}
+
+long long BartFit::pipe_sweeps_done()
+{
+  if (d_pipe_ran_ == nullptr) return 0;
+  unsigned long long k = 0;
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  S4B_CUDA(cudaMemcpy(&k, d_pipe_ran_, sizeof k, cudaMemcpyDeviceToHost));
+  return (long long) k;
 }
 
 void BartFit::bin_matrix(const double* x, long long rows, long long rows_pad, std::vector<uint8_t>& out) const

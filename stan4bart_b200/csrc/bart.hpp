@@ -150,6 +150,21 @@ class BartFit {
   std::vector<double> split_probs_;       // normalised bart_args split.probs (empty = uniform)
   DTree* d_store_ = nullptr; double* d_store_scale_ = nullptr; long long store_cap_ = 0, store_len_ = 0;
   size_t persistent_smem_ = 0;
+  // pipelined sweep kernel (sweep_pipe.cuh): ring of partial rows, barrier counters, per-step cell tables, per-sweep flag
+  bool pipe_enabled_ = false;
+  int pipe_count_words_ = 0, pipe_ring_stride_ = 0;
+  size_t pipe_smem_ = 0;
+  double* d_pipe_ring_ = nullptr; unsigned int* d_pipe_counters_ = nullptr; unsigned int* d_pipe_flag_ = nullptr; void* d_pipe_infos_ = nullptr;
+  long long pipe_sweeps_ = 0;
+  unsigned long long* d_pipe_ran_ = nullptr;
+ public:
+  // sweeps that really ran in the pipelined kernel (counted on the device)
+  long long pipe_sweeps_done();
+  // sweeps launched through the pipelined kernel path so far (whether a given sweep ran pipelined is decided on the device)
+  long long pipe_sweeps() const { return pipe_sweeps_; }
+  bool pipe_enabled() const { return pipe_enabled_; }
+  void set_pipe_enabled(bool on) { pipe_enabled_ = on && pipe_smem_ > 0; }
+ private:
   unsigned int* d_barrier_ = nullptr;
   double* d_partials2_ = nullptr;
   double* d_tables_ = nullptr;

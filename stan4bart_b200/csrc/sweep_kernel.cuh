@@ -1062,8 +1062,68 @@ __device__ inline void w_copy_desc(StepDesc& dst, const StepDesc& src, int lane)
 constexpr int kPrepWarps = 4;
 struct PrepSmemWarp { DTree tree; CtlScratch cs; StepDesc sd; };
 
+// ---- pipelined sweep (sweep_pipe.cuh): data-independent description of a step's cells ----
+constexpr int kPipeCells = 16;            // capacity of the per-step cell tables
+constexpr int kPipeRing = 4;
+constexpr int kPipeDescs = 3;
+
+// data-independent description of step t's cells (k_prepare_sweep): which node a cell's rows sit in now (cell_a) and in the
+// accepted tree (cell_f; the rejected tree keeps cell_a)
+struct PipeInfo {
+  int32_t ncells;
+  int32_t ok;                              // this step fits the pipelined kernel
+  uint8_t cellbase[32];                    // change / swap: first cell of bottom node a (outside the branch: its only cell)
+  uint8_t cell_a[kPipeCells], cell_f[kPipeCells];
+};
+
+// one warp per tree, after w_propose: fills infos[t]; returns whether the step fits
+__device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& pi, int max_cells, int lane)
+{
+  const int nn = t.num_nodes, kind = d.b_kind, node = d.b_node, L = d.b_num_leaves, nslots = d.b_nslots;
+  const bool bd = kind == 0 || kind == 1;
+  bool ok = nn + 2 <= 32 && nslots + (bd ? 1 : 0) <= 32 && nslots <= kBinSlots;
+  int ncells = nslots;
+  if (lane < kPipeCells) { pi.cell_a[lane] = 0; pi.cell_f[lane] = 0; }
+  pi.cellbase[lane] = 0;
+  __syncwarp();
+  if (ok) {
+    const bool leaf = lane < nn && t.nodes[lane].var < 0;
+    const int slot = lane < nn ? (int) d.b_cur.slot[lane] : 255;
+    if (kind == 2 || kind == 3) {
+      const bool inside = leaf && d.b_prop.slot[lane] != 255;
+      const unsigned m_in = __ballot_sync(0xffffffffu, inside), m_out = __ballot_sync(0xffffffffu, leaf && !inside);
+      const int k_in = __popc(m_in), n_out = __popc(m_out);
+      ncells = n_out + k_in * k_in;
+      ok = ncells <= max_cells && ncells <= kPipeCells;
+      if (ok) {
+        const unsigned below = (1u << lane) - 1u;
+        if (leaf && !inside) { const int c = __popc(m_out & below); pi.cellbase[lane] = (uint8_t) c; pi.cell_a[c] = (uint8_t) lane; pi.cell_f[c] = (uint8_t) lane; }
+        if (inside) {
+          const int r = __popc(m_in & below);
+          pi.cellbase[lane] = (uint8_t) (n_out + r * k_in);
+          // pair (this node now, j-th node of the branch after an accepted change / swap): prop slot L + j belongs to the j-th inside node
+          for (int j = 0; j < k_in; ++j) { const int f = nth_set_bit(m_in, j); pi.cell_a[n_out + r * k_in + j] = (uint8_t) lane; pi.cell_f[n_out + r * k_in + j] = (uint8_t) f; }
+        }
+      }
+    } else {
+      ok = ncells <= max_cells && ncells <= kPipeCells;
+      if (ok && leaf && slot < kPipeCells) {
+        int f = lane;
+        if (kind == 0) f = lane > node ? lane + 2 : lane;
+        else if (kind == 1) f = (lane == node + 1 || lane == node + 2) ? node : (lane > node + 2 ? lane - 2 : lane);
+        pi.cell_a[slot] = (uint8_t) lane; pi.cell_f[slot] = (uint8_t) f;
+      }
+      if (ok && kind == 0 && lane < 2) { pi.cell_a[L + lane] = (uint8_t) node; pi.cell_f[L + lane] = (uint8_t) (node + 1 + lane); }
+    }
+  }
+  if (lane == 0) { pi.ncells = ncells; pi.ok = ok ? 1 : 0; }
+  __syncwarp();
+  return ok;
+}
+
 __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, StepDesc* __restrict__ descs, double2* __restrict__ draws,
-                                                                   const double* __restrict__ tables)
+                                                                   const double* __restrict__ tables, PipeInfo* __restrict__ infos,
+                                                                   unsigned int* __restrict__ pipe_not_ok, int pipe_max_cells)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* tab = reinterpret_cast<double*>(smem_raw);
@@ -1091,6 +1151,11 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
   w_propose(W.tree, *prm, tab, rngp, W.sd, W.cs, t, lane);
   rngp.commit();
   w_copy_desc(descs[t], W.sd, lane);
+  // does this step fit the pipelined kernel?  one step that does not sends the whole sweep to the synchronous kernel
+  if (infos != nullptr) {
+    const bool ok = w_pipe_info(W.tree, W.sd, infos[t], pipe_max_cells, lane);
+    if (!ok && lane == 0) atomicOr(pipe_not_ok, 1u);
+  }
   // decision draws of this step: (uniform, normal) pairs for draw indices 0..31
   {
     const double u = keyed_stream_uniform(rng->key0, rng->key1, rng->stream, step, 1u, (uint32_t) lane);
@@ -1252,8 +1317,10 @@ __device__ __forceinline__ void stream_update(const UpdateDesc& upd, double* Rg,
 template <int NQ, bool SEQ, bool STREAM = false, bool SQ = true>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
                                                                const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
-                                                               const __grid_constant__ ShardDev sh_param)
+                                                               const __grid_constant__ ShardDev sh_param, const unsigned int* __restrict__ run_flag)
 {
+  // the pipelined kernel (sweep_pipe.cuh) was launched before this one and has done the sweep unless the flag says otherwise
+  if (run_flag != nullptr && *run_flag == 0u) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
   // lane-private statistic bins: [slot][thread] -> (sum, sum^2) and count; no atomics, no bank conflicts

@@ -222,6 +222,15 @@ class GpuBart:
         _lib.check(self.L.gpubart_get_sweep_mode(self.h, C.byref(m)))
         return m.value
 
+    def set_pipeline(self, on):
+        """Software-pipelined sweep kernel on / off (on by default where it applies)."""
+        _lib.check(self.L.gpubart_set_pipeline(self.h, int(bool(on))))
+
+    def pipeline(self):
+        en, a, b = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        _lib.check(self.L.gpubart_get_pipeline(self.h, C.byref(en), C.byref(a), C.byref(b)))
+        return dict(enabled=bool(en.value), sweeps_offered=int(a.value), sweeps_pipelined=int(b.value))
+
     def time_leaf_stats(self, tree=0, reps=20):
         ms = C.c_double(0.0)
         _lib.check(self.L.gpubart_time_leaf_stats(self.h, tree, reps, C.byref(ms)))

@@ -207,7 +207,7 @@ int main(int argc, char** argv)
       bartFunctions.setResponse(fit, y2.data());
       dbarts::Results r(n, p, nt, 1, 1, !bartModel.kPrior->isFixed);
       bartFunctions.runSamplerWithResults(fit, 0, &r);
-      write_vec(out, "after_setresponse", r.trainingSamples, n);
+      write_vec(out, "after_setresp", r.trainingSamples, n);
     }
     bartFunctions.invalidateFit(fit); ::operator delete(fit);
     bartFunctions.invalidateModel(&bartModel); bartFunctions.invalidateData(&bartData);

@@ -581,3 +581,38 @@ def test_cut_counts_per_predictor():
     assert births.shape[0] > 0 and np.all(births[:, 3] < counts[births[:, 2].astype(int)])
     tg, to = g.trees(), o.trees()
     assert np.array_equal(tg["var"], to["var"]) and rel_err(tg["value"], to["value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-9
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_pipelined_sweep_kernel_equals_the_synchronous_one(binary):
+    """csrc/sweep_pipe.cuh: workers one step ahead of the controller, slot sums corrected with the cross table (slot of t) x (cell
+    of t - 1).  Same decisions, draws and trees as the synchronous kernel; fits / residuals differ only by the rounding of the
+    slot sums.  Also against the oracle, and the kernel really ran (device-side counter)."""
+    n, p, T, sweeps = 6000, 6, 40, 12
+    x, y, _ = bart_problem(n=n, p=p, binary=binary, seed=31)
+    off = 0.2 * np.sin(np.arange(n) * 0.05)
+    res = {}
+    for mode in ("pipe", "sync", "oracle"):
+        cfg = bart_config(n, p, num_trees=T, is_binary=binary, seed=777)
+        s = O.OracleBart(cfg, y, x) if mode == "oracle" else GpuBart(cfg, y, x)
+        if mode == "sync":
+            s.set_pipeline(False)
+        s.set_offset(off, True)
+        if not binary:
+            s.set_sigma(0.9)
+        s.sample_trees_from_prior()
+        for _ in range(sweeps):
+            r = s.run()
+        res[mode] = dict(train=r["train"], trees=s.trees(), resid=s.residual(), vc=r["varcount"])
+        if mode == "pipe":
+            pl = s.pipeline()
+            assert pl["enabled"] and pl["sweeps_offered"] == sweeps and pl["sweeps_pipelined"] >= sweeps - 2, pl
+        if mode == "sync":
+            assert not s.pipeline()["enabled"] and s.pipeline()["sweeps_pipelined"] == 0
+    for other in ("sync", "oracle"):
+        a, b = res["pipe"], res[other]
+        assert np.array_equal(a["trees"]["var"], b["trees"]["var"]) and np.array_equal(a["trees"]["n"], b["trees"]["n"]), other
+        assert np.array_equal(a["vc"], b["vc"])
+        assert rel_err(a["trees"]["value"], b["trees"]["value"], scale=np.abs(b["trees"]["value"]) + 1e-3) <= 1e-9
+        assert rel_err(a["train"], b["train"], scale=np.abs(b["train"]) + 1.0) <= 1e-10
+        assert rel_err(a["resid"], b["resid"], scale=np.abs(b["resid"]) + 1.0) <= 1e-10

@@ -144,5 +144,5 @@ def test_table_driven_run_equals_the_direct_c_abi(binary, kmod):
     # setResponse + one more draw (store switched off again)
     g.set_keep_trees_active(False)
     g.set_response(y2)
-    assert np.array_equal(got["after_setresponse"], g.run()["train"])
+    assert np.array_equal(got["after_setresp"], g.run()["train"])
     assert g.num_stored() == iters

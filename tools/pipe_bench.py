@@ -1,0 +1,31 @@
+"""BART-only timing of the sweep kernels at the benchmark shape: pipelined (sweep_pipe.cuh) against synchronous.
+usage: python tools/pipe_bench.py [n] [trees] [sweeps]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from stan4bart_b200.frontend import friedman_problem
+from stan4bart_b200.sampler import GpuBart
+from stan4bart_b200.structs import bart_config
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+pr = friedman_problem(n, binary=True)
+out = {}
+for mode in ("sync", "pipe"):
+    cfg = bart_config(n, 9, num_trees=T, seed=1, is_binary=True)
+    g = GpuBart(cfg, pr["y"], pr["x_bart"])
+    g.set_pipeline(mode == "pipe")
+    for _ in range(40):
+        g.run()
+    g.tree_step_ms()
+    t0 = time.time()
+    for _ in range(sweeps):
+        g.run()
+    dt = time.time() - t0
+    dev = g.tree_step_ms()
+    tr = g.trees()
+    out[mode] = {"wall_ms_per_sweep": dt / sweeps * 1e3, "device_ms_per_sweep": dev / sweeps, "us_per_tree_step": dev / sweeps / T * 1e3,
+                 "nodes_per_tree": len(tr["var"]) / T, "pipeline": g.pipeline()}
+    del g
+print(json.dumps({"n": n, "trees": T, "sweeps": sweeps, **out}, indent=1))
