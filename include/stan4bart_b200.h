@@ -180,10 +180,12 @@ int gpubart_set_use_graph(gpubart_fit* fit, int use_graph);
 int gpubart_set_sweep_mode(gpubart_fit* fit, int mode);
 int gpubart_get_sweep_mode(gpubart_fit* fit, int* mode);
 /* the software-pipelined sweep kernel (csrc/sweep_pipe.cuh): on by default for unweighted, unsharded, register-resident chains
- * without parity trace / replay; decided per sweep on the device (every tree small enough), otherwise the synchronous kernel
- * runs.  get: whether it is enabled, sweeps offered to it, sweeps it actually ran */
+ * without parity trace / replay.  Decided per tree step on the device: runs of steps whose trees are small enough go through it,
+ * the steps in between through the synchronous kernel.  get: whether it is enabled, sweeps offered to it, tree steps it ran */
 int gpubart_set_pipeline(gpubart_fit* fit, int on);
-int gpubart_get_pipeline(gpubart_fit* fit, int* enabled, int64_t* sweeps_launched, int64_t* sweeps_pipelined);
+int gpubart_get_pipeline(gpubart_fit* fit, int* enabled, int64_t* sweeps_launched, int64_t* steps_pipelined);
+/* tree steps that did not fit the pipelined kernel so far: [0] all, [1] tree too large, [2] more than 8 statistic slots, [3] too many cells */
+int gpubart_pipeline_misfits(gpubart_fit* fit, uint32_t* out4);
 /* micro-benchmark hook: `reps` launches of the leaf-statistics pass for `tree`, returns mean ms per launch */
 int gpubart_time_leaf_stats(gpubart_fit* fit, int tree, int reps, double* ms_per_launch);
 int gpubart_num_tree_steps(gpubart_fit* fit, int64_t* out);

@@ -103,6 +103,7 @@ SIGNATURES = {
     "glmm_stan_row_names": (C.c_int, [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "gpubart_set_pipeline": (C.c_int, [vp, C.c_int]),
     "gpubart_get_pipeline": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gpubart_pipeline_misfits": (C.c_int, [vp, c_uint32_p]),
     "gpubart_set_keep_trees_active": (C.c_int, [vp, C.c_int]),
     "gpubart_set_response": (C.c_int, [vp, c_double_p]),
     "gpubart_get_stored_scales": (C.c_int, [vp, C.c_int64, C.c_int64, c_double_p]),

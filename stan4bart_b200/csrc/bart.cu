@@ -854,7 +854,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_counters_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_counters_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_pipe_pos_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -952,20 +952,25 @@ void BartFit::setup_persistent()
                      : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
       const size_t fixed = ((sizeof(PipeSmem) + 15) / 16) * 16 + (size_t) (kBinSlots + 1) * kWorkers * sizeof(double)
                          + (size_t) p_ * persistent_nq_ * kWorkers * sizeof(uint32_t);
-      int words = 0;
-      if (fixed < (size_t) max_smem) words = (int) std::min<size_t>(32, ((size_t) max_smem - fixed) / (kWorkers * sizeof(uint32_t))) - 1;
-      if (words >= 8) {
-        const size_t smem = fixed + (size_t) (words + 1) * kWorkers * sizeof(uint32_t);
+      // the cross table (slot of this step) x (cell of the previous step) gets what shared memory is left: one byte counter per entry and thread
+      int entries = 0;
+      if (fixed < (size_t) max_smem) entries = (int) std::min<size_t>((size_t) kBinSlots * kPipeCells, ((size_t) max_smem - fixed) / kWorkers - 1);
+      entries &= ~3;
+      if (entries >= 4 * kBinSlots) {
+        const int words = entries;            // (member name kept: capacity of the cross table in entries)
+        const size_t smem = fixed + (size_t) (entries + 1) * kWorkers;
         int per_sm = 0;
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) == cudaSuccess && per_sm >= 1) {
-          pipe_count_words_ = words; pipe_smem_ = smem; pipe_ring_stride_ = (kBinSlots + words) * persistent_grid_;
-          S4B_CUDA(cudaMalloc(&d_pipe_ring_, sizeof(double) * kPipeRing * (size_t) pipe_ring_stride_));
-          zero_device_sync(d_pipe_ring_, sizeof(double) * kPipeRing * (size_t) pipe_ring_stride_, stream_);
+          pipe_count_words_ = words; pipe_smem_ = smem;
+          S4B_CUDA(cudaMalloc(&d_pipe_ring_, sizeof(unsigned long long) * kPipeRing * kPipeAcc));
+          zero_device_sync(d_pipe_ring_, sizeof(unsigned long long) * kPipeRing * kPipeAcc, stream_);
           S4B_CUDA(cudaMalloc(&d_pipe_counters_, sizeof(unsigned int) * kPipeRing));
-          S4B_CUDA(cudaMalloc(&d_pipe_flag_, sizeof(unsigned int)));
+          S4B_CUDA(cudaMalloc(&d_pipe_flag_, sizeof(unsigned int) * 4));
+          zero_device_sync(d_pipe_flag_, sizeof(unsigned int) * 4, stream_);
           S4B_CUDA(cudaMalloc(&d_pipe_infos_, sizeof(PipeInfo) * (size_t) T_));
           zero_device_sync(d_pipe_infos_, sizeof(PipeInfo) * (size_t) T_, stream_);
+          S4B_CUDA(cudaMalloc(&d_pipe_pos_, sizeof(int) * (2 * kPipeSegments + 1)));
           S4B_CUDA(cudaMalloc(&d_pipe_ran_, sizeof(unsigned long long)));
           zero_device_sync(d_pipe_ran_, sizeof(unsigned long long), stream_);
           pipe_enabled_ = true;
@@ -998,35 +1003,20 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   // replay / record keep strict program order inside the kernel; otherwise proposals and decision draws are produced up front
   const StepDesc* descs = sequential_rng_ ? nullptr : d_descs_;
   const double2* draws = sequential_rng_ ? nullptr : d_draws_;
-  // the pipelined kernel takes the sweep when this is a production run (no parity trace, no replay, no cycle counters) and,
-  // decided on the device by k_prepare_sweep, every tree of the sweep is small enough for it; otherwise it returns at once
-  // and the synchronous kernel below does the sweep (it returns at once in the other case)
+  // Production runs (no parity trace, no replay, no cycle counters) of chains the pipelined kernel supports split the sweep
+  // into segments, decided on the device from k_prepare_sweep's per-step flags: the pipelined kernel takes every run of
+  // consecutive steps that fit it, the synchronous kernel the single steps in between (and whatever is left after
+  // kPipeSegments rounds).  Launches with nothing to do return at once.
   const bool pipe = pipe_enabled_ && !sequential_rng_ && trace_cap_ == 0 && !profile_on_;
   PipeInfo* infos = pipe ? static_cast<PipeInfo*>(d_pipe_infos_) : nullptr;
-  unsigned int* flag = pipe ? d_pipe_flag_ : nullptr;
   if (!sequential_rng_) {
     size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
-    if (pipe) {
-      S4B_CUDA(cudaMemsetAsync(d_pipe_flag_, 0, sizeof(unsigned int), stream_));
-      S4B_CUDA(cudaMemsetAsync(d_pipe_counters_, 0, sizeof(unsigned int) * kPipeRing, stream_));
-    }
-    k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_, infos, flag,
-                                                                                         std::min(kPipeCells, 4 * pipe_count_words_ / kBinSlots));
-  }
-  if (pipe) {
-    const void* pfn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
-                    : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
-    unsigned int* ctrs = d_pipe_counters_; double* ring = d_pipe_ring_; int rstride = pipe_ring_stride_; int words = pipe_count_words_;
-    const StepDesc* pdescs = d_descs_; const PipeInfo* pinfos = infos; const double2* pdraws = d_draws_; const unsigned int* pflag = flag;
-    unsigned long long* ran = d_pipe_ran_;
-    void* pargs[] = { &dv, &ctrs, &ring, &rstride, &pdescs, &pinfos, &pdraws, &pflag, &words, &ran };
-    S4B_CUDA(cudaLaunchCooperativeKernel(pfn, dim3(persistent_grid_), dim3(kSweepBlock), pargs, pipe_smem_, stream_));
-    ++pipe_sweeps_;
+    if (pipe) S4B_CUDA(cudaMemsetAsync(d_pipe_pos_, 0, sizeof(int) * (2 * kPipeSegments + 1), stream_));
+    k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_, infos, d_pipe_flag_,
+                                                                                         std::min(kPipeCells, pipe_count_words_ / kBinSlots));
   }
   int overlap = overlap_walk_;
   ShardDev sh = shard_dev();
-  const unsigned int* run_flag = flag;
-  void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &run_flag };
   // the sums of squares are accumulated only when the parity trace (which reports the individual log-likelihoods) is on
   // (weighted fits use the two-value bins for sum w r and sum w)
   const bool sq = trace_cap_ > 0 || sequential_rng_ || d_wt_ != nullptr;
@@ -1038,11 +1028,43 @@ void BartFit::launch_persistent_sweep(bool last_thin)
   else if (persistent_nq_ == 4) fn = S4B_PICK(4);
   else fn = S4B_PICK(6);
 #undef S4B_PICK
-  S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
+  if (!pipe) {
+    const int* pos_in = nullptr; int* pos_out = nullptr; int max_steps = T_;
+    void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &pos_in, &pos_out, &max_steps };
+    S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
+  } else {
+    const void* pfn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
+                    : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
+    unsigned long long* ring = d_pipe_ring_; int words = pipe_count_words_;
+    static const int pipe_dbg = getenv("S4B_PIPE_DBG") ? atoi(getenv("S4B_PIPE_DBG")) : 0;      // timing experiments only (wrong results)
+    int dbg = pipe_dbg;
+    const StepDesc* pdescs = d_descs_; const PipeInfo* pinfos = infos; const double2* pdraws = d_draws_; unsigned long long* ran = d_pipe_ran_;
+    static const bool pipe_prof = getenv("S4B_PIPE_PROF") != nullptr;
+    unsigned long long* pprof = pipe_prof ? d_prof_ : nullptr;
+    for (int k = 0; k < kPipeSegments; ++k) {
+      const int* pin = d_pipe_pos_ + 2 * k; int* pmid = d_pipe_pos_ + 2 * k + 1; int* pout = d_pipe_pos_ + 2 * k + 2;
+      S4B_CUDA(cudaMemsetAsync(d_pipe_ring_, 0, sizeof(unsigned long long) * kPipeRing * kPipeAcc, stream_));
+      void* pargs[] = { &dv, &ring, &pdescs, &pinfos, &pdraws, &pin, &pmid, &words, &ran, &pprof, &dbg };
+      S4B_CUDA(cudaLaunchCooperativeKernel(pfn, dim3(persistent_grid_), dim3(kSweepBlock), pargs, pipe_smem_, stream_));
+      if (k > 0) S4B_CUDA(cudaMemsetAsync(d_barrier_, 0, sizeof(unsigned int), stream_));
+      const int* sin = pmid; int max_steps = k + 1 < kPipeSegments ? 1 : T_;
+      void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &sin, &pout, &max_steps };
+      S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
+    }
+    ++pipe_sweeps_;
+  }
   k_finish_sweep<<<grid_ew_, kBlock, 0, stream_>>>(dv, last_thin ? d_train_out_ : nullptr, d_latent_out_, add_offset_ ? 1 : 0,
                                                    (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
   S4B_CUDA(cudaGetLastError());
+}
+
+void BartFit::pipe_reasons(unsigned int* out4)
+{
+  for (int i = 0; i < 4; ++i) out4[i] = 0;
+  if (d_pipe_flag_ == nullptr) return;
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  S4B_CUDA(cudaMemcpy(out4, d_pipe_flag_, sizeof(unsigned int) * 4, cudaMemcpyDeviceToHost));
 }
 
 long long BartFit::pipe_sweeps_done()

@@ -152,14 +152,17 @@ class BartFit {
   size_t persistent_smem_ = 0;
   // pipelined sweep kernel (sweep_pipe.cuh): ring of partial rows, barrier counters, per-step cell tables, per-sweep flag
   bool pipe_enabled_ = false;
-  int pipe_count_words_ = 0, pipe_ring_stride_ = 0;
+  int pipe_count_words_ = 0;
   size_t pipe_smem_ = 0;
-  double* d_pipe_ring_ = nullptr; unsigned int* d_pipe_counters_ = nullptr; unsigned int* d_pipe_flag_ = nullptr; void* d_pipe_infos_ = nullptr;
+  unsigned long long* d_pipe_ring_ = nullptr; unsigned int* d_pipe_counters_ = nullptr; unsigned int* d_pipe_flag_ = nullptr; void* d_pipe_infos_ = nullptr;
   long long pipe_sweeps_ = 0;
   unsigned long long* d_pipe_ran_ = nullptr;
+  int* d_pipe_pos_ = nullptr;          // first step still to do, one entry per launch of a sweep's segment sequence
  public:
-  // sweeps that really ran in the pipelined kernel (counted on the device)
+  // tree steps that ran in the pipelined kernel (counted on the device)
   long long pipe_sweeps_done();
+  // steps that did not fit the pipelined kernel so far: [0] all, [1] tree too large, [2] more than 8 statistic slots, [3] too many cells
+  void pipe_reasons(unsigned int* out4);
   // sweeps launched through the pipelined kernel path so far (whether a given sweep ran pipelined is decided on the device)
   long long pipe_sweeps() const { return pipe_sweeps_; }
   bool pipe_enabled() const { return pipe_enabled_; }

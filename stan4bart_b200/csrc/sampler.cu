@@ -457,15 +457,16 @@ int s4b_sampler_set_host_plumbing(s4b_sampler* s, int on, int64_t* h2d, int64_t*
 int gpubart_get_profile(gpubart_fit* f, uint64_t* out24, int reset) { S4B_API_BEGIN S4B_REQUIRE(f && out24); f->fit->get_profile((unsigned long long*) out24, reset != 0); S4B_API_END }
 int gpubart_set_keep_trees(gpubart_fit* f, int64_t capacity) { S4B_API_BEGIN S4B_REQUIRE(f && capacity >= 0); f->fit->set_keep_trees(capacity); S4B_API_END }
 int gpubart_set_pipeline(gpubart_fit* f, int on) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_pipe_enabled(on != 0); S4B_API_END }
-int gpubart_get_pipeline(gpubart_fit* f, int* enabled, int64_t* sweeps_launched, int64_t* sweeps_pipelined)
+int gpubart_get_pipeline(gpubart_fit* f, int* enabled, int64_t* sweeps_launched, int64_t* steps_pipelined)
 {
   S4B_API_BEGIN
   S4B_REQUIRE(f);
   if (enabled) *enabled = f->fit->pipe_enabled() ? 1 : 0;
   if (sweeps_launched) *sweeps_launched = f->fit->pipe_sweeps();
-  if (sweeps_pipelined) *sweeps_pipelined = f->fit->pipe_sweeps_done();
+  if (steps_pipelined) *steps_pipelined = f->fit->pipe_sweeps_done();
   S4B_API_END
 }
+int gpubart_pipeline_misfits(gpubart_fit* f, uint32_t* out4) { S4B_API_BEGIN S4B_REQUIRE(f && out4); f->fit->pipe_reasons(out4); S4B_API_END }
 int gpubart_set_keep_trees_active(gpubart_fit* f, int on) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->set_keep_trees_active(on != 0); S4B_API_END }
 int gpubart_set_response(gpubart_fit* f, const double* y) { S4B_API_BEGIN S4B_REQUIRE(f && y); f->fit->set_response_host(y); S4B_API_END }
 int gpubart_get_stored_scales(gpubart_fit* f, int64_t first, int64_t count, double* out2)

@@ -1063,17 +1063,25 @@ constexpr int kPrepWarps = 4;
 struct PrepSmemWarp { DTree tree; CtlScratch cs; StepDesc sd; };
 
 // ---- pipelined sweep (sweep_pipe.cuh): data-independent description of a step's cells ----
+constexpr int kPipeSegments = 4;          // (pipelined run, synchronous step) rounds per sweep; the last synchronous launch takes the rest
 constexpr int kPipeCells = 16;            // capacity of the per-step cell tables
 constexpr int kPipeRing = 4;
 constexpr int kPipeDescs = 3;
 
-// data-independent description of step t's cells (k_prepare_sweep): which node a cell's rows sit in now (cell_a) and in the
-// accepted tree (cell_f; the rejected tree keeps cell_a)
+// data-independent description of step t for the pipelined kernel (k_prepare_sweep): everything keyed by STATISTIC SLOT, so
+// that the workers go from a row's rule pattern straight to its slot (one table look-up) and from the slot to the current leaf
+// value; and the step's cells: which node a cell's rows sit in now (cell_a) and in the accepted tree (cell_f; the rejected
+// tree keeps cell_a)
 struct PipeInfo {
   int32_t ncells;
   int32_t ok;                              // this step fits the pipelined kernel
-  uint8_t cellbase[32];                    // change / swap: first cell of bottom node a (outside the branch: its only cell)
+  int32_t slot_b;                          // birth: slot of the node to split (its rows take slot L + side); 255 otherwise
+  int32_t pad;
+  double vs[kBinSlots + 2];                // leaf value of the current tree by slot (a birth's two new slots repeat the parent's)
+  uint8_t cellbase[16];                    // change / swap: first cell of slot s (a slot outside the branch: its only cell)
   uint8_t cell_a[kPipeCells], cell_f[kPipeCells];
+  uint8_t stab[1 << S4B_BITMAP_INT];       // rule pattern -> slot under the current rules
+  uint8_t ptab[1 << S4B_BITMAP_INT];       // change / swap: pattern under the proposed rules -> proposed slot (255 outside the branch)
 };
 
 // one warp per tree, after w_propose: fills infos[t]; returns whether the step fits
@@ -1081,14 +1089,17 @@ __device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& 
 {
   const int nn = t.num_nodes, kind = d.b_kind, node = d.b_node, L = d.b_num_leaves, nslots = d.b_nslots;
   const bool bd = kind == 0 || kind == 1;
-  bool ok = nn + 2 <= 32 && nslots + (bd ? 1 : 0) <= 32 && nslots <= kBinSlots;
+  const int n_int = d.b_cur.n_int;
+  bool ok = nn + 2 <= 32 && nslots + (bd ? 1 : 0) <= 32 && nslots <= kBinSlots && n_int <= S4B_BITMAP_INT;
   int ncells = nslots;
-  if (lane < kPipeCells) { pi.cell_a[lane] = 0; pi.cell_f[lane] = 0; }
-  pi.cellbase[lane] = 0;
+  if (lane < kPipeCells) { pi.cell_a[lane] = 0; pi.cell_f[lane] = 0; pi.cellbase[lane] = 0; }
+  if (lane < kBinSlots + 2) pi.vs[lane] = 0.0;
   __syncwarp();
   if (ok) {
     const bool leaf = lane < nn && t.nodes[lane].var < 0;
     const int slot = lane < nn ? (int) d.b_cur.slot[lane] : 255;
+    if (leaf) pi.vs[slot] = d.b_cur.val[lane];
+    if (kind == 0 && lane < 2) pi.vs[L + lane] = d.b_cur.val[node];
     if (kind == 2 || kind == 3) {
       const bool inside = leaf && d.b_prop.slot[lane] != 255;
       const unsigned m_in = __ballot_sync(0xffffffffu, inside), m_out = __ballot_sync(0xffffffffu, leaf && !inside);
@@ -1097,10 +1108,10 @@ __device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& 
       ok = ncells <= max_cells && ncells <= kPipeCells;
       if (ok) {
         const unsigned below = (1u << lane) - 1u;
-        if (leaf && !inside) { const int c = __popc(m_out & below); pi.cellbase[lane] = (uint8_t) c; pi.cell_a[c] = (uint8_t) lane; pi.cell_f[c] = (uint8_t) lane; }
+        if (leaf && !inside) { const int c = __popc(m_out & below); pi.cellbase[slot] = (uint8_t) c; pi.cell_a[c] = (uint8_t) lane; pi.cell_f[c] = (uint8_t) lane; }
         if (inside) {
           const int r = __popc(m_in & below);
-          pi.cellbase[lane] = (uint8_t) (n_out + r * k_in);
+          pi.cellbase[slot] = (uint8_t) (n_out + r * k_in);
           // pair (this node now, j-th node of the branch after an accepted change / swap): prop slot L + j belongs to the j-th inside node
           for (int j = 0; j < k_in; ++j) { const int f = nth_set_bit(m_in, j); pi.cell_a[n_out + r * k_in + j] = (uint8_t) lane; pi.cell_f[n_out + r * k_in + j] = (uint8_t) f; }
         }
@@ -1115,8 +1126,16 @@ __device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& 
       }
       if (ok && kind == 0 && lane < 2) { pi.cell_a[L + lane] = (uint8_t) node; pi.cell_f[L + lane] = (uint8_t) (node + 1 + lane); }
     }
+    if (ok) {
+      const bool two = kind == 2 || kind == 3;
+      for (int e = lane; e < (1 << n_int); e += 32) {
+        const int nd = d.b_cur.table[e];
+        pi.stab[e] = d.b_cur.slot[nd];
+        pi.ptab[e] = two ? d.b_prop.slot[nd] : (uint8_t) 255;
+      }
+    }
   }
-  if (lane == 0) { pi.ncells = ncells; pi.ok = ok ? 1 : 0; }
+  if (lane == 0) { pi.ncells = ncells; pi.ok = ok ? 1 : 0; pi.slot_b = (ok && kind == 0) ? (int) d.b_cur.slot[node] : 255; pi.pad = 0; }
   __syncwarp();
   return ok;
 }
@@ -1154,7 +1173,13 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
   // does this step fit the pipelined kernel?  one step that does not sends the whole sweep to the synchronous kernel
   if (infos != nullptr) {
     const bool ok = w_pipe_info(W.tree, W.sd, infos[t], pipe_max_cells, lane);
-    if (!ok && lane == 0) atomicOr(pipe_not_ok, 1u);
+    if (!ok && lane == 0) {                                    // (diagnostics: steps that took the synchronous kernel, by reason)
+      atomicAdd(pipe_not_ok, 1u);
+      const bool bd = W.sd.b_kind == 0 || W.sd.b_kind == 1;
+      if (W.tree.num_nodes + 2 > 32 || W.sd.b_nslots + (bd ? 1 : 0) > 32) atomicAdd(pipe_not_ok + 1, 1u);
+      else if (W.sd.b_nslots > kBinSlots) atomicAdd(pipe_not_ok + 2, 1u);
+      else atomicAdd(pipe_not_ok + 3, 1u);
+    }
   }
   // decision draws of this step: (uniform, normal) pairs for draw indices 0..31
   {
@@ -1317,10 +1342,13 @@ __device__ __forceinline__ void stream_update(const UpdateDesc& upd, double* Rg,
 template <int NQ, bool SEQ, bool STREAM = false, bool SQ = true>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
                                                                const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
-                                                               const __grid_constant__ ShardDev sh_param, const unsigned int* __restrict__ run_flag)
+                                                               const __grid_constant__ ShardDev sh_param, const int* __restrict__ pos_in,
+                                                               int* __restrict__ pos_out, int max_steps)
 {
-  // the pipelined kernel (sweep_pipe.cuh) was launched before this one and has done the sweep unless the flag says otherwise
-  if (run_flag != nullptr && *run_flag == 0u) return;
+  // A sweep can be split into segments of consecutive tree steps handled by alternating launches of the pipelined kernel
+  // (sweep_pipe.cuh: runs of steps that fit it) and of this one (the steps that do not): *pos_in = first step still to do,
+  // max_steps = how many this launch may take.  pos_in == nullptr: the whole sweep.
+  if (pos_in != nullptr && *pos_in >= dv.params->num_trees) { if (blockIdx.x == 0 && threadIdx.x == 0) *pos_out = *pos_in; return; }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SweepSmem& S = *reinterpret_cast<SweepSmem*>(smem_raw);
   // lane-private statistic bins: [slot][thread] -> (sum, sum^2) and count; no atomics, no bank conflicts
@@ -1365,6 +1393,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
   for (int i = tid; i < 3 * S4B_MAX_SLOTS; i += kSweepBlock) reinterpret_cast<double*>(S.st)[i] = 0.0;
   __syncthreads();
   const int p = S.prm.p, T = S.prm.num_trees;
+  const int t_begin = pos_in != nullptr ? *pos_in : 0;
+  const int t_end = pos_in != nullptr ? min(T, t_begin + max_steps) : T;
   const unsigned long long step0 = S.prm.step_id;
   // replay / record need strict program order: proposals and draws are then produced inside the loop
   constexpr bool sequential_rng = SEQ;
@@ -1379,32 +1409,32 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       }
   }
   {
-    const DTree& g = dv.trees[0];
+    const DTree& g = dv.trees[t_begin];
     int nn = g.num_nodes;
-    if (tid == 0) { S.tree[0].num_nodes = nn; S.tree[0].pad = 0; }
-    for (int i = tid; i < nn * (int) (sizeof(DNode) / 4); i += kSweepBlock) reinterpret_cast<uint32_t*>(S.tree[0].nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+    if (tid == 0) { S.tree[t_begin & 1].num_nodes = nn; S.tree[t_begin & 1].pad = 0; }
+    for (int i = tid; i < nn * (int) (sizeof(DNode) / 4); i += kSweepBlock) reinterpret_cast<uint32_t*>(S.tree[t_begin & 1].nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
   }
   __syncthreads();
   WarpRng rngp; rngp.g = &S.rng; rngp.cs = &S.csp; rngp.lane = lane; rngp.writer = cta == 0;     // proposal draws
   WarpRng rngd; rngd.g = &S.rng; rngd.cs = &S.csd; rngd.lane = lane; rngd.writer = cta == 0;     // decision draws
   if (!is_worker) {
     if (sequential_rng) {
-      rngp.enter(step0, 0u); rngp.fill();
-      w_propose(S.tree[0], S.prm, S.tab, rngp, S.sd[0], S.csp, 0, lane);
+      rngp.enter(step0 + (unsigned long long) t_begin, 0u); rngp.fill();
+      w_propose(S.tree[t_begin & 1], S.prm, S.tab, rngp, S.sd[t_begin & 1], S.csp, t_begin, lane);
       rngp.commit();
-    } else w_copy_desc(S.sd[0], descs[0], lane);
+    } else w_copy_desc(S.sd[t_begin & 1], descs[t_begin], lane);
   }
   __syncthreads();
   uint32_t leaf_pack[NQ], aux_pack[NQ];
   if (is_worker) {
-    if (STREAM) stream_walk(S.sd[0], xt32, col_words, q_lo, q_hi, tid, dv.packs);
-    else walk_step<NQ>(S.sd[0], tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
+    if (STREAM) stream_walk(S.sd[t_begin & 1], xt32, col_words, q_lo, q_hi, tid, dv.packs + (size_t) (t_begin & 1) * (size_t) nquad);
+    else walk_step<NQ>(S.sd[t_begin & 1], tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
   }
 
   // phase counters live in shared memory (thread 0, profiling runs only): as registers they would be carried through the
   // whole loop by every thread.  S.wk[0..3]: worker sub-phases (zero bins, accumulate, wait + row reduce, second barrier)
   const bool prof_on = dv.prof != nullptr;
-  for (int t = 0; t < T; ++t) {
+  for (int t = t_begin; t < t_end; ++t) {
     const long long c0 = clock64();
     StepDesc& sd = S.sd[t & 1];
     StepDesc& sd_next = S.sd[(t + 1) & 1];
@@ -1433,7 +1463,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         // branch-free: every observation adds into exactly one bin row (row kBinSlots is a trash row for padding and for
         // slots outside this pass); loads first (independent), then the read-modify-write chain
         if (STREAM) {
-          stream_accumulate<SQ>(sd, (t > 0 && chunk == 0) ? &S.upd[(t - 1) & 1] : nullptr, dv.R, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad,
+          stream_accumulate<SQ>(sd, (t > t_begin && chunk == 0) ? &S.upd[(t - 1) & 1] : nullptr, dv.R, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad,
                             dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, n, tid, base, kmax, bin_s, cpk, dv.wt);
         } else if (!two_trees) {
 #pragma unroll
@@ -1519,7 +1549,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         if (prof_on) S.pc[0] += clock64() - c0;
         // release-arrive: orders this CTA's partial rows (made visible to thread 0 by the named barrier) before the count
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(barrier_counter) : "memory");
-        const unsigned int target = (unsigned int) (t + 1) * (unsigned int) G;
+        const unsigned int target = (unsigned int) (t - t_begin + 1) * (unsigned int) G;
         unsigned int v;
         const long long w0 = clock64();
         do {
@@ -1531,7 +1561,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       // ---- controller warp: plan this step's decision, fetch tree t+1, pre-compute this step's decision draws, propose for t+1 ----
       { const FastPlan pl = w_plan(tree, sd, S.upd[t & 1], S.csd, lane); plan_store(S.plan, pl, lane); }
       const long long h0 = clock64();
-      if (t + 1 < T) {
+      if (t + 1 < t_end) {
         const DTree& g = dv.trees[t + 1];
         int nn = g.num_nodes;
         if (lane == 0) { tree_next.num_nodes = nn; tree_next.pad = 0; }
@@ -1546,7 +1576,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         S.csd.ubuf[lane] = dz.x; S.csd.zbuf[lane] = dz.y;
         rngd.adopt();
         const long long h2 = clock64();
-        if (t + 1 < T) w_copy_desc(sd_next, descs[t + 1], lane);
+        if (t + 1 < t_end) w_copy_desc(sd_next, descs[t + 1], lane);
         if (lane == 0 && S.csd.prof_on) { S.csd.dbg[4] += h1 - h0; S.csd.dbg[5] += h2 - h1; S.csd.dbg[7] += clock64() - h2; }
       }
     }
@@ -1620,12 +1650,12 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       if (S.plan.valid) { const FastPlan plan = plan_load(S.plan, lane); w_decide_fast<SQ>(plan, tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq, thr); }
       else w_decide<SQ>(tree, S.prm, rngd, sd, S.st, S.upd[t & 1], S.csd, trec, lane, S.inv_sigsq, thr);
       rngd.commit();
-      if (sequential_rng && t + 1 < T) {
+      if (sequential_rng && t + 1 < t_end) {
         rngp.enter(step0 + (unsigned long long) (t + 1), 0u); rngp.fill();
         w_propose(tree_next, S.prm, S.tab, rngp, sd_next, S.csp, t + 1, lane);
         rngp.commit();
       }
-    } else if (!sequential_rng && overlap_walk && t + 1 < T) {
+    } else if (!sequential_rng && overlap_walk && t + 1 < t_end) {
       // ---- workers, concurrently: walk tree t+1 (independent of this step's decision) ----
       if (STREAM) stream_walk(sd_next, xt32, col_words, q_lo, q_hi, tid, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad);
       else walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_next, aux_next);
@@ -1638,7 +1668,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       const int amode = upd.mode, unode = upd.node;
       if (STREAM) {
         // applied together with the next step's accumulation (one read and one write of R per step); the last step has no successor
-        if (t + 1 == T) stream_update(upd, dv.R, dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, tid);
+        if (t + 1 == t_end) stream_update(upd, dv.R, dv.packs + (size_t) (t & 1) * (size_t) nquad, q_lo, q_hi, tid);
       } else if (amode == 0) {
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
@@ -1660,8 +1690,8 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
         }
       }
       if (STREAM) {
-        if (t + 1 < T && (sequential_rng || !overlap_walk)) stream_walk(sd_next, xt32, col_words, q_lo, q_hi, tid, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad);
-      } else if (t + 1 < T) {
+        if (t + 1 < t_end && (sequential_rng || !overlap_walk)) stream_walk(sd_next, xt32, col_words, q_lo, q_hi, tid, dv.packs + (size_t) ((t + 1) & 1) * (size_t) nquad);
+      } else if (t + 1 < t_end) {
         if (sequential_rng || !overlap_walk) walk_step<NQ>(sd_next, tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
         else {
 #pragma unroll
@@ -1693,14 +1723,15 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
     *dv.rng = out;
     if (out.tape_underrun) dv.params->error_flag |= 2u;
     if (S.peer_dead) dv.params->error_flag |= (S.peer_dead == 2 ? 8u : 4u);
-    dv.params->step_id = step0 + (unsigned long long) T;
+    if (t_end == T) dv.params->step_id = step0 + (unsigned long long) T;
+    if (pos_out != nullptr) *pos_out = t_end;
     if (world > 1) S.sh.mail[S.sh.rank]->kseq = S.seq_base + (unsigned long long) T;
     dv.desc->a_valid = 0;
     if (dv.prof != nullptr) {
       // [0] accumulate + CTA reduction (CTA 0), [1] ... + grid barrier + controller wait, [2] statistics reduce,
       // [3] decision (overlapped with the next walk), [4] cross-rank exchange (sharded chains), [5] update, [7] steps
       for (int i = 0; i < 6; ++i) dv.prof[i] += (unsigned long long) S.pc[i];
-      dv.prof[7] += (unsigned long long) T;
+      dv.prof[7] += (unsigned long long) (t_end - t_begin);
       // [8..11] decision: slot summaries + accept, structure, leaf draws, update descriptor; [12..15] controller before the
       // barrier: tree fetch, decision-draw prefill, proposal-draw prefill, proposal
       for (int i = 0; i < 8; ++i) dv.prof[8 + i] += (unsigned long long) S.csd.dbg[i];

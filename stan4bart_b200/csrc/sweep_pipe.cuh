@@ -18,7 +18,16 @@
 // own previous output).  Every CTA's controller does the same arithmetic in the same order on the same global partial rows,
 // so all CTAs hold bitwise identical statistics and take identical decisions, as before.
 //
-// Rings: partial rows and barrier counters are 4 deep (a CTA can run at most two steps ahead of another CTA's controller
+// Cross-CTA reduction: per step every CTA adds its partial results into ONE small accumulator row with integer atomics
+// (red.global.add.u64) before it arrives at the barrier: the cross-table counts as packed integers, the per-slot sums as exact
+// two-limb fixed point (value = hi 2^-20 + lo 2^-72: every double of magnitude < 2^43 is represented exactly, integer addition
+// is associative), so the totals do not depend on the order in which the CTAs arrive -- bitwise reproducible run to run, and
+// identical in every CTA because all read the same words.  Every accumulator word also counts its contributions in its top
+// byte (each CTA adds 1 << 56 together with its data), so a word tells by itself when it is complete: there is no separate
+// barrier counter, no release fence on the workers' side and no flag-then-data double round trip on the controller's --
+// it polls the very words it needs, one L2 round trip per step instead of reading 148 partial rows.
+//
+// Rings: accumulator rows and barrier counters are 4 deep (a CTA can run at most two steps ahead of another CTA's controller
 // reading rows); descriptors 3 deep; update tables 2 deep.  Decisions, draws and tree updates are the synchronous kernel's
 // (w_plan / w_decide_fast), so both kernels produce the same chain up to the rounding of the slot sums.
 #pragma once
@@ -27,13 +36,16 @@
 
 namespace s4b {
 
+constexpr int kPipeAcc = 2 * kBinSlots + (kBinSlots * kPipeCells) / 2;     // per step: (hi, lo) per slot sum, then one word per pair of cross-table entries
 struct PipeSmem {
   StepDesc sd[kPipeDescs];
   PipeInfo info[kPipeDescs];
   DTree tree[2];
   UpdateDesc upd[2];
+  unsigned long long accprev[kPipeRing][kPipeAcc];   // accumulator rows as last read (a row is reused every kPipeRing steps and never zeroed)
   double dcell[2][kPipeCells];              // delta of step parity: mu_old - mu_new per cell
-  int ncnt[kBinSlots * kPipeCells];         // the reduced cross table of the step being decided
+  int ncnt[4 * kBinSlots];                  // staging of the (hi, lo) limbs of the slot sums
+  int cross[kBinSlots * kPipeCells + 2];    // the cross table of the step being decided
   CtlScratch csd;
   LeafStat st[S4B_MAX_SLOTS];
   FastPlanSmem plan;
@@ -45,28 +57,101 @@ struct PipeSmem {
 
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// Asynchronous fetch of a step descriptor (the part the sweep reads: from b_tree on) and its cell table into the shared-memory
+// ring: one warp issues cp.async copies and goes on with its work -- no register staging, no stall on the L2 round trip.  The
+// descriptors in global memory were laid out by w_copy_desc in k_prepare_sweep, so a plain copy gives the same contents.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+{
+  const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ inline void w_fetch_desc_async(StepDesc& dst, const StepDesc& src, PipeInfo& idst, const PipeInfo& isrc, int lane)
+{
+  constexpr size_t kFrom = offsetof(StepDesc, b_tree);
+  static_assert(kFrom % 8 == 0 && sizeof(StepDesc) % 8 == 0 && sizeof(PipeInfo) % 8 == 0, "8-byte copies");
+  const char* s = reinterpret_cast<const char*>(&src) + kFrom;
+  char* d = reinterpret_cast<char*>(&dst) + kFrom;
+  for (int i = lane; i < (int) ((sizeof(StepDesc) - kFrom) / 8); i += 32) cp_async8(d + 8 * i, s + 8 * i);
+  for (int i = lane; i < (int) (sizeof(PipeInfo) / 8); i += 32) cp_async8(reinterpret_cast<char*>(&idst) + 8 * i, reinterpret_cast<const char*>(&isrc) + 8 * i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ inline void w_copy_info(PipeInfo& dst, const PipeInfo& src, int lane)
 {
-  if (lane == 0) { dst.ncells = src.ncells; dst.ok = src.ok; }
-  dst.cellbase[lane] = src.cellbase[lane];
-  if (lane < kPipeCells) { dst.cell_a[lane] = src.cell_a[lane]; dst.cell_f[lane] = src.cell_f[lane]; }
+  for (int i = lane; i < (int) (sizeof(PipeInfo) / 8); i += 32) reinterpret_cast<unsigned long long*>(&dst)[i] = reinterpret_cast<const unsigned long long*>(&src)[i];
   __syncwarp();
 }
 
-// partial rows of one step in the ring: [0, kBinSlots) per-slot sums (double), then `count_words` rows of packed counts
-// (4 x 16 bit per CTA: a CTA holds at most 480 x 24 rows); row r of CTA c at ring + r * G + c
+// rule patterns of the owned quads -> statistic slots (one table look-up per row); a change / swap step also under the proposed
+// rules; a birth step moves the rows of the node to split to the two new slots L + side
 template <int NQ>
-__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsigned int* counters, double* ring, int ring_stride,
-                                                                const StepDesc* __restrict__ descs, const PipeInfo* __restrict__ infos,
-                                                                const double2* __restrict__ draws, const unsigned int* __restrict__ not_ok, int count_words,
-                                                                unsigned long long* __restrict__ ran)
+__device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi, const uint32_t* __restrict__ tile, int tile_stride, int tid,
+                                          uint32_t (&sp)[NQ], uint32_t (&pp)[NQ])
 {
-  if (*not_ok != 0u) return;               // some tree of this sweep does not fit: the synchronous kernel (launched next) runs instead
+  const int kind = sd.b_kind, n_int = sd.b_cur.n_int;
+  uint32_t pat[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) pat[j] = 0u;
+#pragma unroll 1
+  for (int i = 0; i < n_int; ++i) {
+    const uint32_t rec = sd.b_cur.irec[i];
+    const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
+    const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+  }
+#pragma unroll
+  for (int j = 0; j < NQ; ++j)
+    sp[j] = (uint32_t) pi.stab[pat[j] & 0xFFu] | ((uint32_t) pi.stab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.stab[(pat[j] >> 16) & 0xFFu] << 16) |
+            ((uint32_t) pi.stab[pat[j] >> 24] << 24);
+  if (kind == 2 || kind == 3) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) pat[j] = 0u;
+#pragma unroll 1
+    for (int i = 0; i < n_int; ++i) {
+      const uint32_t rec = sd.b_prop.irec[i];
+      const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
+      const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+    }
+#pragma unroll
+    for (int j = 0; j < NQ; ++j)
+      pp[j] = (uint32_t) pi.ptab[pat[j] & 0xFFu] | ((uint32_t) pi.ptab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.ptab[(pat[j] >> 16) & 0xFFu] << 16) |
+              ((uint32_t) pi.ptab[pat[j] >> 24] << 24);
+  } else if (kind == 0) {
+    const uint32_t* col = tile + sd.b_var * tile_stride + tid;
+    const uint32_t cut4 = (uint32_t) sd.b_cut * 0x01010101u;
+    const uint32_t sb4 = (uint32_t) pi.slot_b * 0x01010101u, l4 = (uint32_t) sd.b_num_leaves * 0x01010101u;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const uint32_t side = __vcmpgtu4(col[j * kWorkers], cut4) & 0x01010101u;
+      const uint32_t at_b = __vcmpeq4(sp[j], sb4);                 // 0xFF in the bytes of rows that sit in the node to split
+      sp[j] = (sp[j] & ~at_b) | ((l4 + side) & at_b);
+    }
+  }
+}
+
+// acc_ring: kPipeRing accumulator rows of kPipeAcc 64-bit words (zeroed by the host before every launch)
+template <int NQ>
+__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsigned long long* acc_ring,
+                                                                const StepDesc* __restrict__ descs, const PipeInfo* __restrict__ infos,
+                                                                const double2* __restrict__ draws, const int* __restrict__ pos_in, int* __restrict__ pos_out,
+                                                                int count_entries, unsigned long long* __restrict__ ran, unsigned long long* __restrict__ prof, int dbg)
+{
+  // this launch takes the run of consecutive steps that fit, starting at *pos_in; the synchronous kernel (launched next) takes
+  // the step that stopped it.  Every CTA scans the same flags, so all agree on the range without talking to each other.
+  const int T_all = dv.params->num_trees;
+  const int t_begin = *pos_in;
+  int t_end = t_begin;
+  while (t_end < T_all && infos[t_end].ok != 0) ++t_end;
+  if (t_end == t_begin) { if (blockIdx.x == 0 && threadIdx.x == 0) *pos_out = t_begin; return; }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PipeSmem& S = *reinterpret_cast<PipeSmem*>(smem_raw);
   double* bins = reinterpret_cast<double*>(smem_raw + ((sizeof(PipeSmem) + 15) / 16) * 16);                    // [kBinSlots + 1][kWorkers]
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(bins + (kBinSlots + 1) * kWorkers);                               // [count_words + 1][kWorkers]
-  uint32_t* tile = cnt + (size_t) (count_words + 1) * kWorkers;                                                   // [p][NQ * kWorkers]
+  uint8_t* cnt = reinterpret_cast<uint8_t*>(bins + (kBinSlots + 1) * kWorkers);                                  // [count_entries + 1][kWorkers] bytes
+  uint32_t* tile = reinterpret_cast<uint32_t*>(cnt + (size_t) (count_entries + 1) * kWorkers);                    // [p][NQ * kWorkers]
   constexpr int tile_stride = NQ * kWorkers;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -95,6 +180,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
   for (int i = tid; i < (int) (2 * sizeof(UpdateDesc) / sizeof(uint32_t)); i += kSweepBlock) reinterpret_cast<uint32_t*>(S.upd)[i] = 0u;
   for (int i = tid; i < 3 * S4B_MAX_SLOTS; i += kSweepBlock) reinterpret_cast<double*>(S.st)[i] = 0.0;
   if (tid < 2 * kPipeCells) (&S.dcell[0][0])[tid] = 0.0;
+  for (int i = tid; i < kPipeRing * kPipeAcc; i += kSweepBlock) (&S.accprev[0][0])[i] = 0ull;
   __syncthreads();
   const int p = S.prm.p, T = S.prm.num_trees;
   const unsigned long long step0 = S.prm.step_id;
@@ -108,123 +194,162 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
         tile[v * tile_stride + j * kWorkers + tid] = ((valid_mask >> j) & 1u) ? __ldg(xt32 + (long long) v * col_words + q) : 0u;
       }
   } else {
-    const DTree& g = dv.trees[0];
+    const DTree& g = dv.trees[t_begin];
     const int nn = g.num_nodes;
-    if (lane == 0) { S.tree[0].num_nodes = nn; S.tree[0].pad = 0; }
-    for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(S.tree[0].nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
-    w_copy_desc(S.sd[0], descs[0], lane);
-    w_copy_info(S.info[0], infos[0], lane);
+    if (lane == 0) { S.tree[t_begin & 1].num_nodes = nn; S.tree[t_begin & 1].pad = 0; }
+    for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(S.tree[t_begin & 1].nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+    w_copy_desc(S.sd[t_begin % kPipeDescs], descs[t_begin], lane);
+    w_copy_info(S.info[t_begin % kPipeDescs], infos[t_begin], lane);
   }
   __syncthreads();
 
   if (is_worker) {
     // =====================================================================================  workers
-    uint32_t leaf_pack[NQ], aux_pack[NQ], cprev[NQ], cprev2[NQ];
+    uint32_t sp[NQ], pp[NQ], cprev[NQ], cprev2[NQ];
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) { cprev[j] = 0u; cprev2[j] = 0u; }
-    for (int t = 0; t < T; ++t) {
+    for (int j = 0; j < NQ; ++j) { cprev[j] = 0u; cprev2[j] = 0u; pp[j] = 0u; }
+    // rows beyond the data (the tail of the last quad, quads beyond q_hi) are parked in the trash slot kBinSlots at every step
+    constexpr unsigned kAllObs = NQ == 8 ? 0xFFFFFFFFu : ((1u << (4 * NQ)) - 1u);
+    const bool ragged = obs_mask != kAllObs;
+    int C = 1;                                 // cells of the previous step (its descriptor's ring slot is recycled two steps later)
+    // cycle counters (thread 0 of CTA 0, only when asked for): [0] wait for decision t-2, [1] U, [2] W, [3] A, [4] CTA reduce + arrive
+    long long wp0 = 0, wp1 = 0, wp2 = 0, wp3 = 0, wp4 = 0;
+    const bool wprof = prof != nullptr && cta == 0 && tid == 0;
+    const int e_trash = count_entries;
+    uint32_t* cntw = reinterpret_cast<uint32_t*>(cnt);
+    for (int k = 0; k <= kBinSlots; ++k) bins[k * kWorkers + tid] = 0.0;
+    for (int i = tid; i < (count_entries + 1) * (kWorkers / 4); i += kWorkers) cntw[i] = 0u;
+    named_bar_sync(1, kWorkers);
+    for (int t = t_begin; t < t_end; ++t) {
       const StepDesc& sd = S.sd[t % kPipeDescs];
       const PipeInfo& pi = S.info[t % kPipeDescs];
-      if (t >= 2) {
+      const long long k0 = clock64();
+      long long k1 = k0;
+      if (t >= t_begin + 2) {
         // ---- U(t-2): wait for decision t-2, add its per-cell deltas ----
         named_bar_sync(2 + (t & 1), kSweepBlock);
+        k1 = clock64();
         const double* dc = S.dcell[t & 1];
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
 #pragma unroll
           for (int o = 0; o < 4; ++o) R[j][o] += dc[(cprev2[j] >> (8 * o)) & 0xFF];
       }
+      const long long k2 = clock64();
       // one warp fetches the next step's descriptor (its ring slot held step t-2, which has been decided)
-      if (warp == kWorkerWarps - 1 && t + 1 < T) { w_copy_desc(S.sd[(t + 1) % kPipeDescs], descs[t + 1], lane); w_copy_info(S.info[(t + 1) % kPipeDescs], infos[t + 1], lane); }
-      // ---- W(t) ----
-      walk_step<NQ>(sd, tile, tile_stride, tid, valid_mask, leaf_pack, aux_pack);
+      if (warp == kWorkerWarps - 1 && t + 1 < t_end)
+        w_fetch_desc_async(S.sd[(t + 1) % kPipeDescs], descs[t + 1], S.info[(t + 1) % kPipeDescs], infos[t + 1], lane);
+      // ---- W(t): slots of every owned row ----
+      pipe_walk<NQ>(sd, pi, tile, tile_stride, tid, sp, pp);
+      if (ragged) {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) if (!((obs_mask >> (4 * j + o)) & 1u)) { sp[j] = (sp[j] & ~(0xFFu << (8 * o))) | ((uint32_t) kBinSlots << (8 * o)); pp[j] |= 0xFFu << (8 * o); }
+      }
+      const long long k3 = clock64();
       const int kind = sd.b_kind, L = sd.b_num_leaves, nslots = sd.b_nslots;
       const bool two_trees = (kind == 2 || kind == 3);
-      const int birth_node = kind == 0 ? sd.b_node : -1;
-      const int C = t > 0 ? S.info[(t - 1) % kPipeDescs].ncells : 1;
-      const int nwords = (nslots * C + 3) >> 2;
-      for (int k = 0; k < nslots; ++k) bins[k * kWorkers + tid] = 0.0;
-      for (int k = 0; k < nwords; ++k) cnt[k * kWorkers + tid] = 0u;
+      const int E = nslots * C;
+      const int C_next = pi.ncells;
+      // the previous step's reduction tasks have read the bins and the count table
+      // (which have also put them back to zero: every bin row and counter row is zero between steps)
+      if (t > t_begin) named_bar_sync(1, kWorkers);
       // ---- A(t): per-slot sums of (residual after t-2) + mu_t, and the cross table (slot of t) x (cell of t-1) ----
       uint32_t ccur[NQ];
+      if (!two_trees) {
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) {
-        double pr[4]; int row[4], row2[4], ent[4], ent2[4];
-        uint32_t cc = 0u;
+        for (int j = 0; j < NQ; ++j) {
+          double pr[4]; int s[4], e[4];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const int leaf = (leaf_pack[j] >> (8 * o)) & 0xFF;
-          const int aux = (aux_pack[j] >> (8 * o)) & 0xFF;
-          const int cp = (cprev[j] >> (8 * o)) & 0xFF;
-          const bool ok = (obs_mask >> (4 * j + o)) & 1u;
-          pr[o] = R[j][o] + sd.b_cur.val[leaf];
-          int sa, sb = 255, cell;
-          if (two_trees) {
-            sa = sd.b_cur.slot[leaf]; sb = sd.b_prop.slot[aux];
-            cell = (int) pi.cellbase[leaf] + (sb != 255 ? sb - L : 0);
-          } else {
-            sa = leaf == birth_node ? L + aux : (int) sd.b_cur.slot[leaf];
-            cell = sa;
+          for (int o = 0; o < 4; ++o) {
+            s[o] = (sp[j] >> (8 * o)) & 0xFF;
+            const int cp = (cprev[j] >> (8 * o)) & 0xFF;
+            pr[o] = R[j][o] + pi.vs[s[o]];
+            e[o] = s[o] >= kBinSlots ? e_trash : s[o] * C + cp;
           }
-          cc |= (uint32_t) (ok ? cell : 0) << (8 * o);
-          row[o] = ok ? sa : kBinSlots;
-          ent[o] = ok ? sa * C + cp : 4 * count_words;
-          const bool second = two_trees && sb != 255 && ok;
-          row2[o] = second ? sb : kBinSlots;
-          ent2[o] = second ? sb * C + cp : 4 * count_words;
+#pragma unroll
+          for (int o = 0; o < 4; ++o) { bins[s[o] * kWorkers + tid] += pr[o]; cnt[e[o] * kWorkers + tid] += 1; }
+          ccur[j] = sp[j];                                         // cells of this step = its slots
         }
-        ccur[j] = cc;
+      } else {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          bins[row[o] * kWorkers + tid] += pr[o];
-          cnt[(ent[o] >> 2) * kWorkers + tid] += 1u << (8 * (ent[o] & 3));
-          if (two_trees) {
-            bins[row2[o] * kWorkers + tid] += pr[o];
-            cnt[(ent2[o] >> 2) * kWorkers + tid] += 1u << (8 * (ent2[o] & 3));
+        for (int j = 0; j < NQ; ++j) {
+          double pr[4]; int s[4], q[4], e[4], e2[4];
+          uint32_t cc = 0u;
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            s[o] = (sp[j] >> (8 * o)) & 0xFF;
+            const int pq = (pp[j] >> (8 * o)) & 0xFF;
+            const int cp = (cprev[j] >> (8 * o)) & 0xFF;
+            const bool in = pq != 255;
+            pr[o] = R[j][o] + pi.vs[s[o]];
+            q[o] = in ? pq : kBinSlots;
+            e[o] = s[o] >= kBinSlots ? e_trash : s[o] * C + cp;
+            e2[o] = in ? pq * C + cp : e_trash;
+            const int cell = s[o] >= kBinSlots ? kBinSlots : (int) pi.cellbase[s[o]] + (in ? pq - L : 0);
+            cc |= (uint32_t) cell << (8 * o);
           }
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            bins[s[o] * kWorkers + tid] += pr[o]; cnt[e[o] * kWorkers + tid] += 1;
+            bins[q[o] * kWorkers + tid] += pr[o]; cnt[e2[o] * kWorkers + tid] += 1;
+          }
+          ccur[j] = cc;
         }
       }
 #pragma unroll
       for (int j = 0; j < NQ; ++j) { cprev2[j] = cprev[j]; cprev[j] = ccur[j]; }
+      const long long k4 = clock64();
+      if (warp == kWorkerWarps - 1) cp_async_wait_all();          // the next step's descriptor has landed (issued a whole step ago)
       named_bar_sync(1, kWorkers);
-      // ---- CTA reduction: one partial row per slot / count word ----
-      double* rows = ring + (size_t) (t & (kPipeRing - 1)) * ring_stride;
-      for (int task = warp; task < nslots + nwords; task += kWorkerWarps) {
+      // ---- CTA reduction, then integer atomics into the step's accumulator row ----
+      unsigned long long* acc = acc_ring + (size_t) ((t - t_begin) & (kPipeRing - 1)) * kPipeAcc;
+      const int npairs = (E + 1) >> 1;
+      for (int task = warp; task < nslots + npairs; task += kWorkerWarps) {
         if (task < nslots) {
           double a = 0.0;
 #pragma unroll
-          for (int i = 0; i < kWorkerWarps; ++i) a += bins[task * kWorkers + i * 32 + lane];
+          for (int i = 0; i < kWorkerWarps; ++i) { a += bins[task * kWorkers + i * 32 + lane]; bins[task * kWorkers + i * 32 + lane] = 0.0; }
           a = w_sum(a);
-          if (lane == 0) rows[(size_t) task * G + cta] = a;
+          if (lane == 0) {
+            // two-limb fixed point: hi = floor(a 2^20) (biased by 2^47 to stay non-negative), lo = (a 2^20 - hi) 2^48; bits 56..63 count
+            // the contributions.  |a| < 2^27 per CTA; 148 CTAs x 2^48 stay below the count field.
+            const double xs = a * 1048576.0, fl = floor(xs);
+            const unsigned long long hi = (unsigned long long) ((long long) fl + (1ll << 47)), lo = (unsigned long long) ((xs - fl) * 281474976710656.0);
+            atomicAdd(acc + 2 * task, (1ull << 56) | hi);
+            atomicAdd(acc + 2 * task + 1, (1ull << 56) | lo);
+          }
         } else {
-          const int w = task - nslots;
-          int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+          // two cross-table entries per task: 480 byte counters each, four at a time with dp4a
+          const int e0 = 2 * (task - nslots), e1 = e0 + 1;
+          int c0 = 0, c1 = 0;
 #pragma unroll
-          for (int i = 0; i < kWorkerWarps; ++i) {
-            const uint32_t v = cnt[w * kWorkers + i * 32 + lane];
-            c0 += (int) (v & 0xFFu); c1 += (int) ((v >> 8) & 0xFFu); c2 += (int) ((v >> 16) & 0xFFu); c3 += (int) (v >> 24);
+          for (int i = 0; i < 4; ++i) {
+            const int w = i * 32 + lane;
+            if (w < kWorkers / 4) {
+              c0 = __dp4a(cntw[e0 * (kWorkers / 4) + w], 0x01010101u, (unsigned) c0); cntw[e0 * (kWorkers / 4) + w] = 0u;
+              if (e1 < E) { c1 = __dp4a(cntw[e1 * (kWorkers / 4) + w], 0x01010101u, (unsigned) c1); cntw[e1 * (kWorkers / 4) + w] = 0u; }
+            }
           }
           c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
-          c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
-          if (lane == 0) {
-            const unsigned long long packed = (unsigned long long) c0 | ((unsigned long long) c1 << 16) | ((unsigned long long) c2 << 32) | ((unsigned long long) c3 << 48);
-            reinterpret_cast<unsigned long long*>(rows)[(size_t) (kBinSlots + w) * G + cta] = packed;
-          }
+          if (lane == 0) atomicAdd(acc + 2 * kBinSlots + (task - nslots), (1ull << 56) | (unsigned long long) (unsigned) c0 | ((unsigned long long) (unsigned) c1 << 28));
         }
       }
-      // every row of this CTA is stored before thread 0 publishes them; nobody waits here
-      named_bar_sync(1, kWorkers);
-      if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + (t & (kPipeRing - 1))) : "memory");
+      // (the bins and the count table are rewritten by the next step only after the next named barrier)
+      C = C_next;
+      if (wprof) { const long long k5 = clock64(); wp0 += k1 - k0; wp1 += k2 - k1; wp2 += k3 - k2; wp3 += k4 - k3; wp4 += k5 - k4; }
     }
+    if (wprof) { prof[0] += (unsigned long long) wp0; prof[1] += (unsigned long long) wp1; prof[2] += (unsigned long long) wp2; prof[3] += (unsigned long long) wp3; prof[4] += (unsigned long long) wp4; prof[5] += (unsigned long long) (t_end - t_begin); }
     // ---- drain: the last two updates ----
-    for (int u = T - 2; u < T; ++u) {
-      if (u < 0) continue;
+    for (int u = t_end - 2; u < t_end; ++u) {
+      if (u < t_begin) continue;
       named_bar_sync(2 + (u & 1), kSweepBlock);
       const double* dc = S.dcell[u & 1];
 #pragma unroll
       for (int j = 0; j < NQ; ++j)
 #pragma unroll
-        for (int o = 0; o < 4; ++o) R[j][o] += dc[((u == T - 1 ? cprev[j] : cprev2[j]) >> (8 * o)) & 0xFF];
+        for (int o = 0; o < 4; ++o) R[j][o] += dc[((u == t_end - 1 ? cprev[j] : cprev2[j]) >> (8 * o)) & 0xFF];
     }
 #pragma unroll
     for (int j = 0; j < NQ; ++j) if ((valid_mask >> j) & 1u) {
@@ -235,13 +360,18 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
   } else {
     // =====================================================================================  controller warp
     WarpRng rngd; rngd.g = &S.rng; rngd.cs = &S.csd; rngd.lane = lane; rngd.writer = cta == 0;
-    for (int u = 0; u < T; ++u) {
+    int C = 1;                                 // cells of step u - 1 (kept here: the workers recycle that step's descriptor slot while this step is decided)
+    // cycle counters (lane 0 of CTA 0): [8] plan + tree fetch + draws, [9] wait for the rows, [10] row reduction + correction, [11] decision, [12] deltas + arrive
+    long long cp0 = 0, cp1 = 0, cp2 = 0, cp3 = 0, cp4 = 0;
+    const bool cprof = prof != nullptr && cta == 0 && lane == 0;
+    for (int u = t_begin; u < t_end; ++u) {
+      const long long h0 = clock64();
       StepDesc& sd = S.sd[u % kPipeDescs];
       const PipeInfo& pi = S.info[u % kPipeDescs];
       DTree& tree = S.tree[u & 1];
       // ---- before the barrier: plan the decision, fetch the next tree, adopt this step's pre-computed draws ----
       { const FastPlan pl = w_plan(tree, sd, S.upd[u & 1], S.csd, lane); plan_store(S.plan, pl, lane); }
-      if (u + 1 < T) {
+      if (u + 1 < t_end) {
         DTree& tn = S.tree[(u + 1) & 1];
         const DTree& g = dv.trees[u + 1];
         const int nn = g.num_nodes;
@@ -251,77 +381,69 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       rngd.enter(step0 + (unsigned long long) u, 1u);
       { const double2 dz = __ldcg(draws + u * 32 + lane); S.csd.ubuf[lane] = dz.x; S.csd.zbuf[lane] = dz.y; }
       rngd.adopt();
-      // ---- wait until every CTA has published its rows of step u ----
-      if (lane == 0) {
-        const unsigned int target = (unsigned int) (u / kPipeRing + 1) * (unsigned int) G;
-        const unsigned int* ctr = counters + (u & (kPipeRing - 1));
-        unsigned int v;
-        const long long w0 = clock64();
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-          if (v < target && (S.fail || clock64() - w0 > 4000000000LL)) { S.fail = 1; break; }
-        } while (v < target);
-      }
+      const long long h1 = clock64();
+      // (no separate barrier: the accumulator words themselves tell when every CTA has contributed, see below)
       __syncwarp();
+      const long long h2 = clock64();
       // ---- reduce the partial rows of all CTAs (fixed order), correct the sums with the previous step's deltas ----
       const int nslots = sd.b_nslots;
-      const int C = u > 0 ? S.info[(u - 1) % kPipeDescs].ncells : 1;
-      const int nwords = (nslots * C + 3) >> 2;
-      const double* rows = ring + (size_t) (u & (kPipeRing - 1)) * ring_stride;
-      for (int r0 = 0; r0 < nslots; r0 += 4) {
-        double acc[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double* src = rows + (size_t) (r0 + k) * G;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
-          if (r0 + k < nslots) {
-            { int b = lane;       if (b < G) a0 = __ldcg(src + b); }
-            { int b = lane + 32;  if (b < G) a1 = __ldcg(src + b); }
-            { int b = lane + 64;  if (b < G) a2 = __ldcg(src + b); }
-            { int b = lane + 96;  if (b < G) a3 = __ldcg(src + b); }
-            { int b = lane + 128; if (b < G) a4 = __ldcg(src + b); }
-            for (int b = lane + 160; b < G; b += 32) a4 += __ldcg(src + b);
-          }
-          acc[k] = (((a0 + a1) + a2) + a3) + a4;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const double a = w_sum(acc[k]); if (lane == 0 && r0 + k < nslots) S.st[r0 + k].sum = a; }
-      }
-      for (int w0 = 0; w0 < nwords; w0 += 4) {
-        int c[4][4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned long long* src = reinterpret_cast<const unsigned long long*>(rows) + (size_t) (kBinSlots + w0 + k) * G;
-          c[k][0] = c[k][1] = c[k][2] = c[k][3] = 0;
-          if (w0 + k < nwords)
-            for (int b = lane; b < G; b += 32) {
-              const unsigned long long v = __ldcg(src + b);
-              c[k][0] += (int) (v & 0xFFFFull); c[k][1] += (int) ((v >> 16) & 0xFFFFull); c[k][2] += (int) ((v >> 32) & 0xFFFFull); c[k][3] += (int) (v >> 48);
+      const int npairs = (nslots * C + 1) >> 1;
+      {
+        // One load per lane and 32 values: this step's totals = accumulator row now - the row as read kPipeRing steps ago; a word
+        // is complete when its top byte has advanced by the number of CTAs.  (Shared-memory data written by this CTA's workers
+        // before they issued their atomics -- the descriptor ring -- is read only after this loop has seen those atomics.)
+        const int slot_b = (u - t_begin) & (kPipeRing - 1);
+        const unsigned long long* acc = acc_ring + (size_t) slot_b * kPipeAcc;
+        const int nvals = 2 * kBinSlots + npairs;
+        const unsigned long long want = (unsigned long long) (G & 0xFF);
+        for (int i0 = 0; i0 < nvals; i0 += 32) {
+          const int i = i0 + lane;
+          const bool used = i < nvals && (i >= 2 * kBinSlots || i < 2 * nslots);
+          unsigned long long v = 0ull;
+          const unsigned long long prev = used ? S.accprev[slot_b][i] : 0ull;
+          const long long w0 = clock64();
+          bool done = !used;
+          for (;;) {
+            if (!done) {
+              unsigned long long now;
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(now) : "l"(acc + i) : "memory");
+              v = now - prev;
+              if ((v >> 56) == want) { done = true; S.accprev[slot_b][i] = now; }
             }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const int tot = __reduce_add_sync(0xffffffffu, c[k][f]);
-            if (lane == 0 && w0 + k < nwords) S.ncnt[4 * (w0 + k) + f] = tot;
+            if (__all_sync(0xffffffffu, done)) break;
+            if (S.fail || clock64() - w0 > 4000000000LL) { S.fail = 1; break; }
           }
+          v &= (1ull << 56) - 1ull;
+          if (i < 2 * kBinSlots) reinterpret_cast<unsigned long long*>(S.ncnt)[i] = v;       // staged: (hi, lo) pairs, combined below
+          else if (i < nvals) {
+            const int k = i - 2 * kBinSlots;
+            S.cross[2 * k] = (int) (v & 0xFFFFFFFull); S.cross[2 * k + 1] = (int) ((v >> 28) & 0xFFFFFFFull);
+          }
+        }
+        __syncwarp();
+        if (lane < nslots) {
+          const long long hi = (long long) reinterpret_cast<unsigned long long*>(S.ncnt)[2 * lane] - (long long) G * (1ll << 47);
+          const long long lo = (long long) reinterpret_cast<unsigned long long*>(S.ncnt)[2 * lane + 1];
+          S.st[lane].sum = (double) hi * 9.5367431640625e-07 + (double) lo * 3.3881317890172014e-21;       // 2^-20, 2^-68
+        }
       }
       __syncwarp();
       if (lane < nslots) {
         const double* dprev = S.dcell[(u + 1) & 1];          // deltas of step u-1 (zeros before the first step)
         int cnt_s = 0; double corr = 0.0;
-        for (int cidx = 0; cidx < C; ++cidx) { const int m = S.ncnt[lane * C + cidx]; cnt_s += m; if (m != 0) corr += (double) m * dprev[cidx]; }   // (an empty cell's delta is undefined)
+        for (int cidx = 0; cidx < C; ++cidx) { const int m = S.cross[lane * C + cidx]; cnt_s += m; if (m != 0) corr += (double) m * dprev[cidx]; }   // (an empty cell's delta is undefined)
         S.st[lane].n = (double) cnt_s;
         S.st[lane].sum += corr;
       }
       __syncwarp();
+      const long long h3 = clock64();
       // ---- Metropolis decision + leaf draws (same code as the synchronous kernel) ----
       {
         const FastPlan plan = plan_load(S.plan, lane);
         w_decide_fast<false>(plan, tree, S.prm, rngd, sd, S.st, S.upd[u & 1], S.csd, nullptr, lane, S.inv_sigsq, sd.accept_thr);
       }
       rngd.commit();
+      const long long h4 = clock64();
       // ---- per-cell deltas of this step: what the workers add to the residuals, and the next step's correction ----
       {
         const UpdateDesc& upd = S.upd[u & 1];
@@ -333,7 +455,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
         }
       }
       __syncwarp();
+      C = pi.ncells;
       named_bar_arrive(2 + (u & 1), kSweepBlock);            // decision u is done: the workers may apply it
+      if (cprof) { const long long h5 = clock64(); cp0 += h1 - h0; cp1 += h2 - h1; cp2 += h3 - h2; cp3 += h4 - h3; cp4 += h5 - h4; }
       if (cta == 0) {
         DTree& g = dv.trees[u];
         const int nn = tree.num_nodes;
@@ -342,14 +466,16 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       }
       __syncwarp();
     }
+    if (cprof) { prof[8] += (unsigned long long) cp0; prof[9] += (unsigned long long) cp1; prof[10] += (unsigned long long) cp2; prof[11] += (unsigned long long) cp3; prof[12] += (unsigned long long) cp4; }
     if (cta == 0 && lane == 0) {
       RngState out = S.rng;
       out.counter += (unsigned long long) S.csd.draws_total;
       *dv.rng = out;
       if (S.fail) dv.params->error_flag |= 8u;
-      dv.params->step_id = step0 + (unsigned long long) T;
+      if (t_end == T) dv.params->step_id = step0 + (unsigned long long) T;
       dv.desc->a_valid = 0;
-      *ran += 1ull;
+      *pos_out = t_end;
+      *ran += (unsigned long long) (t_end - t_begin);
     }
   }
 }

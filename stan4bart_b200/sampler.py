@@ -229,7 +229,10 @@ class GpuBart:
     def pipeline(self):
         en, a, b = C.c_int(0), C.c_int64(0), C.c_int64(0)
         _lib.check(self.L.gpubart_get_pipeline(self.h, C.byref(en), C.byref(a), C.byref(b)))
-        return dict(enabled=bool(en.value), sweeps_offered=int(a.value), sweeps_pipelined=int(b.value))
+        mis = (C.c_uint32 * 4)()
+        _lib.check(self.L.gpubart_pipeline_misfits(self.h, mis))
+        return dict(enabled=bool(en.value), sweeps_offered=int(a.value), steps_pipelined=int(b.value),
+                    misfits=dict(all=int(mis[0]), tree_too_large=int(mis[1]), too_many_slots=int(mis[2]), too_many_cells=int(mis[3])))
 
     def time_leaf_stats(self, tree=0, reps=20):
         ms = C.c_double(0.0)

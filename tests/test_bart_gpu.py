@@ -606,9 +606,9 @@ def test_pipelined_sweep_kernel_equals_the_synchronous_one(binary):
         res[mode] = dict(train=r["train"], trees=s.trees(), resid=s.residual(), vc=r["varcount"])
         if mode == "pipe":
             pl = s.pipeline()
-            assert pl["enabled"] and pl["sweeps_offered"] == sweeps and pl["sweeps_pipelined"] >= sweeps - 2, pl
+            assert pl["enabled"] and pl["sweeps_offered"] == sweeps and pl["steps_pipelined"] >= 0.5 * sweeps * T, pl
         if mode == "sync":
-            assert not s.pipeline()["enabled"] and s.pipeline()["sweeps_pipelined"] == 0
+            assert not s.pipeline()["enabled"] and s.pipeline()["steps_pipelined"] == 0
     for other in ("sync", "oracle"):
         a, b = res["pipe"], res[other]
         assert np.array_equal(a["trees"]["var"], b["trees"]["var"]) and np.array_equal(a["trees"]["n"], b["trees"]["n"]), other

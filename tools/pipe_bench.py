@@ -29,3 +29,19 @@ for mode in ("sync", "pipe"):
                  "nodes_per_tree": len(tr["var"]) / T, "pipeline": g.pipeline()}
     del g
 print(json.dumps({"n": n, "trees": T, "sweeps": sweeps, **out}, indent=1))
+if os.environ.get("S4B_PIPE_PROF"):
+    cfg = bart_config(n, 9, num_trees=T, seed=1, is_binary=True)
+    g = GpuBart(cfg, pr["y"], pr["x_bart"])
+    for _ in range(40):
+        g.run()
+    g.profile()          # reset the counters
+    for _ in range(10):
+        g.run()
+    import ctypes as C
+    from stan4bart_b200 import _lib
+    out = (C.c_uint64 * 24)()
+    _lib.check(g.L.gpubart_get_profile(g.h, out, 1))
+    v = [int(x) for x in out]
+    steps = max(1, v[5])
+    print("pipe profile (cycles per pipelined step):", json.dumps({"steps": v[5], "worker": dict(zip(["wait_decision", "update", "walk", "accumulate", "reduce_arrive"], [x / steps for x in v[0:5]])),
+          "controller": dict(zip(["plan_fetch", "wait_rows", "row_reduce", "decide", "deltas_arrive"], [x / steps for x in v[8:13]]))}))
