@@ -7,6 +7,7 @@
 #include "bart_kernels.cuh"
 #include "sweep_kernel.cuh"
 #include "sweep_pipe.cuh"
+#include "leaf_stats.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -854,7 +855,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_counters_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_pipe_pos_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_counters_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_pipe_pos_); cudaFree(d_leaf_partials_); cudaFree(d_leaf_ticket_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -950,21 +951,21 @@ void BartFit::setup_persistent()
     if (persistent_nq_ != kStreamNq && d_wt_ == nullptr && !sharded() && !(getenv("S4B_PIPE") && atoi(getenv("S4B_PIPE")) == 0)) {
       const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
                      : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
-      const size_t fixed = ((sizeof(PipeSmem) + 15) / 16) * 16 + (size_t) (kBinSlots + 1) * kWorkers * sizeof(double)
+      const size_t fixed = ((sizeof(PipeSmem) + 15) / 16) * 16 + (size_t) (kPipeSlots + 1) * kWorkers * sizeof(double)
                          + (size_t) p_ * persistent_nq_ * kWorkers * sizeof(uint32_t);
       // the cross table (slot of this step) x (cell of the previous step) gets what shared memory is left: one byte counter per entry and thread
       int entries = 0;
-      if (fixed < (size_t) max_smem) entries = (int) std::min<size_t>((size_t) kBinSlots * kPipeCells, ((size_t) max_smem - fixed) / kWorkers - 1);
+      if (fixed < (size_t) max_smem) entries = (int) std::min<size_t>((size_t) kPipeSlots * kPipeCells, ((size_t) max_smem - fixed) / kWorkers - 1);
       entries &= ~3;
-      if (entries >= 4 * kBinSlots) {
+      if (entries >= 4 * kPipeSlots) {
         const int words = entries;            // (member name kept: capacity of the cross table in entries)
         const size_t smem = fixed + (size_t) (entries + 1) * kWorkers;
         int per_sm = 0;
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) == cudaSuccess && per_sm >= 1) {
           pipe_count_words_ = words; pipe_smem_ = smem;
-          S4B_CUDA(cudaMalloc(&d_pipe_ring_, sizeof(unsigned long long) * kPipeRing * kPipeAcc));
-          zero_device_sync(d_pipe_ring_, sizeof(unsigned long long) * kPipeRing * kPipeAcc, stream_);
+          S4B_CUDA(cudaMalloc(&d_pipe_ring_, sizeof(unsigned long long) * 2 * kPipeRing * kPipeAcc));
+          zero_device_sync(d_pipe_ring_, sizeof(unsigned long long) * 2 * kPipeRing * kPipeAcc, stream_);
           S4B_CUDA(cudaMalloc(&d_pipe_counters_, sizeof(unsigned int) * kPipeRing));
           S4B_CUDA(cudaMalloc(&d_pipe_flag_, sizeof(unsigned int) * 4));
           zero_device_sync(d_pipe_flag_, sizeof(unsigned int) * 4, stream_);
@@ -1013,7 +1014,7 @@ void BartFit::launch_persistent_sweep(bool last_thin)
     size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
     if (pipe) S4B_CUDA(cudaMemsetAsync(d_pipe_pos_, 0, sizeof(int) * (2 * kPipeSegments + 1), stream_));
     k_prepare_sweep<<<(T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, stream_>>>(dv, d_descs_, d_draws_, d_tables_, infos, d_pipe_flag_,
-                                                                                         std::min(kPipeCells, pipe_count_words_ / kBinSlots));
+                                                                                         kPipeCells);
   }
   int overlap = overlap_walk_;
   ShardDev sh = shard_dev();
@@ -1043,8 +1044,8 @@ void BartFit::launch_persistent_sweep(bool last_thin)
     unsigned long long* pprof = pipe_prof ? d_prof_ : nullptr;
     for (int k = 0; k < kPipeSegments; ++k) {
       const int* pin = d_pipe_pos_ + 2 * k; int* pmid = d_pipe_pos_ + 2 * k + 1; int* pout = d_pipe_pos_ + 2 * k + 2;
-      S4B_CUDA(cudaMemsetAsync(d_pipe_ring_, 0, sizeof(unsigned long long) * kPipeRing * kPipeAcc, stream_));
-      void* pargs[] = { &dv, &ring, &pdescs, &pinfos, &pdraws, &pin, &pmid, &words, &ran, &pprof, &dbg };
+      int parity = (int) (pipe_launches_++ & 1);
+      void* pargs[] = { &dv, &ring, &parity, &pdescs, &pinfos, &pdraws, &pin, &pmid, &words, &ran, &pprof, &dbg };
       S4B_CUDA(cudaLaunchCooperativeKernel(pfn, dim3(persistent_grid_), dim3(kSweepBlock), pargs, pipe_smem_, stream_));
       if (k > 0) S4B_CUDA(cudaMemsetAsync(d_barrier_, 0, sizeof(unsigned int), stream_));
       const int* sin = pmid; int max_steps = k + 1 < kPipeSegments ? 1 : T_;
@@ -1564,6 +1565,12 @@ int BartFit::leaf_stats(int tree, int max_leaves, long long* heap, long long* co
 {
   if (tree < 0 || tree >= T_) throw std::invalid_argument("tree index out of range");
   launch_leaf_stats(tree);
+  if (d_leaf_ticket_ != nullptr && !leaf_generic_) {
+    int fits = 1;
+    S4B_CUDA(cudaMemcpyAsync(&fits, reinterpret_cast<int*>(d_leaf_ticket_ + 1), sizeof fits, cudaMemcpyDeviceToHost, stream_));
+    S4B_CUDA(cudaStreamSynchronize(stream_));
+    if (!fits) { leaf_generic_ = true; launch_leaf_stats(tree); leaf_generic_ = false; }      // a tree with more than kLeafSlots bottom nodes
+  }
   std::vector<double> st((size_t) 3 * S4B_MAX_SLOTS);
   S4B_CUDA(cudaMemcpyAsync(st.data(), d_stats_out_, sizeof(double) * st.size(), cudaMemcpyDeviceToHost, stream_));
   std::vector<DTree> trees = download_trees();       // (sharded chains: the kernel already exchanged the statistics)
@@ -1584,6 +1591,22 @@ int BartFit::leaf_stats(int tree, int max_leaves, long long* heap, long long* co
 
 void BartFit::launch_leaf_stats(int tree)
 {
+  // the dedicated one-launch kernel (leaf_stats.cuh) for unweighted, unsharded fits; it reports through d_leaf_fits_ when a tree has
+  // more bottom nodes than it handles, and leaf_stats() then repeats the pass with the generic per-tree kernels below
+  if (d_wt_ == nullptr && !sharded() && !leaf_generic_) {
+    if (d_leaf_partials_ == nullptr) {
+      leaf_grid_ = (int) std::max<long long>(1, std::min<long long>(((n_ + 3) / 4 + 2 * kLeafBlock - 1) / (2 * kLeafBlock), (long long) num_sms_ * 2));
+      leaf_smem_ = ((sizeof(LeafSmem) + 15) / 16) * 16 + (size_t) (kLeafSlots + 1) * kLeafBlock * (sizeof(double2) + sizeof(int));
+      S4B_CUDA(cudaFuncSetAttribute(k_leaf_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) leaf_smem_));
+      S4B_CUDA(cudaMalloc(&d_leaf_partials_, sizeof(double) * 3 * kLeafSlots * (size_t) leaf_grid_));
+      S4B_CUDA(cudaMalloc(&d_leaf_ticket_, sizeof(unsigned int) + sizeof(int)));
+      zero_device_sync(d_leaf_ticket_, sizeof(unsigned int) + sizeof(int), stream_);
+    }
+    int* fits = reinterpret_cast<int*>(d_leaf_ticket_ + 1);
+    k_leaf_stats<<<leaf_grid_, kLeafBlock, leaf_smem_, stream_>>>(n_, npad_, d_xt_, d_R_, d_trees_, tree, d_leaf_partials_, d_leaf_ticket_, d_stats_out_, fits);
+    S4B_CUDA(cudaGetLastError());
+    return;
+  }
   BartDev dv = dev();
   k_build_stats_desc<<<1, 32, 0, stream_>>>(dv, tree);
   k_tree_step<<<grid_, kBlock, 0, stream_>>>(dv, kModeStatsOnly, 0, shard_dev());

@@ -155,7 +155,7 @@ class BartFit {
   int pipe_count_words_ = 0;
   size_t pipe_smem_ = 0;
   unsigned long long* d_pipe_ring_ = nullptr; unsigned int* d_pipe_counters_ = nullptr; unsigned int* d_pipe_flag_ = nullptr; void* d_pipe_infos_ = nullptr;
-  long long pipe_sweeps_ = 0;
+  long long pipe_sweeps_ = 0, pipe_launches_ = 0;
   unsigned long long* d_pipe_ran_ = nullptr;
   int* d_pipe_pos_ = nullptr;          // first step still to do, one entry per launch of a sweep's segment sequence
  public:
@@ -178,6 +178,8 @@ class BartFit {
   int overlap_walk_ = 1;
   bool profile_on_ = false;
   bool keep_trees_active_ = true;
+  // stand-alone leaf-statistics kernel (leaf_stats.cuh)
+  double* d_leaf_partials_ = nullptr; unsigned int* d_leaf_ticket_ = nullptr; int leaf_grid_ = 0; size_t leaf_smem_ = 0; bool leaf_generic_ = false;
   long long num_tree_steps_ = 0;
 
   uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;

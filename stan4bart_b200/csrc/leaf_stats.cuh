@@ -1,0 +1,163 @@
+// stan4bart_b200/csrc/leaf_stats.cuh
+// Stand-alone leaf sufficient statistics of one tree (the "leaf-stat" half of BASELINE.json's metric): per bottom
+// node (n, sum, sum of squares) of the partial residual r_i + mu_leaf(i), in ONE launch.
+//
+//   * grid = a multiple of the SM count; every thread streams quads of 4 rows: the residuals as 2 x 16-byte loads, the binned
+//     predictors as one 32-bit word per rule and quad (coalesced: column major, 4 rows per word); two quads per iteration so that
+//     ~80 bytes per thread are in flight;
+//   * the tree's rules sit in shared memory; a row's rule outcomes form a bit pattern that indexes a 256-entry table of leaf
+//     slots (trees with more than 8 rules walk node by node);
+//   * accumulation into lane-private shared-memory bins (no atomics), then a fixed-order reduction: threads -> warp (shuffles)
+//     -> CTA -> one partial row per CTA -> the last CTA to finish sums the rows in CTA order.  Deterministic run to run.
+// Algorithmic bytes per row: 8 (residual) + 2 (node id) + 1 (split column) = 11; actually read: 8 + the number of
+// rules of the tree.
+#pragma once
+
+#include "s4b_common.cuh"
+
+namespace s4b {
+
+constexpr int kLeafBlock = 256;
+constexpr int kLeafSlots = 16;             // bottom nodes handled by the fast kernel (more: the generic per-tree pass)
+
+struct LeafSmem {
+  uint32_t irec[S4B_NODE_CAP];             // rule i (internal nodes in index order): var << 8 | cut
+  uint8_t table[256];                      // rule pattern -> slot (n_int <= 8)
+  uint32_t trav[S4B_NODE_CAP];             // node walk (n_int > 8): var << 16 | cut << 8 | right ; 0xFFFF.. for a bottom node
+  uint8_t slot[S4B_NODE_CAP];
+  double val[kLeafSlots + 1];
+  int n_int, n_leaves, nn, fits;
+  int last;
+};
+
+__device__ __forceinline__ double leaf_wsum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out: [3 * slot + {0, 1, 2}] = n, sum, sum of squares; *fits_out = 0 when the tree has more than kLeafSlots bottom nodes
+__global__ void __launch_bounds__(kLeafBlock) k_leaf_stats(long long n, long long npad, const uint8_t* __restrict__ xt, const double* __restrict__ R,
+                                                           const DTree* __restrict__ trees, int tree_index, double* __restrict__ partials,
+                                                           unsigned int* __restrict__ ticket, double* __restrict__ out, int* __restrict__ fits_out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LeafSmem& S = *reinterpret_cast<LeafSmem*>(smem_raw);
+  double2* bins = reinterpret_cast<double2*>(smem_raw + ((sizeof(LeafSmem) + 15) / 16) * 16);        // [kLeafSlots + 1][kLeafBlock]: (sum, sum of squares)
+  int* cnts = reinterpret_cast<int*>(bins + (kLeafSlots + 1) * kLeafBlock);                            // [kLeafSlots + 1][kLeafBlock]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DTree& t = trees[tree_index];
+  const int nn = t.num_nodes;
+  if (warp == 0) {
+    // rules in internal-node order, slots in bottom-node order, the pattern table
+    int n_int = 0, n_leaf = 0;
+    for (int base = 0; base < nn; base += 32) {
+      const int k = base + lane;
+      const bool in = k < nn && t.nodes[k].var >= 0, lf = k < nn && t.nodes[k].var < 0;
+      const unsigned mi = __ballot_sync(0xffffffffu, in), ml = __ballot_sync(0xffffffffu, lf);
+      const unsigned below = (1u << lane) - 1u;
+      if (in) S.irec[n_int + __popc(mi & below)] = ((uint32_t) t.nodes[k].var << 8) | (uint32_t) (t.nodes[k].cut & 0xFF);
+      if (k < nn) {
+        S.slot[k] = lf ? (uint8_t) min(n_leaf + __popc(ml & below), kLeafSlots) : (uint8_t) 255;
+        S.trav[k] = lf ? 0xFFFFFFFFu : (((uint32_t) t.nodes[k].var << 16) | ((uint32_t) (t.nodes[k].cut & 0xFF) << 8) | (uint32_t) (t.nodes[k].right & 0xFF));
+        if (lf && n_leaf + __popc(ml & below) < kLeafSlots) S.val[n_leaf + __popc(ml & below)] = t.nodes[k].mu;
+      }
+      n_int += __popc(mi); n_leaf += __popc(ml);
+    }
+    __syncwarp();
+    if (lane == 0) { S.n_int = n_int; S.n_leaves = n_leaf; S.nn = nn; S.fits = n_leaf <= kLeafSlots ? 1 : 0; S.val[kLeafSlots] = 0.0; }
+    if (n_int <= 8 && nn <= 32) {
+      // internal-node mask of the (<= 32-node) tree, then every pattern's bottom node
+      const unsigned imask = __ballot_sync(0xffffffffu, lane < nn && t.nodes[lane].var >= 0);
+      for (int e = lane; e < (1 << n_int); e += 32) {
+        int node = 0;
+        while ((imask >> node) & 1u) { const int id = __popc(imask & ((1u << node) - 1u)); node = ((e >> id) & 1) ? node + 1 : (int) t.nodes[node].right; }
+        S.table[e] = S.slot[node];
+      }
+    }
+  }
+  for (int k = tid; k < (kLeafSlots + 1) * kLeafBlock; k += kLeafBlock) { bins[k] = make_double2(0.0, 0.0); cnts[k] = 0; }
+  __syncthreads();
+  if (!S.fits) { if (blockIdx.x == 0 && tid == 0) *fits_out = 0; return; }
+  const int n_int = S.n_int;
+  const bool bitmap = n_int <= 8 && S.nn <= 32;
+  const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(xt);
+  const long long col_words = npad >> 2, nquad = (n + 3) >> 2;
+  const long long stride = (long long) gridDim.x * kLeafBlock;
+
+  auto slots_of = [&](long long q) -> uint32_t {
+    if (bitmap) {
+      uint32_t pat = 0u;
+      for (int i = 0; i < n_int; ++i) {
+        const uint32_t rec = S.irec[i];
+        pat |= (__vcmpleu4(__ldg(xt32 + (long long) (rec >> 8) * col_words + q), (rec & 0xFFu) * 0x01010101u) & 0x01010101u) << i;
+      }
+      return (uint32_t) S.table[pat & 0xFFu] | ((uint32_t) S.table[(pat >> 8) & 0xFFu] << 8) | ((uint32_t) S.table[(pat >> 16) & 0xFFu] << 16) |
+             ((uint32_t) S.table[pat >> 24] << 24);
+    }
+    uint32_t res = 0u;
+    for (int o = 0; o < 4; ++o) {
+      int node = 0;
+      uint32_t tr = S.trav[0];
+      while (tr != 0xFFFFFFFFu) {
+        const uint32_t w = __ldg(xt32 + (long long) (tr >> 16) * col_words + q);
+        node = ((w >> (8 * o)) & 0xFFu) <= ((tr >> 8) & 0xFFu) ? node + 1 : (int) (tr & 0xFFu);
+        tr = S.trav[node];
+      }
+      res |= (uint32_t) S.slot[node] << (8 * o);
+    }
+    return res;
+  };
+  auto add_quad = [&](long long q, double2 a, double2 b, uint32_t sl) {
+    const double r[4] = { a.x, a.y, b.x, b.y };
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      int s = (sl >> (8 * o)) & 0xFF;
+      if (4 * q + o >= n) s = kLeafSlots;                       // padding rows of the last quad: trash row
+      const double pr = r[o] + S.val[s];
+      double2 v = bins[s * kLeafBlock + tid];
+      v.x += pr; v.y = fma(pr, pr, v.y);
+      bins[s * kLeafBlock + tid] = v;
+      cnts[s * kLeafBlock + tid] += 1;
+    }
+  };
+  for (long long q0 = (long long) blockIdx.x * kLeafBlock + tid; q0 < nquad; q0 += 2 * stride) {
+    const long long q1 = q0 + stride;
+    const bool two = q1 < nquad;
+    const double2 a0 = __ldg(reinterpret_cast<const double2*>(R + 4 * q0)), b0 = __ldg(reinterpret_cast<const double2*>(R + 4 * q0 + 2));
+    double2 a1 = make_double2(0.0, 0.0), b1 = a1;
+    if (two) { a1 = __ldg(reinterpret_cast<const double2*>(R + 4 * q1)); b1 = __ldg(reinterpret_cast<const double2*>(R + 4 * q1 + 2)); }
+    const uint32_t s0 = slots_of(q0);
+    const uint32_t s1 = two ? slots_of(q1) : 0u;
+    add_quad(q0, a0, b0, s0);
+    if (two) add_quad(q1, a1, b1, s1);
+  }
+  __syncthreads();
+  // ---- CTA reduction in a fixed order: warp w takes slots w, w + 8, ...; one partial row (n, sum, sum of squares) per slot and CTA ----
+  const int L = S.n_leaves, G = gridDim.x;
+  for (int s = warp; s < L; s += kLeafBlock / 32) {
+    double a = 0.0, b = 0.0; int c = 0;
+#pragma unroll
+    for (int i = 0; i < kLeafBlock / 32; ++i) { const double2 v = bins[s * kLeafBlock + i * 32 + lane]; a += v.x; b += v.y; c += cnts[s * kLeafBlock + i * 32 + lane]; }
+    a = leaf_wsum(a); b = leaf_wsum(b); c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) { partials[(size_t) (3 * s) * G + blockIdx.x] = (double) c; partials[(size_t) (3 * s + 1) * G + blockIdx.x] = a; partials[(size_t) (3 * s + 2) * G + blockIdx.x] = b; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) S.last = atomicAdd(ticket, 1u) == (unsigned) (G - 1) ? 1 : 0;
+  __syncthreads();
+  if (!S.last) return;
+  __threadfence();
+  // ---- the last CTA sums the partial rows of all CTAs in CTA order (lane-strided, then a shuffle tree: the same order every run) ----
+  for (int v = warp; v < 3 * L; v += kLeafBlock / 32) {
+    const double* src = partials + (size_t) v * G;
+    double acc = 0.0;
+    for (int b = lane; b < G; b += 32) acc += __ldcg(src + b);
+    acc = leaf_wsum(acc);
+    if (lane == 0) out[v] = acc;
+  }
+  if (tid == 0) { *ticket = 0u; *fits_out = 1; }
+}
+
+}  // namespace s4b

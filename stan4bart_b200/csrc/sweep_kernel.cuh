@@ -1063,8 +1063,9 @@ constexpr int kPrepWarps = 4;
 struct PrepSmemWarp { DTree tree; CtlScratch cs; StepDesc sd; };
 
 // ---- pipelined sweep (sweep_pipe.cuh): data-independent description of a step's cells ----
-constexpr int kPipeSegments = 4;          // (pipelined run, synchronous step) rounds per sweep; the last synchronous launch takes the rest
-constexpr int kPipeCells = 16;            // capacity of the per-step cell tables
+constexpr int kPipeSegments = 2;          // (pipelined run, synchronous step) rounds per sweep; the last synchronous launch takes the rest
+constexpr int kPipeSlots = 12;            // statistic slots a step of the pipelined kernel may have (+ 1 trash row of bins)
+constexpr int kPipeCells = 24;            // capacity of the per-step cell tables
 constexpr int kPipeRing = 4;
 constexpr int kPipeDescs = 3;
 
@@ -1076,8 +1077,8 @@ struct PipeInfo {
   int32_t ncells;
   int32_t ok;                              // this step fits the pipelined kernel
   int32_t slot_b;                          // birth: slot of the node to split (its rows take slot L + side); 255 otherwise
-  int32_t pad;
-  double vs[kBinSlots + 2];                // leaf value of the current tree by slot (a birth's two new slots repeat the parent's)
+  int32_t nslots;                          // statistic slots of the step (the cross table of step t has nslots_t x ncells_{t-1} entries)
+  double vs[kPipeSlots + 2];               // leaf value of the current tree by slot (a birth's two new slots repeat the parent's)
   uint8_t cellbase[16];                    // change / swap: first cell of slot s (a slot outside the branch: its only cell)
   uint8_t cell_a[kPipeCells], cell_f[kPipeCells];
   uint8_t stab[1 << S4B_BITMAP_INT];       // rule pattern -> slot under the current rules
@@ -1085,15 +1086,16 @@ struct PipeInfo {
 };
 
 // one warp per tree, after w_propose: fills infos[t]; returns whether the step fits
-__device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& pi, int max_cells, int lane)
+__device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& pi, int /* max_cells: the pair limit is checked by the kernel */, int lane)
 {
   const int nn = t.num_nodes, kind = d.b_kind, node = d.b_node, L = d.b_num_leaves, nslots = d.b_nslots;
   const bool bd = kind == 0 || kind == 1;
   const int n_int = d.b_cur.n_int;
-  bool ok = nn + 2 <= 32 && nslots + (bd ? 1 : 0) <= 32 && nslots <= kBinSlots && n_int <= S4B_BITMAP_INT;
+  bool ok = nn + 2 <= 32 && nslots + (bd ? 1 : 0) <= 32 && nslots <= kPipeSlots && n_int <= S4B_BITMAP_INT;
   int ncells = nslots;
-  if (lane < kPipeCells) { pi.cell_a[lane] = 0; pi.cell_f[lane] = 0; pi.cellbase[lane] = 0; }
-  if (lane < kBinSlots + 2) pi.vs[lane] = 0.0;
+  if (lane < kPipeCells) { pi.cell_a[lane] = 0; pi.cell_f[lane] = 0; }
+  if (lane < 16) pi.cellbase[lane] = 0;
+  if (lane < kPipeSlots + 2) pi.vs[lane] = 0.0;
   __syncwarp();
   if (ok) {
     const bool leaf = lane < nn && t.nodes[lane].var < 0;
@@ -1105,7 +1107,7 @@ __device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& 
       const unsigned m_in = __ballot_sync(0xffffffffu, inside), m_out = __ballot_sync(0xffffffffu, leaf && !inside);
       const int k_in = __popc(m_in), n_out = __popc(m_out);
       ncells = n_out + k_in * k_in;
-      ok = ncells <= max_cells && ncells <= kPipeCells;
+      ok = ncells <= kPipeCells;
       if (ok) {
         const unsigned below = (1u << lane) - 1u;
         if (leaf && !inside) { const int c = __popc(m_out & below); pi.cellbase[slot] = (uint8_t) c; pi.cell_a[c] = (uint8_t) lane; pi.cell_f[c] = (uint8_t) lane; }
@@ -1117,7 +1119,7 @@ __device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& 
         }
       }
     } else {
-      ok = ncells <= max_cells && ncells <= kPipeCells;
+      ok = ncells <= kPipeCells;
       if (ok && leaf && slot < kPipeCells) {
         int f = lane;
         if (kind == 0) f = lane > node ? lane + 2 : lane;
@@ -1135,7 +1137,7 @@ __device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& 
       }
     }
   }
-  if (lane == 0) { pi.ncells = ncells; pi.ok = ok ? 1 : 0; pi.slot_b = (ok && kind == 0) ? (int) d.b_cur.slot[node] : 255; pi.pad = 0; }
+  if (lane == 0) { pi.ncells = ncells; pi.ok = ok ? 1 : 0; pi.slot_b = (ok && kind == 0) ? (int) d.b_cur.slot[node] : 255; pi.nslots = nslots; }
   __syncwarp();
   return ok;
 }
@@ -1177,7 +1179,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_prepare_sweep(BartDev dv, S
       atomicAdd(pipe_not_ok, 1u);
       const bool bd = W.sd.b_kind == 0 || W.sd.b_kind == 1;
       if (W.tree.num_nodes + 2 > 32 || W.sd.b_nslots + (bd ? 1 : 0) > 32) atomicAdd(pipe_not_ok + 1, 1u);
-      else if (W.sd.b_nslots > kBinSlots) atomicAdd(pipe_not_ok + 2, 1u);
+      else if (W.sd.b_nslots > kPipeSlots) atomicAdd(pipe_not_ok + 2, 1u);
       else atomicAdd(pipe_not_ok + 3, 1u);
     }
   }

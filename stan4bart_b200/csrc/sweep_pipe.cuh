@@ -36,16 +36,17 @@
 
 namespace s4b {
 
-constexpr int kPipeAcc = 2 * kBinSlots + (kBinSlots * kPipeCells) / 2;     // per step: (hi, lo) per slot sum, then one word per pair of cross-table entries
+constexpr int kPipeAcc = 2 * kPipeSlots + (kPipeSlots * kPipeCells) / 2;     // per step: (hi, lo) per slot sum, then one word per pair of cross-table entries
 struct PipeSmem {
   StepDesc sd[kPipeDescs];
   PipeInfo info[kPipeDescs];
   DTree tree[2];
   UpdateDesc upd[2];
   unsigned long long accprev[kPipeRing][kPipeAcc];   // accumulator rows as last read (a row is reused every kPipeRing steps and never zeroed)
+  double2 draws[2][32];                     // decision draws of the step being decided / the next one
   double dcell[2][kPipeCells];              // delta of step parity: mu_old - mu_new per cell
-  int ncnt[4 * kBinSlots];                  // staging of the (hi, lo) limbs of the slot sums
-  int cross[kBinSlots * kPipeCells + 2];    // the cross table of the step being decided
+  int ncnt[4 * kPipeSlots];                  // staging of the (hi, lo) limbs of the slot sums
+  int cross[kPipeSlots * kPipeCells + 2];    // the cross table of the step being decided
   CtlScratch csd;
   LeafStat st[S4B_MAX_SLOTS];
   FastPlanSmem plan;
@@ -135,22 +136,31 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
 
 // acc_ring: kPipeRing accumulator rows of kPipeAcc 64-bit words (zeroed by the host before every launch)
 template <int NQ>
-__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsigned long long* acc_ring,
+__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsigned long long* acc_rings, int launch_parity,
                                                                 const StepDesc* __restrict__ descs, const PipeInfo* __restrict__ infos,
                                                                 const double2* __restrict__ draws, const int* __restrict__ pos_in, int* __restrict__ pos_out,
                                                                 int count_entries, unsigned long long* __restrict__ ran, unsigned long long* __restrict__ prof, int dbg)
 {
   // this launch takes the run of consecutive steps that fit, starting at *pos_in; the synchronous kernel (launched next) takes
   // the step that stopped it.  Every CTA scans the same flags, so all agree on the range without talking to each other.
+  // two accumulator rings alternate by launch: this launch adds into one (zero on entry) and clears the other for the next
+  // launch, so no host-side memset sits between the launches of a sweep
+  unsigned long long* acc_ring = acc_rings + (size_t) (launch_parity & 1) * kPipeRing * kPipeAcc;
+  if (blockIdx.x == 0) {
+    unsigned long long* other = acc_rings + (size_t) ((launch_parity + 1) & 1) * kPipeRing * kPipeAcc;
+    for (int i = threadIdx.x; i < kPipeRing * kPipeAcc; i += blockDim.x) other[i] = 0ull;
+  }
   const int T_all = dv.params->num_trees;
   const int t_begin = *pos_in;
+  // a step fits when its trees are small (k_prepare_sweep's flag) and its cross table -- (its slots) x (the previous step's cells) --
+  // fits the shared-memory counters; the first step of a run has no predecessor in flight (one cell)
   int t_end = t_begin;
-  while (t_end < T_all && infos[t_end].ok != 0) ++t_end;
+  while (t_end < T_all && infos[t_end].ok != 0 && (t_end == t_begin || infos[t_end].nslots * infos[t_end - 1].ncells <= count_entries)) ++t_end;
   if (t_end == t_begin) { if (blockIdx.x == 0 && threadIdx.x == 0) *pos_out = t_begin; return; }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PipeSmem& S = *reinterpret_cast<PipeSmem*>(smem_raw);
-  double* bins = reinterpret_cast<double*>(smem_raw + ((sizeof(PipeSmem) + 15) / 16) * 16);                    // [kBinSlots + 1][kWorkers]
-  uint8_t* cnt = reinterpret_cast<uint8_t*>(bins + (kBinSlots + 1) * kWorkers);                                  // [count_entries + 1][kWorkers] bytes
+  double* bins = reinterpret_cast<double*>(smem_raw + ((sizeof(PipeSmem) + 15) / 16) * 16);                    // [kPipeSlots + 1][kWorkers]
+  uint8_t* cnt = reinterpret_cast<uint8_t*>(bins + (kPipeSlots + 1) * kWorkers);                                  // [count_entries + 1][kWorkers] bytes
   uint32_t* tile = reinterpret_cast<uint32_t*>(cnt + (size_t) (count_entries + 1) * kWorkers);                    // [p][NQ * kWorkers]
   constexpr int tile_stride = NQ * kWorkers;
 
@@ -198,6 +208,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     const int nn = g.num_nodes;
     if (lane == 0) { S.tree[t_begin & 1].num_nodes = nn; S.tree[t_begin & 1].pad = 0; }
     for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(S.tree[t_begin & 1].nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+    S.draws[t_begin & 1][lane] = __ldcg(draws + t_begin * 32 + lane);
     w_copy_desc(S.sd[t_begin % kPipeDescs], descs[t_begin], lane);
     w_copy_info(S.info[t_begin % kPipeDescs], infos[t_begin], lane);
   }
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     uint32_t sp[NQ], pp[NQ], cprev[NQ], cprev2[NQ];
 #pragma unroll
     for (int j = 0; j < NQ; ++j) { cprev[j] = 0u; cprev2[j] = 0u; pp[j] = 0u; }
-    // rows beyond the data (the tail of the last quad, quads beyond q_hi) are parked in the trash slot kBinSlots at every step
+    // rows beyond the data (the tail of the last quad, quads beyond q_hi) are parked in the trash slot kPipeSlots at every step
     constexpr unsigned kAllObs = NQ == 8 ? 0xFFFFFFFFu : ((1u << (4 * NQ)) - 1u);
     const bool ragged = obs_mask != kAllObs;
     int C = 1;                                 // cells of the previous step (its descriptor's ring slot is recycled two steps later)
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     const bool wprof = prof != nullptr && cta == 0 && tid == 0;
     const int e_trash = count_entries;
     uint32_t* cntw = reinterpret_cast<uint32_t*>(cnt);
-    for (int k = 0; k <= kBinSlots; ++k) bins[k * kWorkers + tid] = 0.0;
+    for (int k = 0; k <= kPipeSlots; ++k) bins[k * kWorkers + tid] = 0.0;
     for (int i = tid; i < (count_entries + 1) * (kWorkers / 4); i += kWorkers) cntw[i] = 0u;
     named_bar_sync(1, kWorkers);
     for (int t = t_begin; t < t_end; ++t) {
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
 #pragma unroll
-          for (int o = 0; o < 4; ++o) if (!((obs_mask >> (4 * j + o)) & 1u)) { sp[j] = (sp[j] & ~(0xFFu << (8 * o))) | ((uint32_t) kBinSlots << (8 * o)); pp[j] |= 0xFFu << (8 * o); }
+          for (int o = 0; o < 4; ++o) if (!((obs_mask >> (4 * j + o)) & 1u)) { sp[j] = (sp[j] & ~(0xFFu << (8 * o))) | ((uint32_t) kPipeSlots << (8 * o)); pp[j] |= 0xFFu << (8 * o); }
       }
       const long long k3 = clock64();
       const int kind = sd.b_kind, L = sd.b_num_leaves, nslots = sd.b_nslots;
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
             s[o] = (sp[j] >> (8 * o)) & 0xFF;
             const int cp = (cprev[j] >> (8 * o)) & 0xFF;
             pr[o] = R[j][o] + pi.vs[s[o]];
-            e[o] = s[o] >= kBinSlots ? e_trash : s[o] * C + cp;
+            e[o] = s[o] >= kPipeSlots ? e_trash : s[o] * C + cp;
           }
 #pragma unroll
           for (int o = 0; o < 4; ++o) { bins[s[o] * kWorkers + tid] += pr[o]; cnt[e[o] * kWorkers + tid] += 1; }
@@ -284,10 +295,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
             const int cp = (cprev[j] >> (8 * o)) & 0xFF;
             const bool in = pq != 255;
             pr[o] = R[j][o] + pi.vs[s[o]];
-            q[o] = in ? pq : kBinSlots;
-            e[o] = s[o] >= kBinSlots ? e_trash : s[o] * C + cp;
+            q[o] = in ? pq : kPipeSlots;
+            e[o] = s[o] >= kPipeSlots ? e_trash : s[o] * C + cp;
             e2[o] = in ? pq * C + cp : e_trash;
-            const int cell = s[o] >= kBinSlots ? kBinSlots : (int) pi.cellbase[s[o]] + (in ? pq - L : 0);
+            const int cell = s[o] >= kPipeSlots ? kPipeSlots : (int) pi.cellbase[s[o]] + (in ? pq - L : 0);
             cc |= (uint32_t) cell << (8 * o);
           }
 #pragma unroll
@@ -333,7 +344,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
             }
           }
           c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
-          if (lane == 0) atomicAdd(acc + 2 * kBinSlots + (task - nslots), (1ull << 56) | (unsigned long long) (unsigned) c0 | ((unsigned long long) (unsigned) c1 << 28));
+          if (lane == 0) atomicAdd(acc + 2 * kPipeSlots + (task - nslots), (1ull << 56) | (unsigned long long) (unsigned) c0 | ((unsigned long long) (unsigned) c1 << 28));
         }
       }
       // (the bins and the count table are rewritten by the next step only after the next named barrier)
@@ -371,15 +382,17 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       DTree& tree = S.tree[u & 1];
       // ---- before the barrier: plan the decision, fetch the next tree, adopt this step's pre-computed draws ----
       { const FastPlan pl = w_plan(tree, sd, S.upd[u & 1], S.csd, lane); plan_store(S.plan, pl, lane); }
+      // the next step's tree (a tree fits 32 nodes here: 8 + 32 x 24 bytes) and decision draws come in asynchronously: needed one step from now
       if (u + 1 < t_end) {
-        DTree& tn = S.tree[(u + 1) & 1];
-        const DTree& g = dv.trees[u + 1];
-        const int nn = g.num_nodes;
-        if (lane == 0) { tn.num_nodes = nn; tn.pad = 0; }
-        for (int i = lane; i < nn * (int) (sizeof(DNode) / 4); i += 32) reinterpret_cast<uint32_t*>(tn.nodes)[i] = reinterpret_cast<const uint32_t*>(g.nodes)[i];
+        const char* g = reinterpret_cast<const char*>(&dv.trees[u + 1]);
+        char* tn = reinterpret_cast<char*>(&S.tree[(u + 1) & 1]);
+        for (int i = lane; i < (int) ((8 + 32 * sizeof(DNode)) / 8); i += 32) cp_async8(tn + 8 * i, g + 8 * i);
+        cp_async8(reinterpret_cast<char*>(&S.draws[(u + 1) & 1][lane]), reinterpret_cast<const char*>(draws + (u + 1) * 32 + lane));
+        cp_async8(reinterpret_cast<char*>(&S.draws[(u + 1) & 1][lane]) + 8, reinterpret_cast<const char*>(draws + (u + 1) * 32 + lane) + 8);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
       rngd.enter(step0 + (unsigned long long) u, 1u);
-      { const double2 dz = __ldcg(draws + u * 32 + lane); S.csd.ubuf[lane] = dz.x; S.csd.zbuf[lane] = dz.y; }
+      { const double2 dz = S.draws[u & 1][lane]; S.csd.ubuf[lane] = dz.x; S.csd.zbuf[lane] = dz.y; }
       rngd.adopt();
       const long long h1 = clock64();
       // (no separate barrier: the accumulator words themselves tell when every CTA has contributed, see below)
@@ -394,11 +407,11 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
         // before they issued their atomics -- the descriptor ring -- is read only after this loop has seen those atomics.)
         const int slot_b = (u - t_begin) & (kPipeRing - 1);
         const unsigned long long* acc = acc_ring + (size_t) slot_b * kPipeAcc;
-        const int nvals = 2 * kBinSlots + npairs;
+        const int nvals = 2 * kPipeSlots + npairs;
         const unsigned long long want = (unsigned long long) (G & 0xFF);
         for (int i0 = 0; i0 < nvals; i0 += 32) {
           const int i = i0 + lane;
-          const bool used = i < nvals && (i >= 2 * kBinSlots || i < 2 * nslots);
+          const bool used = i < nvals && (i >= 2 * kPipeSlots || i < 2 * nslots);
           unsigned long long v = 0ull;
           const unsigned long long prev = used ? S.accprev[slot_b][i] : 0ull;
           const long long w0 = clock64();
@@ -414,9 +427,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
             if (S.fail || clock64() - w0 > 4000000000LL) { S.fail = 1; break; }
           }
           v &= (1ull << 56) - 1ull;
-          if (i < 2 * kBinSlots) reinterpret_cast<unsigned long long*>(S.ncnt)[i] = v;       // staged: (hi, lo) pairs, combined below
+          if (i < 2 * kPipeSlots) reinterpret_cast<unsigned long long*>(S.ncnt)[i] = v;       // staged: (hi, lo) pairs, combined below
           else if (i < nvals) {
-            const int k = i - 2 * kBinSlots;
+            const int k = i - 2 * kPipeSlots;
             S.cross[2 * k] = (int) (v & 0xFFFFFFFull); S.cross[2 * k + 1] = (int) ((v >> 28) & 0xFFFFFFFull);
           }
         }
@@ -457,6 +470,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       __syncwarp();
       C = pi.ncells;
       named_bar_arrive(2 + (u & 1), kSweepBlock);            // decision u is done: the workers may apply it
+      cp_async_wait_all(); __syncwarp();                     // next tree and draws are in shared memory
       if (cprof) { const long long h5 = clock64(); cp0 += h1 - h0; cp1 += h2 - h1; cp2 += h3 - h2; cp3 += h4 - h3; cp4 += h5 - h4; }
       if (cta == 0) {
         DTree& g = dv.trees[u];
