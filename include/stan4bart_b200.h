@@ -284,6 +284,14 @@ int s4b_shard_attach(s4b_shard* sh, const unsigned char* handles);
 int s4b_shard_set_obs_range(s4b_shard* sh, int64_t first_obs, int64_t total_obs);
 /* in-place all-reduce of a host vector over the ranks (op 0 = sum in rank order, 1 = max); collective */
 int s4b_shard_allreduce(s4b_shard* sh, double* vec, int64_t n, int op);
+/* Reference collective ("NCCL ncclAllReduce as reference implementation"): the small all-reduces of a sharded chain
+ * (cut-point ranges, response range of the rescale, the (1 + K + q) GLMM reductions, the Gram matrix, s4b_shard_allreduce) through
+ * ncclAllReduce over NVLink instead of the peer-mapped mailboxes.  Rank 0 obtains the 128-byte unique id, every rank passes it to
+ * nccl_init (collective), use_nccl switches the path.  NCCL is loaded at run time.  The per-tree-step exchange stays inside the
+ * sweep kernel (NCCL's launch latency per call is several times the whole tree step); tests check both paths against each other. */
+int s4b_shard_nccl_unique_id(unsigned char* out128);
+int s4b_shard_nccl_init(s4b_shard* sh, const unsigned char* id128);
+int s4b_shard_use_nccl(s4b_shard* sh, int on);
 /* initializeFit / glmm / stan4bart_create on this rank's rows; n, N are the local row counts */
 int gpubart_create_sharded(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test, s4b_shard* sh, gpubart_fit** out);
 int glmm_create_sharded(const s4b_glmm_data* d, s4b_shard* sh, glmm_model** out);

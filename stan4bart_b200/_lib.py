@@ -108,6 +108,9 @@ SIGNATURES = {
     "gpubart_set_response": (C.c_int, [vp, c_double_p]),
     "gpubart_get_stored_scales": (C.c_int, [vp, C.c_int64, C.c_int64, c_double_p]),
     "gpubart_stored_get_scales": (C.c_int, [vp, C.c_int64, C.c_int64, c_double_p]),
+    "s4b_shard_nccl_unique_id": (C.c_int, [c_ubyte_p]),
+    "s4b_shard_nccl_init": (C.c_int, [vp, c_ubyte_p]),
+    "s4b_shard_use_nccl": (C.c_int, [vp, C.c_int]),
     "gpubart_create_sharded": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, vp, vpp]),
     "glmm_create_sharded": (C.c_int, [C.POINTER(GlmmData), vp, vpp]),
     "s4b_sampler_create_sharded": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, C.POINTER(GlmmData),

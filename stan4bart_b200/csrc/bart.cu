@@ -1595,7 +1595,7 @@ void BartFit::launch_leaf_stats(int tree)
   // more bottom nodes than it handles, and leaf_stats() then repeats the pass with the generic per-tree kernels below
   if (d_wt_ == nullptr && !sharded() && !leaf_generic_) {
     if (d_leaf_partials_ == nullptr) {
-      leaf_grid_ = (int) std::max<long long>(1, std::min<long long>(((n_ + 3) / 4 + 2 * kLeafBlock - 1) / (2 * kLeafBlock), (long long) num_sms_ * 2));
+      leaf_grid_ = (int) std::max<long long>(1, std::min<long long>(((n_ + 3) / 4 + 4 * kLeafBlock - 1) / (4 * kLeafBlock), (long long) num_sms_ * 4));   // >= 4 quads per thread
       leaf_smem_ = ((sizeof(LeafSmem) + 15) / 16) * 16 + (size_t) (kLeafSlots + 1) * kLeafBlock * (sizeof(double2) + sizeof(int));
       S4B_CUDA(cudaFuncSetAttribute(k_leaf_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) leaf_smem_));
       S4B_CUDA(cudaMalloc(&d_leaf_partials_, sizeof(double) * 3 * kLeafSlots * (size_t) leaf_grid_));

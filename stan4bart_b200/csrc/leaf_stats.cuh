@@ -3,8 +3,7 @@
 // node (n, sum, sum of squares) of the partial residual r_i + mu_leaf(i), in ONE launch.
 //
 //   * grid = a multiple of the SM count; every thread streams quads of 4 rows: the residuals as 2 x 16-byte loads, the binned
-//     predictors as one 32-bit word per rule and quad (coalesced: column major, 4 rows per word); two quads per iteration so that
-//     ~80 bytes per thread are in flight;
+//     predictors as one 32-bit word per rule and quad (coalesced: column major, 4 rows per word); four quads per iteration (~150 bytes per thread in flight, 1024 threads per SM);
 //   * the tree's rules sit in shared memory; a row's rule outcomes form a bit pattern that indexes a 256-entry table of leaf
 //     slots (trees with more than 8 rules walk node by node);
 //   * accumulation into lane-private shared-memory bins (no atomics), then a fixed-order reduction: threads -> warp (shuffles)
@@ -18,7 +17,7 @@
 namespace s4b {
 
 constexpr int kLeafBlock = 256;
-constexpr int kLeafSlots = 16;             // bottom nodes handled by the fast kernel (more: the generic per-tree pass)
+constexpr int kLeafSlots = 8;              // bottom nodes handled by the fast kernel (more: the generic per-tree pass); 46 KB of bins => 4 CTAs per SM
 
 struct LeafSmem {
   uint32_t irec[S4B_NODE_CAP];             // rule i (internal nodes in index order): var << 8 | cut
@@ -122,16 +121,20 @@ __global__ void __launch_bounds__(kLeafBlock) k_leaf_stats(long long n, long lon
       cnts[s * kLeafBlock + tid] += 1;
     }
   };
-  for (long long q0 = (long long) blockIdx.x * kLeafBlock + tid; q0 < nquad; q0 += 2 * stride) {
-    const long long q1 = q0 + stride;
-    const bool two = q1 < nquad;
-    const double2 a0 = __ldg(reinterpret_cast<const double2*>(R + 4 * q0)), b0 = __ldg(reinterpret_cast<const double2*>(R + 4 * q0 + 2));
-    double2 a1 = make_double2(0.0, 0.0), b1 = a1;
-    if (two) { a1 = __ldg(reinterpret_cast<const double2*>(R + 4 * q1)); b1 = __ldg(reinterpret_cast<const double2*>(R + 4 * q1 + 2)); }
-    const uint32_t s0 = slots_of(q0);
-    const uint32_t s1 = two ? slots_of(q1) : 0u;
-    add_quad(q0, a0, b0, s0);
-    if (two) add_quad(q1, a1, b1, s1);
+  for (long long q0 = (long long) blockIdx.x * kLeafBlock + tid; q0 < nquad; q0 += 4 * stride) {
+    // all global loads of four quads are issued before the first is used
+    double2 a[4], b[4]; uint32_t sl[4]; bool live[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long q = q0 + k * stride;
+      live[k] = q < nquad;
+      a[k] = make_double2(0.0, 0.0); b[k] = a[k];
+      if (live[k]) { a[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q)); b[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q + 2)); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sl[k] = live[k] ? slots_of(q0 + k * stride) : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (live[k]) add_quad(q0 + k * stride, a[k], b[k], sl[k]);
   }
   __syncthreads();
   // ---- CTA reduction in a fixed order: warp w takes slots w, w + 8, ...; one partial row (n, sum, sum of squares) per slot and CTA ----

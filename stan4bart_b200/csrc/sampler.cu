@@ -527,6 +527,9 @@ int s4b_shard_set_obs_range(s4b_shard* sh, int64_t first_obs, int64_t total_obs)
 { S4B_API_BEGIN S4B_REQUIRE(sh && first_obs >= 0 && total_obs >= first_obs); sh->ctx->set_obs_range(first_obs, total_obs); S4B_API_END }
 int s4b_shard_allreduce(s4b_shard* sh, double* vec, int64_t n, int op)
 { S4B_API_BEGIN S4B_REQUIRE(sh && vec && n >= 0 && (op == 0 || op == 1)); sh->ctx->allreduce_host(vec, n, op == 0 ? kOpSum : kOpMax, current_stream()); S4B_API_END }
+int s4b_shard_nccl_unique_id(unsigned char* out128) { S4B_API_BEGIN S4B_REQUIRE(out128); ShardContext::nccl_unique_id(out128); S4B_API_END }
+int s4b_shard_nccl_init(s4b_shard* sh, const unsigned char* id128) { S4B_API_BEGIN S4B_REQUIRE(sh && id128); sh->ctx->nccl_init(id128); S4B_API_END }
+int s4b_shard_use_nccl(s4b_shard* sh, int on) { S4B_API_BEGIN S4B_REQUIRE(sh); sh->ctx->use_nccl(on != 0); S4B_API_END }
 int gpubart_create_sharded(const s4b_bart_config* cfg, const double* y, const double* x, const double* x_test, s4b_shard* sh, gpubart_fit** out)
 {
   S4B_API_BEGIN

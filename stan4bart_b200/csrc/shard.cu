@@ -1,10 +1,13 @@
 // stan4bart_b200/csrc/shard.cu -- see shard.hpp
 #include "shard.hpp"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 namespace s4b {
@@ -39,6 +42,60 @@ __global__ void __launch_bounds__(256) k_allreduce_small(ShardDev sh, double* __
   }
 }
 
+// ---- NCCL, bound at run time: the library is the reference collective, not a link-time dependency of the product path ----
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api()
+{
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (h != nullptr) {
+      api.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(h, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(h, "ncclCommInitRank"));
+      api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+      api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+      api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    }
+  }
+  if (!api.ok) throw std::runtime_error("NCCL (libnccl.so.2) could not be loaded");
+  return api;
+}
+void nccl_check(int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + nccl_api().GetErrorString(rc)); }
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;       // nccl.h: ncclFloat64, ncclSum, ncclMax
+}  // namespace
+
+void ShardContext::nccl_unique_id(void* out128)
+{
+  NcclId id;
+  nccl_check(nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(out128, &id, sizeof id);
+}
+
+void ShardContext::nccl_init(const void* id128)
+{
+  if (nccl_comm_ != nullptr) return;
+  NcclId id; std::memcpy(&id, id128, sizeof id);
+  nccl_check(nccl_api().CommInitRank(&nccl_comm_, dev_.world, id, dev_.rank), "ncclCommInitRank");
+}
+
+void ShardContext::use_nccl(bool on)
+{
+  if (on && nccl_comm_ == nullptr) throw std::runtime_error("shard context: nccl_init first");
+  use_nccl_ = on;
+}
+
 ShardContext::ShardContext(int rank, int world)
 {
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) throw std::invalid_argument("shard context: bad rank / world");
@@ -56,6 +113,7 @@ ShardContext::ShardContext(int rank, int world)
 
 ShardContext::~ShardContext()
 {
+  if (nccl_comm_ != nullptr) nccl_api().CommDestroy(nccl_comm_);
   for (int r = 0; r < dev_.world; ++r) if (r != dev_.rank && dev_.mail[r] != nullptr) cudaIpcCloseMemHandle(dev_.mail[r]);
   cudaFree(local_); cudaFree(d_tmp_); cudaFree(d_err_);
 }
@@ -86,6 +144,10 @@ void ShardContext::allreduce(double* d_vec, int n, ReduceOp op, cudaStream_t str
   if (dev_.world == 1) return;
   if (!attached_) throw std::runtime_error("shard context: peers not attached");
   if (n < 0 || n > kMailVec) throw std::invalid_argument("shard all-reduce: vector too long");
+  if (use_nccl_) {        // the reference collective: same payload, same ranks, NCCL's ring / tree over NVLink
+    nccl_check(nccl_api().AllReduce(d_vec, d_vec, (size_t) n, kNcclFloat64, op == kOpSum ? kNcclSum : kNcclMax, nccl_comm_, stream), "ncclAllReduce");
+    return;
+  }
   ++vec_seq_;
   static const bool debug = getenv("S4B_SHARD_DEBUG") != nullptr;
   if (debug) fprintf(stderr, "[s4b shard] rank %d allreduce seq %llu n %d op %d\n", dev_.rank, vec_seq_, n, (int) op);

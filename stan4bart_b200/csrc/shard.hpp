@@ -56,6 +56,13 @@ class ShardContext {
   const ShardDev& dev() const { return dev_; }
   // in-place all-reduce of a small device vector (n <= kMailVec), identical result on every rank
   void allreduce(double* d_vec, int n, ReduceOp op, cudaStream_t stream);
+  // Reference collective: the same small all-reduces through ncclAllReduce over NVLink instead of the
+  // peer-mapped mailboxes.  NCCL is loaded at run time (libnccl.so.2); every rank calls nccl_init with the 128-byte unique id
+  // that rank 0 obtained from nccl_unique_id (hand it round with any transport).  use_nccl(true) routes allreduce() through it.
+  static void nccl_unique_id(void* out128);
+  void nccl_init(const void* id128);
+  void use_nccl(bool on);
+  bool using_nccl() const { return use_nccl_; }
   // host convenience (any length; chunks of kMailVec)
   void allreduce_host(double* h_vec, long long n, ReduceOp op, cudaStream_t stream);
 
@@ -67,6 +74,8 @@ class ShardContext {
   long long total_obs_ = 0;
   double* d_tmp_ = nullptr;
   unsigned int* d_err_ = nullptr;
+  void* nccl_comm_ = nullptr;
+  bool use_nccl_ = false;
 };
 
 // device side of the generic all-reduce, callable from any single CTA

@@ -61,6 +61,23 @@ class ShardContext:
         _lib.check(self.L.s4b_shard_allreduce(self.h, dptr(v), v.size, {"sum": 0, "max": 1}[op]))
         return v
 
+    def init_nccl(self):
+        """Reference collective: create the NCCL communicator of this context's ranks (collective; the unique id travels through
+        the torch.distributed process group) -- `use_nccl(True)` then routes the small all-reduces through ncclAllReduce."""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            _lib.check(self.L.s4b_shard_nccl_unique_id(buf))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        ident = (C.c_ubyte * 128).from_buffer_copy(bytes(t.cpu().tolist()))
+        _lib.check(self.L.s4b_shard_nccl_init(self.h, ident))
+
+    def use_nccl(self, on):
+        _lib.check(self.L.s4b_shard_use_nccl(self.h, int(bool(on))))
+
     @classmethod
     def from_torch_distributed(cls, total_obs=None):
         """Build and attach a context for the current torch.distributed process group (one rank per GPU)."""

@@ -45,6 +45,30 @@ def main():
     long_v = SC.allreduce_long_input(rank)
     res["allreduce_long"] = ctx.allreduce(long_v, "sum")
 
+    # ---- the reference collective: the same small all-reduces through ncclAllReduce (needs one GPU per rank) ----
+    res["nccl"] = np.array([0.0])
+    if ndev >= world:
+        ctx.init_nccl()
+        ctx.use_nccl(True)
+        res["nccl"] = np.array([1.0])
+        res["nccl_allreduce_sum"] = ctx.allreduce(v, "sum")
+        res["nccl_allreduce_max"] = ctx.allreduce(v, "max")
+        res["nccl_allreduce_long"] = ctx.allreduce(long_v, "sum")
+        pr = friedman_problem(SC.GLMM_N)
+        lo, hi = row_range(SC.GLMM_N, rank, world)
+        ctx.set_obs_range(lo, SC.GLMM_N)
+        sp = shard_problem(pr, lo, hi)
+        m = GlmmModel(sp["stan_data"], shard=ctx)        # Gram matrix and every data pass all-reduced by NCCL
+        m.set_mode(0)
+        m.set_offset(SC.glmm_offset()[lo:hi])
+        out = []
+        for q in SC.glmm_points(m.d):
+            lp, grad, st = m.log_prob_grad(q)
+            out.append(np.concatenate([[lp, st], grad]))
+        res["glmm_nccl"] = np.array(out)
+        del m
+        ctx.use_nccl(False)
+
     # ---- stand-alone BART on sharded rows ----
     for binary in (False, True):
         tag = "bin" if binary else "cont"

@@ -176,3 +176,26 @@ def test_sharded_weighted_gibbs_matches_whole_data_oracle(ranks):
     assert np.array_equal(ranks[0]["gibbs_wt_trace"], ranks[1]["gibbs_wt_trace"])
     got = _cat(ranks, "gibbs_wt_train", axis=0)
     assert rel_err(w["bart"]["train"], got, scale=np.abs(w["bart"]["train"]) + 1.0) <= 1e-7
+
+
+def test_nccl_reference_collective_agrees_with_the_mailbox_exchange(ranks):
+    """`ncclAllReduce` as the reference implementation of the exchange.  With one GPU per rank the worker repeats the
+    small all-reduces and the sharded GLMM density through NCCL (`s4b_shard_use_nccl`); both transports must give the same numbers
+    (two ranks: a + b either way round, so bit for bit) and the oracle's density.  On a one-GPU box NCCL cannot place two ranks on
+    the same device; the mailbox path (the product path) is what the other tests of this file exercise there."""
+    if not all(r["nccl"][0] == 1.0 for r in ranks):
+        pytest.skip("NCCL needs one GPU per rank (run with gpurun --gpus 2)")
+    for r in ranks:
+        assert np.array_equal(r["nccl_allreduce_sum"], r["allreduce_sum"])
+        assert np.array_equal(r["nccl_allreduce_max"], r["allreduce_max"])
+        assert np.array_equal(r["nccl_allreduce_long"], r["allreduce_long"])
+        assert np.allclose(r["glmm_nccl"], r["glmm_mode0"], rtol=1e-13, atol=0.0)
+    pr = friedman_problem(SC.GLMM_N)
+    g = O.OracleGlmm(pr["stan_data"])
+    g.set_offset(SC.glmm_offset())
+    for k, q in enumerate(SC.glmm_points(g.d)):
+        lp, grad, st = g.log_prob_grad(q)
+        for r in ranks:
+            row = r["glmm_nccl"][k]
+            assert int(row[1]) == st and abs(row[0] - lp) <= 1e-10 * max(1.0, abs(lp))
+            assert rel_err(grad, row[2:], scale=np.abs(grad) + 1.0) <= 1e-10
