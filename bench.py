@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--chains-per-gpu", type=int, default=2,
                     help="chains resident on every GPU, each on its own host thread and stream (value = aggregate over all chains; the "
                          "one-chain-per-GPU figure is reported beside it)")
+    ap.add_argument("--scaled-levels", action="store_true",
+                    help="grouping factors with max(5 | 8, n / 2000) levels each (SURVEY.md 8d: 'scale to max(5, N/2000) levels for big N and "
+                         "report it'): q = 3 n / 2000 random-effect coefficients instead of 18")
     ap.add_argument("--no-mode0", action="store_true", help="skip the glmm mode 0 leg (one device pass per gradient evaluation)")
     ap.add_argument("--shard-rows", action="store_true",
                     help="N > 1 only: ONE chain whose --n rows are sharded over the N GPUs (BASELINE config E; strong scaling) instead of "
@@ -57,8 +60,9 @@ def workload_config(args):
     what = "continuous Friedman causal" if args.continuous else "config C: binary probit Friedman causal"
     if args.weighted:
         what += " with observation weights"
-    return {"workload": "%s, n=%d, %d trees, p_bart=9, K=2, q=18, n_test=%d, "
-                        "1 chain per GPU" % (what, args.n, args.trees, args.n),
+    q = 18 if not getattr(args, "scaled_levels", False) else 2 * max(5, args.n // 2000) + max(8, args.n // 2000)
+    return {"workload": "%s, n=%d, %d trees, p_bart=9, K=2, q=%d, n_test=%d, "
+                        "1 chain per GPU" % (what, args.n, args.trees, q, args.n),
             "n": args.n, "trees": args.trees, "chains_per_gpu": 1, "parallelism": "chains over GPUs, no data-path collective",
             "l2": "inputs larger than L2, no explicit flush: one sweep streams ~%d MB of distinct N-length arrays (BART: binned X, "
                   "residual, response, offset, fits, latents; GLMM: X, Z index / value streams, response, offset, residual; running "
@@ -69,7 +73,8 @@ def workload_config(args):
 
 def make_problem(args):
     from stan4bart_b200.frontend import friedman_problem
-    pr = friedman_problem(args.n, binary=not args.continuous, seed=99)
+    lv = {"n_g1": max(5, args.n // 2000), "n_g2": max(8, args.n // 2000)} if getattr(args, "scaled_levels", False) else {}
+    pr = friedman_problem(args.n, binary=not args.continuous, seed=99, **lv)
     return add_weights(pr, args.n) if args.weighted else pr
 
 
@@ -625,11 +630,22 @@ def run_ours(args):
                    "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors; "
                    "bytes are per step of the GPU (all %d chain(s) on it advance one sweep)" % cpg}
 
-    # kernels launched inside the timed region, per sweep and chain: k_prepare_sweep + k_sweep + epilogue + epoch bump (BART block),
-    # the offset kernel + its epoch bump (1 kernel for a continuous response), parametric mean, the fused GLMM input refresh,
-    # the fused running-mean accumulation, plus the GLMM data passes
-    per_sweep_bart = 4 if bart.sweep_mode() == 2 else T + 3
+    # kernels launched inside the timed region, per sweep and chain.  BART block with the pipelined sweep: k_prepare_sweep +
+    # 2 x (k_sweep_pipe + k_sweep) segment launches (those with nothing to do return at once) + epilogue + epoch bump;
+    # synchronous sweep: k_prepare_sweep + k_sweep + epilogue + epoch bump; per-tree kernels: T + 3.  Then the offset kernel + its
+    # epoch bump (1 kernel for a continuous response), parametric mean, the fused GLMM input refresh, the fused running-mean
+    # accumulation, plus the GLMM data passes.
+    pl = bart.pipeline()
+    if bart.sweep_mode() == 2:
+        per_sweep_bart = (1 + 4 + 2) if pl["enabled"] else 4
+    else:
+        per_sweep_bart = T + 3
     launches = cpg * K * (per_sweep_bart + (1 if args.continuous else 2) + 1 + 1 + 1) + glmm_passes
+    sweeps_done = max(1, pl["sweeps_offered"])
+    roofline["pipelined_sweep"] = {"enabled": pl["enabled"], "tree_steps_pipelined_frac": pl["steps_pipelined"] / (sweeps_done * T) if pl["enabled"] else 0.0,
+                                   "misfits": pl["misfits"],
+                                   "note": "csrc/sweep_pipe.cuh: workers one tree step ahead of the controller; steps whose trees are too large for it "
+                                           "run in the synchronous kernel (csrc/sweep_kernel.cuh)"}
 
     cfg_out = workload_config(args)
     cfg_out["chains_per_gpu"] = cpg
