@@ -438,7 +438,11 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     for (size_t c = 0; c < q; ++c) gz_ptr_[c + 1] += gz_ptr_[c];
     sparse_gram_ = true;
     theta0_.assign((size_t) nb, 0.0); g0_.assign((size_t) nb, 0.0);
-    mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : 1;
+    // crossed grouping factors with many levels fill Z'WZ in (500 x 500 levels => 10^6 entries): the host-side expansion then costs
+    // more per evaluation (~1 ns per entry) than one device pass (tens of microseconds), so the per-evaluation device path is the
+    // default there
+    const bool expansion_pays = gz_val_.size() <= 60000;
+    mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : (expansion_pays ? 1 : 0);
   }
   dl_.assign((size_t) nb + 1, 0.0); Gd_.assign((size_t) nb + 1, 0.0);
   refresh_r();
