@@ -194,7 +194,6 @@ void gpubart_shim_initializeFit(BARTFit* fit, Control* control, Model* model, Da
   fit->sharedScratch.dataScale.min = -0.5; fit->sharedScratch.dataScale.max = 0.5; fit->sharedScratch.dataScale.range = 1.0;
   fit->currentNumSamples = 0; fit->impl = NULL; fit->stored = NULL; fit->storeEnabled = false; fit->storeBase = 0;
   if (control->numChains > 1 && !control->keepTrees) fail("the device sampler runs one chain per fit (stan4bart sets n.chains = 1, R/stan4bart_fit.R:438)");
-  if (control->useQuantiles) fail("quantile cut points are not implemented on the device (uniform cut points only)");
   if (data->y == NULL || data->x == NULL) return;           // a prediction-only fit: initializeState supplies the trees
 
   s4b_bart_config cfg; std::memset(&cfg, 0, sizeof cfg);
@@ -209,7 +208,7 @@ void gpubart_shim_initializeFit(BARTFit* fit, Control* control, Model* model, Da
   std::vector<int32_t> ncuts(data->numPredictors);
   int32_t mx = 1;
   for (std::size_t j = 0; j < data->numPredictors; ++j) { ncuts[j] = (int32_t) data->maxNumCuts[j]; if (ncuts[j] > mx) mx = ncuts[j]; }
-  cfg.n_cuts = mx; cfg.n_cuts_var = ncuts.data();
+  cfg.n_cuts = mx; cfg.n_cuts_var = ncuts.data(); cfg.use_quantiles = control->useQuantiles ? 1 : 0;
   gpubart_fit* g = NULL;
   check(gpubart_create(&cfg, data->y, data->x, data->x_test, &g), "initializeFit");
   fit->impl = g;

@@ -13,7 +13,7 @@ namespace dbarts {
     bool responseIsBinary;      // init.cpp:222
     bool verbose;               // init.cpp:265-266, :295
     bool keepTrainingFits;
-    bool useQuantiles;          // quantile cut points are not implemented on the device: refused by initializeFit
+    bool useQuantiles;          // cut points between the distinct sorted values (s4b_bart_config::use_quantiles)
     bool keepTrees;             // init.cpp:216-217, :739-741, :375
     std::size_t defaultNumSamples;   // init.cpp:219
     std::size_t defaultNumBurnIn;    // init.cpp:220

@@ -60,7 +60,10 @@ typedef struct s4b_bart_config {
    * tests/test_exact_posterior.py checks by brute-force enumeration.  1 = prior x likelihood ratio only, the form the change
    * step is remembered to have in dbarts / BayesTree (not verifiable here: dbarts is not vendored); exact only for p = 1. */
   int32_t change_symmetric;
-  int32_t reserved;
+  /* bart_args use.quantiles (R/stan4bart_fit.R:437-451 passes it on to dbartsControl): cut points between the distinct sorted values of
+   * every predictor (all gaps when there are at most n.cuts + 1 distinct values, else n.cuts of them evenly spaced in rank) instead of
+   * uniform over the range; not available for observation-sharded chains */
+  int32_t use_quantiles;
 } s4b_bart_config;
 
 /* the `data.stan` list, R/stan4bart_fit.R:259-365 / src/stan_sampler.cpp:112-380 (default path) */

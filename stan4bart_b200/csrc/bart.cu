@@ -721,11 +721,14 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   if (cfg.n_cuts_var != nullptr) {
     ncuts_var_.assign(cfg.n_cuts_var, cfg.n_cuts_var + p_);
     for (int j = 0; j < p_; ++j) if (ncuts_var_[(size_t) j] < 1 || ncuts_var_[(size_t) j] > cfg.n_cuts) throw std::invalid_argument("n_cuts_var entries must be in [1, n_cuts]");
-    S4B_CUDA(cudaMalloc(&d_ncuts_var_, sizeof(int) * (size_t) p_));
-    S4B_CUDA(cudaMemcpy(d_ncuts_var_, ncuts_var_.data(), sizeof(int) * (size_t) p_, cudaMemcpyHostToDevice));
   }
   cfg_.n_cuts_var = nullptr;
-  // ---- cut points (uniform over the training range) and binning, host side (setup only) ----
+  if (cfg.use_quantiles != 0) {
+    // bart_args use.quantiles: every predictor gets its own number of cuts (at most its n.cuts; fewer when it has few distinct values)
+    if (sharded()) throw std::invalid_argument("use_quantiles is not available for an observation-sharded chain (the cut points would need a global sort; uniform cuts only)");
+    if (ncuts_var_.empty()) ncuts_var_.assign((size_t) p_, cfg.n_cuts);
+  }
+  // ---- cut points (uniform over the training range, or between the distinct sorted values) and binning, host side (setup only) ----
   cuts_.resize((size_t) p_ * cfg.n_cuts);
   std::vector<uint8_t> xt((size_t) p_ * npad_, 0);
   std::vector<double> range((size_t) 2 * p_);          // (-min, max) per predictor: one max-reduction over the shards
@@ -740,12 +743,32 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
     const double* col = x + (size_t) j * n_;
     const double mn = -range[(size_t) 2 * j], mx = range[(size_t) 2 * j + 1];
     // a predictor with fewer cuts than n_cuts (bart_args n.cuts as a vector) pads its row with +inf: binning never goes past its last cut
-    const int mj = ncuts_var_.empty() ? cfg.n_cuts : ncuts_var_[(size_t) j];
-    double inc = (mx - mn) / (double) (mj + 1);
+    int mj = ncuts_var_.empty() ? cfg.n_cuts : ncuts_var_[(size_t) j];
     double* c = cuts_.data() + (size_t) j * cfg.n_cuts;
-    for (int k = 0; k < cfg.n_cuts; ++k) c[k] = k < mj ? mn + (double) (k + 1) * inc : std::numeric_limits<double>::infinity();
+    if (cfg.use_quantiles != 0) {
+      // dbarts' quantile rule (as recalled; dbarts is not vendored -- DESIGN.md section 6): distinct values sorted; few of them => a cut in
+      // every gap, otherwise mj cuts every (distinct / mj) values starting half a step in; a cut = midpoint of two neighbouring values
+      std::vector<double> u(col, col + n_);
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      const size_t nu = u.size();
+      size_t num, step, offset;
+      if (nu <= (size_t) mj + 1) { num = nu - 1; step = 1; offset = 0; }
+      else { num = (size_t) mj; step = nu / num; offset = step / 2; }
+      for (size_t k = 0; k < num; ++k) { const size_t idx = std::min(k * step + offset, nu - 2); c[k] = 0.5 * (u[idx] + u[idx + 1]); }
+      for (int k = (int) num; k < cfg.n_cuts; ++k) c[k] = std::numeric_limits<double>::infinity();
+      mj = (int) num;
+      ncuts_var_[(size_t) j] = mj;                  // 0 for a constant predictor: never available for a split
+    } else {
+      const double inc = (mx - mn) / (double) (mj + 1);
+      for (int k = 0; k < cfg.n_cuts; ++k) c[k] = k < mj ? mn + (double) (k + 1) * inc : std::numeric_limits<double>::infinity();
+    }
     uint8_t* dst = xt.data() + (size_t) j * npad_;
     for (long long i = 0; i < n_; ++i) dst[i] = (uint8_t) (std::lower_bound(c, c + cfg.n_cuts, col[i]) - c);
+  }
+  if (!ncuts_var_.empty()) {
+    S4B_CUDA(cudaMalloc(&d_ncuts_var_, sizeof(int) * (size_t) p_));
+    S4B_CUDA(cudaMemcpy(d_ncuts_var_, ncuts_var_.data(), sizeof(int) * (size_t) p_, cudaMemcpyHostToDevice));
   }
   S4B_CUDA(cudaMalloc(&d_xt_, xt.size()));
   S4B_CUDA(cudaMemcpy(d_xt_, xt.data(), xt.size(), cudaMemcpyHostToDevice));
@@ -1637,10 +1660,11 @@ std::string BartFit::summary() const
     snprintf(line, sizeof line, "%g%s", split_probs_.empty() ? 1.0 / (double) p_ : split_probs_[(size_t) j], j + 1 < p_ ? ", " : "\n");
     out += line;
   }
-  snprintf(line, sizeof line, "\tuse quantiles for rule cut points: false\n\tproposal probabilities: birth/death %.2f, swap %.2f, change %.2f; birth %.2f\n",
-           cfg_.birth_death_prob, cfg_.swap_prob, cfg_.change_prob, cfg_.birth_prob);
+  snprintf(line, sizeof line, "\tuse quantiles for rule cut points: %s\n\tproposal probabilities: birth/death %.2f, swap %.2f, change %.2f; birth %.2f\n",
+           cfg_.use_quantiles != 0 ? "true" : "false", cfg_.birth_death_prob, cfg_.swap_prob, cfg_.change_prob, cfg_.birth_prob);
   out += line;
-  snprintf(line, sizeof line, "Cutoff rules c in x<=c vs x>c\nnumber of cuts: %d per predictor (uniform over the training range)\n", cfg_.n_cuts);
+  snprintf(line, sizeof line, "Cutoff rules c in x<=c vs x>c\nnumber of cuts: %d per predictor (%s)\n", cfg_.n_cuts,
+           cfg_.use_quantiles != 0 ? "at most; between the distinct sorted training values" : "uniform over the training range");
   out += line;
   return out;
 }

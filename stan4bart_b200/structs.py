@@ -27,7 +27,7 @@ class BartConfig(C.Structure):
         ("birth_prob", C.c_double), ("base", C.c_double), ("power", C.c_double), ("k", C.c_double),
         ("node_scale", C.c_double), ("seed", C.c_uint64), ("split_probs", C.POINTER(C.c_double)),
         ("weights", C.POINTER(C.c_double)), ("k_df", C.c_double), ("k_scale", C.c_double),
-        ("n_cuts_var", C.POINTER(C.c_int32)), ("change_symmetric", C.c_int32), ("reserved", C.c_int32),
+        ("n_cuts_var", C.POINTER(C.c_int32)), ("change_symmetric", C.c_int32), ("use_quantiles", C.c_int32),
     ]
 
 
@@ -82,7 +82,7 @@ def i32(a):
 def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_binary=False,
                 base=0.95, power=2.0, k=2.0, node_scale=None, seed=0,
                 birth_death_prob=0.5, swap_prob=0.1, change_prob=0.4, birth_prob=0.5, split_probs=None, max_ctas=0, weights=None,
-                k_df=0.0, k_scale=float("inf"), change_symmetric=False):
+                k_df=0.0, k_scale=float("inf"), change_symmetric=False, use_quantiles=False):
     """dbarts defaults as used by stan4bart (R/stan4bart_fit.R:437-479).  split_probs: relative probabilities of the p
     predictors (bart_args split.probs), None = uniform."""
     if node_scale is None:
@@ -94,7 +94,8 @@ def bart_config(n, p, n_test=0, num_trees=75, n_cuts=100, thin=1, min_obs=5, is_
     cfg = BartConfig(n=n, p=p, n_test=n_test, num_trees=num_trees, n_cuts=n_cuts, thin=thin, min_obs=min_obs,
                      is_binary=int(is_binary), max_ctas=int(max_ctas), birth_death_prob=birth_death_prob, swap_prob=swap_prob,
                      change_prob=change_prob, birth_prob=birth_prob, base=base, power=power, k=k,
-                     node_scale=node_scale, seed=seed, k_df=float(k_df), k_scale=float(k_scale), change_symmetric=int(bool(change_symmetric)))
+                     node_scale=node_scale, seed=seed, k_df=float(k_df), k_scale=float(k_scale), change_symmetric=int(bool(change_symmetric)),
+                     use_quantiles=int(bool(use_quantiles)))
     if split_probs is not None:
         sp = np.ascontiguousarray(split_probs, dtype=np.float64)
         if sp.shape != (p,) or np.any(sp < 0) or not np.any(sp > 0):

@@ -528,6 +528,8 @@ def test_randomised_configurations_against_the_oracle(case, monkeypatch):
         kw["k_df"] = float(rng.uniform(0.5, 3.0))
     if case >= 10:               # bart_args n.cuts as a vector: one count per predictor
         kw["n_cuts"] = rng.integers(1, 60, p)
+    if case in (3, 7, 11, 13):   # bart_args use.quantiles
+        kw["use_quantiles"] = True
     variant = rng.choice(["auto", "stream", "nq2", "nq6"])
     if variant == "stream":
         monkeypatch.setenv("S4B_FORCE_STREAM", "1")
@@ -581,6 +583,37 @@ def test_cut_counts_per_predictor():
     assert births.shape[0] > 0 and np.all(births[:, 3] < counts[births[:, 2].astype(int)])
     tg, to = g.trees(), o.trees()
     assert np.array_equal(tg["var"], to["var"]) and rel_err(tg["value"], to["value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-9
+
+
+def test_quantile_cut_points():
+    """bart_args use.quantiles: cut points between the distinct sorted values (discrete predictors get a cut in every gap, a
+    constant predictor none); same cuts, bins, decisions and fits as the oracle; test rows are binned against the same cuts."""
+    n, T = 3000, 15
+    rng = np.random.default_rng(12)
+    x = np.empty((n, 5)); xt = np.empty((40, 5))
+    for a, m in ((x, n), (xt, 40)):
+        a[:, 0] = rng.integers(0, 2, m); a[:, 1] = rng.integers(0, 6, m) * 1.5; a[:, 2] = rng.standard_normal(m) ** 3
+        a[:, 3] = 7.0; a[:, 4] = rng.random(m)
+    x, xt = np.asfortranarray(x), np.asfortranarray(xt)
+    y = 2.0 * x[:, 0] + 0.4 * x[:, 1] + np.tanh(x[:, 2]) + x[:, 4] + 0.2 * rng.standard_normal(n)
+    cfg = bart_config(n, 5, n_test=40, num_trees=T, seed=9, n_cuts=np.array([100, 100, 30, 100, 255]), use_quantiles=True)
+    o, g = O.OracleBart(cfg, y, x, xt), GpuBart(cfg, y, x, xt)
+    for b in (o, g):
+        b.set_sigma(0.7); b.sample_trees_from_prior()
+    o.set_trace(T * 10); g.set_trace(T * 10)
+    for s in range(10):
+        ro, rg = o.run(), g.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9
+        assert rel_err(ro["test"], rg["test"], scale=np.abs(ro["test"]) + 1.0) <= 1e-9
+        assert np.array_equal(ro["varcount"], rg["varcount"]) and ro["varcount"][3] == 0
+    compare_traces(o.trace(), g.trace())
+    assert_same_partition(o, g, T)
+    tg, to = g.trees(), o.trees()
+    assert np.array_equal(tg["var"], to["var"]) and np.array_equal(tg["value"], to["value"])          # cut values bit for bit
+    rules = tg["var"] >= 0
+    assert set(np.unique(tg["value"][rules & (tg["var"] == 0)])) <= {0.5}
+    assert set(np.unique(tg["value"][rules & (tg["var"] == 1)])) <= {0.75, 2.25, 3.75, 5.25, 6.75}
+    assert "use quantiles for rule cut points: true" in g.summary()
 
 
 @pytest.mark.parametrize("binary", [False, True])

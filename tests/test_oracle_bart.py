@@ -237,3 +237,36 @@ def test_cut_counts_per_predictor_in_the_oracle():
     assert rules.shape[0] > 0 and np.all(rules[:, 3] < counts[rules[:, 2].astype(int)])
     with pytest.raises(Exception):
         O.OracleBart(bart_config(n, 3, num_trees=T, n_cuts=np.array([0, 3, 50])), y, x, xt)
+
+
+def test_quantile_cut_points_in_the_oracle():
+    """bart_args use.quantiles (R/stan4bart_fit.R:437-451 -> dbartsControl): cuts between the distinct sorted values.  Known answers of
+    the rule as restated in oracle_bart.c:quantile_cuts: few distinct values => a cut in every gap; many => n.cuts of them, every
+    (distinct / n.cuts) values starting half a step in; a constant predictor has no cut and is never split on."""
+    n, T = 400, 8
+    rng = np.random.default_rng(8)
+    x = np.empty((n, 4))
+    x[:, 0] = rng.integers(0, 2, n)                 # binary: one cut at 0.5
+    x[:, 1] = rng.integers(0, 5, n) * 2.0           # 0, 2, .. 8: cuts 1, 3, 5, 7
+    x[:, 2] = rng.permutation(n) + 0.0              # 400 distinct values, 7 cuts: step 57, offset 28 => between ranks 28|29, 85|86, ...
+    x[:, 3] = 3.25                                  # constant: no cut
+    x = np.asfortranarray(x)
+    y = x[:, 0] + 0.3 * x[:, 1] + np.sin(x[:, 2] / 50.0) + 0.1 * rng.standard_normal(n)
+    o = O.OracleBart(bart_config(n, 4, num_trees=T, seed=3, n_cuts=7, use_quantiles=True), y, x)
+    o.set_sigma(0.5); o.sample_trees_from_prior()
+    for _ in range(30):
+        r = o.run()
+    tr = o.trees()
+    rules = tr["var"] >= 0
+    assert rules.sum() > 0 and not np.any(tr["var"][rules] == 3)
+    allowed = {0: {0.5}, 1: {1.0, 3.0, 5.0, 7.0}, 2: {28.5 + 57.0 * k for k in range(7)}}
+    for v, c in zip(tr["var"][rules], tr["value"][rules]):
+        assert float(c) in allowed[int(v)], (v, c)
+    # every cut of the evenly-ranked predictor gets used over a long enough run of prior draws
+    seen = set()
+    for _ in range(60):
+        o.sample_trees_from_prior()
+        t2 = o.trees()
+        seen |= {float(c) for v, c in zip(t2["var"], t2["value"]) if v == 2}
+    assert seen == allowed[2]
+
