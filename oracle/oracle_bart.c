@@ -508,36 +508,42 @@ or_bart* or_bart_create(const s4b_bart_config* cfg, const double* y, const doubl
   f->offset = (double*) calloc(n ? n : 1, sizeof(double));
   f->ncuts = (int*) malloc(sizeof(int) * p); f->cuts = (double**) malloc(sizeof(double*) * p);
   f->split_w = NULL;
-  if (cfg->split_probs) {
-    /* integer weights: round(2^30 sp_j / sum sp), at least 1 for a positive probability */
-    double sum = 0.0;
-    for (size_t j = 0; j < p; ++j) sum += cfg->split_probs[j];
-    f->split_w = (uint32_t*) malloc(sizeof(uint32_t) * p);
-    for (size_t j = 0; j < p; ++j) {
-      double t = cfg->split_probs[j] / sum;
-      double w = floor(ldexp(t, 30) + 0.5);
-      f->split_w[j] = cfg->split_probs[j] > 0.0 ? (w < 1.0 ? 1u : (uint32_t) w) : 0u;
-    }
-  }
   f->cfg.split_probs = NULL;       /* the caller's array is not kept */
   f->weights = NULL;
   if (cfg->weights) { f->weights = (double*) malloc(sizeof(double) * (n ? n : 1)); memcpy(f->weights, cfg->weights, sizeof(double) * n); }
   f->cfg.weights = NULL;
   f->cfg.n_cuts_var = NULL;
   f->xt = (uint8_t*) malloc(n * p + 1);
+  int* cutless = NULL;
   for (size_t j = 0; j < p; ++j) {
     const double* col = x + j * n;
     double mn = col[0], mx = col[0];
     for (size_t i = 1; i < n; ++i) { if (col[i] < mn) mn = col[i]; if (col[i] > mx) mx = col[i]; }
     f->ncuts[j] = cfg->n_cuts_var ? cfg->n_cuts_var[j] : cfg->n_cuts;      /* bart_args n.cuts, possibly one count per predictor */
     f->cuts[j] = (double*) malloc(sizeof(double) * (size_t) cfg->n_cuts);
-    if (cfg->use_quantiles) f->ncuts[j] = quantile_cuts(col, n, f->ncuts[j], f->cuts[j]);
-    else {
+    if (cfg->use_quantiles) {
+      f->ncuts[j] = quantile_cuts(col, n, f->ncuts[j], f->cuts[j]);
+      /* a constant predictor has no cut: out of the variable selection (split weight 0 below), one unreachable cut keeps the intervals defined */
+      if (f->ncuts[j] == 0) { if (!cutless) cutless = (int*) calloc(p, sizeof(int)); cutless[j] = 1; f->ncuts[j] = 1; f->cuts[j][0] = INFINITY; }
+    } else {
       double inc = (mx - mn) / (double) (f->ncuts[j] + 1);
       for (int k = 0; k < f->ncuts[j]; ++k) f->cuts[j][k] = mn + (double) (k + 1) * inc;
     }
     for (size_t i = 0; i < n; ++i) f->xt[j * n + i] = bin_value(f->cuts[j], f->ncuts[j], col[i]);
   }
+  if (cfg->split_probs || cutless) {
+    /* integer weights: round(2^30 sp_j / sum sp), at least 1 for a positive probability; predictors without a cut weigh 0 */
+    double sum = 0.0;
+    for (size_t j = 0; j < p; ++j) sum += (cutless && cutless[j]) ? 0.0 : (cfg->split_probs ? cfg->split_probs[j] : 1.0);
+    f->split_w = (uint32_t*) malloc(sizeof(uint32_t) * p);
+    for (size_t j = 0; j < p; ++j) {
+      double spj = (cutless && cutless[j]) ? 0.0 : (cfg->split_probs ? cfg->split_probs[j] : 1.0);
+      double t = spj / sum;
+      double w = floor(ldexp(t, 30) + 0.5);
+      f->split_w[j] = spj > 0.0 ? (w < 1.0 ? 1u : (uint32_t) w) : 0u;
+    }
+  }
+  free(cutless);
   if (nt > 0) {
     f->x_test = (double*) malloc(sizeof(double) * nt * p); memcpy(f->x_test, x_test, sizeof(double) * nt * p);
     f->xt_test = (uint8_t*) malloc(nt * p);

@@ -757,8 +757,11 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
       else { num = (size_t) mj; step = nu / num; offset = step / 2; }
       for (size_t k = 0; k < num; ++k) { const size_t idx = std::min(k * step + offset, nu - 2); c[k] = 0.5 * (u[idx] + u[idx + 1]); }
       for (int k = (int) num; k < cfg.n_cuts; ++k) c[k] = std::numeric_limits<double>::infinity();
+      // a constant predictor has no cut: it is taken out of the variable selection (split weight 0, exactly like split.probs = 0)
+      // and keeps one unreachable cut at +inf so that the interval bookkeeping stays well defined
+      if (num == 0) { cutless_.push_back(j); num = 1; c[0] = std::numeric_limits<double>::infinity(); }
       mj = (int) num;
-      ncuts_var_[(size_t) j] = mj;                  // 0 for a constant predictor: never available for a split
+      ncuts_var_[(size_t) j] = mj;
     } else {
       const double inc = (mx - mn) / (double) (mj + 1);
       for (int k = 0; k < cfg.n_cuts; ++k) c[k] = k < mj ? mn + (double) (k + 1) * inc : std::numeric_limits<double>::infinity();
@@ -813,25 +816,32 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   P.k_inv_scale2 = (cfg.k_scale > 0.0 && std::isfinite(cfg.k_scale)) ? 1.0 / (cfg.k_scale * cfg.k_scale) : 0.0;
   P.sigma = 1.0; P.smin = -0.5; P.smax = 0.5; P.srange = cfg.is_binary ? 1.0 : 0.0;
   P.key0 = (uint32_t) cfg.seed; P.key1 = (uint32_t) (cfg.seed >> 32);
-  if (cfg.split_probs != nullptr) {
+  std::vector<double> sp_eff;
+  if (cfg.split_probs != nullptr) sp_eff.assign(cfg.split_probs, cfg.split_probs + p_);
+  if (!cutless_.empty()) {
+    if (sp_eff.empty()) sp_eff.assign((size_t) p_, 1.0);
+    for (int j : cutless_) sp_eff[(size_t) j] = 0.0;
+  }
+  if (!sp_eff.empty()) {
     // bart_args split.probs -> integer weights round(2^30 p_j / sum p), at least 1 for a positive probability (same recipe
     // as the oracle: selection and rule priors are then exact integer arithmetic on both sides)
+    const double* split_probs = sp_eff.data();
     double sum = 0.0;
-    for (int j = 0; j < p_; ++j) { if (!(cfg.split_probs[j] >= 0.0)) throw std::invalid_argument("split_probs must be non-negative"); sum += cfg.split_probs[j]; }
-    if (!(sum > 0.0)) throw std::invalid_argument("split_probs must not all be zero");
+    for (int j = 0; j < p_; ++j) { if (!(split_probs[j] >= 0.0)) throw std::invalid_argument("split_probs must be non-negative"); sum += split_probs[j]; }
+    if (!(sum > 0.0)) throw std::invalid_argument("split_probs must not all be zero (and with use_quantiles at least one predictor must take two values)");
     std::vector<uint32_t> w((size_t) p_);
     unsigned long long total = 0; int pos = 0;
     for (int j = 0; j < p_; ++j) {
-      const double tj = cfg.split_probs[j] / sum;
+      const double tj = split_probs[j] / sum;
       const double wj = std::floor(std::ldexp(tj, 30) + 0.5);
-      w[(size_t) j] = cfg.split_probs[j] > 0.0 ? (wj < 1.0 ? 1u : (uint32_t) wj) : 0u;
+      w[(size_t) j] = split_probs[j] > 0.0 ? (wj < 1.0 ? 1u : (uint32_t) wj) : 0u;
       total += w[(size_t) j]; pos += w[(size_t) j] != 0u;
     }
     S4B_CUDA(cudaMalloc(&d_split_w_, sizeof(uint32_t) * (size_t) p_));
     S4B_CUDA(cudaMemcpy(d_split_w_, w.data(), sizeof(uint32_t) * (size_t) p_, cudaMemcpyHostToDevice));
     P.split_w = d_split_w_; P.split_total = total; P.p_pos = pos;
     split_probs_.resize((size_t) p_);
-    for (int j = 0; j < p_; ++j) split_probs_[(size_t) j] = cfg.split_probs[j] / sum;
+    for (int j = 0; j < p_; ++j) split_probs_[(size_t) j] = split_probs[j] / sum;
   }
   cfg_.split_probs = nullptr;        // the caller's array is not kept
   if (cfg.weights != nullptr) {
@@ -974,11 +984,11 @@ void BartFit::setup_persistent()
     if (persistent_nq_ != kStreamNq && d_wt_ == nullptr && !sharded() && !(getenv("S4B_PIPE") && atoi(getenv("S4B_PIPE")) == 0)) {
       const void* fn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
                      : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
-      const size_t fixed = ((sizeof(PipeSmem) + 15) / 16) * 16 + (size_t) (kPipeSlots + 1) * kWorkers * sizeof(double)
+      const size_t fixed = ((sizeof(PipeSmem) + 15) / 16) * 16 + (size_t) (kPipeSlots + 1) * kWorkers * sizeof(double) + 2 * (size_t) kWorkers * sizeof(unsigned long long)
                          + (size_t) p_ * persistent_nq_ * kWorkers * sizeof(uint32_t);
       // the cross table (slot of this step) x (cell of the previous step) gets what shared memory is left: one byte counter per entry and thread
       int entries = 0;
-      if (fixed < (size_t) max_smem) entries = (int) std::min<size_t>((size_t) kPipeSlots * kPipeCells, ((size_t) max_smem - fixed) / kWorkers - 1);
+      if (fixed < (size_t) max_smem) entries = (int) std::min<size_t>((size_t) kPipeCross, ((size_t) max_smem - fixed) / kWorkers - 1);
       entries &= ~3;
       if (entries >= 4 * kPipeSlots) {
         const int words = entries;            // (member name kept: capacity of the cross table in entries)

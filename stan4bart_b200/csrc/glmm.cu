@@ -36,7 +36,10 @@ __device__ __forceinline__ double g_warp_sum(double v)
 }
 
 // algorithmic bytes per observation: r 8 + X 8K + Z (4 + 8 [0 if the slot is an indicator]) per slot
-__global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
+// KT, ST: compile-time bounds of the fast path (K <= KT dense columns, <= ST non-zeros per row of Z), so that the register arrays of
+// the loads in flight are as small as the model allows; <4, 4> also carries the general path
+template <int KT, int ST>
+__global__ void __launch_bounds__(kGBlock, 2) k_glmm_data_terms(GlmmDev g)
 {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -50,13 +53,16 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
   const long long N = g.N, npad = g.npad;
   const int K = g.K, slots = g.slots;
   double S = 0.0;
-  if (K <= kGFast && slots <= kGFast) {
+  double gx[KT];                                     // fast path: X'e in registers (the dense columns are the same for every row)
+#pragma unroll
+  for (int k = 0; k < KT; ++k) gx[k] = 0.0;
+  if (K <= KT && slots <= ST) {
     // fast path (K, non-zeros per row <= 4: every BASELINE config): two observations per thread and load, two such pairs
     // in flight per iteration, every global load of the iteration issued before the first use -- the pass is bound by
     // memory latency otherwise (ncu: long-scoreboard stalls, 1.1 TB/s)
     const long long stride = (long long) gridDim.x * kGBlock * 2;
     for (long long i0 = ((long long) blockIdx.x * kGBlock + tid) * 2; i0 < N; i0 += 2 * stride) {
-      double2 r2[2], w2[2], x2[2][kGFast], v2[2][kGFast]; int2 c2[2][kGFast];
+      double2 r2[2], w2[2], x2[2][KT], v2[2][ST]; int2 c2[2][ST];
       bool live[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -66,9 +72,9 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
           r2[u] = __ldg(reinterpret_cast<const double2*>(g.r + i));
           w2[u] = g.wt != nullptr ? __ldg(reinterpret_cast<const double2*>(g.wt + i)) : make_double2(1.0, 1.0);
 #pragma unroll
-          for (int k = 0; k < kGFast; ++k) if (k < K) x2[u][k] = __ldg(reinterpret_cast<const double2*>(g.X + (long long) k * npad + i));
+          for (int k = 0; k < KT; ++k) if (k < K) x2[u][k] = __ldg(reinterpret_cast<const double2*>(g.X + (long long) k * npad + i));
 #pragma unroll
-          for (int s_ = 0; s_ < kGFast; ++s_) if (s_ < slots) {
+          for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) {
             c2[u][s_] = __ldg(reinterpret_cast<const int2*>(g.zidx + (long long) s_ * npad + i));
             v2[u][s_] = ((g.ones_mask >> s_) & 1u) ? make_double2(1.0, 1.0) : __ldg(reinterpret_cast<const double2*>(g.zval + (long long) s_ * npad + i));
           }
@@ -81,9 +87,9 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
         const bool second = i + 1 < N;            // the padded tail holds zeros, but indicator slots are forced to 1
         double eta0 = 0.0, eta1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < kGFast; ++k) if (k < K) { eta0 += x2[u][k].x * sth[k]; eta1 += x2[u][k].y * sth[k]; }
+        for (int k = 0; k < KT; ++k) if (k < K) { eta0 += x2[u][k].x * sth[k]; eta1 += x2[u][k].y * sth[k]; }
 #pragma unroll
-        for (int s_ = 0; s_ < kGFast; ++s_) if (s_ < slots) { eta0 += v2[u][s_].x * sth[K + c2[u][s_].x]; eta1 += v2[u][s_].y * sth[K + c2[u][s_].y]; }
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) { eta0 += v2[u][s_].x * sth[K + c2[u][s_].x]; eta1 += v2[u][s_].y * sth[K + c2[u][s_].y]; }
         double e0 = r2[u].x - eta0, e1 = second ? r2[u].y - eta1 : 0.0;
         if (g.wt != nullptr) {       // continuous.stan:365: sum w e^2; its gradient carries w e
           const double we0 = w2[u].x * e0, we1 = w2[u].y * e1;
@@ -91,15 +97,30 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
           e0 = we0; e1 = we1;
         } else { S += e0 * e0; S += e1 * e1; }
 #pragma unroll
-        for (int k = 0; k < kGFast; ++k) if (k < K) { double a = wb[k * 32 + lane]; a += x2[u][k].x * e0; a += x2[u][k].y * e1; wb[k * 32 + lane] = a; }
+        for (int k = 0; k < KT; ++k) if (k < K) { gx[k] = fma(x2[u][k].x, e0, gx[k]); gx[k] = fma(x2[u][k].y, e1, gx[k]); }
+        // the non-zeros of one row of Z sit in distinct columns (compressed sparse rows), so a row's bin updates are independent of each
+        // other: all loads, then all stores -- one shared-memory round trip per row instead of one per non-zero; the second row of the
+        // pair may share columns with the first and follows it
+        if (g.row_distinct) {
+          double b0[ST];
 #pragma unroll
-        for (int s_ = 0; s_ < kGFast; ++s_) if (s_ < slots) {
-          wb[(K + c2[u][s_].x) * 32 + lane] += v2[u][s_].x * e0;
-          wb[(K + c2[u][s_].y) * 32 + lane] += v2[u][s_].y * e1;
+          for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wb[(K + c2[u][s_].x) * 32 + lane];
+#pragma unroll
+          for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wb[(K + c2[u][s_].x) * 32 + lane] = fma(v2[u][s_].x, e0, b0[s_]);
+#pragma unroll
+          for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wb[(K + c2[u][s_].y) * 32 + lane];
+#pragma unroll
+          for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wb[(K + c2[u][s_].y) * 32 + lane] = fma(v2[u][s_].y, e1, b0[s_]);
+        } else {
+#pragma unroll
+          for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) {
+            wb[(K + c2[u][s_].x) * 32 + lane] += v2[u][s_].x * e0;
+            wb[(K + c2[u][s_].y) * 32 + lane] += v2[u][s_].y * e1;
+          }
         }
       }
     }
-  } else
+  } else if (KT == kGFast && ST == kGFast)
   for (long long i = (long long) blockIdx.x * kGBlock + tid; i < N; i += (long long) gridDim.x * kGBlock) {
     double eta = 0.0;
     for (int k = 0; k < K; ++k) eta += __ldg(g.X + (long long) k * npad + i) * sth[k];
@@ -117,12 +138,23 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
       wb[(K + c) * 32 + lane] += v * e;
     }
   }
+  if (K <= KT && slots <= ST) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (k < K) wb[k * 32 + lane] = gx[k];
+  }
   wb[nb * 32 + lane] = S;
   __syncwarp();
-  for (int j = 0; j <= nb; ++j) {
-    double v = g_warp_sum(wb[j * 32 + lane]);
+  // warp reduction of the (nb + 1) x 32 lane-private bins, transposed: lane l sums row j0 + l over its 32 copies, starting at copy l
+  // (conflict-free: the 32 lanes touch 32 different banks), in a fixed order
+  for (int j0 = 0; j0 <= nb; j0 += 32) {
+    const int j = j0 + lane;
+    double v = 0.0;
+    if (j <= nb) {
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) v += wb[j * 32 + ((c + lane) & 31)];
+    }
     __syncwarp();
-    if (lane == 0) wb[j * 32] = v;
+    if (j <= nb) wb[j * 32] = v;
   }
   __syncthreads();
   const int G = gridDim.x;
@@ -148,6 +180,14 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_data_terms(GlmmDev g)
     if (lane == 0) g.result[v] = acc;
   }
   if (tid == 0) *g.ticket = 0u;
+}
+
+using DataTermsKernel = void (*)(GlmmDev);
+static DataTermsKernel data_terms_kernel(int K, int slots)
+{
+  if (K > kGFast || slots > kGFast) return k_glmm_data_terms<4, 4>;
+  if (K <= 2) return slots <= 2 ? k_glmm_data_terms<2, 2> : k_glmm_data_terms<2, 4>;
+  return slots <= 2 ? k_glmm_data_terms<4, 2> : k_glmm_data_terms<4, 4>;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -344,6 +384,26 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     }
     if (all_one) ones_mask_ |= 1u << s;
   }
+  // padding of rows with fewer non-zeros: columns the row does not use (value 0), so that the column indices of a row stay pairwise
+  // distinct and its bin updates in the data pass are independent of each other
+  row_distinct_ = 1;
+  {
+    std::vector<int> used;
+    for (long long i = 0; i < N_; ++i) {
+      const int nnz = d.u[i + 1] - d.u[i];
+      bool dup = false;
+      for (int a = 0; a < nnz && !dup; ++a) for (int b = a + 1; b < nnz; ++b) if (d.v[d.u[i] + a] == d.v[d.u[i] + b]) { dup = true; break; }
+      if (dup) row_distinct_ = 0;
+      if (nnz == slots_) continue;
+      if (q_ < slots_) { row_distinct_ = 0; continue; }
+      used.assign(d.v + d.u[i], d.v + d.u[i + 1]);
+      int c = 0;
+      for (int s = nnz; s < slots_; ++s) {
+        while (std::find(used.begin(), used.end(), c) != used.end()) ++c;
+        zidx[(size_t) s * npad_ + i] = c; used.push_back(c);
+      }
+    }
+  }
   auto dalloc = [&](double** p, size_t count) { S4B_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1))); zero_device_sync(*p, sizeof(double) * std::max<size_t>(count, 1), stream_); };
   dalloc(&d_X_, (size_t) std::max(1, K_) * npad_);
   for (int k = 0; k < K_; ++k) S4B_CUDA(cudaMemcpy(d_X_ + (size_t) k * npad_, d.X + (size_t) k * N_, sizeof(double) * (size_t) N_, cudaMemcpyHostToDevice));
@@ -384,8 +444,8 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     dalloc(&d_we_, (size_t) npad_);
     per_sm = 4;
   } else {
-    S4B_CUDA(cudaFuncSetAttribute(k_glmm_data_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_glmm_data_terms, kGBlock, smem_bytes_) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    S4B_CUDA(cudaFuncSetAttribute(data_terms_kernel(K_, slots_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_terms_kernel(K_, slots_), kGBlock, smem_bytes_) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
   }
   num_sms_ = sms;
   long long want = (N_ + 2 * kGBlock - 1) / (2 * kGBlock);
@@ -581,8 +641,11 @@ void GlmmModel::data_terms(const double* beta, const double* b, double* S, doubl
   if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
   GlmmDev g;
   g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
-  g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
-  if (!columns_) k_glmm_data_terms<<<grid_, kGBlock, smem_bytes_, stream_>>>(g);
+  g.ones_mask = ones_mask_; g.row_distinct = row_distinct_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
+  if (!columns_) {
+    void* args[] = { &g };
+    S4B_CUDA(cudaLaunchKernel((const void*) data_terms_kernel(K_, slots_), dim3(grid_), dim3(kGBlock), args, smem_bytes_, stream_));
+  }
   else {
     k_glmm_resid_we<<<grid_, kGBlock, 0, stream_>>>(g, d_we_, d_partials_);
     if (K_ > 0) k_glmm_dense_cols<<<dim3((unsigned) grid_, (unsigned) K_), kGBlock, 0, stream_>>>(g, d_we_, d_partials_);
@@ -610,7 +673,7 @@ void GlmmModel::parametric_mean_device(const double* beta, const double* b, doub
   if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
   GlmmDev g;
   g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
-  g.ones_mask = ones_mask_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
+  g.ones_mask = ones_mask_; g.row_distinct = row_distinct_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
   int grid = elementwise_grid(N_, kGBlock, num_sms_);
   k_glmm_linear_predictor<<<grid, kGBlock, (size_t) nb * sizeof(double) <= kThetaSmemMax ? sizeof(double) * (size_t) std::max(1, nb) : 8, stream_>>>(g, d_out, include_fixed ? 1 : 0, include_random ? 1 : 0);
   S4B_CUDA(cudaGetLastError());

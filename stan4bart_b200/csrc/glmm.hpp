@@ -17,9 +17,10 @@ struct GlmmDev {
   const double* X;        // [K][npad]
   const double* r;        // y - offset, [npad]
   const double* wt;       // observation weights [npad], nullptr = unweighted
-  const int* zidx;        // [slots][npad]   (ELL, padded rows point at column 0 with value 0)
+  const int* zidx;        // [slots][npad]   (ELL; the padding of a short row points at columns the row does not use, with value 0)
   const double* zval;     // [slots][npad]
   unsigned int ones_mask; // bit s set => every stored value of slot s is exactly 1.0
+  int row_distinct;       // every row's `slots` column indices are pairwise distinct (padding included): a row's bin updates are independent
   const double* theta;    // [K + q] : beta then b
   double* partials;       // [(1 + K + q)][G]
   double* result;         // [1 + K + q]
@@ -89,6 +90,7 @@ class GlmmModel {
   std::vector<int> p_, l_;
   int slots_ = 0, grid_ = 1, block_ = 256, num_sms_ = 1;
   unsigned int ones_mask_ = 0;
+  int row_distinct_ = 0;
   size_t smem_bytes_ = 0;
   long long num_grad_ = 0, num_passes_ = 0;
   // sweep-level sufficient statistics: with e = r - A theta (A = [X Z]) the data terms are an exact quadratic in theta,

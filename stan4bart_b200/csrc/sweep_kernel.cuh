@@ -1065,7 +1065,8 @@ struct PrepSmemWarp { DTree tree; CtlScratch cs; StepDesc sd; };
 // ---- pipelined sweep (sweep_pipe.cuh): data-independent description of a step's cells ----
 constexpr int kPipeSegments = 2;          // (pipelined run, synchronous step) rounds per sweep; the last synchronous launch takes the rest
 constexpr int kPipeSlots = 12;            // statistic slots a step of the pipelined kernel may have (+ 1 trash row of bins)
-constexpr int kPipeCells = 24;            // capacity of the per-step cell tables
+constexpr int kPipeCells = 48;            // capacity of the per-step cell tables (change / swap on a branch of k leaves: k^2 cells; slots <= 12 => k <= 6)
+constexpr int kPipeCross = 288;           // capacity of a step's cross table (its slots) x (the previous step's cells); a pair of steps beyond it drains the pipeline
 constexpr int kPipeRing = 4;
 constexpr int kPipeDescs = 3;
 
@@ -1093,7 +1094,7 @@ __device__ inline bool w_pipe_info(const DTree& t, const StepDesc& d, PipeInfo& 
   const int n_int = d.b_cur.n_int;
   bool ok = nn + 2 <= 32 && nslots + (bd ? 1 : 0) <= 32 && nslots <= kPipeSlots && n_int <= S4B_BITMAP_INT;
   int ncells = nslots;
-  if (lane < kPipeCells) { pi.cell_a[lane] = 0; pi.cell_f[lane] = 0; }
+  for (int c = lane; c < kPipeCells; c += 32) { pi.cell_a[c] = 0; pi.cell_f[c] = 0; }
   if (lane < 16) pi.cellbase[lane] = 0;
   if (lane < kPipeSlots + 2) pi.vs[lane] = 0.0;
   __syncwarp();

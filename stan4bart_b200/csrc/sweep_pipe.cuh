@@ -27,6 +27,12 @@
 // barrier counter, no release fence on the workers' side and no flag-then-data double round trip on the controller's --
 // it polls the very words it needs, one L2 round trip per step instead of reading 148 partial rows.
 //
+// Drained steps: a step whose cross table would not fit the counters -- (its slots) x (the previous step's cells) above the capacity
+// the launch was given -- waits for the previous decision as well and applies it before it accumulates: its rows then have no
+// update pending (one cell, no correction), at the price of one synchronous step; every thread derives the same flag from the step
+// descriptors, so nothing is communicated.  The workers add the plain residuals: the leaf values of the current tree enter as
+// count x value on the controller's side (one multiply per slot instead of one add per row).
+//
 // Rings: accumulator rows and barrier counters are 4 deep (a CTA can run at most two steps ahead of another CTA's controller
 // reading rows); descriptors 3 deep; update tables 2 deep.  Decisions, draws and tree updates are the synchronous kernel's
 // (w_plan / w_decide_fast), so both kernels produce the same chain up to the rounding of the slot sums.
@@ -36,7 +42,8 @@
 
 namespace s4b {
 
-constexpr int kPipeAcc = 2 * kPipeSlots + (kPipeSlots * kPipeCells) / 2;     // per step: (hi, lo) per slot sum, then one word per pair of cross-table entries
+constexpr int kPipeAcc = 2 * kPipeSlots + kPipeCross / 2;     // per step: (hi, lo) per slot sum, then one word per pair of cross-table entries
+constexpr int kPipePacked = 24;            // cross tables up to this many entries are counted in two packed registers per thread (5-bit fields)
 struct PipeSmem {
   StepDesc sd[kPipeDescs];
   PipeInfo info[kPipeDescs];
@@ -46,7 +53,7 @@ struct PipeSmem {
   double2 draws[2][32];                     // decision draws of the step being decided / the next one
   double dcell[2][kPipeCells];              // delta of step parity: mu_old - mu_new per cell
   int ncnt[4 * kPipeSlots];                  // staging of the (hi, lo) limbs of the slot sums
-  int cross[kPipeSlots * kPipeCells + 2];    // the cross table of the step being decided
+  int cross[kPipeCross + 2];                 // the cross table of the step being decided
   CtlScratch csd;
   LeafStat st[S4B_MAX_SLOTS];
   FastPlanSmem plan;
@@ -55,6 +62,14 @@ struct PipeSmem {
   RngState rng;
   BartParams prm;
 };
+
+// 1 << sh for sh < 64, 0 otherwise (PTX shl clamps the shift amount; an amount that wrapped below zero is a large unsigned number)
+__device__ __forceinline__ unsigned long long shl64_clamp(unsigned sh)
+{
+  unsigned long long r;
+  asm("shl.b64 %0, 1, %1;" : "=l"(r) : "r"(sh));
+  return r;
+}
 
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -152,15 +167,30 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
   }
   const int T_all = dv.params->num_trees;
   const int t_begin = *pos_in;
-  // a step fits when its trees are small (k_prepare_sweep's flag) and its cross table -- (its slots) x (the previous step's cells) --
-  // fits the shared-memory counters; the first step of a run has no predecessor in flight (one cell)
-  int t_end = t_begin;
-  while (t_end < T_all && infos[t_end].ok != 0 && (t_end == t_begin || infos[t_end].nslots * infos[t_end - 1].ncells <= count_entries)) ++t_end;
+  // a step fits when its trees are small (k_prepare_sweep's flag); when its cross table -- (its slots) x (the previous step's cells) --
+  // does not fit the shared-memory counters it runs drained (below); the first step of a run has no predecessor in flight (one cell)
+  // (every warp scans by itself, 8 x 32 flags per round with all loads issued before the first is used: a thread-serial scan costs one L2
+  // round trip per step, ~0.1 ms for a 200-tree sweep)
+  int t_end = T_all;
+  {
+    const int ln = threadIdx.x & 31;
+    for (int base = t_begin; base < T_all && t_end == T_all; base += 256) {
+      int okv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int t = base + 32 * k + ln; okv[k] = t < T_all ? __ldg(&infos[t].ok) : 0; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned bad = __ballot_sync(0xffffffffu, okv[k] == 0);
+        if (bad != 0u && t_end == T_all) t_end = min(T_all, base + 32 * k + __ffs(bad) - 1);
+      }
+    }
+  }
   if (t_end == t_begin) { if (blockIdx.x == 0 && threadIdx.x == 0) *pos_out = t_begin; return; }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PipeSmem& S = *reinterpret_cast<PipeSmem*>(smem_raw);
   double* bins = reinterpret_cast<double*>(smem_raw + ((sizeof(PipeSmem) + 15) / 16) * 16);                    // [kPipeSlots + 1][kWorkers]
-  uint8_t* cnt = reinterpret_cast<uint8_t*>(bins + (kPipeSlots + 1) * kWorkers);                                  // [count_entries + 1][kWorkers] bytes
+  unsigned long long* pkw = reinterpret_cast<unsigned long long*>(bins + (kPipeSlots + 1) * kWorkers);            // [2][kWorkers]: packed counters of small cross tables
+  uint8_t* cnt = reinterpret_cast<uint8_t*>(pkw + 2 * kWorkers);                                                   // [count_entries + 1][kWorkers] bytes
   uint32_t* tile = reinterpret_cast<uint32_t*>(cnt + (size_t) (count_entries + 1) * kWorkers);                    // [p][NQ * kWorkers]
   constexpr int tile_stride = NQ * kWorkers;
 
@@ -222,9 +252,16 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     // rows beyond the data (the tail of the last quad, quads beyond q_hi) are parked in the trash slot kPipeSlots at every step
     constexpr unsigned kAllObs = NQ == 8 ? 0xFFFFFFFFu : ((1u << (4 * NQ)) - 1u);
     const bool ragged = obs_mask != kAllObs;
-    int C = 1;                                 // cells of the previous step (its descriptor's ring slot is recycled two steps later)
-    // cycle counters (thread 0 of CTA 0, only when asked for): [0] wait for decision t-2, [1] U, [2] W, [3] A, [4] CTA reduce + arrive
-    long long wp0 = 0, wp1 = 0, wp2 = 0, wp3 = 0, wp4 = 0;
+    uint32_t tmask[NQ];                        // 0xFF in the bytes of rows beyond the data
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const uint32_t nib = (~obs_mask >> (4 * j)) & 0xFu;
+      tmask[j] = (((nib * 0x00204081u) & 0x01010101u) * 0xFFu);
+    }
+    int C = 1;                                 // cells of the previous step as the cross table sees them (1 at the start and after a drained step)
+    int na = t_begin;                          // the next decision whose update the residuals have not seen yet
+    // cycle counters (thread 0 of CTA 0, only when asked for): [0] wait for decisions, [1] U, [2] W, [3] A, [4] CTA reduce + arrive, [6] drained steps
+    long long wp0 = 0, wp1 = 0, wp2 = 0, wp3 = 0, wp4 = 0, wp6 = 0;
     const bool wprof = prof != nullptr && cta == 0 && tid == 0;
     const int e_trash = count_entries;
     uint32_t* cntw = reinterpret_cast<uint32_t*>(cnt);
@@ -235,16 +272,28 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       const StepDesc& sd = S.sd[t % kPipeDescs];
       const PipeInfo& pi = S.info[t % kPipeDescs];
       const long long k0 = clock64();
-      long long k1 = k0;
-      if (t >= t_begin + 2) {
-        // ---- U(t-2): wait for decision t-2, add its per-cell deltas ----
-        named_bar_sync(2 + (t & 1), kSweepBlock);
-        k1 = clock64();
-        const double* dc = S.dcell[t & 1];
+      const int kind = sd.b_kind, L = sd.b_num_leaves, nslots = sd.b_nslots;
+      // a cross table beyond the counters' capacity: this step waits for the previous decision too and starts from updated residuals
+      const bool drained = t > t_begin && nslots * C > count_entries;
+      // ---- U: apply the decisions up to t-2 (t-1 as well when drained): per-cell deltas ----
+      long long kw = 0;
+      for (const int need = drained ? t - 1 : t - 2; na <= need; ++na) {
+        const long long w0 = clock64();
+        named_bar_sync(2 + (na & 1), kSweepBlock);
+        kw += clock64() - w0;
+        const double* dc = S.dcell[na & 1];
+        const bool newest = na == t - 1;
 #pragma unroll
-        for (int j = 0; j < NQ; ++j)
+        for (int j = 0; j < NQ; ++j) {
+          const uint32_t cw = newest ? cprev[j] : cprev2[j];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) R[j][o] += dc[(cprev2[j] >> (8 * o)) & 0xFF];
+          for (int o = 0; o < 4; ++o) R[j][o] += dc[(cw >> (8 * o)) & 0xFF];
+        }
+      }
+      if (drained) {
+        C = 1;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) cprev[j] = 0u;
       }
       const long long k2 = clock64();
       // one warp fetches the next step's descriptor (its ring slot held step t-2, which has been decided)
@@ -254,33 +303,42 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       pipe_walk<NQ>(sd, pi, tile, tile_stride, tid, sp, pp);
       if (ragged) {
 #pragma unroll
-        for (int j = 0; j < NQ; ++j)
-#pragma unroll
-          for (int o = 0; o < 4; ++o) if (!((obs_mask >> (4 * j + o)) & 1u)) { sp[j] = (sp[j] & ~(0xFFu << (8 * o))) | ((uint32_t) kPipeSlots << (8 * o)); pp[j] |= 0xFFu << (8 * o); }
+        for (int j = 0; j < NQ; ++j) { sp[j] = (sp[j] & ~tmask[j]) | (((uint32_t) kPipeSlots * 0x01010101u) & tmask[j]); pp[j] |= tmask[j]; }
       }
       const long long k3 = clock64();
-      const int kind = sd.b_kind, L = sd.b_num_leaves, nslots = sd.b_nslots;
       const bool two_trees = (kind == 2 || kind == 3);
       const int E = nslots * C;
       const int C_next = pi.ncells;
+      // small cross tables (the usual case) are counted in two packed registers per thread, 12 five-bit fields each (a thread owns at
+      // most 24 rows and an entry sees a row at most once); larger ones in the shared-memory byte counters
+      const bool packed = E <= kPipePacked;
+      unsigned long long pk0 = 0ull, pk1 = 0ull;
       // the previous step's reduction tasks have read the bins and the count table
       // (which have also put them back to zero: every bin row and counter row is zero between steps)
       if (t > t_begin) named_bar_sync(1, kWorkers);
-      // ---- A(t): per-slot sums of (residual after t-2) + mu_t, and the cross table (slot of t) x (cell of t-1) ----
+      // ---- A(t): per-slot sums of the residuals (after t-2, or after t-1 when drained), and the cross table (slot of t) x (cell of t-1);
+      //      the leaf values of the current tree are added by the controller (count x value); rows of a proposed slot come from
+      //      several current leaves, so their sums carry the leaf values themselves ----
       uint32_t ccur[NQ];
       if (!two_trees) {
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
-          double pr[4]; int s[4], e[4];
+          int s[4], e[4];
 #pragma unroll
           for (int o = 0; o < 4; ++o) {
             s[o] = (sp[j] >> (8 * o)) & 0xFF;
             const int cp = (cprev[j] >> (8 * o)) & 0xFF;
-            pr[o] = R[j][o] + pi.vs[s[o]];
-            e[o] = s[o] >= kPipeSlots ? e_trash : s[o] * C + cp;
+            e[o] = s[o] * C + cp;                                    // rows in the trash slot: beyond E
           }
 #pragma unroll
-          for (int o = 0; o < 4; ++o) { bins[s[o] * kWorkers + tid] += pr[o]; cnt[e[o] * kWorkers + tid] += 1; }
+          for (int o = 0; o < 4; ++o) bins[s[o] * kWorkers + tid] += R[j][o];
+          if (packed) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) { const unsigned sh = (unsigned) e[o] * 5u; pk0 += shl64_clamp(sh); pk1 += shl64_clamp(sh - 60u); }
+          } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) cnt[(s[o] >= kPipeSlots ? e_trash : e[o]) * kWorkers + tid] += 1;
+          }
           ccur[j] = sp[j];                                         // cells of this step = its slots
         }
       } else {
@@ -296,19 +354,30 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
             const bool in = pq != 255;
             pr[o] = R[j][o] + pi.vs[s[o]];
             q[o] = in ? pq : kPipeSlots;
-            e[o] = s[o] >= kPipeSlots ? e_trash : s[o] * C + cp;
-            e2[o] = in ? pq * C + cp : e_trash;
+            e[o] = s[o] * C + cp;
+            e2[o] = in ? pq * C + cp : 0xFFFF;
             const int cell = s[o] >= kPipeSlots ? kPipeSlots : (int) pi.cellbase[s[o]] + (in ? pq - L : 0);
             cc |= (uint32_t) cell << (8 * o);
           }
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            bins[s[o] * kWorkers + tid] += pr[o]; cnt[e[o] * kWorkers + tid] += 1;
-            bins[q[o] * kWorkers + tid] += pr[o]; cnt[e2[o] * kWorkers + tid] += 1;
+          for (int o = 0; o < 4; ++o) { bins[s[o] * kWorkers + tid] += R[j][o]; bins[q[o] * kWorkers + tid] += pr[o]; }
+          if (packed) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const unsigned sh = (unsigned) e[o] * 5u, sh2 = (unsigned) e2[o] * 5u;
+              pk0 += shl64_clamp(sh) + shl64_clamp(sh2); pk1 += shl64_clamp(sh - 60u) + shl64_clamp(sh2 - 60u);
+            }
+          } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              cnt[(s[o] >= kPipeSlots ? e_trash : e[o]) * kWorkers + tid] += 1;
+              cnt[(e2[o] == 0xFFFF ? e_trash : e2[o]) * kWorkers + tid] += 1;
+            }
           }
           ccur[j] = cc;
         }
       }
+      if (packed) { pkw[tid] = pk0; pkw[kWorkers + tid] = pk1; }
 #pragma unroll
       for (int j = 0; j < NQ; ++j) { cprev2[j] = cprev[j]; cprev[j] = ccur[j]; }
       const long long k4 = clock64();
@@ -331,6 +400,17 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
             atomicAdd(acc + 2 * task, (1ull << 56) | hi);
             atomicAdd(acc + 2 * task + 1, (1ull << 56) | lo);
           }
+        } else if (packed) {
+          // two cross-table entries per task (both in the same packed word: 12 fields per word)
+          const int e0 = 2 * (task - nslots);
+          const unsigned long long* wsrc = pkw + (e0 >= 12 ? kWorkers : 0);
+          const int f0 = 5 * (e0 >= 12 ? e0 - 12 : e0);
+          int c0 = 0, c1 = 0;
+#pragma unroll
+          for (int i = 0; i < kWorkerWarps; ++i) { const unsigned long long w = wsrc[i * 32 + lane] >> f0; c0 += (int) (w & 31ull); c1 += (int) ((w >> 5) & 31ull); }
+          c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
+          if (e0 + 1 >= E) c1 = 0;
+          if (lane == 0) atomicAdd(acc + 2 * kPipeSlots + (task - nslots), (1ull << 56) | (unsigned long long) (unsigned) c0 | ((unsigned long long) (unsigned) c1 << 28));
         } else {
           // two cross-table entries per task: 480 byte counters each, four at a time with dp4a
           const int e0 = 2 * (task - nslots), e1 = e0 + 1;
@@ -347,20 +427,22 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
           if (lane == 0) atomicAdd(acc + 2 * kPipeSlots + (task - nslots), (1ull << 56) | (unsigned long long) (unsigned) c0 | ((unsigned long long) (unsigned) c1 << 28));
         }
       }
-      // (the bins and the count table are rewritten by the next step only after the next named barrier)
+      // (the bins, the packed words and the count table are rewritten by the next step only after the next named barrier)
       C = C_next;
-      if (wprof) { const long long k5 = clock64(); wp0 += k1 - k0; wp1 += k2 - k1; wp2 += k3 - k2; wp3 += k4 - k3; wp4 += k5 - k4; }
+      if (wprof) { const long long k5 = clock64(); wp0 += kw; wp1 += k2 - k0 - kw; wp2 += k3 - k2; wp3 += k4 - k3; wp4 += k5 - k4; wp6 += drained ? 1 : 0; }
     }
-    if (wprof) { prof[0] += (unsigned long long) wp0; prof[1] += (unsigned long long) wp1; prof[2] += (unsigned long long) wp2; prof[3] += (unsigned long long) wp3; prof[4] += (unsigned long long) wp4; prof[5] += (unsigned long long) (t_end - t_begin); }
-    // ---- drain: the last two updates ----
-    for (int u = t_end - 2; u < t_end; ++u) {
-      if (u < t_begin) continue;
-      named_bar_sync(2 + (u & 1), kSweepBlock);
-      const double* dc = S.dcell[u & 1];
+    if (wprof) { prof[0] += (unsigned long long) wp0; prof[1] += (unsigned long long) wp1; prof[2] += (unsigned long long) wp2; prof[3] += (unsigned long long) wp3; prof[4] += (unsigned long long) wp4; prof[5] += (unsigned long long) (t_end - t_begin); prof[6] += (unsigned long long) wp6; }
+    // ---- drain: the updates not yet applied ----
+    for (; na < t_end; ++na) {
+      named_bar_sync(2 + (na & 1), kSweepBlock);
+      const double* dc = S.dcell[na & 1];
+      const bool newest = na == t_end - 1;
 #pragma unroll
-      for (int j = 0; j < NQ; ++j)
+      for (int j = 0; j < NQ; ++j) {
+        const uint32_t cw = newest ? cprev[j] : cprev2[j];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) R[j][o] += dc[((u == t_end - 1 ? cprev[j] : cprev2[j]) >> (8 * o)) & 0xFF];
+        for (int o = 0; o < 4; ++o) R[j][o] += dc[(cw >> (8 * o)) & 0xFF];
+      }
     }
 #pragma unroll
     for (int j = 0; j < NQ; ++j) if ((valid_mask >> j) & 1u) {
@@ -400,6 +482,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       const long long h2 = clock64();
       // ---- reduce the partial rows of all CTAs (fixed order), correct the sums with the previous step's deltas ----
       const int nslots = sd.b_nslots;
+      // a pair of steps whose cross table exceeds the counters: the workers ran this step drained (update u-1 applied first), one cell
+      const bool drained = u > t_begin && nslots * C > count_entries;
+      if (drained) C = 1;
       const int npairs = (nslots * C + 1) >> 1;
       {
         // One load per lane and 32 values: this step's totals = accumulator row now - the row as read kPipeRing steps ago; a word
@@ -442,9 +527,13 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       }
       __syncwarp();
       if (lane < nslots) {
-        const double* dprev = S.dcell[(u + 1) & 1];          // deltas of step u-1 (zeros before the first step)
+        const double* dprev = S.dcell[(u + 1) & 1];          // deltas of step u-1 (zeros before the first step; already applied when drained)
         int cnt_s = 0; double corr = 0.0;
-        for (int cidx = 0; cidx < C; ++cidx) { const int m = S.cross[lane * C + cidx]; cnt_s += m; if (m != 0) corr += (double) m * dprev[cidx]; }   // (an empty cell's delta is undefined)
+        for (int cidx = 0; cidx < C; ++cidx) { const int m = S.cross[lane * C + cidx]; cnt_s += m; if (m != 0 && !drained) corr += (double) m * dprev[cidx]; }   // (an empty cell's delta is undefined)
+        // the workers summed the plain residuals of the current slots: the partial residual adds the slot's current leaf value per row
+        // (the rows of a proposed slot of a change / swap step sit in several current leaves: those sums carry the values already)
+        const bool two = sd.b_kind == 2 || sd.b_kind == 3;
+        if (!two || lane < sd.b_num_leaves) corr += (double) cnt_s * pi.vs[lane];
         S.st[lane].n = (double) cnt_s;
         S.st[lane].sum += corr;
       }
@@ -461,10 +550,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       {
         const UpdateDesc& upd = S.upd[u & 1];
         const bool accepted = upd.mode != 0;
-        if (lane < kPipeCells) {
+        for (int c = lane; c < kPipeCells; c += 32) {
           double dlt = 0.0;
-          if (lane < pi.ncells) { const int a = pi.cell_a[lane]; const int f = accepted ? (int) pi.cell_f[lane] : a; dlt = upd.val_old[a] - upd.val_new[f]; }
-          S.dcell[u & 1][lane] = dlt;
+          if (c < pi.ncells) { const int a = pi.cell_a[c]; const int f = accepted ? (int) pi.cell_f[c] : a; dlt = upd.val_old[a] - upd.val_new[f]; }
+          S.dcell[u & 1][c] = dlt;
         }
       }
       __syncwarp();
