@@ -566,14 +566,34 @@ def run_ours(args):
             reps = 50
             leaf_ms = float(np.median([bart.time_leaf_stats(t, reps) for t in (0, T // 2, T - 1)]))
             leaf_gbs = 11.0 * n / (leaf_ms * 1e-3) / 1e9
-            leaf_stat = {"kernel": "k_tree_step (statistics only): one launch = one tree's per-leaf (n, sum r, sum r^2) over all rows",
+            leaf_stat = {"kernel": "k_leaf_stats (csrc/leaf_stats.cuh): one launch = one tree's per-leaf (n, sum r, sum r^2) over all rows",
                          "algorithmic_bytes_per_obs": 11.0, "launch_us": leaf_ms * 1e3, "achieved": leaf_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": leaf_gbs / peak, "traffic": traffic_file.get("k_tree_step_dram_bytes_per_launch"),
-                         "timing": "CUDA events around %d back-to-back launches on the launching stream, median over 3 trees; the 9 MB + 8 MB "
-                                   "working set stays in the 126 MB L2 between launches, so this is an L2-resident rate unless flushed" % reps}
+                         "frac": leaf_gbs / peak, "traffic": traffic_file.get("k_leaf_stats_dram_bytes_per_launch"),
+                         "timing": "CUDA events around %d back-to-back launches on the launching stream, median over 3 trees; at n = 1 M the "
+                                   "pass reads ~10 MB (1.5 us at peak) and is bound by ~10 us of fixed cost (launch, tree set-up, two-level "
+                                   "reduction), and the working set stays in L2 between launches; bandwidth-bound sizes (16 M - 32 M rows: "
+                                   "0.55 - 0.64 of peak) are in profiles/leaf_stat_sizes_r2.json" % reps}
         except Exception as e:      # pragma: no cover
             leaf_stat = {"error": repr(e)}
-    roofline = {"bound": "hbm", "kernel": "k_sweep (one launch = one %d-tree sweep)" % T if persistent else "k_tree_step (one launch = one tree)",
+    # the GLMM data pass (S, X'e, Z'e over all rows: 44 algorithmic B per row for this model), L2-warm and from HBM
+    glmm_pass = None
+    if not sharded:
+        try:
+            gm = glmm
+            bpr = 8.0 + 8.0 * sd.K + 4.0 * 3 + 8.0 * 1
+            warm_ms, is_bulk = gm.time_data_pass(30, False)
+            cold_ms, _ = gm.time_data_pass(20, True)
+            glmm_pass = {"kernel": "k_glmm_data_terms_bulk (cp.async.bulk + mbarrier ring)" if is_bulk else "k_glmm_data_terms", "algorithmic_bytes_per_obs": bpr,
+                         "launch_us_l2_warm": warm_ms * 1e3, "launch_us_l2_flushed": cold_ms * 1e3,
+                         "achieved_l2_warm": bpr * n / warm_ms / 1e6, "achieved": bpr * n / cold_ms / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": bpr * n / cold_ms / 1e6 / peak, "frac_l2_warm": bpr * n / warm_ms / 1e6 / peak,
+                         "traffic": traffic_file.get("k_glmm_data_terms_dram_bytes_per_launch"),
+                         "timing": "CUDA events around single launches (L2 flushed by a 256 MB memset before each) and around 30 back-to-back launches; "
+                                   "44 MB is 7 us at peak, ~8 us of the launch are fixed cost (profiles/glmm_pass_r2.json: 0.54 - 0.67 of peak at 4 M rows)"}
+        except Exception as e:      # pragma: no cover
+            glmm_pass = {"error": repr(e)}
+    roofline = {"bound": "hbm", "kernel": ("k_sweep_pipe + k_sweep (one sweep = one %d-tree pass over all rows: the pipelined kernel takes the steps that fit it, "
+                                           "the synchronous kernel the rest)" % T) if persistent else "k_tree_step (one launch = one tree)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_tree_obs": bytes_per_obs,
                 "units_per_launch": units_per_launch, "avg_tree_levels": lv,
@@ -582,7 +602,7 @@ def run_ours(args):
                 "achieved_lean_model_gbs": bytes_per_obs_lean * units_per_launch / (launch_ms * 1e-3) / 1e9,
                 "lean_bytes_per_tree_obs": bytes_per_obs_lean,
                 "whole_sweep_frac": bytes_per_obs * T * n * (value / max(1, world)) / 1e9 / peak,
-                "leaf_stat": leaf_stat,
+                "leaf_stat": leaf_stat, "glmm_data_pass": glmm_pass,
                 # where a sweep's time goes, per rank (max / min over ranks): kept here so that the scaling record can attribute a loss
                 "step_breakdown": {"ms_stan_block_max": max_over_ranks(ms_stan), "ms_stan_block_min": min_over_ranks(ms_stan),
                                    "ms_bart_block_max": max_over_ranks(ms_bart), "ms_bart_block_min": min_over_ranks(ms_bart),

@@ -228,6 +228,9 @@ int glmm_num_grad_evals(glmm_model* m, int64_t* out);
 int glmm_set_mode(glmm_model* m, int mode);
 int glmm_get_mode(glmm_model* m, int* mode);
 int glmm_num_device_passes(glmm_model* m, int64_t* out);
+/* measurement: device milliseconds of the data pass alone (CUDA events on the model's stream, mean of `reps` launches); flush_l2 != 0
+ * evicts the L2 before every timed launch; *bulk (optional) = 1 when the pass is the bulk-copy (TMA) kernel */
+int glmm_time_data_pass(glmm_model* m, int reps, int flush_l2, double* ms, int* bulk);
 
 /* ------------------------------------------------------------------ s4b_sampler_* */
 typedef struct s4b_sampler s4b_sampler;

@@ -994,6 +994,7 @@ void BartFit::setup_persistent()
         const int words = entries;            // (member name kept: capacity of the cross table in entries)
         const size_t smem = fixed + (size_t) (entries + 1) * kWorkers;
         int per_sm = 0;
+        if (persistent_nq_ == 4) cudaFuncSetAttribute((const void*) k_sweep_pipe<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) == cudaSuccess && per_sm >= 1) {
           pipe_count_words_ = words; pipe_smem_ = smem;
@@ -1067,13 +1068,13 @@ void BartFit::launch_persistent_sweep(bool last_thin)
     void* args[] = { &dv, &bar, &stride, &tabs, &descs, &draws, &overlap, &sh, &pos_in, &pos_out, &max_steps };
     S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3(persistent_grid_), dim3(kSweepBlock), args, persistent_smem_, stream_));
   } else {
+    static const bool pipe_prof = getenv("S4B_PIPE_PROF") != nullptr;
     const void* pfn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
-                    : persistent_nq_ == 4 ? (const void*) k_sweep_pipe<4> : (const void*) k_sweep_pipe<6>;
+                    : persistent_nq_ == 4 ? (pipe_prof ? (const void*) k_sweep_pipe<4, true> : (const void*) k_sweep_pipe<4>) : (const void*) k_sweep_pipe<6>;
     unsigned long long* ring = d_pipe_ring_; int words = pipe_count_words_;
     static const int pipe_dbg = getenv("S4B_PIPE_DBG") ? atoi(getenv("S4B_PIPE_DBG")) : 0;      // timing experiments only (wrong results)
     int dbg = pipe_dbg;
     const StepDesc* pdescs = d_descs_; const PipeInfo* pinfos = infos; const double2* pdraws = d_draws_; unsigned long long* ran = d_pipe_ran_;
-    static const bool pipe_prof = getenv("S4B_PIPE_PROF") != nullptr;
     unsigned long long* pprof = pipe_prof ? d_prof_ : nullptr;
     for (int k = 0; k < kPipeSegments; ++k) {
       const int* pin = d_pipe_pos_ + 2 * k; int* pmid = d_pipe_pos_ + 2 * k + 1; int* pout = d_pipe_pos_ + 2 * k + 2;

@@ -35,6 +35,63 @@ __device__ __forceinline__ double g_warp_sum(double v)
   return v;
 }
 
+// Shared tail of the binned data passes: the (nb + 1) x 32 lane-private bins of every consumer warp -> one partial row per CTA -> the
+// last CTA to finish sums the rows of all CTAs in CTA order.  `bins0` = the bins of warp 0, `wb` = this warp's (ignored when the
+// warp holds none: `has_bins` false, e.g. a producer warp); every thread of the block calls this.
+__device__ __forceinline__ void data_terms_epilogue(const GlmmDev& g, double* bins0, double* wb, bool has_bins)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = g.K + g.q;
+  if (has_bins) {
+    __syncwarp();
+    // warp reduction, transposed: lane l sums row j0 + l over its 32 copies, starting at copy l (conflict-free: the 32 lanes touch 32
+    // different banks), in a fixed order
+    for (int j0 = 0; j0 <= nb; j0 += 32) {
+      const int j = j0 + lane;
+      double v = 0.0;
+      if (j <= nb) {
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) v += wb[j * 32 + ((c + lane) & 31)];
+      }
+      __syncwarp();
+      if (j <= nb) wb[j * 32] = v;
+    }
+  }
+  __syncthreads();
+  const int G = gridDim.x;
+  for (int j = tid; j <= nb; j += blockDim.x) {
+    double acc = 0.0;
+    for (int w = 0; w < kGBlock / 32; ++w) acc += bins0[(size_t) w * (nb + 1) * 32 + j * 32];
+    // value order in partials / result: S, X'e, Z'e
+    int out_j = j == nb ? 0 : j + 1;
+    g.partials[(long long) out_j * G + blockIdx.x] = acc;
+  }
+  __shared__ unsigned int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(g.ticket, 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned int) G - 1) return;
+  __threadfence();
+  // one warp per row of partials, four rows at a time with every load issued before the first sum: the rows were written by other SMs a
+  // moment ago, so each round of loads is one L2 round trip -- serialising them per row costs microseconds at the tail of the pass
+  const int W = blockDim.x / 32;
+  for (int v0 = warp; v0 <= nb; v0 += 4 * W) {
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (int b = lane; b < G; b += 32) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { const int v = v0 + r * W; if (v <= nb) acc[r] += __ldcg(g.partials + (long long) v * G + b); }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int v = v0 + r * W;
+      const double a = g_warp_sum(acc[r]);
+      if (v <= nb && lane == 0) g.result[v] = a;
+    }
+  }
+  if (tid == 0) *g.ticket = 0u;
+}
+
 // algorithmic bytes per observation: r 8 + X 8K + Z (4 + 8 [0 if the slot is an indicator]) per slot
 // KT, ST: compile-time bounds of the fast path (K <= KT dense columns, <= ST non-zeros per row of Z), so that the register arrays of
 // the loads in flight are as small as the model allows; <4, 4> also carries the general path
@@ -143,43 +200,161 @@ __global__ void __launch_bounds__(kGBlock, 2) k_glmm_data_terms(GlmmDev g)
     for (int k = 0; k < KT; ++k) if (k < K) wb[k * 32 + lane] = gx[k];
   }
   wb[nb * 32 + lane] = S;
-  __syncwarp();
-  // warp reduction of the (nb + 1) x 32 lane-private bins, transposed: lane l sums row j0 + l over its 32 copies, starting at copy l
-  // (conflict-free: the 32 lanes touch 32 different banks), in a fixed order
-  for (int j0 = 0; j0 <= nb; j0 += 32) {
-    const int j = j0 + lane;
-    double v = 0.0;
-    if (j <= nb) {
-#pragma unroll 8
-      for (int c = 0; c < 32; ++c) v += wb[j * 32 + ((c + lane) & 31)];
+  data_terms_epilogue(g, smem + nb, wb, true);
+}
+
+// ---------------------------------------------------------------------------------------
+// The same pass with the operand streams staged through shared memory by the bulk-copy engine (TMA, cp.async.bulk + mbarrier):
+// one persistent CTA per SM, 8 consumer warps + 1 producer warp, a ring of `stages` tiles of `tile` observations.  The producer
+// keeps `stages` tiles (~45 KB each for the Friedman model) in flight per SM regardless of what the consumers are doing, so the
+// memory system never waits for the arithmetic and the consumers need no registers for loads in flight -- the register version
+// above alternates between a burst of loads and a burst of shared-memory bin updates (ncu: long scoreboard, 2.1 TB/s).
+// Tile layout in shared memory, every stream contiguous: r | weights (if any) | X[0..K) | zidx[0..slots) | zval of the slots whose
+// values are not all 1.  Same bins, same fixed-order reductions, same results as k_glmm_data_terms up to the order of the sums.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kGMaxStages = 4;
+struct BulkBars { unsigned long long full[kGMaxStages], empty[kGMaxStages]; };
+
+template <int KT, int ST>
+__global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDev g, int tile, int stages, int tile_bytes)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BulkBars& bars = *reinterpret_cast<BulkBars*>(smem_raw);
+  double* sth = reinterpret_cast<double*>(smem_raw + sizeof(BulkBars));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = g.K + g.q, K = g.K, slots = g.slots;
+  double* bins0 = sth + nb;
+  double* wb = bins0 + (size_t) (warp < kGBlock / 32 ? warp : 0) * (nb + 1) * 32;
+  unsigned char* ring = smem_raw + (((sizeof(BulkBars) + sizeof(double) * ((size_t) nb + (size_t) (kGBlock / 32) * (nb + 1) * 32)) + 127) / 128) * 128;
+  const bool weighted = g.wt != nullptr;
+  if (tid == 0) {
+    for (int s_ = 0; s_ < stages; ++s_) { mbar_init(&bars.full[s_], 1u); mbar_init(&bars.empty[s_], (unsigned) (kGBlock / 32)); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();                                      // the barriers exist: the producer starts streaming at once
+  if (warp < kGBlock / 32) {
+    // consumers: coefficients and zeroed bins while the first tiles are in flight
+    for (int j = tid; j < nb; j += kGBlock) sth[j] = g.theta[j];
+    for (int j = lane; j < (nb + 1) * 32; j += 32) wb[j] = 0.0;
+    asm volatile("bar.sync 1, %0;" ::"n"(kGBlock) : "memory");
+  }
+  const long long N = g.N, npad = g.npad;
+  const long long ntiles = (N + tile - 1) / tile;
+  // stream offsets inside a tile
+  const int off_w = tile * 8, off_x = off_w + (weighted ? tile * 8 : 0), off_i = off_x + K * tile * 8, off_v = off_i + slots * tile * 4;
+  if (warp == kGBlock / 32) {
+    // ------------------------------------------------------------- producer warp: one lane issues the bulk copies
+    if (lane == 0) {
+      int k = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+        const int st = k % stages;
+        if (k >= stages) mbar_wait(&bars.empty[st], (unsigned) ((k / stages - 1) & 1));
+        const long long base = t * tile;
+        const unsigned rows = (unsigned) (npad - base < tile ? npad - base : tile);          // npad and tile are multiples of 16 rows
+        unsigned char* dst = ring + (size_t) st * tile_bytes;
+        int nval = 0;
+        for (int s_ = 0; s_ < slots; ++s_) nval += ((g.ones_mask >> s_) & 1u) ? 0 : 1;
+        mbar_expect_tx(&bars.full[st], rows * (8u * (1u + (weighted ? 1u : 0u) + (unsigned) K + (unsigned) nval) + 4u * (unsigned) slots));
+        bulk_g2s(dst, g.r + base, rows * 8u, &bars.full[st]);
+        if (weighted) bulk_g2s(dst + off_w, g.wt + base, rows * 8u, &bars.full[st]);
+        for (int c = 0; c < K; ++c) bulk_g2s(dst + off_x + c * tile * 8, g.X + (long long) c * npad + base, rows * 8u, &bars.full[st]);
+        for (int s_ = 0; s_ < slots; ++s_) bulk_g2s(dst + off_i + s_ * tile * 4, g.zidx + (long long) s_ * npad + base, rows * 4u, &bars.full[st]);
+        int v = 0;
+        for (int s_ = 0; s_ < slots; ++s_) if (!((g.ones_mask >> s_) & 1u)) { bulk_g2s(dst + off_v + v * tile * 8, g.zval + (long long) s_ * npad + base, rows * 8u, &bars.full[st]); ++v; }
+      }
     }
     __syncwarp();
-    if (j <= nb) wb[j * 32] = v;
+    data_terms_epilogue(g, bins0, wb, false);
+    return;
   }
-  __syncthreads();
-  const int G = gridDim.x;
-  for (int j = tid; j <= nb; j += kGBlock) {
-    double acc = 0.0;
-    for (int w = 0; w < kGBlock / 32; ++w) acc += smem[nb + (size_t) w * (nb + 1) * 32 + j * 32];
-    // value order in partials / result: S, X'e, Z'e
-    int out_j = j == nb ? 0 : j + 1;
-    g.partials[(long long) out_j * G + blockIdx.x] = acc;
+  // --------------------------------------------------------------- consumer warps
+  double S = 0.0;
+  double gx[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) gx[k] = 0.0;
+  // position of slot s_'s values in the tile (slots whose values are all 1 have none)
+  int vpos[ST];
+  { int v = 0;
+#pragma unroll
+    for (int s_ = 0; s_ < ST; ++s_) { vpos[s_] = ((g.ones_mask >> s_) & 1u) ? -1 : v; if (s_ < slots && vpos[s_] >= 0) ++v; } }
+  int k = 0;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+    const int st = k % stages;
+    mbar_wait(&bars.full[st], (unsigned) ((k / stages) & 1));
+    const unsigned char* src = ring + (size_t) st * tile_bytes;
+    const long long base = t * tile;
+    for (int o = 2 * tid; o < tile; o += 2 * kGBlock) {
+      const long long i = base + o;
+      if (i >= N) break;
+      const bool second = i + 1 < N;
+      const double2 r2 = *reinterpret_cast<const double2*>(src + (size_t) o * 8);
+      double2 x2[KT], v2[ST]; int2 c2[ST];
+#pragma unroll
+      for (int c = 0; c < KT; ++c) if (c < K) x2[c] = *reinterpret_cast<const double2*>(src + off_x + ((size_t) c * tile + o) * 8);
+#pragma unroll
+      for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) {
+        c2[s_] = *reinterpret_cast<const int2*>(src + off_i + ((size_t) s_ * tile + o) * 4);
+        v2[s_] = vpos[s_] < 0 ? make_double2(1.0, 1.0) : *reinterpret_cast<const double2*>(src + off_v + ((size_t) vpos[s_] * tile + o) * 8);
+      }
+      double eta0 = 0.0, eta1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < KT; ++c) if (c < K) { eta0 += x2[c].x * sth[c]; eta1 += x2[c].y * sth[c]; }
+#pragma unroll
+      for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) { eta0 += v2[s_].x * sth[K + c2[s_].x]; eta1 += v2[s_].y * sth[K + c2[s_].y]; }
+      double e0 = r2.x - eta0, e1 = second ? r2.y - eta1 : 0.0;
+      if (weighted) {
+        const double2 w2 = *reinterpret_cast<const double2*>(src + off_w + (size_t) o * 8);
+        const double we0 = w2.x * e0, we1 = w2.y * e1;
+        S += we0 * e0; S += we1 * e1;
+        e0 = we0; e1 = we1;
+      } else { S += e0 * e0; S += e1 * e1; }
+#pragma unroll
+      for (int c = 0; c < KT; ++c) if (c < K) { gx[c] = fma(x2[c].x, e0, gx[c]); gx[c] = fma(x2[c].y, e1, gx[c]); }
+      if (g.row_distinct) {
+        double b0[ST];
+#pragma unroll
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wb[(K + c2[s_].x) * 32 + lane];
+#pragma unroll
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wb[(K + c2[s_].x) * 32 + lane] = fma(v2[s_].x, e0, b0[s_]);
+#pragma unroll
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wb[(K + c2[s_].y) * 32 + lane];
+#pragma unroll
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wb[(K + c2[s_].y) * 32 + lane] = fma(v2[s_].y, e1, b0[s_]);
+      } else {
+#pragma unroll
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) {
+          wb[(K + c2[s_].x) * 32 + lane] += v2[s_].x * e0;
+          wb[(K + c2[s_].y) * 32 + lane] += v2[s_].y * e1;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars.empty[st]);              // this warp has read everything it needs from the stage
   }
-  __shared__ unsigned int s_ticket;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(g.ticket, 1u);
-  __syncthreads();
-  if (s_ticket != (unsigned int) G - 1) return;
-  __threadfence();
-  for (int v = warp; v <= nb; v += kGBlock / 32) {
-    const double* src = g.partials + (long long) v * G;
-    double acc = 0.0;
-    for (int b = lane; b < G; b += 32) acc += __ldcg(src + b);
-    acc = g_warp_sum(acc);
-    if (lane == 0) g.result[v] = acc;
-  }
-  if (tid == 0) *g.ticket = 0u;
+#pragma unroll
+  for (int c = 0; c < KT; ++c) if (c < K) wb[c * 32 + lane] = gx[c];
+  wb[nb * 32 + lane] = S;
+  data_terms_epilogue(g, bins0, wb, true);
+}
+
+using DataTermsBulkKernel = void (*)(GlmmDev, int, int, int);
+static DataTermsBulkKernel data_terms_bulk_kernel(int K, int slots)
+{
+  if (K <= 2) return slots <= 2 ? k_glmm_data_terms_bulk<2, 2> : k_glmm_data_terms_bulk<2, 4>;
+  return slots <= 2 ? k_glmm_data_terms_bulk<4, 2> : k_glmm_data_terms_bulk<4, 4>;
 }
 
 using DataTermsKernel = void (*)(GlmmDev);
@@ -450,6 +625,25 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
   num_sms_ = sms;
   long long want = (N_ + 2 * kGBlock - 1) / (2 * kGBlock);
   grid_ = (int) std::max<long long>(1, std::min<long long>(want, (long long) sms * per_sm));
+  // the bulk-copy (TMA) version of the binned pass: small models (K, non-zeros per row <= 4) whose bins leave room for a ring of tiles;
+  // from ~64 k rows on (below that the pass is a few microseconds of latency either way); S4B_GLMM_BULK = 0 / 1 overrides
+  if (!columns_ && K_ <= kGFast && slots_ <= kGFast) {
+    int nval = 0;
+    for (int s = 0; s < slots_; ++s) nval += ((ones_mask_ >> s) & 1u) ? 0 : 1;
+    const size_t per_obs = 8u * (size_t) (1 + (d.weights != nullptr ? 1 : 0) + K_ + nval) + 4u * (size_t) slots_;
+    const size_t head = ((sizeof(BulkBars) + smem_bytes_ + 127) / 128) * 128;
+    for (int tile : { 1024, 512, 256 }) {
+      const size_t need = head + 3 * (size_t) tile * per_obs;
+      if (need <= (size_t) max_smem) { bulk_tile_ = tile; bulk_stages_ = 3; bulk_tile_bytes_ = (int) ((size_t) tile * per_obs); bulk_smem_ = need; break; }
+    }
+    const char* ev = getenv("S4B_GLMM_BULK");
+    bulk_ = bulk_tile_ > 0 && (ev != nullptr ? atoi(ev) != 0 : N_ >= 65536);
+    if (bulk_) {
+      if (cudaFuncSetAttribute((const void*) data_terms_bulk_kernel(K_, slots_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bulk_smem_) != cudaSuccess) { cudaGetLastError(); bulk_ = false; }
+      const long long ntiles = (N_ + bulk_tile_ - 1) / bulk_tile_;
+      bulk_grid_ = (int) std::max<long long>(1, std::min<long long>(std::min<long long>(ntiles, sms), grid_));
+    }
+  }
   dalloc(&d_theta_, (size_t) nb + 1); dalloc(&d_partials_, (size_t) ((columns_ ? K_ : nb) + 1) * grid_); dalloc(&d_result_, (size_t) nb + 1);
   S4B_CUDA(cudaMalloc(&d_ticket_, sizeof(unsigned int))); zero_device_sync(d_ticket_, sizeof(unsigned int), stream_);
   S4B_CUDA(cudaMallocHost(&h_pinned_, sizeof(double) * 2 * ((size_t) nb + 1)));
@@ -630,19 +824,52 @@ void GlmmModel::set_inputs_device(const double* d_offset, const double* d_y)
 void GlmmModel::set_offset_device(const double* d_offset) { set_inputs_device(d_offset, nullptr); }
 void GlmmModel::set_response_device(const double* d_y) { set_inputs_device(nullptr, d_y); }
 
-void GlmmModel::data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb)
+// device time of the data pass alone (the kernels data_terms() launches, coefficients as last uploaded): CUDA events around `reps`
+// launches; flush_l2 != 0 writes a 256 MB scratch buffer before every launch (not timed) so that each pass starts from HBM
+double GlmmModel::time_data_pass(int reps, int flush_l2)
 {
-  ++num_passes_;
   const int nb = K_ + q_;
-  double* h_theta = h_pinned_;
-  double* h_res = h_pinned_ + nb + 1;
-  for (int k = 0; k < K_; ++k) h_theta[k] = beta[k];
-  for (int k = 0; k < q_; ++k) h_theta[K_ + k] = b[k];
-  if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
+  std::vector<double> th((size_t) nb + 1, 0.01);
+  S4B_CUDA(cudaMemcpyAsync(d_theta_, th.data(), sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
+  void* scratch = nullptr;
+  const size_t flush_bytes = (size_t) 256 << 20;
+  if (flush_l2) S4B_CUDA(cudaMalloc(&scratch, flush_bytes));
+  cudaEvent_t a, b; S4B_CUDA(cudaEventCreate(&a)); S4B_CUDA(cudaEventCreate(&b));
+  launch_data_pass();
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  double total = 0.0;
+  if (!flush_l2) {
+    S4B_CUDA(cudaEventRecord(a, stream_));
+    for (int r = 0; r < reps; ++r) launch_data_pass();
+    S4B_CUDA(cudaEventRecord(b, stream_));
+    S4B_CUDA(cudaEventSynchronize(b));
+    float t = 0.f; S4B_CUDA(cudaEventElapsedTime(&t, a, b)); total = t;
+  } else {
+    for (int r = 0; r < reps; ++r) {
+      S4B_CUDA(cudaMemsetAsync(scratch, r & 0xFF, flush_bytes, stream_));
+      S4B_CUDA(cudaEventRecord(a, stream_));
+      launch_data_pass();
+      S4B_CUDA(cudaEventRecord(b, stream_));
+      S4B_CUDA(cudaEventSynchronize(b));
+      float t = 0.f; S4B_CUDA(cudaEventElapsedTime(&t, a, b)); total += t;
+    }
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(scratch);
+  expansion_valid_ = false;
+  return total / reps;
+}
+
+void GlmmModel::launch_data_pass()
+{
+  const int nb = K_ + q_;
   GlmmDev g;
   g.N = N_; g.npad = npad_; g.K = K_; g.q = q_; g.slots = slots_; g.bins = nb; g.X = d_X_; g.r = d_r_; g.wt = d_wt_; g.zidx = d_zidx_; g.zval = d_zval_;
   g.ones_mask = ones_mask_; g.row_distinct = row_distinct_; g.theta = d_theta_; g.partials = d_partials_; g.result = d_result_; g.ticket = d_ticket_;
-  if (!columns_) {
+  if (!columns_ && bulk_) {
+    int tile = bulk_tile_, stages = bulk_stages_, tile_bytes = bulk_tile_bytes_;
+    void* args[] = { &g, &tile, &stages, &tile_bytes };
+    S4B_CUDA(cudaLaunchKernel((const void*) data_terms_bulk_kernel(K_, slots_), dim3(bulk_grid_), dim3(kGBlock + 32), args, bulk_smem_, stream_));
+  } else if (!columns_) {
     void* args[] = { &g };
     S4B_CUDA(cudaLaunchKernel((const void*) data_terms_kernel(K_, slots_), dim3(grid_), dim3(kGBlock), args, smem_bytes_, stream_));
   }
@@ -656,6 +883,18 @@ void GlmmModel::data_terms(const double* beta, const double* b, double* S, doubl
     }
   }
   S4B_CUDA(cudaGetLastError());
+}
+
+void GlmmModel::data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb)
+{
+  ++num_passes_;
+  const int nb = K_ + q_;
+  double* h_theta = h_pinned_;
+  double* h_res = h_pinned_ + nb + 1;
+  for (int k = 0; k < K_; ++k) h_theta[k] = beta[k];
+  for (int k = 0; k < q_; ++k) h_theta[K_ + k] = b[k];
+  if (nb) S4B_CUDA(cudaMemcpyAsync(d_theta_, h_theta, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
+  launch_data_pass();
   if (sharded()) for (int off = 0; off < nb + 1; off += kMailVec) shard_->allreduce(d_result_ + off, std::min(kMailVec, nb + 1 - off), kOpSum, stream_);
   S4B_CUDA(cudaMemcpyAsync(h_res, d_result_, sizeof(double) * (size_t) (nb + 1), cudaMemcpyDeviceToHost, stream_));
   S4B_CUDA(cudaStreamSynchronize(stream_));

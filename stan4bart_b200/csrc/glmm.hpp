@@ -58,6 +58,9 @@ class GlmmModel {
   void parametric_mean_host(const double* constrained, double* out, bool include_fixed, bool include_random);
   // device pass: S = sum e^2, X'e, Z'e at (beta, b)
   void data_terms(const double* beta, const double* b, double* S, double* gbeta, double* gb);
+  void launch_data_pass();
+  double time_data_pass(int reps, int flush_l2);
+  bool bulk_pass() const { return bulk_; }
   // the same three quantities through the sweep-level expansion (mode 1) or the device pass (mode 0)
   void data_terms_auto(const double* beta, const double* b, double* S, double* gbeta, double* gb);
   // 0: one device pass per evaluation; 1: one device pass per Gibbs sweep + exact quadratic expansion (default when K + q is small)
@@ -92,6 +95,9 @@ class GlmmModel {
   unsigned int ones_mask_ = 0;
   int row_distinct_ = 0;
   size_t smem_bytes_ = 0;
+  bool bulk_ = false;                       // binned data pass staged through shared memory by bulk copies (k_glmm_data_terms_bulk)
+  int bulk_tile_ = 0, bulk_stages_ = 0, bulk_tile_bytes_ = 0, bulk_grid_ = 1;
+  size_t bulk_smem_ = 0;
   long long num_grad_ = 0, num_passes_ = 0;
   // sweep-level sufficient statistics: with e = r - A theta (A = [X Z]) the data terms are an exact quadratic in theta,
   //   S(theta0 + d) = S0 - 2 g0'd + d'G d,   A'e(theta0 + d) = g0 - G d,   G = A'A (fixed), (S0, g0) from one pass at theta0

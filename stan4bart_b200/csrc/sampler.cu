@@ -410,6 +410,14 @@ int glmm_stan_row_names(glmm_model* m, char* out, size_t cap, size_t* needed)
 int glmm_set_mode(glmm_model* m, int mode) { S4B_API_BEGIN S4B_REQUIRE(m); m->m->set_mode(mode); S4B_API_END }
 int glmm_get_mode(glmm_model* m, int* mode) { S4B_API_BEGIN S4B_REQUIRE(m && mode); *mode = m->m->mode(); S4B_API_END }
 int glmm_num_device_passes(glmm_model* m, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(m && out); *out = m->m->num_device_passes(); S4B_API_END }
+int glmm_time_data_pass(glmm_model* m, int reps, int flush_l2, double* ms, int* bulk)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(m && ms && reps > 0);
+  *ms = m->m->time_data_pass(reps, flush_l2);
+  if (bulk) *bulk = m->m->bulk_pass() ? 1 : 0;
+  S4B_API_END
+}
 int glmm_num_grad_evals(glmm_model* m, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(m && out); *out = m->m->num_grad_evals(); S4B_API_END }
 
 // ---- sampler ----

@@ -150,7 +150,7 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
 }
 
 // acc_ring: kPipeRing accumulator rows of kPipeAcc 64-bit words (zeroed by the host before every launch)
-template <int NQ>
+template <int NQ, bool PROF = false>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsigned long long* acc_rings, int launch_parity,
                                                                 const StepDesc* __restrict__ descs, const PipeInfo* __restrict__ infos,
                                                                 const double2* __restrict__ draws, const int* __restrict__ pos_in, int* __restrict__ pos_out,
@@ -252,17 +252,12 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     // rows beyond the data (the tail of the last quad, quads beyond q_hi) are parked in the trash slot kPipeSlots at every step
     constexpr unsigned kAllObs = NQ == 8 ? 0xFFFFFFFFu : ((1u << (4 * NQ)) - 1u);
     const bool ragged = obs_mask != kAllObs;
-    uint32_t tmask[NQ];                        // 0xFF in the bytes of rows beyond the data
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-      const uint32_t nib = (~obs_mask >> (4 * j)) & 0xFu;
-      tmask[j] = (((nib * 0x00204081u) & 0x01010101u) * 0xFFu);
-    }
+
     int C = 1;                                 // cells of the previous step as the cross table sees them (1 at the start and after a drained step)
     int na = t_begin;                          // the next decision whose update the residuals have not seen yet
     // cycle counters (thread 0 of CTA 0, only when asked for): [0] wait for decisions, [1] U, [2] W, [3] A, [4] CTA reduce + arrive, [6] drained steps
     long long wp0 = 0, wp1 = 0, wp2 = 0, wp3 = 0, wp4 = 0, wp6 = 0;
-    const bool wprof = prof != nullptr && cta == 0 && tid == 0;
+    const bool wprof = PROF && prof != nullptr && cta == 0 && tid == 0;
     const int e_trash = count_entries;
     uint32_t* cntw = reinterpret_cast<uint32_t*>(cnt);
     for (int k = 0; k <= kPipeSlots; ++k) bins[k * kWorkers + tid] = 0.0;
@@ -271,16 +266,16 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     for (int t = t_begin; t < t_end; ++t) {
       const StepDesc& sd = S.sd[t % kPipeDescs];
       const PipeInfo& pi = S.info[t % kPipeDescs];
-      const long long k0 = clock64();
+      const long long k0 = PROF ? clock64() : 0;
       const int kind = sd.b_kind, L = sd.b_num_leaves, nslots = sd.b_nslots;
       // a cross table beyond the counters' capacity: this step waits for the previous decision too and starts from updated residuals
       const bool drained = t > t_begin && nslots * C > count_entries;
       // ---- U: apply the decisions up to t-2 (t-1 as well when drained): per-cell deltas ----
       long long kw = 0;
       for (const int need = drained ? t - 1 : t - 2; na <= need; ++na) {
-        const long long w0 = clock64();
+        const long long w0 = PROF ? clock64() : 0;
         named_bar_sync(2 + (na & 1), kSweepBlock);
-        kw += clock64() - w0;
+        if (PROF) kw += clock64() - w0;
         const double* dc = S.dcell[na & 1];
         const bool newest = na == t - 1;
 #pragma unroll
@@ -295,7 +290,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
 #pragma unroll
         for (int j = 0; j < NQ; ++j) cprev[j] = 0u;
       }
-      const long long k2 = clock64();
+      const long long k2 = PROF ? clock64() : 0;
       // one warp fetches the next step's descriptor (its ring slot held step t-2, which has been decided)
       if (warp == kWorkerWarps - 1 && t + 1 < t_end)
         w_fetch_desc_async(S.sd[(t + 1) % kPipeDescs], descs[t + 1], S.info[(t + 1) % kPipeDescs], infos[t + 1], lane);
@@ -303,9 +298,13 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       pipe_walk<NQ>(sd, pi, tile, tile_stride, tid, sp, pp);
       if (ragged) {
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) { sp[j] = (sp[j] & ~tmask[j]) | (((uint32_t) kPipeSlots * 0x01010101u) & tmask[j]); pp[j] |= tmask[j]; }
+        for (int j = 0; j < NQ; ++j) {
+          const uint32_t nib = (~obs_mask >> (4 * j)) & 0xFu;                                   // rows beyond the data
+          const uint32_t tm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;                      // 0xFF in their bytes
+          sp[j] = (sp[j] & ~tm) | (((uint32_t) kPipeSlots * 0x01010101u) & tm); pp[j] |= tm;
+        }
       }
-      const long long k3 = clock64();
+      const long long k3 = PROF ? clock64() : 0;
       const bool two_trees = (kind == 2 || kind == 3);
       const int E = nslots * C;
       const int C_next = pi.ncells;
@@ -380,7 +379,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       if (packed) { pkw[tid] = pk0; pkw[kWorkers + tid] = pk1; }
 #pragma unroll
       for (int j = 0; j < NQ; ++j) { cprev2[j] = cprev[j]; cprev[j] = ccur[j]; }
-      const long long k4 = clock64();
+      const long long k4 = PROF ? clock64() : 0;
       if (warp == kWorkerWarps - 1) cp_async_wait_all();          // the next step's descriptor has landed (issued a whole step ago)
       named_bar_sync(1, kWorkers);
       // ---- CTA reduction, then integer atomics into the step's accumulator row ----
@@ -456,9 +455,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     int C = 1;                                 // cells of step u - 1 (kept here: the workers recycle that step's descriptor slot while this step is decided)
     // cycle counters (lane 0 of CTA 0): [8] plan + tree fetch + draws, [9] wait for the rows, [10] row reduction + correction, [11] decision, [12] deltas + arrive
     long long cp0 = 0, cp1 = 0, cp2 = 0, cp3 = 0, cp4 = 0;
-    const bool cprof = prof != nullptr && cta == 0 && lane == 0;
+    const bool cprof = PROF && prof != nullptr && cta == 0 && lane == 0;
     for (int u = t_begin; u < t_end; ++u) {
-      const long long h0 = clock64();
+      const long long h0 = PROF ? clock64() : 0;
       StepDesc& sd = S.sd[u % kPipeDescs];
       const PipeInfo& pi = S.info[u % kPipeDescs];
       DTree& tree = S.tree[u & 1];
@@ -476,10 +475,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       rngd.enter(step0 + (unsigned long long) u, 1u);
       { const double2 dz = S.draws[u & 1][lane]; S.csd.ubuf[lane] = dz.x; S.csd.zbuf[lane] = dz.y; }
       rngd.adopt();
-      const long long h1 = clock64();
+      const long long h1 = PROF ? clock64() : 0;
       // (no separate barrier: the accumulator words themselves tell when every CTA has contributed, see below)
       __syncwarp();
-      const long long h2 = clock64();
+      const long long h2 = PROF ? clock64() : 0;
       // ---- reduce the partial rows of all CTAs (fixed order), correct the sums with the previous step's deltas ----
       const int nslots = sd.b_nslots;
       // a pair of steps whose cross table exceeds the counters: the workers ran this step drained (update u-1 applied first), one cell
@@ -538,14 +537,14 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
         S.st[lane].sum += corr;
       }
       __syncwarp();
-      const long long h3 = clock64();
+      const long long h3 = PROF ? clock64() : 0;
       // ---- Metropolis decision + leaf draws (same code as the synchronous kernel) ----
       {
         const FastPlan plan = plan_load(S.plan, lane);
         w_decide_fast<false>(plan, tree, S.prm, rngd, sd, S.st, S.upd[u & 1], S.csd, nullptr, lane, S.inv_sigsq, sd.accept_thr);
       }
       rngd.commit();
-      const long long h4 = clock64();
+      const long long h4 = PROF ? clock64() : 0;
       // ---- per-cell deltas of this step: what the workers add to the residuals, and the next step's correction ----
       {
         const UpdateDesc& upd = S.upd[u & 1];

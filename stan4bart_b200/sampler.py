@@ -371,6 +371,12 @@ class GlmmModel:
         _lib.check(self.L.glmm_num_device_passes(self.h, C.byref(k)))
         return int(k.value)
 
+    def time_data_pass(self, reps=20, flush_l2=False):
+        """(milliseconds per data pass on the device, whether it is the bulk-copy kernel)"""
+        ms, bulk = C.c_double(0.0), C.c_int(0)
+        _lib.check(self.L.glmm_time_data_pass(self.h, int(reps), int(bool(flush_l2)), C.byref(ms), C.byref(bulk)))
+        return ms.value, bool(bulk.value)
+
     def set_mode(self, mode):
         _lib.check(self.L.glmm_set_mode(self.h, int(mode)))
 

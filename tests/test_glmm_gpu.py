@@ -190,6 +190,54 @@ def test_column_path_matches_golden(monkeypatch, name, mode):
         assert rel_err(g_g, grad, scale=np.abs(grad) + 1e-8 * np.max(np.abs(grad))) <= REL_TOL
 
 
+@pytest.mark.parametrize("bulk", ["0", "1"])
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: os.path.basename(p)[5:-5])
+def test_bulk_copy_data_pass_matches_golden(monkeypatch, path, bulk):
+    """k_glmm_data_terms_bulk (operand streams staged through shared memory by cp.async.bulk + mbarrier, producer warp + consumer
+    warps) forced on / off on the golden models (tiny n: one ragged tile per CTA); models outside its scope (K or non-zeros per row
+    above 4, no coefficients) take the register version either way."""
+    monkeypatch.setenv("S4B_GLMM_BULK", bulk)
+    sd, c = load_glmm_case(path)
+    m = GlmmModel(sd)
+    if sd.K + sd.q > 0:
+        m.set_mode(0)
+    m.set_offset(np.asarray(c["offset"]))
+    for q, lp, grad in zip(c["q"], c["lp"], c["grad"]):
+        lp_g, g_g, status = m.log_prob_grad(np.asarray(q))
+        assert status == 0
+        assert abs(lp_g - lp) <= REL_TOL * abs(lp)
+        assert rel_err(g_g, grad, scale=np.abs(grad) + 1e-8 * np.max(np.abs(grad))) <= REL_TOL
+
+
+@pytest.mark.parametrize("n,binary,weighted", [(1023, False, False), (1025, True, False), (70001, False, True), (300017, True, False)])
+def test_bulk_copy_data_pass_matches_oracle_and_register_version(monkeypatch, n, binary, weighted):
+    """Sizes around the tile boundaries (1024 rows per tile, three tiles in flight, several tiles per CTA at the largest size),
+    weighted and unweighted: against the oracle at 1e-10 and against the register version of the same pass."""
+    pr = friedman_problem(n, binary=binary, seed=21)
+    sd = pr["stan_data"]
+    rng = np.random.default_rng(n)
+    if weighted:
+        sd.weights = rng.gamma(2.0, 0.5, n)
+    off = rng.standard_normal(sd.N)
+    monkeypatch.setenv("S4B_GLMM_BULK", "1")
+    mb = GlmmModel(sd)
+    monkeypatch.setenv("S4B_GLMM_BULK", "0")
+    mr = GlmmModel(sd)
+    mo = O.OracleGlmm(sd)
+    for m in (mb, mr, mo):
+        m.set_offset(off)
+    mb.set_mode(0); mr.set_mode(0)
+    for _ in range(4):
+        q = rng.uniform(-1, 1, mo.d)
+        lo, go, so = mo.log_prob_grad(q)
+        lb, gb, sb = mb.log_prob_grad(q)
+        lr, gr, sr = mr.log_prob_grad(q)
+        assert so == sb == sr == 0
+        assert abs(lo - lb) <= REL_TOL * abs(lo) and abs(lr - lb) <= 1e-12 * abs(lr)
+        assert rel_err(go, gb, scale=np.abs(go) + 1e-8 * np.max(np.abs(go))) <= REL_TOL
+        assert rel_err(gr, gb, scale=np.abs(gr) + 1e-8 * np.max(np.abs(gr))) <= 1e-11
+
+
 @pytest.mark.parametrize("levels,weighted", [(150, False), (1500, True)])
 def test_many_grouping_levels(levels, weighted):
     """Hundreds to thousands of grouping levels (K + q far beyond the ~110 columns of the binned pass): random intercept and
