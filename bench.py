@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--continuous", action="store_true", help="continuous response (configs B / E) instead of the probit model of config C")
     ap.add_argument("--weighted", action="store_true", help="observation weights (`weights` of stan4bart()): a non-default branch, not the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chains-per-gpu", type=int, default=2,
+    ap.add_argument("--chains-per-gpu", type=int, default=3,
                     help="chains resident on every GPU, each on its own host thread and stream (value = aggregate over all chains; the "
                          "one-chain-per-GPU figure is reported beside it)")
     ap.add_argument("--scaled-levels", action="store_true",
@@ -69,6 +69,16 @@ def workload_config(args):
                   "means) against 126 MB of L2, so every step's kernels start from HBM; inside k_sweep the chain's residuals and "
                   "predictors are then held on chip for the 200 tree steps by design" % int(round((9 + 8 * 19 + 12 + 8) * args.n / 1e6)),
             "adapt_sweeps": args.adapt}
+
+
+def ref_config(args, procs):
+    """The reference arm runs the GPU arm's configuration: the same chains (chains-per-gpu x gpus), one single-threaded process each."""
+    cfg = workload_config(args)
+    cpg = max(1, args.chains_per_gpu)
+    cfg["chains_per_gpu"] = cpg
+    cfg["workload"] = cfg["workload"].replace("1 chain per GPU", "%d chain(s) per GPU" % cpg)
+    cfg["cpu_processes"] = procs
+    return cfg
 
 
 def make_problem(args):
@@ -240,7 +250,7 @@ def run_reference(args):
     O.use_fast(True)
     O.lib()                 # loaded in this process too (the workers are forked from it): the CPU arm's native code is visible here
     build = "-O3 -march=native" if O.fast_build_is_native() else "-O2 (strict build)"
-    chains = max(1, args.gpus)
+    chains = max(1, args.gpus) * max(1, args.chains_per_gpu)      # the same chains as the GPU arm's configuration, one process each
     cores = os.cpu_count() or 1
     procs = min(chains, cores)
     ctx = mp.get_context("fork")
@@ -277,7 +287,7 @@ def run_reference(args):
               "(requested steps=%d warmup=%d bounded by --ref-budget-s)" % (build, procs, procs, args.n, args.trees, k, warm_done, args.steps, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": warm_done,
             "ms_per_step": 1000.0 * dt / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args),
+            "data": "synthetic", "config": ref_config(args, procs),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -447,7 +457,8 @@ def run_ours(args):
     n, T = args.n, args.trees
     sharded = bool(args.shard_rows) and world > 1
     shard_ctx = None
-    cpg = 1 if sharded else max(1, args.chains_per_gpu)
+    # every chain needs a host core for its NUTS thread (one is left to the main thread)
+    cpg = 1 if sharded else max(1, min(args.chains_per_gpu, max(1, (cores_per_rank or 4) - 1)))
     chains_total = 1 if sharded else world * cpg
     if sharded:
         # one chain, rows dealt out in contiguous blocks; every rank runs the replicated controller with the same seeds
