@@ -103,7 +103,7 @@ __device__ inline void w_copy_info(PipeInfo& dst, const PipeInfo& src, int lane)
 // rules; a birth step moves the rows of the node to split to the two new slots L + side
 template <int NQ>
 __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi, const uint32_t* __restrict__ tile, int tile_stride, int tid,
-                                          uint32_t (&sp)[NQ], uint32_t (&pp)[NQ])
+                                          uint32_t (&sp)[NQ], uint32_t (&pp)[NQ], int nq /* quads this warp owns (warp uniform): the others are skipped */)
 {
   const int kind = sd.b_kind, n_int = sd.b_cur.n_int;
   uint32_t pat[NQ];
@@ -115,10 +115,10 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
     const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
     const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+    for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
   }
 #pragma unroll
-  for (int j = 0; j < NQ; ++j)
+  for (int j = 0; j < NQ; ++j) if (j < nq)
     sp[j] = (uint32_t) pi.stab[pat[j] & 0xFFu] | ((uint32_t) pi.stab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.stab[(pat[j] >> 16) & 0xFFu] << 16) |
             ((uint32_t) pi.stab[pat[j] >> 24] << 24);
   if (kind == 2 || kind == 3) {
@@ -130,10 +130,10 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
       const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
       const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+      for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
     }
 #pragma unroll
-    for (int j = 0; j < NQ; ++j)
+    for (int j = 0; j < NQ; ++j) if (j < nq)
       pp[j] = (uint32_t) pi.ptab[pat[j] & 0xFFu] | ((uint32_t) pi.ptab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.ptab[(pat[j] >> 16) & 0xFFu] << 16) |
               ((uint32_t) pi.ptab[pat[j] >> 24] << 24);
   } else if (kind == 0) {
@@ -141,7 +141,7 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
     const uint32_t cut4 = (uint32_t) sd.b_cut * 0x01010101u;
     const uint32_t sb4 = (uint32_t) pi.slot_b * 0x01010101u, l4 = (uint32_t) sd.b_num_leaves * 0x01010101u;
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) {
+    for (int j = 0; j < NQ; ++j) if (j < nq) {
       const uint32_t side = __vcmpgtu4(col[j * kWorkers], cut4) & 0x01010101u;
       const uint32_t at_b = __vcmpeq4(sp[j], sb4);                 // 0xFF in the bytes of rows that sit in the node to split
       sp[j] = (sp[j] & ~at_b) | ((l4 + side) & at_b);
@@ -252,6 +252,9 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
     // rows beyond the data (the tail of the last quad, quads beyond q_hi) are parked in the trash slot kPipeSlots at every step
     constexpr unsigned kAllObs = NQ == 8 ? 0xFFFFFFFFu : ((1u << (4 * NQ)) - 1u);
     const bool ragged = obs_mask != kAllObs;
+    // quads that hold data in at least one lane of this warp: the rows are dealt out quad-major (q_lo + j * 480 + tid), so at n = 1 M
+    // the last quad is empty for the upper half of the warps -- they skip it altogether instead of computing on trash rows
+    const int nq = __reduce_max_sync(0xffffffffu, 32 - __clz(valid_mask));
 
     int C = 1;                                 // cells of the previous step as the cross table sees them (1 at the start and after a drained step)
     int na = t_begin;                          // the next decision whose update the residuals have not seen yet
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
         const double* dc = S.dcell[na & 1];
         const bool newest = na == t - 1;
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
+        for (int j = 0; j < NQ; ++j) if (j < nq) {
           const uint32_t cw = newest ? cprev[j] : cprev2[j];
 #pragma unroll
           for (int o = 0; o < 4; ++o) R[j][o] += dc[(cw >> (8 * o)) & 0xFF];
@@ -295,10 +298,10 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       if (warp == kWorkerWarps - 1 && t + 1 < t_end)
         w_fetch_desc_async(S.sd[(t + 1) % kPipeDescs], descs[t + 1], S.info[(t + 1) % kPipeDescs], infos[t + 1], lane);
       // ---- W(t): slots of every owned row ----
-      pipe_walk<NQ>(sd, pi, tile, tile_stride, tid, sp, pp);
+      pipe_walk<NQ>(sd, pi, tile, tile_stride, tid, sp, pp, nq);
       if (ragged) {
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
+        for (int j = 0; j < NQ; ++j) if (j < nq) {
           const uint32_t nib = (~obs_mask >> (4 * j)) & 0xFu;                                   // rows beyond the data
           const uint32_t tm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;                      // 0xFF in their bytes
           sp[j] = (sp[j] & ~tm) | (((uint32_t) kPipeSlots * 0x01010101u) & tm); pp[j] |= tm;
@@ -319,9 +322,11 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       //      the leaf values of the current tree are added by the controller (count x value); rows of a proposed slot come from
       //      several current leaves, so their sums carry the leaf values themselves ----
       uint32_t ccur[NQ];
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) ccur[j] = 0u;
       if (!two_trees) {
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
+        for (int j = 0; j < NQ; ++j) if (j < nq) {
           int s[4], e[4];
 #pragma unroll
           for (int o = 0; o < 4; ++o) {
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < NQ; ++j) {
+        for (int j = 0; j < NQ; ++j) if (j < nq) {
           double pr[4]; int s[4], q[4], e[4], e2[4];
           uint32_t cc = 0u;
 #pragma unroll
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsig
       const double* dc = S.dcell[na & 1];
       const bool newest = na == t_end - 1;
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) {
+      for (int j = 0; j < NQ; ++j) if (j < nq) {
         const uint32_t cw = newest ? cprev[j] : cprev2[j];
 #pragma unroll
         for (int o = 0; o < 4; ++o) R[j][o] += dc[(cw >> (8 * o)) & 0xFF];
