@@ -85,6 +85,7 @@ __device__ inline void w_fetch_desc_async(StepDesc& dst, const StepDesc& src, Pi
 {
   constexpr size_t kFrom = offsetof(StepDesc, b_tree);
   static_assert(kFrom % 8 == 0 && sizeof(StepDesc) % 8 == 0 && sizeof(PipeInfo) % 8 == 0, "8-byte copies");
+  static_assert(offsetof(PipeInfo, stab) % 4 == 0 && offsetof(PipeInfo, ptab) % 4 == 0, "the pattern tables are read as 32-bit words");
   const char* s = reinterpret_cast<const char*>(&src) + kFrom;
   char* d = reinterpret_cast<char*>(&dst) + kFrom;
   for (int i = lane; i < (int) ((sizeof(StepDesc) - kFrom) / 8); i += 32) cp_async8(d + 8 * i, s + 8 * i);
@@ -117,10 +118,19 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
 #pragma unroll
     for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
   }
+  // pattern -> slot.  Up to three rules (eight patterns) the table is two registers and the four look-ups of a quad are two byte
+  // permutes: the pattern bytes are folded into the four selector nibbles, PRMT then picks the four slot bytes at once
+  const bool small = n_int <= 3;
+  if (small) {
+    const uint32_t tlo = *reinterpret_cast<const uint32_t*>(pi.stab), thi = *reinterpret_cast<const uint32_t*>(pi.stab + 4);
 #pragma unroll
-  for (int j = 0; j < NQ; ++j) if (j < nq)
-    sp[j] = (uint32_t) pi.stab[pat[j] & 0xFFu] | ((uint32_t) pi.stab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.stab[(pat[j] >> 16) & 0xFFu] << 16) |
-            ((uint32_t) pi.stab[pat[j] >> 24] << 24);
+    for (int j = 0; j < NQ; ++j) if (j < nq) { const uint32_t x = pat[j] | (pat[j] >> 4); sp[j] = __byte_perm(tlo, thi, __byte_perm(x, 0u, 0x4420u)); }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) if (j < nq)
+      sp[j] = (uint32_t) pi.stab[pat[j] & 0xFFu] | ((uint32_t) pi.stab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.stab[(pat[j] >> 16) & 0xFFu] << 16) |
+              ((uint32_t) pi.stab[pat[j] >> 24] << 24);
+  }
   if (kind == 2 || kind == 3) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) pat[j] = 0u;
@@ -132,10 +142,16 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
 #pragma unroll
       for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
     }
+    if (small) {
+      const uint32_t tlo = *reinterpret_cast<const uint32_t*>(pi.ptab), thi = *reinterpret_cast<const uint32_t*>(pi.ptab + 4);
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) if (j < nq)
-      pp[j] = (uint32_t) pi.ptab[pat[j] & 0xFFu] | ((uint32_t) pi.ptab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.ptab[(pat[j] >> 16) & 0xFFu] << 16) |
-              ((uint32_t) pi.ptab[pat[j] >> 24] << 24);
+      for (int j = 0; j < NQ; ++j) if (j < nq) { const uint32_t x = pat[j] | (pat[j] >> 4); pp[j] = __byte_perm(tlo, thi, __byte_perm(x, 0u, 0x4420u)); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) if (j < nq)
+        pp[j] = (uint32_t) pi.ptab[pat[j] & 0xFFu] | ((uint32_t) pi.ptab[(pat[j] >> 8) & 0xFFu] << 8) | ((uint32_t) pi.ptab[(pat[j] >> 16) & 0xFFu] << 16) |
+                ((uint32_t) pi.ptab[pat[j] >> 24] << 24);
+    }
   } else if (kind == 0) {
     const uint32_t* col = tile + sd.b_var * tile_stride + tid;
     const uint32_t cut4 = (uint32_t) sd.b_cut * 0x01010101u;
