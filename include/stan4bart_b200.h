@@ -232,6 +232,18 @@ int glmm_num_device_passes(glmm_model* m, int64_t* out);
  * evicts the L2 before every timed launch; *bulk (optional) = 1 when the pass is the bulk-copy (TMA) kernel */
 int glmm_time_data_pass(glmm_model* m, int reps, int flush_l2, double* ms, int* bulk);
 
+/* The Stan half alone: the reference's StanSampler over a model (src/stan_sampler.cpp:382-476 constructor: diag_e NUTS with the
+ * windowed adaptation of `ctl`; run(isWarmup) :478-489: `ctl.skip` transitions, the last one written to out[num_pars] -- lp__,
+ * accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, then the constrained parameters).  The model must
+ * outlive the sampler.  Used by the Gibbs sampler below; exposed for tests of the NUTS control against exact posteriors. */
+typedef struct glmm_nuts glmm_nuts;
+int glmm_nuts_create(glmm_model* m, const s4b_stan_control* ctl, int chain_id, int num_warmup, glmm_nuts** out);
+int glmm_nuts_free(glmm_nuts* s);
+int glmm_nuts_num_pars(glmm_nuts* s, int* out);
+int glmm_nuts_run(glmm_nuts* s, int is_warmup, double* out);
+int glmm_nuts_disengage_adaptation(glmm_nuts* s);
+int glmm_nuts_stepsize(glmm_nuts* s, double* out);
+
 /* ------------------------------------------------------------------ s4b_sampler_* */
 typedef struct s4b_sampler s4b_sampler;
 /* stan4bart_create (init.cpp:190-310) */

@@ -79,6 +79,12 @@ SIGNATURES = {
     "glmm_set_mode": (C.c_int, [vp, C.c_int]),
     "glmm_get_mode": (C.c_int, [vp, c_int_p]),
     "glmm_num_device_passes": (C.c_int, [vp, c_int64_p]),
+    "glmm_nuts_create": (C.c_int, [vp, C.POINTER(StanControl), C.c_int, C.c_int, vpp]),
+    "glmm_nuts_free": (C.c_int, [vp]),
+    "glmm_nuts_num_pars": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "glmm_nuts_run": (C.c_int, [vp, C.c_int, c_double_p]),
+    "glmm_nuts_disengage_adaptation": (C.c_int, [vp]),
+    "glmm_nuts_stepsize": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "glmm_time_data_pass": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "s4b_sampler_create": (C.c_int, [C.POINTER(BartConfig), c_double_p, c_double_p, c_double_p, C.POINTER(GlmmData),
                                      C.POINTER(StanControl), C.POINTER(CommonControl), c_double_p, vpp]),

@@ -268,6 +268,7 @@ using namespace s4b;
 
 struct gpubart_fit { std::unique_ptr<BartFit> owned; BartFit* fit; };
 struct glmm_model { std::unique_ptr<GlmmModel> owned; GlmmModel* m; };
+struct glmm_nuts { std::unique_ptr<NutsSampler> s; };
 struct s4b_shard { std::unique_ptr<ShardContext> ctx; };
 struct gpubart_stored { std::unique_ptr<StoredBart> st; };
 struct s4b_sampler { std::unique_ptr<GibbsSampler> s; gpubart_fit bart_view; glmm_model glmm_view; };
@@ -419,6 +420,22 @@ int glmm_time_data_pass(glmm_model* m, int reps, int flush_l2, double* ms, int* 
   S4B_API_END
 }
 int glmm_num_grad_evals(glmm_model* m, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(m && out); *out = m->m->num_grad_evals(); S4B_API_END }
+
+// ---- the Stan half alone: StanSampler over a model (src/stan_sampler.cpp:382-476, run(isWarmup) :478-489) ----
+int glmm_nuts_create(glmm_model* m, const s4b_stan_control* ctl, int chain_id, int num_warmup, glmm_nuts** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(m && ctl && out && num_warmup >= 0);
+  auto* h = new glmm_nuts;
+  h->s.reset(new NutsSampler(*m->m, *ctl, chain_id, num_warmup));
+  *out = h;
+  S4B_API_END
+}
+int glmm_nuts_free(glmm_nuts* s) { S4B_API_BEGIN delete s; S4B_API_END }
+int glmm_nuts_num_pars(glmm_nuts* s, int* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); *out = s->s->num_pars(); S4B_API_END }
+int glmm_nuts_run(glmm_nuts* s, int is_warmup, double* out) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->run(is_warmup != 0, out); S4B_API_END }
+int glmm_nuts_disengage_adaptation(glmm_nuts* s) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->disengage_adaptation(); S4B_API_END }
+int glmm_nuts_stepsize(glmm_nuts* s, double* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); *out = s->s->stepsize(); S4B_API_END }
 
 // ---- sampler ----
 int s4b_sampler_create(const s4b_bart_config* bcfg, const double* y_bart, const double* x_bart, const double* x_test,

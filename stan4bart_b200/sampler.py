@@ -386,6 +386,40 @@ class GlmmModel:
         return m.value
 
 
+class StanSampler:
+    """The Stan half alone: NUTS (diag_e, windowed adaptation) over a GlmmModel, like the reference's StanSampler
+    (src/stan_sampler.cpp:382-489).  run(warmup) makes `ctl.skip` transitions and returns the last row
+    (lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__, constrained parameters)."""
+
+    def __init__(self, glmm, ctl, chain_id=1, num_warmup=1000):
+        self.L = _lib.load()
+        self.glmm, self.ctl = glmm, ctl               # the model must outlive the sampler
+        h = C.c_void_p()
+        _lib.check(self.L.glmm_nuts_create(glmm.h, C.byref(ctl), int(chain_id), int(num_warmup), C.byref(h)))
+        self.h = h
+        k = C.c_int(0)
+        _lib.check(self.L.glmm_nuts_num_pars(self.h, C.byref(k)))
+        self.num_pars = k.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.glmm_nuts_free(self.h)
+            self.h = None
+
+    def run(self, warmup=True):
+        out = np.zeros(self.num_pars)
+        _lib.check(self.L.glmm_nuts_run(self.h, int(bool(warmup)), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def disengage_adaptation(self):
+        _lib.check(self.L.glmm_nuts_disengage_adaptation(self.h))
+
+    def stepsize(self):
+        v = C.c_double(0.0)
+        _lib.check(self.L.glmm_nuts_stepsize(self.h, C.byref(v)))
+        return v.value
+
+
 class Sampler:
     """stan4bart_create(...) -> sampler object with run / disengage_adaptation / ... methods."""
 
