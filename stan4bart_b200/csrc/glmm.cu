@@ -277,9 +277,7 @@ __global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDe
       }
     }
     __syncwarp();
-    data_terms_epilogue(g, bins0, wb, false);
-    return;
-  }
+  } else {
   // --------------------------------------------------------------- consumer warps
   double S = 0.0;
   double gx[KT];
@@ -347,7 +345,9 @@ __global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDe
 #pragma unroll
   for (int c = 0; c < KT; ++c) if (c < K) wb[c * 32 + lane] = gx[c];
   wb[nb * 32 + lane] = S;
-  data_terms_epilogue(g, bins0, wb, true);
+  }
+  // one call site for the whole block: the epilogue's block-wide barriers must be reached by producer and consumers alike
+  data_terms_epilogue(g, bins0, wb, warp < kGBlock / 32);
 }
 
 using DataTermsBulkKernel = void (*)(GlmmDev, int, int, int);
