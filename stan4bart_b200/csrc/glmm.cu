@@ -467,6 +467,23 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_linear_predictor(GlmmDev g, do
   }
 }
 
+// out = G d for the dense symmetric Gram matrix G = [X Z]' W [X Z] kept on the device (models whose Z'WZ fills in: crossed grouping
+// factors with many levels).  One warp per row, lanes stride over the columns with two accumulators, shuffle tree: a fixed order,
+// so the product is reproducible.  nb^2 x 8 bytes per product (18 MB at nb = 1 500: L2 resident).
+__global__ void __launch_bounds__(kGBlock) k_gram_matvec(int nb, const double* __restrict__ G, const double* __restrict__ d, double* __restrict__ out)
+{
+  const int lane = threadIdx.x & 31;
+  const int row = (int) (((long long) blockIdx.x * kGBlock + threadIdx.x) >> 5);
+  if (row >= nb) return;
+  const double* __restrict__ g = G + (size_t) row * nb;
+  double a0 = 0.0, a1 = 0.0;
+  int c = lane;
+  for (; c + 32 < nb; c += 64) { a0 = fma(__ldg(g + c), __ldg(d + c), a0); a1 = fma(__ldg(g + c + 32), __ldg(d + c + 32), a1); }
+  if (c < nb) a0 = fma(__ldg(g + c), __ldg(d + c), a0);
+  const double acc = g_warp_sum(a0 + a1);
+  if (lane == 0) out[row] = acc;
+}
+
 __global__ void k_glmm_residual(long long N, const double* __restrict__ y, const double* __restrict__ offset, double* __restrict__ r)
 {
   for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long) gridDim.x * blockDim.x) r[i] = y[i] - offset[i];
@@ -695,8 +712,24 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     // crossed grouping factors with many levels fill Z'WZ in (500 x 500 levels => 10^6 entries): the host-side expansion then costs
     // more per evaluation (~1 ns per entry) than one device pass (tens of microseconds), so the per-evaluation device path is the
     // default there
+    // ... unless the Gram matrix fits the device densely (nb <= 4096: 134 MB): then G d is one small kernel (k_gram_matvec, L2 resident)
+    // and the sweep-level expansion stays the default
     const bool expansion_pays = gz_val_.size() <= 60000;
-    mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : (expansion_pays ? 1 : 0);
+    const bool device_gram = !expansion_pays && nb <= 4096 && !(getenv("S4B_GLMM_DEVICE_GRAM") && atoi(getenv("S4B_GLMM_DEVICE_GRAM")) == 0);
+    if (device_gram) {
+      std::vector<double> G((size_t) nb * nb, 0.0);
+      const size_t K = (size_t) K_, q = (size_t) q_;
+      for (size_t a = 0; a < K; ++a) {
+        for (size_t bb = 0; bb < K; ++bb) G[a * nb + bb] = gxx_[a * K + bb];
+        for (size_t c = 0; c < q; ++c) { G[a * nb + K + c] = gxz_[a * q + c]; G[(K + c) * nb + a] = gxz_[a * q + c]; }
+      }
+      for (size_t r = 0; r < q; ++r) for (long long k = gz_ptr_[r]; k < gz_ptr_[r + 1]; ++k) G[(K + r) * nb + K + (size_t) gz_col_[(size_t) k]] = gz_val_[(size_t) k];
+      S4B_CUDA(cudaMalloc(&d_gram_, sizeof(double) * G.size()));
+      S4B_CUDA(cudaMemcpy(d_gram_, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice));
+      S4B_CUDA(cudaMalloc(&d_dl_, sizeof(double) * 2 * ((size_t) nb + 1)));
+      S4B_CUDA(cudaMallocHost(&h_dl_, sizeof(double) * 2 * ((size_t) nb + 1)));
+    }
+    mode_ = getenv("S4B_GLMM_MODE") ? atoi(getenv("S4B_GLMM_MODE")) : ((expansion_pays || device_gram) ? 1 : 0);
   }
   dl_.assign((size_t) nb + 1, 0.0); Gd_.assign((size_t) nb + 1, 0.0);
   refresh_r();
@@ -707,6 +740,7 @@ GlmmModel::~GlmmModel()
 {
   cudaFree(d_X_); cudaFree(d_y_); cudaFree(d_offset_); cudaFree(d_r_); cudaFree(d_wt_); cudaFree(d_we_); cudaFree(d_col_ptr_); cudaFree(d_col_obs_); cudaFree(d_col_val_); cudaFree(d_tmp_); cudaFree(d_zval_); cudaFree(d_zidx_);
   cudaFree(d_theta_); cudaFree(d_partials_); cudaFree(d_result_); cudaFree(d_ticket_); cudaFreeHost(h_pinned_);
+  cudaFree(d_gram_); cudaFree(d_dl_); cudaFreeHost(h_dl_);
   delete scratch_;
 }
 
@@ -763,6 +797,17 @@ void GlmmModel::expand_sparse(const double* beta, const double* b, double* S, do
   double* dl = dl_.data(); double* Gd = Gd_.data();
   for (int k = 0; k < K_; ++k) dl[k] = beta[k] - theta0_[(size_t) k];
   for (int k = 0; k < q_; ++k) dl[K_ + k] = b[k] - theta0_[(size_t) (K_ + k)];
+  if (d_gram_ != nullptr) {
+    // G d on the device: 12 KB up, one kernel over the L2-resident matrix, 12 KB down
+    ++num_gram_products_;
+    std::memcpy(h_dl_, dl, sizeof(double) * (size_t) nb);
+    S4B_CUDA(cudaMemcpyAsync(d_dl_, h_dl_, sizeof(double) * (size_t) nb, cudaMemcpyHostToDevice, stream_));
+    const int blocks = (int) (((long long) nb * 32 + kGBlock - 1) / kGBlock);
+    k_gram_matvec<<<blocks, kGBlock, 0, stream_>>>(nb, d_gram_, d_dl_, d_dl_ + nb + 1);
+    S4B_CUDA(cudaMemcpyAsync(h_dl_ + nb + 1, d_dl_ + nb + 1, sizeof(double) * (size_t) nb, cudaMemcpyDeviceToHost, stream_));
+    S4B_CUDA(cudaStreamSynchronize(stream_));
+    std::memcpy(Gd, h_dl_ + nb + 1, sizeof(double) * (size_t) nb);
+  } else {
   for (int a = 0; a < nb; ++a) Gd[a] = 0.0;
   const double* db = dl + K;
   for (size_t a = 0; a < K; ++a) {
@@ -780,6 +825,7 @@ void GlmmModel::expand_sparse(const double* beta, const double* b, double* S, do
     double acc = 0.0;
     for (long long k = gz_ptr_[r]; k < gz_ptr_[r + 1]; ++k) acc += gz_val_[(size_t) k] * db[gz_col_[(size_t) k]];
     Gd[K + r] += acc;
+  }
   }
   double quad = 0.0, lin = 0.0;
   for (int a = 0; a < nb; ++a) { quad += dl[a] * Gd[a]; lin += g0_[(size_t) a] * dl[a]; }

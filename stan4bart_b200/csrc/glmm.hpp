@@ -106,6 +106,8 @@ class GlmmModel {
   std::vector<double> gram_, theta0_, g0_, dl_, Gd_;
   // K + q > 512: the Gram matrix in pieces -- X'WX, X'WZ dense, Z'WZ as compressed sparse rows
   bool sparse_gram_ = false;
+  double* d_gram_ = nullptr; double* d_dl_ = nullptr; double* h_dl_ = nullptr;    // dense Gram matrix on the device (filled-in Z'WZ), its operand / result
+  long long num_gram_products_ = 0;
   void expand_sparse(const double* beta, const double* b, double* S, double* gbeta, double* gb);
   std::vector<double> gxx_, gxz_, gz_val_; std::vector<long long> gz_ptr_; std::vector<int> gz_col_;
   double S0_ = 0.0;

@@ -270,6 +270,47 @@ def test_many_grouping_levels(levels, weighted):
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
 
 
+@pytest.mark.parametrize("weighted", [False, True])
+def test_crossed_factors_with_many_levels_use_the_gram_matrix_on_the_device(weighted, monkeypatch):
+    """Two crossed grouping factors with hundreds of levels each fill Z'WZ in (300 x 300 cross block): the host-side sparse expansion
+    would cost more than a device pass, so the Gram matrix lives on the device and G d is one kernel (k_gram_matvec).  Same
+    density and gradient as the per-evaluation path, the host-side expansion and the oracle; one data pass per residual."""
+    from stan4bart_b200.frontend import build_stan_data
+    rng = np.random.default_rng(11)
+    N, L1, L2 = 120000, 300, 300
+    g1 = rng.integers(0, L1, N); g1[:L1] = np.arange(L1)
+    g2 = rng.integers(0, L2, N); g2[:L2] = np.arange(L2)
+    M1 = np.column_stack([np.ones(N), rng.standard_normal(N)])
+    wt = rng.gamma(2.0, 0.5, N) if weighted else None
+    sd = build_stan_data(rng.standard_normal((N, 2)), rng.standard_normal(N), [(g1, M1), (g2, np.ones((N, 1)))], weights=wt)
+    assert sd.q == 2 * L1 + L2
+    off = rng.standard_normal(N)
+    mo, mg = O.OracleGlmm(sd), GlmmModel(sd)
+    assert mg.mode() == 1                                   # the expansion stays the default thanks to the device-side product
+    monkeypatch.setenv("S4B_GLMM_DEVICE_GRAM", "0")
+    mh = GlmmModel(sd)                                       # host-side sparse expansion (default mode there: 0)
+    mh.set_mode(1)
+    for m in (mo, mg, mh):
+        m.set_offset(off)
+    passes0 = mg.num_device_passes()
+    q0 = rng.uniform(-0.5, 0.5, mo.d)
+    for scale in (0.0, 1e-3, 0.3):
+        q = q0 + scale * rng.standard_normal(mo.d)
+        lo, go, so = mo.log_prob_grad(q)
+        lg, gg, sg = mg.log_prob_grad(q)
+        lh, gh, sh = mh.log_prob_grad(q)
+        assert so == sg == sh == 0
+        assert abs(lo - lg) <= REL_TOL * abs(lo) and abs(lh - lg) <= 1e-12 * abs(lh)
+        assert rel_err(go, gg, scale=np.abs(go) + 1e-8 * np.max(np.abs(go))) <= REL_TOL
+        assert rel_err(gh, gg, scale=np.abs(gh) + 1e-8 * np.max(np.abs(gh))) <= 1e-11
+    assert mg.num_device_passes() == passes0 + 1            # one data pass anchors all three evaluations
+    mg.set_mode(0)
+    l0, g0, _ = mg.log_prob_grad(q)
+    assert abs(l0 - lg) <= 1e-12 * abs(l0) and rel_err(g0, gg, scale=np.abs(g0) + 1e-8 * np.max(np.abs(g0))) <= 1e-10
+    a, b = mg.log_prob_grad(q), mg.log_prob_grad(q)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
 @pytest.mark.parametrize("prior_dist", [1, 3, 4, 5, 6, 7])
 def test_stan_row_names_match_the_reference_naming(prior_dist):
     """The names the library reports for the stored Stan rows (dimnames of the reference's `stan` result, src/stan_sampler.cpp:478-489,
