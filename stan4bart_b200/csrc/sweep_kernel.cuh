@@ -1059,7 +1059,7 @@ __device__ inline void w_copy_desc(StepDesc& dst, const StepDesc& src, int lane)
 
 // Everything of a sweep that does not depend on the data: with keyed RNG substreams the proposal of every tree (it needs
 // only that tree's structure) and the decision draws of every step can be produced before the sweep, one warp per tree.
-constexpr int kPrepWarps = 4;
+constexpr int kPrepWarps = 8;            // trees per block: the kernel is bound by instruction fetch (large, cold code): many warps per SM share the fetched lines
 struct PrepSmemWarp { DTree tree; CtlScratch cs; StepDesc sd; };
 
 // ---- pipelined sweep (sweep_pipe.cuh): data-independent description of a step's cells ----
