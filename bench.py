@@ -295,14 +295,31 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+RANK_CORES = []          # this rank's logical CPUs, one per physical core first (chain threads are pinned to them in that order)
+
+
 def pin_rank_to_cores(local_rank, local_world):
     """Every rank gets its own slice of the host's cores (its chain threads and their NUTS run there): eight ranks sharing one
-    NUMA node's scheduler was what bent the 8-GPU curve."""
+    NUMA node's scheduler was what bent the 8-GPU curve.  Inside the slice the logical CPUs are ordered one per physical core
+    first, so that two chain threads (one running NUTS, one spinning on a stream) do not share a core's two hyper-threads."""
+    global RANK_CORES
     try:
         cores = sorted(os.sched_getaffinity(0))
         per = max(1, len(cores) // max(1, local_world))
         mine = cores[local_rank * per:(local_rank + 1) * per] or cores
         os.sched_setaffinity(0, mine)
+        first, rest, seen = [], [], set()
+        for c in mine:
+            try:
+                with open("/sys/devices/system/cpu/cpu%d/topology/core_id" % c) as f:
+                    core = int(f.read())
+                with open("/sys/devices/system/cpu/cpu%d/topology/physical_package_id" % c) as f:
+                    core = (int(f.read()), core)
+            except (OSError, ValueError):
+                core = ("cpu", c)
+            (rest if core in seen else first).append(c)
+            seen.add(core)
+        RANK_CORES = first + rest
         return len(mine)
     except (AttributeError, OSError):
         return None
@@ -327,6 +344,11 @@ class ChainThread(threading.Thread):
 
         from stan4bart_b200 import _lib
         try:
+            if RANK_CORES:      # chain c of this rank -> its own physical core (the last logical CPU of the slice stays with the main thread)
+                try:
+                    os.sched_setaffinity(0, {RANK_CORES[self.index % max(1, len(RANK_CORES) - 1)]})
+                except OSError:
+                    pass
             torch.cuda.set_device(self.device)
             L = _lib.load()
             _lib.check(L.s4b_set_device(self.device))
