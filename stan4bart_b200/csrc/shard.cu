@@ -141,7 +141,7 @@ void ShardContext::attach(const void* handles64_by_rank)
 
 void ShardContext::allreduce(double* d_vec, int n, ReduceOp op, cudaStream_t stream)
 {
-  if (dev_.world == 1) return;
+  if (dev_.world == 1 && !use_nccl_) return;         // (a one-rank NCCL communicator still goes through ncclAllReduce: the cross-check on one GPU)
   if (!attached_) throw std::runtime_error("shard context: peers not attached");
   if (n < 0 || n > kMailVec) throw std::invalid_argument("shard all-reduce: vector too long");
   if (use_nccl_) {        // the reference collective: same payload, same ranks, NCCL's ring / tree over NVLink
@@ -157,7 +157,7 @@ void ShardContext::allreduce(double* d_vec, int n, ReduceOp op, cudaStream_t str
 
 void ShardContext::allreduce_host(double* h_vec, long long n, ReduceOp op, cudaStream_t stream)
 {
-  if (dev_.world == 1) return;
+  if (dev_.world == 1 && !use_nccl_) return;
   for (long long off = 0; off < n; off += kMailVec) {
     int m = (int) std::min<long long>(kMailVec, n - off);
     S4B_CUDA(cudaMemcpyAsync(d_tmp_, h_vec + off, sizeof(double) * (size_t) m, cudaMemcpyHostToDevice, stream));

@@ -64,11 +64,14 @@ class ShardContext:
     def init_nccl(self):
         """Reference collective: create the NCCL communicator of this context's ranks (collective; the unique id travels through
         the torch.distributed process group) -- `use_nccl(True)` then routes the small all-reduces through ncclAllReduce."""
-        import torch
-        import torch.distributed as dist
         buf = (C.c_ubyte * 128)()
         if self.rank == 0:
             _lib.check(self.L.s4b_shard_nccl_unique_id(buf))
+        if self.world == 1:                # a communicator of one rank: nothing to broadcast
+            _lib.check(self.L.s4b_shard_nccl_init(self.h, buf))
+            return
+        import torch
+        import torch.distributed as dist
         dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
         t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
         dist.broadcast(t, src=0)

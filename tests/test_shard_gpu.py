@@ -184,7 +184,30 @@ def test_nccl_reference_collective_agrees_with_the_mailbox_exchange(ranks):
     (two ranks: a + b either way round, so bit for bit) and the oracle's density.  On a one-GPU box NCCL cannot place two ranks on
     the same device; the mailbox path (the product path) is what the other tests of this file exercise there."""
     if not all(r["nccl"][0] == 1.0 for r in ranks):
-        pytest.skip("NCCL needs one GPU per rank (run with gpurun --gpus 2)")
+        # one GPU: NCCL refuses two ranks on one device, so the cross-check runs on a communicator of ONE rank in this process -- the
+        # library is loaded, the communicator built and ncclAllReduce launched on the fit's stream exactly as with more ranks (the
+        # two-rank comparison is in profiles/shard_and_nuts_tests_2gpu_r2.log)
+        from stan4bart_b200.sampler import GlmmModel
+        from stan4bart_b200.shard import ShardContext
+        ctx = ShardContext(0, 1)
+        ctx.init_nccl()
+        v, long_v = SC.allreduce_input(0), SC.allreduce_long_input(0)
+        plain = [ctx.allreduce(v, "sum"), ctx.allreduce(v, "max"), ctx.allreduce(long_v, "sum")]
+        ctx.use_nccl(True)
+        through_nccl = [ctx.allreduce(v, "sum"), ctx.allreduce(v, "max"), ctx.allreduce(long_v, "sum")]
+        for a, b, want in zip(plain, through_nccl, (v, v, long_v)):
+            assert np.array_equal(a, want) and np.array_equal(b, want)
+        pr = friedman_problem(SC.GLMM_N)
+        ctx.set_obs_range(0, SC.GLMM_N)
+        m, g = GlmmModel(pr["stan_data"], shard=ctx), O.OracleGlmm(pr["stan_data"])     # every data pass all-reduced by NCCL
+        m.set_mode(0); m.set_offset(SC.glmm_offset()); g.set_offset(SC.glmm_offset())
+        for q in SC.glmm_points(g.d):
+            lp, grad, st = g.log_prob_grad(q)
+            lp2, grad2, st2 = m.log_prob_grad(q)
+            assert st == st2 and abs(lp - lp2) <= 1e-10 * max(1.0, abs(lp)) and rel_err(grad, grad2, scale=np.abs(grad) + 1.0) <= 1e-10
+        del m
+        ctx.use_nccl(False)
+        return
     for r in ranks:
         assert np.array_equal(r["nccl_allreduce_sum"], r["allreduce_sum"])
         assert np.array_equal(r["nccl_allreduce_max"], r["allreduce_max"])
