@@ -888,7 +888,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_counters_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_pipe_pos_); cudaFree(d_leaf_partials_); cudaFree(d_leaf_ticket_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_pipe_pos_); cudaFree(d_leaf_partials_); cudaFree(d_leaf_ticket_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -1000,7 +1000,6 @@ void BartFit::setup_persistent()
           pipe_count_words_ = words; pipe_smem_ = smem;
           S4B_CUDA(cudaMalloc(&d_pipe_ring_, sizeof(unsigned long long) * 2 * kPipeRing * kPipeAcc));
           zero_device_sync(d_pipe_ring_, sizeof(unsigned long long) * 2 * kPipeRing * kPipeAcc, stream_);
-          S4B_CUDA(cudaMalloc(&d_pipe_counters_, sizeof(unsigned int) * kPipeRing));
           S4B_CUDA(cudaMalloc(&d_pipe_flag_, sizeof(unsigned int) * 4));
           zero_device_sync(d_pipe_flag_, sizeof(unsigned int) * 4, stream_);
           S4B_CUDA(cudaMalloc(&d_pipe_infos_, sizeof(PipeInfo) * (size_t) T_));
@@ -1072,14 +1071,12 @@ void BartFit::launch_persistent_sweep(bool last_thin)
     const void* pfn = persistent_nq_ == 1 ? (const void*) k_sweep_pipe<1> : persistent_nq_ == 2 ? (const void*) k_sweep_pipe<2>
                     : persistent_nq_ == 4 ? (pipe_prof ? (const void*) k_sweep_pipe<4, true> : (const void*) k_sweep_pipe<4>) : (const void*) k_sweep_pipe<6>;
     unsigned long long* ring = d_pipe_ring_; int words = pipe_count_words_;
-    static const int pipe_dbg = getenv("S4B_PIPE_DBG") ? atoi(getenv("S4B_PIPE_DBG")) : 0;      // timing experiments only (wrong results)
-    int dbg = pipe_dbg;
     const StepDesc* pdescs = d_descs_; const PipeInfo* pinfos = infos; const double2* pdraws = d_draws_; unsigned long long* ran = d_pipe_ran_;
     unsigned long long* pprof = pipe_prof ? d_prof_ : nullptr;
     for (int k = 0; k < kPipeSegments; ++k) {
       const int* pin = d_pipe_pos_ + 2 * k; int* pmid = d_pipe_pos_ + 2 * k + 1; int* pout = d_pipe_pos_ + 2 * k + 2;
       int parity = (int) (pipe_launches_++ & 1);
-      void* pargs[] = { &dv, &ring, &parity, &pdescs, &pinfos, &pdraws, &pin, &pmid, &words, &ran, &pprof, &dbg };
+      void* pargs[] = { &dv, &ring, &parity, &pdescs, &pinfos, &pdraws, &pin, &pmid, &words, &ran, &pprof };
       S4B_CUDA(cudaLaunchCooperativeKernel(pfn, dim3(persistent_grid_), dim3(kSweepBlock), pargs, pipe_smem_, stream_));
       if (k > 0) S4B_CUDA(cudaMemsetAsync(d_barrier_, 0, sizeof(unsigned int), stream_));
       const int* sin = pmid; int max_steps = k + 1 < kPipeSegments ? 1 : T_;

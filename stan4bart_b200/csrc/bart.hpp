@@ -155,7 +155,7 @@ class BartFit {
   bool pipe_enabled_ = false;
   int pipe_count_words_ = 0;
   size_t pipe_smem_ = 0;
-  unsigned long long* d_pipe_ring_ = nullptr; unsigned int* d_pipe_counters_ = nullptr; unsigned int* d_pipe_flag_ = nullptr; void* d_pipe_infos_ = nullptr;
+  unsigned long long* d_pipe_ring_ = nullptr; unsigned int* d_pipe_flag_ = nullptr; void* d_pipe_infos_ = nullptr;
   long long pipe_sweeps_ = 0, pipe_launches_ = 0;
   unsigned long long* d_pipe_ran_ = nullptr;
   int* d_pipe_pos_ = nullptr;          // first step still to do, one entry per launch of a sweep's segment sequence

@@ -455,6 +455,29 @@ __global__ void __launch_bounds__(kGBlock) k_glmm_linear_predictor(GlmmDev g, do
   const bool staged = (size_t) nb * sizeof(double) <= kThetaSmemMax;      // otherwise the coefficients are read through L1 / L2
   if (staged) { for (int j = threadIdx.x; j < nb; j += kGBlock) smem[j] = g.theta[j]; __syncthreads(); }
   const double* th = staged ? smem : g.theta;
+  if (g.K <= kGFast && g.slots <= kGFast) {
+    const bool out_aligned = (reinterpret_cast<unsigned long long>(out) & 15ull) == 0ull;
+    // small models: two rows per thread and load (16-byte loads; the arrays are padded to a multiple of 16 rows), every load of the
+    // pair issued before the first use -- the pass is latency bound otherwise (ncu: long scoreboard)
+    for (long long i = ((long long) blockIdx.x * kGBlock + threadIdx.x) * 2; i < g.N; i += (long long) gridDim.x * kGBlock * 2) {
+      double2 x2[kGFast], v2[kGFast]; int2 c2[kGFast];
+#pragma unroll
+      for (int k = 0; k < kGFast; ++k) if (include_fixed && k < g.K) x2[k] = __ldg(reinterpret_cast<const double2*>(g.X + (long long) k * g.npad + i));
+#pragma unroll
+      for (int s = 0; s < kGFast; ++s) if (include_random && s < g.slots) {
+        c2[s] = __ldg(reinterpret_cast<const int2*>(g.zidx + (long long) s * g.npad + i));
+        v2[s] = ((g.ones_mask >> s) & 1u) ? make_double2(1.0, 1.0) : __ldg(reinterpret_cast<const double2*>(g.zval + (long long) s * g.npad + i));
+      }
+      double eta0 = 0.0, eta1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kGFast; ++k) if (include_fixed && k < g.K) { eta0 += x2[k].x * th[k]; eta1 += x2[k].y * th[k]; }
+#pragma unroll
+      for (int s = 0; s < kGFast; ++s) if (include_random && s < g.slots) { eta0 += v2[s].x * th[g.K + c2[s].x]; eta1 += v2[s].y * th[g.K + c2[s].y]; }
+      if (i + 1 < g.N && out_aligned) *reinterpret_cast<double2*>(out + i) = make_double2(eta0, eta1);
+      else { out[i] = eta0; if (i + 1 < g.N) out[i + 1] = eta1; }
+    }
+    return;
+  }
   for (long long i = (long long) blockIdx.x * kGBlock + threadIdx.x; i < g.N; i += (long long) gridDim.x * kGBlock) {
     double eta = 0.0;
     if (include_fixed) for (int k = 0; k < g.K; ++k) eta += __ldg(g.X + (long long) k * g.npad + i) * th[k];

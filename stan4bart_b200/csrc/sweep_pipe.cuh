@@ -170,7 +170,7 @@ template <int NQ, bool PROF = false>
 __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_pipe(BartDev dv, unsigned long long* acc_rings, int launch_parity,
                                                                 const StepDesc* __restrict__ descs, const PipeInfo* __restrict__ infos,
                                                                 const double2* __restrict__ draws, const int* __restrict__ pos_in, int* __restrict__ pos_out,
-                                                                int count_entries, unsigned long long* __restrict__ ran, unsigned long long* __restrict__ prof, int dbg)
+                                                                int count_entries, unsigned long long* __restrict__ ran, unsigned long long* __restrict__ prof)
 {
   // this launch takes the run of consecutive steps that fit, starting at *pos_in; the synchronous kernel (launched next) takes
   // the step that stopped it.  Every CTA scans the same flags, so all agree on the range without talking to each other.
