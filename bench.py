@@ -678,9 +678,10 @@ def run_ours(args):
         c.sampler.set_host_plumbing(False)
     if clocks:
         clocks.stop()
-    e2e = {"value": chains_total * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * cpg, "d2h_bytes_per_step": int(d2h + 2 * 8 * n + 8 * s0.num_pars) * cpg,
+    e2e = {"value": chains_total * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * cpg, "d2h_bytes_per_step": int(d2h + 8 * n + 8 * s0.num_pars) * cpg,
            "note": "s4b_sampler_run with host result buffers (train + test fits, Stan row) and every N-vector of the sweep "
-                   "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors; "
+                   "(parametric mean, BART fit, latents) round-tripped through pinned host memory like the reference's host vectors "
+                   "(the training fit makes its round trip through the result buffer, as in init.cpp:828-835: counted once); "
                    "bytes are per step of the GPU (all %d chain(s) on it advance one sweep)" % cpg}
 
     # kernels launched inside the timed region, per sweep and chain.  BART block with the pipelined sweep: k_prepare_sweep +

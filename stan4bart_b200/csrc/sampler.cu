@@ -147,8 +147,11 @@ class GibbsSampler {
           S4B_CUDA(cudaMemcpyAsync(h_plumb_ + 2 * n, bart_.d_latent_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, copy_stream_));
           S4B_CUDA(cudaEventRecord(ev_b_, copy_stream_));
         }
-        S4B_CUDA(cudaMemcpyAsync(h_plumb_ + n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
-        S4B_CUDA(cudaMemcpyAsync(bart_.d_train_out(), h_plumb_ + n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+        // the reference computes `stanOffset` on the host FROM the results buffer dbarts filled (init.cpp:828-835): when the caller
+        // collects the training fits, that buffer is the host vector of the round trip -- one device-to-host copy, not two
+        double* h_train = train != nullptr ? train + slot * n : h_plumb_ + n;
+        S4B_CUDA(cudaMemcpyAsync(h_train, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+        S4B_CUDA(cudaMemcpyAsync(bart_.d_train_out(), h_train, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
         if (cc_.is_binary) {
           S4B_CUDA(cudaStreamWaitEvent(stream_, ev_b_, 0));
           S4B_CUDA(cudaMemcpyAsync(bart_.d_latent_out(), h_plumb_ + 2 * n, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
@@ -160,11 +163,12 @@ class GibbsSampler {
                                                      nt_, nt_ > 0 ? bart_.d_test_out() : nullptr, d_mean_test_);
         ++num_mean_draws_;
       }
-      if (train || (test && nt_ > 0)) {
+      const bool train_copied = host_plumbing_ && train != nullptr;      // (already in the caller's buffer: the round trip above)
+      if ((train && !train_copied) || (test && nt_ > 0)) {
         // the N-length results leave on the copy stream and overlap the next iteration's Stan block
         S4B_CUDA(cudaEventRecord(ev_a_, stream_));
         S4B_CUDA(cudaStreamWaitEvent(copy_stream_, ev_a_, 0));
-        if (train) S4B_CUDA(cudaMemcpyAsync(train + slot * n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, copy_stream_));
+        if (train && !train_copied) S4B_CUDA(cudaMemcpyAsync(train + slot * n, bart_.d_train_out(), sizeof(double) * n, cudaMemcpyDeviceToHost, copy_stream_));
         if (test && nt_ > 0) S4B_CUDA(cudaMemcpyAsync(test + slot * nt, bart_.d_test_out(), sizeof(double) * nt, cudaMemcpyDeviceToHost, copy_stream_));
         S4B_CUDA(cudaEventRecord(ev_c_, copy_stream_));
         copy_pending_ = true;
