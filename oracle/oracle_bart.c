@@ -14,7 +14,11 @@
  * dbarts itself (>= 0.9-34) is an un-vendored dependency; the algorithm below
  * follows SURVEY.md App. B / section 8 rows a3-a10 (upstream files named there:
  * bartFit.cpp, tree.cpp, node.cpp, birthDeathRule.cpp, changeRule.cpp,
- * swapRule.cpp, likelihood.cpp).  PARITY UNPINNED against real dbarts.
+ * swapRule.cpp, likelihood.cpp).  PARITY UNPINNED against real dbarts (none of its
+ * outputs or test vectors exist here).  What does pin this file: the exact posterior of
+ * an enumerable one-tree model computed from the model alone
+ * (tests/exact_posterior.py, tests/test_exact_posterior.py) and the reference's own
+ * acceptance bounds (tests/test_acceptance_gpu.py).
  *
  * Data model here is deliberately dbarts-like (per-node index partitions,
  * per-tree fits, two-pass mean/variance) and therefore independent of the CUDA

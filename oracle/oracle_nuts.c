@@ -14,6 +14,8 @@
  *   services/util/initialize.hpp:60-216, generate_transitions.hpp:43-77, mcmc_writer.hpp:97-129
  * Randomness is s4b-rng v1 (stream 1), NOT boost::ecuyer1988: the reference's own
  * NUTS draws cannot be replayed here ("parity unpinned" vs the reference binary).
+ * What does pin this file: exact posterior moments by quadrature of an independent
+ * transcription of the density (tests/test_exact_stan_posterior.py).
  */
 #include "s4b_oracle.h"
 #include "s4b_rng.h"
