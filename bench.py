@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--scaled-levels", action="store_true",
                     help="grouping factors with max(5 | 8, n / 2000) levels each (SURVEY.md 8d: 'scale to max(5, N/2000) levels for big N and "
                          "report it'): q = 3 n / 2000 random-effect coefficients instead of 18")
+    ap.add_argument("--no-leaf-large", action="store_true", help="skip the 32 M-row leg of the leaf-statistics kernel (HBM-bound size)")
     ap.add_argument("--no-mode0", action="store_true", help="skip the glmm mode 0 leg (one device pass per gradient evaluation)")
     ap.add_argument("--shard-rows", action="store_true",
                     help="N > 1 only: ONE chain whose --n rows are sharded over the N GPUs (BASELINE config E; strong scaling) instead of "
@@ -608,6 +609,37 @@ def run_ours(args):
                                    "0.55 - 0.64 of peak) are in profiles/leaf_stat_sizes_r2.json" % reps}
         except Exception as e:      # pragma: no cover
             leaf_stat = {"error": repr(e)}
+        # the same kernel where it IS bound by HBM: 32 M rows (working set 8 B residual + 1 B per rule and row = 290-320 MB, beyond the
+        # 126 MB L2, so back-to-back launches stream from HBM); rank 0 of a one-GPU run only
+        if leaf_stat is not None and "error" not in leaf_stat and world == 1 and not args.no_leaf_large:
+            try:
+                from stan4bart_b200.sampler import GpuBart
+                nl = 32_000_000
+                rg = np.random.default_rng(1)
+                xl = np.asfortranarray(rg.random((nl, 3)))
+                yl = 10 * np.sin(np.pi * xl[:, 0] * xl[:, 1]) + 5 * xl[:, 2] + rg.standard_normal(nl)
+                gl = GpuBart(bart_config(nl, 3, num_trees=8, seed=3), yl, xl)
+                gl.set_sigma(1.0)
+                gl.sample_trees_from_prior()
+                gl.run()
+                tr = gl.trees()
+                rows = []
+                for t in range(8):
+                    rules = int(np.sum(tr["var"][tr["tree"] == t] >= 0))
+                    if 1 <= rules <= 7:
+                        ms_l = gl.time_leaf_stats(t, 20)
+                        rows.append((rules, ms_l))
+                del gl, xl, yl
+                if rows:
+                    rules, ms_l = rows[len(rows) // 2]
+                    leaf_stat["hbm_bound_size"] = {"n": nl, "rules_of_the_tree": rules, "launch_us": ms_l * 1e3,
+                                                   "achieved": 11.0 * nl / ms_l / 1e6, "frac": 11.0 * nl / ms_l / 1e6 / peak,
+                                                   "achieved_bytes_actually_read": (8.0 + rules) * nl / ms_l / 1e6,
+                                                   "frac_bytes_actually_read": (8.0 + rules) * nl / ms_l / 1e6 / peak,
+                                                   "note": "k_leaf_stats on a synthetic 32 M-row fit (3 predictors): 11 algorithmic B per row as above; "
+                                                           "the kernel actually reads 8 + (rules of the tree) B per row"}
+            except Exception as e:      # pragma: no cover
+                leaf_stat["hbm_bound_size"] = {"error": repr(e)}
     # the GLMM data pass (S, X'e, Z'e over all rows: 44 algorithmic B per row for this model), L2-warm and from HBM
     glmm_pass = None
     if not sharded:

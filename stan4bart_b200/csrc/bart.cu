@@ -919,7 +919,7 @@ void BartFit::setup_persistent()
     auto try_nq = [&](int nq, size_t smem, const void* fn, const void* fn_seq, const void* fn_nosq) -> bool {
       if (smem > (size_t) max_smem || p_ > 511) return false;      // traversal records carry 9 bits of variable index
       for (const void* f : { fn, fn_seq, fn_nosq }) {
-        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (s4b_allow_max_dynamic_smem((const void*) f) != cudaSuccess) { cudaGetLastError(); return false; }
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, kSweepBlock, smem) != cudaSuccess) { cudaGetLastError(); return false; }
         if (per_sm < 1) return false;
@@ -945,7 +945,7 @@ void BartFit::setup_persistent()
       bool ok = smem <= (size_t) max_smem && p_ <= 511 && rounds <= 63;      // 8-bit count fields: at most 63 rounds of 4 observations
       for (const void* f : { (const void*) k_sweep<1, false, true>, (const void*) k_sweep<1, true, true>, (const void*) k_sweep<1, false, true, false> }) {
         if (!ok) break;
-        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        if (s4b_allow_max_dynamic_smem((const void*) f) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, kSweepBlock, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); ok = false; }
       }
@@ -975,7 +975,7 @@ void BartFit::setup_persistent()
     S4B_CUDA(cudaMalloc(&d_draws_, sizeof(double2) * 32 * (size_t) T_));
     {
       size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
-      S4B_CUDA(cudaFuncSetAttribute(k_prepare_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) psmem));
+      S4B_CUDA(s4b_allow_max_dynamic_smem((const void*) k_prepare_sweep));
     }
     S4B_CUDA(cudaMalloc(&d_tables_, sizeof(double) * tab.size()));
     S4B_CUDA(cudaMemcpy(d_tables_, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
@@ -994,8 +994,8 @@ void BartFit::setup_persistent()
         const int words = entries;            // (member name kept: capacity of the cross table in entries)
         const size_t smem = fixed + (size_t) (entries + 1) * kWorkers;
         int per_sm = 0;
-        if (persistent_nq_ == 4) cudaFuncSetAttribute((const void*) k_sweep_pipe<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) == cudaSuccess &&
+        if (persistent_nq_ == 4) s4b_allow_max_dynamic_smem((const void*) k_sweep_pipe<4, true>);
+        if (s4b_allow_max_dynamic_smem((const void*) fn) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSweepBlock, smem) == cudaSuccess && per_sm >= 1) {
           pipe_count_words_ = words; pipe_smem_ = smem;
           S4B_CUDA(cudaMalloc(&d_pipe_ring_, sizeof(unsigned long long) * 2 * kPipeRing * kPipeAcc));
@@ -1506,7 +1506,7 @@ void StoredBart::predict(const double* x_test, long long rows, const double* tes
   BartDev dv; std::memset(&dv, 0, sizeof dv);
   dv.params = d_params_;
   const size_t smem = (sizeof(uint32_t) + sizeof(double)) * 2048 + (size_t) p_ * kBlock;
-  if (smem > 48 * 1024) S4B_CUDA(cudaFuncSetAttribute(k_test_fits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (smem > 48 * 1024) S4B_CUDA(s4b_allow_max_dynamic_smem((const void*) k_test_fits));
   const int grid = (int) ((rows + kBlock - 1) / kBlock);
   for (long long s = 0; s < count; ++s) {
     k_test_fits<<<grid, kBlock, smem, stream_>>>(dv, d_x, rows, rows_pad, d_off, d_o, is_binary_ ? 0 : 1, p_, d_store_ + (size_t) (first + s) * (size_t) T_,
@@ -1542,7 +1542,7 @@ void BartFit::test_fits_device(const uint8_t* d_xt, long long rows, long long ro
                                const double* scale)
 {
   size_t smem = (sizeof(uint32_t) + sizeof(double)) * 2048 + (size_t) p_ * kBlock;
-  if (smem > 48 * 1024) S4B_CUDA(cudaFuncSetAttribute(k_test_fits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (smem > 48 * 1024) S4B_CUDA(s4b_allow_max_dynamic_smem((const void*) k_test_fits));
   int grid = (int) ((rows + kBlock - 1) / kBlock);
   k_test_fits<<<grid, kBlock, smem, stream_>>>(dev(), d_xt, rows, rows_pad, d_off, d_out, cfg_.is_binary ? 0 : 1, p_, trees, scale);
   S4B_CUDA(cudaGetLastError());
@@ -1628,7 +1628,7 @@ void BartFit::launch_leaf_stats(int tree)
     if (d_leaf_partials_ == nullptr) {
       leaf_grid_ = (int) std::max<long long>(1, std::min<long long>(((n_ + 3) / 4 + 4 * kLeafBlock - 1) / (4 * kLeafBlock), (long long) num_sms_ * 4));   // >= 4 quads per thread
       leaf_smem_ = ((sizeof(LeafSmem) + 15) / 16) * 16 + (size_t) (kLeafSlots + 1) * kLeafBlock * (sizeof(double2) + sizeof(int));
-      S4B_CUDA(cudaFuncSetAttribute(k_leaf_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) leaf_smem_));
+      S4B_CUDA(s4b_allow_max_dynamic_smem((const void*) k_leaf_stats));
       S4B_CUDA(cudaMalloc(&d_leaf_partials_, sizeof(double) * 3 * kLeafSlots * (size_t) leaf_grid_));
       S4B_CUDA(cudaMalloc(&d_leaf_ticket_, sizeof(unsigned int) + sizeof(int)));
       zero_device_sync(d_leaf_ticket_, sizeof(unsigned int) + sizeof(int), stream_);

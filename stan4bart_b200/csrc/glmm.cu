@@ -659,7 +659,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     dalloc(&d_we_, (size_t) npad_);
     per_sm = 4;
   } else {
-    S4B_CUDA(cudaFuncSetAttribute(data_terms_kernel(K_, slots_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes_));
+    S4B_CUDA(s4b_allow_max_dynamic_smem((const void*) data_terms_kernel(K_, slots_)));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, data_terms_kernel(K_, slots_), kGBlock, smem_bytes_) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
   }
   num_sms_ = sms;
@@ -679,7 +679,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     const char* ev = getenv("S4B_GLMM_BULK");
     bulk_ = bulk_tile_ > 0 && (ev != nullptr ? atoi(ev) != 0 : N_ >= 65536);
     if (bulk_) {
-      if (cudaFuncSetAttribute((const void*) data_terms_bulk_kernel(K_, slots_), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bulk_smem_) != cudaSuccess) { cudaGetLastError(); bulk_ = false; }
+      if (s4b_allow_max_dynamic_smem((const void*) data_terms_bulk_kernel(K_, slots_)) != cudaSuccess) { cudaGetLastError(); bulk_ = false; }
       const long long ntiles = (N_ + bulk_tile_ - 1) / bulk_tile_;
       bulk_grid_ = (int) std::max<long long>(1, std::min<long long>(std::min<long long>(ntiles, sms), grid_));
     }

@@ -307,4 +307,20 @@ struct BartParams {
   int change_symmetric, pad_cs;
 };
 
+// The opt-in limit of dynamic shared memory is an attribute of the kernel FUNCTION, not of a launch: every kernel that needs more than
+// the default gets the most its static shared memory leaves, once and for all, so that two fits of different shapes in one process
+// (other predictors, other tree counts, other models) cannot lower each other's limit between their launches.
+inline cudaError_t s4b_allow_max_dynamic_smem(const void* fn)
+{
+  int dev = 0, optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes attr;
+  e = cudaFuncGetAttributes(&attr, fn);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) attr.sharedSizeBytes);
+}
+
 }  // namespace s4b

@@ -585,6 +585,29 @@ def test_cut_counts_per_predictor():
     assert np.array_equal(tg["var"], to["var"]) and rel_err(tg["value"], to["value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-9
 
 
+def test_two_fits_of_different_shapes_in_one_process():
+    """The opt-in limit of dynamic shared memory is an attribute of the kernel FUNCTION: a second fit with fewer predictors (a smaller
+    predictor tile) must not lower the limit under the first fit's launches (two stan4bart fits in one session).  Regression test:
+    fit A runs, fit B (other shape) is created and runs, fit A runs again -- and still equals its oracle."""
+    xa, ya, _ = bart_problem(n=9000, p=9, binary=False, seed=41)
+    xb, yb, _ = bart_problem(n=4000, p=2, binary=True, seed=42)
+    cfg_a = bart_config(9000, 9, num_trees=12, seed=5)
+    oa, ga = O.OracleBart(cfg_a, ya, xa), GpuBart(cfg_a, ya, xa)
+    for b in (oa, ga):
+        b.set_sigma(1.0); b.sample_trees_from_prior()
+    for _ in range(2):
+        ro, rg = oa.run(), ga.run()
+    gb = GpuBart(bart_config(4000, 2, num_trees=7, seed=6, is_binary=True), yb, xb)
+    gb.sample_trees_from_prior()
+    for _ in range(2):
+        gb.run()
+    for _ in range(3):
+        ro, rg = oa.run(), ga.run()
+        assert rel_err(ro["train"], rg["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9
+    gb.run()
+    assert_same_partition(oa, ga, 12)
+
+
 def test_quantile_cut_points():
     """bart_args use.quantiles: cut points between the distinct sorted values (discrete predictors get a cut in every gap, a
     constant predictor none); same cuts, bins, decisions and fits as the oracle; test rows are binned against the same cuts."""
