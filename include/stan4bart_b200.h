@@ -130,6 +130,12 @@ int gpubart_get_k(gpubart_fit* fit, double* k);
 int gpubart_sample_trees_from_prior(gpubart_fit* fit);
 /* runSamplerWithResults(fit, 0, results[numSamples = 1]) (init.cpp:273, :824); layout src/bart_util.hpp:14-35 */
 int gpubart_run_sampler_with_results(gpubart_fit* fit, double* train, double* test, uint32_t* varcount, double* sigma);
+/* Several chains, one launch (grid.y = chain): one runSamplerWithResults step of `count` fits whose sweep kernels
+ * run as ONE cooperative launch, chain c on the CTAs of row c.  The fits must have been created on the same thread / stream with the
+ * same shape class (rows per thread, predictors, `thin`) and max_ctas = SMs / count (or less); traced, replayed, weighted and sharded
+ * fits are refused.  The chains evolve exactly as if run one by one.  Results of each fit: gpubart_collect_results (any pointer NULL). */
+int gpubart_run_batched(gpubart_fit* const* fits, int count);
+int gpubart_collect_results(gpubart_fit* fit, double* train, double* test, uint32_t* varcount, double* sigma);
 /* storeLatents / getLatentVariables (init.cpp:289, :845) */
 int gpubart_store_latents(gpubart_fit* fit, double* out);
 /* fit->sharedScratch.dataScale.{min,max,range} (init.cpp:324-325) */

@@ -47,6 +47,8 @@ SIGNATURES = {
     "gpubart_get_k": (C.c_int, [vp, c_double_p]),
     "gpubart_sample_trees_from_prior": (C.c_int, [vp]),
     "gpubart_run_sampler_with_results": (C.c_int, [vp, c_double_p, c_double_p, c_uint32_p, c_double_p]),
+    "gpubart_run_batched": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "gpubart_collect_results": (C.c_int, [vp, c_double_p, c_double_p, c_uint32_p, c_double_p]),
     "gpubart_store_latents": (C.c_int, [vp, c_double_p]),
     "gpubart_get_data_range": (C.c_int, [vp, c_double_p]),
     "gpubart_predict": (C.c_int, [vp, c_double_p, C.c_int64, c_double_p, c_double_p]),

@@ -888,7 +888,7 @@ BartFit::~BartFit()
   cudaFree(d_train_out_); cudaFree(d_latent_out_); cudaFree(d_offset_in_); cudaFree(d_test_out_);
   cudaFree(d_partials_); cudaFree(d_minmax_); cudaFree(d_stats_out_); cudaFree(d_desc_); cudaFree(d_ticket_);
   cudaFree(d_trace_len_); cudaFree(d_trees_); cudaFree(d_params_); cudaFree(d_pgrow_); cudaFree(d_rng_); cudaFree(d_scale_factor_);
-  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_pipe_ran_); cudaFree(d_pipe_pos_); cudaFree(d_leaf_partials_); cudaFree(d_leaf_ticket_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
+  cudaFree(d_split_w_); cudaFree(d_wt_); cudaFree(d_ncuts_var_); cudaFree(d_store_); cudaFree(d_store_scale_); cudaFree(d_packs_); cudaFree(d_barrier_); cudaFree(d_partials2_); cudaFree(d_pipe_ring_); cudaFree(d_pipe_flag_); cudaFree(d_pipe_infos_); cudaFree(d_batch_args_); cudaFree(d_pipe_ran_); cudaFree(d_pipe_pos_); cudaFree(d_leaf_partials_); cudaFree(d_leaf_ticket_); cudaFree(d_tables_); cudaFree(d_descs_); cudaFree(d_draws_); cudaFree(d_prof_); cudaFree(d_trace_); cudaFree(d_tape_); cudaFree(d_rec_); cudaFree(d_varcount_);
 }
 
 template <int NQ>
@@ -1089,6 +1089,82 @@ void BartFit::launch_persistent_sweep(bool last_thin)
                                                    (last_thin && test_aliases_train_) ? d_test_out_ : nullptr);
   k_bump_epoch_clear_update<<<1, 32, 0, stream_>>>(dv, cfg_.is_binary ? 1 : 0);
   S4B_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// Several chains, one launch (config D, grid.y = chain).  Every fit of the batch was created with the same shape
+// class (same kernel instantiation and shared-memory size) and a share of the SMs (s4b_bart_config::max_ctas) such that all the
+// grids are co-resident; they live on one stream.  Per sweep: every chain's k_prepare_sweep, ONE cooperative k_sweep_batch over
+// (CTAs per chain) x (chains), every chain's epilogue.  The chains' results are those of running them one by one (same kernels'
+// code, same draws): tests/test_bart_gpu.py::test_chains_batched_in_one_launch.
+// ---------------------------------------------------------------------------------------
+void BartFit::run_sweeps_batched(BartFit* const* fits, int count)
+{
+  if (count < 1) return;
+  BartFit& f0 = *fits[0];
+  long long ctas = 0;
+  for (int c = 0; c < count; ++c) {
+    BartFit& f = *fits[c];
+    if (f.sweep_mode_ != 2 || f.persistent_nq_ == 0) throw std::invalid_argument("batched sweep: every fit needs the persistent sweep kernel");
+    if (f.sequential_rng_ || f.trace_cap_ > 0 || f.profile_on_ || f.d_wt_ != nullptr || f.sharded())
+      throw std::invalid_argument("batched sweep: traced, replayed, profiled, weighted and sharded fits run on their own");
+    if (f.persistent_nq_ != f0.persistent_nq_ || f.persistent_smem_ != f0.persistent_smem_ || f.persistent_grid_ != f0.persistent_grid_ ||
+        f.cfg_.thin != f0.cfg_.thin || f.stream_ != f0.stream_)
+      throw std::invalid_argument("batched sweep: the fits must share the kernel layout (rows per thread, predictors), the CTA count, `thin` and the stream");
+    ctas += f.persistent_grid_;
+  }
+  if (ctas > f0.num_sms_) throw std::invalid_argument("batched sweep: the chains' CTAs exceed the SMs (create the fits with max_ctas = SMs / chains)");
+  cudaStream_t st = f0.stream_;
+  if (f0.d_batch_args_ == nullptr || f0.batch_cap_ < count) {
+    cudaFree(f0.d_batch_args_);
+    S4B_CUDA(cudaMalloc(&f0.d_batch_args_, sizeof(SweepBatchArgs) * (size_t) count));
+    f0.batch_cap_ = count;
+  }
+  const void* fn = f0.persistent_nq_ == kStreamNq ? (const void*) k_sweep_batch<1, true> : f0.persistent_nq_ == 1 ? (const void*) k_sweep_batch<1>
+                 : f0.persistent_nq_ == 2 ? (const void*) k_sweep_batch<2> : f0.persistent_nq_ == 4 ? (const void*) k_sweep_batch<4> : (const void*) k_sweep_batch<6>;
+  S4B_CUDA(s4b_allow_max_dynamic_smem(fn));
+  for (int c = 0; c < count; ++c) { fits[c]->tree_step_ms(false); }
+  S4B_CUDA(cudaEventRecord(f0.ev_start_, st));
+  std::vector<SweepBatchArgs> args((size_t) count);
+  const size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
+  for (int k = 0; k < f0.cfg_.thin; ++k) {
+    const bool last = (k + 1) == f0.cfg_.thin;
+    for (int c = 0; c < count; ++c) {
+      BartFit& f = *fits[c];
+      if (k > 0) f.draw_k();
+      BartDev dv = f.dev();
+      dv.partials = f.d_partials2_;
+      S4B_CUDA(cudaMemsetAsync(f.d_barrier_, 0, sizeof(unsigned int), st));
+      k_prepare_sweep<<<(f.T_ + kPrepWarps - 1) / kPrepWarps, kPrepWarps * 32, psmem, st>>>(dv, f.d_descs_, f.d_draws_, f.d_tables_, nullptr, f.d_pipe_flag_, kPipeCells);
+      SweepBatchArgs& a = args[(size_t) c];
+      std::memset(&a, 0, sizeof a);
+      a.dv = dv; a.barrier_counter = f.d_barrier_; a.partial_stride = f.partial_stride_; a.tables = f.d_tables_; a.descs = f.d_descs_; a.draws = f.d_draws_;
+      a.overlap_walk = f.overlap_walk_; a.sh = f.shard_dev(); a.max_steps = f.T_;
+    }
+    S4B_CUDA(cudaMemcpyAsync(f0.d_batch_args_, args.data(), sizeof(SweepBatchArgs) * (size_t) count, cudaMemcpyHostToDevice, st));
+    S4B_CUDA(cudaStreamSynchronize(st));      // (the pageable staging copy has left `args` before it is rewritten)
+    const SweepBatchArgs* d_args = static_cast<const SweepBatchArgs*>(f0.d_batch_args_);
+    void* kargs[] = { &d_args };
+    S4B_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned) f0.persistent_grid_, (unsigned) count), dim3(kSweepBlock), kargs, f0.persistent_smem_, st));
+    for (int c = 0; c < count; ++c) {
+      BartFit& f = *fits[c];
+      BartDev dv = f.dev();
+      dv.partials = f.d_partials2_;
+      k_finish_sweep<<<f.grid_ew_, kBlock, 0, st>>>(dv, last ? f.d_train_out_ : nullptr, f.d_latent_out_, f.add_offset_ ? 1 : 0,
+                                                    (last && f.test_aliases_train_) ? f.d_test_out_ : nullptr);
+      k_bump_epoch_clear_update<<<1, 32, 0, st>>>(dv, f.cfg_.is_binary ? 1 : 0);
+    }
+    S4B_CUDA(cudaGetLastError());
+  }
+  S4B_CUDA(cudaEventRecord(f0.ev_end_, st));
+  f0.ev_pending_ = true;
+  for (int c = 0; c < count; ++c) {
+    BartFit& f = *fits[c];
+    f.draw_k();
+    f.num_tree_steps_ += (long long) f.cfg_.thin * f.T_;
+    if (f.nt_ > 0 && !f.test_aliases_train_) f.test_fits_device(f.d_xt_test_, f.nt_, f.npad_t_, nullptr, f.d_test_out_);
+    if (f.keep_trees_active_) f.snapshot_trees();
+  }
 }
 
 void BartFit::pipe_reasons(unsigned int* out4)
@@ -1551,6 +1627,12 @@ void BartFit::test_fits_device(const uint8_t* d_xt, long long rows, long long ro
 void BartFit::run(double* train, double* test, uint32_t* varcount, double* sigma)
 {
   run_sweeps();
+  collect_results(train, test, varcount, sigma);
+}
+
+// the results of the last run_sweeps() / run_sweeps_batched(): what runSamplerWithResults hands back (any pointer may be NULL)
+void BartFit::collect_results(double* train, double* test, uint32_t* varcount, double* sigma)
+{
   if (train) S4B_CUDA(cudaMemcpyAsync(train, d_train_out_, sizeof(double) * (size_t) n_, cudaMemcpyDeviceToHost, stream_));
   if (test && nt_ > 0) S4B_CUDA(cudaMemcpyAsync(test, d_test_out_, sizeof(double) * (size_t) nt_, cudaMemcpyDeviceToHost, stream_));
   if (varcount) {

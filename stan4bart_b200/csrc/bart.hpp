@@ -48,6 +48,8 @@ class BartFit {
   double config_k() const { return cfg_.k; }
   // `thin` sweeps; results stay on device (train_out / test_out / latent_out)
   void run_sweeps();
+  static void run_sweeps_batched(BartFit* const* fits, int count);       // several chains, one launch (grid.y = chain)
+  void collect_results(double* train, double* test, uint32_t* varcount, double* sigma);
   // runSamplerWithResults with host result buffers (any may be NULL)
   void run(double* train, double* test, uint32_t* varcount, double* sigma);
   void store_latents(double* out);
@@ -152,6 +154,7 @@ class BartFit {
   DTree* d_store_ = nullptr; double* d_store_scale_ = nullptr; long long store_cap_ = 0, store_len_ = 0;
   size_t persistent_smem_ = 0;
   // pipelined sweep kernel (sweep_pipe.cuh): ring of partial rows, barrier counters, per-step cell tables, per-sweep flag
+  void* d_batch_args_ = nullptr; int batch_cap_ = 0;        // argument block of a batched launch (owned by the first fit of the batch)
   bool pipe_enabled_ = false;
   int pipe_count_words_ = 0;
   size_t pipe_smem_ = 0;

@@ -338,6 +338,17 @@ int gpubart_set_sigma(gpubart_fit* f, double sigma) { S4B_API_BEGIN S4B_REQUIRE(
 int gpubart_sample_trees_from_prior(gpubart_fit* f) { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->sample_trees_from_prior(); S4B_API_END }
 int gpubart_run_sampler_with_results(gpubart_fit* f, double* train, double* test, uint32_t* varcount, double* sigma)
 { S4B_API_BEGIN S4B_REQUIRE(f); f->fit->run(train, test, varcount, sigma); S4B_API_END }
+int gpubart_run_batched(gpubart_fit* const* fits, int count)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(fits && count >= 1);
+  std::vector<BartFit*> v((size_t) count);
+  for (int c = 0; c < count; ++c) { S4B_REQUIRE(fits[c]); v[(size_t) c] = fits[c]->fit; }
+  BartFit::run_sweeps_batched(v.data(), count);
+  S4B_API_END
+}
+int gpubart_collect_results(gpubart_fit* f, double* train, double* test, uint32_t* varcount, double* sigma)
+{ S4B_API_BEGIN S4B_REQUIRE(f); f->fit->collect_results(train, test, varcount, sigma); S4B_API_END }
 int gpubart_store_latents(gpubart_fit* f, double* out) { S4B_API_BEGIN S4B_REQUIRE(f && out); f->fit->store_latents(out); S4B_API_END }
 int gpubart_get_data_range(gpubart_fit* f, double* o) { S4B_API_BEGIN S4B_REQUIRE(f && o); BartParams P = f->fit->params(); o[0] = P.smin; o[1] = P.smax; o[2] = P.srange; S4B_API_END }
 int gpubart_predict(gpubart_fit* f, const double* x_test, int64_t n, const double* test_offset, double* out)

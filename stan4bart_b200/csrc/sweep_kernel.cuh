@@ -1342,11 +1342,13 @@ __device__ __forceinline__ void stream_update(const UpdateDesc& upd, double* Rg,
 // the production instantiation (SEQ = false) carries none of that code
 // SQ: also accumulate the per-slot sums of squares (needed only to report the individual log-likelihoods in the parity
 // trace; the Metropolis ratios do not depend on them, see slot_summary)
+// The body of the sweep: everything of a chain comes in through its arguments, and the grid is used through blockIdx.x / gridDim.x only,
+// so the same code serves one chain per launch (k_sweep) and several chains in one launch, one per blockIdx.y (k_sweep_batch)
 template <int NQ, bool SEQ, bool STREAM = false, bool SQ = true>
-__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
-                                                               const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
-                                                               const __grid_constant__ ShardDev sh_param, const int* __restrict__ pos_in,
-                                                               int* __restrict__ pos_out, int max_steps)
+__device__ __forceinline__ void sweep_body(const BartDev& dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
+                                           const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
+                                           const ShardDev& sh_param, const int* __restrict__ pos_in,
+                                           int* __restrict__ pos_out, int max_steps)
 {
   // A sweep can be split into segments of consecutive tree steps handled by alternating launches of the pipelined kernel
   // (sweep_pipe.cuh: runs of steps that fit it) and of this one (the steps that do not): *pos_in = first step still to do,
@@ -1742,6 +1744,31 @@ __global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(BartDev dv, unsigned i
       for (int i = 0; i < 4; ++i) dv.prof[20 + i] += (unsigned long long) S.csd.fine[i];
     }
   }
+}
+
+template <int NQ, bool SEQ, bool STREAM = false, bool SQ = true>
+__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep(const __grid_constant__ BartDev dv, unsigned int* barrier_counter, int partial_stride, const double* __restrict__ tables,
+                                                               const StepDesc* __restrict__ descs, const double2* __restrict__ draws, int overlap_walk,
+                                                               const __grid_constant__ ShardDev sh_param, const int* __restrict__ pos_in,
+                                                               int* __restrict__ pos_out, int max_steps)
+{
+  sweep_body<NQ, SEQ, STREAM, SQ>(dv, barrier_counter, partial_stride, tables, descs, draws, overlap_walk, sh_param, pos_in, pos_out, max_steps);
+}
+
+// Several chains in ONE cooperative launch (grid.y = chain): chain c = blockIdx.y runs its sweep on the gridDim.x
+// CTAs of its row with its own state, barrier counter and partial rows; the chains share nothing but the launch.  All chains of a
+// batch use the same instantiation (same rows-per-thread layout and shared-memory size) and gridDim.x * gridDim.y <= the SM count.
+struct SweepBatchArgs {
+  BartDev dv; unsigned int* barrier_counter; int partial_stride; const double* tables; const StepDesc* descs; const double2* draws;
+  int overlap_walk; ShardDev sh; int max_steps;
+};
+template <int NQ, bool STREAM = false>
+__global__ void __launch_bounds__(kSweepBlock, 1) k_sweep_batch(const SweepBatchArgs* __restrict__ chains)
+{
+  __shared__ SweepBatchArgs a;
+  for (int i = threadIdx.x; i < (int) (sizeof(SweepBatchArgs) / 4); i += kSweepBlock) reinterpret_cast<uint32_t*>(&a)[i] = reinterpret_cast<const uint32_t*>(chains + blockIdx.y)[i];
+  __syncthreads();
+  sweep_body<NQ, false, STREAM, false>(a.dv, a.barrier_counter, a.partial_stride, a.tables, a.descs, a.draws, a.overlap_walk, a.sh, nullptr, nullptr, a.max_steps);
 }
 
 }  // namespace s4b

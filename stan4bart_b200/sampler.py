@@ -83,6 +83,24 @@ class GpuBart:
         _lib.check(self.L.gpubart_run_sampler_with_results(self.h, dptr(train), dptr(test), vc.ctypes.data_as(c_uint32_p), C.byref(sig)))
         return dict(train=train, test=test, varcount=vc, sigma=sig.value)
 
+    def results(self):
+        """The results of the last sweep (after run_batched: the chain's own)."""
+        train = np.zeros(self.n)
+        test = np.zeros(self.nt) if self.nt else None
+        vc = np.zeros(self.p, dtype=np.uint32)
+        sig = C.c_double(0.0)
+        _lib.check(self.L.gpubart_collect_results(self.h, dptr(train), dptr(test), vc.ctypes.data_as(c_uint32_p), C.byref(sig)))
+        return dict(train=train, test=test, varcount=vc, sigma=sig.value)
+
+    @staticmethod
+    def run_batched(fits, results=True):
+        """One sweep step of several chains with their sweep kernels batched into ONE launch (grid.y = chain): the fits were created with
+        the same shape class and max_ctas = SMs // len(fits).  Returns every chain's results (or None)."""
+        L = _lib.load()
+        arr = (C.c_void_p * len(fits))(*[f.h for f in fits])
+        _lib.check(L.gpubart_run_batched(arr, len(fits)))
+        return [f.results() for f in fits] if results else None
+
     def latents(self):
         out = np.zeros(self.n)
         _lib.check(self.L.gpubart_store_latents(self.h, dptr(out)))

@@ -585,6 +585,41 @@ def test_cut_counts_per_predictor():
     assert np.array_equal(tg["var"], to["var"]) and rel_err(tg["value"], to["value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-9
 
 
+@pytest.mark.parametrize("binary", [False, True])
+def test_chains_batched_in_one_launch(binary):
+    """several chains, ONE cooperative launch (k_sweep_batch, grid.y = chain), every chain on its share of the SMs.
+    Four chains with different data and seeds: each must evolve exactly like the same chain run on its own (same kernel code, same
+    draws: bit for bit) and like its oracle."""
+    from stan4bart_b200 import _lib
+    sms = 148
+    chains, n, T = 4, 5000, 10
+    data = [bart_problem(n=n, p=6, binary=binary, seed=60 + c) for c in range(chains)]
+    mk = lambda c: bart_config(n, 6, num_trees=T, is_binary=binary, seed=900 + c, max_ctas=sms // chains)
+    batch = [GpuBart(mk(c), data[c][1], data[c][0]) for c in range(chains)]
+    solo = [GpuBart(mk(c), data[c][1], data[c][0]) for c in range(chains)]
+    orc = [O.OracleBart(mk(c), data[c][1], data[c][0]) for c in range(chains)]
+    for group in (batch, solo, orc):
+        for b in group:
+            if not binary:
+                b.set_sigma(1.0)
+            b.sample_trees_from_prior()
+    for g in solo:
+        g.set_pipeline(False)                      # the batched launch runs the synchronous kernel's code
+    for s in range(6):
+        rb = GpuBart.run_batched(batch)
+        for c in range(chains):
+            rs, ro = solo[c].run(), orc[c].run()
+            assert np.array_equal(rb[c]["train"], rs["train"]) and np.array_equal(rb[c]["varcount"], rs["varcount"]), (s, c)
+            assert rel_err(ro["train"], rb[c]["train"], scale=np.abs(ro["train"]) + 1.0) <= 1e-9
+    for c in range(chains):
+        tb, ts = batch[c].trees(), solo[c].trees()
+        assert np.array_equal(tb["var"], ts["var"]) and np.array_equal(tb["value"], ts["value"])
+        assert batch[c].rng_counter() == solo[c].rng_counter() == orc[c].rng_counter()
+    with pytest.raises(Exception):                 # a fit of another shape class (other predictor tile) cannot join the batch
+        xo, yo, _ = bart_problem(n=n, p=3, binary=binary, seed=1)
+        GpuBart.run_batched(batch + [GpuBart(bart_config(n, 3, num_trees=T, is_binary=binary, seed=1, max_ctas=sms // chains), yo, xo)])
+
+
 def test_two_fits_of_different_shapes_in_one_process():
     """The opt-in limit of dynamic shared memory is an attribute of the kernel FUNCTION: a second fit with fewer predictors (a smaller
     predictor tile) must not lower the limit under the first fit's launches (two stan4bart fits in one session).  Regression test:
