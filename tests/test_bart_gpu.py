@@ -585,12 +585,13 @@ def test_cut_counts_per_predictor():
     assert np.array_equal(tg["var"], to["var"]) and rel_err(tg["value"], to["value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-9
 
 
-@pytest.mark.parametrize("binary", [False, True])
-def test_chains_batched_in_one_launch(binary):
+@pytest.mark.parametrize("binary,streamed", [(False, False), (True, False), (False, True)])
+def test_chains_batched_in_one_launch(binary, streamed, monkeypatch):
     """several chains, ONE cooperative launch (k_sweep_batch, grid.y = chain), every chain on its share of the SMs.
     Four chains with different data and seeds: each must evolve exactly like the same chain run on its own (same kernel code, same
     draws: bit for bit) and like its oracle."""
-    from stan4bart_b200 import _lib
+    if streamed:                                   # residuals and node indices streamed from global memory (large shards): k_sweep_batch<1, true>
+        monkeypatch.setenv("S4B_FORCE_STREAM", "1")
     sms = 148
     chains, n, T = 4, 5000, 10
     data = [bart_problem(n=n, p=6, binary=binary, seed=60 + c) for c in range(chains)]
@@ -615,6 +616,8 @@ def test_chains_batched_in_one_launch(binary):
         tb, ts = batch[c].trees(), solo[c].trees()
         assert np.array_equal(tb["var"], ts["var"]) and np.array_equal(tb["value"], ts["value"])
         assert batch[c].rng_counter() == solo[c].rng_counter() == orc[c].rng_counter()
+    if streamed:
+        return                                     # (the streamed layout has no predictor tile: any number of predictors may share a batch)
     with pytest.raises(Exception):                 # a fit of another shape class (other predictor tile) cannot join the batch
         xo, yo, _ = bart_problem(n=n, p=3, binary=binary, seed=1)
         GpuBart.run_batched(batch + [GpuBart(bart_config(n, 3, num_trees=T, is_binary=binary, seed=1, max_ctas=sms // chains), yo, xo)])
