@@ -261,6 +261,16 @@ int s4b_sampler_free(s4b_sampler* s);
 int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out);
 /* stan4bart_run(sampler, numIter, isWarmup, "both") (init.cpp:678-965).  Output buffers may be NULL.
  * stan [num_pars x S], train [n x S], test [n_test x S], varcount [p x S], sigma [S]; S = keep_fits ? num_iter : 1 */
+/* Several chains of one GPU with their BART sweeps batched into ONE launch per Gibbs iteration (grid.y = chain).
+ * Create a group for `count` samplers (all on the same device, each created with max_ctas = SMs / count and the same BART shape class),
+ * attach every sampler, then call s4b_sampler_run for each of them from its OWN host thread with the same num_iter: at its BART block a
+ * chain waits for the others, the last one enqueues k_sweep_batch for all.  The chains advance in lock-step; each evolves exactly as on
+ * its own with the synchronous sweep kernel.  A chain that stops early times the others out (error) instead of hanging them. */
+typedef struct s4b_batch_group s4b_batch_group;
+int s4b_batch_group_create(int count, s4b_batch_group** out);
+int s4b_batch_group_free(s4b_batch_group* g);
+int s4b_batch_group_launches(s4b_batch_group* g, int64_t* out);
+int s4b_sampler_set_batch_group(s4b_sampler* s, s4b_batch_group* g);   /* NULL detaches */
 int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma);
 /* k of every iteration of the last s4b_sampler_run (the `k` row of the reference's BART results when k is modelled,
  * src/bart_util.hpp:25); *count = how many were written (<= capacity) */

@@ -81,6 +81,10 @@ SIGNATURES = {
     "glmm_set_mode": (C.c_int, [vp, C.c_int]),
     "glmm_get_mode": (C.c_int, [vp, c_int_p]),
     "glmm_num_device_passes": (C.c_int, [vp, c_int64_p]),
+    "s4b_batch_group_create": (C.c_int, [C.c_int, vpp]),
+    "s4b_batch_group_free": (C.c_int, [vp]),
+    "s4b_batch_group_launches": (C.c_int, [vp, c_int64_p]),
+    "s4b_sampler_set_batch_group": (C.c_int, [vp, vp]),
     "glmm_nuts_create": (C.c_int, [vp, C.POINTER(StanControl), C.c_int, C.c_int, vpp]),
     "glmm_nuts_free": (C.c_int, [vp]),
     "glmm_nuts_num_pars": (C.c_int, [vp, C.POINTER(C.c_int)]),

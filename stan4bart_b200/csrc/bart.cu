@@ -1101,6 +1101,27 @@ void BartFit::launch_persistent_sweep(bool last_thin)
 void BartFit::run_sweeps_batched(BartFit* const* fits, int count)
 {
   if (count < 1) return;
+  for (int c = 0; c < count; ++c) if (fits[c]->stream_ != fits[0]->stream_) throw std::invalid_argument("batched sweep: the fits must share the stream");
+  for (int c = 0; c < count; ++c) fits[c]->tree_step_ms(false);
+  S4B_CUDA(cudaEventRecord(fits[0]->ev_start_, fits[0]->stream_));
+  batched_sweeps_on(fits, count, fits[0]->stream_);
+  S4B_CUDA(cudaEventRecord(fits[0]->ev_end_, fits[0]->stream_));
+  fits[0]->ev_pending_ = true;
+  for (int c = 0; c < count; ++c) fits[c]->after_batched_sweeps();
+}
+
+// what follows the sweep kernels of one runSamplerWithResults step, on the fit's own stream (run_sweeps() does the same)
+void BartFit::after_batched_sweeps()
+{
+  draw_k();
+  num_tree_steps_ += (long long) cfg_.thin * T_;
+  if (nt_ > 0 && !test_aliases_train_) test_fits_device(d_xt_test_, nt_, npad_t_, nullptr, d_test_out_);
+  if (keep_trees_active_) snapshot_trees();
+}
+
+// the kernels of the batched step on stream `st` (the fits' own streams are not touched: the caller orders them against `st`)
+void BartFit::batched_sweeps_on(BartFit* const* fits, int count, cudaStream_t st)
+{
   BartFit& f0 = *fits[0];
   long long ctas = 0;
   for (int c = 0; c < count; ++c) {
@@ -1109,12 +1130,11 @@ void BartFit::run_sweeps_batched(BartFit* const* fits, int count)
     if (f.sequential_rng_ || f.trace_cap_ > 0 || f.profile_on_ || f.d_wt_ != nullptr || f.sharded())
       throw std::invalid_argument("batched sweep: traced, replayed, profiled, weighted and sharded fits run on their own");
     if (f.persistent_nq_ != f0.persistent_nq_ || f.persistent_smem_ != f0.persistent_smem_ || f.persistent_grid_ != f0.persistent_grid_ ||
-        f.cfg_.thin != f0.cfg_.thin || f.stream_ != f0.stream_)
-      throw std::invalid_argument("batched sweep: the fits must share the kernel layout (rows per thread, predictors), the CTA count, `thin` and the stream");
+        f.cfg_.thin != f0.cfg_.thin)
+      throw std::invalid_argument("batched sweep: the fits must share the kernel layout (rows per thread, predictors), the CTA count and `thin`");
     ctas += f.persistent_grid_;
   }
   if (ctas > f0.num_sms_) throw std::invalid_argument("batched sweep: the chains' CTAs exceed the SMs (create the fits with max_ctas = SMs / chains)");
-  cudaStream_t st = f0.stream_;
   if (f0.d_batch_args_ == nullptr || f0.batch_cap_ < count) {
     cudaFree(f0.d_batch_args_);
     S4B_CUDA(cudaMalloc(&f0.d_batch_args_, sizeof(SweepBatchArgs) * (size_t) count));
@@ -1123,15 +1143,13 @@ void BartFit::run_sweeps_batched(BartFit* const* fits, int count)
   const void* fn = f0.persistent_nq_ == kStreamNq ? (const void*) k_sweep_batch<1, true> : f0.persistent_nq_ == 1 ? (const void*) k_sweep_batch<1>
                  : f0.persistent_nq_ == 2 ? (const void*) k_sweep_batch<2> : f0.persistent_nq_ == 4 ? (const void*) k_sweep_batch<4> : (const void*) k_sweep_batch<6>;
   S4B_CUDA(s4b_allow_max_dynamic_smem(fn));
-  for (int c = 0; c < count; ++c) { fits[c]->tree_step_ms(false); }
-  S4B_CUDA(cudaEventRecord(f0.ev_start_, st));
   std::vector<SweepBatchArgs> args((size_t) count);
   const size_t psmem = ((sizeof(double) * kTabSize + sizeof(BartParams) + sizeof(RngState) + 15) / 16) * 16 + sizeof(PrepSmemWarp) * kPrepWarps;
   for (int k = 0; k < f0.cfg_.thin; ++k) {
     const bool last = (k + 1) == f0.cfg_.thin;
     for (int c = 0; c < count; ++c) {
       BartFit& f = *fits[c];
-      if (k > 0) f.draw_k();
+      if (k > 0) f.draw_k_on(st);
       BartDev dv = f.dev();
       dv.partials = f.d_partials2_;
       S4B_CUDA(cudaMemsetAsync(f.d_barrier_, 0, sizeof(unsigned int), st));
@@ -1155,15 +1173,6 @@ void BartFit::run_sweeps_batched(BartFit* const* fits, int count)
       k_bump_epoch_clear_update<<<1, 32, 0, st>>>(dv, f.cfg_.is_binary ? 1 : 0);
     }
     S4B_CUDA(cudaGetLastError());
-  }
-  S4B_CUDA(cudaEventRecord(f0.ev_end_, st));
-  f0.ev_pending_ = true;
-  for (int c = 0; c < count; ++c) {
-    BartFit& f = *fits[c];
-    f.draw_k();
-    f.num_tree_steps_ += (long long) f.cfg_.thin * f.T_;
-    if (f.nt_ > 0 && !f.test_aliases_train_) f.test_fits_device(f.d_xt_test_, f.nt_, f.npad_t_, nullptr, f.d_test_out_);
-    if (f.keep_trees_active_) f.snapshot_trees();
   }
 }
 
@@ -1399,10 +1408,11 @@ void BartFit::run_sweeps()
   if (keep_trees_active_) snapshot_trees();
 }
 
-void BartFit::draw_k()
+void BartFit::draw_k() { draw_k_on(stream_); }
+void BartFit::draw_k_on(cudaStream_t st)
 {
   if (!(cfg_.k_df > 0.0)) return;
-  k_draw_k<<<1, 256, 0, stream_>>>(dev());
+  k_draw_k<<<1, 256, 0, st>>>(dev());
   S4B_CUDA(cudaGetLastError());
 }
 

@@ -49,6 +49,10 @@ class BartFit {
   // `thin` sweeps; results stay on device (train_out / test_out / latent_out)
   void run_sweeps();
   static void run_sweeps_batched(BartFit* const* fits, int count);       // several chains, one launch (grid.y = chain)
+  static void batched_sweeps_on(BartFit* const* fits, int count, cudaStream_t st);
+  void after_batched_sweeps();
+  void draw_k_on(cudaStream_t st);
+  int num_sms() const { return num_sms_; }
   void collect_results(double* train, double* test, uint32_t* varcount, double* sigma);
   // runSamplerWithResults with host result buffers (any may be NULL)
   void run(double* train, double* test, uint32_t* varcount, double* sigma);

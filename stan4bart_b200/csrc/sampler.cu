@@ -10,8 +10,10 @@
 #include "nuts.hpp"
 
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 
 namespace s4b {
@@ -34,6 +36,56 @@ __global__ void k_accumulate3(long long n, const double* __restrict__ s0, double
     if (i < n2) a2[i] += s2[i];
   }
 }
+
+// Several chains of one GPU whose BART sweeps are batched into ONE launch per Gibbs iteration (grid.y = chain).
+// Every chain keeps its own host thread (its NUTS runs there) and stream; at its BART block the thread arrives here instead of
+// launching its own sweep kernels.  The last chain to arrive orders the group's stream after every chain's stream, enqueues the
+// batched step for all of them and records an event every chain's stream then waits for.  The chains advance in lock-step, one
+// sweep at a time; a chain that never arrives (an error in its thread) times the others out instead of hanging them.
+class BatchGroup {
+ public:
+  explicit BatchGroup(int count) : count_(count), fits_((size_t) count, nullptr), ready_((size_t) count, nullptr)
+  {
+    if (count < 1) throw std::invalid_argument("batch group: count < 1");
+    S4B_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    for (auto& e : ready_) S4B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    S4B_CUDA(cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
+  }
+  ~BatchGroup() { for (auto e : ready_) cudaEventDestroy(e); cudaEventDestroy(done_); cudaStreamDestroy(st_); }
+  int count() const { return count_; }
+  long long launches() const { return launches_; }
+  void run(BartFit* fit, cudaStream_t chain_stream)
+  {
+    std::unique_lock<std::mutex> lk(m_);
+    const int idx = arrived_++;
+    fits_[(size_t) idx] = fit;
+    S4B_CUDA(cudaEventRecord(ready_[(size_t) idx], chain_stream));
+    const unsigned long long gen = gen_;
+    if (arrived_ == count_) {
+      failed_.clear();
+      try {
+        for (int i = 0; i < count_; ++i) S4B_CUDA(cudaStreamWaitEvent(st_, ready_[(size_t) i], 0));
+        BartFit::batched_sweeps_on(fits_.data(), count_, st_);
+        S4B_CUDA(cudaEventRecord(done_, st_));
+        ++launches_;
+      } catch (const std::exception& e) { failed_ = e.what(); }
+      arrived_ = 0; ++gen_;
+      cv_.notify_all();
+    } else if (!cv_.wait_for(lk, std::chrono::seconds(120), [&] { return gen_ != gen; })) {
+      --arrived_;
+      throw std::runtime_error("batch group: the other chains did not reach their BART block within 120 s");
+    }
+    if (!failed_.empty()) throw std::runtime_error("batch group: " + failed_);
+    S4B_CUDA(cudaStreamWaitEvent(chain_stream, done_, 0));
+    lk.unlock();
+    fit->after_batched_sweeps();
+  }
+ private:
+  int count_, arrived_ = 0; unsigned long long gen_ = 0; long long launches_ = 0;
+  std::mutex m_; std::condition_variable cv_;
+  std::vector<BartFit*> fits_; std::vector<cudaEvent_t> ready_; cudaEvent_t done_ = nullptr; cudaStream_t st_ = nullptr;
+  std::string failed_;
+};
 
 class GibbsSampler {
  public:
@@ -87,6 +139,7 @@ class GibbsSampler {
   BartFit& bart() { return bart_; }
   GlmmModel& glmm() { return glmm_; }
   NutsSampler& nuts() { return nuts_; }
+  void set_batch_group(BatchGroup* g) { batch_group_ = g; }
 
   void run(int num_iter, bool is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma)
   {
@@ -138,7 +191,8 @@ class GibbsSampler {
       // ---- B. BART block (init.cpp:821-916) ----
       // the previous iteration's result copies (second stream) must be out of the fit buffers before they are rewritten
       if (copy_pending_) { S4B_CUDA(cudaStreamWaitEvent(stream_, ev_c_, 0)); copy_pending_ = false; }
-      bart_.run_sweeps();                                                                // :824
+      if (batch_group_ != nullptr) batch_group_->run(&bart_, stream_);                   // several chains, one launch
+      else bart_.run_sweeps();                                                           // :824
       if (host_plumbing_) {   // `stanOffset` and `bartLatents` as host vectors (init.cpp:144-145, :835, :845-846)
         // the latents leave on the copy stream while the fit makes its round trip on the main stream: PCIe is full duplex
         if (cc_.is_binary) {
@@ -259,6 +313,7 @@ class GibbsSampler {
   long long num_mean_draws_ = 0, last_grad_evals_ = 0, last_tree_steps_ = 0;
   double ms_stan_ = 0.0, ms_bart_ = 0.0;
   bool host_plumbing_ = false, copy_pending_ = false;
+  BatchGroup* batch_group_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
   double* h_plumb_ = nullptr;
 };
@@ -273,6 +328,7 @@ using namespace s4b;
 struct gpubart_fit { std::unique_ptr<BartFit> owned; BartFit* fit; };
 struct glmm_model { std::unique_ptr<GlmmModel> owned; GlmmModel* m; };
 struct glmm_nuts { std::unique_ptr<NutsSampler> s; };
+struct s4b_batch_group { std::unique_ptr<BatchGroup> g; };
 struct s4b_shard { std::unique_ptr<ShardContext> ctx; };
 struct gpubart_stored { std::unique_ptr<StoredBart> st; };
 struct s4b_sampler { std::unique_ptr<GibbsSampler> s; gpubart_fit bart_view; glmm_model glmm_view; };
@@ -470,6 +526,16 @@ int s4b_sampler_create(const s4b_bart_config* bcfg, const double* y_bart, const 
 }
 int s4b_sampler_free(s4b_sampler* s) { S4B_API_BEGIN delete s; S4B_API_END }
 int s4b_sampler_num_stan_pars(s4b_sampler* s, int* out) { S4B_API_BEGIN S4B_REQUIRE(s && out); *out = s->s->num_pars(); S4B_API_END }
+int s4b_batch_group_create(int count, s4b_batch_group** out)
+{
+  S4B_API_BEGIN
+  S4B_REQUIRE(out && count >= 1);
+  auto* h = new s4b_batch_group; h->g.reset(new BatchGroup(count)); *out = h;
+  S4B_API_END
+}
+int s4b_batch_group_free(s4b_batch_group* g) { S4B_API_BEGIN delete g; S4B_API_END }
+int s4b_batch_group_launches(s4b_batch_group* g, int64_t* out) { S4B_API_BEGIN S4B_REQUIRE(g && out); *out = g->g->launches(); S4B_API_END }
+int s4b_sampler_set_batch_group(s4b_sampler* s, s4b_batch_group* g) { S4B_API_BEGIN S4B_REQUIRE(s); s->s->set_batch_group(g ? g->g.get() : nullptr); S4B_API_END }
 int s4b_sampler_run(s4b_sampler* s, int num_iter, int is_warmup, double* stan, double* train, double* test, uint32_t* varcount, double* sigma)
 { S4B_API_BEGIN S4B_REQUIRE(s); s->s->run(num_iter, is_warmup != 0, stan, train, test, varcount, sigma); S4B_API_END }
 int s4b_sampler_last_k(s4b_sampler* s, double* out, int capacity, int* count)

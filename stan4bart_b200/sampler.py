@@ -438,6 +438,27 @@ class StanSampler:
         return v.value
 
 
+class BatchGroup:
+    """Several chains of one GPU whose BART sweeps are batched into one launch per Gibbs iteration (config D: grid.y = chain).
+    Attach `count` samplers (created with max_ctas = SMs // count), then call run() of each from its own host thread."""
+
+    def __init__(self, count):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.L.s4b_batch_group_create(int(count), C.byref(h)))
+        self.h, self.count = h, int(count)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.s4b_batch_group_free(self.h)
+            self.h = None
+
+    def launches(self):
+        k = C.c_int64(0)
+        _lib.check(self.L.s4b_batch_group_launches(self.h, C.byref(k)))
+        return int(k.value)
+
+
 class Sampler:
     """stan4bart_create(...) -> sampler object with run / disengage_adaptation / ... methods."""
 
@@ -523,6 +544,11 @@ class Sampler:
 
         self._cb = _lib.ITERATION_CALLBACK(tramp)          # keep the trampoline alive
         _lib.check(self.L.s4b_sampler_set_callback(self.h, self._cb, None))
+
+    def set_batch_group(self, group):
+        """Join (or, with None, leave) a BatchGroup: this chain's BART sweeps are then launched together with the group's other chains."""
+        _lib.check(self.L.s4b_sampler_set_batch_group(self.h, group.h if group is not None else None))
+        self._batch_group = group
 
     def disengage_adaptation(self):
         _lib.check(self.L.s4b_sampler_disengage_adaptation(self.h))

@@ -193,6 +193,55 @@ def test_chains_on_concurrent_host_threads_match_sequential_runs():
         assert np.array_equal(seq[c]["bart"]["train"], out[c]["bart"]["train"])
 
 
+def test_chains_batched_in_one_launch_through_the_gibbs_loop():
+    """Config D as SURVEY.md 8e states it: the chains of one GPU with their BART sweeps batched into ONE launch per Gibbs iteration
+    (k_sweep_batch, grid.y = chain), every chain on its own host thread for its NUTS.  Four chains joined in a BatchGroup must
+    produce exactly the draws of the same chains run one by one with the synchronous sweep kernel, and the group must have
+    launched once per iteration."""
+    import threading
+    from stan4bart_b200.sampler import BatchGroup
+    pr, cfg0, ctl0, kw = _ihdp_pair(n=600)
+    chains, iters = 4, 6
+
+    def make(c):
+        cfg = bart_config(600, 25, n_test=600, num_trees=9, is_binary=False, seed=100 + c, max_ctas=148 // chains)
+        return Sampler(cfg, pr["y"], pr["x_bart"], pr["x_test"], pr["stan_data"], stan_control(seed=200 + c), **kw)
+
+    seq = []
+    for c in range(chains):
+        s = make(c)
+        s.bart().set_pipeline(False)
+        seq.append(s.run(iters, True))
+        del s
+    group = BatchGroup(chains)
+    out, err = [None] * chains, [None] * chains
+    samplers = [None] * chains
+
+    def work(c):
+        try:
+            samplers[c] = make(c)
+            samplers[c].set_batch_group(group)
+            out[c] = samplers[c].run(iters, True)
+        except Exception as e:      # pragma: no cover
+            err[c] = e
+
+    th = [threading.Thread(target=work, args=(c,)) for c in range(chains)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert all(e is None for e in err), err
+    assert group.launches() == iters
+    for c in range(chains):
+        assert np.array_equal(seq[c]["stan"], out[c]["stan"])
+        assert np.array_equal(seq[c]["bart"]["train"], out[c]["bart"]["train"])
+        assert np.array_equal(seq[c]["bart"]["test"], out[c]["bart"]["test"])
+        assert np.array_equal(seq[c]["bart"]["varcount"], out[c]["bart"]["varcount"])
+    for s in samplers:
+        s.set_batch_group(None)
+    del samplers
+
+
 @pytest.mark.parametrize("binary", [False, True])
 def test_host_boundary_path_gives_the_same_draws(binary):
     """bench.py's `e2e` leg: results written into caller-provided host buffers (on a second stream, overlapping the next

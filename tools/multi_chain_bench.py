@@ -30,6 +30,10 @@ if not binary:
     kw.update(sigma_init=pr["sigma_init"], bart_offset_init=pr["bart_offset_init"])
 samplers = [None] * chains
 barrier = threading.Barrier(chains + 1)
+group = None
+if max_ctas > 0 and os.environ.get("S4B_NO_BATCH_LEG") is None:
+    from stan4bart_b200.sampler import BatchGroup
+    group = BatchGroup(chains)
 times = {}
 
 
@@ -43,7 +47,14 @@ def work(c):
     barrier.wait()          # everybody adapted
     barrier.wait()          # sequential leg done by the main thread
     s.run(sweeps, False, results=False)
-    barrier.wait()
+    barrier.wait()          # threaded leg done
+    if group is not None:   # the same chains with their BART sweeps batched into one launch per iteration (grid.y = chain)
+        s.set_batch_group(group)
+        s.run(3, False, results=False)
+        barrier.wait()
+        s.run(sweeps, False, results=False)
+        barrier.wait()
+        s.set_batch_group(None)
 
 
 th = [threading.Thread(target=work, args=(c,)) for c in range(chains)]
@@ -59,10 +70,17 @@ barrier.wait()
 t0 = time.time()
 barrier.wait()
 t_par = time.time() - t0
+t_batch = None
+if group is not None:
+    barrier.wait()
+    t0 = time.time()
+    barrier.wait()
+    t_batch = time.time() - t0
 for t in th:
     t.join()
 what = "config C: binary probit Friedman" if binary else "config D shape: IHDP-like continuous"
 print(json.dumps({"workload": "%s, n=%d, p=%d, %d trees, %d chains on one GPU, %s SMs per chain" % (what, n, p_bart, trees, chains, max_ctas or "all"),
                   "sweeps_per_s_sequential": chains * sweeps / t_seq, "sweeps_per_s_threaded": chains * sweeps / t_par,
+                  "sweeps_per_s_batched_one_launch_per_iteration": (chains * sweeps / t_batch) if t_batch else None,
                   "ms_stan_block": stats["ms_stan"] / sweeps, "ms_bart_block": stats["ms_bart"] / sweeps,
                   "bart_sweep_mode": samplers[0].bart().sweep_mode()}))
