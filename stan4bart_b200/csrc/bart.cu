@@ -700,6 +700,32 @@ __global__ void __launch_bounds__(kBlock) k_node_assignment(BartDev dv, int tree
 // ---------------------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
+// use_quantiles on an observation-sharded chain: every rank holds the sorted distinct values of its own rows; the cut points are a
+// function of the sorted distinct values of all rows, so the ranks exchange theirs (setup only).  The exchange is an all-gather
+// written as a rank-ordered sum over the peer mailboxes: every rank contributes its values at its own offset of a zero vector
+// (x + 0 is exact), first the counts, then the values.  Every rank ends with the same vector and therefore the same cuts.
+void BartFit::gather_distinct_over_shards(std::vector<double>& u)
+{
+  const int world = shard_->world(), rank = shard_->rank();
+  std::vector<double> counts((size_t) world, 0.0);
+  counts[(size_t) rank] = (double) u.size();
+  shard_->allreduce_host(counts.data(), world, kOpSum, stream_);
+  size_t total = 0, first = 0;
+  for (int r = 0; r < world; ++r) { if (r < rank) first += (size_t) counts[(size_t) r]; total += (size_t) counts[(size_t) r]; }
+  std::vector<double> all(total, 0.0);
+  std::copy(u.begin(), u.end(), all.begin() + (std::ptrdiff_t) first);
+  shard_->allreduce_host(all.data(), (long long) total, kOpSum, stream_);
+  // the segments are sorted: merge them pairwise in rank order, then drop the values that several shards hold
+  size_t done = (size_t) counts[0];
+  for (int r = 1; r < world; ++r) {
+    const size_t next = done + (size_t) counts[(size_t) r];
+    std::inplace_merge(all.begin(), all.begin() + (std::ptrdiff_t) done, all.begin() + (std::ptrdiff_t) next);
+    done = next;
+  }
+  all.erase(std::unique(all.begin(), all.end()), all.end());
+  u.swap(all);
+}
+
 BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, const double* x_test, cudaStream_t stream, ShardContext* shard)
     : cfg_(cfg), stream_(stream), shard_(shard)
 {
@@ -725,7 +751,6 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
   cfg_.n_cuts_var = nullptr;
   if (cfg.use_quantiles != 0) {
     // bart_args use.quantiles: every predictor gets its own number of cuts (at most its n.cuts; fewer when it has few distinct values)
-    if (sharded()) throw std::invalid_argument("use_quantiles is not available for an observation-sharded chain (the cut points would need a global sort; uniform cuts only)");
     if (ncuts_var_.empty()) ncuts_var_.assign((size_t) p_, cfg.n_cuts);
   }
   // ---- cut points (uniform over the training range, or between the distinct sorted values) and binning, host side (setup only) ----
@@ -751,6 +776,7 @@ BartFit::BartFit(const s4b_bart_config& cfg, const double* y, const double* x, c
       std::vector<double> u(col, col + n_);
       std::sort(u.begin(), u.end());
       u.erase(std::unique(u.begin(), u.end()), u.end());
+      if (sharded()) gather_distinct_over_shards(u);      // the rule is stated on the distinct values of the WHOLE column
       const size_t nu = u.size();
       size_t num, step, offset;
       if (nu <= (size_t) mj + 1) { num = nu - 1; step = 1; offset = 0; }

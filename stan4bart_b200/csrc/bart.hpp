@@ -150,6 +150,7 @@ class BartFit {
   int sweep_mode_ = 1;
   int persistent_nq_ = 0, persistent_grid_ = 0;       // nq = kStreamNq: residuals streamed from global memory (L2)
   uint2* d_packs_ = nullptr;
+  void gather_distinct_over_shards(std::vector<double>& sorted_distinct);   // use_quantiles on sharded rows (setup only)
   std::vector<int> cutless_;                                  // use_quantiles: constant predictors (no cut point; split weight 0)
   int* d_ncuts_var_ = nullptr; std::vector<int> ncuts_var_;   // bart_args n.cuts per predictor (empty = n_cuts everywhere)
   double* d_wt_ = nullptr;       // observation weights (zero padded), nullptr = unweighted

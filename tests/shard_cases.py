@@ -24,6 +24,19 @@ def bart_data(binary):
     return x, y, off
 
 
+def quantile_bart_data():
+    """Predictors for use.quantiles on sharded rows: continuous, rounded (values shared between the shards), a few integers, one that is
+    constant inside the first shard only (it has cut points because the OTHER shard varies), one constant everywhere (no cut at all)."""
+    x, y, off = bart_data(False)
+    x = x.copy()
+    n = len(y)
+    x[:, 1] = np.round(x[:, 1], 1)
+    x[:, 2] = np.floor(4.0 * x[:, 2])
+    x[: (n + 1) // 2 + 7, 3] = 0.25
+    x[:, 4] = 1.5
+    return x, y, off
+
+
 def glmm_offset():
     return 0.5 * np.sin(np.arange(GLMM_N) * 0.37)
 

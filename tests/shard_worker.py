@@ -124,6 +124,28 @@ def main():
             res[f"bart_{tag}_train_mode{mode}"] = r["train"]
             del g
 
+    # ---- bart_args use.quantiles on sharded rows: the cut points come from the distinct values of the whole column ----
+    x, y, off = SC.quantile_bart_data()
+    n = len(y)
+    lo, hi = row_range(n, rank, world)
+    ctx.set_obs_range(lo, n)
+    cfg = bart_config(hi - lo, x.shape[1], n_test=0, num_trees=SC.BART_TREES, seed=SC.BART_SEED, n_cuts=40, use_quantiles=True)
+    g = GpuBart(cfg, y[lo:hi], x[lo:hi], shard=ctx)
+    g.set_offset(off[lo:hi], True)
+    g.set_sigma(1.3)
+    g.sample_trees_from_prior()
+    g.set_trace(SC.BART_TREES * SC.BART_SWEEPS)
+    for _ in range(SC.BART_SWEEPS):
+        r = g.run()
+    res["bart_quant_trace"] = g.trace()
+    res["bart_quant_train"] = r["train"]
+    tr = g.trees()
+    res["bart_quant_trees_var"] = tr["var"]
+    res["bart_quant_trees_n"] = tr["n"]
+    res["bart_quant_trees_value"] = tr["value"]
+    res["bart_quant_varcount"] = r["varcount"]
+    del g
+
     # ---- GLMM density on sharded rows ----
     pr = friedman_problem(SC.GLMM_N)
     lo, hi = row_range(SC.GLMM_N, rank, world)

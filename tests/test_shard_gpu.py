@@ -107,6 +107,32 @@ def test_sharded_bart_matches_whole_data_oracle(ranks, binary):
         assert rel_err(to["value"], r[f"bart_{tag}_trees_value"], scale=np.abs(to["value"]) + 1e-3) <= 1e-8
 
 
+def test_sharded_quantile_cut_points_match_whole_data_oracle(ranks):
+    """bart_args use.quantiles on sharded rows: the cut points are a function of the distinct values of the WHOLE column, so the ranks
+    exchange their sorted distinct values at setup.  Cut values bit for bit those of the whole-data oracle - also for values that several
+    shards hold, for a predictor that is constant inside one shard only, and for one that is constant everywhere (no cut, never chosen)."""
+    x, y, off = SC.quantile_bart_data()
+    cfg = bart_config(len(y), x.shape[1], n_test=0, num_trees=SC.BART_TREES, seed=SC.BART_SEED, n_cuts=40, use_quantiles=True)
+    o = O.OracleBart(cfg, y, x)
+    o.set_offset(off, True)
+    o.set_sigma(1.3)
+    o.sample_trees_from_prior()
+    o.set_trace(SC.BART_TREES * SC.BART_SWEEPS)
+    for _ in range(SC.BART_SWEEPS):
+        ro = o.run()
+    to = o.trees()
+    rules = to["var"] >= 0
+    assert rules.any() and ro["varcount"][4] == 0
+    for r in ranks:
+        compare_traces(o.trace(), r["bart_quant_trace"], tol=1e-8)
+        assert np.array_equal(to["var"], r["bart_quant_trees_var"]) and np.array_equal(to["n"], r["bart_quant_trees_n"])
+        assert np.array_equal(to["value"][rules], r["bart_quant_trees_value"][rules])                   # cut values bit for bit
+        assert np.array_equal(ro["varcount"], r["bart_quant_varcount"])
+    assert np.array_equal(ranks[0]["bart_quant_trace"], ranks[1]["bart_quant_trace"])
+    train = _cat(ranks, "bart_quant_train")
+    assert rel_err(ro["train"], train, scale=np.abs(ro["train"]) + 1.0) <= 1e-8
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_sharded_glmm_density_matches_whole_data_oracle(ranks, mode):
     pr = friedman_problem(SC.GLMM_N)
