@@ -600,13 +600,13 @@ def run_ours(args):
             reps = 50
             leaf_ms = float(np.median([bart.time_leaf_stats(t, reps) for t in (0, T // 2, T - 1)]))
             leaf_gbs = 11.0 * n / (leaf_ms * 1e-3) / 1e9
-            leaf_stat = {"kernel": "k_leaf_stats (csrc/leaf_stats.cuh): one launch = one tree's per-leaf (n, sum r, sum r^2) over all rows",
+            leaf_stat = {"kernel": "k_leaf_stats / k_leaf_stats_small (csrc/leaf_stats.cuh): one launch = one tree's per-leaf (n, sum r, sum r^2) over all rows",
                          "algorithmic_bytes_per_obs": 11.0, "launch_us": leaf_ms * 1e3, "achieved": leaf_gbs, "peak": peak, "unit": "GB/s",
                          "frac": leaf_gbs / peak, "traffic": traffic_file.get("k_leaf_stats_dram_bytes_per_launch"),
                          "timing": "CUDA events around %d back-to-back launches on the launching stream, median over 3 trees; at n = 1 M the "
                                    "pass reads ~10 MB (1.5 us at peak) and is bound by ~10 us of fixed cost (launch, tree set-up, two-level "
                                    "reduction), and the working set stays in L2 between launches; bandwidth-bound sizes (16 M - 32 M rows: "
-                                   "0.55 - 0.64 of peak) are in profiles/leaf_stat_sizes_r2.json" % reps}
+                                   "see hbm_bound_size) are in profiles/leaf_stat_sizes_r2b.json" % reps}
         except Exception as e:      # pragma: no cover
             leaf_stat = {"error": repr(e)}
         # the same kernel where it IS bound by HBM: 32 M rows (working set 8 B residual + 1 B per rule and row = 290-320 MB, beyond the
@@ -632,12 +632,22 @@ def run_ours(args):
                 del gl, xl, yl
                 if rows:
                     rules, ms_l = rows[len(rows) // 2]
+                    by_rules = {}
+                    for rr, mm in rows:
+                        by_rules.setdefault(rr, []).append(mm)
                     leaf_stat["hbm_bound_size"] = {"n": nl, "rules_of_the_tree": rules, "launch_us": ms_l * 1e3,
+                                                   "by_rules": {str(rr): {"trees": len(v), "launch_us": float(np.median(v)) * 1e3,
+                                                                          "frac": 11.0 * nl / float(np.median(v)) / 1e6 / peak,
+                                                                          "frac_bytes_actually_read": (8.0 + rr) * nl / float(np.median(v)) / 1e6 / peak,
+                                                                          "kernel": "k_leaf_stats_small<2,4,1>" if rr <= 1 else "k_leaf_stats_small<4,3,2>" if rr <= 3 else "k_leaf_stats"}
+                                                                for rr, v in sorted(by_rules.items())},
                                                    "achieved": 11.0 * nl / ms_l / 1e6, "frac": 11.0 * nl / ms_l / 1e6 / peak,
                                                    "achieved_bytes_actually_read": (8.0 + rules) * nl / ms_l / 1e6,
                                                    "frac_bytes_actually_read": (8.0 + rules) * nl / ms_l / 1e6 / peak,
-                                                   "note": "k_leaf_stats on a synthetic 32 M-row fit (3 predictors): 11 algorithmic B per row as above; "
-                                                           "the kernel actually reads 8 + (rules of the tree) B per row"}
+                                                   "note": "the leaf-statistics pass on a synthetic 32 M-row fit (3 predictors), the tree in the middle of the 8 prior trees "
+                                                           "(by_rules: every tree shape of the fit): 11 algorithmic B per row as above; the kernels actually read "
+                                                           "8 + (rules of the tree) B per row; trees with <= 2 / <= 4 bottom nodes take the software-pipelined "
+                                                           "kernels with register bins / register counts (csrc/leaf_stats.cuh)"}
             except Exception as e:      # pragma: no cover
                 leaf_stat["hbm_bound_size"] = {"error": repr(e)}
     # the GLMM data pass (S, X'e, Z'e over all rows: 44 algorithmic B per row for this model), L2-warm and from HBM

@@ -1738,21 +1738,45 @@ int BartFit::leaf_stats(int tree, int max_leaves, long long* heap, long long* co
   return leaf;
 }
 
-void BartFit::launch_leaf_stats(int tree)
+int BartFit::tree_num_leaves(int tree)
 {
-  // the dedicated one-launch kernel (leaf_stats.cuh) for unweighted, unsharded fits; it reports through d_leaf_fits_ when a tree has
-  // more bottom nodes than it handles, and leaf_stats() then repeats the pass with the generic per-tree kernels below
+  if (tree < 0 || tree >= T_) throw std::invalid_argument("tree index out of range");
+  int nn = 1;
+  S4B_CUDA(cudaMemcpyAsync(&nn, &d_trees_[tree].num_nodes, sizeof nn, cudaMemcpyDeviceToHost, stream_));
+  S4B_CUDA(cudaStreamSynchronize(stream_));
+  return (nn + 1) / 2;                      // a binary tree
+}
+
+void BartFit::launch_leaf_stats(int tree, int num_leaves)
+{
+  // the dedicated one-launch kernels (leaf_stats.cuh) for unweighted, unsharded fits: register bins + software pipelining for trees with
+  // at most 4 bottom nodes, shared-memory bins up to kLeafSlots; the latter reports through d_leaf_fits_ when a tree has more bottom
+  // nodes than it handles, and leaf_stats() then repeats the pass with the generic per-tree kernels below
   if (d_wt_ == nullptr && !sharded() && !leaf_generic_) {
+    using LeafKernel = void (*)(long long, long long, const uint8_t*, const double*, const DTree*, int, double*, unsigned int*, double*, int*);
+    static const LeafKernel kernels[kLeafVariants] = { k_leaf_stats, k_leaf_stats_small<2, 4, 1>, k_leaf_stats_small<4, 3, 2> };
     if (d_leaf_partials_ == nullptr) {
-      leaf_grid_ = (int) std::max<long long>(1, std::min<long long>(((n_ + 3) / 4 + 4 * kLeafBlock - 1) / (4 * kLeafBlock), (long long) num_sms_ * 4));   // >= 4 quads per thread
       leaf_smem_ = ((sizeof(LeafSmem) + 15) / 16) * 16 + (size_t) (kLeafSlots + 1) * kLeafBlock * (sizeof(double2) + sizeof(int));
-      S4B_CUDA(s4b_allow_max_dynamic_smem((const void*) k_leaf_stats));
-      S4B_CUDA(cudaMalloc(&d_leaf_partials_, sizeof(double) * 3 * kLeafSlots * (size_t) leaf_grid_));
+      int max_grid = 1;
+      for (int v = 0; v < kLeafVariants; ++v) {
+        S4B_CUDA(s4b_allow_max_dynamic_smem((const void*) kernels[v]));
+        // one wave: as many CTAs as are resident at once (registers and the 46 KB of bins decide), every thread >= 4 quads
+        int per_sm = 0;
+        S4B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[v], kLeafBlock, leaf_smem_));
+        per_sm = std::max(1, per_sm);
+        leaf_grid_[v] = (int) std::max<long long>(1, std::min<long long>(((n_ + 3) / 4 + 4 * kLeafBlock - 1) / (4 * kLeafBlock), (long long) num_sms_ * per_sm));
+        max_grid = std::max(max_grid, leaf_grid_[v]);
+      }
+      S4B_CUDA(cudaMalloc(&d_leaf_partials_, sizeof(double) * 3 * kLeafSlots * (size_t) max_grid));
       S4B_CUDA(cudaMalloc(&d_leaf_ticket_, sizeof(unsigned int) + sizeof(int)));
       zero_device_sync(d_leaf_ticket_, sizeof(unsigned int) + sizeof(int), stream_);
     }
     int* fits = reinterpret_cast<int*>(d_leaf_ticket_ + 1);
-    k_leaf_stats<<<leaf_grid_, kLeafBlock, leaf_smem_, stream_>>>(n_, npad_, d_xt_, d_R_, d_trees_, tree, d_leaf_partials_, d_leaf_ticket_, d_stats_out_, fits);
+    if (num_leaves < 0) num_leaves = tree_num_leaves(tree);
+    // S4B_LEAF_REG_BINS=0: the shared-memory bins for every tree
+    const char* rb = getenv("S4B_LEAF_REG_BINS");
+    const int v = (rb != nullptr && atoi(rb) == 0) ? 0 : num_leaves <= 2 ? 1 : num_leaves <= 4 ? 2 : 0;
+    kernels[v]<<<leaf_grid_[v], kLeafBlock, leaf_smem_, stream_>>>(n_, npad_, d_xt_, d_R_, d_trees_, tree, d_leaf_partials_, d_leaf_ticket_, d_stats_out_, fits);
     S4B_CUDA(cudaGetLastError());
     return;
   }

@@ -83,7 +83,8 @@ class BartFit {
   // parity / measurement instrumentation
   void node_assignment(int tree, long long* out);
   int leaf_stats(int tree, int max_leaves, long long* heap, long long* count, double* sum, double* sumsq);
-  void launch_leaf_stats(int tree);
+  void launch_leaf_stats(int tree, int num_leaves = -1);      // num_leaves < 0: asked from the device (one small synchronous copy)
+  int tree_num_leaves(int tree);
   void get_residual(double* out);
   void set_trace(size_t cap_records);
   size_t get_trace(double* out, size_t cap_records);
@@ -188,7 +189,7 @@ class BartFit {
   bool profile_on_ = false;
   bool keep_trees_active_ = true;
   // stand-alone leaf-statistics kernel (leaf_stats.cuh)
-  double* d_leaf_partials_ = nullptr; unsigned int* d_leaf_ticket_ = nullptr; int leaf_grid_ = 0; size_t leaf_smem_ = 0; bool leaf_generic_ = false;
+  double* d_leaf_partials_ = nullptr; unsigned int* d_leaf_ticket_ = nullptr; static constexpr int kLeafVariants = 3; int leaf_grid_[kLeafVariants] = {}; size_t leaf_smem_ = 0; bool leaf_generic_ = false;
   long long num_tree_steps_ = 0;
 
   uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;

