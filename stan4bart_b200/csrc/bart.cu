@@ -1775,7 +1775,8 @@ void BartFit::launch_leaf_stats(int tree, int num_leaves)
     if (num_leaves < 0) num_leaves = tree_num_leaves(tree);
     // S4B_LEAF_REG_BINS=0: the shared-memory bins for every tree
     const char* rb = getenv("S4B_LEAF_REG_BINS");
-    const int v = (rb != nullptr && atoi(rb) == 0) ? 0 : num_leaves <= 2 ? 1 : num_leaves <= 4 ? 2 : 0;
+    int v = (rb != nullptr && atoi(rb) == 0) ? 0 : num_leaves <= 2 ? 1 : num_leaves <= 4 ? 2 : 0;
+    if (v == 2 && n_ / ((long long) leaf_grid_[2] * kLeafBlock) + 8 > 65535) v = 0;      // its row counts are 16-bit fields per thread
     kernels[v]<<<leaf_grid_[v], kLeafBlock, leaf_smem_, stream_>>>(n_, npad_, d_xt_, d_R_, d_trees_, tree, d_leaf_partials_, d_leaf_ticket_, d_stats_out_, fits);
     S4B_CUDA(cudaGetLastError());
     return;

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
                                                                     unsigned int* __restrict__ ticket, double* __restrict__ out, int* __restrict__ fits_out)
 {
   static_assert(LM >= 1 && LM <= 4, "at most 3 rules: 8 patterns x 4 bits in one register");
+  static_assert(MODE == 2 || (MODE == 1 && LM == 2), "register bins: two bottom nodes");
   constexpr int NR = LM > 1 ? LM - 1 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LeafSmem& S = *reinterpret_cast<LeafSmem*>(smem_raw);
@@ -207,27 +208,50 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
   if (MODE == 2) {
 #pragma unroll
     for (int j = 0; j < LM; ++j) bins[j * kLeafBlock + tid] = make_double2(0.0, 0.0);
-    bins[kLeafSlots * kLeafBlock + tid] = make_double2(0.0, 0.0);
   }
   __syncthreads();
   if (S.n_leaves > LM) { if (blockIdx.x == 0 && tid == 0) *fits_out = 0; return; }       // (the host picks the kernel by the tree's size)
   const int n_int = S.n_int;
   const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(xt);
-  const long long col_words = npad >> 2, nquad = (n + 3) >> 2;
+  const long long col_words = npad >> 2, nquad = n >> 2;         // full quads only in the loop: a ragged last quad is added at the end
   const long long stride = (long long) gridDim.x * kLeafBlock;
-  // rules in registers; a rule the tree does not have reads nothing and always says "left", the table ignores its bit
-  const uint32_t* col[NR]; uint32_t cut[NR];
+  // rules in registers; a rule the tree does not have reads nothing and always says "left", the table ignores its bit.
+  // x <= cut for the four rows of a quad at once, in 16-bit lanes: (cut + 256) - x has bit 8 set iff x <= cut
+  const uint32_t* col[NR]; uint32_t cutk[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
     const uint32_t rec = i < n_int ? S.irec[i] : 0xFFu;
-    col[i] = xt32 + (long long) (rec >> 8) * col_words; cut[i] = rec & 0xFFu;
+    col[i] = xt32 + (long long) (rec >> 8) * col_words; cutk[i] = ((rec & 0xFFu) | 0x100u) * 0x00010001u;
   }
+  // pattern -> slot, 4 bits per pattern; the pattern arrives multiplied by 4 (rule i sets bit i + 2)
   uint32_t tbl = 0u;
 #pragma unroll
   for (int e = 0; e < 8; ++e) tbl |= ((uint32_t) S.table[e & ((1 << n_int) - 1)] & 0xFu) << (4 * e);
-  double sum[LM], sq[LM], val[LM]; int cnt[LM];
+  double sum[LM], sq[LM], val[LM];
+  int cnt1 = 0, rows_done = 0;             // MODE 1 (two bins): rows of bin 1 and all rows
+  unsigned long long cntp = 0ull;          // MODE 2: four 16-bit counts (the host keeps rows per thread below 65536)
 #pragma unroll
-  for (int j = 0; j < LM; ++j) { sum[j] = 0.0; sq[j] = 0.0; cnt[j] = 0; val[j] = S.val[j]; }
+  for (int j = 0; j < LM; ++j) { sum[j] = 0.0; sq[j] = 0.0; val[j] = S.val[j]; }
+
+  auto add_row = [&](double r, int s) {
+    if (MODE == 1) {
+      // branch free: a row is added to every bin, as +0.0 / fma(0, pr, .) to the bins it does not belong to (bit for bit the same sums)
+#pragma unroll
+      for (int j = 0; j < LM; ++j) {
+        const double pr = r + val[j];
+        const double pm = s == j ? pr : 0.0;
+        sum[j] += pm; sq[j] = fma(pm, pr, sq[j]);
+      }
+      cnt1 += s == 1 ? 1 : 0; rows_done += 1;
+    } else {
+      // (sum, sum of squares) in the thread's shared-memory bin, the counts packed in a register pair
+      const double pr = r + S.val[s];
+      double2 v = bins[s * kLeafBlock + tid];
+      v.x += pr; v.y = fma(pr, pr, v.y);
+      bins[s * kLeafBlock + tid] = v;
+      cntp += 1ull << (16 * s);
+    }
+  };
 
   struct Buf { double2 a[QB], b[QB]; uint32_t w[QB][NR]; };
   auto prefetch = [&](Buf& B, long long q0) {
@@ -244,37 +268,20 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
   auto accumulate = [&](const Buf& B, long long q0) {
 #pragma unroll
     for (int k = 0; k < QB; ++k) {
-      const long long q = q0 + k * stride;
-      if (q >= nquad) break;
-      const int rows = (int) (n - 4 * q < 4 ? n - 4 * q : 4);          // only the last quad can be ragged
-      const double r[4] = { B.a[k].x, B.a[k].y, B.b[k].x, B.b[k].y };
+      if (q0 + k * stride >= nquad) break;
+      // rows 0 and 2 of the quad in the 16-bit lanes of pe, rows 1 and 3 in those of po: 4 x (pattern of the row)
+      uint32_t pe = 0u, po = 0u;
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        uint32_t pat = 0u;
-#pragma unroll
-        for (int i = 0; i < NR; ++i) pat |= (((B.w[k][i] >> (8 * o)) & 0xFFu) <= cut[i] ? 1u : 0u) << i;
-        int s = (int) ((tbl >> (4 * pat)) & 0xFu);
-        if (o >= rows) s = 15;
-        if (MODE == 1) {
-          // branch free: a row is added to every bin, as +0.0 / fma(0, pr, .) to the bins it does not belong to (bit for bit the same sums)
-#pragma unroll
-          for (int j = 0; j < LM; ++j) {
-            const bool m = s == j;
-            const double pr = r[o] + val[j];
-            const double pm = m ? pr : 0.0;
-            sum[j] += pm; sq[j] = fma(pm, pr, sq[j]); cnt[j] += m ? 1 : 0;
-          }
-        } else {
-          // (sum, sum of squares) in the thread's shared-memory bins, the counts in registers; a padding row goes to the trash bin
-          const int sb = s < LM ? s : kLeafSlots;
-          const double pr = r[o] + S.val[sb];
-          double2 v = bins[sb * kLeafBlock + tid];
-          v.x += pr; v.y = fma(pr, pr, v.y);
-          bins[sb * kLeafBlock + tid] = v;
-#pragma unroll
-          for (int j = 0; j < LM; ++j) cnt[j] += s == j ? 1 : 0;
-        }
+      for (int i = 0; i < NR; ++i) {
+        const uint32_t w = B.w[k][i];
+        const uint32_t te = cutk[i] - (w & 0x00FF00FFu), to = cutk[i] - ((w >> 8) & 0x00FF00FFu);
+        pe |= (te >> (6 - i)) & (0x00010001u << (i + 2));
+        po |= (to >> (6 - i)) & (0x00010001u << (i + 2));
       }
+      add_row(B.a[k].x, (int) ((tbl >> (pe & 0xFFFFu)) & 0xFu));
+      add_row(B.a[k].y, (int) ((tbl >> (po & 0xFFFFu)) & 0xFu));
+      add_row(B.b[k].x, (int) ((tbl >> (pe >> 16)) & 0xFu));
+      add_row(B.b[k].y, (int) ((tbl >> (po >> 16)) & 0xFu));
     }
   };
   {
@@ -292,8 +299,19 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
       q0 += step;
     }
   }
+  if ((n & 3) != 0 && blockIdx.x == 0 && tid == 0) {
+    // the ragged last quad, row by row
+    for (long long row = 4 * nquad; row < n; ++row) {
+      int pat = 0;
+      for (int i = 0; i < n_int; ++i) { const uint32_t rec = S.irec[i]; pat |= ((uint32_t) xt[(long long) (rec >> 8) * npad + row] <= (rec & 0xFFu) ? 1 : 0) << i; }
+      add_row(R[row], (int) S.table[pat]);
+    }
+  }
 #pragma unroll
-  for (int j = 0; j < LM; ++j) { if (MODE != 2) bins[j * kLeafBlock + tid] = make_double2(sum[j], sq[j]); cnts[j * kLeafBlock + tid] = cnt[j]; }
+  for (int j = 0; j < LM; ++j) {
+    if (MODE == 1) { bins[j * kLeafBlock + tid] = make_double2(sum[j], sq[j]); cnts[j * kLeafBlock + tid] = j == 0 ? rows_done - cnt1 : j == 1 ? cnt1 : 0; }
+    else cnts[j * kLeafBlock + tid] = (int) ((cntp >> (16 * j)) & 0xFFFFull);
+  }
   leaf_epilogue(S, bins, cnts, partials, ticket, out, fits_out);
 }
 
