@@ -62,7 +62,7 @@ typedef struct s4b_bart_config {
   int32_t change_symmetric;
   /* bart_args use.quantiles (R/stan4bart_fit.R:437-451 passes it on to dbartsControl): cut points between the distinct sorted values of
    * every predictor (all gaps when there are at most n.cuts + 1 distinct values, else n.cuts of them evenly spaced in rank) instead of
-   * uniform over the range; not available for observation-sharded chains */
+   * uniform over the range; observation-sharded chains exchange their distinct values at create, so every rank gets the cuts of the whole column */
   int32_t use_quantiles;
 } s4b_bart_config;
 
