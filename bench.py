@@ -639,7 +639,7 @@ def run_ours(args):
                                                    "by_rules": {str(rr): {"trees": len(v), "launch_us": float(np.median(v)) * 1e3,
                                                                           "frac": 11.0 * nl / float(np.median(v)) / 1e6 / peak,
                                                                           "frac_bytes_actually_read": (8.0 + rr) * nl / float(np.median(v)) / 1e6 / peak,
-                                                                          "kernel": "k_leaf_stats_small<2,4,1>" if rr <= 1 else "k_leaf_stats_small<4,3,2>" if rr <= 3 else "k_leaf_stats"}
+                                                                          "kernel": "k_leaf_stats_small<2,4,1>" if rr <= 1 else "k_leaf_stats_small<4,3,2>" if rr <= 3 else "k_leaf_stats_small<8,2,2>"}
                                                                 for rr, v in sorted(by_rules.items())},
                                                    "achieved": 11.0 * nl / ms_l / 1e6, "frac": 11.0 * nl / ms_l / 1e6 / peak,
                                                    "achieved_bytes_actually_read": (8.0 + rules) * nl / ms_l / 1e6,

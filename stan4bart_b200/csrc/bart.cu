@@ -1754,7 +1754,7 @@ void BartFit::launch_leaf_stats(int tree, int num_leaves)
   // nodes than it handles, and leaf_stats() then repeats the pass with the generic per-tree kernels below
   if (d_wt_ == nullptr && !sharded() && !leaf_generic_) {
     using LeafKernel = void (*)(long long, long long, const uint8_t*, const double*, const DTree*, int, double*, unsigned int*, double*, int*);
-    static const LeafKernel kernels[kLeafVariants] = { k_leaf_stats, k_leaf_stats_small<2, 4, 1>, k_leaf_stats_small<4, 3, 2> };
+    static const LeafKernel kernels[kLeafVariants] = { k_leaf_stats, k_leaf_stats_small<2, 4, 1>, k_leaf_stats_small<4, 3, 2>, k_leaf_stats_small<8, 2, 2> };
     if (d_leaf_partials_ == nullptr) {
       leaf_smem_ = ((sizeof(LeafSmem) + 15) / 16) * 16 + (size_t) (kLeafSlots + 1) * kLeafBlock * (sizeof(double2) + sizeof(int));
       int max_grid = 1;
@@ -1775,7 +1775,7 @@ void BartFit::launch_leaf_stats(int tree, int num_leaves)
     if (num_leaves < 0) num_leaves = tree_num_leaves(tree);
     // S4B_LEAF_REG_BINS=0: the shared-memory bins for every tree
     const char* rb = getenv("S4B_LEAF_REG_BINS");
-    int v = (rb != nullptr && atoi(rb) == 0) ? 0 : num_leaves <= 2 ? 1 : num_leaves <= 4 ? 2 : 0;
+    int v = (rb != nullptr && atoi(rb) == 0) ? 0 : num_leaves <= 2 ? 1 : num_leaves <= 4 ? 2 : num_leaves <= kLeafSlots ? 3 : 0;
     if (v == 2 && n_ / ((long long) leaf_grid_[2] * kLeafBlock) + 8 > 65535) v = 0;      // its row counts are 16-bit fields per thread
     kernels[v]<<<leaf_grid_[v], kLeafBlock, leaf_smem_, stream_>>>(n_, npad_, d_xt_, d_R_, d_trees_, tree, d_leaf_partials_, d_leaf_ticket_, d_stats_out_, fits);
     S4B_CUDA(cudaGetLastError());

@@ -189,7 +189,7 @@ class BartFit {
   bool profile_on_ = false;
   bool keep_trees_active_ = true;
   // stand-alone leaf-statistics kernel (leaf_stats.cuh)
-  double* d_leaf_partials_ = nullptr; unsigned int* d_leaf_ticket_ = nullptr; static constexpr int kLeafVariants = 3; int leaf_grid_[kLeafVariants] = {}; size_t leaf_smem_ = 0; bool leaf_generic_ = false;
+  double* d_leaf_partials_ = nullptr; unsigned int* d_leaf_ticket_ = nullptr; static constexpr int kLeafVariants = 4; int leaf_grid_[kLeafVariants] = {}; size_t leaf_smem_ = 0; bool leaf_generic_ = false;
   long long num_tree_steps_ = 0;
 
   uint8_t* d_xt_ = nullptr; uint8_t* d_xt_test_ = nullptr;

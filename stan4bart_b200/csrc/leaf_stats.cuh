@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kLeafBlock) k_leaf_stats(long long n, long lon
 }
 
 // ---------------------------------------------------------------------------------------
-// The same pass for trees with at most LM <= 4 bottom nodes (BART trees average 2-3), as ncu asked for it (profiles/README.md, round 2:
+// The same pass, software-pipelined, templated on the number of bottom nodes it holds (LM; BART trees average 2-3), as ncu asked for it (profiles/README.md, round 2:
 // ncu_k_leaf_stats_r2_*): with k_leaf_stats a row costs ~12 shared-memory wavefronts per warp and the L1 / shared-memory pipe was the
 // busiest unit (75 %) at 3.3 TB/s; and every warp of the SM issued its loads, waited and computed in step, so memory and arithmetic did
 // not overlap (long scoreboard 6 per issue at 46 % issue utilisation).  Here
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kLeafBlock) k_leaf_stats(long long n, long lon
 //     it does not belong to, which leaves them bit for bit unchanged - so the loop has no branch and no shared-memory access at all;
 //   * MODE 2 (3-4 bottom nodes, where the selects of MODE 1 cost more than they save): (sum, sum of squares) in the thread's
 //     shared-memory bins, the counts in registers.
+//   * 5-8 bottom nodes (LM = 8): the same pipelining and compares, the pattern table and the counts in shared memory.
 // Per-thread sums are formed in the same order as in k_leaf_stats; results differ only through the grid size (the order of the final
 // sums); counts are exact.  32 M rows: 59 us (<= 2 bottom nodes) / 80 us (3-4) against 86 / 88-109 us with k_leaf_stats.
 // ---------------------------------------------------------------------------------------
@@ -196,8 +197,9 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
                                                                     const DTree* __restrict__ trees, int tree_index, double* __restrict__ partials,
                                                                     unsigned int* __restrict__ ticket, double* __restrict__ out, int* __restrict__ fits_out)
 {
-  static_assert(LM >= 1 && LM <= 4, "at most 3 rules: 8 patterns x 4 bits in one register");
+  static_assert(LM >= 1 && LM <= kLeafSlots, "bins for kLeafSlots bottom nodes");
   static_assert(MODE == 2 || (MODE == 1 && LM == 2), "register bins: two bottom nodes");
+  constexpr bool kRegTable = LM <= 4;        // <= 3 rules: 8 patterns x 4 bits in one register; more: the table in shared memory
   constexpr int NR = LM > 1 ? LM - 1 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LeafSmem& S = *reinterpret_cast<LeafSmem*>(smem_raw);
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
   if (warp == 0) leaf_setup(S, trees[tree_index], lane);
   if (MODE == 2) {
 #pragma unroll
-    for (int j = 0; j < LM; ++j) bins[j * kLeafBlock + tid] = make_double2(0.0, 0.0);
+    for (int j = 0; j < LM; ++j) { bins[j * kLeafBlock + tid] = make_double2(0.0, 0.0); if (!kRegTable) cnts[j * kLeafBlock + tid] = 0; }
   }
   __syncthreads();
   if (S.n_leaves > LM) { if (blockIdx.x == 0 && tid == 0) *fits_out = 0; return; }       // (the host picks the kernel by the tree's size)
@@ -215,13 +217,14 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
   const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(xt);
   const long long col_words = npad >> 2, nquad = n >> 2;         // full quads only in the loop: a ragged last quad is added at the end
   const long long stride = (long long) gridDim.x * kLeafBlock;
-  // rules in registers; a rule the tree does not have reads nothing and always says "left", the table ignores its bit.
+  // rules in registers; a rule the tree does not have reads nothing and never sets its bit.
   // x <= cut for the four rows of a quad at once, in 16-bit lanes: (cut + 256) - x has bit 8 set iff x <= cut
   const uint32_t* col[NR]; uint32_t cutk[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
-    const uint32_t rec = i < n_int ? S.irec[i] : 0xFFu;
-    col[i] = xt32 + (long long) (rec >> 8) * col_words; cutk[i] = ((rec & 0xFFu) | 0x100u) * 0x00010001u;
+    const uint32_t rec = i < n_int ? S.irec[i] : 0u;
+    col[i] = xt32 + (long long) (rec >> 8) * col_words;
+    cutk[i] = i < n_int ? ((rec & 0xFFu) | 0x100u) * 0x00010001u : 0x00FF00FFu;       // (no such rule: 255 - 0, bit 8 never set)
   }
   // pattern -> slot, 4 bits per pattern; the pattern arrives multiplied by 4 (rule i sets bit i + 2)
   uint32_t tbl = 0u;
@@ -249,7 +252,8 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
       double2 v = bins[s * kLeafBlock + tid];
       v.x += pr; v.y = fma(pr, pr, v.y);
       bins[s * kLeafBlock + tid] = v;
-      cntp += 1ull << (16 * s);
+      if (kRegTable) cntp += 1ull << (16 * s);
+      else cnts[s * kLeafBlock + tid] += 1;
     }
   };
 
@@ -278,10 +282,17 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
         pe |= (te >> (6 - i)) & (0x00010001u << (i + 2));
         po |= (to >> (6 - i)) & (0x00010001u << (i + 2));
       }
-      add_row(B.a[k].x, (int) ((tbl >> (pe & 0xFFFFu)) & 0xFu));
-      add_row(B.a[k].y, (int) ((tbl >> (po & 0xFFFFu)) & 0xFu));
-      add_row(B.b[k].x, (int) ((tbl >> (pe >> 16)) & 0xFu));
-      add_row(B.b[k].y, (int) ((tbl >> (po >> 16)) & 0xFu));
+      if (kRegTable) {
+        add_row(B.a[k].x, (int) ((tbl >> (pe & 0xFFFFu)) & 0xFu));
+        add_row(B.a[k].y, (int) ((tbl >> (po & 0xFFFFu)) & 0xFu));
+        add_row(B.b[k].x, (int) ((tbl >> (pe >> 16)) & 0xFu));
+        add_row(B.b[k].y, (int) ((tbl >> (po >> 16)) & 0xFu));
+      } else {
+        add_row(B.a[k].x, (int) S.table[(pe & 0xFFFFu) >> 2]);
+        add_row(B.a[k].y, (int) S.table[(po & 0xFFFFu) >> 2]);
+        add_row(B.b[k].x, (int) S.table[pe >> 18]);
+        add_row(B.b[k].y, (int) S.table[po >> 18]);
+      }
     }
   };
   {
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
 #pragma unroll
   for (int j = 0; j < LM; ++j) {
     if (MODE == 1) { bins[j * kLeafBlock + tid] = make_double2(sum[j], sq[j]); cnts[j * kLeafBlock + tid] = j == 0 ? rows_done - cnt1 : j == 1 ? cnt1 : 0; }
-    else cnts[j * kLeafBlock + tid] = (int) ((cntp >> (16 * j)) & 0xFFFFull);
+    else if (kRegTable) cnts[j * kLeafBlock + tid] = (int) ((cntp >> (16 * j)) & 0xFFFFull);
   }
   leaf_epilogue(S, bins, cnts, partials, ticket, out, fits_out);
 }

@@ -57,10 +57,10 @@ def test_leaf_stats_small_tree_kernels(monkeypatch):
     in a register, software-pipelined loads), larger ones k_leaf_stats (shared-memory bins).  Counts bit exact, sums 1e-10 against the
     oracle, and the small-tree kernels against the shared-memory one (S4B_LEAF_REG_BINS=0) to rounding.  Trees after a few sweeps
     (1-6 bottom nodes), a ragged last quad, several CTAs."""
-    n, T = 150_003, 16
+    n, T = 150_003, 30
     o, g, _ = make_pair(n=n, num_trees=T)
     o.sample_trees_from_prior(); g.sample_trees_from_prior()
-    for _ in range(4):
+    for _ in range(8):
         o.run(); g.run()
     sizes = set()
     for t in range(T):
@@ -77,7 +77,7 @@ def test_leaf_stats_small_tree_kernels(monkeypatch):
         assert rel_err(sso, ssr) <= REL_TOL
         assert rel_err(so, sr, scale=scale) <= REL_TOL
         sizes.add(len(hr))
-    assert min(sizes) <= 2 and any(3 <= k <= 4 for k in sizes), sizes
+    assert min(sizes) <= 2 and any(3 <= k <= 4 for k in sizes) and any(5 <= k <= 8 for k in sizes), sizes
 
 
 @pytest.mark.parametrize("binary", [False, True])

@@ -13,7 +13,8 @@ y = 10 * np.sin(np.pi * x[:, 0] * x[:, 1]) + 5 * x[:, 2] + rg.standard_normal(n)
 g = GpuBart(bart_config(n, 3, num_trees=8, seed=3), y, x)
 g.set_sigma(1.0)
 g.sample_trees_from_prior()
-g.run()
+for _ in range(int(os.environ.get("LEAF_SWEEPS", "1"))):
+    g.run()
 tr = g.trees()
 for t in range(8):
     rules = int(np.sum(tr["var"][tr["tree"] == t] >= 0))
