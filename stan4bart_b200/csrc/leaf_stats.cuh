@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kLeafBlock) k_leaf_stats(long long n, long lon
       uint32_t pat = 0u;
       for (int i = 0; i < n_int; ++i) {
         const uint32_t rec = S.irec[i];
-        pat |= (__vcmpleu4(__ldg(xt32 + (long long) (rec >> 8) * col_words + q), (rec & 0xFFu) * 0x01010101u) & 0x01010101u) << i;
+        pat |= __vsetleu4(__ldg(xt32 + (long long) (rec >> 8) * col_words + q), (rec & 0xFFu) * 0x01010101u) << i;
       }
       return (uint32_t) S.table[pat & 0xFFu] | ((uint32_t) S.table[(pat >> 8) & 0xFFu] << 8) | ((uint32_t) S.table[(pat >> 16) & 0xFFu] << 16) |
              ((uint32_t) S.table[pat >> 24] << 24);

@@ -982,7 +982,7 @@ __device__ __forceinline__ void bitmap_walk(const TravTree& tv, const uint8_t* _
     const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
     const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+    for (int j = 0; j < NQ; ++j) pat[j] |= __vsetleu4(col[j * kWorkers], cut4) << i;
   }
 #pragma unroll
   for (int j = 0; j < NQ; ++j)

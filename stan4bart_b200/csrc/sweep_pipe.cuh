@@ -116,7 +116,7 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
     const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
     const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+    for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= __vsetleu4(col[j * kWorkers], cut4) << i;
   }
   // pattern -> slot.  Up to three rules (eight patterns) the table is two registers and the four look-ups of a quad are two byte
   // permutes: the pattern bytes are folded into the four selector nibbles, PRMT then picks the four slot bytes at once
@@ -140,7 +140,7 @@ __device__ __forceinline__ void pipe_walk(const StepDesc& sd, const PipeInfo& pi
       const uint32_t* col = tile + (rec >> 8) * tile_stride + tid;
       const uint32_t cut4 = (rec & 0xFFu) * 0x01010101u;
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= (__vcmpleu4(col[j * kWorkers], cut4) & 0x01010101u) << i;
+      for (int j = 0; j < NQ; ++j) if (j < nq) pat[j] |= __vsetleu4(col[j * kWorkers], cut4) << i;
     }
     if (small) {
       const uint32_t tlo = *reinterpret_cast<const uint32_t*>(pi.ptab), thi = *reinterpret_cast<const uint32_t*>(pi.ptab + 4);
