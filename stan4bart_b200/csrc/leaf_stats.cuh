@@ -38,22 +38,30 @@ __device__ __forceinline__ double leaf_wsum(double v)
   return v;
 }
 
-// warp 0 of the CTA: the tree's rules in internal-node order, its bottom nodes' slots in node order, the rule-pattern -> slot table
+// warp 0 of the CTA: the tree's rules in internal-node order, its bottom nodes' slots in node order, the rule-pattern -> slot table.
+// The node count and the first 32 nodes are read in the same round trip (the node array has S4B_NODE_CAP >= 32 entries, so the read
+// is in bounds whatever the count is), and the table is walked in shared memory: one L2 latency instead of one per dependent read --
+// at n = 1 M the pass itself takes ~2 us, so this set-up is a visible share of the launch.
 __device__ __forceinline__ void leaf_setup(LeafSmem& S, const DTree& t, int lane)
 {
+  static_assert(S4B_NODE_CAP >= 32, "the first pass reads 32 nodes unconditionally");
+  const uint2 first = *reinterpret_cast<const uint2*>(&t.nodes[lane]);          // var | cut << 16, right | parent << 16
+  const double first_mu = t.nodes[lane].mu;
   const int nn = t.num_nodes;
-  // rules in internal-node order, slots in bottom-node order, the pattern table
   int n_int = 0, n_leaf = 0;
   for (int base = 0; base < nn; base += 32) {
     const int k = base + lane;
-    const bool in = k < nn && t.nodes[k].var >= 0, lf = k < nn && t.nodes[k].var < 0;
+    uint2 rec = first; double mu = first_mu;
+    if (base > 0 && k < nn) { rec = *reinterpret_cast<const uint2*>(&t.nodes[k]); mu = t.nodes[k].mu; }
+    const int var = (int) (int16_t) (rec.x & 0xFFFFu), cut = (int) (int16_t) (rec.x >> 16), right = (int) (int16_t) (rec.y & 0xFFFFu);
+    const bool in = k < nn && var >= 0, lf = k < nn && var < 0;
     const unsigned mi = __ballot_sync(0xffffffffu, in), ml = __ballot_sync(0xffffffffu, lf);
     const unsigned below = (1u << lane) - 1u;
-    if (in) S.irec[n_int + __popc(mi & below)] = ((uint32_t) t.nodes[k].var << 8) | (uint32_t) (t.nodes[k].cut & 0xFF);
+    if (in) S.irec[n_int + __popc(mi & below)] = ((uint32_t) var << 8) | (uint32_t) (cut & 0xFF);
     if (k < nn) {
       S.slot[k] = lf ? (uint8_t) min(n_leaf + __popc(ml & below), kLeafSlots) : (uint8_t) 255;
-      S.trav[k] = lf ? 0xFFFFFFFFu : (((uint32_t) t.nodes[k].var << 16) | ((uint32_t) (t.nodes[k].cut & 0xFF) << 8) | (uint32_t) (t.nodes[k].right & 0xFF));
-      if (lf && n_leaf + __popc(ml & below) < kLeafSlots) S.val[n_leaf + __popc(ml & below)] = t.nodes[k].mu;
+      S.trav[k] = lf ? 0xFFFFFFFFu : (((uint32_t) var << 16) | ((uint32_t) (cut & 0xFF) << 8) | (uint32_t) (right & 0xFF));
+      if (lf && n_leaf + __popc(ml & below) < kLeafSlots) S.val[n_leaf + __popc(ml & below)] = mu;
     }
     n_int += __popc(mi); n_leaf += __popc(ml);
   }
@@ -61,10 +69,10 @@ __device__ __forceinline__ void leaf_setup(LeafSmem& S, const DTree& t, int lane
   if (lane == 0) { S.n_int = n_int; S.n_leaves = n_leaf; S.nn = nn; S.fits = n_leaf <= kLeafSlots ? 1 : 0; S.val[kLeafSlots] = 0.0; }
   if (n_int <= 8 && nn <= 32) {
     // internal-node mask of the (<= 32-node) tree, then every pattern's bottom node
-    const unsigned imask = __ballot_sync(0xffffffffu, lane < nn && t.nodes[lane].var >= 0);
+    const unsigned imask = __ballot_sync(0xffffffffu, lane < nn && S.trav[lane < nn ? lane : 0] != 0xFFFFFFFFu);
     for (int e = lane; e < (1 << n_int); e += 32) {
       int node = 0;
-      while ((imask >> node) & 1u) { const int id = __popc(imask & ((1u << node) - 1u)); node = ((e >> id) & 1) ? node + 1 : (int) t.nodes[node].right; }
+      while ((imask >> node) & 1u) { const int id = __popc(imask & ((1u << node) - 1u)); node = ((e >> id) & 1) ? node + 1 : (int) (S.trav[node] & 0xFFu); }
       S.table[e] = S.slot[node];
     }
   }
@@ -206,6 +214,19 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
   double2* bins = reinterpret_cast<double2*>(smem_raw + ((sizeof(LeafSmem) + 15) / 16) * 16);
   int* cnts = reinterpret_cast<int*>(bins + (kLeafSlots + 1) * kLeafBlock);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long nquad = n >> 2;                                // full quads only in the loop: a ragged last quad is added at the end
+  const long long stride = (long long) gridDim.x * kLeafBlock;
+  struct Buf { double2 a[QB], b[QB]; uint32_t w[QB][NR]; };
+  auto prefetch_r = [&](Buf& B, long long q0) {
+#pragma unroll
+    for (int k = 0; k < QB; ++k) {
+      const long long q = q0 + k * stride;
+      if (q < nquad) { B.a[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q)); B.b[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q + 2)); }
+    }
+  };
+  Buf A, B;
+  // the residuals of the first quads do not depend on the tree: their loads are in flight while warp 0 reads and prepares the tree
+  prefetch_r(A, (long long) blockIdx.x * kLeafBlock + tid);
   if (warp == 0) leaf_setup(S, trees[tree_index], lane);
   if (MODE == 2) {
 #pragma unroll
@@ -215,8 +236,7 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
   if (S.n_leaves > LM) { if (blockIdx.x == 0 && tid == 0) *fits_out = 0; return; }       // (the host picks the kernel by the tree's size)
   const int n_int = S.n_int;
   const uint32_t* xt32 = reinterpret_cast<const uint32_t*>(xt);
-  const long long col_words = npad >> 2, nquad = n >> 2;         // full quads only in the loop: a ragged last quad is added at the end
-  const long long stride = (long long) gridDim.x * kLeafBlock;
+  const long long col_words = npad >> 2;
   // rules in registers; a rule the tree does not have reads nothing and never sets its bit.
   // x <= cut for the four rows of a quad at once, in 16-bit lanes: (cut + 256) - x has bit 8 set iff x <= cut
   const uint32_t* col[NR]; uint32_t cutk[NR];
@@ -257,18 +277,17 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
     }
   };
 
-  struct Buf { double2 a[QB], b[QB]; uint32_t w[QB][NR]; };
-  auto prefetch = [&](Buf& B, long long q0) {
+  auto prefetch_w = [&](Buf& B, long long q0) {
 #pragma unroll
     for (int k = 0; k < QB; ++k) {
       const long long q = q0 + k * stride;
       if (q < nquad) {
-        B.a[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q)); B.b[k] = __ldg(reinterpret_cast<const double2*>(R + 4 * q + 2));
 #pragma unroll
         for (int i = 0; i < NR; ++i) B.w[k][i] = i < n_int ? __ldg(col[i] + q) : 0u;
       }
     }
   };
+  auto prefetch = [&](Buf& B, long long q0) { prefetch_r(B, q0); prefetch_w(B, q0); };
   auto accumulate = [&](const Buf& B, long long q0) {
 #pragma unroll
     for (int k = 0; k < QB; ++k) {
@@ -296,10 +315,9 @@ __global__ void __launch_bounds__(kLeafBlock, 2) k_leaf_stats_small(long long n,
     }
   };
   {
-    Buf A, B;
     long long q0 = (long long) blockIdx.x * kLeafBlock + tid;
     const long long step = QB * stride;
-    prefetch(A, q0);
+    prefetch_w(A, q0);
     while (q0 < nquad) {
       prefetch(B, q0 + step);
       accumulate(A, q0);
