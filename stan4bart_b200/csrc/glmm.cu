@@ -288,33 +288,44 @@ __global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDe
   { int v = 0;
 #pragma unroll
     for (int s_ = 0; s_ < ST; ++s_) { vpos[s_] = ((g.ones_mask >> s_) & 1u) ? -1 : v; if (s_ < slots && vpos[s_] >= 0) ++v; } }
+  // byte offsets of this thread's pair of rows inside every stream of a tile, formed once: the loop below then addresses shared memory
+  // with one add per access (the pass is bound by the consumers' instruction latency: 8 warps per SM, ~2 fixed-latency stall cycles per
+  // instruction in ncu, and address arithmetic was most of the instruction stream)
+  int offx[KT], offi[ST], offv[ST];
+#pragma unroll
+  for (int c = 0; c < KT; ++c) offx[c] = off_x + c * tile * 8;
+#pragma unroll
+  for (int s_ = 0; s_ < ST; ++s_) { offi[s_] = off_i + s_ * tile * 4; offv[s_] = vpos[s_] < 0 ? -1 : off_v + vpos[s_] * tile * 8; }
+  double* const wbl = wb + lane + K * 32;               // bin of column K + c: wbl[c * 32]
+  const double* const sthK = sth + K;
   int k = 0;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
     const int st = k % stages;
     mbar_wait(&bars.full[st], (unsigned) ((k / stages) & 1));
-    const unsigned char* src = ring + (size_t) st * tile_bytes;
+    const unsigned char* src = ring + (unsigned) st * (unsigned) tile_bytes;
     const long long base = t * tile;
-    for (int o = 2 * tid; o < tile; o += 2 * kGBlock) {
-      const long long i = base + o;
-      if (i >= N) break;
-      const bool second = i + 1 < N;
-      const double2 r2 = *reinterpret_cast<const double2*>(src + (size_t) o * 8);
+    const int rows_here = (int) (N - base < tile ? N - base : tile);       // rows of this tile that exist
+    for (int o = 2 * tid; o < rows_here; o += 2 * kGBlock) {
+      const bool second = o + 1 < rows_here;
+      const unsigned char* p8 = src + o * 8;
+      const unsigned char* p4 = src + o * 4;
+      const double2 r2 = *reinterpret_cast<const double2*>(p8);
       double2 x2[KT], v2[ST]; int2 c2[ST];
 #pragma unroll
-      for (int c = 0; c < KT; ++c) if (c < K) x2[c] = *reinterpret_cast<const double2*>(src + off_x + ((size_t) c * tile + o) * 8);
+      for (int c = 0; c < KT; ++c) if (c < K) x2[c] = *reinterpret_cast<const double2*>(p8 + offx[c]);
 #pragma unroll
       for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) {
-        c2[s_] = *reinterpret_cast<const int2*>(src + off_i + ((size_t) s_ * tile + o) * 4);
-        v2[s_] = vpos[s_] < 0 ? make_double2(1.0, 1.0) : *reinterpret_cast<const double2*>(src + off_v + ((size_t) vpos[s_] * tile + o) * 8);
+        c2[s_] = *reinterpret_cast<const int2*>(p4 + offi[s_]);
+        v2[s_] = offv[s_] < 0 ? make_double2(1.0, 1.0) : *reinterpret_cast<const double2*>(p8 + offv[s_]);
       }
       double eta0 = 0.0, eta1 = 0.0;
 #pragma unroll
       for (int c = 0; c < KT; ++c) if (c < K) { eta0 += x2[c].x * sth[c]; eta1 += x2[c].y * sth[c]; }
 #pragma unroll
-      for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) { eta0 += v2[s_].x * sth[K + c2[s_].x]; eta1 += v2[s_].y * sth[K + c2[s_].y]; }
+      for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) { eta0 += v2[s_].x * sthK[c2[s_].x]; eta1 += v2[s_].y * sthK[c2[s_].y]; }
       double e0 = r2.x - eta0, e1 = second ? r2.y - eta1 : 0.0;
       if (weighted) {
-        const double2 w2 = *reinterpret_cast<const double2*>(src + off_w + (size_t) o * 8);
+        const double2 w2 = *reinterpret_cast<const double2*>(p8 + off_w);
         const double we0 = w2.x * e0, we1 = w2.y * e1;
         S += we0 * e0; S += we1 * e1;
         e0 = we0; e1 = we1;
@@ -324,18 +335,18 @@ __global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDe
       if (g.row_distinct) {
         double b0[ST];
 #pragma unroll
-        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wb[(K + c2[s_].x) * 32 + lane];
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wbl[c2[s_].x * 32];
 #pragma unroll
-        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wb[(K + c2[s_].x) * 32 + lane] = fma(v2[s_].x, e0, b0[s_]);
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wbl[c2[s_].x * 32] = fma(v2[s_].x, e0, b0[s_]);
 #pragma unroll
-        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wb[(K + c2[s_].y) * 32 + lane];
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) b0[s_] = wbl[c2[s_].y * 32];
 #pragma unroll
-        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wb[(K + c2[s_].y) * 32 + lane] = fma(v2[s_].y, e1, b0[s_]);
+        for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) wbl[c2[s_].y * 32] = fma(v2[s_].y, e1, b0[s_]);
       } else {
 #pragma unroll
         for (int s_ = 0; s_ < ST; ++s_) if (s_ < slots) {
-          wb[(K + c2[s_].x) * 32 + lane] += v2[s_].x * e0;
-          wb[(K + c2[s_].y) * 32 + lane] += v2[s_].y * e1;
+          wbl[c2[s_].x * 32] += v2[s_].x * e0;
+          wbl[c2[s_].y * 32] += v2[s_].y * e1;
         }
       }
     }
