@@ -663,7 +663,7 @@ def run_ours(args):
                          "achieved_l2_warm": bpr * n / warm_ms / 1e6, "achieved": bpr * n / cold_ms / 1e6, "peak": peak, "unit": "GB/s",
                          "frac": bpr * n / cold_ms / 1e6 / peak, "frac_l2_warm": bpr * n / warm_ms / 1e6 / peak,
                          "traffic": traffic_file.get("k_glmm_data_terms_dram_bytes_per_launch"),
-                         "timing": "CUDA events around single launches (L2 flushed by a 256 MB memset before each) and around 30 back-to-back launches; "
+                         "timing": "CUDA events around single launches (L2 flushed before each by a 256 MB memset followed by a 256 MB read pass, so that the write-back of the memset's dirty lines is not charged to the launch) and around 30 back-to-back launches; "
                                    "44 MB is 7 us at peak, ~8 us of the launch are fixed cost (profiles/glmm_pass_r2.json: 0.54 - 0.67 of peak at 4 M rows)"}
         except Exception as e:      # pragma: no cover
             glmm_pass = {"error": repr(e)}
