@@ -24,6 +24,8 @@
 namespace s4b {
 
 constexpr int kGBlock = 256;
+constexpr int kGBulkWarps = 16;      // consumer warps of the bulk-copy data pass (its consumers are latency bound: 8 warps left the issue slots 70 % idle)
+constexpr int kGBulk = kGBulkWarps * 32;
 constexpr int kMaxNc = 16;         // coefficients per ranef block
 constexpr size_t kThetaSmemMax = 40 * 1024;   // coefficient vector staged in (default-limit) shared memory up to this size
 constexpr int kGFast = 4;          // fast path of the data pass: K and non-zeros per row of Z up to this
@@ -38,6 +40,7 @@ __device__ __forceinline__ double g_warp_sum(double v)
 // Shared tail of the binned data passes: the (nb + 1) x 32 lane-private bins of every consumer warp -> one partial row per CTA -> the
 // last CTA to finish sums the rows of all CTAs in CTA order.  `bins0` = the bins of warp 0, `wb` = this warp's (ignored when the
 // warp holds none: `has_bins` false, e.g. a producer warp); every thread of the block calls this.
+template <int WARPS>
 __device__ __forceinline__ void data_terms_epilogue(const GlmmDev& g, double* bins0, double* wb, bool has_bins)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -61,7 +64,7 @@ __device__ __forceinline__ void data_terms_epilogue(const GlmmDev& g, double* bi
   const int G = gridDim.x;
   for (int j = tid; j <= nb; j += blockDim.x) {
     double acc = 0.0;
-    for (int w = 0; w < kGBlock / 32; ++w) acc += bins0[(size_t) w * (nb + 1) * 32 + j * 32];
+    for (int w = 0; w < WARPS; ++w) acc += bins0[(size_t) w * (nb + 1) * 32 + j * 32];
     // value order in partials / result: S, X'e, Z'e
     int out_j = j == nb ? 0 : j + 1;
     g.partials[(long long) out_j * G + blockIdx.x] = acc;
@@ -200,12 +203,12 @@ __global__ void __launch_bounds__(kGBlock, 2) k_glmm_data_terms(GlmmDev g)
     for (int k = 0; k < KT; ++k) if (k < K) wb[k * 32 + lane] = gx[k];
   }
   wb[nb * 32 + lane] = S;
-  data_terms_epilogue(g, smem + nb, wb, true);
+  data_terms_epilogue<kGBlock / 32>(g, smem + nb, wb, true);
 }
 
 // ---------------------------------------------------------------------------------------
 // The same pass with the operand streams staged through shared memory by the bulk-copy engine (TMA, cp.async.bulk + mbarrier):
-// one persistent CTA per SM, 8 consumer warps + 1 producer warp, a ring of `stages` tiles of `tile` observations.  The producer
+// one persistent CTA per SM, 16 consumer warps + 1 producer warp, a ring of `stages` tiles of `tile` observations.  The producer
 // keeps `stages` tiles (~45 KB each for the Friedman model) in flight per SM regardless of what the consumers are doing, so the
 // memory system never waits for the arithmetic and the consumers need no registers for loads in flight -- the register version
 // above alternates between a burst of loads and a burst of shared-memory bin updates (ncu: long scoreboard, 2.1 TB/s).
@@ -229,7 +232,7 @@ constexpr int kGMaxStages = 4;
 struct BulkBars { unsigned long long full[kGMaxStages], empty[kGMaxStages]; };
 
 template <int KT, int ST>
-__global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDev g, int tile, int stages, int tile_bytes)
+__global__ void __launch_bounds__(kGBulk + 32, 1) k_glmm_data_terms_bulk(GlmmDev g, int tile, int stages, int tile_bytes)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BulkBars& bars = *reinterpret_cast<BulkBars*>(smem_raw);
@@ -237,25 +240,25 @@ __global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDe
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = g.K + g.q, K = g.K, slots = g.slots;
   double* bins0 = sth + nb;
-  double* wb = bins0 + (size_t) (warp < kGBlock / 32 ? warp : 0) * (nb + 1) * 32;
-  unsigned char* ring = smem_raw + (((sizeof(BulkBars) + sizeof(double) * ((size_t) nb + (size_t) (kGBlock / 32) * (nb + 1) * 32)) + 127) / 128) * 128;
+  double* wb = bins0 + (size_t) (warp < kGBulkWarps ? warp : 0) * (nb + 1) * 32;
+  unsigned char* ring = smem_raw + (((sizeof(BulkBars) + sizeof(double) * ((size_t) nb + (size_t) (kGBulkWarps) * (nb + 1) * 32)) + 127) / 128) * 128;
   const bool weighted = g.wt != nullptr;
   if (tid == 0) {
-    for (int s_ = 0; s_ < stages; ++s_) { mbar_init(&bars.full[s_], 1u); mbar_init(&bars.empty[s_], (unsigned) (kGBlock / 32)); }
+    for (int s_ = 0; s_ < stages; ++s_) { mbar_init(&bars.full[s_], 1u); mbar_init(&bars.empty[s_], (unsigned) (kGBulkWarps)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();                                      // the barriers exist: the producer starts streaming at once
-  if (warp < kGBlock / 32) {
+  if (warp < kGBulkWarps) {
     // consumers: coefficients and zeroed bins while the first tiles are in flight
-    for (int j = tid; j < nb; j += kGBlock) sth[j] = g.theta[j];
+    for (int j = tid; j < nb; j += kGBulk) sth[j] = g.theta[j];
     for (int j = lane; j < (nb + 1) * 32; j += 32) wb[j] = 0.0;
-    asm volatile("bar.sync 1, %0;" ::"n"(kGBlock) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kGBulk) : "memory");
   }
   const long long N = g.N, npad = g.npad;
   const long long ntiles = (N + tile - 1) / tile;
   // stream offsets inside a tile
   const int off_w = tile * 8, off_x = off_w + (weighted ? tile * 8 : 0), off_i = off_x + K * tile * 8, off_v = off_i + slots * tile * 4;
-  if (warp == kGBlock / 32) {
+  if (warp == kGBulkWarps) {
     // ------------------------------------------------------------- producer warp: one lane issues the bulk copies
     if (lane == 0) {
       int k = 0;
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDe
     const unsigned char* src = ring + (unsigned) st * (unsigned) tile_bytes;
     const long long base = t * tile;
     const int rows_here = (int) (N - base < tile ? N - base : tile);       // rows of this tile that exist
-    for (int o = 2 * tid; o < rows_here; o += 2 * kGBlock) {
+    for (int o = 2 * tid; o < rows_here; o += 2 * kGBulk) {
       const bool second = o + 1 < rows_here;
       const unsigned char* p8 = src + o * 8;
       const unsigned char* p4 = src + o * 4;
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(kGBlock + 32, 1) k_glmm_data_terms_bulk(GlmmDe
   wb[nb * 32 + lane] = S;
   }
   // one call site for the whole block: the epilogue's block-wide barriers must be reached by producer and consumers alike
-  data_terms_epilogue(g, bins0, wb, warp < kGBlock / 32);
+  data_terms_epilogue<kGBulkWarps>(g, bins0, wb, warp < kGBulkWarps);
 }
 
 using DataTermsBulkKernel = void (*)(GlmmDev, int, int, int);
@@ -682,7 +685,7 @@ GlmmModel::GlmmModel(const s4b_glmm_data& d, cudaStream_t stream, ShardContext* 
     int nval = 0;
     for (int s = 0; s < slots_; ++s) nval += ((ones_mask_ >> s) & 1u) ? 0 : 1;
     const size_t per_obs = 8u * (size_t) (1 + (d.weights != nullptr ? 1 : 0) + K_ + nval) + 4u * (size_t) slots_;
-    const size_t head = ((sizeof(BulkBars) + smem_bytes_ + 127) / 128) * 128;
+    const size_t head = ((sizeof(BulkBars) + sizeof(double) * ((size_t) nb + (size_t) kGBulkWarps * (nb + 1) * 32) + 127) / 128) * 128;
     for (int tile : { 1024, 512, 256 }) {
       const size_t need = head + 3 * (size_t) tile * per_obs;
       if (need <= (size_t) max_smem) { bulk_tile_ = tile; bulk_stages_ = 3; bulk_tile_bytes_ = (int) ((size_t) tile * per_obs); bulk_smem_ = need; break; }
@@ -959,7 +962,7 @@ void GlmmModel::launch_data_pass()
   if (!columns_ && bulk_) {
     int tile = bulk_tile_, stages = bulk_stages_, tile_bytes = bulk_tile_bytes_;
     void* args[] = { &g, &tile, &stages, &tile_bytes };
-    S4B_CUDA(cudaLaunchKernel((const void*) data_terms_bulk_kernel(K_, slots_), dim3(bulk_grid_), dim3(kGBlock + 32), args, bulk_smem_, stream_));
+    S4B_CUDA(cudaLaunchKernel((const void*) data_terms_bulk_kernel(K_, slots_), dim3(bulk_grid_), dim3(kGBulk + 32), args, bulk_smem_, stream_));
   } else if (!columns_) {
     void* args[] = { &g };
     S4B_CUDA(cudaLaunchKernel((const void*) data_terms_kernel(K_, slots_), dim3(grid_), dim3(kGBlock), args, smem_bytes_, stream_));
