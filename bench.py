@@ -664,7 +664,7 @@ def run_ours(args):
                          "frac": bpr * n / cold_ms / 1e6 / peak, "frac_l2_warm": bpr * n / warm_ms / 1e6 / peak,
                          "traffic": traffic_file.get("k_glmm_data_terms_dram_bytes_per_launch"),
                          "timing": "CUDA events around single launches (L2 flushed before each by a 256 MB memset followed by a 256 MB read pass, so that the write-back of the memset's dirty lines is not charged to the launch) and around 30 back-to-back launches; "
-                                   "44 MB is 7 us at peak, ~8 us of the launch are fixed cost (profiles/glmm_pass_r2.json: 0.54 - 0.67 of peak at 4 M rows)"}
+                                   "44 MB is 7 us at peak, ~8 us of the launch are fixed cost (profiles/glmm_pass_r2b.json: 9 us for 70 000 rows; 0.68 / 0.73 of peak at 4 M rows)"}
         except Exception as e:      # pragma: no cover
             glmm_pass = {"error": repr(e)}
     roofline = {"bound": "hbm", "kernel": ("k_sweep_pipe + k_sweep (one sweep = one %d-tree pass over all rows: the pipelined kernel takes the steps that fit it, "
